@@ -1,0 +1,383 @@
+// polyrl_b200 — Python bindings (pybind11 through torch) for the sm_100a kernels in csrc/*.cu.
+// Kernel translation units are torch-free (raw pointers + cudaStream_t) so they compile in seconds;
+// this file is the only one that sees torch headers.
+#include <ATen/cuda/CUDAContext.h>
+#include <c10/cuda/CUDAGuard.h>
+#include <torch/extension.h>
+
+#include <cstdint>
+#include <string>
+#include <vector>
+
+extern "C" {
+int prl_gemm_bf16(const void*, const void*, void*, const void*, int, int, int, int64_t, int64_t, int64_t, int, cudaStream_t);
+int prl_gemm_fp8(const void*, const void*, void*, const float*, const float*, int, int, int, int64_t, int64_t, int64_t, int, cudaStream_t);
+int prl_gemm_swiglu_bf16(const void*, const void*, void*, void*, int, int, int, int64_t, int64_t, int64_t, int64_t, cudaStream_t);
+int prl_linear_ce_num_splits(int, int);
+int prl_linear_ce_fwd(const void*, const void*, const int64_t*, float, int, int, int, int64_t, int64_t, float*, int, float*, float*, float*, float*, cudaStream_t);
+int prl_linear_ce_dz(const void*, const void*, const int64_t*, const float*, const float*, const float*, const float*, float, int, int, int, int, int64_t, int64_t, void*, int64_t, cudaStream_t);
+int prl_rmsnorm_fwd(const void*, const void*, void*, float*, int, int, float, cudaStream_t);
+int prl_rmsnorm_bwd(const void*, const void*, const void*, const float*, void*, float*, int, int, cudaStream_t);
+int prl_rope(void*, const int64_t*, const float*, const float*, int, int, int, int, int64_t, float, void*, void*, const int64_t*, int, cudaStream_t);
+int prl_swiglu_bwd(const void*, const void*, void*, int64_t, int, cudaStream_t);
+int prl_quant_fp8_rowwise(const void*, void*, float*, int, int, cudaStream_t);
+int prl_grad_accum(float*, const void*, int, float, int64_t, float*, cudaStream_t);
+int prl_sumsq(const float*, int64_t, float*, cudaStream_t);
+int prl_adamw(float*, float*, float*, float*, void*, int64_t, float, float, float, float, float, int, float, const float*, int*, int, cudaStream_t);
+int prl_paged_decode_workspace_floats(int, int, int, int);
+int prl_paged_decode(const void*, int64_t, const void*, const void*, const int32_t*, int64_t, const int32_t*, int, int, int, int, float, int, float*, void*, int64_t, cudaStream_t);
+int prl_sample(const void*, int, int64_t, int, int, const float*, const uint64_t*, int, int64_t*, float*, cudaStream_t);
+int prl_ipc_get_handle(void*, void*);
+int prl_ipc_open_handle(const void*, void**);
+int prl_ipc_close_handle(void*);
+int prl_cuda_malloc(void**, int64_t);
+int prl_cuda_free(void*);
+int prl_enable_peer_access(int);
+int prl_p2p_barrier(void* const*, int, int, uint32_t, cudaStream_t);
+int prl_p2p_copy(const void*, void*, int64_t, int, cudaStream_t);
+int prl_p2p_push_fp8(const void*, void*, float*, int, int, int, cudaStream_t);
+int prl_p2p_allgather_pull(void* const*, void*, int64_t, int, int, int, cudaStream_t);
+int prl_p2p_reduce_scatter_accum(void* const*, int64_t, float*, int64_t, float, int, int, float*, int, cudaStream_t);
+int prl_ag_gemm_bf16(const void*, void* const*, void*, void*, uint32_t*, uint32_t, int, int, int, int64_t, int64_t, int, int, int, cudaStream_t);
+}
+
+namespace {
+
+inline cudaStream_t cur_stream() { return at::cuda::getCurrentCUDAStream().stream(); }
+
+inline void check(int rc, const char* what) {
+  TORCH_CHECK(rc == 0, "polyrl_b200 kernel '", what, "' failed with code ", rc);
+}
+#define CHECK_BF16(t) TORCH_CHECK((t).is_cuda() && (t).scalar_type() == at::kBFloat16, #t " must be a CUDA bf16 tensor")
+#define CHECK_F32(t) TORCH_CHECK((t).is_cuda() && (t).scalar_type() == at::kFloat, #t " must be a CUDA fp32 tensor")
+#define CHECK_LASTDIM(t) TORCH_CHECK((t).stride(-1) == 1, #t " must be contiguous in the last dim")
+
+at::Tensor gemm_bf16(const at::Tensor& a, const at::Tensor& b, const c10::optional<at::Tensor>& residual,
+                     c10::optional<at::Tensor> out, int64_t force_bn) {
+  CHECK_BF16(a); CHECK_BF16(b);
+  TORCH_CHECK(a.dim() == 2 && b.dim() == 2 && a.size(1) == b.size(1), "gemm_bf16: A[M,K] B[N,K]");
+  CHECK_LASTDIM(a); CHECK_LASTDIM(b);
+  const int M = a.size(0), K = a.size(1), N = b.size(0);
+  TORCH_CHECK(K % 8 == 0 && N % 8 == 0, "K and N must be multiples of 8");
+  TORCH_CHECK(a.stride(0) % 8 == 0 && b.stride(0) % 8 == 0, "row pitch must be a multiple of 8 elements");
+  c10::cuda::CUDAGuard g(a.device());
+  at::Tensor d = out.has_value() ? *out : at::empty({M, N}, a.options());
+  CHECK_BF16(d); CHECK_LASTDIM(d);
+  const void* r = nullptr;
+  if (residual.has_value()) {
+    CHECK_BF16(*residual);
+    TORCH_CHECK(residual->sizes() == d.sizes() && residual->stride(0) == d.stride(0) && residual->stride(1) == 1);
+    r = residual->data_ptr();
+  }
+  check(prl_gemm_bf16(a.data_ptr(), b.data_ptr(), d.data_ptr(), r, M, N, K, a.stride(0), b.stride(0), d.stride(0),
+                      static_cast<int>(force_bn), cur_stream()), "gemm_bf16");
+  return d;
+}
+
+at::Tensor gemm_fp8(const at::Tensor& a, const at::Tensor& b, const at::Tensor& row_scale, const at::Tensor& col_scale,
+                    int64_t force_bn) {
+  TORCH_CHECK(a.is_cuda() && b.is_cuda() && a.element_size() == 1 && b.element_size() == 1, "fp8 operands expected");
+  CHECK_F32(row_scale); CHECK_F32(col_scale);
+  const int M = a.size(0), K = a.size(1), N = b.size(0);
+  TORCH_CHECK(b.size(1) == K && K % 16 == 0 && N % 8 == 0);
+  c10::cuda::CUDAGuard g(a.device());
+  at::Tensor d = at::empty({M, N}, a.options().dtype(at::kBFloat16));
+  check(prl_gemm_fp8(a.data_ptr(), b.data_ptr(), d.data_ptr(), row_scale.data_ptr<float>(),
+                     col_scale.data_ptr<float>(), M, N, K, a.stride(0), b.stride(0), d.stride(0),
+                     static_cast<int>(force_bn), cur_stream()), "gemm_fp8");
+  return d;
+}
+
+std::vector<at::Tensor> gemm_swiglu(const at::Tensor& a, const at::Tensor& wgu, bool save_gu) {
+  CHECK_BF16(a); CHECK_BF16(wgu); CHECK_LASTDIM(a); CHECK_LASTDIM(wgu);
+  const int M = a.size(0), K = a.size(1), N2 = wgu.size(0);
+  TORCH_CHECK(wgu.size(1) == K && N2 % 256 == 0 && K % 8 == 0);
+  c10::cuda::CUDAGuard g(a.device());
+  at::Tensor h = at::empty({M, N2 / 2}, a.options());
+  at::Tensor gu = save_gu ? at::empty({M, N2}, a.options()) : at::Tensor();
+  check(prl_gemm_swiglu_bf16(a.data_ptr(), wgu.data_ptr(), h.data_ptr(), save_gu ? gu.data_ptr() : nullptr, M, N2, K,
+                             a.stride(0), wgu.stride(0), h.stride(0), save_gu ? gu.stride(0) : 0, cur_stream()),
+        "gemm_swiglu");
+  if (save_gu) return {h, gu};
+  return {h};
+}
+
+std::vector<at::Tensor> linear_ce_fwd(const at::Tensor& hidden, const at::Tensor& w, const at::Tensor& labels,
+                                      double inv_tau) {
+  CHECK_BF16(hidden); CHECK_BF16(w); CHECK_LASTDIM(hidden); CHECK_LASTDIM(w);
+  TORCH_CHECK(labels.is_cuda() && labels.scalar_type() == at::kLong && labels.is_contiguous());
+  const int T = hidden.size(0), H = hidden.size(1), V = w.size(0);
+  TORCH_CHECK(w.size(1) == H && labels.numel() == T && H % 8 == 0);
+  c10::cuda::CUDAGuard g(hidden.device());
+  const int S = prl_linear_ce_num_splits(T, V);
+  auto fopt = hidden.options().dtype(at::kFloat);
+  at::Tensor scratch = at::empty({static_cast<int64_t>(T) * (3 * S + 1)}, fopt);
+  at::Tensor lp = at::empty({T}, fopt), ent = at::empty({T}, fopt), lse = at::empty({T}, fopt), ez = at::empty({T}, fopt);
+  check(prl_linear_ce_fwd(hidden.data_ptr(), w.data_ptr(), labels.data_ptr<int64_t>(), static_cast<float>(inv_tau), T,
+                          V, H, hidden.stride(0), w.stride(0), scratch.data_ptr<float>(), S, lp.data_ptr<float>(),
+                          ent.data_ptr<float>(), lse.data_ptr<float>(), ez.data_ptr<float>(), cur_stream()),
+        "linear_ce_fwd");
+  return {lp, ent, lse, ez};
+}
+
+at::Tensor linear_ce_dz(const at::Tensor& hidden, const at::Tensor& w_slice, const at::Tensor& labels,
+                        const at::Tensor& lse, const at::Tensor& ez, const c10::optional<at::Tensor>& g_lp,
+                        const c10::optional<at::Tensor>& g_ent, double inv_tau, int64_t v0) {
+  CHECK_BF16(hidden); CHECK_BF16(w_slice); CHECK_F32(lse); CHECK_F32(ez);
+  const int T = hidden.size(0), H = hidden.size(1), Vc = w_slice.size(0);
+  TORCH_CHECK(Vc % 8 == 0);
+  c10::cuda::CUDAGuard g(hidden.device());
+  at::Tensor dz = at::empty({T, Vc}, hidden.options());
+  const float* glp = g_lp.has_value() ? g_lp->data_ptr<float>() : nullptr;
+  const float* gent = g_ent.has_value() ? g_ent->data_ptr<float>() : nullptr;
+  check(prl_linear_ce_dz(hidden.data_ptr(), w_slice.data_ptr(), labels.data_ptr<int64_t>(), lse.data_ptr<float>(),
+                         ez.data_ptr<float>(), glp, gent, static_cast<float>(inv_tau), T, Vc, H, static_cast<int>(v0),
+                         hidden.stride(0), w_slice.stride(0), dz.data_ptr(), dz.stride(0), cur_stream()),
+        "linear_ce_dz");
+  return dz;
+}
+
+std::vector<at::Tensor> rmsnorm_fwd(const at::Tensor& x, const at::Tensor& w, double eps) {
+  CHECK_BF16(x); CHECK_BF16(w);
+  TORCH_CHECK(x.is_contiguous() && w.is_contiguous());
+  const int H = x.size(-1);
+  const int T = x.numel() / H;
+  c10::cuda::CUDAGuard g(x.device());
+  at::Tensor y = at::empty_like(x);
+  at::Tensor rstd = at::empty({T}, x.options().dtype(at::kFloat));
+  check(prl_rmsnorm_fwd(x.data_ptr(), w.data_ptr(), y.data_ptr(), rstd.data_ptr<float>(), T, H,
+                        static_cast<float>(eps), cur_stream()), "rmsnorm_fwd");
+  return {y, rstd};
+}
+
+std::vector<at::Tensor> rmsnorm_bwd(const at::Tensor& x, const at::Tensor& w, const at::Tensor& dy,
+                                    const at::Tensor& rstd) {
+  CHECK_BF16(x); CHECK_BF16(w); CHECK_BF16(dy); CHECK_F32(rstd);
+  TORCH_CHECK(x.is_contiguous() && dy.is_contiguous());
+  const int H = x.size(-1);
+  const int T = x.numel() / H;
+  c10::cuda::CUDAGuard g(x.device());
+  at::Tensor dx = at::empty_like(x);
+  at::Tensor dw = at::zeros({H}, x.options().dtype(at::kFloat));
+  check(prl_rmsnorm_bwd(x.data_ptr(), w.data_ptr(), dy.data_ptr(), rstd.data_ptr<float>(), dx.data_ptr(),
+                        dw.data_ptr<float>(), T, H, cur_stream()), "rmsnorm_bwd");
+  return {dx, dw};
+}
+
+void rope_(at::Tensor qkv, const at::Tensor& pos, const at::Tensor& cos_tab, const at::Tensor& sin_tab, int64_t nq,
+           int64_t nkv, int64_t d, double sign, const c10::optional<at::Tensor>& k_cache,
+           const c10::optional<at::Tensor>& v_cache, const c10::optional<at::Tensor>& slot_mapping,
+           int64_t block_size) {
+  CHECK_BF16(qkv); CHECK_F32(cos_tab); CHECK_F32(sin_tab);
+  TORCH_CHECK(pos.is_cuda() && pos.scalar_type() == at::kLong && pos.is_contiguous());
+  TORCH_CHECK(qkv.dim() == 2 && qkv.stride(1) == 1);
+  c10::cuda::CUDAGuard g(qkv.device());
+  void* kc = nullptr; void* vc = nullptr; const int64_t* sm = nullptr;
+  if (slot_mapping.has_value()) {
+    TORCH_CHECK(k_cache.has_value() && v_cache.has_value());
+    kc = k_cache->data_ptr(); vc = v_cache->data_ptr();
+    TORCH_CHECK(slot_mapping->scalar_type() == at::kLong);
+    sm = slot_mapping->data_ptr<int64_t>();
+  }
+  check(prl_rope(qkv.data_ptr(), pos.data_ptr<int64_t>(), cos_tab.data_ptr<float>(), sin_tab.data_ptr<float>(),
+                 qkv.size(0), nq, nkv, d, qkv.stride(0), static_cast<float>(sign), kc, vc, sm, block_size,
+                 cur_stream()), "rope");
+}
+
+at::Tensor swiglu_bwd(const at::Tensor& gu, const at::Tensor& dh) {
+  CHECK_BF16(gu); CHECK_BF16(dh);
+  TORCH_CHECK(gu.is_contiguous() && dh.is_contiguous());
+  const int F = dh.size(-1);
+  const int64_t T = dh.numel() / F;
+  c10::cuda::CUDAGuard g(gu.device());
+  at::Tensor dgu = at::empty_like(gu);
+  check(prl_swiglu_bwd(gu.data_ptr(), dh.data_ptr(), dgu.data_ptr(), T, F, cur_stream()), "swiglu_bwd");
+  return dgu;
+}
+
+std::vector<at::Tensor> quant_fp8_rowwise(const at::Tensor& x) {
+  CHECK_BF16(x); TORCH_CHECK(x.is_contiguous() && x.dim() == 2);
+  c10::cuda::CUDAGuard g(x.device());
+  at::Tensor q = at::empty(x.sizes(), x.options().dtype(at::kFloat8_e4m3fn));
+  at::Tensor s = at::empty({x.size(0)}, x.options().dtype(at::kFloat));
+  check(prl_quant_fp8_rowwise(x.data_ptr(), q.data_ptr(), s.data_ptr<float>(), x.size(0), x.size(1), cur_stream()),
+        "quant_fp8_rowwise");
+  return {q, s};
+}
+
+void grad_accum_(at::Tensor acc, const at::Tensor& g, double scale, const c10::optional<at::Tensor>& sumsq) {
+  CHECK_F32(acc); TORCH_CHECK(acc.is_contiguous() && g.is_contiguous() && acc.numel() == g.numel());
+  const int dt = g.scalar_type() == at::kFloat ? 0 : 1;
+  TORCH_CHECK(dt == 0 || g.scalar_type() == at::kBFloat16);
+  c10::cuda::CUDAGuard gd(acc.device());
+  check(prl_grad_accum(acc.data_ptr<float>(), g.data_ptr(), dt, static_cast<float>(scale), acc.numel(),
+                       sumsq.has_value() ? sumsq->data_ptr<float>() : nullptr, cur_stream()), "grad_accum");
+}
+
+void sumsq_(const at::Tensor& g, at::Tensor out) {
+  CHECK_F32(g); CHECK_F32(out);
+  c10::cuda::CUDAGuard gd(g.device());
+  check(prl_sumsq(g.data_ptr<float>(), g.numel(), out.data_ptr<float>(), cur_stream()), "sumsq");
+}
+
+void adamw_(at::Tensor master, at::Tensor m, at::Tensor v, at::Tensor grad, const c10::optional<at::Tensor>& param_bf16,
+            double lr, double beta1, double beta2, double eps, double wd, int64_t step, double max_norm,
+            const c10::optional<at::Tensor>& total_sumsq, const c10::optional<at::Tensor>& status, bool zero_grad) {
+  CHECK_F32(master); CHECK_F32(m); CHECK_F32(v); CHECK_F32(grad);
+  TORCH_CHECK(master.is_contiguous() && m.is_contiguous() && v.is_contiguous() && grad.is_contiguous());
+  c10::cuda::CUDAGuard gd(master.device());
+  void* pb = nullptr;
+  if (param_bf16.has_value()) { CHECK_BF16(*param_bf16); TORCH_CHECK(param_bf16->is_contiguous()); pb = param_bf16->data_ptr(); }
+  check(prl_adamw(master.data_ptr<float>(), m.data_ptr<float>(), v.data_ptr<float>(), grad.data_ptr<float>(), pb,
+                  master.numel(), lr, beta1, beta2, eps, wd, static_cast<int>(step), max_norm,
+                  total_sumsq.has_value() ? total_sumsq->data_ptr<float>() : nullptr,
+                  status.has_value() ? status->data_ptr<int>() : nullptr, zero_grad ? 1 : 0, cur_stream()), "adamw");
+}
+
+at::Tensor paged_decode(const at::Tensor& q, const at::Tensor& k_cache, const at::Tensor& v_cache,
+                        const at::Tensor& block_table, const at::Tensor& seq_lens, int64_t nq, int64_t nkv, int64_t d,
+                        double sm_scale, int64_t splits, c10::optional<at::Tensor> out) {
+  CHECK_BF16(q); CHECK_BF16(k_cache); CHECK_BF16(v_cache);
+  TORCH_CHECK(block_table.scalar_type() == at::kInt && seq_lens.scalar_type() == at::kInt);
+  TORCH_CHECK(q.dim() == 2 && q.stride(1) == 1 && k_cache.is_contiguous() && v_cache.is_contiguous());
+  TORCH_CHECK(k_cache.size(2) == 16, "KV page size must be 16 tokens");
+  const int B = q.size(0);
+  c10::cuda::CUDAGuard g(q.device());
+  at::Tensor o = out.has_value() ? *out : at::empty({B, nq * d}, q.options());
+  const int64_t ws = prl_paged_decode_workspace_floats(B, nq, d, splits);
+  at::Tensor workspace = at::empty({ws}, q.options().dtype(at::kFloat));
+  check(prl_paged_decode(q.data_ptr(), q.stride(0), k_cache.data_ptr(), v_cache.data_ptr(),
+                         block_table.data_ptr<int32_t>(), block_table.stride(0), seq_lens.data_ptr<int32_t>(), B, nq,
+                         nkv, d, static_cast<float>(sm_scale), splits, workspace.data_ptr<float>(), o.data_ptr(),
+                         o.stride(0), cur_stream()), "paged_decode");
+  return o;
+}
+
+std::vector<at::Tensor> sample(const at::Tensor& logits, const c10::optional<at::Tensor>& inv_temp,
+                               const c10::optional<at::Tensor>& seeds, bool greedy) {
+  TORCH_CHECK(logits.is_cuda() && logits.dim() == 2 && logits.stride(1) == 1);
+  const int dt = logits.scalar_type() == at::kFloat ? 0 : 1;
+  TORCH_CHECK(dt == 0 || logits.scalar_type() == at::kBFloat16);
+  const int B = logits.size(0), V = logits.size(1);
+  c10::cuda::CUDAGuard g(logits.device());
+  at::Tensor tok = at::empty({B}, logits.options().dtype(at::kLong));
+  at::Tensor lp = at::empty({B}, logits.options().dtype(at::kFloat));
+  const uint64_t* sd = nullptr;
+  if (seeds.has_value()) { TORCH_CHECK(seeds->scalar_type() == at::kLong); sd = reinterpret_cast<const uint64_t*>(seeds->data_ptr<int64_t>()); }
+  check(prl_sample(logits.data_ptr(), dt, logits.stride(0), B, V,
+                   inv_temp.has_value() ? inv_temp->data_ptr<float>() : nullptr, sd, greedy ? 1 : 0,
+                   tok.data_ptr<int64_t>(), lp.data_ptr<float>(), cur_stream()), "sample");
+  return {tok, lp};
+}
+
+// ---------------------------------------------------------------- symmetric heap / peer kernels
+int64_t sym_malloc(int64_t bytes) {
+  void* p = nullptr;
+  check(prl_cuda_malloc(&p, bytes), "cuda_malloc");
+  return reinterpret_cast<int64_t>(p);
+}
+void sym_free(int64_t ptr) { check(prl_cuda_free(reinterpret_cast<void*>(ptr)), "cuda_free"); }
+py::bytes ipc_get_handle(int64_t ptr) {
+  char buf[64];
+  check(prl_ipc_get_handle(reinterpret_cast<void*>(ptr), buf), "ipc_get_handle");
+  return py::bytes(buf, 64);
+}
+int64_t ipc_open_handle(const std::string& h) {
+  TORCH_CHECK(h.size() == 64);
+  void* p = nullptr;
+  check(prl_ipc_open_handle(h.data(), &p), "ipc_open_handle");
+  return reinterpret_cast<int64_t>(p);
+}
+void ipc_close_handle(int64_t ptr) { check(prl_ipc_close_handle(reinterpret_cast<void*>(ptr)), "ipc_close_handle"); }
+void enable_peer_access(int64_t dev) { check(prl_enable_peer_access(static_cast<int>(dev)), "enable_peer_access"); }
+
+at::Tensor tensor_from_ptr(int64_t ptr, std::vector<int64_t> sizes, at::ScalarType dtype, int64_t device) {
+  auto opts = at::TensorOptions().dtype(dtype).device(at::kCUDA, device);
+  return at::from_blob(reinterpret_cast<void*>(ptr), sizes, [](void*) {}, opts);
+}
+
+std::vector<void*> to_ptrs(const std::vector<int64_t>& v) {
+  std::vector<void*> r;
+  for (auto x : v) r.push_back(reinterpret_cast<void*>(x));
+  return r;
+}
+
+void p2p_barrier(const std::vector<int64_t>& flag_ptrs, int64_t rank, int64_t epoch) {
+  auto p = to_ptrs(flag_ptrs);
+  check(prl_p2p_barrier(p.data(), rank, p.size(), static_cast<uint32_t>(epoch), cur_stream()), "p2p_barrier");
+}
+void p2p_copy(int64_t src, int64_t dst, int64_t nbytes, int64_t max_ctas) {
+  check(prl_p2p_copy(reinterpret_cast<void*>(src), reinterpret_cast<void*>(dst), nbytes, max_ctas, cur_stream()), "p2p_copy");
+}
+void p2p_push_fp8(const at::Tensor& src, int64_t dst_q, int64_t dst_scale, int64_t max_ctas) {
+  CHECK_BF16(src); TORCH_CHECK(src.is_contiguous() && src.dim() == 2);
+  check(prl_p2p_push_fp8(src.data_ptr(), reinterpret_cast<void*>(dst_q), reinterpret_cast<float*>(dst_scale),
+                         src.size(0), src.size(1), max_ctas, cur_stream()), "p2p_push_fp8");
+}
+void p2p_allgather_pull(const std::vector<int64_t>& shard_ptrs, int64_t out, int64_t shard_bytes, int64_t rank,
+                        int64_t max_ctas) {
+  auto p = to_ptrs(shard_ptrs);
+  check(prl_p2p_allgather_pull(p.data(), reinterpret_cast<void*>(out), shard_bytes, rank, p.size(), max_ctas,
+                               cur_stream()), "p2p_allgather_pull");
+}
+void p2p_reduce_scatter_accum(const std::vector<int64_t>& grad_ptrs, int64_t shard_off, at::Tensor acc, double scale,
+                              int64_t rank, const c10::optional<at::Tensor>& sumsq, int64_t max_ctas) {
+  CHECK_F32(acc);
+  auto p = to_ptrs(grad_ptrs);
+  check(prl_p2p_reduce_scatter_accum(p.data(), shard_off, acc.data_ptr<float>(), acc.numel(), scale, p.size(), rank,
+                                     sumsq.has_value() ? sumsq->data_ptr<float>() : nullptr, max_ctas, cur_stream()),
+        "p2p_reduce_scatter_accum");
+}
+
+// All-gather fused GEMM: D = A · gather(W_shards)^T with the gather done by copy warps of the same kernel.
+at::Tensor ag_gemm_bf16(const at::Tensor& a, const std::vector<int64_t>& shard_ptrs, int64_t gathered_ptr,
+                        int64_t flags_ptr, int64_t epoch, int64_t rows_per_rank, int64_t rank, int64_t comm_chunks) {
+  CHECK_BF16(a); CHECK_LASTDIM(a);
+  const int M = a.size(0), K = a.size(1);
+  const int world = shard_ptrs.size();
+  const int N = rows_per_rank * world;
+  c10::cuda::CUDAGuard g(a.device());
+  at::Tensor d = at::empty({M, N}, a.options());
+  auto p = to_ptrs(shard_ptrs);
+  check(prl_ag_gemm_bf16(a.data_ptr(), p.data(), reinterpret_cast<void*>(gathered_ptr), d.data_ptr(),
+                         reinterpret_cast<uint32_t*>(flags_ptr), static_cast<uint32_t>(epoch), M, N, K, a.stride(0),
+                         d.stride(0), world, rank, comm_chunks, cur_stream()), "ag_gemm_bf16");
+  return d;
+}
+
+}  // namespace
+
+PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
+  m.def("gemm_bf16", &gemm_bf16, py::arg("a"), py::arg("b"), py::arg("residual") = py::none(),
+        py::arg("out") = py::none(), py::arg("force_bn") = 0);
+  m.def("gemm_fp8", &gemm_fp8, py::arg("a"), py::arg("b"), py::arg("row_scale"), py::arg("col_scale"),
+        py::arg("force_bn") = 0);
+  m.def("gemm_swiglu", &gemm_swiglu);
+  m.def("linear_ce_fwd", &linear_ce_fwd);
+  m.def("linear_ce_dz", &linear_ce_dz);
+  m.def("rmsnorm_fwd", &rmsnorm_fwd);
+  m.def("rmsnorm_bwd", &rmsnorm_bwd);
+  m.def("rope_", &rope_);
+  m.def("swiglu_bwd", &swiglu_bwd);
+  m.def("quant_fp8_rowwise", &quant_fp8_rowwise);
+  m.def("grad_accum_", &grad_accum_);
+  m.def("sumsq_", &sumsq_);
+  m.def("adamw_", &adamw_);
+  m.def("paged_decode", &paged_decode, py::arg("q"), py::arg("k_cache"), py::arg("v_cache"), py::arg("block_table"),
+        py::arg("seq_lens"), py::arg("nq"), py::arg("nkv"), py::arg("d"), py::arg("sm_scale"), py::arg("splits") = 1,
+        py::arg("out") = py::none());
+  m.def("sample", &sample);
+  m.def("sym_malloc", &sym_malloc);
+  m.def("sym_free", &sym_free);
+  m.def("ipc_get_handle", &ipc_get_handle);
+  m.def("ipc_open_handle", &ipc_open_handle);
+  m.def("ipc_close_handle", &ipc_close_handle);
+  m.def("enable_peer_access", &enable_peer_access);
+  m.def("tensor_from_ptr", &tensor_from_ptr);
+  m.def("p2p_barrier", &p2p_barrier);
+  m.def("p2p_copy", &p2p_copy);
+  m.def("p2p_push_fp8", &p2p_push_fp8);
+  m.def("p2p_allgather_pull", &p2p_allgather_pull);
+  m.def("p2p_reduce_scatter_accum", &p2p_reduce_scatter_accum);
+  m.def("ag_gemm_bf16", &ag_gemm_bf16);
+}

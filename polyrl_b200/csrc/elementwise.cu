@@ -1,0 +1,333 @@
+// polyrl_b200 — memory-bound transformer kernels: RMSNorm fwd/bwd, RoPE (+ paged-KV append),
+// SwiGLU backward, per-row fp8 quantisation.  All are 128-bit vectorised, one pass over HBM.
+//
+// Reference capability: HF eager RMSNorm/RoPE/SiLU·mul (optionally liger Triton) inside the verl
+// FSDP actor (3rdparty/verl/verl/workers/fsdp_workers.py:386-389, models/transformers/*).
+#include "common.cuh"
+
+namespace prl {
+
+constexpr int kNormThreads = 256;
+constexpr int kMaxVPT = 4;   // up to H = 256*8*4 = 8192
+
+__device__ __forceinline__ float block_sum_256(float v, float* red) {
+  v = warp_sum(v);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __syncthreads();
+  if (l == 0) red[w] = v;
+  __syncthreads();
+  float t = (l < kNormThreads / 32) ? red[l] : 0.f;
+  t = warp_sum(t);
+  return t;
+}
+
+// y = x * rsqrt(mean(x^2)+eps) * w ; rstd saved for backward.
+__global__ void __launch_bounds__(kNormThreads)
+rmsnorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ w,
+                   __nv_bfloat16* __restrict__ y, float* __restrict__ rstd_out, int T, int H, float eps) {
+  __shared__ float red[8];
+  const int nvec = H >> 3;
+  int4 wv[kMaxVPT];
+#pragma unroll
+  for (int i = 0; i < kMaxVPT; ++i) {
+    const int v = threadIdx.x + i * kNormThreads;
+    if (v < nvec) wv[i] = *reinterpret_cast<const int4*>(w + 8 * v);
+  }
+  for (int row = blockIdx.x; row < T; row += gridDim.x) {
+    const __nv_bfloat16* xr = x + static_cast<int64_t>(row) * H;
+    int4 xv[kMaxVPT];
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < kMaxVPT; ++i) {
+      const int v = threadIdx.x + i * kNormThreads;
+      if (v < nvec) {
+        xv[i] = ld_nc_v4(xr + 8 * v);
+        const uint32_t* u = reinterpret_cast<const uint32_t*>(&xv[i]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = unpack_bf16(u[j]);
+          ss += f.x * f.x + f.y * f.y;
+        }
+      }
+    }
+    ss = block_sum_256(ss, red);
+    const float rstd = rsqrtf(ss / static_cast<float>(H) + eps);
+    if (threadIdx.x == 0 && rstd_out) rstd_out[row] = rstd;
+    __nv_bfloat16* yr = y + static_cast<int64_t>(row) * H;
+#pragma unroll
+    for (int i = 0; i < kMaxVPT; ++i) {
+      const int v = threadIdx.x + i * kNormThreads;
+      if (v < nvec) {
+        const uint32_t* u = reinterpret_cast<const uint32_t*>(&xv[i]);
+        const uint32_t* wu = reinterpret_cast<const uint32_t*>(&wv[i]);
+        int4 o;
+        uint32_t* ou = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = unpack_bf16(u[j]);
+          const float2 g = unpack_bf16(wu[j]);
+          ou[j] = pack_bf16(f.x * rstd * g.x, f.y * rstd * g.y);
+        }
+        st_v4(yr + 8 * v, o);
+      }
+    }
+  }
+}
+
+// dx = rstd * (dy*w - xhat * mean(dy*w*xhat)), dw += sum_rows dy*xhat  (fp32 atomics, one per CTA/col)
+__global__ void __launch_bounds__(kNormThreads)
+rmsnorm_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ w,
+                   const __nv_bfloat16* __restrict__ dy, const float* __restrict__ rstd_in,
+                   __nv_bfloat16* __restrict__ dx, float* __restrict__ dw, int T, int H) {
+  __shared__ float red[8];
+  const int nvec = H >> 3;
+  float wf[kMaxVPT][8];
+  float dwacc[kMaxVPT][8];
+#pragma unroll
+  for (int i = 0; i < kMaxVPT; ++i) {
+    const int v = threadIdx.x + i * kNormThreads;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { dwacc[i][j] = 0.f; wf[i][j] = 0.f; }
+    if (v < nvec) {
+      const int4 q = *reinterpret_cast<const int4*>(w + 8 * v);
+      const uint32_t* u = reinterpret_cast<const uint32_t*>(&q);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = unpack_bf16(u[j]);
+        wf[i][2 * j] = f.x; wf[i][2 * j + 1] = f.y;
+      }
+    }
+  }
+  for (int row = blockIdx.x; row < T; row += gridDim.x) {
+    const float rstd = rstd_in[row];
+    const __nv_bfloat16* xr = x + static_cast<int64_t>(row) * H;
+    const __nv_bfloat16* dyr = dy + static_cast<int64_t>(row) * H;
+    float xh[kMaxVPT][8], g[kMaxVPT][8];
+    float dot = 0.f;
+#pragma unroll
+    for (int i = 0; i < kMaxVPT; ++i) {
+      const int v = threadIdx.x + i * kNormThreads;
+      if (v < nvec) {
+        const int4 xq = ld_nc_v4(xr + 8 * v);
+        const int4 dq = ld_nc_v4(dyr + 8 * v);
+        const uint32_t* xu = reinterpret_cast<const uint32_t*>(&xq);
+        const uint32_t* du = reinterpret_cast<const uint32_t*>(&dq);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 xf = unpack_bf16(xu[j]);
+          const float2 df = unpack_bf16(du[j]);
+          xh[i][2 * j] = xf.x * rstd; xh[i][2 * j + 1] = xf.y * rstd;
+          g[i][2 * j] = df.x; g[i][2 * j + 1] = df.y;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          dwacc[i][j] += g[i][j] * xh[i][j];
+          g[i][j] *= wf[i][j];
+          dot += g[i][j] * xh[i][j];
+        }
+      }
+    }
+    dot = block_sum_256(dot, red) / static_cast<float>(H);
+    __nv_bfloat16* dxr = dx + static_cast<int64_t>(row) * H;
+#pragma unroll
+    for (int i = 0; i < kMaxVPT; ++i) {
+      const int v = threadIdx.x + i * kNormThreads;
+      if (v < nvec) {
+        int4 o;
+        uint32_t* ou = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          ou[j] = pack_bf16(rstd * (g[i][2 * j] - xh[i][2 * j] * dot), rstd * (g[i][2 * j + 1] - xh[i][2 * j + 1] * dot));
+        st_v4(dxr + 8 * v, o);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < kMaxVPT; ++i) {
+    const int v = threadIdx.x + i * kNormThreads;
+    if (v < nvec) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) atomicAdd(dw + 8 * v + j, dwacc[i][j]);
+    }
+  }
+}
+
+// Rotary embedding (rotate-half / NeoX convention), in place on the q and k heads of a packed
+// qkv row [nq*d | nkv*d | nkv*d]; optionally appends the rotated k and the v of each token to a
+// paged KV cache laid out [num_blocks, n_kv, block_size, d] at slot_mapping[t] (= block*bs + off).
+// `sign` = +1 forward, -1 backward (inverse rotation applied to gradients).
+__global__ void rope_kernel(__nv_bfloat16* __restrict__ qkv, const int64_t* __restrict__ pos,
+                            const float* __restrict__ cos_tab, const float* __restrict__ sin_tab, int T, int nq,
+                            int nkv, int d, int64_t ld, float sign, __nv_bfloat16* __restrict__ k_cache,
+                            __nv_bfloat16* __restrict__ v_cache, const int64_t* __restrict__ slot_mapping,
+                            int block_size) {
+  const int t = blockIdx.x;
+  if (t >= T) return;
+  const int half = d >> 1;
+  const int64_t p = pos[t];
+  const float* ct = cos_tab + p * half;
+  const float* st = sin_tab + p * half;
+  __nv_bfloat16* row = qkv + static_cast<int64_t>(t) * ld;
+  const int nrot = (nq + nkv) * half;
+  int64_t slot = -1;
+  if (slot_mapping) slot = slot_mapping[t];
+  const int64_t blk = slot >= 0 ? slot / block_size : 0;
+  const int64_t off = slot >= 0 ? slot % block_size : 0;
+  for (int i = threadIdx.x; i < nrot; i += blockDim.x) {
+    const int h = i / half, j = i - h * half;
+    __nv_bfloat16* hp = row + h * d;
+    const float x1 = __bfloat162float(hp[j]), x2 = __bfloat162float(hp[j + half]);
+    const float c = ct[j], s = st[j] * sign;
+    const __nv_bfloat16 o1 = __float2bfloat16(x1 * c - x2 * s);
+    const __nv_bfloat16 o2 = __float2bfloat16(x2 * c + x1 * s);
+    hp[j] = o1;
+    hp[j + half] = o2;
+    if (slot >= 0 && h >= nq) {
+      __nv_bfloat16* kc = k_cache + ((blk * nkv + (h - nq)) * block_size + off) * d;
+      kc[j] = o1;
+      kc[j + half] = o2;
+    }
+  }
+  if (slot >= 0) {
+    const __nv_bfloat16* vrow = row + (nq + nkv) * d;
+    for (int i = threadIdx.x; i < nkv * d; i += blockDim.x) {
+      const int h = i / d, j = i - h * d;
+      v_cache[((blk * nkv + h) * block_size + off) * d + j] = vrow[i];
+    }
+  }
+}
+
+// SwiGLU backward on the block-interleaved layout ([128 gate | 128 up] per 256 columns):
+// dG = dH * u * sig(g) * (1 + g*(1-sig(g))),  dU = dH * silu(g)
+__global__ void swiglu_bwd_kernel(const __nv_bfloat16* __restrict__ gu, const __nv_bfloat16* __restrict__ dh,
+                                  __nv_bfloat16* __restrict__ dgu, int64_t T, int F) {
+  const int64_t nvec = T * (F >> 3);
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < nvec;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t t = i / (F >> 3);
+    const int c = static_cast<int>(i - t * (F >> 3)) * 8;       // column in H
+    const int blk = c >> 7, in = c & 127;
+    const int64_t gcol = static_cast<int64_t>(blk) * 256 + in;
+    const __nv_bfloat16* gp = gu + t * 2 * F + gcol;
+    const int4 gq = ld_nc_v4(gp), uq = ld_nc_v4(gp + 128), dq = ld_nc_v4(dh + t * F + c);
+    const uint32_t* gu32 = reinterpret_cast<const uint32_t*>(&gq);
+    const uint32_t* uu32 = reinterpret_cast<const uint32_t*>(&uq);
+    const uint32_t* du32 = reinterpret_cast<const uint32_t*>(&dq);
+    int4 og, ou;
+    uint32_t* ogu = reinterpret_cast<uint32_t*>(&og);
+    uint32_t* ouu = reinterpret_cast<uint32_t*>(&ou);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 g = unpack_bf16(gu32[j]), u = unpack_bf16(uu32[j]), d = unpack_bf16(du32[j]);
+      const float s0 = 1.f / (1.f + __expf(-g.x)), s1 = 1.f / (1.f + __expf(-g.y));
+      ogu[j] = pack_bf16(d.x * u.x * s0 * (1.f + g.x * (1.f - s0)), d.y * u.y * s1 * (1.f + g.y * (1.f - s1)));
+      ouu[j] = pack_bf16(d.x * g.x * s0, d.y * g.y * s1);
+    }
+    __nv_bfloat16* op = dgu + t * 2 * F + gcol;
+    st_v4(op, og);
+    st_v4(op + 128, ou);
+  }
+}
+
+// Per-row dynamic fp8 (e4m3) quantisation: scale = amax/448; q = x/scale.
+__global__ void __launch_bounds__(256)
+quant_fp8_rowwise_kernel(const __nv_bfloat16* __restrict__ x, uint8_t* __restrict__ q, float* __restrict__ scale,
+                         int T, int H) {
+  __shared__ float red[8];
+  for (int row = blockIdx.x; row < T; row += gridDim.x) {
+    const __nv_bfloat16* xr = x + static_cast<int64_t>(row) * H;
+    float amax = 0.f;
+    for (int i = threadIdx.x * 8; i < H; i += 256 * 8) {
+      const int4 v = ld_nc_v4(xr + i);
+      const uint32_t* u = reinterpret_cast<const uint32_t*>(&v);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = unpack_bf16(u[j]);
+        amax = fmaxf(amax, fmaxf(fabsf(f.x), fabsf(f.y)));
+      }
+    }
+    amax = warp_max(amax);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = amax;
+    __syncthreads();
+    amax = red[0];
+#pragma unroll
+    for (int i = 1; i < 8; ++i) amax = fmaxf(amax, red[i]);
+    const float sc = fmaxf(amax, 1e-12f) / 448.f;
+    const float inv = 1.f / sc;
+    if (threadIdx.x == 0) scale[row] = sc;
+    uint8_t* qr = q + static_cast<int64_t>(row) * H;
+    for (int i = threadIdx.x * 8; i < H; i += 256 * 8) {
+      const int4 v = ld_nc_v4(xr + i);
+      const uint32_t* u = reinterpret_cast<const uint32_t*>(&v);
+      uint32_t o[2];
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const float2 a = unpack_bf16(u[2 * j]), b = unpack_bf16(u[2 * j + 1]);
+        uint16_t lo, hi;
+        asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(lo) : "f"(a.y * inv), "f"(a.x * inv));
+        asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(hi) : "f"(b.y * inv), "f"(b.x * inv));
+        o[j] = static_cast<uint32_t>(lo) | (static_cast<uint32_t>(hi) << 16);
+      }
+      *reinterpret_cast<uint2*>(qr + i) = make_uint2(o[0], o[1]);
+    }
+  }
+}
+
+}  // namespace prl
+
+using namespace prl;
+
+extern "C" int prl_rmsnorm_fwd(const void* x, const void* w, void* y, float* rstd, int T, int H, float eps,
+                               cudaStream_t s) {
+  if (H % 8 != 0 || H > 8 * kNormThreads * kMaxVPT) return -20;
+  if (T <= 0) return 0;
+  const int grid = T < 148 * 8 ? T : 148 * 8;
+  rmsnorm_fwd_kernel<<<grid, kNormThreads, 0, s>>>(static_cast<const __nv_bfloat16*>(x),
+                                                  static_cast<const __nv_bfloat16*>(w),
+                                                  static_cast<__nv_bfloat16*>(y), rstd, T, H, eps);
+  PRL_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+extern "C" int prl_rmsnorm_bwd(const void* x, const void* w, const void* dy, const float* rstd, void* dx, float* dw,
+                               int T, int H, cudaStream_t s) {
+  if (H % 8 != 0 || H > 8 * kNormThreads * kMaxVPT) return -20;
+  if (T <= 0) return 0;
+  const int grid = T < 148 * 2 ? T : 148 * 2;
+  rmsnorm_bwd_kernel<<<grid, kNormThreads, 0, s>>>(static_cast<const __nv_bfloat16*>(x),
+                                                  static_cast<const __nv_bfloat16*>(w),
+                                                  static_cast<const __nv_bfloat16*>(dy), rstd,
+                                                  static_cast<__nv_bfloat16*>(dx), dw, T, H);
+  PRL_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+extern "C" int prl_rope(void* qkv, const int64_t* pos, const float* cos_tab, const float* sin_tab, int T, int nq,
+                        int nkv, int d, int64_t ld, float sign, void* k_cache, void* v_cache,
+                        const int64_t* slot_mapping, int block_size, cudaStream_t s) {
+  if (T <= 0) return 0;
+  rope_kernel<<<T, 256, 0, s>>>(static_cast<__nv_bfloat16*>(qkv), pos, cos_tab, sin_tab, T, nq, nkv, d, ld, sign,
+                                static_cast<__nv_bfloat16*>(k_cache), static_cast<__nv_bfloat16*>(v_cache),
+                                slot_mapping, block_size);
+  PRL_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+extern "C" int prl_swiglu_bwd(const void* gu, const void* dh, void* dgu, int64_t T, int F, cudaStream_t s) {
+  if (F % 128 != 0) return -21;
+  if (T <= 0) return 0;
+  const int64_t nvec = T * (F / 8);
+  int grid = static_cast<int>((nvec + 255) / 256);
+  if (grid > 148 * 16) grid = 148 * 16;
+  swiglu_bwd_kernel<<<grid, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(gu), static_cast<const __nv_bfloat16*>(dh),
+                                         static_cast<__nv_bfloat16*>(dgu), T, F);
+  PRL_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+extern "C" int prl_quant_fp8_rowwise(const void* x, void* q, float* scale, int T, int H, cudaStream_t s) {
+  if (H % 8 != 0) return -22;
+  if (T <= 0) return 0;
+  const int grid = T < 148 * 8 ? T : 148 * 8;
+  quant_fp8_rowwise_kernel<<<grid, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(x), static_cast<uint8_t*>(q), scale,
+                                                T, H);
+  PRL_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}

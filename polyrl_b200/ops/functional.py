@@ -1,0 +1,297 @@
+"""Autograd-aware wrappers over the sm_100a kernels (CUDA) and the PyTorch references (CPU)."""
+from __future__ import annotations
+
+import os
+
+import torch
+
+from . import reference as ref
+
+
+def _C():
+    from . import ext
+
+    return ext()
+
+
+def _cublas() -> bool:
+    return os.environ.get("POLYRL_GEMM_BACKEND", "tcgen05") == "cublas"
+
+
+def _is_kernel_tensor(x: torch.Tensor) -> bool:
+    return x.is_cuda and x.dtype == torch.bfloat16
+
+
+# --------------------------------------------------------------------------------------------
+# linear (+ residual) : tcgen05 GEMM forward with fused residual epilogue
+# --------------------------------------------------------------------------------------------
+class _LinearFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, residual):
+        x2 = x.reshape(-1, x.shape[-1])
+        r2 = residual.reshape(-1, w.shape[0]) if residual is not None else None
+        if _cublas():
+            y = x2 @ w.t()
+            if r2 is not None:
+                y = y + r2
+        else:
+            if x2.stride(-1) != 1 or x2.stride(0) % 8 != 0:
+                x2 = x2.contiguous()
+            if r2 is not None and not r2.is_contiguous():
+                r2 = r2.contiguous()
+            y = _C().gemm_bf16(x2, w, r2)
+        ctx.save_for_backward(x2, w)
+        ctx.has_res = residual is not None
+        ctx.x_shape = x.shape
+        return y.reshape(*x.shape[:-1], w.shape[0])
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, w = ctx.saved_tensors
+        dy2 = dy.reshape(-1, dy.shape[-1])
+        dx = dw = dres = None
+        if ctx.needs_input_grad[0]:
+            dx = (dy2 @ w).reshape(ctx.x_shape)
+        if ctx.needs_input_grad[1]:
+            dw = dy2.t() @ x2
+        if ctx.has_res and ctx.needs_input_grad[2]:
+            dres = dy
+        return dx, dw, dres
+
+
+def linear(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None = None,
+           residual: torch.Tensor | None = None) -> torch.Tensor:
+    """y = x @ w.T (+ bias) (+ residual).  w is [out, in] (nn.Linear layout)."""
+    if _is_kernel_tensor(x) and w.dtype == torch.bfloat16 and w.shape[0] % 8 == 0 and w.shape[1] % 8 == 0:
+        y = _LinearFn.apply(x, w, residual if bias is None else None)
+        if bias is not None:
+            y = y + bias
+            if residual is not None:
+                y = y + residual
+        return y
+    if x.is_cuda and x.dtype == torch.bfloat16 and w.dtype == torch.bfloat16:
+        # odd shapes (e.g. vocab not multiple of 8): library GEMM
+        y = torch.nn.functional.linear(x, w, bias)
+        return y + residual if residual is not None else y
+    y = torch.nn.functional.linear(x, w.to(x.dtype), None if bias is None else bias.to(x.dtype))
+    return y + residual if residual is not None else y
+
+
+# --------------------------------------------------------------------------------------------
+# gate/up projection with SwiGLU fused into the GEMM epilogue
+# --------------------------------------------------------------------------------------------
+class _LinearSwigluFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, wgu):
+        x2 = x.reshape(-1, x.shape[-1])
+        if x2.stride(-1) != 1 or x2.stride(0) % 8 != 0:
+            x2 = x2.contiguous()
+        need = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        outs = _C().gemm_swiglu(x2, wgu, bool(need))
+        h = outs[0]
+        if need:
+            ctx.save_for_backward(x2, wgu, outs[1])
+        ctx.x_shape = x.shape
+        return h.reshape(*x.shape[:-1], wgu.shape[0] // 2)
+
+    @staticmethod
+    def backward(ctx, dh):
+        x2, wgu, gu = ctx.saved_tensors
+        dh2 = dh.reshape(-1, dh.shape[-1]).contiguous()
+        dgu = _C().swiglu_bwd(gu, dh2)
+        dx = (dgu @ wgu).reshape(ctx.x_shape) if ctx.needs_input_grad[0] else None
+        dw = dgu.t() @ x2 if ctx.needs_input_grad[1] else None
+        return dx, dw
+
+
+def linear_swiglu(x: torch.Tensor, wgu: torch.Tensor) -> torch.Tensor:
+    """silu(x @ Wg.T) * (x @ Wu.T) with W_gu stored block-interleaved ([128 gate | 128 up] rows)."""
+    if _is_kernel_tensor(x) and wgu.dtype == torch.bfloat16 and not _cublas():
+        return _LinearSwigluFn.apply(x, wgu)
+    gu = torch.nn.functional.linear(x, wgu.to(x.dtype))
+    return ref.swiglu(gu)
+
+
+# --------------------------------------------------------------------------------------------
+# RMSNorm
+# --------------------------------------------------------------------------------------------
+class _RmsNormFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, eps):
+        xc = x.contiguous()
+        y, rstd = _C().rmsnorm_fwd(xc, w, eps)
+        ctx.save_for_backward(xc, w, rstd)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w, rstd = ctx.saved_tensors
+        dx, dw = _C().rmsnorm_bwd(x, w, dy.contiguous(), rstd)
+        return dx, dw.to(w.dtype), None
+
+
+def rmsnorm(x: torch.Tensor, w: torch.Tensor, eps: float = 1e-6) -> torch.Tensor:
+    if _is_kernel_tensor(x) and w.dtype == torch.bfloat16 and x.shape[-1] % 8 == 0 and x.shape[-1] <= 8192:
+        return _RmsNormFn.apply(x, w, eps)
+    return ref.rmsnorm(x, w, eps)
+
+
+# --------------------------------------------------------------------------------------------
+# RoPE (in place on packed qkv), optional paged-KV append
+# --------------------------------------------------------------------------------------------
+class _RopeFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, qkv, pos, cos, sin, nq, nkv, d):
+        ctx.mark_dirty(qkv)
+        _C().rope_(qkv, pos, cos, sin, nq, nkv, d, 1.0, None, None, None, 16)
+        ctx.save_for_backward(pos, cos, sin)
+        ctx.dims = (nq, nkv, d)
+        return qkv
+
+    @staticmethod
+    def backward(ctx, dy):
+        pos, cos, sin = ctx.saved_tensors
+        nq, nkv, d = ctx.dims
+        g = dy.contiguous().clone()
+        _C().rope_(g, pos, cos, sin, nq, nkv, d, -1.0, None, None, None, 16)
+        return g, None, None, None, None, None, None
+
+
+def apply_rope(qkv: torch.Tensor, pos: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor, nq: int, nkv: int,
+               d: int) -> torch.Tensor:
+    """Rotate q/k heads of packed rows [T, (nq+2*nkv)*d].  CUDA path works in place on ``qkv``."""
+    if _is_kernel_tensor(qkv):
+        if not qkv.requires_grad and not torch.is_grad_enabled():
+            _C().rope_(qkv, pos, cos, sin, nq, nkv, d, 1.0, None, None, None, 16)
+            return qkv
+        return _RopeFn.apply(qkv, pos, cos, sin, nq, nkv, d)
+    return ref.rope(qkv, pos, cos, sin, nq, nkv, d)
+
+
+def rope_and_cache_(qkv, pos, cos, sin, nq, nkv, d, k_cache, v_cache, slot_mapping, page: int = 16):
+    """Inference: rotate in place and append rotated k / v to the paged cache at ``slot_mapping``."""
+    if _is_kernel_tensor(qkv):
+        _C().rope_(qkv, pos, cos, sin, nq, nkv, d, 1.0, k_cache, v_cache, slot_mapping, page)
+        return qkv
+    out = ref.rope(qkv, pos, cos, sin, nq, nkv, d)
+    t = out.shape[0]
+    k = out[:, nq * d:(nq + nkv) * d].reshape(t, nkv, d)
+    v = out[:, (nq + nkv) * d:].reshape(t, nkv, d)
+    blk = torch.div(slot_mapping, page, rounding_mode="floor")
+    off = slot_mapping % page
+    k_cache[blk, :, off] = k.to(k_cache.dtype)
+    v_cache[blk, :, off] = v.to(v_cache.dtype)
+    qkv.copy_(out)
+    return qkv
+
+
+# --------------------------------------------------------------------------------------------
+# fused LM head: log-prob + entropy without materialising logits
+# --------------------------------------------------------------------------------------------
+_CE_CHUNK = int(os.environ.get("POLYRL_CE_BWD_CHUNK", "16384"))
+
+
+class _LinearCEFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, hidden, weight, labels, inv_tau):
+        h2 = hidden.reshape(-1, hidden.shape[-1])
+        if not h2.is_contiguous():
+            h2 = h2.contiguous()
+        lab = labels.reshape(-1).contiguous()
+        lp, ent, lse, ez = _C().linear_ce_fwd(h2, weight, lab, inv_tau)
+        ctx.save_for_backward(h2, weight, lab, lse, ez)
+        ctx.inv_tau = inv_tau
+        ctx.h_shape = hidden.shape
+        return lp.reshape(labels.shape), ent.reshape(labels.shape)
+
+    @staticmethod
+    def backward(ctx, g_lp, g_ent):
+        h2, w, lab, lse, ez = ctx.saved_tensors
+        C = _C()
+        g_lp = g_lp.reshape(-1).float().contiguous() if g_lp is not None else None
+        g_ent = g_ent.reshape(-1).float().contiguous() if g_ent is not None else None
+        V = w.shape[0]
+        need_h, need_w = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        dh = torch.zeros_like(h2, dtype=torch.float32) if need_h else None
+        dw = torch.empty_like(w) if need_w else None
+        for v0 in range(0, V, _CE_CHUNK):
+            v1 = min(V, v0 + _CE_CHUNK)
+            ws = w[v0:v1]
+            dz = C.linear_ce_dz(h2, ws, lab, lse, ez, g_lp, g_ent, ctx.inv_tau, v0)
+            if need_h:
+                dh.add_(dz @ ws)
+            if need_w:
+                torch.mm(dz.t(), h2, out=dw[v0:v1])
+        dh_out = dh.to(h2.dtype).reshape(ctx.h_shape) if need_h else None
+        return dh_out, dw, None, None
+
+
+def linear_cross_entropy(hidden: torch.Tensor, weight: torch.Tensor, labels: torch.Tensor,
+                         temperature: float = 1.0) -> tuple[torch.Tensor, torch.Tensor]:
+    """(log p(labels), entropy) of softmax(hidden @ weight.T / temperature); fp32 outputs, shape of labels."""
+    if _is_kernel_tensor(hidden) and weight.dtype == torch.bfloat16 and weight.shape[0] % 8 == 0:
+        return _LinearCEFn.apply(hidden, weight, labels, 1.0 / float(temperature))
+    lp, ent = ref.linear_cross_entropy(hidden.reshape(-1, hidden.shape[-1]), weight, labels.reshape(-1), temperature)
+    return lp.reshape(labels.shape), ent.reshape(labels.shape)
+
+
+# --------------------------------------------------------------------------------------------
+# rollout-side ops (no autograd)
+# --------------------------------------------------------------------------------------------
+def _auto_splits(num_seqs: int, nkv: int, max_len: int) -> int:
+    ctas = num_seqs * nkv
+    if ctas >= 4 * 148:
+        return 1
+    want = (4 * 148 + ctas - 1) // ctas
+    by_len = max(1, max_len // 256)
+    return max(1, min(want, by_len, 32))
+
+
+@torch.no_grad()
+def paged_decode_attention(q, k_cache, v_cache, block_table, seq_lens, nq, nkv, d, sm_scale, splits: int = 0,
+                           max_len: int = 0, out=None):
+    if _is_kernel_tensor(q):
+        if splits <= 0:
+            splits = _auto_splits(q.shape[0], nkv, max_len if max_len > 0 else 1024)
+        return _C().paged_decode(q, k_cache, v_cache, block_table, seq_lens, nq, nkv, d, sm_scale, splits, out)
+    return ref.paged_decode_attention(q, k_cache, v_cache, block_table, seq_lens, nq, nkv, d, sm_scale)
+
+
+@torch.no_grad()
+def sample_tokens(logits: torch.Tensor, temperature: torch.Tensor | float = 1.0, seeds: torch.Tensor | None = None,
+                  greedy: bool = False, top_k: int = -1, top_p: float = 1.0):
+    """Sample one token per row and return (token ids int64, log-prob of the sampled token fp32)."""
+    b, v = logits.shape
+    if not torch.is_tensor(temperature):
+        temperature = torch.full((b,), float(temperature), device=logits.device, dtype=torch.float32)
+    simple = top_k <= 0 and top_p >= 1.0
+    if logits.is_cuda and simple:
+        inv_t = torch.where(temperature > 0, 1.0 / temperature.clamp_min(1e-6), torch.zeros_like(temperature))
+        if seeds is None:
+            seeds = torch.randint(0, 2 ** 62, (b,), device=logits.device, dtype=torch.int64)
+        tok, lp = _C().sample(logits, inv_t.float().contiguous(), seeds, bool(greedy))
+        return tok, lp
+    z = logits.float()
+    t = temperature.to(z.device).clamp_min(1e-6).unsqueeze(-1)
+    is_greedy = greedy or bool((temperature <= 0).all())
+    if not is_greedy:
+        z = z / t
+    if top_k > 0:
+        kth = torch.topk(z, min(top_k, v), dim=-1).values[..., -1:]
+        z = z.masked_fill(z < kth, float("-inf"))
+    if top_p < 1.0:
+        sz, si = torch.sort(z, dim=-1, descending=True)
+        cp = torch.softmax(sz, dim=-1).cumsum(-1)
+        drop = cp - torch.softmax(sz, dim=-1) >= top_p
+        sz = sz.masked_fill(drop, float("-inf"))
+        z = torch.full_like(z, float("-inf")).scatter(-1, si, sz)
+    logp = torch.log_softmax(z, dim=-1)
+    if is_greedy:
+        tok = z.argmax(-1)
+    else:
+        gen = None
+        if seeds is not None:
+            gen = torch.Generator(device=z.device)
+            gen.manual_seed(int(seeds.reshape(-1)[0].item()) & 0x7FFFFFFF)
+        tok = torch.multinomial(logp.exp(), 1, generator=gen).squeeze(-1)
+    return tok, logp.gather(-1, tok.unsqueeze(-1)).squeeze(-1)

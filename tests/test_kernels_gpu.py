@@ -1,0 +1,241 @@
+"""Numerics of every sm_100a kernel vs a plain PyTorch fp32 reference of the same op.
+
+Mirrors the reference's Triton-vs-torch tier (3rdparty/verl/tests/utils/test_linear_cross_entropy.py).
+"""
+import math
+
+import pytest
+import torch
+
+from polyrl_b200.ops import reference as ref
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def C():
+    from polyrl_b200.ops import ext
+
+    return ext()
+
+
+def _rel_err(a, b):
+    a, b = a.float(), b.float()
+    return ((a - b).norm() / (b.norm() + 1e-12)).item()
+
+
+@pytest.mark.parametrize("M,N,K,bn", [
+    (128, 256, 64, 0), (256, 512, 512, 0), (1000, 1032, 520, 0), (4096, 4096, 4096, 256),
+    (256, 6144, 4096, 64), (256, 6144, 4096, 128), (333, 264, 776, 128), (64, 128, 128, 64),
+])
+def test_gemm_bf16(C, M, N, K, bn):
+    torch.manual_seed(0)
+    a = torch.randn(M, K, device="cuda", dtype=torch.bfloat16)
+    b = torch.randn(N, K, device="cuda", dtype=torch.bfloat16)
+    d = C.gemm_bf16(a, b, None, None, bn)
+    want = a.float() @ b.float().t()
+    assert _rel_err(d, want) < 5e-3
+
+
+def test_gemm_bf16_residual_and_strided(C):
+    torch.manual_seed(1)
+    big = torch.randn(512, 1024 + 64, device="cuda", dtype=torch.bfloat16)
+    a = big[:, :1024]                       # row pitch != K
+    b = torch.randn(768, 1024, device="cuda", dtype=torch.bfloat16)
+    r = torch.randn(512, 768, device="cuda", dtype=torch.bfloat16)
+    d = C.gemm_bf16(a, b, r, None, 0)
+    want = a.float() @ b.float().t() + r.float()
+    assert _rel_err(d, want) < 5e-3
+
+
+def test_gemm_fp8(C):
+    torch.manual_seed(2)
+    M, N, K = 256, 1024, 2048
+    a = torch.randn(M, K, device="cuda", dtype=torch.bfloat16)
+    w = torch.randn(N, K, device="cuda", dtype=torch.bfloat16) * 0.05
+    aq, a_s = C.quant_fp8_rowwise(a)
+    wq, w_s = C.quant_fp8_rowwise(w)
+    # quantiser vs torch
+    want_q = (a.float() / a_s[:, None]).to(torch.float8_e4m3fn)
+    assert (aq.float() - want_q.float()).abs().max().item() <= 32.0   # at most one e4m3 ulp at the top bin
+    d = C.gemm_fp8(aq, wq, a_s, w_s, 0)
+    want = (aq.float() * a_s[:, None]) @ (wq.float() * w_s[:, None]).t()
+    assert _rel_err(d, want) < 5e-3
+    assert _rel_err(d, a.float() @ w.float().t()) < 6e-2
+
+
+def test_gemm_swiglu(C):
+    torch.manual_seed(3)
+    M, F, K = 300, 1024, 512
+    x = torch.randn(M, K, device="cuda", dtype=torch.bfloat16)
+    wg = torch.randn(F, K, device="cuda", dtype=torch.bfloat16) * 0.05
+    wu = torch.randn(F, K, device="cuda", dtype=torch.bfloat16) * 0.05
+    wgu = ref.interleave_gate_up(wg, wu).contiguous()
+    h, gu = C.gemm_swiglu(x, wgu, True)
+    g = x.float() @ wg.float().t()
+    u = x.float() @ wu.float().t()
+    want = torch.nn.functional.silu(g) * u
+    assert _rel_err(h, want) < 1e-2
+    g2, u2 = ref.split_gate_up(gu)
+    assert _rel_err(g2, g) < 5e-3 and _rel_err(u2, u) < 5e-3
+    # backward kernel
+    dh = torch.randn(M, F, device="cuda", dtype=torch.bfloat16)
+    dgu = C.swiglu_bwd(gu, dh)
+    guf = gu.float().requires_grad_(True)
+    gg, uu = ref.split_gate_up(guf)
+    (torch.nn.functional.silu(gg) * uu * dh.float()).sum().backward()
+    assert _rel_err(dgu, guf.grad) < 1e-2
+
+
+@pytest.mark.parametrize("T,V,H,tau", [(256, 4096, 512, 1.0), (700, 32008, 1024, 0.7), (130, 1000, 256, 1.3)])
+def test_linear_ce_fwd_bwd(C, T, V, H, tau):
+    from polyrl_b200.ops import linear_cross_entropy
+
+    torch.manual_seed(4)
+    h = (torch.randn(T, H, device="cuda") * 0.5).to(torch.bfloat16).requires_grad_(True)
+    w = (torch.randn(V, H, device="cuda") * 0.05).to(torch.bfloat16).requires_grad_(True)
+    labels = torch.randint(0, V, (T,), device="cuda")
+    lp, ent = linear_cross_entropy(h, w, labels, tau)
+    hf = h.detach().float().requires_grad_(True)
+    wf = w.detach().float().requires_grad_(True)
+    lp_r, ent_r = ref.linear_cross_entropy(hf, wf, labels, tau)
+    assert (lp - lp_r).abs().max().item() < 3e-2
+    assert (ent - ent_r).abs().max().item() < 3e-2
+    glp = torch.randn(T, device="cuda")
+    gent = torch.randn(T, device="cuda") * 0.1
+    (lp * glp + ent * gent).sum().backward()
+    (lp_r * glp + ent_r * gent).sum().backward()
+    assert _rel_err(h.grad, hf.grad) < 3e-2
+    assert _rel_err(w.grad, wf.grad) < 3e-2
+
+
+@pytest.mark.parametrize("T,H", [(257, 4096), (64, 768), (1000, 2048), (33, 8192)])
+def test_rmsnorm(C, T, H):
+    torch.manual_seed(5)
+    x = torch.randn(T, H, device="cuda", dtype=torch.bfloat16)
+    w = (1 + 0.1 * torch.randn(H, device="cuda")).to(torch.bfloat16)
+    y, rstd = C.rmsnorm_fwd(x, w, 1e-6)
+    assert _rel_err(y, ref.rmsnorm(x.float(), w.float(), 1e-6)) < 5e-3
+    dy = torch.randn(T, H, device="cuda", dtype=torch.bfloat16)
+    dx, dw = C.rmsnorm_bwd(x, w, dy, rstd)
+    xf = x.float().requires_grad_(True)
+    wf = w.float().requires_grad_(True)
+    (ref.rmsnorm(xf, wf, 1e-6) * dy.float()).sum().backward()
+    assert _rel_err(dx, xf.grad) < 1e-2
+    assert _rel_err(dw, wf.grad) < 1e-2
+
+
+def test_rope_and_cache(C):
+    torch.manual_seed(6)
+    T, nq, nkv, d = 100, 8, 2, 128
+    qkv = torch.randn(T, (nq + 2 * nkv) * d, device="cuda", dtype=torch.bfloat16)
+    pos = torch.randint(0, 500, (T,), device="cuda")
+    cos, sin = ref.rope_tables(512, d, 10000.0, device="cuda")
+    want = ref.rope(qkv, pos, cos, sin, nq, nkv, d)
+    kc = torch.zeros(16, nkv, 16, d, device="cuda", dtype=torch.bfloat16)
+    vc = torch.zeros_like(kc)
+    slots = torch.randperm(16 * 16, device="cuda")[:T]
+    got = qkv.clone()
+    C.rope_(got, pos, cos, sin, nq, nkv, d, 1.0, kc, vc, slots, 16)
+    assert _rel_err(got, want) < 5e-3
+    blk, off = slots // 16, slots % 16
+    k_want = want[:, nq * d:(nq + nkv) * d].reshape(T, nkv, d)
+    v_want = want[:, (nq + nkv) * d:].reshape(T, nkv, d)
+    assert torch.equal(kc[blk, :, off], got[:, nq * d:(nq + nkv) * d].reshape(T, nkv, d))
+    assert _rel_err(kc[blk, :, off], k_want) < 5e-3
+    assert torch.equal(vc[blk, :, off], v_want)
+    # inverse rotation
+    back = got.clone()
+    C.rope_(back, pos, cos, sin, nq, nkv, d, -1.0, None, None, None, 16)
+    assert _rel_err(back, qkv) < 1e-2
+
+
+def test_adamw_and_grad_accum(C):
+    torch.manual_seed(7)
+    n = 100003
+    master = torch.randn(n, device="cuda")
+    m = torch.zeros(n, device="cuda")
+    v = torch.zeros(n, device="cuda")
+    acc = torch.zeros(n, device="cuda")
+    p16 = torch.empty(n, device="cuda", dtype=torch.bfloat16)
+    rm, rmm, rv = master.clone(), m.clone(), v.clone()
+    for step in range(1, 4):
+        g16 = torch.randn(n, device="cuda", dtype=torch.bfloat16)
+        g32 = torch.randn(n, device="cuda")
+        ss = torch.zeros(1, device="cuda")
+        C.grad_accum_(acc, g16, 0.5, None)
+        C.grad_accum_(acc, g32, 0.25, ss)
+        want_g = 0.5 * g16.float() + 0.25 * g32
+        assert torch.allclose(acc, want_g, atol=1e-5)
+        assert math.isclose(ss.item(), want_g.pow(2).sum().item(), rel_tol=1e-3)
+        coef = min(1.0, 1.0 / (math.sqrt(ss.item()) + 1e-6))
+        status = torch.zeros(1, device="cuda", dtype=torch.int32)
+        C.adamw_(master, m, v, acc, p16, 1e-2, 0.9, 0.95, 1e-8, 0.1, step, 1.0, ss, status, True)
+        ref.adamw_step(rm, rmm, rv, want_g, 1e-2, 0.9, 0.95, 1e-8, 0.1, step, coef)
+        assert torch.allclose(master, rm, atol=2e-5, rtol=1e-4)
+        assert torch.equal(p16, master.to(torch.bfloat16))
+        assert acc.abs().max().item() == 0.0 and status.item() == 0
+    # non-finite norm => skipped, grads zeroed
+    acc.fill_(1.0)
+    before = master.clone()
+    ss = torch.full((1,), float("inf"), device="cuda")
+    status = torch.zeros(1, device="cuda", dtype=torch.int32)
+    C.adamw_(master, m, v, acc, p16, 1e-2, 0.9, 0.95, 1e-8, 0.1, 4, 1.0, ss, status, True)
+    assert torch.equal(master, before) and status.item() == 1 and acc.abs().max().item() == 0.0
+
+
+@pytest.mark.parametrize("nq,nkv,d,splits", [(32, 8, 128, 1), (32, 8, 128, 4), (28, 4, 128, 2), (12, 12, 64, 1), (64, 8, 128, 3)])
+def test_paged_decode(C, nq, nkv, d, splits):
+    torch.manual_seed(8)
+    B, page, max_len = 9, 16, 700
+    seq_lens = torch.randint(1, max_len, (B,), device="cuda", dtype=torch.int32)
+    seq_lens[0] = 1
+    seq_lens[1] = 16
+    seq_lens[2] = 17
+    nblk_per = (max_len + page - 1) // page
+    num_blocks = B * nblk_per + 3
+    kc = torch.randn(num_blocks, nkv, page, d, device="cuda", dtype=torch.bfloat16)
+    vc = torch.randn(num_blocks, nkv, page, d, device="cuda", dtype=torch.bfloat16)
+    perm = torch.randperm(num_blocks, device="cuda")[: B * nblk_per].to(torch.int32)
+    bt = perm.reshape(B, nblk_per).contiguous()
+    q = torch.randn(B, nq * d, device="cuda", dtype=torch.bfloat16)
+    scale = 1.0 / math.sqrt(d)
+    got = C.paged_decode(q, kc, vc, bt, seq_lens, nq, nkv, d, scale, splits, None)
+    want = ref.paged_decode_attention(q, kc, vc, bt, seq_lens, nq, nkv, d, scale)
+    assert _rel_err(got, want) < 1.5e-2
+
+
+def test_sampling(C):
+    torch.manual_seed(9)
+    B, V = 64, 5000
+    logits = torch.randn(B, V, device="cuda") * 2
+    # greedy
+    tok, lp = C.sample(logits, None, None, True)
+    assert torch.equal(tok, logits.argmax(-1))
+    want_lp = torch.log_softmax(logits, -1).gather(-1, tok[:, None]).squeeze(-1)
+    assert torch.allclose(lp, want_lp, atol=1e-3)
+    # sampled: log-prob consistent with temperature-scaled softmax, distribution roughly right
+    inv_t = torch.full((B,), 1 / 0.8, device="cuda")
+    small = torch.tensor([[2.0, 1.0, 0.0, -1.0]], device="cuda").repeat(20000, 1)
+    seeds = torch.arange(20000, device="cuda", dtype=torch.int64) * 7919 + 13
+    tok, lp = C.sample(small, torch.ones(20000, device="cuda"), seeds, False)
+    freq = torch.bincount(tok, minlength=4).float() / 20000
+    assert (freq - torch.softmax(small[0], -1)).abs().max().item() < 0.02
+    seeds = torch.randint(0, 2 ** 40, (B,), device="cuda")
+    tok, lp = C.sample(logits.to(torch.bfloat16), inv_t, seeds, False)
+    want_lp = torch.log_softmax(logits.to(torch.bfloat16).float() / 0.8, -1).gather(-1, tok[:, None]).squeeze(-1)
+    assert torch.allclose(lp, want_lp, atol=2e-3)
+
+
+def test_functional_autograd_linear():
+    from polyrl_b200 import ops
+
+    torch.manual_seed(10)
+    x = torch.randn(3, 50, 256, device="cuda", dtype=torch.bfloat16, requires_grad=True)
+    w = (torch.randn(512, 256, device="cuda") * 0.05).to(torch.bfloat16).requires_grad_(True)
+    r = torch.randn(3, 50, 512, device="cuda", dtype=torch.bfloat16, requires_grad=True)
+    y = ops.linear(x, w, residual=r)
+    y.float().pow(2).sum().backward()
+    xf, wf, rf = (t.detach().float().requires_grad_(True) for t in (x, w, r))
+    (xf @ wf.t() + rf).pow(2).sum().backward()
+    assert _rel_err(x.grad, xf.grad) < 2e-2 and _rel_err(w.grad, wf.grad) < 2e-2 and _rel_err(r.grad, rf.grad) < 2e-2
