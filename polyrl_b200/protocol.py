@@ -1,0 +1,487 @@
+"""Batch protocol exchanged between the driver and the workers.
+
+``DataProto`` carries three parts: ``batch`` (name -> tensor, all sharing dim 0), ``non_tensor_batch``
+(name -> numpy object array of the same length) and ``meta_info`` (free-form dict that is *not* split).
+It provides the transformations the PPO loop needs: chunk / split / concat / union / select / slice /
+repeat / reorder / pop / pad-to-divisor, plus picklable (de)serialisation and a future type for
+asynchronous worker calls.
+
+Capability parity with the reference's protocol (3rdparty/verl/verl/protocol.py:329-1237), built on a
+small in-house ``TensorBatch`` instead of the ``tensordict`` package (not installed on the target image).
+"""
+from __future__ import annotations
+
+import copy
+import io
+import pickle
+from dataclasses import dataclass, field
+from typing import Any, Callable, Iterable, Iterator, Sequence
+
+import numpy as np
+import torch
+
+__all__ = [
+    "TensorBatch",
+    "DataProto",
+    "DataProtoFuture",
+    "pad_dataproto_to_divisor",
+    "unpad_dataproto",
+    "union_tensor_batches",
+    "collate_fn",
+    "all_gather_data_proto",
+]
+
+
+class TensorBatch:
+    """Ordered mapping name -> tensor where every tensor has the same leading (batch) dimension."""
+
+    def __init__(self, tensors: dict[str, torch.Tensor] | None = None, batch_size: int | None = None):
+        self._t: dict[str, torch.Tensor] = {}
+        self._n = batch_size
+        for k, v in (tensors or {}).items():
+            self[k] = v
+
+    # -- mapping protocol -----------------------------------------------------------------
+    def __setitem__(self, key: str, value: torch.Tensor) -> None:
+        if not torch.is_tensor(value):
+            raise TypeError(f"TensorBatch[{key!r}] must be a tensor, got {type(value)}")
+        if value.dim() == 0:
+            raise ValueError(f"TensorBatch[{key!r}] needs a batch dimension")
+        if self._n is None:
+            self._n = value.shape[0]
+        elif value.shape[0] != self._n:
+            raise ValueError(f"batch dim mismatch for {key!r}: {value.shape[0]} vs {self._n}")
+        self._t[key] = value
+
+    def __getitem__(self, key):
+        if isinstance(key, str):
+            return self._t[key]
+        return self.index(key)
+
+    def __delitem__(self, key: str) -> None:
+        del self._t[key]
+
+    def __contains__(self, key: str) -> bool:
+        return key in self._t
+
+    def __iter__(self) -> Iterator[str]:
+        return iter(self._t)
+
+    def __len__(self) -> int:
+        return 0 if self._n is None else self._n
+
+    def keys(self):
+        return self._t.keys()
+
+    def values(self):
+        return self._t.values()
+
+    def items(self):
+        return self._t.items()
+
+    def get(self, key, default=None):
+        return self._t.get(key, default)
+
+    def pop(self, key, *default):
+        return self._t.pop(key, *default)
+
+    @property
+    def batch_size(self) -> int:
+        return len(self)
+
+    @property
+    def device(self):
+        for v in self._t.values():
+            return v.device
+        return None
+
+    # -- transforms ------------------------------------------------------------------------
+    def index(self, idx) -> "TensorBatch":
+        if isinstance(idx, int):
+            idx = slice(idx, idx + 1)
+        out = {k: v[idx] for k, v in self._t.items()}
+        if out:
+            n = next(iter(out.values())).shape[0]
+        elif isinstance(idx, slice):
+            n = len(range(*idx.indices(len(self))))
+        else:
+            n = int(torch.as_tensor(idx).sum()) if torch.as_tensor(idx).dtype == torch.bool else len(idx)
+        return TensorBatch(out, batch_size=n)
+
+    def select(self, keys: Iterable[str]) -> "TensorBatch":
+        return TensorBatch({k: self._t[k] for k in keys}, batch_size=len(self))
+
+    def to(self, device, non_blocking: bool = False) -> "TensorBatch":
+        return TensorBatch({k: v.to(device, non_blocking=non_blocking) for k, v in self._t.items()}, batch_size=len(self))
+
+    def clone(self) -> "TensorBatch":
+        return TensorBatch({k: v.clone() for k, v in self._t.items()}, batch_size=len(self))
+
+    def contiguous(self) -> "TensorBatch":
+        return TensorBatch({k: v.contiguous() for k, v in self._t.items()}, batch_size=len(self))
+
+    def pin_memory(self) -> "TensorBatch":
+        return TensorBatch({k: v.pin_memory() for k, v in self._t.items()}, batch_size=len(self))
+
+    @staticmethod
+    def cat(batches: Sequence["TensorBatch"]) -> "TensorBatch":
+        if not batches:
+            return TensorBatch()
+        keys = list(batches[0].keys())
+        for b in batches[1:]:
+            if list(b.keys()) != keys and set(b.keys()) != set(keys):
+                raise ValueError(f"cannot concat batches with different keys: {keys} vs {list(b.keys())}")
+        return TensorBatch({k: torch.cat([b[k] for b in batches], dim=0) for k in keys},
+                           batch_size=sum(len(b) for b in batches))
+
+    def __repr__(self) -> str:
+        body = ", ".join(f"{k}: {tuple(v.shape)} {str(v.dtype).replace('torch.', '')}" for k, v in self._t.items())
+        return f"TensorBatch(n={len(self)}, {{{body}}})"
+
+
+def union_tensor_batches(a: TensorBatch, b: TensorBatch) -> TensorBatch:
+    """Merge ``b`` into ``a``; a key present in both must hold equal tensors."""
+    if len(a) != len(b) and len(a) and len(b):
+        raise ValueError(f"cannot union batches of size {len(a)} and {len(b)}")
+    for k, v in b.items():
+        if k in a:
+            if a[k].shape != v.shape or not torch.equal(a[k].to(v.device), v):
+                raise ValueError(f"union conflict on key {k!r}")
+        else:
+            a[k] = v
+    return a
+
+
+def _union_numpy(a: dict[str, np.ndarray], b: dict[str, np.ndarray]) -> dict[str, np.ndarray]:
+    for k, v in b.items():
+        if k in a:
+            same = a[k].shape == v.shape and all(_obj_eq(x, y) for x, y in zip(a[k].reshape(-1), v.reshape(-1)))
+            if not same:
+                raise ValueError(f"union conflict on non-tensor key {k!r}")
+        else:
+            a[k] = v
+    return a
+
+
+def _obj_eq(x, y) -> bool:
+    try:
+        r = x == y
+        if isinstance(r, np.ndarray):
+            return bool(r.all())
+        if torch.is_tensor(r):
+            return bool(r.all())
+        return bool(r)
+    except Exception:
+        return x is y
+
+
+def _as_object_array(v) -> np.ndarray:
+    if isinstance(v, np.ndarray):
+        return v
+    arr = np.empty(len(v), dtype=object)
+    for i, x in enumerate(v):
+        arr[i] = x
+    return arr
+
+
+def collate_fn(samples: list[dict]) -> dict:
+    """Stack tensor fields, gather everything else into object arrays (dataset -> batch dict)."""
+    tensors: dict[str, list] = {}
+    others: dict[str, list] = {}
+    for s in samples:
+        for k, v in s.items():
+            (tensors if torch.is_tensor(v) else others).setdefault(k, []).append(v)
+    out: dict[str, Any] = {k: torch.stack(v, dim=0) for k, v in tensors.items()}
+    for k, v in others.items():
+        out[k] = _as_object_array(v)
+    return out
+
+
+@dataclass
+class DataProto:
+    batch: TensorBatch | None = None
+    non_tensor_batch: dict[str, np.ndarray] = field(default_factory=dict)
+    meta_info: dict[str, Any] = field(default_factory=dict)
+
+    def __post_init__(self):
+        self.check_consistency()
+
+    # -- construction ----------------------------------------------------------------------
+    @classmethod
+    def from_dict(cls, tensors: dict[str, torch.Tensor] | None = None, non_tensors: dict | None = None,
+                  meta_info: dict | None = None) -> "DataProto":
+        tb = TensorBatch(tensors) if tensors else None
+        nt = {k: _as_object_array(v) for k, v in (non_tensors or {}).items()}
+        return cls(batch=tb, non_tensor_batch=nt, meta_info=dict(meta_info or {}))
+
+    @classmethod
+    def from_single_dict(cls, data: dict[str, Any], meta_info: dict | None = None) -> "DataProto":
+        tensors = {k: v for k, v in data.items() if torch.is_tensor(v)}
+        others = {k: v for k, v in data.items() if not torch.is_tensor(v)}
+        return cls.from_dict(tensors, others, meta_info)
+
+    def check_consistency(self) -> None:
+        n = len(self.batch) if self.batch is not None and len(self.batch.keys()) else None
+        for k, v in self.non_tensor_batch.items():
+            if not isinstance(v, np.ndarray):
+                raise TypeError(f"non_tensor_batch[{k!r}] must be a numpy array")
+            if n is None:
+                n = v.shape[0]
+            elif v.shape[0] != n:
+                raise ValueError(f"non_tensor_batch[{k!r}] has length {v.shape[0]}, expected {n}")
+
+    # -- basics ------------------------------------------------------------------------------
+    def __len__(self) -> int:
+        if self.batch is not None and len(self.batch.keys()):
+            return len(self.batch)
+        for v in self.non_tensor_batch.values():
+            return v.shape[0]
+        return 0
+
+    def __getitem__(self, item):
+        if isinstance(item, str):
+            if self.batch is not None and item in self.batch:
+                return self.batch[item]
+            return self.non_tensor_batch[item]
+        if isinstance(item, (int, np.integer)):
+            item = slice(int(item), int(item) + 1)
+        if isinstance(item, slice):
+            return self.slice(*item.indices(len(self)))
+        return self.select_idxs(item)
+
+    def keys(self) -> list[str]:
+        ks = list(self.batch.keys()) if self.batch is not None else []
+        return ks + list(self.non_tensor_batch.keys())
+
+    def to(self, device, non_blocking: bool = False) -> "DataProto":
+        if self.batch is not None:
+            self.batch = self.batch.to(device, non_blocking=non_blocking)
+        return self
+
+    def clone(self) -> "DataProto":
+        return DataProto(batch=self.batch.clone() if self.batch is not None else None,
+                         non_tensor_batch={k: v.copy() for k, v in self.non_tensor_batch.items()},
+                         meta_info=copy.deepcopy(self.meta_info))
+
+    # -- selection ---------------------------------------------------------------------------
+    def select(self, batch_keys: Sequence[str] | None = None, non_tensor_batch_keys: Sequence[str] | None = None,
+               meta_info_keys: Sequence[str] | None = None, deepcopy: bool = False) -> "DataProto":
+        tb = self.batch
+        if batch_keys is not None and tb is not None:
+            tb = tb.select(batch_keys)
+        nt = self.non_tensor_batch
+        if non_tensor_batch_keys is not None:
+            nt = {k: nt[k] for k in non_tensor_batch_keys}
+        mi = self.meta_info
+        if meta_info_keys is not None:
+            mi = {k: mi[k] for k in meta_info_keys}
+        out = DataProto(batch=tb, non_tensor_batch=dict(nt), meta_info=dict(mi))
+        return out.clone() if deepcopy else out
+
+    def select_idxs(self, idxs) -> "DataProto":
+        if isinstance(idxs, list):
+            idxs = torch.tensor(idxs)
+        if isinstance(idxs, np.ndarray):
+            idxs_np, idxs_t = idxs, torch.from_numpy(idxs)
+        else:
+            idxs_t, idxs_np = idxs, idxs.detach().cpu().numpy()
+        tb = None
+        if self.batch is not None:
+            dev = self.batch.device
+            tb = self.batch.index(idxs_t.to(dev) if dev is not None else idxs_t)
+        nt = {k: v[idxs_np] for k, v in self.non_tensor_batch.items()}
+        return DataProto(batch=tb, non_tensor_batch=nt, meta_info=self.meta_info)
+
+    def slice(self, start: int | None = None, end: int | None = None, step: int | None = None) -> "DataProto":
+        s = slice(start, end, step)
+        tb = self.batch.index(s) if self.batch is not None else None
+        nt = {k: v[s] for k, v in self.non_tensor_batch.items()}
+        return DataProto(batch=tb, non_tensor_batch=nt, meta_info=self.meta_info)
+
+    def pop(self, batch_keys: Sequence[str] | None = None, non_tensor_batch_keys: Sequence[str] | None = None,
+            meta_info_keys: Sequence[str] | None = None) -> "DataProto":
+        tensors = {k: self.batch.pop(k) for k in (batch_keys or [])}
+        nts = {k: self.non_tensor_batch.pop(k) for k in (non_tensor_batch_keys or [])}
+        mis = {k: self.meta_info.pop(k) for k in (meta_info_keys or [])}
+        return DataProto.from_dict(tensors, nts, mis)
+
+    def rename(self, old_keys, new_keys) -> "DataProto":
+        old_keys = [old_keys] if isinstance(old_keys, str) else list(old_keys)
+        new_keys = [new_keys] if isinstance(new_keys, str) else list(new_keys)
+        if len(old_keys) != len(new_keys):
+            raise ValueError("rename needs as many new keys as old keys")
+        for o, n in zip(old_keys, new_keys):
+            self.batch[n] = self.batch.pop(o)
+        return self
+
+    # -- combination -------------------------------------------------------------------------
+    def union(self, other: "DataProto") -> "DataProto":
+        if self.batch is None:
+            self.batch = other.batch
+        elif other.batch is not None:
+            self.batch = union_tensor_batches(self.batch, other.batch)
+        self.non_tensor_batch = _union_numpy(self.non_tensor_batch, other.non_tensor_batch)
+        for k, v in other.meta_info.items():
+            if k in self.meta_info and not _obj_eq(self.meta_info[k], v):
+                raise ValueError(f"union conflict on meta_info key {k!r}")
+            self.meta_info[k] = v
+        return self
+
+    @staticmethod
+    def concat(data: Sequence["DataProto"]) -> "DataProto":
+        data = [d for d in data if d is not None]
+        if not data:
+            return DataProto()
+        tbs = [d.batch for d in data if d.batch is not None]
+        tb = TensorBatch.cat(tbs) if tbs else None
+        nt = {}
+        for k in data[0].non_tensor_batch:
+            nt[k] = np.concatenate([d.non_tensor_batch[k] for d in data], axis=0)
+        meta = dict(data[0].meta_info)
+        # per-chunk metric dicts are merged list-wise so the driver can reduce them
+        metrics = [d.meta_info.get("metrics") for d in data if isinstance(d.meta_info.get("metrics"), dict)]
+        if len(metrics) > 1:
+            merged: dict[str, list] = {}
+            for m in metrics:
+                for k, v in m.items():
+                    merged.setdefault(k, []).extend(v if isinstance(v, list) else [v])
+            meta["metrics"] = merged
+        return DataProto(batch=tb, non_tensor_batch=nt, meta_info=meta)
+
+    def chunk(self, chunks: int) -> list["DataProto"]:
+        n = len(self)
+        if n % chunks != 0:
+            raise ValueError(f"batch of {n} is not divisible into {chunks} chunks (pad with pad_dataproto_to_divisor)")
+        return self.split(n // chunks) if n else [DataProto(meta_info=self.meta_info) for _ in range(chunks)]
+
+    def split(self, split_size: int) -> list["DataProto"]:
+        return [self.slice(i, min(i + split_size, len(self))) for i in range(0, len(self), split_size)]
+
+    def repeat(self, repeat_times: int = 2, interleave: bool = True) -> "DataProto":
+        tb = None
+        if self.batch is not None:
+            if interleave:
+                tb = TensorBatch({k: v.repeat_interleave(repeat_times, dim=0) for k, v in self.batch.items()})
+            else:
+                tb = TensorBatch({k: v.repeat(repeat_times, *([1] * (v.dim() - 1))) for k, v in self.batch.items()})
+        nt = {}
+        for k, v in self.non_tensor_batch.items():
+            nt[k] = np.repeat(v, repeat_times, axis=0) if interleave else np.tile(v, (repeat_times,) + (1,) * (v.ndim - 1))
+        return DataProto(batch=tb, non_tensor_batch=nt, meta_info=self.meta_info)
+
+    def reorder(self, indices: torch.Tensor) -> None:
+        """In-place permutation of the batch."""
+        idx_np = indices.detach().cpu().numpy()
+        if self.batch is not None:
+            dev = self.batch.device
+            self.batch = self.batch.index(indices.to(dev) if dev is not None else indices)
+        self.non_tensor_batch = {k: v[idx_np] for k, v in self.non_tensor_batch.items()}
+
+    def make_iterator(self, mini_batch_size: int, epochs: int, seed: int | None = None) -> Iterator["DataProto"]:
+        n = len(self)
+        if n % mini_batch_size != 0:
+            raise ValueError(f"{n} % {mini_batch_size} != 0")
+        g = torch.Generator()
+        if seed is not None:
+            g.manual_seed(seed)
+        for _ in range(epochs):
+            perm = torch.randperm(n, generator=g)
+            for i in range(0, n, mini_batch_size):
+                yield self.select_idxs(perm[i:i + mini_batch_size])
+
+    # -- serialisation -----------------------------------------------------------------------
+    def __getstate__(self):
+        buf = io.BytesIO()
+        tensors = {k: v.detach().cpu().contiguous() for k, v in self.batch.items()} if self.batch is not None else None
+        torch.save(tensors, buf)
+        return {"tensors": buf.getvalue(), "n": len(self), "non_tensor": self.non_tensor_batch, "meta": self.meta_info}
+
+    def __setstate__(self, state):
+        tensors = torch.load(io.BytesIO(state["tensors"]), weights_only=False, map_location="cpu")
+        self.batch = TensorBatch(tensors, batch_size=state["n"]) if tensors is not None else None
+        self.non_tensor_batch = state["non_tensor"]
+        self.meta_info = state["meta"]
+
+    def save_to_disk(self, path: str) -> None:
+        with open(path, "wb") as f:
+            pickle.dump(self, f)
+
+    @staticmethod
+    def load_from_disk(path: str) -> "DataProto":
+        with open(path, "rb") as f:
+            return pickle.load(f)
+
+    def __repr__(self) -> str:
+        return (f"DataProto(n={len(self)}, batch={self.batch}, non_tensor={list(self.non_tensor_batch)}, "
+                f"meta={list(self.meta_info)})")
+
+
+def pad_dataproto_to_divisor(data: DataProto, divisor: int) -> tuple[DataProto, int]:
+    """Pad by cycling the first rows so that ``len % divisor == 0``; returns (padded, pad_size)."""
+    n = len(data)
+    if divisor <= 0 or n % divisor == 0:
+        return data, 0
+    pad = divisor - n % divisor
+    parts = [data]
+    remaining = pad
+    while remaining > 0:
+        take = min(remaining, n)
+        parts.append(data.slice(0, take))
+        remaining -= take
+    return DataProto.concat(parts), pad
+
+
+def unpad_dataproto(data: DataProto, pad_size: int) -> DataProto:
+    return data.slice(0, len(data) - pad_size) if pad_size else data
+
+
+class DataProtoFuture:
+    """Deferred result of an asynchronous worker-group call: resolves to the collected DataProto.
+
+    ``futures`` are objects with ``.result()`` (concurrent futures) or callables; ``collect_fn`` merges
+    their results; ``dispatch_fn`` optionally selects this consumer's shard (chunking a future).
+    """
+
+    def __init__(self, futures: list, collect_fn: Callable[[list], DataProto],
+                 dispatch_fn: Callable[[DataProto], DataProto] | None = None):
+        self.futures = futures
+        self.collect_fn = collect_fn
+        self.dispatch_fn = dispatch_fn
+
+    @staticmethod
+    def concat(futures: list) -> "DataProtoFuture":
+        return DataProtoFuture(futures, DataProto.concat)
+
+    def chunk(self, chunks: int) -> list["DataProtoFuture"]:
+        out = []
+        for i in range(chunks):
+            def pick(x, i=i):
+                return x.chunk(chunks)[i]
+            out.append(DataProtoFuture(self.futures, self.collect_fn, pick))
+        return out
+
+    def get(self) -> DataProto:
+        vals = [f.result() if hasattr(f, "result") else f() for f in self.futures]
+        out = self.collect_fn(vals)
+        return self.dispatch_fn(out) if self.dispatch_fn is not None else out
+
+
+def all_gather_data_proto(data: DataProto, group=None) -> DataProto:
+    """All-gather a DataProto across a process group (tensors via all_gather, the rest as objects)."""
+    import torch.distributed as dist
+
+    ws = dist.get_world_size(group)
+    if ws == 1:
+        return data
+    tb = None
+    if data.batch is not None:
+        out = {}
+        for k, v in data.batch.items():
+            bufs = [torch.empty_like(v) for _ in range(ws)]
+            dist.all_gather(bufs, v.contiguous(), group=group)
+            out[k] = torch.cat(bufs, dim=0)
+        tb = TensorBatch(out)
+    gathered: list = [None] * ws
+    dist.all_gather_object(gathered, data.non_tensor_batch, group=group)
+    nt = {k: np.concatenate([g[k] for g in gathered], axis=0) for k in data.non_tensor_batch}
+    return DataProto(batch=tb, non_tensor_batch=nt, meta_info=data.meta_info)
