@@ -1,0 +1,478 @@
+"""Typed configuration tree with the reference's key names, YAML loading and Hydra-style
+dotted overrides (``actor_rollout_ref.actor.optim.lr=1e-6``).  Hydra/OmegaConf are not available on the
+target image, so composition is implemented here: defaults from dataclasses < YAML file(s) < CLI
+overrides, then ``validate_config`` cross-field checks (reference: 3rdparty/verl/verl/utils/config.py:23-200,
+verl/trainer/config/ppo_trainer.yaml, rlboost/verl_stream/trainer/config/ppo_stream_trainer.yaml:9-23,
+rlboost/verl_stream/workers/config/rollout.py:94-208).
+"""
+from __future__ import annotations
+
+import copy
+import dataclasses
+from dataclasses import dataclass, field, fields, is_dataclass
+from typing import Any, Mapping
+
+import yaml
+
+
+class BaseConfig(Mapping):
+    """Dataclass mixin: mapping access (cfg['a'], cfg.get('a')), frozen-by-convention with an explicit
+    allow-list of fields that may be mutated after construction (``_mutable_fields``)."""
+
+    _mutable_fields: set = set()
+
+    def __getitem__(self, k):
+        try:
+            return getattr(self, k)
+        except AttributeError as e:
+            raise KeyError(k) from e
+
+    def __iter__(self):
+        return (f.name for f in fields(self))
+
+    def __len__(self):
+        return len(fields(self))
+
+    def get(self, k, default=None):
+        return getattr(self, k, default)
+
+    def to_dict(self) -> dict:
+        return dataclasses.asdict(self)
+
+
+@dataclass
+class OptimConfig(BaseConfig):
+    lr: float = 1e-6
+    lr_warmup_steps: int = -1
+    lr_warmup_steps_ratio: float = 0.0
+    min_lr_ratio: float = 0.0
+    num_cycles: float = 0.5
+    warmup_style: str = "constant"      # constant | cosine
+    total_training_steps: int = -1
+    weight_decay: float = 0.01
+    betas: tuple = (0.9, 0.999)
+    eps: float = 1e-8
+    clip_grad: float = 1.0
+
+
+@dataclass
+class FSDPConfig(BaseConfig):
+    param_offload: bool = False
+    optimizer_offload: bool = False
+    fsdp_size: int = -1
+    reshard_after_forward: bool = True
+    forward_prefetch: bool = True
+    comm_backend: str = "p2p"           # "p2p" (NVLink peer-memory kernels) | "nccl" (baseline)
+    model_dtype: str = "bf16"
+
+
+@dataclass
+class PolicyLossConfig(BaseConfig):
+    loss_mode: str = "vanilla"
+    clip_cov_ratio: float = 0.0002
+    clip_cov_lb: float = 1.0
+    clip_cov_ub: float = 5.0
+    kl_cov_ratio: float = 0.0002
+    ppo_kl_coef: float = 0.1
+
+
+@dataclass
+class CheckpointConfig(BaseConfig):
+    save_contents: list = field(default_factory=lambda: ["model", "optimizer", "extra"])
+    load_contents: list = field(default_factory=lambda: ["model", "optimizer", "extra"])
+    async_save: bool = False
+
+
+@dataclass
+class ProfilerConfig(BaseConfig):
+    enable: bool = False
+    all_ranks: bool = False
+    ranks: list = field(default_factory=list)
+    tool_config: dict = field(default_factory=dict)
+
+
+@dataclass
+class ActorConfig(BaseConfig):
+    strategy: str = "fsdp"
+    ppo_mini_batch_size: int = 256
+    ppo_micro_batch_size: int | None = None
+    ppo_micro_batch_size_per_gpu: int | None = None
+    use_dynamic_bsz: bool = False
+    ppo_max_token_len_per_gpu: int = 16384
+    clip_ratio: float = 0.2
+    clip_ratio_low: float = 0.2
+    clip_ratio_high: float = 0.2
+    clip_ratio_c: float = 3.0
+    policy_loss: PolicyLossConfig = field(default_factory=PolicyLossConfig)
+    loss_agg_mode: str = "token-mean"
+    entropy_coeff: float = 0.0
+    use_kl_loss: bool = False
+    kl_loss_coef: float = 0.001
+    kl_loss_type: str = "low_var_kl"
+    ppo_epochs: int = 1
+    shuffle: bool = False
+    ulysses_sequence_parallel_size: int = 1
+    grad_clip: float = 1.0
+    optim: OptimConfig = field(default_factory=OptimConfig)
+    fsdp_config: FSDPConfig = field(default_factory=FSDPConfig)
+    checkpoint: CheckpointConfig = field(default_factory=CheckpointConfig)
+    profiler: ProfilerConfig = field(default_factory=ProfilerConfig)
+    _mutable_fields = {"ppo_mini_batch_size", "ppo_micro_batch_size", "ppo_micro_batch_size_per_gpu"}
+
+
+@dataclass
+class RolloutManagerConfig(BaseConfig):
+    port: int = 5000
+    endpoint: str | None = None
+    config_path: str | None = None
+    max_local_gen_s: float = 150.0
+
+
+@dataclass
+class RolloutConfig(BaseConfig):
+    name: str = "native"                # native | native-disaggregated | sglang-disaggregated (alias) | hf | naive
+    mode: str = "sync"
+    n: int = 1
+    temperature: float = 1.0
+    top_k: int = -1
+    top_p: float = 1.0
+    do_sample: bool = True
+    prompt_length: int = 512
+    response_length: int = 512
+    dtype: str = "bfloat16"
+    weight_dtype: str = "bf16"          # bf16 | fp8 (row-scaled e4m3 rollout weights)
+    gpu_memory_utilization: float = 0.5
+    free_cache_engine: bool = True
+    tensor_model_parallel_size: int = 1
+    data_parallel_size: int = 1
+    pipeline_model_parallel_size: int = 1
+    expert_parallel_size: int = 1
+    max_num_batched_tokens: int = 16384
+    max_num_seqs: int = 256
+    max_model_len: int | None = None
+    enable_chunked_prefill: bool = True
+    load_format: str = "dummy"
+    calculate_log_probs: bool = False
+    log_prob_micro_batch_size_per_gpu: int | None = None
+    log_prob_use_dynamic_bsz: bool = False
+    log_prob_max_token_len_per_gpu: int = 16384
+    min_stream_batch_size: int = 16
+    cuda_graph: bool = True
+    rollout_manager: RolloutManagerConfig = field(default_factory=RolloutManagerConfig)
+    val_kwargs: dict = field(default_factory=lambda: {"n": 1, "temperature": 0.0, "do_sample": False})
+
+    def __post_init__(self):
+        if self.pipeline_model_parallel_size > 1:
+            raise NotImplementedError("rollout pipeline parallelism is not supported")
+        if self.expert_parallel_size > 1 and self.expert_parallel_size != self.tensor_model_parallel_size * self.data_parallel_size:
+            raise ValueError("expert_parallel_size must equal tensor_model_parallel_size * data_parallel_size")
+        if self.name == "sglang-disaggregated":
+            self.name = "native-disaggregated"
+
+
+@dataclass
+class RefConfig(BaseConfig):
+    strategy: str = "fsdp"
+    log_prob_micro_batch_size_per_gpu: int | None = None
+    log_prob_use_dynamic_bsz: bool = False
+    log_prob_max_token_len_per_gpu: int = 16384
+    fsdp_config: FSDPConfig = field(default_factory=FSDPConfig)
+
+
+@dataclass
+class ModelCfg(BaseConfig):
+    path: str = "tiny-llama"
+    use_remove_padding: bool = True
+    enable_gradient_checkpointing: bool = True
+    use_fused_kernels: bool = True
+    lora_rank: int = 0
+    lora_alpha: int = 16
+    target_modules: str = "all-linear"
+    override_config: dict = field(default_factory=dict)
+    tokenizer_path: str | None = None
+
+
+@dataclass
+class ActorRolloutRefConfig(BaseConfig):
+    hybrid_engine: bool = True
+    nccl_timeout: int = 600
+    model: ModelCfg = field(default_factory=ModelCfg)
+    actor: ActorConfig = field(default_factory=ActorConfig)
+    rollout: RolloutConfig = field(default_factory=RolloutConfig)
+    ref: RefConfig = field(default_factory=RefConfig)
+
+
+@dataclass
+class CriticConfig(BaseConfig):
+    enable: bool | None = None
+    strategy: str = "fsdp"
+    model: ModelCfg = field(default_factory=ModelCfg)
+    optim: OptimConfig = field(default_factory=lambda: OptimConfig(lr=1e-5))
+    ppo_mini_batch_size: int = 256
+    ppo_micro_batch_size_per_gpu: int | None = None
+    use_dynamic_bsz: bool = False
+    ppo_max_token_len_per_gpu: int = 32768
+    forward_max_token_len_per_gpu: int = 32768
+    cliprange_value: float = 0.5
+    loss_agg_mode: str = "token-mean"
+    grad_clip: float = 1.0
+    ppo_epochs: int = 1
+    fsdp_config: FSDPConfig = field(default_factory=FSDPConfig)
+    checkpoint: CheckpointConfig = field(default_factory=CheckpointConfig)
+
+
+@dataclass
+class RewardModelConfig(BaseConfig):
+    enable: bool = False
+    reward_manager: str = "naive"       # naive | batch | dapo | prime
+    launch_reward_fn_async: bool = False
+    model: ModelCfg = field(default_factory=ModelCfg)
+    micro_batch_size_per_gpu: int | None = None
+
+
+@dataclass
+class CustomRewardFunction(BaseConfig):
+    path: str | None = None
+    name: str = "compute_score"
+
+
+@dataclass
+class KLCtrlConfig(BaseConfig):
+    type: str = "fixed"
+    kl_coef: float = 0.001
+    horizon: int = 10000
+    target_kl: float = 0.1
+
+
+@dataclass
+class RolloutCorrectionConfig(BaseConfig):
+    rollout_is: str | None = None        # None | token | sequence | geometric
+    rollout_is_threshold: float = 2.0
+    rollout_rs: str | None = None        # None | token | sequence | geometric
+    rollout_rs_threshold: float | None = None
+    rollout_rs_threshold_lower: float | None = None
+    rollout_token_veto_threshold: float | None = None
+    bypass_mode: bool = False
+
+
+@dataclass
+class AlgorithmConfig(BaseConfig):
+    gamma: float = 1.0
+    lam: float = 1.0
+    adv_estimator: str = "gae"
+    norm_adv_by_std_in_grpo: bool = True
+    use_kl_in_reward: bool = False
+    kl_penalty: str = "kl"
+    kl_ctrl: KLCtrlConfig = field(default_factory=KLCtrlConfig)
+    rollout_correction: RolloutCorrectionConfig = field(default_factory=RolloutCorrectionConfig)
+
+
+@dataclass
+class DataConfig(BaseConfig):
+    train_files: Any = None
+    val_files: Any = None
+    prompt_key: str = "prompt"
+    reward_fn_key: str = "data_source"
+    max_prompt_length: int = 512
+    max_response_length: int = 512
+    train_batch_size: int = 1024
+    val_batch_size: int | None = None
+    shuffle: bool = True
+    seed: int = 1
+    filter_overlong_prompts: bool = False
+    truncation: str = "error"
+    return_raw_chat: bool = False
+    dataloader_num_workers: int = 0
+    synthetic: bool = False               # synthetic GSM8K-shaped prompts (no network on the target box)
+    synthetic_num_samples: int = 4096
+    synthetic_prompt_len_range: tuple = (64, 192)
+
+
+@dataclass
+class GlobalProfilerConfig(BaseConfig):
+    tool: str | None = None              # nsys | torch | torch_memory
+    steps: list | None = None
+    profile_continuous_steps: bool = False
+    save_path: str = "outputs/profile"
+    global_tool_config: dict = field(default_factory=dict)
+
+
+@dataclass
+class TrainerConfig(BaseConfig):
+    total_epochs: int = 1
+    total_training_steps: int | None = None
+    project_name: str = "polyrl_b200"
+    experiment_name: str = "run"
+    logger: list = field(default_factory=lambda: ["console"])
+    nnodes: int = 1
+    n_gpus_per_node: int = 8
+    save_freq: int = -1
+    test_freq: int = -1
+    val_before_train: bool = False
+    val_only: bool = False
+    balance_batch: bool = True
+    critic_warmup: int = 0
+    resume_mode: str = "auto"            # disable | auto | resume_path
+    resume_from_path: str | None = None
+    default_local_dir: str = "checkpoints"
+    default_hdfs_dir: str | None = None
+    max_actor_ckpt_to_keep: int | None = None
+    max_critic_ckpt_to_keep: int | None = None
+    esi_redundant_time: float = 0.0
+    rollout_data_dir: str | None = None
+    validation_data_dir: str | None = None
+    log_val_generations: int = 0
+    device: str = "cuda"
+    controller_backend: str = "spmd"     # spmd | local | mp | ray
+    n_rollout_gpus: int = 0              # >0 => disaggregated: dedicated rollout GPUs
+
+
+@dataclass
+class PPOConfig(BaseConfig):
+    data: DataConfig = field(default_factory=DataConfig)
+    actor_rollout_ref: ActorRolloutRefConfig = field(default_factory=ActorRolloutRefConfig)
+    critic: CriticConfig = field(default_factory=CriticConfig)
+    reward_model: RewardModelConfig = field(default_factory=RewardModelConfig)
+    custom_reward_function: CustomRewardFunction = field(default_factory=CustomRewardFunction)
+    algorithm: AlgorithmConfig = field(default_factory=AlgorithmConfig)
+    trainer: TrainerConfig = field(default_factory=TrainerConfig)
+    global_profiler: GlobalProfilerConfig = field(default_factory=GlobalProfilerConfig)
+
+
+# ---------------------------------------------------------------------------------------------
+# loading / overrides
+# ---------------------------------------------------------------------------------------------
+def _coerce(value: Any, target: Any) -> Any:
+    """Parse a CLI string into the type of the current value."""
+    if not isinstance(value, str):
+        return value
+    parsed = yaml.safe_load(value)
+    if isinstance(target, float) and isinstance(parsed, (int, str)):
+        try:
+            return float(parsed)
+        except (TypeError, ValueError):
+            return parsed
+    if isinstance(target, tuple) and isinstance(parsed, list):
+        return tuple(parsed)
+    return parsed
+
+
+def _apply_dict(obj: Any, d: Mapping, path: str = "") -> None:
+    for k, v in d.items():
+        if not hasattr(obj, k):
+            raise KeyError(f"unknown config key {path + k!r}")
+        cur = getattr(obj, k)
+        if is_dataclass(cur) and isinstance(v, Mapping):
+            _apply_dict(cur, v, path + k + ".")
+        else:
+            setattr(obj, k, _coerce(v, cur) if not isinstance(v, Mapping) else dict(v))
+
+
+def apply_overrides(cfg: Any, overrides: list[str]) -> Any:
+    """``a.b.c=value`` (set), ``+a.b.c=value`` (set, key may be new inside a dict field), ``~a.b.c`` (reset)."""
+    for ov in overrides:
+        ov = ov.strip()
+        if not ov:
+            continue
+        if ov.startswith("~"):
+            key, value, reset = ov[1:], None, True
+        else:
+            if "=" not in ov:
+                raise ValueError(f"override {ov!r} is not of the form key=value")
+            key, value = ov.split("=", 1)
+            reset = False
+        key = key.lstrip("+")
+        parts = key.split(".")
+        obj = cfg
+        for i, p in enumerate(parts[:-1]):
+            nxt = obj[p] if isinstance(obj, dict) else getattr(obj, p, None)
+            if nxt is None and not isinstance(obj, dict):
+                raise KeyError(f"unknown config key {'.'.join(parts[:i + 1])!r}")
+            if nxt is None:
+                nxt = obj.setdefault(p, {})
+            obj = nxt
+        leaf = parts[-1]
+        if isinstance(obj, dict):
+            obj[leaf] = None if reset else yaml.safe_load(value)
+            continue
+        if not hasattr(obj, leaf):
+            raise KeyError(f"unknown config key {key!r}")
+        cur = getattr(obj, leaf)
+        if reset:
+            default = {f.name: f for f in fields(obj)}[leaf]
+            setattr(obj, leaf, default.default if default.default is not dataclasses.MISSING else default.default_factory())
+        else:
+            setattr(obj, leaf, _coerce(value, cur))
+        if hasattr(obj, "__post_init__"):
+            obj.__post_init__()
+    return cfg
+
+
+def load_config(yaml_paths: list[str] | str | None = None, overrides: list[str] | None = None,
+                base: PPOConfig | None = None) -> PPOConfig:
+    cfg = copy.deepcopy(base) if base is not None else PPOConfig()
+    if isinstance(yaml_paths, str):
+        yaml_paths = [yaml_paths]
+    for p in yaml_paths or []:
+        with open(p) as f:
+            d = yaml.safe_load(f) or {}
+        _apply_dict(cfg, d)
+    apply_overrides(cfg, overrides or [])
+    return cfg
+
+
+def config_to_flat_dict(cfg: Any, prefix: str = "") -> dict[str, Any]:
+    out = {}
+    d = dataclasses.asdict(cfg) if is_dataclass(cfg) else cfg
+    for k, v in d.items():
+        if isinstance(v, dict):
+            out.update(config_to_flat_dict(v, prefix + k + "."))
+        else:
+            out[prefix + k] = v
+    return out
+
+
+def need_critic(cfg: PPOConfig) -> bool:
+    if cfg.critic.enable is not None:
+        return bool(cfg.critic.enable)
+    return cfg.algorithm.adv_estimator == "gae"
+
+
+def need_reference_policy(cfg: PPOConfig) -> bool:
+    return cfg.algorithm.use_kl_in_reward or cfg.actor_rollout_ref.actor.use_kl_loss
+
+
+def validate_config(cfg: PPOConfig, n_gpus: int | None = None) -> None:
+    """Cross-field validation (reference: verl/utils/config.py:74-200 and
+    rlboost/verl_stream/trainer/main_stream.py:372-389)."""
+    t, a, r = cfg.trainer, cfg.actor_rollout_ref.actor, cfg.actor_rollout_ref.rollout
+    n_gpus = n_gpus or t.n_gpus_per_node * t.nnodes
+    n_train = n_gpus - t.n_rollout_gpus
+    if n_train <= 0:
+        raise ValueError("no trainer GPUs left after reserving rollout GPUs")
+    real_bsz = cfg.data.train_batch_size * r.n
+    if real_bsz % n_train != 0:
+        raise ValueError(f"train_batch_size*n ({real_bsz}) must be divisible by the number of trainer GPUs ({n_train})")
+    if a.ppo_epochs != 1:
+        raise ValueError("the streaming trainer requires actor.ppo_epochs == 1")
+    if a.strategy not in ("fsdp", "fsdp2", "zero3"):
+        raise NotImplementedError(f"actor strategy {a.strategy!r}: only ZeRO-3/FSDP is supported by the streaming path")
+    if not a.use_dynamic_bsz:
+        if a.ppo_micro_batch_size_per_gpu is None and a.ppo_micro_batch_size is None:
+            raise ValueError("set actor.ppo_micro_batch_size_per_gpu (or enable use_dynamic_bsz)")
+        mb = a.ppo_micro_batch_size_per_gpu or max(1, a.ppo_micro_batch_size // n_train)
+        if r.min_stream_batch_size % (mb * n_train) != 0:
+            raise ValueError(f"min_stream_batch_size ({r.min_stream_batch_size}) must be divisible by "
+                             f"micro_batch_size_per_gpu*n_gpus ({mb * n_train})")
+    if r.min_stream_batch_size % r.n != 0:
+        raise ValueError("min_stream_batch_size must be divisible by rollout.n (whole GRPO groups per streamed batch)")
+    if need_critic(cfg) and not a.use_dynamic_bsz:
+        cm = cfg.critic.ppo_micro_batch_size_per_gpu
+        if cm is not None and a.ppo_micro_batch_size_per_gpu is not None and cm != a.ppo_micro_batch_size_per_gpu:
+            raise ValueError("with GAE the critic and actor micro-batch sizes must match in streaming mode")
+    if a.loss_agg_mode not in ("token-mean", "seq-mean-token-sum", "seq-mean-token-mean", "seq-mean-token-sum-norm"):
+        raise ValueError(f"invalid loss_agg_mode {a.loss_agg_mode}")
+    if cfg.algorithm.use_kl_in_reward and a.use_kl_loss:
+        print("[config] NOTICE: both in-reward KL and KL loss are enabled")
+    if r.tensor_model_parallel_size < 1:
+        raise ValueError("tensor_model_parallel_size must be >= 1")

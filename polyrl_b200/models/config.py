@@ -1,0 +1,150 @@
+"""Model architecture configs (decoder-only transformers) and named presets.
+
+Families: ``llama`` (Llama-2/3, Qwen2/2.5/3 — RMSNorm, RoPE, SwiGLU, GQA, optional qkv bias / qk-norm) and
+``gpt2`` (LayerNorm, learned positions, GELU MLP, biases).  Shapes for the presets follow the public
+HF configs (the reference loads the same families through HF AutoModel:
+3rdparty/verl/verl/workers/fsdp_workers.py:269-577).
+"""
+from __future__ import annotations
+
+import json
+from dataclasses import asdict, dataclass, field
+from pathlib import Path
+
+
+@dataclass
+class ModelConfig:
+    family: str = "llama"            # "llama" | "gpt2"
+    vocab_size: int = 32000
+    hidden_size: int = 4096
+    intermediate_size: int = 11008
+    num_layers: int = 32
+    num_heads: int = 32
+    num_kv_heads: int = 32
+    head_dim: int = 0                # 0 -> hidden_size // num_heads
+    max_position_embeddings: int = 8192
+    rope_theta: float = 10000.0
+    rms_norm_eps: float = 1e-6
+    qkv_bias: bool = False           # Qwen2
+    tie_word_embeddings: bool = False
+    pad_token_id: int = 0
+    eos_token_id: int = 1
+    bos_token_id: int = 1
+    name: str = "custom"
+    value_head: bool = False         # critic: scalar head instead of lm_head
+
+    def __post_init__(self):
+        if self.head_dim == 0:
+            self.head_dim = self.hidden_size // self.num_heads
+        if self.num_heads % self.num_kv_heads != 0:
+            raise ValueError("num_heads must be a multiple of num_kv_heads")
+        if self.family not in ("llama", "gpt2"):
+            raise ValueError(f"unknown model family {self.family!r}")
+
+    @property
+    def q_size(self) -> int:
+        return self.num_heads * self.head_dim
+
+    @property
+    def kv_size(self) -> int:
+        return self.num_kv_heads * self.head_dim
+
+    def num_params(self) -> int:
+        h, f, v = self.hidden_size, self.intermediate_size, self.vocab_size
+        if self.family == "llama":
+            per = h * (self.q_size + 2 * self.kv_size) + self.q_size * h + 3 * h * f + 2 * h
+            if self.qkv_bias:
+                per += self.q_size + 2 * self.kv_size
+        else:
+            per = 4 * h * h + 2 * h * f + 9 * h + f + 4 * h
+        emb = v * h * (1 if self.tie_word_embeddings else 2)
+        if self.family == "gpt2":
+            emb += self.max_position_embeddings * h
+        return per * self.num_layers + emb + h
+
+    def to_dict(self) -> dict:
+        return asdict(self)
+
+    def save(self, path: str | Path) -> None:
+        Path(path).write_text(json.dumps(self.to_dict(), indent=2))
+
+    @classmethod
+    def load(cls, path: str | Path) -> "ModelConfig":
+        return cls(**json.loads(Path(path).read_text()))
+
+    @classmethod
+    def from_hf_config(cls, hf: dict) -> "ModelConfig":
+        """Translate a HuggingFace ``config.json`` dict (Llama / Qwen2 / Qwen3 / GPT-2)."""
+        mt = hf.get("model_type", "llama")
+        if mt == "gpt2":
+            return cls(family="gpt2", vocab_size=hf["vocab_size"], hidden_size=hf["n_embd"],
+                       intermediate_size=hf.get("n_inner") or 4 * hf["n_embd"], num_layers=hf["n_layer"],
+                       num_heads=hf["n_head"], num_kv_heads=hf["n_head"], max_position_embeddings=hf["n_positions"],
+                       rms_norm_eps=hf.get("layer_norm_epsilon", 1e-5), tie_word_embeddings=True,
+                       eos_token_id=hf.get("eos_token_id", 50256), bos_token_id=hf.get("bos_token_id", 50256),
+                       pad_token_id=hf.get("pad_token_id") or hf.get("eos_token_id", 50256), name=hf.get("_name_or_path", "gpt2"))
+        eos = hf.get("eos_token_id", 2)
+        if isinstance(eos, list):
+            eos = eos[0]
+        return cls(family="llama", vocab_size=hf["vocab_size"], hidden_size=hf["hidden_size"],
+                   intermediate_size=hf["intermediate_size"], num_layers=hf["num_hidden_layers"],
+                   num_heads=hf["num_attention_heads"], num_kv_heads=hf.get("num_key_value_heads", hf["num_attention_heads"]),
+                   head_dim=hf.get("head_dim") or 0, max_position_embeddings=hf.get("max_position_embeddings", 8192),
+                   rope_theta=hf.get("rope_theta", 10000.0), rms_norm_eps=hf.get("rms_norm_eps", 1e-6),
+                   qkv_bias=(mt == "qwen2") or hf.get("attention_bias", False),
+                   tie_word_embeddings=hf.get("tie_word_embeddings", False), eos_token_id=eos,
+                   bos_token_id=hf.get("bos_token_id") or eos, pad_token_id=hf.get("pad_token_id") or eos,
+                   name=hf.get("_name_or_path", mt))
+
+
+PRESETS: dict[str, dict] = {
+    "llama3-8b": dict(family="llama", vocab_size=128256, hidden_size=4096, intermediate_size=14336, num_layers=32,
+                      num_heads=32, num_kv_heads=8, max_position_embeddings=8192, rope_theta=500000.0,
+                      rms_norm_eps=1e-5, eos_token_id=128001, bos_token_id=128000, pad_token_id=128001),
+    "llama3-70b": dict(family="llama", vocab_size=128256, hidden_size=8192, intermediate_size=28672, num_layers=80,
+                       num_heads=64, num_kv_heads=8, max_position_embeddings=8192, rope_theta=500000.0,
+                       rms_norm_eps=1e-5, eos_token_id=128001, bos_token_id=128000, pad_token_id=128001),
+    "qwen2-7b": dict(family="llama", vocab_size=152064, hidden_size=3584, intermediate_size=18944, num_layers=28,
+                     num_heads=28, num_kv_heads=4, max_position_embeddings=32768, rope_theta=1000000.0,
+                     rms_norm_eps=1e-6, qkv_bias=True, eos_token_id=151643, bos_token_id=151643, pad_token_id=151643),
+    "qwen3-1.7b": dict(family="llama", vocab_size=151936, hidden_size=2048, intermediate_size=6144, num_layers=28,
+                       num_heads=16, num_kv_heads=8, head_dim=128, max_position_embeddings=40960,
+                       rope_theta=1000000.0, rms_norm_eps=1e-6, tie_word_embeddings=True, eos_token_id=151645,
+                       bos_token_id=151643, pad_token_id=151643),
+    "qwen2.5-0.5b": dict(family="llama", vocab_size=151936, hidden_size=896, intermediate_size=4864, num_layers=24,
+                         num_heads=14, num_kv_heads=2, max_position_embeddings=32768, rope_theta=1000000.0,
+                         rms_norm_eps=1e-6, qkv_bias=True, tie_word_embeddings=True, eos_token_id=151645,
+                         bos_token_id=151643, pad_token_id=151643),
+    "gpt2-small": dict(family="gpt2", vocab_size=50257, hidden_size=768, intermediate_size=3072, num_layers=12,
+                       num_heads=12, num_kv_heads=12, max_position_embeddings=1024, rms_norm_eps=1e-5,
+                       tie_word_embeddings=True, eos_token_id=50256, bos_token_id=50256, pad_token_id=50256),
+    # tiny configs for tests (2-layer, like the reference's test fixtures
+    # 3rdparty/verl/tests/models/test_transformers_ulysses.py:49-70)
+    "tiny-llama": dict(family="llama", vocab_size=512, hidden_size=256, intermediate_size=512, num_layers=2,
+                       num_heads=4, num_kv_heads=2, head_dim=64, max_position_embeddings=512, rope_theta=10000.0,
+                       eos_token_id=1, bos_token_id=2, pad_token_id=0),
+    "tiny-llama-128": dict(family="llama", vocab_size=1024, hidden_size=512, intermediate_size=1024, num_layers=2,
+                           num_heads=4, num_kv_heads=2, head_dim=128, max_position_embeddings=1024,
+                           rope_theta=10000.0, eos_token_id=1, bos_token_id=2, pad_token_id=0),
+    "tiny-gpt2": dict(family="gpt2", vocab_size=512, hidden_size=128, intermediate_size=512, num_layers=2,
+                      num_heads=4, num_kv_heads=4, max_position_embeddings=256, rms_norm_eps=1e-5,
+                      tie_word_embeddings=True, eos_token_id=1, bos_token_id=2, pad_token_id=0),
+}
+
+
+def get_model_config(name_or_path: str, **overrides) -> ModelConfig:
+    """Resolve a preset name, a directory containing ``config.json`` (HF or ours), or a json path."""
+    if name_or_path in PRESETS:
+        cfg = dict(PRESETS[name_or_path], name=name_or_path)
+        cfg.update(overrides)
+        return ModelConfig(**cfg)
+    p = Path(name_or_path)
+    if p.is_dir():
+        p = p / "config.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        cfg = ModelConfig(**d) if "family" in d else ModelConfig.from_hf_config(d)
+        for k, v in overrides.items():
+            setattr(cfg, k, v)
+        return cfg
+    raise ValueError(f"unknown model {name_or_path!r}; presets: {sorted(PRESETS)}")

@@ -10,6 +10,34 @@ import os
 
 _EXT = None
 _EXT_ERR: Exception | None = None
+LAUNCHES: dict[str, int] = {}
+
+
+class _CountingExt:
+    """Thin proxy over the compiled module that counts calls per kernel entry point, so benchmarks can
+    report how many of OUR kernels ran (CUDA-graph replays add the count recorded at capture)."""
+
+    def __init__(self, mod):
+        self._mod = mod
+        self._cache: dict = {}
+
+    def __getattr__(self, name):
+        fn = self._cache.get(name)
+        if fn is None:
+            raw = getattr(self._mod, name)
+            if not callable(raw):
+                return raw
+
+            def fn(*a, _raw=raw, _n=name, **kw):
+                LAUNCHES[_n] = LAUNCHES.get(_n, 0) + 1
+                return _raw(*a, **kw)
+
+            self._cache[name] = fn
+        return fn
+
+
+def total_launches() -> int:
+    return sum(v for k, v in LAUNCHES.items() if not k.startswith(("sym_", "ipc_", "tensor_from", "enable_peer")))
 
 
 def ext():
@@ -19,7 +47,7 @@ def ext():
         try:
             import torch  # noqa: F401  (must be imported before the extension)
 
-            _EXT = importlib.import_module("polyrl_b200._C")
+            _EXT = _CountingExt(importlib.import_module("polyrl_b200._C"))
         except Exception as e:  # pragma: no cover - depends on build state
             _EXT_ERR = e
     if _EXT is None:
@@ -55,6 +83,8 @@ from .functional import (  # noqa: E402
 
 __all__ = [
     "ext",
+    "LAUNCHES",
+    "total_launches",
     "have_ext",
     "linear",
     "linear_swiglu",

@@ -1,0 +1,65 @@
+"""Packed (varlen) causal self-attention for training / prefill.
+
+Backends, in order: flash-attn varlen (library call, the same provider the reference uses —
+3rdparty/verl/verl/models/transformers/monkey_patch.py:108) on CUDA; PyTorch SDPA over a padded
+[B, S] view otherwise (CPU tests, or CUDA when flash-attn cannot be imported).  Decode-time
+attention is NOT here: it is the hand-written paged kernel in csrc/decode_attn.cu.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn.functional as F
+
+_FLASH = None
+
+
+def _flash():
+    global _FLASH
+    if _FLASH is None:
+        try:
+            from flash_attn import flash_attn_varlen_func
+
+            _FLASH = flash_attn_varlen_func
+        except Exception:  # pragma: no cover
+            _FLASH = False
+    return _FLASH
+
+
+def _sdpa_varlen(q, k, v, cu_seqlens, max_seqlen, causal, scale):
+    """q:[T,nq,d] k,v:[T,nkv,d] -> [T,nq,d] via a padded batch (supports autograd)."""
+    t, nq, d = q.shape
+    nkv = k.shape[1]
+    b = cu_seqlens.numel() - 1
+    lens = (cu_seqlens[1:] - cu_seqlens[:-1]).long()
+    s = int(max_seqlen)
+    seq_id = torch.repeat_interleave(torch.arange(b, device=q.device), lens, output_size=t)
+    pos = torch.arange(t, device=q.device) - cu_seqlens[:-1].long()[seq_id]
+    flat = seq_id * s + pos
+
+    def pad(x):
+        out = x.new_zeros(b * s, x.shape[1], x.shape[2])
+        out = out.index_copy(0, flat, x)
+        return out.view(b, s, x.shape[1], x.shape[2]).transpose(1, 2)      # [B, h, S, d]
+
+    qp, kp, vp = pad(q), pad(k), pad(v)
+    if nkv != nq:
+        kp = kp.repeat_interleave(nq // nkv, dim=1)
+        vp = vp.repeat_interleave(nq // nkv, dim=1)
+    key_ok = torch.arange(s, device=q.device)[None, :] < lens[:, None]          # [B, S]
+    mask = key_ok[:, None, None, :]
+    if causal:
+        mask = mask & torch.ones(s, s, dtype=torch.bool, device=q.device).tril()[None, None]
+    o = F.scaled_dot_product_attention(qp, kp, vp, attn_mask=mask, scale=scale)
+    return o.transpose(1, 2).reshape(b * s, nq, d).index_select(0, flat)
+
+
+def attention_varlen(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, cu_seqlens: torch.Tensor, max_seqlen: int,
+                     causal: bool = True, scale: float | None = None) -> torch.Tensor:
+    """q:[T,nq,d], k/v:[T,nkv,d] packed over sequences delimited by ``cu_seqlens`` (int32 [B+1])."""
+    if scale is None:
+        scale = q.shape[-1] ** -0.5
+    fa = _flash() if q.is_cuda and q.dtype in (torch.bfloat16, torch.float16) else False
+    if fa:
+        return fa(q, k, v, cu_seqlens, cu_seqlens, int(max_seqlen), int(max_seqlen), 0.0, softmax_scale=scale,
+                  causal=causal)
+    return _sdpa_varlen(q, k, v, cu_seqlens, max_seqlen, causal, scale)

@@ -1,0 +1,528 @@
+"""Native in-process rollout engine: paged KV cache, continuous batching, CUDA-graph decode.
+
+Replaces the patched SGLang server the reference launches per TP group
+(rlboost/verl_stream/workers/rollout/sglang_rollout/sglang_rollout_remote.py:103-182,
+rlboost/verl_stream/workers/rollout/sglang_rollout/sglang_http_async_engine.py:43-113).  The engine
+lives in the trainer process, so colocated weight hand-off is pointer aliasing (no CUDA-IPC
+serialisation, SURVEY §2.5c last rows) and ``release/resume_memory_occupation`` is dropping /
+re-creating the KV pool.
+
+Per step the scheduler either *prefills* newly admitted prompts (packed varlen forward that also fills
+the KV pages) or *decodes* one token for every running sequence.  The decode step — embedding, all
+layers (fused GEMM epilogues, RoPE+KV append, paged flash-decode), LM head, Gumbel-max sampling with
+log-prob, and the on-device bookkeeping for the next step — is captured once per batch-size bucket in a
+CUDA graph and replayed; the host only feeds page-table deltas and reads back tokens one step late.
+"""
+from __future__ import annotations
+
+import itertools
+import time
+import zlib
+from collections import deque
+from dataclasses import dataclass, field
+
+import torch
+
+from .. import ops
+from ..models import transformer as tf
+from ..models.config import ModelConfig
+
+PAGE = 16
+
+
+@dataclass
+class SamplingParams:
+    max_new_tokens: int = 128
+    temperature: float = 1.0
+    top_p: float = 1.0
+    top_k: int = -1
+    n: int = 1
+    stop_token_ids: tuple = ()
+    ignore_eos: bool = False
+    seed: int | None = None
+
+    @classmethod
+    def from_dict(cls, d: dict | None) -> "SamplingParams":
+        d = dict(d or {})
+        keep = {k: d[k] for k in ("max_new_tokens", "temperature", "top_p", "top_k", "n", "ignore_eos", "seed") if k in d}
+        if "stop_token_ids" in d and d["stop_token_ids"]:
+            keep["stop_token_ids"] = tuple(d["stop_token_ids"])
+        return cls(**keep)
+
+
+@dataclass
+class Request:
+    rid: str
+    prompt_ids: list[int]
+    params: SamplingParams
+    output_ids: list[int] = field(default_factory=list)
+    logprobs: list[float] = field(default_factory=list)
+    finish_reason: str | None = None       # "stop" | "length" | "abort"
+    slot: int = -1
+    blocks: list[int] = field(default_factory=list)
+    shared_prefix_blocks: int = 0
+    t_arrival: float = 0.0
+    group: object = None                   # requests of one n-sample group share prompt KV pages
+
+    @property
+    def finished(self) -> bool:
+        return self.finish_reason is not None
+
+    @property
+    def num_tokens(self) -> int:
+        return len(self.prompt_ids) + len(self.output_ids)
+
+
+class BlockAllocator:
+    """Ref-counted KV page allocator; block 0 is a scratch page for idle batch slots."""
+
+    def __init__(self, num_blocks: int):
+        self.num_blocks = num_blocks
+        self.free = deque(range(1, num_blocks))
+        self.ref = [0] * num_blocks
+
+    def available(self) -> int:
+        return len(self.free)
+
+    def alloc(self, n: int) -> list[int]:
+        if n > len(self.free):
+            raise MemoryError("KV cache exhausted")
+        out = [self.free.popleft() for _ in range(n)]
+        for b in out:
+            self.ref[b] = 1
+        return out
+
+    def share(self, blocks: list[int]) -> None:
+        for b in blocks:
+            self.ref[b] += 1
+
+    def release(self, blocks: list[int]) -> None:
+        for b in blocks:
+            self.ref[b] -= 1
+            if self.ref[b] == 0:
+                self.free.append(b)
+
+
+class RolloutEngine:
+    def __init__(self, cfg: ModelConfig, device, max_num_seqs: int = 256, max_model_len: int = 2048,
+                 kv_cache_tokens: int | None = None, gpu_memory_utilization: float = 0.5, dtype=None,
+                 use_cuda_graph: bool = True, max_prefill_tokens: int = 16384, seed: int = 0):
+        self.cfg = cfg
+        self.device = torch.device(device)
+        self.is_cuda = self.device.type == "cuda"
+        self.dtype = dtype or (torch.bfloat16 if self.is_cuda else torch.float32)
+        self.max_num_seqs = max_num_seqs
+        self.max_model_len = max_model_len
+        self.max_blocks_per_seq = (max_model_len + PAGE - 1) // PAGE
+        self.max_prefill_tokens = max_prefill_tokens
+        self.use_cuda_graph = use_cuda_graph and self.is_cuda
+        self.gpu_memory_utilization = gpu_memory_utilization
+        self._kv_tokens_req = kv_cache_tokens
+        self.embed_w: dict | None = None
+        self.layer_w: list[dict] | None = None
+        self.head_w: dict | None = None
+        self.weight_version = 0
+        self.k_cache: list[torch.Tensor] = []
+        self.v_cache: list[torch.Tensor] = []
+        self.alloc: BlockAllocator | None = None
+        self.waiting: deque[Request] = deque()
+        self.running: dict[int, Request] = {}          # slot -> request
+        self.free_slots = list(range(max_num_seqs - 1, -1, -1))
+        self._rid = itertools.count()
+        self._graphs: dict[int, tuple] = {}
+        self._pending = None        # (event, cpu tokens, cpu logprobs, slots snapshot) of the step in flight
+        self._base_seed = seed
+        self._step_count = 0
+        self._top_k, self._top_p = -1, 1.0
+        self.stats = {"prefill_tokens": 0, "decode_tokens": 0, "steps": 0, "last_gen_throughput": 0.0}
+        self._alloc_static()
+
+    # ------------------------------------------------------------------ weights / memory
+    def set_weights(self, embed_w: dict, layer_w: list[dict], head_w: dict, version: int | None = None) -> None:
+        """Point the engine at (possibly trainer-owned) weight tensors.  Pointers that change invalidate
+        captured graphs; in-place updates of the same storage do not."""
+        old = self._weight_ptrs()
+        self.embed_w, self.layer_w, self.head_w = embed_w, layer_w, head_w
+        if old != self._weight_ptrs():
+            self._graphs.clear()
+        if version is not None:
+            self.weight_version = version
+
+    def _weight_ptrs(self):
+        if self.layer_w is None:
+            return None
+        return tuple(t.data_ptr() for w in [self.embed_w, *self.layer_w, self.head_w] for t in w.values())
+
+    def kv_bytes_per_token(self) -> int:
+        c = self.cfg
+        return 2 * c.num_layers * c.num_kv_heads * c.head_dim * torch.empty(0, dtype=self.dtype).element_size()
+
+    def init_kv_cache(self) -> None:
+        """(Re)create the paged KV pool (``resume_memory_occupation(['kv_cache'])``)."""
+        if self.k_cache:
+            return
+        if self._kv_tokens_req is not None:
+            tokens = self._kv_tokens_req
+        elif self.is_cuda:
+            free, total = torch.cuda.mem_get_info(self.device)
+            tokens = int(free * self.gpu_memory_utilization) // self.kv_bytes_per_token()
+        else:
+            tokens = self.max_num_seqs * self.max_model_len
+        tokens = min(tokens, self.max_num_seqs * self.max_blocks_per_seq * PAGE + PAGE)
+        num_blocks = max(2, tokens // PAGE)
+        c = self.cfg
+        shape = (num_blocks, c.num_kv_heads, PAGE, c.head_dim)
+        self.k_cache = [torch.zeros(shape, device=self.device, dtype=self.dtype) for _ in range(c.num_layers)]
+        self.v_cache = [torch.zeros(shape, device=self.device, dtype=self.dtype) for _ in range(c.num_layers)]
+        self.alloc = BlockAllocator(num_blocks)
+        self._graphs.clear()
+
+    def release_memory(self, tags=("kv_cache",)) -> None:
+        """Free engine memory so the trainer can use it (colocated mode).  Requires no running requests."""
+        if "kv_cache" in tags:
+            if self.running or self.waiting:
+                raise RuntimeError("cannot release the KV cache with requests in flight")
+            self.k_cache, self.v_cache, self.alloc = [], [], None
+            self._graphs.clear()
+            if self.is_cuda:
+                torch.cuda.empty_cache()
+        if "weights" in tags:
+            self.embed_w = self.layer_w = self.head_w = None
+            self._graphs.clear()
+
+    def resume_memory(self, tags=("kv_cache",)) -> None:
+        if "kv_cache" in tags:
+            self.init_kv_cache()
+
+    def flush_cache(self) -> None:
+        return None     # no cross-request prefix cache to invalidate (prompt pages are shared per n-group only)
+
+    # ------------------------------------------------------------------ static decode state
+    def _alloc_static(self) -> None:
+        s, dev = self.max_num_seqs, self.device
+        self.st_input_ids = torch.zeros(s, dtype=torch.long, device=dev)
+        self.st_positions = torch.zeros(s, dtype=torch.long, device=dev)
+        self.st_seq_lens = torch.zeros(s, dtype=torch.int32, device=dev)
+        self.st_active = torch.zeros(s, dtype=torch.long, device=dev)
+        self.st_block_table = torch.zeros(s, self.max_blocks_per_seq + 1, dtype=torch.int32, device=dev)
+        self.st_temp = torch.ones(s, dtype=torch.float32, device=dev)
+        self.st_seeds = torch.zeros(s, dtype=torch.long, device=dev)
+        self.st_out_tok = torch.zeros(s, dtype=torch.long, device=dev)
+        self.st_out_lp = torch.zeros(s, dtype=torch.float32, device=dev)
+        pin = self.is_cuda
+        self.h_tok = [torch.zeros(s, dtype=torch.long, pin_memory=pin) for _ in range(2)]
+        self.h_lp = [torch.zeros(s, dtype=torch.float32, pin_memory=pin) for _ in range(2)]
+
+    # ------------------------------------------------------------------ request API
+    def add_request(self, prompt_ids: list[int], params: SamplingParams | dict | None = None, rid: str | None = None,
+                    group=None) -> Request:
+        if not isinstance(params, SamplingParams):
+            params = SamplingParams.from_dict(params)
+        if len(prompt_ids) + 1 > self.max_model_len:
+            prompt_ids = prompt_ids[-(self.max_model_len - 1):]
+        budget = self.max_model_len - len(prompt_ids)
+        if params.max_new_tokens > budget:
+            params = SamplingParams(**{**params.__dict__, "max_new_tokens": budget})
+        r = Request(rid or f"r{next(self._rid)}", list(prompt_ids), params, t_arrival=time.time(), group=group)
+        self.waiting.append(r)
+        return r
+
+    def abort(self, rid: str | None = None, abort_all: bool = False) -> list[Request]:
+        out = []
+        for r in list(self.waiting):
+            if abort_all or r.rid == rid:
+                self.waiting.remove(r)
+                r.finish_reason = "abort"
+                out.append(r)
+        self._drain_pending()
+        for slot, r in list(self.running.items()):
+            if abort_all or r.rid == rid:
+                self._finish(r, "abort")
+                out.append(r)
+        return out
+
+    def has_work(self) -> bool:
+        return bool(self.waiting or self.running or self._pending)
+
+    def num_running(self) -> int:
+        return len(self.running)
+
+    def num_waiting(self) -> int:
+        return len(self.waiting)
+
+    # ------------------------------------------------------------------ scheduling
+    def _blocks_needed(self, r: Request) -> int:
+        total = len(r.prompt_ids) + r.params.max_new_tokens
+        return (total + PAGE - 1) // PAGE
+
+    def _admit(self) -> list[Request]:
+        """Pop waiting requests that fit (slots, KV pages reserved up front, prefill token budget)."""
+        admitted, tokens = [], 0
+        shared: dict = {}
+        while self.waiting and self.free_slots:
+            r = self.waiting[0]
+            need = self._blocks_needed(r)
+            full_prompt_pages = len(r.prompt_ids) // PAGE
+            donor = shared.get(id(r.group)) if r.group is not None else None
+            fresh = need - (full_prompt_pages if donor is not None else 0)
+            if fresh > self.alloc.available():
+                break
+            if tokens + len(r.prompt_ids) > self.max_prefill_tokens and admitted:
+                break
+            self.waiting.popleft()
+            if donor is not None:
+                pre = donor.blocks[:full_prompt_pages]
+                self.alloc.share(pre)
+                r.blocks = pre + self.alloc.alloc(fresh)
+                r.shared_prefix_blocks = full_prompt_pages
+            else:
+                r.blocks = self.alloc.alloc(need)
+                if r.group is not None:
+                    shared[id(r.group)] = r
+            r.slot = self.free_slots.pop()
+            self.running[r.slot] = r
+            admitted.append(r)
+            tokens += len(r.prompt_ids)
+        return admitted
+
+    def _finish(self, r: Request, reason: str) -> None:
+        r.finish_reason = reason
+        if r.slot >= 0:
+            self.running.pop(r.slot, None)
+            self.st_active[r.slot] = 0
+            self.st_seq_lens[r.slot] = 0
+            self.free_slots.append(r.slot)
+            r.slot = -1
+        if r.blocks and self.alloc is not None:
+            self.alloc.release(r.blocks)
+        r.blocks = []
+
+    # ------------------------------------------------------------------ forward passes
+    def _lm_logits(self, h: torch.Tensor) -> torch.Tensor:
+        w = tf.lm_head_weight(self.cfg, self.head_w, self.embed_w)
+        return ops.linear(h, w.to(h.dtype))
+
+    @torch.no_grad()
+    def _prefill(self, reqs: list[Request]) -> None:
+        cfg, dev = self.cfg, self.device
+        # requests that share prompt pages with a donor in the same batch still run the full prompt here
+        # (their page writes of the shared pages are redundant but identical); simple and correct.
+        ids, pos, slots, lens = [], [], [], []
+        for r in reqs:
+            n = len(r.prompt_ids)
+            ids += r.prompt_ids
+            pos += list(range(n))
+            slots += [r.blocks[t // PAGE] * PAGE + t % PAGE for t in range(n)]
+            lens.append(n)
+        cu = torch.zeros(len(reqs) + 1, dtype=torch.int32)
+        cu[1:] = torch.tensor(lens, dtype=torch.int32).cumsum(0)
+        inp = tf.PackedInput(torch.tensor(ids, dtype=torch.long, device=dev), torch.tensor(pos, dtype=torch.long, device=dev),
+                             cu.to(dev), max(lens))
+        slot_t = torch.tensor(slots, dtype=torch.long, device=dev)
+        x = tf.embed_forward(cfg, self.embed_w, inp).to(self.dtype)
+        for i, w in enumerate(self.layer_w):
+            x = tf.layer_forward(cfg, w, x, inp, kv_sink=(self.k_cache[i], self.v_cache[i], slot_t))
+        last = (cu[1:] - 1).long().to(dev)
+        h = tf.final_norm(cfg, self.head_w, x.index_select(0, last))
+        logits = self._lm_logits(h)
+        temps = torch.tensor([r.params.temperature for r in reqs], dtype=torch.float32, device=dev)
+        seeds = torch.tensor([self._seed_for(r, 0) for r in reqs], dtype=torch.long, device=dev)
+        p0 = reqs[0].params
+        tok, lp = ops.sample_tokens(logits, temps, seeds, greedy=False, top_k=p0.top_k, top_p=p0.top_p)
+        tok_c, lp_c = tok.tolist(), lp.tolist()
+        self.stats["prefill_tokens"] += len(ids)
+        live, rows = [], []
+        for r, t, l in zip(reqs, tok_c, lp_c):
+            self._append_token(r, t, l)
+            if r.finished:
+                continue
+            n = r.num_tokens            # tokens so far; the new token sits at position n-1
+            live.append((r.slot, t, n - 1, n, 1, r.params.temperature, self._seed_for(r, 1)))
+            row = r.blocks + [0] * (self.max_blocks_per_seq + 1 - len(r.blocks))
+            rows.append(row)
+        if live:
+            cols = list(zip(*live))
+            sl = torch.tensor(cols[0], dtype=torch.long, device=dev)
+            self.st_input_ids[sl] = torch.tensor(cols[1], dtype=torch.long, device=dev)
+            self.st_positions[sl] = torch.tensor(cols[2], dtype=torch.long, device=dev)
+            self.st_seq_lens[sl] = torch.tensor(cols[3], dtype=torch.int32, device=dev)
+            self.st_active[sl] = torch.tensor(cols[4], dtype=torch.long, device=dev)
+            self.st_temp[sl] = torch.tensor(cols[5], dtype=torch.float32, device=dev)
+            self.st_seeds[sl] = torch.tensor(cols[6], dtype=torch.long, device=dev)
+            self.st_block_table[sl] = torch.tensor(rows, dtype=torch.int32, device=dev)
+
+    def _seed_for(self, r: Request, step: int) -> int:
+        base = r.params.seed if r.params.seed is not None else self._base_seed
+        return (zlib.crc32(f"{base}/{r.rid}".encode()) << 12) + step * 1000003
+
+    def _append_token(self, r: Request, tok: int, lp: float) -> None:
+        r.output_ids.append(int(tok))
+        r.logprobs.append(float(lp))
+        p = r.params
+        if not p.ignore_eos and (tok == self.cfg.eos_token_id or tok in p.stop_token_ids):
+            self._finish(r, "stop")
+        elif len(r.output_ids) >= p.max_new_tokens or r.num_tokens >= self.max_model_len:
+            self._finish(r, "length")
+
+    def _decode_body(self, bs: int) -> None:
+        """One decode step over the first ``bs`` batch slots (captured into a CUDA graph)."""
+        cfg = self.cfg
+        ids, pos = self.st_input_ids[:bs], self.st_positions[:bs]
+        bt, sl, act = self.st_block_table[:bs], self.st_seq_lens[:bs], self.st_active[:bs]
+        page_idx = torch.div(pos, PAGE, rounding_mode="floor").clamp_(max=self.max_blocks_per_seq)
+        blk = bt.gather(1, page_idx.unsqueeze(1)).squeeze(1).long()
+        slot = (blk * PAGE + pos % PAGE) * act          # idle slots write into scratch page 0
+        inp = tf.DecodeInput(ids, pos, slot, bt, sl, self.max_model_len)
+        x = torch.nn.functional.embedding(ids, self.embed_w["embed"]).to(self.dtype)
+        if cfg.family == "gpt2":
+            x = x + torch.nn.functional.embedding(pos, self.embed_w["pos_embed"]).to(self.dtype)
+        for i, w in enumerate(self.layer_w):
+            x = tf.layer_decode(cfg, w, x, inp, self.k_cache[i], self.v_cache[i])
+        h = tf.final_norm(cfg, self.head_w, x)
+        logits = self._lm_logits(h)
+        tok, lp = ops.sample_tokens(logits, self.st_temp[:bs], self.st_seeds[:bs], top_k=self._top_k, top_p=self._top_p)
+        self.st_out_tok[:bs].copy_(tok)
+        self.st_out_lp[:bs].copy_(lp)
+        # on-device bookkeeping for the next step
+        self.st_input_ids[:bs].copy_(tok)
+        self.st_positions[:bs].add_(act)
+        self.st_seq_lens[:bs].add_(act.to(torch.int32))
+        self.st_seeds[:bs].add_(1000003)
+
+    def _bucket(self, n: int) -> int:
+        b = 8
+        while b < n:
+            b *= 2
+        return min(b, self.max_num_seqs)
+
+    def _run_decode(self, bs: int) -> None:
+        if not self.use_cuda_graph:
+            self._decode_body(bs)
+            return
+        key = (bs, self._top_k, self._top_p)
+        g = self._graphs.get(key)
+        if g is None:
+            # warm-up on a side stream (also sets kernel attributes), then capture
+            snap = [t.clone() for t in (self.st_input_ids, self.st_positions, self.st_seq_lens, self.st_seeds)]
+            s = torch.cuda.Stream(device=self.device)
+            s.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(s):
+                self._decode_body(bs)
+            torch.cuda.current_stream(self.device).wait_stream(s)
+            for dst, src in zip((self.st_input_ids, self.st_positions, self.st_seq_lens, self.st_seeds), snap):
+                dst.copy_(src)
+            graph = torch.cuda.CUDAGraph()
+            n0 = ops.total_launches()
+            with torch.cuda.graph(graph):
+                self._decode_body(bs)
+            per_replay = ops.total_launches() - n0
+            for dst, src in zip((self.st_input_ids, self.st_positions, self.st_seq_lens, self.st_seeds), snap):
+                dst.copy_(src)
+            self._graphs[key] = (graph, per_replay)
+            g = self._graphs[key]
+        g[0].replay()
+        ops.LAUNCHES["graph_replayed_kernels"] = ops.LAUNCHES.get("graph_replayed_kernels", 0) + g[1]
+
+    def _compact_slots(self) -> None:
+        """Keep running sequences in the lowest slots so a smaller graph bucket can be used."""
+        if not self.running:
+            return
+        n = len(self.running)
+        bucket = self._bucket(n)
+        high = sorted(s for s in self.running if s >= bucket)
+        if not high:
+            return
+        low_free = sorted(s for s in range(bucket) if s not in self.running)
+        for src, dst in zip(high, low_free):
+            r = self.running.pop(src)
+            for t in (self.st_input_ids, self.st_positions, self.st_seq_lens, self.st_active, self.st_temp,
+                      self.st_seeds):
+                t[dst] = t[src]
+            self.st_block_table[dst] = self.st_block_table[src]
+            self.st_active[src] = 0
+            self.st_seq_lens[src] = 0
+            r.slot = dst
+            self.running[dst] = r
+            self.free_slots.remove(dst)
+            self.free_slots.append(src)
+        self.free_slots.sort(reverse=True)
+
+    def _drain_pending(self) -> list[Request]:
+        """Consume the tokens of the decode step in flight; returns requests that finished."""
+        done = []
+        if self._pending is None:
+            return done
+        ev, h_tok, h_lp, slots = self._pending
+        self._pending = None
+        if ev is not None:
+            ev.synchronize()
+        for s, r in slots:
+            if r.finished:
+                continue
+            self._append_token(r, int(h_tok[s]), float(h_lp[s]))
+            if r.finished:
+                done.append(r)
+        return done
+
+    @torch.no_grad()
+    def step(self) -> list[Request]:
+        """Run one scheduler iteration; returns requests that finished during it."""
+        if self.layer_w is None:
+            raise RuntimeError("RolloutEngine has no weights (call set_weights)")
+        self.init_kv_cache()
+        finished: list[Request] = []
+        if self.waiting and self.free_slots and self.alloc.available() > 0:
+            finished = self._drain_pending()
+            admitted = self._admit()
+            if admitted:
+                self._top_k, self._top_p = admitted[0].params.top_k, admitted[0].params.top_p
+                self._prefill(admitted)
+                finished += [r for r in admitted if r.finished]
+                self.stats["steps"] += 1
+                return finished
+        if not self.running:
+            return finished + self._drain_pending()
+        self._compact_slots()
+        bs = self._bucket(max(self.running) + 1)
+        # launch step k+1 first, then consume step k's tokens while the GPU works (one-step lag:
+        # a sequence that ended at step k rides along for one harmless extra token)
+        self._run_decode(bs)
+        i = self._step_count & 1
+        self._step_count += 1
+        self.h_tok[i].copy_(self.st_out_tok, non_blocking=True)
+        self.h_lp[i].copy_(self.st_out_lp, non_blocking=True)
+        ev = None
+        if self.is_cuda:
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(self.device))
+        new_pending = (ev, self.h_tok[i], self.h_lp[i], list(self.running.items()))
+        self.stats["decode_tokens"] += len(self.running)
+        finished += self._drain_pending()
+        self._pending = new_pending
+        self.stats["steps"] += 1
+        return finished
+
+    # ------------------------------------------------------------------ batch API
+    @torch.no_grad()
+    def generate(self, prompts: list[list[int]], params: SamplingParams | dict | None = None,
+                 on_finish=None) -> list[list[Request]]:
+        """Generate ``params.n`` samples for every prompt; returns, per prompt, its list of requests."""
+        if not isinstance(params, SamplingParams):
+            params = SamplingParams.from_dict(params)
+        groups: list[list[Request]] = []
+        for pi, p in enumerate(prompts):
+            tag = object()
+            groups.append([self.add_request(p, params, group=tag if params.n > 1 else None) for _ in range(params.n)])
+        t0 = time.time()
+        ntok0 = self.stats["decode_tokens"]
+        while self.has_work():
+            for r in self.step():
+                if on_finish is not None:
+                    on_finish(r)
+        dt = max(time.time() - t0, 1e-9)
+        self.stats["last_gen_throughput"] = (self.stats["decode_tokens"] - ntok0) / dt
+        return groups
+
+    def server_info(self) -> dict:
+        return {"#running_req": len(self.running), "#queue_req": len(self.waiting),
+                "last_gen_throughput": self.stats["last_gen_throughput"], "weight_version": self.weight_version}

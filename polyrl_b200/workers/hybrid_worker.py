@@ -1,0 +1,346 @@
+"""Per-GPU workers: the hybrid actor / rollout / reference worker and the critic worker.
+
+API surface mirrors the reference's stream workers (rlboost/verl_stream/workers/stream_fsdp_workers.py:
+``init_model`` :262, ``update_actor_stream`` :378-431, ``update_weight_remote`` :435-444,
+``generate_sequences_remote`` :448-495, ``get_stream_batches`` :497-507; critic :511-595) and verl's
+``ActorRolloutRefWorker`` (3rdparty/verl/verl/workers/fsdp_workers.py:863-1108), but one worker = one
+OS process = one GPU with everything native and in-process: ZeRO-3 engine, rollout engine sharing the
+trainer's bf16 weights, and the peer-memory weight-transfer path instead of shm/TCP/ZMQ agents.
+"""
+from __future__ import annotations
+
+import math
+import os
+import time
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from ..config.schema import PPOConfig
+from ..models import get_model_config
+from ..parallel.zero3 import Zero3Engine
+from ..protocol import DataProto
+from ..rollout.engine import RolloutEngine, SamplingParams
+from .actor import ActorConfig as ActorRuntimeConfig
+from .actor import DataParallelPPOActor, DataParallelPPOCritic
+
+
+def get_response_mask(responses: torch.Tensor, eos_token_id: int, lengths: torch.Tensor | None = None) -> torch.Tensor:
+    """1 up to and including the first EOS (reference: verl/utils/torch_functional.py:226)."""
+    if lengths is not None:
+        ar = torch.arange(responses.shape[1], device=responses.device)[None]
+        return (ar < lengths[:, None]).long()
+    is_eos = responses == eos_token_id
+    after = (is_eos.cumsum(-1) - is_eos.long()) > 0
+    return (~after).long()
+
+
+def lr_at_step(optim, step: int, total_steps: int) -> float:
+    """Warmup + constant / cosine schedule (reference: verl/utils/torch_functional.py:509-700)."""
+    warm = optim.lr_warmup_steps
+    if warm < 0:
+        warm = int(optim.lr_warmup_steps_ratio * max(total_steps, 0))
+    if warm > 0 and step < warm:
+        return optim.lr * (step + 1) / warm
+    if optim.warmup_style == "cosine" and total_steps > warm:
+        prog = min(1.0, (step - warm) / max(1, total_steps - warm))
+        cos = 0.5 * (1.0 + math.cos(math.pi * 2.0 * optim.num_cycles * prog))
+        return optim.lr * (optim.min_lr_ratio + (1 - optim.min_lr_ratio) * cos)
+    return optim.lr
+
+
+class ActorRolloutRefWorker:
+    """role in {"actor_rollout", "actor_rollout_ref", "actor", "rollout", "ref"}."""
+
+    def __init__(self, config: PPOConfig, role: str = "actor_rollout_ref", device=None, group=None):
+        self.config = config
+        self.role = role
+        self.group = group
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        if device is None:
+            device = f"cuda:{int(os.environ.get('LOCAL_RANK', 0))}" if torch.cuda.is_available() else "cpu"
+        self.device = torch.device(device)
+        if self.device.type == "cuda":
+            torch.cuda.set_device(self.device)
+        self.has_actor = "actor" in role
+        self.has_rollout = "rollout" in role
+        self.has_ref = "ref" in role
+        self.actor_engine: Zero3Engine | None = None
+        self.ref_engine: Zero3Engine | None = None
+        self.rollout: RolloutEngine | None = None
+        self.actor: DataParallelPPOActor | None = None
+        self.lr_step = 0
+        self.weight_version = 0
+        self._rollout_full: dict | None = None
+        self.profiler = None
+
+    # ------------------------------------------------------------------ init
+    def init_model(self) -> None:
+        cfg = self.config
+        arr = cfg.actor_rollout_ref
+        self.model_cfg = get_model_config(arr.model.path, **arr.model.override_config)
+        comm = arr.actor.fsdp_config.comm_backend
+        opt = arr.actor.optim
+        seed = cfg.data.seed
+        if self.has_actor:
+            self.actor_engine = Zero3Engine(self.model_cfg, self.device, group=self.group, comm=comm, trainable=True,
+                                            seed=seed, lr=opt.lr, betas=tuple(opt.betas), eps=opt.eps,
+                                            weight_decay=opt.weight_decay, max_grad_norm=arr.actor.grad_clip)
+            n_dp = self.world
+            a = arr.actor
+            mini = max(1, a.ppo_mini_batch_size * arr.rollout.n // n_dp)      # per-GPU samples per optimizer step
+            micro = a.ppo_micro_batch_size_per_gpu or (max(1, a.ppo_micro_batch_size // n_dp) if a.ppo_micro_batch_size else None)
+            rt = ActorRuntimeConfig(ppo_mini_batch_size=mini, ppo_micro_batch_size_per_gpu=micro,
+                                    use_dynamic_bsz=a.use_dynamic_bsz, ppo_max_token_len_per_gpu=a.ppo_max_token_len_per_gpu,
+                                    clip_ratio=a.clip_ratio, clip_ratio_low=a.clip_ratio_low, clip_ratio_high=a.clip_ratio_high,
+                                    clip_ratio_c=a.clip_ratio_c, loss_agg_mode=a.loss_agg_mode, entropy_coeff=a.entropy_coeff,
+                                    use_kl_loss=a.use_kl_loss, kl_loss_coef=a.kl_loss_coef, kl_loss_type=a.kl_loss_type,
+                                    ppo_epochs=a.ppo_epochs, policy_loss_mode=a.policy_loss.loss_mode,
+                                    policy_loss=a.policy_loss.to_dict(), grad_clip=a.grad_clip)
+            self.actor = DataParallelPPOActor(self.actor_engine, rt, dp_group=self.group)
+        if self.has_ref:
+            # reference policy = frozen copy of the initial actor weights (same seed => identical init)
+            self.ref_engine = Zero3Engine(self.model_cfg, self.device, group=self.group, comm=comm, trainable=False,
+                                          seed=seed, heap=self.actor_engine.heap if self.actor_engine else None)
+            self.ref_actor = DataParallelPPOActor(self.ref_engine, ActorRuntimeConfig(), dp_group=self.group)
+        if self.has_rollout:
+            r = arr.rollout
+            max_len = r.max_model_len or (cfg.data.max_prompt_length + cfg.data.max_response_length)
+            self.rollout = RolloutEngine(self.model_cfg, self.device, max_num_seqs=r.max_num_seqs, max_model_len=max_len,
+                                         gpu_memory_utilization=r.gpu_memory_utilization, use_cuda_graph=r.cuda_graph,
+                                         max_prefill_tokens=r.max_num_batched_tokens, seed=seed + 17 * self.rank)
+            if self.has_actor:
+                self.update_weight_remote()
+
+    # ------------------------------------------------------------------ weight sync (colocated)
+    def update_weight_remote(self) -> bool:
+        """Publish the current actor weights to the rollout engine.  world==1: the engine *aliases* the
+        trainer's bf16 shard (zero copies).  world>1: every rank gathers a full bf16 replica into
+        engine-owned buffers with the peer-memory all-gather (or NCCL in baseline mode)."""
+        eng = self.actor_engine
+        if eng is None or self.rollout is None:
+            return False
+        self.weight_version += 1
+        if eng.world == 1:
+            views = [u.views(u.shard) for u in eng.units]
+        else:
+            if self._rollout_full is None:
+                self._rollout_full = {u.name: torch.empty(u.full_numel, device=self.device, dtype=eng.param_dtype)
+                                      for u in eng.units}
+            if eng.heap is not None:
+                eng.heap.barrier()
+            for u in eng.units:
+                u._gather_into(self._rollout_full[u.name])
+            views = [u.views(self._rollout_full[u.name]) for u in eng.units]
+        self.rollout.set_weights(views[0], views[1:-1], views[-1], version=self.weight_version)
+        return True
+
+    # ------------------------------------------------------------------ rollout
+    @torch.no_grad()
+    def generate_sequences(self, prompts: DataProto) -> DataProto:
+        """Generate ``n`` responses per prompt with the colocated engine (sync path / validation)."""
+        cfg = self.config
+        r = cfg.actor_rollout_ref.rollout
+        meta = prompts.meta_info
+        do_sample = meta.get("do_sample", r.do_sample)
+        validate = meta.get("validate", False)
+        n = 1 if validate else meta.get("n", r.n)
+        temperature = (r.val_kwargs.get("temperature", 0.0) if validate else meta.get("temperature", r.temperature))
+        if not do_sample:
+            temperature = 0.0
+        resp_len = meta.get("response_length", cfg.data.max_response_length)
+        sp = SamplingParams(max_new_tokens=resp_len, temperature=temperature, top_p=meta.get("top_p", r.top_p),
+                            top_k=meta.get("top_k", r.top_k), n=n, ignore_eos=meta.get("ignore_eos", False))
+        raw = prompts.non_tensor_batch.get("raw_prompt_ids")
+        if raw is None:
+            ids, mask = prompts.batch["input_ids"], prompts.batch["attention_mask"].bool()
+            raw = [ids[i][mask[i]].tolist() for i in range(len(prompts))]
+        t0 = time.time()
+        self.rollout.resume_memory(("kv_cache",))
+        groups = self.rollout.generate([list(map(int, p)) for p in raw], sp)
+        gen_s = time.time() - t0
+        out = self._postprocess(prompts, groups, n, resp_len)
+        out.meta_info["timing"] = {"generate_sequences": gen_s}
+        if r.free_cache_engine and not meta.get("keep_cache", False):
+            self.rollout.release_memory(("kv_cache",))
+        return out
+
+    def _postprocess(self, prompts: DataProto, groups, n: int, resp_len: int) -> DataProto:
+        """Pad responses to ``response_length`` and build input_ids / masks / position ids (reference:
+        sglang_rollout_remote.py:318-391)."""
+        pad = self.model_cfg.pad_token_id
+        dev = prompts.batch["input_ids"].device
+        rep = prompts.repeat(n, interleave=True) if n > 1 else prompts
+        b = len(rep)
+        resp = torch.full((b, resp_len), pad, dtype=torch.long)
+        lps = torch.zeros(b, resp_len, dtype=torch.float32)
+        lens = torch.zeros(b, dtype=torch.long)
+        aborted = np.zeros(b, dtype=bool)
+        k = 0
+        for g in groups:
+            for req in g:
+                m = min(len(req.output_ids), resp_len)
+                resp[k, :m] = torch.tensor(req.output_ids[:m], dtype=torch.long)
+                lps[k, :m] = torch.tensor(req.logprobs[:m])
+                lens[k] = m
+                aborted[k] = req.finish_reason == "abort"
+                k += 1
+        resp, lps, lens = resp.to(dev), lps.to(dev), lens.to(dev)
+        p_ids, p_mask = rep.batch["input_ids"], rep.batch["attention_mask"]
+        response_mask = get_response_mask(resp, self.model_cfg.eos_token_id, lens)
+        input_ids = torch.cat([p_ids, resp], dim=1)
+        attention_mask = torch.cat([p_mask, response_mask], dim=1)
+        p_pos = rep.batch.get("position_ids")
+        if p_pos is None:
+            p_pos = (p_mask.cumsum(-1) - 1).clamp_min(0)
+        delta = torch.arange(1, resp_len + 1, device=dev)[None]
+        position_ids = torch.cat([p_pos, p_pos[:, -1:] + delta], dim=1)
+        rep.batch["prompts"] = p_ids
+        rep.batch["responses"] = resp
+        rep.batch["input_ids"] = input_ids
+        rep.batch["attention_mask"] = attention_mask
+        rep.batch["position_ids"] = position_ids
+        rep.batch["response_mask"] = response_mask
+        rep.batch["rollout_log_probs"] = lps
+        rep.non_tensor_batch["aborted"] = aborted
+        return rep
+
+    # ------------------------------------------------------------------ log-probs
+    @torch.no_grad()
+    def compute_log_prob(self, data: DataProto) -> DataProto:
+        r = self.config.actor_rollout_ref.rollout
+        data.meta_info.setdefault("micro_batch_size", r.log_prob_micro_batch_size_per_gpu)
+        data.meta_info.setdefault("max_token_len", r.log_prob_max_token_len_per_gpu)
+        data.meta_info.setdefault("use_dynamic_bsz", r.log_prob_use_dynamic_bsz)
+        data.meta_info.setdefault("temperature", r.temperature)
+        lp, ent = self.actor.compute_log_prob(data)
+        return DataProto.from_dict({"old_log_probs": lp, "entropys": ent}, meta_info={"temperature": r.temperature})
+
+    @torch.no_grad()
+    def compute_ref_log_prob(self, data: DataProto) -> DataProto:
+        ref = self.config.actor_rollout_ref.ref
+        data.meta_info["micro_batch_size"] = ref.log_prob_micro_batch_size_per_gpu
+        data.meta_info["max_token_len"] = ref.log_prob_max_token_len_per_gpu
+        data.meta_info["use_dynamic_bsz"] = ref.log_prob_use_dynamic_bsz
+        data.meta_info.setdefault("temperature", self.config.actor_rollout_ref.rollout.temperature)
+        lp, _ = self.ref_actor.compute_log_prob(data, calculate_entropy=False)
+        return DataProto.from_dict({"ref_log_prob": lp})
+
+    # ------------------------------------------------------------------ update
+    def update_actor_stream(self, data: DataProto) -> DataProto:
+        meta = data.meta_info
+        is_opt = meta.get("is_opt_step", True)
+        is_lr = meta.get("is_lr_step", is_opt)
+        opt = self.config.actor_rollout_ref.actor.optim
+        total = opt.total_training_steps if opt.total_training_steps > 0 else (self.config.trainer.total_training_steps or 0)
+        lr = lr_at_step(opt, self.lr_step, total)
+        t0 = time.time()
+        metrics = self.actor.update_policy_stream(data, is_opt_step=is_opt, lr=lr)
+        metrics["actor/lr"] = [lr]
+        if is_lr:
+            self.lr_step += 1
+        metrics["perf/update_actor_s"] = [time.time() - t0]
+        if self.device.type == "cuda":
+            metrics["perf/max_memory_allocated_gb"] = [torch.cuda.max_memory_allocated(self.device) / 2 ** 30]
+            metrics["perf/max_memory_reserved_gb"] = [torch.cuda.max_memory_reserved(self.device) / 2 ** 30]
+        return DataProto(meta_info={"metrics": metrics})
+
+    update_actor = update_actor_stream
+
+    # ------------------------------------------------------------------ checkpoint / profile
+    def save_checkpoint(self, local_path: str, hdfs_path: str | None = None, global_step: int = 0,
+                        max_ckpt_to_keep: int | None = None) -> None:
+        from ..utils.checkpoint import ShardedCheckpointManager
+
+        ShardedCheckpointManager(self.actor_engine, self.model_cfg).save(local_path, global_step, max_ckpt_to_keep,
+                                                                        extra={"lr_step": self.lr_step})
+
+    def load_checkpoint(self, local_path: str | None, hdfs_path: str | None = None, del_local_after_load: bool = False) -> None:
+        if not local_path:
+            return
+        from ..utils.checkpoint import ShardedCheckpointManager
+
+        extra = ShardedCheckpointManager(self.actor_engine, self.model_cfg).load(local_path)
+        self.lr_step = (extra or {}).get("lr_step", 0)
+        if self.rollout is not None:
+            self.update_weight_remote()
+
+    def start_profile(self, **kw) -> None:
+        from ..utils.profiler import DistProfiler
+
+        self.profiler = self.profiler or DistProfiler(self.rank, self.config.global_profiler)
+        self.profiler.start(**kw)
+
+    def stop_profile(self) -> None:
+        if self.profiler is not None:
+            self.profiler.stop()
+
+    def dump_memory_snapshot(self, tag: str = "manual", sub_dir: str | None = None) -> None:
+        from ..utils.profiler import dump_memory_snapshot
+
+        dump_memory_snapshot(self.config.global_profiler.save_path, tag, sub_dir, self.rank)
+
+
+class CriticWorker:
+    def __init__(self, config: PPOConfig, device=None, group=None):
+        self.config, self.group = config, group
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        if device is None:
+            device = f"cuda:{int(os.environ.get('LOCAL_RANK', 0))}" if torch.cuda.is_available() else "cpu"
+        self.device = torch.device(device)
+        self.lr_step = 0
+
+    def init_model(self, heap=None) -> None:
+        cfg = self.config
+        c = cfg.critic
+        path = c.model.path if c.model.path != "tiny-llama" or cfg.actor_rollout_ref.model.path == "tiny-llama" \
+            else cfg.actor_rollout_ref.model.path
+        self.model_cfg = get_model_config(path, **{**c.model.override_config, "value_head": True})
+        self.engine = Zero3Engine(self.model_cfg, self.device, group=self.group, comm=c.fsdp_config.comm_backend,
+                                  trainable=True, seed=cfg.data.seed + 1, lr=c.optim.lr, betas=tuple(c.optim.betas),
+                                  eps=c.optim.eps, weight_decay=c.optim.weight_decay, max_grad_norm=c.grad_clip, heap=heap)
+        n_dp = self.world
+        mini = max(1, c.ppo_mini_batch_size * cfg.actor_rollout_ref.rollout.n // n_dp)
+        rt = ActorRuntimeConfig(ppo_mini_batch_size=mini, ppo_micro_batch_size_per_gpu=c.ppo_micro_batch_size_per_gpu,
+                                use_dynamic_bsz=c.use_dynamic_bsz, ppo_max_token_len_per_gpu=c.ppo_max_token_len_per_gpu,
+                                loss_agg_mode=c.loss_agg_mode, grad_clip=c.grad_clip, cliprange_value=c.cliprange_value)
+        self.critic = DataParallelPPOCritic(self.engine, rt, dp_group=self.group)
+
+    @torch.no_grad()
+    def compute_values(self, data: DataProto) -> DataProto:
+        c = self.config.critic
+        data.meta_info.setdefault("micro_batch_size", c.ppo_micro_batch_size_per_gpu)
+        data.meta_info.setdefault("max_token_len", c.forward_max_token_len_per_gpu)
+        data.meta_info.setdefault("use_dynamic_bsz", c.use_dynamic_bsz)
+        return DataProto.from_dict({"values": self.critic.compute_values(data)})
+
+    def update_critic_stream(self, data: DataProto) -> DataProto:
+        meta = data.meta_info
+        is_opt = meta.get("is_opt_step", True)
+        opt = self.config.critic.optim
+        total = opt.total_training_steps if opt.total_training_steps > 0 else (self.config.trainer.total_training_steps or 0)
+        lr = lr_at_step(opt, self.lr_step, total)
+        metrics = self.critic.update_critic_stream(data, is_opt_step=is_opt, lr=lr)
+        metrics["critic/lr"] = [lr]
+        if meta.get("is_lr_step", is_opt):
+            self.lr_step += 1
+        return DataProto(meta_info={"metrics": metrics})
+
+    update_critic = update_critic_stream
+
+    def save_checkpoint(self, local_path, hdfs_path=None, global_step=0, max_ckpt_to_keep=None) -> None:
+        from ..utils.checkpoint import ShardedCheckpointManager
+
+        ShardedCheckpointManager(self.engine, self.model_cfg).save(local_path, global_step, max_ckpt_to_keep,
+                                                                  extra={"lr_step": self.lr_step})
+
+    def load_checkpoint(self, local_path, hdfs_path=None, del_local_after_load=False) -> None:
+        if not local_path:
+            return
+        from ..utils.checkpoint import ShardedCheckpointManager
+
+        extra = ShardedCheckpointManager(self.engine, self.model_cfg).load(local_path)
+        self.lr_step = (extra or {}).get("lr_step", 0)
