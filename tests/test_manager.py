@@ -1,0 +1,204 @@
+"""C++ rollout manager: unit tests of the socket-free core + integration tests against in-process fake
+engines with fault injection (crash mid-stream, abort -> continuation, time-boxed local window,
+weight-version gating, balance feedback).  The reference's Rust manager ships no tests."""
+import json
+import os
+import subprocess
+import time
+import urllib.request
+from pathlib import Path
+
+import pytest
+
+from polyrl_b200.manager.build import build_manager
+from polyrl_b200.manager.fake_engine import FakeEngine, reference_generation
+
+ROOT = Path(__file__).resolve().parent.parent
+SRC = ROOT / "polyrl_b200" / "manager" / "src"
+
+
+def _http(method, url, body=None, timeout=30):
+    data = None if body is None else json.dumps(body).encode()
+    req = urllib.request.Request(url, data=data, method=method, headers={"Content-Type": "application/json"})
+    try:
+        with urllib.request.urlopen(req, timeout=timeout) as r:
+            return r.status, r.read().decode()
+    except urllib.error.HTTPError as e:
+        return e.code, e.read().decode()
+
+
+@pytest.fixture(scope="module")
+def manager_bin():
+    return build_manager()
+
+
+class Manager:
+    def __init__(self, binary, *extra):
+        self.p = subprocess.Popen([str(binary), "--bind-addr", "127.0.0.1:0", "--stats-interval-ms", "100",
+                                   "--health-interval-ms", "100", "--log-level", "error", *extra],
+                                  stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        line = self.p.stdout.readline()
+        assert line.startswith("ROLLOUT_MANAGER_PORT="), line
+        self.port = int(line.strip().split("=")[1])
+        self.url = f"http://127.0.0.1:{self.port}"
+
+    def close(self):
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+
+
+def test_core_unit_tests_cpp(tmp_path):
+    exe = tmp_path / "test_core"
+    subprocess.run(["g++", "-O1", "-std=c++17", "-I", str(SRC), str(ROOT / "polyrl_b200/manager/tests_cpp/test_core.cpp"),
+                    "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True)
+    assert "OK" in out.stdout
+
+
+def test_health_and_status(manager_bin):
+    m = Manager(manager_bin)
+    try:
+        code, body = _http("GET", m.url + "/health")
+        assert code == 200 and json.loads(body)["status"] == "healthy"
+        code, body = _http("GET", m.url + "/get_instances_status")
+        st = json.loads(body)
+        assert st["ready_instances"] == 0 and st["pending_instances"] == 0
+        assert _http("POST", m.url + "/batch_generate_requests", [])[0] == 400
+        assert _http("GET", m.url + "/nope")[0] == 404
+    finally:
+        m.close()
+
+
+def _batch(m, reqs, timeout=60):
+    code, body = _http("POST", m.url + "/batch_generate_requests", reqs, timeout=timeout)
+    assert code == 200
+    lines = [json.loads(l) for l in body.strip().split("\n")]
+    assert lines[0] == {"id": 0, "success": True}          # notifier first
+    return {l["id"]: l for l in lines[1:]}
+
+
+def _tokens(resp):
+    return [t[1] for t in resp["meta_info"]["output_token_logprobs"]]
+
+
+def test_local_generation_and_grouped_requests(manager_bin):
+    m = Manager(manager_bin)
+    e1, e2 = FakeEngine(), FakeEngine()
+    try:
+        assert _http("POST", m.url + "/register_local_rollout_instances", [["127.0.0.1", e1.port], ["127.0.0.1", e2.port]])[0] == 200
+        st = json.loads(_http("GET", m.url + "/get_instances_status")[1])
+        assert st["ready_instances"] == 2
+        reqs = [[i + 1, {"input_ids": [[5, i, 9]] * 3, "sampling_params": {"max_new_tokens": 12}, "return_logprob": True}]
+                for i in range(10)]
+        res = _batch(m, reqs)
+        assert len(res) == 10
+        for i in range(10):
+            r = res[i + 1]
+            assert r["success"] and len(r["data"]) == 3
+            for sub in r["data"]:
+                assert _tokens(sub) == reference_generation([5, i, 9], 12)
+                assert sub["meta_info"]["completion_tokens"] == 12
+        assert e1.generate_calls > 0 and e2.generate_calls > 0       # round-robin used both engines
+    finally:
+        m.close(); e1.stop(); e2.stop()
+
+
+def test_engine_crash_continuation(manager_bin):
+    """A remote engine dies mid-stream: it is evicted and the partial generation continues on another engine
+    with the generated tokens appended to the prompt; the merged result equals an uninterrupted run."""
+    m = Manager(manager_bin, "--weight-sender-rpyc-endpoints", "127.0.0.1:18861")
+    bad, good = FakeEngine(die_after_tokens=5), FakeEngine()
+    try:
+        for e in (bad, good):
+            code, body = _http("POST", m.url + "/register_rollout_instance", {"host": "127.0.0.1", "port": e.port})
+            assert code == 200 and json.loads(body)["weight_sender_rpyc_endpoint"] == "127.0.0.1:18861"
+        assert _http("POST", m.url + "/register_rollout_instance", {"host": "127.0.0.1", "port": good.port})[0] == 409
+        time.sleep(0.5)                                   # health gate
+        v = json.loads(_http("POST", m.url + "/update_weight_version")[1])["new_weight_version"]
+        inst = json.loads(_http("POST", m.url + "/get_receive_instances",
+                                {"weight_sender_endpoint": "127.0.0.1:18861", "sender_weight_version": v})[1])["instances"]
+        assert len(inst) == 2
+        # a second poll must not hand out the same instances again (updating_weight CAS)
+        again = json.loads(_http("POST", m.url + "/get_receive_instances",
+                                 {"weight_sender_endpoint": "127.0.0.1:18861", "sender_weight_version": v})[1])["instances"]
+        assert again == []
+        eps = [i["instance"]["endpoint"] for i in inst]
+        code, body = _http("POST", m.url + "/update_weights", {"instance_endpoints": eps, "weight_version": v,
+                                                               "tensors_meta": [["w", [[2, 2], "bfloat16"]]], "bootstrap": False})
+        assert code == 200 and json.loads(body)["success"]
+        assert len(good.weight_updates) == 1 and good.weight_updates[0]["weight_version"] == v
+        st = json.loads(_http("GET", m.url + "/get_instances_status")[1])
+        assert st["ready_instances"] == 2
+        reqs = [[i + 1, {"input_ids": [3, 4, i], "sampling_params": {"max_new_tokens": 20}}] for i in range(6)]
+        res = _batch(m, reqs)
+        for i in range(6):
+            assert res[i + 1]["success"], res[i + 1]
+            assert _tokens(res[i + 1]["data"]) == reference_generation([3, 4, i], 20)
+            assert res[i + 1]["data"]["meta_info"]["completion_tokens"] == 20
+        st = json.loads(_http("GET", m.url + "/get_instances_status")[1])
+        assert bad.endpoint not in st["ready_instance_endpoints"] + st["pending_instance_endpoints"]    # evicted
+        assert bad.shutdown_called.wait(2.0)
+    finally:
+        m.close(); bad.stop(); good.stop()
+
+
+def test_timed_local_window_abort_and_remote_continuation(manager_bin):
+    """Local engines get a time budget; at expiry they are aborted and the partials finish on the remote engine."""
+    m = Manager(manager_bin, "--weight-sender-rpyc-endpoints", "127.0.0.1:18861", "--initial-local-gen-s", "1",
+                "--max-assigned-batches-per-stats-check", "64")
+    local, remote = FakeEngine(token_delay_s=0.05), FakeEngine(token_delay_s=0.001)
+    try:
+        _http("POST", m.url + "/register_rollout_instance", {"host": "127.0.0.1", "port": remote.port})
+        _http("POST", m.url + "/register_local_rollout_instances", [["127.0.0.1", local.port]])
+        time.sleep(0.4)
+        v = json.loads(_http("POST", m.url + "/update_weight_version")[1])["new_weight_version"]
+        # remote engine has stale weights -> not schedulable until updated; keep it parked for now
+        reqs = [[i + 1, {"input_ids": [[7, i]] * 2, "sampling_params": {"max_new_tokens": 60}}] for i in range(3)]
+        t0 = time.time()
+        import threading
+        out = {}
+        th = threading.Thread(target=lambda: out.update(res=_batch(m, reqs, timeout=120)))
+        th.start()
+        time.sleep(0.3)
+        # now bring the remote engine to the latest version: it joins the active pool mid-batch (elastic join)
+        inst = json.loads(_http("POST", m.url + "/get_receive_instances",
+                                {"weight_sender_endpoint": "127.0.0.1:18861", "sender_weight_version": v})[1])["instances"]
+        _http("POST", m.url + "/update_weights", {"instance_endpoints": [i["instance"]["endpoint"] for i in inst],
+                                                  "weight_version": v, "tensors_meta": [], "bootstrap": False})
+        th.join(timeout=120)
+        res = out["res"]
+        for i in range(3):
+            assert res[i + 1]["success"], res[i + 1]
+            for sub in res[i + 1]["data"]:
+                assert _tokens(sub) == reference_generation([7, i], 60)
+        assert remote.generate_calls >= 1                      # continuation really moved to the remote engine
+        assert time.time() - t0 < 60
+        # balance feedback
+        code, body = _http("POST", m.url + "/update_metrics", {"step_time_s": 30, "trainer_bubble_time_s": 12, "step_throughput": 10.0})
+        fb = json.loads(body)
+        assert code == 200 and fb["success"] and fb["new_max_gen_s"] >= 5 and fb["new_num_rollout_instances"] == 1
+    finally:
+        m.close(); local.stop(); remote.stop()
+
+
+def test_weight_senders_cidr_and_shutdown(manager_bin, tmp_path):
+    cfg = tmp_path / "config.toml"
+    cfg.write_text('allowed_sender_ips = "10.0.0.0/8"\nweight_sender_rpyc_base_port = 19000\nnum_mooncake_groups_per_sender = 2\n')
+    m = Manager(manager_bin, "--config-file", str(cfg))
+    e = FakeEngine()
+    try:
+        code, _ = _http("PUT", m.url + "/update_weight_senders", {"weight_sender_ips": [["192.168.1.2"]]})
+        assert code == 400
+        code, _ = _http("PUT", m.url + "/update_weight_senders", {"weight_sender_ips": [["192.168.1.2", "10.1.1.1"], ["10.2.2.2"]]})
+        assert code == 200
+        r1 = json.loads(_http("POST", m.url + "/register_rollout_instance", {"host": "127.0.0.1", "port": e.port})[1])
+        assert r1["weight_sender_rpyc_endpoint"] == "10.1.1.1:19000" and r1["sender_group_idx"] == 0
+        code, body = _http("POST", m.url + "/shutdown_instances", {"endpoints": [e.endpoint]})
+        assert json.loads(body)["shutdown_endpoints"] == [e.endpoint]
+        assert e.shutdown_called.wait(2.0)
+        assert json.loads(_http("GET", m.url + "/get_instances_status")[1])["pending_instances"] == 0
+    finally:
+        m.close(); e.stop()
