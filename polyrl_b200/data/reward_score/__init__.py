@@ -1,0 +1,22 @@
+"""Rule-based scorers and the ``default_compute_score`` router (reference:
+3rdparty/verl/verl/utils/reward_score/__init__.py, rlboost/verl_stream/utils/reward_score/__init__.py:47-54
+which adds ``open-r1/OpenR1-Math-220k`` to the math family)."""
+from __future__ import annotations
+
+from . import gsm8k, math as math_score
+
+MATH_SOURCES = {"lighteval/MATH", "DigitalLearningGmbH/MATH-lighteval", "HuggingFaceH4/MATH-500", "open-r1/OpenR1-Math-220k",
+                "math_dapo", "math", "aime"}
+
+
+def default_compute_score(data_source: str, solution_str: str, ground_truth, extra_info=None, **kwargs) -> float:
+    if data_source == "openai/gsm8k":
+        return gsm8k.compute_score(solution_str, ground_truth)
+    if data_source in MATH_SOURCES or str(data_source).startswith("aime"):
+        return math_score.compute_score(solution_str, ground_truth)
+    if str(data_source).startswith("synthetic/"):
+        from ..synthetic import synthetic_token_reward
+
+        ids = (extra_info or {}).get("response_ids")
+        return synthetic_token_reward(ids if ids is not None else [ord(c) for c in solution_str], ground_truth, 0)
+    raise NotImplementedError(f"no reward function for data_source={data_source!r}; pass custom_reward_function")

@@ -1,0 +1,149 @@
+"""Prompt dataset for RL: parquet / jsonl rows -> chat template -> tokenise -> left-pad / truncate, with
+over-long filtering and resumable sampling (reference: 3rdparty/verl/verl/utils/dataset/rl_dataset.py:69-463).
+A whitespace/byte tokenizer is provided for offline tests (the reference's digit-completion env plays the
+same role, tests/special_e2e/envs/digit_completion/)."""
+from __future__ import annotations
+
+import json
+from pathlib import Path
+from typing import Any
+
+import numpy as np
+import torch
+from torch.utils.data import Dataset, Sampler
+
+
+class ByteTokenizer:
+    """Offline tokenizer: UTF-8 bytes + specials; enough for plumbing tests and synthetic runs."""
+
+    pad_token_id, eos_token_id, bos_token_id = 0, 1, 2
+    vocab_size = 259
+
+    def encode(self, text: str, add_special_tokens: bool = False) -> list[int]:
+        ids = [b + 3 for b in text.encode("utf-8")]
+        return ([self.bos_token_id] + ids) if add_special_tokens else ids
+
+    def decode(self, ids, skip_special_tokens: bool = True) -> str:
+        bs = bytes(int(i) - 3 for i in ids if int(i) >= 3)
+        return bs.decode("utf-8", errors="replace")
+
+    def apply_chat_template(self, messages: list[dict], add_generation_prompt: bool = True, tokenize: bool = False):
+        text = "".join(f"<{m['role']}>{m['content']}\n" for m in messages) + ("<assistant>" if add_generation_prompt else "")
+        return self.encode(text) if tokenize else text
+
+
+def load_tokenizer(path: str | None):
+    if not path or path == "byte":
+        return ByteTokenizer()
+    from transformers import AutoTokenizer
+
+    tok = AutoTokenizer.from_pretrained(path)
+    if tok.pad_token_id is None:
+        tok.pad_token_id = tok.eos_token_id
+    return tok
+
+
+def _read_rows(files) -> list[dict]:
+    if isinstance(files, (str, Path)):
+        files = [files]
+    rows: list[dict] = []
+    for f in files:
+        f = str(f)
+        if f.endswith(".parquet"):
+            import pyarrow.parquet as pq
+
+            rows += pq.read_table(f).to_pylist()
+        elif f.endswith(".jsonl"):
+            rows += [json.loads(l) for l in Path(f).read_text().splitlines() if l.strip()]
+        elif f.endswith(".json"):
+            rows += json.loads(Path(f).read_text())
+        else:
+            raise ValueError(f"unsupported data file {f}")
+    return rows
+
+
+def left_pad(ids: list[int], max_len: int, pad_id: int, truncation: str = "error"):
+    if len(ids) > max_len:
+        if truncation == "left":
+            ids = ids[-max_len:]
+        elif truncation == "right":
+            ids = ids[:max_len]
+        elif truncation == "middle":
+            half = max_len // 2
+            ids = ids[:half] + ids[-(max_len - half):]
+        else:
+            raise ValueError(f"prompt of {len(ids)} tokens exceeds max_prompt_length={max_len} (truncation='error')")
+    n = len(ids)
+    input_ids = torch.full((max_len,), pad_id, dtype=torch.long)
+    input_ids[max_len - n:] = torch.tensor(ids, dtype=torch.long)
+    mask = torch.zeros(max_len, dtype=torch.long)
+    mask[max_len - n:] = 1
+    pos = (mask.cumsum(0) - 1).clamp_min(0)
+    return input_ids, mask, pos, ids
+
+
+class RLHFDataset(Dataset):
+    def __init__(self, data_files, tokenizer, prompt_key: str = "prompt", max_prompt_length: int = 512,
+                 filter_overlong_prompts: bool = False, truncation: str = "error", return_raw_chat: bool = False):
+        self.tok, self.key, self.max_len = tokenizer, prompt_key, max_prompt_length
+        self.truncation, self.return_raw_chat = truncation, return_raw_chat
+        self.rows = _read_rows(data_files)
+        if filter_overlong_prompts:
+            self.rows = [r for r in self.rows if len(self._tokenize(r)) <= max_prompt_length]
+
+    def _tokenize(self, row: dict) -> list[int]:
+        p = row[self.key]
+        if isinstance(p, (list, np.ndarray)) and len(p) and isinstance(p[0], dict):
+            text = self.tok.apply_chat_template(list(p), add_generation_prompt=True, tokenize=False)
+        else:
+            text = str(p)
+        return list(self.tok.encode(text, add_special_tokens=False))
+
+    def __len__(self) -> int:
+        return len(self.rows)
+
+    def __getitem__(self, i: int) -> dict[str, Any]:
+        row = dict(self.rows[i])
+        ids, mask, pos, raw = left_pad(self._tokenize(row), self.max_len, self.tok.pad_token_id, self.truncation)
+        out = {"input_ids": ids, "attention_mask": mask, "position_ids": pos, "raw_prompt_ids": raw,
+               "data_source": row.get("data_source", "unknown"), "reward_model": row.get("reward_model", {"ground_truth": ""}),
+               "extra_info": row.get("extra_info", {}), "index": (row.get("extra_info") or {}).get("index", i)}
+        if self.return_raw_chat:
+            out["raw_prompt"] = row[self.key]
+        return out
+
+
+class ResumableRandomSampler(Sampler):
+    """Seeded shuffling with a checkpointable cursor (plays the role of StatefulDataLoader state,
+    reference ray_trainer.py:346-426,777-835)."""
+
+    def __init__(self, n: int, seed: int = 1, shuffle: bool = True):
+        self.n, self.seed, self.shuffle = n, seed, shuffle
+        self.epoch, self.cursor = 0, 0
+
+    def __iter__(self):
+        while self.cursor < self.n:
+            order = self._order()
+            i = order[self.cursor]
+            self.cursor += 1
+            yield int(i)
+        self.cursor, self.epoch = 0, self.epoch + 1
+
+    def _order(self):
+        if not self.shuffle:
+            return np.arange(self.n)
+        return np.random.default_rng(self.seed + self.epoch).permutation(self.n)
+
+    def __len__(self) -> int:
+        return self.n
+
+    def state_dict(self) -> dict:
+        return {"epoch": self.epoch, "cursor": self.cursor, "seed": self.seed}
+
+    def load_state_dict(self, sd: dict) -> None:
+        self.epoch, self.cursor, self.seed = sd["epoch"], sd["cursor"], sd["seed"]
+
+
+def gsm8k_prompt(question: str) -> list[dict]:
+    """GSM8K prompt template used by the reference's preprocessing (examples/data_preprocess/gsm8k.py:57-70)."""
+    return [{"role": "user", "content": question + " Let's think step by step and output the final answer after \"####\"."}]

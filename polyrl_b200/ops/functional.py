@@ -43,7 +43,7 @@ class _LinearFn(torch.autograd.Function):
         ctx.save_for_backward(x2, w)
         ctx.has_res = residual is not None
         ctx.x_shape = x.shape
-        return y.reshape(*x.shape[:-1], w.shape[0])
+        return y if x.dim() == 2 else y.reshape(*x.shape[:-1], w.shape[0])
 
     @staticmethod
     def backward(ctx, dy):
@@ -92,7 +92,7 @@ class _LinearSwigluFn(torch.autograd.Function):
         if need:
             ctx.save_for_backward(x2, wgu, outs[1])
         ctx.x_shape = x.shape
-        return h.reshape(*x.shape[:-1], wgu.shape[0] // 2)
+        return h if x.dim() == 2 else h.reshape(*x.shape[:-1], wgu.shape[0] // 2)
 
     @staticmethod
     def backward(ctx, dh):

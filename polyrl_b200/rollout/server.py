@@ -1,0 +1,279 @@
+"""HTTP front-end of the native rollout engine, wire-compatible with the SGLang endpoints the rollout
+manager and the reference trainer use (reference patches:
+rlboost/sglang/patches.py:390-566, rlboost/verl_stream/workers/rollout/sglang_rollout/sglang_http_async_engine.py:155-299):
+
+  POST /generate (stream => SSE ``data: {...}`` cumulative chunks, ``data: [DONE]``), GET /health_generate,
+  GET /get_server_info (``#running_req`` / ``#queue_req`` / ``last_gen_throughput``), POST /abort_request,
+  POST /shutdown, POST /update_weights_from_agent, POST /update_weights_from_tensor,
+  POST /release_memory_occupation, /resume_memory_occupation, /flush_cache.
+
+One background thread owns the engine (``step()`` loop); HTTP handler threads only enqueue requests and read
+per-request event queues.  ``register_with_manager`` self-registers the instance (remote or local).
+"""
+from __future__ import annotations
+
+import json
+import queue
+import threading
+import time
+import urllib.request
+from http.server import BaseHTTPRequestHandler, ThreadingHTTPServer
+
+from .engine import Request, RolloutEngine, SamplingParams
+
+
+class _Tracked:
+    def __init__(self, req: Request, index: int):
+        self.req, self.index = req, index
+        self.sent = 0
+
+
+class EngineServer:
+    def __init__(self, engine: RolloutEngine, host: str = "127.0.0.1", port: int = 0, stream_interval: int = 20,
+                 weight_update_fn=None):
+        self.engine = engine
+        self.stream_interval = stream_interval
+        self.weight_update_fn = weight_update_fn        # callable(payload dict) -> (ok, message)
+        self._lock = threading.Lock()
+        self._inbox: list = []                          # (kind, payload) commands for the engine thread
+        self._streams: dict[str, tuple[queue.Queue, list[_Tracked]]] = {}
+        self._stop = threading.Event()
+        self._paused = threading.Event()
+        self.weight_version = 0
+        srv = self
+
+        class H(BaseHTTPRequestHandler):
+            protocol_version = "HTTP/1.1"
+
+            def log_message(self, *a):
+                return
+
+            def _json(self, code, obj):
+                data = json.dumps(obj).encode()
+                self.send_response(code)
+                self.send_header("Content-Type", "application/json")
+                self.send_header("Content-Length", str(len(data)))
+                self.end_headers()
+                self.wfile.write(data)
+
+            def do_GET(self):
+                path = self.path.split("?")[0]
+                if path in ("/health", "/health_generate"):
+                    self._json(200, {"status": "ok"})
+                elif path == "/get_server_info":
+                    info = srv.engine.server_info()
+                    self._json(200, {"internal_states": [info], "weight_version": srv.weight_version})
+                else:
+                    self._json(404, {"error": "not found"})
+
+            def do_POST(self):
+                n = int(self.headers.get("Content-Length", 0))
+                raw = self.rfile.read(n) if n else b""
+                try:
+                    body = json.loads(raw) if raw else {}
+                except Exception:
+                    self._json(400, {"error": "invalid json"})
+                    return
+                path = self.path.split("?")[0]
+                if path == "/generate":
+                    srv._handle_generate(self, body)
+                elif path == "/abort_request":
+                    srv._command("abort", body)
+                    self._json(200, {"success": True})
+                elif path == "/shutdown":
+                    self._json(200, {"success": True})
+                    srv._stop.set()
+                elif path == "/update_weights_from_agent":
+                    ok, msg = srv._update_weights(body)
+                    self._json(200 if ok else 500, {"success": ok, "message": msg})
+                elif path == "/update_weights_from_tensor":
+                    self._json(501, {"success": False, "message": "in-process engines alias trainer weights; no tensor upload needed"})
+                elif path == "/release_memory_occupation":
+                    srv._command("release", body, wait=True)
+                    self._json(200, {"success": True})
+                elif path == "/resume_memory_occupation":
+                    srv._command("resume", body, wait=True)
+                    self._json(200, {"success": True})
+                elif path == "/flush_cache":
+                    self._json(200, {"success": True})
+                else:
+                    self._json(404, {"error": "not found"})
+
+        self.httpd = ThreadingHTTPServer((host, port), H)
+        self.httpd.daemon_threads = True
+        self.host, self.port = host, self.httpd.server_address[1]
+        self._http_thread = threading.Thread(target=self.httpd.serve_forever, daemon=True)
+        self._engine_thread = threading.Thread(target=self._engine_loop, daemon=True)
+
+    @property
+    def endpoint(self) -> str:
+        return f"{self.host}:{self.port}"
+
+    def start(self) -> "EngineServer":
+        self._http_thread.start()
+        self._engine_thread.start()
+        return self
+
+    def stop(self) -> None:
+        self._stop.set()
+        self.httpd.shutdown()
+        self.httpd.server_close()
+
+    def serve_until_shutdown(self, poll_s: float = 0.2) -> None:
+        while not self._stop.is_set():
+            time.sleep(poll_s)
+        self.stop()
+
+    # ------------------------------------------------------------------ manager registration
+    def register_with_manager(self, manager_endpoint: str, local: bool = False, handshake_port: int = 21000, timeout: float = 600) -> dict:
+        url = f"http://{manager_endpoint}"
+        if local:
+            body, path = [[self.host, self.port]], "/register_local_rollout_instances"
+        else:
+            body, path = {"host": self.host, "port": self.port, "mooncake_handshake_port": handshake_port}, "/register_rollout_instance"
+        req = urllib.request.Request(url + path, data=json.dumps(body).encode(), method="POST",
+                                     headers={"Content-Type": "application/json"})
+        with urllib.request.urlopen(req, timeout=timeout) as r:
+            return json.loads(r.read().decode())
+
+    # ------------------------------------------------------------------ commands executed on the engine thread
+    def _command(self, kind: str, payload, wait: bool = False):
+        done = threading.Event() if wait else None
+        with self._lock:
+            self._inbox.append((kind, payload, done))
+        if done is not None:
+            done.wait(timeout=120)
+
+    def _update_weights(self, body: dict):
+        """The payload data already sits in this GPU's weight buffers (peer-memory push) or is fetched by
+        ``weight_update_fn``; here we only fence: drain the engine, apply, bump the version."""
+        done = threading.Event()
+        result = {}
+        with self._lock:
+            self._inbox.append(("update_weights", (body, result), done))
+        done.wait(timeout=600)
+        return result.get("ok", False), result.get("msg", "timeout")
+
+    def _handle_generate(self, h, body: dict):
+        ids = body.get("input_ids")
+        if ids is None:
+            h._json(400, {"error": "input_ids required (text prompts need a tokenizer front-end)"})
+            return
+        batch = bool(ids) and isinstance(ids[0], list)
+        prompts = ids if batch else [ids]
+        sp = SamplingParams.from_dict(body.get("sampling_params") or {})
+        stream = bool(body.get("stream", False))
+        q: queue.Queue = queue.Queue()
+        key = f"g{id(q)}"
+        with self._lock:
+            self._inbox.append(("generate", (key, prompts, sp, q), None))
+        n = len(prompts)
+        latest = [None] * n
+        if stream:
+            h.send_response(200)
+            h.send_header("Content-Type", "text/event-stream")
+            h.send_header("Transfer-Encoding", "chunked")
+            h.end_headers()
+
+        def write(s: str):
+            d = s.encode()
+            h.wfile.write(f"{len(d):x}\r\n".encode() + d + b"\r\n")
+            h.wfile.flush()
+
+        finished = 0
+        try:
+            while finished < n:
+                ev = q.get(timeout=3600)
+                idx, payload, fin = ev
+                latest[idx] = payload
+                if fin:
+                    finished += 1
+                if stream:
+                    write("data: " + json.dumps(payload) + "\n\n")
+            if stream:
+                write("data: [DONE]\n\n")
+                h.wfile.write(b"0\r\n\r\n")
+                h.wfile.flush()
+            else:
+                h._json(200, latest if batch else latest[0])
+        except (BrokenPipeError, ConnectionResetError, OSError, queue.Empty):
+            self._command("abort_key", key)
+
+    # ------------------------------------------------------------------ engine thread
+    @staticmethod
+    def _payload(t: _Tracked) -> dict:
+        r = t.req
+        fr = None
+        if r.finished:
+            fr = {"type": r.finish_reason}
+            if r.finish_reason == "length":
+                fr["length"] = len(r.output_ids)
+        return {"text": "", "index": t.index, "output_ids": list(r.output_ids),
+                "meta_info": {"id": r.rid, "finish_reason": fr, "prompt_tokens": len(r.prompt_ids),
+                              "completion_tokens": len(r.output_ids),
+                              "output_token_logprobs": [[lp, tok, None] for lp, tok in zip(r.logprobs, r.output_ids)]}}
+
+    def _engine_loop(self) -> None:
+        eng = self.engine
+        while not self._stop.is_set():
+            with self._lock:
+                cmds, self._inbox = self._inbox, []
+            for kind, payload, done in cmds:
+                try:
+                    if kind == "generate":
+                        key, prompts, sp, q = payload
+                        tag = object() if len(prompts) > 1 and all(p == prompts[0] for p in prompts) else None
+                        tracked = [_Tracked(eng.add_request(list(map(int, p)), sp, group=tag), i) for i, p in enumerate(prompts)]
+                        self._streams[key] = (q, tracked)
+                    elif kind == "abort":
+                        eng.abort(payload.get("rid") or None, abort_all=bool(payload.get("abort_all", not payload.get("rid"))))
+                    elif kind == "abort_key":
+                        ent = self._streams.pop(payload, None)
+                        if ent:
+                            for t in ent[1]:
+                                eng.abort(t.req.rid)
+                    elif kind == "release":
+                        eng.abort(abort_all=True)
+                        eng.release_memory(tuple((payload or {}).get("tags") or ("kv_cache",)))
+                    elif kind == "resume":
+                        eng.resume_memory(tuple((payload or {}).get("tags") or ("kv_cache",)))
+                    elif kind == "update_weights":
+                        body, result = payload
+                        while eng.has_work() and not body.get("bootstrap"):
+                            eng.step()              # drain in-flight requests on the old weights
+                            self._flush_streams()
+                        ok, msg = True, "ok"
+                        if self.weight_update_fn is not None:
+                            ok, msg = self.weight_update_fn(body)
+                        if ok and not body.get("bootstrap"):
+                            self.weight_version = int(body.get("weight_version", self.weight_version + 1))
+                            eng.weight_version = self.weight_version
+                        result["ok"], result["msg"] = ok, msg
+                except Exception as e:  # keep the engine thread alive
+                    if kind == "update_weights":
+                        payload[1]["ok"], payload[1]["msg"] = False, repr(e)
+                finally:
+                    if done is not None:
+                        done.set()
+            if eng.layer_w is not None and eng.has_work():
+                eng.step()
+                self._flush_streams()
+            else:
+                time.sleep(0.002)
+
+    def _flush_streams(self) -> None:
+        for key in list(self._streams):
+            q, tracked = self._streams[key]
+            alive = False
+            for t in tracked:
+                n = len(t.req.output_ids)
+                if t.req.finished and t.sent >= 0:
+                    q.put((t.index, self._payload(t), True))
+                    t.sent = -1
+                elif t.sent >= 0:
+                    alive = True
+                    if n - t.sent >= self.stream_interval:
+                        q.put((t.index, self._payload(t), False))
+                        t.sent = n
+            if not alive:
+                self._streams.pop(key, None)

@@ -1,0 +1,204 @@
+"""Entry point of the streaming trainer:  ``python -m polyrl_b200.trainer.main_stream [--config-file F] key=value ...``
+
+Launch it once per GPU (``torchrun --nproc-per-node N -m polyrl_b200.trainer.main_stream ...`` or the
+``--spawn`` helper).  Ranks ``[0, N - n_rollout_gpus)`` are trainer ranks (ZeRO-3 group); with
+``trainer.n_rollout_gpus > 0`` the remaining ranks host native rollout engines behind the SGLang-compatible
+HTTP front-end and register with the C++ rollout manager, which rank 0 spawns.  With ``n_rollout_gpus = 0``
+the run is colocated (every GPU rolls out, then trains).
+
+Reference flow: rlboost/verl_stream/trainer/main_stream.py:40-391 (Hydra main -> TaskRunner: build workers,
+datasets, reward fns, spawn manager via ``cargo run``, init_workers, register_weight_senders, validate
+``min_stream_batch_size``, ``fit()``).
+"""
+from __future__ import annotations
+
+import argparse
+import os
+import sys
+import time
+
+import torch
+import torch.distributed as dist
+
+from ..config.schema import PPOConfig, load_config, need_critic, need_reference_policy, validate_config
+
+
+def _init_dist(device_type: str):
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    if world > 1 and not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29511")
+        if device_type == "cuda":
+            torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", 0)))
+            dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ.get("LOCAL_RANK", 0))))
+        else:
+            dist.init_process_group("gloo")
+    return int(os.environ.get("RANK", 0)), world
+
+
+def build_datasets(cfg: PPOConfig, model_cfg, tokenizer=None):
+    from ..data.rl_dataset import ResumableRandomSampler, RLHFDataset, load_tokenizer
+    from ..data.synthetic import SyntheticPromptDataset
+
+    d = cfg.data
+    if d.synthetic or not d.train_files:
+        train = SyntheticPromptDataset(model_cfg.vocab_size, d.synthetic_num_samples, tuple(d.synthetic_prompt_len_range),
+                                       d.max_prompt_length, model_cfg.pad_token_id, seed=d.seed)
+        val = SyntheticPromptDataset(model_cfg.vocab_size, max(8, d.val_batch_size or 64), tuple(d.synthetic_prompt_len_range),
+                                     d.max_prompt_length, model_cfg.pad_token_id, seed=d.seed + 7)
+        tok = None
+    else:
+        tok = tokenizer or load_tokenizer(cfg.actor_rollout_ref.model.tokenizer_path or cfg.actor_rollout_ref.model.path)
+        train = RLHFDataset(d.train_files, tok, d.prompt_key, d.max_prompt_length, d.filter_overlong_prompts, d.truncation)
+        val = RLHFDataset(d.val_files, tok, d.prompt_key, d.max_prompt_length, d.filter_overlong_prompts, d.truncation) if d.val_files else None
+    sampler = ResumableRandomSampler(len(train), d.seed, d.shuffle)
+    return train, val, sampler, tok
+
+
+def run_rollout_rank(cfg: PPOConfig, rank: int, trainer_ranks, rollout_ranks, device, manager_endpoint: str) -> None:
+    from ..models import get_model_config
+    from ..rollout.engine import RolloutEngine
+    from ..rollout.server import EngineServer
+    from ..weight_transfer.sync import WeightSync
+
+    arr = cfg.actor_rollout_ref
+    model_cfg = get_model_config(arr.model.path, **arr.model.override_config)
+    r = arr.rollout
+    sync = WeightSync(model_cfg, trainer_ranks, rollout_ranks, device, backend=arr.actor.fsdp_config.comm_backend)
+    max_len = r.max_model_len or (cfg.data.max_prompt_length + cfg.data.max_response_length)
+    eng = RolloutEngine(model_cfg, device, max_num_seqs=r.max_num_seqs, max_model_len=max_len,
+                        gpu_memory_utilization=r.gpu_memory_utilization, use_cuda_graph=r.cuda_graph,
+                        max_prefill_tokens=r.max_num_batched_tokens, seed=cfg.data.seed + 17 * rank)
+    e, l, h = sync.engine_views()
+    eng.set_weights(e, l, h)
+
+    def on_update(body: dict):
+        sync.receive(int(body.get("weight_version", 0)))
+        return True, "ok"
+
+    srv = EngineServer(eng, port=int(os.environ.get("POLYRL_ENGINE_PORT_BASE", 30000)) + rank, weight_update_fn=on_update).start()
+    srv.register_with_manager(manager_endpoint, local=False)
+    print(f"[rollout rank {rank}] engine serving on {srv.endpoint}", flush=True)
+    srv.serve_until_shutdown()
+
+
+def run_trainer_rank(cfg: PPOConfig, rank: int, trainer_ranks, rollout_ranks, device, manager_endpoint: str | None, trainer_group):
+    from ..data.reward_manager import load_reward_manager
+    from ..rollout.remote_client import RemoteRolloutClient
+    from ..utils.tracking import Tracking
+    from ..weight_transfer.agent import TrainerWeightSender
+    from ..weight_transfer.sync import WeightSync
+    from ..workers.hybrid_worker import ActorRolloutRefWorker, CriticWorker
+    from .stream_trainer import StreamPPOTrainer
+
+    disagg = len(rollout_ranks) > 0
+    role = ("actor" if disagg else "actor_rollout") + ("_ref" if need_reference_policy(cfg) else "")
+    worker = ActorRolloutRefWorker(cfg, role=role, device=device, group=trainer_group)
+    worker.init_model()
+    critic = None
+    if need_critic(cfg):
+        critic = CriticWorker(cfg, device=device, group=trainer_group)
+        critic.init_model(heap=worker.actor_engine.heap)
+    train, val, sampler, tok = build_datasets(cfg, worker.model_cfg)
+    reward_fn = None if tok is None else load_reward_manager(cfg, tok)
+    client = None
+    if disagg:
+        sync = WeightSync(worker.model_cfg, trainer_ranks, rollout_ranks, device, backend=cfg.actor_rollout_ref.actor.fsdp_config.comm_backend)
+        sender = TrainerWeightSender(manager_endpoint, sync, group=trainer_group)
+        r = cfg.actor_rollout_ref.rollout
+        if rank == 0:
+            client = RemoteRolloutClient(manager_endpoint, r.n, cfg.data.max_response_length, worker.model_cfg.pad_token_id,
+                                         worker.model_cfg.eos_token_id, stream_size=r.min_stream_batch_size)
+            client.wait_healthy()
+            sender.register_as_sender()
+            # wait until every rollout rank has registered and passed the health gate
+            t0 = time.time()
+            while time.time() - t0 < 600:
+                st = client.instances_status()
+                if st.get("pending_instances", 0) + st.get("ready_instances", 0) >= len(rollout_ranks):
+                    break
+                time.sleep(0.2)
+            time.sleep(0.5)
+        if dist.is_initialized():
+            dist.barrier(group=trainer_group)
+
+        def update_weight_remote():
+            sender.update(worker.actor_engine, rank)
+            return True
+
+        worker.update_weight_remote = update_weight_remote      # disaggregated: push over NVLink / broadcast
+
+        class _NoopVersion:
+            """the sender bumps the version itself; the trainer's explicit bump becomes a no-op"""
+
+        if client is not None:
+            client.update_weight_version = lambda: sender.version
+    tracking = Tracking(cfg.trainer.project_name, cfg.trainer.experiment_name, cfg.trainer.logger) if rank == 0 else None
+    trainer = StreamPPOTrainer(cfg, worker, critic, reward_fn, reward_fn, train, val, client, trainer_group, tracking, sampler)
+    out = trainer.fit()
+    return out
+
+
+def main(argv: list[str] | None = None) -> int:
+    ap = argparse.ArgumentParser(add_help=True)
+    ap.add_argument("--config-file", action="append", default=[])
+    ap.add_argument("--manager-endpoint", default=None, help="use an already running rollout manager")
+    ap.add_argument("overrides", nargs="*")
+    a = ap.parse_args(argv)
+    cfg = load_config(a.config_file, a.overrides)
+    device_type = cfg.trainer.device if (cfg.trainer.device != "cuda" or torch.cuda.is_available()) else "cpu"
+    rank, world = _init_dist(device_type)
+    n_roll = cfg.trainer.n_rollout_gpus
+    n_train = world - n_roll
+    validate_config(cfg, n_gpus=world)
+    trainer_ranks = list(range(n_train))
+    rollout_ranks = list(range(n_train, world))
+    device = torch.device("cuda", int(os.environ.get("LOCAL_RANK", 0))) if device_type == "cuda" else torch.device("cpu")
+    trainer_group = dist.new_group(trainer_ranks) if (dist.is_initialized() and n_roll > 0) else None
+    manager_endpoint = a.manager_endpoint or cfg.actor_rollout_ref.rollout.rollout_manager.endpoint
+    mgr_proc = None
+    if n_roll > 0 and manager_endpoint is None:
+        from ..weight_transfer.launcher import spawn_rollout_manager
+
+        port = cfg.actor_rollout_ref.rollout.rollout_manager.port
+        if rank == 0:
+            mgr_proc, port = spawn_rollout_manager(port=port, config_path=cfg.actor_rollout_ref.rollout.rollout_manager.config_path,
+                                                   initial_local_gen_s=int(cfg.actor_rollout_ref.rollout.rollout_manager.max_local_gen_s))
+        box = [port]
+        if dist.is_initialized():
+            dist.broadcast_object_list(box, src=0)
+        manager_endpoint = f"127.0.0.1:{box[0]}"
+    try:
+        if rank in rollout_ranks:
+            run_rollout_rank(cfg, rank, trainer_ranks, rollout_ranks, device, manager_endpoint)
+        else:
+            out = run_trainer_rank(cfg, rank, trainer_ranks, rollout_ranks, device, manager_endpoint if n_roll > 0 else None,
+                                   trainer_group)
+            if rank == 0:
+                print("[main_stream] final metrics:", {k: v for k, v in sorted(out.items()) if k.startswith(("perf/", "critic/score", "actor/pg_loss", "training/"))}, flush=True)
+                if n_roll > 0:        # tell the rollout ranks to exit
+                    import http.client
+                    import json as _json
+
+                    h, p = manager_endpoint.rsplit(":", 1)
+                    c = http.client.HTTPConnection(h, int(p), timeout=10)
+                    c.request("GET", "/get_instances_status")
+                    st = _json.loads(c.getresponse().read().decode())
+                    eps = st.get("ready_instance_endpoints", []) + st.get("pending_instance_endpoints", [])
+                    c.request("POST", "/shutdown_instances", body=_json.dumps({"endpoints": eps}), headers={"Content-Type": "application/json"})
+                    c.getresponse().read()
+    finally:
+        if mgr_proc is not None:
+            time.sleep(0.5)
+            mgr_proc.terminate()
+    if dist.is_initialized():
+        try:
+            dist.barrier()
+            dist.destroy_process_group()
+        except Exception:
+            pass
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

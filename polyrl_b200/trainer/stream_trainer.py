@@ -1,0 +1,373 @@
+"""Streaming PPO/GRPO trainer: rollout results arrive in micro-batches and the actor/critic forward/backward
+run while generation is still in flight; optimizer steps happen at mini-batch boundaries.
+
+Behavioural parity with ``StreamRayPPOTrainer.fit`` (rlboost/verl_stream/trainer/ppo/stream_ray_trainer.py:
+282-689; mini-batch boundaries :239-278,500-564; metrics feedback :691-704) and verl's ``RayPPOTrainer``
+checkpoint / validation / balance logic (3rdparty/verl/verl/trainer/ppo/ray_trainer.py:529-668,777-954).
+Execution model is SPMD: every trainer rank runs this loop; rank 0 owns the manager connection and
+broadcasts each streamed batch, every rank then takes its data-parallel shard (no driver<->worker object-store
+round trips).  Without a manager (colocated sync mode) the batch is generated locally and then consumed in
+``min_stream_batch_size`` slices, so both modes share one code path.
+"""
+from __future__ import annotations
+
+import os
+import time
+import uuid
+from pathlib import Path
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from ..algos import core_algos
+from ..config.schema import PPOConfig, need_critic, need_reference_policy
+from ..protocol import DataProto, collate_fn, pad_dataproto_to_divisor
+from ..utils import metrics as M
+from ..utils.checkpoint import find_latest_ckpt_path, write_latest
+from ..utils.profiler import marked_timer
+from ..utils.seqlen_balancing import get_seqlen_balanced_partitions, log_seqlen_unbalance
+from . import core
+
+
+def _bcast_obj(obj, src: int = 0, group=None):
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return obj
+    box = [obj]
+    dist.broadcast_object_list(box, src=src, group=group)
+    return box[0]
+
+
+class StreamPPOTrainer:
+    def __init__(self, config: PPOConfig, worker, critic=None, reward_fn=None, val_reward_fn=None, train_dataset=None,
+                 val_dataset=None, rollout_client=None, group=None, tracking=None, train_sampler=None):
+        self.config = config
+        self.worker, self.critic = worker, critic
+        self.reward_fn, self.val_reward_fn = reward_fn, val_reward_fn or reward_fn
+        self.train_dataset, self.val_dataset = train_dataset, val_dataset
+        self.client = rollout_client
+        self.group = group
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.tracking = tracking
+        self.sampler = train_sampler
+        self.device = worker.device
+        self.global_steps = 0
+        self.use_critic = critic is not None
+        self.use_reference = worker.has_ref
+        self.kl_ctrl = core_algos.get_kl_controller(config.algorithm.kl_ctrl) if config.algorithm.use_kl_in_reward else None
+        bs = config.data.train_batch_size
+        n_batches = max(1, len(train_dataset) // bs) if train_dataset is not None else 0
+        self.total_training_steps = config.trainer.total_training_steps or n_batches * config.trainer.total_epochs
+        config.actor_rollout_ref.actor.optim.total_training_steps = self.total_training_steps
+        self._esi_deadline = float(os.environ.get("POLYRL_ESI_EXPIRATION_TS", "0") or 0)
+
+    # ------------------------------------------------------------------ data
+    def _iter_batches(self):
+        bs = self.config.data.train_batch_size
+        ds = self.train_dataset
+        for _ in range(self.config.trainer.total_epochs):
+            order = list(iter(self.sampler)) if self.sampler is not None else list(range(len(ds)))
+            for i in range(0, len(order) - bs + 1, bs):
+                yield DataProto.from_single_dict(collate_fn([ds[j] for j in order[i:i + bs]]))
+
+    def _mini_batch_boundaries(self, total: int) -> list[int]:
+        """Cumulative sample counts at which the optimizer steps (global samples = prompts * n)."""
+        a = self.config.actor_rollout_ref
+        mini = a.actor.ppo_mini_batch_size * a.rollout.n
+        b = list(range(mini, total + 1, mini))
+        if not b or b[-1] != total:
+            b.append(total)           # clamp: the reference crashes when train_batch_size*n < mini
+        return b
+
+    # ------------------------------------------------------------------ rollout stream
+    def _stream(self, prompts: DataProto):
+        """Yield streamed rollout batches (identical on every rank)."""
+        r = self.config.actor_rollout_ref.rollout
+        if self.client is None:
+            batch = self.worker.generate_sequences(prompts.to(self.device))
+            self._timing["gen"] = batch.meta_info.get("timing", {}).get("generate_sequences", 0.0)
+            step = r.min_stream_batch_size
+            for i in range(0, len(batch), step):
+                yield batch.slice(i, min(i + step, len(batch)))
+            return
+        it = None
+        if self.rank == 0:
+            sp = {"temperature": r.temperature, "top_p": r.top_p, "top_k": r.top_k}
+            it = iter(self.client.generate_sequences_remote(prompts, sp))
+        while True:
+            item = None
+            if self.rank == 0:
+                try:
+                    item = next(it)
+                except StopIteration:
+                    item = None
+            item = _bcast_obj(item, 0, self.group)
+            if item is None:
+                break
+            yield item.to(self.device)
+        if self.rank == 0:
+            self._timing["gen"] = self.client.timing.get("gen", 0.0)
+            self._timing["local_gen"] = self.client.timing.get("local_gen", 0.0)
+
+    def _balance_and_shard(self, batch: DataProto, metrics: dict) -> DataProto:
+        """Karmarkar-Karp reorder so every DP rank gets a similar token count, then take this rank's shard."""
+        if self.world == 1:
+            return batch
+        batch, pad = pad_dataproto_to_divisor(batch, self.world)
+        if pad:
+            batch.batch["response_mask"][-pad:] = 0        # padded duplicates carry no loss
+        if self.config.trainer.balance_batch:
+            lens = batch.batch["attention_mask"].sum(-1).tolist()
+            parts = get_seqlen_balanced_partitions([int(x) for x in lens], self.world, equal_size=True)
+            metrics.update(log_seqlen_unbalance([int(x) for x in lens], parts, "global_seqlen"))
+            batch.reorder(torch.tensor([i for p in parts for i in p], dtype=torch.long))
+        return batch.chunk(self.world)[self.rank]
+
+    def _reward(self, batch: DataProto) -> torch.Tensor:
+        if self.reward_fn is None:
+            from ..data.synthetic import synthetic_token_reward
+
+            mask = batch.batch["response_mask"]
+            resp, lens = batch.batch["responses"].cpu().numpy(), mask.sum(-1).cpu().numpy()
+            rm = batch.non_tensor_batch["reward_model"]
+            scores = [synthetic_token_reward(resp[i, : lens[i]], rm[i]["ground_truth"], 0) for i in range(len(batch))]
+            return core.place_outcome_rewards(scores, mask)
+        out = self.reward_fn(batch)
+        return out.to(self.device) if torch.is_tensor(out) else out["reward_tensor"].to(self.device)
+
+    # ------------------------------------------------------------------ one streamed batch
+    def _process_ibatch(self, ibatch: DataProto, seen: int, boundaries: list[int], metrics: dict) -> None:
+        cfg, algo = self.config, self.config.algorithm
+        t = self._timing
+        with marked_timer("reward", t):
+            ibatch.batch["token_level_scores"] = self._reward(ibatch)
+        full_len = len(ibatch)
+        uid_full = ibatch.non_tensor_batch["uid"]
+        # advantages that need whole groups are computed on the full streamed batch (groups arrive together)
+        group_level = algo.adv_estimator not in ("gae", "reinforce_plus_plus", "remax")
+        if group_level and not algo.use_kl_in_reward:
+            ibatch.batch["token_level_rewards"] = ibatch.batch["token_level_scores"]
+            with marked_timer("adv", t):
+                ibatch = core.compute_advantage(ibatch, algo.adv_estimator, algo.gamma, algo.lam, cfg.actor_rollout_ref.rollout.n,
+                                                algo.norm_adv_by_std_in_grpo, algo)
+        local = self._balance_and_shard(ibatch, metrics)
+        local.meta_info["temperature"] = cfg.actor_rollout_ref.rollout.temperature
+        with marked_timer("old_log_prob", t):
+            old = self.worker.compute_log_prob(local)
+            local.batch["old_log_probs"] = old.batch["old_log_probs"]
+            metrics.setdefault("actor/entropy_rollout", []).append(
+                core_algos.masked_mean(old.batch["entropys"], local.batch["response_mask"].float()).item())
+            if "rollout_log_probs" in local.batch:
+                m = local.batch["response_mask"].bool()
+                diff = (local.batch["rollout_log_probs"] - local.batch["old_log_probs"]).abs()[m]
+                if diff.numel():
+                    metrics.setdefault("training/rollout_probs_diff_mean", []).append(diff.mean().item())
+                    metrics.setdefault("training/rollout_probs_diff_max", []).append(diff.max().item())
+        if self.use_reference:
+            with marked_timer("ref", t):
+                local.batch["ref_log_prob"] = self.worker.compute_ref_log_prob(local).batch["ref_log_prob"]
+        if self.use_critic:
+            with marked_timer("values", t):
+                local.batch["values"] = self.critic.compute_values(local).batch["values"]
+        if not (group_level and not algo.use_kl_in_reward):
+            with marked_timer("adv", t):
+                if algo.use_kl_in_reward:
+                    local, klm = core.apply_kl_penalty(local, self.kl_ctrl, algo.kl_penalty)
+                    for k, v in klm.items():
+                        metrics.setdefault(k, []).append(v)
+                else:
+                    local.batch["token_level_rewards"] = local.batch["token_level_scores"]
+                local = core.compute_advantage(local, algo.adv_estimator, algo.gamma, algo.lam, cfg.actor_rollout_ref.rollout.n,
+                                               algo.norm_adv_by_std_in_grpo, algo)
+        self._step_batches.append(local)
+        # ---- split at cumulative mini-batch boundaries (in global sample counts)
+        end_global = seen + full_len
+        cuts = [b for b in boundaries if seen < b <= end_global]
+        per_rank = len(local)
+        start = 0
+        for b in cuts + ([end_global] if (not cuts or cuts[-1] != end_global) else []):
+            frac = (b - seen) / full_len
+            stop = per_rank if b == end_global else int(round(frac * per_rank))
+            if stop <= start and b not in cuts:
+                continue
+            part = local.slice(start, stop) if stop > start else None
+            is_opt = b in cuts
+            is_lr = is_opt and b == boundaries[-1]
+            if part is not None and len(part):
+                part.meta_info = {**local.meta_info, "is_opt_step": is_opt, "is_lr_step": is_lr}
+                if self.use_critic:
+                    with marked_timer("update_critic", t):
+                        M.append_to_dict(metrics, self.critic.update_critic_stream(part).meta_info["metrics"])
+                if self.global_steps >= cfg.trainer.critic_warmup or not self.use_critic:
+                    with marked_timer("update_actor", t):
+                        M.append_to_dict(metrics, self.worker.update_actor_stream(part).meta_info["metrics"])
+            elif is_opt:
+                # boundary hit exactly at a batch edge with nothing left in this slice: step on accumulated grads
+                st = self.worker.actor_engine.step()
+                metrics.setdefault("actor/grad_norm", []).append(st["grad_norm"])
+            start = stop
+
+    # ------------------------------------------------------------------ validation / checkpoint
+    def _validate(self) -> dict:
+        if self.val_dataset is None:
+            return {}
+        cfg = self.config
+        bs = cfg.data.val_batch_size or len(self.val_dataset)
+        scores, sources, uids = [], [], []
+        for i in range(0, len(self.val_dataset), bs):
+            rows = [self.val_dataset[j] for j in range(i, min(i + bs, len(self.val_dataset)))]
+            shard = rows[self.rank::self.world] if self.world > 1 else rows
+            if not shard:
+                continue
+            batch = DataProto.from_single_dict(collate_fn(shard)).to(self.device)
+            batch.meta_info = {"validate": True, "do_sample": cfg.actor_rollout_ref.rollout.val_kwargs.get("do_sample", False)}
+            out = self.worker.generate_sequences(batch)
+            fn = self.val_reward_fn
+            if fn is None:
+                old, self.reward_fn = self.reward_fn, None
+                r = self._reward(out)
+                self.reward_fn = old
+            else:
+                r = fn(out)
+                r = r if torch.is_tensor(r) else r["reward_tensor"]
+            scores += r.sum(-1).tolist()
+            sources += list(out.non_tensor_batch.get("data_source", ["unknown"] * len(out)))
+            uids += [str(uuid.uuid4()) for _ in range(len(out))]
+        if self.world > 1:
+            gathered = [None] * self.world
+            dist.all_gather_object(gathered, (scores, sources, uids), group=self.group)
+            scores = [s for g in gathered for s in g[0]]
+            sources = [s for g in gathered for s in g[1]]
+            uids = [s for g in gathered for s in g[2]]
+        res = M.process_validation_metrics(sources, uids, {"reward": scores})
+        out = {}
+        for ds, vars_ in res.items():
+            for var, ms in vars_.items():
+                for mname, v in ms.items():
+                    out[f"val-core/{ds}/{var}/{mname}"] = v
+        return out
+
+    def _ckpt_root(self) -> Path:
+        return Path(self.config.trainer.default_local_dir)
+
+    def _save_checkpoint(self) -> None:
+        root = self._ckpt_root() / f"global_step_{self.global_steps}"
+        t = self.config.trainer
+        self.worker.save_checkpoint(str(root / "actor"), None, self.global_steps, t.max_actor_ckpt_to_keep)
+        if self.use_critic:
+            self.critic.save_checkpoint(str(root / "critic"), None, self.global_steps, t.max_critic_ckpt_to_keep)
+        if self.rank == 0:
+            torch.save({"sampler": self.sampler.state_dict() if self.sampler is not None else None,
+                        "global_steps": self.global_steps,
+                        "kl_ctrl": getattr(self.kl_ctrl, "value", None)}, root / "data.pt")
+            write_latest(self._ckpt_root(), self.global_steps)
+        if dist.is_initialized() and self.world > 1:
+            dist.barrier(group=self.group)
+
+    def _load_checkpoint(self) -> int:
+        t = self.config.trainer
+        if t.resume_mode == "disable":
+            return 0
+        path = t.resume_from_path if t.resume_mode == "resume_path" else find_latest_ckpt_path(self._ckpt_root())
+        if not path:
+            return 0
+        path = Path(path)
+        self.worker.load_checkpoint(str(path / "actor"))
+        if self.use_critic and (path / "critic").exists():
+            self.critic.load_checkpoint(str(path / "critic"))
+        data = path / "data.pt"
+        if data.exists():
+            sd = torch.load(data, weights_only=False)
+            self.global_steps = sd.get("global_steps", int(path.name.split("_")[-1]))
+            if self.sampler is not None and sd.get("sampler"):
+                self.sampler.load_state_dict(sd["sampler"])
+            if self.kl_ctrl is not None and sd.get("kl_ctrl") is not None:
+                self.kl_ctrl.value = sd["kl_ctrl"]
+        else:
+            self.global_steps = int(path.name.split("_")[-1])
+        if self.rank == 0:
+            print(f"[trainer] resumed from {path} at global step {self.global_steps}", flush=True)
+        return self.global_steps
+
+    def _should_save(self, is_last: bool, step_time: float) -> bool:
+        t = self.config.trainer
+        if t.save_freq > 0 and (is_last or self.global_steps % t.save_freq == 0):
+            return True
+        # ESI (spot-instance expiry) aware: force a checkpoint when the lease is about to end
+        if self._esi_deadline > 0 and time.time() + step_time + t.esi_redundant_time >= self._esi_deadline:
+            return True
+        return False
+
+    # ------------------------------------------------------------------ main loop
+    def fit(self) -> dict:
+        cfg = self.config
+        self._load_checkpoint()
+        last_metrics: dict = {}
+        if cfg.trainer.val_before_train and self.val_dataset is not None:
+            vm = self._validate()
+            if self.rank == 0 and self.tracking:
+                self.tracking.log(vm, self.global_steps)
+            if cfg.trainer.val_only:
+                return vm
+        if self.client is not None and self.rank == 0:
+            self.client.update_weight_version()
+        self.worker.update_weight_remote()
+        prof = cfg.global_profiler
+        for prompts in self._iter_batches():
+            if self.global_steps >= self.total_training_steps:
+                break
+            self.global_steps += 1
+            do_profile = bool(prof.tool and prof.steps and self.global_steps in prof.steps)
+            if do_profile:
+                self.worker.start_profile()
+            self._timing = {}
+            self._step_batches = []
+            metrics: dict = {}
+            t_step = time.time()
+            n = cfg.actor_rollout_ref.rollout.n
+            prompts.non_tensor_batch["uid"] = core.uid_array(len(prompts), 1, prefix=f"{self.global_steps}-")
+            total = len(prompts) * n
+            boundaries = self._mini_batch_boundaries(total)
+            seen = 0
+            for ibatch in self._stream(prompts):
+                self._process_ibatch(ibatch, seen, boundaries, metrics)
+                seen += len(ibatch)
+            with marked_timer("update_weight", self._timing):
+                if self.client is not None and self.rank == 0:
+                    self.client.update_weight_version()
+                self.worker.update_weight_remote()
+            step_time = time.time() - t_step
+            self._timing["step"] = step_time
+            is_last = self.global_steps >= self.total_training_steps
+            if self.val_dataset is not None and cfg.trainer.test_freq > 0 and (is_last or self.global_steps % cfg.trainer.test_freq == 0):
+                with marked_timer("testing", self._timing):
+                    metrics.update(self._validate())
+            if self._should_save(is_last, step_time):
+                with marked_timer("save_checkpoint", self._timing):
+                    self._save_checkpoint()
+            if do_profile:
+                self.worker.stop_profile()
+            # ---- metrics
+            full = DataProto.concat(self._step_batches)
+            out = M.reduce_metrics(metrics)
+            out.update(M.compute_data_metrics(full, use_critic=self.use_critic))
+            out.update(M.compute_timing_metrics(full, self._timing))
+            ntok = torch.tensor([float(full.batch["attention_mask"].sum().item())], device=self.device)
+            if self.world > 1:
+                dist.all_reduce(ntok, group=self.group)
+            full.meta_info["global_token_num"] = [int(ntok.item())]
+            out.update(M.compute_throughout_metrics(full, self._timing, self.world))
+            out["training/global_step"] = self.global_steps
+            out["perf/samples_per_sec"] = total / step_time
+            if self.client is not None and self.rank == 0:
+                try:
+                    fb = self.client.update_metrics(step_time, self._timing.get("gen", 0.0), out["perf/throughput_all_gpus"])
+                    out["training/num_rollout_instances"] = fb.get("new_num_rollout_instances", 0)
+                    out["training/new_max_gen_s"] = fb.get("new_max_gen_s", 0)
+                except Exception as e:  # the feedback loop must never kill training
+                    print(f"[trainer] update_metrics failed: {e}")
+            if self.rank == 0 and self.tracking:
+                self.tracking.log(out, self.global_steps)
+            last_metrics = out
+        return last_metrics

@@ -1,0 +1,84 @@
+"""Native engine behind its SGLang-compatible HTTP front-end, driven through the C++ manager (CPU, tiny model)."""
+import json
+import time
+import urllib.request
+
+import pytest
+import torch
+
+from polyrl_b200.manager.build import build_manager
+from polyrl_b200.models import TransformerWeights, get_model_config
+from polyrl_b200.rollout.engine import RolloutEngine, SamplingParams
+from polyrl_b200.rollout.server import EngineServer
+from tests.test_manager import Manager, _http
+
+
+def _engine():
+    cfg = get_model_config("tiny-llama")
+    w = TransformerWeights(cfg, seed=3)
+    eng = RolloutEngine(cfg, "cpu", max_num_seqs=16, max_model_len=96, kv_cache_tokens=16 * 96)
+    eng.set_weights(w.embed, w.layers, w.head)
+    return cfg, w, eng
+
+
+def test_generate_stream_and_abort():
+    cfg, w, eng = _engine()
+    direct = RolloutEngine(cfg, "cpu", max_num_seqs=16, max_model_len=96, kv_cache_tokens=16 * 96)
+    direct.set_weights(w.embed, w.layers, w.head)
+    want = direct.generate([[5, 6, 7]], SamplingParams(max_new_tokens=10, temperature=0.0, ignore_eos=True))[0][0].output_ids
+    srv = EngineServer(eng, stream_interval=3).start()
+    try:
+        url = f"http://{srv.endpoint}"
+        assert _http("GET", url + "/health_generate")[0] == 200
+        body = {"input_ids": [5, 6, 7], "sampling_params": {"max_new_tokens": 10, "temperature": 0.0, "ignore_eos": True}}
+        code, out = _http("POST", url + "/generate", body)
+        out = json.loads(out)
+        assert code == 200 and [t[1] for t in out["meta_info"]["output_token_logprobs"]] == want
+        assert out["meta_info"]["finish_reason"]["type"] == "length" and out["meta_info"]["completion_tokens"] == 10
+        # SSE stream, cumulative chunks
+        req = urllib.request.Request(url + "/generate", data=json.dumps({**body, "stream": True}).encode(), method="POST",
+                                     headers={"Content-Type": "application/json"})
+        chunks = []
+        with urllib.request.urlopen(req, timeout=60) as r:
+            for line in r:
+                line = line.decode().strip()
+                if line.startswith("data:"):
+                    chunks.append(line[5:].strip())
+        assert chunks[-1] == "[DONE]" and len(chunks) >= 3
+        last = json.loads(chunks[-2])
+        assert [t[1] for t in last["meta_info"]["output_token_logprobs"]] == want
+        info = json.loads(_http("GET", url + "/get_server_info")[1])["internal_states"][0]
+        assert info["#running_req"] == 0 and info["#queue_req"] == 0
+    finally:
+        srv.stop()
+
+
+def test_manager_drives_native_engines():
+    mbin = build_manager()
+    m = Manager(mbin)
+    servers = []
+    try:
+        cfg, w, _ = _engine()
+        for _ in range(2):
+            e = RolloutEngine(cfg, "cpu", max_num_seqs=16, max_model_len=96, kv_cache_tokens=16 * 96)
+            e.set_weights(w.embed, w.layers, w.head)
+            s = EngineServer(e, stream_interval=4).start()
+            s.register_with_manager(f"127.0.0.1:{m.port}", local=True)
+            servers.append(s)
+        ref = RolloutEngine(cfg, "cpu", max_num_seqs=16, max_model_len=96, kv_cache_tokens=16 * 96)
+        ref.set_weights(w.embed, w.layers, w.head)
+        reqs = [[i + 1, {"input_ids": [[9, 8, i + 3]] * 2, "sampling_params": {"max_new_tokens": 8, "temperature": 0.0, "ignore_eos": True},
+                         "return_logprob": True}] for i in range(5)]
+        code, body = _http("POST", m.url + "/batch_generate_requests", reqs, timeout=120)
+        lines = [json.loads(l) for l in body.strip().split("\n")]
+        assert lines[0] == {"id": 0, "success": True}
+        got = {l["id"]: l for l in lines[1:]}
+        for i in range(5):
+            want = ref.generate([[9, 8, i + 3]], SamplingParams(max_new_tokens=8, temperature=0.0, ignore_eos=True))[0][0].output_ids
+            assert got[i + 1]["success"]
+            for sub in got[i + 1]["data"]:
+                assert [t[1] for t in sub["meta_info"]["output_token_logprobs"]] == want
+    finally:
+        for s in servers:
+            s.stop()
+        m.close()
