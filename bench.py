@@ -175,6 +175,9 @@ def main() -> int:
         ev[k][0].record()
         m = ppo.step(hb)                         # includes H2D of hb and D2H of losses/metrics (.item())
         ev[k][1].record()
+        if rank == 0:
+            print("[bench] step", k, {kk: round(v, 3) for kk, v in m.items() if kk.startswith("timing_s/")},
+                  "launches", dict(sorted(ops.LAUNCHES.items())), file=sys.stderr, flush=True)
         d2h_bytes += 8 * sum(1 for v in m.values() if isinstance(v, float))
         samples += int(m["num_samples"])
     sync_all()

@@ -38,6 +38,8 @@ int prl_p2p_copy(const void*, void*, int64_t, int, cudaStream_t);
 int prl_p2p_push_fp8(const void*, void*, float*, int, int, int, cudaStream_t);
 int prl_p2p_allgather_pull(void* const*, void*, int64_t, int, int, int, cudaStream_t);
 int prl_p2p_reduce_scatter_accum(void* const*, int64_t, float*, int64_t, float, int, int, float*, int, cudaStream_t);
+int prl_skinny_workspace_floats(int, int, int);
+int prl_skinny_gemm(const void*, const void*, void*, const void*, const void*, const float*, const float*, float*, int*, int, int, int, int64_t, int64_t, int64_t, int, int, int, cudaStream_t);
 int prl_ag_gemm_bf16(const void*, void* const*, void*, void*, uint32_t*, uint32_t, int, int, int, int64_t, int64_t, int, int, int, cudaStream_t);
 }
 
@@ -270,6 +272,38 @@ std::vector<at::Tensor> sample(const at::Tensor& logits, const c10::optional<at:
   return {tok, lp};
 }
 
+// Decode-shape GEMM (swap-AB + split-K).  mode 0: out = x @ w.T (+bias)(+residual); mode 1: SwiGLU on interleaved W.
+at::Tensor skinny_gemm(const at::Tensor& x, const at::Tensor& w, const c10::optional<at::Tensor>& residual,
+                       const c10::optional<at::Tensor>& bias, const c10::optional<at::Tensor>& x_scale,
+                       const c10::optional<at::Tensor>& w_scale, at::Tensor workspace, at::Tensor counters, int64_t mode,
+                       int64_t splits) {
+  TORCH_CHECK(x.is_cuda() && w.is_cuda() && x.dim() == 2 && w.dim() == 2 && x.stride(1) == 1 && w.stride(1) == 1);
+  const bool fp8 = x.element_size() == 1;
+  TORCH_CHECK(fp8 == (w.element_size() == 1), "x and w must both be bf16 or both fp8");
+  if (!fp8) { CHECK_BF16(x); CHECK_BF16(w); }
+  const int B = x.size(0), K = x.size(1), N = w.size(0);
+  TORCH_CHECK(w.size(1) == K && B <= 256 && K % 16 == 0);
+  CHECK_F32(workspace);
+  TORCH_CHECK(counters.scalar_type() == at::kInt && counters.numel() >= (N + 127) / 128);
+  c10::cuda::CUDAGuard g(x.device());
+  const int n_out = mode == 1 ? N / 2 : N;
+  at::Tensor out = at::empty({B, n_out}, x.options().dtype(at::kBFloat16));
+  const void* r = nullptr;
+  if (residual.has_value()) { CHECK_BF16(*residual); TORCH_CHECK(residual->is_contiguous() && residual->numel() == out.numel()); r = residual->data_ptr(); }
+  const void* bs = nullptr;
+  if (bias.has_value()) { CHECK_BF16(*bias); bs = bias->data_ptr(); }
+  const float* xs = x_scale.has_value() ? x_scale->data_ptr<float>() : nullptr;
+  const float* ws = w_scale.has_value() ? w_scale->data_ptr<float>() : nullptr;
+  TORCH_CHECK(!fp8 || (xs && ws), "fp8 skinny GEMM needs x_scale and w_scale");
+  const int64_t need = prl_skinny_workspace_floats(B, N, splits > 0 ? splits : 16);
+  TORCH_CHECK(splits == 1 || workspace.numel() >= need || workspace.numel() >= (int64_t)(148 + (N + 127) / 128) * 128 * (((B + 15) / 16) * 16),
+              "skinny GEMM workspace too small");
+  check(prl_skinny_gemm(x.data_ptr(), w.data_ptr(), out.data_ptr(), r, bs, xs, ws, workspace.data_ptr<float>(), counters.data_ptr<int>(),
+                        B, N, K, x.stride(0), w.stride(0), out.stride(0), static_cast<int>(mode), fp8 ? 1 : 0,
+                        static_cast<int>(splits), cur_stream()), "skinny_gemm");
+  return out;
+}
+
 // ---------------------------------------------------------------- symmetric heap / peer kernels
 int64_t sym_malloc(int64_t bytes) {
   void* p = nullptr;
@@ -353,6 +387,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("gemm_fp8", &gemm_fp8, py::arg("a"), py::arg("b"), py::arg("row_scale"), py::arg("col_scale"),
         py::arg("force_bn") = 0);
   m.def("gemm_swiglu", &gemm_swiglu);
+  m.def("skinny_gemm", &skinny_gemm);
   m.def("linear_ce_fwd", &linear_ce_fwd);
   m.def("linear_ce_dz", &linear_ce_dz);
   m.def("rmsnorm_fwd", &rmsnorm_fwd);

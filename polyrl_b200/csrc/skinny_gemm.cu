@@ -1,0 +1,287 @@
+// polyrl_b200 — decode-shape ("skinny") tcgen05 GEMM:  out[B, N] = X[B, K] · W[N, K]^T  with B <= 256.
+//
+// At decode batch sizes the weight matrix is the only large operand, so the kernel is oriented around it
+// ("swap-AB"): the 128-row UMMA M dimension walks the WEIGHT rows (output features), the UMMA N dimension is
+// the (padded) batch.  Every CTA streams a unique [128 x Kslice] weight panel from HBM exactly once through a
+// deep TMA ring while the small activation panel comes from L2.  K is split across CTAs (split-K) so that all
+// 148 SMs pull weights concurrently even for N = 4096; partial accumulators meet in an L2-resident fp32
+// workspace and the LAST CTA to arrive (ticket counter) reduces and runs the fused epilogue:
+//   plain store | + bias | + residual | fp8 row/col scales | SwiGLU (gate and up tiles of the block-interleaved
+//   weight accumulate in two TMEM buffers of the same CTA and are combined lane-wise).
+// Outputs are written transposed back to [B, N] row-major with 64-byte coalesced segments.
+//
+// This is the rollout engine's replacement for the cuBLAS / sgl-kernel decode GEMMs of the reference stack
+// (SURVEY §2.5b "Decode GEMMs"); measured against cuBLAS in profiles/.
+#include "common.cuh"
+
+namespace prl {
+
+constexpr int kSkThreads = 192;          // warp0 TMA, warp1 MMA, warps 2-5 epilogue
+constexpr int kSkSmemBudget = 196 * 1024;
+
+struct SkinnyParams {
+  __nv_bfloat16* out;          // [B, ldo]
+  const __nv_bfloat16* res;    // optional residual [B, ldo]
+  const __nv_bfloat16* bias;   // optional [N]
+  const float* x_scale;        // optional fp8: per batch row
+  const float* w_scale;        // optional fp8: per weight row
+  float* workspace;            // split-K partials
+  int* counters;               // [num_tiles], zero on entry, zero on exit
+  int64_t ldo;
+  int B, N, K, BP, splits, kb_per_split, swiglu;
+};
+
+template <int MT, bool FP8>
+__global__ void __launch_bounds__(kSkThreads, 1)
+skinny_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmX, SkinnyParams p) {
+  constexpr int BLOCK_K = FP8 ? 128 : 64;
+  constexpr int A_BYTES = MT * 128 * 128;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int b_bytes = p.BP * 128;
+  const int stage_bytes = A_BYTES + b_bytes;
+  int stages = kSkSmemBudget / stage_bytes;
+  if (stages > 8) stages = 8;
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + stages * A_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + stages * stage_bytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + 8;
+  uint64_t* acc_bar = bars + 16;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
+  int* last_flag = reinterpret_cast<int*>(bars + 18);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tile = blockIdx.x / p.splits;
+  const int split = blockIdx.x - tile * p.splits;
+  const int num_kb_total = (p.K + BLOCK_K - 1) / BLOCK_K;
+  const int kb0 = split * p.kb_per_split;
+  const int kb1 = min(num_kb_total, kb0 + p.kb_per_split);
+  const int nkb = max(0, kb1 - kb0);
+  const int row0 = tile * (MT * 128);                       // first weight row of this tile
+  uint32_t tmem_cols = 32;
+  while (tmem_cols < static_cast<uint32_t>(MT * p.BP)) tmem_cols <<= 1;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmW);
+    tma_prefetch_desc(&tmX);
+    for (int i = 0; i < stages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    mbar_init(acc_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) { tmem_alloc(tmem_slot, tmem_cols); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        mbar_expect_tx(&full_bar[stage], stage_bytes);
+        // weights are read exactly once: do not let them displace the activations in L2
+        tma_load_2d_hint(&tmW, &full_bar[stage], smem_a + stage * A_BYTES, kb * BLOCK_K, row0, kEvictFirst);
+        tma_load_2d_hint(&tmX, &full_bar[stage], smem_b + stage * b_bytes, kb * BLOCK_K, 0, kEvictLast);
+        if (++stage == stages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = FP8 ? umma_idesc(128, p.BP, 0, 0) : umma_idesc(128, p.BP, 1, 1);
+      int stage = 0; uint32_t phase = 0;
+      for (int kb = 0; kb < nkb; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint64_t db = umma_desc_sw128_kmajor(smem_b + stage * b_bytes);
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+          const uint64_t da = umma_desc_sw128_kmajor(smem_a + stage * A_BYTES + mt * 128 * 128);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint32_t acc = (kb | k) != 0;
+            if constexpr (FP8) umma_f8_ss(tmem_base + mt * p.BP, da + 2 * k, db + 2 * k, idesc, acc);
+            else umma_bf16_ss(tmem_base + mt * p.BP, da + 2 * k, db + 2 * k, idesc, acc);
+          }
+        }
+        umma_commit(&empty_bar[stage]);
+        if (++stage == stages) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(acc_bar);
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (128 threads = 128 weight rows)
+    const int quad = warp & 3;
+    const int r = quad * 32 + lane;                              // row inside a 128-row tile
+    const int et = (warp - 2) * 32 + lane;                       // 0..127 epilogue thread id
+    const uint32_t lane_base = static_cast<uint32_t>(quad * 32) << 16;
+    if (nkb > 0) { mbar_wait(acc_bar, 0); tc_fence_after(); }
+    const int64_t tile_ws = static_cast<int64_t>(MT) * 128 * p.BP;          // floats per (tile, split)
+    float* ws_tile = p.workspace + static_cast<int64_t>(tile) * p.splits * tile_ws;
+    bool is_last = true;
+    if (p.splits > 1) {
+      float* mine = ws_tile + static_cast<int64_t>(split) * tile_ws;
+      for (int mt = 0; mt < MT; ++mt)
+        for (int c = 0; c < p.BP; c += 32) {
+          uint32_t v[32];
+          __syncwarp();
+          if (nkb > 0) { tmem_ld_32x32(tmem_base + lane_base + mt * p.BP + c, v); tmem_ld_wait(); }
+          else { for (int i = 0; i < 32; ++i) v[i] = 0; }
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (c + i < p.BP) mine[(static_cast<int64_t>(mt) * p.BP + c + i) * 128 + r] = __uint_as_float(v[i]);
+        }
+      __threadfence();
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (et == 0) {
+        const int t = atomicAdd(p.counters + tile, 1);
+        *last_flag = (t == p.splits - 1) ? 1 : 0;
+        if (t == p.splits - 1) p.counters[tile] = 0;             // self-cleaning for the next launch
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      is_last = *last_flag != 0;
+      if (is_last) __threadfence();
+    }
+    if (is_last) {
+      const int n_feat = p.swiglu ? (tile * 128 + r) : (row0 + r);       // output column owned by this thread
+      const int n_out = p.swiglu ? p.N / 2 : p.N;
+      const bool n_ok = n_feat < n_out;
+      const float ws0 = (p.w_scale && n_ok) ? p.w_scale[p.swiglu ? row0 + r : n_feat] : 1.f;
+      const float ws1 = (p.w_scale && n_ok && p.swiglu) ? p.w_scale[row0 + 128 + r] : 1.f;
+      const float bias0 = (p.bias && n_ok && !p.swiglu) ? __bfloat162float(p.bias[n_feat]) : 0.f;
+      for (int c = 0; c < p.BP; c += 32) {
+        float a0[32], a1[32];
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+          float(&acc)[32] = mt == 0 ? a0 : a1;
+          if (p.splits == 1 || nkb > 0) {
+            uint32_t v[32];
+            __syncwarp();
+            tmem_ld_32x32(tmem_base + lane_base + mt * p.BP + c, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) acc[i] = __uint_as_float(v[i]);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) acc[i] = 0.f;
+          }
+          for (int s = 0; s < p.splits; ++s) {
+            if (s == split) continue;
+            const float* other = ws_tile + static_cast<int64_t>(s) * tile_ws + (static_cast<int64_t>(mt) * p.BP + c) * 128 + r;
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (c + i < p.BP) acc[i] += __ldcg(other + i * 128);
+          }
+        }
+        if (!n_ok) continue;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int b = c + i;
+          if (b >= p.B) break;
+          const float xs = p.x_scale ? p.x_scale[b] : 1.f;
+          float y;
+          if (MT == 2 && p.swiglu) {
+            const float g = a0[i] * ws0 * xs, u = a1[i] * ws1 * xs;
+            y = g / (1.f + __expf(-g)) * u;
+          } else {
+            y = a0[i] * ws0 * xs + bias0;
+          }
+          const int64_t o = static_cast<int64_t>(b) * p.ldo + n_feat;
+          if (p.res) y += __bfloat162float(p.res[o]);
+          p.out[o] = __float2bfloat16(y);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, tmem_cols); }
+}
+
+using EncodeTiledFn2 = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn2 sk_encode_fn() {
+  static EncodeTiledFn2 fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || !p) return nullptr;
+    fn = reinterpret_cast<EncodeTiledFn2>(p);
+  }
+  return fn;
+}
+static int sk_tmap(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld_bytes, uint32_t box_rows, int eb) {
+  auto fn = sk_encode_fn();
+  if (!fn) return -1;
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstride[1] = {ld_bytes};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(128 / eb), box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, eb == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(ptr), gdim,
+                  gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : -static_cast<int>(r);
+}
+
+template <int MT, bool FP8>
+static int launch_skinny(const void* X, const void* W, SkinnyParams p, int64_t ldx_bytes, int64_t ldw_bytes, cudaStream_t s) {
+  constexpr int EB = FP8 ? 1 : 2;
+  CUtensorMap tmW, tmX;
+  if (sk_tmap(&tmW, W, p.N, p.K, ldw_bytes, MT * 128, EB)) return -61;  // one box = all MT 128-row tiles of the CTA
+  if (sk_tmap(&tmX, X, p.B, p.K, ldx_bytes, p.BP, EB)) return -62;
+  auto kern = skinny_gemm_kernel<MT, FP8>;
+  static bool attr = false;
+  const int smem = kSkSmemBudget + 1024 + 256;
+  if (!attr) { PRL_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr = true; }
+  const int tiles = (p.N + MT * 128 - 1) / (MT * 128);
+  kern<<<tiles * p.splits, kSkThreads, smem, s>>>(tmW, tmX, p);
+  PRL_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace prl
+
+using namespace prl;
+
+extern "C" int prl_skinny_workspace_floats(int B, int N, int max_splits) {
+  const int BP = ((B + 15) / 16) * 16;
+  const int tiles = (N + 127) / 128;
+  return tiles * max_splits * 128 * BP;
+}
+
+// mode: 0 = store (+bias, +residual), 1 = SwiGLU (W block-interleaved, out is [B, N/2]).
+// dtype: 0 = bf16, 1 = fp8 e4m3 (x_scale per batch row, w_scale per weight row required).
+extern "C" int prl_skinny_gemm(const void* X, const void* W, void* out, const void* res, const void* bias, const float* x_scale,
+                               const float* w_scale, float* workspace, int* counters, int B, int N, int K, int64_t ldx,
+                               int64_t ldw, int64_t ldo, int mode, int dtype, int splits, cudaStream_t stream) {
+  if (B <= 0 || B > 256) return -60;
+  SkinnyParams p;
+  p.out = static_cast<__nv_bfloat16*>(out);
+  p.res = static_cast<const __nv_bfloat16*>(res);
+  p.bias = static_cast<const __nv_bfloat16*>(bias);
+  p.x_scale = x_scale; p.w_scale = w_scale;
+  p.workspace = workspace; p.counters = counters;
+  p.ldo = ldo; p.B = B; p.N = N; p.K = K;
+  p.BP = ((B + 15) / 16) * 16;
+  p.swiglu = mode == 1;
+  const int MT = mode == 1 ? 2 : 1;
+  if (mode == 1 && N % 256 != 0) return -63;
+  const int block_k = dtype == 1 ? 128 : 64;
+  const int num_kb = (K + block_k - 1) / block_k;
+  const int tiles = (N + MT * 128 - 1) / (MT * 128);
+  if (splits <= 0) {                      // fill ~148 SMs, keep >= 8 k-blocks per split
+    splits = (148 + tiles - 1) / tiles;
+    if (splits > num_kb / 8) splits = num_kb / 8;
+    if (splits < 1) splits = 1;
+    if (splits > 16) splits = 16;
+  }
+  p.kb_per_split = (num_kb + splits - 1) / splits;
+  p.splits = (num_kb + p.kb_per_split - 1) / p.kb_per_split;
+  const int eb = dtype == 1 ? 1 : 2;
+  if (MT == 2) return dtype == 1 ? launch_skinny<2, true>(X, W, p, ldx * eb, ldw * eb, stream)
+                                 : launch_skinny<2, false>(X, W, p, ldx * eb, ldw * eb, stream);
+  return dtype == 1 ? launch_skinny<1, true>(X, W, p, ldx * eb, ldw * eb, stream)
+                    : launch_skinny<1, false>(X, W, p, ldx * eb, ldw * eb, stream);
+}

@@ -22,6 +22,36 @@ def _is_kernel_tensor(x: torch.Tensor) -> bool:
     return x.is_cuda and x.dtype == torch.bfloat16
 
 
+# ---- decode-shape ("skinny") GEMM: swap-AB + split-K tcgen05 kernel for <= 256 rows, inference only ----
+_SKINNY_WS: dict = {}
+_SKINNY_MAX_ROWS = int(os.environ.get("POLYRL_SKINNY_MAX_ROWS", "256"))
+
+
+def _skinny_buffers(device):
+    key = (device.type, device.index)
+    if key not in _SKINNY_WS:
+        ws = torch.empty(24 * 1024 * 1024, device=device, dtype=torch.float32)       # 96 MB of split-K partials
+        ctr = torch.zeros(4096, device=device, dtype=torch.int32)
+        _SKINNY_WS[key] = (ws, ctr)
+    return _SKINNY_WS[key]
+
+
+def _use_skinny(x2: torch.Tensor, w: torch.Tensor) -> bool:
+    if _cublas() or os.environ.get("POLYRL_DECODE_GEMM", "skinny") != "skinny":
+        return False
+    return (not torch.is_grad_enabled() or not (x2.requires_grad or w.requires_grad)) and x2.shape[0] <= _SKINNY_MAX_ROWS \
+        and x2.shape[1] % 16 == 0 and w.shape[0] >= 128
+
+
+def skinny_linear(x2: torch.Tensor, w: torch.Tensor, bias=None, residual=None, mode: int = 0, splits: int = 0) -> torch.Tensor:
+    ws, ctr = _skinny_buffers(x2.device)
+    if x2.stride(-1) != 1 or x2.stride(0) % 8 != 0:
+        x2 = x2.contiguous()
+    if residual is not None and not residual.is_contiguous():
+        residual = residual.contiguous()
+    return _C().skinny_gemm(x2, w, residual, bias, None, None, ws, ctr, mode, splits)
+
+
 # --------------------------------------------------------------------------------------------
 # linear (+ residual) : tcgen05 GEMM forward with fused residual epilogue
 # --------------------------------------------------------------------------------------------
@@ -62,6 +92,8 @@ class _LinearFn(torch.autograd.Function):
 def linear(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None = None,
            residual: torch.Tensor | None = None) -> torch.Tensor:
     """y = x @ w.T (+ bias) (+ residual).  w is [out, in] (nn.Linear layout)."""
+    if _is_kernel_tensor(x) and w.dtype == torch.bfloat16 and x.dim() == 2 and _use_skinny(x, w):
+        return skinny_linear(x, w, bias, residual, 0)
     if _is_kernel_tensor(x) and w.dtype == torch.bfloat16 and w.shape[0] % 8 == 0 and w.shape[1] % 8 == 0:
         y = _LinearFn.apply(x, w, residual if bias is None else None)
         if bias is not None:
@@ -106,6 +138,8 @@ class _LinearSwigluFn(torch.autograd.Function):
 
 def linear_swiglu(x: torch.Tensor, wgu: torch.Tensor) -> torch.Tensor:
     """silu(x @ Wg.T) * (x @ Wu.T) with W_gu stored block-interleaved ([128 gate | 128 up] rows)."""
+    if _is_kernel_tensor(x) and wgu.dtype == torch.bfloat16 and x.dim() == 2 and _use_skinny(x, wgu):
+        return skinny_linear(x, wgu, None, None, 1)
     if _is_kernel_tensor(x) and wgu.dtype == torch.bfloat16 and not _cublas():
         return _LinearSwigluFn.apply(x, wgu)
     gu = torch.nn.functional.linear(x, wgu.to(x.dtype))

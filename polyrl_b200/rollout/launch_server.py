@@ -1,0 +1,66 @@
+"""Stand-alone rollout engine server (elastic remote instance):
+    python -m polyrl_b200.rollout.launch_server --model-path llama3-8b --port 30000 --rollout-manager-address H:P
+CLI mirrors the flags the reference adds to SGLang's launcher (rlboost/sglang/patches.py:35-75):
+--enable-weight-transfer-agent, --transfer-agent-handshake-port, --weight-sender-rpyc-endpoint,
+--weight-receiver-zmq-bind-host, --rollout-manager-address, --transfer-agent-sender-group-idx,
+--num-transfer-engines-per-group.  Weights arrive through the TCP transfer engine (other hosts) or are
+random/dummy initialised (``--load-format dummy``) until the first update."""
+from __future__ import annotations
+
+import argparse
+
+import torch
+
+from ..models import TransformerWeights, get_model_config
+from .engine import RolloutEngine
+from .server import EngineServer
+
+
+def main(argv=None) -> int:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--model-path", required=True)
+    ap.add_argument("--host", default="127.0.0.1")
+    ap.add_argument("--port", type=int, default=30000)
+    ap.add_argument("--device", default="cuda" if torch.cuda.is_available() else "cpu")
+    ap.add_argument("--max-num-seqs", type=int, default=256)
+    ap.add_argument("--max-model-len", type=int, default=2048)
+    ap.add_argument("--mem-fraction-static", type=float, default=0.6)
+    ap.add_argument("--load-format", default="dummy")
+    ap.add_argument("--stream-interval", type=int, default=20)
+    ap.add_argument("--rollout-manager-address", default=None)
+    ap.add_argument("--enable-weight-transfer-agent", action="store_true")
+    ap.add_argument("--transfer-agent-handshake-port", type=int, default=21000)
+    ap.add_argument("--weight-sender-rpyc-endpoint", default=None)
+    ap.add_argument("--weight-receiver-zmq-bind-host", default="0.0.0.0")
+    ap.add_argument("--transfer-agent-sender-group-idx", type=int, default=0)
+    ap.add_argument("--num-transfer-engines-per-group", type=int, default=1)
+    a = ap.parse_args(argv)
+    cfg = get_model_config(a.model_path)
+    dtype = torch.bfloat16 if a.device.startswith("cuda") else torch.float32
+    w = TransformerWeights(cfg, device=a.device, dtype=dtype, init=True)
+    eng = RolloutEngine(cfg, a.device, max_num_seqs=a.max_num_seqs, max_model_len=a.max_model_len,
+                        gpu_memory_utilization=a.mem_fraction_static)
+    eng.set_weights(w.embed, w.layers, w.head)
+    receiver = None
+    if a.enable_weight_transfer_agent:
+        from ..weight_transfer.tcp_engine import TCPWeightReceiver
+
+        receiver = TCPWeightReceiver(w, bind_host=a.weight_receiver_zmq_bind_host, port=a.transfer_agent_handshake_port,
+                                     num_streams=a.num_transfer_engines_per_group)
+
+    def on_update(body):
+        if receiver is not None and not body.get("bootstrap"):
+            receiver.wait_and_apply(timeout=3600)
+        return True, "ok"
+
+    srv = EngineServer(eng, host=a.host, port=a.port, stream_interval=a.stream_interval, weight_update_fn=on_update).start()
+    if a.rollout_manager_address:
+        info = srv.register_with_manager(a.rollout_manager_address, local=False, handshake_port=a.transfer_agent_handshake_port)
+        print(f"[engine] registered with manager: {info}", flush=True)
+    print(f"[engine] serving {cfg.name} on {srv.endpoint}", flush=True)
+    srv.serve_until_shutdown()
+    return 0
+
+
+if __name__ == "__main__":
+    raise SystemExit(main())

@@ -46,6 +46,29 @@ def main():
                 rec[f"own_bn{fbn}_ms"] = round(bench(lambda: C.gemm_bf16(a, b, None, d, fbn)), 4)
         print(json.dumps(rec), flush=True)
         out.append(rec)
+    # decode-shape GEMMs: skinny (swap-AB + split-K) kernel vs cuBLAS vs the 128-row-tile kernel
+    ws = torch.empty(24 * 1024 * 1024, device="cuda", dtype=torch.float32)
+    ctr = torch.zeros(4096, device="cuda", dtype=torch.int32)
+    for B in (64, 128, 256):
+        tot = {"skinny": 0.0, "cublas": 0.0}
+        for N, K in ((6144, 4096), (4096, 4096), (28672, 4096), (4096, 14336), (128256, 4096)):
+            x = torch.randn(B, K, device="cuda", dtype=torch.bfloat16)
+            w = torch.randn(N, K, device="cuda", dtype=torch.bfloat16) * 0.02
+            mode = 1 if N == 28672 else 0
+            t_s = bench(lambda: C.skinny_gemm(x, w, None, None, None, None, ws, ctr, mode, 0))
+            if mode == 1:
+                def lib():
+                    gu = x @ w.t()
+                    return torch.nn.functional.silu(gu[:, :N // 2]) * gu[:, N // 2:]
+            else:
+                lib = lambda: x @ w.t()
+            t_l = bench(lib)
+            rec = {"op": "decode_gemm", "B": B, "N": N, "K": K, "swiglu": bool(mode), "skinny_ms": round(t_s, 4), "cublas_ms": round(t_l, 4),
+                   "skinny_GBps": round(N * K * 2 / t_s / 1e6, 1), "hbm_frac_of_measured": round(N * K * 2 / t_s / 1e6 / 6569.6, 3)}
+            print(json.dumps(rec), flush=True)
+            if N != 128256:
+                tot["skinny"] += t_s; tot["cublas"] += t_l
+        print(json.dumps({"op": "decode_layer_gemms_total", "B": B, "skinny_ms": round(tot["skinny"], 4), "cublas_ms": round(tot["cublas"], 4)}), flush=True)
     # fused swiglu vs unfused
     M, F, K = 16384, 14336, 4096
     x = torch.randn(M, K, device="cuda", dtype=torch.bfloat16)

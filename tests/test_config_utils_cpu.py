@@ -1,0 +1,111 @@
+"""Config system, seqlen balancing, checkpoint manager, scorers, metrics (CPU)."""
+import json
+
+import numpy as np
+import pytest
+import torch
+
+from polyrl_b200.config.schema import PPOConfig, apply_overrides, load_config, validate_config, need_critic
+from polyrl_b200.data.reward_score import default_compute_score, gsm8k, math as math_score
+from polyrl_b200.utils.seqlen_balancing import get_seqlen_balanced_partitions, rearrange_micro_batches
+
+
+def test_overrides_yaml_and_validation(tmp_path):
+    y = tmp_path / "c.yaml"
+    y.write_text("algorithm:\n  adv_estimator: grpo\nactor_rollout_ref:\n  actor:\n    optim:\n      lr: 3.0e-6\n")
+    cfg = load_config(str(y), ["actor_rollout_ref.rollout.n=8", "data.train_batch_size=16", "trainer.logger=[console,file]",
+                               "actor_rollout_ref.actor.ppo_micro_batch_size_per_gpu=2", "actor_rollout_ref.rollout.name=sglang-disaggregated",
+                               "actor_rollout_ref.actor.clip_ratio_high=0.28", "trainer.n_gpus_per_node=2",
+                               "+actor_rollout_ref.model.override_config.num_layers=4"])
+    assert cfg.algorithm.adv_estimator == "grpo" and cfg.actor_rollout_ref.actor.optim.lr == 3.0e-6
+    assert cfg.actor_rollout_ref.rollout.n == 8 and cfg.trainer.logger == ["console", "file"]
+    assert cfg.actor_rollout_ref.rollout.name == "native-disaggregated"
+    assert cfg.actor_rollout_ref.model.override_config == {"num_layers": 4}
+    assert not need_critic(cfg)
+    validate_config(cfg)
+    with pytest.raises(KeyError):
+        apply_overrides(cfg, ["actor_rollout_ref.actor.nonexistent=1"])
+    cfg.actor_rollout_ref.rollout.min_stream_batch_size = 12          # not divisible by n=8
+    with pytest.raises(ValueError):
+        validate_config(cfg)
+    with pytest.raises(NotImplementedError):
+        apply_overrides(PPOConfig(), ["actor_rollout_ref.rollout.pipeline_model_parallel_size=2"])
+    assert cfg["trainer"]["total_epochs"] == 1 and "data" in cfg
+
+
+def test_seqlen_balancing():
+    rng = np.random.default_rng(0)
+    lens = rng.integers(10, 2000, size=64).tolist()
+    parts = get_seqlen_balanced_partitions(lens, 8, equal_size=True)
+    sums = [sum(lens[i] for i in p) for p in parts]
+    assert all(len(p) == 8 for p in parts) and sorted(i for p in parts for i in p) == list(range(64))
+    assert max(sums) - min(sums) < 0.05 * np.mean(sums)
+    mbs = rearrange_micro_batches(lens, 8192)
+    assert all(sum(lens[i] for i in p) <= 8192 for p in mbs) and sorted(i for p in mbs for i in p) == list(range(64))
+    with pytest.raises(ValueError):
+        rearrange_micro_batches([100, 9000], 8192)
+
+
+def test_scorers():
+    assert gsm8k.compute_score("so the answer is #### 1,234", "1234") == 1.0
+    assert gsm8k.compute_score("#### 12 then #### 13", "12") == 0.0
+    assert gsm8k.compute_score("no answer", "1") == 0.0
+    assert math_score.compute_score("thus \\boxed{\\frac{1}{2}}", "0.5") == 1.0
+    assert math_score.compute_score("\\boxed{3}", "4") == 0.0
+    assert default_compute_score("openai/gsm8k", "#### 7", "7") == 1.0
+    assert default_compute_score("open-r1/OpenR1-Math-220k", "\\boxed{x+1}", "x+1") == 1.0
+    with pytest.raises(NotImplementedError):
+        default_compute_score("unknown/ds", "", "")
+
+
+def test_checkpoint_roundtrip_and_rotation(tmp_path):
+    from polyrl_b200.models import get_model_config, pack_padded
+    from polyrl_b200.parallel.zero3 import Zero3Engine
+    from polyrl_b200.utils.checkpoint import ShardedCheckpointManager, find_latest_ckpt_path, write_latest
+
+    cfg = get_model_config("tiny-llama")
+    eng = Zero3Engine(cfg, "cpu", lr=1e-2)
+    ids = torch.randint(3, cfg.vocab_size, (2, 8))
+    inp, _ = pack_padded(ids, torch.ones_like(ids))
+    labels = torch.randint(0, cfg.vocab_size, (16,))
+    lp, _ = eng.forward_logprob_entropy(inp, labels)
+    (-lp.mean()).backward()
+    eng.step()
+    mgr = ShardedCheckpointManager(eng, cfg)
+    for s in (1, 2, 3):
+        mgr.save(str(tmp_path / f"global_step_{s}" / "actor"), s, max_ckpt_to_keep=2, extra={"lr_step": s})
+        write_latest(tmp_path, s)
+    assert not (tmp_path / "global_step_1" / "actor").exists() and (tmp_path / "global_step_3" / "actor" / "config.json").exists()
+    assert find_latest_ckpt_path(tmp_path).endswith("global_step_3")
+    want = [u.master.clone() for u in eng.units]
+    lp2, _ = eng.forward_logprob_entropy(inp, labels)
+    (-lp2.mean()).backward()
+    eng.step()
+    assert not torch.equal(eng.units[1].master, want[1])
+    extra = ShardedCheckpointManager(eng, cfg).load(str(tmp_path / "global_step_3" / "actor"))
+    assert extra == {"lr_step": 3} and eng.opt_step == 1
+    assert all(torch.equal(u.master, w) for u, w in zip(eng.units, want))
+
+
+def test_metrics_and_reward_manager():
+    from polyrl_b200.data.reward_manager import get_reward_manager_cls
+    from polyrl_b200.protocol import DataProto
+    from polyrl_b200.utils.metrics import compute_data_metrics, process_validation_metrics, reduce_metrics
+
+    b, p, r = 4, 3, 5
+    mask = torch.ones(b, p + r, dtype=torch.long)
+    mask[1, -2:] = 0
+    d = DataProto.from_dict({"responses": torch.randint(0, 9, (b, r)), "attention_mask": mask, "response_mask": mask[:, -r:],
+                             "token_level_scores": torch.rand(b, r), "token_level_rewards": torch.rand(b, r),
+                             "advantages": torch.randn(b, r), "returns": torch.randn(b, r), "values": torch.randn(b, r)},
+                            {"data_source": ["synthetic/x"] * b, "reward_model": [{"ground_truth": "1"}] * b})
+    m = compute_data_metrics(d, use_critic=True)
+    assert m["response_length/max"] == 5 and m["response_length/min"] == 3 and "critic/vf_explained_var" in m
+    assert reduce_metrics({"a": [1.0, 3.0], "x/max": [1, 5]}) == {"a": 2.0, "x/max": 5.0}
+    rm = get_reward_manager_cls("naive")(tokenizer=None)
+    t = rm(d)
+    assert t.shape == (b, r) and (t != 0).sum(-1).max() <= 1
+    dapo = get_reward_manager_cls("dapo")(tokenizer=None, max_resp_len=5, overlong_buffer_len=2, penalty_factor=1.0)
+    assert dapo(d).shape == (b, r)
+    v = process_validation_metrics(["a", "a", "a", "a"], ["u1", "u1", "u2", "u2"], {"reward": [1.0, 0.0, 1.0, 1.0]})
+    assert v["a"]["reward"]["mean@2"] == pytest.approx(0.75)

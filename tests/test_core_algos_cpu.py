@@ -1,0 +1,139 @@
+"""Advantage estimators, losses, KL (spirit of 3rdparty/verl/tests/trainer/ppo/test_core_algos_on_cpu.py)."""
+import numpy as np
+import pytest
+import torch
+
+from polyrl_b200.algos import core_algos as A
+
+
+def _mask(b=6, t=5):
+    m = torch.ones(b, t)
+    m[1, 3:] = 0
+    m[4, 1:] = 0
+    return m
+
+
+def test_registry():
+    assert A.get_adv_estimator_fn("grpo") is A.get_adv_estimator_fn(A.AdvantageEstimator.GRPO)
+    with pytest.raises(ValueError):
+        A.get_adv_estimator_fn("nope")
+    for name in ["vanilla", "gspo", "gpg", "clip_cov", "kl_cov", "geo_mean", "rollout_correction"]:
+        assert callable(A.get_policy_loss_fn(name))
+
+
+def test_grpo_matches_loop_reference():
+    torch.manual_seed(0)
+    m = _mask()
+    r = torch.zeros(6, 5)
+    r[:, 0] = torch.tensor([1.0, 0.0, 1.0, 3.0, 2.0, 5.0])
+    idx = np.array(["a", "a", "a", "b", "b", "c"], dtype=object)
+    adv, ret = A.compute_grpo_outcome_advantage(r, m, idx)
+    s = r.sum(-1)
+    want = torch.zeros(6)
+    for g in ["a", "b"]:
+        sel = torch.tensor([i for i in range(6) if idx[i] == g])
+        want[sel] = (s[sel] - s[sel].mean()) / (s[sel].std() + 1e-6)
+    want[5] = s[5] / (1 + 1e-6)        # singleton group: mean 0, std 1
+    assert torch.allclose(adv, want[:, None] * m, atol=1e-5) and torch.equal(adv, ret)
+    adv2, _ = A.compute_grpo_outcome_advantage(r, m, idx, norm_adv_by_std_in_grpo=False)
+    assert torch.allclose(adv2[0, 0], s[0] - s[:3].mean())
+
+
+def test_rloo_opo_gpg_passk():
+    m = torch.ones(4, 3)
+    r = torch.zeros(4, 3)
+    r[:, -1] = torch.tensor([1.0, 2.0, 6.0, 4.0])
+    idx = np.array([0, 0, 0, 1])
+    adv, _ = A.compute_rloo_outcome_advantage(r, m, idx)
+    assert torch.allclose(adv[0, 0], torch.tensor(1.0 - (2.0 + 6.0) / 2))
+    assert torch.allclose(adv[3, 0], torch.tensor(4.0))
+    advv, _ = A.compute_rloo_vectorized_outcome_advantage(r, m, idx)
+    assert torch.allclose(advv[:3], adv[:3]) and advv[3].abs().sum() == 0
+    m2 = torch.tensor([[1.0, 1, 1], [1, 0, 0], [1, 1, 0], [1, 1, 1]])
+    opo, _ = A.compute_opo_outcome_advantage(r, m2, idx)
+    base = (3 * 1 + 1 * 2 + 2 * 6) / 6
+    assert torch.allclose(opo[2, 0], torch.tensor(6.0 - base))
+    pk, _ = A.compute_grpo_passk_outcome_advantage(r, m, np.array([0, 0, 0, 0]), config={"norm_adv_by_std_in_grpo": False})
+    assert pk[2, 0] == 2.0 and pk[[0, 1, 3]].abs().sum() == 0
+    gpg, _ = A.compute_gpg_outcome_advantage(r, m, idx)
+    assert gpg.shape == (4, 3)
+
+
+def test_gae_matches_manual_scan():
+    torch.manual_seed(1)
+    b, t = 3, 6
+    r, v = torch.randn(b, t), torch.randn(b, t)
+    m = torch.ones(b, t)
+    m[1, 4:] = 0
+    gamma, lam = 0.99, 0.95
+    adv, ret = A.compute_gae_advantage_return(r, v, m, gamma, lam)
+    raw = torch.zeros(b, t)
+    for i in range(b):
+        nv, last = 0.0, 0.0
+        for k in reversed(range(t)):
+            if m[i, k] == 0:
+                raw[i, k] = last
+                continue
+            delta = r[i, k] + gamma * nv - v[i, k]
+            last = delta + gamma * lam * last
+            nv = v[i, k]
+            raw[i, k] = last
+    assert torch.allclose(ret, raw + v, atol=1e-5)
+    assert torch.allclose(adv, A.masked_whiten(raw, m), atol=1e-5)
+
+
+def test_reinforce_pp_and_remax():
+    r = torch.tensor([[0.0, 0.0, 1.0, 0.0]])
+    m = torch.tensor([[1.0, 1.0, 1.0, 0.0]])
+    adv, ret = A.compute_reinforce_plus_plus_outcome_advantage(r, m, gamma=0.5)
+    assert torch.allclose(ret[0, :3], torch.tensor([0.25, 0.5, 1.0]))
+    adv2, ret2 = A.compute_remax_outcome_advantage(r, torch.tensor([0.3]), m)
+    assert torch.allclose(ret2[0], torch.tensor([1.0, 1.0, 1.0, 0.0])) and torch.allclose(adv2[0, 0], torch.tensor(0.7))
+
+
+def test_agg_loss_modes():
+    x = torch.tensor([[1.0, 2.0, 3.0], [4.0, 5.0, 6.0]])
+    m = torch.tensor([[1.0, 1.0, 0.0], [1.0, 0.0, 0.0]])
+    assert torch.isclose(A.agg_loss(x, m, "token-mean"), torch.tensor(7.0 / 3))
+    assert torch.isclose(A.agg_loss(x, m, "seq-mean-token-sum"), torch.tensor((3.0 + 4.0) / 2))
+    assert torch.isclose(A.agg_loss(x, m, "seq-mean-token-mean"), torch.tensor((1.5 + 4.0) / 2))
+    assert torch.isclose(A.agg_loss(x, m, "seq-mean-token-sum-norm"), torch.tensor(7.0 / 3))
+    with pytest.raises(ValueError):
+        A.agg_loss(x, m, "bad")
+
+
+def test_vanilla_ppo_dual_clip():
+    old = torch.zeros(1, 4)
+    lp = torch.log(torch.tensor([[1.0, 1.5, 0.5, 5.0]]))
+    adv = torch.tensor([[1.0, 1.0, -1.0, -1.0]])
+    m = torch.ones(1, 4)
+    loss, met = A.compute_policy_loss_vanilla(old, lp, adv, m, "token-mean", config={"clip_ratio": 0.2, "clip_ratio_c": 3.0})
+    # token losses: -1*1 ; -1*1.2 (clipped) ; max(0.5, 0.8)=0.8 ; min(3, max(5,1.2))=3
+    assert torch.isclose(loss, torch.tensor((-1.0 - 1.2 + 0.8 + 3.0) / 4))
+    assert met["actor/pg_clipfrac"] == pytest.approx(0.5) and met["actor/pg_clipfrac_lower"] == pytest.approx(0.25)
+    lp.requires_grad_(True)
+    for name in ["gspo", "gpg", "clip_cov", "kl_cov", "geo_mean", "rollout_correction"]:
+        l, _ = A.get_policy_loss_fn(name)(old, lp, adv, m, "token-mean", config={"clip_ratio": 0.2}, rollout_is_weights=None)
+        l.backward()
+        assert torch.isfinite(l) and torch.isfinite(lp.grad).all()
+        lp.grad = None
+
+
+def test_value_loss_and_kl():
+    v, ret, old = torch.tensor([[1.0, 3.0]]), torch.tensor([[0.0, 0.0]]), torch.tensor([[0.5, 0.5]])
+    loss, frac = A.compute_value_loss(v, ret, old, torch.ones(1, 2), 0.5)
+    # clipped preds: 1.0, 1.0 -> max((1)^2,(1)^2)=1 ; max(9,1)=9 -> 0.5*mean = 2.5
+    assert torch.isclose(loss, torch.tensor(2.5)) and frac == 0
+    a, b = torch.tensor([0.1, -0.3]), torch.tensor([0.0, 0.2])
+    assert torch.allclose(A.kl_penalty(a, b, "kl"), a - b)
+    assert torch.allclose(A.kl_penalty(a, b, "mse"), 0.5 * (a - b) ** 2)
+    d = b - a
+    assert torch.allclose(A.kl_penalty(a, b, "low_var_kl"), torch.exp(d) - d - 1)
+    a.requires_grad_(True)
+    k = A.kl_penalty(a, b, "low_var_kl+")
+    k.sum().backward()
+    assert torch.allclose(a.grad, (a - b).detach())          # straight-through k2 gradient
+    c = A.AdaptiveKLController(0.1, 0.05, 100)
+    c.update(0.1, 10)
+    assert c.value == pytest.approx(0.1 * (1 + 0.2 * 10 / 100))
+    assert A.get_kl_controller({"type": "fixed", "kl_coef": 0.3}).value == 0.3

@@ -239,3 +239,41 @@ def test_functional_autograd_linear():
     xf, wf, rf = (t.detach().float().requires_grad_(True) for t in (x, w, r))
     (xf @ wf.t() + rf).pow(2).sum().backward()
     assert _rel_err(x.grad, xf.grad) < 2e-2 and _rel_err(w.grad, wf.grad) < 2e-2 and _rel_err(r.grad, rf.grad) < 2e-2
+
+
+@pytest.mark.parametrize("B,N,K,splits", [(128, 4096, 4096, 0), (128, 6144, 4096, 4), (7, 512, 256, 1), (256, 1024, 14336, 0),
+                                          (33, 1000, 4096, 3), (128, 128256, 1024, 0), (200, 4096, 4096, 1)])
+def test_skinny_gemm(C, B, N, K, splits):
+    torch.manual_seed(20)
+    x = torch.randn(B, K, device="cuda", dtype=torch.bfloat16)
+    w = (torch.randn(N, K, device="cuda") * 0.05).to(torch.bfloat16)
+    r = torch.randn(B, N, device="cuda", dtype=torch.bfloat16)
+    bias = torch.randn(N, device="cuda", dtype=torch.bfloat16)
+    ws = torch.empty(24 * 1024 * 1024, device="cuda", dtype=torch.float32)
+    ctr = torch.zeros(4096, device="cuda", dtype=torch.int32)
+    want = x.float() @ w.float().t()
+    got = C.skinny_gemm(x, w, None, None, None, None, ws, ctr, 0, splits)
+    assert _rel_err(got, want) < 5e-3
+    got = C.skinny_gemm(x, w, r, bias, None, None, ws, ctr, 0, splits)          # counters must have self-reset
+    assert _rel_err(got, want + bias.float() + r.float()) < 5e-3
+    assert int(ctr.abs().sum().item()) == 0
+
+
+def test_skinny_gemm_swiglu_and_fp8(C):
+    torch.manual_seed(21)
+    B, F, K = 96, 2048, 1024
+    x = torch.randn(B, K, device="cuda", dtype=torch.bfloat16)
+    wg = (torch.randn(F, K, device="cuda") * 0.05).to(torch.bfloat16)
+    wu = (torch.randn(F, K, device="cuda") * 0.05).to(torch.bfloat16)
+    wgu = ref.interleave_gate_up(wg, wu).contiguous()
+    ws = torch.empty(24 * 1024 * 1024, device="cuda", dtype=torch.float32)
+    ctr = torch.zeros(4096, device="cuda", dtype=torch.int32)
+    want = torch.nn.functional.silu(x.float() @ wg.float().t()) * (x.float() @ wu.float().t())
+    for splits in (1, 0, 4):
+        got = C.skinny_gemm(x, wgu, None, None, None, None, ws, ctr, 1, splits)
+        assert got.shape == (B, F) and _rel_err(got, want) < 1e-2
+    xq, xs = C.quant_fp8_rowwise(x)
+    wq, wsc = C.quant_fp8_rowwise(wg)
+    got = C.skinny_gemm(xq, wq, None, None, xs, wsc, ws, ctr, 0, 0)
+    want8 = (xq.float() * xs[:, None]) @ (wq.float() * wsc[:, None]).t()
+    assert _rel_err(got, want8) < 5e-3

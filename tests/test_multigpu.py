@@ -1,0 +1,26 @@
+"""Launch tests/multigpu_worker.py under torchrun on all visible GPUs (>= 2) and check its report."""
+import json
+import os
+import subprocess
+import sys
+from pathlib import Path
+
+import pytest
+import torch
+
+ROOT = Path(__file__).resolve().parent.parent
+pytestmark = [pytest.mark.gpu, pytest.mark.multigpu]
+
+
+def test_peer_memory_paths_match_nccl():
+    n = min(torch.cuda.device_count(), 8)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1",
+                        "--master-port", "29655", str(ROOT / "tests" / "multigpu_worker.py")], capture_output=True, text=True,
+                       timeout=600, env={**os.environ, "PYTHONPATH": str(ROOT)})
+    line = [l for l in r.stdout.splitlines() if l.startswith("MULTIGPU_RESULTS ")]
+    assert r.returncode == 0 and line, r.stdout[-2000:] + r.stderr[-3000:]
+    res = json.loads(line[0].split(" ", 1)[1])
+    assert res["allgather_pull_exact"] and res["ag_gemm_gather_exact"] and res["weight_push_exact"]
+    assert res["reduce_scatter_accum_err"] < 1e-5 and res["reduce_scatter_sumsq_err"] < 1e-3
+    assert res["ag_gemm_err"] < 5e-3
+    assert res["zero3_p2p_weight_err"] < 2e-2 and res["zero3_nccl_weight_err"] < 2e-2
