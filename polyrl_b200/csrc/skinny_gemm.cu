@@ -29,6 +29,13 @@ struct SkinnyParams {
   int* counters;               // [num_tiles], zero on entry, zero on exit
   int64_t ldo;
   int B, N, K, BP, splits, kb_per_split, swiglu;
+  // tensor-parallel all-reduce fused into the epilogue (row-parallel layers): every rank pushes its fp32 partial
+  // tile into each peer's inbox over NVLink, signals, waits for the peers' tiles and reduces in rank order.
+  int tp_world, tp_rank;
+  uint32_t tp_epoch;
+  int64_t inbox_half;          // floats per parity half of an inbox (double-buffered by epoch parity)
+  float* inbox[8];             // inbox[r] = base of rank r's inbox: [tp_world slots][tiles][BP][128] fp32
+  uint32_t* tp_flags[8];       // tp_flags[r] = rank r's flag array: [tp_world][tiles]
 };
 
 template <int MT, bool FP8>
@@ -150,46 +157,84 @@ skinny_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
       const float ws0 = (p.w_scale && n_ok) ? p.w_scale[p.swiglu ? row0 + r : n_feat] : 1.f;
       const float ws1 = (p.w_scale && n_ok && p.swiglu) ? p.w_scale[row0 + 128 + r] : 1.f;
       const float bias0 = (p.bias && n_ok && !p.swiglu) ? __bfloat162float(p.bias[n_feat]) : 0.f;
-      for (int c = 0; c < p.BP; c += 32) {
-        float a0[32], a1[32];
-#pragma unroll
-        for (int mt = 0; mt < MT; ++mt) {
-          float(&acc)[32] = mt == 0 ? a0 : a1;
-          if (p.splits == 1 || nkb > 0) {
-            uint32_t v[32];
-            __syncwarp();
-            tmem_ld_32x32(tmem_base + lane_base + mt * p.BP + c, v);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) acc[i] = __uint_as_float(v[i]);
-          } else {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) acc[i] = 0.f;
-          }
-          for (int s = 0; s < p.splits; ++s) {
-            if (s == split) continue;
-            const float* other = ws_tile + static_cast<int64_t>(s) * tile_ws + (static_cast<int64_t>(mt) * p.BP + c) * 128 + r;
-#pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (c + i < p.BP) acc[i] += __ldcg(other + i * 128);
-          }
+      const bool tp = p.tp_world > 1;
+      const int tiles = gridDim.x / p.splits;
+      const int64_t inbox_tile = static_cast<int64_t>(p.BP) * 128;
+      const int64_t inbox_par = static_cast<int64_t>(p.tp_epoch & 1) * p.inbox_half;
+      for (int pass = tp ? 0 : 1; pass < 2; ++pass) {
+        if (tp && pass == 1) {
+          // publish: all partial chunks of this tile are in every peer's inbox
+          __threadfence_system();
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          if (et < p.tp_world) st_release_sys(p.tp_flags[et] + p.tp_rank * tiles + tile, p.tp_epoch);
+          if (et < p.tp_world) wait_ge_sys(p.tp_flags[p.tp_rank] + et * tiles + tile, p.tp_epoch);
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          __threadfence_system();
         }
-        if (!n_ok) continue;
+        for (int c = 0; c < p.BP; c += 32) {
+          float a0[32], a1[32];
+          if (!tp || pass == 0) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int b = c + i;
-          if (b >= p.B) break;
-          const float xs = p.x_scale ? p.x_scale[b] : 1.f;
-          float y;
-          if (MT == 2 && p.swiglu) {
-            const float g = a0[i] * ws0 * xs, u = a1[i] * ws1 * xs;
-            y = g / (1.f + __expf(-g)) * u;
-          } else {
-            y = a0[i] * ws0 * xs + bias0;
+            for (int mt = 0; mt < MT; ++mt) {
+              float(&acc)[32] = mt == 0 ? a0 : a1;
+              if (p.splits == 1 || nkb > 0) {
+                uint32_t v[32];
+                __syncwarp();
+                tmem_ld_32x32(tmem_base + lane_base + mt * p.BP + c, v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) acc[i] = __uint_as_float(v[i]);
+              } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) acc[i] = 0.f;
+              }
+              for (int s = 0; s < p.splits; ++s) {
+                if (s == split) continue;
+                const float* other = ws_tile + static_cast<int64_t>(s) * tile_ws + (static_cast<int64_t>(mt) * p.BP + c) * 128 + r;
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                  if (c + i < p.BP) acc[i] += __ldcg(other + i * 128);
+              }
+            }
           }
-          const int64_t o = static_cast<int64_t>(b) * p.ldo + n_feat;
-          if (p.res) y += __bfloat162float(p.res[o]);
-          p.out[o] = __float2bfloat16(y);
+          if (tp && pass == 0) {
+            // push this chunk of the partial tile to every rank's inbox slot [tp_rank][tile] (coalesced 128 B rows)
+            for (int dst = 0; dst < p.tp_world; ++dst) {
+              float* ib = p.inbox[dst] + inbox_par + (static_cast<int64_t>(p.tp_rank) * tiles + tile) * inbox_tile + static_cast<int64_t>(c) * 128 + r;
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (c + i < p.BP) ib[i * 128] = a0[i];
+            }
+            continue;
+          }
+          if (tp) {
+            // reduce in rank order so every rank obtains bit-identical sums (lock-step engines)
+#pragma unroll
+            for (int i = 0; i < 32; ++i) a0[i] = 0.f;
+            for (int src = 0; src < p.tp_world; ++src) {
+              const float* ib = p.inbox[p.tp_rank] + inbox_par + (static_cast<int64_t>(src) * tiles + tile) * inbox_tile + static_cast<int64_t>(c) * 128 + r;
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (c + i < p.BP) a0[i] += __ldcg(ib + i * 128);
+            }
+          }
+          if (!n_ok) continue;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int b = c + i;
+            if (b >= p.B) break;
+            const float xs = p.x_scale ? p.x_scale[b] : 1.f;
+            float y;
+            if (MT == 2 && p.swiglu) {
+              const float g = a0[i] * ws0 * xs, u = a1[i] * ws1 * xs;
+              y = g / (1.f + __expf(-g)) * u;
+            } else {
+              y = a0[i] * ws0 * xs + bias0;
+            }
+            const int64_t o = static_cast<int64_t>(b) * p.ldo + n_feat;
+            if (p.res) y += __bfloat162float(p.res[o]);
+            p.out[o] = __float2bfloat16(y);
+          }
         }
       }
     }
@@ -253,11 +298,32 @@ extern "C" int prl_skinny_workspace_floats(int B, int N, int max_splits) {
 
 // mode: 0 = store (+bias, +residual), 1 = SwiGLU (W block-interleaved, out is [B, N/2]).
 // dtype: 0 = bf16, 1 = fp8 e4m3 (x_scale per batch row, w_scale per weight row required).
+extern "C" int prl_skinny_gemm_tp(const void* X, const void* W, void* out, const void* res, const void* bias, const float* x_scale,
+                                  const float* w_scale, float* workspace, int* counters, int B, int N, int K, int64_t ldx,
+                                  int64_t ldw, int64_t ldo, int mode, int dtype, int splits, int tp_world, int tp_rank,
+                                  uint32_t tp_epoch, int64_t inbox_half, void* const* inbox_ptrs, void* const* flag_ptrs, cudaStream_t stream);
+
 extern "C" int prl_skinny_gemm(const void* X, const void* W, void* out, const void* res, const void* bias, const float* x_scale,
                                const float* w_scale, float* workspace, int* counters, int B, int N, int K, int64_t ldx,
                                int64_t ldw, int64_t ldo, int mode, int dtype, int splits, cudaStream_t stream) {
+  return prl_skinny_gemm_tp(X, W, out, res, bias, x_scale, w_scale, workspace, counters, B, N, K, ldx, ldw, ldo, mode, dtype, splits,
+                            1, 0, 0, 0, nullptr, nullptr, stream);
+}
+
+// Row-parallel tensor-parallel variant: X is this rank's K-slice [B, K_local], W its [N, K_local] slice; the epilogue
+// all-reduces over `tp_world` ranks through peer-mapped inboxes (inbox_ptrs[r], flag_ptrs[r] = rank r's buffers).
+extern "C" int prl_skinny_gemm_tp(const void* X, const void* W, void* out, const void* res, const void* bias, const float* x_scale,
+                                  const float* w_scale, float* workspace, int* counters, int B, int N, int K, int64_t ldx,
+                                  int64_t ldw, int64_t ldo, int mode, int dtype, int splits, int tp_world, int tp_rank,
+                                  uint32_t tp_epoch, int64_t inbox_half, void* const* inbox_ptrs, void* const* flag_ptrs, cudaStream_t stream) {
   if (B <= 0 || B > 256) return -60;
+  if (tp_world > 8 || (tp_world > 1 && mode == 1)) return -64;
   SkinnyParams p;
+  p.tp_world = tp_world; p.tp_rank = tp_rank; p.tp_epoch = tp_epoch; p.inbox_half = inbox_half;
+  for (int i = 0; i < 8; ++i) {
+    p.inbox[i] = (tp_world > 1 && i < tp_world) ? static_cast<float*>(inbox_ptrs[i]) : nullptr;
+    p.tp_flags[i] = (tp_world > 1 && i < tp_world) ? static_cast<uint32_t*>(flag_ptrs[i]) : nullptr;
+  }
   p.out = static_cast<__nv_bfloat16*>(out);
   p.res = static_cast<const __nv_bfloat16*>(res);
   p.bias = static_cast<const __nv_bfloat16*>(bias);

@@ -46,29 +46,51 @@ def main():
                 rec[f"own_bn{fbn}_ms"] = round(bench(lambda: C.gemm_bf16(a, b, None, d, fbn)), 4)
         print(json.dumps(rec), flush=True)
         out.append(rec)
-    # decode-shape GEMMs: skinny (swap-AB + split-K) kernel vs cuBLAS vs the 128-row-tile kernel
+    # decode-shape GEMMs measured INSIDE a CUDA graph (as the engine runs them: no host launch overhead), cycling over
+    # enough distinct weight copies that every call streams its weights from HBM (sum of copies > L2).
     ws = torch.empty(24 * 1024 * 1024, device="cuda", dtype=torch.float32)
     ctr = torch.zeros(4096, device="cuda", dtype=torch.int32)
+
+    def graph_time(fns, reps=5):
+        for f in fns:
+            f()
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for f in fns:
+                f()
+        g.replay(); torch.cuda.synchronize()
+        ts = []
+        for _ in range(reps):
+            s_, e_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s_.record(); g.replay(); e_.record(); torch.cuda.synchronize()
+            ts.append(s_.elapsed_time(e_) / len(fns))
+        return sorted(ts)[len(ts) // 2]
+
     for B in (64, 128, 256):
-        tot = {"skinny": 0.0, "cublas": 0.0}
+        tot = {"skinny": 0.0, "cublas": 0.0, "tile128": 0.0}
         for N, K in ((6144, 4096), (4096, 4096), (28672, 4096), (4096, 14336), (128256, 4096)):
+            copies = max(2, int(300e6 // (N * K * 2)) + 1)
             x = torch.randn(B, K, device="cuda", dtype=torch.bfloat16)
-            w = torch.randn(N, K, device="cuda", dtype=torch.bfloat16) * 0.02
+            Ws = [torch.randn(N, K, device="cuda", dtype=torch.bfloat16) * 0.02 for _ in range(copies)]
             mode = 1 if N == 28672 else 0
-            t_s = bench(lambda: C.skinny_gemm(x, w, None, None, None, None, ws, ctr, mode, 0))
+            t_s = graph_time([(lambda w=w: C.skinny_gemm(x, w, None, None, None, None, ws, ctr, mode, 0)) for w in Ws])
             if mode == 1:
-                def lib():
-                    gu = x @ w.t()
-                    return torch.nn.functional.silu(gu[:, :N // 2]) * gu[:, N // 2:]
+                t_l = graph_time([(lambda w=w: torch.nn.functional.silu((x @ w.t())[:, :N // 2]) * (x @ w.t())[:, N // 2:]) for w in Ws[:1]]) if False else \
+                    graph_time([(lambda w=w: (lambda gu: torch.nn.functional.silu(gu[:, :N // 2]) * gu[:, N // 2:])(x @ w.t())) for w in Ws])
+                t_o = graph_time([(lambda w=w: C.gemm_swiglu(x, w, False)) for w in Ws])
             else:
-                lib = lambda: x @ w.t()
-            t_l = bench(lib)
-            rec = {"op": "decode_gemm", "B": B, "N": N, "K": K, "swiglu": bool(mode), "skinny_ms": round(t_s, 4), "cublas_ms": round(t_l, 4),
-                   "skinny_GBps": round(N * K * 2 / t_s / 1e6, 1), "hbm_frac_of_measured": round(N * K * 2 / t_s / 1e6 / 6569.6, 3)}
+                t_l = graph_time([(lambda w=w: x @ w.t()) for w in Ws])
+                t_o = graph_time([(lambda w=w: C.gemm_bf16(x, w, None, None, 0)) for w in Ws])
+            rec = {"op": "decode_gemm_in_graph", "B": B, "N": N, "K": K, "swiglu": bool(mode), "skinny_ms": round(t_s, 4),
+                   "cublas_ms": round(t_l, 4), "tile128_ms": round(t_o, 4), "skinny_GBps": round(N * K * 2 / t_s / 1e6, 1),
+                   "skinny_hbm_frac_of_measured": round(N * K * 2 / t_s / 1e6 / 6569.6, 3),
+                   "cublas_hbm_frac_of_measured": round(N * K * 2 / t_l / 1e6 / 6569.6, 3)}
             print(json.dumps(rec), flush=True)
             if N != 128256:
-                tot["skinny"] += t_s; tot["cublas"] += t_l
-        print(json.dumps({"op": "decode_layer_gemms_total", "B": B, "skinny_ms": round(tot["skinny"], 4), "cublas_ms": round(tot["cublas"], 4)}), flush=True)
+                tot["skinny"] += t_s; tot["cublas"] += t_l; tot["tile128"] += t_o
+            del Ws
+        print(json.dumps({"op": "decode_layer_gemms_total_in_graph", "B": B, **{k: round(v, 4) for k, v in tot.items()}}), flush=True)
     # fused swiglu vs unfused
     M, F, K = 16384, 14336, 4096
     x = torch.randn(M, K, device="cuda", dtype=torch.bfloat16)
