@@ -40,7 +40,7 @@ int prl_p2p_allgather_pull(void* const*, void*, int64_t, int, int, int, cudaStre
 int prl_p2p_reduce_scatter_accum(void* const*, int64_t, float*, int64_t, float, int, int, float*, int, cudaStream_t);
 int prl_skinny_workspace_floats(int, int, int);
 int prl_skinny_gemm(const void*, const void*, void*, const void*, const void*, const float*, const float*, float*, int*, int, int, int, int64_t, int64_t, int64_t, int, int, int, cudaStream_t);
-int prl_skinny_gemm_tp(const void*, const void*, void*, const void*, const void*, const float*, const float*, float*, int*, int, int, int, int64_t, int64_t, int64_t, int, int, int, int, int, uint32_t, int64_t, void* const*, void* const*, cudaStream_t);
+int prl_skinny_gemm_tp(const void*, const void*, void*, const void*, const void*, const float*, const float*, float*, int*, int, int, int, int64_t, int64_t, int64_t, int, int, int, int, int, uint32_t*, int*, int64_t, void* const*, void* const*, cudaStream_t);
 int prl_ag_gemm_bf16(const void*, void* const*, void*, void*, uint32_t*, uint32_t, int, int, int, int64_t, int64_t, int, int, int, cudaStream_t);
 }
 
@@ -309,13 +309,14 @@ at::Tensor skinny_gemm(const at::Tensor& x, const at::Tensor& w, const c10::opti
 // Row-parallel TP linear with the all-reduce fused into the GEMM epilogue over NVLink peer memory.
 at::Tensor skinny_gemm_tp(const at::Tensor& x, const at::Tensor& w, const c10::optional<at::Tensor>& residual,
                           at::Tensor workspace, at::Tensor counters, int64_t splits, const std::vector<int64_t>& inbox_ptrs,
-                          const std::vector<int64_t>& flag_ptrs, int64_t tp_rank, int64_t epoch, int64_t inbox_half) {
+                          const std::vector<int64_t>& flag_ptrs, int64_t tp_rank, at::Tensor epoch_state, int64_t inbox_half) {
   CHECK_BF16(x); CHECK_BF16(w);
   TORCH_CHECK(x.dim() == 2 && w.dim() == 2 && x.stride(1) == 1 && w.stride(1) == 1 && x.size(1) == w.size(1));
   const int B = x.size(0), K = x.size(1), N = w.size(0);
   const int world = inbox_ptrs.size();
   const int BP = ((B + 15) / 16) * 16;
   TORCH_CHECK((int64_t)world * ((N + 127) / 128) * BP * 128 <= inbox_half, "TP inbox too small");
+  TORCH_CHECK(epoch_state.is_cuda() && epoch_state.scalar_type() == at::kInt && epoch_state.numel() >= 2);
   c10::cuda::CUDAGuard g(x.device());
   at::Tensor out = at::empty({B, N}, x.options());
   const void* r = nullptr;
@@ -324,7 +325,8 @@ at::Tensor skinny_gemm_tp(const at::Tensor& x, const at::Tensor& w, const c10::o
   auto fl = to_ptrs(flag_ptrs);
   check(prl_skinny_gemm_tp(x.data_ptr(), w.data_ptr(), out.data_ptr(), r, nullptr, nullptr, nullptr, workspace.data_ptr<float>(),
                            counters.data_ptr<int>(), B, N, K, x.stride(0), w.stride(0), out.stride(0), 0, 0, static_cast<int>(splits),
-                           world, static_cast<int>(tp_rank), static_cast<uint32_t>(epoch), inbox_half, ib.data(), fl.data(), cur_stream()),
+                           world, static_cast<int>(tp_rank), reinterpret_cast<uint32_t*>(epoch_state.data_ptr<int>()), epoch_state.data_ptr<int>() + 1,
+                           inbox_half, ib.data(), fl.data(), cur_stream()),
         "skinny_gemm_tp");
   return out;
 }

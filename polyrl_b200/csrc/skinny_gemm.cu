@@ -32,7 +32,8 @@ struct SkinnyParams {
   // tensor-parallel all-reduce fused into the epilogue (row-parallel layers): every rank pushes its fp32 partial
   // tile into each peer's inbox over NVLink, signals, waits for the peers' tiles and reduces in rank order.
   int tp_world, tp_rank;
-  uint32_t tp_epoch;
+  uint32_t* tp_epoch_ptr;      // device-resident epoch (CUDA-graph safe): launch k uses *ptr + 1, last CTA publishes it
+  int* tp_done;                // CTA completion counter (self-resetting)
   int64_t inbox_half;          // floats per parity half of an inbox (double-buffered by epoch parity)
   float* inbox[8];             // inbox[r] = base of rank r's inbox: [tp_world slots][tiles][BP][128] fp32
   uint32_t* tp_flags[8];       // tp_flags[r] = rank r's flag array: [tp_world][tiles]
@@ -66,6 +67,7 @@ skinny_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
   const int kb1 = min(num_kb_total, kb0 + p.kb_per_split);
   const int nkb = max(0, kb1 - kb0);
   const int row0 = tile * (MT * 128);                       // first weight row of this tile
+  const uint32_t tp_epoch = p.tp_world > 1 ? *reinterpret_cast<volatile uint32_t*>(p.tp_epoch_ptr) + 1u : 0u;
   uint32_t tmem_cols = 32;
   while (tmem_cols < static_cast<uint32_t>(MT * p.BP)) tmem_cols <<= 1;
 
@@ -160,14 +162,14 @@ skinny_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
       const bool tp = p.tp_world > 1;
       const int tiles = gridDim.x / p.splits;
       const int64_t inbox_tile = static_cast<int64_t>(p.BP) * 128;
-      const int64_t inbox_par = static_cast<int64_t>(p.tp_epoch & 1) * p.inbox_half;
+      const int64_t inbox_par = static_cast<int64_t>(tp_epoch & 1) * p.inbox_half;
       for (int pass = tp ? 0 : 1; pass < 2; ++pass) {
         if (tp && pass == 1) {
           // publish: all partial chunks of this tile are in every peer's inbox
           __threadfence_system();
           asm volatile("bar.sync 1, 128;" ::: "memory");
-          if (et < p.tp_world) st_release_sys(p.tp_flags[et] + p.tp_rank * tiles + tile, p.tp_epoch);
-          if (et < p.tp_world) wait_ge_sys(p.tp_flags[p.tp_rank] + et * tiles + tile, p.tp_epoch);
+          if (et < p.tp_world) st_release_sys(p.tp_flags[et] + p.tp_rank * tiles + tile, tp_epoch);
+          if (et < p.tp_world) wait_ge_sys(p.tp_flags[p.tp_rank] + et * tiles + tile, tp_epoch);
           asm volatile("bar.sync 1, 128;" ::: "memory");
           __threadfence_system();
         }
@@ -242,6 +244,14 @@ skinny_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
   tc_fence_before();
   __syncthreads();
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, tmem_cols); }
+  if (p.tp_world > 1 && threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(p.tp_done, 1) == static_cast<int>(gridDim.x) - 1) {      // every CTA has read the old epoch
+      *p.tp_done = 0;
+      *reinterpret_cast<volatile uint32_t*>(p.tp_epoch_ptr) = tp_epoch;
+      __threadfence();
+    }
+  }
 }
 
 using EncodeTiledFn2 = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -301,13 +311,13 @@ extern "C" int prl_skinny_workspace_floats(int B, int N, int max_splits) {
 extern "C" int prl_skinny_gemm_tp(const void* X, const void* W, void* out, const void* res, const void* bias, const float* x_scale,
                                   const float* w_scale, float* workspace, int* counters, int B, int N, int K, int64_t ldx,
                                   int64_t ldw, int64_t ldo, int mode, int dtype, int splits, int tp_world, int tp_rank,
-                                  uint32_t tp_epoch, int64_t inbox_half, void* const* inbox_ptrs, void* const* flag_ptrs, cudaStream_t stream);
+                                  uint32_t* tp_epoch_ptr, int* tp_done, int64_t inbox_half, void* const* inbox_ptrs, void* const* flag_ptrs, cudaStream_t stream);
 
 extern "C" int prl_skinny_gemm(const void* X, const void* W, void* out, const void* res, const void* bias, const float* x_scale,
                                const float* w_scale, float* workspace, int* counters, int B, int N, int K, int64_t ldx,
                                int64_t ldw, int64_t ldo, int mode, int dtype, int splits, cudaStream_t stream) {
   return prl_skinny_gemm_tp(X, W, out, res, bias, x_scale, w_scale, workspace, counters, B, N, K, ldx, ldw, ldo, mode, dtype, splits,
-                            1, 0, 0, 0, nullptr, nullptr, stream);
+                            1, 0, nullptr, nullptr, 0, nullptr, nullptr, stream);
 }
 
 // Row-parallel tensor-parallel variant: X is this rank's K-slice [B, K_local], W its [N, K_local] slice; the epilogue
@@ -315,11 +325,11 @@ extern "C" int prl_skinny_gemm(const void* X, const void* W, void* out, const vo
 extern "C" int prl_skinny_gemm_tp(const void* X, const void* W, void* out, const void* res, const void* bias, const float* x_scale,
                                   const float* w_scale, float* workspace, int* counters, int B, int N, int K, int64_t ldx,
                                   int64_t ldw, int64_t ldo, int mode, int dtype, int splits, int tp_world, int tp_rank,
-                                  uint32_t tp_epoch, int64_t inbox_half, void* const* inbox_ptrs, void* const* flag_ptrs, cudaStream_t stream) {
+                                  uint32_t* tp_epoch_ptr, int* tp_done, int64_t inbox_half, void* const* inbox_ptrs, void* const* flag_ptrs, cudaStream_t stream) {
   if (B <= 0 || B > 256) return -60;
   if (tp_world > 8 || (tp_world > 1 && mode == 1)) return -64;
   SkinnyParams p;
-  p.tp_world = tp_world; p.tp_rank = tp_rank; p.tp_epoch = tp_epoch; p.inbox_half = inbox_half;
+  p.tp_world = tp_world; p.tp_rank = tp_rank; p.tp_epoch_ptr = tp_epoch_ptr; p.tp_done = tp_done; p.inbox_half = inbox_half;
   for (int i = 0; i < 8; ++i) {
     p.inbox[i] = (tp_world > 1 && i < tp_world) ? static_cast<float*>(inbox_ptrs[i]) : nullptr;
     p.tp_flags[i] = (tp_world > 1 && i < tp_world) ? static_cast<uint32_t*>(flag_ptrs[i]) : nullptr;
@@ -337,8 +347,8 @@ extern "C" int prl_skinny_gemm_tp(const void* X, const void* W, void* out, const
   const int block_k = dtype == 1 ? 128 : 64;
   const int num_kb = (K + block_k - 1) / block_k;
   const int tiles = (N + MT * 128 - 1) / (MT * 128);
-  if (splits <= 0) {                      // fill ~148 SMs, keep >= 8 k-blocks per split
-    splits = (148 + tiles - 1) / tiles;
+  if (splits <= 0) {                      // one wave: tiles*splits <= #SMs (ncu: a 160-CTA grid paid a second wave), >= 8 k-blocks per split
+    splits = 148 / tiles;
     if (splits > num_kb / 8) splits = num_kb / 8;
     if (splits < 1) splits = 1;
     if (splits > 16) splits = 16;

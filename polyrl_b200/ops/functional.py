@@ -36,11 +36,21 @@ def _skinny_buffers(device):
     return _SKINNY_WS[key]
 
 
+def _decode_policy() -> str:
+    """Decode-shape (<= 256 rows, inference) GEMM backend.  ``auto`` follows the in-graph measurements in
+    profiles/r1_decode_gemm_in_graph_v0.jsonl: library GEMM for plain projections, own fused tile kernel for gate/up+SwiGLU;
+    ``skinny`` forces the swap-AB split-K kernel, ``tile`` the 128-row-tile kernel, ``cublas`` the library everywhere."""
+    return os.environ.get("POLYRL_DECODE_GEMM", "auto")
+
+
+def _is_decode_shape(x2: torch.Tensor, w: torch.Tensor) -> bool:
+    return (not torch.is_grad_enabled() or not (x2.requires_grad or w.requires_grad)) and x2.shape[0] <= _SKINNY_MAX_ROWS
+
+
 def _use_skinny(x2: torch.Tensor, w: torch.Tensor) -> bool:
-    if _cublas() or os.environ.get("POLYRL_DECODE_GEMM", "skinny") != "skinny":
+    if _cublas() or _decode_policy() != "skinny":
         return False
-    return (not torch.is_grad_enabled() or not (x2.requires_grad or w.requires_grad)) and x2.shape[0] <= _SKINNY_MAX_ROWS \
-        and x2.shape[1] % 16 == 0 and w.shape[0] >= 128
+    return _is_decode_shape(x2, w) and x2.shape[1] % 16 == 0 and w.shape[0] >= 128
 
 
 def skinny_linear(x2: torch.Tensor, w: torch.Tensor, bias=None, residual=None, mode: int = 0, splits: int = 0) -> torch.Tensor:
@@ -94,6 +104,10 @@ def linear(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None = None,
     """y = x @ w.T (+ bias) (+ residual).  w is [out, in] (nn.Linear layout)."""
     if _is_kernel_tensor(x) and w.dtype == torch.bfloat16 and x.dim() == 2 and _use_skinny(x, w):
         return skinny_linear(x, w, bias, residual, 0)
+    if _is_kernel_tensor(x) and w.dtype == torch.bfloat16 and x.dim() == 2 and _decode_policy() in ("auto", "cublas") \
+            and _is_decode_shape(x, w):
+        y = torch.nn.functional.linear(x, w, bias)
+        return y.add_(residual) if residual is not None else y
     if _is_kernel_tensor(x) and w.dtype == torch.bfloat16 and w.shape[0] % 8 == 0 and w.shape[1] % 8 == 0:
         y = _LinearFn.apply(x, w, residual if bias is None else None)
         if bias is not None:

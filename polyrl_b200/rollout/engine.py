@@ -106,7 +106,10 @@ class BlockAllocator:
 class RolloutEngine:
     def __init__(self, cfg: ModelConfig, device, max_num_seqs: int = 256, max_model_len: int = 2048,
                  kv_cache_tokens: int | None = None, gpu_memory_utilization: float = 0.5, dtype=None,
-                 use_cuda_graph: bool = True, max_prefill_tokens: int = 16384, seed: int = 0):
+                 use_cuda_graph: bool = True, max_prefill_tokens: int = 16384, seed: int = 0, tp=None):
+        self.tp = tp                               # rollout.tp.TPContext for tensor-parallel engines
+        self.full_cfg = cfg
+        cfg = tp.local_cfg() if tp is not None else cfg   # per-rank view: local heads / kv heads / intermediate
         self.cfg = cfg
         self.device = torch.device(device)
         self.is_cuda = self.device.type == "cuda"
@@ -142,6 +145,8 @@ class RolloutEngine:
         """Point the engine at (possibly trainer-owned) weight tensors.  Pointers that change invalidate
         captured graphs; in-place updates of the same storage do not."""
         old = self._weight_ptrs()
+        if self.tp is not None:
+            layer_w = [self.tp.shard_layer(w) for w in layer_w]
         self.embed_w, self.layer_w, self.head_w = embed_w, layer_w, head_w
         if old != self._weight_ptrs():
             self._graphs.clear()
@@ -321,7 +326,12 @@ class RolloutEngine:
         slot_t = torch.tensor(slots, dtype=torch.long, device=dev)
         x = tf.embed_forward(cfg, self.embed_w, inp).to(self.dtype)
         for i, w in enumerate(self.layer_w):
-            x = tf.layer_forward(cfg, w, x, inp, kv_sink=(self.k_cache[i], self.v_cache[i], slot_t))
+            if self.tp is not None:
+                from .tp import layer_prefill_tp
+
+                x = layer_prefill_tp(self.tp, cfg, w, x, inp, (self.k_cache[i], self.v_cache[i], slot_t))
+            else:
+                x = tf.layer_forward(cfg, w, x, inp, kv_sink=(self.k_cache[i], self.v_cache[i], slot_t))
         last = (cu[1:] - 1).long().to(dev)
         h = tf.final_norm(cfg, self.head_w, x.index_select(0, last))
         logits = self._lm_logits(h)
@@ -377,7 +387,12 @@ class RolloutEngine:
         if cfg.family == "gpt2":
             x = x + torch.nn.functional.embedding(pos, self.embed_w["pos_embed"]).to(self.dtype)
         for i, w in enumerate(self.layer_w):
-            x = tf.layer_decode(cfg, w, x, inp, self.k_cache[i], self.v_cache[i])
+            if self.tp is not None:
+                from .tp import layer_decode_tp
+
+                x = layer_decode_tp(self.tp, cfg, w, x, inp, self.k_cache[i], self.v_cache[i])
+            else:
+                x = tf.layer_decode(cfg, w, x, inp, self.k_cache[i], self.v_cache[i])
         h = tf.final_norm(cfg, self.head_w, x)
         logits = self._lm_logits(h)
         tok, lp = ops.sample_tokens(logits, self.st_temp[:bs], self.st_seeds[:bs], top_k=self._top_k, top_p=self._top_p)

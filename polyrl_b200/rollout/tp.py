@@ -1,0 +1,113 @@
+"""Tensor-parallel rollout: weight slicing, the fused GEMM -> all-reduce over NVLink peer memory, and lock-step
+driving of the TP ranks.
+
+Megatron-style sharding (what SGLang does for the reference's ``rollout.tensor_model_parallel_size``,
+rlboost/verl_stream/workers/rollout/sglang_rollout/sglang_rollout_remote.py:152): QKV and gate/up are
+column-parallel (each rank owns nq/W query heads, nkv/W kv heads and F/W intermediate channels — its KV cache
+only holds its heads), O and down projections are row-parallel and need an all-reduce.  The reference stack
+issues that all-reduce as a separate NCCL / custom-all-reduce kernel after a cuBLAS GEMM; here the decode path
+uses ``skinny_gemm_tp``: the GEMM's epilogue pushes its partial tile into every peer's inbox with NVLink
+stores, signals per-tile flags and reduces in rank order — one kernel, no NCCL (SURVEY §2.5c "SGLang TP
+all-reduce x2 per layer per decode step").  Prefill (large M) uses the NCCL all-reduce.
+
+Lock-step: all TP ranks run identical engines on identical request streams with identical seeds; hidden states
+are bit-identical after the rank-ordered reduction, so sampling agrees without any host communication.  Rank 0
+broadcasts the request/abort commands it receives over a gloo control group.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+from .. import ops
+from ..models import transformer as tf
+from ..models.config import ModelConfig
+from ..ops.attention import attention_varlen
+from ..ops.functional import rope_and_cache_, _skinny_buffers
+
+
+class TPContext:
+    def __init__(self, cfg: ModelConfig, heap, tp_rank: int, tp_world: int, max_batch: int, group=None):
+        if cfg.num_heads % tp_world or cfg.num_kv_heads % tp_world or (cfg.intermediate_size // 128) % tp_world:
+            raise ValueError("heads, kv heads and intermediate_size/128 must be divisible by the TP size")
+        self.cfg, self.heap, self.rank, self.world, self.group = cfg, heap, tp_rank, tp_world, group
+        self.max_batch = max_batch
+        bp = ((min(max_batch, 256) + 15) // 16) * 16
+        tiles = (cfg.hidden_size + 127) // 128
+        self.inbox_half = tp_world * tiles * bp * 128
+        self.inbox = heap.alloc(2 * self.inbox_half, torch.float32)
+        self.flags = heap.alloc(tp_world * tiles + 64, torch.int32)
+        self.epoch_state = torch.zeros(2, device=heap.device, dtype=torch.int32)   # [epoch, done-counter] (device side)
+        self.C = ops.ext()
+        heap.barrier()
+
+    def local_cfg(self) -> ModelConfig:
+        """Model config as seen by one TP rank (for KV-cache sizing and the attention kernels)."""
+        c = self.cfg
+        d = c.to_dict()
+        d.update(num_heads=c.num_heads // self.world, num_kv_heads=c.num_kv_heads // self.world,
+                 intermediate_size=c.intermediate_size // self.world, head_dim=c.head_dim)
+        out = ModelConfig(**d)
+        out.hidden_size = c.hidden_size
+        return out
+
+    # ---------------------------------------------------------------- weight slicing
+    def shard_layer(self, w: dict) -> dict:
+        """Slice one layer's full weights for this rank.  Row/column slices that are contiguous (or strided with a
+        row pitch TMA can express) are views; the fused qkv needs a compact copy (three disjoint row ranges)."""
+        c, r, W = self.cfg, self.rank, self.world
+        d, nq, nkv = c.head_dim, c.num_heads // W, c.num_kv_heads // W
+        q0, k0, v0 = r * nq * d, c.q_size + r * nkv * d, c.q_size + c.kv_size + r * nkv * d
+        out = {"ln1": w["ln1"], "ln2": w["ln2"]}
+        out["wqkv"] = torch.cat([w["wqkv"][q0:q0 + nq * d], w["wqkv"][k0:k0 + nkv * d], w["wqkv"][v0:v0 + nkv * d]], dim=0).contiguous()
+        if "bqkv" in w:
+            out["bqkv"] = torch.cat([w["bqkv"][q0:q0 + nq * d], w["bqkv"][k0:k0 + nkv * d], w["bqkv"][v0:v0 + nkv * d]]).contiguous()
+        out["wo"] = w["wo"][:, q0:q0 + nq * d]                      # [H, nq_local*d] view, row pitch = full
+        f2 = 2 * c.intermediate_size // W
+        out["wgu"] = w["wgu"][r * f2:(r + 1) * f2]                  # contiguous rows (block-interleaved layout)
+        fl = c.intermediate_size // W
+        out["wd"] = w["wd"][:, r * fl:(r + 1) * fl]                 # [H, F_local] view
+        return out
+
+    # ---------------------------------------------------------------- row-parallel linear
+    def row_parallel(self, x_local: torch.Tensor, w_local: torch.Tensor, residual: torch.Tensor | None) -> torch.Tensor:
+        b = x_local.shape[0]
+        if x_local.is_cuda and b <= 256 and b <= self.max_batch:
+            ws, ctr = _skinny_buffers(x_local.device)
+            res = residual.contiguous() if residual is not None else None
+            return self.C.skinny_gemm_tp(x_local.contiguous(), w_local, res, ws, ctr, 0, self.inbox.ptrs, self.flags.ptrs,
+                                         self.rank, self.epoch_state, self.inbox_half)
+        y = torch.nn.functional.linear(x_local, w_local)
+        dist.all_reduce(y, group=self.group)
+        return y + residual if residual is not None else y
+
+
+def layer_decode_tp(tp: TPContext, lcfg: ModelConfig, w: dict, x: torch.Tensor, inp: tf.DecodeInput, k_cache, v_cache) -> torch.Tensor:
+    nq, nkv, d = lcfg.num_heads, lcfg.num_kv_heads, lcfg.head_dim
+    h = ops.rmsnorm(x, w["ln1"], lcfg.rms_norm_eps)
+    qkv = ops.linear(h, w["wqkv"], bias=w.get("bqkv"))
+    cos, sin = tf.rope_tables(lcfg, x.device)
+    rope_and_cache_(qkv, inp.position_ids, cos, sin, nq, nkv, d, k_cache, v_cache, inp.slot_mapping, k_cache.shape[2])
+    a = ops.paged_decode_attention(qkv[:, : nq * d], k_cache, v_cache, inp.block_table, inp.seq_lens, nq, nkv, d, d ** -0.5,
+                                   max_len=inp.max_len)
+    x = tp.row_parallel(a, w["wo"], x)
+    h = ops.rmsnorm(x, w["ln2"], lcfg.rms_norm_eps)
+    a = ops.linear_swiglu(h, w["wgu"])
+    return tp.row_parallel(a, w["wd"], x)
+
+
+def layer_prefill_tp(tp: TPContext, lcfg: ModelConfig, w: dict, x: torch.Tensor, inp: tf.PackedInput, kv_sink) -> torch.Tensor:
+    nq, nkv, d = lcfg.num_heads, lcfg.num_kv_heads, lcfg.head_dim
+    t = x.shape[0]
+    h = ops.rmsnorm(x, w["ln1"], lcfg.rms_norm_eps)
+    qkv = ops.linear(h, w["wqkv"], bias=w.get("bqkv"))
+    cos, sin = tf.rope_tables(lcfg, x.device)
+    qkv = rope_and_cache_(qkv, inp.position_ids, cos, sin, nq, nkv, d, *kv_sink)
+    q = qkv[:, : nq * d].view(t, nq, d)
+    k = qkv[:, nq * d:(nq + nkv) * d].view(t, nkv, d)
+    v = qkv[:, (nq + nkv) * d:].view(t, nkv, d)
+    a = attention_varlen(q, k, v, inp.cu_seqlens, inp.max_seqlen, causal=True).reshape(t, nq * d)
+    x = tp.row_parallel(a, w["wo"], x)
+    h = ops.rmsnorm(x, w["ln2"], lcfg.rms_norm_eps)
+    a = ops.linear_swiglu(h, w["wgu"])
+    return tp.row_parallel(a, w["wd"], x)

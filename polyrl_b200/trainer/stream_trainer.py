@@ -164,6 +164,19 @@ class StreamPPOTrainer:
                 if diff.numel():
                     metrics.setdefault("training/rollout_probs_diff_mean", []).append(diff.mean().item())
                     metrics.setdefault("training/rollout_probs_diff_max", []).append(diff.max().item())
+        rc = cfg.algorithm.rollout_correction
+        if (rc.rollout_is or rc.rollout_rs) and "rollout_log_probs" in local.batch:
+            from ..algos.rollout_corr import compute_rollout_correction
+
+            w, new_mask, rcm = compute_rollout_correction(local.batch["old_log_probs"], local.batch["rollout_log_probs"],
+                                                          local.batch["response_mask"], rc.rollout_is, rc.rollout_is_threshold,
+                                                          rc.rollout_rs, rc.rollout_rs_threshold, rc.rollout_rs_threshold_lower,
+                                                          rc.rollout_token_veto_threshold)
+            if w is not None:
+                local.batch["rollout_is_weights"] = w
+            local.batch["response_mask"] = new_mask
+            for k, v in rcm.items():
+                metrics.setdefault(k, []).append(v)
         if self.use_reference:
             with marked_timer("ref", t):
                 local.batch["ref_log_prob"] = self.worker.compute_ref_log_prob(local).batch["ref_log_prob"]
