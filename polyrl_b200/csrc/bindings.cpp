@@ -17,6 +17,7 @@ int prl_linear_ce_num_splits(int, int);
 int prl_linear_ce_fwd(const void*, const void*, const int64_t*, float, int, int, int, int64_t, int64_t, float*, int, float*, float*, float*, float*, cudaStream_t);
 int prl_linear_ce_dz(const void*, const void*, const int64_t*, const float*, const float*, const float*, const float*, float, int, int, int, int, int64_t, int64_t, void*, int64_t, cudaStream_t);
 int prl_rmsnorm_fwd(const void*, const void*, void*, float*, int, int, float, cudaStream_t);
+int prl_add_rmsnorm(void*, const void*, const void*, void*, int, int, float, cudaStream_t);
 int prl_rmsnorm_bwd(const void*, const void*, const void*, const float*, void*, float*, int, int, cudaStream_t);
 int prl_rope(void*, const int64_t*, const float*, const float*, int, int, int, int, int64_t, float, void*, void*, const int64_t*, int, cudaStream_t);
 int prl_swiglu_bwd(const void*, const void*, void*, int64_t, int, cudaStream_t);
@@ -152,6 +153,18 @@ std::vector<at::Tensor> rmsnorm_fwd(const at::Tensor& x, const at::Tensor& w, do
   check(prl_rmsnorm_fwd(x.data_ptr(), w.data_ptr(), y.data_ptr(), rstd.data_ptr<float>(), T, H,
                         static_cast<float>(eps), cur_stream()), "rmsnorm_fwd");
   return {y, rstd};
+}
+
+// x += r (in place), returns rmsnorm(x) * w  — decode-path fusion of the residual add into the following norm.
+at::Tensor add_rmsnorm_(at::Tensor x, const at::Tensor& r, const at::Tensor& w, double eps) {
+  CHECK_BF16(x); CHECK_BF16(r); CHECK_BF16(w);
+  TORCH_CHECK(x.is_contiguous() && r.is_contiguous() && x.sizes() == r.sizes());
+  const int H = x.size(-1);
+  const int T = x.numel() / H;
+  c10::cuda::CUDAGuard g(x.device());
+  at::Tensor y = at::empty_like(x);
+  check(prl_add_rmsnorm(x.data_ptr(), r.data_ptr(), w.data_ptr(), y.data_ptr(), T, H, static_cast<float>(eps), cur_stream()), "add_rmsnorm");
+  return y;
 }
 
 std::vector<at::Tensor> rmsnorm_bwd(const at::Tensor& x, const at::Tensor& w, const at::Tensor& dy,
@@ -420,6 +433,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("linear_ce_dz", &linear_ce_dz);
   m.def("rmsnorm_fwd", &rmsnorm_fwd);
   m.def("rmsnorm_bwd", &rmsnorm_bwd);
+  m.def("add_rmsnorm_", &add_rmsnorm_);
   m.def("rope_", &rope_);
   m.def("swiglu_bwd", &swiglu_bwd);
   m.def("quant_fp8_rowwise", &quant_fp8_rowwise);

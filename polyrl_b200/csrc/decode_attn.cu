@@ -36,7 +36,7 @@ paged_decode_kernel(const __nv_bfloat16* __restrict__ q, int64_t ldq,     // [nu
                     const __nv_bfloat16* __restrict__ k_cache, const __nv_bfloat16* __restrict__ v_cache,
                     const int32_t* __restrict__ block_table, int64_t ld_bt, const int32_t* __restrict__ seq_lens,
                     int nq, int nkv, int splits, float scale_log2, float* __restrict__ o_part,
-                    float* __restrict__ ml_part) {
+                    float* __restrict__ ml_part, __nv_bfloat16* __restrict__ out_direct, int64_t ldo) {
   static_assert(D % 64 == 0, "head dim must be a multiple of 64");
   constexpr int KC = D / 32;     // 32-wide d chunks for QK (two MMAs each)
   constexpr int DB = D / 64;     // 64-wide d blocks for PV (eight n-tiles each)
@@ -201,6 +201,10 @@ paged_decode_kernel(const __nv_bfloat16* __restrict__ q, int64_t ldq,     // [nu
       ll += sm_l[w][g] * f;
     }
     const int head = kvh * G + g;
+    if (out_direct) {        // single split: normalise and write the final bf16 output here (no merge kernel)
+      out_direct[static_cast<int64_t>(seq) * ldo + head * D + dcol] = __float2bfloat16(ll > 0.f ? acc / ll : 0.f);
+      continue;
+    }
     const int64_t base = (static_cast<int64_t>(seq) * nq + head) * splits + split;
     o_part[base * D + dcol] = acc;
     if (dcol == 0) { ml_part[base * 2] = mm; ml_part[base * 2 + 1] = ll; }
@@ -256,16 +260,16 @@ extern "C" int prl_paged_decode(const void* q, int64_t ldq, const void* k_cache,
     paged_decode_kernel<128><<<grid, kAttnWarps * 32, 0, s>>>(
         static_cast<const __nv_bfloat16*>(q), ldq, static_cast<const __nv_bfloat16*>(k_cache),
         static_cast<const __nv_bfloat16*>(v_cache), block_table, ld_bt, seq_lens, nq, nkv, splits, scale_log2, o_part,
-        ml_part);
-    decode_merge_kernel<128><<<num_seqs * nq, 128, 0, s>>>(o_part, ml_part, splits, static_cast<__nv_bfloat16*>(out),
-                                                          ldo, nq);
+        ml_part, splits == 1 ? static_cast<__nv_bfloat16*>(out) : nullptr, ldo);
+    if (splits > 1)
+      decode_merge_kernel<128><<<num_seqs * nq, 128, 0, s>>>(o_part, ml_part, splits, static_cast<__nv_bfloat16*>(out), ldo, nq);
   } else if (d == 64) {
     paged_decode_kernel<64><<<grid, kAttnWarps * 32, 0, s>>>(
         static_cast<const __nv_bfloat16*>(q), ldq, static_cast<const __nv_bfloat16*>(k_cache),
         static_cast<const __nv_bfloat16*>(v_cache), block_table, ld_bt, seq_lens, nq, nkv, splits, scale_log2, o_part,
-        ml_part);
-    decode_merge_kernel<64><<<num_seqs * nq, 64, 0, s>>>(o_part, ml_part, splits, static_cast<__nv_bfloat16*>(out), ldo,
-                                                        nq);
+        ml_part, splits == 1 ? static_cast<__nv_bfloat16*>(out) : nullptr, ldo);
+    if (splits > 1)
+      decode_merge_kernel<64><<<num_seqs * nq, 64, 0, s>>>(o_part, ml_part, splits, static_cast<__nv_bfloat16*>(out), ldo, nq);
   } else {
     return -31;
   }

@@ -74,6 +74,60 @@ rmsnorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __r
   }
 }
 
+// Decode-path fusion: x_out = x + r (new residual stream, written in place of x), y = rmsnorm(x_out) * w.
+__global__ void __launch_bounds__(kNormThreads)
+add_rmsnorm_kernel(__nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ r, const __nv_bfloat16* __restrict__ w,
+                   __nv_bfloat16* __restrict__ y, int T, int H, float eps) {
+  __shared__ float red[8];
+  const int nvec = H >> 3;
+  for (int row = blockIdx.x; row < T; row += gridDim.x) {
+    __nv_bfloat16* xr = x + static_cast<int64_t>(row) * H;
+    const __nv_bfloat16* rr = r + static_cast<int64_t>(row) * H;
+    float v[kMaxVPT][8];
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < kMaxVPT; ++i) {
+      const int vi = threadIdx.x + i * kNormThreads;
+      if (vi < nvec) {
+        const int4 a = *reinterpret_cast<const int4*>(xr + 8 * vi);
+        const int4 b = ld_nc_v4(rr + 8 * vi);
+        const uint32_t* au = reinterpret_cast<const uint32_t*>(&a);
+        const uint32_t* bu = reinterpret_cast<const uint32_t*>(&b);
+        int4 o;
+        uint32_t* ou = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 fa = unpack_bf16(au[j]), fb = unpack_bf16(bu[j]);
+          ou[j] = pack_bf16(fa.x + fb.x, fa.y + fb.y);
+          const float2 s2 = unpack_bf16(ou[j]);          // norm over the bf16-rounded residual stream (what the next op reads)
+          v[i][2 * j] = s2.x; v[i][2 * j + 1] = s2.y;
+          ss += s2.x * s2.x + s2.y * s2.y;
+        }
+        st_v4(xr + 8 * vi, o);
+      }
+    }
+    ss = block_sum_256(ss, red);
+    const float rstd = rsqrtf(ss / static_cast<float>(H) + eps);
+    __nv_bfloat16* yr = y + static_cast<int64_t>(row) * H;
+#pragma unroll
+    for (int i = 0; i < kMaxVPT; ++i) {
+      const int vi = threadIdx.x + i * kNormThreads;
+      if (vi < nvec) {
+        const int4 wq = *reinterpret_cast<const int4*>(w + 8 * vi);
+        const uint32_t* wu = reinterpret_cast<const uint32_t*>(&wq);
+        int4 o;
+        uint32_t* ou = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 g = unpack_bf16(wu[j]);
+          ou[j] = pack_bf16(v[i][2 * j] * rstd * g.x, v[i][2 * j + 1] * rstd * g.y);
+        }
+        st_v4(yr + 8 * vi, o);
+      }
+    }
+  }
+}
+
 // dx = rstd * (dy*w - xhat * mean(dy*w*xhat)), dw += sum_rows dy*xhat  (fp32 atomics, one per CTA/col)
 __global__ void __launch_bounds__(kNormThreads)
 rmsnorm_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ w,
@@ -286,6 +340,15 @@ extern "C" int prl_rmsnorm_fwd(const void* x, const void* w, void* y, float* rst
   rmsnorm_fwd_kernel<<<grid, kNormThreads, 0, s>>>(static_cast<const __nv_bfloat16*>(x),
                                                   static_cast<const __nv_bfloat16*>(w),
                                                   static_cast<__nv_bfloat16*>(y), rstd, T, H, eps);
+  PRL_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+extern "C" int prl_add_rmsnorm(void* x, const void* r, const void* w, void* y, int T, int H, float eps, cudaStream_t s) {
+  if (H % 8 != 0 || H > 8 * kNormThreads * kMaxVPT) return -20;
+  if (T <= 0) return 0;
+  const int grid = T < 148 * 8 ? T : 148 * 8;
+  add_rmsnorm_kernel<<<grid, kNormThreads, 0, s>>>(static_cast<__nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(r),
+                                                  static_cast<const __nv_bfloat16*>(w), static_cast<__nv_bfloat16*>(y), T, H, eps);
   PRL_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

@@ -25,7 +25,8 @@ __global__ void p2p_barrier_kernel(PeerPtrs flag_ptrs, int rank, int world, uint
   const int t = threadIdx.x;
   if (t < world) {
     __threadfence_system();
-    st_release_sys(static_cast<uint32_t*>(flag_ptrs.p[t]) + rank, epoch);
+    // max (not store): barriers issued from different streams of one process may execute out of launch order
+    asm volatile("red.release.sys.global.max.u32 [%0], %1;" ::"l"(static_cast<uint32_t*>(flag_ptrs.p[t]) + rank), "r"(epoch) : "memory");
   }
   if (t < world) wait_ge_sys(static_cast<uint32_t*>(flag_ptrs.p[rank]) + t, epoch);
   __syncthreads();

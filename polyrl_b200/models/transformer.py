@@ -209,6 +209,27 @@ def layer_decode(cfg: ModelConfig, w: dict, x: torch.Tensor, inp: DecodeInput, k
     return x + F.linear(F.gelu(F.linear(h, w["wfc"], w["bfc"]), approximate="tanh"), w["wproj"], w["bproj"])
 
 
+def layer_decode_fused(cfg: ModelConfig, w: dict, x: torch.Tensor, delta: torch.Tensor | None, inp: DecodeInput,
+                       k_cache: torch.Tensor, v_cache: torch.Tensor):
+    """Decode block with the residual adds folded into the following RMSNorm (one kernel: x += delta; h = norm(x)).
+    ``x`` is the residual stream (updated in place), ``delta`` the not-yet-added output of the previous block.
+    Returns (x, new_delta).  Llama family, CUDA bf16."""
+    from ..ops import ext
+
+    C = ext()
+    nq, nkv, d = cfg.num_heads, cfg.num_kv_heads, cfg.head_dim
+    h = ops.rmsnorm(x, w["ln1"], cfg.rms_norm_eps) if delta is None else C.add_rmsnorm_(x, delta, w["ln1"], cfg.rms_norm_eps)
+    qkv = ops.linear(h, w["wqkv"], bias=w.get("bqkv"))
+    cos, sin = rope_tables(cfg, x.device)
+    rope_and_cache_(qkv, inp.position_ids, cos, sin, nq, nkv, d, k_cache, v_cache, inp.slot_mapping, k_cache.shape[2])
+    a = ops.paged_decode_attention(qkv[:, : nq * d], k_cache, v_cache, inp.block_table, inp.seq_lens, nq, nkv, d, d ** -0.5,
+                                   max_len=inp.max_len)
+    o = ops.linear(a, w["wo"])
+    h = C.add_rmsnorm_(x, o, w["ln2"], cfg.rms_norm_eps)
+    g = ops.linear_swiglu(h, w["wgu"])
+    return x, ops.linear(g, w["wd"])
+
+
 # --------------------------------------------------------------------------------------------
 # a plain (unsharded) weight container — single-process inference, tests, HF import/export
 # --------------------------------------------------------------------------------------------

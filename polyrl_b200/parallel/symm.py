@@ -76,16 +76,20 @@ class SymmetricHeap:
         return self._C.tensor_from_ptr(buf.ptrs[rank] + elem_offset * _DTYPE_SIZE[dtype], [numel], dtype,
                                        self.device.index)
 
-    def barrier(self) -> None:
-        """Device-side barrier across the heap's ranks on the current stream (no host sync)."""
+    def barrier(self, channel: int = 0) -> None:
+        """Device-side barrier across the heap's ranks on the current stream (no host sync).
+
+        Barriers on one *channel* must all be issued on the same CUDA stream (epochs are assigned in launch order);
+        use a different channel per stream — the ZeRO-3 engine uses channel 1 for its communication stream."""
         if self.world == 1:
             return
         if self._flags is None:
-            self._flags = self.alloc(64, torch.int32)
+            self._flags = self.alloc(64 * 4, torch.int32)        # 4 channels x 64 flag words
+            self._epochs = [0, 0, 0, 0]
             torch.cuda.synchronize(self.device)
             dist.barrier(group=self.group)       # everyone's flag words are zeroed and mapped
-        self._epoch += 1
-        self._C.p2p_barrier(self._flags.ptrs, self.rank, self._epoch)
+        self._epochs[channel] += 1
+        self._C.p2p_barrier(self._flags.peer_ptrs(channel * 64 * 4), self.rank, self._epochs[channel])
 
     def close(self) -> None:
         torch.cuda.synchronize(self.device)

@@ -204,12 +204,12 @@ class ShardedUnit:
             cur = torch.cuda.current_stream(eng.device)
             eng.comm_stream.wait_stream(cur)
             with torch.cuda.stream(eng.comm_stream):
-                eng.heap.barrier()                      # every rank finished writing its grads
+                eng.heap.barrier(1)                     # every rank finished writing its grads (comm-stream channel)
                 es = flat.element_size()
                 for chunk, so, fo in zip(self.chunks, self.shard_offsets, self.full_offsets):
                     eng.C.p2p_reduce_scatter_accum(slot.peer_ptrs(), fo + eng.rank * chunk,
                                                    self.grad_acc[so:so + chunk], scale_eff, eng.rank, None, eng.comm_ctas)
-                eng.heap.barrier()                      # every rank finished reading -> slot reusable
+                eng.heap.barrier(1)                     # every rank finished reading -> slot reusable
                 ev = torch.cuda.Event()
                 ev.record(eng.comm_stream)
             eng.mark_grad_slot_busy(slot, ev)
@@ -494,6 +494,8 @@ class Zero3Engine:
     def step(self, lr: float | None = None) -> dict:
         """Clip + AdamW on every shard.  Returns {'grad_norm': float, 'skipped': bool}."""
         lr = self.lr if lr is None else lr
+        for u in self.units:
+            u.wait_grads()            # comm-stream reduce-scatters (and their barriers) precede this stream's barrier
         if self.heap is not None and self.world > 1:
             self.heap.barrier()       # nobody may still be pulling the shards we are about to rewrite
         tot = self.grad_norm_sq()

@@ -386,14 +386,21 @@ class RolloutEngine:
         x = torch.nn.functional.embedding(ids, self.embed_w["embed"]).to(self.dtype)
         if cfg.family == "gpt2":
             x = x + torch.nn.functional.embedding(pos, self.embed_w["pos_embed"]).to(self.dtype)
+        fused = self.tp is None and cfg.family == "llama" and self.is_cuda and self.dtype == torch.bfloat16
+        delta = None
         for i, w in enumerate(self.layer_w):
             if self.tp is not None:
                 from .tp import layer_decode_tp
 
                 x = layer_decode_tp(self.tp, cfg, w, x, inp, self.k_cache[i], self.v_cache[i])
+            elif fused:
+                x, delta = tf.layer_decode_fused(cfg, w, x, delta, inp, self.k_cache[i], self.v_cache[i])
             else:
                 x = tf.layer_decode(cfg, w, x, inp, self.k_cache[i], self.v_cache[i])
-        h = tf.final_norm(cfg, self.head_w, x)
+        if delta is not None:
+            h = ops.ext().add_rmsnorm_(x, delta, self.head_w["norm_w"], cfg.rms_norm_eps)
+        else:
+            h = tf.final_norm(cfg, self.head_w, x)
         logits = self._lm_logits(h)
         tok, lp = ops.sample_tokens(logits, self.st_temp[:bs], self.st_seeds[:bs], top_k=self._top_k, top_p=self._top_p)
         self.st_out_tok[:bs].copy_(tok)

@@ -74,7 +74,7 @@ class WeightSync:
         self.version = 0
         self.flat = None
         # every process must take part in new_group, in the same order
-        self.bcast_group = dist.new_group([self.trainer_ranks[0], *self.rollout_ranks]) if dist.is_initialized() else None
+        self.bcast_group = dist.new_group(sorted({self.trainer_ranks[0], *self.rollout_ranks})) if dist.is_initialized() else None
         if self.backend == "p2p":
             from ..parallel.symm import SymmetricHeap
 

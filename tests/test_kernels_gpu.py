@@ -277,3 +277,14 @@ def test_skinny_gemm_swiglu_and_fp8(C):
     got = C.skinny_gemm(xq, wq, None, None, xs, wsc, ws, ctr, 0, 0)
     want8 = (xq.float() * xs[:, None]) @ (wq.float() * wsc[:, None]).t()
     assert _rel_err(got, want8) < 5e-3
+
+
+def test_add_rmsnorm(C):
+    torch.manual_seed(22)
+    x = torch.randn(130, 4096, device="cuda", dtype=torch.bfloat16)
+    r = torch.randn(130, 4096, device="cuda", dtype=torch.bfloat16)
+    w = (1 + 0.1 * torch.randn(4096, device="cuda")).to(torch.bfloat16)
+    xs = (x.float() + r.float()).to(torch.bfloat16)
+    want = ref.rmsnorm(xs.float(), w.float(), 1e-5)
+    y = C.add_rmsnorm_(x, r, w, 1e-5)
+    assert torch.equal(x, xs) and _rel_err(y, want) < 5e-3

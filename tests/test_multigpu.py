@@ -24,3 +24,16 @@ def test_peer_memory_paths_match_nccl():
     assert res["reduce_scatter_accum_err"] < 1e-5 and res["reduce_scatter_sumsq_err"] < 1e-3
     assert res["ag_gemm_err"] < 5e-3
     assert res["zero3_p2p_weight_err"] < 2e-2 and res["zero3_nccl_weight_err"] < 2e-2
+
+
+def test_tensor_parallel_rollout_engine():
+    n = 2
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1",
+                        "--master-port", "29656", str(ROOT / "tests" / "tp_worker.py")], capture_output=True, text=True,
+                       timeout=600, env={**os.environ, "PYTHONPATH": str(ROOT)})
+    line = [l for l in r.stdout.splitlines() if l.startswith("TP_RESULTS ")]
+    assert r.returncode == 0 and line, r.stdout[-2000:] + r.stderr[-3000:]
+    res = json.loads(line[0].split(" ", 1)[1])
+    assert res["lockstep_graph0"] and res["lockstep_graph1"]
+    assert res["first8_agreement_graph0"] > 0.9 and res["first8_agreement_graph1"] > 0.9
+    assert res["token_agreement_vs_single_gpu_graph0"] > 0.6 and res["token_agreement_vs_single_gpu_graph1"] > 0.6
