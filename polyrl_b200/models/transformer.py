@@ -97,6 +97,8 @@ class PackedInput:
     position_ids: torch.Tensor     # [T] int64
     cu_seqlens: torch.Tensor       # [B+1] int32
     max_seqlen: int
+    sp_group: object = None        # Ulysses SP: ids/positions are this rank's slice, cu_seqlens describe the full stream
+    total_tokens: int = 0          # un-padded length of the full packed stream (SP only)
 
 
 # --------------------------------------------------------------------------------------------
@@ -125,7 +127,12 @@ def layer_forward(cfg: ModelConfig, w: dict, x: torch.Tensor, inp: PackedInput, 
         q = qkv[:, : nq * d].view(t, nq, d)
         k = qkv[:, nq * d:(nq + nkv) * d].view(t, nkv, d)
         v = qkv[:, (nq + nkv) * d:].view(t, nkv, d)
-        a = attention_varlen(q, k, v, inp.cu_seqlens, inp.max_seqlen, causal=True)
+        if inp.sp_group is not None:
+            from ..parallel.ulysses import ulysses_attention
+
+            a = ulysses_attention(q, k, v, inp.cu_seqlens, inp.max_seqlen, inp.sp_group, inp.total_tokens, causal=True)
+        else:
+            a = attention_varlen(q, k, v, inp.cu_seqlens, inp.max_seqlen, causal=True)
         x = ops.linear(a.reshape(t, nq * d), w["wo"], residual=x)
         h = ops.rmsnorm(x, w["ln2"], cfg.rms_norm_eps)
         a = ops.linear_swiglu(h, w["wgu"])

@@ -335,8 +335,9 @@ class Zero3Engine:
 
     def __init__(self, cfg: ModelConfig, device, group=None, comm: str = "nccl", param_dtype=None, trainable: bool = True,
                  seed: int = 0, lr: float = 1e-6, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.01,
-                 max_grad_norm: float = 1.0, heap=None, comm_ctas: int = 32, init: bool = True):
+                 max_grad_norm: float = 1.0, heap=None, comm_ctas: int = 32, init: bool = True, sp_group=None):
         self.cfg = cfg
+        self.sp_group = sp_group       # Ulysses sequence-parallel group (subset of `group`), or None
         self.device = torch.device(device)
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -454,6 +455,18 @@ class Zero3Engine:
             r.next_bwd = chain[-1].units[0]
 
     def forward_hidden(self, inp: tf.PackedInput) -> torch.Tensor:
+        sp = self.sp_group
+        if sp is not None and dist.get_world_size(sp) > 1:
+            from .ulysses import GatherSeq, ulysses_pad_and_slice, validate_sp
+
+            validate_sp(self.cfg.num_heads, self.cfg.num_kv_heads, dist.get_world_size(sp))
+            total = inp.input_ids.shape[0]
+            ids, pos, _ = ulysses_pad_and_slice(inp.input_ids, inp.position_ids, sp, self.cfg.pad_token_id)
+            local = tf.PackedInput(ids, pos, inp.cu_seqlens, inp.max_seqlen, sp_group=sp, total_tokens=total)
+            x = self.embed_runner(local, ids, pos)
+            for r in self.layer_runners:
+                x = r(local, x)
+            return GatherSeq.apply(x, sp, True)[:total]      # full hidden on every SP rank; grads scaled by sp on the way back
         x = self.embed_runner(inp, inp.input_ids, inp.position_ids)
         for r in self.layer_runners:
             x = r(inp, x)

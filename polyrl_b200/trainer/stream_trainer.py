@@ -112,17 +112,18 @@ class StreamPPOTrainer:
 
     def _balance_and_shard(self, batch: DataProto, metrics: dict) -> DataProto:
         """Karmarkar-Karp reorder so every DP rank gets a similar token count, then take this rank's shard."""
-        if self.world == 1:
+        dp, dp_rank = getattr(self.worker, "dp_size", self.world), getattr(self.worker, "dp_rank", self.rank)
+        if dp == 1:
             return batch
-        batch, pad = pad_dataproto_to_divisor(batch, self.world)
+        batch, pad = pad_dataproto_to_divisor(batch, dp)
         if pad:
             batch.batch["response_mask"][-pad:] = 0        # padded duplicates carry no loss
         if self.config.trainer.balance_batch:
             lens = batch.batch["attention_mask"].sum(-1).tolist()
-            parts = get_seqlen_balanced_partitions([int(x) for x in lens], self.world, equal_size=True)
+            parts = get_seqlen_balanced_partitions([int(x) for x in lens], dp, equal_size=True)
             metrics.update(log_seqlen_unbalance([int(x) for x in lens], parts, "global_seqlen"))
             batch.reorder(torch.tensor([i for p in parts for i in p], dtype=torch.long))
-        return batch.chunk(self.world)[self.rank]
+        return batch.chunk(dp)[dp_rank]       # ranks of one Ulysses SP group share the same shard
 
     def _reward(self, batch: DataProto) -> torch.Tensor:
         if self.reward_fn is None:

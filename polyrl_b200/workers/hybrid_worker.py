@@ -75,6 +75,7 @@ class ActorRolloutRefWorker:
         self.weight_version = 0
         self._rollout_full: dict | None = None
         self.profiler = None
+        self.sp_size, self.dp_size, self.dp_rank, self.sp_group = 1, self.world, self.rank, None
 
     # ------------------------------------------------------------------ init
     def init_model(self) -> None:
@@ -84,11 +85,24 @@ class ActorRolloutRefWorker:
         comm = arr.actor.fsdp_config.comm_backend
         opt = arr.actor.optim
         seed = cfg.data.seed
+        # Ulysses SP: consecutive ranks form an SP group; data parallelism is over the remaining dimension
+        sp = max(1, arr.actor.ulysses_sequence_parallel_size)
+        if self.world % sp != 0:
+            raise ValueError(f"world size {self.world} not divisible by ulysses_sequence_parallel_size {sp}")
+        self.sp_size, self.dp_size, self.dp_rank = sp, self.world // sp, self.rank // sp
+        self.sp_group = None
+        if sp > 1:
+            base = dist.get_process_group_ranks(self.group) if self.group is not None else list(range(self.world))
+            for g in range(self.dp_size):       # every process creates every group, in the same order
+                grp = dist.new_group([base[g * sp + i] for i in range(sp)])
+                if g == self.dp_rank:
+                    self.sp_group = grp
         if self.has_actor:
             self.actor_engine = Zero3Engine(self.model_cfg, self.device, group=self.group, comm=comm, trainable=True,
                                             seed=seed, lr=opt.lr, betas=tuple(opt.betas), eps=opt.eps,
-                                            weight_decay=opt.weight_decay, max_grad_norm=arr.actor.grad_clip)
-            n_dp = self.world
+                                            weight_decay=opt.weight_decay, max_grad_norm=arr.actor.grad_clip,
+                                            sp_group=self.sp_group)
+            n_dp = self.dp_size
             a = arr.actor
             mini = max(1, a.ppo_mini_batch_size * arr.rollout.n // n_dp)      # per-GPU samples per optimizer step
             micro = a.ppo_micro_batch_size_per_gpu or (max(1, a.ppo_micro_batch_size // n_dp) if a.ppo_micro_batch_size else None)
@@ -103,7 +117,8 @@ class ActorRolloutRefWorker:
         if self.has_ref:
             # reference policy = frozen copy of the initial actor weights (same seed => identical init)
             self.ref_engine = Zero3Engine(self.model_cfg, self.device, group=self.group, comm=comm, trainable=False,
-                                          seed=seed, heap=self.actor_engine.heap if self.actor_engine else None)
+                                          seed=seed, heap=self.actor_engine.heap if self.actor_engine else None,
+                                          sp_group=self.sp_group)
             self.ref_actor = DataParallelPPOActor(self.ref_engine, ActorRuntimeConfig(), dp_group=self.group)
         if self.has_rollout:
             r = arr.rollout

@@ -54,3 +54,13 @@ def test_grpo_colocated_single_process(tmp_path):
     r = _run(1, ov)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "step:2" in r.stdout and "actor/kl_loss" in r.stdout and "val-core/" in r.stdout
+
+
+def test_ulysses_sp_equivalence_gloo():
+    env = {**os.environ, "PYTHONPATH": str(ROOT), "OMP_NUM_THREADS": "2", "ULYSSES_DEVICE": "cpu"}
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29677", str(ROOT / "tests" / "ulysses_worker.py")], capture_output=True, text=True, timeout=600, env=env)
+    line = [l for l in r.stdout.splitlines() if l.startswith("ULYSSES_RESULTS")]
+    assert r.returncode == 0 and line, r.stdout[-2000:] + r.stderr[-2000:]
+    vals = dict(kv.split("=") for kv in line[0].split()[1:])
+    assert float(vals["lp_err"]) < 1e-4 and float(vals["w_err"]) < 1e-3

@@ -1,0 +1,47 @@
+"""Ulysses SP equivalence (torchrun, gloo/CPU or nccl/GPU): SP=world vs no-SP logprobs and parameter gradients."""
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+
+def main():
+    cuda = torch.cuda.is_available() and os.environ.get("ULYSSES_DEVICE", "auto") != "cpu"
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    if cuda:
+        torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
+        dev = torch.device("cuda", int(os.environ["LOCAL_RANK"]))
+        dist.init_process_group("nccl", device_id=dev)
+    else:
+        dev = torch.device("cpu")
+        dist.init_process_group("gloo")
+    from polyrl_b200.models import get_model_config, pack_padded
+    from polyrl_b200.parallel.zero3 import Zero3Engine
+
+    cfg = get_model_config("tiny-llama-128" if cuda else "tiny-llama")
+    torch.manual_seed(5)
+    ids = torch.randint(3, cfg.vocab_size, (3, 21), device=dev)
+    mask = torch.ones_like(ids)
+    mask[1, 15:] = 0
+    inp, _ = pack_padded(ids, mask)
+    labels = torch.randint(0, cfg.vocab_size, (inp.input_ids.numel(),), device=dev)
+    outs = {}
+    for name, sp_group in (("nosp", None), ("sp", dist.group.WORLD)):
+        eng = Zero3Engine(cfg, dev, comm="nccl", lr=1e-2, weight_decay=0.0, seed=7, sp_group=sp_group)
+        lp, ent = eng.forward_logprob_entropy(inp, labels, 1.0)
+        (-(lp.mean()) + 0.01 * ent.mean()).backward()
+        eng.step()
+        outs[name] = (lp.detach().float().cpu(), {n: t.float().cpu().clone() for n, t in eng.named_full_tensors()})
+    lp_err = (outs["sp"][0] - outs["nosp"][0]).abs().max().item()
+    w_err = max(((outs["sp"][1][k] - outs["nosp"][1][k]).norm() / (outs["nosp"][1][k].norm() + 1e-9)).item() for k in outs["sp"][1])
+    if rank == 0:
+        print(f"ULYSSES_RESULTS lp_err={lp_err:.3e} w_err={w_err:.3e}", flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
