@@ -540,6 +540,31 @@ class Zero3Engine:
             self.heap.barrier()       # peers must see the new shards before the next pull
         return {"grad_norm": norm, "skipped": skipped}
 
+    # ---- optimizer-state offload (reference: verl/utils/fsdp_utils.py:204-225 offload/load_fsdp_optimizer) ------
+    def offload_optimizer(self) -> None:
+        """Move fp32 master weights and Adam moments to pinned host memory (frees 12 B/param of HBM for the rollout
+        phase of a colocated step); ``load_optimizer`` brings them back before the next update."""
+        if not self.trainable or not self.is_cuda or getattr(self, "_opt_offloaded", False):
+            return
+        for u in self.units:
+            for name in ("master", "exp_avg", "exp_avg_sq", "grad_acc"):
+                t = getattr(u, name)
+                host = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+                host.copy_(t, non_blocking=True)
+                setattr(u, name, host)
+        torch.cuda.synchronize(self.device)
+        torch.cuda.empty_cache()
+        self._opt_offloaded = True
+
+    def load_optimizer(self) -> None:
+        if not getattr(self, "_opt_offloaded", False):
+            return
+        for u in self.units:
+            for name in ("master", "exp_avg", "exp_avg_sq", "grad_acc"):
+                setattr(u, name, getattr(u, name).to(self.device, non_blocking=True))
+        torch.cuda.synchronize(self.device)
+        self._opt_offloaded = False
+
     # ---- full-weight access (rollout sync / export) ---------------------------------------------
     def gather_unit_full(self, unit: ShardedUnit) -> dict[str, torch.Tensor]:
         full = unit.acquire()

@@ -222,6 +222,32 @@ class ActorRolloutRefWorker:
         rep.non_tensor_batch["aborted"] = aborted
         return rep
 
+    # ------------------------------------------------------------------ streaming rollout through the manager
+    def attach_rollout_client(self, client) -> None:
+        """Rank 0 holds the manager connection (``rollout.remote_client.RemoteRolloutClient``)."""
+        self.rollout_client = client
+        self._stream_iter = None
+
+    def generate_sequences_remote(self, prompts: DataProto) -> bool:
+        """Submit the (unsharded) prompt batch to the rollout manager; returns once the request is in flight.
+        Results are consumed with ``get_stream_batches`` (reference API: stream_fsdp_workers.py:448-507)."""
+        if getattr(self, "rollout_client", None) is not None and self.rank == 0:
+            r = self.config.actor_rollout_ref.rollout
+            self._stream_iter = iter(self.rollout_client.generate_sequences_remote(
+                prompts, {"temperature": r.temperature, "top_p": r.top_p, "top_k": r.top_k}))
+        return True
+
+    def get_stream_batches(self) -> DataProto | None:
+        """Next streamed micro-batch (rank 0) or ``None`` at the end of the stream."""
+        it = getattr(self, "_stream_iter", None)
+        if it is None:
+            return None
+        try:
+            return next(it)
+        except StopIteration:
+            self._stream_iter = None
+            return None
+
     # ------------------------------------------------------------------ log-probs
     @torch.no_grad()
     def compute_log_prob(self, data: DataProto) -> DataProto:
@@ -252,8 +278,19 @@ class ActorRolloutRefWorker:
         total = opt.total_training_steps if opt.total_training_steps > 0 else (self.config.trainer.total_training_steps or 0)
         lr = lr_at_step(opt, self.lr_step, total)
         t0 = time.time()
+        offload = self.config.actor_rollout_ref.actor.fsdp_config.optimizer_offload
+        if offload:
+            self.actor_engine.load_optimizer()
         metrics = self.actor.update_policy_stream(data, is_opt_step=is_opt, lr=lr)
+        if offload and is_opt:
+            self.actor_engine.offload_optimizer()
         metrics["actor/lr"] = [lr]
+        # MFU of this update (fwd + recompute + bwd counted as the standard 6·N·T model FLOPs)
+        from ..utils.flops_counter import FlopsCounter
+
+        seqlens = data.batch["attention_mask"].sum(-1).tolist()
+        achieved, peak = FlopsCounter(self.model_cfg).estimate_flops([int(x) for x in seqlens], time.time() - t0)
+        metrics["perf/mfu/actor"] = [achieved / peak if peak != float("inf") else 0.0]
         if is_lr:
             self.lr_step += 1
         metrics["perf/update_actor_s"] = [time.time() - t0]
@@ -296,6 +333,36 @@ class ActorRolloutRefWorker:
         from ..utils.profiler import dump_memory_snapshot
 
         dump_memory_snapshot(self.config.global_profiler.save_path, tag, sub_dir, self.rank)
+
+
+class RewardModelWorker:
+    """Model-based reward: a value-head transformer scores each (prompt, response); the scalar at the last valid response
+    token becomes ``rm_scores`` (reference: verl/workers/fsdp_workers.py:1573-1925 ``RewardModelWorker.compute_rm_score``)."""
+
+    def __init__(self, config: PPOConfig, device=None, group=None):
+        self.config, self.group = config, group
+        if device is None:
+            device = f"cuda:{int(os.environ.get('LOCAL_RANK', 0))}" if torch.cuda.is_available() else "cpu"
+        self.device = torch.device(device)
+
+    def init_model(self, heap=None) -> None:
+        rm = self.config.reward_model
+        self.model_cfg = get_model_config(rm.model.path, **{**rm.model.override_config, "value_head": True})
+        self.engine = Zero3Engine(self.model_cfg, self.device, group=self.group, comm="nccl", trainable=False,
+                                  seed=self.config.data.seed + 2, heap=heap)
+        rt = ActorRuntimeConfig(ppo_micro_batch_size_per_gpu=rm.micro_batch_size_per_gpu)
+        self.scorer = DataParallelPPOCritic(self.engine, rt, dp_group=self.group)
+
+    @torch.no_grad()
+    def compute_rm_score(self, data: DataProto) -> DataProto:
+        data.meta_info.setdefault("micro_batch_size", self.config.reward_model.micro_batch_size_per_gpu)
+        values = self.scorer.compute_values(data)                     # value BEFORE each response token
+        mask = data.batch["response_mask"] if "response_mask" in data.batch else data.batch["attention_mask"][:, -values.shape[1]:]
+        last = (mask.sum(-1).long() - 1).clamp_min(0)
+        score = values.gather(1, last[:, None]).squeeze(1)
+        out = torch.zeros_like(values)
+        out[torch.arange(out.shape[0], device=out.device), last] = score
+        return DataProto.from_dict({"rm_scores": out * (mask.sum(-1, keepdim=True) > 0)})
 
 
 class CriticWorker:
