@@ -37,7 +37,7 @@ __device__ __forceinline__ void merge(SampleState& a, const SampleState& b) {
 }
 
 template <typename T>
-__global__ void __launch_bounds__(512)
+__global__ void __launch_bounds__(1024)
 sample_kernel(const T* __restrict__ logits, int64_t ld, int V, const float* __restrict__ inv_temp,
               const uint64_t* __restrict__ seeds, int greedy_all, int64_t* __restrict__ out_tok,
               float* __restrict__ out_lp) {
@@ -48,14 +48,34 @@ sample_kernel(const T* __restrict__ logits, int64_t ld, int V, const float* __re
   const float scale = greedy ? 1.f : it;
   const uint64_t seed = seeds ? seeds[row] : 0;
   SampleState st{-INFINITY, 0x7fffffff, 0.f, -INFINITY, 0.f};
-  for (int c = threadIdx.x; c < V; c += blockDim.x) {
-    const float z = static_cast<float>(lr[c]) * scale;
+  auto visit = [&](int c, float raw) {
+    const float z = raw * scale;
     const float key = greedy ? z : z + gumbel_noise(seed, row, c);
     if (key > st.best) { st.best = key; st.best_idx = c; st.best_z = z; }
     const float nm = fmaxf(st.m, z);
     st.s = st.s * __expf(st.m - nm) + __expf(z - nm);
     st.m = nm;
+  };
+  int c0 = 0;
+  if constexpr (sizeof(T) == 2) {
+    // 128-bit vector loads (8 bf16) when the row is 16-byte aligned: 8x fewer load instructions (profile: the scalar
+    // version took 131 us per step for [128, 128256] logits)
+    if ((reinterpret_cast<uintptr_t>(lr) & 15) == 0) {
+      const int nvec = V >> 3;
+      for (int v = threadIdx.x; v < nvec; v += blockDim.x) {
+        const int4 q = ld_nc_v4(reinterpret_cast<const __nv_bfloat16*>(lr) + 8 * v);
+        const uint32_t* u = reinterpret_cast<const uint32_t*>(&q);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = unpack_bf16(u[j]);
+          visit(8 * v + 2 * j, f.x);
+          visit(8 * v + 2 * j + 1, f.y);
+        }
+      }
+      c0 = nvec << 3;
+    }
   }
+  for (int c = c0 + threadIdx.x; c < V; c += blockDim.x) visit(c, static_cast<float>(lr[c]));
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     SampleState other;
@@ -66,7 +86,7 @@ sample_kernel(const T* __restrict__ logits, int64_t ld, int V, const float* __re
     other.s = __shfl_xor_sync(0xffffffffu, st.s, o);
     merge(st, other);
   }
-  __shared__ SampleState red[16];
+  __shared__ SampleState red[32];
   const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
   if (l == 0) red[w] = st;
   __syncthreads();
@@ -87,10 +107,10 @@ extern "C" int prl_sample(const void* logits, int dtype, int64_t ld, int B, int 
                           const uint64_t* seeds, int greedy_all, int64_t* out_tok, float* out_lp, cudaStream_t s) {
   if (B <= 0) return 0;
   if (dtype == 0)
-    sample_kernel<float><<<B, 512, 0, s>>>(static_cast<const float*>(logits), ld, V, inv_temp, seeds, greedy_all,
+    sample_kernel<float><<<B, 1024, 0, s>>>(static_cast<const float*>(logits), ld, V, inv_temp, seeds, greedy_all,
                                            out_tok, out_lp);
   else
-    sample_kernel<__nv_bfloat16><<<B, 512, 0, s>>>(static_cast<const __nv_bfloat16*>(logits), ld, V, inv_temp, seeds,
+    sample_kernel<__nv_bfloat16><<<B, 1024, 0, s>>>(static_cast<const __nv_bfloat16*>(logits), ld, V, inv_temp, seeds,
                                                    greedy_all, out_tok, out_lp);
   PRL_CUDA_CHECK(cudaGetLastError());
   return 0;

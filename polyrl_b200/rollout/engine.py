@@ -63,6 +63,7 @@ class Request:
     shared_prefix_blocks: int = 0
     t_arrival: float = 0.0
     group: object = None                   # requests of one n-sample group share prompt KV pages
+    donor: object = None                   # the group member whose prefill this request re-uses
 
     @property
     def finished(self) -> bool:
@@ -280,6 +281,7 @@ class RolloutEngine:
                 self.alloc.share(pre)
                 r.blocks = pre + self.alloc.alloc(fresh)
                 r.shared_prefix_blocks = full_prompt_pages
+                r.donor = donor
             else:
                 r.blocks = self.alloc.alloc(need)
                 if r.group is not None:
@@ -310,16 +312,18 @@ class RolloutEngine:
     @torch.no_grad()
     def _prefill(self, reqs: list[Request]) -> None:
         cfg, dev = self.cfg, self.device
-        # requests that share prompt pages with a donor in the same batch still run the full prompt here
-        # (their page writes of the shared pages are redundant but identical); simple and correct.
+        # n-sample groups: only the donor runs the prompt; followers share its full KV pages, copy its partial last
+        # page and sample their own first token from the donor's last-position logits.
+        donors = [r for r in reqs if r.donor is None]
+        d_index = {id(r): i for i, r in enumerate(donors)}
         ids, pos, slots, lens = [], [], [], []
-        for r in reqs:
+        for r in donors:
             n = len(r.prompt_ids)
             ids += r.prompt_ids
             pos += list(range(n))
             slots += [r.blocks[t // PAGE] * PAGE + t % PAGE for t in range(n)]
             lens.append(n)
-        cu = torch.zeros(len(reqs) + 1, dtype=torch.int32)
+        cu = torch.zeros(len(donors) + 1, dtype=torch.int32)
         cu[1:] = torch.tensor(lens, dtype=torch.int32).cumsum(0)
         inp = tf.PackedInput(torch.tensor(ids, dtype=torch.long, device=dev), torch.tensor(pos, dtype=torch.long, device=dev),
                              cu.to(dev), max(lens))
@@ -334,13 +338,29 @@ class RolloutEngine:
                 x = tf.layer_forward(cfg, w, x, inp, kv_sink=(self.k_cache[i], self.v_cache[i], slot_t))
         last = (cu[1:] - 1).long().to(dev)
         h = tf.final_norm(cfg, self.head_w, x.index_select(0, last))
-        logits = self._lm_logits(h)
+        logits_d = self._lm_logits(h)
+        src_blk, dst_blk = [], []
+        for r in reqs:
+            if r.donor is not None and len(r.prompt_ids) % PAGE != 0:
+                fp = len(r.prompt_ids) // PAGE
+                src_blk.append(r.donor.blocks[fp])
+                dst_blk.append(r.blocks[fp])
+        if dst_blk:
+            s_t = torch.tensor(src_blk, dtype=torch.long, device=dev)
+            d_t = torch.tensor(dst_blk, dtype=torch.long, device=dev)
+            for i in range(len(self.layer_w)):
+                self.k_cache[i].index_copy_(0, d_t, self.k_cache[i].index_select(0, s_t))
+                self.v_cache[i].index_copy_(0, d_t, self.v_cache[i].index_select(0, s_t))
+        row = torch.tensor([d_index[id(r.donor if r.donor is not None else r)] for r in reqs], dtype=torch.long, device=dev)
+        logits = logits_d.index_select(0, row)
         temps = torch.tensor([r.params.temperature for r in reqs], dtype=torch.float32, device=dev)
         seeds = torch.tensor([self._seed_for(r, 0) for r in reqs], dtype=torch.long, device=dev)
         p0 = reqs[0].params
         tok, lp = ops.sample_tokens(logits, temps, seeds, greedy=False, top_k=p0.top_k, top_p=p0.top_p)
         tok_c, lp_c = tok.tolist(), lp.tolist()
         self.stats["prefill_tokens"] += len(ids)
+        for r in reqs:
+            r.donor = None            # release the reference; pages stay shared through the allocator's ref-counts
         live, rows = [], []
         for r, t, l in zip(reqs, tok_c, lp_c):
             self._append_token(r, t, l)
@@ -478,10 +498,11 @@ class RolloutEngine:
         self._pending = None
         if ev is not None:
             ev.synchronize()
+        toks, lps = h_tok.tolist(), h_lp.tolist()      # one bulk conversion instead of 2 tensor-scalar reads per request
         for s, r in slots:
             if r.finished:
                 continue
-            self._append_token(r, int(h_tok[s]), float(h_lp[s]))
+            self._append_token(r, toks[s], lps[s])
             if r.finished:
                 done.append(r)
         return done
