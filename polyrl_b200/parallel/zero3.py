@@ -335,9 +335,14 @@ class Zero3Engine:
 
     def __init__(self, cfg: ModelConfig, device, group=None, comm: str = "nccl", param_dtype=None, trainable: bool = True,
                  seed: int = 0, lr: float = 1e-6, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.01,
-                 max_grad_norm: float = 1.0, heap=None, comm_ctas: int = 32, init: bool = True, sp_group=None):
+                 max_grad_norm: float = 1.0, heap=None, comm_ctas: int = 32, init: bool = True, sp_group=None,
+                 replica_group=None):
         self.cfg = cfg
         self.sp_group = sp_group       # Ulysses sequence-parallel group (subset of `group`), or None
+        # HSDP (reference: fsdp_size < world => 2-D mesh ["ddp","fsdp"], verl/workers/fsdp_workers.py:99-118):
+        # `group` is the shard (ZeRO) group, `replica_group` links the ranks that own the same shard in each replica;
+        # shard gradients are averaged over it right before the optimizer step.
+        self.replica_group = replica_group
         self.device = torch.device(device)
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -511,6 +516,11 @@ class Zero3Engine:
             u.wait_grads()            # comm-stream reduce-scatters (and their barriers) precede this stream's barrier
         if self.heap is not None and self.world > 1:
             self.heap.barrier()       # nobody may still be pulling the shards we are about to rewrite
+        if self.replica_group is not None and dist.get_world_size(self.replica_group) > 1:
+            nrep = dist.get_world_size(self.replica_group)
+            for u in self.units:
+                dist.all_reduce(u.grad_acc, group=self.replica_group)
+                u.grad_acc.div_(nrep)
         tot = self.grad_norm_sq()
         self.opt_step += 1
         b1, b2 = self.betas

@@ -97,11 +97,26 @@ class ActorRolloutRefWorker:
                 grp = dist.new_group([base[g * sp + i] for i in range(sp)])
                 if g == self.dp_rank:
                     self.sp_group = grp
+        # HSDP: fsdp_size < world => shard inside consecutive blocks of fsdp_size ranks, replicate across blocks
+        fs = arr.actor.fsdp_config.fsdp_size
+        self.shard_group, self.replica_group = self.group, None
+        if dist.is_initialized() and 0 < fs < self.world:
+            if self.world % fs != 0:
+                raise ValueError(f"world size {self.world} not divisible by fsdp_size {fs}")
+            base = dist.get_process_group_ranks(self.group) if self.group is not None else list(range(self.world))
+            for b in range(self.world // fs):
+                grp = dist.new_group(base[b * fs:(b + 1) * fs])
+                if b == self.rank // fs:
+                    self.shard_group = grp
+            for i in range(fs):
+                grp = dist.new_group(base[i::fs])
+                if i == self.rank % fs:
+                    self.replica_group = grp
         if self.has_actor:
-            self.actor_engine = Zero3Engine(self.model_cfg, self.device, group=self.group, comm=comm, trainable=True,
+            self.actor_engine = Zero3Engine(self.model_cfg, self.device, group=self.shard_group, comm=comm, trainable=True,
                                             seed=seed, lr=opt.lr, betas=tuple(opt.betas), eps=opt.eps,
                                             weight_decay=opt.weight_decay, max_grad_norm=arr.actor.grad_clip,
-                                            sp_group=self.sp_group)
+                                            sp_group=self.sp_group, replica_group=self.replica_group)
             n_dp = self.dp_size
             a = arr.actor
             mini = max(1, a.ppo_mini_batch_size * arr.rollout.n // n_dp)      # per-GPU samples per optimizer step
@@ -116,7 +131,7 @@ class ActorRolloutRefWorker:
             self.actor = DataParallelPPOActor(self.actor_engine, rt, dp_group=self.group)
         if self.has_ref:
             # reference policy = frozen copy of the initial actor weights (same seed => identical init)
-            self.ref_engine = Zero3Engine(self.model_cfg, self.device, group=self.group, comm=comm, trainable=False,
+            self.ref_engine = Zero3Engine(self.model_cfg, self.device, group=self.shard_group, comm=comm, trainable=False,
                                           seed=seed, heap=self.actor_engine.heap if self.actor_engine else None,
                                           sp_group=self.sp_group)
             self.ref_actor = DataParallelPPOActor(self.ref_engine, ActorRuntimeConfig(), dp_group=self.group)

@@ -64,3 +64,14 @@ def test_ulysses_sp_equivalence_gloo():
     assert r.returncode == 0 and line, r.stdout[-2000:] + r.stderr[-2000:]
     vals = dict(kv.split("=") for kv in line[0].split()[1:])
     assert float(vals["lp_err"]) < 1e-4 and float(vals["w_err"]) < 1e-3
+
+
+def test_hsdp_equivalence_gloo():
+    """fsdp_size=2 x 2 replicas must match plain ZeRO-3 over 4 ranks (reference HSDP mesh: fsdp_workers.py:99-118)."""
+    env = {**os.environ, "PYTHONPATH": str(ROOT), "OMP_NUM_THREADS": "1", "HSDP_DEVICE": "cpu"}
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=4", "--master-addr", "127.0.0.1",
+                        "--master-port", "29688", str(ROOT / "tests" / "hsdp_worker.py")], capture_output=True, text=True, timeout=600, env=env)
+    line = [l for l in r.stdout.splitlines() if l.startswith("HSDP_RESULTS")]
+    assert r.returncode == 0 and line, r.stdout[-2000:] + r.stderr[-2000:]
+    vals = dict(kv.split("=") for kv in line[0].split()[1:])
+    assert float(vals["w_err"]) < 1e-4 and float(vals["gn_err"]) < 1e-4
