@@ -1,0 +1,201 @@
+"""Tool abstraction for multi-turn rollouts.
+
+A tool has an OpenAI-function style schema (rendered into the system prompt by the chat template) and a
+per-trajectory lifecycle: ``create`` -> ``execute``* -> ``calc_reward`` -> ``release``.
+
+Capability parity: 3rdparty/verl/verl/tools/base_tool.py:24-95 (BaseTool lifecycle), tools/schemas.py:21-80
+(OpenAI function schema + parsed call), tools/gsm8k_tool.py:31-110 (answer-checking tool with step rewards),
+tools/utils/tool_registry.py (config-driven instantiation).  The implementation is synchronous — the batched
+``MultiTurnRollout`` scheduler runs tool calls on a thread pool while the engine keeps decoding the other
+trajectories of the continuous batch.
+"""
+from __future__ import annotations
+
+import ast
+import importlib
+import json
+import operator
+import uuid
+from dataclasses import dataclass, field
+from typing import Any
+
+
+@dataclass
+class ToolSchema:
+    name: str
+    description: str = ""
+    parameters: dict = field(default_factory=lambda: {"type": "object", "properties": {}, "required": []})
+    strict: bool = False
+
+    def to_openai(self) -> dict:
+        return {"type": "function", "function": {"name": self.name, "description": self.description,
+                                                 "parameters": self.parameters, "strict": self.strict}}
+
+    @classmethod
+    def from_openai(cls, d: dict) -> "ToolSchema":
+        f = d.get("function", d)
+        return cls(name=f["name"], description=f.get("description", ""),
+                   parameters=f.get("parameters") or {"type": "object", "properties": {}, "required": []},
+                   strict=bool(f.get("strict", False)))
+
+    def validate_arguments(self, args: Any) -> tuple[dict, str | None]:
+        """Returns (arguments, error).  Checks JSON-object-ness and required keys."""
+        if isinstance(args, str):
+            try:
+                args = json.loads(args)
+            except json.JSONDecodeError as e:
+                return {}, f"arguments are not valid JSON: {e}"
+        if not isinstance(args, dict):
+            return {}, "arguments must be a JSON object"
+        missing = [k for k in self.parameters.get("required", []) if k not in args]
+        if missing:
+            return args, f"missing required argument(s): {', '.join(missing)}"
+        return args, None
+
+
+@dataclass
+class ToolResponse:
+    text: str = ""
+    image: Any = None          # multimodal payloads are carried through untouched
+    video: Any = None
+
+    def is_empty(self) -> bool:
+        return not self.text and self.image is None and self.video is None
+
+
+class BaseTool:
+    """Override ``execute`` (and optionally ``create`` / ``calc_reward`` / ``release``)."""
+
+    def __init__(self, config: dict | None = None, schema: ToolSchema | None = None):
+        self.config = config or {}
+        self.schema = schema or self.default_schema()
+        self.name = self.schema.name
+        self._instances: dict[str, dict] = {}
+
+    @classmethod
+    def default_schema(cls) -> ToolSchema:
+        return ToolSchema(name=cls.__name__.lower())
+
+    def create(self, instance_id: str | None = None, **kwargs) -> tuple[str, ToolResponse]:
+        iid = instance_id or uuid.uuid4().hex
+        self._instances[iid] = dict(kwargs)
+        return iid, ToolResponse()
+
+    def execute(self, instance_id: str, parameters: dict[str, Any], **kwargs) -> tuple[ToolResponse, float, dict]:
+        """Returns (response shown to the model, step reward, metrics)."""
+        return ToolResponse(text="ok"), 0.0, {}
+
+    def calc_reward(self, instance_id: str, **kwargs) -> float:
+        return 0.0
+
+    def release(self, instance_id: str, **kwargs) -> None:
+        self._instances.pop(instance_id, None)
+
+
+# ------------------------------------------------------------------------------------------------ built-in tools
+_BIN = {ast.Add: operator.add, ast.Sub: operator.sub, ast.Mult: operator.mul, ast.Div: operator.truediv,
+        ast.FloorDiv: operator.floordiv, ast.Mod: operator.mod, ast.Pow: operator.pow}
+_UN = {ast.UAdd: operator.pos, ast.USub: operator.neg}
+
+
+def safe_arith(expr: str) -> float:
+    """Evaluate + - * / // % ** and parentheses over numbers — no names, calls or attribute access."""
+    def ev(node):
+        if isinstance(node, ast.Expression):
+            return ev(node.body)
+        if isinstance(node, ast.Constant) and isinstance(node.value, (int, float)):
+            return node.value
+        if isinstance(node, ast.BinOp) and type(node.op) in _BIN:
+            a, b = ev(node.left), ev(node.right)
+            if isinstance(node.op, ast.Pow) and (abs(a) > 1e6 or abs(b) > 64):
+                raise ValueError("exponent too large")
+            return _BIN[type(node.op)](a, b)
+        if isinstance(node, ast.UnaryOp) and type(node.op) in _UN:
+            return _UN[type(node.op)](ev(node.operand))
+        raise ValueError(f"unsupported expression element: {type(node).__name__}")
+    return ev(ast.parse(expr.strip(), mode="eval"))
+
+
+class CalculatorTool(BaseTool):
+    @classmethod
+    def default_schema(cls) -> ToolSchema:
+        return ToolSchema(name="calculator", description="Evaluate an arithmetic expression.",
+                          parameters={"type": "object", "required": ["expression"],
+                                      "properties": {"expression": {"type": "string", "description": "e.g. (3+4)*5"}}})
+
+    def execute(self, instance_id, parameters, **kwargs):
+        try:
+            val = safe_arith(str(parameters.get("expression", "")))
+            return ToolResponse(text=f"{val:g}" if isinstance(val, float) else str(val)), 0.0, {"calc_ok": 1}
+        except Exception as e:                                     # the model sees the error and may retry
+            return ToolResponse(text=f"error: {e}"), 0.0, {"calc_ok": 0}
+
+
+class Gsm8kTool(BaseTool):
+    """`calc_gsm8k_reward(answer)`: tells the model whether its answer matches the ground truth; repeated
+    non-improving submissions get a small penalty (same shaping as the reference tool)."""
+
+    @classmethod
+    def default_schema(cls) -> ToolSchema:
+        return ToolSchema(name="calc_gsm8k_reward", description="Check a candidate final answer for the GSM8K problem.",
+                          parameters={"type": "object", "required": ["answer"],
+                                      "properties": {"answer": {"type": "string", "description": "the numeric answer"}}})
+
+    def create(self, instance_id=None, ground_truth: str | None = None, **kwargs):
+        iid, resp = super().create(instance_id, **kwargs)
+        self._instances[iid] = {"ground_truth": ground_truth, "response": "", "reward": 0.0}
+        return iid, resp
+
+    def execute(self, instance_id, parameters, **kwargs):
+        st = self._instances[instance_id]
+        ans = str(parameters.get("answer", "")).strip()
+        st["response"] = ans if ans.startswith("#### ") else "#### " + ans
+        reward = self.calc_reward(instance_id)
+        step = -0.05 if reward <= st["reward"] else 0.0
+        st["reward"] = max(st["reward"], reward)
+        return ToolResponse(text=f"Current parsed answer={ans!r} reward={reward}"), step, {}
+
+    def calc_reward(self, instance_id, **kwargs) -> float:
+        from ..data.reward_score import gsm8k
+
+        st = self._instances[instance_id]
+        return float(gsm8k.compute_score(st["response"], st["ground_truth"], method="flexible", format_score=0.0, score=1.0))
+
+
+_TOOLS: dict[str, type] = {"calculator": CalculatorTool, "calc_gsm8k_reward": Gsm8kTool, "gsm8k": Gsm8kTool}
+
+
+def register_tool(name: str):
+    def deco(cls):
+        _TOOLS[name] = cls
+        return cls
+    return deco
+
+
+def _resolve(class_name: str) -> type:
+    if class_name in _TOOLS:
+        return _TOOLS[class_name]
+    mod, _, attr = class_name.rpartition(".")
+    return getattr(importlib.import_module(mod), attr)
+
+
+def load_tools(spec) -> list[BaseTool]:
+    """``spec``: path to a YAML/JSON file or an in-memory dict/list shaped like the reference's tool config:
+    ``{"tools": [{"class_name": "...", "config": {...}, "tool_schema": {...openai...}}]}``."""
+    if spec is None:
+        return []
+    if isinstance(spec, str):
+        import yaml
+
+        with open(spec) as f:
+            spec = yaml.safe_load(f)
+    items = spec.get("tools", []) if isinstance(spec, dict) else list(spec)
+    tools = []
+    for it in items:
+        if isinstance(it, BaseTool):
+            tools.append(it)
+            continue
+        cls = _resolve(it.get("class_name") or it.get("name"))
+        schema = ToolSchema.from_openai(it["tool_schema"]) if it.get("tool_schema") else None
+        tools.append(cls(config=it.get("config") or {}, schema=schema))
+    return tools

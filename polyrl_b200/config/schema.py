@@ -129,6 +129,20 @@ class RolloutManagerConfig(BaseConfig):
 
 
 @dataclass
+class MultiTurnConfig(BaseConfig):
+    """Multi-turn / tool rollouts (reference: verl/workers/config/rollout.py MultiTurnConfig)."""
+    enable: bool = False
+    max_assistant_turns: int = 4
+    max_user_turns: int = 4
+    max_parallel_calls: int = 1
+    max_tool_response_length: int = 256
+    tool_response_truncate_side: str = "middle"
+    tool_config_path: str | None = None
+    interaction_config_path: str | None = None
+    format: str = "hermes"
+
+
+@dataclass
 class RolloutConfig(BaseConfig):
     name: str = "native"                # native | native-disaggregated | sglang-disaggregated (alias) | hf | naive
     mode: str = "sync"
@@ -159,6 +173,7 @@ class RolloutConfig(BaseConfig):
     min_stream_batch_size: int = 16
     cuda_graph: bool = True
     rollout_manager: RolloutManagerConfig = field(default_factory=RolloutManagerConfig)
+    multi_turn: MultiTurnConfig = field(default_factory=MultiTurnConfig)
     val_kwargs: dict = field(default_factory=lambda: {"n": 1, "temperature": 0.0, "do_sample": False})
 
     def __post_init__(self):

@@ -189,13 +189,52 @@ class ActorRolloutRefWorker:
             raw = [ids[i][mask[i]].tolist() for i in range(len(prompts))]
         t0 = time.time()
         self.rollout.resume_memory(("kv_cache",))
-        groups = self.rollout.generate([list(map(int, p)) for p in raw], sp)
+        if r.multi_turn.enable:
+            out = self._generate_multi_turn(prompts, raw, sp, n, resp_len)
+        else:
+            groups = self.rollout.generate([list(map(int, p)) for p in raw], sp)
+            out = self._postprocess(prompts, groups, n, resp_len)
         gen_s = time.time() - t0
-        out = self._postprocess(prompts, groups, n, resp_len)
         out.meta_info["timing"] = {"generate_sequences": gen_s}
         if r.free_cache_engine and not meta.get("keep_cache", False):
             self.rollout.release_memory(("kv_cache",))
         return out
+
+    def _generate_multi_turn(self, prompts: DataProto, raw, sp: SamplingParams, n: int, resp_len: int) -> DataProto:
+        """Tool / interaction trajectories inside the engine's continuous batch (reference: request-level path of
+        sglang_rollout.py:807-1497 and experimental/agent_loop/tool_agent_loop.py)."""
+        from ..agent import MultiTurnRollout, load_tools
+        from ..agent.agent_loop import outputs_to_dataproto
+        from ..agent.interactions import load_interactions
+        from ..data.rl_dataset import load_tokenizer
+
+        mt = self.config.actor_rollout_ref.rollout.multi_turn
+        if getattr(self, "_multi_turn", None) is None:
+            tok = load_tokenizer(self.config.actor_rollout_ref.model.tokenizer_path)
+            self._multi_turn = MultiTurnRollout(
+                self.rollout, tok, tools=load_tools(mt.tool_config_path), interactions=load_interactions(mt.interaction_config_path),
+                parser=mt.format, response_length=resp_len, max_assistant_turns=mt.max_assistant_turns,
+                max_user_turns=mt.max_user_turns, max_parallel_calls=mt.max_parallel_calls,
+                max_tool_response_length=mt.max_tool_response_length, tool_response_truncate_side=mt.tool_response_truncate_side)
+        self._multi_turn.response_length = resp_len
+        nt = prompts.non_tensor_batch
+        samples = []
+        for i, p in enumerate(raw):
+            s = {"prompt_ids": list(map(int, p))}
+            for key in ("tools_kwargs", "interaction_kwargs"):
+                if key in nt and nt[key][i] is not None:
+                    s[key] = nt[key][i]
+            if "raw_prompt" in nt:
+                s["messages"] = list(nt["raw_prompt"][i])
+            samples += [dict(s) for _ in range(n)]
+        outs = self._multi_turn.generate(samples, {"temperature": sp.temperature, "top_p": sp.top_p, "top_k": sp.top_k})
+        rep = prompts.repeat(n, interleave=True) if n > 1 else prompts
+        dp = outputs_to_dataproto(outs, rep.batch["input_ids"].shape[1], resp_len, self.model_cfg.pad_token_id)
+        dev = rep.batch["input_ids"].device
+        for k, v in dp.batch.items():
+            rep.batch[k] = v.to(dev)
+        rep.non_tensor_batch.update(dp.non_tensor_batch)
+        return rep
 
     def _postprocess(self, prompts: DataProto, groups, n: int, resp_len: int) -> DataProto:
         """Pad responses to ``response_length`` and build input_ids / masks / position ids (reference:
