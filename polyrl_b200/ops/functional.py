@@ -320,10 +320,10 @@ def sample_tokens(logits: torch.Tensor, temperature: torch.Tensor | float = 1.0,
         tok, lp = _C().sample(logits, inv_t.float().contiguous(), seeds, bool(greedy))
         return tok, lp
     z = logits.float()
-    t = temperature.to(z.device).clamp_min(1e-6).unsqueeze(-1)
-    is_greedy = greedy or bool((temperature <= 0).all())
-    if not is_greedy:
-        z = z / t
+    temperature = temperature.to(z.device)
+    row_greedy = torch.ones_like(temperature, dtype=torch.bool) if greedy else temperature <= 0     # per row, like the kernel
+    is_greedy = bool(row_greedy.all())
+    z = z / torch.where(row_greedy, torch.ones_like(temperature), temperature).unsqueeze(-1)
     if top_k > 0:
         kth = torch.topk(z, min(top_k, v), dim=-1).values[..., -1:]
         z = z.masked_fill(z < kth, float("-inf"))
@@ -342,4 +342,5 @@ def sample_tokens(logits: torch.Tensor, temperature: torch.Tensor | float = 1.0,
             gen = torch.Generator(device=z.device)
             gen.manual_seed(int(seeds.reshape(-1)[0].item()) & 0x7FFFFFFF)
         tok = torch.multinomial(logp.exp(), 1, generator=gen).squeeze(-1)
+        tok = torch.where(row_greedy, z.argmax(-1), tok)
     return tok, logp.gather(-1, tok.unsqueeze(-1)).squeeze(-1)

@@ -82,3 +82,25 @@ def test_manager_drives_native_engines():
         for s in servers:
             s.stop()
         m.close()
+
+
+def test_rollout_registry_and_naive_oracle():
+    """The cache-less naive rollout is the oracle for the paged engine: greedy decoding must agree token by token."""
+    import torch
+
+    from polyrl_b200.models import TransformerWeights, get_model_config
+    from polyrl_b200.rollout.registry import get_rollout_cls
+
+    cfg = get_model_config("tiny-llama")
+    w = TransformerWeights(cfg, "cpu", torch.float32, seed=11)
+    prompts = [[5, 9, 33, 7], [12, 4, 4, 8, 19, 3, 77]]
+    outs = {}
+    for name in ("native", "naive"):
+        eng = get_rollout_cls(name)(cfg, "cpu", max_model_len=64, seed=0, **({"max_num_seqs": 4, "use_cuda_graph": False} if name == "native" else {}))
+        eng.set_weights(w.embed, w.layers, w.head)
+        g = eng.generate(prompts, {"max_new_tokens": 10, "temperature": 0.0, "ignore_eos": True})
+        outs[name] = [(r.output_ids, r.logprobs) for grp in g for r in grp]
+    for (a, la), (b, lb) in zip(outs["native"], outs["naive"]):
+        assert a == b
+        assert max(abs(x - y) for x, y in zip(la, lb)) < 1e-4
+    assert get_rollout_cls("sglang") is get_rollout_cls("native")
