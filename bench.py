@@ -177,6 +177,8 @@ def main() -> int:
         ev[k][1].record()
         if rank == 0:
             print("[bench] step", k, {kk: round(v, 3) for kk, v in m.items() if kk.startswith("timing_s/")},
+                  "saved_act_layers", ppo.worker.actor_engine.saved_layers_last, "resident", ppo.worker.actor_engine.resident,
+                  "mem_GB", round(torch.cuda.max_memory_allocated() / 2**30, 1),
                   "launches", dict(sorted(ops.LAUNCHES.items())), file=sys.stderr, flush=True)
         d2h_bytes += 8 * sum(1 for v in m.values() if isinstance(v, float))
         samples += int(m["num_samples"])
@@ -203,7 +205,10 @@ def main() -> int:
             "dtype": "bf16", "data": "synthetic GSM8K-shaped prompts (64-192 tok), random-init weights",
             "config": {"model": args.model, "algorithm": "GRPO", "global_batch": P * world, "samples_per_step": per_gpu * world,
                        "n": n, "seq_len": args.prompt_len_max + R, "response_length": R,
-                       "parallelism": f"colocated dp{world} rollout replicas + zero3 x{world} ({args.comm})",
+                       "parallelism": f"colocated dp{world} rollout replicas + zero x{world} ({args.comm}; fp32 master/moments/grads "
+                                      f"sharded, bf16 replica {'resident' if ppo.worker.actor_engine.resident or world == 1 else 'gathered per layer'})",
+                       "activation_checkpoint": f"auto: {ppo.worker.actor_engine.saved_layers_last}/{ppo.worker.model_cfg.num_layers} blocks "
+                                                "saved, rest recomputed",
                        "l2": "working set >> L2: 16 GB bf16 weights + KV cache streamed every step; no cache reuse across iterations",
                        "optimizer": "AdamW fp32 master+moments, grad clip 1.0", "old_log_prob_recompute": True,
                        "cuda_graph_decode": not args.no_graph},

@@ -64,6 +64,12 @@ class FSDPConfig(BaseConfig):
     forward_prefetch: bool = True
     comm_backend: str = "p2p"           # "p2p" (NVLink peer-memory kernels) | "nccl" (baseline)
     model_dtype: str = "bf16"
+    # keep a full bf16 replica on every GPU, re-gathered once per optimizer step and aliased by the colocated rollout
+    # engine ("auto": when the replica is <= 1/4 of HBM; reshard_after_forward=False in FSDP terms)
+    resident_params: str = "auto"       # auto | true | false
+    # full = recompute every block in backward; none = save all activations; auto = save what fits in free HBM; or an int
+    activation_checkpoint: str = "auto"
+    activation_reserve_gb: float = 16.0
 
 
 @dataclass

@@ -69,6 +69,7 @@ class ShardedUnit:
         self.grad_acc = torch.zeros_like(self.master) if engine.trainable else None
         self._full: torch.Tensor | None = None
         self._full_event = None
+        self._resident: torch.Tensor | None = None      # persistent full bf16 replica (engine.resident mode)
         self._pending_rs = None       # event of the last async reduce-scatter into grad_acc
 
     # ---- initialisation ---------------------------------------------------------------------
@@ -95,6 +96,7 @@ class ShardedUnit:
         self.shard[so:so + chunk] = piece.to(self.shard.dtype)
 
     def load_full_state(self, named: dict[str, torch.Tensor], prefix: str = "") -> None:
+        self.engine._resident_stale = True
         for (n, shp), numel, chunk, so in zip(self.specs, self.numels, self.chunks, self.shard_offsets):
             self._load_param_chunk(named[prefix + n].reshape(-1), numel, chunk, so)
 
@@ -112,6 +114,10 @@ class ShardedUnit:
             return
         if eng.world == 1:
             self._full = self.shard
+            return
+        if eng.resident:
+            eng.ensure_resident()
+            self._full = self._resident
             return
         buf = eng.pool_acquire(self.full_numel)
         if eng.comm_stream is not None:
@@ -157,14 +163,14 @@ class ShardedUnit:
         eng = self.engine
         if self._full is None:
             return
-        if eng.world > 1 and not eng.keep_gathered:
+        if eng.world > 1 and not eng.keep_gathered and not eng.resident:
             if self._full.is_cuda:
                 self._full.record_stream(torch.cuda.current_stream(eng.device))
             eng.pool_release(self._full)
             self._full = None
 
     def drop_gathered(self) -> None:
-        if self._full is not None and self.engine.world > 1:
+        if self._full is not None and self.engine.world > 1 and self._full is not self._resident:
             self.engine.pool_release(self._full)
         self._full = None
 
@@ -246,6 +252,7 @@ class ShardedUnit:
         return {"master": self.master, "exp_avg": self.exp_avg, "exp_avg_sq": self.exp_avg_sq, "shard": self.shard}
 
     def load_state_dict(self, sd: dict) -> None:
+        self.engine._resident_stale = True
         self.shard.copy_(sd["shard"])
         if self.master is not None and sd.get("master") is not None:
             self.master.copy_(sd["master"])
@@ -262,10 +269,27 @@ class _UnitFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, runner: "UnitRunner", static, anchor, *tensors):
         ctx.runner, ctx.static = runner, static
-        ctx.save_for_backward(*tensors)
+        ctx.graph = None
         fulls = [u.acquire() for u in runner.units]
         if runner.next_fwd is not None:
             runner.next_fwd.prefetch()
+        if runner.save_activations:
+            # no recompute: run the unit under autograd now and keep its graph (parameter storage is stable:
+            # world == 1 shard or the resident replica), backward differentiates the stored graph
+            view_dicts, leaves = [], []
+            for u, f in zip(runner.units, fulls):
+                vd = {n: v.detach().requires_grad_(True) for n, v in u.views(f).items()}
+                view_dicts.append(vd)
+                leaves.append(list(vd.values()))
+            need = ctx.needs_input_grad[3:]
+            ins = [t.detach().requires_grad_(bool(t.is_floating_point() and nd)) for t, nd in zip(tensors, need)]
+            with torch.enable_grad():
+                out = runner.fn(view_dicts, static, *ins)
+            ctx.graph = (ins, leaves, out)
+            for u in runner.units:
+                u.release()
+            return tuple(o.detach() for o in out) if isinstance(out, tuple) else out.detach()
+        ctx.save_for_backward(*tensors)
         with torch.no_grad():
             out = runner.fn([u.views(f) for u, f in zip(runner.units, fulls)], static, *tensors)
         for u in runner.units:
@@ -275,19 +299,27 @@ class _UnitFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, *grad_out):
         runner = ctx.runner
-        tensors = ctx.saved_tensors
-        fulls = [u.acquire() for u in runner.units]
-        if runner.next_bwd is not None:
-            runner.next_bwd.prefetch()
-        view_dicts, leaves = [], []
-        for u, f in zip(runner.units, fulls):
-            vd = {n: v.detach().requires_grad_(True) for n, v in u.views(f).items()}
-            view_dicts.append(vd)
-            leaves.append(list(vd.values()))
-        need = ctx.needs_input_grad[3:]
-        ins = [t.detach().requires_grad_(bool(t.is_floating_point() and nd)) for t, nd in zip(tensors, need)]
-        with torch.enable_grad():
-            out = runner.fn(view_dicts, ctx.static, *ins)
+        if ctx.graph is not None:
+            ins, leaves, out = ctx.graph
+            ctx.graph = None
+            for u in runner.units:
+                u.acquire()
+            if runner.next_bwd is not None:
+                runner.next_bwd.prefetch()
+        else:
+            tensors = ctx.saved_tensors
+            fulls = [u.acquire() for u in runner.units]
+            if runner.next_bwd is not None:
+                runner.next_bwd.prefetch()
+            view_dicts, leaves = [], []
+            for u, f in zip(runner.units, fulls):
+                vd = {n: v.detach().requires_grad_(True) for n, v in u.views(f).items()}
+                view_dicts.append(vd)
+                leaves.append(list(vd.values()))
+            need = ctx.needs_input_grad[3:]
+            ins = [t.detach().requires_grad_(bool(t.is_floating_point() and nd)) for t, nd in zip(tensors, need)]
+            with torch.enable_grad():
+                out = runner.fn(view_dicts, ctx.static, *ins)
         outs = out if isinstance(out, tuple) else (out,)
         pairs = [(o, g) for o, g in zip(outs, grad_out) if g is not None and o.requires_grad]
         diff_ins = [t for t in ins if t.requires_grad]
@@ -316,6 +348,7 @@ class UnitRunner:
         self.engine, self.units, self.fn = engine, units, fn
         self.next_fwd: ShardedUnit | None = None
         self.next_bwd: ShardedUnit | None = None
+        self.save_activations = False
 
     def __call__(self, static, *tensors):
         if not self.engine.trainable or not torch.is_grad_enabled():
@@ -354,6 +387,18 @@ class Zero3Engine:
         self.comm = comm if (self.is_cuda and self.world > 1) else "nccl"
         self.comm_ctas = comm_ctas
         self.keep_gathered = False
+        # resident mode: keep a full bf16 replica of every unit on every rank, re-gathered ONCE per optimizer step
+        # (ZeRO-1/2 layout: fp32 master, moments and gradients stay sharded).  16 GB for an 8B model on a 180 GB GPU —
+        # removes the per-layer per-micro-batch all-gathers, lets the rollout engine alias the same buffers, and
+        # gives saved activations stable parameter storage (see `act_ckpt`).
+        self.resident = False
+        self._resident_stale = True
+        # activation checkpointing: "full" = recompute every layer in backward (reference default,
+        # enable_gradient_checkpointing=True); "none" = save activations for every layer; "auto" = save as many layers
+        # as fit in free HBM at the first forward of a micro-batch; an int = that many layers.
+        self.act_ckpt = "full"
+        self.act_reserve_bytes = 16 << 30
+        self.saved_layers_last = 0
         self.grad_scale = 1.0
         self.lr, self.betas, self.eps, self.weight_decay, self.max_grad_norm = lr, betas, eps, weight_decay, max_grad_norm
         self.opt_step = 0
@@ -387,6 +432,28 @@ class Zero3Engine:
             big = max(u.full_numel for u in self.units)
             self._grad_slots = [self.heap.alloc(big, self.param_dtype) for _ in range(2)]
         self._build_runners()
+
+    # ---- resident replica ---------------------------------------------------------------------
+    def make_resident(self) -> None:
+        if self.world == 1 or self.resident:
+            return
+        for u in self.units:
+            u.drop_gathered()
+            u._resident = torch.empty(u.full_numel, device=self.device, dtype=self.param_dtype)
+        self.resident, self._resident_stale = True, True
+
+    def ensure_resident(self) -> None:
+        """Re-gather every unit after the shards changed (collective: every rank of the group must call it)."""
+        if not self.resident or not self._resident_stale:
+            return
+        self._resident_stale = False
+        if self.heap is not None:
+            self.heap.barrier()
+        for u in self.units:
+            u._gather_into(u._resident)
+            u._full = u._resident
+        if self.heap is not None:
+            self.heap.barrier()
 
     # ---- buffer pool (full-size gather buffers are recycled) ------------------------------------
     def pool_acquire(self, numel: int, tag: str = "full", dtype=None) -> torch.Tensor:
@@ -459,7 +526,42 @@ class Zero3Engine:
         for r in (self.head_lp_runner, self.head_value_runner, self.head_logits_runner):
             r.next_bwd = chain[-1].units[0]
 
+    def act_bytes_per_token_layer(self) -> int:
+        """Autograd-saved bytes per token of one decoder block (bf16): block input, 2 norm outputs, qkv, attention out,
+        post-attention residual, gate/up pre-activations and the SwiGLU output."""
+        c = self.cfg
+        inter = getattr(c, "intermediate_size", 4 * c.hidden_size)
+        qkv = (c.num_heads + 2 * c.num_kv_heads) * c.head_dim
+        return 2 * (5 * c.hidden_size + qkv + 3 * inter) + 64
+
+    def _plan_activation_saving(self, tokens: int) -> None:
+        n = len(self.layer_runners)
+        mode = self.act_ckpt
+        stable = self.world == 1 or self.resident
+        if not (self.trainable and torch.is_grad_enabled()) or mode == "full" or not stable:
+            k = 0
+        elif mode == "none":
+            k = n
+        elif mode == "auto":
+            if not self.is_cuda:
+                k = n
+            else:
+                free, _ = torch.cuda.mem_get_info(self.device)
+                cached = torch.cuda.memory_reserved(self.device) - torch.cuda.memory_allocated(self.device)
+                budget = free + cached - self.act_reserve_bytes
+                k = max(0, min(n, int(budget // max(1, tokens * self.act_bytes_per_token_layer()))))
+                if self.world > 1:                       # every rank must agree (keeps ranks in lock-step on comm)
+                    t = torch.tensor([k], device=self.device, dtype=torch.int32)
+                    dist.all_reduce(t, op=dist.ReduceOp.MIN, group=self.group)
+                    k = int(t.item())
+        else:
+            k = max(0, min(n, int(mode)))
+        for i, r in enumerate(self.layer_runners):
+            r.save_activations = i < k
+        self.saved_layers_last = k
+
     def forward_hidden(self, inp: tf.PackedInput) -> torch.Tensor:
+        self._plan_activation_saving(int(inp.input_ids.shape[0]))
         sp = self.sp_group
         if sp is not None and dist.get_world_size(sp) > 1:
             from .ulysses import GatherSeq, ulysses_pad_and_slice, validate_sp
@@ -548,6 +650,7 @@ class Zero3Engine:
             u.drop_gathered()
         if self.heap is not None and self.world > 1:
             self.heap.barrier()       # peers must see the new shards before the next pull
+        self._resident_stale = True
         return {"grad_norm": norm, "skipped": skipped}
 
     # ---- optimizer-state offload (reference: verl/utils/fsdp_utils.py:204-225 offload/load_fsdp_optimizer) ------
@@ -596,6 +699,7 @@ class Zero3Engine:
                 "world": self.world, "rank": self.rank}
 
     def load_state_dict(self, sd: dict) -> None:
+        self._resident_stale = True
         if sd["world"] != self.world:
             raise ValueError(f"checkpoint was written with world_size={sd['world']}, now {self.world}")
         for u in self.units:

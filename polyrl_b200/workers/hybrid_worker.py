@@ -117,6 +117,15 @@ class ActorRolloutRefWorker:
                                             seed=seed, lr=opt.lr, betas=tuple(opt.betas), eps=opt.eps,
                                             weight_decay=opt.weight_decay, max_grad_norm=arr.actor.grad_clip,
                                             sp_group=self.sp_group, replica_group=self.replica_group)
+            fc = arr.actor.fsdp_config
+            eng = self.actor_engine
+            want = str(fc.resident_params).lower()
+            replica_bytes = 2 * eng.num_params()
+            hbm = torch.cuda.get_device_properties(self.device).total_memory if self.device.type == "cuda" else 1 << 62
+            if eng.world > 1 and (want == "true" or (want == "auto" and replica_bytes <= hbm // 4)):
+                eng.make_resident()
+            eng.act_ckpt = str(fc.activation_checkpoint) if arr.model.enable_gradient_checkpointing else "none"
+            eng.act_reserve_bytes = int(fc.activation_reserve_gb * (1 << 30))
             n_dp = self.dp_size
             a = arr.actor
             mini = max(1, a.ppo_mini_batch_size * arr.rollout.n // n_dp)      # per-GPU samples per optimizer step
@@ -155,6 +164,9 @@ class ActorRolloutRefWorker:
         self.weight_version += 1
         if eng.world == 1:
             views = [u.views(u.shard) for u in eng.units]
+        elif eng.resident:
+            eng.ensure_resident()           # one gather per optimizer step; the engine aliases the trainer's replica
+            views = [u.views(u._resident) for u in eng.units]
         else:
             if self._rollout_full is None:
                 self._rollout_full = {u.name: torch.empty(u.full_numel, device=self.device, dtype=eng.param_dtype)

@@ -38,8 +38,12 @@ def main():
     inp, _ = pack_padded(ids, torch.ones_like(ids))
     labels = torch.randint(0, cfg.vocab_size, (inp.input_ids.numel(),), device=dev)
     outs = {}
-    for name, kw in (("zero", dict(group=None)), ("hsdp", dict(group=shard_group, replica_group=replica_group))):
+    for name, kw in (("zero", dict(group=None)), ("hsdp", dict(group=shard_group, replica_group=replica_group)),
+                     ("resident", dict(group=None))):
         eng = Zero3Engine(cfg, dev, comm="nccl", lr=1e-2, weight_decay=0.0, seed=7, **kw)
+        if name == "resident":              # full replica kept on every rank + activations saved (no recompute)
+            eng.make_resident()
+            eng.act_ckpt = "none"
         for _ in range(2):
             lp, ent = eng.forward_logprob_entropy(inp, labels, 1.0)
             (-(lp.mean()) + 0.01 * ent.mean()).backward()
@@ -48,8 +52,10 @@ def main():
     w_err = max(((outs["hsdp"][0][k] - outs["zero"][0][k]).norm() / (outs["zero"][0][k].norm() + 1e-9)).item()
                 for k in outs["zero"][0])
     gn_err = abs(outs["hsdp"][1] - outs["zero"][1]) / (abs(outs["zero"][1]) + 1e-9)
+    r_err = max(((outs["resident"][0][k] - outs["zero"][0][k]).norm() / (outs["zero"][0][k].norm() + 1e-9)).item()
+                for k in outs["zero"][0])
     if rank == 0:
-        print(f"HSDP_RESULTS w_err={w_err:.3e} gn_err={gn_err:.3e}", flush=True)
+        print(f"HSDP_RESULTS w_err={w_err:.3e} gn_err={gn_err:.3e} resident_err={r_err:.3e}", flush=True)
     dist.barrier()
     dist.destroy_process_group()
 

@@ -75,3 +75,4 @@ def test_hsdp_equivalence_gloo():
     assert r.returncode == 0 and line, r.stdout[-2000:] + r.stderr[-2000:]
     vals = dict(kv.split("=") for kv in line[0].split()[1:])
     assert float(vals["w_err"]) < 1e-4 and float(vals["gn_err"]) < 1e-4
+    assert float(vals["resident_err"]) < 1e-4          # resident replica + saved activations == ZeRO-3 + recompute
