@@ -1,0 +1,153 @@
+"""LoRA adapters for the fused-projection transformer blocks.
+
+The reference trains LoRA through peft on top of FSDP (``lora_rank`` / ``lora_alpha`` / ``target_modules``,
+3rdparty/verl/verl/workers/fsdp_workers.py:269-577) and merges the adapters layer by layer before handing weights
+to the rollout engine (verl/utils/fsdp_utils.py:569-694 "layered summon").  Here an adapter is an extra, trainable
+ZeRO unit per decoder block next to a FROZEN base unit (no fp32 master / moments / gradient storage for the base:
+12 bytes per base parameter saved), the low-rank path is added to the fused qkv / o / gate-up / down projections,
+and ``merge_layer_`` folds ``scale * B @ A`` into a weight replica for the rollout engine.
+
+Adapters are kept per HF projection (q/k/v/o/gate/up/down) so they export 1:1 to peft names.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import torch
+
+from ..ops import reference as ref
+from .config import ModelConfig
+
+ALL_LINEAR = ("q_proj", "k_proj", "v_proj", "o_proj", "gate_proj", "up_proj", "down_proj")
+
+
+@dataclass
+class LoraConfig:
+    rank: int = 8
+    alpha: float = 16.0
+    target_modules: tuple = ALL_LINEAR
+
+    @property
+    def scale(self) -> float:
+        return self.alpha / self.rank
+
+    @classmethod
+    def from_model_cfg(cls, rank: int, alpha: float, target_modules) -> "LoraConfig | None":
+        if not rank or rank <= 0:
+            return None
+        if target_modules in (None, "all-linear", "all_linear"):
+            tm = ALL_LINEAR
+        elif isinstance(target_modules, str):
+            tm = tuple(t.strip() for t in target_modules.strip("[]").split(",") if t.strip())
+        else:
+            tm = tuple(target_modules)
+        bad = [t for t in tm if t not in ALL_LINEAR]
+        if bad:
+            raise ValueError(f"unsupported LoRA target module(s) {bad}; supported: {ALL_LINEAR}")
+        return cls(rank=int(rank), alpha=float(alpha), target_modules=tm)
+
+
+def _proj_dims(cfg: ModelConfig) -> dict[str, tuple[int, int]]:
+    """projection -> (out_features, in_features)"""
+    h, f, d = cfg.hidden_size, cfg.intermediate_size, cfg.head_dim
+    return {"q_proj": (cfg.num_heads * d, h), "k_proj": (cfg.num_kv_heads * d, h), "v_proj": (cfg.num_kv_heads * d, h),
+            "o_proj": (h, cfg.num_heads * d), "gate_proj": (f, h), "up_proj": (f, h), "down_proj": (h, f)}
+
+
+def lora_param_specs(cfg: ModelConfig, lcfg: LoraConfig) -> list[tuple[str, tuple[int, ...]]]:
+    if cfg.family != "llama":
+        raise NotImplementedError("LoRA is implemented for the llama/qwen block family")
+    dims = _proj_dims(cfg)
+    specs = []
+    for p in ALL_LINEAR:
+        if p in lcfg.target_modules:
+            out_f, in_f = dims[p]
+            specs.append((f"lora_{p}_A", (lcfg.rank, in_f)))
+            specs.append((f"lora_{p}_B", (out_f, lcfg.rank)))
+    return specs
+
+
+def _delta(x: torch.Tensor, w: dict, proj: str) -> torch.Tensor | None:
+    a = w.get(f"lora_{proj}_A")
+    if a is None:
+        return None
+    b = w[f"lora_{proj}_B"]
+    return torch.nn.functional.linear(torch.nn.functional.linear(x, a.to(x.dtype)), b.to(x.dtype))
+
+
+def has_lora(w: dict, *projs: str) -> bool:
+    return any(f"lora_{p}_A" in w for p in projs)
+
+
+def qkv_delta(cfg: ModelConfig, w: dict, h: torch.Tensor) -> torch.Tensor:
+    """Low-rank update of the fused [q | k | v] projection output."""
+    dims = _proj_dims(cfg)
+    parts = []
+    for p in ("q_proj", "k_proj", "v_proj"):
+        d = _delta(h, w, p)
+        parts.append(d if d is not None else h.new_zeros(h.shape[0], dims[p][0]))
+    return torch.cat(parts, dim=-1) * w["_lora_scale"]
+
+
+def single_delta(w: dict, x: torch.Tensor, proj: str) -> torch.Tensor:
+    return _delta(x, w, proj) * w["_lora_scale"]
+
+
+def gate_up_delta(cfg: ModelConfig, w: dict, h: torch.Tensor) -> torch.Tensor:
+    """Update of the block-interleaved [128 gate | 128 up] fused projection output."""
+    f = cfg.intermediate_size
+    t = h.shape[0]
+    dg, du = _delta(h, w, "gate_proj"), _delta(h, w, "up_proj")
+    dg = dg if dg is not None else h.new_zeros(t, f)
+    du = du if du is not None else h.new_zeros(t, f)
+    return torch.stack([dg.view(t, f // 128, 128), du.view(t, f // 128, 128)], dim=2).reshape(t, 2 * f) * w["_lora_scale"]
+
+
+@torch.no_grad()
+def merge_layer_(cfg: ModelConfig, base: dict, lora: dict, scale: float) -> None:
+    """In place: fold the adapters of one block into (a copy of) its fused base weights."""
+    nq, nkv, d = cfg.num_heads, cfg.num_kv_heads, cfg.head_dim
+
+    def ba(p):
+        a = lora.get(f"lora_{p}_A")
+        return None if a is None else (lora[f"lora_{p}_B"].float() @ a.float()) * scale
+
+    row = 0
+    for p, rows in (("q_proj", nq * d), ("k_proj", nkv * d), ("v_proj", nkv * d)):
+        m = ba(p)
+        if m is not None:
+            base["wqkv"][row:row + rows] += m.to(base["wqkv"].dtype)
+        row += rows
+    m = ba("o_proj")
+    if m is not None:
+        base["wo"] += m.to(base["wo"].dtype)
+    g, u = ba("gate_proj"), ba("up_proj")
+    if g is not None or u is not None:
+        f, h = cfg.intermediate_size, cfg.hidden_size
+        z = torch.zeros(f, h, device=base["wgu"].device)
+        base["wgu"] += ref.interleave_gate_up(g if g is not None else z, u if u is not None else z).to(base["wgu"].dtype)
+    m = ba("down_proj")
+    if m is not None:
+        base["wd"] += m.to(base["wd"].dtype)
+
+
+_PEFT_MODULE = {"q_proj": "self_attn.q_proj", "k_proj": "self_attn.k_proj", "v_proj": "self_attn.v_proj",
+                "o_proj": "self_attn.o_proj", "gate_proj": "mlp.gate_proj", "up_proj": "mlp.up_proj", "down_proj": "mlp.down_proj"}
+
+
+def export_peft_state_dict(named: dict[str, torch.Tensor]) -> dict[str, torch.Tensor]:
+    """``layers.{i}.lora.lora_{proj}_{A|B}`` -> peft ``base_model.model.model.layers.{i}.<module>.lora_{A|B}.weight``"""
+    out = {}
+    for k, v in named.items():
+        if ".lora.lora_" not in k:
+            continue
+        layer = k.split(".")[1]
+        tail = k.split(".lora.lora_")[1]
+        proj, ab = tail.rsplit("_", 1)
+        out[f"base_model.model.model.layers.{layer}.{_PEFT_MODULE[proj]}.lora_{ab}.weight"] = v
+    return out
+
+
+def peft_adapter_config(cfg: ModelConfig, lcfg: LoraConfig) -> dict:
+    return {"peft_type": "LORA", "r": lcfg.rank, "lora_alpha": lcfg.alpha, "target_modules": list(lcfg.target_modules),
+            "bias": "none", "task_type": "CAUSAL_LM", "lora_dropout": 0.0}

@@ -64,6 +64,13 @@ def head_param_specs(cfg: ModelConfig) -> ParamSpec:
 def init_param_(name: str, t: torch.Tensor, cfg: ModelConfig, generator: torch.Generator | None = None) -> None:
     """Random init (weights ~ N(0, 0.02), norm gains 1, biases 0), in place, any dtype/device."""
     base = name.split(".")[-1]
+    if base.startswith("lora_"):                    # peft default: A ~ U(-1/sqrt(in), 1/sqrt(in)), B = 0
+        if base.endswith("_B"):
+            t.zero_()
+        else:
+            bound = 1.0 / math.sqrt(t.shape[-1])
+            t.uniform_(-bound, bound, generator=generator)
+        return
     if base in ("ln1", "ln2", "norm_w", "ln1_w", "ln2_w"):
         t.fill_(1.0)
     elif base.startswith("b") or base.endswith("_b"):
@@ -117,8 +124,13 @@ def layer_forward(cfg: ModelConfig, w: dict, x: torch.Tensor, inp: PackedInput, 
     nq, nkv, d = cfg.num_heads, cfg.num_kv_heads, cfg.head_dim
     t = x.shape[0]
     if cfg.family == "llama":
+        lora = "_lora_scale" in w
+        if lora:
+            from . import lora as L
         h = ops.rmsnorm(x, w["ln1"], cfg.rms_norm_eps)
         qkv = ops.linear(h, w["wqkv"], bias=w.get("bqkv"))
+        if lora and L.has_lora(w, "q_proj", "k_proj", "v_proj"):
+            qkv = qkv + L.qkv_delta(cfg, w, h)
         cos, sin = rope_tables(cfg, x.device)
         if kv_sink is not None:
             qkv = rope_and_cache_(qkv, inp.position_ids, cos, sin, nq, nkv, d, *kv_sink)
@@ -133,10 +145,19 @@ def layer_forward(cfg: ModelConfig, w: dict, x: torch.Tensor, inp: PackedInput, 
             a = ulysses_attention(q, k, v, inp.cu_seqlens, inp.max_seqlen, inp.sp_group, inp.total_tokens, causal=True)
         else:
             a = attention_varlen(q, k, v, inp.cu_seqlens, inp.max_seqlen, causal=True)
-        x = ops.linear(a.reshape(t, nq * d), w["wo"], residual=x)
+        a = a.reshape(t, nq * d)
+        x = ops.linear(a, w["wo"], residual=x)
+        if lora and L.has_lora(w, "o_proj"):
+            x = x + L.single_delta(w, a, "o_proj")
         h = ops.rmsnorm(x, w["ln2"], cfg.rms_norm_eps)
-        a = ops.linear_swiglu(h, w["wgu"])
-        return ops.linear(a, w["wd"], residual=x)
+        if lora and L.has_lora(w, "gate_proj", "up_proj"):
+            a = ref.swiglu(ops.linear(h, w["wgu"]) + L.gate_up_delta(cfg, w, h))    # adapters act before the activation
+        else:
+            a = ops.linear_swiglu(h, w["wgu"])
+        y = ops.linear(a, w["wd"], residual=x)
+        if lora and L.has_lora(w, "down_proj"):
+            y = y + L.single_delta(w, a, "down_proj")
+        return y
     # ---- gpt2 block (library ops; plumbing / CPU config)
     h = F.layer_norm(x, (cfg.hidden_size,), w["ln1_w"], w["ln1_b"], cfg.rms_norm_eps)
     qkv = F.linear(h, w["wqkv"], w["bqkv"])

@@ -42,9 +42,10 @@ def _ceil_to(x: int, m: int) -> int:
 class ShardedUnit:
     """Flat per-parameter-chunked storage of one FSDP unit."""
 
-    def __init__(self, name: str, specs: tf.ParamSpec, engine: "Zero3Engine"):
+    def __init__(self, name: str, specs: tf.ParamSpec, engine: "Zero3Engine", trainable: bool | None = None):
         self.name = name
         self.engine = engine
+        self.trainable = engine.trainable if trainable is None else (trainable and engine.trainable)
         self.specs = specs
         w = engine.world
         self.numels = [math.prod(s) for _, s in specs]
@@ -63,10 +64,10 @@ class ShardedUnit:
         else:
             self.symm = None
             self.shard = torch.zeros(self.shard_numel, device=dev, dtype=pd)
-        self.master = torch.zeros(self.shard_numel, device=dev, dtype=torch.float32) if engine.trainable else None
-        self.exp_avg = torch.zeros_like(self.master) if engine.trainable else None
-        self.exp_avg_sq = torch.zeros_like(self.master) if engine.trainable else None
-        self.grad_acc = torch.zeros_like(self.master) if engine.trainable else None
+        self.master = torch.zeros(self.shard_numel, device=dev, dtype=torch.float32) if self.trainable else None
+        self.exp_avg = torch.zeros_like(self.master) if self.trainable else None
+        self.exp_avg_sq = torch.zeros_like(self.master) if self.trainable else None
+        self.grad_acc = torch.zeros_like(self.master) if self.trainable else None
         self._full: torch.Tensor | None = None
         self._full_event = None
         self._resident: torch.Tensor | None = None      # persistent full bf16 replica (engine.resident mode)
@@ -278,9 +279,9 @@ class _UnitFn(torch.autograd.Function):
             # world == 1 shard or the resident replica), backward differentiates the stored graph
             view_dicts, leaves = [], []
             for u, f in zip(runner.units, fulls):
-                vd = {n: v.detach().requires_grad_(True) for n, v in u.views(f).items()}
+                vd = {n: v.detach().requires_grad_(u.trainable) for n, v in u.views(f).items()}
                 view_dicts.append(vd)
-                leaves.append(list(vd.values()))
+                leaves.append(list(vd.values()) if u.trainable else [])
             need = ctx.needs_input_grad[3:]
             ins = [t.detach().requires_grad_(bool(t.is_floating_point() and nd)) for t, nd in zip(tensors, need)]
             with torch.enable_grad():
@@ -313,9 +314,9 @@ class _UnitFn(torch.autograd.Function):
                 runner.next_bwd.prefetch()
             view_dicts, leaves = [], []
             for u, f in zip(runner.units, fulls):
-                vd = {n: v.detach().requires_grad_(True) for n, v in u.views(f).items()}
+                vd = {n: v.detach().requires_grad_(u.trainable) for n, v in u.views(f).items()}
                 view_dicts.append(vd)
-                leaves.append(list(vd.values()))
+                leaves.append(list(vd.values()) if u.trainable else [])
             need = ctx.needs_input_grad[3:]
             ins = [t.detach().requires_grad_(bool(t.is_floating_point() and nd)) for t, nd in zip(tensors, need)]
             with torch.enable_grad():
@@ -330,7 +331,8 @@ class _UnitFn(torch.autograd.Function):
         gpar = grads[len(diff_ins):]
         k = 0
         for u, l in zip(runner.units, leaves):
-            u.accumulate_grads(gpar[k:k + len(l)], runner.engine.grad_scale)
+            if l:
+                u.accumulate_grads(gpar[k:k + len(l)], runner.engine.grad_scale)
             k += len(l)
             u.release()
         res, j = [None, None, None], 0
@@ -351,7 +353,9 @@ class UnitRunner:
         self.save_activations = False
 
     def __call__(self, static, *tensors):
-        if not self.engine.trainable or not torch.is_grad_enabled():
+        frozen_leaf = not any(u.trainable for u in self.units) and not any(
+            t.requires_grad for t in tensors if torch.is_tensor(t))        # e.g. the frozen embedding under LoRA
+        if not self.engine.trainable or not torch.is_grad_enabled() or frozen_leaf:
             fulls = [u.acquire() for u in self.units]
             if self.next_fwd is not None:
                 self.next_fwd.prefetch()
@@ -369,7 +373,7 @@ class Zero3Engine:
     def __init__(self, cfg: ModelConfig, device, group=None, comm: str = "nccl", param_dtype=None, trainable: bool = True,
                  seed: int = 0, lr: float = 1e-6, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.01,
                  max_grad_norm: float = 1.0, heap=None, comm_ctas: int = 32, init: bool = True, sp_group=None,
-                 replica_group=None):
+                 replica_group=None, lora=None):
         self.cfg = cfg
         self.sp_group = sp_group       # Ulysses sequence-parallel group (subset of `group`), or None
         # HSDP (reference: fsdp_size < world => 2-D mesh ["ddp","fsdp"], verl/workers/fsdp_workers.py:99-118):
@@ -418,10 +422,22 @@ class Zero3Engine:
         self._grad_slot_events: dict = {}
         self._grad_slot_idx = 0
 
-        self.embed = ShardedUnit("embed", tf.embed_param_specs(cfg), self)
-        self.layers = [ShardedUnit(f"layers.{i}", tf.layer_param_specs(cfg), self) for i in range(cfg.num_layers)]
-        self.head = ShardedUnit("head", tf.head_param_specs(cfg), self)
-        self.units = [self.embed, *self.layers, self.head]
+        # LoRA (models/lora.py): the base units are frozen (bf16 shard only), one small trainable adapter unit per block
+        self.lora = lora if trainable else None
+        base_tr = None if self.lora is None else False
+        self.embed = ShardedUnit("embed", tf.embed_param_specs(cfg), self, trainable=base_tr)
+        self.layers = [ShardedUnit(f"layers.{i}", tf.layer_param_specs(cfg), self, trainable=base_tr)
+                       for i in range(cfg.num_layers)]
+        self.head = ShardedUnit("head", tf.head_param_specs(cfg), self, trainable=base_tr)
+        self.base_units = [self.embed, *self.layers, self.head]
+        self.lora_layers = []
+        if self.lora is not None:
+            from ..models.lora import lora_param_specs
+
+            lspecs = lora_param_specs(cfg, self.lora)
+            self.lora_layers = [ShardedUnit(f"layers.{i}.lora", lspecs, self) for i in range(cfg.num_layers)]
+        self.units = [*self.base_units, *self.lora_layers]
+        self.opt_units = [u for u in self.units if u.trainable]
         if init:
             for u in self.units:
                 u.init_random(cfg, seed)
@@ -429,7 +445,7 @@ class Zero3Engine:
             self.total_sumsq = torch.zeros(1, device=self.device, dtype=torch.float32)
             self.status = torch.zeros(1, device=self.device, dtype=torch.int32)
         if self.comm == "p2p" and trainable:
-            big = max(u.full_numel for u in self.units)
+            big = max(u.full_numel for u in self.opt_units)
             self._grad_slots = [self.heap.alloc(big, self.param_dtype) for _ in range(2)]
         self._build_runners()
 
@@ -492,6 +508,8 @@ class Zero3Engine:
             return x
 
         def layer_fn(ws, inp, x):
+            if len(ws) > 1:         # base + adapter views
+                return tf.layer_forward(cfg, {**ws[0], **ws[1], "_lora_scale": self.lora.scale}, x, inp)
             return tf.layer_forward(cfg, ws[0], x, inp)
 
         tied = cfg.tie_word_embeddings and not cfg.value_head
@@ -513,7 +531,8 @@ class Zero3Engine:
             return torch.nn.functional.linear(h, w_lm.to(h.dtype))
 
         self.embed_runner = UnitRunner(self, [self.embed], embed_fn)
-        self.layer_runners = [UnitRunner(self, [u], layer_fn) for u in self.layers]
+        self.layer_runners = [UnitRunner(self, [u] + ([self.lora_layers[i]] if self.lora_layers else []), layer_fn)
+                              for i, u in enumerate(self.layers)]
         self.head_lp_runner = UnitRunner(self, head_units, head_lp_fn)
         self.head_value_runner = UnitRunner(self, [self.head], head_value_fn)
         self.head_logits_runner = UnitRunner(self, head_units, head_logits_fn)
@@ -591,21 +610,21 @@ class Zero3Engine:
 
     # ---- optimizer ------------------------------------------------------------------------------
     def zero_grad(self) -> None:
-        for u in self.units:
+        for u in self.opt_units:
             u.wait_grads()
             u.grad_acc.zero_()
 
     def grad_norm_sq(self) -> torch.Tensor:
-        for u in self.units:
+        for u in self.opt_units:
             u.wait_grads()
         if self.use_kernels:
             self.total_sumsq.zero_()
-            for u in self.units:
+            for u in self.opt_units:
                 self.C.sumsq_(u.grad_acc, self.total_sumsq)
             tot = self.total_sumsq
         else:
             tot = torch.zeros(1, device=self.device)
-            for u in self.units:
+            for u in self.opt_units:
                 tot += u.grad_acc.pow(2).sum()
         if self.world > 1:
             dist.all_reduce(tot, group=self.group)
@@ -614,13 +633,13 @@ class Zero3Engine:
     def step(self, lr: float | None = None) -> dict:
         """Clip + AdamW on every shard.  Returns {'grad_norm': float, 'skipped': bool}."""
         lr = self.lr if lr is None else lr
-        for u in self.units:
+        for u in self.opt_units:
             u.wait_grads()            # comm-stream reduce-scatters (and their barriers) precede this stream's barrier
         if self.heap is not None and self.world > 1:
             self.heap.barrier()       # nobody may still be pulling the shards we are about to rewrite
         if self.replica_group is not None and dist.get_world_size(self.replica_group) > 1:
             nrep = dist.get_world_size(self.replica_group)
-            for u in self.units:
+            for u in self.opt_units:
                 dist.all_reduce(u.grad_acc, group=self.replica_group)
                 u.grad_acc.div_(nrep)
         tot = self.grad_norm_sq()
@@ -628,7 +647,7 @@ class Zero3Engine:
         b1, b2 = self.betas
         if self.use_kernels:
             self.status.zero_()
-            for u in self.units:
+            for u in self.opt_units:
                 self.C.adamw_(u.master, u.exp_avg, u.exp_avg_sq, u.grad_acc, u.shard, lr, b1, b2, self.eps,
                               self.weight_decay, self.opt_step, self.max_grad_norm, tot, self.status, True)
             norm = float(tot.sqrt().item())
@@ -638,11 +657,11 @@ class Zero3Engine:
             skipped = not math.isfinite(norm)
             if not skipped:
                 coef = min(1.0, self.max_grad_norm / (norm + 1e-6)) if self.max_grad_norm > 0 else 1.0
-                for u in self.units:
+                for u in self.opt_units:
                     ref.adamw_step(u.master, u.exp_avg, u.exp_avg_sq, u.grad_acc, lr, b1, b2, self.eps,
                                    self.weight_decay, self.opt_step, coef)
                     u.shard.copy_(u.master.to(u.shard.dtype))
-            for u in self.units:
+            for u in self.opt_units:
                 u.grad_acc.zero_()
         if skipped:
             self.opt_step -= 1
@@ -659,7 +678,7 @@ class Zero3Engine:
         phase of a colocated step); ``load_optimizer`` brings them back before the next update."""
         if not self.trainable or not self.is_cuda or getattr(self, "_opt_offloaded", False):
             return
-        for u in self.units:
+        for u in self.opt_units:
             for name in ("master", "exp_avg", "exp_avg_sq", "grad_acc"):
                 t = getattr(u, name)
                 host = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
@@ -672,7 +691,7 @@ class Zero3Engine:
     def load_optimizer(self) -> None:
         if not getattr(self, "_opt_offloaded", False):
             return
-        for u in self.units:
+        for u in self.opt_units:
             for name in ("master", "exp_avg", "exp_avg_sq", "grad_acc"):
                 setattr(u, name, getattr(u, name).to(self.device, non_blocking=True))
         torch.cuda.synchronize(self.device)

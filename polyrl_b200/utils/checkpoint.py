@@ -82,7 +82,8 @@ class ShardedCheckpointManager:
                         for u in eng.units}, mp)
         if "optimizer" in self.save_contents and eng.trainable:
             torch.save({"opt_step": eng.opt_step,
-                        "units": {u.name: {"exp_avg": u.exp_avg.cpu(), "exp_avg_sq": u.exp_avg_sq.cpu()} for u in eng.units}}, op)
+                        "units": {u.name: {"exp_avg": u.exp_avg.cpu(), "exp_avg_sq": u.exp_avg_sq.cpu()} for u in eng.units
+                                  if u.exp_avg is not None}}, op)
         if "extra" in self.save_contents:
             torch.save({"extra": extra or {}, "rng": _rng_state(eng.device), "global_step": global_step}, ep)
         if eng.rank == 0:
@@ -107,10 +108,13 @@ class ShardedCheckpointManager:
                 if u.master is not None and sd[u.name]["master"] is not None:
                     u.master.copy_(sd[u.name]["master"])
                 u.drop_gathered()
+            eng._resident_stale = True
         if "optimizer" in self.load_contents and eng.trainable and op.exists():
             sd = torch.load(op, map_location="cpu", weights_only=False)
             eng.opt_step = sd["opt_step"]
             for u in eng.units:
+                if u.exp_avg is None:
+                    continue
                 u.exp_avg.copy_(sd["units"][u.name]["exp_avg"])
                 u.exp_avg_sq.copy_(sd["units"][u.name]["exp_avg_sq"])
         extra = None

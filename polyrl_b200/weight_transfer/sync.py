@@ -104,7 +104,9 @@ class WeightSync:
     # ---------------------------------------------------------------- trainer side
     def push(self, engine, version: int | None = None) -> None:
         """Called on every trainer rank with its ZeRO-3 engine."""
-        units = engine.units
+        units = engine.base_units
+        if getattr(engine, "lora", None) is not None:
+            raise NotImplementedError("LoRA adapters are merged on the colocated path only; export + reload for disaggregated rollouts")
         t_idx = self.trainer_ranks.index(self.rank)
         if self.backend == "p2p":
             C = engine.C

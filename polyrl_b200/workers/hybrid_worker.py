@@ -112,11 +112,15 @@ class ActorRolloutRefWorker:
                 grp = dist.new_group(base[i::fs])
                 if i == self.rank % fs:
                     self.replica_group = grp
+        from ..models.lora import LoraConfig
+
+        m = arr.model
+        self.lora_cfg = LoraConfig.from_model_cfg(m.lora_rank, m.lora_alpha, m.target_modules)
         if self.has_actor:
             self.actor_engine = Zero3Engine(self.model_cfg, self.device, group=self.shard_group, comm=comm, trainable=True,
                                             seed=seed, lr=opt.lr, betas=tuple(opt.betas), eps=opt.eps,
                                             weight_decay=opt.weight_decay, max_grad_norm=arr.actor.grad_clip,
-                                            sp_group=self.sp_group, replica_group=self.replica_group)
+                                            sp_group=self.sp_group, replica_group=self.replica_group, lora=self.lora_cfg)
             fc = arr.actor.fsdp_config
             eng = self.actor_engine
             want = str(fc.resident_params).lower()
@@ -162,20 +166,37 @@ class ActorRolloutRefWorker:
         if eng is None or self.rollout is None:
             return False
         self.weight_version += 1
-        if eng.world == 1:
-            views = [u.views(u.shard) for u in eng.units]
+        base = eng.base_units
+        if eng.lora is not None:
+            # adapters are merged into an engine-owned replica (reference: layered summon + merge, fsdp_utils.py:569-694)
+            from ..models.lora import merge_layer_
+
+            if self._rollout_full is None:
+                self._rollout_full = {u.name: torch.empty(u.full_numel, device=self.device, dtype=eng.param_dtype) for u in base}
+            views = []
+            for u in base:
+                full = u.acquire()
+                self._rollout_full[u.name].copy_(full)
+                u.release()
+                views.append(u.views(self._rollout_full[u.name]))
+            for i, lu in enumerate(eng.lora_layers):
+                lfull = lu.acquire()
+                merge_layer_(self.model_cfg, views[1 + i], lu.views(lfull), eng.lora.scale)
+                lu.release()
+        elif eng.world == 1:
+            views = [u.views(u.shard) for u in base]
         elif eng.resident:
             eng.ensure_resident()           # one gather per optimizer step; the engine aliases the trainer's replica
-            views = [u.views(u._resident) for u in eng.units]
+            views = [u.views(u._resident) for u in base]
         else:
             if self._rollout_full is None:
                 self._rollout_full = {u.name: torch.empty(u.full_numel, device=self.device, dtype=eng.param_dtype)
-                                      for u in eng.units}
+                                      for u in base}
             if eng.heap is not None:
                 eng.heap.barrier()
-            for u in eng.units:
+            for u in base:
                 u._gather_into(self._rollout_full[u.name])
-            views = [u.views(self._rollout_full[u.name]) for u in eng.units]
+            views = [u.views(self._rollout_full[u.name]) for u in base]
         self.rollout.set_weights(views[0], views[1:-1], views[-1], version=self.weight_version)
         return True
 
