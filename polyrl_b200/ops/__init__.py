@@ -77,6 +77,7 @@ from .functional import (  # noqa: E402
     rmsnorm,
     apply_rope,
     linear_cross_entropy,
+    linear_cross_entropy_tp,
     paged_decode_attention,
     sample_tokens,
 )
@@ -91,6 +92,7 @@ __all__ = [
     "rmsnorm",
     "apply_rope",
     "linear_cross_entropy",
+    "linear_cross_entropy_tp",
     "paged_decode_attention",
     "sample_tokens",
 ]

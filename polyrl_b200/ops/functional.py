@@ -283,6 +283,80 @@ def linear_cross_entropy(hidden: torch.Tensor, weight: torch.Tensor, labels: tor
     return lp.reshape(labels.shape), ent.reshape(labels.shape)
 
 
+class _LinearCETPFn(torch.autograd.Function):
+    """Vocab-parallel fused linear + cross-entropy: every TP rank holds ``weight[V/tp, H]``.  Local online-softmax
+    stats come from the same tcgen05 kernel; ONE all-gather of [T, 3] (lse, E[z], label logit) replaces the three
+    all-reduces of the reference's TP mode (verl/utils/kernel/kernels.py:642-694), and the backward all-reduces dH."""
+
+    @staticmethod
+    def forward(ctx, hidden, w_shard, labels, inv_tau, group, vocab_start):
+        import torch.distributed as dist
+
+        h2 = hidden.reshape(-1, hidden.shape[-1])
+        if not h2.is_contiguous():
+            h2 = h2.contiguous()
+        vs = w_shard.shape[0]
+        lab_local = (labels.reshape(-1) - vocab_start).contiguous()
+        in_shard = (lab_local >= 0) & (lab_local < vs)
+        kernel = _is_kernel_tensor(h2) and w_shard.dtype == torch.bfloat16 and vs % 8 == 0
+        if kernel:
+            lp_l, _, lse_l, ez_l = _C().linear_ce_fwd(h2, w_shard, lab_local, inv_tau)
+            zlab = torch.where(in_shard, lp_l + lse_l, torch.zeros_like(lp_l))
+        else:
+            z = (h2.float() @ w_shard.float().t()) * inv_tau
+            lse_l = torch.logsumexp(z, -1)
+            ez_l = (torch.softmax(z, -1) * z).sum(-1)
+            zlab = torch.where(in_shard, z.gather(-1, lab_local.clamp(0, vs - 1).unsqueeze(-1)).squeeze(-1), torch.zeros_like(lse_l))
+        tp = dist.get_world_size(group)
+        stats = torch.stack([lse_l, ez_l, zlab], dim=-1).contiguous()                  # [T, 3]
+        allst = [torch.empty_like(stats) for _ in range(tp)]
+        dist.all_gather(allst, stats, group=group)
+        allst = torch.stack(allst)                                                      # [tp, T, 3]
+        lse = torch.logsumexp(allst[..., 0], dim=0)
+        ez = (torch.exp(allst[..., 0] - lse) * allst[..., 1]).sum(0)
+        lp = allst[..., 2].sum(0) - lse
+        ent = lse - ez
+        ctx.save_for_backward(h2, w_shard, lab_local, lse.contiguous(), ez.contiguous())
+        ctx.inv_tau, ctx.group, ctx.kernel, ctx.h_shape = inv_tau, group, kernel, hidden.shape
+        return lp.reshape(labels.shape), ent.reshape(labels.shape)
+
+    @staticmethod
+    def backward(ctx, g_lp, g_ent):
+        import torch.distributed as dist
+
+        h2, w, lab, lse, ez = ctx.saved_tensors
+        g_lp = g_lp.reshape(-1).float().contiguous() if g_lp is not None else torch.zeros_like(lse)
+        g_ent = g_ent.reshape(-1).float().contiguous() if g_ent is not None else torch.zeros_like(lse)
+        vs = w.shape[0]
+        need_h, need_w = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        dh = torch.zeros_like(h2, dtype=torch.float32)
+        dw = torch.empty_like(w) if need_w else None
+        for v0 in range(0, vs, _CE_CHUNK):
+            v1 = min(vs, v0 + _CE_CHUNK)
+            ws = w[v0:v1]
+            if ctx.kernel:
+                dz = _C().linear_ce_dz(h2, ws, lab, lse, ez, g_lp, g_ent, ctx.inv_tau, v0)
+            else:
+                z = (h2.float() @ ws.float().t()) * ctx.inv_tau
+                p = torch.exp(z - lse[:, None])
+                onehot = (torch.arange(v0, v1, device=z.device)[None] == lab[:, None]).float()
+                dz = ctx.inv_tau * (g_lp[:, None] * (onehot - p) - g_ent[:, None] * p * (z - ez[:, None]))
+                dz = dz.to(h2.dtype)
+            if need_h:
+                dh.add_((dz @ ws).float())
+            if need_w:
+                torch.mm(dz.t(), h2, out=dw[v0:v1])
+        if need_h:
+            dist.all_reduce(dh, group=ctx.group)
+        return (dh.to(h2.dtype).reshape(ctx.h_shape) if need_h else None), dw, None, None, None, None
+
+
+def linear_cross_entropy_tp(hidden: torch.Tensor, weight_shard: torch.Tensor, labels: torch.Tensor, temperature: float,
+                            group, vocab_start: int) -> tuple[torch.Tensor, torch.Tensor]:
+    """Vocab-parallel variant of ``linear_cross_entropy``: ``weight_shard`` = rows [vocab_start, vocab_start + V/tp)."""
+    return _LinearCETPFn.apply(hidden, weight_shard, labels, 1.0 / float(temperature), group, int(vocab_start))
+
+
 # --------------------------------------------------------------------------------------------
 # rollout-side ops (no autograd)
 # --------------------------------------------------------------------------------------------

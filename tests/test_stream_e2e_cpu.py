@@ -76,3 +76,14 @@ def test_hsdp_equivalence_gloo():
     vals = dict(kv.split("=") for kv in line[0].split()[1:])
     assert float(vals["w_err"]) < 1e-4 and float(vals["gn_err"]) < 1e-4
     assert float(vals["resident_err"]) < 1e-4          # resident replica + saved activations == ZeRO-3 + recompute
+
+
+def test_vocab_parallel_linear_ce_gloo():
+    """TP (vocab-parallel) fused linear-CE == unsharded op, values and gradients (reference TP mode: kernels.py:642-694)."""
+    env = {**os.environ, "PYTHONPATH": str(ROOT), "OMP_NUM_THREADS": "2", "CE_TP_DEVICE": "cpu"}
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29691", str(ROOT / "tests" / "ce_tp_worker.py")], capture_output=True, text=True, timeout=300, env=env)
+    line = [l for l in r.stdout.splitlines() if l.startswith("CE_TP_RESULTS")]
+    assert r.returncode == 0 and line, r.stdout[-2000:] + r.stderr[-2000:]
+    vals = dict(kv.split("=") for kv in line[0].split()[1:])
+    assert all(float(v) < 1e-4 for v in vals.values()), vals
