@@ -34,13 +34,37 @@ def main(argv=None) -> int:
     ap.add_argument("--weight-receiver-zmq-bind-host", default="0.0.0.0")
     ap.add_argument("--transfer-agent-sender-group-idx", type=int, default=0)
     ap.add_argument("--num-transfer-engines-per-group", type=int, default=1)
+    ap.add_argument("--tp-size", type=int, default=1, help="tensor-parallel degree; launch with torchrun --nproc-per-node TP")
     a = ap.parse_args(argv)
     cfg = get_model_config(a.model_path)
     dtype = torch.bfloat16 if a.device.startswith("cuda") else torch.float32
-    w = TransformerWeights(cfg, device=a.device, dtype=dtype, init=True)
+    tp_ctx = cmd_group = None
+    tp_rank = 0
+    if a.tp_size > 1:
+        # one process per TP rank (torchrun); rank 0 owns the HTTP front-end, the others mirror its commands
+        import os
+
+        import torch.distributed as dist
+
+        from ..parallel.symm import SymmetricHeap
+        from .tp import TPContext
+
+        tp_rank = int(os.environ["RANK"])
+        a.device = f"cuda:{int(os.environ.get('LOCAL_RANK', 0))}"
+        torch.cuda.set_device(a.device)
+        dist.init_process_group("nccl", device_id=torch.device(a.device))
+        cmd_group = dist.new_group(list(range(a.tp_size)), backend="gloo")
+        heap = SymmetricHeap(group=None, device=torch.device(a.device))
+        tp_ctx = TPContext(cfg, heap, tp_rank, a.tp_size, max_batch=a.max_num_seqs)
+    w = TransformerWeights(cfg, device=a.device, dtype=dtype, init=True)          # same seed on every TP rank
     eng = RolloutEngine(cfg, a.device, max_num_seqs=a.max_num_seqs, max_model_len=a.max_model_len,
-                        gpu_memory_utilization=a.mem_fraction_static)
+                        gpu_memory_utilization=a.mem_fraction_static, tp=tp_ctx)
     eng.set_weights(w.embed, w.layers, w.head)
+    if tp_rank > 0:
+        from .server import run_tp_follower
+
+        run_tp_follower(eng, cmd_group)
+        return 0
     receiver = None
     if a.enable_weight_transfer_agent:
         from ..weight_transfer.tcp_engine import TCPWeightReceiver
@@ -53,7 +77,8 @@ def main(argv=None) -> int:
             receiver.wait_and_apply(timeout=3600)
         return True, "ok"
 
-    srv = EngineServer(eng, host=a.host, port=a.port, stream_interval=a.stream_interval, weight_update_fn=on_update).start()
+    srv = EngineServer(eng, host=a.host, port=a.port, stream_interval=a.stream_interval, weight_update_fn=on_update,
+                       tp_cmd_group=cmd_group).start()
     if a.rollout_manager_address:
         info = srv.register_with_manager(a.rollout_manager_address, local=False, handshake_port=a.transfer_agent_handshake_port)
         print(f"[engine] registered with manager: {info}", flush=True)

@@ -30,8 +30,14 @@ class _Tracked:
 
 class EngineServer:
     def __init__(self, engine: RolloutEngine, host: str = "127.0.0.1", port: int = 0, stream_interval: int = 20,
-                 weight_update_fn=None):
+                 weight_update_fn=None, tp_cmd_group=None):
         self.engine = engine
+        # tensor-parallel serving: this object lives on TP rank 0; every scheduler iteration its command list is
+        # broadcast over ``tp_cmd_group`` (a gloo group of the TP ranks) so that followers (``run_tp_follower``) apply the
+        # same requests / aborts / weight updates and then take the same engine step (reference: SGLang broadcasts
+        # scheduler inputs to its TP workers; weight fan-out rlboost/sglang/patches.py:185-241)
+        self.tp_cmd_group = tp_cmd_group
+        self._rid = 0
         self.stream_interval = stream_interval
         self.weight_update_fn = weight_update_fn        # callable(payload dict) -> (ok, message)
         self._lock = threading.Lock()
@@ -218,30 +224,35 @@ class EngineServer:
         while not self._stop.is_set():
             with self._lock:
                 cmds, self._inbox = self._inbox, []
+            wire = []                                   # serialisable mirror of the commands (TP followers)
             for kind, payload, done in cmds:
                 try:
                     if kind == "generate":
                         key, prompts, sp, q = payload
-                        tag = object() if len(prompts) > 1 and all(p == prompts[0] for p in prompts) else None
-                        tracked = [_Tracked(eng.add_request(list(map(int, p)), sp, group=tag), i) for i, p in enumerate(prompts)]
+                        rids = []
+                        for _ in prompts:
+                            self._rid += 1
+                            rids.append(f"s{self._rid}")
+                        wire.append(("generate", {"prompts": prompts, "sp": sp.__dict__, "rids": rids}))
+                        tracked = [_Tracked(r, i) for i, r in enumerate(_add_group(eng, prompts, sp, rids))]
                         self._streams[key] = (q, tracked)
-                    elif kind == "abort":
-                        eng.abort(payload.get("rid") or None, abort_all=bool(payload.get("abort_all", not payload.get("rid"))))
                     elif kind == "abort_key":
                         ent = self._streams.pop(payload, None)
-                        if ent:
-                            for t in ent[1]:
-                                eng.abort(t.req.rid)
-                    elif kind == "release":
-                        eng.abort(abort_all=True)
-                        eng.release_memory(tuple((payload or {}).get("tags") or ("kv_cache",)))
-                    elif kind == "resume":
-                        eng.resume_memory(tuple((payload or {}).get("tags") or ("kv_cache",)))
+                        rids = [t.req.rid for t in ent[1]] if ent else []
+                        wire.append(("abort_rids", rids))
+                        _apply_wire(eng, "abort_rids", rids, None)
                     elif kind == "update_weights":
                         body, result = payload
+                        if self.tp_cmd_group is not None:
+                            _tp_broadcast(self.tp_cmd_group, wire + [("update_weights", body)], 0)
+                            wire = []
                         while eng.has_work() and not body.get("bootstrap"):
+                            if self.tp_cmd_group is not None:
+                                _tp_broadcast(self.tp_cmd_group, [], 1)
                             eng.step()              # drain in-flight requests on the old weights
                             self._flush_streams()
+                        if self.tp_cmd_group is not None:
+                            _tp_broadcast(self.tp_cmd_group, [("apply_weights", body)], 0)
                         ok, msg = True, "ok"
                         if self.weight_update_fn is not None:
                             ok, msg = self.weight_update_fn(body)
@@ -249,17 +260,25 @@ class EngineServer:
                             self.weight_version = int(body.get("weight_version", self.weight_version + 1))
                             eng.weight_version = self.weight_version
                         result["ok"], result["msg"] = ok, msg
+                    else:                           # abort / release / resume
+                        wire.append((kind, payload))
+                        _apply_wire(eng, kind, payload, None)
                 except Exception as e:  # keep the engine thread alive
                     if kind == "update_weights":
                         payload[1]["ok"], payload[1]["msg"] = False, repr(e)
                 finally:
                     if done is not None:
                         done.set()
-            if eng.layer_w is not None and eng.has_work():
+            do_step = eng.layer_w is not None and eng.has_work()
+            if self.tp_cmd_group is not None and (wire or do_step):
+                _tp_broadcast(self.tp_cmd_group, wire, int(do_step))
+            if do_step:
                 eng.step()
                 self._flush_streams()
             else:
                 time.sleep(0.002)
+        if self.tp_cmd_group is not None:
+            _tp_broadcast(self.tp_cmd_group, [("shutdown", None)], 0)
 
     def _flush_streams(self) -> None:
         for key in list(self._streams):
@@ -277,3 +296,58 @@ class EngineServer:
                         t.sent = n
             if not alive:
                 self._streams.pop(key, None)
+
+
+# ---------------------------------------------------------------------------------------------- TP lock-step helpers
+def _add_group(eng: RolloutEngine, prompts, sp: SamplingParams, rids) -> list[Request]:
+    tag = object() if len(prompts) > 1 and all(p == prompts[0] for p in prompts) else None
+    return [eng.add_request(list(map(int, p)), sp, rid=rid, group=tag) for p, rid in zip(prompts, rids)]
+
+
+def _apply_wire(eng: RolloutEngine, kind: str, payload, weight_update_fn) -> bool:
+    """Apply one broadcast command on an engine replica.  Returns False on shutdown."""
+    if kind == "generate":
+        _add_group(eng, payload["prompts"], SamplingParams(**{**payload["sp"], "stop_token_ids": tuple(payload["sp"].get("stop_token_ids", ()))}),
+                   payload["rids"])
+    elif kind == "abort_rids":
+        for rid in payload:
+            eng.abort(rid)
+    elif kind == "abort":
+        eng.abort(payload.get("rid") or None, abort_all=bool(payload.get("abort_all", not payload.get("rid"))))
+    elif kind == "release":
+        eng.abort(abort_all=True)
+        eng.release_memory(tuple((payload or {}).get("tags") or ("kv_cache",)))
+    elif kind == "resume":
+        eng.resume_memory(tuple((payload or {}).get("tags") or ("kv_cache",)))
+    elif kind == "apply_weights":
+        if weight_update_fn is not None:
+            weight_update_fn(payload)
+        if not payload.get("bootstrap"):
+            eng.weight_version = int(payload.get("weight_version", eng.weight_version + 1))
+    elif kind == "shutdown":
+        return False
+    return True
+
+
+def _tp_broadcast(group, wire: list, do_step: int, src_is_me: bool = True):
+    """One scheduler tick on the command channel: [commands, do_step] from TP rank 0 to the followers."""
+    import torch.distributed as dist
+
+    box = [(wire, do_step)] if src_is_me else [None]
+    dist.broadcast_object_list(box, src=dist.get_process_group_ranks(group)[0], group=group)
+    return box[0]
+
+
+def run_tp_follower(engine: RolloutEngine, tp_cmd_group, weight_update_fn=None) -> None:
+    """Main loop of TP ranks > 0: mirror rank 0's commands, then take the same engine step."""
+    while True:
+        wire, do_step = _tp_broadcast(tp_cmd_group, None, 0, src_is_me=False)
+        alive = True
+        for kind, payload in wire:
+            if kind == "update_weights":
+                continue                    # rank 0 drains with explicit do_step ticks, then sends apply_weights
+            alive = _apply_wire(engine, kind, payload, weight_update_fn) and alive
+        if not alive:
+            return
+        if do_step:
+            engine.step()

@@ -104,3 +104,20 @@ def test_rollout_registry_and_naive_oracle():
         assert a == b
         assert max(abs(x - y) for x, y in zip(la, lb)) < 1e-4
     assert get_rollout_cls("sglang") is get_rollout_cls("native")
+
+
+def test_tp_server_lockstep_gloo():
+    """Rank-0 HTTP front-end + follower rank mirror the same commands and produce identical generations."""
+    import os
+    import subprocess
+    import sys
+    from pathlib import Path
+
+    root = Path(__file__).resolve().parent.parent
+    env = {**os.environ, "PYTHONPATH": str(root), "OMP_NUM_THREADS": "2"}
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29693", str(root / "tests" / "tp_server_worker.py")], capture_output=True, text=True,
+                       timeout=300, env=env)
+    line = [l for l in r.stdout.splitlines() if l.startswith("TP_SERVER_RESULTS")]
+    assert r.returncode == 0 and line, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "same=1 http_ok=1 n=4 versions=True wv=True" in line[0]
