@@ -76,6 +76,8 @@ from .functional import (  # noqa: E402
     linear_swiglu,
     rmsnorm,
     apply_rope,
+    Fp8Weight,
+    quantize_weight_fp8,
     linear_cross_entropy,
     linear_cross_entropy_tp,
     paged_decode_attention,
@@ -91,6 +93,8 @@ __all__ = [
     "linear_swiglu",
     "rmsnorm",
     "apply_rope",
+    "Fp8Weight",
+    "quantize_weight_fp8",
     "linear_cross_entropy",
     "linear_cross_entropy_tp",
     "paged_decode_attention",

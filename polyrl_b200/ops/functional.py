@@ -63,6 +63,61 @@ def skinny_linear(x2: torch.Tensor, w: torch.Tensor, bias=None, residual=None, m
 
 
 # --------------------------------------------------------------------------------------------
+# fp8 (e4m3, per-output-row scale) inference weights: rollout-side only (BASELINE config "fp8 rollout, bf16 update")
+# --------------------------------------------------------------------------------------------
+class Fp8Weight:
+    """``q`` [N, K] float8_e4m3fn + ``scale`` [N] fp32 (w ~= q * scale[:, None]).  Activations are quantised per token
+    on the fly; the GEMM is the tcgen05 kind::f8f6f4 kernel with both scale vectors applied in the epilogue."""
+    __slots__ = ("q", "scale")
+
+    def __init__(self, q: torch.Tensor, scale: torch.Tensor):
+        self.q, self.scale = q, scale
+
+    @property
+    def shape(self):
+        return self.q.shape
+
+    @property
+    def dtype(self):
+        return self.q.dtype
+
+    def dequant(self, dtype=torch.float32) -> torch.Tensor:
+        return (self.q.float() * self.scale[:, None]).to(dtype)
+
+
+def quantize_fp8_rowwise(x: torch.Tensor):
+    if x.is_cuda and x.dtype == torch.bfloat16 and x.dim() == 2:
+        q, s = _C().quant_fp8_rowwise(x.contiguous())
+        return q, s
+    xf = x.float()
+    s = xf.abs().amax(-1).clamp_min(1e-12) / 448.0
+    return (xf / s[:, None]).to(torch.float8_e4m3fn), s
+
+
+def quantize_weight_fp8(w: torch.Tensor) -> Fp8Weight:
+    return Fp8Weight(*quantize_fp8_rowwise(w))
+
+
+def _linear_fp8(x: torch.Tensor, w: Fp8Weight, bias=None, residual=None, swiglu: bool = False) -> torch.Tensor:
+    if x.is_cuda and x.dtype == torch.bfloat16:
+        xq, xs = quantize_fp8_rowwise(x)
+        n = w.q.shape[0]
+        if x.shape[0] <= _SKINNY_MAX_ROWS and n >= 128 and (not swiglu or n % 256 == 0):
+            wsb, ctr = _skinny_buffers(x.device)              # swap-AB split-K kernel: fp8 operands, fused scales/residual/SwiGLU
+            r = residual.contiguous() if residual is not None else None
+            return _C().skinny_gemm(xq, w.q, r, bias, xs, w.scale, wsb, ctr, 1 if swiglu else 0, 0)
+        y = _C().gemm_fp8(xq, w.q, xs, w.scale, 0)
+    else:                                                       # CPU emulation: same quantisation, fp32 matmul
+        xq, xs = quantize_fp8_rowwise(x)
+        y = ((xq.float() * xs[:, None]) @ w.dequant().t()).to(x.dtype)
+    if swiglu:
+        return ref.swiglu(y)
+    if bias is not None:
+        y = y + bias.to(y.dtype)
+    return y + residual if residual is not None else y
+
+
+# --------------------------------------------------------------------------------------------
 # linear (+ residual) : tcgen05 GEMM forward with fused residual epilogue
 # --------------------------------------------------------------------------------------------
 class _LinearFn(torch.autograd.Function):
@@ -102,6 +157,8 @@ class _LinearFn(torch.autograd.Function):
 def linear(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None = None,
            residual: torch.Tensor | None = None) -> torch.Tensor:
     """y = x @ w.T (+ bias) (+ residual).  w is [out, in] (nn.Linear layout)."""
+    if isinstance(w, Fp8Weight):
+        return _linear_fp8(x, w, bias, residual)
     if _is_kernel_tensor(x) and w.dtype == torch.bfloat16 and x.dim() == 2 and _use_skinny(x, w):
         return skinny_linear(x, w, bias, residual, 0)
     if _is_kernel_tensor(x) and w.dtype == torch.bfloat16 and x.dim() == 2 and _decode_policy() in ("auto", "cublas") \
@@ -152,6 +209,8 @@ class _LinearSwigluFn(torch.autograd.Function):
 
 def linear_swiglu(x: torch.Tensor, wgu: torch.Tensor) -> torch.Tensor:
     """silu(x @ Wg.T) * (x @ Wu.T) with W_gu stored block-interleaved ([128 gate | 128 up] rows)."""
+    if isinstance(wgu, Fp8Weight):
+        return _linear_fp8(x, wgu, swiglu=True)
     if _is_kernel_tensor(x) and wgu.dtype == torch.bfloat16 and x.dim() == 2 and _use_skinny(x, wgu):
         return skinny_linear(x, wgu, None, None, 1)
     if _is_kernel_tensor(x) and wgu.dtype == torch.bfloat16 and not _cublas():

@@ -107,7 +107,14 @@ class BlockAllocator:
 class RolloutEngine:
     def __init__(self, cfg: ModelConfig, device, max_num_seqs: int = 256, max_model_len: int = 2048,
                  kv_cache_tokens: int | None = None, gpu_memory_utilization: float = 0.5, dtype=None,
-                 use_cuda_graph: bool = True, max_prefill_tokens: int = 16384, seed: int = 0, tp=None):
+                 use_cuda_graph: bool = True, max_prefill_tokens: int = 16384, seed: int = 0, tp=None,
+                 weight_dtype: str = "bf16"):
+        if weight_dtype not in ("bf16", "fp8"):
+            raise ValueError("weight_dtype must be 'bf16' or 'fp8'")
+        if weight_dtype == "fp8" and tp is not None:
+            raise NotImplementedError("fp8 rollout weights with tensor parallelism")
+        self.weight_dtype = weight_dtype               # fp8: projections re-quantised (e4m3, per-row scale) at every sync
+        self._fp8_cache: list[dict] = []
         self.tp = tp                               # rollout.tp.TPContext for tensor-parallel engines
         self.full_cfg = cfg
         cfg = tp.local_cfg() if tp is not None else cfg   # per-rank view: local heads / kv heads / intermediate
@@ -148,16 +155,45 @@ class RolloutEngine:
         old = self._weight_ptrs()
         if self.tp is not None:
             layer_w = [self.tp.shard_layer(w) for w in layer_w]
+        if self.weight_dtype == "fp8":
+            layer_w = self._quantize_layers(layer_w)
         self.embed_w, self.layer_w, self.head_w = embed_w, layer_w, head_w
         if old != self._weight_ptrs():
             self._graphs.clear()
         if version is not None:
             self.weight_version = version
 
+    _FP8_KEYS = ("wqkv", "wo", "wgu", "wd")
+
+    @torch.no_grad()
+    def _quantize_layers(self, layer_w: list[dict]) -> list[dict]:
+        """bf16 -> (e4m3, row scale) for the four block projections; buffers are reused across syncs so captured decode
+        graphs stay valid (reference capability: fp8 rollout with bf16 update, BASELINE config 4)."""
+        fresh = len(self._fp8_cache) != len(layer_w)
+        if fresh:
+            self._fp8_cache = [dict() for _ in layer_w]
+        out = []
+        for w, cache in zip(layer_w, self._fp8_cache):
+            nw = dict(w)
+            for k in self._FP8_KEYS:
+                if k not in w:
+                    continue
+                src = w[k] if w[k].dtype in (torch.bfloat16, torch.float32) else w[k].float()
+                fw = ops.quantize_weight_fp8(src.to(self.dtype) if src.dtype != self.dtype else src)
+                if k in cache and cache[k].q.shape == fw.q.shape:
+                    cache[k].q.copy_(fw.q)
+                    cache[k].scale.copy_(fw.scale)
+                else:
+                    cache[k] = fw
+                nw[k] = cache[k]
+            out.append(nw)
+        return out
+
     def _weight_ptrs(self):
         if self.layer_w is None:
             return None
-        return tuple(t.data_ptr() for w in [self.embed_w, *self.layer_w, self.head_w] for t in w.values())
+        return tuple((t.q if isinstance(t, ops.Fp8Weight) else t).data_ptr()
+                     for w in [self.embed_w, *self.layer_w, self.head_w] for t in w.values())
 
     def kv_bytes_per_token(self) -> int:
         c = self.cfg

@@ -153,7 +153,8 @@ class ActorRolloutRefWorker:
             max_len = r.max_model_len or (cfg.data.max_prompt_length + cfg.data.max_response_length)
             self.rollout = RolloutEngine(self.model_cfg, self.device, max_num_seqs=r.max_num_seqs, max_model_len=max_len,
                                          gpu_memory_utilization=r.gpu_memory_utilization, use_cuda_graph=r.cuda_graph,
-                                         max_prefill_tokens=r.max_num_batched_tokens, seed=seed + 17 * self.rank)
+                                         max_prefill_tokens=r.max_num_batched_tokens, seed=seed + 17 * self.rank,
+                                         weight_dtype=r.weight_dtype)
             if self.has_actor:
                 self.update_weight_remote()
 

@@ -121,3 +121,31 @@ def test_tp_server_lockstep_gloo():
     line = [l for l in r.stdout.splitlines() if l.startswith("TP_SERVER_RESULTS")]
     assert r.returncode == 0 and line, r.stdout[-2000:] + r.stderr[-2000:]
     assert "same=1 http_ok=1 n=4 versions=True wv=True" in line[0]
+
+
+def test_fp8_rollout_weights_cpu_emulation():
+    """weight_dtype=fp8: projections quantised to e4m3 with per-row scales, log-probs stay close to the bf16/fp32 engine and
+    re-syncing re-quantises into the same buffers."""
+    import torch
+
+    from polyrl_b200 import ops
+    from polyrl_b200.models import TransformerWeights, get_model_config
+    from polyrl_b200.rollout.engine import RolloutEngine
+
+    cfg = get_model_config("tiny-llama")
+    w = TransformerWeights(cfg, "cpu", torch.float32, seed=21)
+    prompts = [[5, 9, 33, 7, 21, 8], [12, 4, 4, 8, 19, 3, 77]]
+    res = {}
+    for wd in ("bf16", "fp8"):
+        eng = RolloutEngine(cfg, "cpu", max_num_seqs=4, max_model_len=64, use_cuda_graph=False, seed=0, weight_dtype=wd)
+        eng.set_weights(w.embed, w.layers, w.head)
+        g = eng.generate(prompts, {"max_new_tokens": 6, "temperature": 0.0, "ignore_eos": True})
+        res[wd] = [(r.output_ids, r.logprobs) for grp in g for r in grp]
+        if wd == "fp8":
+            assert isinstance(eng.layer_w[0]["wqkv"], ops.Fp8Weight) and eng.layer_w[0]["wqkv"].q.dtype == torch.float8_e4m3fn
+            ptr = eng.layer_w[0]["wd"].q.data_ptr()
+            eng.set_weights(w.embed, w.layers, w.head)
+            assert eng.layer_w[0]["wd"].q.data_ptr() == ptr
+    # first-token log-probs (same context) differ only by quantisation noise
+    for (a, la), (b, lb) in zip(res["bf16"], res["fp8"]):
+        assert abs(la[0] - lb[0]) < 0.15

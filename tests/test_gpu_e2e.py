@@ -37,3 +37,27 @@ def test_engine_greedy_matches_forward_gpu():
                 gap = (top2.values[t, 0] - pred[t, tok]).item()
                 agree += gap < 0.05 * max(1.0, abs(top2.values[t, 0].item()))
     assert agree / total > 0.97, (agree, total)
+
+
+def test_engine_fp8_weights_gpu():
+    """fp8 rollout weights: the engine's sampled-token log-probs stay close to the bf16 engine's on the same context
+    (tcgen05 kind::f8f6f4 GEMMs with per-token / per-row scales in the decode and prefill paths)."""
+    from polyrl_b200 import ops
+    from polyrl_b200.models import TransformerWeights, get_model_config
+    from polyrl_b200.rollout.engine import RolloutEngine, SamplingParams
+
+    cfg = get_model_config("tiny-llama-128")
+    w = TransformerWeights(cfg, device="cuda", dtype=torch.bfloat16)
+    prompts = [[5, 6, 7, 8, 9, 10, 11], [20, 21, 22, 23], [3, 9] * 20]
+    first = {}
+    for wd in ("bf16", "fp8"):
+        eng = RolloutEngine(cfg, "cuda", max_num_seqs=8, max_model_len=128, kv_cache_tokens=8 * 128, weight_dtype=wd)
+        eng.set_weights(w.embed, w.layers, w.head)
+        n0 = ops.total_launches()
+        groups = eng.generate(prompts, SamplingParams(max_new_tokens=8, temperature=0.0, ignore_eos=True))
+        assert ops.total_launches() > n0
+        first[wd] = [(g[0].output_ids[0], g[0].logprobs[0]) for g in groups]
+        if wd == "fp8":
+            assert isinstance(eng.layer_w[0]["wgu"], ops.Fp8Weight)
+    close = sum(abs(a[1] - b[1]) < 0.25 for a, b in zip(first["bf16"], first["fp8"]))
+    assert close == len(prompts), first
