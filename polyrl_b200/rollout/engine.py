@@ -203,6 +203,8 @@ class RolloutEngine:
         """(Re)create the paged KV pool (``resume_memory_occupation(['kv_cache'])``)."""
         if self.k_cache:
             return
+        if self.is_cuda:
+            torch.cuda.empty_cache()       # hand the trainer's cached activation blocks back before sizing the pool
         if self._kv_tokens_req is not None:
             tokens = self._kv_tokens_req
         elif self.is_cuda:
