@@ -56,6 +56,13 @@ def test_scorers():
     assert default_compute_score("open-r1/OpenR1-Math-220k", "\\boxed{x+1}", "x+1") == 1.0
     with pytest.raises(NotImplementedError):
         default_compute_score("unknown/ds", "", "")
+    f = default_compute_score
+    assert f("math_dapo", "blah\nAnswer: $\\frac{1}{2}$", "\\frac12") == 1.0 and f("aime24", "no answer here", "3") == -1.0
+    assert f("numina_cn_k12", "so we get \\boxed{0.5}", "1/2") == 1.0 and f("numina_olympiads", "the result is 3.14159", "3.1416") == 1.0
+    assert abs(f("hiyouga/geometry3k", "<think>x</think> so \\boxed{12}", "12") - 1.0) < 1e-9
+    assert abs(f("hiyouga/geometry3k", "\\boxed{12}", "12") - 0.9) < 1e-9
+    assert f("searchR1_nq", "<answer>The Eiffel Tower!</answer>", {"target": ["eiffel tower"]}) == 1.0
+    assert f("searchR1_nq", "<answer>London</answer>", {"target": ["Paris"]}) == 0.0
 
 
 def test_checkpoint_roundtrip_and_rotation(tmp_path):
