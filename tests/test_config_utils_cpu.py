@@ -116,3 +116,16 @@ def test_metrics_and_reward_manager():
     assert dapo(d).shape == (b, r)
     v = process_validation_metrics(["a", "a", "a", "a"], ["u1", "u1", "u2", "u2"], {"reward": [1.0, 0.0, 1.0, 1.0]})
     assert v["a"]["reward"]["mean@2"] == pytest.approx(0.75)
+
+
+def test_memory_utils(tmp_path):
+    import time
+
+    from polyrl_b200.utils.memory import MemorySnapshotSampler, aggressive_empty_cache, log_gpu_memory_usage
+
+    assert "allocated_gb" in aggressive_empty_cache()
+    s = MemorySnapshotSampler(str(tmp_path), interval_s=0.02).start()
+    time.sleep(0.1)
+    s.stop()
+    assert s.dump("t").exists() and len(s.samples) >= 2
+    assert "free_gb" in log_gpu_memory_usage("test", rank=None)
