@@ -84,6 +84,30 @@ def main():
     t_copy = timeit(lambda: C.p2p_copy(big.local.data_ptr(), big.ptrs[peer], nb, 0))
     results["peer_write_GBps"] = round(nb / t_copy / 1e6, 1)
 
+    # reduce-scatter (+ fp32 accumulate, scale) of a layer-sized bf16 gradient buffer vs NCCL reduce_scatter + accumulate kernel
+    rs_n = (218_112_000 // (8 * world)) * 8                       # one Llama-3-8B block / world, bf16 elements per rank chunk
+    gbuf = heap.alloc(world * rs_n, torch.bfloat16)
+    gbuf.local.normal_()
+    acc_big = torch.zeros(rs_n, device=dev)
+    heap.barrier()
+
+    def rs_p2p():
+        heap.barrier()
+        C.p2p_reduce_scatter_accum(gbuf.ptrs, rank * rs_n, acc_big, 0.5, rank, None, 32)
+        heap.barrier()
+
+    rs_in = torch.empty(world * rs_n, device=dev)
+    rs_out = torch.empty(rs_n, device=dev)
+
+    def rs_nccl():                                                  # the reference path: cast to fp32, NCCL reduce-scatter, accumulate
+        rs_in.copy_(gbuf.local)
+        dist.reduce_scatter_tensor(rs_out, rs_in)
+        C.grad_accum_(acc_big, rs_out, 0.5, None)
+
+    t_rs, t_rs_nccl = timeit(rs_p2p, 5), timeit(rs_nccl, 5)
+    results["reduce_scatter_layer_ms"] = {"p2p_fused_accum": round(t_rs, 3), "nccl_fp32_rs_plus_accum": round(t_rs_nccl, 3),
+                                          "p2p_GBps_per_gpu_in": round((world - 1) * rs_n * 2 / t_rs / 1e6, 1)}
+
     # ---- 3. all-gather fused GEMM vs (NCCL all-gather + matmul)
     M, K, R = 4096, 4096, 1536 // (world // 2 if world > 2 else 1)
     R = max(256, (R // 256) * 256)

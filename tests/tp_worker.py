@@ -46,6 +46,62 @@ def main():
             head = sum(int(a == b) for o, t in zip(out, want) for a, b in zip(o[:8], t[:8])) / (8 * len(want))
             res[f"first8_agreement_graph{int(graph)}"] = round(head, 4)
         dist.barrier()
+    if os.environ.get("TP_TIMING", "1") == "1":
+        # fused row-parallel GEMM -> all-reduce (one kernel, NVLink peer stores) vs cuBLAS + NCCL all-reduce, at the
+        # Llama-3-8B decode shapes (B=128; o-proj K=4096/W, down-proj K=14336/W), both replayed from CUDA graphs
+        big = get_model_config("llama3-8b", num_layers=1)
+        heap = SymmetricHeap(device=dev)
+        tp = TPContext(big, heap, rank, world, max_batch=128)
+        B, H = 128, big.hidden_size
+        torch.manual_seed(11)
+        timing = {}
+        for name, K in (("o_proj", big.num_heads * big.head_dim // world), ("down_proj", big.intermediate_size // world)):
+            x = torch.randn(B, K, device=dev, dtype=torch.bfloat16)
+            wts = [(torch.randn(H, K, device=dev) * 0.02).to(torch.bfloat16) for _ in range(6)]     # cycle > L2
+            resid = torch.randn(B, H, device=dev, dtype=torch.bfloat16)
+
+            def fused():
+                for wt in wts:
+                    tp.row_parallel(x, wt, resid)
+
+            def lib():
+                for wt in wts:
+                    y = torch.nn.functional.linear(x, wt)
+                    dist.all_reduce(y)
+                    y.add_(resid)
+
+            got = tp.row_parallel(x, wts[0], resid).float()
+            y = torch.nn.functional.linear(x, wts[0]).float()
+            dist.all_reduce(y)
+            timing[f"{name}_err"] = round(((got - (y + resid.float())).norm() / (y + resid.float()).norm()).item(), 5)
+            out = {}
+            for label, fn in (("fused_gemm_allreduce", fused), ("cublas_plus_nccl_allreduce", lib)):
+                s_ = torch.cuda.Stream()
+                s_.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(s_):
+                    for _ in range(3):
+                        fn()
+                torch.cuda.current_stream().wait_stream(s_)
+                torch.cuda.synchronize()
+                dist.barrier()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    fn()
+                for _ in range(3):
+                    g.replay()
+                torch.cuda.synchronize()
+                dist.barrier()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(20):
+                    g.replay()
+                e1.record()
+                torch.cuda.synchronize()
+                t = torch.tensor([e0.elapsed_time(e1) / (20 * len(wts)) * 1e3], device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                out[label + "_us"] = round(t.item(), 2)
+            timing[name] = out
+        res["row_parallel_decode_B128"] = timing
     if rank == 0:
         print("TP_RESULTS " + json.dumps(res), flush=True)
     dist.barrier()
