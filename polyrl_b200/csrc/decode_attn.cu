@@ -74,10 +74,22 @@ paged_decode_kernel(const __nv_bfloat16* __restrict__ q, int64_t ldq,     // [nu
   float m_lo = -INFINITY, m_hi = -INFINITY, l_lo = 0.f, l_hi = 0.f;   // rows gq and gq+8
 
   const int32_t* bt = block_table + static_cast<int64_t>(seq) * ld_bt;
+  constexpr int kLinesPerPage = kPage * D * 2 / 128;          // 128-byte lines in one K (or V) page of one kv head
+  int64_t blk_next = (p_begin + warp < p_end) ? bt[p_begin + warp] : 0;
   for (int p = p_begin + warp; p < p_end; p += kAttnWarps) {
-    const int64_t blk = bt[p];
+    const int64_t blk = blk_next;
     const __nv_bfloat16* kp = k_cache + ((blk * nkv + kvh) * kPage) * D;
     const __nv_bfloat16* vp = v_cache + ((blk * nkv + kvh) * kPage) * D;
+    // ---- software prefetch: look up this warp's NEXT page now (breaks the block-table -> KV dependent-load chain) and pull
+    // its K and V lines into L2 while the current page is being consumed (zero register cost, doubles bytes in flight)
+    if (p + kAttnWarps < p_end) {
+      blk_next = bt[p + kAttnWarps];
+      if (lane < kLinesPerPage) {
+        const int64_t off = ((blk_next * nkv + kvh) * kPage) * D + lane * 64;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(k_cache + off));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(v_cache + off));
+      }
+    }
     // ---- issue every load of this page up front (16 x LDG.128 in flight per lane)
     uint4 kr[2][KC];
 #pragma unroll

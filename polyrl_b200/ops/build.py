@@ -96,11 +96,13 @@ def build(force: bool = False, verbose: bool = False) -> Path:
             list(ex.map(lambda c: _run(c, verbose), jobs))
     if jobs or force or not OUT.exists():
         lib_dirs = ce.library_paths("cuda") if "device_type" in ce.library_paths.__code__.co_varnames else ce.library_paths(True)
-        link = ["g++", "-shared", "-o", str(OUT), *map(str, objs)]
+        tmp_out = OUT.with_suffix(".so.tmp")           # link next to the target, then rename: readers never see a half-written .so
+        link = ["g++", "-shared", "-o", str(tmp_out), *map(str, objs)]
         for d in lib_dirs:
             link += [f"-L{d}", f"-Wl,-rpath,{d}"]
         link += ["-lc10", "-lc10_cuda", "-ltorch_cpu", "-ltorch_cuda", "-ltorch", "-ltorch_python", "-lcudart"]
         _run(link, verbose)
+        tmp_out.replace(OUT)
     return OUT
 
 
