@@ -15,12 +15,51 @@ import torch
 import torch.distributed as dist
 
 
+class PeerAllToAll:
+    """All-to-all over NVLink peer memory: every rank WRITES chunk j straight into rank j's receive slot with the peer-copy
+    kernel (csrc/p2p.cu), bracketed by device-side barriers — no NCCL, no staging, stream-ordered and graph-safe.
+    Replaces ``dist.all_to_all`` on list-of-chunks (reference: verl/utils/ulysses.py:133-152) on one NVSwitch domain.
+    Two receive buffers alternate so a rank may start the next exchange while peers still read the previous one."""
+
+    def __init__(self, heap, max_bytes: int):
+        self.heap, self.world, self.rank = heap, heap.world, heap.rank
+        self.slot_bytes = ((max_bytes + 255) // 256) * 256
+        self.bufs = [heap.alloc(self.world * self.slot_bytes, torch.uint8) for _ in range(2)]
+        self.turn = 0
+        self.C = heap._C
+
+    def __call__(self, parts: list[torch.Tensor]) -> list[torch.Tensor]:
+        nbytes = parts[0].numel() * parts[0].element_size()
+        if nbytes > self.slot_bytes:
+            raise ValueError(f"all-to-all chunk of {nbytes} B exceeds the symmetric slot ({self.slot_bytes} B)")
+        buf = self.bufs[self.turn]
+        self.turn ^= 1
+        self.heap.barrier()                                    # peers finished reading this buffer two exchanges ago
+        for j, p in enumerate(parts):
+            self.C.p2p_copy(p.data_ptr(), buf.ptrs[j] + self.rank * self.slot_bytes, nbytes, 16)
+        self.heap.barrier()                                    # every rank's chunks have landed
+        flat = buf.local
+        return [flat[i * self.slot_bytes:i * self.slot_bytes + nbytes].view(parts[0].dtype).view(parts[0].shape)
+                for i in range(self.world)]
+
+
+_PEER_A2A: dict = {}
+
+
+def enable_peer_all_to_all(group, heap, max_bytes: int) -> None:
+    """Route this SP group's all-to-alls through NVLink peer memory (``heap`` must span exactly ``group``)."""
+    _PEER_A2A[id(group)] = PeerAllToAll(heap, max_bytes)
+
+
 def _all_to_all(x: torch.Tensor, scatter_dim: int, gather_dim: int, group) -> torch.Tensor:
     """Split ``x`` into sp chunks along ``scatter_dim``, exchange, concatenate along ``gather_dim``."""
     sp = dist.get_world_size(group)
     if sp == 1:
         return x
     parts = [p.contiguous() for p in x.chunk(sp, dim=scatter_dim)]
+    peer = _PEER_A2A.get(id(group))
+    if peer is not None and x.is_cuda:
+        return torch.cat(peer(parts), dim=gather_dim)
     if x.is_cuda:
         out = [torch.empty_like(parts[0]) for _ in range(sp)]
         dist.all_to_all(out, parts, group=group)

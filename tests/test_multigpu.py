@@ -37,3 +37,31 @@ def test_tensor_parallel_rollout_engine():
     assert res["lockstep_graph0"] and res["lockstep_graph1"]
     assert res["first8_agreement_graph0"] > 0.9 and res["first8_agreement_graph1"] > 0.9
     assert res["token_agreement_vs_single_gpu_graph0"] > 0.6 and res["token_agreement_vs_single_gpu_graph1"] > 0.6
+
+
+def _torchrun(worker: str, n: int, port: int, tag: str, timeout: int = 600) -> dict:
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1",
+                        "--master-port", str(port), str(ROOT / "tests" / worker)], capture_output=True, text=True,
+                       timeout=timeout, env={**os.environ, "PYTHONPATH": str(ROOT)})
+    line = [l for l in r.stdout.splitlines() if l.startswith(tag)]
+    assert r.returncode == 0 and line, r.stdout[-2000:] + r.stderr[-3000:]
+    return dict(kv.split("=") for kv in line[0].split()[1:])
+
+
+def test_ulysses_sp_nccl_and_peer_memory():
+    """SP=2 == no SP (bf16 tolerances), and the NVLink peer-memory all-to-all == the NCCL all-to-all."""
+    v = _torchrun("ulysses_worker.py", 2, 29657, "ULYSSES_RESULTS")
+    assert float(v["lp_err"]) < 5e-2 and float(v["w_err"]) < 5e-2
+    assert float(v["peer_lp_err"]) < 1e-6 and float(v["peer_w_err"]) < 1e-6
+
+
+def test_vocab_parallel_linear_ce_kernels():
+    v = _torchrun("ce_tp_worker.py", 2, 29658, "CE_TP_RESULTS")
+    assert float(v["lp"]) < 3e-2 and float(v["ent"]) < 3e-2 and float(v["dh"]) < 3e-2 and float(v["dw"]) < 3e-2
+
+
+def test_hsdp_and_resident_replica():
+    if torch.cuda.device_count() < 4:
+        pytest.skip("needs 4 GPUs")
+    v = _torchrun("hsdp_worker.py", 4, 29659, "HSDP_RESULTS")
+    assert float(v["w_err"]) < 2e-2 and float(v["resident_err"]) < 2e-2

@@ -29,7 +29,15 @@ def main():
     inp, _ = pack_padded(ids, mask)
     labels = torch.randint(0, cfg.vocab_size, (inp.input_ids.numel(),), device=dev)
     outs = {}
-    for name, sp_group in (("nosp", None), ("sp", dist.group.WORLD)):
+    variants = [("nosp", None), ("sp", dist.group.WORLD)]
+    if cuda:
+        variants.append(("sp_peer", dist.group.WORLD))        # same exchange over NVLink peer memory instead of NCCL
+    for name, sp_group in variants:
+        if name == "sp_peer":
+            from polyrl_b200.parallel.symm import SymmetricHeap
+            from polyrl_b200.parallel.ulysses import enable_peer_all_to_all
+
+            enable_peer_all_to_all(dist.group.WORLD, SymmetricHeap(device=dev), 1 << 22)
         eng = Zero3Engine(cfg, dev, comm="nccl", lr=1e-2, weight_decay=0.0, seed=7, sp_group=sp_group)
         lp, ent = eng.forward_logprob_entropy(inp, labels, 1.0)
         (-(lp.mean()) + 0.01 * ent.mean()).backward()
@@ -37,8 +45,13 @@ def main():
         outs[name] = (lp.detach().float().cpu(), {n: t.float().cpu().clone() for n, t in eng.named_full_tensors()})
     lp_err = (outs["sp"][0] - outs["nosp"][0]).abs().max().item()
     w_err = max(((outs["sp"][1][k] - outs["nosp"][1][k]).norm() / (outs["nosp"][1][k].norm() + 1e-9)).item() for k in outs["sp"][1])
+    extra = ""
+    if "sp_peer" in outs:
+        p_lp = (outs["sp_peer"][0] - outs["sp"][0]).abs().max().item()
+        p_w = max(((outs["sp_peer"][1][k] - outs["sp"][1][k]).norm() / (outs["sp"][1][k].norm() + 1e-9)).item() for k in outs["sp"][1])
+        extra = f" peer_lp_err={p_lp:.3e} peer_w_err={p_w:.3e}"
     if rank == 0:
-        print(f"ULYSSES_RESULTS lp_err={lp_err:.3e} w_err={w_err:.3e}", flush=True)
+        print(f"ULYSSES_RESULTS lp_err={lp_err:.3e} w_err={w_err:.3e}{extra}", flush=True)
     dist.barrier()
     dist.destroy_process_group()
 
