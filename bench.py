@@ -177,6 +177,7 @@ def main() -> int:
         ev[k][1].record()
         if rank == 0:
             print("[bench] step", k, {kk: round(v, 3) for kk, v in m.items() if kk.startswith("timing_s/")},
+                  "engine", {kk: round(float(v), 3) for kk, v in ppo.worker.rollout.stats.items()}, "cpus", len(os.sched_getaffinity(0)),
                   "saved_act_layers", ppo.worker.actor_engine.saved_layers_last, "resident", ppo.worker.actor_engine.resident,
                   "mem_GB", round(torch.cuda.max_memory_allocated() / 2**30, 1),
                   "launches", dict(sorted(ops.LAUNCHES.items())), file=sys.stderr, flush=True)

@@ -535,7 +535,9 @@ class RolloutEngine:
         ev, h_tok, h_lp, slots = self._pending
         self._pending = None
         if ev is not None:
+            t0 = time.perf_counter()
             ev.synchronize()
+            self.stats["gpu_wait_s"] = self.stats.get("gpu_wait_s", 0.0) + time.perf_counter() - t0     # ~0 => host-bound loop
         toks, lps = h_tok.tolist(), h_lp.tolist()      # one bulk conversion instead of 2 tensor-scalar reads per request
         for s, r in slots:
             if r.finished:

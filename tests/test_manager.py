@@ -33,10 +33,10 @@ def manager_bin():
 
 
 class Manager:
-    def __init__(self, binary, *extra):
+    def __init__(self, binary, *extra, stderr=subprocess.DEVNULL, env=None):
         self.p = subprocess.Popen([str(binary), "--bind-addr", "127.0.0.1:0", "--stats-interval-ms", "100",
                                    "--health-interval-ms", "100", "--log-level", "error", *extra],
-                                  stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                  stdout=subprocess.PIPE, stderr=stderr, text=True, env=env)
         line = self.p.stdout.readline()
         assert line.startswith("ROLLOUT_MANAGER_PORT="), line
         self.port = int(line.strip().split("=")[1])
@@ -202,3 +202,34 @@ def test_weight_senders_cidr_and_shutdown(manager_bin, tmp_path):
         assert json.loads(_http("GET", m.url + "/get_instances_status")[1])["pending_instances"] == 0
     finally:
         m.close(); e.stop()
+
+
+def test_thread_sanitizer_build_is_race_free(tmp_path):
+    """The manager built with -fsanitize=thread serves the crash-continuation scenario (concurrent request tasks, stats
+    worker, eviction, weight-version bump, metrics feedback) without a single ThreadSanitizer report."""
+    import os
+
+    binary = build_manager(sanitize="thread")
+    log = open(tmp_path / "tsan.log", "w")
+    m = Manager(binary, "--weight-sender-rpyc-endpoints", "127.0.0.1:18861", stderr=log,
+                env={**os.environ, "TSAN_OPTIONS": "halt_on_error=0 report_signal_unsafe=0"})
+    bad, good = FakeEngine(die_after_tokens=5), FakeEngine()
+    try:
+        for e in (bad, good):
+            assert _http("POST", m.url + "/register_rollout_instance", {"host": "127.0.0.1", "port": e.port})[0] == 200
+        time.sleep(0.6)
+        v = json.loads(_http("POST", m.url + "/update_weight_version")[1])["new_weight_version"]
+        inst = json.loads(_http("POST", m.url + "/get_receive_instances",
+                                {"weight_sender_endpoint": "127.0.0.1:18861", "sender_weight_version": v})[1])["instances"]
+        eps = [i["instance"]["endpoint"] for i in inst]
+        _http("POST", m.url + "/update_weights", {"instance_endpoints": eps, "weight_version": v,
+                                                  "tensors_meta": [["w", [[2, 2], "bfloat16"]]], "bootstrap": False})
+        reqs = [[i + 1, {"input_ids": [3, 4, i], "sampling_params": {"max_new_tokens": 16}}] for i in range(8)]
+        res = _batch(m, reqs, timeout=120)
+        assert all(res[i + 1]["success"] for i in range(8))
+        _http("POST", m.url + "/update_metrics", {"step_time_s": 10.0, "trainer_bubble_time_s": 2.0, "step_throughput": 100.0})
+        _http("GET", m.url + "/get_instances_status")
+    finally:
+        m.close(); bad.stop(); good.stop(); log.close()
+    report = (tmp_path / "tsan.log").read_text()
+    assert "ThreadSanitizer" not in report, report[:4000]
