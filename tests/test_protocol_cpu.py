@@ -86,3 +86,29 @@ def test_collate_and_iterator():
     assert b.batch["x"].shape == (4, 2) and b.non_tensor_batch["meta"][2] == {"i": 2}
     seen = [len(m) for m in b.make_iterator(2, epochs=2, seed=0)]
     assert seen == [2, 2, 2, 2]
+
+
+def test_rollout_skip_replays_dumped_generations(tmp_path):
+    import torch
+
+    from polyrl_b200.protocol import DataProto
+    from polyrl_b200.utils.rollout_skip import RolloutSkip
+
+    calls = []
+
+    class W:
+        def generate_sequences(self, prompts):
+            calls.append(1)
+            return DataProto.from_dict({"input_ids": prompts.batch["input_ids"], "responses": torch.full((2, 3), len(calls))})
+
+    p = DataProto.from_dict({"input_ids": torch.arange(8).view(2, 4)})
+    w = W()
+    RolloutSkip(str(tmp_path), n=2, train_batch_size=2).wrap_generate_sequences(w)
+    first = w.generate_sequences(p)
+    w2 = W()
+    skip2 = RolloutSkip(str(tmp_path), n=2, train_batch_size=2)
+    skip2.wrap_generate_sequences(w2)
+    again = w2.generate_sequences(p)
+    assert len(calls) == 1 and skip2.hits == 1 and torch.equal(first.batch["responses"], again.batch["responses"])
+    w2.generate_sequences(p)                      # step 1 was never dumped: falls through to the engine
+    assert len(calls) == 2
