@@ -149,3 +149,40 @@ def test_fp8_rollout_weights_cpu_emulation():
     # first-token log-probs (same context) differ only by quantisation noise
     for (a, la), (b, lb) in zip(res["bf16"], res["fp8"]):
         assert abs(la[0] - lb[0]) < 0.15
+
+
+def test_engine_http_adapter_sync_and_async():
+    import asyncio
+
+    import torch
+
+    from polyrl_b200.models import TransformerWeights, get_model_config
+    from polyrl_b200.rollout.engine import RolloutEngine
+    from polyrl_b200.rollout.http_adapter import AsyncEngineHttpAdapter, EngineHttpAdapter
+    from polyrl_b200.rollout.server import EngineServer
+
+    cfg = get_model_config("tiny-llama")
+    w = TransformerWeights(cfg, "cpu", torch.float32, seed=2)
+    eng = RolloutEngine(cfg, "cpu", max_num_seqs=4, max_model_len=64, use_cuda_graph=False)
+    eng.set_weights(w.embed, w.layers, w.head)
+    srv = EngineServer(eng, port=0).start()
+    try:
+        ad = EngineHttpAdapter("127.0.0.1", srv.port, timeout=60)
+        ad.wait_healthy(30)
+        out = ad.generate([5, 6, 7], {"max_new_tokens": 4, "temperature": 0.0, "ignore_eos": True})
+        assert len(out["output_ids"]) == 4 and len(out["meta_info"]["output_token_logprobs"]) == 4
+        assert "last_gen_throughput" in ad.server_info() or "internal_states" in ad.server_info()
+        assert ad.release_memory_occupation().get("http_status") == 200 and ad.resume_memory_occupation().get("http_status") == 200
+        assert ad.update_weights_from_agent(7)["success"] and srv.weight_version == 7
+        ad.flush_cache(); ad.abort_request(abort_all=True)
+        aad = AsyncEngineHttpAdapter("127.0.0.1", srv.port, timeout=60)
+
+        async def go():
+            a, b = await asyncio.gather(aad.generate([5, 6, 7], {"max_new_tokens": 4, "temperature": 0.0, "ignore_eos": True}),
+                                        aad.generate([9, 9], {"max_new_tokens": 2, "temperature": 0.0, "ignore_eos": True}))
+            return a, b
+
+        a, b = asyncio.run(go())
+        assert a["output_ids"] == out["output_ids"] and len(b["output_ids"]) == 2
+    finally:
+        srv.stop()
