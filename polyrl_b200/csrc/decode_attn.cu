@@ -10,6 +10,8 @@
 //     the k-index of an MMA is a free permutation, so each lane's 16-byte load is wired to the
 //     k-slots it feeds; V fragments are built with two PRMTs per register pair)
 //   * fp32 online softmax in registers, split results merged by a second tiny kernel.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace prl {
@@ -30,8 +32,10 @@ __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
 }
 
 // partial outputs: o_part [num_seqs, nq, splits, D] fp32, ml_part [num_seqs, nq, splits, 2] (max2, sum)
-template <int D>
-__global__ void __launch_bounds__(kAttnWarps * 32)
+// MINB = minimum resident CTAs per SM (register budget): 3 -> 168 regs, no spills; 4 -> 128 regs, ~76 B of spills but a third
+// more warps in flight to hide HBM latency.  Both are compiled; POLYRL_DECODE_MINB picks (default from the microbench).
+template <int D, int MINB>
+__global__ void __launch_bounds__(kAttnWarps * 32, MINB)
 paged_decode_kernel(const __nv_bfloat16* __restrict__ q, int64_t ldq,     // [num_seqs, nq*D] (row pitch ldq)
                     const __nv_bfloat16* __restrict__ k_cache, const __nv_bfloat16* __restrict__ v_cache,
                     const int32_t* __restrict__ block_table, int64_t ld_bt, const int32_t* __restrict__ seq_lens,
@@ -268,15 +272,17 @@ extern "C" int prl_paged_decode(const void* q, int64_t ldq, const void* k_cache,
   float* ml_part = workspace + static_cast<int64_t>(num_seqs) * nq * splits * d;
   const float scale_log2 = sm_scale * 1.4426950408889634f;
   const int grid = num_seqs * nkv * splits;
+  static const int minb = [] { const char* e = getenv("POLYRL_DECODE_MINB"); return e ? atoi(e) : 4; }();
   if (d == 128) {
-    paged_decode_kernel<128><<<grid, kAttnWarps * 32, 0, s>>>(
+    auto kern = minb >= 4 ? paged_decode_kernel<128, 4> : paged_decode_kernel<128, 3>;
+    kern<<<grid, kAttnWarps * 32, 0, s>>>(
         static_cast<const __nv_bfloat16*>(q), ldq, static_cast<const __nv_bfloat16*>(k_cache),
         static_cast<const __nv_bfloat16*>(v_cache), block_table, ld_bt, seq_lens, nq, nkv, splits, scale_log2, o_part,
         ml_part, splits == 1 ? static_cast<__nv_bfloat16*>(out) : nullptr, ldo);
     if (splits > 1)
       decode_merge_kernel<128><<<num_seqs * nq, 128, 0, s>>>(o_part, ml_part, splits, static_cast<__nv_bfloat16*>(out), ldo, nq);
   } else if (d == 64) {
-    paged_decode_kernel<64><<<grid, kAttnWarps * 32, 0, s>>>(
+    paged_decode_kernel<64, 3><<<grid, kAttnWarps * 32, 0, s>>>(
         static_cast<const __nv_bfloat16*>(q), ldq, static_cast<const __nv_bfloat16*>(k_cache),
         static_cast<const __nv_bfloat16*>(v_cache), block_table, ld_bt, seq_lens, nq, nkv, splits, scale_log2, o_part,
         ml_part, splits == 1 ? static_cast<__nv_bfloat16*>(out) : nullptr, ldo);

@@ -55,4 +55,13 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    import os
+    import subprocess
+    import sys
+
+    if os.environ.get("_DECODE_ATTN_CHILD") == "1":
+        main()
+    else:                                   # the occupancy variant is latched per process: one child per setting
+        for minb in ("3", "4"):
+            print(f"== POLYRL_DECODE_MINB={minb}", flush=True)
+            subprocess.run([sys.executable, __file__], env={**os.environ, "_DECODE_ATTN_CHILD": "1", "POLYRL_DECODE_MINB": minb})
