@@ -1,0 +1,202 @@
+"""Training-engine abstraction used by the role workers (reference: 3rdparty/verl/verl/workers/engine/base.py:26
+``BaseEngine`` and its FSDP implementations ``FSDPEngineWithLMHead`` / ``WithValueHead``, fsdp/transformer_impl.py:81-974;
+role-level losses verl/workers/roles/utils/losses.py:27-108).
+
+``ZeroEngine`` adapts ``parallel.zero3.Zero3Engine`` to that surface: mode switches, forward-only inference over packed
+micro-batches, forward+backward with a pluggable loss, optimizer / LR step, (sharded) checkpoint IO.
+"""
+from __future__ import annotations
+
+import contextlib
+from typing import Callable
+
+import torch
+
+from ..models import get_model_config, pack_padded, unpack_to_padded
+from ..parallel.zero3 import Zero3Engine
+from ..utils.checkpoint import ShardedCheckpointManager
+
+_ENGINES: dict[tuple[str, str], type] = {}
+
+
+def register_engine(model_type: str, backend: str = "zero"):
+    def deco(cls):
+        _ENGINES[(model_type, backend)] = cls
+        return cls
+    return deco
+
+
+def get_engine_cls(model_type: str, backend: str = "zero"):
+    backend = {"fsdp": "zero", "fsdp2": "zero"}.get(backend, backend)
+    if (model_type, backend) not in _ENGINES:
+        raise NotImplementedError(f"no training engine for model_type={model_type!r} backend={backend!r}")
+    return _ENGINES[(model_type, backend)]
+
+
+class BaseEngine:
+    def initialize(self) -> None:
+        raise NotImplementedError
+
+    def train_mode(self):
+        raise NotImplementedError
+
+    def eval_mode(self):
+        raise NotImplementedError
+
+    def infer_batch(self, batch: dict, **kw) -> dict:
+        raise NotImplementedError
+
+    def train_batch(self, batch: dict, loss_fn: Callable, **kw) -> dict:
+        raise NotImplementedError
+
+    def optimizer_zero_grad(self) -> None:
+        raise NotImplementedError
+
+    def optimizer_step(self) -> dict:
+        raise NotImplementedError
+
+    def lr_scheduler_step(self) -> float:
+        raise NotImplementedError
+
+    def save_checkpoint(self, path: str, global_step: int = 0, max_ckpt_to_keep=None) -> None:
+        raise NotImplementedError
+
+    def load_checkpoint(self, path: str):
+        raise NotImplementedError
+
+
+@register_engine("language_model")
+class ZeroEngine(BaseEngine):
+    """LM-head engine: ``infer_batch`` -> log_probs / entropy of the response tokens; ``train_batch`` back-propagates
+    ``loss_fn(outputs, batch)`` (called once per micro-batch, gradients accumulate in the sharded fp32 buffers)."""
+
+    value_head = False
+
+    def __init__(self, model: str | dict, device, group=None, lr: float = 1e-6, lr_schedule: Callable[[int], float] | None = None,
+                 micro_batch_size: int = 8, **engine_kw):
+        self.model_cfg = get_model_config(model, value_head=self.value_head) if isinstance(model, str) else model
+        self.device, self.group = torch.device(device), group
+        self.base_lr, self.lr_schedule = lr, lr_schedule
+        self.micro_batch_size = micro_batch_size
+        self.engine_kw = engine_kw
+        self.engine: Zero3Engine | None = None
+        self.lr_step = 0
+        self._training = False
+
+    def initialize(self) -> None:
+        self.engine = Zero3Engine(self.model_cfg, self.device, group=self.group, lr=self.base_lr, **self.engine_kw)
+        self.ckpt = ShardedCheckpointManager(self.engine, self.model_cfg)
+
+    @contextlib.contextmanager
+    def train_mode(self):
+        prev, self._training = self._training, True
+        try:
+            yield self
+        finally:
+            self._training = prev
+
+    @contextlib.contextmanager
+    def eval_mode(self):
+        prev, self._training = self._training, False
+        try:
+            with torch.no_grad():
+                yield self
+        finally:
+            self._training = prev
+
+    # ------------------------------------------------------------------ compute
+    def _forward_micro(self, mb: dict, temperature: float) -> dict:
+        ids, mask = mb["input_ids"].to(self.device), mb["attention_mask"].to(self.device)
+        resp_len = mb["responses"].shape[1]
+        inp, idx = pack_padded(ids, mask, mb.get("position_ids"))
+        labels = torch.roll(inp.input_ids, -1)
+        if self.value_head:
+            v = self.engine.forward_values(inp)
+            values = unpack_to_padded(v, idx, ids.shape[0], ids.shape[1])
+            return {"values": values[:, -resp_len - 1:-1]}
+        lp, ent = self.engine.forward_logprob_entropy(inp, labels, temperature)
+        lp = unpack_to_padded(lp, idx, ids.shape[0], ids.shape[1])[:, -resp_len - 1:-1]
+        ent = unpack_to_padded(ent, idx, ids.shape[0], ids.shape[1])[:, -resp_len - 1:-1]
+        return {"log_probs": lp, "entropy": ent}
+
+    def _micro_batches(self, batch: dict):
+        n = batch["input_ids"].shape[0]
+        for s in range(0, n, self.micro_batch_size):
+            yield {k: (v[s:s + self.micro_batch_size] if torch.is_tensor(v) else v) for k, v in batch.items()}
+
+    def infer_batch(self, batch: dict, temperature: float = 1.0) -> dict:
+        outs: dict[str, list] = {}
+        with torch.no_grad():
+            for mb in self._micro_batches(batch):
+                for k, v in self._forward_micro(mb, temperature).items():
+                    outs.setdefault(k, []).append(v)
+        return {k: torch.cat(v) for k, v in outs.items()}
+
+    def train_batch(self, batch: dict, loss_fn: Callable, temperature: float = 1.0) -> dict:
+        assert self._training, "call inside `with engine.train_mode():`"
+        metrics: dict[str, list] = {}
+        n = batch["input_ids"].shape[0]
+        for mb in self._micro_batches(batch):
+            out = self._forward_micro(mb, temperature)
+            loss, m = loss_fn(out, mb)
+            (loss * (mb["input_ids"].shape[0] / n)).backward()
+            for k, v in m.items():
+                metrics.setdefault(k, []).append(float(v))
+        return {k: sum(v) / len(v) for k, v in metrics.items()}
+
+    # ------------------------------------------------------------------ optimizer
+    def optimizer_zero_grad(self) -> None:
+        self.engine.zero_grad()
+
+    def optimizer_step(self) -> dict:
+        lr = self.lr_schedule(self.lr_step) if self.lr_schedule is not None else self.base_lr
+        return {**self.engine.step(lr), "lr": lr}
+
+    def lr_scheduler_step(self) -> float:
+        self.lr_step += 1
+        return self.lr_schedule(self.lr_step) if self.lr_schedule is not None else self.base_lr
+
+    # ------------------------------------------------------------------ checkpoint
+    def save_checkpoint(self, path: str, global_step: int = 0, max_ckpt_to_keep=None) -> None:
+        self.ckpt.save(path, global_step, max_ckpt_to_keep, extra={"lr_step": self.lr_step})
+
+    def load_checkpoint(self, path: str):
+        extra = self.ckpt.load(path)
+        if extra and "lr_step" in extra:
+            self.lr_step = int(extra["lr_step"])
+        return extra
+
+
+@register_engine("value_model")
+class ZeroEngineWithValueHead(ZeroEngine):
+    value_head = True
+
+
+# ---- role-level losses (reference: workers/roles/utils/losses.py) --------------------------------------------------------
+def sft_loss(out: dict, mb: dict):
+    mask = mb["response_mask"].to(out["log_probs"].device).float()
+    loss = -(out["log_probs"] * mask).sum() / mask.sum().clamp_min(1)
+    return loss, {"sft/loss": loss.item()}
+
+
+def ppo_loss(config=None, clip_ratio: float = 0.2, loss_agg_mode: str = "token-mean"):
+    from ..algos import core_algos
+
+    def fn(out: dict, mb: dict):
+        dev = out["log_probs"].device
+        mask = mb["response_mask"].to(dev).float()
+        pg, m = core_algos.compute_policy_loss_vanilla(mb["old_log_probs"].to(dev), out["log_probs"], mb["advantages"].to(dev), mask,
+                                                       loss_agg_mode=loss_agg_mode, config=config, cliprange=clip_ratio)
+        return pg, {"actor/pg_loss": pg.item(), **m}
+    return fn
+
+
+def value_loss(cliprange_value: float = 0.5):
+    from ..algos import core_algos
+
+    def fn(out: dict, mb: dict):
+        dev = out["values"].device
+        mask = mb["response_mask"].to(dev).float()
+        vf, clipfrac = core_algos.compute_value_loss(out["values"], mb["returns"].to(dev), mb["values"].to(dev), mask, cliprange_value)
+        return vf, {"critic/vf_loss": vf.item(), "critic/vf_clipfrac": float(clipfrac)}
+    return fn
