@@ -108,7 +108,11 @@ class RolloutEngine:
     def __init__(self, cfg: ModelConfig, device, max_num_seqs: int = 256, max_model_len: int = 2048,
                  kv_cache_tokens: int | None = None, gpu_memory_utilization: float = 0.5, dtype=None,
                  use_cuda_graph: bool = True, max_prefill_tokens: int = 16384, seed: int = 0, tp=None,
-                 weight_dtype: str = "bf16"):
+                 weight_dtype: str = "bf16", steps_per_sync: int | None = None):
+        # decode steps launched back to back per host round trip (tokens are read back once per window; a sequence that
+        # ends mid-window rides along for a few ignored tokens).  1 = one-step lag only.
+        import os as _os
+        self.steps_per_sync = max(1, min(8, int(steps_per_sync or _os.environ.get("POLYRL_DECODE_STEPS_PER_SYNC", "1"))))
         if weight_dtype not in ("bf16", "fp8"):
             raise ValueError("weight_dtype must be 'bf16' or 'fp8'")
         if weight_dtype == "fp8" and tp is not None:
@@ -248,14 +252,15 @@ class RolloutEngine:
         self.st_positions = torch.zeros(s, dtype=torch.long, device=dev)
         self.st_seq_lens = torch.zeros(s, dtype=torch.int32, device=dev)
         self.st_active = torch.zeros(s, dtype=torch.long, device=dev)
-        self.st_block_table = torch.zeros(s, self.max_blocks_per_seq + 1, dtype=torch.int32, device=dev)
+        self.st_block_table = torch.zeros(s, self.max_blocks_per_seq + 2, dtype=torch.int32, device=dev)   # + overshoot slack -> scratch page 0
         self.st_temp = torch.ones(s, dtype=torch.float32, device=dev)
         self.st_seeds = torch.zeros(s, dtype=torch.long, device=dev)
         self.st_out_tok = torch.zeros(s, dtype=torch.long, device=dev)
         self.st_out_lp = torch.zeros(s, dtype=torch.float32, device=dev)
         pin = self.is_cuda
-        self.h_tok = [torch.zeros(s, dtype=torch.long, pin_memory=pin) for _ in range(2)]
-        self.h_lp = [torch.zeros(s, dtype=torch.float32, pin_memory=pin) for _ in range(2)]
+        k = self.steps_per_sync
+        self.h_tok = [torch.zeros(k, s, dtype=torch.long, pin_memory=pin) for _ in range(2)]
+        self.h_lp = [torch.zeros(k, s, dtype=torch.float32, pin_memory=pin) for _ in range(2)]
 
     # ------------------------------------------------------------------ request API
     def add_request(self, prompt_ids: list[int], params: SamplingParams | dict | None = None, rid: str | None = None,
@@ -406,7 +411,7 @@ class RolloutEngine:
                 continue
             n = r.num_tokens            # tokens so far; the new token sits at position n-1
             live.append((r.slot, t, n - 1, n, 1, r.params.temperature, self._seed_for(r, 1)))
-            row = r.blocks + [0] * (self.max_blocks_per_seq + 1 - len(r.blocks))
+            row = r.blocks + [0] * (self.st_block_table.shape[1] - len(r.blocks))
             rows.append(row)
         if live:
             cols = list(zip(*live))
@@ -542,9 +547,11 @@ class RolloutEngine:
         for s, r in slots:
             if r.finished:
                 continue
-            self._append_token(r, toks[s], lps[s])
-            if r.finished:
-                done.append(r)
+            for tk, lp in zip(toks, lps):                # the window's steps, oldest first
+                self._append_token(r, tk[s], lp[s])
+                if r.finished:
+                    done.append(r)
+                    break
         return done
 
     @torch.no_grad()
@@ -569,17 +576,18 @@ class RolloutEngine:
         bs = self._bucket(max(self.running) + 1)
         # launch step k+1 first, then consume step k's tokens while the GPU works (one-step lag:
         # a sequence that ended at step k rides along for one harmless extra token)
-        self._run_decode(bs)
         i = self._step_count & 1
         self._step_count += 1
-        self.h_tok[i].copy_(self.st_out_tok, non_blocking=True)
-        self.h_lp[i].copy_(self.st_out_lp, non_blocking=True)
+        for j in range(self.steps_per_sync):
+            self._run_decode(bs)
+            self.h_tok[i][j].copy_(self.st_out_tok, non_blocking=True)
+            self.h_lp[i][j].copy_(self.st_out_lp, non_blocking=True)
         ev = None
         if self.is_cuda:
             ev = torch.cuda.Event()
             ev.record(torch.cuda.current_stream(self.device))
         new_pending = (ev, self.h_tok[i], self.h_lp[i], list(self.running.items()))
-        self.stats["decode_tokens"] += len(self.running)
+        self.stats["decode_tokens"] += len(self.running) * self.steps_per_sync
         finished += self._drain_pending()
         self._pending = new_pending
         self.stats["steps"] += 1

@@ -186,3 +186,24 @@ def test_engine_http_adapter_sync_and_async():
         assert a["output_ids"] == out["output_ids"] and len(b["output_ids"]) == 2
     finally:
         srv.stop()
+
+
+def test_multi_step_decode_windows_match_single_step():
+    """steps_per_sync=4 (tokens read back once per 4-step window) generates exactly what the step-by-step loop does,
+    including EOS / length stops in the middle of a window and slot reuse by queued requests."""
+    import torch
+
+    from polyrl_b200.models import TransformerWeights, get_model_config
+    from polyrl_b200.rollout.engine import RolloutEngine
+
+    cfg = get_model_config("tiny-llama")
+    w = TransformerWeights(cfg, "cpu", torch.float32, seed=13)
+    prompts = [[5 + i, 9, 33, 7 + i] for i in range(7)]           # 7 prompts x n=2 on 4 slots: forces queueing + slot reuse
+    outs = {}
+    for k in (1, 4):
+        eng = RolloutEngine(cfg, "cpu", max_num_seqs=4, max_model_len=48, use_cuda_graph=False, seed=3, steps_per_sync=k)
+        eng.set_weights(w.embed, w.layers, w.head)
+        g = eng.generate(prompts, {"max_new_tokens": 11, "temperature": 0.0, "n": 2})
+        outs[k] = [(r.output_ids, r.finish_reason, [round(x, 4) for x in r.logprobs]) for grp in g for r in grp]
+        assert all(len(o[0]) <= 11 for o in outs[k])
+    assert outs[1] == outs[4]
