@@ -29,7 +29,10 @@ def parse():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="own", choices=["own", "reference"])
+    ap.add_argument("--impl", default="own", choices=["own", "reference", "baseline"],
+                    help="own = product; reference = the unmodified reference (unavailable offline); baseline = this framework with the "
+                         "named ops routed through stock libraries (BASELINE.md section 3): cuBLAS GEMMs + unfused SwiGLU, materialised-"
+                         "logits chunked CE, NCCL all-gather per layer / fp32 reduce-scatter, full recompute")
     ap.add_argument("--model", default=os.environ.get("BENCH_MODEL", "llama3-8b"))
     ap.add_argument("--prompts-per-gpu", type=int, default=int(os.environ.get("BENCH_PROMPTS_PER_GPU", 16)))
     ap.add_argument("--n", type=int, default=int(os.environ.get("BENCH_N", 8)))
@@ -103,6 +106,11 @@ def main() -> int:
     args = parse()
     if args.impl == "reference":
         return reference_arm(args)
+    if args.impl == "baseline":
+        os.environ["POLYRL_GEMM_BACKEND"] = "cublas"
+        os.environ["POLYRL_CE_BACKEND"] = "torch"
+        os.environ["POLYRL_DECODE_GEMM"] = "cublas"
+        args.comm = "nccl"
 
     import torch
     import torch.distributed as dist
@@ -140,6 +148,8 @@ def main() -> int:
         f"actor_rollout_ref.rollout.max_num_seqs={per_gpu}", f"actor_rollout_ref.rollout.cuda_graph={not args.no_graph}",
         f"actor_rollout_ref.actor.fsdp_config.comm_backend={args.comm}", "actor_rollout_ref.rollout.free_cache_engine=True",
         f"trainer.n_gpus_per_node={world}", "actor_rollout_ref.actor.optim.lr=1e-6",
+        *(["actor_rollout_ref.actor.fsdp_config.resident_params=false", "actor_rollout_ref.actor.fsdp_config.activation_checkpoint=full"]
+          if args.impl == "baseline" else []),
     ])
     ppo = ColocatedPPO(cfg, device=device, group=None)
     mcfg = ppo.worker.model_cfg
@@ -216,7 +226,7 @@ def main() -> int:
             "clocks": clocks,
             "e2e": {"value": round(e2e, 4), "unit": "samples/s", "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": int(d2h_bytes / max(1, args.steps)) + per_gpu * R * 12},
-            "gpu_launches": int(launches),
+            "gpu_launches": int(launches), "impl": args.impl,
             "tokens_per_s": round(value * (args.prompt_len_max / 2 + R), 1),
         }
         print(json.dumps(out), flush=True)

@@ -333,9 +333,36 @@ class _LinearCEFn(torch.autograd.Function):
         return dh_out, dw, None, None
 
 
+def _chunked_torch_ce(hidden, weight, labels, temperature, chunk: int = 2048):
+    """Library baseline: materialise [chunk, V] logits with cuBLAS, eager softmax statistics, recompute per chunk in backward
+    (the reference's non-fused path: verl/utils/experimental/torch_functional.py:75-216 ``FusedLinearForPPO`` chunks of tokens)."""
+    from torch.utils.checkpoint import checkpoint
+
+    h2, lab = hidden.reshape(-1, hidden.shape[-1]), labels.reshape(-1)
+
+    def piece(h, w, l):
+        z = (h @ w.t()).float() / temperature
+        lse = torch.logsumexp(z, -1)
+        lp = z.gather(-1, l.unsqueeze(-1)).squeeze(-1) - lse
+        ent = lse - (torch.softmax(z, -1) * z).sum(-1)
+        return lp, ent
+
+    lps, ents = [], []
+    for s in range(0, h2.shape[0], chunk):
+        if torch.is_grad_enabled() and (h2.requires_grad or weight.requires_grad):
+            lp, ent = checkpoint(piece, h2[s:s + chunk], weight, lab[s:s + chunk], use_reentrant=False)
+        else:
+            lp, ent = piece(h2[s:s + chunk], weight, lab[s:s + chunk])
+        lps.append(lp)
+        ents.append(ent)
+    return torch.cat(lps).reshape(labels.shape), torch.cat(ents).reshape(labels.shape)
+
+
 def linear_cross_entropy(hidden: torch.Tensor, weight: torch.Tensor, labels: torch.Tensor,
                          temperature: float = 1.0) -> tuple[torch.Tensor, torch.Tensor]:
     """(log p(labels), entropy) of softmax(hidden @ weight.T / temperature); fp32 outputs, shape of labels."""
+    if os.environ.get("POLYRL_CE_BACKEND", "fused") == "torch" and hidden.is_cuda:
+        return _chunked_torch_ce(hidden, weight, labels, temperature)
     if _is_kernel_tensor(hidden) and weight.dtype == torch.bfloat16 and weight.shape[0] % 8 == 0:
         return _LinearCEFn.apply(hidden, weight, labels, 1.0 / float(temperature))
     lp, ent = ref.linear_cross_entropy(hidden.reshape(-1, hidden.shape[-1]), weight, labels.reshape(-1), temperature)
