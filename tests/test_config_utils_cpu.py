@@ -129,3 +129,19 @@ def test_memory_utils(tmp_path):
     s.stop()
     assert s.dump("t").exists() and len(s.samples) >= 2
     assert "free_gb" in log_gpu_memory_usage("test", rank=None)
+
+
+def test_hbm_sizing_planner():
+    from polyrl_b200.utils.hbm_sizing import count_params, plan
+    from polyrl_b200.models import get_model_config
+
+    assert abs(count_params(get_model_config("llama3-8b")) / 1e9 - 8.03) < 0.01
+    p1 = plan("llama3-8b", n_gpus=1, max_num_seqs=128, max_model_len=768)
+    assert p1.decisions["fits_training"] and 0 < p1.saved_blocks < 32 and p1.resident_replica == 0
+    p8 = plan("llama3-8b", n_gpus=8, max_num_seqs=128, max_model_len=768)
+    assert p8.saved_blocks == 32 and p8.resident_replica > 14 and p8.decisions["fits_training"]
+    p70 = plan("llama3-70b", n_gpus=8, rollout_tp=8, critic="llama3-8b", max_model_len=4096)
+    d = p70.decisions
+    assert p70.resident_replica == 0 and p70.saved_blocks == 0 and d["optimizer_offload_during_rollout"]
+    assert d["release_rollout_weights_during_training"] and d["fits_rollout"] and d["fits_training"]
+    assert d["max_tokens_per_microbatch"] < 16384
