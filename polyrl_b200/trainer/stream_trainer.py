@@ -137,12 +137,37 @@ class StreamPPOTrainer:
         out = self.reward_fn(batch)
         return out.to(self.device) if torch.is_tensor(out) else out["reward_tensor"].to(self.device)
 
+    def _dump_generations(self, batch: DataProto, scores: torch.Tensor, dump_dir: str | None, tag: str) -> None:
+        """Append one JSONL line per sample (prompt / response text or ids, score, step) — reference:
+        ray_trainer.py:428-486 ``_dump_generations`` / ``trainer.rollout_data_dir`` / ``trainer.validation_data_dir``."""
+        if not dump_dir or self.rank != 0:
+            return
+        import json
+
+        path = Path(dump_dir)
+        path.mkdir(parents=True, exist_ok=True)
+        tok = getattr(self, "tokenizer", None)
+        prompts, resp = batch.batch["prompts"].cpu(), batch.batch["responses"].cpu()
+        pm = batch.batch["attention_mask"][:, : prompts.shape[1]].bool().cpu()
+        rm = batch.batch["attention_mask"][:, prompts.shape[1]:].bool().cpu()
+        srcs = batch.non_tensor_batch.get("data_source")
+        with open(path / f"{tag}_{self.global_steps}.jsonl", "a") as f:
+            for i in range(len(batch)):
+                p_ids, r_ids = prompts[i][pm[i]].tolist(), resp[i][rm[i]].tolist()
+                row = {"step": self.global_steps, "score": float(scores[i]), "data_source": None if srcs is None else str(srcs[i])}
+                if tok is not None:
+                    row["input"], row["output"] = tok.decode(p_ids), tok.decode(r_ids)
+                else:
+                    row["input_ids"], row["output_ids"] = p_ids, r_ids
+                f.write(json.dumps(row) + "\n")
+
     # ------------------------------------------------------------------ one streamed batch
     def _process_ibatch(self, ibatch: DataProto, seen: int, boundaries: list[int], metrics: dict) -> None:
         cfg, algo = self.config, self.config.algorithm
         t = self._timing
         with marked_timer("reward", t):
             ibatch.batch["token_level_scores"] = self._reward(ibatch)
+            self._dump_generations(ibatch, ibatch.batch["token_level_scores"].sum(-1).tolist(), self.config.trainer.rollout_data_dir, "train")
         full_len = len(ibatch)
         uid_full = ibatch.non_tensor_batch["uid"]
         # advantages that need whole groups are computed on the full streamed batch (groups arrive together)
@@ -245,6 +270,7 @@ class StreamPPOTrainer:
             else:
                 r = fn(out)
                 r = r if torch.is_tensor(r) else r["reward_tensor"]
+            self._dump_generations(out, r.sum(-1).tolist(), cfg.trainer.validation_data_dir, "val")
             scores += r.sum(-1).tolist()
             sources += list(out.non_tensor_batch.get("data_source", ["unknown"] * len(out)))
             uids += [str(uuid.uuid4()) for _ in range(len(out))]
