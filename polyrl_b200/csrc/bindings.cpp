@@ -38,6 +38,7 @@ int prl_p2p_barrier(void* const*, int, int, uint32_t, cudaStream_t);
 int prl_p2p_copy(const void*, void*, int64_t, int, cudaStream_t);
 int prl_p2p_push_fp8(const void*, void*, float*, int, int, int, cudaStream_t);
 int prl_p2p_allgather_pull(void* const*, void*, int64_t, int, int, int, cudaStream_t);
+int prl_p2p_allreduce(void* const*, int64_t, void*, const void*, int64_t, int, int, cudaStream_t);
 int prl_p2p_reduce_scatter_accum(void* const*, int64_t, float*, int64_t, float, int, int, float*, int, cudaStream_t);
 int prl_skinny_workspace_floats(int, int, int);
 int prl_skinny_gemm(const void*, const void*, void*, const void*, const void*, const float*, const float*, float*, int*, int, int, int, int64_t, int64_t, int64_t, int, int, int, cudaStream_t);
@@ -388,6 +389,18 @@ void p2p_push_fp8(const at::Tensor& src, int64_t dst_q, int64_t dst_scale, int64
   check(prl_p2p_push_fp8(src.data_ptr(), reinterpret_cast<void*>(dst_q), reinterpret_cast<float*>(dst_scale),
                          src.size(0), src.size(1), max_ctas, cur_stream()), "p2p_push_fp8");
 }
+// out = sum over ranks of bf16 partials living at buf_ptrs[r] + elem_off (+ residual); rank-ordered fp32 sum.
+void p2p_allreduce(const std::vector<int64_t>& buf_ptrs, int64_t elem_off, at::Tensor out, const c10::optional<at::Tensor>& residual,
+                   int64_t max_ctas) {
+  CHECK_BF16(out);
+  TORCH_CHECK(out.is_contiguous() && out.numel() % 8 == 0);
+  if (residual.has_value()) { CHECK_BF16(*residual); TORCH_CHECK(residual->is_contiguous() && residual->numel() == out.numel()); }
+  c10::cuda::CUDAGuard g(out.device());
+  auto p = to_ptrs(buf_ptrs);
+  check(prl_p2p_allreduce(p.data(), elem_off, out.data_ptr(), residual.has_value() ? residual->data_ptr() : nullptr, out.numel(),
+                          static_cast<int>(p.size()), static_cast<int>(max_ctas), cur_stream()), "p2p_allreduce");
+}
+
 void p2p_allgather_pull(const std::vector<int64_t>& shard_ptrs, int64_t out, int64_t shard_bytes, int64_t rank,
                         int64_t max_ctas) {
   auto p = to_ptrs(shard_ptrs);
@@ -455,6 +468,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("p2p_copy", &p2p_copy);
   m.def("p2p_push_fp8", &p2p_push_fp8);
   m.def("p2p_allgather_pull", &p2p_allgather_pull);
+  m.def("p2p_allreduce", &p2p_allreduce);
   m.def("p2p_reduce_scatter_accum", &p2p_reduce_scatter_accum);
   m.def("ag_gemm_bf16", &ag_gemm_bf16);
 }

@@ -100,36 +100,117 @@ __global__ void p2p_allgather_pull_kernel(PeerPtrs shards, int4* __restrict__ ou
 }
 
 // acc[i] += scale * sum_r grads_r[shard_off + i]   (bf16 peer grads, fp32 accumulate), optional sumsq.
-__global__ void p2p_reduce_scatter_accum_kernel(PeerPtrs grads, int64_t shard_off, float* __restrict__ acc,
-                                                int64_t n, float scale, int world, int rank,
-                                                float* __restrict__ sumsq) {
-  const int64_t n8 = n >> 3;
-  float local = 0.f;
-  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n8;
-       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    float s[8];
+// Bandwidth notes (profiles/: the first version kept ONE 16-byte load per peer in flight per thread and reached 49 GB/s of
+// NVLink ingest): every thread now owns U = 4 consecutive-in-stride vectors, issues the U loads of two peers (and the fp32
+// accumulator loads) before the first add, so >= 8 x 16 B are in flight per thread and ~1 MB per 32-CTA launch.
+template <int U>
+__device__ __forceinline__ void rs_accum_vec(const PeerPtrs& grads, int64_t shard_off, float* __restrict__ acc, const int64_t (&idx)[U],
+                                             int nvalid, float scale, int world, int rank, float& local) {
+  float s[U][8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) s[j] = 0.f;
-    for (int rr = 0; rr < world; ++rr) {
-      const int r = (rr + rank) % world;
-      const int4 v = ld_v4(static_cast<const __nv_bfloat16*>(grads.p[r]) + shard_off + 8 * i);
-      const uint32_t* u = reinterpret_cast<const uint32_t*>(&v);
+  for (int u = 0; u < U; ++u)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float2 f = unpack_bf16(u[j]);
-        s[2 * j] += f.x; s[2 * j + 1] += f.y;
-      }
+    for (int j = 0; j < 8; ++j) s[u][j] = 0.f;
+  float4 a0[U], a1[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u)
+    if (u < nvalid) {
+      a0[u] = *reinterpret_cast<const float4*>(acc + 8 * idx[u]);
+      a1[u] = *reinterpret_cast<const float4*>(acc + 8 * idx[u] + 4);
     }
-    float4 a0 = *reinterpret_cast<float4*>(acc + 8 * i), a1 = *reinterpret_cast<float4*>(acc + 8 * i + 4);
-    a0.x += scale * s[0]; a0.y += scale * s[1]; a0.z += scale * s[2]; a0.w += scale * s[3];
-    a1.x += scale * s[4]; a1.y += scale * s[5]; a1.z += scale * s[6]; a1.w += scale * s[7];
-    *reinterpret_cast<float4*>(acc + 8 * i) = a0;
-    *reinterpret_cast<float4*>(acc + 8 * i + 4) = a1;
-    local += a0.x * a0.x + a0.y * a0.y + a0.z * a0.z + a0.w * a0.w + a1.x * a1.x + a1.y * a1.y + a1.z * a1.z + a1.w * a1.w;
+  for (int rr = 0; rr < world; rr += 2) {
+    int4 v[2][U];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int r = (rr + h + rank) % world;
+      const __nv_bfloat16* base = static_cast<const __nv_bfloat16*>(grads.p[r]) + shard_off;
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        v[h][u] = (rr + h < world && u < nvalid) ? ld_v4(base + 8 * idx[u]) : make_int4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const uint32_t* w = reinterpret_cast<const uint32_t*>(&v[h][u]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = unpack_bf16(w[j]);
+          s[u][2 * j] += f.x; s[u][2 * j + 1] += f.y;
+        }
+      }
+  }
+#pragma unroll
+  for (int u = 0; u < U; ++u)
+    if (u < nvalid) {
+      float4 x = a0[u], y = a1[u];
+      x.x += scale * s[u][0]; x.y += scale * s[u][1]; x.z += scale * s[u][2]; x.w += scale * s[u][3];
+      y.x += scale * s[u][4]; y.y += scale * s[u][5]; y.z += scale * s[u][6]; y.w += scale * s[u][7];
+      *reinterpret_cast<float4*>(acc + 8 * idx[u]) = x;
+      *reinterpret_cast<float4*>(acc + 8 * idx[u] + 4) = y;
+      local += x.x * x.x + x.y * x.y + x.z * x.z + x.w * x.w + y.x * y.x + y.y * y.y + y.z * y.z + y.w * y.w;
+    }
+}
+
+__global__ void __launch_bounds__(512)
+p2p_reduce_scatter_accum_kernel(PeerPtrs grads, int64_t shard_off, float* __restrict__ acc, int64_t n, float scale, int world,
+                                int rank, float* __restrict__ sumsq) {
+  constexpr int U = 4;
+  const int64_t n8 = n >> 3;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  float local = 0.f;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n8; i += U * stride) {
+    int64_t idx[U];
+    int nvalid = 0;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      idx[u] = i + u * stride;
+      nvalid += idx[u] < n8;
+    }
+    rs_accum_vec<U>(grads, shard_off, acc, idx, nvalid, scale, world, rank, local);
   }
   if (sumsq) {
     local = warp_sum(local);
     if ((threadIdx.x & 31) == 0) atomicAdd(sumsq, local);
+  }
+}
+
+// One-shot all-reduce for small tensors (TP decode activations, <= a few MB): every rank has written its bf16 partial into its
+// symmetric buffer (and a device barrier has passed); each rank reads ALL peers' partials over NVLink, sums in fp32 IN RANK
+// ORDER (bit-identical results on every rank: TP engines stay in lock-step without host traffic), adds the residual and
+// writes its own output.  out may alias residual.
+__global__ void __launch_bounds__(256)
+p2p_allreduce_kernel(PeerPtrs bufs, int64_t elem_off, __nv_bfloat16* __restrict__ out, const __nv_bfloat16* __restrict__ residual,
+                     int64_t n, int world) {
+  const int64_t n8 = n >> 3;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n8;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    int4 v[kMaxPeers];
+#pragma unroll
+    for (int r = 0; r < kMaxPeers; ++r)
+      if (r < world) v[r] = ld_v4(static_cast<const __nv_bfloat16*>(bufs.p[r]) + elem_off + 8 * i);
+    float s[8];
+    if (residual) {
+      const int4 rv = ld_v4(residual + 8 * i);
+      const uint32_t* u = reinterpret_cast<const uint32_t*>(&rv);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { const float2 f = unpack_bf16(u[j]); s[2 * j] = f.x; s[2 * j + 1] = f.y; }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s[j] = 0.f;
+    }
+#pragma unroll
+    for (int r = 0; r < kMaxPeers; ++r)
+      if (r < world) {
+        const uint32_t* u = reinterpret_cast<const uint32_t*>(&v[r]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { const float2 f = unpack_bf16(u[j]); s[2 * j] += f.x; s[2 * j + 1] += f.y; }
+      }
+    int4 o;
+    uint32_t* ou = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) ou[j] = pack_bf16(s[2 * j], s[2 * j + 1]);
+    *reinterpret_cast<int4*>(out + 8 * i) = o;
   }
 }
 
@@ -220,15 +301,28 @@ extern "C" int prl_p2p_allgather_pull(void* const* shard_ptrs, void* out, int64_
   PRL_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
+extern "C" int prl_p2p_allreduce(void* const* buf_ptrs, int64_t elem_off, void* out, const void* residual, int64_t n, int world,
+                                 int max_ctas, cudaStream_t s) {
+  if (world > kMaxPeers || n % 8 != 0) return -46;
+  if (n == 0) return 0;
+  int grid = static_cast<int>((n / 8 + 255) / 256);
+  const int cap = max_ctas > 0 ? max_ctas : 148;
+  if (grid > cap) grid = cap;
+  p2p_allreduce_kernel<<<grid, 256, 0, s>>>(to_ptrs(buf_ptrs, world), elem_off, static_cast<__nv_bfloat16*>(out),
+                                            static_cast<const __nv_bfloat16*>(residual), n, world);
+  PRL_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
 extern "C" int prl_p2p_reduce_scatter_accum(void* const* grad_ptrs, int64_t shard_off, float* acc, int64_t n,
                                             float scale, int world, int rank, float* sumsq, int max_ctas,
                                             cudaStream_t s) {
   if (world > kMaxPeers || n % 8 != 0 || shard_off % 8 != 0) return -45;
   if (n == 0) return 0;
-  int grid = static_cast<int>((n / 8 + 255) / 256);
-  const int cap = max_ctas > 0 ? max_ctas : 148 * 4;
+  int grid = static_cast<int>((n / 8 + 2047) / 2048);
+  if (grid < 1) grid = 1;
+  const int cap = max_ctas > 0 ? max_ctas : 148 * 2;
   if (grid > cap) grid = cap;
-  p2p_reduce_scatter_accum_kernel<<<grid, 256, 0, s>>>(to_ptrs(grad_ptrs, world), shard_off, acc, n, scale, world, rank,
+  p2p_reduce_scatter_accum_kernel<<<grid, 512, 0, s>>>(to_ptrs(grad_ptrs, world), shard_off, acc, n, scale, world, rank,
                                                       sumsq);
   PRL_CUDA_CHECK(cudaGetLastError());
   return 0;

@@ -39,6 +39,17 @@ class TPContext:
         self.flags = heap.alloc(tp_world * tiles + 64, torch.int32)
         self.epoch_state = torch.zeros(2, device=heap.device, dtype=torch.int32)   # [epoch, done-counter] (device side)
         self.C = ops.ext()
+        # row-parallel all-reduce on the decode path (measured, profiles/r1_tp2_rowparallel_*.json):
+        #   "oneshot" (default): library GEMM straight into a symmetric buffer -> device barrier -> one-shot peer-memory
+        #             all-reduce kernel (every rank reads all partials over NVLink, rank-ordered fp32 sum, fused residual)
+        #   "fused":  the swap-AB split-K GEMM whose epilogue pushes fp32 tiles into the peers' inboxes (one kernel)
+        #   "nccl":   library GEMM + NCCL all-reduce (baseline)
+        import os
+
+        self.ar_mode = os.environ.get("POLYRL_TP_ALLREDUCE", "oneshot")
+        rows = ((min(max_batch, 256) + 7) // 8) * 8
+        self.ar_bufs = [heap.alloc(rows * cfg.hidden_size, torch.bfloat16) for _ in range(2)]   # alternate: see row_parallel
+        self.ar_turn = 0
         heap.barrier()
 
     def local_cfg(self) -> ModelConfig:
@@ -70,9 +81,24 @@ class TPContext:
         return out
 
     # ---------------------------------------------------------------- row-parallel linear
-    def row_parallel(self, x_local: torch.Tensor, w_local: torch.Tensor, residual: torch.Tensor | None) -> torch.Tensor:
+    def row_parallel(self, x_local: torch.Tensor, w_local: torch.Tensor, residual: torch.Tensor | None,
+                     decode: bool = True) -> torch.Tensor:
         b = x_local.shape[0]
-        if x_local.is_cuda and b <= 256 and b <= self.max_batch:
+        small = x_local.is_cuda and decode and b <= 256 and b <= self.max_batch
+        if small and self.ar_mode == "oneshot":
+            # Two symmetric buffers alternate: a rank may overwrite buffer p for call c+2 only after passing the barrier of
+            # call c+1, which every peer reaches after it finished READING buffer p in call c.  (Decode issues an even
+            # number of calls per step, so captured graphs replay a consistent alternation.)
+            buf = self.ar_bufs[self.ar_turn]
+            self.ar_turn ^= 1
+            h = w_local.shape[0]
+            part = buf.local[: b * h].view(b, h)
+            torch.mm(x_local, w_local.t(), out=part)
+            self.heap.barrier()
+            out = torch.empty(b, h, device=x_local.device, dtype=torch.bfloat16)
+            self.C.p2p_allreduce(buf.ptrs, 0, out, residual.contiguous() if residual is not None else None, 32)
+            return out
+        if small and self.ar_mode == "fused":
             ws, ctr = _skinny_buffers(x_local.device)
             res = residual.contiguous() if residual is not None else None
             return self.C.skinny_gemm_tp(x_local.contiguous(), w_local, res, ws, ctr, 0, self.inbox.ptrs, self.flags.ptrs,
@@ -107,7 +133,7 @@ def layer_prefill_tp(tp: TPContext, lcfg: ModelConfig, w: dict, x: torch.Tensor,
     k = qkv[:, nq * d:(nq + nkv) * d].view(t, nkv, d)
     v = qkv[:, (nq + nkv) * d:].view(t, nkv, d)
     a = attention_varlen(q, k, v, inp.cu_seqlens, inp.max_seqlen, causal=True).reshape(t, nq * d)
-    x = tp.row_parallel(a, w["wo"], x)
+    x = tp.row_parallel(a, w["wo"], x, decode=False)
     h = ops.rmsnorm(x, w["ln2"], lcfg.rms_norm_eps)
     a = ops.linear_swiglu(h, w["wgu"])
-    return tp.row_parallel(a, w["wd"], x)
+    return tp.row_parallel(a, w["wd"], x, decode=False)

@@ -61,6 +61,12 @@ def main():
             resid = torch.randn(B, H, device=dev, dtype=torch.bfloat16)
 
             def fused():
+                tp.ar_mode = "fused"
+                for wt in wts:
+                    tp.row_parallel(x, wt, resid)
+
+            def oneshot():
+                tp.ar_mode = "oneshot"
                 for wt in wts:
                     tp.row_parallel(x, wt, resid)
 
@@ -70,12 +76,18 @@ def main():
                     dist.all_reduce(y)
                     y.add_(resid)
 
+            tp.ar_mode = "oneshot"
+            got1 = tp.row_parallel(x, wts[0], resid).float()
+            tp.row_parallel(x, wts[1], resid)                    # keep the buffer alternation even
+            tp.ar_mode = "fused"
             got = tp.row_parallel(x, wts[0], resid).float()
             y = torch.nn.functional.linear(x, wts[0]).float()
             dist.all_reduce(y)
             timing[f"{name}_err"] = round(((got - (y + resid.float())).norm() / (y + resid.float()).norm()).item(), 5)
+            timing[f"{name}_oneshot_err"] = round(((got1 - (y + resid.float())).norm() / (y + resid.float()).norm()).item(), 5)
             out = {}
-            for label, fn in (("fused_gemm_allreduce", fused), ("cublas_plus_nccl_allreduce", lib)):
+            for label, fn in (("fused_gemm_allreduce", fused), ("cublas_plus_oneshot_p2p_allreduce", oneshot),
+                              ("cublas_plus_nccl_allreduce", lib)):
                 s_ = torch.cuda.Stream()
                 s_.wait_stream(torch.cuda.current_stream())
                 with torch.cuda.stream(s_):
@@ -101,6 +113,7 @@ def main():
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
                 out[label + "_us"] = round(t.item(), 2)
             timing[name] = out
+        tp.ar_mode = "oneshot"
         res["row_parallel_decode_B128"] = timing
     if rank == 0:
         print("TP_RESULTS " + json.dumps(res), flush=True)
