@@ -272,7 +272,7 @@ extern "C" int prl_paged_decode(const void* q, int64_t ldq, const void* k_cache,
   float* ml_part = workspace + static_cast<int64_t>(num_seqs) * nq * splits * d;
   const float scale_log2 = sm_scale * 1.4426950408889634f;
   const int grid = num_seqs * nkv * splits;
-  static const int minb = [] { const char* e = getenv("POLYRL_DECODE_MINB"); return e ? atoi(e) : 4; }();
+  static const int minb = [] { const char* e = getenv("POLYRL_DECODE_MINB"); return e ? atoi(e) : 3; }();
   if (d == 128) {
     auto kern = minb >= 4 ? paged_decode_kernel<128, 4> : paged_decode_kernel<128, 3>;
     kern<<<grid, kAttnWarps * 32, 0, s>>>(

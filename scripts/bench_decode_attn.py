@@ -12,7 +12,10 @@ def main():
     dev = "cuda"
     nq, nkv, d, page = 32, 8, 128, 16
     out_rows = []
-    for B, ctx in ((128, 428), (128, 640), (256, 640), (32, 2048)):
+    import os
+
+    for B, ctx, splits in [(b, c, sp) for (b, c) in ((128, 428), (128, 640), (256, 640), (32, 2048))
+                           for sp in ([0] if os.environ.get("DECODE_ATTN_SPLITS", "") == "" else [int(x) for x in os.environ["DECODE_ATTN_SPLITS"].split(",")])]:
         pages = (ctx + page - 1) // page
         nblk = B * pages + 1
         layers = 4
@@ -24,7 +27,7 @@ def main():
 
         def fn():
             for i in range(layers):
-                paged_decode_attention(q, kc[i], vc[i], bt, sl, nq, nkv, d, d ** -0.5, max_len=ctx)
+                paged_decode_attention(q, kc[i], vc[i], bt, sl, nq, nkv, d, d ** -0.5, max_len=ctx, splits=splits)
 
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
@@ -47,7 +50,7 @@ def main():
         torch.cuda.synchronize()
         us = e0.elapsed_time(e1) / (reps * layers) * 1e3
         bytes_ = 2 * B * ctx * nkv * d * 2
-        out_rows.append({"B": B, "ctx": ctx, "us": round(us, 2), "TBps": round(bytes_ / us / 1e6, 3),
+        out_rows.append({"B": B, "ctx": ctx, "splits": splits, "us": round(us, 2), "TBps": round(bytes_ / us / 1e6, 3),
                          "frac_of_hbm_copy_6.57": round(bytes_ / us / 1e6 / 6.57, 3)})
         del kc, vc
     for r in out_rows:
@@ -62,6 +65,6 @@ if __name__ == "__main__":
     if os.environ.get("_DECODE_ATTN_CHILD") == "1":
         main()
     else:                                   # the occupancy variant is latched per process: one child per setting
-        for minb in ("3", "4"):
+        for minb in os.environ.get("DECODE_ATTN_MINB", "3").split(","):
             print(f"== POLYRL_DECODE_MINB={minb}", flush=True)
             subprocess.run([sys.executable, __file__], env={**os.environ, "_DECODE_ATTN_CHILD": "1", "POLYRL_DECODE_MINB": minb})
