@@ -30,7 +30,7 @@ def test_tensor_parallel_rollout_engine():
     n = 2
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1",
                         "--master-port", "29656", str(ROOT / "tests" / "tp_worker.py")], capture_output=True, text=True,
-                       timeout=600, env={**os.environ, "PYTHONPATH": str(ROOT)})
+                       timeout=600, env={**os.environ, "PYTHONPATH": str(ROOT), "TP_TIMING": "0"})   # timing: run the worker directly
     line = [l for l in r.stdout.splitlines() if l.startswith("TP_RESULTS ")]
     assert r.returncode == 0 and line, r.stdout[-2000:] + r.stderr[-3000:]
     res = json.loads(line[0].split(" ", 1)[1])
