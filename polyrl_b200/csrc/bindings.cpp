@@ -34,7 +34,7 @@ int prl_ipc_close_handle(void*);
 int prl_cuda_malloc(void**, int64_t);
 int prl_cuda_free(void*);
 int prl_enable_peer_access(int);
-int prl_p2p_barrier(void* const*, int, int, uint32_t, cudaStream_t);
+int prl_p2p_barrier(void* const*, int, int, uint32_t*, cudaStream_t);
 int prl_p2p_copy(const void*, void*, int64_t, int, cudaStream_t);
 int prl_p2p_push_fp8(const void*, void*, float*, int, int, int, cudaStream_t);
 int prl_p2p_allgather_pull(void* const*, void*, int64_t, int, int, int, cudaStream_t);
@@ -377,9 +377,12 @@ std::vector<void*> to_ptrs(const std::vector<int64_t>& v) {
   return r;
 }
 
-void p2p_barrier(const std::vector<int64_t>& flag_ptrs, int64_t rank, int64_t epoch) {
+// epoch_ctr: int32 device tensor (1 element) owned by this rank; the kernel increments it (graph-replay safe).
+void p2p_barrier(const std::vector<int64_t>& flag_ptrs, int64_t rank, at::Tensor epoch_ctr) {
+  TORCH_CHECK(epoch_ctr.is_cuda() && epoch_ctr.scalar_type() == at::kInt && epoch_ctr.numel() >= 1);
+  c10::cuda::CUDAGuard g(epoch_ctr.device());
   auto p = to_ptrs(flag_ptrs);
-  check(prl_p2p_barrier(p.data(), rank, p.size(), static_cast<uint32_t>(epoch), cur_stream()), "p2p_barrier");
+  check(prl_p2p_barrier(p.data(), rank, p.size(), reinterpret_cast<uint32_t*>(epoch_ctr.data_ptr<int>()), cur_stream()), "p2p_barrier");
 }
 void p2p_copy(int64_t src, int64_t dst, int64_t nbytes, int64_t max_ctas) {
   check(prl_p2p_copy(reinterpret_cast<void*>(src), reinterpret_cast<void*>(dst), nbytes, max_ctas, cur_stream()), "p2p_copy");

@@ -21,8 +21,15 @@ struct PeerPtrs {
 };
 
 // flags layout per rank: uint32 flags[kMaxPeers]; rank r writes `epoch` into flags[r] on every peer.
-__global__ void p2p_barrier_kernel(PeerPtrs flag_ptrs, int rank, int world, uint32_t epoch) {
+// The epoch lives in DEVICE memory (one counter per barrier channel, bumped by the kernel itself): a barrier captured into a
+// CUDA graph therefore advances on every replay — a host-assigned epoch would be frozen at capture time and later replays
+// would fall straight through (found on B200: TP engines lost lock-step under graph replay).
+__global__ void p2p_barrier_kernel(PeerPtrs flag_ptrs, int rank, int world, uint32_t* __restrict__ epoch_ctr) {
   const int t = threadIdx.x;
+  __shared__ uint32_t s_epoch;
+  if (t == 0) { s_epoch = *epoch_ctr + 1; *epoch_ctr = s_epoch; }
+  __syncthreads();
+  const uint32_t epoch = s_epoch;
   if (t < world) {
     __threadfence_system();
     // max (not store): barriers issued from different streams of one process may execute out of launch order
@@ -260,9 +267,9 @@ static PeerPtrs to_ptrs(void* const* ptrs, int world) {
   return pp;
 }
 
-extern "C" int prl_p2p_barrier(void* const* flag_ptrs, int rank, int world, uint32_t epoch, cudaStream_t s) {
+extern "C" int prl_p2p_barrier(void* const* flag_ptrs, int rank, int world, uint32_t* epoch_ctr, cudaStream_t s) {
   if (world > kMaxPeers) return -41;
-  p2p_barrier_kernel<<<1, 32, 0, s>>>(to_ptrs(flag_ptrs, world), rank, world, epoch);
+  p2p_barrier_kernel<<<1, 32, 0, s>>>(to_ptrs(flag_ptrs, world), rank, world, epoch_ctr);
   PRL_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

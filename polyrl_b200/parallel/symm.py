@@ -79,16 +79,16 @@ class SymmetricHeap:
     def barrier(self, channel: int = 0) -> None:
         """Device-side barrier across the heap's ranks on the current stream (no host sync).
 
-        Barriers on one *channel* must all be issued on the same CUDA stream (epochs are assigned in launch order);
+        Barriers on one *channel* must all be issued on the same CUDA stream (the device-side epoch advances in execution order);
         use a different channel per stream — the ZeRO-3 engine uses channel 1 for its communication stream."""
         if self.world == 1:
             return
         if self._flags is None:
             self._flags = self.alloc(64 * 4, torch.int32)        # 4 channels x 64 flag words
-            self._epochs = [0, 0, 0, 0]
+            # device-resident epoch counter per channel (the barrier kernel bumps it: CUDA-graph replays stay in step)
+            self._epochs = [torch.zeros(1, dtype=torch.int32, device=self.device) for _ in range(4)]
             torch.cuda.synchronize(self.device)
             dist.barrier(group=self.group)       # everyone's flag words are zeroed and mapped
-        self._epochs[channel] += 1
         self._C.p2p_barrier(self._flags.peer_ptrs(channel * 64 * 4), self.rank, self._epochs[channel])
 
     def close(self) -> None:

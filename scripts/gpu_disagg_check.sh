@@ -14,4 +14,4 @@ python -m torch.distributed.run --nnodes=1 --nproc-per-node=$NGPU --master-addr 
   actor_rollout_ref.rollout.min_stream_batch_size=16 actor_rollout_ref.rollout.max_num_seqs=64 \
   actor_rollout_ref.rollout.rollout_manager.port=0 actor_rollout_ref.rollout.rollout_manager.max_local_gen_s=60 \
   trainer.n_gpus_per_node=$NGPU trainer.n_rollout_gpus=$NROLL trainer.logger=[console] \
-  trainer.total_training_steps=3 trainer.total_epochs=1 trainer.save_freq=-1 trainer.test_freq=-1 "$@" 2>&1 | tail -40
+  trainer.total_training_steps=3 trainer.total_epochs=1 trainer.save_freq=-1 trainer.test_freq=-1 "$@" 2>&1
