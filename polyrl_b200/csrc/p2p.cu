@@ -312,8 +312,8 @@ extern "C" int prl_p2p_allreduce(void* const* buf_ptrs, int64_t elem_off, void* 
                                  int max_ctas, cudaStream_t s) {
   if (world > kMaxPeers || n % 8 != 0) return -46;
   if (n == 0) return 0;
-  int grid = static_cast<int>((n / 8 + 255) / 256);
-  const int cap = max_ctas > 0 ? max_ctas : 148;
+  int grid = static_cast<int>((n / 8 + 255) / 256);       // one 16-byte vector per thread: a single NVLink round trip deep
+  const int cap = max_ctas > 0 ? max_ctas : 148 * 4;
   if (grid > cap) grid = cap;
   p2p_allreduce_kernel<<<grid, 256, 0, s>>>(to_ptrs(buf_ptrs, world), elem_off, static_cast<__nv_bfloat16*>(out),
                                             static_cast<const __nv_bfloat16*>(residual), n, world);

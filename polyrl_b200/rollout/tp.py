@@ -96,7 +96,7 @@ class TPContext:
             torch.mm(x_local, w_local.t(), out=part)
             self.heap.barrier()
             out = torch.empty(b, h, device=x_local.device, dtype=torch.bfloat16)
-            self.C.p2p_allreduce(buf.ptrs, 0, out, residual.contiguous() if residual is not None else None, 32)
+            self.C.p2p_allreduce(buf.ptrs, 0, out, residual.contiguous() if residual is not None else None, 0)
             return out
         if small and self.ar_mode == "fused":
             ws, ctr = _skinny_buffers(x_local.device)
