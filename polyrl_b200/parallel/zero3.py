@@ -180,13 +180,18 @@ class ShardedUnit:
         """Reduce-scatter the unit's full bf16 grads (one tensor per spec, None = zero) into grad_acc."""
         eng = self.engine
         w = eng.world
+        fold = eng.total_sumsq if (eng._fold and eng.use_kernels) else None
+        if fold is not None:
+            eng._folded.add(self.name)
         if w == 1:
             for g, numel, so in zip(grads, self.numels, self.shard_offsets):
-                if g is None:
-                    continue
                 acc = self.grad_acc[so:so + numel]
+                if g is None:
+                    if fold is not None:
+                        eng.C.sumsq_(acc, fold)            # untouched this micro-batch: still part of the norm
+                    continue
                 if eng.use_kernels:
-                    eng.C.grad_accum_(acc, g.reshape(-1).contiguous(), scale, None)
+                    eng.C.grad_accum_(acc, g.reshape(-1).contiguous(), scale, fold)
                 else:
                     acc.add_(g.reshape(-1).float(), alpha=scale)
             return
@@ -215,7 +220,7 @@ class ShardedUnit:
                 es = flat.element_size()
                 for chunk, so, fo in zip(self.chunks, self.shard_offsets, self.full_offsets):
                     eng.C.p2p_reduce_scatter_accum(slot.peer_ptrs(), fo + eng.rank * chunk,
-                                                   self.grad_acc[so:so + chunk], scale_eff, eng.rank, None, eng.comm_ctas)
+                                                   self.grad_acc[so:so + chunk], scale_eff, eng.rank, fold, eng.comm_ctas)
                 eng.heap.barrier(1)                     # every rank finished reading -> slot reusable
                 ev = torch.cuda.Event()
                 ev.record(eng.comm_stream)
@@ -231,7 +236,7 @@ class ShardedUnit:
                 rm2[:, so:so + chunk].copy_(flat[fo:fo + chunk * w].view(w, chunk))
             dist.reduce_scatter_tensor(out, rm, op=dist.ReduceOp.SUM, group=eng.group)   # fp32 reduce
             if eng.use_kernels:
-                eng.C.grad_accum_(self.grad_acc, out, scale_eff, None)
+                eng.C.grad_accum_(self.grad_acc, out, scale_eff, fold)
             else:
                 self.grad_acc.add_(out, alpha=scale_eff)
             eng.pool_release(out, tag="rs_out")
@@ -401,6 +406,7 @@ class Zero3Engine:
         # enable_gradient_checkpointing=True); "none" = save activations for every layer; "auto" = save as many layers
         # as fit in free HBM at the first forward of a micro-batch; an int = that many layers.
         self.act_ckpt = "full"
+        self._fold, self._folded = False, set()
         self.act_reserve_bytes = 16 << 30
         self.saved_layers_last = 0
         self.grad_scale = 1.0
@@ -609,6 +615,15 @@ class Zero3Engine:
         return self.head_logits_runner(None, self.forward_hidden(inp))
 
     # ---- optimizer ------------------------------------------------------------------------------
+    def arm_norm_fold(self) -> None:
+        """Call right before the LAST backward of a mini-batch: that micro-batch's reduce-scatter / accumulate kernels also
+        accumulate sum(grad_acc^2) of the values they just produced, so ``step()`` needs no separate pass over the fp32
+        gradients (SURVEY 2.5b "grad clip: norm accumulated in RS kernel")."""
+        if not (self.use_kernels and self.trainable) or self.replica_group is not None:
+            return
+        self.total_sumsq.zero_()
+        self._fold, self._folded = True, set()
+
     def zero_grad(self) -> None:
         for u in self.opt_units:
             u.wait_grads()
@@ -617,7 +632,11 @@ class Zero3Engine:
     def grad_norm_sq(self) -> torch.Tensor:
         for u in self.opt_units:
             u.wait_grads()
-        if self.use_kernels:
+        folded = self._fold and self._folded == {u.name for u in self.opt_units}
+        self._fold = False
+        if self.use_kernels and folded:
+            tot = self.total_sumsq                           # accumulated by the last micro-batch's RS / accumulate kernels
+        elif self.use_kernels:
             self.total_sumsq.zero_()
             for u in self.opt_units:
                 self.C.sumsq_(u.grad_acc, self.total_sumsq)

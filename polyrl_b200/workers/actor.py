@@ -149,7 +149,8 @@ class DataParallelPPOActor:
                                   cfg.use_dynamic_bsz)
         grad_accum = max(1, cfg.ppo_mini_batch_size // max(1, (cfg.ppo_micro_batch_size_per_gpu or n)))
         loss_fn = core_algos.get_policy_loss_fn(cfg.policy_loss_mode)
-        for mb, idx in mbs:
+        mbs = list(mbs)
+        for mi, (mb, idx) in enumerate(mbs):
             b = mb.batch
             mask = b["response_mask"].float()
             scale = (len(mb) / cfg.ppo_mini_batch_size) if cfg.use_dynamic_bsz else 1.0 / grad_accum
@@ -169,6 +170,8 @@ class DataParallelPPOActor:
                 loss = loss + cfg.kl_loss_coef * kl_loss
                 m["actor/kl_loss"] = kl_loss.detach().item()
                 m["actor/kl_coef"] = cfg.kl_loss_coef
+            if is_opt_step and mi == len(mbs) - 1:
+                self.engine.arm_norm_fold()         # the last reduce-scatter of the mini-batch also produces the grad norm
             (loss * scale).backward()
             for k, v in m.items():
                 metrics.setdefault(k, []).append(v)
@@ -217,13 +220,16 @@ class DataParallelPPOCritic:
         n = len(data)
         mbs = self._mb(data, cfg.ppo_micro_batch_size_per_gpu, cfg.ppo_max_token_len_per_gpu, cfg.use_dynamic_bsz)
         grad_accum = max(1, cfg.ppo_mini_batch_size // max(1, (cfg.ppo_micro_batch_size_per_gpu or n)))
-        for mb, idx in mbs:
+        mbs = list(mbs)
+        for mi, (mb, idx) in enumerate(mbs):
             b = mb.batch
             mask = b["response_mask"].float()
             scale = (len(mb) / cfg.ppo_mini_batch_size) if cfg.use_dynamic_bsz else 1.0 / grad_accum
             vpred = self._forward_micro_batch(mb)
             vf_loss, clipfrac = core_algos.compute_value_loss(vpred, b["returns"], b["values"], mask,
                                                               cfg.cliprange_value, cfg.loss_agg_mode)
+            if is_opt_step and mi == len(mbs) - 1:
+                self.engine.arm_norm_fold()
             (vf_loss * scale).backward()
             metrics.setdefault("critic/vf_loss", []).append(vf_loss.detach().item())
             metrics.setdefault("critic/vf_clipfrac", []).append(clipfrac.detach().item())

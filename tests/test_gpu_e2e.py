@@ -61,3 +61,27 @@ def test_engine_fp8_weights_gpu():
             assert isinstance(eng.layer_w[0]["wgu"], ops.Fp8Weight)
     close = sum(abs(a[1] - b[1]) < 0.25 for a, b in zip(first["bf16"], first["fp8"]))
     assert close == len(prompts), first
+
+
+def test_grad_norm_folded_into_last_accumulate_gpu():
+    """The last micro-batch's accumulate kernels also produce sum(grad^2): it must equal a separate pass over the fp32 grads."""
+    from polyrl_b200.models import get_model_config, pack_padded
+    from polyrl_b200.parallel.zero3 import Zero3Engine
+
+    cfg = get_model_config("tiny-llama-128")
+    eng = Zero3Engine(cfg, "cuda", lr=1e-3, seed=2)
+    torch.manual_seed(0)
+    for i in range(2):
+        ids = torch.randint(3, cfg.vocab_size, (3, 40), device="cuda")
+        inp, _ = pack_padded(ids, torch.ones_like(ids))
+        labels = torch.roll(inp.input_ids, -1)
+        lp, ent = eng.forward_logprob_entropy(inp, labels, 1.0)
+        if i == 1:
+            eng.arm_norm_fold()
+        (-(lp.mean()) + 0.01 * ent.mean()).backward()
+    want = sum(u.grad_acc.double().pow(2).sum().item() for u in eng.opt_units)
+    assert eng._fold and eng._folded == {u.name for u in eng.opt_units}
+    got = eng.total_sumsq.item()
+    assert abs(got - want) / want < 1e-4, (got, want)
+    st = eng.step()
+    assert abs(st["grad_norm"] - want ** 0.5) / want ** 0.5 < 1e-3 and not eng._fold
