@@ -182,7 +182,7 @@ class ShardedUnit:
         w = eng.world
         fold = eng.total_sumsq if (eng._fold and eng.use_kernels) else None
         if fold is not None:
-            eng._folded.add(self.name)
+            eng._folded[self.name] = eng._folded.get(self.name, 0) + 1      # twice (tied embeddings) => fold invalid, recompute
         if w == 1:
             for g, numel, so in zip(grads, self.numels, self.shard_offsets):
                 acc = self.grad_acc[so:so + numel]
@@ -406,7 +406,7 @@ class Zero3Engine:
         # enable_gradient_checkpointing=True); "none" = save activations for every layer; "auto" = save as many layers
         # as fit in free HBM at the first forward of a micro-batch; an int = that many layers.
         self.act_ckpt = "full"
-        self._fold, self._folded = False, set()
+        self._fold, self._folded = False, {}
         self.act_reserve_bytes = 16 << 30
         self.saved_layers_last = 0
         self.grad_scale = 1.0
@@ -622,7 +622,7 @@ class Zero3Engine:
         if not (self.use_kernels and self.trainable) or self.replica_group is not None:
             return
         self.total_sumsq.zero_()
-        self._fold, self._folded = True, set()
+        self._fold, self._folded = True, {}
 
     def zero_grad(self) -> None:
         for u in self.opt_units:
@@ -632,7 +632,7 @@ class Zero3Engine:
     def grad_norm_sq(self) -> torch.Tensor:
         for u in self.opt_units:
             u.wait_grads()
-        folded = self._fold and self._folded == {u.name for u in self.opt_units}
+        folded = self._fold and self._folded == {u.name: 1 for u in self.opt_units}
         self._fold = False
         if self.use_kernels and folded:
             tot = self.total_sumsq                           # accumulated by the last micro-batch's RS / accumulate kernels

@@ -80,7 +80,7 @@ def test_grad_norm_folded_into_last_accumulate_gpu():
             eng.arm_norm_fold()
         (-(lp.mean()) + 0.01 * ent.mean()).backward()
     want = sum(u.grad_acc.double().pow(2).sum().item() for u in eng.opt_units)
-    assert eng._fold and eng._folded == {u.name for u in eng.opt_units}
+    assert eng._fold and eng._folded == {u.name: 1 for u in eng.opt_units}
     got = eng.total_sumsq.item()
     assert abs(got - want) / want < 1e-4, (got, want)
     st = eng.step()
