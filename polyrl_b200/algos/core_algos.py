@@ -9,7 +9,7 @@ with ``torch.unique`` + ``index_add`` instead of per-sample Python dict loops.
 from __future__ import annotations
 
 from enum import Enum
-from typing import Any, Callable
+from typing import Callable
 
 import numpy as np
 import torch

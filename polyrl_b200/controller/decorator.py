@@ -10,7 +10,7 @@ from __future__ import annotations
 import functools
 import inspect
 from enum import Enum
-from typing import Any, Callable
+from typing import Callable
 
 from ..protocol import DataProto, DataProtoFuture, pad_dataproto_to_divisor, unpad_dataproto
 

@@ -24,7 +24,7 @@ import threading
 import time
 import traceback
 from concurrent.futures import Future, ThreadPoolExecutor
-from typing import Any, Callable
+from typing import Callable
 
 from .decorator import MAGIC_ATTR, Execute, dispatch_attr, get_predefined_dispatch_fn
 

@@ -8,7 +8,7 @@ HF configs (the reference loads the same families through HF AutoModel:
 from __future__ import annotations
 
 import json
-from dataclasses import asdict, dataclass, field
+from dataclasses import asdict, dataclass
 from pathlib import Path
 
 

@@ -16,12 +16,11 @@ import time
 import uuid
 from pathlib import Path
 
-import numpy as np
 import torch
 import torch.distributed as dist
 
 from ..algos import core_algos
-from ..config.schema import PPOConfig, need_critic, need_reference_policy
+from ..config.schema import PPOConfig
 from ..protocol import DataProto, collate_fn, pad_dataproto_to_divisor
 from ..utils import metrics as M
 from ..utils.checkpoint import find_latest_ckpt_path, write_latest

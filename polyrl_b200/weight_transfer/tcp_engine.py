@@ -12,9 +12,7 @@ import os
 import socket
 import struct
 import threading
-import time
 
-import numpy as np
 import torch
 
 HEADER = struct.Struct("<QQ")          # (offset, length)
