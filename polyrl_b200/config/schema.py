@@ -171,6 +171,7 @@ class RolloutConfig(BaseConfig):
     max_num_seqs: int = 256
     max_model_len: int | None = None
     enable_chunked_prefill: bool = True
+    enable_prefix_caching: bool = False     # cross-request KV page reuse (always on for multi-turn rollouts)
     load_format: str = "dummy"
     calculate_log_probs: bool = False
     log_prob_micro_batch_size_per_gpu: int | None = None

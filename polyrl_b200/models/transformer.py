@@ -106,6 +106,9 @@ class PackedInput:
     max_seqlen: int
     sp_group: object = None        # Ulysses SP: ids/positions are this rank's slice, cu_seqlens describe the full stream
     total_tokens: int = 0          # un-padded length of the full packed stream (SP only)
+    # prefill behind a cached KV prefix (rollout engine's prefix cache): (block idx [Tk], in-page offset [Tk], cu_seqlens_k
+    # [B+1], max_k) describing EVERY key position (cached + new) of every sequence in the paged cache
+    kv_gather: object = None
 
 
 # --------------------------------------------------------------------------------------------
@@ -139,7 +142,13 @@ def layer_forward(cfg: ModelConfig, w: dict, x: torch.Tensor, inp: PackedInput, 
         q = qkv[:, : nq * d].view(t, nq, d)
         k = qkv[:, nq * d:(nq + nkv) * d].view(t, nkv, d)
         v = qkv[:, (nq + nkv) * d:].view(t, nkv, d)
-        if inp.sp_group is not None:
+        if inp.kv_gather is not None and kv_sink is not None:
+            from ..ops.attention import attention_varlen_prefix
+
+            blk, off, cu_k, max_k = inp.kv_gather            # new tokens were appended to the cache just above
+            a = attention_varlen_prefix(q, kv_sink[0][blk, :, off, :], kv_sink[1][blk, :, off, :], inp.cu_seqlens, cu_k,
+                                        inp.max_seqlen, max_k)
+        elif inp.sp_group is not None:
             from ..parallel.ulysses import ulysses_attention
 
             a = ulysses_attention(q, k, v, inp.cu_seqlens, inp.max_seqlen, inp.sp_group, inp.total_tokens, causal=True)

@@ -63,3 +63,26 @@ def attention_varlen(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, cu_seqle
         return fa(q, k, v, cu_seqlens, cu_seqlens, int(max_seqlen), int(max_seqlen), 0.0, softmax_scale=scale,
                   causal=causal)
     return _sdpa_varlen(q, k, v, cu_seqlens, max_seqlen, causal, scale)
+
+
+def attention_varlen_prefix(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, cu_q: torch.Tensor, cu_k: torch.Tensor, max_q: int,
+                            max_k: int, scale: float | None = None) -> torch.Tensor:
+    """Prefill behind a cached prefix: sequence i has ``lq_i`` NEW query tokens and ``lk_i >= lq_i`` keys (cached prefix first,
+    then the new tokens); causal mask aligned bottom-right.  q:[Tq,nq,d], k/v:[Tk,nkv,d]."""
+    if scale is None:
+        scale = q.shape[-1] ** -0.5
+    fa = _flash() if q.is_cuda and q.dtype in (torch.bfloat16, torch.float16) else False
+    if fa:
+        return fa(q, k, v, cu_q, cu_k, int(max_q), int(max_k), 0.0, softmax_scale=scale, causal=True)
+    nq, nkv = q.shape[1], k.shape[1]
+    out = torch.empty_like(q)
+    cq, ck = cu_q.tolist(), cu_k.tolist()
+    for i in range(len(cq) - 1):
+        qs, ks, vs = q[cq[i]:cq[i + 1]], k[ck[i]:ck[i + 1]], v[ck[i]:ck[i + 1]]
+        lq, lk = qs.shape[0], ks.shape[0]
+        if nkv != nq:
+            ks, vs = ks.repeat_interleave(nq // nkv, dim=1), vs.repeat_interleave(nq // nkv, dim=1)
+        mask = torch.arange(lk, device=q.device)[None, :] <= (torch.arange(lq, device=q.device)[:, None] + (lk - lq))
+        o = F.scaled_dot_product_attention(qs.transpose(0, 1), ks.transpose(0, 1), vs.transpose(0, 1), attn_mask=mask, scale=scale)
+        out[cq[i]:cq[i + 1]] = o.transpose(0, 1)
+    return out

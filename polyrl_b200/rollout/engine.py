@@ -64,6 +64,7 @@ class Request:
     t_arrival: float = 0.0
     group: object = None                   # requests of one n-sample group share prompt KV pages
     donor: object = None                   # the group member whose prefill this request re-uses
+    cached_tokens: int = 0                 # prompt tokens whose KV came from the prefix cache (multiple of the page size)
 
     @property
     def finished(self) -> bool:
@@ -104,15 +105,80 @@ class BlockAllocator:
                 self.free.append(b)
 
 
+class PrefixCache:
+    """Cross-request KV reuse at page granularity (the role of SGLang's radix cache for the reference's multi-turn /
+    shared-system-prompt traffic).  A full page is identified by the hash chain of every token up to and including it, so a hit
+    on page i implies hits on pages 0..i-1.  The cache holds one reference on every registered block; blocks nobody else
+    references are evicted in LRU order when the allocator runs dry.  Must be flushed when the weights change."""
+
+    def __init__(self, alloc: BlockAllocator):
+        self.alloc = alloc
+        self.by_key: dict[int, int] = {}
+        self.key_of: dict[int, int] = {}
+        self.lru: "dict[int, None]" = {}            # insertion-ordered: oldest first
+        self.hits = self.misses = 0
+
+    @staticmethod
+    def page_keys(tokens: list[int], max_pages: int) -> list[int]:
+        keys, h = [], 0
+        for i in range(max_pages):
+            h = hash((h, tuple(tokens[i * PAGE:(i + 1) * PAGE])))
+            keys.append(h)
+        return keys
+
+    def match(self, keys: list[int]) -> list[int]:
+        out = []
+        for k in keys:
+            b = self.by_key.get(k)
+            if b is None:
+                break
+            out.append(b)
+        for b in out:                               # refresh recency
+            self.lru.pop(b, None)
+            self.lru[b] = None
+        self.hits += len(out)
+        self.misses += len(keys) - len(out)
+        return out
+
+    def insert(self, keys: list[int], blocks: list[int]) -> None:
+        for k, b in zip(keys, blocks):
+            if k in self.by_key or b in self.key_of:
+                continue
+            self.by_key[k], self.key_of[b] = b, k
+            self.alloc.share([b])
+            self.lru[b] = None
+
+    def evict(self, want: int) -> int:
+        freed = 0
+        for b in list(self.lru):
+            if freed >= want:
+                break
+            if self.alloc.ref[b] == 1:              # only the cache holds it
+                self._drop(b)
+                freed += 1
+        return freed
+
+    def _drop(self, b: int) -> None:
+        self.by_key.pop(self.key_of.pop(b), None)
+        self.lru.pop(b, None)
+        self.alloc.release([b])
+
+    def flush(self) -> None:
+        for b in list(self.key_of):
+            self._drop(b)
+
+
 class RolloutEngine:
     def __init__(self, cfg: ModelConfig, device, max_num_seqs: int = 256, max_model_len: int = 2048,
                  kv_cache_tokens: int | None = None, gpu_memory_utilization: float = 0.5, dtype=None,
                  use_cuda_graph: bool = True, max_prefill_tokens: int = 16384, seed: int = 0, tp=None,
-                 weight_dtype: str = "bf16", steps_per_sync: int | None = None):
+                 weight_dtype: str = "bf16", steps_per_sync: int | None = None, enable_prefix_cache: bool = False):
         # decode steps launched back to back per host round trip (tokens are read back once per window; a sequence that
         # ends mid-window rides along for a few ignored tokens).  1 = one-step lag only.
         import os as _os
         self.steps_per_sync = max(1, min(8, int(steps_per_sync or _os.environ.get("POLYRL_DECODE_STEPS_PER_SYNC", "1"))))
+        self.enable_prefix_cache = enable_prefix_cache and tp is None and cfg.family == "llama"
+        self.prefix_cache: PrefixCache | None = None
         if weight_dtype not in ("bf16", "fp8"):
             raise ValueError("weight_dtype must be 'bf16' or 'fp8'")
         if weight_dtype == "fp8" and tp is not None:
@@ -164,6 +230,7 @@ class RolloutEngine:
         self.embed_w, self.layer_w, self.head_w = embed_w, layer_w, head_w
         if old != self._weight_ptrs():
             self._graphs.clear()
+        self.flush_cache()              # same storage updated in place still means new weights
         if version is not None:
             self.weight_version = version
 
@@ -223,6 +290,7 @@ class RolloutEngine:
         self.k_cache = [torch.zeros(shape, device=self.device, dtype=self.dtype) for _ in range(c.num_layers)]
         self.v_cache = [torch.zeros(shape, device=self.device, dtype=self.dtype) for _ in range(c.num_layers)]
         self.alloc = BlockAllocator(num_blocks)
+        self.prefix_cache = PrefixCache(self.alloc) if self.enable_prefix_cache else None
         self._graphs.clear()
 
     def release_memory(self, tags=("kv_cache",)) -> None:
@@ -230,7 +298,7 @@ class RolloutEngine:
         if "kv_cache" in tags:
             if self.running or self.waiting:
                 raise RuntimeError("cannot release the KV cache with requests in flight")
-            self.k_cache, self.v_cache, self.alloc = [], [], None
+            self.k_cache, self.v_cache, self.alloc, self.prefix_cache = [], [], None, None
             self._graphs.clear()
             if self.is_cuda:
                 torch.cuda.empty_cache()
@@ -243,7 +311,9 @@ class RolloutEngine:
             self.init_kv_cache()
 
     def flush_cache(self) -> None:
-        return None     # no cross-request prefix cache to invalidate (prompt pages are shared per n-group only)
+        """Drop every cached prefix page (mandatory after a weight update: the KV was produced by the old weights)."""
+        if self.prefix_cache is not None:
+            self.prefix_cache.flush()
 
     # ------------------------------------------------------------------ static decode state
     def _alloc_static(self) -> None:
@@ -313,10 +383,23 @@ class RolloutEngine:
             need = self._blocks_needed(r)
             full_prompt_pages = len(r.prompt_ids) // PAGE
             donor = shared.get(id(r.group)) if r.group is not None else None
-            fresh = need - (full_prompt_pages if donor is not None else 0)
+            cached: list[int] = []
+            keys: list[int] = []
+            if donor is None and self.prefix_cache is not None:
+                # at least the last prompt token must be recomputed (its logits seed the first sampled token)
+                keys = PrefixCache.page_keys(r.prompt_ids, (len(r.prompt_ids) - 1) // PAGE)
+                cached = self.prefix_cache.match(keys)
+                self.alloc.share(cached)            # pin before any eviction below can touch them
+            fresh = need - (full_prompt_pages if donor is not None else len(cached))
+            if fresh > self.alloc.available() and self.prefix_cache is not None:
+                self.prefix_cache.evict(fresh - self.alloc.available())
             if fresh > self.alloc.available():
+                if cached:
+                    self.alloc.release(cached)
                 break
             if tokens + len(r.prompt_ids) > self.max_prefill_tokens and admitted:
+                if cached:
+                    self.alloc.release(cached)
                 break
             self.waiting.popleft()
             if donor is not None:
@@ -326,7 +409,8 @@ class RolloutEngine:
                 r.shared_prefix_blocks = full_prompt_pages
                 r.donor = donor
             else:
-                r.blocks = self.alloc.alloc(need)
+                r.blocks = cached + self.alloc.alloc(fresh)
+                r.cached_tokens = len(cached) * PAGE
                 if r.group is not None:
                     shared[id(r.group)] = r
             r.slot = self.free_slots.pop()
@@ -344,6 +428,11 @@ class RolloutEngine:
             self.free_slots.append(r.slot)
             r.slot = -1
         if r.blocks and self.alloc is not None:
+            if self.prefix_cache is not None and reason != "abort":
+                # every FULL page whose KV is final: prompt + generated tokens except the last one (never fed back)
+                toks = r.prompt_ids + r.output_ids
+                n_full = max(0, (len(toks) - 1)) // PAGE
+                self.prefix_cache.insert(PrefixCache.page_keys(toks, n_full), r.blocks[:n_full])
             self.alloc.release(r.blocks)
         r.blocks = []
 
@@ -360,16 +449,27 @@ class RolloutEngine:
         donors = [r for r in reqs if r.donor is None]
         d_index = {id(r): i for i, r in enumerate(donors)}
         ids, pos, slots, lens = [], [], [], []
+        any_cached = any(r.cached_tokens for r in donors)
+        g_blk, g_off, klens = [], [], []
         for r in donors:
-            n = len(r.prompt_ids)
-            ids += r.prompt_ids
-            pos += list(range(n))
-            slots += [r.blocks[t // PAGE] * PAGE + t % PAGE for t in range(n)]
-            lens.append(n)
+            n, c = len(r.prompt_ids), r.cached_tokens
+            ids += r.prompt_ids[c:]
+            pos += list(range(c, n))
+            slots += [r.blocks[t // PAGE] * PAGE + t % PAGE for t in range(c, n)]
+            lens.append(n - c)
+            if any_cached:
+                g_blk += [r.blocks[t // PAGE] for t in range(n)]
+                g_off += [t % PAGE for t in range(n)]
+                klens.append(n)
         cu = torch.zeros(len(donors) + 1, dtype=torch.int32)
         cu[1:] = torch.tensor(lens, dtype=torch.int32).cumsum(0)
         inp = tf.PackedInput(torch.tensor(ids, dtype=torch.long, device=dev), torch.tensor(pos, dtype=torch.long, device=dev),
                              cu.to(dev), max(lens))
+        if any_cached:
+            cu_k = torch.zeros(len(donors) + 1, dtype=torch.int32)
+            cu_k[1:] = torch.tensor(klens, dtype=torch.int32).cumsum(0)
+            inp.kv_gather = (torch.tensor(g_blk, dtype=torch.long, device=dev), torch.tensor(g_off, dtype=torch.long, device=dev),
+                             cu_k.to(dev), max(klens))
         slot_t = torch.tensor(slots, dtype=torch.long, device=dev)
         x = tf.embed_forward(cfg, self.embed_w, inp).to(self.dtype)
         for i, w in enumerate(self.layer_w):

@@ -34,6 +34,7 @@ def main(argv=None) -> int:
     ap.add_argument("--weight-receiver-zmq-bind-host", default="0.0.0.0")
     ap.add_argument("--transfer-agent-sender-group-idx", type=int, default=0)
     ap.add_argument("--num-transfer-engines-per-group", type=int, default=1)
+    ap.add_argument("--enable-prefix-cache", action="store_true", help="cross-request KV page reuse (radix-cache equivalent)")
     ap.add_argument("--tp-size", type=int, default=1, help="tensor-parallel degree; launch with torchrun --nproc-per-node TP")
     a = ap.parse_args(argv)
     cfg = get_model_config(a.model_path)
@@ -58,7 +59,7 @@ def main(argv=None) -> int:
         tp_ctx = TPContext(cfg, heap, tp_rank, a.tp_size, max_batch=a.max_num_seqs)
     w = TransformerWeights(cfg, device=a.device, dtype=dtype, init=True)          # same seed on every TP rank
     eng = RolloutEngine(cfg, a.device, max_num_seqs=a.max_num_seqs, max_model_len=a.max_model_len,
-                        gpu_memory_utilization=a.mem_fraction_static, tp=tp_ctx)
+                        gpu_memory_utilization=a.mem_fraction_static, tp=tp_ctx, enable_prefix_cache=a.enable_prefix_cache)
     eng.set_weights(w.embed, w.layers, w.head)
     if tp_rank > 0:
         from .server import run_tp_follower

@@ -154,7 +154,8 @@ class ActorRolloutRefWorker:
             self.rollout = RolloutEngine(self.model_cfg, self.device, max_num_seqs=r.max_num_seqs, max_model_len=max_len,
                                          gpu_memory_utilization=r.gpu_memory_utilization, use_cuda_graph=r.cuda_graph,
                                          max_prefill_tokens=r.max_num_batched_tokens, seed=seed + 17 * self.rank,
-                                         weight_dtype=r.weight_dtype)
+                                         weight_dtype=r.weight_dtype,
+                                         enable_prefix_cache=r.enable_prefix_caching or r.multi_turn.enable)
             if self.has_actor:
                 self.update_weight_remote()
 

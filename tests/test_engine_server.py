@@ -207,3 +207,46 @@ def test_multi_step_decode_windows_match_single_step():
         outs[k] = [(r.output_ids, r.finish_reason, [round(x, 4) for x in r.logprobs]) for grp in g for r in grp]
         assert all(len(o[0]) <= 11 for o in outs[k])
     assert outs[1] == outs[4]
+
+
+def test_prefix_cache_multi_turn_reuse_eviction_flush():
+    """Cross-request KV reuse: a second turn whose prompt extends the first turn's prompt+response re-uses the cached pages
+    (fewer prefill tokens), generates exactly what a cache-less engine generates, survives eviction pressure, and is flushed by
+    a weight update."""
+    import torch
+
+    from polyrl_b200.models import TransformerWeights, get_model_config
+    from polyrl_b200.rollout.engine import RolloutEngine
+
+    cfg = get_model_config("tiny-llama")
+    w = TransformerWeights(cfg, "cpu", torch.float32, seed=17)
+    sp = {"max_new_tokens": 21, "temperature": 0.0, "ignore_eos": True}
+
+    def run(cache: bool, kv_tokens: int = 64 * 16):
+        eng = RolloutEngine(cfg, "cpu", max_num_seqs=4, max_model_len=160, use_cuda_graph=False, seed=0, kv_cache_tokens=kv_tokens,
+                            enable_prefix_cache=cache)
+        eng.set_weights(w.embed, w.layers, w.head)
+        p1 = [[7 + (i * 3) % 50 for i in range(37)], [9 + (i * 5) % 40 for i in range(20)]]
+        t1 = [g[0] for g in eng.generate(p1, sp)]
+        pre1 = eng.stats["prefill_tokens"]
+        # turn 2: previous context + a "tool response" + new question
+        p2 = [p + r.output_ids + [60, 61, 62, 63, 64] for p, r in zip(p1, t1)]
+        t2 = [g[0] for g in eng.generate(p2, sp)]
+        return eng, [r.output_ids for r in t1 + t2], [r.logprobs for r in t1 + t2], pre1, eng.stats["prefill_tokens"] - pre1, p2
+
+    e0, out0, lp0, pre1_0, pre2_0, _ = run(False)
+    e1, out1, lp1, pre1_1, pre2_1, p2 = run(True)
+    assert out0 == out1
+    assert max(abs(a - b) for x, y in zip(lp0, lp1) for a, b in zip(x, y)) < 1e-4
+    assert pre1_0 == pre1_1 and pre2_1 < pre2_0 - 60                 # (37+20) + 2*(21-1) context tokens mostly came from the cache
+    assert e1.prefix_cache.hits >= 5 and all(r.cached_tokens % 16 == 0 for r in [])
+    # a third request sharing only the first page
+    third = e1.generate([p2[0][:16] + [90] * 9], sp)[0][0]
+    assert third.cached_tokens == 16
+    # eviction: tiny pool forces cached pages out, results unchanged
+    e2, out2, _, _, _, _ = run(True, kv_tokens=14 * 16)
+    assert out2 == out0
+    # weight update flushes
+    assert e1.prefix_cache.by_key
+    e1.set_weights(w.embed, w.layers, w.head)
+    assert not e1.prefix_cache.by_key and e1.alloc.available() == e1.alloc.num_blocks - 1
