@@ -221,6 +221,11 @@ class EngineServer:
 
     def _engine_loop(self) -> None:
         eng = self.engine
+        if eng.is_cuda:
+            import torch
+
+            torch.cuda.set_device(eng.device)       # the current CUDA device is per THREAD: without this the engine thread issues
+                                                    # its barrier kernels / NCCL calls on cuda:0 (found on the 2-GPU disaggregated run)
         while not self._stop.is_set():
             with self._lock:
                 cmds, self._inbox = self._inbox, []

@@ -117,8 +117,10 @@ def main():
         res["row_parallel_decode_B128"] = timing
     if rank == 0:
         print("TP_RESULTS " + json.dumps(res), flush=True)
+    torch.cuda.synchronize()
     dist.barrier()
-    dist.destroy_process_group()
+    sys.stdout.flush()
+    os._exit(0)          # graphs that captured NCCL collectives are still alive: skip communicator teardown
 
 
 if __name__ == "__main__":
