@@ -65,6 +65,12 @@ class Request:
     group: object = None                   # requests of one n-sample group share prompt KV pages
     donor: object = None                   # the group member whose prefill this request re-uses
     cached_tokens: int = 0                 # prompt tokens whose KV came from the prefix cache (multiple of the page size)
+    prefilled: int = -1                    # prompt tokens whose KV is in the cache (-1: not admitted yet); < len(prompt) while
+                                           # a long prompt is being prefilled chunk by chunk
+
+    @property
+    def decoding(self) -> bool:
+        return self.prefilled >= len(self.prompt_ids) and self.finish_reason is None
 
     @property
     def finished(self) -> bool:
@@ -212,6 +218,8 @@ class RolloutEngine:
         self._rid = itertools.count()
         self._graphs: dict[int, tuple] = {}
         self._pending = None        # (event, cpu tokens, cpu logprobs, slots snapshot) of the step in flight
+        self._prefill_queue: list[Request] = []     # admitted requests whose prompt is not completely prefilled yet
+        self._prefill_turn = True                    # alternate prefill chunks with decode steps
         self._base_seed = seed
         self._step_count = 0
         self._top_k, self._top_p = -1, 1.0
@@ -361,7 +369,7 @@ class RolloutEngine:
         return out
 
     def has_work(self) -> bool:
-        return bool(self.waiting or self.running or self._pending)
+        return bool(self.waiting or self.running or self._pending or self._prefill_queue)
 
     def num_running(self) -> int:
         return len(self.running)
@@ -397,7 +405,7 @@ class RolloutEngine:
                 if cached:
                     self.alloc.release(cached)
                 break
-            if tokens + len(r.prompt_ids) > self.max_prefill_tokens and admitted:
+            if tokens >= self.max_prefill_tokens and admitted:      # this round's chunk budget is spent
                 if cached:
                     self.alloc.release(cached)
                 break
@@ -408,15 +416,16 @@ class RolloutEngine:
                 r.blocks = pre + self.alloc.alloc(fresh)
                 r.shared_prefix_blocks = full_prompt_pages
                 r.donor = donor
+                r.prefilled = 0
             else:
                 r.blocks = cached + self.alloc.alloc(fresh)
-                r.cached_tokens = len(cached) * PAGE
+                r.cached_tokens = r.prefilled = len(cached) * PAGE
                 if r.group is not None:
                     shared[id(r.group)] = r
             r.slot = self.free_slots.pop()
             self.running[r.slot] = r
             admitted.append(r)
-            tokens += len(r.prompt_ids)
+            tokens += 0 if donor is not None else len(r.prompt_ids) - r.prefilled
         return admitted
 
     def _finish(self, r: Request, reason: str) -> None:
@@ -446,21 +455,41 @@ class RolloutEngine:
         cfg, dev = self.cfg, self.device
         # n-sample groups: only the donor runs the prompt; followers share its full KV pages, copy its partial last
         # page and sample their own first token from the donor's last-position logits.
-        donors = [r for r in reqs if r.donor is None]
+        # Chunked prefill: at most ``max_prefill_tokens`` new tokens per call; a prompt longer than the remaining budget is
+        # cut, the rest is processed by later calls (attending to the KV already in the cache) interleaved with decode
+        # steps.  Requests whose prompt is complete after this call get their first token sampled below.
+        self._prefill_queue = [r for r in self._prefill_queue if not r.finished]
+        for r in reqs:                          # a follower whose donor was aborted mid-prefill becomes its own donor
+            if r.donor is not None and r.donor.finished and r.donor.prefilled < len(r.donor.prompt_ids):
+                r.donor, r.prefilled = None, 0
+        budget = self.max_prefill_tokens
+        donors, spans = [], []
+        for r in reqs:
+            if r.donor is not None or r.finished:
+                continue
+            c = r.prefilled
+            e = min(len(r.prompt_ids), c + max(budget, 0))
+            if e <= c:
+                continue                        # no budget left for this one in this round
+            donors.append(r)
+            spans.append((c, e))
+            budget -= e - c
+        if not donors:
+            return
         d_index = {id(r): i for i, r in enumerate(donors)}
         ids, pos, slots, lens = [], [], [], []
-        any_cached = any(r.cached_tokens for r in donors)
+        any_cached = any(c > 0 for c, _ in spans)
         g_blk, g_off, klens = [], [], []
-        for r in donors:
-            n, c = len(r.prompt_ids), r.cached_tokens
-            ids += r.prompt_ids[c:]
-            pos += list(range(c, n))
-            slots += [r.blocks[t // PAGE] * PAGE + t % PAGE for t in range(c, n)]
-            lens.append(n - c)
+        for r, (c, e) in zip(donors, spans):
+            ids += r.prompt_ids[c:e]
+            pos += list(range(c, e))
+            slots += [r.blocks[t // PAGE] * PAGE + t % PAGE for t in range(c, e)]
+            lens.append(e - c)
             if any_cached:
-                g_blk += [r.blocks[t // PAGE] for t in range(n)]
-                g_off += [t % PAGE for t in range(n)]
-                klens.append(n)
+                g_blk += [r.blocks[t // PAGE] for t in range(e)]
+                g_off += [t % PAGE for t in range(e)]
+                klens.append(e)
+            r.prefilled = e
         cu = torch.zeros(len(donors) + 1, dtype=torch.int32)
         cu[1:] = torch.tensor(lens, dtype=torch.int32).cumsum(0)
         inp = tf.PackedInput(torch.tensor(ids, dtype=torch.long, device=dev), torch.tensor(pos, dtype=torch.long, device=dev),
@@ -479,11 +508,19 @@ class RolloutEngine:
                 x = layer_prefill_tp(self.tp, cfg, w, x, inp, (self.k_cache[i], self.v_cache[i], slot_t))
             else:
                 x = tf.layer_forward(cfg, w, x, inp, kv_sink=(self.k_cache[i], self.v_cache[i], slot_t))
+        self.stats["prefill_tokens"] += len(ids)
+        done_ids = {id(r) for r in donors if r.prefilled >= len(r.prompt_ids)}
+        reqs = [r for r in reqs if not r.finished and (id(r) in done_ids or (r.donor is not None and id(r.donor) in done_ids))]
+        self._prefill_queue = [r for r in self._prefill_queue if not r.finished and not any(r is q for q in reqs)]
+        if not reqs:
+            return
         last = (cu[1:] - 1).long().to(dev)
         h = tf.final_norm(cfg, self.head_w, x.index_select(0, last))
         logits_d = self._lm_logits(h)
         src_blk, dst_blk = [], []
         for r in reqs:
+            if r.donor is not None:
+                r.prefilled = len(r.prompt_ids)
             if r.donor is not None and len(r.prompt_ids) % PAGE != 0:
                 fp = len(r.prompt_ids) // PAGE
                 src_blk.append(r.donor.blocks[fp])
@@ -501,7 +538,6 @@ class RolloutEngine:
         p0 = reqs[0].params
         tok, lp = ops.sample_tokens(logits, temps, seeds, greedy=False, top_k=p0.top_k, top_p=p0.top_p)
         tok_c, lp_c = tok.tolist(), lp.tolist()
-        self.stats["prefill_tokens"] += len(ids)
         for r in reqs:
             r.donor = None            # release the reference; pages stay shared through the allocator's ref-counts
         live, rows = [], []
@@ -661,16 +697,28 @@ class RolloutEngine:
             raise RuntimeError("RolloutEngine has no weights (call set_weights)")
         self.init_kv_cache()
         finished: list[Request] = []
-        if self.waiting and self.free_slots and self.alloc.available() > 0:
+        decoding = any(r.decoding for r in self.running.values())
+        if self._prefill_queue and (self._prefill_turn or not decoding):
+            # continue a chunked prefill (alternating with decode steps so running sequences keep advancing)
+            finished = self._drain_pending()
+            self._prefill_turn = False
+            batch = list(self._prefill_queue)
+            self._prefill(batch)
+            finished += [r for r in batch if r.finished]
+            self.stats["steps"] += 1
+            return finished
+        self._prefill_turn = True
+        if not self._prefill_queue and self.waiting and self.free_slots and self.alloc.available() > 0:
             finished = self._drain_pending()
             admitted = self._admit()
             if admitted:
                 self._top_k, self._top_p = admitted[0].params.top_k, admitted[0].params.top_p
+                self._prefill_queue = list(admitted)
                 self._prefill(admitted)
                 finished += [r for r in admitted if r.finished]
                 self.stats["steps"] += 1
                 return finished
-        if not self.running:
+        if not decoding:
             return finished + self._drain_pending()
         self._compact_slots()
         bs = self._bucket(max(self.running) + 1)
@@ -686,8 +734,9 @@ class RolloutEngine:
         if self.is_cuda:
             ev = torch.cuda.Event()
             ev.record(torch.cuda.current_stream(self.device))
-        new_pending = (ev, self.h_tok[i], self.h_lp[i], list(self.running.items()))
-        self.stats["decode_tokens"] += len(self.running) * self.steps_per_sync
+        live = [(s_, r_) for s_, r_ in self.running.items() if r_.decoding]      # mid-prefill requests hold idle slots
+        new_pending = (ev, self.h_tok[i], self.h_lp[i], live)
+        self.stats["decode_tokens"] += len(live) * self.steps_per_sync
         finished += self._drain_pending()
         self._pending = new_pending
         self.stats["steps"] += 1

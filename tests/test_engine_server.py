@@ -250,3 +250,37 @@ def test_prefix_cache_multi_turn_reuse_eviction_flush():
     assert e1.prefix_cache.by_key
     e1.set_weights(w.embed, w.layers, w.head)
     assert not e1.prefix_cache.by_key and e1.alloc.available() == e1.alloc.num_blocks - 1
+
+
+def test_chunked_prefill_matches_whole_prompt_prefill():
+    """max_prefill_tokens=16: long prompts are prefilled in 16-token chunks interleaved with decode steps of the sequences
+    already running; generations equal the unchunked engine's (n-sample groups and queueing included)."""
+    import torch
+
+    from polyrl_b200.models import TransformerWeights, get_model_config
+    from polyrl_b200.rollout.engine import RolloutEngine
+
+    cfg = get_model_config("tiny-llama")
+    w = TransformerWeights(cfg, "cpu", torch.float32, seed=23)
+    prompts = [[5 + (i * 7) % 90 for i in range(53)], [9, 4, 33], [11 + (i * 3) % 70 for i in range(37)], [8] * 18, [6, 7]]
+    sp = {"max_new_tokens": 9, "temperature": 0.0, "n": 2, "ignore_eos": True}
+    outs = {}
+    for budget in (4096, 16):
+        eng = RolloutEngine(cfg, "cpu", max_num_seqs=6, max_model_len=96, use_cuda_graph=False, seed=1, max_prefill_tokens=budget)
+        eng.set_weights(w.embed, w.layers, w.head)
+        g = eng.generate(prompts, sp)
+        outs[budget] = [(r.output_ids, [round(x, 4) for x in r.logprobs]) for grp in g for r in grp]
+        assert not eng._prefill_queue and not eng.running
+        if budget == 16:
+            assert eng.stats["steps"] > 20            # chunk steps really happened
+    assert outs[4096] == outs[16]
+    # abort in the middle of a chunked prefill
+    eng = RolloutEngine(cfg, "cpu", max_num_seqs=4, max_model_len=96, use_cuda_graph=False, seed=1, max_prefill_tokens=16)
+    eng.set_weights(w.embed, w.layers, w.head)
+    r = eng.add_request(prompts[0], {"max_new_tokens": 4, "temperature": 0.0})
+    eng.step()
+    assert 0 < r.prefilled < len(r.prompt_ids) and not r.decoding
+    eng.abort(r.rid)
+    while eng.has_work():
+        eng.step()
+    assert r.finish_reason == "abort" and eng.alloc.available() == eng.alloc.num_blocks - 1
