@@ -59,7 +59,8 @@ class ClockSampler:
     """nvidia-smi clock / throttle sampling DURING the timed region (B200_PROFILING.md recipe)."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,"
+         "clocks.mem,temperature.gpu")
 
     def __init__(self, gpu_index: int):
         self.gpu, self.rows, self.proc, self.thr = gpu_index, [], None, None
@@ -75,8 +76,23 @@ class ClockSampler:
         self.thr.start()
 
     def _read(self):
+        import time as _t
+
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append([x.strip() for x in line.split(",")] + [_t.time()])
+
+    def phase_medians(self, intervals: list[tuple[float, float]]) -> dict:
+        """Median SM / memory clock and max temperature inside vs outside the given wall-clock intervals (rollout phases)."""
+        inside, outside, mem, temp = [], [], [], []
+        for r in self.rows:
+            try:
+                smv, t = float(r[1]), float(r[-1])
+                mem.append(float(r[9])); temp.append(float(r[10]))
+            except Exception:
+                continue
+            (inside if any(a <= t <= b for a, b in intervals) else outside).append(smv)
+        med = lambda v: sorted(v)[len(v) // 2] if v else None
+        return {"sm_mhz_rollout": med(inside), "sm_mhz_train": med(outside), "mem_mhz": med(mem), "temp_c_max": max(temp) if temp else None}
 
     def stop(self) -> dict:
         if self.proc is None:
@@ -180,11 +196,14 @@ def main() -> int:
     d2h_bytes = 0
     samples = 0
     t_wall0 = time.perf_counter()
+    gen_intervals = []
     for k in range(args.steps):
         hb = host_batch(args.warmup + k)         # host-side batch assembly is part of the e2e region
         ev[k][0].record()
+        t_wall = time.time()
         m = ppo.step(hb)                         # includes H2D of hb and D2H of losses/metrics (.item())
         ev[k][1].record()
+        gen_intervals.append((t_wall, t_wall + m.get("timing_s/gen", 0.0)))
         if rank == 0:
             print("[bench] step", k, {kk: round(v, 3) for kk, v in m.items() if kk.startswith("timing_s/")},
                   "engine", {kk: round(float(v), 3) for kk, v in ppo.worker.rollout.stats.items()}, "cpus", len(os.sched_getaffinity(0)),
@@ -196,6 +215,7 @@ def main() -> int:
     sync_all()
     t_wall = time.perf_counter() - t_wall0
     clocks = sampler.stop()
+    clocks.update(sampler.phase_medians(gen_intervals))
     dev_ms = sum(a.elapsed_time(b) for a, b in ev)
     t = torch.tensor([dev_ms, t_wall * 1e3, float(samples), float(ops.total_launches() - launches0)], device=device, dtype=torch.float64)
     if world > 1:
