@@ -13,7 +13,7 @@ pytestmark = [pytest.mark.gpu, pytest.mark.multigpu]
 
 
 def test_peer_memory_paths_match_nccl():
-    n = min(torch.cuda.device_count(), 8)
+    n = min(torch.cuda.device_count(), int(os.environ.get("POLYRL_TEST_MULTIGPU_WORLD", "2")))   # 2 = the measured configuration
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1",
                         "--master-port", "29655", str(ROOT / "tests" / "multigpu_worker.py")], capture_output=True, text=True,
                        timeout=600, env={**os.environ, "PYTHONPATH": str(ROOT)})
