@@ -172,6 +172,7 @@ class RolloutConfig(BaseConfig):
     max_model_len: int | None = None
     enable_chunked_prefill: bool = True
     enable_prefix_caching: bool = False     # cross-request KV page reuse (always on for multi-turn rollouts)
+    kv_vmm: bool = False                    # KV pool in a CUDA-VMM range: release/resume keep addresses (graphs survive)
     load_format: str = "dummy"
     calculate_log_probs: bool = False
     log_prob_micro_batch_size_per_gpu: int | None = None

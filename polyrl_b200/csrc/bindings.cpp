@@ -39,6 +39,12 @@ int prl_p2p_copy(const void*, void*, int64_t, int, cudaStream_t);
 int prl_p2p_push_fp8(const void*, void*, float*, int, int, int, cudaStream_t);
 int prl_p2p_allgather_pull(void* const*, void*, int64_t, int, int, int, cudaStream_t);
 int prl_p2p_allreduce(void* const*, int64_t, void*, const void*, int64_t, int, int, cudaStream_t);
+int64_t prl_vmm_granularity(int);
+int prl_vmm_reserve(int64_t, int, int64_t*, int64_t*);
+int prl_vmm_map(int64_t);
+int prl_vmm_unmap(int64_t);
+int prl_vmm_free(int64_t);
+int prl_vmm_is_mapped(int64_t);
 int prl_p2p_reduce_scatter_accum(void* const*, int64_t, float*, int64_t, float, int, int, float*, int, cudaStream_t);
 int prl_skinny_workspace_floats(int, int, int);
 int prl_skinny_gemm(const void*, const void*, void*, const void*, const void*, const float*, const float*, float*, int*, int, int, int, int64_t, int64_t, int64_t, int, int, int, cudaStream_t);
@@ -366,6 +372,17 @@ int64_t ipc_open_handle(const std::string& h) {
 void ipc_close_handle(int64_t ptr) { check(prl_ipc_close_handle(reinterpret_cast<void*>(ptr)), "ipc_close_handle"); }
 void enable_peer_access(int64_t dev) { check(prl_enable_peer_access(static_cast<int>(dev)), "enable_peer_access"); }
 
+// ---- CUDA VMM ranges (csrc/vmm.cu): fixed virtual address, physical backing released / re-created on demand
+std::vector<int64_t> vmm_reserve(int64_t bytes, int64_t device) {
+  int64_t ptr = 0, size = 0;
+  check(prl_vmm_reserve(bytes, static_cast<int>(device), &ptr, &size), "vmm_reserve");
+  return {ptr, size};
+}
+void vmm_map(int64_t ptr) { check(prl_vmm_map(ptr), "vmm_map (out of device memory?)"); }
+void vmm_unmap(int64_t ptr) { check(prl_vmm_unmap(ptr), "vmm_unmap"); }
+void vmm_free(int64_t ptr) { check(prl_vmm_free(ptr), "vmm_free"); }
+bool vmm_is_mapped(int64_t ptr) { return prl_vmm_is_mapped(ptr) != 0; }
+
 at::Tensor tensor_from_ptr(int64_t ptr, std::vector<int64_t> sizes, at::ScalarType dtype, int64_t device) {
   auto opts = at::TensorOptions().dtype(dtype).device(at::kCUDA, device);
   return at::from_blob(reinterpret_cast<void*>(ptr), sizes, [](void*) {}, opts);
@@ -467,6 +484,12 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("ipc_close_handle", &ipc_close_handle);
   m.def("enable_peer_access", &enable_peer_access);
   m.def("tensor_from_ptr", &tensor_from_ptr);
+  m.def("vmm_reserve", &vmm_reserve);
+  m.def("vmm_map", &vmm_map);
+  m.def("vmm_unmap", &vmm_unmap);
+  m.def("vmm_free", &vmm_free);
+  m.def("vmm_is_mapped", &vmm_is_mapped);
+  m.def("vmm_granularity", [](int64_t d) { return prl_vmm_granularity(static_cast<int>(d)); });
   m.def("p2p_barrier", &p2p_barrier);
   m.def("p2p_copy", &p2p_copy);
   m.def("p2p_push_fp8", &p2p_push_fp8);

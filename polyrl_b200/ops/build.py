@@ -24,6 +24,7 @@ OUT = PKG / "_C.so"
 CU_SOURCES = [
     "gemm_tcgen05.cu",
     "skinny_gemm.cu",
+    "vmm.cu",
     "linear_ce.cu",
     "ag_gemm.cu",
     "elementwise.cu",

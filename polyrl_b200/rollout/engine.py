@@ -178,11 +178,19 @@ class RolloutEngine:
     def __init__(self, cfg: ModelConfig, device, max_num_seqs: int = 256, max_model_len: int = 2048,
                  kv_cache_tokens: int | None = None, gpu_memory_utilization: float = 0.5, dtype=None,
                  use_cuda_graph: bool = True, max_prefill_tokens: int = 16384, seed: int = 0, tp=None,
-                 weight_dtype: str = "bf16", steps_per_sync: int | None = None, enable_prefix_cache: bool = False):
+                 weight_dtype: str = "bf16", steps_per_sync: int | None = None, enable_prefix_cache: bool = False,
+                 kv_vmm: bool | None = None):
         # decode steps launched back to back per host round trip (tokens are read back once per window; a sequence that
         # ends mid-window rides along for a few ignored tokens).  1 = one-step lag only.
         import os as _os
         self.steps_per_sync = max(1, min(8, int(steps_per_sync or _os.environ.get("POLYRL_DECODE_STEPS_PER_SYNC", "1"))))
+        # KV pool in a CUDA-VMM range: release_memory / resume_memory swap the PHYSICAL pages only, addresses (and therefore
+        # captured decode graphs) stay valid across PPO steps (utils/vmm.py)
+        import os as _os2
+        self.kv_vmm = (kv_vmm if kv_vmm is not None else _os2.environ.get("POLYRL_KV_VMM", "0") == "1") and str(device).startswith("cuda")
+        self._vmm = None
+        self._kv_views: tuple[list, list] | None = None
+        self._kv_blocks = 0
         self.enable_prefix_cache = enable_prefix_cache and tp is None and cfg.family == "llama"
         self.prefix_cache: PrefixCache | None = None
         if weight_dtype not in ("bf16", "fp8"):
@@ -295,6 +303,26 @@ class RolloutEngine:
         num_blocks = max(2, tokens // PAGE)
         c = self.cfg
         shape = (num_blocks, c.num_kv_heads, PAGE, c.head_dim)
+        if self.kv_vmm:
+            if self._vmm is None:                      # sized once; later resumes re-back the same virtual range
+                from ..utils.vmm import VmmBuffer
+
+                per = num_blocks * c.num_kv_heads * PAGE * c.head_dim * torch.empty(0, dtype=self.dtype).element_size()
+                per = (per + 255) // 256 * 256
+                self._vmm = VmmBuffer(2 * c.num_layers * per, self.device)
+                self._vmm.map()
+                self._kv_views = ([self._vmm.tensor((2 * i) * per, shape, self.dtype) for i in range(c.num_layers)],
+                                  [self._vmm.tensor((2 * i + 1) * per, shape, self.dtype) for i in range(c.num_layers)])
+                self._kv_blocks = num_blocks
+                self._graphs.clear()
+            else:
+                self._vmm.map()
+            self.k_cache, self.v_cache = self._kv_views
+            for t in (*self.k_cache, *self.v_cache):
+                t.zero_()                              # fresh physical pages: masked tail slots must hold finite values
+            self.alloc = BlockAllocator(self._kv_blocks)
+            self.prefix_cache = PrefixCache(self.alloc) if self.enable_prefix_cache else None
+            return
         self.k_cache = [torch.zeros(shape, device=self.device, dtype=self.dtype) for _ in range(c.num_layers)]
         self.v_cache = [torch.zeros(shape, device=self.device, dtype=self.dtype) for _ in range(c.num_layers)]
         self.alloc = BlockAllocator(num_blocks)
@@ -307,7 +335,11 @@ class RolloutEngine:
             if self.running or self.waiting:
                 raise RuntimeError("cannot release the KV cache with requests in flight")
             self.k_cache, self.v_cache, self.alloc, self.prefix_cache = [], [], None, None
-            self._graphs.clear()
+            if self.kv_vmm and self._vmm is not None:
+                torch.cuda.synchronize(self.device)        # nothing may still read the pool
+                self._vmm.unmap()                          # graphs stay valid: same addresses after the next resume
+            else:
+                self._graphs.clear()
             if self.is_cuda:
                 torch.cuda.empty_cache()
         if "weights" in tags:

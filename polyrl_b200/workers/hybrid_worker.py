@@ -155,7 +155,8 @@ class ActorRolloutRefWorker:
                                          gpu_memory_utilization=r.gpu_memory_utilization, use_cuda_graph=r.cuda_graph,
                                          max_prefill_tokens=r.max_num_batched_tokens, seed=seed + 17 * self.rank,
                                          weight_dtype=r.weight_dtype,
-                                         enable_prefix_cache=r.enable_prefix_caching or r.multi_turn.enable)
+                                         enable_prefix_cache=r.enable_prefix_caching or r.multi_turn.enable,
+                                         kv_vmm=True if r.kv_vmm else None)
             if self.has_actor:
                 self.update_weight_remote()
 

@@ -109,3 +109,30 @@ def test_prefix_cache_gpu_matches_uncached():
         res[cache] = ([r.logprobs[0] for r in t2], eng.stats["prefill_tokens"] - pre, [r.cached_tokens for r in t2])
     assert res[True][1] < res[False][1] and all(c > 0 for c in res[True][2])
     assert all(abs(a - b) < 0.1 for a, b in zip(res[False][0], res[True][0])), res
+
+
+def test_kv_pool_in_vmm_range_release_resume_keeps_graphs():
+    """CUDA-VMM backed KV pool: release gives the physical memory back, resume re-backs the same addresses, captured decode
+    graphs are re-used (no re-capture) and generations are unchanged."""
+    from polyrl_b200.models import TransformerWeights, get_model_config
+    from polyrl_b200.rollout.engine import RolloutEngine, SamplingParams
+
+    cfg = get_model_config("tiny-llama-128")
+    w = TransformerWeights(cfg, device="cuda", dtype=torch.bfloat16)
+    eng = RolloutEngine(cfg, "cuda", max_num_seqs=8, max_model_len=256, kv_cache_tokens=64 * 1024, kv_vmm=True)
+    eng.set_weights(w.embed, w.layers, w.head)
+    prompts = [[5, 6, 7, 8, 9], [20, 21, 22], [3, 9] * 10]
+    sp = SamplingParams(max_new_tokens=16, temperature=0.0, ignore_eos=True)
+    out1 = [g[0].output_ids for g in eng.generate(prompts, sp)]
+    ptr = eng.k_cache[0].data_ptr()
+    graphs = dict(eng._graphs)
+    assert graphs and eng._vmm.mapped
+    torch.cuda.synchronize()
+    free0 = torch.cuda.mem_get_info()[0]
+    eng.release_memory(("kv_cache",))
+    assert not eng._vmm.mapped and torch.cuda.mem_get_info()[0] > free0 + (32 << 20)
+    eng.resume_memory(("kv_cache",))
+    assert eng._vmm.mapped and eng.k_cache[0].data_ptr() == ptr
+    out2 = [g[0].output_ids for g in eng.generate(prompts, sp)]
+    assert out1 == out2
+    assert all(eng._graphs.get(k) is v for k, v in graphs.items())       # same graph objects: nothing was re-captured
