@@ -130,7 +130,7 @@ def test_kv_pool_in_vmm_range_release_resume_keeps_graphs():
     torch.cuda.synchronize()
     free0 = torch.cuda.mem_get_info()[0]
     eng.release_memory(("kv_cache",))
-    assert not eng._vmm.mapped and torch.cuda.mem_get_info()[0] > free0 + (32 << 20)
+    assert not eng._vmm.mapped and torch.cuda.mem_get_info()[0] >= free0 + eng._vmm.nbytes // 2     # physical pages returned
     eng.resume_memory(("kv_cache",))
     assert eng._vmm.mapped and eng.k_cache[0].data_ptr() == ptr
     out2 = [g[0].output_ids for g in eng.generate(prompts, sp)]
