@@ -25,6 +25,7 @@ from ..protocol import DataProto
 from .interactions import BaseInteraction
 from .tool_parser import FunctionCall, get_tool_parser
 from .tools import BaseTool, ToolResponse
+from ..utils.rollout_trace import rollout_trace_attr, rollout_trace_op
 
 
 class AgentState(str, Enum):
@@ -151,6 +152,7 @@ class MultiTurnRollout:
             if it is not None:
                 it.finalize_interaction(tr.interaction_id)
 
+    @rollout_trace_op
     def _call_tool(self, tr: _Traj, call: FunctionCall) -> tuple[ToolResponse, float, dict]:
         tool = self.tools.get(call.name)
         if tool is None:
@@ -172,7 +174,8 @@ class MultiTurnRollout:
         t0 = time.time()
         msgs = []
         for c in calls[: self.max_parallel_calls]:
-            resp, reward, _ = self._call_tool(tr, c)
+            with rollout_trace_attr(sample_index=tr.index, name="tool_call"):
+                resp, reward, _ = self._call_tool(tr, c)
             tr.tool_rewards.append(reward)
             msgs.append({"role": "tool", "content": resp.text})
         tr.metrics["tool_s"] += time.time() - t0

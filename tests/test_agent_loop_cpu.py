@@ -174,3 +174,25 @@ def test_worker_multi_turn_generate_and_update(tmp_path):
     out.meta_info.update({"is_opt_step": True})
     m = w.update_actor_stream(out)
     assert "actor/pg_loss" in m.meta_info["metrics"]
+
+
+def test_rollout_trace_file_backend(tmp_path):
+    import json as _json
+
+    from polyrl_b200.utils.rollout_trace import RolloutTraceConfig, rollout_trace_attr, rollout_trace_op
+
+    RolloutTraceConfig.reset()
+
+    class T:
+        @rollout_trace_op
+        def work(self, x, k=1):
+            return x * k
+
+    t = T()
+    assert t.work(3, k=2) == 6                                   # tracing off: plain call
+    cfg = RolloutTraceConfig.init("proj", "exp", "file", out_dir=str(tmp_path))
+    with rollout_trace_attr(step=5, sample_index=2, rollout_n=1):
+        assert t.work(4, k=3) == 12
+    rows = [_json.loads(l) for l in cfg.path.read_text().splitlines()]
+    assert len(rows) == 1 and rows[0]["step"] == 5 and rows[0]["output"] == 12 and rows[0]["inputs"]["kwargs"] == {"k": 3}
+    RolloutTraceConfig.reset()
