@@ -494,7 +494,7 @@ class RolloutEngine:
         for r in reqs:                          # a follower whose donor was aborted mid-prefill becomes its own donor
             if r.donor is not None and r.donor.finished and r.donor.prefilled < len(r.donor.prompt_ids):
                 r.donor, r.prefilled = None, 0
-        budget = self.max_prefill_tokens
+        budget = self.max_prefill_tokens if self.tp is None else 1 << 60      # the TP prefill path does not chunk
         donors, spans = [], []
         for r in reqs:
             if r.donor is not None or r.finished:

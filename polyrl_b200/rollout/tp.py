@@ -32,6 +32,9 @@ class TPContext:
             raise ValueError("heads, kv heads and intermediate_size/128 must be divisible by the TP size")
         self.cfg, self.heap, self.rank, self.world, self.group = cfg, heap, tp_rank, tp_world, group
         self.max_batch = max_batch
+        if heap is None:            # CPU / gloo (plumbing tests) or explicit library mode: all-reduce through torch.distributed
+            self.ar_mode, self.C = "nccl", None
+            return
         bp = ((min(max_batch, 256) + 15) // 16) * 16
         tiles = (cfg.hidden_size + 127) // 128
         self.inbox_half = tp_world * tiles * bp * 128
@@ -84,7 +87,7 @@ class TPContext:
     def row_parallel(self, x_local: torch.Tensor, w_local: torch.Tensor, residual: torch.Tensor | None,
                      decode: bool = True) -> torch.Tensor:
         b = x_local.shape[0]
-        small = x_local.is_cuda and decode and b <= 256 and b <= self.max_batch
+        small = self.heap is not None and x_local.is_cuda and decode and b <= 256 and b <= self.max_batch
         if small and self.ar_mode == "oneshot":
             # Two symmetric buffers alternate: a rank may overwrite buffer p for call c+2 only after passing the barrier of
             # call c+1, which every peer reaches after it finished READING buffer p in call c.  (Decode issues an even

@@ -151,11 +151,35 @@ class ActorRolloutRefWorker:
         if self.has_rollout:
             r = arr.rollout
             max_len = r.max_model_len or (cfg.data.max_prompt_length + cfg.data.max_response_length)
+            # tensor-parallel rollout (reference: rollout.tensor_model_parallel_size -> SGLang tp_size, mesh (dp, infer_tp),
+            # collect from tp-rank 0; stream_fsdp_workers.py:126-153): consecutive ranks form one engine replica that decodes
+            # the union of its ranks' prompts in lock-step; every rank keeps its own slice of the results.
+            self.rollout_tp = max(1, r.tensor_model_parallel_size)
+            self.tp_group, self.tp_rank, tp_ctx = None, 0, None
+            if self.rollout_tp > 1:
+                if self.world % self.rollout_tp != 0:
+                    raise ValueError(f"world size {self.world} not divisible by rollout TP {self.rollout_tp}")
+                from ..rollout.tp import TPContext
+
+                base = dist.get_process_group_ranks(self.group) if self.group is not None else list(range(self.world))
+                for g in range(self.world // self.rollout_tp):
+                    grp = dist.new_group(base[g * self.rollout_tp:(g + 1) * self.rollout_tp])
+                    if g == self.rank // self.rollout_tp:
+                        self.tp_group = grp
+                self.tp_rank = self.rank % self.rollout_tp
+                heap = None
+                if self.device.type == "cuda":
+                    from ..parallel.symm import SymmetricHeap
+
+                    heap = SymmetricHeap(group=self.tp_group, device=self.device)
+                tp_ctx = TPContext(self.model_cfg, heap, self.tp_rank, self.rollout_tp,
+                                   max_batch=r.max_num_seqs, group=self.tp_group)
             self.rollout = RolloutEngine(self.model_cfg, self.device, max_num_seqs=r.max_num_seqs, max_model_len=max_len,
                                          gpu_memory_utilization=r.gpu_memory_utilization, use_cuda_graph=r.cuda_graph,
-                                         max_prefill_tokens=r.max_num_batched_tokens, seed=seed + 17 * self.rank,
+                                         max_prefill_tokens=r.max_num_batched_tokens,
+                                         seed=seed + 17 * (self.rank // self.rollout_tp), tp=tp_ctx,
                                          weight_dtype=r.weight_dtype,
-                                         enable_prefix_cache=r.enable_prefix_caching or r.multi_turn.enable,
+                                         enable_prefix_cache=(r.enable_prefix_caching or r.multi_turn.enable) and tp_ctx is None,
                                          kv_vmm=True if r.kv_vmm else None)
             if self.has_actor:
                 self.update_weight_remote()
@@ -228,7 +252,15 @@ class ActorRolloutRefWorker:
         if r.multi_turn.enable:
             out = self._generate_multi_turn(prompts, raw, sp, n, resp_len)
         else:
-            groups = self.rollout.generate([list(map(int, p)) for p in raw], sp)
+            mine = [list(map(int, p)) for p in raw]
+            if getattr(self, "rollout_tp", 1) > 1:
+                # every TP rank must feed the SAME request stream to its engine shard
+                parts: list = [None] * self.rollout_tp
+                dist.all_gather_object(parts, mine, group=self.tp_group)
+                off = sum(len(p) for p in parts[: self.tp_rank])
+                groups = self.rollout.generate([p for part in parts for p in part], sp)[off:off + len(mine)]
+            else:
+                groups = self.rollout.generate(mine, sp)
             out = self._postprocess(prompts, groups, n, resp_len)
         gen_s = time.time() - t0
         out.meta_info["timing"] = {"generate_sequences": gen_s}

@@ -284,3 +284,21 @@ def test_chunked_prefill_matches_whole_prompt_prefill():
     while eng.has_work():
         eng.step()
     assert r.finish_reason == "abort" and eng.alloc.available() == eng.alloc.num_blocks - 1
+
+
+def test_tp_rollout_cpu_gloo_engine_and_colocated_worker():
+    """TP=2 engine shards over gloo reproduce the single engine; the colocated worker with
+    rollout.tensor_model_parallel_size=2 decodes the union of the TP group's prompts and hands every rank its own slice."""
+    import os
+    import subprocess
+    import sys
+    from pathlib import Path
+
+    root = Path(__file__).resolve().parent.parent
+    env = {**os.environ, "PYTHONPATH": str(root), "OMP_NUM_THREADS": "2"}
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29741", str(root / "tests" / "tp_cpu_worker.py")], capture_output=True, text=True,
+                       timeout=300, env=env)
+    line = [l for l in r.stdout.splitlines() if l.startswith("TP_CPU_RESULTS")]
+    assert r.returncode == 0 and line, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "tok_ok=1" in line[0] and "lock=1" in line[0] and "slice_ok=1" in line[0] and "differ=1" in line[0]
