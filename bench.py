@@ -128,6 +128,10 @@ def main() -> int:
         os.environ["POLYRL_DECODE_GEMM"] = "cublas"
         args.comm = "nccl"
 
+    # stdout carries exactly ONE JSON line: keep NCCL's "NCCL version ..." banner (NCCL_DEBUG=VERSION) off it
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"
+
     import torch
     import torch.distributed as dist
 
