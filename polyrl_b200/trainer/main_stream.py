@@ -55,10 +55,13 @@ def build_datasets(cfg: PPOConfig, model_cfg, tokenizer=None):
     return train, val, sampler, tok
 
 
-def run_rollout_rank(cfg: PPOConfig, rank: int, trainer_ranks, rollout_ranks, device, manager_endpoint: str) -> None:
+def run_rollout_rank(cfg: PPOConfig, rank: int, trainer_ranks, rollout_ranks, device, manager_endpoint: str, tp_groups=None) -> None:
+    """One rollout GPU.  With ``rollout.tensor_model_parallel_size = t > 1`` consecutive rollout ranks form one TP-t engine:
+    its first rank owns the HTTP front-end and the manager registration, the others mirror its scheduler commands in
+    lock-step (rollout/server.py); every rank holds a full bf16 replica that the trainers push into and slices it locally."""
     from ..models import get_model_config
     from ..rollout.engine import RolloutEngine
-    from ..rollout.server import EngineServer
+    from ..rollout.server import EngineServer, run_tp_follower
     from ..weight_transfer.sync import WeightSync
 
     arr = cfg.actor_rollout_ref
@@ -66,17 +69,36 @@ def run_rollout_rank(cfg: PPOConfig, rank: int, trainer_ranks, rollout_ranks, de
     r = arr.rollout
     sync = WeightSync(model_cfg, trainer_ranks, rollout_ranks, device, backend=arr.actor.fsdp_config.comm_backend)
     max_len = r.max_model_len or (cfg.data.max_prompt_length + cfg.data.max_response_length)
+    tp = max(1, r.tensor_model_parallel_size)
+    tp_ctx, cmd_group, tp_rank, replica = None, None, 0, rollout_ranks.index(rank)
+    if tp > 1:
+        from ..rollout.tp import TPContext
+
+        nccl_group, cmd_group = tp_groups
+        tp_rank, replica = rollout_ranks.index(rank) % tp, rollout_ranks.index(rank) // tp
+        heap = None
+        if torch.device(device).type == "cuda":
+            from ..parallel.symm import SymmetricHeap
+
+            heap = SymmetricHeap(group=nccl_group, device=torch.device(device))
+        tp_ctx = TPContext(model_cfg, heap, tp_rank, tp, max_batch=r.max_num_seqs, group=nccl_group)
     eng = RolloutEngine(model_cfg, device, max_num_seqs=r.max_num_seqs, max_model_len=max_len,
                         gpu_memory_utilization=r.gpu_memory_utilization, use_cuda_graph=r.cuda_graph,
-                        max_prefill_tokens=r.max_num_batched_tokens, seed=cfg.data.seed + 17 * rank)
+                        max_prefill_tokens=r.max_num_batched_tokens, seed=cfg.data.seed + 17 * replica, tp=tp_ctx)
     e, l, h = sync.engine_views()
     eng.set_weights(e, l, h)
 
     def on_update(body: dict):
         sync.receive(int(body.get("weight_version", 0)))
+        if tp_ctx is not None:
+            eng.set_weights(*sync.engine_views())          # re-slice the compacted qkv copies from the fresh replica
         return True, "ok"
 
-    srv = EngineServer(eng, port=int(os.environ.get("POLYRL_ENGINE_PORT_BASE", 30000)) + rank, weight_update_fn=on_update).start()
+    if tp_rank > 0:
+        run_tp_follower(eng, cmd_group, weight_update_fn=on_update)
+        return
+    srv = EngineServer(eng, port=int(os.environ.get("POLYRL_ENGINE_PORT_BASE", 30000)) + rank, weight_update_fn=on_update,
+                       tp_cmd_group=cmd_group).start()
     srv.register_with_manager(manager_endpoint, local=False)
     print(f"[rollout rank {rank}] engine serving on {srv.endpoint}", flush=True)
     srv.serve_until_shutdown()
@@ -115,7 +137,8 @@ def run_trainer_rank(cfg: PPOConfig, rank: int, trainer_ranks, rollout_ranks, de
             t0 = time.time()
             while time.time() - t0 < 600:
                 st = client.instances_status()
-                if st.get("pending_instances", 0) + st.get("ready_instances", 0) >= len(rollout_ranks):
+                n_inst = len(rollout_ranks) // max(1, cfg.actor_rollout_ref.rollout.tensor_model_parallel_size)
+                if st.get("pending_instances", 0) + st.get("ready_instances", 0) >= n_inst:
                     break
                 time.sleep(0.2)
             time.sleep(0.5)
@@ -155,6 +178,17 @@ def main(argv: list[str] | None = None) -> int:
     rollout_ranks = list(range(n_train, world))
     device = torch.device("cuda", int(os.environ.get("LOCAL_RANK", 0))) if device_type == "cuda" else torch.device("cpu")
     trainer_group = dist.new_group(trainer_ranks) if (dist.is_initialized() and n_roll > 0) else None
+    # TP groups of the rollout ranks: every process must take part in every new_group call, in the same order
+    my_tp_groups = None
+    tp = max(1, cfg.actor_rollout_ref.rollout.tensor_model_parallel_size)
+    if dist.is_initialized() and n_roll > 0 and tp > 1:
+        if n_roll % tp != 0:
+            raise ValueError(f"trainer.n_rollout_gpus ({n_roll}) must be a multiple of rollout.tensor_model_parallel_size ({tp})")
+        for c in range(n_roll // tp):
+            chunk = rollout_ranks[c * tp:(c + 1) * tp]
+            g_main, g_cmd = dist.new_group(chunk), dist.new_group(chunk, backend="gloo")
+            if rank in chunk:
+                my_tp_groups = (g_main, g_cmd)
     manager_endpoint = a.manager_endpoint or cfg.actor_rollout_ref.rollout.rollout_manager.endpoint
     mgr_proc = None
     if n_roll > 0 and manager_endpoint is None:
@@ -170,7 +204,7 @@ def main(argv: list[str] | None = None) -> int:
         manager_endpoint = f"127.0.0.1:{box[0]}"
     try:
         if rank in rollout_ranks:
-            run_rollout_rank(cfg, rank, trainer_ranks, rollout_ranks, device, manager_endpoint)
+            run_rollout_rank(cfg, rank, trainer_ranks, rollout_ranks, device, manager_endpoint, my_tp_groups)
         else:
             out = run_trainer_rank(cfg, rank, trainer_ranks, rollout_ranks, device, manager_endpoint if n_roll > 0 else None,
                                    trainer_group)

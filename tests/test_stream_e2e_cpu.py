@@ -93,3 +93,15 @@ def test_vocab_parallel_linear_ce_gloo():
     assert r.returncode == 0 and line, r.stdout[-2000:] + r.stderr[-2000:]
     vals = dict(kv.split("=") for kv in line[0].split()[1:])
     assert all(float(v) < 1e-4 for v in vals.values()), vals
+
+
+def test_disaggregated_tp2_rollout_gloo_ws3(tmp_path):
+    """BASELINE config 3 in miniature: 1 trainer rank + a TP-2 rollout engine (2 ranks: HTTP front-end + lock-step follower),
+    weights broadcast to both rollout ranks every step."""
+    ov = COMMON + ["actor_rollout_ref.model.path=tiny-llama", "algorithm.adv_estimator=grpo", "trainer.n_rollout_gpus=2",
+                   "trainer.n_gpus_per_node=3", "trainer.total_training_steps=2", "actor_rollout_ref.rollout.tensor_model_parallel_size=2",
+                   "actor_rollout_ref.rollout.rollout_manager.port=0", "actor_rollout_ref.rollout.rollout_manager.max_local_gen_s=30",
+                   "actor_rollout_ref.rollout.cuda_graph=False"]
+    r = _run(3, ov)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "step:2" in r.stdout and "actor/pg_loss" in r.stdout and "training/num_rollout_instances:1" in r.stdout
