@@ -235,11 +235,12 @@ class RolloutEngine:
         self._alloc_static()
 
     # ------------------------------------------------------------------ weights / memory
-    def set_weights(self, embed_w: dict, layer_w: list[dict], head_w: dict, version: int | None = None) -> None:
+    def set_weights(self, embed_w: dict, layer_w: list[dict], head_w: dict, version: int | None = None,
+                    presharded: bool = False) -> None:
         """Point the engine at (possibly trainer-owned) weight tensors.  Pointers that change invalidate
         captured graphs; in-place updates of the same storage do not."""
         old = self._weight_ptrs()
-        if self.tp is not None:
+        if self.tp is not None and not presharded:
             layer_w = [self.tp.shard_layer(w) for w in layer_w]
         if self.weight_dtype == "fp8":
             layer_w = self._quantize_layers(layer_w)

@@ -215,6 +215,31 @@ class ActorRolloutRefWorker:
         elif eng.resident:
             eng.ensure_resident()           # one gather per optimizer step; the engine aliases the trainer's replica
             views = [u.views(u._resident) for u in base]
+        elif getattr(self, "rollout_tp", 1) > 1:
+            # ZeRO-3 (no resident replica: 70B-class) + TP rollout: gather ONE block at a time, keep only this rank's TP slice.
+            # Peak extra memory = one full block + 1/tp of the model (a full replica per GPU would not fit in HBM).
+            tp = self.rollout.tp
+            keep = self._rollout_full if isinstance(self._rollout_full, dict) else {}
+
+            def stash(name: str, tensors: dict) -> dict:
+                out = {}
+                for k, v in tensors.items():
+                    dst = keep.get((name, k))
+                    if dst is None or dst.shape != v.shape:
+                        dst = keep[(name, k)] = torch.empty(v.shape, device=self.device, dtype=v.dtype)
+                    dst.copy_(v)
+                    out[k] = dst
+                return out
+
+            sliced = []
+            for i, u in enumerate(base):
+                full = u.acquire()
+                v = u.views(full)
+                sliced.append(stash(u.name, tp.shard_layer(v) if 0 < i < len(base) - 1 else v))
+                u.release()
+            self._rollout_full = keep
+            self.rollout.set_weights(sliced[0], sliced[1:-1], sliced[-1], version=self.weight_version, presharded=True)
+            return True
         else:
             if self._rollout_full is None:
                 self._rollout_full = {u.name: torch.empty(u.full_numel, device=self.device, dtype=eng.param_dtype)

@@ -301,4 +301,4 @@ def test_tp_rollout_cpu_gloo_engine_and_colocated_worker():
                        timeout=300, env=env)
     line = [l for l in r.stdout.splitlines() if l.startswith("TP_CPU_RESULTS")]
     assert r.returncode == 0 and line, r.stdout[-2000:] + r.stderr[-2000:]
-    assert "tok_ok=1" in line[0] and "lock=1" in line[0] and "slice_ok=1" in line[0] and "differ=1" in line[0]
+    assert "tok_ok=1" in line[0] and "lock=1" in line[0] and "slice_ok=1" in line[0] and "differ=1" in line[0] and "zero3_tp_slices_ok=1" in line[0]

@@ -49,12 +49,21 @@ def main():
     batch = DataProto.from_dict({"input_ids": ids, "attention_mask": torch.ones_like(ids), "position_ids": torch.arange(8).repeat(2, 1)})
     batch.meta_info = {"do_sample": False}
     out = wk.generate_sequences(batch)
+    c2 = load_config(None, ["trainer.device=cpu", "actor_rollout_ref.model.path=tiny-llama", "data.max_prompt_length=8",
+                            "data.max_response_length=6", "actor_rollout_ref.rollout.n=2", "actor_rollout_ref.rollout.max_num_seqs=8",
+                            "actor_rollout_ref.rollout.cuda_graph=False", "actor_rollout_ref.rollout.tensor_model_parallel_size=2",
+                            "actor_rollout_ref.actor.fsdp_config.comm_backend=nccl",
+                            "actor_rollout_ref.actor.fsdp_config.resident_params=false"])
+    wk2 = ActorRolloutRefWorker(c2, role="actor_rollout", device="cpu")       # ZeRO-3 + block-by-block TP-sliced gather
+    wk2.init_model()
+    out2 = wk2.generate_sequences(batch)
+    zero3_ok = (not wk2.actor_engine.resident) and torch.equal(out2.batch["responses"], out.batch["responses"])
     mine_ok = out.batch["responses"].shape == (4, 6) and torch.equal(out.batch["prompts"][::2], ids)
     resp = [None] * world
     dist.all_gather_object(resp, out.batch["responses"].tolist())
     differ = resp[0] != resp[1]                      # different prompts -> different slices came back
     if rank == 0:
-        print(f"TP_CPU_RESULTS tok_ok={int(tok_ok)} lp_err={lp_err:.2e} lock={int(lock)} slice_ok={int(mine_ok)} differ={int(differ)}", flush=True)
+        print(f"TP_CPU_RESULTS tok_ok={int(tok_ok)} lp_err={lp_err:.2e} lock={int(lock)} slice_ok={int(mine_ok)} differ={int(differ)} zero3_tp_slices_ok={int(zero3_ok)}", flush=True)
     dist.barrier()
     dist.destroy_process_group()
 
