@@ -173,8 +173,9 @@ class ActorRolloutRefWorker:
 
                     heap = SymmetricHeap(group=self.tp_group, device=self.device)
                 tp_ctx = TPContext(self.model_cfg, heap, self.tp_rank, self.rollout_tp,
-                                   max_batch=r.max_num_seqs, group=self.tp_group)
-            self.rollout = RolloutEngine(self.model_cfg, self.device, max_num_seqs=r.max_num_seqs, max_model_len=max_len,
+                                   max_batch=r.max_num_seqs * self.rollout_tp, group=self.tp_group)
+            # a TP replica serves the prompts of all its ranks: tp x the per-GPU sequence slots (each holds 1/tp of the KV heads)
+            self.rollout = RolloutEngine(self.model_cfg, self.device, max_num_seqs=r.max_num_seqs * self.rollout_tp, max_model_len=max_len,
                                          gpu_memory_utilization=r.gpu_memory_utilization, use_cuda_graph=r.cuda_graph,
                                          max_prefill_tokens=r.max_num_batched_tokens,
                                          seed=seed + 17 * (self.rank // self.rollout_tp), tp=tp_ctx,
