@@ -22,6 +22,6 @@ python -m torch.distributed.run --nnodes=1 --nproc-per-node=$NGPU --master-addr 
   actor_rollout_ref.rollout.log_prob_use_dynamic_bsz=True \
   actor_rollout_ref.rollout.max_num_seqs=256 \
   actor_rollout_ref.rollout.rollout_manager.port=5000 \
-  trainer.n_gpus_per_node=$NGPU trainer.n_rollout_gpus=$NROLL \
+  trainer.n_gpus_per_node=$NGPU trainer.n_rollout_gpus=$NROLL trainer.local_rollout=True \
   trainer.logger=[console,file] trainer.project_name=polyrl_b200 trainer.experiment_name=qwen3_1p7b_async_grpo \
   trainer.save_freq=20 trainer.test_freq=10 trainer.total_epochs=1 "$@"

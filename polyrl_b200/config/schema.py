@@ -348,6 +348,10 @@ class TrainerConfig(BaseConfig):
     device: str = "cuda"
     controller_backend: str = "spmd"     # spmd | local | mp | ray
     n_rollout_gpus: int = 0              # >0 => disaggregated: dedicated rollout GPUs
+    # PolyRL's hybrid mode: in a disaggregated job every trainer GPU ALSO hosts a local engine (aliasing the trainer's weights)
+    # that generates during the manager's time-boxed local window, then hands its HBM back to training while the remote
+    # instances finish the partial generations (reference: local SGLang per trainer + /register_local_rollout_instances)
+    local_rollout: bool = False
 
 
 @dataclass

@@ -114,7 +114,8 @@ def run_trainer_rank(cfg: PPOConfig, rank: int, trainer_ranks, rollout_ranks, de
     from .stream_trainer import StreamPPOTrainer
 
     disagg = len(rollout_ranks) > 0
-    role = ("actor" if disagg else "actor_rollout") + ("_ref" if need_reference_policy(cfg) else "")
+    hybrid = disagg and cfg.trainer.local_rollout
+    role = ("actor" if (disagg and not hybrid) else "actor_rollout") + ("_ref" if need_reference_policy(cfg) else "")
     worker = ActorRolloutRefWorker(cfg, role=role, device=device, group=trainer_group)
     worker.init_model()
     critic = None
@@ -142,11 +143,17 @@ def run_trainer_rank(cfg: PPOConfig, rank: int, trainer_ranks, rollout_ranks, de
                     break
                 time.sleep(0.2)
             time.sleep(0.5)
+        if hybrid:
+            worker.start_local_server(manager_endpoint, int(os.environ.get("POLYRL_ENGINE_PORT_BASE", 30000)) + 100 + rank)
         if dist.is_initialized():
             dist.barrier(group=trainer_group)
 
+        alias_local = worker.update_weight_remote      # colocated path: the local engine aliases the trainer's fresh weights
+
         def update_weight_remote():
             sender.update(worker.actor_engine, rank)
+            if hybrid:
+                alias_local()
             return True
 
         worker.update_weight_remote = update_weight_remote      # disaggregated: push over NVLink / broadcast

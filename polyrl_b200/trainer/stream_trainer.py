@@ -91,17 +91,26 @@ class StreamPPOTrainer:
                 yield batch.slice(i, min(i + step, len(batch)))
             return
         it = None
+        hybrid = getattr(self.worker, "local_server", None) is not None
+        if hybrid:
+            self.worker.rollout_mode()                  # every trainer GPU generates during the manager's local window
+            if dist.is_initialized() and self.world > 1:
+                dist.barrier(group=self.group)
         if self.rank == 0:
             sp = {"temperature": r.temperature, "top_p": r.top_p, "top_k": r.top_k}
             it = iter(self.client.generate_sequences_remote(prompts, sp))
+        first = True
         while True:
             item = None
             if self.rank == 0:
                 try:
-                    item = next(it)
+                    item = next(it)                     # the first item arrives after the notifier = end of the local window
                 except StopIteration:
                     item = None
             item = _bcast_obj(item, 0, self.group)
+            if first and hybrid:
+                self.worker.trainer_mode()              # local engines were aborted by the manager: HBM goes back to training
+            first = False
             if item is None:
                 break
             yield item.to(self.device)

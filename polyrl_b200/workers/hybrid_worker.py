@@ -253,6 +253,29 @@ class ActorRolloutRefWorker:
         self.rollout.set_weights(views[0], views[1:-1], views[-1], version=self.weight_version)
         return True
 
+    # ------------------------------------------------------------------ local instance (disaggregated hybrid mode)
+    def start_local_server(self, manager_endpoint: str, port: int) -> None:
+        """Serve this rank's colocated engine to the rollout manager as a LOCAL instance (time-boxed by the manager)."""
+        from ..rollout.server import EngineServer
+
+        self.local_server = EngineServer(self.rollout, port=port).start()
+        self.local_server.register_with_manager(manager_endpoint, local=True)
+        self._in_rollout_mode = True          # the engine owns its KV pool until the first trainer_mode()
+
+    def rollout_mode(self) -> None:
+        """Give HBM to the local engine (resume its KV pool) — reference: fsdp_workers.py:651-750 rollout_mode()."""
+        srv = getattr(self, "local_server", None)
+        if srv is not None and not self._in_rollout_mode:
+            srv._command("resume", {"tags": ["kv_cache"]}, wait=True)
+            self._in_rollout_mode = True
+
+    def trainer_mode(self) -> None:
+        """Abort whatever the local engine still runs (the manager already re-dispatched it) and take the HBM back."""
+        srv = getattr(self, "local_server", None)
+        if srv is not None and self._in_rollout_mode:
+            srv._command("release", {"tags": ["kv_cache"]}, wait=True)
+            self._in_rollout_mode = False
+
     # ------------------------------------------------------------------ rollout
     @torch.no_grad()
     def generate_sequences(self, prompts: DataProto) -> DataProto:

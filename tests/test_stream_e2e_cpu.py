@@ -105,3 +105,16 @@ def test_disaggregated_tp2_rollout_gloo_ws3(tmp_path):
     r = _run(3, ov)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "step:2" in r.stdout and "actor/pg_loss" in r.stdout and "training/num_rollout_instances:1" in r.stdout
+
+
+def test_hybrid_local_plus_remote_instances_gloo_ws2(tmp_path):
+    """PolyRL's hybrid mode: the trainer rank also serves a LOCAL engine (aliasing its weights) to the manager; generation is
+    shared between the local and the remote instance, the local one is released before training."""
+    ov = COMMON + ["actor_rollout_ref.model.path=tiny-llama", "algorithm.adv_estimator=grpo", "trainer.n_rollout_gpus=1",
+                   "trainer.n_gpus_per_node=2", "trainer.total_training_steps=2", "trainer.local_rollout=True",
+                   "actor_rollout_ref.rollout.rollout_manager.port=0", "actor_rollout_ref.rollout.rollout_manager.max_local_gen_s=30",
+                   "actor_rollout_ref.rollout.cuda_graph=False", "data.train_batch_size=8"]
+    r = _run(2, ov)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "step:2" in r.stdout and "actor/pg_loss" in r.stdout
+    assert "registered local instance" in (r.stdout + r.stderr) or "local" in r.stdout
