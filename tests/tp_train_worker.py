@@ -1,0 +1,90 @@
+"""TP (x DP) training equivalence (torchrun 2 or 4 ranks; gloo/CPU or nccl/GPU): a (dp x tp=2) TPTrainEngine must track a
+single-process reference (plain autograd over TransformerWeights) step by step — log-probs, grad norm and updated weights."""
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+
+def main():
+    cuda = torch.cuda.is_available() and os.environ.get("TP_TRAIN_DEVICE", "auto") != "cpu"
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    if cuda:
+        dev = torch.device("cuda", int(os.environ["LOCAL_RANK"]))
+        torch.cuda.set_device(dev)
+        dist.init_process_group("nccl", device_id=dev)
+    else:
+        dev = torch.device("cpu")
+        dist.init_process_group("gloo")
+    from polyrl_b200 import ops
+    from polyrl_b200.models import TransformerWeights, get_model_config, pack_padded
+    from polyrl_b200.models import transformer as tf
+    from polyrl_b200.ops import reference as ref
+    from polyrl_b200.parallel.tp_train import TPTrainEngine
+
+    tp = 2
+    dp = world // tp
+    tp_group = dp_group = None
+    for d in range(dp):
+        g = dist.new_group(list(range(d * tp, (d + 1) * tp)))
+        if d == rank // tp:
+            tp_group = g
+    for t in range(tp):
+        g = dist.new_group(list(range(t, world, tp)))
+        if t == rank % tp:
+            dp_group = g
+    cfg = get_model_config("tiny-llama-128" if cuda else "tiny-llama")
+    dtype = torch.bfloat16 if cuda else torch.float32
+    eng = TPTrainEngine(cfg, dev, tp_group, dp_group if dp > 1 else None, lr=1e-2, weight_decay=0.0, seed=11, dtype=dtype)
+
+    def batch(dp_rank: int):
+        gen = torch.Generator().manual_seed(500 + dp_rank)
+        ids = torch.randint(3, cfg.vocab_size, (2, 19), generator=gen).to(dev)
+        inp, _ = pack_padded(ids, torch.ones_like(ids))
+        labels = torch.randint(0, cfg.vocab_size, (inp.input_ids.numel(),), generator=gen).to(dev)
+        return inp, labels
+
+    # ---- single-process reference on every rank: plain autograd over the full weights, mean gradient over the dp batches
+    w = TransformerWeights(cfg, device=dev, dtype=torch.float32, init=True, seed=11)
+    params = {n: t.requires_grad_(True) for n, t in w.named_tensors()}
+    m = {n: torch.zeros_like(t) for n, t in params.items()}
+    v = {n: torch.zeros_like(t) for n, t in params.items()}
+    lp_err = gn_err = 0.0
+    for step in range(2):
+        inp, labels = batch(rank // tp)
+        lp, ent = eng.forward_logprob_entropy(inp, labels, 1.0)
+        (-(lp.mean()) + 0.01 * ent.mean()).backward()
+        st = eng.step()
+        # reference
+        for p in params.values():
+            p.grad = None
+        ref_lps = []
+        for d in range(dp):
+            ri, rl = batch(d)
+            x = tf.forward_hidden(cfg, w, ri)
+            h = tf.final_norm(cfg, w.head, x)
+            rlp, rent = ref.linear_cross_entropy(h, tf.lm_head_weight(cfg, w.head, w.embed), rl, 1.0)
+            ((-(rlp.mean()) + 0.01 * rent.mean()) / dp).backward()
+            ref_lps.append(rlp.detach())
+        gn = torch.sqrt(sum(p.grad.pow(2).sum() for p in params.values())).item()
+        coef = min(1.0, 1.0 / (gn + 1e-6))
+        with torch.no_grad():
+            for n, p in params.items():
+                ref.adamw_step(p, m[n], v[n], p.grad, 1e-2, 0.9, 0.999, 1e-8, 0.0, step + 1, coef)
+        lp_err = max(lp_err, (lp.detach().float() - ref_lps[rank // tp]).abs().max().item())
+        gn_err = max(gn_err, abs(st["grad_norm"] - gn) / gn)
+    full = eng.gather_full_state()
+    w_err = max(((full[n].cpu() - params[n].detach().cpu()).norm() / (params[n].detach().cpu().norm() + 1e-9)).item() for n in full)
+    t = torch.tensor([lp_err, gn_err, w_err], device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        print(f"TP_TRAIN_RESULTS dp={dp} tp={tp} lp_err={t[0].item():.3e} gn_err={t[1].item():.3e} w_err={t[2].item():.3e}", flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
