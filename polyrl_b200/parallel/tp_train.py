@@ -134,7 +134,7 @@ class TPTrainEngine:
             for k, v in shard_layer(cfg, w, r, tp).items():
                 named[f"layers.{i}.{k}"] = v
         self.master = {k: v.to(self.device, torch.float32) for k, v in named.items()}
-        self.params = {k: v.to(self.dtype).requires_grad_(True) for k, v in self.master.items()}
+        self.params = {k: v.to(self.dtype).clone().requires_grad_(True) for k, v in self.master.items()}
         self.exp_avg = {k: torch.zeros_like(v) for k, v in self.master.items()}
         self.exp_avg_sq = {k: torch.zeros_like(v) for k, v in self.master.items()}
 
@@ -190,10 +190,10 @@ class TPTrainEngine:
             self.opt_step += 1
             coef = min(1.0, self.max_grad_norm / (norm + 1e-6)) if self.max_grad_norm > 0 else 1.0
             b1, b2 = self.betas
-            for k, g in grads.items():
-                ref.adamw_step(self.master[k], self.exp_avg[k], self.exp_avg_sq[k], g, lr, b1, b2, self.eps, self.weight_decay,
-                               self.opt_step, coef)
-                with torch.no_grad():
+            with torch.no_grad():
+                for k, g in grads.items():
+                    ref.adamw_step(self.master[k], self.exp_avg[k], self.exp_avg_sq[k], g, lr, b1, b2, self.eps, self.weight_decay,
+                                   self.opt_step, coef)
                     self.params[k].copy_(self.master[k].to(self.dtype))
         self.zero_grad()
         return {"grad_norm": norm, "skipped": skipped}

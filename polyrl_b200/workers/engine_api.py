@@ -27,7 +27,13 @@ def register_engine(model_type: str, backend: str = "zero"):
 
 
 def get_engine_cls(model_type: str, backend: str = "zero"):
-    backend = {"fsdp": "zero", "fsdp2": "zero"}.get(backend, backend)
+    """``backend``: zero (aliases fsdp / fsdp2) or tp (alias megatron): ``parallel.tp_train.TPTrainEngine`` — constructed with
+    explicit (tp_group, dp_group), see tests/tp_train_worker.py."""
+    backend = {"fsdp": "zero", "fsdp2": "zero", "megatron": "tp"}.get(backend, backend)
+    if backend == "tp" and model_type == "language_model":
+        from ..parallel.tp_train import TPTrainEngine
+
+        return TPTrainEngine
     if (model_type, backend) not in _ENGINES:
         raise NotImplementedError(f"no training engine for model_type={model_type!r} backend={backend!r}")
     return _ENGINES[(model_type, backend)]

@@ -65,3 +65,9 @@ def test_hsdp_and_resident_replica():
         pytest.skip("needs 4 GPUs")
     v = _torchrun("hsdp_worker.py", 4, 29659, "HSDP_RESULTS")
     assert float(v["w_err"]) < 2e-2 and float(v["resident_err"]) < 2e-2
+
+
+def test_tensor_parallel_training_kernels():
+    """TP=2 training on the bf16 kernel path (tcgen05 GEMMs, fused SwiGLU, vocab-parallel fused CE) vs the fp32 oracle."""
+    v = _torchrun("tp_train_worker.py", 2, 29660, "TP_TRAIN_RESULTS")
+    assert float(v["lp_err"]) < 0.1 and float(v["gn_err"]) < 0.05 and float(v["w_err"]) < 0.05

@@ -118,3 +118,16 @@ def test_hybrid_local_plus_remote_instances_gloo_ws2(tmp_path):
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "step:2" in r.stdout and "actor/pg_loss" in r.stdout
     assert "registered local instance" in (r.stdout + r.stderr) or "local" in r.stdout
+
+
+def test_tensor_parallel_training_dp2_tp2_gloo():
+    """(dp=2 x tp=2) TPTrainEngine (column/row-parallel blocks, vocab-parallel fused CE, DP-averaged grads, global-norm clip,
+    AdamW on local slices) tracks a single-process oracle over two optimizer steps."""
+    env = {**os.environ, "PYTHONPATH": str(ROOT), "OMP_NUM_THREADS": "1", "TP_TRAIN_DEVICE": "cpu"}
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=4", "--master-addr", "127.0.0.1",
+                        "--master-port", "29752", str(ROOT / "tests" / "tp_train_worker.py")], capture_output=True, text=True, timeout=600, env=env)
+    line = [l for l in r.stdout.splitlines() if l.startswith("TP_TRAIN_RESULTS")]
+    assert r.returncode == 0 and line, r.stdout[-2000:] + r.stderr[-2000:]
+    vals = dict(kv.split("=") for kv in line[0].split()[1:])
+    assert vals["dp"] == "2" and vals["tp"] == "2"
+    assert float(vals["lp_err"]) < 1e-3 and float(vals["gn_err"]) < 1e-4 and float(vals["w_err"]) < 2e-3
