@@ -48,7 +48,9 @@ def main():
         return inp, labels
 
     # ---- single-process reference on every rank: plain autograd over the full weights, mean gradient over the dp batches
-    w = TransformerWeights(cfg, device=dev, dtype=torch.float32, init=True, seed=11)
+    w_cpu = TransformerWeights(cfg, device="cpu", dtype=torch.float32, init=True, seed=11)     # same CPU generator as the engine
+    w = TransformerWeights(cfg, device=dev, dtype=torch.float32, init=False)
+    w.load_state_dict({n: t.to(dev) for n, t in w_cpu.state_dict().items()})
     params = {n: t.requires_grad_(True) for n, t in w.named_tensors()}
     m = {n: torch.zeros_like(t) for n, t in params.items()}
     v = {n: torch.zeros_like(t) for n, t in params.items()}
