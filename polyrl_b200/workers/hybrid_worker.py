@@ -130,6 +130,17 @@ class ActorRolloutRefWorker:
                 eng.make_resident()
             eng.act_ckpt = str(fc.activation_checkpoint) if arr.model.enable_gradient_checkpointing else "none"
             eng.act_reserve_bytes = int(fc.activation_reserve_gb * (1 << 30))
+            if self.rank == 0 and self.device.type == "cuda":
+                try:        # what the layout decisions will look like on this box (utils/hbm_sizing.py uses the same arithmetic)
+                    from ..utils.hbm_sizing import plan
+
+                    p = plan(self.model_cfg, n_gpus=eng.world, rollout_tp=max(1, arr.rollout.tensor_model_parallel_size),
+                             tokens_per_microbatch=arr.actor.ppo_max_token_len_per_gpu, max_num_seqs=arr.rollout.max_num_seqs,
+                             max_model_len=cfg.data.max_prompt_length + cfg.data.max_response_length, hbm_gb=hbm / (1 << 30),
+                             reserve_gb=fc.activation_reserve_gb)
+                    print(f"[worker] HBM plan: {p.decisions}", flush=True)
+                except Exception as e:  # the plan is informational only
+                    print(f"[worker] HBM plan unavailable: {e!r}", flush=True)
             n_dp = self.dp_size
             a = arr.actor
             mini = max(1, a.ppo_mini_batch_size * arr.rollout.n // n_dp)      # per-GPU samples per optimizer step
