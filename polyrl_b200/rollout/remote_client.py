@@ -173,11 +173,18 @@ class RemoteRolloutClient:
     def instances_status(self) -> dict:
         return self._post("/get_instances_status", method="GET")
 
-    def generate_sequences_remote(self, prompts: DataProto, sampling_params: dict | None = None) -> Iterator[DataProto]:
+    def submit(self, prompts: DataProto, sampling_params: dict | None = None):
+        """Start the generation NOW (the HTTP request is issued by a background thread) and return a handle for ``collect``."""
         sp = {**self.sampling_params, **(sampling_params or {}), "max_new_tokens": self.response_length}
         payload = build_generate_payload(prompts, self.n, sp)
-        t0 = time.time()
-        it = iter(StreamingBatchIterator(self.host, self.port, "/batch_generate_requests", payload))
+        return prompts, time.time(), StreamingBatchIterator(self.host, self.port, "/batch_generate_requests", payload)
+
+    def generate_sequences_remote(self, prompts: DataProto, sampling_params: dict | None = None) -> Iterator[DataProto]:
+        return self.collect(self.submit(prompts, sampling_params))
+
+    def collect(self, handle) -> Iterator[DataProto]:
+        prompts, t0, sbi = handle
+        it = iter(sbi)
         pending: list[tuple[int, list[dict]]] = []
         per = self.stream_size // self.n
         got_notifier = False

@@ -90,6 +90,18 @@ class StreamPPOTrainer:
             for i in range(0, len(batch), step):
                 yield batch.slice(i, min(i + step, len(batch)))
             return
+        if getattr(self, "_prefetched", None) is not None:
+            # one-step-off: this batch was generated during the previous step (rank 0 holds the list)
+            items, self._prefetched = self._prefetched, None
+            k = 0
+            while True:
+                item = items[k] if (self.rank == 0 and k < len(items)) else None
+                k += 1
+                item = _bcast_obj(item, 0, self.group)
+                if item is None:
+                    break
+                yield item.to(self.device)
+            return
         it = None
         hybrid = getattr(self.worker, "local_server", None) is not None
         if hybrid:
@@ -362,10 +374,22 @@ class StreamPPOTrainer:
             self.client.update_weight_version()
         self.worker.update_weight_remote()
         prof = cfg.global_profiler
-        for prompts in self._iter_batches():
+        one_off = bool(cfg.trainer.one_step_off and self.client is not None)
+        batches = iter(self._iter_batches())
+        lookahead = next(batches, None)
+        self._prefetched = None
+        while lookahead is not None:
+            prompts, lookahead = lookahead, next(batches, None)
             if self.global_steps >= self.total_training_steps:
                 break
             self.global_steps += 1
+            handle_next = None
+            if one_off and lookahead is not None and self.global_steps < self.total_training_steps:
+                # rollout GPUs start on the NEXT batch now (policy = weights of this step), while we train on the current one
+                lookahead.non_tensor_batch["uid"] = core.uid_array(len(lookahead), 1, prefix=f"{self.global_steps + 1}-")
+                if self.rank == 0:
+                    r_ = cfg.actor_rollout_ref.rollout
+                    handle_next = self.client.submit(lookahead, {"temperature": r_.temperature, "top_p": r_.top_p, "top_k": r_.top_k})
             do_profile = bool(prof.tool and prof.steps and self.global_steps in prof.steps)
             if do_profile:
                 self.worker.start_profile()
@@ -374,13 +398,22 @@ class StreamPPOTrainer:
             metrics: dict = {}
             t_step = time.time()
             n = cfg.actor_rollout_ref.rollout.n
-            prompts.non_tensor_batch["uid"] = core.uid_array(len(prompts), 1, prefix=f"{self.global_steps}-")
+            if "uid" not in prompts.non_tensor_batch:
+                prompts.non_tensor_batch["uid"] = core.uid_array(len(prompts), 1, prefix=f"{self.global_steps}-")
             total = len(prompts) * n
             boundaries = self._mini_batch_boundaries(total)
             seen = 0
             for ibatch in self._stream(prompts):
                 self._process_ibatch(ibatch, seen, boundaries, metrics)
                 seen += len(ibatch)
+            if one_off:
+                # the next batch must be complete before the weights under the rollout engines are replaced
+                with marked_timer("wait_next_rollout", self._timing):
+                    if self.rank == 0 and handle_next is not None:
+                        self._prefetched = list(self.client.collect(handle_next))
+                    flag = _bcast_obj(handle_next is not None if self.rank == 0 else None, 0, self.group)
+                    if flag and self.rank != 0:
+                        self._prefetched = []           # non-empty marker: the items come through the broadcast in _stream
             with marked_timer("update_weight", self._timing):
                 if self.client is not None and self.rank == 0:
                     self.client.update_weight_version()

@@ -131,3 +131,15 @@ def test_tensor_parallel_training_dp2_tp2_gloo():
     vals = dict(kv.split("=") for kv in line[0].split()[1:])
     assert vals["dp"] == "2" and vals["tp"] == "2"
     assert float(vals["lp_err"]) < 1e-3 and float(vals["gn_err"]) < 1e-4 and float(vals["w_err"]) < 2e-3
+
+
+def test_one_step_off_policy_gloo_ws2(tmp_path):
+    """trainer.one_step_off: batch k+1 is generated (with the weights of step k) while the trainer updates on batch k; the
+    weights are pushed only after batch k+1 is complete (reference recipe: verl/recipe/one_step_off_policy)."""
+    ov = COMMON + ["actor_rollout_ref.model.path=tiny-llama", "algorithm.adv_estimator=grpo", "trainer.n_rollout_gpus=1",
+                   "trainer.n_gpus_per_node=2", "trainer.total_training_steps=3", "trainer.one_step_off=True",
+                   "actor_rollout_ref.rollout.rollout_manager.port=0", "actor_rollout_ref.rollout.rollout_manager.max_local_gen_s=30",
+                   "actor_rollout_ref.rollout.cuda_graph=False"]
+    r = _run(2, ov)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "step:3" in r.stdout and "timing_s/wait_next_rollout" in r.stdout and "actor/pg_loss" in r.stdout
