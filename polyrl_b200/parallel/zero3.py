@@ -97,7 +97,7 @@ class ShardedUnit:
         self.shard[so:so + chunk] = piece.to(self.shard.dtype)
 
     def load_full_state(self, named: dict[str, torch.Tensor], prefix: str = "") -> None:
-        self.engine._resident_stale = True
+        self.engine._resident_stale = self.engine._reload_all = True
         for (n, shp), numel, chunk, so in zip(self.specs, self.numels, self.chunks, self.shard_offsets):
             self._load_param_chunk(named[prefix + n].reshape(-1), numel, chunk, so)
 
@@ -258,7 +258,7 @@ class ShardedUnit:
         return {"master": self.master, "exp_avg": self.exp_avg, "exp_avg_sq": self.exp_avg_sq, "shard": self.shard}
 
     def load_state_dict(self, sd: dict) -> None:
-        self.engine._resident_stale = True
+        self.engine._resident_stale = self.engine._reload_all = True
         self.shard.copy_(sd["shard"])
         if self.master is not None and sd.get("master") is not None:
             self.master.copy_(sd["master"])
@@ -402,6 +402,7 @@ class Zero3Engine:
         # gives saved activations stable parameter storage (see `act_ckpt`).
         self.resident = False
         self._resident_stale = True
+        self._reload_all = False            # set by checkpoint / state-dict loads: frozen units changed too
         # activation checkpointing: "full" = recompute every layer in backward (reference default,
         # enable_gradient_checkpointing=True); "none" = save activations for every layer; "auto" = save as many layers
         # as fit in free HBM at the first forward of a micro-batch; an int = that many layers.
@@ -471,9 +472,12 @@ class Zero3Engine:
         self._resident_stale = False
         if self.heap is not None:
             self.heap.barrier()
+        first = not getattr(self, "_resident_filled", False)
         for u in self.units:
-            u._gather_into(u._resident)
+            if first or u.trainable or not self.trainable or self._reload_all:
+                u._gather_into(u._resident)         # frozen units (LoRA base) are gathered once, not after every optimizer step
             u._full = u._resident
+        self._resident_filled, self._reload_all = True, False
         if self.heap is not None:
             self.heap.barrier()
 
@@ -737,7 +741,7 @@ class Zero3Engine:
                 "world": self.world, "rank": self.rank}
 
     def load_state_dict(self, sd: dict) -> None:
-        self._resident_stale = True
+        self._resident_stale = self._reload_all = True
         if sd["world"] != self.world:
             raise ValueError(f"checkpoint was written with world_size={sd['world']}, now {self.world}")
         for u in self.units:

@@ -108,7 +108,7 @@ class ShardedCheckpointManager:
                 if u.master is not None and sd[u.name]["master"] is not None:
                     u.master.copy_(sd[u.name]["master"])
                 u.drop_gathered()
-            eng._resident_stale = True
+            eng._resident_stale = eng._reload_all = True
         if "optimizer" in self.load_contents and eng.trainable and op.exists():
             sd = torch.load(op, map_location="cpu", weights_only=False)
             eng.opt_step = sd["opt_step"]

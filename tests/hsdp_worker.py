@@ -54,8 +54,23 @@ def main():
     gn_err = abs(outs["hsdp"][1] - outs["zero"][1]) / (abs(outs["zero"][1]) + 1e-9)
     r_err = max(((outs["resident"][0][k] - outs["zero"][0][k]).norm() / (outs["zero"][0][k].norm() + 1e-9)).item()
                 for k in outs["zero"][0])
+    # LoRA adapters: frozen base gathered once into the resident replica, adapters re-gathered after every step
+    from polyrl_b200.models.lora import LoraConfig
+
+    lo = {}
+    for name in ("lora_zero", "lora_resident"):
+        eng = Zero3Engine(cfg, dev, comm="nccl", lr=1e-2, weight_decay=0.0, seed=7, lora=LoraConfig.from_model_cfg(4, 8, "all-linear"))
+        if name == "lora_resident":
+            eng.make_resident()
+            eng.act_ckpt = "none"
+        for _ in range(3):
+            lp, ent = eng.forward_logprob_entropy(inp, labels, 1.0)
+            (-(lp.mean()) + 0.01 * ent.mean()).backward()
+            eng.step()
+        lo[name] = {n: t.float().cpu().clone() for n, t in eng.named_full_tensors() if ".lora." in n}
+    l_err = max(((lo["lora_resident"][k] - lo["lora_zero"][k]).norm() / (lo["lora_zero"][k].norm() + 1e-9)).item() for k in lo["lora_zero"])
     if rank == 0:
-        print(f"HSDP_RESULTS w_err={w_err:.3e} gn_err={gn_err:.3e} resident_err={r_err:.3e}", flush=True)
+        print(f"HSDP_RESULTS w_err={w_err:.3e} gn_err={gn_err:.3e} resident_err={r_err:.3e} lora_resident_err={l_err:.3e}", flush=True)
     dist.barrier()
     dist.destroy_process_group()
 

@@ -82,6 +82,7 @@ def test_hsdp_equivalence_gloo():
     vals = dict(kv.split("=") for kv in line[0].split()[1:])
     assert float(vals["w_err"]) < 1e-4 and float(vals["gn_err"]) < 1e-4
     assert float(vals["resident_err"]) < 1e-4          # resident replica + saved activations == ZeRO-3 + recompute
+    assert float(vals["lora_resident_err"]) < 1e-4     # LoRA: frozen base gathered once, adapters refreshed every step
 
 
 def test_vocab_parallel_linear_ce_gloo():
