@@ -41,6 +41,8 @@ def parse():
     ap.add_argument("--max-token-len", type=int, default=int(os.environ.get("BENCH_MAX_TOKEN_LEN", 16384)))
     ap.add_argument("--comm", default=os.environ.get("BENCH_COMM", "p2p"), choices=["p2p", "nccl"])
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--rollout-weight-dtype", default="bf16", choices=["bf16", "fp8"],
+                    help="fp8: rollout projections re-quantised to e4m3 every step (BASELINE config 4); training stays bf16")
     return ap.parse_args()
 
 
@@ -168,6 +170,7 @@ def main() -> int:
         f"actor_rollout_ref.rollout.max_num_seqs={per_gpu}", f"actor_rollout_ref.rollout.cuda_graph={not args.no_graph}",
         f"actor_rollout_ref.actor.fsdp_config.comm_backend={args.comm}", "actor_rollout_ref.rollout.free_cache_engine=True",
         f"trainer.n_gpus_per_node={world}", "actor_rollout_ref.actor.optim.lr=1e-6",
+        f"actor_rollout_ref.rollout.weight_dtype={args.rollout_weight_dtype}",
         *(["actor_rollout_ref.actor.fsdp_config.resident_params=false", "actor_rollout_ref.actor.fsdp_config.activation_checkpoint=full"]
           if args.impl == "baseline" else []),
     ])
@@ -246,7 +249,7 @@ def main() -> int:
                                                 "saved, rest recomputed",
                        "l2": "working set >> L2: 16 GB bf16 weights + KV cache streamed every step; no cache reuse across iterations",
                        "optimizer": "AdamW fp32 master+moments, grad clip 1.0", "old_log_prob_recompute": True,
-                       "cuda_graph_decode": not args.no_graph},
+                       "cuda_graph_decode": not args.no_graph, "rollout_weight_dtype": args.rollout_weight_dtype},
             "clocks": clocks,
             "e2e": {"value": round(e2e, 4), "unit": "samples/s", "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": int(d2h_bytes / max(1, args.steps)) + per_gpu * R * 12},
