@@ -302,3 +302,24 @@ def test_tp_rollout_cpu_gloo_engine_and_colocated_worker():
     line = [l for l in r.stdout.splitlines() if l.startswith("TP_CPU_RESULTS")]
     assert r.returncode == 0 and line, r.stdout[-2000:] + r.stderr[-2000:]
     assert "tok_ok=1" in line[0] and "lock=1" in line[0] and "slice_ok=1" in line[0] and "differ=1" in line[0] and "zero3_tp_slices_ok=1" in line[0]
+
+
+def test_prefix_cache_unit_semantics():
+    from polyrl_b200.rollout.engine import PAGE, BlockAllocator, PrefixCache
+
+    alloc = BlockAllocator(8)                       # blocks 1..7 usable
+    pc = PrefixCache(alloc)
+    toks = list(range(100, 100 + 3 * PAGE + 5))
+    keys = PrefixCache.page_keys(toks, 3)
+    assert len(set(keys)) == 3 and PrefixCache.page_keys(toks[: 2 * PAGE] + [0] * PAGE, 3)[:2] == keys[:2]      # chained prefix hashes
+    blocks = alloc.alloc(3)
+    pc.insert(keys, blocks)
+    alloc.release(blocks)                           # the request is gone; the cache still pins the pages
+    assert alloc.available() == 4 and pc.match(keys) == blocks and pc.match([keys[0], 12345]) == blocks[:1]
+    held = pc.match(keys[:2])
+    alloc.share(held)                               # a running request uses the first two pages
+    assert pc.evict(10) == 1 and alloc.available() == 5          # only the unreferenced page could go
+    assert pc.match(keys) == blocks[:2]
+    alloc.release(held)
+    pc.flush()
+    assert alloc.available() == 7 and not pc.by_key and not pc.lru
