@@ -650,7 +650,8 @@ class RolloutEngine:
         return min(b, self.max_num_seqs)
 
     def _run_decode(self, bs: int) -> None:
-        if not self.use_cuda_graph:
+        if not self.use_cuda_graph or self._top_k > 0 or self._top_p < 1.0:
+            # top-k / top-p go through the sort-based library sampler (host-seeded RNG): not captured into a graph
             self._decode_body(bs)
             return
         key = (bs, self._top_k, self._top_p)
