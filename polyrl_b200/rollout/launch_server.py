@@ -54,7 +54,7 @@ def main(argv=None) -> int:
         a.device = f"cuda:{int(os.environ.get('LOCAL_RANK', 0))}"
         torch.cuda.set_device(a.device)
         dist.init_process_group("nccl", device_id=torch.device(a.device))
-        cmd_group = dist.new_group(list(range(a.tp_size)), backend="gloo")
+        cmd_group = dist.group.WORLD          # scheduler commands ride on the TP group itself (no extra gloo rendezvous)
         heap = SymmetricHeap(group=None, device=torch.device(a.device))
         tp_ctx = TPContext(cfg, heap, tp_rank, a.tp_size, max_batch=a.max_num_seqs)
     w = TransformerWeights(cfg, device=a.device, dtype=dtype, init=True)          # same seed on every TP rank

@@ -345,6 +345,10 @@ def _tp_broadcast(group, wire: list, do_step: int, src_is_me: bool = True):
 
 def run_tp_follower(engine: RolloutEngine, tp_cmd_group, weight_update_fn=None) -> None:
     """Main loop of TP ranks > 0: mirror rank 0's commands, then take the same engine step."""
+    if engine.is_cuda:
+        import torch
+
+        torch.cuda.set_device(engine.device)
     while True:
         wire, do_step = _tp_broadcast(tp_cmd_group, None, 0, src_is_me=False)
         alive = True

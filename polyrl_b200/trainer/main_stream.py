@@ -28,6 +28,8 @@ def _init_dist(device_type: str):
     if world > 1 and not dist.is_initialized():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("MASTER_PORT", "29511")
+        if os.environ["MASTER_ADDR"] in ("127.0.0.1", "localhost"):
+            os.environ.setdefault("GLOO_SOCKET_IFNAME", "lo")       # single node: never resolve the (possibly unresolvable) hostname
         if device_type == "cuda":
             torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", 0)))
             dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ.get("LOCAL_RANK", 0))))
@@ -193,7 +195,10 @@ def main(argv: list[str] | None = None) -> int:
             raise ValueError(f"trainer.n_rollout_gpus ({n_roll}) must be a multiple of rollout.tensor_model_parallel_size ({tp})")
         for c in range(n_roll // tp):
             chunk = rollout_ranks[c * tp:(c + 1) * tp]
-            g_main, g_cmd = dist.new_group(chunk), dist.new_group(chunk, backend="gloo")
+            g_main = dist.new_group(chunk)
+            # command channel of the TP engine: on GPUs the TP (NCCL) group itself carries the small scheduler messages — a 4-GPU
+            # run that also created gloo sub-groups hung before the manager was even spawned; gloo only on the CPU plumbing path
+            g_cmd = g_main if device_type == "cuda" else dist.new_group(chunk, backend="gloo")
             if rank in chunk:
                 my_tp_groups = (g_main, g_cmd)
     manager_endpoint = a.manager_endpoint or cfg.actor_rollout_ref.rollout.rollout_manager.endpoint
