@@ -51,12 +51,17 @@ def main(argv=None) -> int:
         from .tp import TPContext
 
         tp_rank = int(os.environ["RANK"])
-        a.device = f"cuda:{int(os.environ.get('LOCAL_RANK', 0))}"
-        torch.cuda.set_device(a.device)
-        dist.init_process_group("nccl", device_id=torch.device(a.device))
-        cmd_group = dist.group.WORLD          # scheduler commands ride on the TP group itself (no extra gloo rendezvous)
-        heap = SymmetricHeap(group=None, device=torch.device(a.device))
-        tp_ctx = TPContext(cfg, heap, tp_rank, a.tp_size, max_batch=a.max_num_seqs)
+        heap = None
+        if a.device.startswith("cuda"):
+            a.device = f"cuda:{int(os.environ.get('LOCAL_RANK', 0))}"
+            torch.cuda.set_device(a.device)
+            dist.init_process_group("nccl", device_id=torch.device(a.device))
+            heap = SymmetricHeap(group=None, device=torch.device(a.device))
+        else:                                  # CPU plumbing path (library all-reduce)
+            os.environ.setdefault("GLOO_SOCKET_IFNAME", "lo")
+            dist.init_process_group("gloo")
+        cmd_group = dist.group.WORLD          # scheduler commands ride on the TP group itself (no extra rendezvous)
+        tp_ctx = TPContext(cfg, heap, tp_rank, a.tp_size, max_batch=a.max_num_seqs, group=dist.group.WORLD)
     w = TransformerWeights(cfg, device=a.device, dtype=dtype, init=True)          # same seed on every TP rank
     eng = RolloutEngine(cfg, a.device, max_num_seqs=a.max_num_seqs, max_model_len=a.max_model_len,
                         gpu_memory_utilization=a.mem_fraction_static, tp=tp_ctx, enable_prefix_cache=a.enable_prefix_cache)

@@ -323,3 +323,46 @@ def test_prefix_cache_unit_semantics():
     alloc.release(held)
     pc.flush()
     assert alloc.available() == 7 and not pc.by_key and not pc.lru
+
+
+def test_launch_server_cli_tp2_cpu(tmp_path):
+    """`torchrun -m polyrl_b200.rollout.launch_server --tp-size 2` (CPU/gloo): rank 0 serves HTTP, rank 1 follows; a request is
+    answered, /shutdown ends both ranks."""
+    import json
+    import os
+    import subprocess
+    import sys
+    import time
+    import urllib.request
+    from pathlib import Path
+
+    root = Path(__file__).resolve().parent.parent
+    env = {**os.environ, "PYTHONPATH": str(root), "OMP_NUM_THREADS": "2"}
+    port = 32471
+    p = subprocess.Popen([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                          "--master-port", "29761", "-m", "polyrl_b200.rollout.launch_server", "--model-path", "tiny-llama", "--device", "cpu",
+                          "--port", str(port), "--tp-size", "2", "--max-num-seqs", "4", "--max-model-len", "64"],
+                         stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env, cwd=root)
+    try:
+        ok = False
+        for _ in range(240):
+            try:
+                with urllib.request.urlopen(f"http://127.0.0.1:{port}/health_generate", timeout=2) as r:
+                    ok = r.status == 200
+                    break
+            except Exception:
+                time.sleep(0.5)
+                assert p.poll() is None, p.stdout.read()[-3000:]
+        assert ok
+        req = urllib.request.Request(f"http://127.0.0.1:{port}/generate", method="POST", headers={"Content-Type": "application/json"},
+                                     data=json.dumps({"input_ids": [5, 6, 7, 8], "sampling_params": {"max_new_tokens": 6, "temperature": 0.0,
+                                                                                                      "ignore_eos": True}}).encode())
+        with urllib.request.urlopen(req, timeout=120) as r:
+            out = json.loads(r.read().decode())
+        assert len(out["output_ids"]) == 6
+        urllib.request.urlopen(urllib.request.Request(f"http://127.0.0.1:{port}/shutdown", method="POST", data=b"{}",
+                                                      headers={"Content-Type": "application/json"}), timeout=30).read()
+        assert p.wait(timeout=120) == 0
+    finally:
+        if p.poll() is None:
+            p.terminate()
