@@ -144,3 +144,12 @@ def test_one_step_off_policy_gloo_ws2(tmp_path):
     r = _run(2, ov)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "step:3" in r.stdout and "timing_s/wait_next_rollout" in r.stdout and "actor/pg_loss" in r.stdout
+
+
+def test_colocated_ws2_bench_topology_gloo():
+    env = {**os.environ, "PYTHONPATH": str(ROOT), "OMP_NUM_THREADS": "2"}
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29771", str(ROOT / "tests" / "colocated_ws2_worker.py")], capture_output=True, text=True, timeout=600, env=env)
+    lines = [l for l in r.stdout.splitlines() if l.startswith("COLO2 step")]
+    assert r.returncode == 0 and len(lines) == 2, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "resident True" in lines[1] and "saved 2" in lines[1] and "n 16" in lines[1]
