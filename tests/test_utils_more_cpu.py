@@ -1,0 +1,130 @@
+"""Direct unit tests for utility modules that were only covered end to end: FLOPs counter, checkpoint merger (incl. HF export),
+tracking back-ends, profiler timers, TCP weight-transfer engine (loopback), sync trainer entry point."""
+import json
+import os
+import subprocess
+import sys
+import time
+from pathlib import Path
+
+import torch
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def test_flops_counter_matches_6nd_rule():
+    from polyrl_b200.models import get_model_config
+    from polyrl_b200.utils.flops_counter import DEVICE_PEAK_BF16, FlopsCounter
+
+    cfg = get_model_config("llama3-8b")
+    fc = FlopsCounter(cfg)
+    n_dense = fc._dense_params()
+    assert 7.4e9 < n_dense < 7.6e9                              # 8.03 B minus the 0.53 B input embedding
+    tf_s, peak = fc.estimate_flops([512] * 32, delta_time=1.0)
+    tokens = 512 * 32
+    assert abs(tf_s * 1e12 - (6 * n_dense * tokens + 12 * cfg.num_layers * cfg.q_size * 32 * 512 * 512)) / (tf_s * 1e12) < 1e-9
+    fwd, _ = fc.estimate_flops([512] * 32, 1.0, forward_only=True)
+    assert abs(fwd * 3 - tf_s) / tf_s < 1e-9
+    assert DEVICE_PEAK_BF16["B200"] == 2.25e15
+
+
+def test_model_merger_roundtrip_and_hf_names(tmp_path):
+    from polyrl_b200.models import get_model_config
+    from polyrl_b200.models import transformer as tf
+    from polyrl_b200.parallel.zero3 import Zero3Engine
+    from polyrl_b200.utils.checkpoint import ShardedCheckpointManager
+    from polyrl_b200.utils.model_merger import merge
+
+    cfg = get_model_config("tiny-llama")
+    eng = Zero3Engine(cfg, "cpu", seed=9)
+    ShardedCheckpointManager(eng, cfg).save(str(tmp_path / "actor"), global_step=1)
+    mcfg, sd = merge(str(tmp_path / "actor"))
+    want = dict(eng.named_full_tensors())
+    assert mcfg.hidden_size == cfg.hidden_size and set(sd) == set(want)
+    assert all(torch.equal(sd[k].float(), want[k].float()) for k in sd)
+    hf = tf.export_hf_state_dict(cfg, sd)
+    assert "model.layers.0.self_attn.q_proj.weight" in hf and "model.embed_tokens.weight" in hf
+    back = tf.convert_hf_state_dict(cfg, hf)                        # HF -> ours restores the fused / interleaved layout
+    assert all(torch.equal(back[k].float(), sd[k].float()) for k in sd)
+    r = subprocess.run([sys.executable, "-m", "polyrl_b200.utils.model_merger", "--ckpt", str(tmp_path / "actor"), "--out",
+                        str(tmp_path / "hf"), "--hf"], capture_output=True, text=True, env={**os.environ, "PYTHONPATH": str(ROOT)})
+    assert r.returncode == 0 and (tmp_path / "hf" / "pytorch_model.bin").exists(), r.stderr[-1000:]
+
+
+def test_tracking_backends_and_validation_logger(tmp_path, monkeypatch):
+    from polyrl_b200.utils.tracking import Tracking, ValidationGenerationsLogger
+
+    monkeypatch.chdir(tmp_path)
+    t = Tracking("proj", "exp", ["console", "file"], config={"a": 1})
+    t.log({"actor/pg_loss": torch.tensor(0.5), "n": 3, "s": "x"}, step=1)
+    t.log({"actor/pg_loss": 0.25}, step=2)
+    t.finish()
+    files = list(tmp_path.rglob("*.jsonl"))
+    assert files, list(tmp_path.rglob("*"))
+    rows = [json.loads(l) for l in files[0].read_text().splitlines()]
+    assert rows[0]["step"] == 1 and abs(rows[0]["actor/pg_loss"] - 0.5) < 1e-9 and rows[0]["s"] == "x" and rows[1]["step"] == 2
+    ValidationGenerationsLogger("proj", "exp", root=str(tmp_path / "val")).log(["file"], [("q", "a", 1.0)], step=3)
+    assert list((tmp_path / "val").rglob("*"))
+    try:
+        Tracking("proj", "exp", ["definitely_not_a_backend"])
+        assert False
+    except (ValueError, AssertionError, ImportError):
+        pass
+
+
+def test_profiler_timers_and_annotate():
+    from polyrl_b200.utils import profiler as P
+
+    timing: dict = {}
+    with P.marked_timer("gen", timing):
+        time.sleep(0.01)
+    with P.marked_timer("gen", timing):
+        time.sleep(0.01)
+    assert timing["gen"] >= 0.02                                   # accumulates across uses
+
+    @P.annotate("unit")
+    def f(x):
+        return x + 1
+
+    assert f(1) == 2
+    assert isinstance(P.log_gpu_memory_usage("here"), str)
+
+
+def test_tcp_transfer_engine_loopback():
+    from polyrl_b200.weight_transfer.tcp_engine import StagingBuffer, TCPWeightReceiver, TCPWeightSender, flat_state_nbytes
+
+    torch.manual_seed(0)
+    src = [("a", torch.randn(1000, 33)), ("b", torch.randn(7).to(torch.bfloat16)), ("c", torch.arange(5000, dtype=torch.int32))]
+    dst = [(n, torch.zeros_like(t)) for n, t in src]
+    n = flat_state_nbytes(src)
+    port = 24871
+    rx = TCPWeightReceiver(dst, bind_host="127.0.0.1", port=port, num_streams=3)
+    tx = TCPWeightSender(num_streams=3)
+    st = StagingBuffer(n, name=f"polyrl_test_{os.getpid()}")
+    try:
+        layout = tx.stage(src, st)
+        assert sum(l[2] for l in layout) == n
+        bid = tx.send(st, "127.0.0.1", port, nbytes=n)              # returns the batch id; status table records the outcome
+        assert tx.status[bid] == "success" and rx.wait_and_apply(timeout=30)
+        assert all(torch.equal(a, b) for (_, a), (_, b) in zip(src, dst))
+        # second transfer re-uses the receiver
+        src[0][1].add_(1.0)
+        tx.stage(src, st)
+        tx.send(st, "127.0.0.1", port, nbytes=n)
+        assert rx.wait_and_apply(timeout=30) and torch.equal(src[0][1], dst[0][1])
+    finally:
+        st.close()
+        rx.close()
+
+
+def test_sync_trainer_entry_main_ppo(tmp_path):
+    ov = ["trainer.device=cpu", "data.synthetic=True", "data.synthetic_num_samples=32", "data.max_prompt_length=16",
+          "data.synthetic_prompt_len_range=[4,12]", "data.max_response_length=6", "data.train_batch_size=4",
+          "actor_rollout_ref.rollout.n=2", "actor_rollout_ref.actor.ppo_mini_batch_size=4", "actor_rollout_ref.actor.ppo_micro_batch_size_per_gpu=4",
+          "actor_rollout_ref.rollout.log_prob_micro_batch_size_per_gpu=8", "actor_rollout_ref.rollout.max_num_seqs=8",
+          "actor_rollout_ref.model.path=tiny-llama", "algorithm.adv_estimator=grpo", "trainer.n_gpus_per_node=1",
+          "trainer.total_training_steps=2", "trainer.logger=[console]", "trainer.total_epochs=1", "actor_rollout_ref.rollout.cuda_graph=False"]
+    r = subprocess.run([sys.executable, "-m", "polyrl_b200.trainer.main_ppo", *ov], capture_output=True, text=True, timeout=600,
+                       env={**os.environ, "PYTHONPATH": str(ROOT), "OMP_NUM_THREADS": "2"}, cwd=ROOT)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "step:2" in r.stdout and "actor/pg_loss" in r.stdout
