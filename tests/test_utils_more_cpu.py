@@ -128,3 +128,41 @@ def test_sync_trainer_entry_main_ppo(tmp_path):
                        env={**os.environ, "PYTHONPATH": str(ROOT), "OMP_NUM_THREADS": "2"}, cwd=ROOT)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "step:2" in r.stdout and "actor/pg_loss" in r.stdout
+
+
+def test_sft_trainer_loss_matches_reference_and_decreases(tmp_path):
+    from polyrl_b200.data.rl_dataset import ByteTokenizer
+    from polyrl_b200.models import TransformerWeights, forward_hidden, lm_head_weight
+    from polyrl_b200.trainer.sft import SFTConfig, SFTDataset, SFTTrainer
+
+    rows = [{"prompt": f"q{i}: what is {i}+{i}?", "response": f" it is {2 * i}"} for i in range(16)]
+    f = tmp_path / "sft.jsonl"
+    f.write_text("\n".join(json.dumps(r) for r in rows))
+    cfg = SFTConfig()
+    cfg.trainer.device, cfg.trainer.total_steps, cfg.trainer.total_epochs = "cpu", 6, 3
+    cfg.data.train_files, cfg.data.max_length, cfg.data.train_batch_size, cfg.data.micro_batch_size_per_gpu = str(f), 48, 8, 4
+    cfg.optim.lr, cfg.optim.weight_decay = 5e-3, 0.0
+    tok = ByteTokenizer()
+    ds = SFTDataset(str(f), tok, cfg.data)
+    s0 = ds[0]
+    n_resp = len(tok.encode(rows[0]["response"])) + 1
+    assert int(s0["loss_mask"].sum()) == n_resp and int(s0["attention_mask"].sum()) == len(tok.encode(rows[0]["prompt"])) + n_resp
+    tr = SFTTrainer(cfg, device="cpu")
+    # loss parity with a plain PyTorch forward on the same weights (padded batch, shifted labels, response-only mask)
+    batch = {k: torch.stack([ds[i][k] for i in range(4)]) for k in s0}
+    w = TransformerWeights(tr.model_cfg, "cpu", torch.float32, init=False)
+    w.load_state_dict(dict(tr.engine.named_full_tensors()))
+    with torch.no_grad():
+        mine = float(tr._loss_on(batch, 1.0))
+        from polyrl_b200.models import pack_padded, unpack_to_padded
+
+        inp, idx = pack_padded(batch["input_ids"], batch["attention_mask"])
+        h = forward_hidden(tr.model_cfg, w, inp)
+        logits = unpack_to_padded(h @ lm_head_weight(tr.model_cfg, w.head, w.embed).t(), idx, 4, 48)
+        lp = torch.log_softmax(logits[:, :-1].float(), -1).gather(-1, batch["input_ids"][:, 1:, None]).squeeze(-1)
+        want = float(-(lp * batch["loss_mask"][:, 1:]).sum())
+    assert abs(mine - want) / abs(want) < 1e-4, (mine, want)
+    before = tr.evaluate(ds)
+    out = tr.fit(ds)
+    after = tr.evaluate(ds)
+    assert tr.step_idx == 6 and after < before - 0.05 and out["train/grad_norm"] > 0
