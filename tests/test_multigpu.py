@@ -53,7 +53,7 @@ def _torchrun(worker: str, n: int, port: int, tag: str, timeout: int = 600) -> d
 def test_ulysses_sp_nccl_and_peer_memory():
     """SP=2 == no SP (bf16 tolerances), and the NVLink peer-memory all-to-all == the NCCL all-to-all."""
     v = _torchrun("ulysses_worker.py", 2, 29657, "ULYSSES_RESULTS")
-    assert float(v["lp_err"]) < 5e-2 and float(v["w_err"]) < 5e-2
+    assert float(v["lp_err"]) < 5e-2 and float(v["w_err"]) < 0.15      # measured 0 / 1.9e-2 (bf16 + AdamW at lr 1e-2)
     assert float(v["peer_lp_err"]) < 1e-6 and float(v["peer_w_err"]) < 1e-6
 
 
