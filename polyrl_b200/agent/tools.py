@@ -162,7 +162,27 @@ class Gsm8kTool(BaseTool):
         return float(gsm8k.compute_score(st["response"], st["ground_truth"], method="flexible", format_score=0.0, score=1.0))
 
 
-_TOOLS: dict[str, type] = {"calculator": CalculatorTool, "calc_gsm8k_reward": Gsm8kTool, "gsm8k": Gsm8kTool}
+class CodeInterpreterTool(BaseTool):
+    """`code_interpreter(code)`: run a Python snippet in the local sandbox and return its stdout / error (reference capability:
+    verl/tools/sandbox_fusion_tools.py)."""
+
+    @classmethod
+    def default_schema(cls) -> ToolSchema:
+        return ToolSchema(name="code_interpreter", description="Execute Python code and return what it prints.",
+                          parameters={"type": "object", "required": ["code"],
+                                      "properties": {"code": {"type": "string", "description": "Python source"}}})
+
+    def execute(self, instance_id, parameters, **kwargs):
+        from ..utils.sandbox import run_python
+
+        r = run_python(str(parameters.get("code", "")), timeout_s=float(self.config.get("timeout_s", 5.0)),
+                       mem_mb=int(self.config.get("memory_limit_mb", 1024)))
+        text = r.stdout if r.status == "ok" else f"[{r.status}] {r.stderr.strip().splitlines()[-1] if r.stderr.strip() else ''}\n{r.stdout}"
+        return ToolResponse(text=text.strip()), 0.0, {"sandbox_status": r.status, "sandbox_wall_s": r.wall_s}
+
+
+_TOOLS: dict[str, type] = {"calculator": CalculatorTool, "calc_gsm8k_reward": Gsm8kTool, "gsm8k": Gsm8kTool,
+                           "code_interpreter": CodeInterpreterTool}
 
 
 def register_tool(name: str):

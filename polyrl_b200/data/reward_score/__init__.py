@@ -3,7 +3,7 @@
 which adds ``open-r1/OpenR1-Math-220k`` to the math family)."""
 from __future__ import annotations
 
-from . import geo3k, gsm8k, math as math_score, math_dapo, prime_math, qa_em
+from . import code_exec, geo3k, gsm8k, math as math_score, math_dapo, prime_math, qa_em
 
 MATH_SOURCES = {"lighteval/MATH", "DigitalLearningGmbH/MATH-lighteval", "HuggingFaceH4/MATH-500", "open-r1/OpenR1-Math-220k", "math"}
 PRIME_MATH_SOURCES = {"numina_aops_forum", "numina_synthetic_math", "numina_amc_aime", "numina_synthetic_amc", "numina_cn_k12",
@@ -23,6 +23,8 @@ def default_compute_score(data_source: str, solution_str: str, ground_truth, ext
         return float(prime_math.compute_score(solution_str, ground_truth)[0])
     if data_source == "hiyouga/geometry3k":
         return geo3k.compute_score(solution_str, ground_truth)
+    if data_source in ("codecontests", "apps", "codeforces", "taco", "code_exec"):
+        return code_exec.compute_score(solution_str, ground_truth, continuous=True)[0]
     if data_source in QA_EM_SOURCES:
         return qa_em.compute_score(solution_str, ground_truth)
     if str(data_source).startswith("synthetic/"):

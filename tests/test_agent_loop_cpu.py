@@ -196,3 +196,30 @@ def test_rollout_trace_file_backend(tmp_path):
     rows = [_json.loads(l) for l in cfg.path.read_text().splitlines()]
     assert len(rows) == 1 and rows[0]["step"] == 5 and rows[0]["output"] == 12 and rows[0]["inputs"]["kwargs"] == {"k": 3}
     RolloutTraceConfig.reset()
+
+
+def test_sandbox_code_reward_and_interpreter_tool():
+    from polyrl_b200.agent.tools import CodeInterpreterTool
+    from polyrl_b200.data.reward_score import code_exec, default_compute_score
+    from polyrl_b200.utils.sandbox import run_python
+
+    assert run_python("print(sum(range(10)))").stdout.strip() == "45"
+    assert run_python("while True: pass", timeout_s=1.0).status == "timeout"
+    assert run_python("raise ValueError('x')").status == "runtime_error"
+    assert run_python("x = bytearray(3 * 1024**3)", mem_mb=256).status in ("runtime_error", "limit")      # address-space limit
+    sol = "Here is my solution:\n```python\nn = int(input())\nprint(n * 2)\n```\n"
+    s, info = code_exec.compute_score(sol, {"inputs": ["3", "10"], "outputs": ["6", "20"]})
+    assert s == 1.0 and info == {"passed": 2, "total": 2}
+    s, _ = code_exec.compute_score(sol, {"inputs": ["3", "10"], "outputs": ["6", "21"]})
+    assert s == 0.5 and code_exec.compute_score(sol, {"inputs": ["3", "10"], "outputs": ["6", "21"]}, continuous=False)[0] == 0.0
+    fn = "```python\ndef add(a, b):\n    return a + b\n```"
+    assert code_exec.compute_score(fn, {"fn_name": "add", "inputs": [[1, 2], [5, 5]], "outputs": [3, 10]})[0] == 1.0
+    assert code_exec.compute_score(fn, {"assert_case": ["assert add(2, 2) == 4", "assert add(1, 1) == 3"]})[0] == 0.5
+    assert code_exec.compute_score("no code", {"inputs": [], "outputs": []})[0] == 0.0
+    assert default_compute_score("code_exec", sol, {"inputs": ["4"], "outputs": ["8"]}) == 1.0
+    tool = CodeInterpreterTool()
+    iid, _ = tool.create()
+    resp, _, m = tool.execute(iid, {"code": "print(6*7)"})
+    assert resp.text == "42" and m["sandbox_status"] == "ok"
+    resp, _, m = tool.execute(iid, {"code": "1/0"})
+    assert "ZeroDivisionError" in resp.text and m["sandbox_status"] == "runtime_error"
