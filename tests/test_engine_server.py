@@ -1,4 +1,9 @@
 """Native engine behind its SGLang-compatible HTTP front-end, driven through the C++ manager (CPU, tiny model)."""
+import os as _os
+import sys as _sys
+
+_sys.path.insert(0, _os.path.dirname(_os.path.abspath(__file__)))
+from _spawn import run_torchrun  # noqa: E402
 import json
 import time
 import urllib.request
@@ -115,7 +120,7 @@ def test_tp_server_lockstep_gloo():
 
     root = Path(__file__).resolve().parent.parent
     env = {**os.environ, "PYTHONPATH": str(root), "OMP_NUM_THREADS": "2"}
-    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+    r = run_torchrun([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
                         "--master-port", "29693", str(root / "tests" / "tp_server_worker.py")], capture_output=True, text=True,
                        timeout=300, env=env)
     line = [l for l in r.stdout.splitlines() if l.startswith("TP_SERVER_RESULTS")]
@@ -296,7 +301,7 @@ def test_tp_rollout_cpu_gloo_engine_and_colocated_worker():
 
     root = Path(__file__).resolve().parent.parent
     env = {**os.environ, "PYTHONPATH": str(root), "OMP_NUM_THREADS": "2"}
-    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+    r = run_torchrun([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
                         "--master-port", "29741", str(root / "tests" / "tp_cpu_worker.py")], capture_output=True, text=True,
                        timeout=300, env=env)
     line = [l for l in r.stdout.splitlines() if l.startswith("TP_CPU_RESULTS")]

@@ -1,8 +1,14 @@
 """Launch tests/multigpu_worker.py under torchrun on all visible GPUs (>= 2) and check its report."""
+import os as _os
+import sys as _sys
+
+_sys.path.insert(0, _os.path.dirname(_os.path.abspath(__file__)))
+from _spawn import run_torchrun  # noqa: E402
 import json
 import os
 import subprocess
 import sys
+
 from pathlib import Path
 
 import pytest
@@ -14,7 +20,7 @@ pytestmark = [pytest.mark.gpu, pytest.mark.multigpu]
 
 def test_peer_memory_paths_match_nccl():
     n = min(torch.cuda.device_count(), int(os.environ.get("POLYRL_TEST_MULTIGPU_WORLD", "2")))   # 2 = the measured configuration
-    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1",
+    r = run_torchrun([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1",
                         "--master-port", "29655", str(ROOT / "tests" / "multigpu_worker.py")], capture_output=True, text=True,
                        timeout=600, env={**os.environ, "PYTHONPATH": str(ROOT)})
     line = [l for l in r.stdout.splitlines() if l.startswith("MULTIGPU_RESULTS ")]
@@ -28,7 +34,7 @@ def test_peer_memory_paths_match_nccl():
 
 def test_tensor_parallel_rollout_engine():
     n = 2
-    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1",
+    r = run_torchrun([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1",
                         "--master-port", "29656", str(ROOT / "tests" / "tp_worker.py")], capture_output=True, text=True,
                        timeout=600, env={**os.environ, "PYTHONPATH": str(ROOT), "TP_TIMING": "0"})   # timing: run the worker directly
     line = [l for l in r.stdout.splitlines() if l.startswith("TP_RESULTS ")]
@@ -42,7 +48,7 @@ def test_tensor_parallel_rollout_engine():
 
 
 def _torchrun(worker: str, n: int, port: int, tag: str, timeout: int = 600) -> dict:
-    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1",
+    r = run_torchrun([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1",
                         "--master-port", str(port), str(ROOT / "tests" / worker)], capture_output=True, text=True,
                        timeout=timeout, env={**os.environ, "PYTHONPATH": str(ROOT)})
     line = [l for l in r.stdout.splitlines() if l.startswith(tag)]

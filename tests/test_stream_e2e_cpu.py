@@ -1,9 +1,15 @@
 """BASELINE config #1 (plumbing, no GPU): GPT-2-family PPO with 1 rollout worker + 1 train worker on CPU/gloo
 world_size=2 — streaming trainer, C++ manager, native engine over HTTP, broadcast weight sync every step,
 mini/micro-batch boundaries, checkpoint save + resume.  Also the colocated single-process GRPO loop."""
+import os as _os
+import sys as _sys
+
+_sys.path.insert(0, _os.path.dirname(_os.path.abspath(__file__)))
+from _spawn import run_torchrun  # noqa: E402
 import os
 import subprocess
 import sys
+
 from pathlib import Path
 
 import pytest
@@ -18,7 +24,7 @@ def _run(nproc: int, overrides: list[str], timeout: int = 600):
     else:
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}", "--master-addr", "127.0.0.1",
                "--master-port", "29641", "-m", "polyrl_b200.trainer.main_stream", *overrides]
-    return subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=env, cwd=ROOT)
+    return run_torchrun(cmd, capture_output=True, text=True, timeout=timeout, env=env, cwd=ROOT)
 
 
 COMMON = ["trainer.device=cpu", "data.synthetic=True", "data.synthetic_num_samples=64", "data.max_prompt_length=24",
@@ -64,7 +70,7 @@ def test_grpo_colocated_single_process(tmp_path):
 
 def test_ulysses_sp_equivalence_gloo():
     env = {**os.environ, "PYTHONPATH": str(ROOT), "OMP_NUM_THREADS": "2", "ULYSSES_DEVICE": "cpu"}
-    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+    r = run_torchrun([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
                         "--master-port", "29677", str(ROOT / "tests" / "ulysses_worker.py")], capture_output=True, text=True, timeout=600, env=env)
     line = [l for l in r.stdout.splitlines() if l.startswith("ULYSSES_RESULTS")]
     assert r.returncode == 0 and line, r.stdout[-2000:] + r.stderr[-2000:]
@@ -75,7 +81,7 @@ def test_ulysses_sp_equivalence_gloo():
 def test_hsdp_equivalence_gloo():
     """fsdp_size=2 x 2 replicas must match plain ZeRO-3 over 4 ranks (reference HSDP mesh: fsdp_workers.py:99-118)."""
     env = {**os.environ, "PYTHONPATH": str(ROOT), "OMP_NUM_THREADS": "1", "HSDP_DEVICE": "cpu"}
-    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=4", "--master-addr", "127.0.0.1",
+    r = run_torchrun([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=4", "--master-addr", "127.0.0.1",
                         "--master-port", "29688", str(ROOT / "tests" / "hsdp_worker.py")], capture_output=True, text=True, timeout=600, env=env)
     line = [l for l in r.stdout.splitlines() if l.startswith("HSDP_RESULTS")]
     assert r.returncode == 0 and line, r.stdout[-2000:] + r.stderr[-2000:]
@@ -88,7 +94,7 @@ def test_hsdp_equivalence_gloo():
 def test_vocab_parallel_linear_ce_gloo():
     """TP (vocab-parallel) fused linear-CE == unsharded op, values and gradients (reference TP mode: kernels.py:642-694)."""
     env = {**os.environ, "PYTHONPATH": str(ROOT), "OMP_NUM_THREADS": "2", "CE_TP_DEVICE": "cpu"}
-    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+    r = run_torchrun([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
                         "--master-port", "29691", str(ROOT / "tests" / "ce_tp_worker.py")], capture_output=True, text=True, timeout=300, env=env)
     line = [l for l in r.stdout.splitlines() if l.startswith("CE_TP_RESULTS")]
     assert r.returncode == 0 and line, r.stdout[-2000:] + r.stderr[-2000:]
@@ -125,7 +131,7 @@ def test_tensor_parallel_training_dp2_tp2_gloo():
     """(dp=2 x tp=2) TPTrainEngine (column/row-parallel blocks, vocab-parallel fused CE, DP-averaged grads, global-norm clip,
     AdamW on local slices) tracks a single-process oracle over two optimizer steps."""
     env = {**os.environ, "PYTHONPATH": str(ROOT), "OMP_NUM_THREADS": "1", "TP_TRAIN_DEVICE": "cpu"}
-    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=4", "--master-addr", "127.0.0.1",
+    r = run_torchrun([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=4", "--master-addr", "127.0.0.1",
                         "--master-port", "29752", str(ROOT / "tests" / "tp_train_worker.py")], capture_output=True, text=True, timeout=600, env=env)
     line = [l for l in r.stdout.splitlines() if l.startswith("TP_TRAIN_RESULTS")]
     assert r.returncode == 0 and line, r.stdout[-2000:] + r.stderr[-2000:]
@@ -148,7 +154,7 @@ def test_one_step_off_policy_gloo_ws2(tmp_path):
 
 def test_colocated_ws2_bench_topology_gloo():
     env = {**os.environ, "PYTHONPATH": str(ROOT), "OMP_NUM_THREADS": "2"}
-    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+    r = run_torchrun([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
                         "--master-port", "29771", str(ROOT / "tests" / "colocated_ws2_worker.py")], capture_output=True, text=True, timeout=600, env=env)
     lines = [l for l in r.stdout.splitlines() if l.startswith("COLO2 step")]
     assert r.returncode == 0 and len(lines) == 2, r.stdout[-2000:] + r.stderr[-2000:]
