@@ -181,7 +181,72 @@ class CodeInterpreterTool(BaseTool):
         return ToolResponse(text=text.strip()), 0.0, {"sandbox_status": r.status, "sandbox_wall_s": r.wall_s}
 
 
-_TOOLS: dict[str, type] = {"calculator": CalculatorTool, "calc_gsm8k_reward": Gsm8kTool, "gsm8k": Gsm8kTool,
+class SearchTool(BaseTool):
+    """`search(query_list)`: BM25 retrieval over a local passage corpus (JSONL rows with ``contents`` / ``text`` and optional
+    ``title``), top-k passages per query — the offline stand-in for the retrieval service of the reference's search tool
+    (verl/tools/search_tool.py, Search-R1 style multi-turn QA; reward: ``reward_score/qa_em.py``)."""
+
+    @classmethod
+    def default_schema(cls) -> ToolSchema:
+        return ToolSchema(name="search", description="Search the knowledge corpus for passages relevant to the queries.",
+                          parameters={"type": "object", "required": ["query_list"],
+                                      "properties": {"query_list": {"type": "array", "items": {"type": "string"},
+                                                                    "description": "one or more search queries"}}})
+
+    def __init__(self, config: dict | None = None, schema: ToolSchema | None = None):
+        super().__init__(config, schema)
+        import math
+        import re
+
+        self._tok = lambda t: re.findall(r"[a-z0-9]+", t.lower())
+        self.topk = int(self.config.get("topk", 3))
+        docs = self.config.get("corpus") or []
+        if isinstance(docs, str):
+            with open(docs) as f:
+                docs = [json.loads(l) for l in f if l.strip()]
+        self.docs = [{"title": d.get("title", ""), "text": d.get("contents") or d.get("text") or ""} if isinstance(d, dict)
+                     else {"title": "", "text": str(d)} for d in docs]
+        self._tf = []
+        df: dict[str, int] = {}
+        for d in self.docs:
+            toks = self._tok(d["title"] + " " + d["text"])
+            tf: dict[str, int] = {}
+            for t in toks:
+                tf[t] = tf.get(t, 0) + 1
+            self._tf.append((tf, len(toks)))
+            for t in tf:
+                df[t] = df.get(t, 0) + 1
+        n = max(1, len(self.docs))
+        self._idf = {t: math.log(1 + (n - c + 0.5) / (c + 0.5)) for t, c in df.items()}
+        self._avg = sum(l for _, l in self._tf) / n if self._tf else 1.0
+
+    def _bm25(self, query: str) -> list[tuple[float, int]]:
+        k1, b = 1.5, 0.75
+        q = self._tok(query)
+        scores = []
+        for i, (tf, ln) in enumerate(self._tf):
+            s = 0.0
+            for t in q:
+                f = tf.get(t, 0)
+                if f:
+                    s += self._idf.get(t, 0.0) * f * (k1 + 1) / (f + k1 * (1 - b + b * ln / self._avg))
+            if s > 0:
+                scores.append((s, i))
+        return sorted(scores, reverse=True)[: self.topk]
+
+    def execute(self, instance_id, parameters, **kwargs):
+        queries = parameters.get("query_list") or ([parameters["query"]] if parameters.get("query") else [])
+        if isinstance(queries, str):
+            queries = [queries]
+        out = []
+        for q in queries:
+            hits = self._bm25(str(q))
+            body = "\n".join(f"Doc {r + 1} (Title: {self.docs[i]['title']}) {self.docs[i]['text']}" for r, (_, i) in enumerate(hits))
+            out.append(body or "no results")
+        return ToolResponse(text="\n---\n".join(out)), 0.0, {"queries": len(queries)}
+
+
+_TOOLS: dict[str, type] = {"search": SearchTool, "calculator": CalculatorTool, "calc_gsm8k_reward": Gsm8kTool, "gsm8k": Gsm8kTool,
                            "code_interpreter": CodeInterpreterTool}
 
 

@@ -223,3 +223,19 @@ def test_sandbox_code_reward_and_interpreter_tool():
     assert resp.text == "42" and m["sandbox_status"] == "ok"
     resp, _, m = tool.execute(iid, {"code": "1/0"})
     assert "ZeroDivisionError" in resp.text and m["sandbox_status"] == "runtime_error"
+
+
+def test_search_tool_bm25_and_qa_reward():
+    from polyrl_b200.agent.tools import SearchTool
+    from polyrl_b200.data.reward_score import qa_em
+
+    corpus = [{"title": "Eiffel Tower", "contents": "The Eiffel Tower is a wrought-iron lattice tower in Paris, France."},
+              {"title": "Big Ben", "contents": "Big Ben is the nickname for the Great Bell of the clock in London."},
+              {"title": "Colosseum", "contents": "The Colosseum is an ancient amphitheatre in the centre of Rome, Italy."}]
+    tool = SearchTool({"corpus": corpus, "topk": 2})
+    iid, _ = tool.create()
+    resp, _, m = tool.execute(iid, {"query_list": ["where is the eiffel tower", "amphitheatre rome"]})
+    first, second = resp.text.split("\n---\n")
+    assert first.startswith("Doc 1 (Title: Eiffel Tower)") and "Colosseum" in second.splitlines()[0] and m["queries"] == 2
+    assert tool.execute(iid, {"query_list": ["zzzz qqqq"]})[0].text == "no results"
+    assert qa_em.compute_score("<answer>Paris</answer>", {"target": ["paris"]}) == 1.0
