@@ -26,6 +26,7 @@ class ModelConfig:
     rope_theta: float = 10000.0
     rms_norm_eps: float = 1e-6
     qkv_bias: bool = False           # Qwen2
+    qk_norm: bool = False            # Qwen3: per-head RMSNorm on q and k (weights [head_dim]) before RoPE
     tie_word_embeddings: bool = False
     pad_token_id: int = 0
     eos_token_id: int = 1
@@ -91,7 +92,7 @@ class ModelConfig:
                    num_heads=hf["num_attention_heads"], num_kv_heads=hf.get("num_key_value_heads", hf["num_attention_heads"]),
                    head_dim=hf.get("head_dim") or 0, max_position_embeddings=hf.get("max_position_embeddings", 8192),
                    rope_theta=hf.get("rope_theta", 10000.0), rms_norm_eps=hf.get("rms_norm_eps", 1e-6),
-                   qkv_bias=(mt == "qwen2") or hf.get("attention_bias", False),
+                   qkv_bias=(mt == "qwen2") or hf.get("attention_bias", False), qk_norm=(mt == "qwen3"),
                    tie_word_embeddings=hf.get("tie_word_embeddings", False), eos_token_id=eos,
                    bos_token_id=hf.get("bos_token_id") or eos, pad_token_id=hf.get("pad_token_id") or eos,
                    name=hf.get("_name_or_path", mt))
@@ -108,7 +109,7 @@ PRESETS: dict[str, dict] = {
                      num_heads=28, num_kv_heads=4, max_position_embeddings=32768, rope_theta=1000000.0,
                      rms_norm_eps=1e-6, qkv_bias=True, eos_token_id=151643, bos_token_id=151643, pad_token_id=151643),
     "qwen3-1.7b": dict(family="llama", vocab_size=151936, hidden_size=2048, intermediate_size=6144, num_layers=28,
-                       num_heads=16, num_kv_heads=8, head_dim=128, max_position_embeddings=40960,
+                       num_heads=16, num_kv_heads=8, head_dim=128, max_position_embeddings=40960, qk_norm=True,
                        rope_theta=1000000.0, rms_norm_eps=1e-6, tie_word_embeddings=True, eos_token_id=151645,
                        bos_token_id=151643, pad_token_id=151643),
     "qwen2.5-0.5b": dict(family="llama", vocab_size=151936, hidden_size=896, intermediate_size=4864, num_layers=24,
@@ -123,6 +124,9 @@ PRESETS: dict[str, dict] = {
     "tiny-llama": dict(family="llama", vocab_size=512, hidden_size=256, intermediate_size=512, num_layers=2,
                        num_heads=4, num_kv_heads=2, head_dim=64, max_position_embeddings=512, rope_theta=10000.0,
                        eos_token_id=1, bos_token_id=2, pad_token_id=0),
+    "tiny-qwen3": dict(family="llama", vocab_size=512, hidden_size=256, intermediate_size=512, num_layers=2, num_heads=4,
+                       num_kv_heads=2, head_dim=64, max_position_embeddings=512, rope_theta=1000000.0, rms_norm_eps=1e-6,
+                       qk_norm=True, tie_word_embeddings=True, eos_token_id=1, bos_token_id=2, pad_token_id=0),
     "tiny-llama-128": dict(family="llama", vocab_size=1024, hidden_size=512, intermediate_size=1024, num_layers=2,
                            num_heads=4, num_kv_heads=2, head_dim=128, max_position_embeddings=1024,
                            rope_theta=10000.0, eos_token_id=1, bos_token_id=2, pad_token_id=0),

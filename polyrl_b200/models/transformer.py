@@ -36,6 +36,8 @@ def layer_param_specs(cfg: ModelConfig) -> ParamSpec:
         specs: ParamSpec = [("ln1", (h,)), ("wqkv", (qkv, h))]
         if cfg.qkv_bias:
             specs.append(("bqkv", (qkv,)))
+        if cfg.qk_norm:
+            specs += [("q_norm", (cfg.head_dim,)), ("k_norm", (cfg.head_dim,))]
         specs += [("wo", (h, cfg.q_size)), ("ln2", (h,)), ("wgu", (2 * f, h)), ("wd", (h, f))]
         return specs
     return [("ln1_w", (h,)), ("ln1_b", (h,)), ("wqkv", (qkv, h)), ("bqkv", (qkv,)), ("wo", (h, h)), ("bo", (h,)),
@@ -71,7 +73,7 @@ def init_param_(name: str, t: torch.Tensor, cfg: ModelConfig, generator: torch.G
             bound = 1.0 / math.sqrt(t.shape[-1])
             t.uniform_(-bound, bound, generator=generator)
         return
-    if base in ("ln1", "ln2", "norm_w", "ln1_w", "ln2_w"):
+    if base in ("ln1", "ln2", "norm_w", "ln1_w", "ln2_w", "q_norm", "k_norm"):
         t.fill_(1.0)
     elif base.startswith("b") or base.endswith("_b"):
         t.zero_()
@@ -95,6 +97,18 @@ def rope_tables(cfg: ModelConfig, device) -> tuple[torch.Tensor, torch.Tensor]:
     if key not in _ROPE_CACHE:
         _ROPE_CACHE[key] = ref.rope_tables(cfg.max_position_embeddings, cfg.head_dim, cfg.rope_theta, device=device)
     return _ROPE_CACHE[key]
+
+
+def qk_norm_(cfg: ModelConfig, w: dict, qkv: torch.Tensor) -> torch.Tensor:
+    """Qwen3: RMS-normalise every q and k head (over head_dim) with learned gains, before RoPE.  Library ops on purpose (rows of
+    128 elements are a poor fit for the row-per-CTA norm kernel); returns a new fused qkv tensor."""
+    if "q_norm" not in w:
+        return qkv
+    t = qkv.shape[0]
+    nq, nkv, d = cfg.num_heads, cfg.num_kv_heads, cfg.head_dim
+    q = ref.rmsnorm(qkv[:, : nq * d].reshape(t, nq, d), w["q_norm"], cfg.rms_norm_eps)
+    k = ref.rmsnorm(qkv[:, nq * d:(nq + nkv) * d].reshape(t, nkv, d), w["k_norm"], cfg.rms_norm_eps)
+    return torch.cat([q.reshape(t, nq * d), k.reshape(t, nkv * d), qkv[:, (nq + nkv) * d:]], dim=-1)
 
 
 @dataclass
@@ -134,6 +148,7 @@ def layer_forward(cfg: ModelConfig, w: dict, x: torch.Tensor, inp: PackedInput, 
         qkv = ops.linear(h, w["wqkv"], bias=w.get("bqkv"))
         if lora and L.has_lora(w, "q_proj", "k_proj", "v_proj"):
             qkv = qkv + L.qkv_delta(cfg, w, h)
+        qkv = qk_norm_(cfg, w, qkv)
         cos, sin = rope_tables(cfg, x.device)
         if kv_sink is not None:
             qkv = rope_and_cache_(qkv, inp.position_ids, cos, sin, nq, nkv, d, *kv_sink)
@@ -223,7 +238,7 @@ def layer_decode(cfg: ModelConfig, w: dict, x: torch.Tensor, inp: DecodeInput, k
     scale = d ** -0.5
     if cfg.family == "llama":
         h = ops.rmsnorm(x, w["ln1"], cfg.rms_norm_eps)
-        qkv = ops.linear(h, w["wqkv"], bias=w.get("bqkv"))
+        qkv = qk_norm_(cfg, w, ops.linear(h, w["wqkv"], bias=w.get("bqkv")))
         cos, sin = rope_tables(cfg, x.device)
         rope_and_cache_(qkv, inp.position_ids, cos, sin, nq, nkv, d, k_cache, v_cache, inp.slot_mapping,
                         k_cache.shape[2])
@@ -256,7 +271,7 @@ def layer_decode_fused(cfg: ModelConfig, w: dict, x: torch.Tensor, delta: torch.
     C = ext()
     nq, nkv, d = cfg.num_heads, cfg.num_kv_heads, cfg.head_dim
     h = ops.rmsnorm(x, w["ln1"], cfg.rms_norm_eps) if delta is None else C.add_rmsnorm_(x, delta, w["ln1"], cfg.rms_norm_eps)
-    qkv = ops.linear(h, w["wqkv"], bias=w.get("bqkv"))
+    qkv = qk_norm_(cfg, w, ops.linear(h, w["wqkv"], bias=w.get("bqkv")))
     cos, sin = rope_tables(cfg, x.device)
     rope_and_cache_(qkv, inp.position_ids, cos, sin, nq, nkv, d, k_cache, v_cache, inp.slot_mapping, k_cache.shape[2])
     a = ops.paged_decode_attention(qkv[:, : nq * d], k_cache, v_cache, inp.block_table, inp.seq_lens, nq, nkv, d, d ** -0.5,
@@ -355,6 +370,8 @@ def convert_hf_state_dict(cfg: ModelConfig, hf_sd: dict[str, torch.Tensor]) -> d
         out[f"layers.{i}.wqkv"] = torch.cat([hf_sd[p + f"self_attn.{n}_proj.weight"] for n in "qkv"], dim=0)
         if cfg.qkv_bias:
             out[f"layers.{i}.bqkv"] = torch.cat([hf_sd[p + f"self_attn.{n}_proj.bias"] for n in "qkv"], dim=0)
+        if cfg.qk_norm:
+            out[f"layers.{i}.q_norm"], out[f"layers.{i}.k_norm"] = hf_sd[p + "self_attn.q_norm.weight"], hf_sd[p + "self_attn.k_norm.weight"]
         out[f"layers.{i}.wo"] = hf_sd[p + "self_attn.o_proj.weight"]
         out[f"layers.{i}.wgu"] = ref.interleave_gate_up(hf_sd[p + "mlp.gate_proj.weight"], hf_sd[p + "mlp.up_proj.weight"])
         out[f"layers.{i}.wd"] = hf_sd[p + "mlp.down_proj.weight"]
@@ -376,6 +393,8 @@ def export_hf_state_dict(cfg: ModelConfig, sd: dict[str, torch.Tensor]) -> dict[
             b = sd[f"layers.{i}.bqkv"]
             out[p + "self_attn.q_proj.bias"], out[p + "self_attn.k_proj.bias"], out[p + "self_attn.v_proj.bias"] = (
                 b[:q], b[q:q + kv], b[q + kv:])
+        if cfg.qk_norm:
+            out[p + "self_attn.q_norm.weight"], out[p + "self_attn.k_norm.weight"] = sd[f"layers.{i}.q_norm"], sd[f"layers.{i}.k_norm"]
         out[p + "self_attn.o_proj.weight"] = sd[f"layers.{i}.wo"]
         g, u = ref.deinterleave_gate_up(sd[f"layers.{i}.wgu"])
         out[p + "mlp.gate_proj.weight"], out[p + "mlp.up_proj.weight"] = g, u

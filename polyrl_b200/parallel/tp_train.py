@@ -69,6 +69,9 @@ def shard_layer(cfg: ModelConfig, w: dict, rank: int, tp: int) -> dict:
     d, nq, nkv = cfg.head_dim, cfg.num_heads // tp, cfg.num_kv_heads // tp
     q0, k0, v0 = rank * nq * d, cfg.q_size + rank * nkv * d, cfg.q_size + cfg.kv_size + rank * nkv * d
     out = {"ln1": w["ln1"].clone(), "ln2": w["ln2"].clone()}
+    for k in ("q_norm", "k_norm"):
+        if k in w:
+            out[k] = w[k].clone()
     out["wqkv"] = torch.cat([w["wqkv"][q0:q0 + nq * d], w["wqkv"][k0:k0 + nkv * d], w["wqkv"][v0:v0 + nkv * d]]).contiguous()
     if "bqkv" in w:
         out["bqkv"] = torch.cat([w["bqkv"][q0:q0 + nq * d], w["bqkv"][k0:k0 + nkv * d], w["bqkv"][v0:v0 + nkv * d]]).contiguous()
@@ -85,7 +88,7 @@ def tp_layer_forward(lcfg: ModelConfig, w: dict, x: torch.Tensor, inp: tf.Packed
     nq, nkv, d = lcfg.num_heads, lcfg.num_kv_heads, lcfg.head_dim
     t = x.shape[0]
     h = _CopyToTP.apply(ops.rmsnorm(x, w["ln1"], lcfg.rms_norm_eps), group)
-    qkv = ops.linear(h, w["wqkv"], bias=w.get("bqkv"))
+    qkv = tf.qk_norm_(lcfg, w, ops.linear(h, w["wqkv"], bias=w.get("bqkv")))
     cos, sin = tf.rope_tables(lcfg, x.device)
     qkv = ops.apply_rope(qkv, inp.position_ids, cos, sin, nq, nkv, d)
     q = qkv[:, : nq * d].view(t, nq, d)
@@ -103,7 +106,7 @@ class TPTrainEngine:
     slices; ``step()`` averages gradients over ``dp_group``, clips by the global norm (sharded params counted once per TP
     rank, replicated params once) and applies AdamW."""
 
-    REPLICATED = ("ln1", "ln2", "embed", "norm_w")
+    REPLICATED = ("ln1", "ln2", "embed", "norm_w", "q_norm", "k_norm")
 
     def __init__(self, cfg: ModelConfig, device, tp_group, dp_group=None, lr: float = 1e-6, betas=(0.9, 0.999), eps: float = 1e-8,
                  weight_decay: float = 0.01, max_grad_norm: float = 1.0, seed: int = 0, dtype=None):
@@ -215,6 +218,9 @@ class TPTrainEngine:
         for i in range(cfg.num_layers):
             pre = f"layers.{i}."
             out[pre + "ln1"], out[pre + "ln2"] = self.master[pre + "ln1"].clone(), self.master[pre + "ln2"].clone()
+            for k in ("q_norm", "k_norm"):
+                if pre + k in self.master:
+                    out[pre + k] = self.master[pre + k].clone()
             qkv = gather(self.master[pre + "wqkv"])
             out[pre + "wqkv"] = torch.cat([torch.cat([p[: nq * d] for p in qkv]), torch.cat([p[nq * d:(nq + nkv) * d] for p in qkv]),
                                            torch.cat([p[(nq + nkv) * d:] for p in qkv])])

@@ -73,6 +73,9 @@ class TPContext:
         d, nq, nkv = c.head_dim, c.num_heads // W, c.num_kv_heads // W
         q0, k0, v0 = r * nq * d, c.q_size + r * nkv * d, c.q_size + c.kv_size + r * nkv * d
         out = {"ln1": w["ln1"], "ln2": w["ln2"]}
+        for k in ("q_norm", "k_norm"):              # Qwen3 per-head gains are shared by every head: replicated
+            if k in w:
+                out[k] = w[k]
         out["wqkv"] = torch.cat([w["wqkv"][q0:q0 + nq * d], w["wqkv"][k0:k0 + nkv * d], w["wqkv"][v0:v0 + nkv * d]], dim=0).contiguous()
         if "bqkv" in w:
             out["bqkv"] = torch.cat([w["bqkv"][q0:q0 + nq * d], w["bqkv"][k0:k0 + nkv * d], w["bqkv"][v0:v0 + nkv * d]]).contiguous()
@@ -114,7 +117,7 @@ class TPContext:
 def layer_decode_tp(tp: TPContext, lcfg: ModelConfig, w: dict, x: torch.Tensor, inp: tf.DecodeInput, k_cache, v_cache) -> torch.Tensor:
     nq, nkv, d = lcfg.num_heads, lcfg.num_kv_heads, lcfg.head_dim
     h = ops.rmsnorm(x, w["ln1"], lcfg.rms_norm_eps)
-    qkv = ops.linear(h, w["wqkv"], bias=w.get("bqkv"))
+    qkv = tf.qk_norm_(lcfg, w, ops.linear(h, w["wqkv"], bias=w.get("bqkv")))
     cos, sin = tf.rope_tables(lcfg, x.device)
     rope_and_cache_(qkv, inp.position_ids, cos, sin, nq, nkv, d, k_cache, v_cache, inp.slot_mapping, k_cache.shape[2])
     a = ops.paged_decode_attention(qkv[:, : nq * d], k_cache, v_cache, inp.block_table, inp.seq_lens, nq, nkv, d, d ** -0.5,
@@ -129,7 +132,7 @@ def layer_prefill_tp(tp: TPContext, lcfg: ModelConfig, w: dict, x: torch.Tensor,
     nq, nkv, d = lcfg.num_heads, lcfg.num_kv_heads, lcfg.head_dim
     t = x.shape[0]
     h = ops.rmsnorm(x, w["ln1"], lcfg.rms_norm_eps)
-    qkv = ops.linear(h, w["wqkv"], bias=w.get("bqkv"))
+    qkv = tf.qk_norm_(lcfg, w, ops.linear(h, w["wqkv"], bias=w.get("bqkv")))
     cos, sin = tf.rope_tables(lcfg, x.device)
     qkv = rope_and_cache_(qkv, inp.position_ids, cos, sin, nq, nkv, d, *kv_sink)
     q = qkv[:, : nq * d].view(t, nq, d)
