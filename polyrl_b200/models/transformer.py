@@ -357,9 +357,20 @@ def unpack_to_padded(values: torch.Tensor, idx: torch.Tensor, batch: int, seqlen
 # HF checkpoint name mapping (import / export)
 # --------------------------------------------------------------------------------------------
 def convert_hf_state_dict(cfg: ModelConfig, hf_sd: dict[str, torch.Tensor]) -> dict[str, torch.Tensor]:
-    """Map HF Llama/Qwen2 parameter names to ours (fusing q/k/v and interleaving gate/up)."""
-    if cfg.family != "llama":
-        raise NotImplementedError("HF import implemented for the llama family")
+    """Map HF Llama / Qwen2 / Qwen3 / GPT-2 parameter names to ours (fusing q/k/v and interleaving gate/up; GPT-2's Conv1D
+    weights are stored [in, out] and get transposed)."""
+    if cfg.family == "gpt2":
+        g = {k.removeprefix("transformer."): v for k, v in hf_sd.items()}
+        out = {"embed": g["wte.weight"], "pos_embed": g["wpe.weight"], "norm_w": g["ln_f.weight"], "norm_b": g["ln_f.bias"]}
+        for i in range(cfg.num_layers):
+            p, q = f"h.{i}.", f"layers.{i}."
+            out[q + "ln1_w"], out[q + "ln1_b"] = g[p + "ln_1.weight"], g[p + "ln_1.bias"]
+            out[q + "ln2_w"], out[q + "ln2_b"] = g[p + "ln_2.weight"], g[p + "ln_2.bias"]
+            out[q + "wqkv"], out[q + "bqkv"] = g[p + "attn.c_attn.weight"].t().contiguous(), g[p + "attn.c_attn.bias"]
+            out[q + "wo"], out[q + "bo"] = g[p + "attn.c_proj.weight"].t().contiguous(), g[p + "attn.c_proj.bias"]
+            out[q + "wfc"], out[q + "bfc"] = g[p + "mlp.c_fc.weight"].t().contiguous(), g[p + "mlp.c_fc.bias"]
+            out[q + "wproj"], out[q + "bproj"] = g[p + "mlp.c_proj.weight"].t().contiguous(), g[p + "mlp.c_proj.bias"]
+        return out
     out = {"embed": hf_sd["model.embed_tokens.weight"], "norm_w": hf_sd["model.norm.weight"]}
     if not cfg.tie_word_embeddings:
         out["lm_head"] = hf_sd["lm_head.weight"]
@@ -379,8 +390,18 @@ def convert_hf_state_dict(cfg: ModelConfig, hf_sd: dict[str, torch.Tensor]) -> d
 
 
 def export_hf_state_dict(cfg: ModelConfig, sd: dict[str, torch.Tensor]) -> dict[str, torch.Tensor]:
-    if cfg.family != "llama":
-        raise NotImplementedError
+    if cfg.family == "gpt2":
+        out = {"transformer.wte.weight": sd["embed"], "transformer.wpe.weight": sd["pos_embed"], "transformer.ln_f.weight": sd["norm_w"],
+               "transformer.ln_f.bias": sd["norm_b"], "lm_head.weight": sd["embed"]}
+        for i in range(cfg.num_layers):
+            p, q = f"transformer.h.{i}.", f"layers.{i}."
+            out[p + "ln_1.weight"], out[p + "ln_1.bias"] = sd[q + "ln1_w"], sd[q + "ln1_b"]
+            out[p + "ln_2.weight"], out[p + "ln_2.bias"] = sd[q + "ln2_w"], sd[q + "ln2_b"]
+            out[p + "attn.c_attn.weight"], out[p + "attn.c_attn.bias"] = sd[q + "wqkv"].t().contiguous(), sd[q + "bqkv"]
+            out[p + "attn.c_proj.weight"], out[p + "attn.c_proj.bias"] = sd[q + "wo"].t().contiguous(), sd[q + "bo"]
+            out[p + "mlp.c_fc.weight"], out[p + "mlp.c_fc.bias"] = sd[q + "wfc"].t().contiguous(), sd[q + "bfc"]
+            out[p + "mlp.c_proj.weight"], out[p + "mlp.c_proj.bias"] = sd[q + "wproj"].t().contiguous(), sd[q + "bproj"]
+        return out
     out = {"model.embed_tokens.weight": sd["embed"], "model.norm.weight": sd["norm_w"]}
     out["lm_head.weight"] = sd["embed"] if cfg.tie_word_embeddings else sd["lm_head"]
     q, kv = cfg.q_size, cfg.kv_size

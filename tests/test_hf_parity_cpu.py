@@ -69,3 +69,29 @@ def test_qk_norm_engine_matches_cacheless_oracle():
         outs[name] = [(r.output_ids, r.logprobs) for grp in g for r in grp]
     for (a, la), (b, lb) in zip(outs["native"], outs["naive"]):
         assert a == b and max(abs(x - y) for x, y in zip(la, lb)) < 1e-4
+
+
+def test_gpt2_logits_match_hf():
+    """BASELINE config 1 trains a GPT-2-family PPO model: the gpt2 block (LayerNorm, learned positions, fused c_attn, GELU-tanh
+    MLP, biases, tied head) must equal HF GPT2LMHeadModel."""
+    torch.manual_seed(1)
+    hc = transformers.GPT2Config(vocab_size=300, n_positions=64, n_embd=96, n_layer=2, n_head=4, resid_pdrop=0.0, embd_pdrop=0.0, attn_pdrop=0.0)
+    m = transformers.GPT2LMHeadModel(hc).eval().float()
+    with torch.no_grad():
+        for n, p in m.named_parameters():
+            if "ln_" in n or n.endswith(".bias"):
+                p.add_(torch.randn_like(p) * 0.1)
+    cfg = ModelConfig.from_hf_config(hc.to_dict())
+    assert cfg.family == "gpt2" and cfg.num_heads == 4
+    sd = tf.convert_hf_state_dict(cfg, m.state_dict())
+    w = TransformerWeights(cfg, "cpu", torch.float32, init=False)
+    w.load_state_dict(sd)
+    ids = torch.randint(0, 300, (2, 19))
+    with torch.no_grad():
+        want = m(ids).logits
+        inp, _ = pack_padded(ids, torch.ones_like(ids))
+        got = (forward_hidden(cfg, w, inp) @ lm_head_weight(cfg, w.head, w.embed).t()).view(2, 19, -1)
+    assert (got - want).abs().max().item() < 2e-4
+    back = tf.export_hf_state_dict(cfg, sd)
+    hf_sd = m.state_dict()
+    assert all(torch.equal(back[k], hf_sd[k]) for k in back if k in hf_sd)
