@@ -1,0 +1,210 @@
+"""HuggingFace checkpoint directories <-> the ZeRO engine / engine weights.
+
+* ``HFCheckpoint(dir)``: lazy tensor access over ``*.safetensors`` (+ ``model.safetensors.index.json``) or ``pytorch_model*.bin``.
+* ``load_into_engine(engine, dir)``: one unit (embedding, one block, head) at a time — read only that unit's HF tensors, convert
+  (fuse q/k/v, interleave gate/up, transpose GPT-2 Conv1D), hand the full tensors to ``ShardedUnit.load_full_state`` which keeps
+  this rank's shard.  Peak host memory = one block, every rank reads only what it needs.
+* ``load_state_dict(cfg, dir)``: the whole model in our naming (rollout servers, tests).
+* ``save_hf(engine_or_state, cfg, dir)``: sharded safetensors + HF ``config.json`` (checkpoint ``save_contents`` ∋ ``hf_model``).
+
+Reference capability: HF AutoModel ``from_pretrained`` + FSDP meta-init / rank-0 broadcast load
+(3rdparty/verl/verl/workers/fsdp_workers.py:269-577, verl/utils/fsdp_utils.py:259-486 parallel safetensors load,
+``fsdp2_load_full_state_dict``) and the ``hf_model`` checkpoint content (fsdp_checkpoint_manager.py:228-300).
+"""
+from __future__ import annotations
+
+import json
+from pathlib import Path
+
+import torch
+
+from . import transformer as tf
+from .config import ModelConfig
+
+
+class HFCheckpoint:
+    def __init__(self, path: str | Path):
+        self.dir = Path(path)
+        if not self.dir.is_dir():
+            raise FileNotFoundError(f"{self.dir} is not a checkpoint directory")
+        self.weight_map: dict[str, str] = {}
+        idx = self.dir / "model.safetensors.index.json"
+        st = sorted(self.dir.glob("*.safetensors"))
+        self._bin_cache: dict[str, dict] = {}
+        if idx.exists():
+            self.weight_map = json.loads(idx.read_text())["weight_map"]
+        elif st:
+            from safetensors import safe_open
+
+            for f in st:
+                with safe_open(str(f), framework="pt") as h:
+                    for k in h.keys():
+                        self.weight_map[k] = f.name
+        else:
+            bins = sorted(self.dir.glob("pytorch_model*.bin"))
+            if not bins:
+                raise FileNotFoundError(f"no *.safetensors or pytorch_model*.bin in {self.dir}")
+            for f in bins:
+                self._bin_cache[f.name] = torch.load(f, map_location="cpu", weights_only=True)
+                for k in self._bin_cache[f.name]:
+                    self.weight_map[k] = f.name
+        self._handles: dict[str, object] = {}
+
+    def has_weights(self) -> bool:
+        return bool(self.weight_map)
+
+    def keys(self):
+        return self.weight_map.keys()
+
+    def get(self, name: str) -> torch.Tensor:
+        if name not in self.weight_map and name == "lm_head.weight" and "model.embed_tokens.weight" in self.weight_map:
+            name = "model.embed_tokens.weight"          # tied checkpoints omit the head
+        fname = self.weight_map[name]
+        if fname in self._bin_cache:
+            return self._bin_cache[fname][name]
+        if fname not in self._handles:
+            from safetensors import safe_open
+
+            self._handles[fname] = safe_open(str(self.dir / fname), framework="pt")
+        return self._handles[fname].get_tensor(name)
+
+
+def _layer_keys(cfg: ModelConfig, i: int) -> list[str]:
+    if cfg.family == "gpt2":
+        p = f"transformer.h.{i}."
+        return [p + s for s in ("ln_1.weight", "ln_1.bias", "ln_2.weight", "ln_2.bias", "attn.c_attn.weight", "attn.c_attn.bias",
+                                "attn.c_proj.weight", "attn.c_proj.bias", "mlp.c_fc.weight", "mlp.c_fc.bias", "mlp.c_proj.weight",
+                                "mlp.c_proj.bias")]
+    p = f"model.layers.{i}."
+    keys = [p + "input_layernorm.weight", p + "post_attention_layernorm.weight", p + "self_attn.o_proj.weight",
+            p + "mlp.gate_proj.weight", p + "mlp.up_proj.weight", p + "mlp.down_proj.weight"]
+    keys += [p + f"self_attn.{n}_proj.weight" for n in "qkv"]
+    if cfg.qkv_bias:
+        keys += [p + f"self_attn.{n}_proj.bias" for n in "qkv"]
+    if cfg.qk_norm:
+        keys += [p + "self_attn.q_norm.weight", p + "self_attn.k_norm.weight"]
+    return keys
+
+
+def _one_layer_cfg(cfg: ModelConfig) -> ModelConfig:
+    c = ModelConfig(**cfg.to_dict())
+    c.num_layers = 1
+    return c
+
+
+def _convert_layer(cfg: ModelConfig, ck: HFCheckpoint, i: int) -> dict[str, torch.Tensor]:
+    """HF tensors of block i -> our names (without the ``layers.i.`` prefix), via the single-layer converter."""
+    if cfg.family == "gpt2":
+        sub = {k.replace(f"transformer.h.{i}.", "transformer.h.0."): ck.get(k) for k in _layer_keys(cfg, i)}
+        sub.update({"transformer.wte.weight": torch.empty(0), "transformer.wpe.weight": torch.empty(0),
+                    "transformer.ln_f.weight": torch.empty(0), "transformer.ln_f.bias": torch.empty(0)})
+    else:
+        sub = {k.replace(f"model.layers.{i}.", "model.layers.0."): ck.get(k) for k in _layer_keys(cfg, i)}
+        sub.update({"model.embed_tokens.weight": torch.empty(0), "model.norm.weight": torch.empty(0), "lm_head.weight": torch.empty(0)})
+    conv = tf.convert_hf_state_dict(_one_layer_cfg(cfg), sub)
+    return {k[len("layers.0."):]: v for k, v in conv.items() if k.startswith("layers.0.")}
+
+
+def _embed_head(cfg: ModelConfig, ck: HFCheckpoint) -> tuple[dict, dict]:
+    if cfg.family == "gpt2":
+        pre = "transformer." if "transformer.wte.weight" in ck.weight_map else ""
+        embed = {"embed": ck.get(pre + "wte.weight"), "pos_embed": ck.get(pre + "wpe.weight")}
+        head = {"norm_w": ck.get(pre + "ln_f.weight"), "norm_b": ck.get(pre + "ln_f.bias")}
+        return embed, head
+    embed = {"embed": ck.get("model.embed_tokens.weight")}
+    head = {"norm_w": ck.get("model.norm.weight")}
+    if not cfg.tie_word_embeddings:
+        head["lm_head"] = ck.get("lm_head.weight")
+    return embed, head
+
+
+def load_state_dict(cfg: ModelConfig, path: str | Path) -> dict[str, torch.Tensor]:
+    ck = HFCheckpoint(path)
+    embed, head = _embed_head(cfg, ck)
+    out = {**embed, **head}
+    for i in range(cfg.num_layers):
+        for k, v in _convert_layer(cfg, ck, i).items():
+            out[f"layers.{i}.{k}"] = v
+    return out
+
+
+def load_into_engine(engine, path: str | Path) -> int:
+    """Fill every ZeRO unit of ``engine`` from the checkpoint; returns the number of tensors loaded.  Value-head engines keep
+    their freshly initialised head projection (an LM checkpoint has none)."""
+    cfg = engine.cfg
+    ck = HFCheckpoint(path)
+    embed, head = _embed_head(cfg, ck)
+    n = 0
+    engine.embed.load_full_state(embed)
+    n += len(embed)
+    for i, unit in enumerate(engine.layers):
+        lw = _convert_layer(cfg, ck, i)
+        unit.load_full_state(lw)
+        n += len(lw)
+    have = {name for name, _ in engine.head.specs}
+    if have <= set(head):
+        engine.head.load_full_state(head)
+        n += len(head)
+    else:                                     # e.g. critic: load the final norm, keep v_head
+        cur = {k: v.clone() for k, v in engine.head.views(engine.head.acquire()).items()}
+        engine.head.release()
+        cur.update({k: v for k, v in head.items() if k in have})
+        engine.head.load_full_state(cur)
+        n += len([k for k in head if k in have])
+    for u in engine.units:
+        u.drop_gathered()
+    return n
+
+
+def hf_config_dict(cfg: ModelConfig) -> dict:
+    if cfg.family == "gpt2":
+        return {"model_type": "gpt2", "architectures": ["GPT2LMHeadModel"], "vocab_size": cfg.vocab_size, "n_embd": cfg.hidden_size,
+                "n_inner": cfg.intermediate_size, "n_layer": cfg.num_layers, "n_head": cfg.num_heads, "n_positions": cfg.max_position_embeddings,
+                "layer_norm_epsilon": cfg.rms_norm_eps, "eos_token_id": cfg.eos_token_id, "bos_token_id": cfg.bos_token_id}
+    mt = "qwen3" if cfg.qk_norm else ("qwen2" if cfg.qkv_bias else "llama")
+    arch = {"qwen3": "Qwen3ForCausalLM", "qwen2": "Qwen2ForCausalLM", "llama": "LlamaForCausalLM"}[mt]
+    return {"model_type": mt, "architectures": [arch], "vocab_size": cfg.vocab_size, "hidden_size": cfg.hidden_size,
+            "intermediate_size": cfg.intermediate_size, "num_hidden_layers": cfg.num_layers, "num_attention_heads": cfg.num_heads,
+            "num_key_value_heads": cfg.num_kv_heads, "head_dim": cfg.head_dim, "max_position_embeddings": cfg.max_position_embeddings,
+            "rope_theta": cfg.rope_theta, "rms_norm_eps": cfg.rms_norm_eps, "tie_word_embeddings": cfg.tie_word_embeddings,
+            "attention_bias": bool(cfg.qkv_bias and mt == "llama"), "hidden_act": "silu", "torch_dtype": "bfloat16",
+            "eos_token_id": cfg.eos_token_id, "bos_token_id": cfg.bos_token_id, "pad_token_id": cfg.pad_token_id}
+
+
+def save_hf(state_or_engine, cfg: ModelConfig, out_dir: str | Path, max_shard_bytes: int = 4 << 30, dtype=torch.bfloat16) -> list[str]:
+    """Write ``config.json`` + sharded safetensors in HF naming.  ``state_or_engine``: our-name state dict or a ZeRO engine (every
+    rank must call; rank 0 writes)."""
+    from safetensors.torch import save_file
+
+    out = Path(out_dir)
+    is_engine = hasattr(state_or_engine, "named_full_tensors")
+    rank0 = (not is_engine) or state_or_engine.rank == 0
+    sd = {n: t.detach().to("cpu", dtype).clone() for n, t in (state_or_engine.named_full_tensors() if is_engine else state_or_engine.items())
+          if ".lora." not in n}
+    if not rank0:
+        return []
+    out.mkdir(parents=True, exist_ok=True)
+    hf = {k: v.contiguous() for k, v in tf.export_hf_state_dict(cfg, sd).items()}
+    if cfg.tie_word_embeddings:
+        hf.pop("lm_head.weight", None)
+    shards, cur, size = [], {}, 0
+    for k, v in hf.items():
+        nb = v.numel() * v.element_size()
+        if cur and size + nb > max_shard_bytes:
+            shards.append(cur)
+            cur, size = {}, 0
+        cur[k] = v
+        size += nb
+    shards.append(cur)
+    names, weight_map = [], {}
+    for i, sh in enumerate(shards):
+        name = "model.safetensors" if len(shards) == 1 else f"model-{i + 1:05d}-of-{len(shards):05d}.safetensors"
+        save_file(sh, str(out / name), metadata={"format": "pt"})
+        names.append(name)
+        weight_map.update({k: name for k in sh})
+    if len(shards) > 1:
+        (out / "model.safetensors.index.json").write_text(json.dumps({"metadata": {}, "weight_map": weight_map}, indent=1))
+    hc = hf_config_dict(cfg)
+    hc["torch_dtype"] = str(dtype).replace("torch.", "")
+    (out / "config.json").write_text(json.dumps(hc, indent=2))
+    return names

@@ -84,6 +84,10 @@ class ShardedCheckpointManager:
             torch.save({"opt_step": eng.opt_step,
                         "units": {u.name: {"exp_avg": u.exp_avg.cpu(), "exp_avg_sq": u.exp_avg_sq.cpu()} for u in eng.units
                                   if u.exp_avg is not None}}, op)
+        if "hf_model" in self.save_contents:
+            from ..models.hf_io import save_hf
+
+            save_hf(eng, self.model_cfg, Path(path) / "huggingface")      # consolidated HF directory (every rank gathers, rank 0 writes)
         if "extra" in self.save_contents:
             torch.save({"extra": extra or {}, "rng": _rng_state(eng.device), "global_step": global_step}, ep)
         if eng.rank == 0:

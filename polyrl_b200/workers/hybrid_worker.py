@@ -121,6 +121,7 @@ class ActorRolloutRefWorker:
                                             seed=seed, lr=opt.lr, betas=tuple(opt.betas), eps=opt.eps,
                                             weight_decay=opt.weight_decay, max_grad_norm=arr.actor.grad_clip,
                                             sp_group=self.sp_group, replica_group=self.replica_group, lora=self.lora_cfg)
+            self._maybe_load_pretrained(self.actor_engine, arr.model.path)
             fc = arr.actor.fsdp_config
             eng = self.actor_engine
             want = str(fc.resident_params).lower()
@@ -158,6 +159,7 @@ class ActorRolloutRefWorker:
             self.ref_engine = Zero3Engine(self.model_cfg, self.device, group=self.shard_group, comm=comm, trainable=False,
                                           seed=seed, heap=self.actor_engine.heap if self.actor_engine else None,
                                           sp_group=self.sp_group)
+            self._maybe_load_pretrained(self.ref_engine, arr.model.path)
             self.ref_actor = DataParallelPPOActor(self.ref_engine, ActorRuntimeConfig(), dp_group=self.group)
         if self.has_rollout:
             r = arr.rollout
@@ -195,6 +197,22 @@ class ActorRolloutRefWorker:
                                          kv_vmm=True if r.kv_vmm else None)
             if self.has_actor:
                 self.update_weight_remote()
+
+    def _maybe_load_pretrained(self, engine, path: str) -> None:
+        """``model.path`` = HF checkpoint directory with weights -> load them (unit by unit); presets / config-only dirs keep the
+        seeded random init (the reference always builds the actor from ``model.path`` through HF ``from_pretrained``)."""
+        from pathlib import Path
+
+        p = Path(str(path))
+        if not p.is_dir():
+            return
+        if not (list(p.glob("*.safetensors")) or list(p.glob("pytorch_model*.bin"))):
+            return
+        from ..models.hf_io import load_into_engine
+
+        n = load_into_engine(engine, p)
+        if self.rank == 0:
+            print(f"[worker] loaded {n} tensors from {p}", flush=True)
 
     # ------------------------------------------------------------------ weight sync (colocated)
     def update_weight_remote(self) -> bool:
