@@ -50,6 +50,22 @@ def lr_at_step(optim, step: int, total_steps: int) -> float:
     return optim.lr
 
 
+def maybe_load_pretrained(engine, path: str, rank: int = 0) -> int:
+    """``path`` = HF checkpoint directory with weights -> load them unit by unit (value-head engines keep their fresh head);
+    presets / config-only directories keep the seeded random init."""
+    from pathlib import Path
+
+    p = Path(str(path))
+    if not p.is_dir() or not (list(p.glob("*.safetensors")) or list(p.glob("pytorch_model*.bin"))):
+        return 0
+    from ..models.hf_io import load_into_engine
+
+    n = load_into_engine(engine, p)
+    if rank == 0:
+        print(f"[worker] loaded {n} tensors from {p}", flush=True)
+    return n
+
+
 class ActorRolloutRefWorker:
     """role in {"actor_rollout", "actor_rollout_ref", "actor", "rollout", "ref"}."""
 
@@ -199,20 +215,7 @@ class ActorRolloutRefWorker:
                 self.update_weight_remote()
 
     def _maybe_load_pretrained(self, engine, path: str) -> None:
-        """``model.path`` = HF checkpoint directory with weights -> load them (unit by unit); presets / config-only dirs keep the
-        seeded random init (the reference always builds the actor from ``model.path`` through HF ``from_pretrained``)."""
-        from pathlib import Path
-
-        p = Path(str(path))
-        if not p.is_dir():
-            return
-        if not (list(p.glob("*.safetensors")) or list(p.glob("pytorch_model*.bin"))):
-            return
-        from ..models.hf_io import load_into_engine
-
-        n = load_into_engine(engine, p)
-        if self.rank == 0:
-            print(f"[worker] loaded {n} tensors from {p}", flush=True)
+        maybe_load_pretrained(engine, path, self.rank)
 
     # ------------------------------------------------------------------ weight sync (colocated)
     def update_weight_remote(self) -> bool:
@@ -550,6 +553,7 @@ class RewardModelWorker:
         self.model_cfg = get_model_config(rm.model.path, **{**rm.model.override_config, "value_head": True})
         self.engine = Zero3Engine(self.model_cfg, self.device, group=self.group, comm="nccl", trainable=False,
                                   seed=self.config.data.seed + 2, heap=heap)
+        maybe_load_pretrained(self.engine, rm.model.path, dist.get_rank(self.group) if dist.is_initialized() else 0)
         rt = ActorRuntimeConfig(ppo_micro_batch_size_per_gpu=rm.micro_batch_size_per_gpu)
         self.scorer = DataParallelPPOCritic(self.engine, rt, dp_group=self.group)
 
@@ -584,6 +588,7 @@ class CriticWorker:
         self.engine = Zero3Engine(self.model_cfg, self.device, group=self.group, comm=c.fsdp_config.comm_backend,
                                   trainable=True, seed=cfg.data.seed + 1, lr=c.optim.lr, betas=tuple(c.optim.betas),
                                   eps=c.optim.eps, weight_decay=c.optim.weight_decay, max_grad_norm=c.grad_clip, heap=heap)
+        maybe_load_pretrained(self.engine, path, self.rank)
         n_dp = self.world
         mini = max(1, c.ppo_mini_batch_size * cfg.actor_rollout_ref.rollout.n // n_dp)
         rt = ActorRuntimeConfig(ppo_mini_batch_size=mini, ppo_micro_batch_size_per_gpu=c.ppo_micro_batch_size_per_gpu,

@@ -158,3 +158,20 @@ def test_worker_starts_from_hf_dir_and_checkpoint_writes_hf_model(tmp_path):
     x = torch.randint(0, 320, (1, 9))
     with torch.no_grad():
         assert (m2(x).logits - m(x).logits).abs().max().item() < 2e-2          # exported in bf16
+
+
+def test_critic_loads_backbone_from_hf_dir_and_keeps_value_head(tmp_path):
+    from polyrl_b200.config.schema import load_config
+    from polyrl_b200.workers.hybrid_worker import CriticWorker
+
+    torch.manual_seed(4)
+    m = _hf("llama").eval().float()
+    m.save_pretrained(tmp_path / "hf")
+    cfg = load_config(None, ["trainer.device=cpu", f"actor_rollout_ref.model.path={tmp_path / 'hf'}", f"critic.model.path={tmp_path / 'hf'}",
+                             "algorithm.adv_estimator=gae"])
+    cw = CriticWorker(cfg, device="cpu")
+    cw.init_model()
+    got = dict(cw.engine.named_full_tensors())
+    want = tf.convert_hf_state_dict(cw.model_cfg, m.state_dict())
+    assert torch.allclose(got["layers.1.wd"].float(), want["layers.1.wd"].float(), atol=1e-6) and "v_head" in got and "lm_head" not in got
+    assert got["v_head"][0].abs().sum() > 0
