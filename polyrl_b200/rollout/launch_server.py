@@ -25,7 +25,7 @@ def main(argv=None) -> int:
     ap.add_argument("--max-num-seqs", type=int, default=256)
     ap.add_argument("--max-model-len", type=int, default=2048)
     ap.add_argument("--mem-fraction-static", type=float, default=0.6)
-    ap.add_argument("--load-format", default="dummy")
+    ap.add_argument("--load-format", default="auto", help="auto: load --model-path weights when it is a checkpoint directory; dummy: random init")
     ap.add_argument("--stream-interval", type=int, default=20)
     ap.add_argument("--rollout-manager-address", default=None)
     ap.add_argument("--enable-weight-transfer-agent", action="store_true")
@@ -63,6 +63,14 @@ def main(argv=None) -> int:
         cmd_group = dist.group.WORLD          # scheduler commands ride on the TP group itself (no extra rendezvous)
         tp_ctx = TPContext(cfg, heap, tp_rank, a.tp_size, max_batch=a.max_num_seqs, group=dist.group.WORLD)
     w = TransformerWeights(cfg, device=a.device, dtype=dtype, init=True)          # same seed on every TP rank
+    from pathlib import Path as _P
+
+    mp = _P(a.model_path)
+    if a.load_format != "dummy" and mp.is_dir() and (list(mp.glob("*.safetensors")) or list(mp.glob("pytorch_model*.bin"))):
+        from ..models.hf_io import load_state_dict as _load_hf
+
+        w.load_state_dict({k: v.to(a.device, dtype) for k, v in _load_hf(cfg, mp).items()})
+        print(f"[engine] loaded weights from {mp}", flush=True)
     eng = RolloutEngine(cfg, a.device, max_num_seqs=a.max_num_seqs, max_model_len=a.max_model_len,
                         gpu_memory_utilization=a.mem_fraction_static, tp=tp_ctx, enable_prefix_cache=a.enable_prefix_cache)
     eng.set_weights(w.embed, w.layers, w.head)
