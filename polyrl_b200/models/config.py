@@ -30,11 +30,13 @@ class ModelConfig:
     tie_word_embeddings: bool = False
     pad_token_id: int = 0
     eos_token_id: int = 1
+    extra_eos_token_ids: tuple = ()  # further stop ids of the HF generation config (e.g. Llama-3 <|eot_id|>)
     bos_token_id: int = 1
     name: str = "custom"
     value_head: bool = False         # critic: scalar head instead of lm_head
 
     def __post_init__(self):
+        self.extra_eos_token_ids = tuple(self.extra_eos_token_ids or ())        # json round trip gives a list
         if self.head_dim == 0:
             self.head_dim = self.hidden_size // self.num_heads
         if self.num_heads % self.num_kv_heads != 0:
@@ -85,15 +87,16 @@ class ModelConfig:
                        eos_token_id=hf.get("eos_token_id", 50256), bos_token_id=hf.get("bos_token_id", 50256),
                        pad_token_id=hf.get("pad_token_id") or hf.get("eos_token_id", 50256), name=hf.get("_name_or_path", "gpt2"))
         eos = hf.get("eos_token_id", 2)
+        extra_eos: tuple = ()
         if isinstance(eos, list):
-            eos = eos[0]
+            eos, extra_eos = eos[0], tuple(int(e) for e in eos[1:])
         return cls(family="llama", vocab_size=hf["vocab_size"], hidden_size=hf["hidden_size"],
                    intermediate_size=hf["intermediate_size"], num_layers=hf["num_hidden_layers"],
                    num_heads=hf["num_attention_heads"], num_kv_heads=hf.get("num_key_value_heads", hf["num_attention_heads"]),
                    head_dim=hf.get("head_dim") or 0, max_position_embeddings=hf.get("max_position_embeddings", 8192),
                    rope_theta=hf.get("rope_theta", 10000.0), rms_norm_eps=hf.get("rms_norm_eps", 1e-6),
                    qkv_bias=(mt == "qwen2") or hf.get("attention_bias", False), qk_norm=(mt == "qwen3"),
-                   tie_word_embeddings=hf.get("tie_word_embeddings", False), eos_token_id=eos,
+                   tie_word_embeddings=hf.get("tie_word_embeddings", False), eos_token_id=eos, extra_eos_token_ids=extra_eos,
                    bos_token_id=hf.get("bos_token_id") or eos, pad_token_id=hf.get("pad_token_id") or eos,
                    name=hf.get("_name_or_path", mt))
 

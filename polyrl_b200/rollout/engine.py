@@ -601,7 +601,7 @@ class RolloutEngine:
         r.output_ids.append(int(tok))
         r.logprobs.append(float(lp))
         p = r.params
-        if not p.ignore_eos and (tok == self.cfg.eos_token_id or tok in p.stop_token_ids):
+        if not p.ignore_eos and (tok == self.cfg.eos_token_id or tok in p.stop_token_ids or tok in self.cfg.extra_eos_token_ids):
             self._finish(r, "stop")
         elif len(r.output_ids) >= p.max_new_tokens or r.num_tokens >= self.max_model_len:
             self._finish(r, "length")

@@ -371,3 +371,23 @@ def test_launch_server_cli_tp2_cpu(tmp_path):
     finally:
         if p.poll() is None:
             p.terminate()
+
+
+def test_extra_eos_ids_stop_generation():
+    import torch
+
+    from polyrl_b200.models import TransformerWeights, get_model_config
+    from polyrl_b200.rollout.engine import RolloutEngine
+
+    cfg = get_model_config("tiny-llama")
+    w = TransformerWeights(cfg, "cpu", torch.float32, seed=8)
+    eng = RolloutEngine(cfg, "cpu", max_num_seqs=2, max_model_len=64, use_cuda_graph=False)
+    eng.set_weights(w.embed, w.layers, w.head)
+    free = eng.generate([[5, 6, 7]], {"max_new_tokens": 12, "temperature": 0.0})[0][0]
+    assert len(free.output_ids) >= 3
+    cfg2 = get_model_config("tiny-llama", extra_eos_token_ids=(free.output_ids[2],))      # third generated token becomes a stop id
+    eng2 = RolloutEngine(cfg2, "cpu", max_num_seqs=2, max_model_len=64, use_cuda_graph=False)
+    eng2.set_weights(w.embed, w.layers, w.head)
+    r = eng2.generate([[5, 6, 7]], {"max_new_tokens": 12, "temperature": 0.0})[0][0]
+    first = free.output_ids.index(free.output_ids[2])
+    assert r.finish_reason == "stop" and r.output_ids == free.output_ids[: first + 1]
