@@ -110,6 +110,13 @@ class RLHFDataset(Dataset):
                "extra_info": row.get("extra_info", {}), "index": (row.get("extra_info") or {}).get("index", i)}
         if self.return_raw_chat:
             out["raw_prompt"] = row[self.key]
+        # multi-turn rollouts: per-sample tool / interaction arguments travel in ``extra_info`` (reference:
+        # verl/utils/dataset/rl_dataset.py:425-445 tools_kwargs / interaction_kwargs, need_tools_kwargs)
+        ei = row.get("extra_info") or {}
+        if ei.get("tools_kwargs") is not None:
+            out["tools_kwargs"] = ei["tools_kwargs"]
+        if ei.get("interaction_kwargs") is not None:
+            out["interaction_kwargs"] = ei["interaction_kwargs"]
         return out
 
 
