@@ -51,8 +51,9 @@ def build_datasets(cfg: PPOConfig, model_cfg, tokenizer=None):
         tok = None
     else:
         tok = tokenizer or load_tokenizer(cfg.actor_rollout_ref.model.tokenizer_path or cfg.actor_rollout_ref.model.path)
-        train = RLHFDataset(d.train_files, tok, d.prompt_key, d.max_prompt_length, d.filter_overlong_prompts, d.truncation)
-        val = RLHFDataset(d.val_files, tok, d.prompt_key, d.max_prompt_length, d.filter_overlong_prompts, d.truncation) if d.val_files else None
+        raw = d.return_raw_chat or cfg.actor_rollout_ref.rollout.multi_turn.enable       # agent loops re-template the chat
+        train = RLHFDataset(d.train_files, tok, d.prompt_key, d.max_prompt_length, d.filter_overlong_prompts, d.truncation, raw)
+        val = RLHFDataset(d.val_files, tok, d.prompt_key, d.max_prompt_length, d.filter_overlong_prompts, d.truncation, raw) if d.val_files else None
     sampler = ResumableRandomSampler(len(train), d.seed, d.shuffle)
     return train, val, sampler, tok
 
