@@ -34,15 +34,28 @@ class ModelConfig:
     bos_token_id: int = 1
     name: str = "custom"
     value_head: bool = False         # critic: scalar head instead of lm_head
+    # vision-language models (Qwen2-VL): a ViT tower feeds merged patch embeddings into the image-token positions and the text
+    # stack rotates with 3-axis (t, h, w) M-RoPE.  ``vision`` holds the tower shape (see models/vision.py), None = text only.
+    vision: dict | None = None
+    mrope_section: tuple = ()        # rotary frequency split between the (t, h, w) position streams, sums to head_dim / 2
+    image_token_id: int = -1
+    video_token_id: int = -1
+    vision_start_token_id: int = -1
 
     def __post_init__(self):
         self.extra_eos_token_ids = tuple(self.extra_eos_token_ids or ())        # json round trip gives a list
+        self.mrope_section = tuple(self.mrope_section or ())
         if self.head_dim == 0:
             self.head_dim = self.hidden_size // self.num_heads
         if self.num_heads % self.num_kv_heads != 0:
             raise ValueError("num_heads must be a multiple of num_kv_heads")
         if self.family not in ("llama", "gpt2"):
             raise ValueError(f"unknown model family {self.family!r}")
+        if self.vision is not None:
+            if self.family != "llama":
+                raise ValueError("vision towers attach to the llama family only")
+            if not self.mrope_section or sum(self.mrope_section) != self.head_dim // 2:
+                raise ValueError("mrope_section must split head_dim / 2 rotary frequencies")
 
     @property
     def q_size(self) -> int:
@@ -63,7 +76,12 @@ class ModelConfig:
         emb = v * h * (1 if self.tie_word_embeddings else 2)
         if self.family == "gpt2":
             emb += self.max_position_embeddings * h
-        return per * self.num_layers + emb + h
+        vis = 0
+        if self.vision is not None:
+            from .vision import vision_num_params
+
+            vis = vision_num_params(self)
+        return per * self.num_layers + emb + h + vis
 
     def to_dict(self) -> dict:
         return asdict(self)
@@ -86,6 +104,21 @@ class ModelConfig:
                        rms_norm_eps=hf.get("layer_norm_epsilon", 1e-5), tie_word_embeddings=True,
                        eos_token_id=hf.get("eos_token_id", 50256), bos_token_id=hf.get("bos_token_id", 50256),
                        pad_token_id=hf.get("pad_token_id") or hf.get("eos_token_id", 50256), name=hf.get("_name_or_path", "gpt2"))
+        vis_kw: dict = {}
+        if mt in ("qwen2_vl",):
+            # transformers >= 4.5x nests the text stack under text_config; older checkpoints keep it flat
+            vc = dict(hf.get("vision_config") or {})
+            top = hf
+            hf = {**{k: v for k, v in hf.items() if k not in ("text_config", "vision_config")}, **(hf.get("text_config") or {})}
+            rope = hf.get("rope_parameters") or hf.get("rope_scaling") or {}
+            hf.setdefault("rope_theta", rope.get("rope_theta", 1000000.0))
+            vis_kw = dict(
+                vision={k: vc[k] for k in ("depth", "embed_dim", "num_heads", "patch_size", "spatial_merge_size",
+                                           "temporal_patch_size", "in_channels", "mlp_ratio") if k in vc},
+                mrope_section=tuple(rope.get("mrope_section", ())), image_token_id=top.get("image_token_id", -1),
+                video_token_id=top.get("video_token_id", -1), vision_start_token_id=top.get("vision_start_token_id", -1))
+            hf["tie_word_embeddings"] = top.get("tie_word_embeddings", hf.get("tie_word_embeddings", False))
+            mt = "qwen2"
         eos = hf.get("eos_token_id", 2)
         extra_eos: tuple = ()
         if isinstance(eos, list):
@@ -98,7 +131,7 @@ class ModelConfig:
                    qkv_bias=(mt == "qwen2") or hf.get("attention_bias", False), qk_norm=(mt == "qwen3"),
                    tie_word_embeddings=hf.get("tie_word_embeddings", False), eos_token_id=eos, extra_eos_token_ids=extra_eos,
                    bos_token_id=hf.get("bos_token_id") or eos, pad_token_id=hf.get("pad_token_id") or eos,
-                   name=hf.get("_name_or_path", mt))
+                   name=hf.get("_name_or_path", mt), **vis_kw)
 
 
 PRESETS: dict[str, dict] = {
@@ -130,6 +163,18 @@ PRESETS: dict[str, dict] = {
     "tiny-qwen3": dict(family="llama", vocab_size=512, hidden_size=256, intermediate_size=512, num_layers=2, num_heads=4,
                        num_kv_heads=2, head_dim=64, max_position_embeddings=512, rope_theta=1000000.0, rms_norm_eps=1e-6,
                        qk_norm=True, tie_word_embeddings=True, eos_token_id=1, bos_token_id=2, pad_token_id=0),
+    "qwen2-vl-7b": dict(family="llama", vocab_size=152064, hidden_size=3584, intermediate_size=18944, num_layers=28,
+                        num_heads=28, num_kv_heads=4, max_position_embeddings=32768, rope_theta=1000000.0,
+                        rms_norm_eps=1e-6, qkv_bias=True, eos_token_id=151645, bos_token_id=151643, pad_token_id=151643,
+                        vision=dict(depth=32, embed_dim=1280, num_heads=16, patch_size=14, spatial_merge_size=2,
+                                    temporal_patch_size=2, in_channels=3, mlp_ratio=4),
+                        mrope_section=(16, 24, 24), image_token_id=151655, video_token_id=151656, vision_start_token_id=151652),
+    "tiny-qwen2-vl": dict(family="llama", vocab_size=512, hidden_size=128, intermediate_size=256, num_layers=2, num_heads=4,
+                          num_kv_heads=2, head_dim=32, max_position_embeddings=512, rope_theta=10000.0, rms_norm_eps=1e-6,
+                          qkv_bias=True, eos_token_id=1, bos_token_id=2, pad_token_id=0,
+                          vision=dict(depth=2, embed_dim=64, num_heads=4, patch_size=4, spatial_merge_size=2,
+                                      temporal_patch_size=2, in_channels=3, mlp_ratio=2),
+                          mrope_section=(4, 6, 6), image_token_id=500, video_token_id=501, vision_start_token_id=499),
     "tiny-llama-128": dict(family="llama", vocab_size=1024, hidden_size=512, intermediate_size=1024, num_layers=2,
                            num_heads=4, num_kv_heads=2, head_dim=128, max_position_embeddings=1024,
                            rope_theta=10000.0, eos_token_id=1, bos_token_id=2, pad_token_id=0),

@@ -123,6 +123,23 @@ class PackedInput:
     # prefill behind a cached KV prefix (rollout engine's prefix cache): (block idx [Tk], in-page offset [Tk], cu_seqlens_k
     # [B+1], max_k) describing EVERY key position (cached + new) of every sequence in the paged cache
     kv_gather: object = None
+    # vision-language inputs (models/vision.py): 3-axis M-RoPE positions [3, T] and the tower's merged patch embeddings that replace
+    # the embedding rows at the image placeholder tokens
+    mrope_pos: torch.Tensor | None = None
+    image_embeds: torch.Tensor | None = None
+
+    def rope_inputs(self, cfg: ModelConfig, device):
+        """(positions, cos, sin) for the rope op; M-RoPE builds per-token tables once per micro-batch and indexes them by row."""
+        cos, sin = rope_tables(cfg, device)
+        if self.mrope_pos is None:
+            return self.position_ids, cos, sin
+        tabs = getattr(self, "_mrope_tabs", None)
+        if tabs is None:
+            from .vision import mrope_tables
+
+            c, s = mrope_tables(cfg, self.mrope_pos, cos, sin)
+            tabs = self._mrope_tabs = (torch.arange(c.shape[0], device=c.device), c, s)
+        return tabs
 
 
 # --------------------------------------------------------------------------------------------
@@ -132,6 +149,10 @@ def embed_forward(cfg: ModelConfig, w: dict, inp: PackedInput) -> torch.Tensor:
     x = F.embedding(inp.input_ids, w["embed"])
     if cfg.family == "gpt2":
         x = x + F.embedding(inp.position_ids, w["pos_embed"])
+    if inp.image_embeds is not None:
+        from .vision import merge_image_embeds
+
+        x = merge_image_embeds(cfg, x, inp.input_ids, inp.image_embeds)
     return x
 
 
@@ -149,11 +170,11 @@ def layer_forward(cfg: ModelConfig, w: dict, x: torch.Tensor, inp: PackedInput, 
         if lora and L.has_lora(w, "q_proj", "k_proj", "v_proj"):
             qkv = qkv + L.qkv_delta(cfg, w, h)
         qkv = qk_norm_(cfg, w, qkv)
-        cos, sin = rope_tables(cfg, x.device)
+        pos, cos, sin = inp.rope_inputs(cfg, x.device)
         if kv_sink is not None:
-            qkv = rope_and_cache_(qkv, inp.position_ids, cos, sin, nq, nkv, d, *kv_sink)
+            qkv = rope_and_cache_(qkv, pos, cos, sin, nq, nkv, d, *kv_sink)
         else:
-            qkv = ops.apply_rope(qkv, inp.position_ids, cos, sin, nq, nkv, d)
+            qkv = ops.apply_rope(qkv, pos, cos, sin, nq, nkv, d)
         q = qkv[:, : nq * d].view(t, nq, d)
         k = qkv[:, nq * d:(nq + nkv) * d].view(t, nkv, d)
         v = qkv[:, (nq + nkv) * d:].view(t, nkv, d)
@@ -371,6 +392,8 @@ def convert_hf_state_dict(cfg: ModelConfig, hf_sd: dict[str, torch.Tensor]) -> d
             out[q + "wfc"], out[q + "bfc"] = g[p + "mlp.c_fc.weight"].t().contiguous(), g[p + "mlp.c_fc.bias"]
             out[q + "wproj"], out[q + "bproj"] = g[p + "mlp.c_proj.weight"].t().contiguous(), g[p + "mlp.c_proj.bias"]
         return out
+    if any(k.startswith("model.language_model.") for k in hf_sd):        # VL checkpoints nest the text stack
+        hf_sd = {k.replace("model.language_model.", "model.", 1): v for k, v in hf_sd.items()}
     out = {"embed": hf_sd["model.embed_tokens.weight"], "norm_w": hf_sd["model.norm.weight"]}
     if not cfg.tie_word_embeddings:
         out["lm_head"] = hf_sd["lm_head.weight"]

@@ -1,0 +1,362 @@
+"""Vision-language support (Qwen2-VL family): ViT tower, patch merger, M-RoPE positions, image preprocessing.
+
+The reference trains VLMs by monkey-patching the HF Qwen2-VL classes (3rdparty/verl/verl/models/transformers/qwen2_vl.py:
+``get_rope_index`` :36-150, flash-attention forward with 3-axis rotary :153-318, ``process_position_ids``) and feeds images through
+the HF processor in the dataset (verl/utils/dataset/rl_dataset.py:181-230, 299-355, vision_utils.py:25-125).  Here the tower is a
+functional model over plain weight dicts like the text stack (models/transformer.py), so it can be sharded by the ZeRO engine as one
+more unit and run by the rollout engine at prefill:
+
+  pixel patches [N, C*Tp*P*P] --linear--> [N, E] --depth x (LN, full attention inside every frame with 2-D rotary, LN, quick-GELU MLP)
+  --> LN --> groups of merge^2 neighbouring patches concatenated --> Linear, GELU, Linear --> [N / merge^2, hidden]
+
+and the merged rows replace the embeddings at the image-token positions of the prompt.  The text stack then rotates q/k with
+M-RoPE: rotary frequency i reads the temporal, height or width position stream depending on ``mrope_section``; text tokens carry the
+same value on all three streams, so decode needs only a per-sequence position offset (``delta``).
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn.functional as F
+
+from .config import ModelConfig
+
+ParamSpec = list[tuple[str, tuple[int, ...]]]
+CLIP_MEAN = (0.48145466, 0.4578275, 0.40821073)
+CLIP_STD = (0.26862954, 0.26130258, 0.27577711)
+
+
+# --------------------------------------------------------------------------------------------
+# parameters
+# --------------------------------------------------------------------------------------------
+def _v(cfg: ModelConfig) -> dict:
+    if cfg.vision is None:
+        raise ValueError(f"model {cfg.name!r} has no vision tower")
+    v = dict(cfg.vision)
+    v.setdefault("in_channels", 3)
+    v.setdefault("temporal_patch_size", 2)
+    v.setdefault("spatial_merge_size", 2)
+    v.setdefault("mlp_ratio", 4)
+    return v
+
+
+def patch_dim(cfg: ModelConfig) -> int:
+    v = _v(cfg)
+    return v["in_channels"] * v["temporal_patch_size"] * v["patch_size"] ** 2
+
+
+def vision_block_specs(cfg: ModelConfig) -> ParamSpec:
+    v = _v(cfg)
+    e, f = v["embed_dim"], int(v["embed_dim"] * v["mlp_ratio"])
+    return [("ln1_w", (e,)), ("ln1_b", (e,)), ("wqkv", (3 * e, e)), ("bqkv", (3 * e,)), ("wo", (e, e)), ("bo", (e,)),
+            ("ln2_w", (e,)), ("ln2_b", (e,)), ("wfc", (f, e)), ("bfc", (f,)), ("wproj", (e, f)), ("bproj", (e,))]
+
+
+def vision_stem_specs(cfg: ModelConfig) -> ParamSpec:
+    """Patch embedding + merger (everything outside the blocks)."""
+    v = _v(cfg)
+    e, m = v["embed_dim"], v["embed_dim"] * v["spatial_merge_size"] ** 2
+    return [("patch_embed", (e, patch_dim(cfg))), ("merger_ln_w", (e,)), ("merger_ln_b", (e,)), ("merger_w1", (m, m)),
+            ("merger_b1", (m,)), ("merger_w2", (cfg.hidden_size, m)), ("merger_b2", (cfg.hidden_size,))]
+
+
+def vision_num_params(cfg: ModelConfig) -> int:
+    n = sum(math.prod(s) for _, s in vision_stem_specs(cfg))
+    return n + _v(cfg)["depth"] * sum(math.prod(s) for _, s in vision_block_specs(cfg))
+
+
+def _init(name: str, t: torch.Tensor, g) -> None:
+    if name.endswith("_w") and "ln" in name:
+        t.fill_(1.0)
+    elif name.startswith("b") or name.endswith("_b") or name.startswith("merger_b"):
+        t.zero_()
+    else:
+        t.normal_(0.0, 0.02, generator=g)
+
+
+class VisionWeights:
+    """Plain (unsharded) tower weights: ``stem`` dict + ``blocks`` list of dicts."""
+
+    def __init__(self, cfg: ModelConfig, device="cpu", dtype=torch.float32, init: bool = True, seed: int = 1):
+        self.cfg = cfg
+        g = torch.Generator(device=device)
+        g.manual_seed(seed)
+
+        def make(specs):
+            out = {}
+            for n, shp in specs:
+                t = torch.empty(shp, device=device, dtype=dtype)
+                if init:
+                    _init(n, t, g)
+                out[n] = t
+            return out
+
+        self.stem = make(vision_stem_specs(cfg))
+        self.blocks = [make(vision_block_specs(cfg)) for _ in range(_v(cfg)["depth"])]
+
+    def named_tensors(self):
+        for n, t in self.stem.items():
+            yield f"vision.{n}", t
+        for i, b in enumerate(self.blocks):
+            for n, t in b.items():
+                yield f"vision.blocks.{i}.{n}", t
+
+    def state_dict(self) -> dict[str, torch.Tensor]:
+        return dict(self.named_tensors())
+
+    def load_state_dict(self, sd: dict[str, torch.Tensor]) -> None:
+        for n, t in self.named_tensors():
+            t.copy_(sd[n])
+
+    def requires_grad_(self, flag: bool = True):
+        for _, t in self.named_tensors():
+            t.requires_grad_(flag)
+        return self
+
+
+# --------------------------------------------------------------------------------------------
+# tower forward
+# --------------------------------------------------------------------------------------------
+def _grid_list(grid_thw) -> list[tuple[int, int, int]]:
+    if isinstance(grid_thw, torch.Tensor):
+        grid_thw = grid_thw.tolist()
+    return [tuple(int(x) for x in g) for g in grid_thw]
+
+
+def vision_rotary(cfg: ModelConfig, grid_thw, device) -> tuple[torch.Tensor, torch.Tensor]:
+    """2-D rotary tables for every patch, [N, head_dim / 2] cos and sin: the first half of the frequencies reads the patch row, the
+    second half the patch column.  Patches are ordered merge-block by merge-block (the order the preprocessor emits)."""
+    v = _v(cfg)
+    m = v["spatial_merge_size"]
+    hd = v["embed_dim"] // v["num_heads"]
+    inv = 1.0 / (10000.0 ** (torch.arange(0, hd // 2, 2, dtype=torch.float32, device=device) / (hd // 2)))      # [hd/4]
+    rows, cols = [], []
+    for t, h, w in _grid_list(grid_thw):
+        r = torch.arange(h, device=device).view(h // m, m, 1, 1).expand(h // m, m, w // m, m)
+        c = torch.arange(w, device=device).view(1, 1, w // m, m).expand(h // m, m, w // m, m)
+        rows.append(r.permute(0, 2, 1, 3).reshape(-1).repeat(t))
+        cols.append(c.permute(0, 2, 1, 3).reshape(-1).repeat(t))
+    r, c = torch.cat(rows).float(), torch.cat(cols).float()
+    ang = torch.cat([torch.outer(r, inv), torch.outer(c, inv)], dim=-1)          # [N, hd/2]
+    return ang.cos(), ang.sin()
+
+
+def _rot_half(x: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor) -> torch.Tensor:
+    """x:[N, heads, hd] rotate-half with per-row tables [N, hd/2] (fp32 math)."""
+    xf = x.float()
+    half = xf.shape[-1] // 2
+    x1, x2 = xf[..., :half], xf[..., half:]
+    c, s = cos.unsqueeze(1), sin.unsqueeze(1)
+    return torch.cat([x1 * c - x2 * s, x2 * c + x1 * s], dim=-1).to(x.dtype)
+
+
+def vision_block(cfg: ModelConfig, w: dict, x: torch.Tensor, cos, sin, cu: torch.Tensor, max_len: int) -> torch.Tensor:
+    from ..ops.attention import attention_varlen
+
+    v = _v(cfg)
+    e, nh = v["embed_dim"], v["num_heads"]
+    n = x.shape[0]
+    h = F.layer_norm(x, (e,), w["ln1_w"], w["ln1_b"], 1e-6)
+    qkv = F.linear(h, w["wqkv"], w["bqkv"]).view(n, 3, nh, e // nh)
+    q, k = _rot_half(qkv[:, 0], cos, sin), _rot_half(qkv[:, 1], cos, sin)
+    a = attention_varlen(q.contiguous(), k.contiguous(), qkv[:, 2].contiguous(), cu, max_len, causal=False)
+    x = x + F.linear(a.reshape(n, e), w["wo"], w["bo"])
+    h = F.layer_norm(x, (e,), w["ln2_w"], w["ln2_b"], 1e-6)
+    h = F.linear(h, w["wfc"], w["bfc"])
+    return x + F.linear(h * torch.sigmoid(1.702 * h), w["wproj"], w["bproj"])          # quick-GELU
+
+
+def vision_stem_in(cfg: ModelConfig, stem: dict, pixel_values: torch.Tensor) -> torch.Tensor:
+    return F.linear(pixel_values.to(stem["patch_embed"].dtype), stem["patch_embed"])
+
+
+def vision_stem_out(cfg: ModelConfig, stem: dict, x: torch.Tensor) -> torch.Tensor:
+    v = _v(cfg)
+    e, m2 = v["embed_dim"], v["spatial_merge_size"] ** 2
+    h = F.layer_norm(x, (e,), stem["merger_ln_w"], stem["merger_ln_b"], 1e-6).view(-1, e * m2)
+    return F.linear(F.gelu(F.linear(h, stem["merger_w1"], stem["merger_b1"])), stem["merger_w2"], stem["merger_b2"])
+
+
+def frame_cu_seqlens(grid_thw, device) -> tuple[torch.Tensor, int]:
+    """Attention is full inside each temporal frame of each image: one varlen segment per (image, frame)."""
+    lens = [h * w for t, h, w in _grid_list(grid_thw) for _ in range(t)]
+    cu = torch.zeros(len(lens) + 1, dtype=torch.int32, device=device)
+    cu[1:] = torch.tensor(lens, dtype=torch.int32, device=device).cumsum(0)
+    return cu, max(lens) if lens else 0
+
+
+def vision_forward(cfg: ModelConfig, vw: "VisionWeights", pixel_values: torch.Tensor, grid_thw) -> torch.Tensor:
+    """pixel_values [N, C*Tp*P*P] (N = sum t*h*w) -> merged image embeddings [N / merge^2, hidden_size]."""
+    x = vision_stem_in(cfg, vw.stem, pixel_values)
+    cos, sin = vision_rotary(cfg, grid_thw, x.device)
+    cu, mx = frame_cu_seqlens(grid_thw, x.device)
+    for b in vw.blocks:
+        x = vision_block(cfg, b, x, cos, sin, cu, mx)
+    return vision_stem_out(cfg, vw.stem, x)
+
+
+def num_image_tokens(cfg: ModelConfig, grid_thw) -> list[int]:
+    m2 = _v(cfg)["spatial_merge_size"] ** 2
+    return [t * h * w // m2 for t, h, w in _grid_list(grid_thw)]
+
+
+def merge_image_embeds(cfg: ModelConfig, x: torch.Tensor, input_ids: torch.Tensor, image_embeds: torch.Tensor) -> torch.Tensor:
+    """Replace the rows of x:[T,H] at image / video placeholder tokens by the tower's output rows, in order."""
+    mask = (input_ids == cfg.image_token_id) | (input_ids == cfg.video_token_id)
+    idx = mask.nonzero(as_tuple=True)[0]
+    if idx.numel() != image_embeds.shape[0]:
+        raise ValueError(f"{idx.numel()} image placeholder tokens but {image_embeds.shape[0]} image embedding rows")
+    return x.index_copy(0, idx, image_embeds.to(x.dtype))
+
+
+# --------------------------------------------------------------------------------------------
+# M-RoPE
+# --------------------------------------------------------------------------------------------
+def mrope_positions(cfg: ModelConfig, input_ids, grid_thw) -> tuple[torch.Tensor, int]:
+    """3-axis positions of ONE sequence -> ([3, T] int64, delta) where ``delta + T`` is the position of the next generated token.
+    Text runs advance all three axes together; an image occupying (t, h/m, w/m) merged cells starts at the running position p and
+    uses (p, p + row, p + col); the run after it resumes at p + max(h/m, w/m)."""
+    ids = input_ids.tolist() if isinstance(input_ids, torch.Tensor) else list(input_ids)
+    m = _v(cfg)["spatial_merge_size"]
+    grids = iter(_grid_list(grid_thw) if grid_thw is not None else [])
+    pos = torch.empty(3, len(ids), dtype=torch.long)
+    i, p = 0, 0
+    n = len(ids)
+    while i < n:
+        if ids[i] in (cfg.image_token_id, cfg.video_token_id):
+            t, h, w = next(grids)
+            gh, gw = h // m, w // m
+            cnt = t * gh * gw
+            if i + cnt > n or any(ids[j] not in (cfg.image_token_id, cfg.video_token_id) for j in (i, i + cnt - 1)):
+                raise ValueError("image placeholder run does not match its grid")
+            pos[0, i:i + cnt] = p
+            pos[1, i:i + cnt] = p + torch.arange(gh).repeat_interleave(gw).repeat(t)
+            pos[2, i:i + cnt] = p + torch.arange(gw).repeat(gh * t)
+            p += max(gh, gw)
+            i += cnt
+        else:
+            j = i
+            while j < n and ids[j] not in (cfg.image_token_id, cfg.video_token_id):
+                j += 1
+            pos[:, i:j] = torch.arange(p, p + j - i)
+            p += j - i
+            i = j
+    delta = (int(pos.max()) + 1 - n) if n else 0
+    return pos, delta
+
+
+def mrope_tables(cfg: ModelConfig, pos3: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor]:
+    """Per-token rotary tables [T, head_dim / 2]: frequency i reads position stream s(i) given by ``mrope_section``.  Feeding them to
+    the rope op with positions arange(T) reuses the 1-D kernel unchanged."""
+    sec = torch.tensor(cfg.mrope_section, device=pos3.device)
+    stream = torch.repeat_interleave(torch.arange(3, device=pos3.device), sec)            # [d/2] -> 0/1/2
+    p = pos3.to(cos.device)[stream.to(cos.device)]                                         # [d/2, T]
+    f = torch.arange(cos.shape[1], device=cos.device).unsqueeze(1)                        # [d/2, 1]
+    return cos[p, f].t().contiguous(), sin[p, f].t().contiguous()
+
+
+# --------------------------------------------------------------------------------------------
+# image preprocessing (PIL / tensor -> patches)
+# --------------------------------------------------------------------------------------------
+def smart_resize(height: int, width: int, factor: int, min_pixels: int, max_pixels: int) -> tuple[int, int]:
+    """Closest (h, w) that are multiples of ``factor``, keep the aspect ratio and fit the pixel budget."""
+    if max(height, width) / max(1, min(height, width)) > 200:
+        raise ValueError("aspect ratio above 200")
+    h = max(factor, round(height / factor) * factor)
+    w = max(factor, round(width / factor) * factor)
+    if h * w > max_pixels:
+        beta = math.sqrt(height * width / max_pixels)
+        h = max(factor, math.floor(height / beta / factor) * factor)
+        w = max(factor, math.floor(width / beta / factor) * factor)
+    elif h * w < min_pixels:
+        beta = math.sqrt(min_pixels / (height * width))
+        h = math.ceil(height * beta / factor) * factor
+        w = math.ceil(width * beta / factor) * factor
+    return h, w
+
+
+def patchify(cfg: ModelConfig, frames: torch.Tensor) -> tuple[torch.Tensor, tuple[int, int, int]]:
+    """frames [F, C, H, W] (normalised; H, W multiples of patch*merge) -> ([t*gh*gw, C*Tp*P*P], (t, gh, gw)).  Frames are padded by
+    repeating the last one up to a multiple of the temporal patch; rows are emitted merge-block by merge-block."""
+    v = _v(cfg)
+    p, m, tp = v["patch_size"], v["spatial_merge_size"], v["temporal_patch_size"]
+    f, c, h, w = frames.shape
+    if f % tp:
+        frames = torch.cat([frames, frames[-1:].expand(tp - f % tp, c, h, w)], dim=0)
+    gt, gh, gw = frames.shape[0] // tp, h // p, w // p
+    x = frames.reshape(gt, tp, c, gh // m, m, p, gw // m, m, p)
+    x = x.permute(0, 3, 6, 4, 7, 2, 1, 5, 8)                  # gt, gh/m, gw/m, m, m, c, tp, p, p
+    return x.reshape(gt * gh * gw, c * tp * p * p).contiguous(), (gt, gh, gw)
+
+
+def preprocess_image(cfg: ModelConfig, image, min_pixels: int | None = None, max_pixels: int | None = None):
+    """One PIL image (or uint8 tensor / array [H, W, C]) -> (pixel_values [n, patch_dim] fp32, (t, gh, gw))."""
+    from PIL import Image
+
+    v = _v(cfg)
+    factor = v["patch_size"] * v["spatial_merge_size"]
+    min_pixels = min_pixels or 4 * factor * factor
+    max_pixels = max_pixels or 1280 * factor * factor
+    if not isinstance(image, Image.Image):
+        import numpy as np
+
+        image = Image.fromarray(np.asarray(image, dtype="uint8"))
+    image = image.convert("RGB")
+    h, w = smart_resize(image.height, image.width, factor, min_pixels, max_pixels)
+    image = image.resize((w, h), resample=Image.BICUBIC)
+    import numpy as np
+
+    x = torch.from_numpy(np.asarray(image).copy()).permute(2, 0, 1).float() / 255.0
+    x = (x - torch.tensor(CLIP_MEAN).view(3, 1, 1)) / torch.tensor(CLIP_STD).view(3, 1, 1)
+    return patchify(cfg, x.unsqueeze(0))
+
+
+def expand_image_placeholders(cfg: ModelConfig, input_ids: list[int], grid_thw) -> list[int]:
+    """A prompt tokenised with ONE placeholder token per image -> the placeholder repeated once per merged patch."""
+    counts = iter(num_image_tokens(cfg, grid_thw))
+    out: list[int] = []
+    for t in input_ids:
+        out.extend([t] * next(counts) if t == cfg.image_token_id else [t])
+    return out
+
+
+# --------------------------------------------------------------------------------------------
+# HF checkpoint names
+# --------------------------------------------------------------------------------------------
+_BLOCK_MAP = {"ln1_w": "norm1.weight", "ln1_b": "norm1.bias", "wqkv": "attn.qkv.weight", "bqkv": "attn.qkv.bias",
+              "wo": "attn.proj.weight", "bo": "attn.proj.bias", "ln2_w": "norm2.weight", "ln2_b": "norm2.bias",
+              "wfc": "mlp.fc1.weight", "bfc": "mlp.fc1.bias", "wproj": "mlp.fc2.weight", "bproj": "mlp.fc2.bias"}
+_STEM_MAP = {"merger_ln_w": "merger.ln_q.weight", "merger_ln_b": "merger.ln_q.bias", "merger_w1": "merger.mlp.0.weight",
+             "merger_b1": "merger.mlp.0.bias", "merger_w2": "merger.mlp.2.weight", "merger_b2": "merger.mlp.2.bias"}
+
+
+def _visual_prefix(hf_sd: dict) -> str:
+    for p in ("model.visual.", "visual."):
+        if any(k.startswith(p) for k in hf_sd):
+            return p
+    raise KeyError("no visual.* tensors in the checkpoint")
+
+
+def convert_hf_vision_state_dict(cfg: ModelConfig, hf_sd: dict[str, torch.Tensor]) -> dict[str, torch.Tensor]:
+    """HF ``visual.*`` names -> ours.  The Conv3d patch embedding [E, C, Tp, P, P] flattens to a linear weight."""
+    p = _visual_prefix(hf_sd)
+    out = {"vision.patch_embed": hf_sd[p + "patch_embed.proj.weight"].reshape(_v(cfg)["embed_dim"], -1)}
+    for ours, theirs in _STEM_MAP.items():
+        out[f"vision.{ours}"] = hf_sd[p + theirs]
+    for i in range(_v(cfg)["depth"]):
+        for ours, theirs in _BLOCK_MAP.items():
+            out[f"vision.blocks.{i}.{ours}"] = hf_sd[f"{p}blocks.{i}.{theirs}"]
+    return out
+
+
+def export_hf_vision_state_dict(cfg: ModelConfig, sd: dict[str, torch.Tensor], prefix: str = "model.visual.") -> dict:
+    v = _v(cfg)
+    out = {prefix + "patch_embed.proj.weight": sd["vision.patch_embed"].reshape(
+        v["embed_dim"], v["in_channels"], v["temporal_patch_size"], v["patch_size"], v["patch_size"])}
+    for ours, theirs in _STEM_MAP.items():
+        out[prefix + theirs] = sd[f"vision.{ours}"]
+    for i in range(v["depth"]):
+        for ours, theirs in _BLOCK_MAP.items():
+            out[f"{prefix}blocks.{i}.{theirs}"] = sd[f"vision.blocks.{i}.{ours}"]
+    return out

@@ -1,0 +1,131 @@
+"""Qwen2-VL family on CPU: the functional ViT tower + M-RoPE text stack reproduce the HF implementation's logits on a tiny random
+model; the image preprocessor matches the HF processor's patches; positions follow the (t, h, w) layout.
+(reference: 3rdparty/verl/verl/models/transformers/qwen2_vl.py:36-150 get_rope_index, verl/utils/dataset/vision_utils.py)"""
+import numpy as np
+import pytest
+import torch
+
+from polyrl_b200.models import transformer as tf
+from polyrl_b200.models import vision as V
+from polyrl_b200.models.config import ModelConfig, get_model_config
+
+
+def _hf_tiny():
+    from transformers import Qwen2VLConfig, Qwen2VLForConditionalGeneration
+
+    torch.manual_seed(0)
+    hc = Qwen2VLConfig(
+        text_config=dict(vocab_size=512, hidden_size=128, intermediate_size=256, num_hidden_layers=2, num_attention_heads=4,
+                         num_key_value_heads=2, max_position_embeddings=512, rms_norm_eps=1e-6, tie_word_embeddings=False,
+                         rope_parameters=dict(rope_type="default", rope_theta=10000.0, mrope_section=[4, 6, 6])),
+        vision_config=dict(depth=2, embed_dim=64, hidden_size=128, num_heads=4, patch_size=4, spatial_merge_size=2,
+                           temporal_patch_size=2, in_channels=3, mlp_ratio=2),
+        image_token_id=500, video_token_id=501, vision_start_token_id=499, vision_end_token_id=498)
+    hc._attn_implementation = "eager"
+    model = Qwen2VLForConditionalGeneration(hc).eval().float()
+    with torch.no_grad():                      # default init leaves biases / norms trivial; randomise so the test sees them
+        for n, p in model.named_parameters():
+            if p.dim() == 1:
+                p.add_(0.1 * torch.randn_like(p))
+    return hc, model
+
+
+def _ours(hc, model):
+    cfg = ModelConfig.from_hf_config(hc.to_dict())
+    sd = model.state_dict()
+    w = tf.TransformerWeights(cfg, init=False)
+    w.load_state_dict(tf.convert_hf_state_dict(cfg, sd))
+    vw = V.VisionWeights(cfg, init=False)
+    vw.load_state_dict(V.convert_hf_vision_state_dict(cfg, sd))
+    return cfg, w, vw
+
+
+def test_vision_tower_and_logits_match_hf():
+    hc, model = _hf_tiny()
+    cfg, w, vw = _ours(hc, model)
+    assert cfg.vision["depth"] == 2 and cfg.mrope_section == (4, 6, 6) and cfg.qkv_bias
+    g = torch.Generator().manual_seed(1)
+    grids = [(1, 4, 6), (1, 8, 4)]                                   # patches (before the 2x2 merge)
+    pix = torch.randn(sum(t * h * w_ for t, h, w_ in grids), V.patch_dim(cfg), generator=g)
+    grid_t = torch.tensor(grids)
+    with torch.no_grad():
+        theirs = model.model.visual(pix, grid_thw=grid_t).pooler_output
+        mine = V.vision_forward(cfg, vw, pix, grids)
+    assert mine.shape == theirs.shape == (sum(V.num_image_tokens(cfg, grids)), cfg.hidden_size)
+    assert (mine - theirs).abs().max() < 2e-4
+
+    # one sequence: text, image 0, text, image 1, text
+    n0, n1 = V.num_image_tokens(cfg, grids)
+    ids = [2, 11, 12, 499] + [500] * n0 + [498, 13, 14, 15, 499] + [500] * n1 + [498, 16, 17]
+    ids_t = torch.tensor([ids])
+    mm_type = (ids_t == 500).int()
+    with torch.no_grad():
+        ref_logits = model(input_ids=ids_t, pixel_values=pix, image_grid_thw=grid_t, mm_token_type_ids=mm_type).logits[0]
+    pos3, delta = V.mrope_positions(cfg, ids, grids)
+    hf_pos, hf_delta = model.model.get_rope_index(ids_t, mm_type, image_grid_thw=grid_t)
+    assert torch.equal(pos3, hf_pos[:, 0]) and delta == int(hf_delta[0, 0])
+    t = len(ids)
+    inp = tf.PackedInput(torch.tensor(ids), pos3[0].clone(), torch.tensor([0, t], dtype=torch.int32), t, mrope_pos=pos3,
+                         image_embeds=mine)
+    with torch.no_grad():
+        h = tf.forward_hidden(cfg, w, inp)
+        logits = tf.logits_forward(cfg, w.head, w.embed, h)
+    assert (logits - ref_logits).abs().max() < 5e-4
+    # a text-only sequence through the M-RoPE path equals the 1-D rope path
+    tids = torch.arange(3, 40)
+    p1 = torch.arange(tids.numel())
+    cu = torch.tensor([0, tids.numel()], dtype=torch.int32)
+    with torch.no_grad():
+        a = tf.forward_hidden(cfg, w, tf.PackedInput(tids, p1, cu, tids.numel()))
+        b = tf.forward_hidden(cfg, w, tf.PackedInput(tids, p1, cu, tids.numel(), mrope_pos=p1.expand(3, -1).contiguous()))
+    assert (a - b).abs().max() < 1e-5
+
+
+def test_mrope_positions_layout_and_errors():
+    cfg = get_model_config("tiny-qwen2-vl")
+    ids = [7, 8, 500, 500, 500, 500, 500, 500, 9]               # a 1 x 4 x 6 patch image = 2 x 3 merged cells
+    pos, delta = V.mrope_positions(cfg, ids, [(1, 4, 6)])
+    assert pos[:, :2].tolist() == [[0, 1]] * 3
+    assert pos[0, 2:8].tolist() == [2] * 6
+    assert pos[1, 2:8].tolist() == [2, 2, 2, 3, 3, 3] and pos[2, 2:8].tolist() == [2, 3, 4, 2, 3, 4]
+    assert pos[:, 8].tolist() == [5, 5, 5] and delta == 6 - 9            # next position 6 for a 9-token prompt
+    with pytest.raises(ValueError):
+        V.mrope_positions(cfg, [7, 500, 500, 9], [(1, 4, 6)])
+    assert V.expand_image_placeholders(cfg, [7, 500, 9], [(1, 4, 6)]) == [7] + [500] * 6 + [9]
+    x = torch.zeros(4, cfg.hidden_size)
+    with pytest.raises(ValueError):
+        V.merge_image_embeds(cfg, x, torch.tensor([1, 500, 500, 2]), torch.ones(3, cfg.hidden_size))
+    y = V.merge_image_embeds(cfg, x, torch.tensor([1, 500, 500, 2]), torch.ones(2, cfg.hidden_size))
+    assert y.sum() == 2 * cfg.hidden_size and x.sum() == 0
+
+
+def test_preprocess_matches_hf_processor():
+    from PIL import Image
+    from transformers.models.qwen2_vl.image_processing_qwen2_vl import Qwen2VLImageProcessor
+
+    cfg = get_model_config("qwen2-vl-7b")
+    rng = np.random.default_rng(0)
+    img = Image.fromarray(rng.integers(0, 255, size=(75, 131, 3), dtype=np.uint8))
+    mine, grid = V.preprocess_image(cfg, img, min_pixels=56 * 56, max_pixels=28 * 28 * 64)
+    proc = Qwen2VLImageProcessor(min_pixels=56 * 56, max_pixels=28 * 28 * 64)
+    out = proc(images=[img], return_tensors="pt")
+    assert tuple(out["image_grid_thw"][0].tolist()) == grid
+    assert mine.shape == out["pixel_values"].shape
+    assert (mine - out["pixel_values"]).abs().max() < 0.05         # resize kernels differ in the last bit of uint8 rounding
+    assert (mine - out["pixel_values"]).abs().mean() < 5e-3
+    # budget clamps: a huge image shrinks under max_pixels, a tiny one grows above min_pixels
+    assert np.prod(V.smart_resize(4000, 3000, 28, 56 * 56, 28 * 28 * 1280)) <= 28 * 28 * 1280
+    h, w = V.smart_resize(20, 30, 28, 56 * 56, 28 * 28 * 1280)
+    assert h * w >= 56 * 56 and h % 28 == 0 and w % 28 == 0
+
+
+def test_vision_state_dict_round_trip_and_param_count():
+    cfg = get_model_config("tiny-qwen2-vl")
+    vw = V.VisionWeights(cfg)
+    sd = vw.state_dict()
+    hf = V.export_hf_vision_state_dict(cfg, sd)
+    assert hf["model.visual.patch_embed.proj.weight"].shape == (64, 3, 2, 4, 4)
+    back = V.convert_hf_vision_state_dict(cfg, hf)
+    assert set(back) == set(sd) and all(torch.equal(back[k], sd[k]) for k in sd)
+    assert V.vision_num_params(cfg) == sum(t.numel() for t in sd.values())
+    assert cfg.num_params() == V.vision_num_params(cfg) + get_model_config("tiny-qwen2-vl", vision=None, mrope_section=()).num_params()
