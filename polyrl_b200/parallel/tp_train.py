@@ -89,8 +89,8 @@ def tp_layer_forward(lcfg: ModelConfig, w: dict, x: torch.Tensor, inp: tf.Packed
     t = x.shape[0]
     h = _CopyToTP.apply(ops.rmsnorm(x, w["ln1"], lcfg.rms_norm_eps), group)
     qkv = tf.qk_norm_(lcfg, w, ops.linear(h, w["wqkv"], bias=w.get("bqkv")))
-    cos, sin = tf.rope_tables(lcfg, x.device)
-    qkv = ops.apply_rope(qkv, inp.position_ids, cos, sin, nq, nkv, d)
+    pos, cos, sin = inp.rope_inputs(lcfg, x.device)
+    qkv = ops.apply_rope(qkv, pos, cos, sin, nq, nkv, d)
     q = qkv[:, : nq * d].view(t, nq, d)
     k = qkv[:, nq * d:(nq + nkv) * d].view(t, nkv, d)
     v = qkv[:, (nq + nkv) * d:].view(t, nkv, d)

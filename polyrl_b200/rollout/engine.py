@@ -67,6 +67,12 @@ class Request:
     cached_tokens: int = 0                 # prompt tokens whose KV came from the prefix cache (multiple of the page size)
     prefilled: int = -1                    # prompt tokens whose KV is in the cache (-1: not admitted yet); < len(prompt) while
                                            # a long prompt is being prefilled chunk by chunk
+    # vision-language prompts: {"pixel_values": [N, patch_dim], "grid_thw": [(t, h, w), ...]}; the prompt carries one placeholder
+    # token per merged patch.  mrope_pos [3, T] / mrope_delta come from models.vision.mrope_positions at admission.
+    mm: dict | None = None
+    mrope_pos: object = None
+    mrope_delta: int = 0
+    image_embeds: object = None            # tower output, computed at the first prefill chunk and dropped after the last
 
     @property
     def decoding(self) -> bool:
@@ -231,6 +237,7 @@ class RolloutEngine:
         self._base_seed = seed
         self._step_count = 0
         self._top_k, self._top_p = -1, 1.0
+        self.vision_w = None                         # VLM tower weights (set_vision_weights)
         self.stats = {"prefill_tokens": 0, "decode_tokens": 0, "steps": 0, "last_gen_throughput": 0.0}
         self._alloc_static()
 
@@ -374,16 +381,34 @@ class RolloutEngine:
         self.h_lp = [torch.zeros(k, s, dtype=torch.float32, pin_memory=pin) for _ in range(2)]
 
     # ------------------------------------------------------------------ request API
+    def set_vision_weights(self, vision_w) -> None:
+        """Tower weights (models.vision.VisionWeights-like: ``.stem`` dict + ``.blocks`` list) for image prompts."""
+        self.vision_w = vision_w
+
     def add_request(self, prompt_ids: list[int], params: SamplingParams | dict | None = None, rid: str | None = None,
-                    group=None) -> Request:
+                    group=None, mm: dict | None = None) -> Request:
         if not isinstance(params, SamplingParams):
             params = SamplingParams.from_dict(params)
+        mrope_pos, mrope_delta = None, 0
+        if mm is not None:
+            from ..models import vision as V
+
+            if self.full_cfg.vision is None:
+                raise ValueError(f"model {self.full_cfg.name!r} has no vision tower; image inputs are not accepted")
+            if len(prompt_ids) + 1 > self.max_model_len:
+                raise ValueError("image prompt longer than max_model_len (image token runs cannot be truncated)")
+            prompt_ids = list(prompt_ids)
+            n_ph = sum(t == self.full_cfg.image_token_id for t in prompt_ids)
+            if n_ph == len(mm["grid_thw"]):                        # one placeholder per image: expand to one per merged patch
+                prompt_ids = V.expand_image_placeholders(self.full_cfg, prompt_ids, mm["grid_thw"])
+            mrope_pos, mrope_delta = V.mrope_positions(self.full_cfg, prompt_ids, mm["grid_thw"])
         if len(prompt_ids) + 1 > self.max_model_len:
             prompt_ids = prompt_ids[-(self.max_model_len - 1):]
         budget = self.max_model_len - len(prompt_ids)
         if params.max_new_tokens > budget:
             params = SamplingParams(**{**params.__dict__, "max_new_tokens": budget})
-        r = Request(rid or f"r{next(self._rid)}", list(prompt_ids), params, t_arrival=time.time(), group=group)
+        r = Request(rid or f"r{next(self._rid)}", list(prompt_ids), params, t_arrival=time.time(), group=group, mm=mm,
+                    mrope_pos=mrope_pos, mrope_delta=mrope_delta)
         self.waiting.append(r)
         return r
 
@@ -426,7 +451,7 @@ class RolloutEngine:
             donor = shared.get(id(r.group)) if r.group is not None else None
             cached: list[int] = []
             keys: list[int] = []
-            if donor is None and self.prefix_cache is not None:
+            if donor is None and self.prefix_cache is not None and r.mm is None:     # placeholder ids do not identify an image
                 # at least the last prompt token must be recomputed (its logits seed the first sampled token)
                 keys = PrefixCache.page_keys(r.prompt_ids, (len(r.prompt_ids) - 1) // PAGE)
                 cached = self.prefix_cache.match(keys)
@@ -470,7 +495,7 @@ class RolloutEngine:
             self.free_slots.append(r.slot)
             r.slot = -1
         if r.blocks and self.alloc is not None:
-            if self.prefix_cache is not None and reason != "abort":
+            if self.prefix_cache is not None and reason != "abort" and r.mm is None:
                 # every FULL page whose KV is final: prompt + generated tokens except the last one (never fed back)
                 toks = r.prompt_ids + r.output_ids
                 n_full = max(0, (len(toks) - 1)) // PAGE
@@ -527,6 +552,8 @@ class RolloutEngine:
         cu[1:] = torch.tensor(lens, dtype=torch.int32).cumsum(0)
         inp = tf.PackedInput(torch.tensor(ids, dtype=torch.long, device=dev), torch.tensor(pos, dtype=torch.long, device=dev),
                              cu.to(dev), max(lens))
+        if any(r.mm is not None for r in donors):
+            inp.mrope_pos, inp.image_embeds = self._mm_prefill_inputs(donors, spans)
         if any_cached:
             cu_k = torch.zeros(len(donors) + 1, dtype=torch.int32)
             cu_k[1:] = torch.tensor(klens, dtype=torch.int32).cumsum(0)
@@ -578,8 +605,8 @@ class RolloutEngine:
             self._append_token(r, t, l)
             if r.finished:
                 continue
-            n = r.num_tokens            # tokens so far; the new token sits at position n-1
-            live.append((r.slot, t, n - 1, n, 1, r.params.temperature, self._seed_for(r, 1)))
+            n = r.num_tokens            # tokens so far; the new token sits at position n-1 (+ the M-RoPE offset of image prompts)
+            live.append((r.slot, t, n - 1 + r.mrope_delta, n, 1, r.params.temperature, self._seed_for(r, 1)))
             row = r.blocks + [0] * (self.st_block_table.shape[1] - len(r.blocks))
             rows.append(row)
         if live:
@@ -592,6 +619,34 @@ class RolloutEngine:
             self.st_temp[sl] = torch.tensor(cols[5], dtype=torch.float32, device=dev)
             self.st_seeds[sl] = torch.tensor(cols[6], dtype=torch.long, device=dev)
             self.st_block_table[sl] = torch.tensor(rows, dtype=torch.int32, device=dev)
+
+    def _mm_prefill_inputs(self, donors: list[Request], spans: list[tuple[int, int]]):
+        """M-RoPE positions [3, T] and tower embeddings for the image-token rows of this prefill chunk.  The tower runs once per
+        request (first chunk) over all of its images; later chunks take their slice of the cached rows."""
+        from ..models import vision as V
+
+        cfg, dev = self.full_cfg, self.device
+        if getattr(self, "vision_w", None) is None:
+            raise RuntimeError("image request but no vision weights were set (RolloutEngine.set_vision_weights)")
+        pos, emb = [], []
+        for r, (c, e) in zip(donors, spans):
+            if r.mm is None:
+                pos.append(torch.arange(c, e).expand(3, -1))
+                continue
+            pos.append(r.mrope_pos[:, c:e])
+            if r.image_embeds is None:
+                pv = r.mm["pixel_values"].to(dev, self.dtype)
+                with torch.no_grad():
+                    r.image_embeds = V.vision_forward(cfg, self.vision_w, pv, r.mm["grid_thw"])
+            ph = [t in (cfg.image_token_id, cfg.video_token_id) for t in r.prompt_ids]
+            lo, hi = sum(ph[:c]), sum(ph[:e])
+            if hi > lo:
+                emb.append(r.image_embeds[lo:hi])
+            if e >= len(r.prompt_ids):
+                r.image_embeds = None
+        pos_t = torch.cat(pos, dim=1).contiguous().to(dev)
+        emb_t = torch.cat(emb, dim=0) if emb else torch.zeros(0, cfg.hidden_size, device=dev, dtype=self.dtype)
+        return pos_t, emb_t
 
     def _seed_for(self, r: Request, step: int) -> int:
         base = r.params.seed if r.params.seed is not None else self._base_seed
@@ -611,9 +666,12 @@ class RolloutEngine:
         cfg = self.cfg
         ids, pos = self.st_input_ids[:bs], self.st_positions[:bs]
         bt, sl, act = self.st_block_table[:bs], self.st_seq_lens[:bs], self.st_active[:bs]
-        page_idx = torch.div(pos, PAGE, rounding_mode="floor").clamp_(max=self.max_blocks_per_seq)
+        # KV index of the new token: equals its rotary position for text models; image prompts shift the rotary position by the
+        # request's M-RoPE delta, so vision-language engines derive the index from the sequence length instead
+        kvpos = pos if self.full_cfg.vision is None else (sl.long() - 1).clamp_(min=0)
+        page_idx = torch.div(kvpos, PAGE, rounding_mode="floor").clamp_(max=self.max_blocks_per_seq)
         blk = bt.gather(1, page_idx.unsqueeze(1)).squeeze(1).long()
-        slot = (blk * PAGE + pos % PAGE) * act          # idle slots write into scratch page 0
+        slot = (blk * PAGE + kvpos % PAGE) * act          # idle slots write into scratch page 0
         inp = tf.DecodeInput(ids, pos, slot, bt, sl, self.max_model_len)
         x = torch.nn.functional.embedding(ids, self.embed_w["embed"]).to(self.dtype)
         if cfg.family == "gpt2":
@@ -779,14 +837,16 @@ class RolloutEngine:
     # ------------------------------------------------------------------ batch API
     @torch.no_grad()
     def generate(self, prompts: list[list[int]], params: SamplingParams | dict | None = None,
-                 on_finish=None) -> list[list[Request]]:
-        """Generate ``params.n`` samples for every prompt; returns, per prompt, its list of requests."""
+                 on_finish=None, mm: list[dict | None] | None = None) -> list[list[Request]]:
+        """Generate ``params.n`` samples for every prompt; returns, per prompt, its list of requests.  ``mm[i]`` carries the image
+        inputs of prompt i (vision-language models)."""
         if not isinstance(params, SamplingParams):
             params = SamplingParams.from_dict(params)
         groups: list[list[Request]] = []
         for pi, p in enumerate(prompts):
             tag = object()
-            groups.append([self.add_request(p, params, group=tag if params.n > 1 else None) for _ in range(params.n)])
+            m = mm[pi] if mm is not None else None
+            groups.append([self.add_request(p, params, group=tag if params.n > 1 else None, mm=m) for _ in range(params.n)])
         t0 = time.time()
         ntok0 = self.stats["decode_tokens"]
         while self.has_work():

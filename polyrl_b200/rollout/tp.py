@@ -133,8 +133,8 @@ def layer_prefill_tp(tp: TPContext, lcfg: ModelConfig, w: dict, x: torch.Tensor,
     t = x.shape[0]
     h = ops.rmsnorm(x, w["ln1"], lcfg.rms_norm_eps)
     qkv = tf.qk_norm_(lcfg, w, ops.linear(h, w["wqkv"], bias=w.get("bqkv")))
-    cos, sin = tf.rope_tables(lcfg, x.device)
-    qkv = rope_and_cache_(qkv, inp.position_ids, cos, sin, nq, nkv, d, *kv_sink)
+    pos, cos, sin = inp.rope_inputs(lcfg, x.device)              # 1-D positions, or per-token M-RoPE tables (VLM prompts)
+    qkv = rope_and_cache_(qkv, pos, cos, sin, nq, nkv, d, *kv_sink)
     q = qkv[:, : nq * d].view(t, nq, d)
     k = qkv[:, nq * d:(nq + nkv) * d].view(t, nkv, d)
     v = qkv[:, (nq + nkv) * d:].view(t, nkv, d)

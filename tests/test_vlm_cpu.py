@@ -129,3 +129,50 @@ def test_vision_state_dict_round_trip_and_param_count():
     assert set(back) == set(sd) and all(torch.equal(back[k], sd[k]) for k in sd)
     assert V.vision_num_params(cfg) == sum(t.numel() for t in sd.values())
     assert cfg.num_params() == V.vision_num_params(cfg) + get_model_config("tiny-qwen2-vl", vision=None, mrope_section=()).num_params()
+
+
+def test_engine_generates_like_hf_with_images():
+    """Rollout engine on image prompts: greedy continuation equals HF generate (prefill with tower embeddings + M-RoPE, decode
+    with the per-request rotary offset), also when the prompt is prefilled in chunks and when n samples share the prompt."""
+    from polyrl_b200.rollout.engine import RolloutEngine, SamplingParams
+
+    hc, model = _hf_tiny()
+    cfg, w, vw = _ours(hc, model)
+    g = torch.Generator().manual_seed(3)
+    grids_a, grids_b = [(1, 4, 6)], [(1, 4, 4), (1, 8, 4)]
+    pix_a = torch.randn(24, V.patch_dim(cfg), generator=g)
+    pix_b = torch.randn(16 + 32, V.patch_dim(cfg), generator=g)
+    pa = [2, 21, 499, 500, 498, 22, 23]                                   # ONE placeholder per image: the engine expands them
+    pb = [2, 499, 500, 498, 31, 32, 33, 34, 499, 500, 498, 35]
+    pt = [2, 40, 41, 42, 43, 44]                                          # text only, same batch
+    new = 12
+
+    def hf_greedy(ids, pix, grids):
+        ids = V.expand_image_placeholders(cfg, ids, grids) if grids else ids
+        ids_t = torch.tensor([ids])
+        kw = {}
+        if grids:
+            kw = dict(pixel_values=pix, image_grid_thw=torch.tensor(grids), mm_token_type_ids=(ids_t == 500).int())
+        with torch.no_grad():
+            out = model.generate(input_ids=ids_t, attention_mask=torch.ones_like(ids_t), max_new_tokens=new, do_sample=False,
+                                 eos_token_id=None, pad_token_id=0, **kw)
+        return out[0, len(ids):].tolist()
+
+    want = [hf_greedy(pa, pix_a, grids_a), hf_greedy(pb, pix_b, grids_b), hf_greedy(pt, None, None)]
+    mm = [dict(pixel_values=pix_a, grid_thw=grids_a), dict(pixel_values=pix_b, grid_thw=grids_b), None]
+    for chunk in (16384, 8):
+        eng = RolloutEngine(cfg, "cpu", max_num_seqs=8, max_model_len=128, kv_cache_tokens=2048, max_prefill_tokens=chunk,
+                            enable_prefix_cache=True)
+        eng.set_weights(w.embed, w.layers, w.head)
+        eng.set_vision_weights(vw)
+        sp = SamplingParams(temperature=0.0, max_new_tokens=new, n=2, ignore_eos=True)
+        groups = eng.generate([pa, pb, pt], sp, mm=mm)
+        for grp, ref_out in zip(groups, want):
+            for r in grp:
+                assert r.output_ids == ref_out, (chunk, r.output_ids, ref_out)
+        assert groups[0][0].mrope_delta == 3 - 6 and groups[2][0].mrope_delta == 0
+    with pytest.raises(ValueError):
+        eng.add_request([2, 499, 500, 500, 498], sp, mm=dict(pixel_values=pix_a, grid_thw=grids_a))     # 2 tokens for a 6-cell image
+    text_cfg = get_model_config("tiny-llama")
+    with pytest.raises(ValueError):
+        RolloutEngine(text_cfg, "cpu", max_num_seqs=2, max_model_len=64, kv_cache_tokens=256).add_request([1, 2], sp, mm=mm[0])
