@@ -57,8 +57,13 @@ class HFCheckpoint:
         return self.weight_map.keys()
 
     def get(self, name: str) -> torch.Tensor:
-        if name not in self.weight_map and name == "lm_head.weight" and "model.embed_tokens.weight" in self.weight_map:
-            name = "model.embed_tokens.weight"          # tied checkpoints omit the head
+        if name not in self.weight_map and name.startswith("model.") and "model.language_model." + name[6:] in self.weight_map:
+            name = "model.language_model." + name[6:]   # vision-language checkpoints nest the text stack
+        if name not in self.weight_map and name == "lm_head.weight":
+            for alias in ("model.embed_tokens.weight", "model.language_model.embed_tokens.weight"):
+                if alias in self.weight_map:
+                    name = alias                        # tied checkpoints omit the head
+                    break
         fname = self.weight_map[name]
         if fname in self._bin_cache:
             return self._bin_cache[fname][name]
@@ -118,10 +123,19 @@ def _embed_head(cfg: ModelConfig, ck: HFCheckpoint) -> tuple[dict, dict]:
     return embed, head
 
 
+def _vision_tensors(cfg: ModelConfig, ck: HFCheckpoint) -> dict[str, torch.Tensor]:
+    """The tower of a vision-language checkpoint in our naming (``vision.*``)."""
+    from .vision import convert_hf_vision_state_dict
+
+    return convert_hf_vision_state_dict(cfg, {k: ck.get(k) for k in ck.keys() if k.startswith(("model.visual.", "visual."))})
+
+
 def load_state_dict(cfg: ModelConfig, path: str | Path) -> dict[str, torch.Tensor]:
     ck = HFCheckpoint(path)
     embed, head = _embed_head(cfg, ck)
     out = {**embed, **head}
+    if cfg.vision is not None:
+        out.update(_vision_tensors(cfg, ck))
     for i in range(cfg.num_layers):
         for k, v in _convert_layer(cfg, ck, i).items():
             out[f"layers.{i}.{k}"] = v
@@ -137,6 +151,10 @@ def load_into_engine(engine, path: str | Path) -> int:
     n = 0
     engine.embed.load_full_state(embed)
     n += len(embed)
+    if getattr(engine, "vision", None) is not None:
+        vt = _vision_tensors(cfg, ck)
+        engine.vision.load_full_state(vt, prefix="vision.")
+        n += len(vt)
     for i, unit in enumerate(engine.layers):
         lw = _convert_layer(cfg, ck, i)
         unit.load_full_state(lw)
@@ -161,6 +179,19 @@ def hf_config_dict(cfg: ModelConfig) -> dict:
         return {"model_type": "gpt2", "architectures": ["GPT2LMHeadModel"], "vocab_size": cfg.vocab_size, "n_embd": cfg.hidden_size,
                 "n_inner": cfg.intermediate_size, "n_layer": cfg.num_layers, "n_head": cfg.num_heads, "n_positions": cfg.max_position_embeddings,
                 "layer_norm_epsilon": cfg.rms_norm_eps, "eos_token_id": cfg.eos_token_id, "bos_token_id": cfg.bos_token_id}
+    if cfg.vision is not None:
+        text = {"vocab_size": cfg.vocab_size, "hidden_size": cfg.hidden_size, "intermediate_size": cfg.intermediate_size,
+                "num_hidden_layers": cfg.num_layers, "num_attention_heads": cfg.num_heads, "num_key_value_heads": cfg.num_kv_heads,
+                "max_position_embeddings": cfg.max_position_embeddings, "rms_norm_eps": cfg.rms_norm_eps, "hidden_act": "silu",
+                "tie_word_embeddings": cfg.tie_word_embeddings, "eos_token_id": cfg.eos_token_id, "bos_token_id": cfg.bos_token_id,
+                "pad_token_id": cfg.pad_token_id,
+                "rope_parameters": {"rope_type": "default", "rope_theta": cfg.rope_theta, "mrope_section": list(cfg.mrope_section)}}
+        return {"model_type": "qwen2_vl", "architectures": ["Qwen2VLForConditionalGeneration"], "text_config": text,
+                "vision_config": {**cfg.vision, "hidden_size": cfg.hidden_size}, "image_token_id": cfg.image_token_id,
+                "video_token_id": cfg.video_token_id, "vision_start_token_id": cfg.vision_start_token_id,
+                "tie_word_embeddings": cfg.tie_word_embeddings, "torch_dtype": "bfloat16",
+                # flat copies for loaders that predate the nested layout
+                "rope_scaling": {"type": "mrope", "mrope_section": list(cfg.mrope_section)}, "rope_theta": cfg.rope_theta}
     mt = "qwen3" if cfg.qk_norm else ("qwen2" if cfg.qkv_bias else "llama")
     arch = {"qwen3": "Qwen3ForCausalLM", "qwen2": "Qwen2ForCausalLM", "llama": "LlamaForCausalLM"}[mt]
     return {"model_type": mt, "architectures": [arch], "vocab_size": cfg.vocab_size, "hidden_size": cfg.hidden_size,
@@ -184,7 +215,12 @@ def save_hf(state_or_engine, cfg: ModelConfig, out_dir: str | Path, max_shard_by
     if not rank0:
         return []
     out.mkdir(parents=True, exist_ok=True)
-    hf = {k: v.contiguous() for k, v in tf.export_hf_state_dict(cfg, sd).items()}
+    hf = {k: v.contiguous() for k, v in tf.export_hf_state_dict(cfg, {k: v for k, v in sd.items() if not k.startswith("vision.")}).items()}
+    if cfg.vision is not None:
+        from .vision import export_hf_vision_state_dict
+
+        hf = {("model.language_model." + k[6:] if k.startswith("model.") else k): v for k, v in hf.items()}
+        hf.update({k: v.contiguous() for k, v in export_hf_vision_state_dict(cfg, sd).items()})
     if cfg.tie_word_embeddings:
         hf.pop("lm_head.weight", None)
     shards, cur, size = [], {}, 0

@@ -73,9 +73,9 @@ def init_param_(name: str, t: torch.Tensor, cfg: ModelConfig, generator: torch.G
             bound = 1.0 / math.sqrt(t.shape[-1])
             t.uniform_(-bound, bound, generator=generator)
         return
-    if base in ("ln1", "ln2", "norm_w", "ln1_w", "ln2_w", "q_norm", "k_norm"):
+    if base in ("ln1", "ln2", "norm_w", "ln1_w", "ln2_w", "q_norm", "k_norm", "merger_ln_w"):
         t.fill_(1.0)
-    elif base.startswith("b") or base.endswith("_b"):
+    elif base.startswith("b") or base.endswith("_b") or base.startswith("merger_b"):
         t.zero_()
     else:
         std = 0.02
@@ -127,6 +127,10 @@ class PackedInput:
     # the embedding rows at the image placeholder tokens
     mrope_pos: torch.Tensor | None = None
     image_embeds: torch.Tensor | None = None
+    # raw tower inputs for engines that own the tower themselves (ZeRO engine: the ``vision`` unit): patches of every image of
+    # the micro-batch in sequence order [N, patch_dim] and their (t, h, w) grids
+    pixel_values: torch.Tensor | None = None
+    grid_thw: object = None
 
     def rope_inputs(self, cfg: ModelConfig, device):
         """(positions, cos, sin) for the rope op; M-RoPE builds per-token tables once per micro-batch and indexes them by row."""

@@ -61,6 +61,26 @@ def vision_stem_specs(cfg: ModelConfig) -> ParamSpec:
             ("merger_b1", (m,)), ("merger_w2", (cfg.hidden_size, m)), ("merger_b2", (cfg.hidden_size,))]
 
 
+def vision_unit_specs(cfg: ModelConfig) -> ParamSpec:
+    """The whole tower as ONE flat spec list (a single ZeRO unit named ``vision``): stem names + ``blocks.{i}.{name}``."""
+    specs = list(vision_stem_specs(cfg))
+    for i in range(_v(cfg)["depth"]):
+        specs += [(f"blocks.{i}.{n}", shp) for n, shp in vision_block_specs(cfg)]
+    return specs
+
+
+class _TowerView:
+    """``.stem`` / ``.blocks`` view over a flat name -> tensor dict (a gathered ZeRO unit, or a state dict with a prefix)."""
+
+    def __init__(self, cfg: ModelConfig, flat: dict[str, torch.Tensor], prefix: str = ""):
+        self.stem = {n: flat[prefix + n] for n, _ in vision_stem_specs(cfg)}
+        self.blocks = [{n: flat[f"{prefix}blocks.{i}.{n}"] for n, _ in vision_block_specs(cfg)} for i in range(_v(cfg)["depth"])]
+
+
+def tower_view(cfg: ModelConfig, flat: dict[str, torch.Tensor], prefix: str = "") -> _TowerView:
+    return _TowerView(cfg, flat, prefix)
+
+
 def vision_num_params(cfg: ModelConfig) -> int:
     n = sum(math.prod(s) for _, s in vision_stem_specs(cfg))
     return n + _v(cfg)["depth"] * sum(math.prod(s) for _, s in vision_block_specs(cfg))

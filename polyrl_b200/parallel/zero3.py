@@ -378,7 +378,7 @@ class Zero3Engine:
     def __init__(self, cfg: ModelConfig, device, group=None, comm: str = "nccl", param_dtype=None, trainable: bool = True,
                  seed: int = 0, lr: float = 1e-6, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.01,
                  max_grad_norm: float = 1.0, heap=None, comm_ctas: int = 32, init: bool = True, sp_group=None,
-                 replica_group=None, lora=None):
+                 replica_group=None, lora=None, freeze_vision_tower: bool = False):
         self.cfg = cfg
         self.sp_group = sp_group       # Ulysses sequence-parallel group (subset of `group`), or None
         # HSDP (reference: fsdp_size < world => 2-D mesh ["ddp","fsdp"], verl/workers/fsdp_workers.py:99-118):
@@ -437,6 +437,14 @@ class Zero3Engine:
                        for i in range(cfg.num_layers)]
         self.head = ShardedUnit("head", tf.head_param_specs(cfg), self, trainable=base_tr)
         self.base_units = [self.embed, *self.layers, self.head]
+        # vision-language models: the ViT tower is one more unit in front of the embedding (models/vision.py); optionally frozen
+        # (reference: actor_rollout_ref.model.freeze_vision_tower, verl/workers/fsdp_workers.py)
+        self.vision = None
+        if cfg.vision is not None and not cfg.value_head:
+            from ..models.vision import vision_unit_specs
+
+            self.vision = ShardedUnit("vision", vision_unit_specs(cfg), self, trainable=False if freeze_vision_tower else base_tr)
+            self.base_units.insert(0, self.vision)
         self.lora_layers = []
         if self.lora is not None:
             from ..models.lora import lora_param_specs
@@ -511,11 +519,20 @@ class Zero3Engine:
         cfg = self.cfg
         self.anchor = torch.zeros(1, device=self.device, requires_grad=True)
 
-        def embed_fn(ws, inp, ids, pos):
+        def embed_fn(ws, inp, ids, pos, *img):
             x = torch.nn.functional.embedding(ids, ws[0]["embed"])
             if cfg.family == "gpt2":
                 x = x + torch.nn.functional.embedding(pos, ws[0]["pos_embed"])
+            if img:                                  # tower rows replace the image placeholder embeddings
+                from ..models.vision import merge_image_embeds
+
+                x = merge_image_embeds(cfg, x, ids, img[0])
             return x
+
+        def vision_fn(ws, grid, pixel_values):
+            from ..models.vision import tower_view, vision_forward
+
+            return vision_forward(cfg, tower_view(cfg, ws[0]), pixel_values, grid)
 
         def layer_fn(ws, inp, x):
             if len(ws) > 1:         # base + adapter views
@@ -541,6 +558,7 @@ class Zero3Engine:
             return torch.nn.functional.linear(h, w_lm.to(h.dtype))
 
         self.embed_runner = UnitRunner(self, [self.embed], embed_fn)
+        self.vision_runner = UnitRunner(self, [self.vision], vision_fn) if self.vision is not None else None
         self.layer_runners = [UnitRunner(self, [u] + ([self.lora_layers[i]] if self.lora_layers else []), layer_fn)
                               for i, u in enumerate(self.layers)]
         self.head_lp_runner = UnitRunner(self, head_units, head_lp_fn)
@@ -552,6 +570,9 @@ class Zero3Engine:
             a.next_fwd = b.units[0]
             b.next_bwd = a.units[0]
         chain[-1].next_fwd = self.head
+        if self.vision_runner is not None:
+            self.vision_runner.next_fwd = self.embed
+            self.embed_runner.next_bwd = self.vision
         for r in (self.head_lp_runner, self.head_value_runner, self.head_logits_runner):
             r.next_bwd = chain[-1].units[0]
 
@@ -596,6 +617,8 @@ class Zero3Engine:
             from .ulysses import GatherSeq, ulysses_pad_and_slice, validate_sp
 
             validate_sp(self.cfg.num_heads, self.cfg.num_kv_heads, dist.get_world_size(sp))
+            if inp.pixel_values is not None or inp.mrope_pos is not None:
+                raise NotImplementedError("image inputs with Ulysses sequence parallelism")
             total = inp.input_ids.shape[0]
             ids, pos, _ = ulysses_pad_and_slice(inp.input_ids, inp.position_ids, sp, self.cfg.pad_token_id)
             local = tf.PackedInput(ids, pos, inp.cu_seqlens, inp.max_seqlen, sp_group=sp, total_tokens=total)
@@ -603,7 +626,14 @@ class Zero3Engine:
             for r in self.layer_runners:
                 x = r(local, x)
             return GatherSeq.apply(x, sp, True)[:total]      # full hidden on every SP rank; grads scaled by sp on the way back
-        x = self.embed_runner(inp, inp.input_ids, inp.position_ids)
+        if inp.pixel_values is not None:
+            if self.vision_runner is None:
+                raise ValueError(f"model {self.cfg.name!r} has no vision tower but the batch carries images")
+            grid = tuple(tuple(int(v) for v in g) for g in (inp.grid_thw.tolist() if torch.is_tensor(inp.grid_thw) else inp.grid_thw))
+            img = self.vision_runner(grid, inp.pixel_values.to(self.device, self.param_dtype))
+            x = self.embed_runner(inp, inp.input_ids, inp.position_ids, img)
+        else:
+            x = self.embed_runner(inp, inp.input_ids, inp.position_ids)
         for r in self.layer_runners:
             x = r(inp, x)
         return x
