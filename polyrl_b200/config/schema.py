@@ -305,6 +305,9 @@ class DataConfig(BaseConfig):
     filter_overlong_prompts: bool = False
     truncation: str = "error"
     return_raw_chat: bool = False
+    image_key: str = "images"             # vision-language datasets: column with the images of a row (verl data.image_key)
+    image_min_pixels: int | None = None   # resize budget of the image preprocessor (None: model default)
+    image_max_pixels: int | None = None
     dataloader_num_workers: int = 0
     synthetic: bool = False               # synthetic GSM8K-shaped prompts (no network on the target box)
     synthetic_num_samples: int = 4096

@@ -82,14 +82,79 @@ def left_pad(ids: list[int], max_len: int, pad_id: int, truncation: str = "error
     return input_ids, mask, pos, ids
 
 
+def load_image(obj):
+    """Dataset image cell -> PIL image: a PIL image, ``{"bytes": ...}`` / ``{"path": ...}`` (HF datasets / parquet encoding), a file
+    path, or an [H, W, C] uint8 array (reference: verl/utils/dataset/vision_utils.py:25-60 process_image)."""
+    import io
+
+    from PIL import Image
+
+    if isinstance(obj, Image.Image):
+        return obj
+    if isinstance(obj, dict):
+        if obj.get("bytes") is not None:
+            return Image.open(io.BytesIO(obj["bytes"]))
+        if obj.get("path"):
+            return Image.open(obj["path"])
+        if obj.get("image") is not None:
+            return load_image(obj["image"])
+        raise ValueError(f"image cell without bytes / path: {list(obj)}")
+    if isinstance(obj, (bytes, bytearray)):
+        return Image.open(io.BytesIO(obj))
+    if isinstance(obj, (str, Path)):
+        return Image.open(obj)
+    return Image.fromarray(np.asarray(obj, dtype=np.uint8))
+
+
 class RLHFDataset(Dataset):
+    """``model_cfg`` with a vision tower turns on the multi-modal path: rows may carry ``image_key`` (list of images) and mark their
+    place in the prompt with ``<image>``; items then hold ``multi_modal_inputs`` (patches + grids), prompt ids with one placeholder
+    token per merged patch and 3-axis ``position_ids`` [3, L] (reference: rl_dataset.py:181-230, 299-405)."""
+
+    IMAGE_MARK = "<image>"
+
     def __init__(self, data_files, tokenizer, prompt_key: str = "prompt", max_prompt_length: int = 512,
-                 filter_overlong_prompts: bool = False, truncation: str = "error", return_raw_chat: bool = False):
+                 filter_overlong_prompts: bool = False, truncation: str = "error", return_raw_chat: bool = False,
+                 model_cfg=None, image_key: str = "images", min_pixels: int | None = None, max_pixels: int | None = None):
         self.tok, self.key, self.max_len = tokenizer, prompt_key, max_prompt_length
         self.truncation, self.return_raw_chat = truncation, return_raw_chat
+        self.vl_cfg = model_cfg if (model_cfg is not None and getattr(model_cfg, "vision", None) is not None) else None
+        self.image_key, self.min_pixels, self.max_pixels = image_key, min_pixels, max_pixels
         self.rows = _read_rows(data_files)
         if filter_overlong_prompts:
-            self.rows = [r for r in self.rows if len(self._tokenize(r)) <= max_prompt_length]
+            self.rows = [r for r in self.rows if self._prompt_len(r) <= max_prompt_length]
+
+    def _prompt_len(self, row: dict) -> int:
+        if self.vl_cfg is not None and row.get(self.image_key):
+            return len(self._tokenize_mm(row)[0])
+        return len(self._tokenize(row))
+
+    def _chat_text(self, row: dict) -> str:
+        p = row[self.key]
+        if isinstance(p, (list, np.ndarray)) and len(p) and isinstance(p[0], dict):
+            return self.tok.apply_chat_template(list(p), add_generation_prompt=True, tokenize=False)
+        return str(p)
+
+    def _tokenize_mm(self, row: dict):
+        """-> (prompt ids with expanded image placeholders, pixel_values [N, patch_dim], grids)."""
+        from ..models import vision as V
+
+        cfg = self.vl_cfg
+        images = [load_image(im) for im in row[self.image_key]]
+        pix, grids = [], []
+        for im in images:
+            pv, g = V.preprocess_image(cfg, im, self.min_pixels, self.max_pixels)
+            pix.append(pv)
+            grids.append(g)
+        parts = self._chat_text(row).split(self.IMAGE_MARK)
+        if len(parts) - 1 != len(images):
+            raise ValueError(f"prompt has {len(parts) - 1} {self.IMAGE_MARK} marks for {len(images)} images")
+        counts = V.num_image_tokens(cfg, grids)
+        ids: list[int] = list(self.tok.encode(parts[0], add_special_tokens=False))
+        for seg, n in zip(parts[1:], counts):
+            ids += [cfg.vision_start_token_id] + [cfg.image_token_id] * n + [cfg.vision_end_token_id]
+            ids += list(self.tok.encode(seg, add_special_tokens=False))
+        return ids, torch.cat(pix, dim=0), grids
 
     def _tokenize(self, row: dict) -> list[int]:
         p = row[self.key]
@@ -104,12 +169,27 @@ class RLHFDataset(Dataset):
 
     def __getitem__(self, i: int) -> dict[str, Any]:
         row = dict(self.rows[i])
-        ids, mask, pos, raw = left_pad(self._tokenize(row), self.max_len, self.tok.pad_token_id, self.truncation)
+        mm = None
+        if self.vl_cfg is not None and row.get(self.image_key):
+            from ..models.vision import mrope_positions
+
+            toks, pixel_values, grids = self._tokenize_mm(row)
+            ids, mask, pos, raw = left_pad(toks, self.max_len, self.tok.pad_token_id, "error")     # image runs cannot be cut
+            pos3, _ = mrope_positions(self.vl_cfg, raw, grids)
+            pos = torch.zeros(3, self.max_len, dtype=torch.long)
+            pos[:, self.max_len - len(raw):] = pos3
+            mm = {"pixel_values": pixel_values, "image_grid_thw": torch.tensor(grids, dtype=torch.long)}
+        else:
+            ids, mask, pos, raw = left_pad(self._tokenize(row), self.max_len, self.tok.pad_token_id, self.truncation)
+            if self.vl_cfg is not None:
+                pos = pos.unsqueeze(0).expand(3, -1).contiguous()          # text rows of a VLM dataset: same value on every axis
         out = {"input_ids": ids, "attention_mask": mask, "position_ids": pos, "raw_prompt_ids": raw,
                "data_source": row.get("data_source", "unknown"), "reward_model": row.get("reward_model", {"ground_truth": ""}),
                "extra_info": row.get("extra_info", {}), "index": (row.get("extra_info") or {}).get("index", i)}
         if self.return_raw_chat:
             out["raw_prompt"] = row[self.key]
+        if self.vl_cfg is not None:
+            out["multi_modal_inputs"] = mm
         # multi-turn rollouts: per-sample tool / interaction arguments travel in ``extra_info`` (reference:
         # verl/utils/dataset/rl_dataset.py:425-445 tools_kwargs / interaction_kwargs, need_tools_kwargs)
         ei = row.get("extra_info") or {}

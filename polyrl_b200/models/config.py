@@ -41,6 +41,7 @@ class ModelConfig:
     image_token_id: int = -1
     video_token_id: int = -1
     vision_start_token_id: int = -1
+    vision_end_token_id: int = -1
 
     def __post_init__(self):
         self.extra_eos_token_ids = tuple(self.extra_eos_token_ids or ())        # json round trip gives a list
@@ -116,7 +117,8 @@ class ModelConfig:
                 vision={k: vc[k] for k in ("depth", "embed_dim", "num_heads", "patch_size", "spatial_merge_size",
                                            "temporal_patch_size", "in_channels", "mlp_ratio") if k in vc},
                 mrope_section=tuple(rope.get("mrope_section", ())), image_token_id=top.get("image_token_id", -1),
-                video_token_id=top.get("video_token_id", -1), vision_start_token_id=top.get("vision_start_token_id", -1))
+                video_token_id=top.get("video_token_id", -1), vision_start_token_id=top.get("vision_start_token_id", -1),
+                vision_end_token_id=top.get("vision_end_token_id", -1))
             hf["tie_word_embeddings"] = top.get("tie_word_embeddings", hf.get("tie_word_embeddings", False))
             mt = "qwen2"
         eos = hf.get("eos_token_id", 2)
@@ -168,13 +170,14 @@ PRESETS: dict[str, dict] = {
                         rms_norm_eps=1e-6, qkv_bias=True, eos_token_id=151645, bos_token_id=151643, pad_token_id=151643,
                         vision=dict(depth=32, embed_dim=1280, num_heads=16, patch_size=14, spatial_merge_size=2,
                                     temporal_patch_size=2, in_channels=3, mlp_ratio=4),
-                        mrope_section=(16, 24, 24), image_token_id=151655, video_token_id=151656, vision_start_token_id=151652),
+                        mrope_section=(16, 24, 24), image_token_id=151655, video_token_id=151656, vision_start_token_id=151652,
+                        vision_end_token_id=151653),
     "tiny-qwen2-vl": dict(family="llama", vocab_size=512, hidden_size=128, intermediate_size=256, num_layers=2, num_heads=4,
                           num_kv_heads=2, head_dim=32, max_position_embeddings=512, rope_theta=10000.0, rms_norm_eps=1e-6,
                           qkv_bias=True, eos_token_id=1, bos_token_id=2, pad_token_id=0,
                           vision=dict(depth=2, embed_dim=64, num_heads=4, patch_size=4, spatial_merge_size=2,
                                       temporal_patch_size=2, in_channels=3, mlp_ratio=2),
-                          mrope_section=(4, 6, 6), image_token_id=500, video_token_id=501, vision_start_token_id=499),
+                          mrope_section=(4, 6, 6), image_token_id=500, video_token_id=501, vision_start_token_id=499, vision_end_token_id=498),
     "tiny-llama-128": dict(family="llama", vocab_size=1024, hidden_size=512, intermediate_size=1024, num_layers=2,
                            num_heads=4, num_kv_heads=2, head_dim=128, max_position_embeddings=1024,
                            rope_theta=10000.0, eos_token_id=1, bos_token_id=2, pad_token_id=0),

@@ -189,6 +189,7 @@ def hf_config_dict(cfg: ModelConfig) -> dict:
         return {"model_type": "qwen2_vl", "architectures": ["Qwen2VLForConditionalGeneration"], "text_config": text,
                 "vision_config": {**cfg.vision, "hidden_size": cfg.hidden_size}, "image_token_id": cfg.image_token_id,
                 "video_token_id": cfg.video_token_id, "vision_start_token_id": cfg.vision_start_token_id,
+                "vision_end_token_id": cfg.vision_end_token_id,
                 "tie_word_embeddings": cfg.tie_word_embeddings, "torch_dtype": "bfloat16",
                 # flat copies for loaders that predate the nested layout
                 "rope_scaling": {"type": "mrope", "mrope_section": list(cfg.mrope_section)}, "rope_theta": cfg.rope_theta}

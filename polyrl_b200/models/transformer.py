@@ -367,8 +367,12 @@ def pack_padded(input_ids: torch.Tensor, attention_mask: torch.Tensor, position_
         position_ids = (mask.long().cumsum(-1) - 1).clamp_min(0)
     cu = torch.zeros(lens.numel() + 1, dtype=torch.int32, device=input_ids.device)
     cu[1:] = lens.cumsum(0)
+    mrope = None
+    if position_ids.dim() == 3:               # M-RoPE [B, 3, S] (vision-language batches): keep all three axes, packed [3, T]
+        mrope = position_ids.permute(1, 0, 2).reshape(3, -1)[:, idx].long().contiguous()
+        position_ids = position_ids[:, 0]
     inp = PackedInput(input_ids.reshape(-1)[idx], position_ids.reshape(-1)[idx].long(), cu,
-                      int(lens.max().item()) if lens.numel() else 0)
+                      int(lens.max().item()) if lens.numel() else 0, mrope_pos=mrope)
     return inp, idx
 
 

@@ -380,3 +380,39 @@ def export_hf_vision_state_dict(cfg: ModelConfig, sd: dict[str, torch.Tensor], p
         for ours, theirs in _BLOCK_MAP.items():
             out[f"{prefix}blocks.{i}.{theirs}"] = sd[f"vision.blocks.{i}.{ours}"]
     return out
+
+
+# --------------------------------------------------------------------------------------------
+# batch / wire helpers
+# --------------------------------------------------------------------------------------------
+def collate_multi_modal(mm_list) -> tuple[torch.Tensor | None, list | None]:
+    """Per-sample ``multi_modal_inputs`` dicts (``pixel_values`` + ``image_grid_thw``; None for text rows) of a micro-batch, in row
+    order -> (all patches concatenated, all grids) matching the order of the image placeholders in the packed token stream."""
+    pix, grids = [], []
+    for m in mm_list:
+        if m is None:
+            continue
+        pix.append(torch.as_tensor(m["pixel_values"]))
+        grids += _grid_list(m["image_grid_thw"] if "image_grid_thw" in m else m["grid_thw"])
+    if not pix:
+        return None, None
+    return torch.cat(pix, dim=0), grids
+
+
+def encode_mm_wire(mm: dict) -> dict:
+    """JSON-safe form of one sample's image inputs for the HTTP generate route (fp16 patches, base64)."""
+    import base64
+
+    pv = torch.as_tensor(mm["pixel_values"]).to(torch.float16).contiguous()
+    grid = mm["image_grid_thw"] if "image_grid_thw" in mm else mm["grid_thw"]
+    return {"pixel_values_b64": base64.b64encode(pv.numpy().tobytes()).decode("ascii"), "shape": list(pv.shape),
+            "grid_thw": [list(g) for g in _grid_list(grid)]}
+
+
+def decode_mm_wire(d: dict) -> dict:
+    import base64
+
+    import numpy as np
+
+    arr = np.frombuffer(base64.b64decode(d["pixel_values_b64"]), dtype=np.float16).reshape(d["shape"])
+    return {"pixel_values": torch.from_numpy(arr.copy()).float(), "grid_thw": [tuple(g) for g in d["grid_thw"]]}

@@ -440,18 +440,18 @@ class Zero3Engine:
         # vision-language models: the ViT tower is one more unit in front of the embedding (models/vision.py); optionally frozen
         # (reference: actor_rollout_ref.model.freeze_vision_tower, verl/workers/fsdp_workers.py)
         self.vision = None
-        if cfg.vision is not None and not cfg.value_head:
+        if cfg.vision is not None:
             from ..models.vision import vision_unit_specs
 
             self.vision = ShardedUnit("vision", vision_unit_specs(cfg), self, trainable=False if freeze_vision_tower else base_tr)
-            self.base_units.insert(0, self.vision)
         self.lora_layers = []
         if self.lora is not None:
             from ..models.lora import lora_param_specs
 
             lspecs = lora_param_specs(cfg, self.lora)
             self.lora_layers = [ShardedUnit(f"layers.{i}.lora", lspecs, self) for i in range(cfg.num_layers)]
-        self.units = [*self.base_units, *self.lora_layers]
+        # base_units stays the text stack [embed, blocks..., head] (weight-sync consumers index it that way)
+        self.units = [*self.base_units, *([self.vision] if self.vision is not None else []), *self.lora_layers]
         self.opt_units = [u for u in self.units if u.trainable]
         if init:
             for u in self.units:

@@ -63,17 +63,27 @@ def main(argv=None) -> int:
         cmd_group = dist.group.WORLD          # scheduler commands ride on the TP group itself (no extra rendezvous)
         tp_ctx = TPContext(cfg, heap, tp_rank, a.tp_size, max_batch=a.max_num_seqs, group=dist.group.WORLD)
     w = TransformerWeights(cfg, device=a.device, dtype=dtype, init=True)          # same seed on every TP rank
+    vw = None
+    if cfg.vision is not None:                  # vision-language model: the engine runs the ViT tower at prefill
+        from ..models.vision import VisionWeights
+
+        vw = VisionWeights(cfg, device=a.device, dtype=dtype, init=True)
     from pathlib import Path as _P
 
     mp = _P(a.model_path)
     if a.load_format != "dummy" and mp.is_dir() and (list(mp.glob("*.safetensors")) or list(mp.glob("pytorch_model*.bin"))):
         from ..models.hf_io import load_state_dict as _load_hf
 
-        w.load_state_dict({k: v.to(a.device, dtype) for k, v in _load_hf(cfg, mp).items()})
+        sd = {k: v.to(a.device, dtype) for k, v in _load_hf(cfg, mp).items()}
+        w.load_state_dict(sd)
+        if vw is not None:
+            vw.load_state_dict(sd)
         print(f"[engine] loaded weights from {mp}", flush=True)
     eng = RolloutEngine(cfg, a.device, max_num_seqs=a.max_num_seqs, max_model_len=a.max_model_len,
                         gpu_memory_utilization=a.mem_fraction_static, tp=tp_ctx, enable_prefix_cache=a.enable_prefix_cache)
     eng.set_weights(w.embed, w.layers, w.head)
+    if vw is not None:
+        eng.set_vision_weights(vw)
     if tp_rank > 0:
         from .server import run_tp_follower
 
@@ -83,7 +93,8 @@ def main(argv=None) -> int:
     if a.enable_weight_transfer_agent:
         from ..weight_transfer.tcp_engine import TCPWeightReceiver
 
-        receiver = TCPWeightReceiver(w, bind_host=a.weight_receiver_zmq_bind_host, port=a.transfer_agent_handshake_port,
+        named = list(w.named_tensors()) + (list(vw.named_tensors()) if vw is not None else [])     # trainer unit order
+        receiver = TCPWeightReceiver(named, bind_host=a.weight_receiver_zmq_bind_host, port=a.transfer_agent_handshake_port,
                                      num_streams=a.num_transfer_engines_per_group)
 
     def on_update(body):

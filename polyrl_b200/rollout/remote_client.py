@@ -80,8 +80,16 @@ def build_generate_payload(prompts: DataProto, n: int, sampling_params: dict) ->
         raw = [ids[i][mask[i]].tolist() for i in range(len(prompts))]
     sp = dict(sampling_params)
     sp.pop("n", None)
-    return [[i + 1, {"input_ids": [list(map(int, raw[i]))] * n, "sampling_params": sp, "return_logprob": True}]
-            for i in range(len(prompts))]
+    out = [[i + 1, {"input_ids": [list(map(int, raw[i]))] * n, "sampling_params": sp, "return_logprob": True}]
+           for i in range(len(prompts))]
+    mm = prompts.non_tensor_batch.get("multi_modal_inputs")
+    if mm is not None:                        # image prompts: the n samples of a request share one ``image_data`` entry
+        from ..models.vision import encode_mm_wire
+
+        for i, m in enumerate(mm):
+            if m is not None:
+                out[i][1]["image_data"] = encode_mm_wire(m)
+    return out
 
 
 def postprocess_samples(prompts: DataProto, results: list[tuple[int, list[dict]]], n: int, response_length: int,
@@ -119,7 +127,12 @@ def postprocess_samples(prompts: DataProto, results: list[tuple[int, list[dict]]
     sel.batch["responses"] = resp
     sel.batch["input_ids"] = torch.cat([p_ids, resp], dim=1)
     sel.batch["attention_mask"] = torch.cat([p_mask, response_mask], dim=1)
-    sel.batch["position_ids"] = torch.cat([p_pos, p_pos[:, -1:] + torch.arange(1, response_length + 1, device=dev)[None]], dim=1)
+    delta = torch.arange(1, response_length + 1, device=dev)
+    if p_pos.dim() == 3:                      # M-RoPE [b, 3, S]: responses continue every axis after the largest prompt position
+        nxt = p_pos.amax(dim=(1, 2)).view(-1, 1, 1) + delta.view(1, 1, -1)
+        sel.batch["position_ids"] = torch.cat([p_pos, nxt.expand(-1, 3, -1)], dim=2)
+    else:
+        sel.batch["position_ids"] = torch.cat([p_pos, p_pos[:, -1:] + delta[None]], dim=1)
     sel.batch["response_mask"] = response_mask
     sel.batch["rollout_log_probs"] = lps
     sel.non_tensor_batch["aborted"] = aborted

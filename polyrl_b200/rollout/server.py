@@ -169,10 +169,16 @@ class EngineServer:
         prompts = ids if batch else [ids]
         sp = SamplingParams.from_dict(body.get("sampling_params") or {})
         stream = bool(body.get("stream", False))
+        mm = None
+        if body.get("image_data") is not None:          # one entry for the whole request, or one per prompt
+            from ..models.vision import decode_mm_wire
+
+            img = body["image_data"]
+            mm = [decode_mm_wire(d) if d is not None else None for d in img] if isinstance(img, list) else [decode_mm_wire(img)] * len(prompts)
         q: queue.Queue = queue.Queue()
         key = f"g{id(q)}"
         with self._lock:
-            self._inbox.append(("generate", (key, prompts, sp, q), None))
+            self._inbox.append(("generate", (key, prompts, sp, q, mm), None))
         n = len(prompts)
         latest = [None] * n
         if stream:
@@ -233,13 +239,13 @@ class EngineServer:
             for kind, payload, done in cmds:
                 try:
                     if kind == "generate":
-                        key, prompts, sp, q = payload
+                        key, prompts, sp, q, mm = payload
                         rids = []
                         for _ in prompts:
                             self._rid += 1
                             rids.append(f"s{self._rid}")
-                        wire.append(("generate", {"prompts": prompts, "sp": sp.__dict__, "rids": rids}))
-                        tracked = [_Tracked(r, i) for i, r in enumerate(_add_group(eng, prompts, sp, rids))]
+                        wire.append(("generate", {"prompts": prompts, "sp": sp.__dict__, "rids": rids, "mm": mm}))
+                        tracked = [_Tracked(r, i) for i, r in enumerate(_add_group(eng, prompts, sp, rids, mm))]
                         self._streams[key] = (q, tracked)
                     elif kind == "abort_key":
                         ent = self._streams.pop(payload, None)
@@ -304,16 +310,19 @@ class EngineServer:
 
 
 # ---------------------------------------------------------------------------------------------- TP lock-step helpers
-def _add_group(eng: RolloutEngine, prompts, sp: SamplingParams, rids) -> list[Request]:
-    tag = object() if len(prompts) > 1 and all(p == prompts[0] for p in prompts) else None
-    return [eng.add_request(list(map(int, p)), sp, rid=rid, group=tag) for p, rid in zip(prompts, rids)]
+def _add_group(eng: RolloutEngine, prompts, sp: SamplingParams, rids, mm=None) -> list[Request]:
+    """Requests of one HTTP call; identical prompts (with the same image inputs) share their prompt KV as an n-sample group."""
+    same_mm = mm is None or all(m is mm[0] for m in mm)
+    tag = object() if len(prompts) > 1 and same_mm and all(p == prompts[0] for p in prompts) else None
+    return [eng.add_request(list(map(int, p)), sp, rid=rid, group=tag, mm=mm[i] if mm is not None else None)
+            for i, (p, rid) in enumerate(zip(prompts, rids))]
 
 
 def _apply_wire(eng: RolloutEngine, kind: str, payload, weight_update_fn) -> bool:
     """Apply one broadcast command on an engine replica.  Returns False on shutdown."""
     if kind == "generate":
         _add_group(eng, payload["prompts"], SamplingParams(**{**payload["sp"], "stop_token_ids": tuple(payload["sp"].get("stop_token_ids", ()))}),
-                   payload["rids"])
+                   payload["rids"], payload.get("mm"))
     elif kind == "abort_rids":
         for rid in payload:
             eng.abort(rid)

@@ -52,8 +52,10 @@ def build_datasets(cfg: PPOConfig, model_cfg, tokenizer=None):
     else:
         tok = tokenizer or load_tokenizer(cfg.actor_rollout_ref.model.tokenizer_path or cfg.actor_rollout_ref.model.path)
         raw = d.return_raw_chat or cfg.actor_rollout_ref.rollout.multi_turn.enable       # agent loops re-template the chat
-        train = RLHFDataset(d.train_files, tok, d.prompt_key, d.max_prompt_length, d.filter_overlong_prompts, d.truncation, raw)
-        val = RLHFDataset(d.val_files, tok, d.prompt_key, d.max_prompt_length, d.filter_overlong_prompts, d.truncation, raw) if d.val_files else None
+        kw = dict(model_cfg=model_cfg, image_key=d.image_key, min_pixels=d.image_min_pixels, max_pixels=d.image_max_pixels)
+        train = RLHFDataset(d.train_files, tok, d.prompt_key, d.max_prompt_length, d.filter_overlong_prompts, d.truncation, raw, **kw)
+        val = (RLHFDataset(d.val_files, tok, d.prompt_key, d.max_prompt_length, d.filter_overlong_prompts, d.truncation, raw, **kw)
+               if d.val_files else None)
     sampler = ResumableRandomSampler(len(train), d.seed, d.shuffle)
     return train, val, sampler, tok
 
@@ -90,6 +92,8 @@ def run_rollout_rank(cfg: PPOConfig, rank: int, trainer_ranks, rollout_ranks, de
                         max_prefill_tokens=r.max_num_batched_tokens, seed=cfg.data.seed + 17 * replica, tp=tp_ctx)
     e, l, h = sync.engine_views()
     eng.set_weights(e, l, h)
+    if model_cfg.vision is not None:
+        eng.set_vision_weights(sync.vision_view())       # the tower lives in the same pushed replica
 
     def on_update(body: dict):
         sync.receive(int(body.get("weight_version", 0)))

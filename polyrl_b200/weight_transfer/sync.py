@@ -35,6 +35,12 @@ class WeightLayout:
         self.units: list[tuple[str, tf.ParamSpec]] = [("embed", tf.embed_param_specs(cfg))]
         self.units += [(f"layers.{i}", tf.layer_param_specs(cfg)) for i in range(cfg.num_layers)]
         self.units.append(("head", tf.head_param_specs(cfg)))
+        self.n_text = len(self.units)                 # vision-language models: the tower follows the text stack
+        if cfg.vision is not None:
+            from ..models.vision import vision_unit_specs
+
+            self.units.append(("vision", vision_unit_specs(cfg)))
+        self.cfg = cfg
         self.entries = []          # (unit_idx, name, shape, numel, chunk, global_offset)
         off = 0
         for ui, (_, specs) in enumerate(self.units):
@@ -47,16 +53,25 @@ class WeightLayout:
 
     def views(self, flat: torch.Tensor):
         embed, head = {}, {}
-        layers = [dict() for _ in range(len(self.units) - 2)]
+        layers = [dict() for _ in range(self.n_text - 2)]
         for ui, n, shp, numel, chunk, off in self.entries:
             v = flat[off:off + numel].view(shp)
             if ui == 0:
                 embed[n] = v
-            elif ui == len(self.units) - 1:
+            elif ui == self.n_text - 1:
                 head[n] = v
-            else:
+            elif ui < self.n_text:
                 layers[ui - 1][n] = v
         return embed, layers, head
+
+    def vision_view(self, flat: torch.Tensor):
+        """Tower weights (``.stem`` / ``.blocks``) over the same flat buffer, or None for text models."""
+        if self.cfg.vision is None:
+            return None
+        from ..models.vision import tower_view
+
+        return tower_view(self.cfg, {n: flat[off:off + numel].view(shp) for ui, n, shp, numel, chunk, off in self.entries
+                                     if ui >= self.n_text})
 
 
 class WeightSync:
@@ -91,6 +106,10 @@ class WeightSync:
         assert self.is_rollout
         return self.layout.views(self.flat)
 
+    def vision_view(self):
+        assert self.is_rollout
+        return self.layout.vision_view(self.flat)
+
     def receive(self, version: int | None = None) -> None:
         """Called on rollout ranks (from the engine thread) while the trainers push."""
         if self.backend == "p2p":
@@ -104,7 +123,7 @@ class WeightSync:
     # ---------------------------------------------------------------- trainer side
     def push(self, engine, version: int | None = None) -> None:
         """Called on every trainer rank with its ZeRO-3 engine."""
-        units = engine.base_units
+        units = engine.base_units + ([engine.vision] if getattr(engine, "vision", None) is not None else [])
         if getattr(engine, "lora", None) is not None:
             raise NotImplementedError("LoRA adapters are merged on the colocated path only; export + reload for disaggregated rollouts")
         t_idx = self.trainer_ranks.index(self.rank)

@@ -84,6 +84,19 @@ class PackedBatch:
         return out
 
 
+def attach_multi_modal(inp: "tf.PackedInput", mb: DataProto) -> None:
+    """Vision-language micro-batches: hand the rows' image patches (row order = placeholder order in the packed stream) to the
+    engine, which runs its tower unit (reference: dp_actor.py multi_modal_inputs concat, verl/workers/actor/dp_actor.py:100-125)."""
+    mm = mb.non_tensor_batch.get("multi_modal_inputs") if mb.non_tensor_batch else None
+    if mm is None:
+        return
+    from ..models.vision import collate_multi_modal
+
+    pix, grids = collate_multi_modal(list(mm))
+    if pix is not None:
+        inp.pixel_values, inp.grid_thw = pix.to(inp.input_ids.device), grids
+
+
 class DataParallelPPOActor:
     def __init__(self, engine: Zero3Engine, config: ActorConfig, dp_group=None):
         self.engine = engine
@@ -114,6 +127,7 @@ class DataParallelPPOActor:
         ids = mb.batch["input_ids"]
         r = mb.batch["responses"].shape[-1]
         pb = PackedBatch(ids, mb.batch["attention_mask"], mb.batch.get("position_ids"), r)
+        attach_multi_modal(pb.inp, mb)
         hidden = self.engine.forward_hidden(pb.inp)
         h_sel = hidden.index_select(0, pb.sel)
         lp, ent = self.engine.head_lp_runner(float(temperature), h_sel, pb.labels)
@@ -197,6 +211,7 @@ class DataParallelPPOCritic:
         ids = mb.batch["input_ids"]
         r = mb.batch["responses"].shape[-1]
         pb = PackedBatch(ids, mb.batch["attention_mask"], mb.batch.get("position_ids"), r)
+        attach_multi_modal(pb.inp, mb)
         hidden = self.engine.forward_hidden(pb.inp)
         v = self.engine.head_value_runner(None, hidden.index_select(0, pb.sel))
         return pb.scatter(v)                 # value of the state BEFORE each response token

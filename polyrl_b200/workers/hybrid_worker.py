@@ -227,6 +227,8 @@ class ActorRolloutRefWorker:
             return False
         self.weight_version += 1
         base = eng.base_units
+        if eng.vision is not None:
+            self._publish_vision_tower(eng)
         if eng.lora is not None:
             # adapters are merged into an engine-owned replica (reference: layered summon + merge, fsdp_utils.py:569-694)
             from ..models.lora import merge_layer_
@@ -285,6 +287,26 @@ class ActorRolloutRefWorker:
         self.rollout.set_weights(views[0], views[1:-1], views[-1], version=self.weight_version)
         return True
 
+    def _publish_vision_tower(self, eng) -> None:
+        """Vision-language actors: the engine runs the tower at prefill.  world == 1 aliases the trainer's shard, otherwise the tower
+        (small next to the text stack) is gathered into an engine-owned replica."""
+        from ..models.vision import tower_view
+
+        u = eng.vision
+        if eng.world == 1:
+            flat = u.shard
+        elif eng.resident:
+            eng.ensure_resident()
+            flat = u._resident
+        else:
+            if getattr(self, "_vision_full", None) is None:
+                self._vision_full = torch.empty(u.full_numel, device=self.device, dtype=eng.param_dtype)
+            if eng.heap is not None:
+                eng.heap.barrier()
+            u._gather_into(self._vision_full)
+            flat = self._vision_full
+        self.rollout.set_vision_weights(tower_view(self.model_cfg, u.views(flat)))
+
     # ------------------------------------------------------------------ local instance (disaggregated hybrid mode)
     def start_local_server(self, manager_endpoint: str, port: int) -> None:
         """Serve this rank's colocated engine to the rollout manager as a LOCAL instance (time-boxed by the manager)."""
@@ -334,6 +356,12 @@ class ActorRolloutRefWorker:
             out = self._generate_multi_turn(prompts, raw, sp, n, resp_len)
         else:
             mine = [list(map(int, p)) for p in raw]
+            mm = None
+            if "multi_modal_inputs" in prompts.non_tensor_batch:
+                if getattr(self, "rollout_tp", 1) > 1:
+                    raise NotImplementedError("image prompts with a tensor-parallel colocated rollout")
+                mm = [None if m is None else {"pixel_values": m["pixel_values"], "grid_thw": torch.as_tensor(m["image_grid_thw"]).tolist()}
+                      for m in prompts.non_tensor_batch["multi_modal_inputs"]]
             if getattr(self, "rollout_tp", 1) > 1:
                 # every TP rank must feed the SAME request stream to its engine shard
                 parts: list = [None] * self.rollout_tp
@@ -341,7 +369,7 @@ class ActorRolloutRefWorker:
                 off = sum(len(p) for p in parts[: self.tp_rank])
                 groups = self.rollout.generate([p for part in parts for p in part], sp)[off:off + len(mine)]
             else:
-                groups = self.rollout.generate(mine, sp)
+                groups = self.rollout.generate(mine, sp, mm=mm)
             out = self._postprocess(prompts, groups, n, resp_len)
         gen_s = time.time() - t0
         out.meta_info["timing"] = {"generate_sequences": gen_s}
@@ -414,7 +442,11 @@ class ActorRolloutRefWorker:
         if p_pos is None:
             p_pos = (p_mask.cumsum(-1) - 1).clamp_min(0)
         delta = torch.arange(1, resp_len + 1, device=dev)[None]
-        position_ids = torch.cat([p_pos, p_pos[:, -1:] + delta], dim=1)
+        if p_pos.dim() == 3:                  # M-RoPE [b, 3, S]: generated tokens continue all three axes after the largest position
+            nxt = p_pos.amax(dim=(1, 2)).view(-1, 1, 1) + delta.view(1, 1, -1)
+            position_ids = torch.cat([p_pos, nxt.expand(-1, 3, -1)], dim=2)
+        else:
+            position_ids = torch.cat([p_pos, p_pos[:, -1:] + delta], dim=1)
         rep.batch["prompts"] = p_ids
         rep.batch["responses"] = resp
         rep.batch["input_ids"] = input_ids

@@ -277,3 +277,144 @@ def test_vlm_hf_checkpoint_round_trip(tmp_path):
     assert set(a) == set(b) and all(torch.equal(a[k], b[k]) for k in a)
     sd = hf_io.load_state_dict(cfg2, tmp_path / "ck")
     assert all(torch.equal(sd[k], a[k]) for k in a)
+
+
+def _png_bytes(rng, h, w):
+    import io
+
+    from PIL import Image
+
+    buf = io.BytesIO()
+    Image.fromarray(rng.integers(0, 255, size=(h, w, 3), dtype=np.uint8)).save(buf, format="PNG")
+    return buf.getvalue()
+
+
+def _vlm_rows(tmp_path, n=4):
+    import json
+
+    rng = np.random.default_rng(0)
+    rows = []
+    for i in range(n):
+        if i % 2 == 0:
+            p = tmp_path / f"img{i}.png"
+            p.write_bytes(_png_bytes(rng, 16 + 8 * (i % 3), 24))
+            rows.append({"prompt": [{"role": "user", "content": f"<image>what is {i}?"}], "images": [{"path": str(p)}],
+                         "data_source": "geo3k", "reward_model": {"ground_truth": str(i)}})
+        else:
+            rows.append({"prompt": [{"role": "user", "content": f"say {i}"}], "data_source": "geo3k",
+                         "reward_model": {"ground_truth": str(i)}})
+    f = tmp_path / "vl.jsonl"
+    f.write_text("\n".join(json.dumps(r) for r in rows))
+    return f
+
+
+def test_dataset_builds_multi_modal_items_and_actor_scores_them(tmp_path):
+    """RLHFDataset with a VLM config: placeholders expanded, 3-axis positions, patches attached; the worker generates with its
+    colocated engine and the actor's log-probs of the generated tokens agree with the engine's (same model, same images)."""
+    from polyrl_b200.data.rl_dataset import ByteTokenizer, RLHFDataset
+    from polyrl_b200.protocol import DataProto, collate_fn
+
+    cfg = get_model_config("tiny-qwen2-vl")
+    ds = RLHFDataset(_vlm_rows(tmp_path), ByteTokenizer(), max_prompt_length=64, model_cfg=cfg, min_pixels=64, max_pixels=8 * 8 * 16)
+    it0, it1 = ds[0], ds[1]
+    g = it0["multi_modal_inputs"]["image_grid_thw"]
+    n_img = int(g[0].prod()) // 4
+    assert it0["raw_prompt_ids"].count(cfg.image_token_id) == n_img and it0["multi_modal_inputs"]["pixel_values"].shape == (int(g[0].prod()), V.patch_dim(cfg))
+    assert it0["position_ids"].shape == (3, 64) and it1["position_ids"].shape == (3, 64) and it1["multi_modal_inputs"] is None
+    k = it0["raw_prompt_ids"].index(cfg.vision_start_token_id)
+    assert it0["raw_prompt_ids"][k + 1] == cfg.image_token_id and it0["raw_prompt_ids"][k + 1 + n_img] == cfg.vision_end_token_id
+    want, _ = V.mrope_positions(cfg, it0["raw_prompt_ids"], g)
+    assert torch.equal(it0["position_ids"][:, 64 - len(it0["raw_prompt_ids"]):], want)
+    with pytest.raises(ValueError):
+        RLHFDataset(_vlm_rows(tmp_path), ByteTokenizer(), max_prompt_length=8, model_cfg=cfg, min_pixels=64, max_pixels=8 * 8 * 16)[0]
+    batch = collate_fn([ds[i] for i in range(4)])
+    tens = {k: v for k, v in batch.items() if torch.is_tensor(v)}
+    dp = DataProto.from_dict(tens, {k: v for k, v in batch.items() if not torch.is_tensor(v)})
+    assert dp.batch["position_ids"].shape == (4, 3, 64)
+
+    from polyrl_b200.config.schema import load_config
+    from polyrl_b200.workers.hybrid_worker import ActorRolloutRefWorker
+
+    c = load_config(None, ["trainer.device=cpu", "actor_rollout_ref.model.path=tiny-qwen2-vl", "data.max_prompt_length=64",
+                           "data.max_response_length=10", "actor_rollout_ref.rollout.max_num_seqs=16", "actor_rollout_ref.rollout.n=2",
+                           "actor_rollout_ref.rollout.cuda_graph=False", "actor_rollout_ref.actor.ppo_mini_batch_size=8",
+                           "actor_rollout_ref.actor.ppo_micro_batch_size_per_gpu=3"])
+    wk = ActorRolloutRefWorker(c, role="actor_rollout", device="cpu")
+    wk.init_model()
+    assert wk.rollout.vision_w is not None
+    dp.meta_info.update(temperature=1.0, ignore_eos=True)
+    out = wk.generate_sequences(dp)
+    assert out.batch["position_ids"].shape == (8, 3, 74) and out.batch["responses"].shape == (8, 10)
+    assert len(out.non_tensor_batch["multi_modal_inputs"]) == 8
+    # response positions continue after the largest prompt position on all three axes
+    p3 = out.batch["position_ids"]
+    assert torch.equal(p3[:, 0, 64:], p3[:, 1, 64:]) and torch.equal(p3[:, 0, 64], p3[:, :, :64].amax(dim=(1, 2)) + 1)
+    out.meta_info.update(temperature=1.0, micro_batch_size=3)
+    lp = wk.compute_log_prob(out).batch["old_log_probs"]
+    assert (lp - out.batch["rollout_log_probs"]).abs().max() < 2e-4          # engine (prefill+decode) == trainer forward
+    # a policy update on the image batch moves tower and text weights, and the refreshed engine sees the new tower
+    before = {n: t.clone() for n, t in wk.actor_engine.named_full_tensors()}
+    out = out.union(wk.compute_log_prob(out))
+    out.batch["advantages"] = torch.randn(8, 10, generator=torch.Generator().manual_seed(0)) * out.batch["response_mask"]
+    out.meta_info.update({"is_opt_step": True})
+    m = wk.update_actor_stream(out)
+    assert "actor/pg_loss" in m.meta_info["metrics"]
+    after = dict(wk.actor_engine.named_full_tensors())
+    assert not torch.equal(after["vision.patch_embed"], before["vision.patch_embed"])
+    assert not torch.equal(after["layers.0.wqkv"], before["layers.0.wqkv"])
+    wk.update_weight_remote()
+    assert wk.rollout.vision_w.stem["patch_embed"].data_ptr() == wk.actor_engine.vision.views(wk.actor_engine.vision.shard)["patch_embed"].data_ptr()
+
+
+def test_image_prompts_over_http_through_the_manager(tmp_path):
+    """The remote path: client payload with ``image_data`` -> C++ manager (forwards the body untouched) -> engine server -> tokens
+    identical to a direct engine call on the same (fp16-rounded) patches; the client rebuilds 3-axis position ids."""
+    import json
+
+    from polyrl_b200.data.rl_dataset import ByteTokenizer, RLHFDataset
+    from polyrl_b200.manager.build import build_manager
+    from polyrl_b200.protocol import DataProto, collate_fn
+    from polyrl_b200.rollout.engine import RolloutEngine, SamplingParams
+    from polyrl_b200.rollout.remote_client import build_generate_payload, postprocess_samples
+    from polyrl_b200.rollout.server import EngineServer
+    from tests.test_manager import Manager, _http
+
+    cfg = get_model_config("tiny-qwen2-vl")
+    w, vw = tf.TransformerWeights(cfg, seed=3), V.VisionWeights(cfg, seed=4)
+
+    def engine():
+        e = RolloutEngine(cfg, "cpu", max_num_seqs=16, max_model_len=128, kv_cache_tokens=16 * 128)
+        e.set_weights(w.embed, w.layers, w.head)
+        e.set_vision_weights(vw)
+        return e
+
+    ds = RLHFDataset(_vlm_rows(tmp_path), ByteTokenizer(), max_prompt_length=64, model_cfg=cfg, min_pixels=64, max_pixels=8 * 8 * 16)
+    batch = collate_fn([ds[i] for i in range(4)])
+    dp = DataProto.from_dict({k: v for k, v in batch.items() if torch.is_tensor(v)}, {k: v for k, v in batch.items() if not torch.is_tensor(v)})
+    reqs = build_generate_payload(dp, 2, {"max_new_tokens": 6, "temperature": 0.0, "ignore_eos": True})
+    assert "image_data" in reqs[0][1] and "image_data" not in reqs[1][1]
+    wire = V.decode_mm_wire(json.loads(json.dumps(reqs[0][1]["image_data"])))
+    assert wire["grid_thw"] == [tuple(dp.non_tensor_batch["multi_modal_inputs"][0]["image_grid_thw"][0].tolist())]
+    assert (wire["pixel_values"] - dp.non_tensor_batch["multi_modal_inputs"][0]["pixel_values"]).abs().max() < 2e-3
+    m = Manager(build_manager())
+    srv = EngineServer(engine(), stream_interval=4).start()
+    try:
+        srv.register_with_manager(f"127.0.0.1:{m.port}", local=True)
+        code, body = _http("POST", m.url + "/batch_generate_requests", reqs, timeout=120)
+        lines = [json.loads(l) for l in body.strip().split("\n")]
+        got = {l["id"]: l for l in lines[1:]}
+        ref = engine()
+        sp = SamplingParams(max_new_tokens=6, temperature=0.0, ignore_eos=True)
+        results = []
+        for i in range(4):
+            assert got[i + 1]["success"], got[i + 1]
+            mm_i = V.decode_mm_wire(reqs[i][1]["image_data"]) if "image_data" in reqs[i][1] else None
+            want = ref.generate([dp.non_tensor_batch["raw_prompt_ids"][i]], sp, mm=[mm_i])[0][0].output_ids
+            for sub in got[i + 1]["data"]:
+                assert [t[1] for t in sub["meta_info"]["output_token_logprobs"]] == want
+            results.append((i, got[i + 1]["data"]))
+        out = postprocess_samples(dp, results, 2, 6, cfg.pad_token_id, cfg.eos_token_id)
+        assert out.batch["position_ids"].shape == (8, 3, 70) and len(out.non_tensor_batch["multi_modal_inputs"]) == 8
+    finally:
+        srv.stop()
+        m.close()
