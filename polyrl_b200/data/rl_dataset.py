@@ -24,7 +24,7 @@ class ByteTokenizer:
         return ([self.bos_token_id] + ids) if add_special_tokens else ids
 
     def decode(self, ids, skip_special_tokens: bool = True) -> str:
-        bs = bytes(int(i) - 3 for i in ids if int(i) >= 3)
+        bs = bytes(int(i) - 3 for i in ids if 3 <= int(i) < 259)      # ids above the byte range (larger model vocab) are dropped
         return bs.decode("utf-8", errors="replace")
 
     def apply_chat_template(self, messages: list[dict], add_generation_prompt: bool = True, tokenize: bool = False):

@@ -192,6 +192,22 @@ class RemoteRolloutClient:
         payload = build_generate_payload(prompts, self.n, sp)
         return prompts, time.time(), StreamingBatchIterator(self.host, self.port, "/batch_generate_requests", payload)
 
+    def generate_once(self, prompts: DataProto, n: int = 1, sampling_params: dict | None = None) -> DataProto:
+        """Blocking one-shot generation (validation): every prompt, ``n`` samples each, in prompt order."""
+        sp = {**self.sampling_params, **(sampling_params or {}), "max_new_tokens": self.response_length}
+        payload = build_generate_payload(prompts, n, sp)
+        results: list[tuple[int, list[dict]]] = []
+        for group in StreamingBatchIterator(self.host, self.port, "/batch_generate_requests", payload):
+            for line in group:
+                if line.get("id") == 0:
+                    continue
+                if not line.get("success"):
+                    raise RuntimeError(f"generation failed for request {line.get('id')}: {line.get('error')}")
+                data = line["data"]
+                results.append((int(line["id"]) - 1, data if isinstance(data, list) else [data]))
+        results.sort(key=lambda t: t[0])
+        return postprocess_samples(prompts, results, n, self.response_length, self.pad, self.eos)
+
     def generate_sequences_remote(self, prompts: DataProto, sampling_params: dict | None = None) -> Iterator[DataProto]:
         return self.collect(self.submit(prompts, sampling_params))
 

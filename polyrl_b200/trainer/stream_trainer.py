@@ -274,14 +274,25 @@ class StreamPPOTrainer:
         cfg = self.config
         bs = cfg.data.val_batch_size or len(self.val_dataset)
         scores, sources, uids = [], [], []
+        # trainers without a colocated engine (disaggregated deployments) validate through the rollout manager like training
+        # does (reference: stream_ray_trainer.py _validate -> generate_sequences on the remote rollout); rank 0 owns the client
+        remote = getattr(self.worker, "rollout", None) is None
+        vk = cfg.actor_rollout_ref.rollout.val_kwargs
         for i in range(0, len(self.val_dataset), bs):
             rows = [self.val_dataset[j] for j in range(i, min(i + bs, len(self.val_dataset)))]
-            shard = rows[self.rank::self.world] if self.world > 1 else rows
+            if remote:
+                shard = rows if self.client is not None and self.rank == 0 else []
+            else:
+                shard = rows[self.rank::self.world] if self.world > 1 else rows
             if not shard:
                 continue
             batch = DataProto.from_single_dict(collate_fn(shard)).to(self.device)
-            batch.meta_info = {"validate": True, "do_sample": cfg.actor_rollout_ref.rollout.val_kwargs.get("do_sample", False)}
-            out = self.worker.generate_sequences(batch)
+            batch.meta_info = {"validate": True, "do_sample": vk.get("do_sample", False)}
+            if remote:
+                temp = vk.get("temperature", 0.0) if vk.get("do_sample", False) else 0.0
+                out = self.client.generate_once(batch, 1, {"temperature": temp, "top_p": vk.get("top_p", 1.0), "top_k": vk.get("top_k", -1)})
+            else:
+                out = self.worker.generate_sequences(batch)
             fn = self.val_reward_fn
             if fn is None:
                 old, self.reward_fn = self.reward_fn, None

@@ -159,3 +159,37 @@ def test_colocated_ws2_bench_topology_gloo():
     lines = [l for l in r.stdout.splitlines() if l.startswith("COLO2 step")]
     assert r.returncode == 0 and len(lines) == 2, r.stdout[-2000:] + r.stderr[-2000:]
     assert "resident True" in lines[1] and "saved 2" in lines[1] and "n 16" in lines[1]
+
+
+def test_vlm_grpo_disaggregated_gloo_ws2(tmp_path):
+    """Vision-language GRPO through the whole streaming stack on CPU: image dataset (jsonl + PNG files, byte tokenizer) ->
+    manager -> remote engine that runs the ViT tower at prefill -> actor update (tower + text) with KL to the reference ->
+    broadcast weight sync including the tower -> validation."""
+    import json
+
+    import numpy as np
+    from PIL import Image
+
+    rng = np.random.default_rng(0)
+    rows = []
+    for i in range(16):
+        row = {"data_source": "hiyouga/geometry3k", "reward_model": {"ground_truth": str(i % 3)}, "extra_info": {"index": i}}
+        if i % 4 != 3:
+            p = tmp_path / f"im{i}.png"
+            Image.fromarray(rng.integers(0, 255, size=(12 + 4 * (i % 3), 20, 3), dtype=np.uint8)).save(p)
+            row["images"] = [{"path": str(p)}]
+            row["prompt"] = [{"role": "user", "content": f"<image>angle {i}?"}]
+        else:
+            row["prompt"] = [{"role": "user", "content": f"no picture {i}"}]
+        rows.append(row)
+    f = tmp_path / "geo.jsonl"
+    f.write_text("\n".join(json.dumps(r) for r in rows))
+    ov = [o for o in COMMON if not o.startswith(("data.synthetic", "data.max_prompt_length"))] + [
+        "actor_rollout_ref.model.path=tiny-qwen2-vl", "actor_rollout_ref.model.tokenizer_path=byte", f"data.train_files={f}",
+        f"data.val_files={f}", "data.max_prompt_length=48", "data.image_min_pixels=64", "data.image_max_pixels=1024",
+        "data.val_batch_size=8", "trainer.test_freq=2", "algorithm.adv_estimator=grpo", "actor_rollout_ref.actor.use_kl_loss=True",
+        "trainer.n_rollout_gpus=1", "trainer.n_gpus_per_node=2", "trainer.total_training_steps=2",
+        "actor_rollout_ref.rollout.rollout_manager.port=0", "actor_rollout_ref.rollout.rollout_manager.max_local_gen_s=30"]
+    r = _run(2, ov)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "step:2" in r.stdout and "actor/pg_loss" in r.stdout and "actor/kl_loss" in r.stdout and "val-core/" in r.stdout
