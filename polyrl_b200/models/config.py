@@ -106,16 +106,20 @@ class ModelConfig:
                        eos_token_id=hf.get("eos_token_id", 50256), bos_token_id=hf.get("bos_token_id", 50256),
                        pad_token_id=hf.get("pad_token_id") or hf.get("eos_token_id", 50256), name=hf.get("_name_or_path", "gpt2"))
         vis_kw: dict = {}
-        if mt in ("qwen2_vl",):
+        if mt in ("qwen2_vl", "qwen2_5_vl"):
             # transformers >= 4.5x nests the text stack under text_config; older checkpoints keep it flat
             vc = dict(hf.get("vision_config") or {})
             top = hf
             hf = {**{k: v for k, v in hf.items() if k not in ("text_config", "vision_config")}, **(hf.get("text_config") or {})}
             rope = hf.get("rope_parameters") or hf.get("rope_scaling") or {}
             hf.setdefault("rope_theta", rope.get("rope_theta", 1000000.0))
+            vision = {k: vc[k] for k in ("depth", "embed_dim", "num_heads", "patch_size", "spatial_merge_size",
+                                         "temporal_patch_size", "in_channels", "mlp_ratio") if k in vc}
+            if mt == "qwen2_5_vl":          # tower width is called hidden_size there; windowed attention + SwiGLU MLP
+                vision.update(arch="qwen2_5", embed_dim=vc["hidden_size"], intermediate_size=vc["intermediate_size"],
+                              window_size=vc.get("window_size", 112), fullatt_block_indexes=list(vc.get("fullatt_block_indexes", ())))
             vis_kw = dict(
-                vision={k: vc[k] for k in ("depth", "embed_dim", "num_heads", "patch_size", "spatial_merge_size",
-                                           "temporal_patch_size", "in_channels", "mlp_ratio") if k in vc},
+                vision=vision,
                 mrope_section=tuple(rope.get("mrope_section", ())), image_token_id=top.get("image_token_id", -1),
                 video_token_id=top.get("video_token_id", -1), vision_start_token_id=top.get("vision_start_token_id", -1),
                 vision_end_token_id=top.get("vision_end_token_id", -1))
@@ -172,12 +176,28 @@ PRESETS: dict[str, dict] = {
                                     temporal_patch_size=2, in_channels=3, mlp_ratio=4),
                         mrope_section=(16, 24, 24), image_token_id=151655, video_token_id=151656, vision_start_token_id=151652,
                         vision_end_token_id=151653),
+    "qwen2.5-vl-7b": dict(family="llama", vocab_size=152064, hidden_size=3584, intermediate_size=18944, num_layers=28,
+                          num_heads=28, num_kv_heads=4, max_position_embeddings=128000, rope_theta=1000000.0,
+                          rms_norm_eps=1e-6, qkv_bias=True, eos_token_id=151645, bos_token_id=151643, pad_token_id=151643,
+                          vision=dict(arch="qwen2_5", depth=32, embed_dim=1280, intermediate_size=3420, num_heads=16, patch_size=14,
+                                      spatial_merge_size=2, temporal_patch_size=2, in_channels=3, window_size=112,
+                                      fullatt_block_indexes=[7, 15, 23, 31]),
+                          mrope_section=(16, 24, 24), image_token_id=151655, video_token_id=151656, vision_start_token_id=151652,
+                          vision_end_token_id=151653),
     "tiny-qwen2-vl": dict(family="llama", vocab_size=512, hidden_size=128, intermediate_size=256, num_layers=2, num_heads=4,
                           num_kv_heads=2, head_dim=32, max_position_embeddings=512, rope_theta=10000.0, rms_norm_eps=1e-6,
                           qkv_bias=True, eos_token_id=1, bos_token_id=2, pad_token_id=0,
                           vision=dict(depth=2, embed_dim=64, num_heads=4, patch_size=4, spatial_merge_size=2,
                                       temporal_patch_size=2, in_channels=3, mlp_ratio=2),
                           mrope_section=(4, 6, 6), image_token_id=500, video_token_id=501, vision_start_token_id=499, vision_end_token_id=498),
+    # kernel-friendly VLM test config (head_dim 128 for the CUDA decode / rope kernels)
+    "tiny-qwen2-vl-128": dict(family="llama", vocab_size=1024, hidden_size=512, intermediate_size=1024, num_layers=2, num_heads=4,
+                              num_kv_heads=2, head_dim=128, max_position_embeddings=1024, rope_theta=10000.0, rms_norm_eps=1e-6,
+                              qkv_bias=True, eos_token_id=1, bos_token_id=2, pad_token_id=0,
+                              vision=dict(depth=2, embed_dim=128, num_heads=2, patch_size=14, spatial_merge_size=2,
+                                          temporal_patch_size=2, in_channels=3, mlp_ratio=2),
+                              mrope_section=(16, 24, 24), image_token_id=1000, video_token_id=1001, vision_start_token_id=999,
+                              vision_end_token_id=998),
     "tiny-llama-128": dict(family="llama", vocab_size=1024, hidden_size=512, intermediate_size=1024, num_layers=2,
                            num_heads=4, num_kv_heads=2, head_dim=128, max_position_embeddings=1024,
                            rope_theta=10000.0, eos_token_id=1, bos_token_id=2, pad_token_id=0),

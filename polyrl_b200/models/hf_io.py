@@ -186,8 +186,15 @@ def hf_config_dict(cfg: ModelConfig) -> dict:
                 "tie_word_embeddings": cfg.tie_word_embeddings, "eos_token_id": cfg.eos_token_id, "bos_token_id": cfg.bos_token_id,
                 "pad_token_id": cfg.pad_token_id,
                 "rope_parameters": {"rope_type": "default", "rope_theta": cfg.rope_theta, "mrope_section": list(cfg.mrope_section)}}
-        return {"model_type": "qwen2_vl", "architectures": ["Qwen2VLForConditionalGeneration"], "text_config": text,
-                "vision_config": {**cfg.vision, "hidden_size": cfg.hidden_size}, "image_token_id": cfg.image_token_id,
+        v25 = cfg.vision.get("arch") == "qwen2_5"
+        vis = {k: v for k, v in cfg.vision.items() if k != "arch"}
+        if v25:
+            vis.update(hidden_size=vis.pop("embed_dim"), out_hidden_size=cfg.hidden_size, hidden_act="silu")
+        else:
+            vis["hidden_size"] = cfg.hidden_size
+        return {"model_type": "qwen2_5_vl" if v25 else "qwen2_vl",
+                "architectures": ["Qwen2_5_VLForConditionalGeneration" if v25 else "Qwen2VLForConditionalGeneration"], "text_config": text,
+                "vision_config": vis, "image_token_id": cfg.image_token_id,
                 "video_token_id": cfg.video_token_id, "vision_start_token_id": cfg.vision_start_token_id,
                 "vision_end_token_id": cfg.vision_end_token_id,
                 "tie_word_embeddings": cfg.tie_word_embeddings, "torch_dtype": "bfloat16",

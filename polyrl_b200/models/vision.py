@@ -46,9 +46,20 @@ def patch_dim(cfg: ModelConfig) -> int:
     return v["in_channels"] * v["temporal_patch_size"] * v["patch_size"] ** 2
 
 
+def is_v25(cfg: ModelConfig) -> bool:
+    """Qwen2.5-VL tower: RMSNorm instead of LayerNorm, biased SwiGLU MLP, attention inside spatial windows except for the
+    ``fullatt_block_indexes`` blocks."""
+    return _v(cfg).get("arch", "qwen2") == "qwen2_5"
+
+
 def vision_block_specs(cfg: ModelConfig) -> ParamSpec:
     v = _v(cfg)
-    e, f = v["embed_dim"], int(v["embed_dim"] * v["mlp_ratio"])
+    e = v["embed_dim"]
+    if is_v25(cfg):
+        f = int(v["intermediate_size"])
+        return [("ln1_w", (e,)), ("wqkv", (3 * e, e)), ("bqkv", (3 * e,)), ("wo", (e, e)), ("bo", (e,)), ("ln2_w", (e,)),
+                ("wg", (f, e)), ("bg", (f,)), ("wu", (f, e)), ("bu", (f,)), ("wproj", (e, f)), ("bproj", (e,))]
+    f = int(e * v["mlp_ratio"])
     return [("ln1_w", (e,)), ("ln1_b", (e,)), ("wqkv", (3 * e, e)), ("bqkv", (3 * e,)), ("wo", (e, e)), ("bo", (e,)),
             ("ln2_w", (e,)), ("ln2_b", (e,)), ("wfc", (f, e)), ("bfc", (f,)), ("wproj", (e, f)), ("bproj", (e,))]
 
@@ -57,7 +68,8 @@ def vision_stem_specs(cfg: ModelConfig) -> ParamSpec:
     """Patch embedding + merger (everything outside the blocks)."""
     v = _v(cfg)
     e, m = v["embed_dim"], v["embed_dim"] * v["spatial_merge_size"] ** 2
-    return [("patch_embed", (e, patch_dim(cfg))), ("merger_ln_w", (e,)), ("merger_ln_b", (e,)), ("merger_w1", (m, m)),
+    ln = [("merger_ln_w", (e,))] if is_v25(cfg) else [("merger_ln_w", (e,)), ("merger_ln_b", (e,))]
+    return [("patch_embed", (e, patch_dim(cfg))), *ln, ("merger_w1", (m, m)),
             ("merger_b1", (m,)), ("merger_w2", (cfg.hidden_size, m)), ("merger_b2", (cfg.hidden_size,))]
 
 
@@ -171,17 +183,26 @@ def _rot_half(x: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor) -> torch.Te
     return torch.cat([x1 * c - x2 * s, x2 * c + x1 * s], dim=-1).to(x.dtype)
 
 
+def _rms(x: torch.Tensor, w: torch.Tensor, eps: float = 1e-6) -> torch.Tensor:
+    xf = x.float()
+    return (w.float() * (xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + eps))).to(x.dtype)
+
+
 def vision_block(cfg: ModelConfig, w: dict, x: torch.Tensor, cos, sin, cu: torch.Tensor, max_len: int) -> torch.Tensor:
     from ..ops.attention import attention_varlen
 
     v = _v(cfg)
     e, nh = v["embed_dim"], v["num_heads"]
     n = x.shape[0]
-    h = F.layer_norm(x, (e,), w["ln1_w"], w["ln1_b"], 1e-6)
+    v25 = "ln1_b" not in w
+    h = _rms(x, w["ln1_w"]) if v25 else F.layer_norm(x, (e,), w["ln1_w"], w["ln1_b"], 1e-6)
     qkv = F.linear(h, w["wqkv"], w["bqkv"]).view(n, 3, nh, e // nh)
     q, k = _rot_half(qkv[:, 0], cos, sin), _rot_half(qkv[:, 1], cos, sin)
     a = attention_varlen(q.contiguous(), k.contiguous(), qkv[:, 2].contiguous(), cu, max_len, causal=False)
     x = x + F.linear(a.reshape(n, e), w["wo"], w["bo"])
+    if v25:
+        h = _rms(x, w["ln2_w"])
+        return x + F.linear(F.silu(F.linear(h, w["wg"], w["bg"])) * F.linear(h, w["wu"], w["bu"]), w["wproj"], w["bproj"])
     h = F.layer_norm(x, (e,), w["ln2_w"], w["ln2_b"], 1e-6)
     h = F.linear(h, w["wfc"], w["bfc"])
     return x + F.linear(h * torch.sigmoid(1.702 * h), w["wproj"], w["bproj"])          # quick-GELU
@@ -194,8 +215,30 @@ def vision_stem_in(cfg: ModelConfig, stem: dict, pixel_values: torch.Tensor) -> 
 def vision_stem_out(cfg: ModelConfig, stem: dict, x: torch.Tensor) -> torch.Tensor:
     v = _v(cfg)
     e, m2 = v["embed_dim"], v["spatial_merge_size"] ** 2
-    h = F.layer_norm(x, (e,), stem["merger_ln_w"], stem["merger_ln_b"], 1e-6).view(-1, e * m2)
+    h = _rms(x, stem["merger_ln_w"]) if "merger_ln_b" not in stem else F.layer_norm(x, (e,), stem["merger_ln_w"], stem["merger_ln_b"], 1e-6)
+    h = h.view(-1, e * m2)
     return F.linear(F.gelu(F.linear(h, stem["merger_w1"], stem["merger_b1"])), stem["merger_w2"], stem["merger_b2"])
+
+
+def window_partition(cfg: ModelConfig, grid_thw) -> tuple[torch.Tensor, list[int]]:
+    """Qwen2.5-VL window attention layout.  Merged cells (groups of merge^2 patches) are re-ordered so that the cells of one
+    ``window_size`` pixel window are contiguous; returns (order [cells] — new position -> original cell, window lengths in PATCHES).
+    Windows tile every frame row-major; border windows are smaller."""
+    v = _v(cfg)
+    m = v["spatial_merge_size"]
+    ws = max(1, int(v["window_size"]) // m // v["patch_size"])
+    order, lens, base = [], [], 0
+    for t, h, w in _grid_list(grid_thw):
+        gh, gw = h // m, w // m
+        idx = torch.arange(t * gh * gw).view(t, gh, gw) + base
+        for ti in range(t):
+            for y in range(0, gh, ws):
+                for x in range(0, gw, ws):
+                    cell = idx[ti, y:y + ws, x:x + ws].reshape(-1)
+                    order.append(cell)
+                    lens.append(cell.numel() * m * m)
+        base += t * gh * gw
+    return torch.cat(order), lens
 
 
 def frame_cu_seqlens(grid_thw, device) -> tuple[torch.Tensor, int]:
@@ -211,9 +254,24 @@ def vision_forward(cfg: ModelConfig, vw: "VisionWeights", pixel_values: torch.Te
     x = vision_stem_in(cfg, vw.stem, pixel_values)
     cos, sin = vision_rotary(cfg, grid_thw, x.device)
     cu, mx = frame_cu_seqlens(grid_thw, x.device)
-    for b in vw.blocks:
-        x = vision_block(cfg, b, x, cos, sin, cu, mx)
-    return vision_stem_out(cfg, vw.stem, x)
+    if not is_v25(cfg):
+        for b in vw.blocks:
+            x = vision_block(cfg, b, x, cos, sin, cu, mx)
+        return vision_stem_out(cfg, vw.stem, x)
+    # Qwen2.5-VL: window-major patch order for the whole tower (full-attention blocks are order-invariant inside a frame because
+    # frames stay contiguous), original order restored on the merged rows
+    m2 = _v(cfg)["spatial_merge_size"] ** 2
+    order, wlens = window_partition(cfg, grid_thw)
+    order = order.to(x.device)
+    gather = (order[:, None] * m2 + torch.arange(m2, device=x.device)[None]).reshape(-1)
+    x, cos, sin = x[gather], cos[gather], sin[gather]
+    cu_w = torch.zeros(len(wlens) + 1, dtype=torch.int32, device=x.device)
+    cu_w[1:] = torch.tensor(wlens, dtype=torch.int32, device=x.device).cumsum(0)
+    full = set(_v(cfg).get("fullatt_block_indexes", ()))
+    for i, b in enumerate(vw.blocks):
+        x = vision_block(cfg, b, x, cos, sin, cu, mx) if i in full else vision_block(cfg, b, x, cos, sin, cu_w, max(wlens))
+    out = vision_stem_out(cfg, vw.stem, x)
+    return out[torch.argsort(order)]
 
 
 def num_image_tokens(cfg: ModelConfig, grid_thw) -> list[int]:
@@ -358,14 +416,26 @@ def _visual_prefix(hf_sd: dict) -> str:
     raise KeyError("no visual.* tensors in the checkpoint")
 
 
+_BLOCK_MAP_25 = {"ln1_w": "norm1.weight", "wqkv": "attn.qkv.weight", "bqkv": "attn.qkv.bias", "wo": "attn.proj.weight",
+                 "bo": "attn.proj.bias", "ln2_w": "norm2.weight", "wg": "mlp.gate_proj.weight", "bg": "mlp.gate_proj.bias",
+                 "wu": "mlp.up_proj.weight", "bu": "mlp.up_proj.bias", "wproj": "mlp.down_proj.weight", "bproj": "mlp.down_proj.bias"}
+
+
+def _maps(cfg: ModelConfig) -> tuple[dict, dict]:
+    if is_v25(cfg):
+        return {k: v for k, v in _STEM_MAP.items() if k != "merger_ln_b"}, _BLOCK_MAP_25
+    return _STEM_MAP, _BLOCK_MAP
+
+
 def convert_hf_vision_state_dict(cfg: ModelConfig, hf_sd: dict[str, torch.Tensor]) -> dict[str, torch.Tensor]:
     """HF ``visual.*`` names -> ours.  The Conv3d patch embedding [E, C, Tp, P, P] flattens to a linear weight."""
     p = _visual_prefix(hf_sd)
+    stem_map, block_map = _maps(cfg)
     out = {"vision.patch_embed": hf_sd[p + "patch_embed.proj.weight"].reshape(_v(cfg)["embed_dim"], -1)}
-    for ours, theirs in _STEM_MAP.items():
+    for ours, theirs in stem_map.items():
         out[f"vision.{ours}"] = hf_sd[p + theirs]
     for i in range(_v(cfg)["depth"]):
-        for ours, theirs in _BLOCK_MAP.items():
+        for ours, theirs in block_map.items():
             out[f"vision.blocks.{i}.{ours}"] = hf_sd[f"{p}blocks.{i}.{theirs}"]
     return out
 
@@ -374,10 +444,11 @@ def export_hf_vision_state_dict(cfg: ModelConfig, sd: dict[str, torch.Tensor], p
     v = _v(cfg)
     out = {prefix + "patch_embed.proj.weight": sd["vision.patch_embed"].reshape(
         v["embed_dim"], v["in_channels"], v["temporal_patch_size"], v["patch_size"], v["patch_size"])}
-    for ours, theirs in _STEM_MAP.items():
+    stem_map, block_map = _maps(cfg)
+    for ours, theirs in stem_map.items():
         out[prefix + theirs] = sd[f"vision.{ours}"]
     for i in range(v["depth"]):
-        for ours, theirs in _BLOCK_MAP.items():
+        for ours, theirs in block_map.items():
             out[f"{prefix}blocks.{i}.{theirs}"] = sd[f"vision.blocks.{i}.{ours}"]
     return out
 

@@ -1,4 +1,6 @@
 """GPU end-to-end: the flagship GRPO step on a tiny Llama (rollout with CUDA-graph decode, fused kernels)."""
+import os
+
 import pytest
 import torch
 
@@ -136,3 +138,60 @@ def test_kv_pool_in_vmm_range_release_resume_keeps_graphs():
     out2 = [g[0].output_ids for g in eng.generate(prompts, sp)]
     assert out1 == out2
     assert all(eng._graphs.get(k) is v for k, v in graphs.items())       # same graph objects: nothing was re-captured
+
+
+@pytest.mark.skipif(os.environ.get("POLYRL_TEST_VLM_GPU") != "1", reason="VLM GPU path not validated on hardware yet (opt in with POLYRL_TEST_VLM_GPU=1)")
+def test_vlm_engine_and_trainer_agree_on_gpu():
+    """Vision-language path on the CUDA kernels (M-RoPE tables on the rope kernel, tower through flash-attn, paged decode with the
+    rotary offset): the bf16 engine's log-probs of its own samples match the bf16 ZeRO engine's and stay close to a CPU fp32
+    model with the same weights."""
+    from polyrl_b200.models import get_model_config
+    from polyrl_b200.models import transformer as tf
+    from polyrl_b200.models import vision as V
+    from polyrl_b200.parallel.zero3 import Zero3Engine
+    from polyrl_b200.rollout.engine import RolloutEngine, SamplingParams
+
+    cfg = get_model_config("tiny-qwen2-vl-128")
+    w32, v32 = tf.TransformerWeights(cfg, seed=3), V.VisionWeights(cfg, seed=4)
+    w = tf.TransformerWeights(cfg, device="cuda", dtype=torch.bfloat16, init=False)
+    w.load_state_dict({k: t.cuda() for k, t in w32.state_dict().items()})
+    vw = V.VisionWeights(cfg, device="cuda", dtype=torch.bfloat16, init=False)
+    vw.load_state_dict({k: t.cuda() for k, t in v32.state_dict().items()})
+    g = torch.Generator().manual_seed(0)
+    grids = [(1, 4, 6)]
+    pix = torch.randn(24, V.patch_dim(cfg), generator=g)
+    prompt = [2, 11, 12, 999, 1000, 998, 13, 14, 15]
+    eng = RolloutEngine(cfg, "cuda", max_num_seqs=8, max_model_len=128, kv_cache_tokens=8 * 128)
+    eng.set_weights(w.embed, w.layers, w.head)
+    eng.set_vision_weights(vw)
+    sp = SamplingParams(max_new_tokens=16, temperature=1.0, n=2, ignore_eos=True, seed=5)
+    reqs = eng.generate([prompt, [2, 20, 21, 22]], sp, mm=[dict(pixel_values=pix, grid_thw=grids), None])
+    ze = Zero3Engine(cfg, "cuda", trainable=False, seed=0)
+    full = {**w32.state_dict(), **v32.state_dict()}
+    for u in ze.units:
+        u.load_full_state({n: full[n if u in (ze.embed, ze.head) else f"{u.name}.{n}"].cuda() for n, _ in u.specs})
+    for r in [q for grp in reqs for q in grp]:
+        ids = r.prompt_ids + r.output_ids
+        has_img = r.mm is not None
+        pos3 = (V.mrope_positions(cfg, r.prompt_ids, grids)[0] if has_img else torch.arange(len(r.prompt_ids)).expand(3, -1))
+        nxt = int(pos3.max()) + 1
+        pos3 = torch.cat([pos3, torch.arange(nxt, nxt + len(r.output_ids)).expand(3, -1)], dim=1)
+        t = len(ids)
+
+        def inp_on(dev):
+            return tf.PackedInput(torch.tensor(ids, device=dev), pos3[0].clone().to(dev), torch.tensor([0, t], dtype=torch.int32, device=dev), t,
+                                  mrope_pos=pos3.contiguous().to(dev), pixel_values=pix.to(dev) if has_img else None,
+                                  grid_thw=grids if has_img else None)
+
+        labels = torch.tensor(ids[1:] + [0])
+        with torch.no_grad():
+            lp_gpu, _ = ze.forward_logprob_entropy(inp_on("cuda"), labels.cuda(), 1.0)
+            i32 = inp_on("cpu")
+            if has_img:
+                i32.image_embeds, i32.pixel_values = V.vision_forward(cfg, v32, pix, grids), None
+            h = tf.forward_hidden(cfg, w32, i32)
+            lp_cpu = torch.log_softmax(tf.logits_forward(cfg, w32.head, w32.embed, h).float(), -1).gather(-1, labels[:, None])[:, 0]
+        k = len(r.prompt_ids) - 1
+        got = torch.tensor(r.logprobs)
+        assert (lp_gpu[k:k + len(r.output_ids)].cpu() - got).abs().max() < 0.15, "engine vs trainer (both bf16)"
+        assert (lp_cpu[k:k + len(r.output_ids)] - got).abs().max() < 0.25, "engine (bf16) vs fp32 reference"

@@ -418,3 +418,66 @@ def test_image_prompts_over_http_through_the_manager(tmp_path):
     finally:
         srv.stop()
         m.close()
+
+
+def test_qwen2_5_vl_window_tower_matches_hf(tmp_path):
+    """Qwen2.5-VL: RMSNorm / SwiGLU tower with windowed attention (full attention only in ``fullatt_block_indexes``) — tower
+    output, LM logits with images and the exported checkpoint all equal HF."""
+    from transformers import Qwen2_5_VLConfig, Qwen2_5_VLForConditionalGeneration
+
+    from polyrl_b200.models import hf_io
+
+    torch.manual_seed(0)
+    hc = Qwen2_5_VLConfig(
+        text_config=dict(vocab_size=512, hidden_size=128, intermediate_size=256, num_hidden_layers=2, num_attention_heads=4,
+                         num_key_value_heads=2, max_position_embeddings=512, rms_norm_eps=1e-6, tie_word_embeddings=False, pad_token_id=0, eos_token_id=1, bos_token_id=2,
+                         rope_parameters=dict(rope_type="default", rope_theta=10000.0, mrope_section=[4, 6, 6])),
+        vision_config=dict(depth=3, hidden_size=64, intermediate_size=96, out_hidden_size=128, num_heads=4, patch_size=4,
+                           spatial_merge_size=2, temporal_patch_size=2, in_channels=3, window_size=16, fullatt_block_indexes=[1]),
+        image_token_id=500, video_token_id=501, vision_start_token_id=499, vision_end_token_id=498)
+    hc._attn_implementation = "eager"
+    model = Qwen2_5_VLForConditionalGeneration(hc).eval().float()
+    with torch.no_grad():
+        for n, p in model.named_parameters():
+            if p.dim() == 1:
+                p.add_(0.1 * torch.randn_like(p))
+    cfg = ModelConfig.from_hf_config(hc.to_dict())
+    assert cfg.vision["arch"] == "qwen2_5" and cfg.vision["window_size"] == 16 and cfg.vision["fullatt_block_indexes"] == [1]
+    sd = model.state_dict()
+    w = tf.TransformerWeights(cfg, init=False)
+    w.load_state_dict(tf.convert_hf_state_dict(cfg, sd))
+    vw = V.VisionWeights(cfg, init=False)
+    vw.load_state_dict(V.convert_hf_vision_state_dict(cfg, sd))
+    g = torch.Generator().manual_seed(1)
+    grids = [(1, 6, 10), (1, 8, 4)]               # 3x5 and 4x2 merged cells, window = 2x2 cells: ragged border windows
+    order, wlens = V.window_partition(cfg, grids)
+    assert sorted(order.tolist()) == list(range(15 + 8)) and sum(wlens) == 60 + 32 and max(wlens) == 16 and min(wlens) == 4
+    pix = torch.randn(60 + 32, V.patch_dim(cfg), generator=g)
+    with torch.no_grad():
+        theirs = model.model.visual(pix, grid_thw=torch.tensor(grids)).pooler_output
+        mine = V.vision_forward(cfg, vw, pix, grids)
+    assert (mine - theirs).abs().max() < 2e-4
+    n0, n1 = V.num_image_tokens(cfg, grids)
+    ids = [2, 11, 499] + [500] * n0 + [498, 13, 499] + [500] * n1 + [498, 16, 17]
+    ids_t = torch.tensor([ids])
+    # positions are passed explicitly: an image's temporal index is its start position (second_per_grid_t = 0, as in the
+    # reference's get_rope_index, verl/models/transformers/qwen2_vl.py:63-150); this transformers release scales it by
+    # tokens_per_second when no second_per_grid_ts is given
+    pos3, _ = V.mrope_positions(cfg, ids, grids)
+    hf_kw = dict(input_ids=ids_t, pixel_values=pix, image_grid_thw=torch.tensor(grids), mm_token_type_ids=(ids_t == 500).int(),
+                 position_ids=pos3[:, None, :])
+    with torch.no_grad():
+        ref_logits = model(**hf_kw).logits[0]
+    inp = tf.PackedInput(torch.tensor(ids), pos3[0].clone(), torch.tensor([0, len(ids)], dtype=torch.int32), len(ids), mrope_pos=pos3,
+                         image_embeds=mine)
+    with torch.no_grad():
+        logits = tf.logits_forward(cfg, w.head, w.embed, tf.forward_hidden(cfg, w, inp))
+    assert (logits - ref_logits).abs().max() < 5e-4
+    # export -> HF loads it
+    full = {**w.state_dict(), **vw.state_dict()}
+    hf_io.save_hf(full, cfg, tmp_path / "ck25", dtype=torch.float32)
+    m2 = Qwen2_5_VLForConditionalGeneration.from_pretrained(tmp_path / "ck25", dtype=torch.float32).eval()
+    with torch.no_grad():
+        again = m2(**hf_kw).logits[0]
+    assert (again - ref_logits).abs().max() < 1e-4
+    assert get_model_config(str(tmp_path / "ck25")).vision == cfg.vision
