@@ -211,6 +211,7 @@ class ModelCfg(BaseConfig):
     lora_rank: int = 0
     lora_alpha: int = 16
     target_modules: str = "all-linear"
+    freeze_vision_tower: bool = False     # vision-language models: train the text stack only (verl model.freeze_vision_tower)
     override_config: dict = field(default_factory=dict)
     tokenizer_path: str | None = None
 

@@ -136,7 +136,8 @@ class ActorRolloutRefWorker:
             self.actor_engine = Zero3Engine(self.model_cfg, self.device, group=self.shard_group, comm=comm, trainable=True,
                                             seed=seed, lr=opt.lr, betas=tuple(opt.betas), eps=opt.eps,
                                             weight_decay=opt.weight_decay, max_grad_norm=arr.actor.grad_clip,
-                                            sp_group=self.sp_group, replica_group=self.replica_group, lora=self.lora_cfg)
+                                            sp_group=self.sp_group, replica_group=self.replica_group, lora=self.lora_cfg,
+                                            freeze_vision_tower=m.freeze_vision_tower)
             self._maybe_load_pretrained(self.actor_engine, arr.model.path)
             fc = arr.actor.fsdp_config
             eng = self.actor_engine
