@@ -280,6 +280,15 @@ class RolloutCorrectionConfig(BaseConfig):
 
 
 @dataclass
+class FilterGroupsConfig(BaseConfig):
+    """DAPO dynamic sampling (reference recipe: 3rdparty/verl/recipe/dapo/dapo_ray_trainer.py filter_groups): prompt groups whose
+    samples all got the same ``metric`` carry no learning signal under group-normalised advantages and are taken out of the loss."""
+    enable: bool = False
+    metric: str = "seq_reward"            # seq_reward | seq_final_reward | acc | score (per-sample scalar looked up in the batch)
+    max_num_gen_batches: int = 0          # accepted for config compatibility; the streaming trainer never re-generates
+
+
+@dataclass
 class AlgorithmConfig(BaseConfig):
     gamma: float = 1.0
     lam: float = 1.0
@@ -289,6 +298,7 @@ class AlgorithmConfig(BaseConfig):
     kl_penalty: str = "kl"
     kl_ctrl: KLCtrlConfig = field(default_factory=KLCtrlConfig)
     rollout_correction: RolloutCorrectionConfig = field(default_factory=RolloutCorrectionConfig)
+    filter_groups: FilterGroupsConfig = field(default_factory=FilterGroupsConfig)
 
 
 @dataclass

@@ -67,3 +67,33 @@ def uid_array(n_prompts: int, n: int, prefix: str = "") -> np.ndarray:
         for j in range(n):
             ids[i * n + j] = f"{prefix}{i}"
     return ids
+
+
+def filter_uninformative_groups(batch: DataProto, metric: str = "seq_reward") -> tuple[DataProto, dict]:
+    """DAPO dynamic sampling for streamed batches (reference: recipe/dapo/dapo_ray_trainer.py:190-260 keeps only prompts whose
+    samples disagree on ``metric``).  Streamed batches hold complete groups and the optimizer-step boundaries are counted in
+    samples, so uninformative groups are not removed but masked out: their ``response_mask`` becomes zero (no policy-gradient, KL,
+    entropy or token-mean weight).  Returns the batch and ``dapo/*`` metrics."""
+    uid = batch.non_tensor_batch["uid"]
+    mask = batch.batch["response_mask"]
+    if metric in ("seq_reward", "seq_final_reward"):
+        key = "token_level_rewards" if metric == "seq_final_reward" and "token_level_rewards" in batch.batch else "token_level_scores"
+        vals = (batch.batch[key] * mask).sum(-1).float().cpu()
+    elif metric in batch.non_tensor_batch:
+        vals = torch.tensor([float(v) for v in batch.non_tensor_batch[metric]])
+    elif metric in batch.batch:
+        vals = batch.batch[metric].float().reshape(len(batch), -1).sum(-1).cpu()
+    else:
+        raise KeyError(f"filter_groups.metric={metric!r} is not in the batch")
+    groups: dict = {}
+    for i, u in enumerate(uid):
+        groups.setdefault(u, []).append(i)
+    drop = [idx for idx in groups.values() if len(idx) > 1 and float(vals[idx].max() - vals[idx].min()) == 0.0]
+    if drop:
+        rows = torch.tensor([i for idx in drop for i in idx], dtype=torch.long, device=mask.device)
+        new_mask = mask.clone()
+        new_mask[rows] = 0
+        batch.batch["response_mask"] = new_mask
+    n = max(1, len(groups))
+    return batch, {"dapo/num_groups": float(len(groups)), "dapo/filtered_groups": float(len(drop)),
+                   "dapo/kept_group_ratio": 1.0 - len(drop) / n}

@@ -190,6 +190,10 @@ class StreamPPOTrainer:
             self._dump_generations(ibatch, ibatch.batch["token_level_scores"].sum(-1).tolist(), self.config.trainer.rollout_data_dir, "train")
         full_len = len(ibatch)
         uid_full = ibatch.non_tensor_batch["uid"]
+        if algo.filter_groups.enable:
+            ibatch, fm = core.filter_uninformative_groups(ibatch, algo.filter_groups.metric)
+            for k, v in fm.items():
+                metrics.setdefault(k, []).append(v)
         # advantages that need whole groups are computed on the full streamed batch (groups arrive together)
         group_level = algo.adv_estimator not in ("gae", "reinforce_plus_plus", "remax")
         if group_level and not algo.use_kl_in_reward:

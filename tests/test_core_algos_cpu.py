@@ -137,3 +137,29 @@ def test_value_loss_and_kl():
     c.update(0.1, 10)
     assert c.value == pytest.approx(0.1 * (1 + 0.2 * 10 / 100))
     assert A.get_kl_controller({"type": "fixed", "kl_coef": 0.3}).value == 0.3
+
+
+def test_dapo_filter_groups_masks_uninformative_prompts():
+    """Dynamic sampling: groups whose samples all got the same score lose their loss mask; mixed groups are untouched."""
+    import numpy as np
+
+    from polyrl_b200.protocol import DataProto
+    from polyrl_b200.trainer.core import filter_uninformative_groups
+
+    mask = torch.ones(6, 4, dtype=torch.long)
+    mask[1, 2:] = 0
+    scores = torch.zeros(6, 4)
+    scores[0, 3], scores[1, 1] = 1.0, 1.0          # group a: both correct -> filtered
+    scores[2, 3] = 1.0                             # group b: 1 and 0 -> kept
+    #                                                group c: both 0 -> filtered
+    dp = DataProto.from_dict({"response_mask": mask, "token_level_scores": scores},
+                             non_tensors={"uid": np.array(["a", "a", "b", "b", "c", "c"], dtype=object),
+                                          "acc": np.array([1, 1, 1, 1, 0, 1], dtype=object)})
+    out, m = filter_uninformative_groups(dp, "seq_reward")
+    assert out.batch["response_mask"].sum(-1).tolist() == [0, 0, 4, 4, 0, 0]
+    assert m == {"dapo/num_groups": 3.0, "dapo/filtered_groups": 2.0, "dapo/kept_group_ratio": 1.0 - 2 / 3}
+    dp.batch["response_mask"] = mask
+    out, m = filter_uninformative_groups(dp, "acc")          # per-sample metric from the non-tensor batch
+    assert out.batch["response_mask"].sum(-1).tolist() == [0, 0, 0, 0, 4, 4] and m["dapo/filtered_groups"] == 2.0
+    with pytest.raises(KeyError):
+        filter_uninformative_groups(dp, "nope")

@@ -56,10 +56,11 @@ def test_gpt2_ppo_disaggregated_gloo_ws2(tmp_path):
 def test_grpo_colocated_single_process(tmp_path):
     ov = COMMON + ["actor_rollout_ref.model.path=tiny-llama", "algorithm.adv_estimator=grpo", "trainer.n_gpus_per_node=1",
                    "trainer.total_training_steps=2", "actor_rollout_ref.actor.use_kl_loss=True", "trainer.test_freq=2",
-                   "data.val_batch_size=8", f"trainer.rollout_data_dir={tmp_path}/gen", f"trainer.validation_data_dir={tmp_path}/val"]
+                   "data.val_batch_size=8", f"trainer.rollout_data_dir={tmp_path}/gen", f"trainer.validation_data_dir={tmp_path}/val",
+                   "algorithm.filter_groups.enable=True"]
     r = _run(1, ov)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
-    assert "step:2" in r.stdout and "actor/kl_loss" in r.stdout and "val-core/" in r.stdout
+    assert "step:2" in r.stdout and "actor/kl_loss" in r.stdout and "val-core/" in r.stdout and "dapo/kept_group_ratio" in r.stdout
     import json
 
     dumps = sorted((tmp_path / "gen").glob("train_*.jsonl"))
