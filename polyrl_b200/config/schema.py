@@ -69,6 +69,8 @@ class FSDPConfig(BaseConfig):
     resident_params: str = "auto"       # auto | true | false
     # full = recompute every block in backward; none = save all activations; auto = save what fits in free HBM; or an int
     activation_checkpoint: str = "auto"
+    activation_offload: bool = False     # park saved activations in pinned host memory (verl enable_activation_offload); slower than
+                                         # recompute on B200, for parity and for models whose saved activations do not fit
     activation_reserve_gb: float = 16.0
 
 

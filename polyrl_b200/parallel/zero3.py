@@ -266,6 +266,52 @@ class ShardedUnit:
             self.exp_avg_sq.copy_(sd["exp_avg_sq"])
 
 
+class _ActivationOffload:
+    """saved-tensor hooks that park a unit's saved activations in pinned host memory between its forward and its backward
+    (reference: verl/utils/activation_offload.py:221-558 — async double-buffered CPU offload of checkpointed layer inputs).
+    The D2H copy runs on a side stream right after the producing kernel; backward waits for it and copies back on the compute
+    stream.  Parameter views (storage of the gathered unit) and small tensors stay on the device.  On a B200 recomputing a block
+    is cheaper than a PCIe round trip of its activations, so this is off by default (``fsdp_config.activation_offload``)."""
+
+    MIN_BYTES = 1 << 20
+
+    def __init__(self, engine: "Zero3Engine", param_storages: set[int]):
+        self.engine, self.skip = engine, param_storages
+
+    def pack(self, t: torch.Tensor):
+        eng = self.engine
+        if not (t.is_cuda or eng._offload_force) or t.numel() * t.element_size() < eng.act_offload_min_bytes:
+            return t
+        if t.untyped_storage().data_ptr() in self.skip:
+            return t
+        eng.offload_stats["bytes"] += t.numel() * t.element_size()
+        eng.offload_stats["tensors"] += 1
+        if not t.is_cuda:                                   # CPU engines (tests): a plain copy exercises the same bookkeeping
+            return ("host", t.detach().clone(), t.device, None)
+        if eng._offload_stream is None:
+            eng._offload_stream = torch.cuda.Stream(device=eng.device)
+        st = eng._offload_stream
+        host = torch.empty(t.shape, dtype=t.dtype, device="cpu", pin_memory=True)
+        st.wait_stream(torch.cuda.current_stream(eng.device))
+        with torch.cuda.stream(st):
+            host.copy_(t, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(st)
+        t.record_stream(st)
+        return ("host", host, t.device, ev)
+
+    def unpack(self, obj):
+        if torch.is_tensor(obj):
+            return obj
+        _, host, dev, ev = obj
+        if ev is not None:
+            torch.cuda.current_stream(dev).wait_event(ev)
+        return host.to(dev, non_blocking=True)
+
+    def hooks(self):
+        return torch.autograd.graph.saved_tensors_hooks(self.pack, self.unpack)
+
+
 class _UnitFn(torch.autograd.Function):
     """Run ``fn(list_of_param_view_dicts, static, *tensors)`` for a group of units with gather + recompute.
 
@@ -289,8 +335,14 @@ class _UnitFn(torch.autograd.Function):
                 leaves.append(list(vd.values()) if u.trainable else [])
             need = ctx.needs_input_grad[3:]
             ins = [t.detach().requires_grad_(bool(t.is_floating_point() and nd)) for t, nd in zip(tensors, need)]
-            with torch.enable_grad():
-                out = runner.fn(view_dicts, static, *ins)
+            eng = runner.engine
+            if eng.act_offload:
+                off = _ActivationOffload(eng, {f.untyped_storage().data_ptr() for f in fulls})
+                with torch.enable_grad(), off.hooks():
+                    out = runner.fn(view_dicts, static, *ins)
+            else:
+                with torch.enable_grad():
+                    out = runner.fn(view_dicts, static, *ins)
             ctx.graph = (ins, leaves, out)
             for u in runner.units:
                 u.release()
@@ -407,6 +459,12 @@ class Zero3Engine:
         # enable_gradient_checkpointing=True); "none" = save activations for every layer; "auto" = save as many layers
         # as fit in free HBM at the first forward of a micro-batch; an int = that many layers.
         self.act_ckpt = "full"
+        # saved (non-recomputed) activations can additionally be parked in pinned host memory (see _ActivationOffload)
+        self.act_offload = False
+        self.act_offload_min_bytes = _ActivationOffload.MIN_BYTES
+        self.offload_stats = {"bytes": 0, "tensors": 0}
+        self._offload_stream = None
+        self._offload_force = False          # tests: run the hooks on CPU tensors too
         self._fold, self._folded = False, {}
         self.act_reserve_bytes = 16 << 30
         self.saved_layers_last = 0

@@ -148,6 +148,7 @@ class ActorRolloutRefWorker:
                 eng.make_resident()
             eng.act_ckpt = str(fc.activation_checkpoint) if arr.model.enable_gradient_checkpointing else "none"
             eng.act_reserve_bytes = int(fc.activation_reserve_gb * (1 << 30))
+            eng.act_offload = bool(fc.activation_offload)
             if self.rank == 0 and self.device.type == "cuda":
                 try:        # what the layout decisions will look like on this box (utils/hbm_sizing.py uses the same arithmetic)
                     from ..utils.hbm_sizing import plan
