@@ -1,6 +1,7 @@
 """Rollout back-end registry.
 
-``native`` is the product (paged-KV continuous-batching engine, rollout/engine.py).  ``naive`` / ``hf`` are
+``native`` is the product (paged-KV continuous-batching engine, rollout/engine.py); ``vllm-lib`` wraps the vLLM library
+(rollout/vllm_adapter.py) as a comparison baseline.  ``naive`` / ``hf`` are
 library-op baselines kept for debugging and as a numerics oracle for the engine: they re-run the full packed
 forward over prompt+generated tokens each step (no KV cache), i.e. the role of the reference's
 ``NaiveRollout`` / ``HFRollout`` (3rdparty/verl/verl/workers/rollout/naive/naive_rollout.py:36,
@@ -103,3 +104,12 @@ class NaiveRollout:
 
 
 register_rollout("hf")(NaiveRollout)
+
+
+def _vllm_lib(*a, **kw):
+    from .vllm_adapter import VLLMRollout          # vLLM itself is imported only when this back-end is constructed
+
+    return VLLMRollout(*a, **kw)
+
+
+register_rollout("vllm-lib")(_vllm_lib)

@@ -391,3 +391,53 @@ def test_extra_eos_ids_stop_generation():
     r = eng2.generate([[5, 6, 7]], {"max_new_tokens": 12, "temperature": 0.0})[0][0]
     first = free.output_ids.index(free.output_ids[2])
     assert r.finish_reason == "stop" and r.output_ids == free.output_ids[: first + 1]
+
+
+def test_vllm_library_adapter_plumbing_with_a_fake_llm():
+    """The vLLM back-end adapter (library baseline): prompts go in as token ids, completions come back as engine Requests with
+    per-token log-probs, weights are handed over in HF naming through collective_rpc, sleep / wake_up bracket training."""
+    from types import SimpleNamespace as NS
+
+    from polyrl_b200.rollout.registry import get_rollout_cls
+
+    calls = {"rpc": [], "sleep": 0, "wake": 0, "reset": 0}
+
+    class FakeLLM:
+        def generate(self, prompts, sp, use_tqdm=False):
+            sp = sp if isinstance(sp, dict) else {"n": sp.n, "max_tokens": sp.max_tokens}
+            outs = []
+            for p in prompts:
+                comps = []
+                for j in range(sp["n"]):
+                    toks = [(p["prompt_token_ids"][-1] + 1 + j + k) % 50 for k in range(sp["max_tokens"])]
+                    comps.append(NS(token_ids=toks, logprobs=[{t: NS(logprob=-0.5 - 0.1 * k)} for k, t in enumerate(toks)], finish_reason="length"))
+                outs.append(NS(outputs=comps))
+            return outs
+
+        def collective_rpc(self, fn, args=()):
+            calls["rpc"].append((fn.__name__, [n for n, _ in args[0]]))
+
+        def sleep(self, level=1):
+            calls["sleep"] += 1
+
+        def wake_up(self):
+            calls["wake"] += 1
+
+        def reset_prefix_cache(self):
+            calls["reset"] += 1
+
+    cfg = get_model_config("tiny-llama")
+    w = TransformerWeights(cfg, seed=3)
+    ro = get_rollout_cls("vllm-lib")(cfg, "cpu", max_model_len=64, llm=FakeLLM())
+    ro.set_weights(w.embed, w.layers, w.head, version=7)
+    name, keys = calls["rpc"][0]
+    assert name == "_load_weights_on_worker" and "model.layers.1.self_attn.q_proj.weight" in keys and "lm_head.weight" in keys
+    assert ro.weight_version == 7 and calls["reset"] == 1
+    ro.release_memory()
+    ro.release_memory()
+    groups = ro.generate([[5, 6, 7], [9]], SamplingParams(max_new_tokens=4, temperature=1.0, n=2))
+    assert calls["sleep"] == 1 and calls["wake"] == 1                     # generate wakes the engine up once
+    assert [len(g) for g in groups] == [2, 2] and groups[0][1].output_ids == [9, 10, 11, 12]
+    assert groups[1][0].logprobs == pytest.approx([-0.5, -0.6, -0.7, -0.8]) and groups[0][0].finish_reason == "length"
+    with pytest.raises(ValueError):
+        get_rollout_cls("vllm-lib")(cfg, "cpu")                         # a real vLLM engine needs a checkpoint directory
