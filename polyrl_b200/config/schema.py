@@ -251,6 +251,10 @@ class CriticConfig(BaseConfig):
 class RewardModelConfig(BaseConfig):
     enable: bool = False
     reward_manager: str = "naive"       # naive | batch | dapo | prime
+    use_reward_loop: bool = False       # async per-sample reward loop (data/reward_loop.py; managers naive | dapo)
+    reward_loop_concurrency: int = 64
+    genrm_endpoints: list = field(default_factory=list)   # "host:port" engine servers judging responses (generative reward model)
+    genrm_max_new_tokens: int = 64
     launch_reward_fn_async: bool = False
     model: ModelCfg = field(default_factory=ModelCfg)
     micro_batch_size_per_gpu: int | None = None
@@ -322,6 +326,10 @@ class DataConfig(BaseConfig):
     image_min_pixels: int | None = None   # resize budget of the image preprocessor (None: model default)
     image_max_pixels: int | None = None
     dataloader_num_workers: int = 0
+    # custom sampler / data generator classes (verl data.sampler.{class_path,class_name}, data.datagen.{path,name}); an empty path
+    # resolves the name inside polyrl_b200.data.dynamic (e.g. SuccessRateCurriculumSampler, MockDataGenerator)
+    sampler: dict = field(default_factory=dict)
+    datagen: dict = field(default_factory=dict)
     synthetic: bool = False               # synthetic GSM8K-shaped prompts (no network on the target box)
     synthetic_num_samples: int = 4096
     synthetic_prompt_len_range: tuple = (64, 192)

@@ -159,6 +159,14 @@ def get_custom_reward_fn(path: str | None, name: str = "compute_score") -> Calla
 def load_reward_manager(config, tokenizer=None, num_examine: int = 0, **kwargs):
     name = config.reward_model.reward_manager
     fn = get_custom_reward_fn(config.custom_reward_function.path, config.custom_reward_function.name)
+    rm = config.reward_model
+    if getattr(rm, "use_reward_loop", False) or getattr(rm, "genrm_endpoints", None):
+        from .reward_loop import GenerativeRewardModel, RewardLoopManager
+
+        if rm.genrm_endpoints and fn is None:          # model-based judge instead of a rule-based scorer
+            fn = GenerativeRewardModel(list(rm.genrm_endpoints), tokenizer, max_new_tokens=rm.genrm_max_new_tokens).compute_score
+        return RewardLoopManager(name if name in ("naive", "dapo") else "naive", tokenizer, max_concurrency=rm.reward_loop_concurrency,
+                                 compute_score=fn, reward_fn_key=config.data.reward_fn_key, **kwargs)
     return get_reward_manager_cls(name)(tokenizer=tokenizer, num_examine=num_examine, compute_score=fn,
                                         reward_fn_key=config.data.reward_fn_key, **kwargs)
 

@@ -53,10 +53,22 @@ def build_datasets(cfg: PPOConfig, model_cfg, tokenizer=None):
         tok = tokenizer or load_tokenizer(cfg.actor_rollout_ref.model.tokenizer_path or cfg.actor_rollout_ref.model.path)
         raw = d.return_raw_chat or cfg.actor_rollout_ref.rollout.multi_turn.enable       # agent loops re-template the chat
         kw = dict(model_cfg=model_cfg, image_key=d.image_key, min_pixels=d.image_min_pixels, max_pixels=d.image_max_pixels)
-        train = RLHFDataset(d.train_files, tok, d.prompt_key, d.max_prompt_length, d.filter_overlong_prompts, d.truncation, raw, **kw)
+        if (d.datagen or {}).get("name"):
+            from ..data.dynamic import DynamicGenDataset, load_extern_type
+
+            gen = load_extern_type(d.datagen.get("path"), d.datagen["name"])(d.datagen)
+            train = DynamicGenDataset(d.train_files, tok, d.prompt_key, d.max_prompt_length, d.filter_overlong_prompts, d.truncation, raw,
+                                      generator=gen, **kw)
+        else:
+            train = RLHFDataset(d.train_files, tok, d.prompt_key, d.max_prompt_length, d.filter_overlong_prompts, d.truncation, raw, **kw)
         val = (RLHFDataset(d.val_files, tok, d.prompt_key, d.max_prompt_length, d.filter_overlong_prompts, d.truncation, raw, **kw)
                if d.val_files else None)
-    sampler = ResumableRandomSampler(len(train), d.seed, d.shuffle)
+    if (d.sampler or {}).get("class_name"):
+        from ..data.dynamic import load_extern_type
+
+        sampler = load_extern_type(d.sampler.get("class_path"), d.sampler["class_name"])(train, d)
+    else:
+        sampler = ResumableRandomSampler(len(train), d.seed, d.shuffle)
     return train, val, sampler, tok
 
 

@@ -66,9 +66,42 @@ class StreamPPOTrainer:
         bs = self.config.data.train_batch_size
         ds = self.train_dataset
         for _ in range(self.config.trainer.total_epochs):
+            if self.sampler is not None and hasattr(self.sampler, "update"):
+                # curriculum samplers are re-weighted after every step: draw lazily, one batch at a time
+                import itertools
+
+                it = iter(self.sampler)
+                while True:
+                    idx = list(itertools.islice(it, bs))
+                    if len(idx) < bs:
+                        for _ in it:                 # run the iterator out so it closes its epoch
+                            pass
+                        break
+                    yield DataProto.from_single_dict(collate_fn([ds[j % len(ds)] for j in idx]))
+                continue
             order = list(iter(self.sampler)) if self.sampler is not None else list(range(len(ds)))
             for i in range(0, len(order) - bs + 1, bs):
                 yield DataProto.from_single_dict(collate_fn([ds[j] for j in order[i:i + bs]]))
+
+    def _data_feedback(self, full: DataProto) -> None:
+        """Dynamic datasets / curriculum samplers learn from the finished step (reference: experimental/dataset/sampler.py
+        ``update(batch)``, dynamicgen_dataset.py ``on_batch_end``).  Every rank must keep an identical dataset and sampler, so the
+        per-rank shards are merged first."""
+        want_s = self.sampler is not None and hasattr(self.sampler, "update")
+        want_d = hasattr(self.train_dataset, "on_batch_end")
+        if not (want_s or want_d):
+            return
+        fb = DataProto.from_dict({"token_level_scores": full.batch["token_level_scores"].detach().cpu(),
+                                  "responses": full.batch["responses"].cpu(), "response_mask": full.batch["response_mask"].cpu()},
+                                 non_tensors={k: full.non_tensor_batch[k] for k in ("index", "uid", "data_source") if k in full.non_tensor_batch})
+        if self.world > 1:
+            parts = [None] * self.world
+            dist.all_gather_object(parts, fb, group=self.group)
+            fb = DataProto.concat(parts)
+        if want_s:
+            self.sampler.update(fb)
+        if want_d:
+            self.train_dataset.on_batch_end(fb)
 
     def _mini_batch_boundaries(self, total: int) -> list[int]:
         """Cumulative sample counts at which the optimizer steps (global samples = prompts * n)."""
@@ -446,6 +479,7 @@ class StreamPPOTrainer:
                 self.worker.stop_profile()
             # ---- metrics
             full = DataProto.concat(self._step_batches)
+            self._data_feedback(full)
             out = M.reduce_metrics(metrics)
             out.update(M.compute_data_metrics(full, use_critic=self.use_critic))
             out.update(M.compute_timing_metrics(full, self._timing))

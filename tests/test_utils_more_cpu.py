@@ -7,6 +7,7 @@ import sys
 import time
 from pathlib import Path
 
+import pytest
 import torch
 
 ROOT = Path(__file__).resolve().parent.parent
@@ -166,3 +167,117 @@ def test_sft_trainer_loss_matches_reference_and_decreases(tmp_path):
     out = tr.fit(ds)
     after = tr.evaluate(ds)
     assert tr.step_idx == 6 and after < before - 0.05 and out["train/grad_norm"] > 0
+
+
+def test_reward_loop_async_scoring_and_generative_reward_model():
+    """Async reward loop: per-sample scoring with bounded concurrency (sync scorers in the executor, async scorers awaited), DAPO
+    over-long shaping, and a generative reward model judged by an engine server over HTTP."""
+    import threading
+    import time
+
+    import numpy as np
+
+    from polyrl_b200.data.reward_loop import GenerativeRewardModel, RewardLoopManager, get_reward_loop_cls
+    from polyrl_b200.data.rl_dataset import ByteTokenizer
+    from polyrl_b200.protocol import DataProto
+
+    tok = ByteTokenizer()
+    texts = ["the answer is #### 4", "no idea", "#### 4", "x" * 30]
+    R = 32
+    resp = torch.zeros(4, R, dtype=torch.long)
+    mask = torch.zeros(4, R, dtype=torch.long)
+    for i, t in enumerate(texts):
+        ids = tok.encode(t)
+        resp[i, : len(ids)] = torch.tensor(ids)
+        mask[i, : len(ids)] = 1
+    dp = DataProto.from_dict({"responses": resp, "response_mask": mask},
+                             non_tensors={"data_source": np.array(["openai/gsm8k"] * 4, dtype=object),
+                                          "reward_model": np.array([{"ground_truth": "4"}] * 4, dtype=object),
+                                          "extra_info": np.array([{"question": f"q{i}"} for i in range(4)], dtype=object)})
+    active, peak = [0], [0]
+    lock = threading.Lock()
+
+    def slow_score(data_source, solution_str, ground_truth, extra_info=None):
+        with lock:
+            active[0] += 1
+            peak[0] = max(peak[0], active[0])
+        time.sleep(0.05)
+        with lock:
+            active[0] -= 1
+        return {"score": float("#### 4" in solution_str), "acc": "#### 4" in solution_str}
+
+    loop = RewardLoopManager("naive", tok, compute_score=slow_score, max_concurrency=3)
+    out = loop(dp, return_dict=True)
+    assert out["reward_tensor"].sum(-1).tolist() == [1.0, 0.0, 1.0, 0.0] and out["reward_extra_info"]["acc"] == [True, False, True, False]
+    assert out["reward_tensor"][0, len(tok.encode(texts[0])) - 1] == 1.0
+    assert 2 <= peak[0] <= 3                                                  # overlapped, bounded by max_concurrency
+    dapo = RewardLoopManager("dapo", tok, compute_score=slow_score, max_resp_len=32, overlong_buffer_len=8, penalty_factor=1.0)
+    o2 = dapo(dp, return_dict=True)
+    assert o2["reward_tensor"][3].sum().item() == pytest.approx(-(30 - 24) / 8) and o2["reward_extra_info"]["overlong"] == [False, False, False, True]
+    with pytest.raises(ValueError):
+        get_reward_loop_cls("nope")
+
+    # generative reward model over the engine's HTTP front-end: the judge text is whatever the tiny random model emits; the parse
+    # function sees exactly the text the engine generated
+    from polyrl_b200.models import TransformerWeights, get_model_config
+    from polyrl_b200.rollout.engine import RolloutEngine
+    from polyrl_b200.rollout.server import EngineServer
+
+    cfg = get_model_config("tiny-llama")
+    w = TransformerWeights(cfg, seed=3)
+    eng = RolloutEngine(cfg, "cpu", max_num_seqs=8, max_model_len=256, kv_cache_tokens=8 * 256)
+    eng.set_weights(w.embed, w.layers, w.head)
+    srv = EngineServer(eng, port=0).start()
+    try:
+        seen = []
+        rm = GenerativeRewardModel([srv.endpoint], tok, parse=lambda text: (seen.append(text), float(len(text) % 2))[1], max_new_tokens=6)
+        loop = RewardLoopManager("naive", tok, compute_score=rm.compute_score, max_concurrency=4)
+        o3 = loop(dp, return_dict=True)
+        assert len(seen) == 4 and len(o3["reward_extra_info"]["judge_text"]) == 4
+        assert set(o3["reward_tensor"].sum(-1).tolist()) <= {0.0, 1.0}
+    finally:
+        srv.stop()
+
+
+def test_dynamic_dataset_and_curriculum_sampler(tmp_path):
+    import json
+
+    import numpy as np
+
+    from polyrl_b200.data.dynamic import DynamicGenDataset, MockDataGenerator, SuccessRateCurriculumSampler, load_extern_type
+    from polyrl_b200.data.rl_dataset import ByteTokenizer
+    from polyrl_b200.protocol import DataProto
+
+    f = tmp_path / "d.jsonl"
+    f.write_text("\n".join(json.dumps({"prompt": f"p{i}", "reward_model": {"ground_truth": str(i)}, "extra_info": {"index": i}}) for i in range(6)))
+    ds = DynamicGenDataset(f, ByteTokenizer(), max_prompt_length=16, generator=MockDataGenerator(), max_rows=8)
+    for _ in range(4):
+        ds.on_batch_end(None)
+    assert len(ds) == 8 and ds.generated == 2 and ds[7]["raw_prompt_ids"] == ds[0]["raw_prompt_ids"]
+    assert load_extern_type(None, "MockDataGenerator") is MockDataGenerator
+    gen_py = tmp_path / "gen.py"
+    gen_py.write_text("from polyrl_b200.data.dynamic import AbstractDataGenerator\n"
+                      "class Hard(AbstractDataGenerator):\n"
+                      "    def generate(self, dataset, batch):\n"
+                      "        return [{'prompt': 'harder ' + str(len(dataset)), 'reward_model': {'ground_truth': '0'}}]\n")
+    ds2 = DynamicGenDataset(f, ByteTokenizer(), max_prompt_length=16, generator=load_extern_type(str(gen_py), "Hard")({}))
+    ds2.on_batch_end(None)
+    assert len(ds2) == 7 and ByteTokenizer().decode(ds2[6]["raw_prompt_ids"]) == "harder 6"
+
+    smp = SuccessRateCurriculumSampler(range(6), seed=3)
+    # prompts 0/1 always solved, 2/3 never, 4/5 half the time
+    scores = torch.zeros(12, 4)
+    idx = np.repeat(np.arange(6), 2)
+    for k, i in enumerate(idx):
+        scores[k, 0] = 1.0 if i < 2 or (i >= 4 and k % 2 == 0) else 0.0
+    fb = DataProto.from_dict({"token_level_scores": scores}, non_tensors={"index": np.array(list(idx), dtype=object)})
+    for _ in range(12):
+        smp.update(fb)
+    w = smp._weights()
+    assert w[4] > 3 * w[0] and w[5] > 3 * w[2] and abs(w.sum() - 1) < 1e-9
+    draws = [i for _ in range(40) for i in smp]
+    assert sum(d >= 4 for d in draws) > 0.5 * len(draws)
+    sd = smp.state_dict()
+    s2 = SuccessRateCurriculumSampler(range(6))
+    s2.load_state_dict(sd)
+    assert np.allclose(s2._weights(), w) and s2.epoch == smp.epoch
