@@ -4,3 +4,4 @@ from .agent_loop import AgentLoopOutput, MultiTurnRollout, SingleTurnAgentLoop, 
 from .interactions import BaseInteraction, Gsm8kInteraction, get_interaction_cls  # noqa: F401
 from .tool_parser import FunctionCall, HermesToolParser, ToolParser, get_tool_parser  # noqa: F401
 from .tools import BaseTool, CalculatorTool, Gsm8kTool, ToolResponse, ToolSchema, load_tools  # noqa: F401
+from . import remote_tools  # noqa: F401,E402 — registers mcp / sandbox_fusion / geo3k / image tools

@@ -31,7 +31,29 @@ def _same(a: str, b: str) -> bool:
         return False
 
 
-def compute_score(solution_str: str, ground_truth, continuous: bool = True, timeout_s: float = 5.0, max_cases: int = 16, **_) -> tuple[float, dict]:
+class _Remote:
+    """Runner with ``run_python``'s result surface over a sandbox-fusion ``/run_code`` endpoint (agent/remote_tools.py)."""
+
+    def __init__(self, url: str):
+        self.url = url
+
+    def __call__(self, code: str, stdin: str = "", timeout_s: float = 5.0):
+        from types import SimpleNamespace
+
+        from ...agent.remote_tools import sandbox_fusion_run
+
+        r = sandbox_fusion_run(self.url, code, stdin=stdin, run_timeout=timeout_s, timeout=timeout_s + 20)
+        return SimpleNamespace(status="ok" if r["ok"] else "error", stdout=r["stdout"], stderr=r["stderr"])
+
+
+def compute_score(solution_str: str, ground_truth, continuous: bool = True, timeout_s: float = 5.0, max_cases: int = 16,
+                  sandbox_fusion_url: str | None = None, **_) -> tuple[float, dict]:
+    """``sandbox_fusion_url`` (or env ``SANDBOX_FUSION_URL``) sends every run to a remote sandbox-fusion service instead of the
+    local sandbox (reference: verl/utils/reward_score/sandbox_fusion/__init__.py)."""
+    import os
+
+    url = sandbox_fusion_url or os.environ.get("SANDBOX_FUSION_URL")
+    run_python = _Remote(url) if url else globals()["run_python"]
     code = extract_code(solution_str)
     if code is None:
         return 0.0, {"error": "no code block"}

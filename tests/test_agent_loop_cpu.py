@@ -239,3 +239,104 @@ def test_search_tool_bm25_and_qa_reward():
     assert first.startswith("Doc 1 (Title: Eiffel Tower)") and "Colosseum" in second.splitlines()[0] and m["queries"] == 2
     assert tool.execute(iid, {"query_list": ["zzzz qqqq"]})[0].text == "no results"
     assert qa_em.compute_score("<answer>Paris</answer>", {"target": ["paris"]}) == 1.0
+
+
+def test_remote_and_image_tools_against_local_fake_services():
+    """MCP (JSON-RPC over HTTP), sandbox-fusion code execution and the image zoom tool, exercised against tiny in-process HTTP
+    servers; the code-exec scorer can run its test cases through the remote sandbox."""
+    import json
+    import threading
+    from http.server import BaseHTTPRequestHandler, HTTPServer
+
+    import numpy as np
+    from PIL import Image
+
+    from polyrl_b200.agent.remote_tools import ImageZoomInTool, MCPSearchTool, MCPTool, SandboxFusionTool, TokenBucket
+    from polyrl_b200.agent.tools import load_tools
+    from polyrl_b200.data.reward_score import code_exec
+    from polyrl_b200.utils.sandbox import run_python
+
+    seen = []
+
+    class H(BaseHTTPRequestHandler):
+        def log_message(self, *a):
+            pass
+
+        def do_POST(self):
+            body = json.loads(self.rfile.read(int(self.headers["Content-Length"])))
+            if self.path == "/mcp":
+                seen.append(body["method"])
+                if body["method"] == "initialize":
+                    res = {"protocolVersion": "2025-03-26", "capabilities": {"tools": {}}}
+                elif body["method"] == "tools/list":
+                    res = {"tools": [{"name": "web_search", "description": "search", "inputSchema": {"type": "object", "required": ["query"], "properties": {"query": {"type": "string"}}}},
+                                     {"name": "echo", "inputSchema": {"type": "object", "properties": {}}}]}
+                elif body["params"]["name"] == "web_search":
+                    res = {"content": [{"type": "text", "text": json.dumps({"results": [{"title": "T", "url": "u", "content": "about " + body["params"]["arguments"]["query"]}]})}]}
+                elif body["params"]["name"] == "echo":
+                    res = {"content": [{"type": "text", "text": json.dumps(body["params"]["arguments"])}], "isError": False}
+                else:
+                    out = {"jsonrpc": "2.0", "id": body["id"], "error": {"code": -32601, "message": "unknown tool"}}
+                    return self._send(out)
+                return self._send({"jsonrpc": "2.0", "id": body["id"], "result": res})
+            if self.path == "/run_code":                # sandbox-fusion: really run it, in the local sandbox
+                r = run_python(body["code"], stdin=body.get("stdin", ""), timeout_s=body.get("run_timeout", 5))
+                return self._send({"status": "Success" if r.status == "ok" else "Failed",
+                                   "run_result": {"stdout": r.stdout, "stderr": r.stderr, "return_code": 0 if r.status == "ok" else 1}})
+            self.send_response(404)
+            self.end_headers()
+
+        def _send(self, obj):
+            d = json.dumps(obj).encode()
+            self.send_response(200)
+            self.send_header("Content-Type", "application/json")
+            self.send_header("Content-Length", str(len(d)))
+            self.end_headers()
+            self.wfile.write(d)
+
+    srv = HTTPServer(("127.0.0.1", 0), H)
+    threading.Thread(target=srv.serve_forever, daemon=True).start()
+    base = f"http://127.0.0.1:{srv.server_port}"
+    try:
+        tools = MCPTool.discover(base + "/mcp")
+        assert [t.name for t in tools] == ["web_search", "echo"] and tools[0].schema.parameters["required"] == ["query"]
+        assert seen.count("initialize") == 1                                  # one handshake, shared client
+        resp, _, m = tools[1].execute("i", {"a": 1})
+        assert json.loads(resp.text) == {"a": 1} and m == {"mcp_error": 0}
+        st = load_tools({"tools": [{"class_name": "mcp_search", "config": {"url": base + "/mcp", "tool_name": "web_search", "rate_limit": 100},
+                                    "tool_schema": {"type": "function", "function": {"name": "search", "parameters": {"type": "object", "properties": {}}}}}]})[0]
+        assert isinstance(st, MCPSearchTool) and st.name == "search"
+        resp, _, _ = st.execute("i", {"query": "blackwell"})
+        assert resp.text == "[1] T (u)\nabout blackwell"
+        bad = MCPTool({"url": base + "/mcp", "tool_name": "nope"})
+        assert "tool call failed" in bad.execute("i", {})[0].text
+        # remote sandbox
+        sb = SandboxFusionTool({"sandbox_fusion_url": base + "/run_code"})
+        assert sb.execute("i", {"code": "print(6*7)"})[0].text.strip() == "42"
+        r, _, m = sb.execute("i", {"code": "raise ValueError('boom')"})
+        assert "boom" in r.text and m == {"sandbox_ok": 0}
+        sol = "```python\nn=int(input())\nprint(n*2)\n```"
+        score, info = code_exec.compute_score(sol, {"inputs": ["2", "5"], "outputs": ["4", "10"]}, sandbox_fusion_url=base + "/run_code")
+        assert score == 1.0 and info == {"passed": 2, "total": 2}
+    finally:
+        srv.shutdown()
+    # token bucket: 3 immediate, then paced
+    import time
+
+    tb = TokenBucket(50, burst=3)
+    t0 = time.monotonic()
+    for _ in range(5):
+        tb.acquire()
+    assert 0.03 <= time.monotonic() - t0 < 0.5
+    # image zoom
+    img = Image.fromarray(np.arange(100 * 80 * 3, dtype=np.uint32).reshape(100, 80, 3).astype(np.uint8))
+    z = ImageZoomInTool({"min_size": 28})
+    iid, _ = z.create(image=img)
+    resp, pen, m = z.execute(iid, {"bbox_2d": [10, 20, 50, 90], "label": "corner"})
+    assert resp.image.size == (40, 70) and "corner" in resp.text and m == {"zoom_ok": 1}
+    resp, _, _ = z.execute(iid, {"bbox_2d": [0, 0, 10, 10]})
+    assert min(resp.image.size) >= 28                                       # tiny crops are enlarged
+    assert z.execute(iid, {"bbox_2d": [200, 200, 300, 300]})[1] < 0 and z.execute(iid, {"bbox_2d": [1, 2]})[1] < 0
+    g = load_tools({"tools": [{"class_name": "calc_geo3k_reward"}]})[0]
+    gid, _ = g.create(ground_truth="45")
+    assert g.execute(gid, {"answer": "45"})[0].text.endswith("reward=1.0") and g.calc_reward(gid) == 1.0
