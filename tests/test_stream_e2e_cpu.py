@@ -194,3 +194,12 @@ def test_vlm_grpo_disaggregated_gloo_ws2(tmp_path):
     r = _run(2, ov)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "step:2" in r.stdout and "actor/pg_loss" in r.stdout and "actor/kl_loss" in r.stdout and "val-core/" in r.stdout
+
+
+def test_pipeline_parallel_training_1f1b_gloo_ws4():
+    """PipelineEngine (1F1B): pp=2 x dp=2, pp=4 with tied embeddings and pp=4 with fewer micro-batches than stages all track a
+    single-process oracle (losses, grad norm, weights after two steps); in-flight micro-batches stay within pp - stage."""
+    env = {**os.environ, "PYTHONPATH": str(ROOT), "OMP_NUM_THREADS": "1"}
+    r = run_torchrun([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=4", "--master-addr", "127.0.0.1",
+                        "--master-port", "29758", str(ROOT / "tests" / "pp_train_worker.py")], capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0 and "PP_TRAIN_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
