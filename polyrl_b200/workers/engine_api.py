@@ -30,6 +30,8 @@ def get_engine_cls(model_type: str, backend: str = "zero"):
     """``backend``: zero (aliases fsdp / fsdp2) or tp (alias megatron): ``parallel.tp_train.TPTrainEngine`` — constructed with
     explicit (tp_group, dp_group), see tests/tp_train_worker.py."""
     backend = {"fsdp": "zero", "fsdp2": "zero", "megatron": "tp"}.get(backend, backend)
+    if backend == "pp" and model_type == "language_model":
+        return PipelineLMEngine
     if backend == "tp" and model_type == "language_model":
         from ..parallel.tp_train import TPTrainEngine
 
@@ -176,6 +178,82 @@ class ZeroEngine(BaseEngine):
 @register_engine("value_model")
 class ZeroEngineWithValueHead(ZeroEngine):
     value_head = True
+
+
+class PipelineLMEngine(ZeroEngine):
+    """``BaseEngine`` surface over ``parallel.pipeline.PipelineEngine`` (dp x pp, 1F1B) — the role of the reference's Megatron
+    engine with ``pipeline_model_parallel_size > 1`` (verl/workers/engine/megatron/transformer_impl.py).  Every stage of a pipeline
+    receives the same batch; losses and metrics exist on the last stage and are broadcast to the others."""
+
+    def __init__(self, model, device, pp_group, dp_group=None, lr: float = 1e-6, lr_schedule=None, micro_batch_size: int = 8, **engine_kw):
+        super().__init__(model, device, group=None, lr=lr, lr_schedule=lr_schedule, micro_batch_size=micro_batch_size, **engine_kw)
+        self.pp_group, self.dp_group = pp_group, dp_group
+
+    def initialize(self) -> None:
+        from ..parallel.pipeline import PipelineEngine
+
+        self.engine = PipelineEngine(self.model_cfg, self.device, self.pp_group, self.dp_group, lr=self.base_lr, **self.engine_kw)
+        self.ckpt = None
+
+    def _packed(self, mb: dict):
+        ids, mask = mb["input_ids"].to(self.device), mb["attention_mask"].to(self.device)
+        inp, idx = pack_padded(ids, mask, mb.get("position_ids"))
+        return inp, torch.roll(inp.input_ids, -1), idx, ids.shape
+
+    def _unpack(self, lp, ent, idx, shape, resp_len):
+        lp = unpack_to_padded(lp, idx, shape[0], shape[1])[:, -resp_len - 1:-1]
+        ent = unpack_to_padded(ent, idx, shape[0], shape[1])[:, -resp_len - 1:-1]
+        return {"log_probs": lp, "entropy": ent}
+
+    def infer_batch(self, batch: dict, temperature: float = 1.0) -> dict:
+        mbs = list(self._micro_batches(batch))
+        packed = [self._packed(mb) for mb in mbs]
+        res = self.engine.forward_only([(p[0], p[1]) for p in packed], temperature)
+        outs = [self._unpack(lp, ent, p[2], p[3], mb["responses"].shape[1]) for (lp, ent), p, mb in zip(res, packed, mbs)]
+        return {k: torch.cat([o[k] for o in outs]) for k in outs[0]}
+
+    def train_batch(self, batch: dict, loss_fn: Callable, temperature: float = 1.0) -> dict:
+        import torch.distributed as dist
+
+        assert self._training, "call inside `with engine.train_mode():`"
+        mbs = list(self._micro_batches(batch))
+        packed = [self._packed(mb) for mb in mbs]
+        n = batch["input_ids"].shape[0]
+        metrics: dict[str, list] = {}
+
+        def stage_loss(lp, ent, k):
+            out = self._unpack(lp, ent, packed[k][2], packed[k][3], mbs[k]["responses"].shape[1])
+            loss, m = loss_fn(out, mbs[k])
+            for key, v in m.items():
+                metrics.setdefault(key, []).append(float(v))
+            return loss * (mbs[k]["input_ids"].shape[0] / n)
+
+        self.engine.train_batch([(p[0], p[1]) for p in packed], stage_loss, temperature)
+        res = [{k: sum(v) / len(v) for k, v in metrics.items()}]
+        dist.broadcast_object_list(res, src=dist.get_process_group_ranks(self.pp_group)[-1], group=self.pp_group)
+        return res[0]
+
+    def save_checkpoint(self, path: str, global_step: int = 0, max_ckpt_to_keep=None) -> None:
+        """Every stage writes its own slice (fp32 masters + moments)."""
+        import os
+
+        e = self.engine
+        os.makedirs(path, exist_ok=True)
+        torch.save({"master": e.master, "exp_avg": e.exp_avg, "exp_avg_sq": e.exp_avg_sq, "opt_step": e.opt_step, "lr_step": self.lr_step,
+                    "global_step": global_step}, os.path.join(path, f"pp_stage_{e.stage}_of_{e.pp}.pt"))
+
+    def load_checkpoint(self, path: str):
+        import os
+
+        e = self.engine
+        sd = torch.load(os.path.join(path, f"pp_stage_{e.stage}_of_{e.pp}.pt"), map_location=e.device, weights_only=True)
+        for k in e.master:
+            e.master[k].copy_(sd["master"][k])
+            e.exp_avg[k].copy_(sd["exp_avg"][k])
+            e.exp_avg_sq[k].copy_(sd["exp_avg_sq"][k])
+            e.params[k].data.copy_(e.master[k].to(e.dtype))
+        e.opt_step, self.lr_step = int(sd["opt_step"]), int(sd["lr_step"])
+        return {"lr_step": self.lr_step, "global_step": sd.get("global_step", 0)}
 
 
 # ---- role-level losses (reference: workers/roles/utils/losses.py) --------------------------------------------------------

@@ -89,6 +89,48 @@ def main():
                 assert (lp - rlp).abs().max() < 1e-4 and (ent - rent).abs().max() < 1e-4
         worst[name] = (loss_err, gn_err, w_err)
         assert loss_err < 1e-5 and gn_err < 1e-4 and w_err < 2e-3, (name, loss_err, gn_err, w_err)
+    # ---- BaseEngine adapter: PPO loss through the pipeline == the ZeRO engine on one rank
+    import tempfile
+
+    from polyrl_b200.workers.engine_api import get_engine_cls, ppo_loss
+
+    pp_group = None
+    for d in range(world // 2):
+        g = dist.new_group([2 * d, 2 * d + 1])
+        if d == rank // 2:
+            pp_group = g
+    solo = [dist.new_group([r]) for r in range(world)][rank]
+    gen = torch.Generator().manual_seed(77)                      # same batch on every rank (dp = 1 here: two independent pipelines)
+    B, S, R = 6, 20, 8
+    ids = torch.randint(3, 500, (B, S), generator=gen)
+    mask = torch.ones(B, S, dtype=torch.long)
+    mask[0, :4] = 0
+    batch = {"input_ids": ids, "attention_mask": mask, "responses": ids[:, -R:], "response_mask": mask[:, -R:],
+             "advantages": torch.randn(B, R, generator=gen), "position_ids": (mask.cumsum(-1) - 1).clamp_min(0)}
+    ppe = get_engine_cls("language_model", "pp")("tiny-llama", "cpu", pp_group, None, lr=1e-2, micro_batch_size=2, weight_decay=0.0, seed=5)
+    ze = get_engine_cls("language_model", "zero")("tiny-llama", "cpu", group=solo, lr=1e-2, micro_batch_size=2, weight_decay=0.0, seed=5)
+    for e in (ppe, ze):
+        e.initialize()
+    full = {n: t.clone() for n, t in ze.engine.named_full_tensors()}          # the engines seed differently: share the ZeRO weights
+    cfg_t = ppe.model_cfg
+    ppe.engine.load_full({"embed": full["embed"]}, [{k.split(".", 2)[2]: v for k, v in full.items() if k.startswith(f"layers.{i}.")}
+                                                    for i in range(cfg_t.num_layers)],
+                         {k: full[k] for k in ("norm_w", "lm_head") if k in full})
+    a, b = ppe.infer_batch(batch), ze.infer_batch(batch)
+    assert (a["log_probs"] - b["log_probs"]).abs().max() < 1e-4 and a["log_probs"].shape == (B, R)
+    batch["old_log_probs"] = b["log_probs"] + 0.05 * torch.randn(B, R, generator=gen)
+    with ppe.train_mode(), ze.train_mode():
+        ma, mb_ = ppe.train_batch(batch, ppo_loss()), ze.train_batch(batch, ppo_loss())
+        sa, sb = ppe.optimizer_step(), ze.optimizer_step()
+    assert abs(ma["actor/pg_loss"] - mb_["actor/pg_loss"]) < 1e-5 and abs(sa["grad_norm"] - sb["grad_norm"]) < 1e-4
+    full_a, full_b = ppe.engine.gather_full_state(), dict(ze.engine.named_full_tensors())
+    assert max(((full_a[n] - full_b[n]).norm() / (full_b[n].norm() + 1e-9)).item() for n in full_b) < 2e-3
+    d = tempfile.gettempdir() + f"/pp_ckpt_{os.environ.get('MASTER_PORT', '0')}_{rank // 2}"
+    ppe.save_checkpoint(d, global_step=3)
+    other = get_engine_cls("language_model", "pp")("tiny-llama", "cpu", pp_group, None, lr=1e-2, micro_batch_size=2, weight_decay=0.0, seed=99)
+    other.initialize()
+    assert other.load_checkpoint(d)["global_step"] == 3
+    assert all(torch.equal(other.engine.master[k], ppe.engine.master[k]) for k in ppe.engine.master)
     t = torch.tensor([max(x[i] for x in worst.values()) for i in range(3)])
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     if rank == 0:
