@@ -34,6 +34,12 @@ class ModelConfig:
     bos_token_id: int = 1
     name: str = "custom"
     value_head: bool = False         # critic: scalar head instead of lm_head
+    # mixture-of-experts MLPs (Qwen3-MoE layout): every block routes each token to ``num_experts_per_tok`` of ``num_experts`` SwiGLU
+    # experts of width ``moe_intermediate_size``; 0 experts = dense MLP
+    num_experts: int = 0
+    num_experts_per_tok: int = 0
+    moe_intermediate_size: int = 0
+    norm_topk_prob: bool = True
     # vision-language models (Qwen2-VL): a ViT tower feeds merged patch embeddings into the image-token positions and the text
     # stack rotates with 3-axis (t, h, w) M-RoPE.  ``vision`` holds the tower shape (see models/vision.py), None = text only.
     vision: dict | None = None
@@ -52,6 +58,11 @@ class ModelConfig:
             raise ValueError("num_heads must be a multiple of num_kv_heads")
         if self.family not in ("llama", "gpt2"):
             raise ValueError(f"unknown model family {self.family!r}")
+        if self.num_experts:
+            if self.family != "llama" or not (0 < self.num_experts_per_tok <= self.num_experts) or self.moe_intermediate_size <= 0:
+                raise ValueError("MoE needs the llama family, 0 < num_experts_per_tok <= num_experts and moe_intermediate_size > 0")
+            if self.moe_intermediate_size % 128:
+                raise ValueError("moe_intermediate_size must be a multiple of 128 (gate / up rows are interleaved in 128-row blocks)")
         if self.vision is not None:
             if self.family != "llama":
                 raise ValueError("vision towers attach to the llama family only")
@@ -69,7 +80,10 @@ class ModelConfig:
     def num_params(self) -> int:
         h, f, v = self.hidden_size, self.intermediate_size, self.vocab_size
         if self.family == "llama":
-            per = h * (self.q_size + 2 * self.kv_size) + self.q_size * h + 3 * h * f + 2 * h
+            mlp = self.num_experts * (3 * h * self.moe_intermediate_size + h) if self.num_experts else 3 * h * f
+            per = h * (self.q_size + 2 * self.kv_size) + self.q_size * h + mlp + 2 * h
+            if self.qk_norm:
+                per += 2 * self.head_dim
             if self.qkv_bias:
                 per += self.q_size + 2 * self.kv_size
         else:
@@ -83,6 +97,13 @@ class ModelConfig:
 
             vis = vision_num_params(self)
         return per * self.num_layers + emb + h + vis
+
+    def num_active_params(self) -> int:
+        """Parameters touched per token (MoE: only the routed experts) — the FLOPs-relevant count."""
+        if not self.num_experts:
+            return self.num_params()
+        idle = (self.num_experts - self.num_experts_per_tok) * 3 * self.hidden_size * self.moe_intermediate_size
+        return self.num_params() - idle * self.num_layers
 
     def to_dict(self) -> dict:
         return asdict(self)
@@ -125,6 +146,13 @@ class ModelConfig:
                 vision_end_token_id=top.get("vision_end_token_id", -1))
             hf["tie_word_embeddings"] = top.get("tie_word_embeddings", hf.get("tie_word_embeddings", False))
             mt = "qwen2"
+        moe_kw: dict = {}
+        if mt == "qwen3_moe":
+            if hf.get("mlp_only_layers") or hf.get("decoder_sparse_step", 1) != 1:
+                raise NotImplementedError("mixed dense / sparse layer stacks (mlp_only_layers, decoder_sparse_step != 1)")
+            moe_kw = dict(num_experts=hf.get("num_experts") or hf["num_local_experts"], num_experts_per_tok=hf["num_experts_per_tok"],
+                          moe_intermediate_size=hf["moe_intermediate_size"], norm_topk_prob=hf.get("norm_topk_prob", False))
+            mt = "qwen3"
         eos = hf.get("eos_token_id", 2)
         extra_eos: tuple = ()
         if isinstance(eos, list):
@@ -137,7 +165,7 @@ class ModelConfig:
                    qkv_bias=(mt == "qwen2") or hf.get("attention_bias", False), qk_norm=(mt == "qwen3"),
                    tie_word_embeddings=hf.get("tie_word_embeddings", False), eos_token_id=eos, extra_eos_token_ids=extra_eos,
                    bos_token_id=hf.get("bos_token_id") or eos, pad_token_id=hf.get("pad_token_id") or eos,
-                   name=hf.get("_name_or_path", mt), **vis_kw)
+                   name=hf.get("_name_or_path", mt), **vis_kw, **moe_kw)
 
 
 PRESETS: dict[str, dict] = {
@@ -198,6 +226,14 @@ PRESETS: dict[str, dict] = {
                                           temporal_patch_size=2, in_channels=3, mlp_ratio=2),
                               mrope_section=(16, 24, 24), image_token_id=1000, video_token_id=1001, vision_start_token_id=999,
                               vision_end_token_id=998),
+    "qwen3-30b-a3b": dict(family="llama", vocab_size=151936, hidden_size=2048, intermediate_size=6144, num_layers=48, num_heads=32,
+                          num_kv_heads=4, head_dim=128, max_position_embeddings=40960, qk_norm=True, rope_theta=1000000.0,
+                          rms_norm_eps=1e-6, num_experts=128, num_experts_per_tok=8, moe_intermediate_size=768, norm_topk_prob=True,
+                          eos_token_id=151645, bos_token_id=151643, pad_token_id=151643),
+    "tiny-qwen3-moe": dict(family="llama", vocab_size=512, hidden_size=128, intermediate_size=256, num_layers=2, num_heads=4,
+                           num_kv_heads=2, head_dim=32, max_position_embeddings=512, rope_theta=1000000.0, rms_norm_eps=1e-6,
+                           qk_norm=True, num_experts=8, num_experts_per_tok=2, moe_intermediate_size=128, norm_topk_prob=True,
+                           eos_token_id=1, bos_token_id=2, pad_token_id=0),
     "tiny-llama-128": dict(family="llama", vocab_size=1024, hidden_size=512, intermediate_size=1024, num_layers=2,
                            num_heads=4, num_kv_heads=2, head_dim=128, max_position_embeddings=1024,
                            rope_theta=10000.0, eos_token_id=1, bos_token_id=2, pad_token_id=0),

@@ -81,8 +81,11 @@ def _layer_keys(cfg: ModelConfig, i: int) -> list[str]:
                                 "attn.c_proj.weight", "attn.c_proj.bias", "mlp.c_fc.weight", "mlp.c_fc.bias", "mlp.c_proj.weight",
                                 "mlp.c_proj.bias")]
     p = f"model.layers.{i}."
-    keys = [p + "input_layernorm.weight", p + "post_attention_layernorm.weight", p + "self_attn.o_proj.weight",
-            p + "mlp.gate_proj.weight", p + "mlp.up_proj.weight", p + "mlp.down_proj.weight"]
+    keys = [p + "input_layernorm.weight", p + "post_attention_layernorm.weight", p + "self_attn.o_proj.weight"]
+    if cfg.num_experts:
+        keys += [p + "mlp.gate.weight", p + "mlp.experts.gate_up_proj", p + "mlp.experts.down_proj"]
+    else:
+        keys += [p + "mlp.gate_proj.weight", p + "mlp.up_proj.weight", p + "mlp.down_proj.weight"]
     keys += [p + f"self_attn.{n}_proj.weight" for n in "qkv"]
     if cfg.qkv_bias:
         keys += [p + f"self_attn.{n}_proj.bias" for n in "qkv"]
@@ -104,7 +107,12 @@ def _convert_layer(cfg: ModelConfig, ck: HFCheckpoint, i: int) -> dict[str, torc
         sub.update({"transformer.wte.weight": torch.empty(0), "transformer.wpe.weight": torch.empty(0),
                     "transformer.ln_f.weight": torch.empty(0), "transformer.ln_f.bias": torch.empty(0)})
     else:
-        sub = {k.replace(f"model.layers.{i}.", "model.layers.0."): ck.get(k) for k in _layer_keys(cfg, i)}
+        keys = _layer_keys(cfg, i)
+        if cfg.num_experts and keys[-1] not in ck.weight_map and f"model.language_model.{keys[-1][6:]}" not in ck.weight_map:
+            # older checkpoints store one module per expert
+            p = f"model.layers.{i}."
+            keys = keys[:-2] + [f"{p}mlp.experts.{e}.{n}_proj.weight" for e in range(cfg.num_experts) for n in ("gate", "up", "down")]
+        sub = {k.replace(f"model.layers.{i}.", "model.layers.0."): ck.get(k) for k in keys}
         sub.update({"model.embed_tokens.weight": torch.empty(0), "model.norm.weight": torch.empty(0), "lm_head.weight": torch.empty(0)})
     conv = tf.convert_hf_state_dict(_one_layer_cfg(cfg), sub)
     return {k[len("layers.0."):]: v for k, v in conv.items() if k.startswith("layers.0.")}
@@ -202,7 +210,12 @@ def hf_config_dict(cfg: ModelConfig) -> dict:
                 "rope_scaling": {"type": "mrope", "mrope_section": list(cfg.mrope_section)}, "rope_theta": cfg.rope_theta}
     mt = "qwen3" if cfg.qk_norm else ("qwen2" if cfg.qkv_bias else "llama")
     arch = {"qwen3": "Qwen3ForCausalLM", "qwen2": "Qwen2ForCausalLM", "llama": "LlamaForCausalLM"}[mt]
-    return {"model_type": mt, "architectures": [arch], "vocab_size": cfg.vocab_size, "hidden_size": cfg.hidden_size,
+    moe = {}
+    if cfg.num_experts:
+        mt, arch = "qwen3_moe", "Qwen3MoeForCausalLM"
+        moe = {"num_experts": cfg.num_experts, "num_experts_per_tok": cfg.num_experts_per_tok, "moe_intermediate_size": cfg.moe_intermediate_size,
+               "norm_topk_prob": cfg.norm_topk_prob, "decoder_sparse_step": 1, "mlp_only_layers": []}
+    return {**moe, "model_type": mt, "architectures": [arch], "vocab_size": cfg.vocab_size, "hidden_size": cfg.hidden_size,
             "intermediate_size": cfg.intermediate_size, "num_hidden_layers": cfg.num_layers, "num_attention_heads": cfg.num_heads,
             "num_key_value_heads": cfg.num_kv_heads, "head_dim": cfg.head_dim, "max_position_embeddings": cfg.max_position_embeddings,
             "rope_theta": cfg.rope_theta, "rms_norm_eps": cfg.rms_norm_eps, "tie_word_embeddings": cfg.tie_word_embeddings,

@@ -38,7 +38,12 @@ def layer_param_specs(cfg: ModelConfig) -> ParamSpec:
             specs.append(("bqkv", (qkv,)))
         if cfg.qk_norm:
             specs += [("q_norm", (cfg.head_dim,)), ("k_norm", (cfg.head_dim,))]
-        specs += [("wo", (h, cfg.q_size)), ("ln2", (h,)), ("wgu", (2 * f, h)), ("wd", (h, f))]
+        specs += [("wo", (h, cfg.q_size)), ("ln2", (h,))]
+        if cfg.num_experts:            # router + stacked experts (gate/up rows interleaved per expert like the dense ``wgu``)
+            fm = cfg.moe_intermediate_size
+            specs += [("router", (cfg.num_experts, h)), ("ewgu", (cfg.num_experts, 2 * fm, h)), ("ewd", (cfg.num_experts, h, fm))]
+        else:
+            specs += [("wgu", (2 * f, h)), ("wd", (h, f))]
         return specs
     return [("ln1_w", (h,)), ("ln1_b", (h,)), ("wqkv", (qkv, h)), ("bqkv", (qkv,)), ("wo", (h, h)), ("bo", (h,)),
             ("ln2_w", (h,)), ("ln2_b", (h,)), ("wfc", (f, h)), ("bfc", (f,)), ("wproj", (h, f)), ("bproj", (h,))]
@@ -79,7 +84,7 @@ def init_param_(name: str, t: torch.Tensor, cfg: ModelConfig, generator: torch.G
         t.zero_()
     else:
         std = 0.02
-        if base in ("wo", "wd", "wproj"):
+        if base in ("wo", "wd", "wproj", "ewd"):
             std = 0.02 / math.sqrt(2 * cfg.num_layers)
         t.normal_(0.0, std, generator=generator)
         if base == "v_head":
@@ -109,6 +114,34 @@ def qk_norm_(cfg: ModelConfig, w: dict, qkv: torch.Tensor) -> torch.Tensor:
     q = ref.rmsnorm(qkv[:, : nq * d].reshape(t, nq, d), w["q_norm"], cfg.rms_norm_eps)
     k = ref.rmsnorm(qkv[:, nq * d:(nq + nkv) * d].reshape(t, nkv, d), w["k_norm"], cfg.rms_norm_eps)
     return torch.cat([q.reshape(t, nq * d), k.reshape(t, nkv * d), qkv[:, (nq + nkv) * d:]], dim=-1)
+
+
+def moe_mlp(cfg: ModelConfig, w: dict, h: torch.Tensor) -> torch.Tensor:
+    """Token-choice top-k mixture of SwiGLU experts on rows h:[T,H] -> [T,H] (Qwen3-MoE semantics: fp32 softmax over all experts,
+    top-k, optional renormalisation of the k weights).  Tokens are grouped by expert and every expert with work runs the same
+    fused projections as a dense MLP (``ops.linear_swiglu`` / ``ops.linear``) on its rows; results are scattered back weighted.
+    Reference capability: HF Qwen3MoeSparseMoeBlock through verl's FSDP path (verl/models/transformers/ + fsdp_workers.py)."""
+    t = h.shape[0]
+    k = cfg.num_experts_per_tok
+    probs = torch.softmax(F.linear(h, w["router"].to(h.dtype)).float(), dim=-1)
+    top_w, top_e = torch.topk(probs, k, dim=-1)                                   # [T, k]
+    if cfg.norm_topk_prob:
+        top_w = top_w / top_w.sum(-1, keepdim=True)
+    flat_e = top_e.reshape(-1)
+    order = torch.argsort(flat_e, stable=True)                                     # assignments grouped by expert
+    tok = torch.div(order, k, rounding_mode="floor")
+    counts = torch.bincount(flat_e, minlength=cfg.num_experts).tolist()
+    gate_w = top_w.reshape(-1)[order].to(h.dtype)
+    xs = h.index_select(0, tok)
+    outs, lo = [], 0
+    for e, n in enumerate(counts):
+        if n == 0:
+            continue
+        a = ops.linear_swiglu(xs[lo:lo + n], w["ewgu"][e])
+        outs.append(ops.linear(a, w["ewd"][e]))
+        lo += n
+    y = torch.cat(outs, dim=0) * gate_w.unsqueeze(-1)
+    return torch.zeros(t, h.shape[1], dtype=y.dtype, device=h.device).index_add(0, tok, y)
 
 
 @dataclass
@@ -199,6 +232,8 @@ def layer_forward(cfg: ModelConfig, w: dict, x: torch.Tensor, inp: PackedInput, 
         if lora and L.has_lora(w, "o_proj"):
             x = x + L.single_delta(w, a, "o_proj")
         h = ops.rmsnorm(x, w["ln2"], cfg.rms_norm_eps)
+        if "router" in w:
+            return x + moe_mlp(cfg, w, h)
         if lora and L.has_lora(w, "gate_proj", "up_proj"):
             a = ref.swiglu(ops.linear(h, w["wgu"]) + L.gate_up_delta(cfg, w, h))    # adapters act before the activation
         else:
@@ -271,6 +306,8 @@ def layer_decode(cfg: ModelConfig, w: dict, x: torch.Tensor, inp: DecodeInput, k
                                        scale, max_len=inp.max_len)
         x = ops.linear(a, w["wo"], residual=x)
         h = ops.rmsnorm(x, w["ln2"], cfg.rms_norm_eps)
+        if "router" in w:
+            return x + moe_mlp(cfg, w, h)
         a = ops.linear_swiglu(h, w["wgu"])
         return ops.linear(a, w["wd"], residual=x)
     h = F.layer_norm(x, (cfg.hidden_size,), w["ln1_w"], w["ln1_b"], cfg.rms_norm_eps)
@@ -415,6 +452,18 @@ def convert_hf_state_dict(cfg: ModelConfig, hf_sd: dict[str, torch.Tensor]) -> d
         if cfg.qk_norm:
             out[f"layers.{i}.q_norm"], out[f"layers.{i}.k_norm"] = hf_sd[p + "self_attn.q_norm.weight"], hf_sd[p + "self_attn.k_norm.weight"]
         out[f"layers.{i}.wo"] = hf_sd[p + "self_attn.o_proj.weight"]
+        if cfg.num_experts:
+            fm = cfg.moe_intermediate_size
+            out[f"layers.{i}.router"] = hf_sd[p + "mlp.gate.weight"]
+            if p + "mlp.experts.gate_up_proj" in hf_sd:          # stacked layout [E, 2f, h] (gate rows then up rows)
+                gu, dn = hf_sd[p + "mlp.experts.gate_up_proj"], hf_sd[p + "mlp.experts.down_proj"]
+                pairs = [(gu[e, :fm], gu[e, fm:]) for e in range(cfg.num_experts)]
+                out[f"layers.{i}.ewd"] = dn.clone()
+            else:                                                # one module per expert
+                pairs = [(hf_sd[f"{p}mlp.experts.{e}.gate_proj.weight"], hf_sd[f"{p}mlp.experts.{e}.up_proj.weight"]) for e in range(cfg.num_experts)]
+                out[f"layers.{i}.ewd"] = torch.stack([hf_sd[f"{p}mlp.experts.{e}.down_proj.weight"] for e in range(cfg.num_experts)])
+            out[f"layers.{i}.ewgu"] = torch.stack([ref.interleave_gate_up(g, u) for g, u in pairs])
+            continue
         out[f"layers.{i}.wgu"] = ref.interleave_gate_up(hf_sd[p + "mlp.gate_proj.weight"], hf_sd[p + "mlp.up_proj.weight"])
         out[f"layers.{i}.wd"] = hf_sd[p + "mlp.down_proj.weight"]
     return out
@@ -448,9 +497,15 @@ def export_hf_state_dict(cfg: ModelConfig, sd: dict[str, torch.Tensor]) -> dict[
         if cfg.qk_norm:
             out[p + "self_attn.q_norm.weight"], out[p + "self_attn.k_norm.weight"] = sd[f"layers.{i}.q_norm"], sd[f"layers.{i}.k_norm"]
         out[p + "self_attn.o_proj.weight"] = sd[f"layers.{i}.wo"]
-        g, u = ref.deinterleave_gate_up(sd[f"layers.{i}.wgu"])
-        out[p + "mlp.gate_proj.weight"], out[p + "mlp.up_proj.weight"] = g, u
-        out[p + "mlp.down_proj.weight"] = sd[f"layers.{i}.wd"]
+        if cfg.num_experts:                                      # stacked HF layout
+            gus = [ref.deinterleave_gate_up(sd[f"layers.{i}.ewgu"][e]) for e in range(cfg.num_experts)]
+            out[p + "mlp.gate.weight"] = sd[f"layers.{i}.router"]
+            out[p + "mlp.experts.gate_up_proj"] = torch.stack([torch.cat([g, u], dim=0) for g, u in gus])
+            out[p + "mlp.experts.down_proj"] = sd[f"layers.{i}.ewd"]
+        else:
+            g, u = ref.deinterleave_gate_up(sd[f"layers.{i}.wgu"])
+            out[p + "mlp.gate_proj.weight"], out[p + "mlp.up_proj.weight"] = g, u
+            out[p + "mlp.down_proj.weight"] = sd[f"layers.{i}.wd"]
         out[p + "input_layernorm.weight"] = sd[f"layers.{i}.ln1"]
         out[p + "post_attention_layernorm.weight"] = sd[f"layers.{i}.ln2"]
     return out

