@@ -231,6 +231,8 @@ def layer_forward(cfg: ModelConfig, w: dict, x: torch.Tensor, inp: PackedInput, 
         x = ops.linear(a, w["wo"], residual=x)
         if lora and L.has_lora(w, "o_proj"):
             x = x + L.single_delta(w, a, "o_proj")
+        if w.get("_skip_mlp"):              # callers that supply their own MLP (expert parallelism, parallel/expert.py)
+            return x
         h = ops.rmsnorm(x, w["ln2"], cfg.rms_norm_eps)
         if "router" in w:
             return x + moe_mlp(cfg, w, h)
