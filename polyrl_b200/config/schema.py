@@ -114,6 +114,7 @@ class ActorConfig(BaseConfig):
     policy_loss: PolicyLossConfig = field(default_factory=PolicyLossConfig)
     loss_agg_mode: str = "token-mean"
     entropy_coeff: float = 0.0
+    router_aux_loss_coef: float = 0.0    # MoE policies: weight of the router load-balancing loss (0 = off; HF default 0.001)
     use_kl_loss: bool = False
     kl_loss_coef: float = 0.001
     kl_loss_type: str = "low_var_kl"

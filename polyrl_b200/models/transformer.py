@@ -116,7 +116,15 @@ def qk_norm_(cfg: ModelConfig, w: dict, qkv: torch.Tensor) -> torch.Tensor:
     return torch.cat([q.reshape(t, nq * d), k.reshape(t, nkv * d), qkv[:, (nq + nkv) * d:]], dim=-1)
 
 
-def moe_mlp(cfg: ModelConfig, w: dict, h: torch.Tensor) -> torch.Tensor:
+def moe_load_balance_loss(cfg: ModelConfig, probs: torch.Tensor, top_e: torch.Tensor) -> torch.Tensor:
+    """Switch-style auxiliary loss of one block: ``E * sum_e f_e * P_e`` with f_e the fraction of (token, slot) assignments routed to
+    expert e and P_e the mean router probability of e (HF ``load_balancing_loss_func`` evaluated per layer)."""
+    e = cfg.num_experts
+    f = torch.bincount(top_e.reshape(-1), minlength=e).to(probs.dtype) / max(1, top_e.shape[0])      # summed over the k slots
+    return e * (f * probs.mean(0)).sum()
+
+
+def moe_mlp(cfg: ModelConfig, w: dict, h: torch.Tensor, aux_out: list | None = None) -> torch.Tensor:
     """Token-choice top-k mixture of SwiGLU experts on rows h:[T,H] -> [T,H] (Qwen3-MoE semantics: fp32 softmax over all experts,
     top-k, optional renormalisation of the k weights).  Tokens are grouped by expert and every expert with work runs the same
     fused projections as a dense MLP (``ops.linear_swiglu`` / ``ops.linear``) on its rows; results are scattered back weighted.
@@ -125,6 +133,8 @@ def moe_mlp(cfg: ModelConfig, w: dict, h: torch.Tensor) -> torch.Tensor:
     k = cfg.num_experts_per_tok
     probs = torch.softmax(F.linear(h, w["router"].to(h.dtype)).float(), dim=-1)
     top_w, top_e = torch.topk(probs, k, dim=-1)                                   # [T, k]
+    if aux_out is not None:
+        aux_out.append(moe_load_balance_loss(cfg, probs, top_e))
     if cfg.norm_topk_prob:
         top_w = top_w / top_w.sum(-1, keepdim=True)
     flat_e = top_e.reshape(-1)
@@ -193,7 +203,7 @@ def embed_forward(cfg: ModelConfig, w: dict, inp: PackedInput) -> torch.Tensor:
     return x
 
 
-def layer_forward(cfg: ModelConfig, w: dict, x: torch.Tensor, inp: PackedInput, kv_sink=None) -> torch.Tensor:
+def layer_forward(cfg: ModelConfig, w: dict, x: torch.Tensor, inp: PackedInput, kv_sink=None, aux_out: list | None = None) -> torch.Tensor:
     """One decoder block on packed activations x:[T,H].  ``kv_sink`` = (k_cache, v_cache, slot_mapping)
     makes this a prefill step that also fills the paged KV cache (rollout engine)."""
     nq, nkv, d = cfg.num_heads, cfg.num_kv_heads, cfg.head_dim
@@ -235,7 +245,7 @@ def layer_forward(cfg: ModelConfig, w: dict, x: torch.Tensor, inp: PackedInput, 
             return x
         h = ops.rmsnorm(x, w["ln2"], cfg.rms_norm_eps)
         if "router" in w:
-            return x + moe_mlp(cfg, w, h)
+            return x + moe_mlp(cfg, w, h, aux_out)
         if lora and L.has_lora(w, "gate_proj", "up_proj"):
             a = ref.swiglu(ops.linear(h, w["wgu"]) + L.gate_up_delta(cfg, w, h))    # adapters act before the activation
         else:

@@ -461,6 +461,9 @@ class Zero3Engine:
         self.act_ckpt = "full"
         # saved (non-recomputed) activations can additionally be parked in pinned host memory (see _ActivationOffload)
         self.act_offload = False
+        # mixture-of-experts: collect the router load-balancing loss of every block during forward_hidden (``last_aux_loss``)
+        self.moe_aux = False
+        self.last_aux_loss = None
         self.act_offload_min_bytes = _ActivationOffload.MIN_BYTES
         self.offload_stats = {"bytes": 0, "tensors": 0}
         self._offload_stream = None
@@ -593,9 +596,12 @@ class Zero3Engine:
             return vision_forward(cfg, tower_view(cfg, ws[0]), pixel_values, grid)
 
         def layer_fn(ws, inp, x):
-            if len(ws) > 1:         # base + adapter views
-                return tf.layer_forward(cfg, {**ws[0], **ws[1], "_lora_scale": self.lora.scale}, x, inp)
-            return tf.layer_forward(cfg, ws[0], x, inp)
+            w = {**ws[0], **ws[1], "_lora_scale": self.lora.scale} if len(ws) > 1 else ws[0]      # base (+ adapter) views
+            if self.moe_aux:        # MoE blocks also return their load-balancing term (a second, differentiable output)
+                aux: list = []
+                y = tf.layer_forward(cfg, w, x, inp, aux_out=aux)
+                return y, aux[0]
+            return tf.layer_forward(cfg, w, x, inp)
 
         tied = cfg.tie_word_embeddings and not cfg.value_head
         head_units = [self.head, self.embed] if tied else [self.head]
@@ -692,6 +698,13 @@ class Zero3Engine:
             x = self.embed_runner(inp, inp.input_ids, inp.position_ids, img)
         else:
             x = self.embed_runner(inp, inp.input_ids, inp.position_ids)
+        if self.moe_aux:
+            auxs = []
+            for r in self.layer_runners:
+                x, a = r(inp, x)
+                auxs.append(a)
+            self.last_aux_loss = torch.stack(auxs).mean()          # mean over blocks; add ``coef * last_aux_loss`` to the loss
+            return x
         for r in self.layer_runners:
             x = r(inp, x)
         return x

@@ -35,6 +35,7 @@ class ActorConfig:
     clip_ratio_c: float = 3.0
     loss_agg_mode: str = "token-mean"
     entropy_coeff: float = 0.0
+    router_aux_loss_coef: float = 0.0         # MoE policies: weight of the router load-balancing loss
     use_kl_loss: bool = False
     kl_loss_coef: float = 0.001
     kl_loss_type: str = "low_var_kl"
@@ -184,6 +185,10 @@ class DataParallelPPOActor:
                 loss = loss + cfg.kl_loss_coef * kl_loss
                 m["actor/kl_loss"] = kl_loss.detach().item()
                 m["actor/kl_coef"] = cfg.kl_loss_coef
+            if getattr(self.engine, "moe_aux", False) and self.engine.last_aux_loss is not None:
+                aux = self.engine.last_aux_loss        # router load-balancing term of the MoE blocks (this micro-batch's forward)
+                loss = loss + cfg.router_aux_loss_coef * aux
+                m["actor/router_aux_loss"] = aux.detach().item()
             if is_opt_step and mi == len(mbs) - 1:
                 self.engine.arm_norm_fold()         # the last reduce-scatter of the mini-batch also produces the grad norm
             (loss * scale).backward()

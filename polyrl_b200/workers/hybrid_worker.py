@@ -149,6 +149,7 @@ class ActorRolloutRefWorker:
             eng.act_ckpt = str(fc.activation_checkpoint) if arr.model.enable_gradient_checkpointing else "none"
             eng.act_reserve_bytes = int(fc.activation_reserve_gb * (1 << 30))
             eng.act_offload = bool(fc.activation_offload)
+            eng.moe_aux = bool(self.model_cfg.num_experts) and arr.actor.router_aux_loss_coef > 0
             if self.rank == 0 and self.device.type == "cuda":
                 try:        # what the layout decisions will look like on this box (utils/hbm_sizing.py uses the same arithmetic)
                     from ..utils.hbm_sizing import plan
@@ -167,7 +168,7 @@ class ActorRolloutRefWorker:
             rt = ActorRuntimeConfig(ppo_mini_batch_size=mini, ppo_micro_batch_size_per_gpu=micro,
                                     use_dynamic_bsz=a.use_dynamic_bsz, ppo_max_token_len_per_gpu=a.ppo_max_token_len_per_gpu,
                                     clip_ratio=a.clip_ratio, clip_ratio_low=a.clip_ratio_low, clip_ratio_high=a.clip_ratio_high,
-                                    clip_ratio_c=a.clip_ratio_c, loss_agg_mode=a.loss_agg_mode, entropy_coeff=a.entropy_coeff,
+                                    clip_ratio_c=a.clip_ratio_c, loss_agg_mode=a.loss_agg_mode, entropy_coeff=a.entropy_coeff, router_aux_loss_coef=a.router_aux_loss_coef,
                                     use_kl_loss=a.use_kl_loss, kl_loss_coef=a.kl_loss_coef, kl_loss_type=a.kl_loss_type,
                                     ppo_epochs=a.ppo_epochs, policy_loss_mode=a.policy_loss.loss_mode,
                                     policy_loss=a.policy_loss.to_dict(), grad_clip=a.grad_clip)

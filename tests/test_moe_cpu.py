@@ -113,3 +113,69 @@ def test_rollout_engine_decodes_moe_like_full_forward():
                 nxt = int(tf.logits_forward(cfg, w.head, w.embed, tf.forward_hidden(cfg, w, inp))[-1].argmax())
             assert nxt == tok
             seq.append(tok)
+
+
+def test_router_aux_loss_matches_hf_and_trains_through_zero_units():
+    from transformers.models.qwen3_moe.modeling_qwen3_moe import load_balancing_loss_func
+
+    from polyrl_b200.ops import reference as ref
+    from polyrl_b200.parallel.zero3 import Zero3Engine
+
+    cfg = get_model_config("tiny-qwen3-moe")
+    g = torch.Generator().manual_seed(4)
+    logits = torch.randn(37, 8, generator=g)
+    probs = torch.softmax(logits, -1)
+    top_e = torch.topk(probs, 2).indices
+    assert abs(tf.moe_load_balance_loss(cfg, probs, top_e).item() - load_balancing_loss_func((logits,), 8, 2).item()) < 1e-5
+    ids = torch.randint(3, 500, (3, 15), generator=g)
+    inp, _ = tf.pack_padded(ids, torch.ones_like(ids))
+    labels = torch.randint(0, 500, (inp.input_ids.numel(),), generator=g)
+    for mode in ("full", "none"):
+        eng = Zero3Engine(cfg, "cpu", lr=1e-2, weight_decay=0.0, seed=3, max_grad_norm=1e9)
+        eng.act_ckpt, eng.moe_aux = mode, True
+        full = {n: t.clone() for n, t in eng.named_full_tensors()}
+        w = tf.TransformerWeights(cfg, init=False)
+        w.load_state_dict(full)
+        w.requires_grad_(True)
+        aux: list = []
+        x = tf.embed_forward(cfg, w.embed, inp)
+        for lw in w.layers:
+            x = tf.layer_forward(cfg, lw, x, inp, aux_out=aux)
+        lp_o, _ = ref.linear_cross_entropy(tf.final_norm(cfg, w.head, x), w.head["lm_head"], labels)
+        aux_o = torch.stack(aux).mean()
+        (-lp_o.mean() + 0.5 * aux_o).backward()
+        lp, _ = eng.forward_logprob_entropy(inp, labels, 1.0)
+        assert abs(eng.last_aux_loss.item() - aux_o.item()) < 1e-6 and eng.last_aux_loss.item() > 0.9      # >= 1 by Cauchy-Schwarz-ish
+        (-lp.mean() + 0.5 * eng.last_aux_loss).backward()
+        grads = dict(w.named_tensors())
+        for u in eng.units:
+            u.wait_grads()
+            for (n, shp), numel, so in zip(u.specs, u.numels, u.shard_offsets):
+                name = n if u in (eng.embed, eng.head) else f"{u.name}.{n}"
+                want = grads[name].grad
+                assert (u.grad_acc[so:so + numel].view(shp) - want).abs().max() < 1e-5 * max(1.0, want.abs().max().item()), (mode, name)
+    # the PPO actor adds the term when the coefficient is set
+    from polyrl_b200.config.schema import load_config
+    from polyrl_b200.workers.hybrid_worker import ActorRolloutRefWorker
+
+    c = load_config(None, ["trainer.device=cpu", "actor_rollout_ref.model.path=tiny-qwen3-moe", "data.max_prompt_length=12",
+                           "data.max_response_length=6", "actor_rollout_ref.rollout.max_num_seqs=8", "actor_rollout_ref.rollout.n=2",
+                           "actor_rollout_ref.rollout.cuda_graph=False", "actor_rollout_ref.actor.ppo_mini_batch_size=4",
+                           "actor_rollout_ref.actor.ppo_micro_batch_size_per_gpu=2", "actor_rollout_ref.actor.router_aux_loss_coef=0.01"])
+    wk = ActorRolloutRefWorker(c, role="actor_rollout", device="cpu")
+    wk.init_model()
+    assert wk.actor_engine.moe_aux
+    import numpy as np
+
+    from polyrl_b200.protocol import DataProto
+
+    pids = torch.randint(3, 200, (2, 12), generator=g)
+    dp = DataProto.from_dict({"input_ids": pids, "attention_mask": torch.ones_like(pids), "position_ids": torch.arange(12).expand(2, -1).contiguous()},
+                             non_tensors={"uid": np.array(["a", "b"], dtype=object)})
+    dp.meta_info.update(temperature=1.0, ignore_eos=True)
+    out = wk.generate_sequences(dp)
+    out = out.union(wk.compute_log_prob(out))
+    out.batch["advantages"] = torch.randn(4, 6, generator=g) * out.batch["response_mask"]
+    out.meta_info.update({"is_opt_step": True})
+    m = wk.update_actor_stream(out).meta_info["metrics"]
+    assert "actor/router_aux_loss" in m and min(m["actor/router_aux_loss"]) > 0.9
