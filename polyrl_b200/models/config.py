@@ -234,6 +234,10 @@ PRESETS: dict[str, dict] = {
                            num_kv_heads=2, head_dim=32, max_position_embeddings=512, rope_theta=1000000.0, rms_norm_eps=1e-6,
                            qk_norm=True, num_experts=8, num_experts_per_tok=2, moe_intermediate_size=128, norm_topk_prob=True,
                            eos_token_id=1, bos_token_id=2, pad_token_id=0),
+    "tiny-qwen3-moe-128": dict(family="llama", vocab_size=1024, hidden_size=512, intermediate_size=1024, num_layers=2, num_heads=4,
+                               num_kv_heads=2, head_dim=128, max_position_embeddings=1024, rope_theta=1000000.0, rms_norm_eps=1e-6,
+                               qk_norm=True, num_experts=8, num_experts_per_tok=2, moe_intermediate_size=256, norm_topk_prob=True,
+                               eos_token_id=1, bos_token_id=2, pad_token_id=0),
     "tiny-llama-128": dict(family="llama", vocab_size=1024, hidden_size=512, intermediate_size=1024, num_layers=2,
                            num_heads=4, num_kv_heads=2, head_dim=128, max_position_embeddings=1024,
                            rope_theta=10000.0, eos_token_id=1, bos_token_id=2, pad_token_id=0),

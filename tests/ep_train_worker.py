@@ -11,7 +11,14 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 def main():
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
-    dist.init_process_group("gloo")
+    cuda = torch.cuda.is_available() and os.environ.get("EP_TRAIN_DEVICE", "cpu") == "cuda"
+    if cuda:                                   # GPU check (next-round verification): NCCL all_to_all_single, or EP_PEER=1 peer writes
+        dev = torch.device("cuda", int(os.environ["LOCAL_RANK"]))
+        torch.cuda.set_device(dev)
+        dist.init_process_group("nccl", device_id=dev)
+    else:
+        dev = torch.device("cpu")
+        dist.init_process_group("gloo")
     from polyrl_b200.models import TransformerWeights, get_model_config, pack_padded
     from polyrl_b200.models import transformer as tf
     from polyrl_b200.ops import reference as ref
@@ -20,24 +27,31 @@ def main():
     # variable all-to-all: rank r sends (r + j + 1) rows to rank j
     send = [rank + j + 1 for j in range(world)]
     recv = [j + rank + 1 for j in range(world)]
-    x = torch.cat([torch.full((n, 3), 100.0 * rank + j) for j, n in enumerate(send)])
+    cfg = get_model_config("tiny-qwen3-moe-128" if cuda else "tiny-qwen3-moe")
+    if cuda and os.environ.get("EP_PEER") == "1":
+        from polyrl_b200.parallel.expert import enable_peer_dispatch
+        from polyrl_b200.parallel.symm import SymmetricHeap
+
+        enable_peer_dispatch(dist.group.WORLD, SymmetricHeap(group=None, device=dev), 4096, cfg.hidden_size, 4)
+    x = torch.cat([torch.full((n, 512), 100.0 * rank + j, device=dev) for j, n in enumerate(send)])
     y = _exchange(x, send, recv, dist.group.WORLD)
-    want = torch.cat([torch.full((n, 3), 100.0 * j + rank) for j, n in enumerate(recv)])
+    want = torch.cat([torch.full((n, 512), 100.0 * j + rank, device=dev) for j, n in enumerate(recv)])
     assert torch.equal(y, want)
 
-    cfg = get_model_config("tiny-qwen3-moe")
     assert local_expert_range(cfg, world, rank) == (2 * rank, 2 * rank + 2)
-    eng = EPTrainEngine(cfg, "cpu", dist.group.WORLD, lr=1e-2, weight_decay=0.0, seed=11)
+    eng = EPTrainEngine(cfg, dev, dist.group.WORLD, lr=1e-2, weight_decay=0.0, seed=11)
     assert eng.master["layers.0.ewgu"].shape[0] == 2 and eng.master["layers.0.router"].shape[0] == 8
 
     def batch(r: int, step: int):
         gen = torch.Generator().manual_seed(900 + 10 * step + r)
-        ids = torch.randint(3, cfg.vocab_size, (2, 11 + 2 * r), generator=gen)
+        ids = torch.randint(3, cfg.vocab_size, (2, 11 + 2 * r), generator=gen).to(dev)
         inp, _ = pack_padded(ids, torch.ones_like(ids))
-        labels = torch.randint(0, cfg.vocab_size, (inp.input_ids.numel(),), generator=gen)
+        labels = torch.randint(0, cfg.vocab_size, (inp.input_ids.numel(),), generator=gen).to(dev)
         return inp, labels
 
-    w = TransformerWeights(cfg, device="cpu", dtype=torch.float32, init=True, seed=11)
+    w_cpu = TransformerWeights(cfg, device="cpu", dtype=torch.float32, init=True, seed=11)
+    w = TransformerWeights(cfg, device=dev, dtype=torch.float32, init=False)
+    w.load_state_dict({n: t.to(dev) for n, t in w_cpu.state_dict().items()})
     params = {n: t.requires_grad_(True) for n, t in w.named_tensors()}
     m = {n: torch.zeros_like(t) for n, t in params.items()}
     v = {n: torch.zeros_like(t) for n, t in params.items()}
@@ -62,15 +76,16 @@ def main():
         with torch.no_grad():
             for n, p in params.items():
                 ref.adamw_step(p, m[n], v[n], p.grad, 1e-2, 0.9, 0.999, 1e-8, 0.0, step + 1, coef)
-        lp_err = max(lp_err, (lp.detach() - mine).abs().max().item())
+        lp_err = max(lp_err, (lp.detach().float() - mine).abs().max().item())
         gn_err = max(gn_err, abs(st["grad_norm"] - gn))
     got = eng.gather_full_state()
     want = {n: t.detach() for n, t in w.named_tensors()}
     assert set(got) == set(want)
     w_err = max(((got[n] - want[n]).norm() / (want[n].norm() + 1e-9)).item() for n in want)
-    t = torch.tensor([lp_err, gn_err, w_err])
+    t = torch.tensor([lp_err, gn_err, w_err], device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    assert t[0] < 1e-4 and t[1] < 1e-4 and t[2] < 2e-3, t
+    tol = (0.2, 5e-2, 0.1) if cuda else (1e-4, 1e-4, 2e-3)            # bf16 kernels vs the fp32 oracle (routing may flip near ties)
+    assert t[0] < tol[0] and t[1] < tol[1] and t[2] < tol[2], t
     if rank == 0:
         print(f"EP_TRAIN_OK lp_err={t[0]:.2e} gn_err={t[1]:.2e} w_err={t[2]:.2e}", flush=True)
     dist.barrier()
