@@ -681,14 +681,30 @@ class Zero3Engine:
             from .ulysses import GatherSeq, ulysses_pad_and_slice, validate_sp
 
             validate_sp(self.cfg.num_heads, self.cfg.num_kv_heads, dist.get_world_size(sp))
-            if inp.pixel_values is not None or inp.mrope_pos is not None:
-                raise NotImplementedError("image inputs with Ulysses sequence parallelism")
             total = inp.input_ids.shape[0]
             ids, pos, _ = ulysses_pad_and_slice(inp.input_ids, inp.position_ids, sp, self.cfg.pad_token_id)
             local = tf.PackedInput(ids, pos, inp.cu_seqlens, inp.max_seqlen, sp_group=sp, total_tokens=total)
-            x = self.embed_runner(local, ids, pos)
-            for r in self.layer_runners:
-                x = r(local, x)
+            n_loc, lo = ids.shape[0], dist.get_rank(sp) * ids.shape[0]
+            if inp.mrope_pos is not None:
+                # vision-language input slicing (reference: verl/models/transformers/monkey_patch.py:120-193): this rank rotates
+                # its token slice with its slice of the 3-axis positions (padding positions are 0)
+                mp = inp.mrope_pos
+                if mp.shape[1] < n_loc * dist.get_world_size(sp):
+                    mp = torch.cat([mp, mp.new_zeros(3, n_loc * dist.get_world_size(sp) - mp.shape[1])], dim=1)
+                local.mrope_pos = mp[:, lo:lo + n_loc].contiguous()
+            if inp.pixel_values is not None:
+                # every SP rank runs the (small) tower on all images and keeps the rows whose placeholders fall into its slice
+                if self.vision_runner is None:
+                    raise ValueError(f"model {self.cfg.name!r} has no vision tower but the batch carries images")
+                grid = tuple(tuple(int(v) for v in g) for g in (inp.grid_thw.tolist() if torch.is_tensor(inp.grid_thw) else inp.grid_thw))
+                img = self.vision_runner(grid, inp.pixel_values.to(self.device, self.param_dtype))
+                ph = (inp.input_ids == self.cfg.image_token_id) | (inp.input_ids == self.cfg.video_token_id)
+                before = int(ph[:lo].sum())
+                here = int(ph[lo:lo + n_loc].sum())
+                x = self.embed_runner(local, ids, pos, img[before:before + here])
+            else:
+                x = self.embed_runner(local, ids, pos)
+            x = self._run_layers(local, x)
             return GatherSeq.apply(x, sp, True)[:total]      # full hidden on every SP rank; grads scaled by sp on the way back
         if inp.pixel_values is not None:
             if self.vision_runner is None:
@@ -698,6 +714,9 @@ class Zero3Engine:
             x = self.embed_runner(inp, inp.input_ids, inp.position_ids, img)
         else:
             x = self.embed_runner(inp, inp.input_ids, inp.position_ids)
+        return self._run_layers(inp, x)
+
+    def _run_layers(self, inp: tf.PackedInput, x: torch.Tensor) -> torch.Tensor:
         if self.moe_aux:
             auxs = []
             for r in self.layer_runners:
