@@ -361,16 +361,18 @@ class ActorRolloutRefWorker:
             mine = [list(map(int, p)) for p in raw]
             mm = None
             if "multi_modal_inputs" in prompts.non_tensor_batch:
-                if getattr(self, "rollout_tp", 1) > 1:
-                    raise NotImplementedError("image prompts with a tensor-parallel colocated rollout")
                 mm = [None if m is None else {"pixel_values": m["pixel_values"], "grid_thw": torch.as_tensor(m["image_grid_thw"]).tolist()}
                       for m in prompts.non_tensor_batch["multi_modal_inputs"]]
             if getattr(self, "rollout_tp", 1) > 1:
-                # every TP rank must feed the SAME request stream to its engine shard
+                # every TP rank must feed the SAME request stream (prompts and their images) to its engine shard
                 parts: list = [None] * self.rollout_tp
-                dist.all_gather_object(parts, mine, group=self.tp_group)
-                off = sum(len(p) for p in parts[: self.tp_rank])
-                groups = self.rollout.generate([p for part in parts for p in part], sp)[off:off + len(mine)]
+                dist.all_gather_object(parts, (mine, mm), group=self.tp_group)
+                off = sum(len(p[0]) for p in parts[: self.tp_rank])
+                all_p = [p for part in parts for p in part[0]]
+                all_mm = None
+                if any(part[1] is not None for part in parts):
+                    all_mm = [m for part in parts for m in (part[1] if part[1] is not None else [None] * len(part[0]))]
+                groups = self.rollout.generate(all_p, sp, mm=all_mm)[off:off + len(mine)]
             else:
                 groups = self.rollout.generate(mine, sp, mm=mm)
             out = self._postprocess(prompts, groups, n, resp_len)

@@ -307,6 +307,8 @@ def test_tp_rollout_cpu_gloo_engine_and_colocated_worker():
     line = [l for l in r.stdout.splitlines() if l.startswith("TP_CPU_RESULTS")]
     assert r.returncode == 0 and line, r.stdout[-2000:] + r.stderr[-2000:]
     assert "tok_ok=1" in line[0] and "lock=1" in line[0] and "slice_ok=1" in line[0] and "differ=1" in line[0] and "zero3_tp_slices_ok=1" in line[0]
+    vlm = [l for l in r.stdout.splitlines() if l.startswith("TP_CPU_VLM")]          # image prompts through the TP engine / worker
+    assert vlm and "tok_ok=1" in vlm[0] and float(vlm[0].split("worker_err=")[1]) < 1e-4
 
 
 def test_prefix_cache_unit_semantics():

@@ -62,6 +62,48 @@ def main():
     resp = [None] * world
     dist.all_gather_object(resp, out.batch["responses"].tolist())
     differ = resp[0] != resp[1]                      # different prompts -> different slices came back
+    # ---- vision-language prompts through the TP engine and the colocated TP worker (tower replicated, M-RoPE per rank)
+    import numpy as np
+
+    from polyrl_b200.models import vision as V
+
+    vcfg = get_model_config("tiny-qwen2-vl")
+    vw_, vt = TransformerWeights(vcfg, "cpu", torch.float32, seed=5), V.VisionWeights(vcfg, seed=6)
+    g = torch.Generator().manual_seed(2)
+    grids = [(1, 4, 6)]
+    pix = torch.randn(24, V.patch_dim(vcfg), generator=g)
+    vprompts, vmm = [[2, 21, 499, 500, 498, 22], [2, 40, 41, 42]], [dict(pixel_values=pix, grid_thw=grids), None]
+    outs_v = []
+    for ctx in (TPContext(vcfg, None, rank, world, max_batch=8, group=dist.group.WORLD), None):
+        e = RolloutEngine(vcfg, "cpu", max_num_seqs=8, max_model_len=64, use_cuda_graph=False, seed=3, tp=ctx)
+        e.set_weights(vw_.embed, vw_.layers, vw_.head)
+        e.set_vision_weights(vt)
+        outs_v.append([(q[0].output_ids, q[0].logprobs) for q in e.generate(vprompts, sp, mm=vmm)])
+    vlm_tok_ok = all(a[0] == b[0] for a, b in zip(*outs_v))
+    vlm_lp_err = max(abs(x - y) for a, b in zip(*outs_v) for x, y in zip(a[1], b[1]))
+    cv = load_config(None, ["trainer.device=cpu", "actor_rollout_ref.model.path=tiny-qwen2-vl", "data.max_prompt_length=16",
+                            "data.max_response_length=6", "actor_rollout_ref.rollout.n=2", "actor_rollout_ref.rollout.max_num_seqs=8",
+                            "actor_rollout_ref.rollout.cuda_graph=False", "actor_rollout_ref.rollout.tensor_model_parallel_size=2",
+                            "actor_rollout_ref.actor.fsdp_config.comm_backend=nccl"])
+    wv = ActorRolloutRefWorker(cv, role="actor_rollout", device="cpu")
+    wv.init_model()
+    raw = V.expand_image_placeholders(vcfg, [2, 21 + rank, 499, 500, 498, 22], grids)          # rank-specific prompt, same image
+    pos3, _ = V.mrope_positions(vcfg, raw, grids)
+    vids = torch.zeros(1, 16, dtype=torch.long)
+    vmask = torch.zeros(1, 16, dtype=torch.long)
+    vpos = torch.zeros(1, 3, 16, dtype=torch.long)
+    vids[0, 16 - len(raw):], vmask[0, 16 - len(raw):], vpos[0, :, 16 - len(raw):] = torch.tensor(raw), 1, pos3
+    vb = DataProto.from_dict({"input_ids": vids, "attention_mask": vmask, "position_ids": vpos},
+                             non_tensors={"raw_prompt_ids": np.array([raw], dtype=object),
+                                          "multi_modal_inputs": np.array([{"pixel_values": pix, "image_grid_thw": torch.tensor(grids)}], dtype=object)})
+    vb.meta_info = {"temperature": 1.0, "ignore_eos": True}
+    vo = wv.generate_sequences(vb)
+    vo.meta_info.update(temperature=1.0)
+    lp_tr = wv.compute_log_prob(vo).batch["old_log_probs"]
+    assert vo.batch["rollout_log_probs"].abs().min() > 1e-3 and vo.batch["response_mask"].sum() == 12
+    vlm_worker_err = (lp_tr - vo.batch["rollout_log_probs"]).abs().max().item()            # TP engine == trainer forward
+    if rank == 0:
+        print(f"TP_CPU_VLM tok_ok={int(vlm_tok_ok)} lp_err={vlm_lp_err:.2e} worker_err={vlm_worker_err:.2e}", flush=True)
     if rank == 0:
         print(f"TP_CPU_RESULTS tok_ok={int(tok_ok)} lp_err={lp_err:.2e} lock={int(lock)} slice_ok={int(mine_ok)} differ={int(differ)} zero3_tp_slices_ok={int(zero3_ok)}", flush=True)
     dist.barrier()
