@@ -324,6 +324,7 @@ class DataConfig(BaseConfig):
     truncation: str = "error"
     return_raw_chat: bool = False
     image_key: str = "images"             # vision-language datasets: column with the images of a row (verl data.image_key)
+    video_key: str = "videos"             # column with the videos of a row: lists of frames, or {"frames": [...], "fps": f}
     image_min_pixels: int | None = None   # resize budget of the image preprocessor (None: model default)
     image_max_pixels: int | None = None
     dataloader_num_workers: int = 0

@@ -112,22 +112,28 @@ class RLHFDataset(Dataset):
     token per merged patch and 3-axis ``position_ids`` [3, L] (reference: rl_dataset.py:181-230, 299-405)."""
 
     IMAGE_MARK = "<image>"
+    VIDEO_MARK = "<video>"
 
     def __init__(self, data_files, tokenizer, prompt_key: str = "prompt", max_prompt_length: int = 512,
                  filter_overlong_prompts: bool = False, truncation: str = "error", return_raw_chat: bool = False,
-                 model_cfg=None, image_key: str = "images", min_pixels: int | None = None, max_pixels: int | None = None):
+                 model_cfg=None, image_key: str = "images", min_pixels: int | None = None, max_pixels: int | None = None,
+                 video_key: str = "videos"):
         self.tok, self.key, self.max_len = tokenizer, prompt_key, max_prompt_length
         self.truncation, self.return_raw_chat = truncation, return_raw_chat
         self.vl_cfg = model_cfg if (model_cfg is not None and getattr(model_cfg, "vision", None) is not None) else None
         self.image_key, self.min_pixels, self.max_pixels = image_key, min_pixels, max_pixels
+        self.video_key = video_key
         self.rows = _read_rows(data_files)
         if filter_overlong_prompts:
             self.rows = [r for r in self.rows if self._prompt_len(r) <= max_prompt_length]
 
     def _prompt_len(self, row: dict) -> int:
-        if self.vl_cfg is not None and row.get(self.image_key):
+        if self._has_vision(row):
             return len(self._tokenize_mm(row)[0])
         return len(self._tokenize(row))
+
+    def _has_vision(self, row: dict) -> bool:
+        return self.vl_cfg is not None and bool(row.get(self.image_key) or row.get(self.video_key))
 
     def _chat_text(self, row: dict) -> str:
         p = row[self.key]
@@ -136,33 +142,44 @@ class RLHFDataset(Dataset):
         return str(p)
 
     def _tokenize_mm(self, row: dict):
-        """-> (prompt ids with expanded image placeholders, pixel_values [N, patch_dim], grids)."""
+        """-> (prompt ids with expanded placeholders, pixel_values [N, patch_dim], grids, seconds per temporal patch of the videos).
+        ``<image>`` / ``<video>`` marks in the prompt consume the row's images / videos in order; a video is a list of frames (or
+        ``{"frames": [...], "fps": f}``)."""
+        import re
+
         from ..models import vision as V
 
         cfg = self.vl_cfg
-        images = [load_image(im) for im in row[self.image_key]]
-        pix, grids = [], []
-        for im in images:
-            pv, g = V.preprocess_image(cfg, im, self.min_pixels, self.max_pixels)
+        images = [load_image(im) for im in (row.get(self.image_key) or [])]
+        videos = list(row.get(self.video_key) or [])
+        parts = re.split(f"({re.escape(self.IMAGE_MARK)}|{re.escape(self.VIDEO_MARK)})", self._chat_text(row))
+        n_img, n_vid = parts.count(self.IMAGE_MARK), parts.count(self.VIDEO_MARK)
+        if n_img != len(images) or n_vid != len(videos):
+            raise ValueError(f"prompt has {n_img} {self.IMAGE_MARK} / {n_vid} {self.VIDEO_MARK} marks for {len(images)} images / {len(videos)} videos")
+        it_img, it_vid = iter(images), iter(videos)
+        ids: list[int] = []
+        pix, grids, secs = [], [], []
+        tp = cfg.vision.get("temporal_patch_size", 2)
+        for seg in parts:
+            if seg == self.IMAGE_MARK:
+                pv, g = V.preprocess_image(cfg, next(it_img), self.min_pixels, self.max_pixels)
+                tok = cfg.image_token_id
+            elif seg == self.VIDEO_MARK:
+                vid = next(it_vid)
+                frames, fps = (vid["frames"], float(vid.get("fps", 2.0))) if isinstance(vid, dict) else (vid, 2.0)
+                pv, g = V.preprocess_video(cfg, [load_image(f) for f in frames], self.min_pixels, self.max_pixels)
+                secs.append(tp / fps)
+                tok = cfg.video_token_id
+            else:
+                ids += list(self.tok.encode(seg, add_special_tokens=False)) if seg else []
+                continue
             pix.append(pv)
             grids.append(g)
-        parts = self._chat_text(row).split(self.IMAGE_MARK)
-        if len(parts) - 1 != len(images):
-            raise ValueError(f"prompt has {len(parts) - 1} {self.IMAGE_MARK} marks for {len(images)} images")
-        counts = V.num_image_tokens(cfg, grids)
-        ids: list[int] = list(self.tok.encode(parts[0], add_special_tokens=False))
-        for seg, n in zip(parts[1:], counts):
-            ids += [cfg.vision_start_token_id] + [cfg.image_token_id] * n + [cfg.vision_end_token_id]
-            ids += list(self.tok.encode(seg, add_special_tokens=False))
-        return ids, torch.cat(pix, dim=0), grids
+            ids += [cfg.vision_start_token_id] + [tok] * V.num_image_tokens(cfg, [g])[0] + [cfg.vision_end_token_id]
+        return ids, torch.cat(pix, dim=0), grids, secs
 
     def _tokenize(self, row: dict) -> list[int]:
-        p = row[self.key]
-        if isinstance(p, (list, np.ndarray)) and len(p) and isinstance(p[0], dict):
-            text = self.tok.apply_chat_template(list(p), add_generation_prompt=True, tokenize=False)
-        else:
-            text = str(p)
-        return list(self.tok.encode(text, add_special_tokens=False))
+        return list(self.tok.encode(self._chat_text(row), add_special_tokens=False))
 
     def __len__(self) -> int:
         return len(self.rows)
@@ -170,15 +187,18 @@ class RLHFDataset(Dataset):
     def __getitem__(self, i: int) -> dict[str, Any]:
         row = dict(self.rows[i])
         mm = None
-        if self.vl_cfg is not None and row.get(self.image_key):
+        if self._has_vision(row):
             from ..models.vision import mrope_positions
 
-            toks, pixel_values, grids = self._tokenize_mm(row)
+            toks, pixel_values, grids, secs = self._tokenize_mm(row)
             ids, mask, pos, raw = left_pad(toks, self.max_len, self.tok.pad_token_id, "error")     # image runs cannot be cut
-            pos3, _ = mrope_positions(self.vl_cfg, raw, grids)
+            pos3, _ = mrope_positions(self.vl_cfg, raw, grids, secs or None)
             pos = torch.zeros(3, self.max_len, dtype=torch.long)
             pos[:, self.max_len - len(raw):] = pos3
+            # one grid list for images and videos, in prompt order (the placeholder token id tells them apart)
             mm = {"pixel_values": pixel_values, "image_grid_thw": torch.tensor(grids, dtype=torch.long)}
+            if secs:
+                mm["second_per_grid_ts"] = secs
         else:
             ids, mask, pos, raw = left_pad(self._tokenize(row), self.max_len, self.tok.pad_token_id, self.truncation)
             if self.vl_cfg is not None:

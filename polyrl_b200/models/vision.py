@@ -291,31 +291,41 @@ def merge_image_embeds(cfg: ModelConfig, x: torch.Tensor, input_ids: torch.Tenso
 # --------------------------------------------------------------------------------------------
 # M-RoPE
 # --------------------------------------------------------------------------------------------
-def mrope_positions(cfg: ModelConfig, input_ids, grid_thw) -> tuple[torch.Tensor, int]:
+def mrope_positions(cfg: ModelConfig, input_ids, grid_thw, second_per_grid_ts=None) -> tuple[torch.Tensor, int]:
     """3-axis positions of ONE sequence -> ([3, T] int64, delta) where ``delta + T`` is the position of the next generated token.
-    Text runs advance all three axes together; an image occupying (t, h/m, w/m) merged cells starts at the running position p and
-    uses (p, p + row, p + col); the run after it resumes at p + max(h/m, w/m)."""
+    Text runs advance all three axes together; a vision block of (t, h/m, w/m) merged cells starts at the running position p and
+    uses (p + frame, p + row, p + col); the run after it resumes at the largest index used + 1.  Images have t = 1.  For videos the
+    frame index advances by 1 per temporal patch (Qwen2-VL) or by ``tokens_per_second * second_per_grid_t`` (Qwen2.5-VL, with
+    ``second_per_grid_ts`` = seconds covered by one temporal patch of each video) — the layout of the reference's get_rope_index
+    (verl/models/transformers/qwen2_vl.py:63-150)."""
     ids = input_ids.tolist() if isinstance(input_ids, torch.Tensor) else list(input_ids)
-    m = _v(cfg)["spatial_merge_size"]
+    v = _v(cfg)
+    m = v["spatial_merge_size"]
     grids = iter(_grid_list(grid_thw) if grid_thw is not None else [])
+    secs = iter(second_per_grid_ts if second_per_grid_ts is not None else [])
     pos = torch.empty(3, len(ids), dtype=torch.long)
     i, p = 0, 0
     n = len(ids)
+    vis = (cfg.image_token_id, cfg.video_token_id)
     while i < n:
-        if ids[i] in (cfg.image_token_id, cfg.video_token_id):
+        if ids[i] in vis:
             t, h, w = next(grids)
             gh, gw = h // m, w // m
             cnt = t * gh * gw
-            if i + cnt > n or any(ids[j] not in (cfg.image_token_id, cfg.video_token_id) for j in (i, i + cnt - 1)):
-                raise ValueError("image placeholder run does not match its grid")
-            pos[0, i:i + cnt] = p
+            if i + cnt > n or any(ids[j] not in vis for j in (i, i + cnt - 1)):
+                raise ValueError("vision placeholder run does not match its grid")
+            step = 1.0
+            if ids[i] == cfg.video_token_id and is_v25(cfg):
+                step = float(v.get("tokens_per_second", 2)) * float(next(secs, 1.0))
+            frame = (torch.arange(t, dtype=torch.float32) * step).long().repeat_interleave(gh * gw)
+            pos[0, i:i + cnt] = p + frame
             pos[1, i:i + cnt] = p + torch.arange(gh).repeat_interleave(gw).repeat(t)
             pos[2, i:i + cnt] = p + torch.arange(gw).repeat(gh * t)
-            p += max(gh, gw)
+            p = int(pos[:, i:i + cnt].max()) + 1
             i += cnt
         else:
             j = i
-            while j < n and ids[j] not in (cfg.image_token_id, cfg.video_token_id):
+            while j < n and ids[j] not in vis:
                 j += 1
             pos[:, i:j] = torch.arange(p, p + j - i)
             p += j - i
@@ -390,12 +400,32 @@ def preprocess_image(cfg: ModelConfig, image, min_pixels: int | None = None, max
     return patchify(cfg, x.unsqueeze(0))
 
 
+def preprocess_video(cfg: ModelConfig, frames, min_pixels: int | None = None, max_pixels: int | None = None):
+    """A video given as a sequence of frames (PIL images / uint8 arrays, all resized to one size) -> (pixel_values, (t, gh, gw)).
+    Frames are grouped ``temporal_patch_size`` at a time (the last one repeated to fill the final group)."""
+    import numpy as np
+    from PIL import Image
+
+    v = _v(cfg)
+    factor = v["patch_size"] * v["spatial_merge_size"]
+    min_pixels = min_pixels or 4 * factor * factor
+    max_pixels = max_pixels or 768 * factor * factor
+    imgs = [f if isinstance(f, Image.Image) else Image.fromarray(np.asarray(f, dtype="uint8")) for f in frames]
+    if not imgs:
+        raise ValueError("empty video")
+    h, w = smart_resize(imgs[0].height, imgs[0].width, factor, min_pixels, max_pixels)
+    mean, std = torch.tensor(CLIP_MEAN).view(3, 1, 1), torch.tensor(CLIP_STD).view(3, 1, 1)
+    xs = [(torch.from_numpy(np.asarray(im.convert("RGB").resize((w, h), resample=Image.BICUBIC)).copy()).permute(2, 0, 1).float() / 255.0 - mean) / std
+          for im in imgs]
+    return patchify(cfg, torch.stack(xs))
+
+
 def expand_image_placeholders(cfg: ModelConfig, input_ids: list[int], grid_thw) -> list[int]:
-    """A prompt tokenised with ONE placeholder token per image -> the placeholder repeated once per merged patch."""
+    """A prompt tokenised with ONE placeholder token per image / video -> the placeholder repeated once per merged patch."""
     counts = iter(num_image_tokens(cfg, grid_thw))
     out: list[int] = []
     for t in input_ids:
-        out.extend([t] * next(counts) if t == cfg.image_token_id else [t])
+        out.extend([t] * next(counts) if t in (cfg.image_token_id, cfg.video_token_id) else [t])
     return out
 
 
@@ -476,8 +506,11 @@ def encode_mm_wire(mm: dict) -> dict:
 
     pv = torch.as_tensor(mm["pixel_values"]).to(torch.float16).contiguous()
     grid = mm["image_grid_thw"] if "image_grid_thw" in mm else mm["grid_thw"]
-    return {"pixel_values_b64": base64.b64encode(pv.numpy().tobytes()).decode("ascii"), "shape": list(pv.shape),
-            "grid_thw": [list(g) for g in _grid_list(grid)]}
+    out = {"pixel_values_b64": base64.b64encode(pv.numpy().tobytes()).decode("ascii"), "shape": list(pv.shape),
+           "grid_thw": [list(g) for g in _grid_list(grid)]}
+    if mm.get("second_per_grid_ts") is not None:
+        out["second_per_grid_ts"] = [float(x) for x in mm["second_per_grid_ts"]]
+    return out
 
 
 def decode_mm_wire(d: dict) -> dict:
@@ -486,4 +519,7 @@ def decode_mm_wire(d: dict) -> dict:
     import numpy as np
 
     arr = np.frombuffer(base64.b64decode(d["pixel_values_b64"]), dtype=np.float16).reshape(d["shape"])
-    return {"pixel_values": torch.from_numpy(arr.copy()).float(), "grid_thw": [tuple(g) for g in d["grid_thw"]]}
+    out = {"pixel_values": torch.from_numpy(arr.copy()).float(), "grid_thw": [tuple(g) for g in d["grid_thw"]]}
+    if d.get("second_per_grid_ts") is not None:
+        out["second_per_grid_ts"] = list(d["second_per_grid_ts"])
+    return out

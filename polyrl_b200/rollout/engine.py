@@ -398,10 +398,10 @@ class RolloutEngine:
             if len(prompt_ids) + 1 > self.max_model_len:
                 raise ValueError("image prompt longer than max_model_len (image token runs cannot be truncated)")
             prompt_ids = list(prompt_ids)
-            n_ph = sum(t == self.full_cfg.image_token_id for t in prompt_ids)
-            if n_ph == len(mm["grid_thw"]):                        # one placeholder per image: expand to one per merged patch
+            n_ph = sum(t in (self.full_cfg.image_token_id, self.full_cfg.video_token_id) for t in prompt_ids)
+            if n_ph == len(mm["grid_thw"]):                        # one placeholder per image / video: expand to one per merged patch
                 prompt_ids = V.expand_image_placeholders(self.full_cfg, prompt_ids, mm["grid_thw"])
-            mrope_pos, mrope_delta = V.mrope_positions(self.full_cfg, prompt_ids, mm["grid_thw"])
+            mrope_pos, mrope_delta = V.mrope_positions(self.full_cfg, prompt_ids, mm["grid_thw"], mm.get("second_per_grid_ts"))
         if len(prompt_ids) + 1 > self.max_model_len:
             prompt_ids = prompt_ids[-(self.max_model_len - 1):]
         budget = self.max_model_len - len(prompt_ids)

@@ -52,7 +52,7 @@ def build_datasets(cfg: PPOConfig, model_cfg, tokenizer=None):
     else:
         tok = tokenizer or load_tokenizer(cfg.actor_rollout_ref.model.tokenizer_path or cfg.actor_rollout_ref.model.path)
         raw = d.return_raw_chat or cfg.actor_rollout_ref.rollout.multi_turn.enable       # agent loops re-template the chat
-        kw = dict(model_cfg=model_cfg, image_key=d.image_key, min_pixels=d.image_min_pixels, max_pixels=d.image_max_pixels)
+        kw = dict(model_cfg=model_cfg, image_key=d.image_key, video_key=d.video_key, min_pixels=d.image_min_pixels, max_pixels=d.image_max_pixels)
         if (d.datagen or {}).get("name"):
             from ..data.dynamic import DynamicGenDataset, load_extern_type
 

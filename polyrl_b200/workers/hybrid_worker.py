@@ -361,7 +361,8 @@ class ActorRolloutRefWorker:
             mine = [list(map(int, p)) for p in raw]
             mm = None
             if "multi_modal_inputs" in prompts.non_tensor_batch:
-                mm = [None if m is None else {"pixel_values": m["pixel_values"], "grid_thw": torch.as_tensor(m["image_grid_thw"]).tolist()}
+                mm = [None if m is None else {"pixel_values": m["pixel_values"], "grid_thw": torch.as_tensor(m["image_grid_thw"]).tolist(),
+                                              "second_per_grid_ts": m.get("second_per_grid_ts")}
                       for m in prompts.non_tensor_batch["multi_modal_inputs"]]
             if getattr(self, "rollout_tp", 1) > 1:
                 # every TP rank must feed the SAME request stream (prompts and their images) to its engine shard

@@ -481,3 +481,65 @@ def test_qwen2_5_vl_window_tower_matches_hf(tmp_path):
         again = m2(**hf_kw).logits[0]
     assert (again - ref_logits).abs().max() < 1e-4
     assert get_model_config(str(tmp_path / "ck25")).vision == cfg.vision
+
+
+def test_video_inputs_positions_tower_and_dataset(tmp_path):
+    """Videos: temporal patches become extra frames of the tower grid (t > 1), M-RoPE advances the temporal axis per frame (scaled by
+    tokens_per_second * seconds-per-patch for Qwen2.5-VL), the dataset turns ``<video>`` + frame lists into placeholders/patches and
+    the engine generates from them exactly like a trainer-side forward."""
+    import json
+
+    from polyrl_b200.data.rl_dataset import ByteTokenizer, RLHFDataset
+    from polyrl_b200.rollout.engine import RolloutEngine, SamplingParams
+
+    cfg = get_model_config("tiny-qwen2-vl")
+    ids = [7, 501, 501, 501, 501, 501, 501, 501, 501, 9]                        # a 2-frame video of 2 x 2 merged cells
+    pos, delta = V.mrope_positions(cfg, ids, [(2, 4, 4)])
+    assert pos[0, 1:9].tolist() == [1] * 4 + [2] * 4 and pos[1, 1:9].tolist() == [1, 1, 2, 2] * 2 and pos[2, 1:9].tolist() == [1, 2] * 4
+    assert pos[:, 9].tolist() == [3, 3, 3] and delta == 4 - 10
+    c25 = get_model_config("tiny-qwen2-vl", vision={**cfg.vision, "arch": "qwen2_5", "intermediate_size": 96, "window_size": 16,
+                                                     "fullatt_block_indexes": [1], "tokens_per_second": 2})
+    p25, _ = V.mrope_positions(c25, ids, [(2, 4, 4)], second_per_grid_ts=[1.5])
+    assert p25[0, 1:9].tolist() == [1] * 4 + [4] * 4 and p25[:, 9].tolist() == [5, 5, 5]          # frame step = 2 tokens/s * 1.5 s
+    # tower with t = 2 equals HF's
+    hc, model = _hf_tiny()
+    hcfg, w, vw = _ours(hc, model)
+    pix = torch.randn(32, V.patch_dim(hcfg), generator=torch.Generator().manual_seed(1))
+    with torch.no_grad():
+        assert (V.vision_forward(hcfg, vw, pix, [(2, 4, 4)]) - model.model.visual(pix, grid_thw=torch.tensor([[2, 4, 4]])).pooler_output).abs().max() < 2e-4
+    # dataset: 3 frames -> 2 temporal patches (last frame repeated)
+    rng = np.random.default_rng(0)
+    frames = []
+    for k in range(3):
+        p = tmp_path / f"f{k}.png"
+        p.write_bytes(_png_bytes(rng, 16, 16))
+        frames.append({"path": str(p)})
+    row = {"prompt": [{"role": "user", "content": "<video>what moves?"}], "videos": [{"frames": frames, "fps": 4.0}],
+           "data_source": "x", "reward_model": {"ground_truth": "1"}}
+    f = tmp_path / "v.jsonl"
+    f.write_text(json.dumps(row))
+    ds = RLHFDataset(f, ByteTokenizer(), max_prompt_length=64, model_cfg=cfg, min_pixels=64, max_pixels=256)
+    it = ds[0]
+    g = it["multi_modal_inputs"]["image_grid_thw"][0].tolist()
+    assert g[0] == 2 and it["multi_modal_inputs"]["second_per_grid_ts"] == [0.5]
+    n_tok = g[0] * g[1] * g[2] // 4
+    assert it["raw_prompt_ids"].count(cfg.video_token_id) == n_tok and it["raw_prompt_ids"].count(cfg.image_token_id) == 0
+    assert it["multi_modal_inputs"]["pixel_values"].shape == (g[0] * g[1] * g[2], V.patch_dim(cfg))
+    # engine: greedy tokens from the video prompt == argmax of a full forward with the same tower rows
+    eng = RolloutEngine(hcfg, "cpu", max_num_seqs=4, max_model_len=128, kv_cache_tokens=512)
+    eng.set_weights(w.embed, w.layers, w.head)
+    eng.set_vision_weights(vw)
+    pv = it["multi_modal_inputs"]["pixel_values"]
+    prompt = [2, 499, 501, 498, 31, 32]
+    r = eng.generate([prompt], SamplingParams(max_new_tokens=4, temperature=0.0, ignore_eos=True), mm=[dict(pixel_values=pv, grid_thw=[tuple(g)])])[0][0]
+    full = r.prompt_ids + r.output_ids
+    assert r.prompt_ids.count(501) == n_tok
+    pos3, _ = V.mrope_positions(hcfg, r.prompt_ids, [tuple(g)])
+    nxt = int(pos3.max()) + 1
+    pos3 = torch.cat([pos3, torch.arange(nxt, nxt + 4).expand(3, -1)], dim=1)
+    inp = tf.PackedInput(torch.tensor(full), pos3[0].clone(), torch.tensor([0, len(full)], dtype=torch.int32), len(full), mrope_pos=pos3,
+                         image_embeds=V.vision_forward(hcfg, vw, pv, [tuple(g)]))
+    with torch.no_grad():
+        logits = tf.logits_forward(hcfg, w.head, w.embed, tf.forward_hidden(hcfg, w, inp))
+    k = len(r.prompt_ids) - 1
+    assert logits[k:k + 4].argmax(-1).tolist() == r.output_ids
