@@ -33,6 +33,7 @@ class SFTDataConfig(BaseConfig):
     val_files: str | None = None
     prompt_key: str = "prompt"
     response_key: str = "response"
+    multiturn_messages_key: str | None = None      # set (e.g. "messages") to train on the assistant turns of chat transcripts
     max_length: int = 1024
     truncation: str = "right"            # right | error
     micro_batch_size_per_gpu: int = 4
@@ -121,6 +122,82 @@ class SFTDataset(Dataset):
         loss_mask = torch.zeros(L, dtype=torch.long)
         loss_mask[np_:n] = 1
         return {"input_ids": input_ids, "attention_mask": attn, "loss_mask": loss_mask}
+
+
+class MultiTurnSFTDataset(Dataset):
+    """rows {messages: [{role, content}, ...]} -> input_ids / attention_mask / loss_mask where only the ASSISTANT turns (their content
+    and end-of-turn tokens, not the generation prompt that introduces them) are trained on.  Turn boundaries come from rendering the
+    chat template on growing prefixes of the conversation, so any prefix-consistent template works (reference:
+    verl/utils/dataset/multiturn_sft_dataset.py)."""
+
+    def __init__(self, files, tokenizer, cfg: SFTDataConfig, messages_key: str = "messages"):
+        self.tok, self.cfg, self.key = tokenizer, cfg, messages_key
+        self.rows = _read_rows(files)
+
+    def __len__(self) -> int:
+        return len(self.rows)
+
+    def tokenize(self, messages: list[dict]) -> tuple[list[int], list[int]]:
+        ids: list[int] = []
+        mask: list[int] = []
+        for i, m in enumerate(messages):
+            cur = list(self.tok.apply_chat_template(messages[:i + 1], add_generation_prompt=False, tokenize=True))
+            if cur[:len(ids)] != ids:
+                raise ValueError("chat template is not prefix-consistent; cannot locate turn boundaries")
+            new = cur[len(ids):]
+            if m["role"] == "assistant":
+                gen = list(self.tok.apply_chat_template(messages[:i], add_generation_prompt=True, tokenize=True))
+                n_prompt = max(0, min(len(new), len(gen) - len(ids)))        # tokens that only announce the assistant turn
+                mask += [0] * n_prompt + [1] * (len(new) - n_prompt)
+            else:
+                mask += [0] * len(new)
+            ids = cur
+        return ids, mask
+
+    def __getitem__(self, i: int) -> dict:
+        ids, mask = self.tokenize(list(self.rows[i][self.key]))
+        L = self.cfg.max_length
+        if len(ids) > L:
+            if self.cfg.truncation == "error":
+                raise ValueError(f"sample {i} has {len(ids)} tokens > max_length {L}")
+            ids, mask = ids[:L], mask[:L]
+        n = len(ids)
+        pad = getattr(self.tok, "pad_token_id", 0) or 0
+        input_ids = torch.full((L,), pad, dtype=torch.long)
+        input_ids[:n] = torch.tensor(ids, dtype=torch.long)
+        attn = torch.zeros(L, dtype=torch.long)
+        attn[:n] = 1
+        loss_mask = torch.zeros(L, dtype=torch.long)
+        loss_mask[:n] = torch.tensor(mask, dtype=torch.long)
+        return {"input_ids": input_ids, "attention_mask": attn, "loss_mask": loss_mask}
+
+
+class PairwiseRMDataset(Dataset):
+    """rows {prompt, chosen, rejected} -> input_ids / attention_mask of shape [2, L] (row 0 = chosen, row 1 = rejected), right-padded —
+    the input format of pairwise reward-model training (reference: verl/utils/dataset/rm_dataset.py)."""
+
+    def __init__(self, files, tokenizer, max_length: int = 1024, prompt_key: str = "prompt", chosen_key: str = "chosen",
+                 rejected_key: str = "rejected"):
+        self.tok, self.L = tokenizer, max_length
+        self.keys = (prompt_key, chosen_key, rejected_key)
+        self.rows = _read_rows(files)
+
+    def __len__(self) -> int:
+        return len(self.rows)
+
+    def __getitem__(self, i: int) -> dict:
+        row = self.rows[i]
+        p = row[self.keys[0]]
+        p_ids = (list(self.tok.apply_chat_template(list(p), add_generation_prompt=True, tokenize=True)) if isinstance(p, (list, tuple))
+                 else list(self.tok.encode(str(p), add_special_tokens=False)))
+        pad = getattr(self.tok, "pad_token_id", 0) or 0
+        ids = torch.full((2, self.L), pad, dtype=torch.long)
+        attn = torch.zeros(2, self.L, dtype=torch.long)
+        for j, k in enumerate(self.keys[1:]):
+            seq = (p_ids + list(self.tok.encode(str(row[k]), add_special_tokens=False)) + [self.tok.eos_token_id])[: self.L]
+            ids[j, :len(seq)] = torch.tensor(seq, dtype=torch.long)
+            attn[j, :len(seq)] = 1
+        return {"input_ids": ids, "attention_mask": attn}
 
 
 def lr_at(o: OptimConfig, step: int, total: int) -> float:
@@ -236,8 +313,12 @@ def main(argv=None) -> int:
             dist.init_process_group("gloo")
     tr = SFTTrainer(cfg)
     tok = load_tokenizer(cfg.model.tokenizer_path or "byte") if not cfg.data.synthetic else None
-    train = SFTDataset(cfg.data.train_files, tok, cfg.data, vocab_size=tr.model_cfg.vocab_size)
-    val = SFTDataset(cfg.data.val_files, tok, cfg.data, vocab_size=tr.model_cfg.vocab_size) if cfg.data.val_files else None
+    if cfg.data.multiturn_messages_key and not cfg.data.synthetic:
+        train = MultiTurnSFTDataset(cfg.data.train_files, tok, cfg.data, cfg.data.multiturn_messages_key)
+        val = MultiTurnSFTDataset(cfg.data.val_files, tok, cfg.data, cfg.data.multiturn_messages_key) if cfg.data.val_files else None
+    else:
+        train = SFTDataset(cfg.data.train_files, tok, cfg.data, vocab_size=tr.model_cfg.vocab_size)
+        val = SFTDataset(cfg.data.val_files, tok, cfg.data, vocab_size=tr.model_cfg.vocab_size) if cfg.data.val_files else None
     out = tr.fit(train, val)
     if tr.rank == 0:
         print("[sft] done:", {k: round(v, 5) for k, v in out.items()}, flush=True)

@@ -281,3 +281,34 @@ def test_dynamic_dataset_and_curriculum_sampler(tmp_path):
     s2 = SuccessRateCurriculumSampler(range(6))
     s2.load_state_dict(sd)
     assert np.allclose(s2._weights(), w) and s2.epoch == smp.epoch
+
+
+def test_multiturn_sft_and_pairwise_rm_datasets(tmp_path):
+    """Chat transcripts: only assistant turns carry loss (not the tokens that announce them); pairwise RM rows: [2, L] chosen/rejected."""
+    from polyrl_b200.data.rl_dataset import ByteTokenizer
+    from polyrl_b200.trainer.sft import MultiTurnSFTDataset, PairwiseRMDataset, SFTDataConfig, main
+
+    tok = ByteTokenizer()
+    msgs = [{"role": "system", "content": "be brief"}, {"role": "user", "content": "2+2?"}, {"role": "assistant", "content": "4"},
+            {"role": "user", "content": "and 3+3?"}, {"role": "assistant", "content": "6!"}]
+    f = tmp_path / "chat.jsonl"
+    f.write_text("\n".join(json.dumps({"messages": msgs}) for _ in range(8)))
+    ds = MultiTurnSFTDataset(f, tok, SFTDataConfig(max_length=96))
+    it = ds[0]
+    ids, mask, attn = it["input_ids"], it["loss_mask"].bool(), it["attention_mask"].bool()
+    assert tok.decode(ids[attn].tolist()) == tok.apply_chat_template(msgs, add_generation_prompt=False)
+    assert tok.decode(ids[mask].tolist()) == "4\n6!\n"                        # assistant contents + their end-of-turn, nothing else
+    assert not (mask & ~attn).any()
+    with pytest.raises(ValueError):
+        MultiTurnSFTDataset(f, tok, SFTDataConfig(max_length=8, truncation="error"))[0]
+    short = MultiTurnSFTDataset(f, tok, SFTDataConfig(max_length=40))[0]
+    assert int(short["attention_mask"].sum()) == 40
+    g = tmp_path / "pairs.jsonl"
+    g.write_text(json.dumps({"prompt": [{"role": "user", "content": "hi"}], "chosen": "hello there", "rejected": "go away"}))
+    rm = PairwiseRMDataset(g, tok, max_length=48)[0]
+    assert rm["input_ids"].shape == (2, 48)
+    c, r = (tok.decode(rm["input_ids"][j][rm["attention_mask"][j].bool()].tolist()) for j in (0, 1))
+    assert c.endswith("hello there") and r.endswith("go away") and c[: c.index("hello")] == r[: r.index("go away")]
+    # the SFT entry point trains on the transcripts
+    assert main(["trainer.device=cpu", f"data.train_files={f}", "data.multiturn_messages_key=messages", "data.max_length=96", "model.path=tiny-llama",
+                 "data.train_batch_size=4", "data.micro_batch_size_per_gpu=2", "trainer.total_steps=2", "optim.lr=1e-3"]) == 0
