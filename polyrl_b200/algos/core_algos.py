@@ -13,6 +13,7 @@ from typing import Callable
 
 import numpy as np
 import torch
+import torch.nn.functional as F
 
 __all__ = [
     "AdvantageEstimator", "register_adv_est", "get_adv_estimator_fn", "register_policy_loss", "get_policy_loss_fn",
@@ -417,6 +418,79 @@ def compute_policy_loss_gpg(old_log_prob, log_prob, advantages, response_mask, l
     if rollout_is_weights is not None:
         losses = losses * rollout_is_weights
     return agg_loss(losses, response_mask, loss_agg_mode), {}
+
+
+@register_policy_loss("cispo")
+def compute_policy_loss_cispo(old_log_prob, log_prob, advantages, response_mask, loss_agg_mode="token-mean",
+                              config=None, rollout_is_weights=None):
+    """CISPO (MiniMax-M1, arXiv:2506.13585): REINFORCE weighted by the CLIPPED, stop-gradient importance ratio — every token keeps
+    a gradient (no PPO-style zeroing of clipped tokens), the clip only bounds its weight."""
+    _, lo, hi = _clip_bounds(config)
+    neg_kl = torch.clamp(log_prob - old_log_prob, -20.0, 20.0)
+    ratio = torch.exp(neg_kl)
+    w = torch.clamp(ratio, 1 - lo, 1 + hi).detach()
+    losses = -w * advantages * log_prob
+    if rollout_is_weights is not None:
+        losses = losses * rollout_is_weights
+    clipped = ((ratio < 1 - lo) | (ratio > 1 + hi)).float()
+    return agg_loss(losses, response_mask, loss_agg_mode), {"actor/pg_clipfrac": masked_mean(clipped, response_mask).item(),
+                                                            "actor/ppo_kl": masked_mean(-neg_kl, response_mask).item()}
+
+
+@register_policy_loss("sppo")
+def compute_policy_loss_sppo(old_log_prob, log_prob, advantages, response_mask, loss_agg_mode="token-mean",
+                             config=None, rollout_is_weights=None):
+    """SPPO (self-play preference optimisation, arXiv:2405.00675; reference recipe/sppo/dp_actor.py:34-57): regress the sequence
+    log-ratio onto ``eta * reward``: ``(sum_t (log pi - log pi_old) - eta * R)^2`` averaged over non-empty samples.  The per-sequence
+    reward is read from ``advantages`` (its masked mean, e.g. an outcome score minus 1/2 broadcast over the response)."""
+    eta = _policy_loss_cfg(config, "sppo_eta", 1.0)
+    mask = response_mask.float()
+    log_ratio = ((log_prob - old_log_prob) * mask).sum(-1)
+    reward = (advantages * mask).sum(-1) / mask.sum(-1).clamp(min=1)
+    have = (mask.sum(-1) > 0).float()
+    loss = (((log_ratio - eta * reward) ** 2) * have).sum() / have.sum().clamp(min=1)
+    return loss, {"actor/sppo_log_ratio": (log_ratio * have).sum().item() / max(1.0, have.sum().item()),
+                  "actor/ppo_kl": masked_mean(old_log_prob - log_prob, response_mask).item()}
+
+
+def pair_preferences(scores: torch.Tensor) -> torch.Tensor:
+    """Rows come in consecutive pairs (two samples of one prompt); True marks the preferred row of each pair (ties: the first)."""
+    if scores.shape[0] % 2:
+        raise ValueError("pairwise preference needs an even number of rows (rollout.n = 2, samples of a prompt adjacent)")
+    s = scores.view(-1, 2)
+    first = s[:, 0] >= s[:, 1]
+    return torch.stack([first, ~first], dim=1).reshape(-1)
+
+
+def dpo_loss(pi_chosen, pi_rejected, ref_chosen, ref_rejected, beta: float = 0.1, label_smoothing: float = 0.0,
+             loss_type: str = "sigmoid") -> torch.Tensor:
+    """Per-pair DPO (sigmoid, optional label smoothing) or IPO loss on sequence log-probabilities."""
+    logits = (pi_chosen - pi_rejected) - (ref_chosen - ref_rejected)
+    if loss_type == "sigmoid":
+        return -F.logsigmoid(beta * logits) * (1 - label_smoothing) - F.logsigmoid(-beta * logits) * label_smoothing
+    if loss_type == "ipo":
+        return (logits - 1 / (2 * beta)) ** 2
+    raise ValueError(f"unsupported dpo loss_type {loss_type!r} (sigmoid | ipo)")
+
+
+@register_policy_loss("online_dpo")
+def compute_policy_loss_online_dpo(old_log_prob, log_prob, advantages, response_mask, loss_agg_mode="token-mean",
+                                   config=None, rollout_is_weights=None):
+    """Online DPO / SPIN-style self-play (reference recipe/spin/core_algos.py:59-158): the two samples of every prompt form a pair,
+    the one with the larger sequence score (read from ``advantages``) is 'chosen'; the reference policy of the DPO logit is the
+    behaviour policy of this iteration (``old_log_prob``).  Needs rollout.n = 2 and whole pairs per micro-batch."""
+    beta = _policy_loss_cfg(config, "dpo_beta", 0.1)
+    mask = response_mask.float()
+    seq_lp, seq_old = (log_prob * mask).sum(-1), (old_log_prob * mask).sum(-1)
+    score = (advantages * mask).sum(-1) / mask.sum(-1).clamp(min=1)
+    chosen = pair_preferences(score)
+    losses = dpo_loss(seq_lp[chosen], seq_lp[~chosen], seq_old[chosen], seq_old[~chosen], beta,
+                      _policy_loss_cfg(config, "dpo_label_smoothing", 0.0), _policy_loss_cfg(config, "dpo_loss_type", "sigmoid"))
+    decided = (score[chosen] != score[~chosen]).float()                  # tied pairs carry no preference
+    loss = (losses * decided).sum() / decided.sum().clamp(min=1)
+    margin = ((seq_lp[chosen] - seq_old[chosen]) - (seq_lp[~chosen] - seq_old[~chosen])).detach()
+    return loss, {"actor/dpo_margin": margin.mean().item(), "actor/dpo_acc": (margin > 0).float().mean().item(),
+                  "actor/ppo_kl": masked_mean(old_log_prob - log_prob, response_mask).item()}
 
 
 def _policy_loss_cfg(config, name, default):

@@ -82,6 +82,10 @@ class PolicyLossConfig(BaseConfig):
     clip_cov_ub: float = 5.0
     kl_cov_ratio: float = 0.0002
     ppo_kl_coef: float = 0.1
+    sppo_eta: float = 1.0                # loss_mode=sppo: scale of the sequence reward the log-ratio is regressed onto
+    dpo_beta: float = 0.1                # loss_mode=online_dpo (SPIN-style pairs, rollout.n = 2)
+    dpo_label_smoothing: float = 0.0
+    dpo_loss_type: str = "sigmoid"       # sigmoid | ipo
 
 
 @dataclass

@@ -163,3 +163,38 @@ def test_dapo_filter_groups_masks_uninformative_prompts():
     assert out.batch["response_mask"].sum(-1).tolist() == [0, 0, 0, 0, 4, 4] and m["dapo/filtered_groups"] == 2.0
     with pytest.raises(KeyError):
         filter_uninformative_groups(dp, "nope")
+
+
+def test_cispo_sppo_online_dpo_losses():
+    g = torch.Generator().manual_seed(0)
+    b, t = 6, 5
+    old = -torch.rand(b, t, generator=g)
+    lp = (old + 0.3 * torch.randn(b, t, generator=g)).requires_grad_(True)
+    adv = torch.randn(b, t, generator=g)
+    mask = torch.ones(b, t)
+    mask[2, 3:] = 0
+    cfg = {"clip_ratio": 0.2, "policy_loss": {"sppo_eta": 2.0, "dpo_beta": 0.5}}
+    # CISPO: gradient = -clip(ratio).detach() * A on EVERY unmasked token (also the clipped ones), token-mean
+    loss, m = A.get_policy_loss_fn("cispo")(old, lp, adv, mask, "token-mean", cfg)
+    (grad,) = torch.autograd.grad(loss, lp)
+    ratio = torch.exp(lp.detach() - old)
+    want = -(ratio.clamp(0.8, 1.2) * adv) * mask / mask.sum()
+    assert torch.allclose(grad, want, atol=1e-6) and 0 < m["actor/pg_clipfrac"] < 1
+    assert (grad[mask.bool()] != 0).all()
+    # SPPO: squared distance between the sequence log-ratio and eta * reward
+    seq_r = torch.tensor([1.0, -1.0, 0.5, 0.0, 1.0, -0.5])
+    loss, _ = A.get_policy_loss_fn("sppo")(old, lp, seq_r[:, None].expand(b, t), mask, "token-mean", cfg)
+    lr_ = ((lp.detach() - old) * mask).sum(-1)
+    assert torch.allclose(loss, ((lr_ - 2.0 * seq_r) ** 2).mean(), atol=1e-6)
+    # online DPO: pairs (0,1), (2,3), (4,5); the higher score is chosen; a tied pair is ignored
+    score = torch.tensor([1.0, 0.0, 0.0, 1.0, 0.5, 0.5])
+    assert A.pair_preferences(score).tolist() == [True, False, False, True, True, False]
+    loss, m = A.get_policy_loss_fn("online_dpo")(old, lp, score[:, None].expand(b, t), mask, "token-mean", cfg)
+    s_lp, s_old = (lp.detach() * mask).sum(-1), (old * mask).sum(-1)
+    logit = lambda c, r: (s_lp[c] - s_lp[r]) - (s_old[c] - s_old[r])                       # noqa: E731
+    want = (-torch.nn.functional.logsigmoid(0.5 * logit(0, 1)) - torch.nn.functional.logsigmoid(0.5 * logit(3, 2))) / 2
+    assert torch.allclose(loss, want, atol=1e-6) and 0.0 <= m["actor/dpo_acc"] <= 1.0
+    ipo = A.dpo_loss(torch.tensor([1.0]), torch.tensor([0.0]), torch.tensor([0.2]), torch.tensor([0.1]), beta=0.5, loss_type="ipo")
+    assert torch.allclose(ipo, torch.tensor([(0.9 - 1.0) ** 2]))
+    with pytest.raises(ValueError):
+        A.pair_preferences(torch.zeros(3))
