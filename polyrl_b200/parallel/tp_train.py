@@ -53,6 +53,65 @@ class _ReduceFromTP(torch.autograd.Function):
         return g, None
 
 
+def _all_gather_rows(x: torch.Tensor, group) -> torch.Tensor:
+    parts = [torch.empty_like(x) for _ in range(dist.get_world_size(group))]
+    dist.all_gather(parts, x.contiguous(), group=group)
+    return torch.cat(parts, dim=0)
+
+
+def _reduce_scatter_rows(x: torch.Tensor, group) -> torch.Tensor:
+    tp, r = dist.get_world_size(group), dist.get_rank(group)
+    n = x.shape[0] // tp
+    if x.is_cuda:
+        out = x.new_empty(n, *x.shape[1:])
+        dist.reduce_scatter_tensor(out, x.contiguous(), group=group)
+        return out
+    x = x.contiguous().clone()                   # gloo has no reduce-scatter: all-reduce and keep this rank's rows
+    dist.all_reduce(x, group=group)
+    return x[r * n:(r + 1) * n].contiguous()
+
+
+class _GatherFromSP(torch.autograd.Function):
+    """Megatron sequence parallelism: activations between the blocks' GEMM regions are sharded by token rows.  Entering a
+    column-parallel region: all-gather rows forward, reduce-scatter the gradient backward."""
+
+    @staticmethod
+    def forward(ctx, x, group):
+        ctx.group = group
+        return _all_gather_rows(x, group)
+
+    @staticmethod
+    def backward(ctx, g):
+        return _reduce_scatter_rows(g, ctx.group), None
+
+
+class _ScatterToSP(torch.autograd.Function):
+    """Leaving a row-parallel region: reduce-scatter rows forward (replaces the all-reduce), all-gather the gradient backward."""
+
+    @staticmethod
+    def forward(ctx, x, group):
+        ctx.group = group
+        return _reduce_scatter_rows(x, group)
+
+    @staticmethod
+    def backward(ctx, g):
+        return _all_gather_rows(g, ctx.group), None
+
+
+class _NoReduceBackward(torch.autograd.Function):
+    """Identity whose gradient is divided by tp: placed between an all-gather (whose backward SUMS the ranks' gradients) and a
+    consumer whose backward already delivers the complete, identical gradient on every rank (the vocab-parallel head)."""
+
+    @staticmethod
+    def forward(ctx, x, tp):
+        ctx.tp = tp
+        return x
+
+    @staticmethod
+    def backward(ctx, g):
+        return g / ctx.tp, None
+
+
 def local_config(cfg: ModelConfig, tp: int) -> ModelConfig:
     if cfg.num_experts:
         raise NotImplementedError("tensor parallelism over mixture-of-experts blocks (shard the experts with ZeRO or pipeline stages)")
@@ -85,9 +144,22 @@ def shard_layer(cfg: ModelConfig, w: dict, rank: int, tp: int) -> dict:
     return out
 
 
-def tp_layer_forward(lcfg: ModelConfig, w: dict, x: torch.Tensor, inp: tf.PackedInput, group) -> torch.Tensor:
-    """One decoder block on this rank's head / channel slice; x is replicated across the TP group."""
+def tp_layer_forward(lcfg: ModelConfig, w: dict, x: torch.Tensor, inp: tf.PackedInput, group, sequence_parallel: bool = False) -> torch.Tensor:
+    """One decoder block on this rank's head / channel slice.  x is replicated across the TP group, or — ``sequence_parallel`` —
+    holds this rank's T/tp token rows: norms and residual adds then run on 1/tp of the tokens, the all-reduces become an
+    all-gather into / a reduce-scatter out of each GEMM region (same bytes on the wire, 1/tp of the norm/residual activations)."""
     nq, nkv, d = lcfg.num_heads, lcfg.num_kv_heads, lcfg.head_dim
+    if sequence_parallel:
+        h = _GatherFromSP.apply(ops.rmsnorm(x, w["ln1"], lcfg.rms_norm_eps), group)
+        t = h.shape[0]
+        qkv = tf.qk_norm_(lcfg, w, ops.linear(h, w["wqkv"], bias=w.get("bqkv")))
+        pos, cos, sin = inp.rope_inputs(lcfg, x.device)
+        qkv = ops.apply_rope(qkv, pos, cos, sin, nq, nkv, d)
+        a = attention_varlen(qkv[:, : nq * d].view(t, nq, d), qkv[:, nq * d:(nq + nkv) * d].view(t, nkv, d),
+                             qkv[:, (nq + nkv) * d:].view(t, nkv, d), inp.cu_seqlens, inp.max_seqlen, causal=True).reshape(t, nq * d)
+        x = x + _ScatterToSP.apply(ops.linear(a, w["wo"]), group)
+        h = _GatherFromSP.apply(ops.rmsnorm(x, w["ln2"], lcfg.rms_norm_eps), group)
+        return x + _ScatterToSP.apply(ops.linear(ops.linear_swiglu(h, w["wgu"]), w["wd"]), group)
     t = x.shape[0]
     h = _CopyToTP.apply(ops.rmsnorm(x, w["ln1"], lcfg.rms_norm_eps), group)
     qkv = tf.qk_norm_(lcfg, w, ops.linear(h, w["wqkv"], bias=w.get("bqkv")))
@@ -111,9 +183,10 @@ class TPTrainEngine:
     REPLICATED = ("ln1", "ln2", "embed", "norm_w", "q_norm", "k_norm")
 
     def __init__(self, cfg: ModelConfig, device, tp_group, dp_group=None, lr: float = 1e-6, betas=(0.9, 0.999), eps: float = 1e-8,
-                 weight_decay: float = 0.01, max_grad_norm: float = 1.0, seed: int = 0, dtype=None):
+                 weight_decay: float = 0.01, max_grad_norm: float = 1.0, seed: int = 0, dtype=None, sequence_parallel: bool = False):
         if cfg.family != "llama":
             raise NotImplementedError("TP training is implemented for the llama / qwen block family")
+        self.sequence_parallel = sequence_parallel      # Megatron SP (reference: megatron.yaml sequence_parallel, utils/megatron/sequence_parallel.py)
         self.cfg, self.device = cfg, torch.device(device)
         self.tp_group, self.dp_group = tp_group, dp_group
         self.tp = dist.get_world_size(tp_group)
@@ -152,12 +225,35 @@ class TPTrainEngine:
 
     # ------------------------------------------------------------------ forward
     def forward_hidden(self, inp: tf.PackedInput) -> torch.Tensor:
-        x = torch.nn.functional.embedding(inp.input_ids, self.params["embed"])
+        if not self.sequence_parallel:
+            x = torch.nn.functional.embedding(inp.input_ids, self.params["embed"])
+            for i in range(self.cfg.num_layers):
+                x = tp_layer_forward(self.lcfg, self.layer(i), x, inp, self.tp_group)
+            return x
+        # sequence parallel: pad the packed stream to a multiple of tp (the pad rows form a dummy tail sequence for attention), embed
+        # and keep this rank's rows; the final norm runs on the local rows, then the rows are gathered for the vocab-parallel head
+        t = inp.input_ids.shape[0]
+        pad = (-t) % self.tp
+        ids, full = inp.input_ids, inp
+        if pad:
+            ids = torch.cat([ids, ids.new_full((pad,), self.cfg.pad_token_id)])
+            pos = torch.cat([inp.position_ids, inp.position_ids.new_zeros(pad)])
+            cu = torch.cat([inp.cu_seqlens, inp.cu_seqlens.new_tensor([t + pad])])
+            full = tf.PackedInput(ids, pos, cu, max(inp.max_seqlen, pad))
+        n = ids.shape[0] // self.tp
+        x = torch.nn.functional.embedding(ids[self.tp_rank * n:(self.tp_rank + 1) * n], self.params["embed"])
         for i in range(self.cfg.num_layers):
-            x = tp_layer_forward(self.lcfg, self.layer(i), x, inp, self.tp_group)
+            x = tp_layer_forward(self.lcfg, self.layer(i), x, full, self.tp_group, sequence_parallel=True)
+        self._sp_rows = (t, pad)
         return x
 
     def forward_logprob_entropy(self, inp: tf.PackedInput, labels: torch.Tensor, temperature: float = 1.0):
+        if self.sequence_parallel:
+            x = self.forward_hidden(inp)
+            h = _GatherFromSP.apply(ops.rmsnorm(x, self.params["norm_w"], self.cfg.rms_norm_eps), self.tp_group)[: self._sp_rows[0]]
+            # the gathered rows feed a vocab-parallel head whose backward already all-reduces dH: scale-free hand-over
+            return ops.linear_cross_entropy_tp(_NoReduceBackward.apply(h, self.tp), self.params["lm_head"], labels, float(temperature),
+                                               self.tp_group, self.vocab_start)
         h = ops.rmsnorm(self.forward_hidden(inp), self.params["norm_w"], self.cfg.rms_norm_eps)
         # vocab-parallel fused linear-CE: its backward all-reduces dH over the TP group, so every rank continues with the
         # complete (identical) gradient — no extra copy-to-TP wrapper here
@@ -173,6 +269,8 @@ class TPTrainEngine:
         grads = {}
         for k, p in self.params.items():
             g = p.grad.float() if p.grad is not None else torch.zeros_like(self.master[k])
+            if self.sequence_parallel and self.is_replicated(k):
+                dist.all_reduce(g, group=self.tp_group)       # norms / embedding saw only this rank's token rows
             if self.dp > 1:
                 dist.all_reduce(g, group=self.dp_group)
                 g /= self.dp

@@ -38,11 +38,13 @@ def main():
             dp_group = g
     cfg = get_model_config("tiny-llama-128" if cuda else "tiny-llama")
     dtype = torch.bfloat16 if cuda else torch.float32
-    eng = TPTrainEngine(cfg, dev, tp_group, dp_group if dp > 1 else None, lr=1e-2, weight_decay=0.0, seed=11, dtype=dtype)
+    sp_mode = os.environ.get("TP_TRAIN_SP", "0") == "1"                 # Megatron sequence parallelism inside the TP group
+    eng = TPTrainEngine(cfg, dev, tp_group, dp_group if dp > 1 else None, lr=1e-2, weight_decay=0.0, seed=11, dtype=dtype,
+                        sequence_parallel=sp_mode)
 
     def batch(dp_rank: int):
         gen = torch.Generator().manual_seed(500 + dp_rank)
-        ids = torch.randint(3, cfg.vocab_size, (2, 19), generator=gen).to(dev)
+        ids = torch.randint(3, cfg.vocab_size, (3 if sp_mode else 2, 19), generator=gen).to(dev)      # 57 tokens: odd, exercises the SP tail padding
         inp, _ = pack_padded(ids, torch.ones_like(ids))
         labels = torch.randint(0, cfg.vocab_size, (inp.input_ids.numel(),), generator=gen).to(dev)
         return inp, labels
