@@ -125,6 +125,18 @@ def main():
     assert abs(ma["actor/pg_loss"] - mb_["actor/pg_loss"]) < 1e-5 and abs(sa["grad_norm"] - sb["grad_norm"]) < 1e-4
     full_a, full_b = ppe.engine.gather_full_state(), dict(ze.engine.named_full_tensors())
     assert max(((full_a[n] - full_b[n]).norm() / (full_b[n].norm() + 1e-9)).item() for n in full_b) < 2e-3
+    # role worker on top of either backend: identical PPO update (two mini-batches -> two optimizer steps)
+    from polyrl_b200.protocol import DataProto
+    from polyrl_b200.workers.roles import ActorWorker
+
+    dp_ = DataProto.from_dict({k: v for k, v in batch.items()})
+    dp_.meta_info["temperature"] = 1.0
+    ra, rb = ActorWorker(ppe, ppo_mini_batch_size=3), ActorWorker(ze, ppo_mini_batch_size=3)
+    la, lb = ra.compute_log_prob(dp_).batch["old_log_probs"], rb.compute_log_prob(dp_).batch["old_log_probs"]
+    assert (la - lb).abs().max() < 1e-4
+    ma2, mb2 = ra.update_actor(dp_), rb.update_actor(dp_)
+    assert abs(ma2["actor/pg_loss"] - mb2["actor/pg_loss"]) < 1e-4 and abs(ma2["actor/grad_norm"] - mb2["actor/grad_norm"]) < 1e-3
+    assert ppe.engine.opt_step == ze.engine.opt_step == 3
     d = tempfile.gettempdir() + f"/pp_ckpt_{os.environ.get('MASTER_PORT', '0')}_{rank // 2}"
     ppe.save_checkpoint(d, global_step=3)
     other = get_engine_cls("language_model", "pp")("tiny-llama", "cpu", pp_group, None, lr=1e-2, micro_batch_size=2, weight_decay=0.0, seed=99)

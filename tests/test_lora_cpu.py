@@ -143,3 +143,48 @@ def test_engine_api_sft_ppo_value_and_checkpoint(tmp_path):
     with veng.train_mode():
         m = veng.train_batch({**batch, "values": vals, "returns": vals + 1.0}, value_loss(0.5))
         assert m["critic/vf_loss"] > 0
+
+
+def test_role_workers_over_base_engine_match_the_streaming_actor():
+    """ActorWorker / CriticWorker (roles over BaseEngine): log-probs equal the hybrid worker's actor on the same weights, an update
+    with two mini-batches takes two optimizer steps and lowers the surrogate loss; the critic role fits returns."""
+    from polyrl_b200.protocol import DataProto
+    from polyrl_b200.workers.engine_api import get_engine_cls
+    from polyrl_b200.workers.roles import ActorWorker, CriticWorker
+
+    g = torch.Generator().manual_seed(0)
+    b, p, r = 8, 6, 5
+    ids = torch.randint(3, 200, (b, p + r), generator=g)
+    mask = torch.ones_like(ids)
+    mask[1, :2] = 0
+    data = DataProto.from_dict({"input_ids": ids, "attention_mask": mask, "position_ids": (mask.cumsum(-1) - 1).clamp_min(0),
+                                "responses": ids[:, p:], "response_mask": mask[:, p:]})
+    data.meta_info["temperature"] = 1.0
+    actor = ActorWorker(get_engine_cls("language_model", "zero")("tiny-llama", "cpu", lr=1e-2, micro_batch_size=2, weight_decay=0.0, seed=4),
+                        ppo_mini_batch_size=4, clip_ratio=0.2)
+    actor.init_model()
+    old = actor.compute_log_prob(data)
+    assert old.batch["old_log_probs"].shape == (b, r) and old.batch["entropys"].min() > 0
+    # oracle: the streaming actor on the same weights
+    from polyrl_b200.workers.actor import ActorConfig, DataParallelPPOActor
+
+    dpa = DataParallelPPOActor(actor.engine.engine, ActorConfig(ppo_mini_batch_size=8, ppo_micro_batch_size_per_gpu=4))
+    lp2, _ = dpa.compute_log_prob(data)
+    assert (lp2 - old.batch["old_log_probs"]).abs().max() < 1e-5
+    data = data.union(old)
+    data.batch["advantages"] = torch.randn(b, r, generator=g)
+    step0 = actor.engine.engine.opt_step
+    m = actor.update_actor(data)
+    assert actor.engine.engine.opt_step == step0 + 2 and m["actor/grad_norm"] > 0 and "actor/pg_loss" in m
+    new = actor.compute_log_prob(data).batch["old_log_probs"]
+    adv, msk = data.batch["advantages"], data.batch["response_mask"].float()
+    surrogate = lambda lp: -((torch.exp(lp - data.batch["old_log_probs"]) * adv) * msk).sum() / msk.sum()      # noqa: E731
+    assert surrogate(new) < surrogate(data.batch["old_log_probs"])
+    critic = CriticWorker(get_engine_cls("value_model", "zero")("tiny-llama", "cpu", lr=5e-4, micro_batch_size=4, weight_decay=0.0, seed=5),
+                          ppo_mini_batch_size=8, ppo_epochs=4)
+    critic.init_model()
+    v0 = critic.compute_values(data).batch["values"]
+    data.batch["values"], data.batch["returns"] = v0, torch.ones(b, r)
+    m = critic.update_critic(data)
+    v1 = critic.compute_values(data).batch["values"]
+    assert "critic/vf_loss" in m and ((v1 - 1) ** 2).mean() < ((v0 - 1) ** 2).mean()
