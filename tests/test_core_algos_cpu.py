@@ -198,3 +198,35 @@ def test_cispo_sppo_online_dpo_losses():
     assert torch.allclose(ipo, torch.tensor([(0.9 - 1.0) ** 2]))
     with pytest.raises(ValueError):
         A.pair_preferences(torch.zeros(3))
+
+
+def test_prime_implicit_reward_blocks():
+    from polyrl_b200.algos import prime as P
+
+    g = torch.Generator().manual_seed(0)
+    b, t, n = 4, 5, 2
+    mask = torch.ones(b, t)
+    mask[1, 3:] = 0
+    prm, refp = -torch.rand(b, t, generator=g), -torch.rand(b, t, generator=g)
+    q = P.implicit_process_rewards(prm, refp, mask, beta=0.5)
+    assert torch.allclose(q, 0.5 * (prm - refp) * mask)
+    whole = P.implicit_process_rewards(prm, refp, mask, beta=0.5, granularity="whole")
+    assert torch.allclose(whole[1, 2], q[1].sum()) and whole[1].abs().sum() == whole[1, 2].abs() and torch.allclose(whole[0, 4], q[0].sum())
+    acc = torch.tensor([1.0, 0.0, 0.0, 0.0])
+    scores = (prm - refp)
+    loss = P.prm_ce_loss(scores, acc, mask, beta=0.5)
+    want = torch.nn.functional.binary_cross_entropy(torch.sigmoid(0.5 * (scores * mask).sum(-1)), acc)
+    assert torch.allclose(loss, want, atol=1e-6)
+    # leave-one-out: with outcome rewards only, pair (1, 0) -> +1*2-1 = 1 and 0*2-1 = -1 on the last tokens; a tied pair -> 0
+    adv, ret = P.prime_advantages(mask, n, acc=acc, reward_gt_coef=1.0, reward_dpo_coef=0.0)
+    assert ret[0].tolist() == [1.0] * 5 and ret[1].tolist() == [-1.0, -1.0, -1.0, 0.0, 0.0] and ret[2].abs().sum() == 0 and ret[3].abs().sum() == 0
+    assert abs(float((adv * mask).sum() / mask.sum())) < 1e-5
+    adv2, ret2 = P.prime_advantages(mask, n, acc=acc, process_rewards=q, reward_gt_coef=1.0, reward_dpo_coef=1.0)
+    assert not torch.allclose(ret2, ret) and torch.isfinite(adv2).all()
+    # ordering accuracy of the implicit reward
+    s = torch.zeros(b, t)
+    s[0, 0], s[1, 0] = 2.0, 1.0            # pair 0 ordered like acc (1 > 0); pair 1 tied labels -> ignored
+    assert P.pairwise_accuracy(s, acc, mask, n) == 1.0 and P.pairwise_accuracy(-s, acc, mask, n) == 0.0
+    assert P.pairwise_accuracy(s, torch.zeros(b), mask, n) == 0.5
+    with pytest.raises(ValueError):
+        P.prime_advantages(mask, 1, acc=acc)
