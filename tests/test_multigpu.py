@@ -6,7 +6,6 @@ _sys.path.insert(0, _os.path.dirname(_os.path.abspath(__file__)))
 from _spawn import run_torchrun  # noqa: E402
 import json
 import os
-import subprocess
 import sys
 
 from pathlib import Path

@@ -7,12 +7,10 @@ import sys as _sys
 _sys.path.insert(0, _os.path.dirname(_os.path.abspath(__file__)))
 from _spawn import run_torchrun  # noqa: E402
 import os
-import subprocess
 import sys
 
 from pathlib import Path
 
-import pytest
 
 ROOT = Path(__file__).resolve().parent.parent
 
