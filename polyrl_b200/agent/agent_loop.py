@@ -48,6 +48,8 @@ class AgentLoopOutput:
     turn_scores: list[float] = field(default_factory=list)
     metrics: dict = field(default_factory=dict)
     finish_reason: str = "stop"
+    # vision-language trajectories: every image of the sequence in order — the prompt's and those returned by tools
+    multi_modal_inputs: dict | None = None
 
 
 @dataclass
@@ -69,6 +71,16 @@ class _Traj:
     finish_reason: str = "stop"
     metrics: dict = field(default_factory=lambda: {"generate_s": 0.0, "tool_s": 0.0, "tool_calls": 0})
     t_submit: float = 0.0
+    mm: dict | None = None                    # {"pixel_values": [N, patch_dim], "grid_thw": [(t, h, w), ...]} so far
+
+
+def _engine_mm(mm: dict | None) -> dict | None:
+    """Dataset-style ``multi_modal_inputs`` (``image_grid_thw`` tensor) -> the engine's {"pixel_values", "grid_thw": [tuples]}."""
+    if mm is None:
+        return None
+    grid = mm["image_grid_thw"] if "image_grid_thw" in mm else mm["grid_thw"]
+    grid = grid.tolist() if hasattr(grid, "tolist") else list(grid)
+    return {"pixel_values": mm["pixel_values"], "grid_thw": [tuple(int(x) for x in g) for g in grid]}
 
 
 def _truncate(text: str, limit: int, side: str) -> str:
@@ -92,8 +104,13 @@ class MultiTurnRollout:
                  interactions: dict[str, BaseInteraction] | None = None, parser: str = "hermes",
                  response_length: int = 512, max_assistant_turns: int = 4, max_user_turns: int = 4,
                  max_parallel_calls: int = 1, max_tool_response_length: int = 256,
-                 tool_response_truncate_side: str = "middle", tool_workers: int = 8):
+                 tool_response_truncate_side: str = "middle", tool_workers: int = 8, model_cfg=None,
+                 image_min_pixels: int | None = None, image_max_pixels: int | None = None):
         self.engine, self.tok = engine, tokenizer
+        # vision-language policies: images returned by tools become image-token runs in the context (reference: the deepeyes /
+        # image_zoom_in_tool path of tool_agent_loop.py) — needs the model config for the patch geometry and token ids
+        self.vl_cfg = model_cfg if (model_cfg is not None and getattr(model_cfg, "vision", None) is not None) else None
+        self.image_pixels = (image_min_pixels, image_max_pixels)
         self.tools = {t.name: t for t in (tools or [])}
         self.tool_schemas = [t.schema.to_openai() for t in (tools or [])]
         self.interactions = interactions or {}
@@ -123,6 +140,29 @@ class MultiTurnRollout:
         """Tokens of tool / user turns followed by the next assistant generation prompt."""
         return self._template(self._base + messages, add_generation_prompt=True)[self._base_len:]
 
+    def _encode_turns_with_images(self, msgs: list[dict]):
+        """Like ``encode_turns`` for turns that carry an image: the turn's text gets an ``<image>`` mark, the rendered text is split
+        at the marks and each mark becomes ``vision_start + image_pad * n + vision_end`` -> (ids, patch tensors, grids)."""
+        from ..models import vision as V
+
+        cfg, mark = self.vl_cfg, "<image>"
+        marked = [{"role": m["role"], "content": (m["content"] + mark) if m.get("image") is not None else m["content"]} for m in msgs]
+        base = self.tok.apply_chat_template(self._base, add_generation_prompt=False, tokenize=False)
+        text = self.tok.apply_chat_template(self._base + marked, add_generation_prompt=True, tokenize=False)[len(base):]
+        parts = text.split(mark)
+        images = [m["image"] for m in msgs if m.get("image") is not None]
+        if len(parts) - 1 != len(images):
+            raise ValueError("chat template dropped or duplicated an <image> mark")
+        ids = list(self.tok.encode(parts[0], add_special_tokens=False))
+        pix, grids = [], []
+        for img, seg in zip(images, parts[1:]):
+            pv, g = V.preprocess_image(cfg, img, *self.image_pixels)
+            pix.append(pv)
+            grids.append(g)
+            ids += [cfg.vision_start_token_id] + [cfg.image_token_id] * V.num_image_tokens(cfg, [g])[0] + [cfg.vision_end_token_id]
+            ids += list(self.tok.encode(seg, add_special_tokens=False))
+        return ids, pix, grids
+
     def encode_prompt(self, messages: list[dict]) -> list[int]:
         return self._template(messages, add_generation_prompt=True, tools=self.tool_schemas or None)
 
@@ -134,7 +174,10 @@ class MultiTurnRollout:
         sp["n"] = 1
         tr.state = AgentState.GENERATING
         tr.t_submit = time.time()
-        req = self.engine.add_request(tr.prompt_ids + tr.response_ids, sp)
+        if tr.mm is not None:
+            req = self.engine.add_request(tr.prompt_ids + tr.response_ids, sp, mm=tr.mm)
+        else:
+            req = self.engine.add_request(tr.prompt_ids + tr.response_ids, sp)
         self._by_rid[req.rid] = tr
 
     def _terminate(self, tr: _Traj, reason: str | None = None) -> None:
@@ -177,17 +220,30 @@ class MultiTurnRollout:
             with rollout_trace_attr(sample_index=tr.index, name="tool_call"):
                 resp, reward, _ = self._call_tool(tr, c)
             tr.tool_rewards.append(reward)
-            msgs.append({"role": "tool", "content": resp.text})
+            msg = {"role": "tool", "content": resp.text}
+            if resp.image is not None and self.vl_cfg is not None:
+                msg["image"] = resp.image
+            msgs.append(msg)
         tr.metrics["tool_s"] += time.time() - t0
         tr.metrics["tool_calls"] += len(msgs)
         return msgs
 
     def _append_context(self, tr: _Traj, msgs: list[dict]) -> bool:
         """Append non-assistant turns (mask 0).  False when the response budget is exhausted."""
-        ids = self.encode_turns(msgs)
+        images = [m["image"] for m in msgs if m.get("image") is not None]
+        if images:
+            ids, pix, grids = self._encode_turns_with_images(msgs)
+        else:
+            ids = self.encode_turns(msgs)
         room = self.response_length - len(tr.response_ids)
         if len(ids) >= room:
             return False
+        if images:
+            if tr.mm is None:
+                tr.mm = {"pixel_values": torch.cat(pix), "grid_thw": list(grids)}
+            else:
+                tr.mm = {"pixel_values": torch.cat([tr.mm["pixel_values"], *pix]), "grid_thw": list(tr.mm["grid_thw"]) + list(grids)}
+            msgs = [{k: v for k, v in m.items() if k != "image"} for m in msgs]
         tr.response_ids += ids
         tr.response_mask += [0] * len(ids)
         tr.logprobs += [0.0] * len(ids)
@@ -232,7 +288,8 @@ class MultiTurnRollout:
         for i, s in enumerate(samples):
             msgs = list(s.get("messages") or [])
             pids = list(map(int, s["prompt_ids"])) if s.get("prompt_ids") is not None else self.encode_prompt(msgs)
-            trajs.append(_Traj(index=i, prompt_ids=pids, messages=msgs, extra=s))
+            mm0 = _engine_mm(s.get("multi_modal_inputs"))
+            trajs.append(_Traj(index=i, prompt_ids=pids, messages=msgs, extra=s, mm=mm0))
         for tr in trajs:
             self._submit(tr, sampling)
         futures: dict[Future, _Traj] = {}
@@ -261,7 +318,9 @@ class MultiTurnRollout:
             outs.append(AgentLoopOutput(prompt_ids=tr.prompt_ids, response_ids=tr.response_ids, response_mask=tr.response_mask,
                                         response_logprobs=tr.logprobs, num_turns=tr.assistant_turns + tr.user_turns + 1
                                         + tr.metrics["tool_calls"], tool_rewards=tr.tool_rewards, turn_scores=tr.turn_scores,
-                                        metrics=tr.metrics, finish_reason=tr.finish_reason))
+                                        metrics=tr.metrics, finish_reason=tr.finish_reason,
+                                        multi_modal_inputs=None if tr.mm is None else
+                                        {"pixel_values": tr.mm["pixel_values"], "image_grid_thw": torch.tensor(tr.mm["grid_thw"])}))
         return outs
 
 
@@ -277,7 +336,7 @@ class SingleTurnAgentLoop(MultiTurnRollout):
 
 
 def outputs_to_dataproto(outs: list[AgentLoopOutput], prompt_length: int, response_length: int, pad_id: int,
-                         non_tensors: dict[str, Any] | None = None) -> DataProto:
+                         non_tensors: dict[str, Any] | None = None, model_cfg=None) -> DataProto:
     """Left-pad prompts / right-pad responses into the trainer batch layout (keys of SURVEY.md Appendix D)."""
     b = len(outs)
     prompts = torch.full((b, prompt_length), pad_id, dtype=torch.long)
@@ -297,9 +356,43 @@ def outputs_to_dataproto(outs: list[AgentLoopOutput], prompt_length: int, respon
         lps[i, :n] = torch.tensor(o.response_logprobs[:n], dtype=torch.float32)
     attention_mask = torch.cat([p_mask, r_att], dim=1)
     position_ids = (attention_mask.cumsum(-1) - 1).clamp_min(0)
+    vl = model_cfg is not None and getattr(model_cfg, "vision", None) is not None
+    if vl:
+        # 3-axis M-RoPE positions over prompt + response: tool images inside the response shift everything after them
+        from ..models.vision import mrope_positions
+
+        pos3 = position_ids.unsqueeze(1).repeat(1, 3, 1)
+        for i, o in enumerate(outs):
+            if o.multi_modal_inputs is None:
+                continue
+            p = o.prompt_ids[-prompt_length:]
+            if len(p) < len(o.prompt_ids):
+                raise ValueError("an image prompt does not fit prompt_length")
+            n = min(len(o.response_ids), response_length)
+            grids = [tuple(int(x) for x in g) for g in o.multi_modal_inputs["image_grid_thw"].tolist()]
+            seq = p + o.response_ids[:n]
+            n_img_tok = sum(t in (model_cfg.image_token_id, model_cfg.video_token_id) for t in seq)
+            m2 = model_cfg.vision.get("spatial_merge_size", 2) ** 2
+            keep, acc = [], 0
+            for g in grids:                                   # a truncated response may have lost its last image run
+                k = g[0] * g[1] * g[2] // m2
+                if acc + k > n_img_tok:
+                    break
+                keep.append(g)
+                acc += k
+            if acc != n_img_tok:
+                raise ValueError("response truncation cut through an image token run")
+            pm, _ = mrope_positions(model_cfg, seq, keep)
+            pos3[i, :, prompt_length - len(p): prompt_length + n] = pm
+        position_ids = pos3
     nt = {"__num_turns__": np.array([o.num_turns for o in outs], dtype=np.int64),
           "tool_rewards": np.array([json.dumps(o.tool_rewards) for o in outs], dtype=object),
           "turn_scores": np.array([json.dumps(o.turn_scores) for o in outs], dtype=object)}
+    if vl or any(o.multi_modal_inputs is not None for o in outs):
+        mm_arr = np.empty(b, dtype=object)
+        for i, o in enumerate(outs):
+            mm_arr[i] = o.multi_modal_inputs
+        nt["multi_modal_inputs"] = mm_arr
     nt.update(non_tensors or {})
     return DataProto.from_dict({"prompts": prompts, "responses": resp, "input_ids": torch.cat([prompts, resp], dim=1),
                                 "attention_mask": attention_mask, "position_ids": position_ids, "response_mask": r_loss,

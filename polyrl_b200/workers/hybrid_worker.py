@@ -398,7 +398,8 @@ class ActorRolloutRefWorker:
                 self.rollout, tok, tools=load_tools(mt.tool_config_path), interactions=load_interactions(mt.interaction_config_path),
                 parser=mt.format, response_length=resp_len, max_assistant_turns=mt.max_assistant_turns,
                 max_user_turns=mt.max_user_turns, max_parallel_calls=mt.max_parallel_calls,
-                max_tool_response_length=mt.max_tool_response_length, tool_response_truncate_side=mt.tool_response_truncate_side)
+                max_tool_response_length=mt.max_tool_response_length, tool_response_truncate_side=mt.tool_response_truncate_side,
+                model_cfg=self.model_cfg, image_min_pixels=self.config.data.image_min_pixels, image_max_pixels=self.config.data.image_max_pixels)
         self._multi_turn.response_length = resp_len
         nt = prompts.non_tensor_batch
         samples = []
@@ -409,10 +410,12 @@ class ActorRolloutRefWorker:
                     s[key] = nt[key][i]
             if "raw_prompt" in nt:
                 s["messages"] = list(nt["raw_prompt"][i])
+            if "multi_modal_inputs" in nt and nt["multi_modal_inputs"][i] is not None:
+                s["multi_modal_inputs"] = nt["multi_modal_inputs"][i]
             samples += [dict(s) for _ in range(n)]
         outs = self._multi_turn.generate(samples, {"temperature": sp.temperature, "top_p": sp.top_p, "top_k": sp.top_k})
         rep = prompts.repeat(n, interleave=True) if n > 1 else prompts
-        dp = outputs_to_dataproto(outs, rep.batch["input_ids"].shape[1], resp_len, self.model_cfg.pad_token_id)
+        dp = outputs_to_dataproto(outs, rep.batch["input_ids"].shape[1], resp_len, self.model_cfg.pad_token_id, model_cfg=self.model_cfg)
         dev = rep.batch["input_ids"].device
         for k, v in dp.batch.items():
             rep.batch[k] = v.to(dev)

@@ -340,3 +340,64 @@ def test_remote_and_image_tools_against_local_fake_services():
     g = load_tools({"tools": [{"class_name": "calc_geo3k_reward"}]})[0]
     gid, _ = g.create(ground_truth="45")
     assert g.execute(gid, {"answer": "45"})[0].text.endswith("reward=1.0") and g.calc_reward(gid) == 1.0
+
+
+def test_image_tool_responses_extend_the_vision_context(tmp_path):
+    """Vision-language multi-turn: the zoom tool's crop enters the context as an image-token run, the trajectory's patches grow, the
+    batch carries 3-axis positions over prompt + response and the trainer can score it (tower rows == placeholders)."""
+    import numpy as np
+    from PIL import Image
+
+    from polyrl_b200.config.schema import load_config
+    from polyrl_b200.models import vision as V
+    from polyrl_b200.models.config import get_model_config
+    from polyrl_b200.workers.hybrid_worker import ActorRolloutRefWorker
+
+    cfg = get_model_config("tiny-qwen2-vl")
+    tok = ByteTokenizer()
+    img = Image.fromarray(np.random.default_rng(0).integers(0, 255, size=(32, 48, 3), dtype=np.uint8))
+    pv, g = V.preprocess_image(cfg, img, 64, 1024)
+    n0 = V.num_image_tokens(cfg, [g])[0]
+    prompt = tok.encode("<user>") + [cfg.vision_start_token_id] + [cfg.image_token_id] * n0 + [cfg.vision_end_token_id] + tok.encode("what is in the corner?\n<assistant>")
+
+    seen_mm = []
+
+    class VLScripted(ScriptedEngine):
+        def add_request(self, prompt_ids, params=None, rid=None, group=None, mm=None):
+            seen_mm.append(None if mm is None else (mm["pixel_values"].shape[0], list(mm["grid_thw"])))
+            return super().add_request(prompt_ids, params, rid, group)
+
+    def policy(ctx: str) -> str:
+        if "<tool>" not in ctx:
+            return 'look closer <tool_call>{"name": "image_zoom_in_tool", "arguments": {"bbox_2d": [0, 0, 24, 16], "label": "corner"}}</tool_call>'
+        return "a cat"
+
+    tools = load_tools({"tools": [{"class_name": "image_zoom_in_tool", "config": {"min_size": 8}}]})
+    roll = MultiTurnRollout(VLScripted(tok, policy), tok, tools=tools, response_length=200, max_assistant_turns=3, model_cfg=cfg,
+                            image_min_pixels=64, image_max_pixels=1024)
+    sample = {"prompt_ids": prompt, "multi_modal_inputs": {"pixel_values": pv, "image_grid_thw": torch.tensor([g])},
+              "tools_kwargs": {"image_zoom_in_tool": {"create_kwargs": {"image": img}}}}
+    (o,) = roll.generate([sample], {"temperature": 1.0})
+    assert o.finish_reason == "stop" and o.metrics["tool_calls"] == 1
+    grids = [tuple(x) for x in o.multi_modal_inputs["image_grid_thw"].tolist()]
+    assert len(grids) == 2 and grids[0] == g and seen_mm[0] == (pv.shape[0], [g]) and seen_mm[1][1] == grids
+    n1 = V.num_image_tokens(cfg, grids)[1]
+    assert o.response_ids.count(cfg.image_token_id) == n1 and o.multi_modal_inputs["pixel_values"].shape[0] == pv.shape[0] + grids[1][0] * grids[1][1] * grids[1][2]
+    img_pos = [k for k, t in enumerate(o.response_ids) if t == cfg.image_token_id]
+    assert all(o.response_mask[k] == 0 for k in img_pos)                      # tool image tokens carry no loss
+    assert tok.decode([t for t, m in zip(o.response_ids, o.response_mask) if m]).endswith("a cat")
+    dp = outputs_to_dataproto([o], prompt_length=96, response_length=200, pad_id=0, model_cfg=cfg)
+    pos3 = dp.batch["position_ids"]
+    n = len(o.response_ids)
+    want, _ = V.mrope_positions(cfg, prompt + o.response_ids, grids)
+    assert pos3.shape == (1, 3, 296) and torch.equal(pos3[0, :, 96 - len(prompt): 96 + n], want)
+    assert not torch.equal(pos3[0, 0], pos3[0, 1])                            # image rows really use separate axes
+    # the trainer consumes it: log-probs over the response, tower fed with both images
+    c = load_config(None, ["trainer.device=cpu", "actor_rollout_ref.model.path=tiny-qwen2-vl", "data.max_prompt_length=96",
+                           "data.max_response_length=200", "actor_rollout_ref.rollout.max_num_seqs=4", "actor_rollout_ref.rollout.cuda_graph=False",
+                           "actor_rollout_ref.actor.ppo_mini_batch_size=1", "actor_rollout_ref.actor.ppo_micro_batch_size_per_gpu=1"])
+    wk = ActorRolloutRefWorker(c, role="actor", device="cpu")
+    wk.init_model()
+    dp.meta_info.update(temperature=1.0, micro_batch_size=1)
+    lp = wk.compute_log_prob(dp).batch["old_log_probs"]
+    assert lp.shape == (1, 200) and torch.isfinite(lp).all() and (lp[0, :n][torch.tensor(o.response_mask, dtype=torch.bool)] < 0).all()
