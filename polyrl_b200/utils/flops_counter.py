@@ -36,7 +36,11 @@ class FlopsCounter:
     def _dense_params(self) -> int:
         c = self.cfg
         h, f, v = c.hidden_size, c.intermediate_size, c.vocab_size
-        per_layer = h * (c.q_size + 2 * c.kv_size) + c.q_size * h + (3 * h * f if c.family == "llama" else 2 * h * f)
+        if c.num_experts:                                 # MoE: only the routed experts (+ the router) do work per token
+            mlp = c.num_experts_per_tok * 3 * h * c.moe_intermediate_size + c.num_experts * h
+        else:
+            mlp = 3 * h * f if c.family == "llama" else 2 * h * f
+        per_layer = h * (c.q_size + 2 * c.kv_size) + c.q_size * h + mlp
         return per_layer * c.num_layers + v * h           # lm_head included, input embedding lookup excluded
 
     def estimate_flops(self, batch_seqlens: list[int], delta_time: float, forward_only: bool = False) -> tuple[float, float]:
