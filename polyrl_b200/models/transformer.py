@@ -116,6 +116,13 @@ def qk_norm_(cfg: ModelConfig, w: dict, qkv: torch.Tensor) -> torch.Tensor:
     return torch.cat([q.reshape(t, nq * d), k.reshape(t, nkv * d), qkv[:, (nq + nkv) * d:]], dim=-1)
 
 
+def _MOE_STATIC_DECODE() -> bool:
+    """``POLYRL_MOE_STATIC_DECODE=1``: decode steps of MoE models use the static-shape expert path (graph-capturable)."""
+    import os
+
+    return os.environ.get("POLYRL_MOE_STATIC_DECODE", "0") == "1"
+
+
 def moe_load_balance_loss(cfg: ModelConfig, probs: torch.Tensor, top_e: torch.Tensor) -> torch.Tensor:
     """Switch-style auxiliary loss of one block: ``E * sum_e f_e * P_e`` with f_e the fraction of (token, slot) assignments routed to
     expert e and P_e the mean router probability of e (HF ``load_balancing_loss_func`` evaluated per layer)."""
@@ -151,6 +158,32 @@ def moe_mlp(cfg: ModelConfig, w: dict, h: torch.Tensor, aux_out: list | None = N
         outs.append(ops.linear(a, w["ewd"][e]))
         lo += n
     y = torch.cat(outs, dim=0) * gate_w.unsqueeze(-1)
+    return torch.zeros(t, h.shape[1], dtype=y.dtype, device=h.device).index_add(0, tok, y)
+
+
+def moe_mlp_static(cfg: ModelConfig, w: dict, h: torch.Tensor) -> torch.Tensor:
+    """``moe_mlp`` with static shapes and no host synchronisation, so a decode step over a fixed batch can be captured in a CUDA
+    graph: assignments are sorted by expert, scattered into an [E, C, H] buffer with capacity C = T (an expert can receive at most
+    every token once, nothing is ever dropped) and all experts run as two batched GEMMs.  Padded rows cost FLOPs but no weight
+    traffic beyond reading each expert once, which a decode step pays anyway — meant for T <= a few hundred rows."""
+    t, k, e = h.shape[0], cfg.num_experts_per_tok, cfg.num_experts
+    probs = torch.softmax(F.linear(h, w["router"].to(h.dtype)).float(), dim=-1)
+    top_w, top_e = torch.topk(probs, k, dim=-1)
+    if cfg.norm_topk_prob:
+        top_w = top_w / top_w.sum(-1, keepdim=True)
+    flat_e = top_e.reshape(-1)
+    order = torch.argsort(flat_e, stable=True)
+    sorted_e = flat_e[order]
+    tok = torch.div(order, k, rounding_mode="floor")
+    counts = torch.bincount(flat_e, minlength=e)
+    start = counts.cumsum(0) - counts
+    slot = torch.arange(t * k, device=h.device) - start[sorted_e]                 # position of the assignment inside its expert
+    x = h.new_zeros(e, t, h.shape[1])
+    x[sorted_e, slot] = h.index_select(0, tok)
+    gu = torch.bmm(x, w["ewgu"].to(h.dtype).transpose(1, 2))                      # [E, T, 2f]
+    a = ref.swiglu(gu.reshape(e * t, -1)).reshape(e, t, -1)
+    y = torch.bmm(a, w["ewd"].to(h.dtype).transpose(1, 2))[sorted_e, slot]          # [T*k, H] in assignment order
+    y = y * top_w.reshape(-1)[order].to(h.dtype).unsqueeze(-1)
     return torch.zeros(t, h.shape[1], dtype=y.dtype, device=h.device).index_add(0, tok, y)
 
 
@@ -319,7 +352,7 @@ def layer_decode(cfg: ModelConfig, w: dict, x: torch.Tensor, inp: DecodeInput, k
         x = ops.linear(a, w["wo"], residual=x)
         h = ops.rmsnorm(x, w["ln2"], cfg.rms_norm_eps)
         if "router" in w:
-            return x + moe_mlp(cfg, w, h)
+            return x + (moe_mlp_static(cfg, w, h) if _MOE_STATIC_DECODE() else moe_mlp(cfg, w, h))
         a = ops.linear_swiglu(h, w["wgu"])
         return ops.linear(a, w["wd"], residual=x)
     h = F.layer_norm(x, (cfg.hidden_size,), w["ln1_w"], w["ln1_b"], cfg.rms_norm_eps)

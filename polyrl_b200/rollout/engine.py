@@ -217,7 +217,8 @@ class RolloutEngine:
         self.max_blocks_per_seq = (max_model_len + PAGE - 1) // PAGE
         self.max_prefill_tokens = max_prefill_tokens
         # MoE blocks group tokens by expert with data-dependent shapes (host-side counts): their decode step cannot be captured
-        self.use_cuda_graph = use_cuda_graph and self.is_cuda and not cfg.num_experts
+        # (POLYRL_MOE_STATIC_DECODE=1 switches decode to the static-shape expert path, which can)
+        self.use_cuda_graph = use_cuda_graph and self.is_cuda and (not cfg.num_experts or tf._MOE_STATIC_DECODE())
         self.gpu_memory_utilization = gpu_memory_utilization
         self._kv_tokens_req = kv_cache_tokens
         self.embed_w: dict | None = None
