@@ -543,3 +543,31 @@ def test_video_inputs_positions_tower_and_dataset(tmp_path):
         logits = tf.logits_forward(hcfg, w.head, w.embed, tf.forward_hidden(hcfg, w, inp))
     k = len(r.prompt_ids) - 1
     assert logits[k:k + 4].argmax(-1).tolist() == r.output_ids
+
+
+def test_model_merger_handles_vlm_checkpoints(tmp_path):
+    """Sharded VLM checkpoint -> merged state (tower included) -> a HF directory that Qwen2VLForConditionalGeneration loads."""
+    import os
+    import subprocess
+    import sys
+    from pathlib import Path
+
+    from transformers import Qwen2VLForConditionalGeneration
+
+    from polyrl_b200.parallel.zero3 import Zero3Engine
+    from polyrl_b200.utils.checkpoint import ShardedCheckpointManager
+    from polyrl_b200.utils.model_merger import merge
+
+    cfg = get_model_config("tiny-qwen2-vl")
+    eng = Zero3Engine(cfg, "cpu", seed=9)
+    ShardedCheckpointManager(eng, cfg).save(str(tmp_path / "actor"), global_step=1)
+    mcfg, sd = merge(str(tmp_path / "actor"))
+    want = dict(eng.named_full_tensors())
+    assert mcfg.vision == cfg.vision and set(sd) == set(want) and all(torch.equal(sd[k].float(), want[k].float()) for k in sd)
+    root = Path(__file__).resolve().parent.parent
+    r = subprocess.run([sys.executable, "-m", "polyrl_b200.utils.model_merger", "--ckpt", str(tmp_path / "actor"), "--out", str(tmp_path / "hf"),
+                        "--hf-dir"], capture_output=True, text=True, env={**os.environ, "PYTHONPATH": str(root)})
+    assert r.returncode == 0, r.stderr[-1500:]
+    m = Qwen2VLForConditionalGeneration.from_pretrained(tmp_path / "hf", dtype=torch.float32)
+    got = m.state_dict()["model.visual.blocks.1.attn.qkv.weight"]
+    assert torch.allclose(got, want["vision.blocks.1.wqkv"].to(torch.bfloat16).float())
