@@ -645,6 +645,8 @@ class Zero3Engine:
         post-attention residual, gate/up pre-activations and the SwiGLU output."""
         c = self.cfg
         inter = getattr(c, "intermediate_size", 4 * c.hidden_size)
+        if c.num_experts:                       # every token passes through k experts of width moe_intermediate_size (+ its copies)
+            inter = c.num_experts_per_tok * (c.moe_intermediate_size + c.hidden_size)
         qkv = (c.num_heads + 2 * c.num_kv_heads) * c.head_dim
         return 2 * (5 * c.hidden_size + qkv + 3 * inter) + 64
 
