@@ -71,3 +71,46 @@ def pairwise_accuracy(token_level_scores: torch.Tensor, acc: torch.Tensor, respo
     if float(w.sum()) == 0.0:
         return 0.5
     return float((((ds > 0) == (da > 0)).float() * w).sum() / w.sum())
+
+
+class ImplicitPRM:
+    """The implicit process reward model as a trainable component: a policy-shaped LM (``engine``, a ZeRO engine) scored against a
+    frozen reference (``ref_engine``).  ``score`` returns dense token rewards for a rollout batch, ``update`` takes one optimizer
+    step of the sequence-level cross-entropy against the outcome labels ``acc`` (reference: recipe/prime/prime_dp_rm.py — compute_rm_score /
+    update_rm).  Micro-batching and packing are the PPO actor's."""
+
+    def __init__(self, engine, ref_engine, beta: float = 0.05, granularity: str = "token", micro_batch_size: int = 8):
+        from ..workers.actor import ActorConfig, DataParallelPPOActor
+
+        self.beta, self.granularity = beta, granularity
+        rt = ActorConfig(ppo_mini_batch_size=micro_batch_size, ppo_micro_batch_size_per_gpu=micro_batch_size)
+        self.prm = DataParallelPPOActor(engine, rt)
+        self.ref = DataParallelPPOActor(ref_engine, rt)
+        self.engine = engine
+
+    @torch.no_grad()
+    def _ref_log_prob(self, data):
+        lp, _ = self.ref.compute_log_prob(data, calculate_entropy=False)
+        return lp
+
+    @torch.no_grad()
+    def score(self, data) -> torch.Tensor:
+        """[b, R] implicit process rewards of the batch's responses."""
+        lp, _ = self.prm.compute_log_prob(data, calculate_entropy=False)
+        return implicit_process_rewards(lp, self._ref_log_prob(data), data.batch["response_mask"].float(), self.beta, self.granularity)
+
+    def update(self, data, acc: torch.Tensor) -> dict:
+        """One optimizer step on the whole batch (gradients accumulated over micro-batches)."""
+        ref_lp = self._ref_log_prob(data)
+        n = len(data)
+        mbs = self.prm._micro_batches(data, self.prm.config.ppo_micro_batch_size_per_gpu, None, False)
+        total = 0.0
+        for mb, idx in mbs:
+            rows = torch.tensor(idx, dtype=torch.long, device=ref_lp.device)
+            _, lp = self.prm._forward_micro_batch(mb, 1.0, calculate_entropy=False)
+            mask = mb.batch["response_mask"].float()
+            loss = prm_ce_loss(lp - ref_lp[rows], acc[rows].to(lp.device), mask, self.beta) * (len(idx) / n)
+            loss.backward()
+            total += float(loss.detach())
+        st = self.engine.step()
+        return {"reward_model/prm_ce_loss": total, "reward_model/grad_norm": st["grad_norm"]}

@@ -230,3 +230,34 @@ def test_prime_implicit_reward_blocks():
     assert P.pairwise_accuracy(s, torch.zeros(b), mask, n) == 0.5
     with pytest.raises(ValueError):
         P.prime_advantages(mask, 1, acc=acc)
+
+
+def test_implicit_prm_learns_the_outcome_labels():
+    """ImplicitPRM over ZeRO engines: starts at zero reward (PRM == reference), its CE loss drops when trained on outcome labels and
+    the sequence reward then separates correct from wrong responses."""
+    import numpy as np
+
+    from polyrl_b200.algos.prime import ImplicitPRM, pairwise_accuracy
+    from polyrl_b200.models import get_model_config
+    from polyrl_b200.parallel.zero3 import Zero3Engine
+    from polyrl_b200.protocol import DataProto
+
+    cfg = get_model_config("tiny-llama")
+    prm_e = Zero3Engine(cfg, "cpu", lr=3e-3, weight_decay=0.0, seed=2)
+    ref_e = Zero3Engine(cfg, "cpu", trainable=False, seed=2)
+    prm = ImplicitPRM(prm_e, ref_e, beta=0.5, micro_batch_size=4)
+    g = torch.Generator().manual_seed(0)
+    b, p, r = 8, 5, 6
+    ids = torch.randint(3, 200, (b, p + r), generator=g)
+    mask = torch.ones_like(ids)
+    data = DataProto.from_dict({"input_ids": ids, "attention_mask": mask, "position_ids": torch.arange(p + r).expand(b, -1).contiguous(),
+                                "responses": ids[:, p:], "response_mask": mask[:, p:]})
+    data.meta_info["temperature"] = 1.0
+    acc = torch.tensor([1.0, 0.0] * 4)
+    q0 = prm.score(data)
+    assert q0.shape == (b, r) and q0.abs().max() < 1e-6                      # identical weights -> zero implicit reward
+    losses = [prm.update(data, acc)["reward_model/prm_ce_loss"] for _ in range(6)]
+    assert abs(losses[0] - 0.6931) < 1e-3 and losses[-1] < 0.5 * losses[0]
+    q = prm.score(data)
+    seq = q.sum(-1)
+    assert (seq[acc > 0].min() > seq[acc == 0].max()) and pairwise_accuracy(q, acc, data.batch["response_mask"].float(), 2) == 1.0
