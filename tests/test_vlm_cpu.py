@@ -571,3 +571,58 @@ def test_model_merger_handles_vlm_checkpoints(tmp_path):
     m = Qwen2VLForConditionalGeneration.from_pretrained(tmp_path / "hf", dtype=torch.float32)
     got = m.state_dict()["model.visual.blocks.1.attn.qkv.weight"]
     assert torch.allclose(got, want["vision.blocks.1.wqkv"].to(torch.bfloat16).float())
+
+
+def test_launch_server_serves_a_vlm_checkpoint_directory(tmp_path):
+    """Stand-alone remote instance: ``launch_server --model-path <HF dir>`` loads text stack + tower and answers an ``image_data``
+    request with the same tokens as an in-process engine built from the same checkpoint."""
+    import json
+    import os
+    import subprocess
+    import sys
+    import time
+    import urllib.request
+    from pathlib import Path
+
+    from polyrl_b200.models import hf_io
+    from polyrl_b200.rollout.engine import RolloutEngine, SamplingParams
+
+    cfg = get_model_config("tiny-qwen2-vl")
+    w, vw = tf.TransformerWeights(cfg, seed=21), V.VisionWeights(cfg, seed=22)
+    hf_io.save_hf({**w.state_dict(), **vw.state_dict()}, cfg, tmp_path / "ck", dtype=torch.float32)
+    grids = [(1, 4, 6)]
+    pix = torch.randn(24, V.patch_dim(cfg), generator=torch.Generator().manual_seed(0))
+    wire = V.encode_mm_wire({"pixel_values": pix, "grid_thw": grids})
+    prompt = [2, 21, 499, 500, 498, 22, 23]
+    eng = RolloutEngine(cfg, "cpu", max_num_seqs=4, max_model_len=64, kv_cache_tokens=256)
+    eng.set_weights(w.embed, w.layers, w.head)
+    eng.set_vision_weights(vw)
+    want = eng.generate([prompt], SamplingParams(max_new_tokens=6, temperature=0.0, ignore_eos=True), mm=[V.decode_mm_wire(wire)])[0][0].output_ids
+    root = Path(__file__).resolve().parent.parent
+    port = 32481
+    p = subprocess.Popen([sys.executable, "-m", "polyrl_b200.rollout.launch_server", "--model-path", str(tmp_path / "ck"), "--device", "cpu",
+                          "--port", str(port), "--max-num-seqs", "4", "--max-model-len", "64"],
+                         stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env={**os.environ, "PYTHONPATH": str(root), "OMP_NUM_THREADS": "2"}, cwd=root)
+    try:
+        ok = False
+        for _ in range(240):
+            try:
+                with urllib.request.urlopen(f"http://127.0.0.1:{port}/health_generate", timeout=2) as r:
+                    ok = r.status == 200
+                    break
+            except Exception:
+                time.sleep(0.5)
+                assert p.poll() is None, p.stdout.read()[-3000:]
+        assert ok
+        body = {"input_ids": prompt, "image_data": wire, "sampling_params": {"max_new_tokens": 6, "temperature": 0.0, "ignore_eos": True}}
+        req = urllib.request.Request(f"http://127.0.0.1:{port}/generate", method="POST", headers={"Content-Type": "application/json"},
+                                     data=json.dumps(body).encode())
+        with urllib.request.urlopen(req, timeout=120) as r:
+            out = json.loads(r.read().decode())
+        assert out["output_ids"] == want
+        urllib.request.urlopen(urllib.request.Request(f"http://127.0.0.1:{port}/shutdown", method="POST", data=b"{}",
+                                                      headers={"Content-Type": "application/json"}), timeout=30).read()
+        assert p.wait(timeout=120) == 0
+    finally:
+        if p.poll() is None:
+            p.terminate()
