@@ -146,7 +146,12 @@ def run_trainer_rank(cfg: PPOConfig, rank: int, trainer_ranks, rollout_ranks, de
     client = None
     if disagg:
         sync = WeightSync(worker.model_cfg, trainer_ranks, rollout_ranks, device, backend=cfg.actor_rollout_ref.actor.fsdp_config.comm_backend)
-        sender = TrainerWeightSender(manager_endpoint, sync, group=trainer_group)
+        # engines of this job's own rollout ranks take the peer-memory / broadcast push; any other registered instance (elastic
+        # engines on other hosts) is served over TCP at its handshake address
+        tp_ = max(1, cfg.actor_rollout_ref.rollout.tensor_model_parallel_size)
+        base_port = int(os.environ.get("POLYRL_ENGINE_PORT_BASE", 30000))
+        own = {f"127.0.0.1:{base_port + r}" for i, r in enumerate(rollout_ranks) if i % tp_ == 0}
+        sender = TrainerWeightSender(manager_endpoint, sync, group=trainer_group, sync_endpoints=own)
         r = cfg.actor_rollout_ref.rollout
         if rank == 0:
             client = RemoteRolloutClient(manager_endpoint, r.n, cfg.data.max_response_length, worker.model_cfg.pad_token_id,

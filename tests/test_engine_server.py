@@ -443,3 +443,60 @@ def test_vllm_library_adapter_plumbing_with_a_fake_llm():
     assert groups[1][0].logprobs == pytest.approx([-0.5, -0.6, -0.7, -0.8]) and groups[0][0].finish_reason == "length"
     with pytest.raises(ValueError):
         get_rollout_cls("vllm-lib")(cfg, "cpu")                         # a real vLLM engine needs a checkpoint directory
+
+
+def test_elastic_remote_instance_receives_weights_over_tcp(tmp_path):
+    """PolyRL's elastic path end to end on CPU: a stand-alone engine (``launch_server --enable-weight-transfer-agent``, random
+    weights) registers with the C++ manager as a remote instance; the trainer-side sender bumps the weight version, learns from the
+    manager that the instance is stale, streams the full state over TCP to its handshake address while the manager fans out
+    ``/update_weights_from_agent``; afterwards the remote engine generates exactly what the trainer's weights generate."""
+    import os
+    import subprocess
+    import sys
+    from pathlib import Path
+
+    from polyrl_b200.parallel.zero3 import Zero3Engine
+    from polyrl_b200.weight_transfer.agent import TrainerWeightSender
+
+    root = Path(__file__).resolve().parent.parent
+    cfg = get_model_config("tiny-llama")
+    m = Manager(build_manager())
+    port, hs_port = 32491, 32551
+    p = subprocess.Popen([sys.executable, "-m", "polyrl_b200.rollout.launch_server", "--model-path", "tiny-llama", "--device", "cpu", "--port", str(port),
+                          "--max-num-seqs", "4", "--max-model-len", "64", "--load-format", "dummy", "--enable-weight-transfer-agent",
+                          "--transfer-agent-handshake-port", str(hs_port), "--weight-receiver-zmq-bind-host", "127.0.0.1",
+                          "--num-transfer-engines-per-group", "2", "--rollout-manager-address", f"127.0.0.1:{m.port}"],
+                         stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env={**os.environ, "PYTHONPATH": str(root), "OMP_NUM_THREADS": "2"}, cwd=root)
+    try:
+        sender = TrainerWeightSender(f"127.0.0.1:{m.port}", sync=None, sender_endpoint="127.0.0.1:18861", tcp_streams=2)
+        sender.register_as_sender()                       # registration of the remote instance waits for a sender to exist
+        for _ in range(240):
+            code, body = _http("GET", m.url + "/get_instances_status")
+            if code == 200 and f"127.0.0.1:{port}" in body:
+                break
+            time.sleep(0.5)
+            assert p.poll() is None, p.stdout.read()[-3000:]
+        trainer = Zero3Engine(cfg, "cpu", seed=77)       # the policy the remote engine must end up with
+        prompt = [5, 9, 33, 7, 2]
+        body = {"input_ids": prompt, "sampling_params": {"max_new_tokens": 8, "temperature": 0.0, "ignore_eos": True}}
+        before = json.loads(_http("POST", f"http://127.0.0.1:{port}/generate", body)[1])["output_ids"]
+        assert sender.update(trainer, rank=0) == 1
+        after = json.loads(_http("POST", f"http://127.0.0.1:{port}/generate", body)[1])["output_ids"]
+        full = dict(trainer.named_full_tensors())
+        w = TransformerWeights(cfg, init=False)
+        w.load_state_dict(full)
+        ref = RolloutEngine(cfg, "cpu", max_num_seqs=4, max_model_len=64, kv_cache_tokens=256)
+        ref.set_weights(w.embed, w.layers, w.head)
+        want = ref.generate([prompt], SamplingParams(max_new_tokens=8, temperature=0.0, ignore_eos=True))[0][0].output_ids
+        assert after == want and before != want
+        st = json.loads(_http("GET", m.url + "/get_instances_status")[1])
+        assert str(sender.version) in json.dumps(st)      # the manager re-activated the instance at the new version
+        assert sender.update(trainer, rank=0, new_version=sender.version) == 0       # nothing is stale now
+    finally:
+        try:
+            _http("POST", f"http://127.0.0.1:{port}/shutdown", {})
+        except Exception:
+            pass
+        if p.poll() is None:
+            p.terminate()
+        m.close()
