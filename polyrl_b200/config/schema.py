@@ -382,6 +382,10 @@ class TrainerConfig(BaseConfig):
     # that generates during the manager's time-boxed local window, then hands its HBM back to training while the remote
     # instances finish the partial generations (reference: local SGLang per trainer + /register_local_rollout_instances)
     local_rollout: bool = False
+    # PolyRL's elastic deployment: no in-job rollout GPUs needed — every rank trains AND serves a hybrid local engine behind the
+    # manager, and external engines (``python -m polyrl_b200.rollout.launch_server`` on other hosts) join or leave at any time; they get
+    # the weights over TCP (weight_transfer/agent.py)
+    elastic_rollout: bool = False
     # one-step-off-policy (reference recipe: 3rdparty/verl/recipe/one_step_off_policy): the rollout GPUs generate batch k+1
     # (with the weights of step k) while the trainers update on batch k; weights are pushed once batch k+1 is complete
     one_step_off: bool = False

@@ -105,10 +105,22 @@ def main(argv=None) -> int:
     srv = EngineServer(eng, host=a.host, port=a.port, stream_interval=a.stream_interval, weight_update_fn=on_update,
                        tp_cmd_group=cmd_group).start()
     if a.rollout_manager_address:
-        info = srv.register_with_manager(a.rollout_manager_address, local=False, handshake_port=a.transfer_agent_handshake_port)
+        import time as _t
+
+        info, t0 = None, _t.time()
+        while info is None:                   # elastic join: the manager may not be up yet (or restarts); keep trying for a while
+            try:
+                info = srv.register_with_manager(a.rollout_manager_address, local=False, handshake_port=a.transfer_agent_handshake_port)
+            except OSError as e:
+                if _t.time() - t0 > 600:
+                    raise
+                print(f"[engine] manager {a.rollout_manager_address} not reachable yet ({e}); retrying", flush=True)
+                _t.sleep(1.0)
         print(f"[engine] registered with manager: {info}", flush=True)
     print(f"[engine] serving {cfg.name} on {srv.endpoint}", flush=True)
     srv.serve_until_shutdown()
+    print(f"[engine] exiting: weight_version={eng.weight_version} decode_tokens={eng.stats['decode_tokens']} "
+          f"prefill_tokens={eng.stats['prefill_tokens']}", flush=True)
     return 0
 
 

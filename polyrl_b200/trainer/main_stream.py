@@ -132,8 +132,9 @@ def run_trainer_rank(cfg: PPOConfig, rank: int, trainer_ranks, rollout_ranks, de
     from ..workers.hybrid_worker import ActorRolloutRefWorker, CriticWorker
     from .stream_trainer import StreamPPOTrainer
 
-    disagg = len(rollout_ranks) > 0
-    hybrid = disagg and cfg.trainer.local_rollout
+    elastic = bool(cfg.trainer.elastic_rollout)
+    disagg = len(rollout_ranks) > 0 or elastic
+    hybrid = disagg and (cfg.trainer.local_rollout or not rollout_ranks)      # without in-job rollout GPUs the local engines must generate
     role = ("actor" if (disagg and not hybrid) else "actor_rollout") + ("_ref" if need_reference_policy(cfg) else "")
     worker = ActorRolloutRefWorker(cfg, role=role, device=device, group=trainer_group)
     worker.init_model()
@@ -145,7 +146,8 @@ def run_trainer_rank(cfg: PPOConfig, rank: int, trainer_ranks, rollout_ranks, de
     reward_fn = None if tok is None else load_reward_manager(cfg, tok)
     client = None
     if disagg:
-        sync = WeightSync(worker.model_cfg, trainer_ranks, rollout_ranks, device, backend=cfg.actor_rollout_ref.actor.fsdp_config.comm_backend)
+        sync = (WeightSync(worker.model_cfg, trainer_ranks, rollout_ranks, device, backend=cfg.actor_rollout_ref.actor.fsdp_config.comm_backend)
+                if rollout_ranks else None)
         # engines of this job's own rollout ranks take the peer-memory / broadcast push; any other registered instance (elastic
         # engines on other hosts) is served over TCP at its handshake address
         tp_ = max(1, cfg.actor_rollout_ref.rollout.tensor_model_parallel_size)
@@ -225,7 +227,8 @@ def main(argv: list[str] | None = None) -> int:
                 my_tp_groups = (g_main, g_cmd)
     manager_endpoint = a.manager_endpoint or cfg.actor_rollout_ref.rollout.rollout_manager.endpoint
     mgr_proc = None
-    if n_roll > 0 and manager_endpoint is None:
+    elastic = bool(cfg.trainer.elastic_rollout)
+    if (n_roll > 0 or elastic) and manager_endpoint is None:
         from ..weight_transfer.launcher import spawn_rollout_manager
 
         port = cfg.actor_rollout_ref.rollout.rollout_manager.port
@@ -240,7 +243,7 @@ def main(argv: list[str] | None = None) -> int:
         if rank in rollout_ranks:
             run_rollout_rank(cfg, rank, trainer_ranks, rollout_ranks, device, manager_endpoint, my_tp_groups)
         else:
-            out = run_trainer_rank(cfg, rank, trainer_ranks, rollout_ranks, device, manager_endpoint if n_roll > 0 else None,
+            out = run_trainer_rank(cfg, rank, trainer_ranks, rollout_ranks, device, manager_endpoint if (n_roll > 0 or elastic) else None,
                                    trainer_group)
             if rank == 0:
                 print("[main_stream] final metrics:", {k: v for k, v in sorted(out.items()) if k.startswith(("perf/", "critic/score", "actor/pg_loss", "training/"))}, flush=True)

@@ -219,3 +219,41 @@ def test_expert_parallel_training_gloo_ws4():
     r = run_torchrun([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=4", "--master-addr", "127.0.0.1",
                         "--master-port", "29761", str(ROOT / "tests" / "ep_train_worker.py")], capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0 and "EP_TRAIN_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_elastic_external_instance_joins_a_running_job(tmp_path):
+    """PolyRL's elastic deployment on CPU: the job has NO in-job rollout ranks (``trainer.elastic_rollout``): the trainer serves a
+    hybrid local engine behind the manager; a stand-alone ``launch_server`` process started separately keeps retrying until the
+    manager exists, registers as a remote instance, receives every new policy over TCP and takes part in generation."""
+    import subprocess
+    import time
+
+    mport = 32611
+    env = {**os.environ, "PYTHONPATH": str(ROOT), "OMP_NUM_THREADS": "2", "POLYRL_ENGINE_PORT_BASE": "31400"}
+    ext = subprocess.Popen([sys.executable, "-m", "polyrl_b200.rollout.launch_server", "--model-path", "tiny-llama", "--device", "cpu", "--port", "32621",
+                            "--max-num-seqs", "8", "--max-model-len", "64", "--load-format", "dummy", "--enable-weight-transfer-agent",
+                            "--transfer-agent-handshake-port", "32631", "--weight-receiver-zmq-bind-host", "127.0.0.1",
+                            "--rollout-manager-address", f"127.0.0.1:{mport}"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env, cwd=ROOT)
+    try:
+        time.sleep(3.0)                                   # the engine is up and retrying before the job (and its manager) exists
+        ov = COMMON + ["actor_rollout_ref.model.path=tiny-llama", "algorithm.adv_estimator=grpo", "trainer.n_gpus_per_node=1",
+                       "trainer.elastic_rollout=True", "trainer.total_training_steps=6", f"actor_rollout_ref.rollout.rollout_manager.port={mport}",
+                       "actor_rollout_ref.rollout.rollout_manager.max_local_gen_s=1", "data.train_batch_size=8",
+                       "actor_rollout_ref.rollout.min_stream_batch_size=4"]
+        r = _run(1, ov)
+        assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+        assert "step:6" in r.stdout and "actor/pg_loss" in r.stdout
+        # the job is gone (and its manager with it): stop the external engine and read what it saw
+        import urllib.request
+
+        urllib.request.urlopen(urllib.request.Request("http://127.0.0.1:32621/shutdown", method="POST", data=b"{}",
+                                                      headers={"Content-Type": "application/json"}), timeout=30).read()
+        out, _ = ext.communicate(timeout=60)
+        assert "registered with manager" in out, out[-2000:]
+        tail = [l for l in out.splitlines() if l.startswith("[engine] exiting")]
+        assert tail, out[-2000:]
+        stats = dict(kv.split("=") for kv in tail[0].split()[2:])
+        assert int(stats["weight_version"]) >= 1, out[-2000:]          # at least one policy arrived over TCP
+    finally:
+        if ext.poll() is None:
+            ext.terminate()
