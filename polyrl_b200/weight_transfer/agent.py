@@ -30,6 +30,7 @@ class TrainerWeightSender:
         self.tcp_streams = tcp_streams
         self._staging = None
         self._tcp = None
+        self.failed_targets: list[str] = []
         self.sender_endpoint = sender_endpoint
         self.group = group
         self.version = 0
@@ -107,6 +108,11 @@ class TrainerWeightSender:
         if rank == 0:
             if torch.cuda.is_available():
                 torch.cuda.synchronize()
+            self.failed_targets = []
             for addr in targets:
                 host, port = addr.rsplit(":", 1)
-                self._tcp.send(self._staging, host, int(port), nbytes)
+                try:                          # a spot instance may vanish at any moment: never let that take the trainer down; the
+                    self._tcp.send(self._staging, host, int(port), nbytes)      # manager drops it at the next failed health check
+                except (OSError, ConnectionError) as e:
+                    self.failed_targets.append(addr)
+                    print(f"[weight-sender] transfer to {addr} failed ({e}); skipping this instance", flush=True)

@@ -500,3 +500,14 @@ def test_elastic_remote_instance_receives_weights_over_tcp(tmp_path):
         if p.poll() is None:
             p.terminate()
         m.close()
+
+
+def test_tcp_push_survives_a_vanished_instance():
+    """A remote instance that died between the manager's listing and the transfer must not crash the trainer."""
+    from polyrl_b200.parallel.zero3 import Zero3Engine
+    from polyrl_b200.weight_transfer.agent import TrainerWeightSender
+
+    eng = Zero3Engine(get_model_config("tiny-llama"), "cpu", seed=1)
+    s = TrainerWeightSender("127.0.0.1:1", sync=None)
+    s._tcp_push(eng, 0, ["127.0.0.1:9"])                # nobody listens there
+    assert s.failed_targets == ["127.0.0.1:9"]
