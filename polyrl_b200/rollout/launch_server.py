@@ -8,6 +8,7 @@ random/dummy initialised (``--load-format dummy``) until the first update."""
 from __future__ import annotations
 
 import argparse
+import os
 
 import torch
 
@@ -99,7 +100,10 @@ def main(argv=None) -> int:
 
     def on_update(body):
         if receiver is not None and not body.get("bootstrap"):
-            receiver.wait_and_apply(timeout=3600)
+            try:
+                receiver.wait_and_apply(timeout=float(os.environ.get("POLYRL_WEIGHT_RECV_TIMEOUT_S", "900")))
+            except TimeoutError as e:         # keep serving the old policy; the manager sees the failure and keeps the instance stale
+                return False, str(e)
         return True, "ok"
 
     srv = EngineServer(eng, host=a.host, port=a.port, stream_interval=a.stream_interval, weight_update_fn=on_update,

@@ -164,6 +164,9 @@ class TCPWeightReceiver:
 
     def wait_and_apply(self, timeout: float = 3600.0) -> bool:
         if not self._done.wait(timeout):
+            with self._lock:                  # a sender that died mid-transfer must not poison the byte count of the next attempt
+                self._received = 0
+                self._done.clear()
             raise TimeoutError("weight transfer did not complete")
         off = 0
         for _, t in self.named:

@@ -312,3 +312,30 @@ def test_multiturn_sft_and_pairwise_rm_datasets(tmp_path):
     # the SFT entry point trains on the transcripts
     assert main(["trainer.device=cpu", f"data.train_files={f}", "data.multiturn_messages_key=messages", "data.max_length=96", "model.path=tiny-llama",
                  "data.train_batch_size=4", "data.micro_batch_size_per_gpu=2", "trainer.total_steps=2", "optim.lr=1e-3"]) == 0
+
+
+def test_tcp_receiver_recovers_from_an_incomplete_transfer():
+    """A transfer that stops half way times out, and the next complete transfer is applied correctly."""
+    import socket
+
+    from polyrl_b200.weight_transfer.tcp_engine import HEADER, StagingBuffer, TCPWeightReceiver, TCPWeightSender
+
+    dst = [("a", torch.zeros(1000)), ("b", torch.zeros(24))]
+    port = 32701
+    rx = TCPWeightReceiver(dst, bind_host="127.0.0.1", port=port, num_streams=1)
+    try:
+        s = socket.create_connection(("127.0.0.1", port))
+        s.sendall(HEADER.pack(0, 4096) + b"\\x01" * 100)          # announces 4096 bytes, sends 100, dies
+        s.close()
+        with pytest.raises(TimeoutError):
+            rx.wait_and_apply(timeout=0.5)
+        src = [("a", torch.arange(1000, dtype=torch.float32)), ("b", torch.ones(24))]
+        st = StagingBuffer(rx.nbytes)
+        tx = TCPWeightSender(num_streams=1)
+        tx.stage(src, st)
+        tx.send(st, "127.0.0.1", port, rx.nbytes)
+        assert rx.wait_and_apply(timeout=10)
+        assert torch.equal(dst[0][1], src[0][1]) and torch.equal(dst[1][1], src[1][1])
+        st.close()
+    finally:
+        rx.close()
