@@ -44,8 +44,6 @@ def main(argv=None) -> int:
     tp_rank = 0
     if a.tp_size > 1:
         # one process per TP rank (torchrun); rank 0 owns the HTTP front-end, the others mirror its commands
-        import os
-
         import torch.distributed as dist
 
         from ..parallel.symm import SymmetricHeap
