@@ -169,6 +169,10 @@ def run_trainer_rank(cfg: PPOConfig, rank: int, trainer_ranks, rollout_ranks, de
                     break
                 time.sleep(0.2)
             time.sleep(0.5)
+        else:
+            from .stream_trainer import RemoteRolloutPlaceholder
+
+            client = RemoteRolloutPlaceholder()      # generation is remote for this rank too; rank 0 owns the connection
         if hybrid:
             worker.start_local_server(manager_endpoint, int(os.environ.get("POLYRL_ENGINE_PORT_BASE", 30000)) + 100 + rank)
         if dist.is_initialized():
@@ -187,7 +191,7 @@ def run_trainer_rank(cfg: PPOConfig, rank: int, trainer_ranks, rollout_ranks, de
         class _NoopVersion:
             """the sender bumps the version itself; the trainer's explicit bump becomes a no-op"""
 
-        if client is not None:
+        if rank == 0:
             client.update_weight_version = lambda: sender.version
     tracking = Tracking(cfg.trainer.project_name, cfg.trainer.experiment_name, cfg.trainer.logger) if rank == 0 else None
     trainer = StreamPPOTrainer(cfg, worker, critic, reward_fn, reward_fn, train, val, client, trainer_group, tracking, sampler)
@@ -204,6 +208,12 @@ def main(argv: list[str] | None = None) -> int:
     cfg = load_config(a.config_file, a.overrides)
     device_type = cfg.trainer.device if (cfg.trainer.device != "cuda" or torch.cuda.is_available()) else "cpu"
     rank, world = _init_dist(device_type)
+    if os.environ.get("POLYRL_DUMP_STACKS_AFTER_S"):
+        # hang diagnosis: every rank writes the Python stacks of all its threads to a file after N seconds (and every N after that)
+        import faulthandler
+
+        _fh = open(os.path.join(os.environ.get("POLYRL_DUMP_STACKS_DIR", "/tmp"), f"polyrl_stacks_rank{rank}.txt"), "w")
+        faulthandler.dump_traceback_later(float(os.environ["POLYRL_DUMP_STACKS_AFTER_S"]), repeat=True, file=_fh)
     n_roll = cfg.trainer.n_rollout_gpus
     n_train = world - n_roll
     validate_config(cfg, n_gpus=world)

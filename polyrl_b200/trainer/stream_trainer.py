@@ -37,6 +37,13 @@ def _bcast_obj(obj, src: int = 0, group=None):
     return box[0]
 
 
+class RemoteRolloutPlaceholder:
+    """What trainer ranks other than 0 hold instead of the manager connection: rank 0 talks to the rollout manager and broadcasts
+    every streamed batch; the other ranks only need to know that generation is remote (``client is not None``)."""
+
+    timing: dict = {}
+
+
 class StreamPPOTrainer:
     def __init__(self, config: PPOConfig, worker, critic=None, reward_fn=None, val_reward_fn=None, train_dataset=None,
                  val_dataset=None, rollout_client=None, group=None, tracking=None, train_sampler=None):

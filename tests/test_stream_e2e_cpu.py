@@ -236,11 +236,11 @@ def test_elastic_external_instance_joins_a_running_job(tmp_path):
                             "--rollout-manager-address", f"127.0.0.1:{mport}"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env, cwd=ROOT)
     try:
         time.sleep(3.0)                                   # the engine is up and retrying before the job (and its manager) exists
-        ov = COMMON + ["actor_rollout_ref.model.path=tiny-llama", "algorithm.adv_estimator=grpo", "trainer.n_gpus_per_node=1",
+        ov = COMMON + ["actor_rollout_ref.model.path=tiny-llama", "algorithm.adv_estimator=grpo", "trainer.n_gpus_per_node=2",
                        "trainer.elastic_rollout=True", "trainer.total_training_steps=6", f"actor_rollout_ref.rollout.rollout_manager.port={mport}",
                        "actor_rollout_ref.rollout.rollout_manager.max_local_gen_s=1", "data.train_batch_size=8",
-                       "actor_rollout_ref.rollout.min_stream_batch_size=4"]
-        r = _run(1, ov)
+                       "actor_rollout_ref.rollout.min_stream_batch_size=4", "actor_rollout_ref.actor.ppo_mini_batch_size=4"]
+        r = _run(2, ov)                                     # two trainer ranks: rank 0 owns the manager connection, both serve engines
         assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
         assert "step:6" in r.stdout and "actor/pg_loss" in r.stdout
         # the job is gone (and its manager with it): stop the external engine and read what it saw
@@ -257,3 +257,15 @@ def test_elastic_external_instance_joins_a_running_job(tmp_path):
     finally:
         if ext.poll() is None:
             ext.terminate()
+
+
+def test_disaggregated_two_trainers_one_rollout_gloo_ws3():
+    """More than one trainer rank in a disaggregated job: rank 0 streams from the manager and broadcasts, the other trainer ranks
+    must follow the remote path too (they hold no manager connection)."""
+    ov = COMMON + ["actor_rollout_ref.model.path=tiny-llama", "algorithm.adv_estimator=grpo", "trainer.n_rollout_gpus=1",
+                   "trainer.n_gpus_per_node=3", "trainer.total_training_steps=2", "actor_rollout_ref.rollout.rollout_manager.port=0",
+                   "actor_rollout_ref.rollout.rollout_manager.max_local_gen_s=30", "data.train_batch_size=8",
+                   "actor_rollout_ref.actor.ppo_mini_batch_size=4"]
+    r = _run(3, ov)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "step:2" in r.stdout and "actor/pg_loss" in r.stdout
