@@ -34,6 +34,7 @@ if [ "$NG" -ge 4 ]; then
   TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node=4 --master-addr 127.0.0.1"
   EP_TRAIN_DEVICE=cuda run ep_nccl $TR --master-port 29741 tests/ep_train_worker.py
   EP_TRAIN_DEVICE=cuda EP_PEER=1 run ep_peer $TR --master-port 29742 tests/ep_train_worker.py
+  T=900 NGPU=4 NROLL=2 run disagg_2trainers_2rollout bash scripts/gpu_disagg_check.sh
   T=900 NGPU=4 NROLL=2 run disagg_tp2 bash scripts/gpu_disagg_check.sh actor_rollout_ref.rollout.tensor_model_parallel_size=2
   POLYRL_TEST_MULTIGPU_WORLD=4 T=1500 run multigpu_suite python -m pytest tests/test_multigpu.py -m gpu -x -q
 fi
