@@ -269,3 +269,6 @@ def test_disaggregated_two_trainers_one_rollout_gloo_ws3():
     r = _run(3, ov)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "step:2" in r.stdout and "actor/pg_loss" in r.stdout
+    r = _run(3, ov + ["trainer.one_step_off=True", "trainer.total_training_steps=3"])      # the prefetched batch reaches both trainers
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "step:3" in r.stdout
