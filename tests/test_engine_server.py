@@ -462,12 +462,13 @@ def test_elastic_remote_instance_receives_weights_over_tcp(tmp_path):
     cfg = get_model_config("tiny-llama")
     m = Manager(build_manager())
     port, hs_port = 32491, 32551
-    p = subprocess.Popen([sys.executable, "-m", "polyrl_b200.rollout.launch_server", "--model-path", "tiny-llama", "--device", "cpu", "--port", str(port),
-                          "--max-num-seqs", "4", "--max-model-len", "64", "--load-format", "dummy", "--enable-weight-transfer-agent",
-                          "--transfer-agent-handshake-port", str(hs_port), "--weight-receiver-zmq-bind-host", "127.0.0.1",
-                          "--num-transfer-engines-per-group", "2", "--rollout-manager-address", f"127.0.0.1:{m.port}"],
-                         stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env={**os.environ, "PYTHONPATH": str(root), "OMP_NUM_THREADS": "2"}, cwd=root)
+    p = None
     try:
+        p = subprocess.Popen(    [sys.executable, "-m", "polyrl_b200.rollout.launch_server", "--model-path", "tiny-llama", "--device", "cpu", "--port", str(port),
+                              "--max-num-seqs", "4", "--max-model-len", "64", "--load-format", "dummy", "--enable-weight-transfer-agent",
+                              "--transfer-agent-handshake-port", str(hs_port), "--weight-receiver-zmq-bind-host", "127.0.0.1",
+                              "--num-transfer-engines-per-group", "2", "--rollout-manager-address", f"127.0.0.1:{m.port}"],
+                             stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env={**os.environ, "PYTHONPATH": str(root), "OMP_NUM_THREADS": "2"}, cwd=root)
         sender = TrainerWeightSender(f"127.0.0.1:{m.port}", sync=None, sender_endpoint="127.0.0.1:18861", tcp_streams=2)
         sender.register_as_sender()                       # registration of the remote instance waits for a sender to exist
         for _ in range(240):
@@ -497,7 +498,7 @@ def test_elastic_remote_instance_receives_weights_over_tcp(tmp_path):
             _http("POST", f"http://127.0.0.1:{port}/shutdown", {})
         except Exception:
             pass
-        if p.poll() is None:
+        if p is not None and p.poll() is None:
             p.terminate()
         m.close()
 
