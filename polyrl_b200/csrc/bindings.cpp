@@ -11,6 +11,7 @@
 
 extern "C" {
 int prl_gemm_bf16(const void*, const void*, void*, const void*, int, int, int, int64_t, int64_t, int64_t, int, cudaStream_t);
+int prl_gemm2_bf16(const void*, const void*, void*, const void*, int, int, int, int64_t, int64_t, int64_t, int, int, int, cudaStream_t);
 int prl_gemm_fp8(const void*, const void*, void*, const float*, const float*, int, int, int, int64_t, int64_t, int64_t, int, cudaStream_t);
 int prl_gemm_swiglu_bf16(const void*, const void*, void*, void*, int, int, int, int64_t, int64_t, int64_t, int64_t, cudaStream_t);
 int prl_linear_ce_num_splits(int, int);
@@ -83,6 +84,36 @@ at::Tensor gemm_bf16(const at::Tensor& a, const at::Tensor& b, const c10::option
   }
   check(prl_gemm_bf16(a.data_ptr(), b.data_ptr(), d.data_ptr(), r, M, N, K, a.stride(0), b.stride(0), d.stride(0),
                       static_cast<int>(force_bn), cur_stream()), "gemm_bf16");
+  return d;
+}
+
+// CTA-pair (cta_group::2) GEMM family.  D[M,N] = sum_k A(m,k) B(n,k) (+residual).
+//   a_mn=false: a is [M,K];  a_mn=true: a is [K,M] (consumed MN-major, never transposed in memory)
+//   b_mn=false: b is [N,K];  b_mn=true: b is [K,N]
+at::Tensor gemm2_bf16(const at::Tensor& a, const at::Tensor& b, bool a_mn, bool b_mn,
+                      const c10::optional<at::Tensor>& residual, c10::optional<at::Tensor> out, int64_t force_bn) {
+  CHECK_BF16(a); CHECK_BF16(b);
+  TORCH_CHECK(a.dim() == 2 && b.dim() == 2, "gemm2_bf16: 2-D operands");
+  CHECK_LASTDIM(a); CHECK_LASTDIM(b);
+  const int M = a_mn ? a.size(1) : a.size(0), K = a_mn ? a.size(0) : a.size(1);
+  const int N = b_mn ? b.size(1) : b.size(0), Kb = b_mn ? b.size(0) : b.size(1);
+  TORCH_CHECK(K == Kb, "gemm2_bf16: reduction lengths differ");
+  TORCH_CHECK(a.size(1) % 8 == 0 && b.size(1) % 8 == 0 && N % 8 == 0, "inner dims must be multiples of 8");
+  TORCH_CHECK(a.stride(0) % 8 == 0 && b.stride(0) % 8 == 0, "row pitch must be a multiple of 8 elements");
+  TORCH_CHECK((reinterpret_cast<uintptr_t>(a.data_ptr()) & 15) == 0 && (reinterpret_cast<uintptr_t>(b.data_ptr()) & 15) == 0,
+              "operands must be 16-byte aligned");
+  c10::cuda::CUDAGuard g(a.device());
+  at::Tensor d = out.has_value() ? *out : at::empty({M, N}, a.options());
+  CHECK_BF16(d); CHECK_LASTDIM(d);
+  TORCH_CHECK(d.size(0) == M && d.size(1) == N && d.stride(0) % 8 == 0 && (reinterpret_cast<uintptr_t>(d.data_ptr()) & 15) == 0);
+  const void* r = nullptr;
+  if (residual.has_value()) {
+    CHECK_BF16(*residual);
+    TORCH_CHECK(residual->sizes() == d.sizes() && residual->stride(0) == d.stride(0) && residual->stride(1) == 1);
+    r = residual->data_ptr();
+  }
+  check(prl_gemm2_bf16(a.data_ptr(), b.data_ptr(), d.data_ptr(), r, M, N, K, a.stride(0), b.stride(0), d.stride(0),
+                       a_mn ? 1 : 0, b_mn ? 1 : 0, static_cast<int>(force_bn), cur_stream()), "gemm2_bf16");
   return d;
 }
 
@@ -457,6 +488,8 @@ at::Tensor ag_gemm_bf16(const at::Tensor& a, const std::vector<int64_t>& shard_p
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("gemm_bf16", &gemm_bf16, py::arg("a"), py::arg("b"), py::arg("residual") = py::none(),
         py::arg("out") = py::none(), py::arg("force_bn") = 0);
+  m.def("gemm2_bf16", &gemm2_bf16, py::arg("a"), py::arg("b"), py::arg("a_mn") = false, py::arg("b_mn") = false,
+        py::arg("residual") = py::none(), py::arg("out") = py::none(), py::arg("force_bn") = 0);
   m.def("gemm_fp8", &gemm_fp8, py::arg("a"), py::arg("b"), py::arg("row_scale"), py::arg("col_scale"),
         py::arg("force_bn") = 0);
   m.def("gemm_swiglu", &gemm_swiglu);

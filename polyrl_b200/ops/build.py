@@ -23,6 +23,7 @@ OUT = PKG / "_C.so"
 
 CU_SOURCES = [
     "gemm_tcgen05.cu",
+    "gemm2.cu",
     "skinny_gemm.cu",
     "vmm.cu",
     "linear_ce.cu",
@@ -33,7 +34,7 @@ CU_SOURCES = [
     "sampling.cu",
     "p2p.cu",
 ]
-HEADERS = ["common.cuh", "gemm_sm100.cuh"]
+HEADERS = ["common.cuh", "gemm_sm100.cuh", "gemm2_sm100.cuh"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",
