@@ -12,6 +12,7 @@
 extern "C" {
 int prl_gemm_bf16(const void*, const void*, void*, const void*, int, int, int, int64_t, int64_t, int64_t, int, cudaStream_t);
 int prl_gemm2_bf16(const void*, const void*, void*, const void*, int, int, int, int64_t, int64_t, int64_t, int, int, int, cudaStream_t);
+int prl_gemm2_bf16_accum_f32(const void*, const void*, float*, float, int, int, int, int64_t, int64_t, int64_t, int, int, cudaStream_t);
 int prl_gemm_fp8(const void*, const void*, void*, const float*, const float*, int, int, int, int64_t, int64_t, int64_t, int, cudaStream_t);
 int prl_gemm_swiglu_bf16(const void*, const void*, void*, void*, int, int, int, int64_t, int64_t, int64_t, int64_t, cudaStream_t);
 int prl_linear_ce_num_splits(int, int);
@@ -115,6 +116,19 @@ at::Tensor gemm2_bf16(const at::Tensor& a, const at::Tensor& b, bool a_mn, bool 
   check(prl_gemm2_bf16(a.data_ptr(), b.data_ptr(), d.data_ptr(), r, M, N, K, a.stride(0), b.stride(0), d.stride(0),
                        a_mn ? 1 : 0, b_mn ? 1 : 0, static_cast<int>(force_bn), cur_stream()), "gemm2_bf16");
   return d;
+}
+
+// out32 = beta * out32 + sum_k A(m,k) B(n,k)   (fp32 output, in place)
+void gemm2_accum_f32_(at::Tensor out32, const at::Tensor& a, const at::Tensor& b, bool a_mn, bool b_mn, double beta) {
+  CHECK_BF16(a); CHECK_BF16(b); CHECK_F32(out32); CHECK_LASTDIM(a); CHECK_LASTDIM(b); CHECK_LASTDIM(out32);
+  const int M = a_mn ? a.size(1) : a.size(0), K = a_mn ? a.size(0) : a.size(1);
+  const int N = b_mn ? b.size(1) : b.size(0), Kb = b_mn ? b.size(0) : b.size(1);
+  TORCH_CHECK(K == Kb && out32.dim() == 2 && out32.size(0) == M && out32.size(1) == N);
+  TORCH_CHECK(a.size(1) % 8 == 0 && b.size(1) % 8 == 0 && a.stride(0) % 8 == 0 && b.stride(0) % 8 == 0 && out32.stride(0) % 4 == 0);
+  c10::cuda::CUDAGuard g(a.device());
+  check(prl_gemm2_bf16_accum_f32(a.data_ptr(), b.data_ptr(), out32.data_ptr<float>(), static_cast<float>(beta), M, N, K,
+                                 a.stride(0), b.stride(0), out32.stride(0), a_mn ? 1 : 0, b_mn ? 1 : 0, cur_stream()),
+        "gemm2_accum_f32");
 }
 
 at::Tensor gemm_fp8(const at::Tensor& a, const at::Tensor& b, const at::Tensor& row_scale, const at::Tensor& col_scale,
@@ -490,6 +504,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
         py::arg("out") = py::none(), py::arg("force_bn") = 0);
   m.def("gemm2_bf16", &gemm2_bf16, py::arg("a"), py::arg("b"), py::arg("a_mn") = false, py::arg("b_mn") = false,
         py::arg("residual") = py::none(), py::arg("out") = py::none(), py::arg("force_bn") = 0);
+  m.def("gemm2_accum_f32_", &gemm2_accum_f32_);
   m.def("gemm_fp8", &gemm_fp8, py::arg("a"), py::arg("b"), py::arg("row_scale"), py::arg("col_scale"),
         py::arg("force_bn") = 0);
   m.def("gemm_swiglu", &gemm_swiglu);

@@ -3,7 +3,7 @@
 // Replaces the cuBLAS `nn.Linear` calls + separate elementwise kernels of the reference's HF/FSDP
 // forward (reference: 3rdparty/verl/verl/workers/actor/dp_actor.py:86-273 runs HF decoder layers
 // whose Linear/SiLU/residual ops are individual library kernels).
-#include "gemm_sm100.cuh"
+#include "gemm2_sm100.cuh"
 
 namespace prl {
 
@@ -132,8 +132,13 @@ static int pick_bn(int M, int N) {
 using namespace prl;
 
 // D = A·B^T (+R).  A:[M,K] B:[N,K] bf16 row-major with pitches lda/ldb/ldd in ELEMENTS.
+extern "C" int prl_gemm2_bf16(const void*, const void*, void*, const void*, int, int, int, int64_t, int64_t, int64_t, int, int,
+                              int, cudaStream_t);
+
 extern "C" int prl_gemm_bf16(const void* A, const void* B, void* D, const void* R, int M, int N, int K, int64_t lda,
                              int64_t ldb, int64_t ldd, int force_bn, cudaStream_t stream) {
+  // more than one 128-row block of tokens: the CTA-pair kernel (256-row tiles, cta_group::2) is the faster mainloop
+  if (M > kBlockM && N > 128 && force_bn == 0) return prl_gemm2_bf16(A, B, D, R, M, N, K, lda, ldb, ldd, 0, 0, 0, stream);
   StoreParams sp{static_cast<__nv_bfloat16*>(D), static_cast<const __nv_bfloat16*>(R), ldd, nullptr, nullptr};
   const int bn = force_bn > 0 ? force_bn : pick_bn(M, N);
   switch (bn) {
@@ -163,6 +168,10 @@ extern "C" int prl_gemm_swiglu_bf16(const void* A, const void* Wgu, void* H, voi
                                     int64_t lda, int64_t ldw, int64_t ldh, int64_t ldgu, cudaStream_t stream) {
   if (N2 % 256 != 0) return -11;
   SwigluParams sp{static_cast<__nv_bfloat16*>(H), static_cast<__nv_bfloat16*>(GU), ldh, ldgu};
+  if (M > kBlockM) {
+    using Cfg2 = Gemm2Cfg<256, false, false, false>;
+    return launch_gemm2<Cfg2, EpiSwiglu>(A, Wgu, nullptr, M, N2, K, lda * 2, ldw * 2, 0, sp, 0, stream);
+  }
   using Cfg = GemmCfg<256, 2>;
   return launch_gemm<Cfg, EpiSwiglu, NoGate, false>(A, Wgu, M, N2, K, lda * 2, ldw * 2, sp, NoGate::Params{}, 0, 0,
                                                     stream);

@@ -6,7 +6,7 @@
 // epilogue) and :1124-1375 (d_logits split-N backward) / linear_cross_entropy.py:119.  Math per
 // m = max z, S = sum exp(z-m), B = sum z·exp(z-m)/S, logprob = z_label - m - log S,
 // entropy = log S + m - B, z = h·W^T / tau.
-#include "gemm_sm100.cuh"
+#include "gemm2_sm100.cuh"
 
 namespace prl {
 
@@ -170,9 +170,11 @@ struct EpiCeBwd {
 using namespace prl;
 
 extern "C" int prl_linear_ce_num_splits(int T, int V) {
-  const int mb = (T + kBlockM - 1) / kBlockM;
+  // T > 128 runs on the CTA-pair kernel: 256-row m-blocks, one work item per SM PAIR
+  const int mb = T > kBlockM ? (T + 255) / 256 : 1;
   const int nb = (V + 255) / 256;
-  int s = (2 * sm_count() + mb - 1) / mb;   // ~2 waves of work items
+  const int workers = T > kBlockM ? sm_count() / 2 : sm_count();
+  int s = (2 * workers + mb - 1) / mb;   // ~2 waves of work items
   if (s < 1) s = 1;
   if (s > nb) s = nb;
   const int per = (nb + s - 1) / s;
@@ -194,8 +196,11 @@ extern "C" int prl_linear_ce_fwd(const void* hidden, const void* W, const int64_
   p.label_logit = scratch + 3 * static_cast<int64_t>(T) * S;
   p.S = S;
   using Cfg = GemmCfg<256, 2>;
-  int rc = launch_gemm<Cfg, EpiCeFwd, NoGate, false>(hidden, W, T, V, H, ldh * 2, ldw * 2, p, NoGate::Params{}, S, 0,
-                                                     stream);
+  using Cfg2 = Gemm2Cfg<256, false, false, false>;
+  int rc = T > kBlockM
+               ? launch_gemm2<Cfg2, EpiCeFwd>(hidden, W, nullptr, T, V, H, ldh * 2, ldw * 2, 0, p, S, stream)
+               : launch_gemm<Cfg, EpiCeFwd, NoGate, false>(hidden, W, T, V, H, ldh * 2, ldw * 2, p, NoGate::Params{}, S, 0,
+                                                           stream);
   if (rc) return rc;
   ce_combine_kernel<<<(T + 127) / 128, 128, 0, stream>>>(p.pmax, p.psum, p.pdot, p.label_logit, labels, T, S, V,
                                                          logprob, entropy, lse, ez);
@@ -209,6 +214,8 @@ extern "C" int prl_linear_ce_dz(const void* hidden, const void* W_slice, const i
                                 int H, int v0, int64_t ldh, int64_t ldw, void* DZ, int64_t lddz, cudaStream_t stream) {
   CeBwdParams p{labels, lse, ez, g_lp, g_ent, inv_tau, v0, static_cast<__nv_bfloat16*>(DZ), lddz};
   using Cfg = GemmCfg<256, 2>;
+  using Cfg2 = Gemm2Cfg<256, false, false, false>;
+  if (T > kBlockM) return launch_gemm2<Cfg2, EpiCeBwd>(hidden, W_slice, nullptr, T, Vc, H, ldh * 2, ldw * 2, 0, p, 0, stream);
   return launch_gemm<Cfg, EpiCeBwd, NoGate, false>(hidden, W_slice, T, Vc, H, ldh * 2, ldw * 2, p, NoGate::Params{}, 0,
                                                    0, stream);
 }

@@ -22,6 +22,31 @@ def _is_kernel_tensor(x: torch.Tensor) -> bool:
     return x.is_cuda and x.dtype == torch.bfloat16
 
 
+def _g2_operand(t: torch.Tensor) -> torch.Tensor:
+    """Operand of the CTA-pair GEMM family: unit inner stride, row pitch a multiple of 8 elements, 16-byte aligned base."""
+    if t.stride(-1) != 1 or t.stride(0) % 8 != 0 or t.data_ptr() % 16 != 0:
+        t = t.contiguous()
+    return t
+
+
+def _g2_ok(*dims: int) -> bool:
+    return all(d % 8 == 0 for d in dims)
+
+
+def mm_nn(dy: torch.Tensor, w: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+    """dgrad: ``dy[M, N] @ w[N, K]`` -> [M, K].  ``w`` is consumed as an MN-major tcgen05 operand (no transpose copy)."""
+    if _cublas() or not (_is_kernel_tensor(dy) and w.dtype == torch.bfloat16 and _g2_ok(dy.shape[1], w.shape[1])):
+        return torch.matmul(dy, w, out=out) if out is not None else dy @ w
+    return _C().gemm2_bf16(_g2_operand(dy), _g2_operand(w), False, True, None, out, 0)
+
+
+def mm_tn(dy: torch.Tensor, x: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+    """wgrad: ``dy[M, N].T @ x[M, K]`` -> [N, K].  Both operands are consumed MN-major straight from their row-major storage."""
+    if _cublas() or not (_is_kernel_tensor(dy) and x.dtype == torch.bfloat16 and _g2_ok(dy.shape[1], x.shape[1])):
+        return torch.mm(dy.t(), x, out=out) if out is not None else dy.t() @ x
+    return _C().gemm2_bf16(_g2_operand(dy), _g2_operand(x), True, True, None, out, 0)
+
+
 # ---- decode-shape ("skinny") GEMM: swap-AB + split-K tcgen05 kernel for <= 256 rows, inference only ----
 _SKINNY_WS: dict = {}
 _SKINNY_MAX_ROWS = int(os.environ.get("POLYRL_SKINNY_MAX_ROWS", "256"))
@@ -146,9 +171,9 @@ class _LinearFn(torch.autograd.Function):
         dy2 = dy.reshape(-1, dy.shape[-1])
         dx = dw = dres = None
         if ctx.needs_input_grad[0]:
-            dx = (dy2 @ w).reshape(ctx.x_shape)
+            dx = mm_nn(dy2, w).reshape(ctx.x_shape)
         if ctx.needs_input_grad[1]:
-            dw = dy2.t() @ x2
+            dw = mm_tn(dy2, x2)
         if ctx.has_res and ctx.needs_input_grad[2]:
             dres = dy
         return dx, dw, dres
@@ -202,8 +227,8 @@ class _LinearSwigluFn(torch.autograd.Function):
         x2, wgu, gu = ctx.saved_tensors
         dh2 = dh.reshape(-1, dh.shape[-1]).contiguous()
         dgu = _C().swiglu_bwd(gu, dh2)
-        dx = (dgu @ wgu).reshape(ctx.x_shape) if ctx.needs_input_grad[0] else None
-        dw = dgu.t() @ x2 if ctx.needs_input_grad[1] else None
+        dx = mm_nn(dgu, wgu).reshape(ctx.x_shape) if ctx.needs_input_grad[0] else None
+        dw = mm_tn(dgu, x2) if ctx.needs_input_grad[1] else None
         return dx, dw
 
 
@@ -319,16 +344,20 @@ class _LinearCEFn(torch.autograd.Function):
         g_ent = g_ent.reshape(-1).float().contiguous() if g_ent is not None else None
         V = w.shape[0]
         need_h, need_w = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
-        dh = torch.zeros_like(h2, dtype=torch.float32) if need_h else None
+        own = not _cublas() and h2.shape[1] % 8 == 0
+        dh = (torch.empty if own else torch.zeros)(h2.shape, device=h2.device, dtype=torch.float32) if need_h else None
         dw = torch.empty_like(w) if need_w else None
         for v0 in range(0, V, _CE_CHUNK):
             v1 = min(V, v0 + _CE_CHUNK)
             ws = w[v0:v1]
             dz = C.linear_ce_dz(h2, ws, lab, lse, ez, g_lp, g_ent, ctx.inv_tau, v0)
             if need_h:
-                dh.add_(dz @ ws)
+                if own:      # dH (fp32) += dz @ W_slice inside the GEMM epilogue
+                    C.gemm2_accum_f32_(dh, dz, ws, False, True, 0.0 if v0 == 0 else 1.0)
+                else:
+                    dh.add_(dz @ ws)
             if need_w:
-                torch.mm(dz.t(), h2, out=dw[v0:v1])
+                mm_tn(dz, h2, out=dw[v0:v1])
         dh_out = dh.to(h2.dtype).reshape(ctx.h_shape) if need_h else None
         return dh_out, dw, None, None
 
@@ -429,9 +458,12 @@ class _LinearCETPFn(torch.autograd.Function):
                 dz = ctx.inv_tau * (g_lp[:, None] * (onehot - p) - g_ent[:, None] * p * (z - ez[:, None]))
                 dz = dz.to(h2.dtype)
             if need_h:
-                dh.add_((dz @ ws).float())
+                if ctx.kernel and not _cublas() and h2.shape[1] % 8 == 0:
+                    _C().gemm2_accum_f32_(dh, dz, ws, False, True, 1.0)
+                else:
+                    dh.add_((dz @ ws).float())
             if need_w:
-                torch.mm(dz.t(), h2, out=dw[v0:v1])
+                mm_tn(dz, h2, out=dw[v0:v1])
         if need_h:
             dist.all_reduce(dh, group=ctx.group)
         return (dh.to(h2.dtype).reshape(ctx.h_shape) if need_h else None), dw, None, None, None, None

@@ -48,6 +48,41 @@ def test_gemm_bf16_residual_and_strided(C):
     assert _rel_err(d, want) < 5e-3
 
 
+@pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, True), (True, False)])
+@pytest.mark.parametrize("M,N,K,bn,res", [
+    (512, 512, 256, 256, False), (1000, 456, 208, 0, False), (2112, 1088, 1024, 0, True), (264, 136, 72, 128, False),
+    (4096, 4096, 2048, 0, False),
+])
+def test_gemm2_cta_pair_layouts(C, a_mn, b_mn, M, N, K, bn, res):
+    """CTA-pair (cta_group::2) GEMM family vs fp32 matmul: NT (forward), NN (dgrad), TN (wgrad) + the mixed layout;
+    ragged M/N/K edges exercise TMA zero-fill on loads and clipping on the TMA store."""
+    torch.manual_seed(4)
+    if b_mn and N % 8:
+        N -= N % 8
+    a = (torch.randn((K, M) if a_mn else (M, K), device="cuda") * 0.5).to(torch.bfloat16)
+    b = (torch.randn((K, N) if b_mn else (N, K), device="cuda") * 0.5).to(torch.bfloat16)
+    r = torch.randn(M, N, device="cuda", dtype=torch.bfloat16) if res else None
+    d = C.gemm2_bf16(a, b, a_mn, b_mn, r, None, bn)
+    want = (a.float().t() if a_mn else a.float()) @ (b.float() if b_mn else b.float().t())
+    if res:
+        want = want + r.float()
+    assert torch.isfinite(d.float()).all()
+    assert _rel_err(d, want) < 5e-3
+
+
+def test_gemm2_accum_f32(C):
+    torch.manual_seed(5)
+    M, N, K = 520, 392, 1032
+    a = torch.randn(M, K, device="cuda", dtype=torch.bfloat16)
+    b = torch.randn(K, N, device="cuda", dtype=torch.bfloat16)
+    out = torch.randn(M, N, device="cuda", dtype=torch.float32)
+    want = out.clone() + a.float() @ b.float()
+    C.gemm2_accum_f32_(out, a, b, False, True, 1.0)
+    assert _rel_err(out, want) < 1e-5 + 2e-3
+    C.gemm2_accum_f32_(out, a, b, False, True, 0.0)
+    assert _rel_err(out, a.float() @ b.float()) < 2e-3
+
+
 def test_gemm_fp8(C):
     torch.manual_seed(2)
     M, N, K = 256, 1024, 2048
