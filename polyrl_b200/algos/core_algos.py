@@ -334,10 +334,14 @@ def compute_rewards(token_level_scores, old_log_prob, ref_log_prob, kl_ratio):
 def agg_loss(loss_mat: torch.Tensor, loss_mask: torch.Tensor, loss_agg_mode: str) -> torch.Tensor:
     if loss_agg_mode == "token-mean":
         return masked_mean(loss_mat, loss_mask)
+    # sequence means run over sequences that still have loss tokens: fully masked rows (padded duplicates, DAPO-filtered
+    # groups, rollout-correction vetoes) must not dilute the mean (reference: verl core_algos.agg_loss seq_mask)
     if loss_agg_mode == "seq-mean-token-sum":
-        return (loss_mat * loss_mask).sum(-1).mean()
+        seq_mask = (loss_mask.sum(-1) > 0).to(loss_mat.dtype)
+        return masked_mean((loss_mat * loss_mask).sum(-1), seq_mask)
     if loss_agg_mode == "seq-mean-token-mean":
-        return ((loss_mat * loss_mask).sum(-1) / (loss_mask.sum(-1) + 1e-8)).mean()
+        seq_mask = (loss_mask.sum(-1) > 0).to(loss_mat.dtype)
+        return masked_mean((loss_mat * loss_mask).sum(-1) / (loss_mask.sum(-1) + 1e-8), seq_mask)
     if loss_agg_mode == "seq-mean-token-sum-norm":
         return (loss_mat * loss_mask).sum(-1).sum() / loss_mask.shape[-1]
     raise ValueError(f"invalid loss_agg_mode {loss_agg_mode!r}")

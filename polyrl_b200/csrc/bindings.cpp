@@ -50,6 +50,7 @@ int prl_vmm_is_mapped(int64_t);
 int prl_p2p_reduce_scatter_accum(void* const*, int64_t, float*, int64_t, float, int, int, float*, int, cudaStream_t);
 int prl_skinny_workspace_floats(int, int, int);
 int prl_skinny_gemm(const void*, const void*, void*, const void*, const void*, const float*, const float*, float*, int*, int, int, int, int64_t, int64_t, int64_t, int, int, int, cudaStream_t);
+int prl_stream_gemm(const void*, const void*, void*, const void*, const void*, const float*, const float*, int, int, int, int64_t, int64_t, int64_t, int, int, int, cudaStream_t);
 int prl_skinny_gemm_tp(const void*, const void*, void*, const void*, const void*, const float*, const float*, float*, int*, int, int, int, int64_t, int64_t, int64_t, int, int, int, int, int, uint32_t*, int*, int64_t, void* const*, void* const*, cudaStream_t);
 int prl_ag_gemm_bf16(const void*, void* const*, void*, void*, uint32_t*, uint32_t, int, int, int, int64_t, int64_t, int, int, int, cudaStream_t);
 }
@@ -371,6 +372,38 @@ at::Tensor skinny_gemm(const at::Tensor& x, const at::Tensor& w, const c10::opti
   return out;
 }
 
+// Decode-shape GEMM v2: streamed weights, cluster split-K with a DSMEM reduce-scatter (csrc/decode_gemm.cu).
+at::Tensor stream_gemm(const at::Tensor& x, const at::Tensor& w, const c10::optional<at::Tensor>& residual,
+                       const c10::optional<at::Tensor>& bias, const c10::optional<at::Tensor>& x_scale,
+                       const c10::optional<at::Tensor>& w_scale, int64_t mode, int64_t splits,
+                       c10::optional<at::Tensor> out_opt) {
+  TORCH_CHECK(x.is_cuda() && w.is_cuda() && x.dim() == 2 && w.dim() == 2 && x.stride(1) == 1 && w.stride(1) == 1);
+  const bool fp8 = x.element_size() == 1;
+  TORCH_CHECK(fp8 == (w.element_size() == 1), "x and w must both be bf16 or both fp8");
+  if (!fp8) { CHECK_BF16(x); CHECK_BF16(w); }
+  const int B = x.size(0), K = x.size(1), N = w.size(0);
+  TORCH_CHECK(w.size(1) == K && B <= 256 && K % 16 == 0);
+  c10::cuda::CUDAGuard g(x.device());
+  const int n_out = mode == 1 ? N / 2 : N;
+  at::Tensor out = out_opt.has_value() ? *out_opt : at::empty({B, n_out}, x.options().dtype(at::kBFloat16));
+  CHECK_BF16(out);
+  TORCH_CHECK(out.dim() == 2 && out.size(0) == B && out.size(1) == n_out && out.stride(1) == 1);
+  const void* r = nullptr;
+  if (residual.has_value()) {
+    CHECK_BF16(*residual);
+    TORCH_CHECK(residual->dim() == 2 && residual->stride(1) == 1 && residual->stride(0) == out.stride(0) && residual->numel() == out.numel());
+    r = residual->data_ptr();
+  }
+  const void* bs = nullptr;
+  if (bias.has_value()) { CHECK_BF16(*bias); bs = bias->data_ptr(); }
+  const float* xs = x_scale.has_value() ? x_scale->data_ptr<float>() : nullptr;
+  const float* ws = w_scale.has_value() ? w_scale->data_ptr<float>() : nullptr;
+  TORCH_CHECK(!fp8 || (xs && ws), "fp8 stream GEMM needs x_scale and w_scale");
+  check(prl_stream_gemm(x.data_ptr(), w.data_ptr(), out.data_ptr(), r, bs, xs, ws, B, N, K, x.stride(0), w.stride(0), out.stride(0),
+                        static_cast<int>(mode), fp8 ? 1 : 0, static_cast<int>(splits), cur_stream()), "stream_gemm");
+  return out;
+}
+
 // Row-parallel TP linear with the all-reduce fused into the GEMM epilogue over NVLink peer memory.
 at::Tensor skinny_gemm_tp(const at::Tensor& x, const at::Tensor& w, const c10::optional<at::Tensor>& residual,
                           at::Tensor workspace, at::Tensor counters, int64_t splits, const std::vector<int64_t>& inbox_ptrs,
@@ -510,6 +543,9 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("gemm_swiglu", &gemm_swiglu);
   m.def("skinny_gemm", &skinny_gemm);
   m.def("skinny_gemm_tp", &skinny_gemm_tp);
+  m.def("stream_gemm", &stream_gemm, py::arg("x"), py::arg("w"), py::arg("residual") = py::none(), py::arg("bias") = py::none(),
+        py::arg("x_scale") = py::none(), py::arg("w_scale") = py::none(), py::arg("mode") = 0, py::arg("splits") = 0,
+        py::arg("out") = py::none());
   m.def("linear_ce_fwd", &linear_ce_fwd);
   m.def("linear_ce_dz", &linear_ce_dz);
   m.def("rmsnorm_fwd", &rmsnorm_fwd);

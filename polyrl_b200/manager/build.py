@@ -1,12 +1,25 @@
-"""Build the native C++ rollout manager binary (polyrl_b200/manager/bin/rollout-manager)."""
+"""Build the native C++ rollout manager binary (polyrl_b200/manager/bin/rollout-manager).
+
+Binaries are never committed: they are built from ``manager/src`` on first use and cached under ``manager/bin/`` (git-ignored)
+next to a stamp holding the hash of the sources + flags that produced them, so a checkout with arbitrary mtimes can never run a
+stale or foreign ELF."""
 from __future__ import annotations
 
+import hashlib
 import subprocess
 from pathlib import Path
 
 HERE = Path(__file__).resolve().parent
 SRC = HERE / "src"
 BIN = HERE / "bin" / "rollout-manager"
+
+
+def _digest(paths: list[Path], flags: list[str]) -> str:
+    h = hashlib.sha256(" ".join(flags).encode())
+    for p in paths:
+        h.update(p.name.encode())
+        h.update(p.read_bytes())
+    return h.hexdigest()
 
 
 def build_manager(force: bool = False, sanitize: str | None = None) -> Path | None:
@@ -19,14 +32,19 @@ def build_manager(force: bool = False, sanitize: str | None = None) -> Path | No
     hdrs = sorted(SRC.glob("*.h*"))
     out = BIN if not sanitize else BIN.with_name(f"{BIN.name}-{sanitize}")
     out.parent.mkdir(parents=True, exist_ok=True)
-    newest = max(p.stat().st_mtime for p in srcs + hdrs)
-    if out.exists() and out.stat().st_mtime >= newest and not force:
-        return out
     flags = ["-O2"] if not sanitize else ["-O1", "-g", f"-fsanitize={sanitize}", "-fno-omit-frame-pointer"]
-    cmd = ["g++", *flags, "-std=c++17", "-pthread", "-I", str(SRC), *map(str, srcs), "-o", str(out)]
+    flags += ["-std=c++17", "-pthread"]
+    want = _digest(srcs + hdrs, flags)
+    stamp = out.with_name(out.name + ".stamp")
+    if out.exists() and stamp.exists() and stamp.read_text().strip() == want and not force:
+        return out
+    tmp = out.with_name(out.name + ".tmp")
+    cmd = ["g++", *flags, "-I", str(SRC), *map(str, srcs), "-o", str(tmp)]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("rollout-manager build failed:\n" + r.stdout + r.stderr)
+    tmp.replace(out)
+    stamp.write_text(want + "\n")
     return out
 
 

@@ -25,6 +25,7 @@ CU_SOURCES = [
     "gemm_tcgen05.cu",
     "gemm2.cu",
     "skinny_gemm.cu",
+    "decode_gemm.cu",
     "vmm.cu",
     "linear_ce.cu",
     "ag_gemm.cu",

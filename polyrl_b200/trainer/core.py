@@ -15,15 +15,55 @@ from ..algos.core_algos import AdvantageEstimator
 from ..protocol import DataProto
 
 
-def apply_kl_penalty(data: DataProto, kl_ctrl, kl_penalty: str = "kl") -> tuple[DataProto, dict]:
+def apply_kl_penalty(data: DataProto, kl_ctrl, kl_penalty: str = "kl", group=None, real_rows: torch.Tensor | None = None,
+                     distributed: bool = False) -> tuple[DataProto, dict]:
+    """Token-level KL-in-reward.  ``data`` may be ONE data-parallel shard of the streamed batch: with ``distributed``
+    (over ``group``, None = default group) the mean KL that drives the adaptive controller is all-reduced (sum of per-sequence KL, count of real sequences), so every
+    rank's ``kl_ctrl`` stays bit-identical — the reference updates one controller on the driver from the whole batch
+    (3rdparty/verl/verl/trainer/ppo/ray_trainer.py:121-159).  ``real_rows`` [n] bool excludes padded duplicates."""
     mask = data.batch["response_mask"].float()
     scores = data.batch["token_level_scores"]
     kld = core_algos.kl_penalty(data.batch["old_log_probs"], data.batch["ref_log_prob"], kl_penalty) * mask
     beta = kl_ctrl.value
     data.batch["token_level_rewards"] = scores - beta * kld
-    current_kl = core_algos.masked_mean(kld, mask, dim=-1).mean().item()
-    kl_ctrl.update(current_kl=current_kl, n_steps=scores.shape[0])
+    per_seq = core_algos.masked_mean(kld, mask, dim=-1)
+    real = torch.ones_like(per_seq) if real_rows is None else real_rows.to(per_seq)
+    stat = torch.stack([(per_seq * real).sum(), real.sum()]).double()
+    if distributed:
+        torch.distributed.all_reduce(stat, group=group)
+    n_real = max(int(round(stat[1].item())), 1)
+    current_kl = float(stat[0].item() / n_real)
+    kl_ctrl.update(current_kl=current_kl, n_steps=n_real)
     return data, {"actor/reward_kl_penalty": current_kl, "actor/reward_kl_penalty_coeff": beta}
+
+
+def compute_group_advantage_sharded(local: DataProto, shard_ctx: dict, adv_estimator, gamma: float, lam: float,
+                                    num_repeat: int, norm_adv_by_std_in_grpo: bool, config, group) -> DataProto:
+    """Group-level advantages (GRPO / RLOO / OPO / GPG / ...) when the rewards only exist per DP shard (KL-in-reward needs
+    the shard's old/ref log-probs).  The shards' ``token_level_rewards`` and masks are all-gathered in the global (balanced)
+    row order recorded by the trainer, the estimator runs on the WHOLE streamed batch exactly like the reference's driver
+    does (stream_ray_trainer.py:516-541), padded duplicates get private group ids so they cannot skew any group's statistics,
+    and the rank keeps its own rows."""
+    import torch.distributed as dist
+
+    dp, dp_rank, sp = shard_ctx["dp"], shard_ctx["dp_rank"], shard_ctx.get("sp", 1)
+    tlr, mask = local.batch["token_level_rewards"].contiguous(), local.batch["response_mask"].contiguous()
+    world = dist.get_world_size(group)
+    def gather(x):
+        parts = [torch.empty_like(x) for _ in range(world)]
+        dist.all_gather(parts, x, group=group)
+        return torch.cat([parts[r * sp] for r in range(dp)], dim=0)      # SP peers hold the same shard: take one per DP rank
+    g_tlr, g_mask = gather(tlr), gather(mask)
+    uid = np.array(shard_ctx["uid"], dtype=object).copy()
+    for i in np.nonzero(shard_ctx["is_pad"])[0]:
+        uid[i] = f"__pad_{i}"
+    whole = DataProto.from_dict({"token_level_rewards": g_tlr, "response_mask": g_mask}, non_tensors={"uid": uid})
+    whole = compute_advantage(whole, adv_estimator, gamma, lam, num_repeat, norm_adv_by_std_in_grpo, config)
+    n = len(local)
+    sl = slice(dp_rank * n, (dp_rank + 1) * n)
+    local.batch["advantages"] = whole.batch["advantages"][sl].clone()
+    local.batch["returns"] = whole.batch["returns"][sl].clone()
+    return local
 
 
 def compute_advantage(data: DataProto, adv_estimator, gamma: float = 1.0, lam: float = 1.0, num_repeat: int = 1,

@@ -16,6 +16,7 @@ import time
 import uuid
 from pathlib import Path
 
+import numpy as np
 import torch
 import torch.distributed as dist
 
@@ -173,16 +174,24 @@ class StreamPPOTrainer:
     def _balance_and_shard(self, batch: DataProto, metrics: dict) -> DataProto:
         """Karmarkar-Karp reorder so every DP rank gets a similar token count, then take this rank's shard."""
         dp, dp_rank = getattr(self.worker, "dp_size", self.world), getattr(self.worker, "dp_rank", self.rank)
+        self._shard_ctx = None
         if dp == 1:
             return batch
         batch, pad = pad_dataproto_to_divisor(batch, dp)
+        is_pad = np.zeros(len(batch), dtype=bool)
         if pad:
             batch.batch["response_mask"][-pad:] = 0        # padded duplicates carry no loss
+            is_pad[-pad:] = True
         if self.config.trainer.balance_batch:
             lens = batch.batch["attention_mask"].sum(-1).tolist()
             parts = get_seqlen_balanced_partitions([int(x) for x in lens], dp, equal_size=True)
             metrics.update(log_seqlen_unbalance([int(x) for x in lens], parts, "global_seqlen"))
-            batch.reorder(torch.tensor([i for p in parts for i in p], dtype=torch.long))
+            order = [i for p in parts for i in p]
+            batch.reorder(torch.tensor(order, dtype=torch.long))
+            is_pad = is_pad[np.asarray(order)]
+        # global (post-balance) row order: lets a shard-local phase re-assemble whole GRPO/RLOO groups across DP ranks
+        self._shard_ctx = {"dp": dp, "dp_rank": dp_rank, "sp": getattr(self.worker, "sp_size", 1), "is_pad": is_pad,
+                           "uid": batch.non_tensor_batch["uid"].copy() if "uid" in batch.non_tensor_batch else None}
         return batch.chunk(dp)[dp_rank]       # ranks of one Ulysses SP group share the same shard
 
     def _reward(self, batch: DataProto) -> torch.Tensor:
@@ -275,14 +284,31 @@ class StreamPPOTrainer:
                 local.batch["values"] = self.critic.compute_values(local).batch["values"]
         if not (group_level and not algo.use_kl_in_reward):
             with marked_timer("adv", t):
+                ctx = getattr(self, "_shard_ctx", None)
+                dp_group = getattr(self.worker, "group", None)
                 if algo.use_kl_in_reward:
-                    local, klm = core.apply_kl_penalty(local, self.kl_ctrl, algo.kl_penalty)
+                    real = None
+                    if ctx is not None:
+                        n = len(local)
+                        real = torch.from_numpy(~ctx["is_pad"][ctx["dp_rank"] * n:(ctx["dp_rank"] + 1) * n]).to(self.device)
+                        if ctx["sp"] > 1:      # SP peers hold the same shard: count it once
+                            real = real & bool(self.rank % ctx["sp"] == 0)
+                    local, klm = core.apply_kl_penalty(local, self.kl_ctrl, algo.kl_penalty,
+                                                       group=dp_group, real_rows=real,
+                                                       distributed=ctx is not None and dist.is_initialized())
                     for k, v in klm.items():
                         metrics.setdefault(k, []).append(v)
                 else:
                     local.batch["token_level_rewards"] = local.batch["token_level_scores"]
-                local = core.compute_advantage(local, algo.adv_estimator, algo.gamma, algo.lam, cfg.actor_rollout_ref.rollout.n,
-                                               algo.norm_adv_by_std_in_grpo, algo)
+                if group_level and ctx is not None and dist.is_initialized():
+                    # groups were split across DP ranks by the balanced sharding: gather rewards, run the estimator on the
+                    # whole streamed batch, keep this rank's rows
+                    local = core.compute_group_advantage_sharded(local, ctx, algo.adv_estimator, algo.gamma, algo.lam,
+                                                                 cfg.actor_rollout_ref.rollout.n, algo.norm_adv_by_std_in_grpo,
+                                                                 algo, dp_group)
+                else:
+                    local = core.compute_advantage(local, algo.adv_estimator, algo.gamma, algo.lam,
+                                                   cfg.actor_rollout_ref.rollout.n, algo.norm_adv_by_std_in_grpo, algo)
         self._step_batches.append(local)
         # ---- split at cumulative mini-batch boundaries (in global sample counts)
         end_global = seen + full_len
@@ -306,9 +332,12 @@ class StreamPPOTrainer:
                     with marked_timer("update_actor", t):
                         M.append_to_dict(metrics, self.worker.update_actor_stream(part).meta_info["metrics"])
             elif is_opt:
-                # boundary hit exactly at a batch edge with nothing left in this slice: step on accumulated grads
-                st = self.worker.actor_engine.step()
-                metrics.setdefault("actor/grad_norm", []).append(st["grad_norm"])
+                # boundary hit exactly at a batch edge with nothing left in this slice: step actor AND critic on the
+                # accumulated grads, at the scheduled learning rate
+                if self.use_critic:
+                    M.append_to_dict(metrics, self.critic.optimizer_step_only(is_lr))
+                if self.global_steps >= cfg.trainer.critic_warmup or not self.use_critic:
+                    M.append_to_dict(metrics, self.worker.optimizer_step_only(is_lr))
             start = stop
 
     # ------------------------------------------------------------------ validation / checkpoint
@@ -369,9 +398,11 @@ class StreamPPOTrainer:
     def _save_checkpoint(self) -> None:
         root = self._ckpt_root() / f"global_step_{self.global_steps}"
         t = self.config.trainer
-        self.worker.save_checkpoint(str(root / "actor"), None, self.global_steps, t.max_actor_ckpt_to_keep)
+        # rotation happens once per step, below, on whole global_step_* directories (a per-role rotation would strand
+        # data.pt / the sibling role of a deleted step)
+        self.worker.save_checkpoint(str(root / "actor"), None, self.global_steps, None)
         if self.use_critic:
-            self.critic.save_checkpoint(str(root / "critic"), None, self.global_steps, t.max_critic_ckpt_to_keep)
+            self.critic.save_checkpoint(str(root / "critic"), None, self.global_steps, None)
         if self.rank == 0:
             torch.save({"sampler": self.sampler.state_dict() if self.sampler is not None else None,
                         "global_steps": self.global_steps,
@@ -379,6 +410,11 @@ class StreamPPOTrainer:
             write_latest(self._ckpt_root(), self.global_steps)
         if dist.is_initialized() and self.world > 1:
             dist.barrier(group=self.group)
+        keeps = [k for k in (t.max_actor_ckpt_to_keep, t.max_critic_ckpt_to_keep if self.use_critic else None) if k]
+        if keeps and self.rank == 0:
+            from ..utils.checkpoint import rotate_checkpoints
+
+            rotate_checkpoints(root, max(keeps))
 
     def _load_checkpoint(self) -> int:
         t = self.config.trainer
@@ -417,7 +453,7 @@ class StreamPPOTrainer:
     # ------------------------------------------------------------------ main loop
     def fit(self) -> dict:
         cfg = self.config
-        self._load_checkpoint()
+        resumed_steps = self._load_checkpoint()
         last_metrics: dict = {}
         if cfg.trainer.val_before_train and self.val_dataset is not None:
             vm = self._validate()
@@ -431,6 +467,11 @@ class StreamPPOTrainer:
         prof = cfg.global_profiler
         one_off = bool(cfg.trainer.one_step_off and self.client is not None)
         batches = iter(self._iter_batches())
+        if resumed_steps and not (self.sampler is not None and hasattr(self.sampler, "state_dict")):
+            # no stateful sampler to restore the data position from: skip the batches the checkpointed steps consumed
+            for _ in range(resumed_steps):
+                if next(batches, None) is None:
+                    break
         lookahead = next(batches, None)
         self._prefetched = None
         while lookahead is not None:

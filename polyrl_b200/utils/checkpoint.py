@@ -60,6 +60,27 @@ def _set_rng_state(st: dict, device) -> None:
         torch.cuda.set_rng_state(st["cuda"], device)
 
 
+def rotate_checkpoints(latest_path: str | Path, keep: int) -> list[str]:
+    """Keep the ``keep`` newest checkpoints, decided from what is ON DISK (a fresh manager per save, or a restarted job,
+    rotates the same way).  ``latest_path`` is either ``<root>/global_step_N`` or a role directory below it
+    (``<root>/global_step_N/actor``): in both cases whole ``global_step_*`` directories are removed, so no orphaned
+    ``data.pt`` / sibling role directory stays behind.  Returns the removed directories."""
+    p = Path(latest_path)
+    step_dir = p if p.name.startswith("global_step_") else p.parent
+    if not step_dir.name.startswith("global_step_") or keep is None or keep <= 0:
+        return []
+    def step_of(d: Path) -> int:
+        try:
+            return int(d.name.rsplit("_", 1)[-1])
+        except ValueError:
+            return -1
+    steps = sorted((d for d in step_dir.parent.glob("global_step_*") if d.is_dir() and step_of(d) >= 0), key=step_of)
+    doomed = [d for d in steps[:-keep] if d != step_dir]
+    for d in doomed:
+        shutil.rmtree(d, ignore_errors=True)
+    return [str(d) for d in doomed]
+
+
 class ShardedCheckpointManager:
     def __init__(self, engine, model_cfg, save_contents=("model", "optimizer", "extra"), load_contents=None):
         self.engine, self.model_cfg = engine, model_cfg
@@ -95,10 +116,8 @@ class ShardedCheckpointManager:
         if dist.is_initialized() and eng.world > 1:
             dist.barrier(group=eng.group)
         self.saved.append(path)
-        if max_ckpt_to_keep and max_ckpt_to_keep > 0 and len(self.saved) > max_ckpt_to_keep and eng.rank == 0:
-            for old in self.saved[:-max_ckpt_to_keep]:
-                shutil.rmtree(old, ignore_errors=True)
-            self.saved = self.saved[-max_ckpt_to_keep:]
+        if max_ckpt_to_keep and max_ckpt_to_keep > 0 and eng.rank == 0:
+            rotate_checkpoints(path, max_ckpt_to_keep)
 
     def load(self, path: str) -> dict | None:
         eng = self.engine

@@ -1,12 +1,15 @@
 """Cross-host weight transfer over N parallel TCP streams (for elastic REMOTE rollout instances that are not on
 the trainer's NVSwitch domain).  Capability parity with the reference's TCPTransferEngine + sender/receiver
-agents (rlboost/weight_transfer/transfer_engine.py:14-291: parallel streams, 16 MiB socket buffers, 16-byte
-(offset, length) header, ``os.sendfile`` from a memfd, ``recv_into`` a registered buffer, per-batch status;
+agents (rlboost/weight_transfer/transfer_engine.py:14-291: parallel streams, 16 MiB socket buffers, (offset, length)
+header — extended here with an auth token, a transfer id and the total length so that a partly failed multi-stream transfer can
+never be completed by streams of the NEXT one, and a stranger that can reach the ports cannot overwrite weights — ``os.sendfile`` from a memfd, ``recv_into`` a registered buffer, per-batch status;
 sender_agent.py:33-99 memfd/shm staging; receiver_agent.py:22-32 shared buffer).  Same-box instances use the
 peer-memory path in ``sync.py`` instead.
 """
 from __future__ import annotations
 
+import hashlib
+import logging
 import mmap
 import os
 import socket
@@ -15,8 +18,15 @@ import threading
 
 import torch
 
-HEADER = struct.Struct("<QQ")          # (offset, length)
+HEADER = struct.Struct("<QQQQQ")       # (token digest, transfer id, total bytes of the transfer, offset, length)
 SOCK_BUF = 16 << 20
+log = logging.getLogger(__name__)
+
+
+def token_digest(token: str | None) -> int:
+    """64-bit digest of the shared secret (``POLYRL_WEIGHT_TOKEN`` unless given); both ends must agree."""
+    token = os.environ.get("POLYRL_WEIGHT_TOKEN", "") if token is None else token
+    return int.from_bytes(hashlib.sha256(token.encode()).digest()[:8], "little")
 
 
 def flat_state_nbytes(named: list[tuple[str, torch.Tensor]]) -> int:
@@ -46,10 +56,12 @@ class StagingBuffer:
 
 
 class TCPWeightSender:
-    def __init__(self, num_streams: int = 4):
+    def __init__(self, num_streams: int = 4, token: str | None = None):
         self.num_streams = num_streams
         self.status: dict[int, str] = {}
         self._batch = 0
+        self._token = token_digest(token)
+        self._nonce = int.from_bytes(os.urandom(4), "little") << 32      # transfer ids are unique across sender restarts
 
     def stage(self, named: list[tuple[str, torch.Tensor]], staging: StagingBuffer) -> list[tuple[str, int, int]]:
         """Copy (full) tensors into the staging buffer at running offsets; returns the layout meta."""
@@ -63,11 +75,12 @@ class TCPWeightSender:
             torch.cuda.synchronize()
         return meta
 
-    def _send_range(self, host: str, port: int, fd: int, lo: int, hi: int, zero_copy: bool, mm) -> None:
+    def _send_range(self, host: str, port: int, fd: int, lo: int, hi: int, zero_copy: bool, mm, tid: int = 0,
+                    total: int = 0) -> None:
         s = socket.create_connection((host, port), timeout=60)
         s.setsockopt(socket.SOL_SOCKET, socket.SO_SNDBUF, SOCK_BUF)
         s.setsockopt(socket.IPPROTO_TCP, socket.TCP_NODELAY, 1)
-        s.sendall(HEADER.pack(lo, hi - lo))
+        s.sendall(HEADER.pack(self._token, tid, total, lo, hi - lo))
         sent = lo
         while sent < hi:
             if zero_copy:
@@ -87,6 +100,7 @@ class TCPWeightSender:
         nbytes = nbytes or staging.nbytes
         self._batch += 1
         bid = self._batch
+        tid = self._nonce | (bid & 0xFFFFFFFF)
         self.status[bid] = "running"
         per = (nbytes + self.num_streams - 1) // self.num_streams
         per = (per + 4095) // 4096 * 4096
@@ -98,7 +112,7 @@ class TCPWeightSender:
             if lo >= hi:
                 return
             try:
-                self._send_range(host, base_port + i, staging.fd, lo, hi, zero_copy, staging.mm)
+                self._send_range(host, base_port + i, staging.fd, lo, hi, zero_copy, staging.mm, tid, nbytes)
             except Exception as e:
                 errs.append(e)
 
@@ -116,7 +130,12 @@ class TCPWeightSender:
 class TCPWeightReceiver:
     """Listens on ``port + i`` for stream i, receives into a host buffer, then copies into the model tensors."""
 
-    def __init__(self, weights, bind_host: str = "0.0.0.0", port: int = 21000, num_streams: int = 4):
+    def __init__(self, weights, bind_host: str | None = None, port: int = 21000, num_streams: int = 4,
+                 token: str | None = None):
+        # bind to the registered NIC when the launcher names one (POLYRL_WEIGHT_BIND); every stream must present the token
+        bind_host = bind_host or os.environ.get("POLYRL_WEIGHT_BIND", "0.0.0.0")
+        self._token = token_digest(token)
+        self._tid = None                 # transfer currently being assembled
         self.named = list(weights.named_tensors()) if hasattr(weights, "named_tensors") else list(weights)
         self.nbytes = flat_state_nbytes(self.named)
         self.buf = torch.empty(self.nbytes, dtype=torch.uint8, pin_memory=torch.cuda.is_available())
@@ -144,8 +163,19 @@ class TCPWeightReceiver:
             try:
                 hdr = b""
                 while len(hdr) < HEADER.size:
-                    hdr += c.recv(HEADER.size - len(hdr))
-                off, ln = HEADER.unpack(hdr)
+                    part = c.recv(HEADER.size - len(hdr))
+                    if not part:
+                        raise ConnectionError("sender closed before the header")
+                    hdr += part
+                tok, tid, total, off, ln = HEADER.unpack(hdr)
+                if tok != self._token:
+                    raise PermissionError("weight stream with a wrong token rejected")
+                if total != self.nbytes or off + ln > self.nbytes:
+                    raise ValueError(f"weight stream out of bounds: total={total} off={off} len={ln} expect {self.nbytes}")
+                with self._lock:
+                    if tid != self._tid:          # first stream of a NEW transfer: forget whatever a failed one left behind
+                        self._tid, self._received = tid, 0
+                        self._done.clear()
                 got = 0
                 while got < ln:
                     n = c.recv_into(self.view[off + got: off + ln], min(ln - got, 16 << 20))
@@ -154,18 +184,23 @@ class TCPWeightReceiver:
                     got += n
                 c.sendall(b"OK")
                 with self._lock:
-                    self._received += ln
-                    if self._received >= self.nbytes:
-                        self._done.set()
-            except Exception:
-                pass
+                    if tid == self._tid:          # a stream of a superseded transfer does not count
+                        self._received += ln
+                        if self._received >= self.nbytes:
+                            self._done.set()
+            except Exception as e:
+                log.warning("weight stream on port %s failed: %r", srv.getsockname()[1], e)
+                try:
+                    c.sendall(b"NO")
+                except OSError:
+                    pass
             finally:
                 c.close()
 
     def wait_and_apply(self, timeout: float = 3600.0) -> bool:
         if not self._done.wait(timeout):
             with self._lock:                  # a sender that died mid-transfer must not poison the byte count of the next attempt
-                self._received = 0
+                self._received, self._tid = 0, None
                 self._done.clear()
             raise TimeoutError("weight transfer did not complete")
         off = 0
@@ -176,7 +211,7 @@ class TCPWeightReceiver:
         if torch.cuda.is_available():
             torch.cuda.synchronize()
         with self._lock:
-            self._received = 0
+            self._received, self._tid = 0, None
             self._done.clear()
         return True
 

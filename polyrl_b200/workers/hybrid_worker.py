@@ -545,20 +545,41 @@ class ActorRolloutRefWorker:
 
     update_actor = update_actor_stream
 
+    def optimizer_step_only(self, is_lr_step: bool = True) -> dict:
+        """Optimizer step on the gradients accumulated so far, with the SCHEDULED learning rate — used when a mini-batch
+        boundary coincides with the end of a streamed slice, so there is no micro-batch left to ride the step on."""
+        opt = self.config.actor_rollout_ref.actor.optim
+        total = opt.total_training_steps if opt.total_training_steps > 0 else (self.config.trainer.total_training_steps or 0)
+        lr = lr_at_step(opt, self.lr_step, total)
+        offload = self.config.actor_rollout_ref.actor.fsdp_config.optimizer_offload
+        if offload:
+            self.actor_engine.load_optimizer()
+        st = self.actor_engine.step(lr)
+        if offload:
+            self.actor_engine.offload_optimizer()
+        if is_lr_step:
+            self.lr_step += 1
+        return {"actor/grad_norm": [st["grad_norm"]], "actor/lr": [lr]}
+
     # ------------------------------------------------------------------ checkpoint / profile
     def save_checkpoint(self, local_path: str, hdfs_path: str | None = None, global_step: int = 0,
                         max_ckpt_to_keep: int | None = None) -> None:
-        from ..utils.checkpoint import ShardedCheckpointManager
+        self._ckpt_manager().save(local_path, global_step, max_ckpt_to_keep, extra={"lr_step": self.lr_step})
 
-        ShardedCheckpointManager(self.actor_engine, self.model_cfg).save(local_path, global_step, max_ckpt_to_keep,
-                                                                        extra={"lr_step": self.lr_step})
+    def _ckpt_manager(self):
+        """ONE manager per worker, configured from ``actor.checkpoint.{save,load}_contents`` (e.g. ``hf_model``)."""
+        if getattr(self, "_ckpt_mgr", None) is None:
+            from ..utils.checkpoint import ShardedCheckpointManager
+
+            ck = self.config.actor_rollout_ref.actor.checkpoint
+            self._ckpt_mgr = ShardedCheckpointManager(self.actor_engine, self.model_cfg, tuple(ck.save_contents),
+                                                      tuple(ck.load_contents))
+        return self._ckpt_mgr
 
     def load_checkpoint(self, local_path: str | None, hdfs_path: str | None = None, del_local_after_load: bool = False) -> None:
         if not local_path:
             return
-        from ..utils.checkpoint import ShardedCheckpointManager
-
-        extra = ShardedCheckpointManager(self.actor_engine, self.model_cfg).load(local_path)
+        extra = self._ckpt_manager().load(local_path)
         self.lr_step = (extra or {}).get("lr_step", 0)
         if self.rollout is not None:
             self.update_weight_remote()
@@ -659,16 +680,28 @@ class CriticWorker:
 
     update_critic = update_critic_stream
 
-    def save_checkpoint(self, local_path, hdfs_path=None, global_step=0, max_ckpt_to_keep=None) -> None:
-        from ..utils.checkpoint import ShardedCheckpointManager
+    def optimizer_step_only(self, is_lr_step: bool = True) -> dict:
+        opt = self.config.critic.optim
+        total = opt.total_training_steps if opt.total_training_steps > 0 else (self.config.trainer.total_training_steps or 0)
+        lr = lr_at_step(opt, self.lr_step, total)
+        st = self.engine.step(lr)
+        if is_lr_step:
+            self.lr_step += 1
+        return {"critic/grad_norm": [st["grad_norm"]], "critic/lr": [lr]}
 
-        ShardedCheckpointManager(self.engine, self.model_cfg).save(local_path, global_step, max_ckpt_to_keep,
-                                                                  extra={"lr_step": self.lr_step})
+    def _ckpt_manager(self):
+        if getattr(self, "_ckpt_mgr", None) is None:
+            from ..utils.checkpoint import ShardedCheckpointManager
+
+            ck = self.config.critic.checkpoint
+            self._ckpt_mgr = ShardedCheckpointManager(self.engine, self.model_cfg, tuple(ck.save_contents), tuple(ck.load_contents))
+        return self._ckpt_mgr
+
+    def save_checkpoint(self, local_path, hdfs_path=None, global_step=0, max_ckpt_to_keep=None) -> None:
+        self._ckpt_manager().save(local_path, global_step, max_ckpt_to_keep, extra={"lr_step": self.lr_step})
 
     def load_checkpoint(self, local_path, hdfs_path=None, del_local_after_load=False) -> None:
         if not local_path:
             return
-        from ..utils.checkpoint import ShardedCheckpointManager
-
-        extra = ShardedCheckpointManager(self.engine, self.model_cfg).load(local_path)
+        extra = self._ckpt_manager().load(local_path)
         self.lr_step = (extra or {}).get("lr_step", 0)

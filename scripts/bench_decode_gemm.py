@@ -1,0 +1,114 @@
+"""Decode-shape GEMMs (B <= 256 rows): stream GEMM v2 (cluster-multicast activations) vs cuBLAS vs the round-1 kernels,
+timed INSIDE CUDA graphs (as the engine runs them) while cycling over enough distinct weight copies that every call streams
+its weights from HBM (sum of copies > L2).  Also a correctness pass against fp32 matmul."""
+import json
+import sys
+
+import torch
+
+from polyrl_b200.ops import ext
+
+
+def graph_time(fns, reps=7):
+    for f in fns:
+        f()
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for f in fns:
+            f()
+    g.replay()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        s_, e_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s_.record()
+        g.replay()
+        e_.record()
+        torch.cuda.synchronize()
+        ts.append(s_.elapsed_time(e_) / len(fns))
+    return sorted(ts)[len(ts) // 2]
+
+
+def rel_err(a, b):
+    a, b = a.float(), b.float()
+    return ((a - b).norm() / (b.norm() + 1e-12)).item()
+
+
+def main():
+    C = ext()
+    ws = torch.empty(48 * 1024 * 1024, device="cuda", dtype=torch.float32)
+    ctr = torch.zeros(4096, device="cuda", dtype=torch.int32)
+    ok = True
+    # ---------------- correctness
+    for (B, N, K, mode, splits) in [(128, 4096, 4096, 0, 1), (128, 4096, 4096, 0, 4), (128, 6144, 4096, 0, 3),
+                                    (128, 4096, 14336, 0, 4), (64, 1024, 512, 0, 0), (7, 512, 256, 0, 2),
+                                    (200, 4096, 4096, 0, 2), (33, 1000, 4096, 0, 5), (128, 28672, 4096, 1, 1),
+                                    (96, 2048, 1024, 1, 3), (128, 128256, 1024, 0, 1), (256, 4096, 4096, 0, 8),
+                                    (128, 4096, 4096, 0, 0), (72, 2048, 2048, 1, 7)]:
+        torch.manual_seed(B + N)
+        x = torch.randn(B, K, device="cuda", dtype=torch.bfloat16)
+        w = (torch.randn(N, K, device="cuda") * 0.05).to(torch.bfloat16)
+        n_out = N // 2 if mode else N
+        r = torch.randn(B, n_out, device="cuda", dtype=torch.bfloat16) if not mode else None
+        bias = torch.randn(N, device="cuda", dtype=torch.bfloat16) if not mode else None
+        got = C.stream_gemm(x, w, r, bias, None, None, mode, splits)
+        torch.cuda.synchronize()
+        z = x.float() @ w.float().t()
+        if mode:
+            zz = z.view(B, N // 256, 2, 128)
+            want = (torch.nn.functional.silu(zz[:, :, 0]) * zz[:, :, 1]).reshape(B, n_out)
+        else:
+            want = z + bias.float() + r.float()
+        e = rel_err(got, want)
+        good = e < 6e-3
+        ok &= good
+        print(json.dumps({"check": "stream_gemm", "B": B, "N": N, "K": K, "mode": mode, "splits": splits,
+                          "rel_err": round(e, 5), "ok": bool(good)}), flush=True)
+    print(json.dumps({"all_checks_ok": bool(ok)}), flush=True)
+    if not ok or "--check" in sys.argv:
+        return 0 if ok else 1
+    # ---------------- timing
+    for B in (128, 64, 256):
+        tot = {"stream": 0.0, "cublas": 0.0}
+        for N, K in ((6144, 4096), (4096, 4096), (28672, 4096), (4096, 14336), (128256, 4096)):
+            copies = max(2, int(300e6 // (N * K * 2)) + 1)
+            x = torch.randn(B, K, device="cuda", dtype=torch.bfloat16)
+            Ws = [torch.randn(N, K, device="cuda", dtype=torch.bfloat16) * 0.02 for _ in range(copies)]
+            mode = 1 if N == 28672 else 0
+            rec = {"op": "decode_gemm_in_graph", "B": B, "N": N, "K": K, "swiglu": bool(mode)}
+            if mode:
+                t_l = graph_time([(lambda w=w: (lambda gu: torch.nn.functional.silu(gu[:, :N // 2]) * gu[:, N // 2:])(x @ w.t())) for w in Ws])
+                t_old = graph_time([(lambda w=w: C.gemm_swiglu(x, w, False)) for w in Ws])
+            else:
+                t_l = graph_time([(lambda w=w: x @ w.t()) for w in Ws])
+                t_old = graph_time([(lambda w=w: C.skinny_gemm(x, w, None, None, None, None, ws, ctr, 0, 0)) for w in Ws])
+            rec["cublas_ms"] = round(t_l, 4)
+            rec["r1_kernel_ms"] = round(t_old, 4)
+            best = None
+            tiles = (N + 127) // 128
+            for splits in range(1, 9):
+                if tiles * splits > 296 and splits > 1:
+                    break
+                t = graph_time([(lambda w=w: C.stream_gemm(x, w, None, None, None, None, mode, splits)) for w in Ws])
+                rec[f"stream_s{splits}_ms"] = round(t, 4)
+                if best is None or t < best[0]:
+                    best = (t, splits)
+            t_auto = graph_time([(lambda w=w: C.stream_gemm(x, w, None, None, None, None, mode, 0)) for w in Ws])
+            rec["stream_auto_ms"] = round(t_auto, 4)
+            rec["best"] = {"ms": round(best[0], 4), "splits": best[1]}
+            rec["best_GBps"] = round(N * K * 2 / best[0] / 1e6, 1)
+            rec["best_hbm_frac_of_measured_6569.6"] = round(N * K * 2 / best[0] / 1e6 / 6569.6, 3)
+            rec["cublas_hbm_frac_of_measured"] = round(N * K * 2 / t_l / 1e6 / 6569.6, 3)
+            rec["best_vs_cublas"] = round(t_l / best[0], 3)
+            print(json.dumps(rec), flush=True)
+            if N != 128256:
+                tot["stream"] += best[0]
+                tot["cublas"] += t_l
+            del Ws
+        print(json.dumps({"op": "decode_layer_gemms_total_in_graph", "B": B, **{k: round(v, 4) for k, v in tot.items()}}), flush=True)
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -100,6 +100,11 @@ def test_agg_loss_modes():
     assert torch.isclose(A.agg_loss(x, m, "seq-mean-token-sum-norm"), torch.tensor(7.0 / 3))
     with pytest.raises(ValueError):
         A.agg_loss(x, m, "bad")
+    # fully masked rows (padded duplicates / filtered groups / vetoed sequences) do not dilute sequence means
+    x2 = torch.cat([x, torch.full((2, x.shape[1]), 100.0)])
+    m2 = torch.cat([m, torch.zeros(2, m.shape[1])])
+    for mode in ("seq-mean-token-sum", "seq-mean-token-mean", "token-mean"):
+        assert torch.isclose(A.agg_loss(x2, m2, mode), A.agg_loss(x, m, mode), atol=1e-6), mode
 
 
 def test_vanilla_ppo_dual_clip():

@@ -113,6 +113,21 @@ def test_tcp_transfer_engine_loopback():
         tx.stage(src, st)
         tx.send(st, "127.0.0.1", port, nbytes=n)
         assert rx.wait_and_apply(timeout=30) and torch.equal(src[0][1], dst[0][1])
+        # a partly delivered transfer (one of three streams) must not be completed by the streams of the next one,
+        # and a stream with the wrong token is refused
+        before = [t.clone() for _, t in dst]
+        per = ((n + 2) // 3 + 4095) // 4096 * 4096
+        tx._send_range("127.0.0.1", port, st.fd, 0, min(per, n), False, st.mm, tid=12345, total=n)
+        src[0][1].add_(1.0)
+        tx.stage(src, st)
+        tx.send(st, "127.0.0.1", port, nbytes=n)
+        assert rx.wait_and_apply(timeout=30)
+        assert all(torch.equal(a, b) for (_, a), (_, b) in zip(src, dst)) and not torch.equal(before[0], dst[0][1])
+        bad = TCPWeightSender(num_streams=3, token="not-the-secret")
+        with pytest.raises(ConnectionError):
+            bad.send(st, "127.0.0.1", port, nbytes=n)
+        with pytest.raises(TimeoutError):
+            rx.wait_and_apply(timeout=0.5)
     finally:
         st.close()
         rx.close()
@@ -318,14 +333,14 @@ def test_tcp_receiver_recovers_from_an_incomplete_transfer():
     """A transfer that stops half way times out, and the next complete transfer is applied correctly."""
     import socket
 
-    from polyrl_b200.weight_transfer.tcp_engine import HEADER, StagingBuffer, TCPWeightReceiver, TCPWeightSender
+    from polyrl_b200.weight_transfer.tcp_engine import HEADER, StagingBuffer, TCPWeightReceiver, TCPWeightSender, token_digest
 
     dst = [("a", torch.zeros(1000)), ("b", torch.zeros(24))]
     port = 32701
     rx = TCPWeightReceiver(dst, bind_host="127.0.0.1", port=port, num_streams=1)
     try:
         s = socket.create_connection(("127.0.0.1", port))
-        s.sendall(HEADER.pack(0, 4096) + b"\\x01" * 100)          # announces 4096 bytes, sends 100, dies
+        s.sendall(HEADER.pack(token_digest(None), 7, rx.nbytes, 0, 4096) + b"\\x01" * 100)   # announces 4096 bytes, sends 100, dies
         s.close()
         with pytest.raises(TimeoutError):
             rx.wait_and_apply(timeout=0.5)
