@@ -30,15 +30,28 @@ def parse():
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="own", choices=["own", "reference", "baseline"],
-                    help="own = product; reference = the unmodified reference (unavailable offline); baseline = this framework with the "
-                         "named ops routed through stock libraries (BASELINE.md section 3): cuBLAS GEMMs + unfused SwiGLU, materialised-"
-                         "logits chunked CE, NCCL all-gather per layer / fp32 reduce-scatter, full recompute")
+                    help="own = product (also times the library baseline afterwards, see --baseline-steps); reference = the unmodified "
+                         "reference (unavailable offline); baseline = ONLY this framework with the named ops routed through stock "
+                         "libraries (BASELINE.md section 3): cuBLAS GEMMs + unfused SwiGLU, materialised-logits chunked CE, cuBLAS "
+                         "decode GEMMs, NCCL collectives.  Memory policy (resident replica, saved activations) is IDENTICAL to own")
+    ap.add_argument("--baseline-steps", type=int, default=int(os.environ.get("BENCH_BASELINE_STEPS", 2)),
+                    help="after the own arm, rebuild the job with the library switches and time this many steps in the same "
+                         "invocation -> vs_baseline (0 = skip)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --prompts-per-gpu prompts on every GPU; strong: --total-prompts split over the GPUs")
+    ap.add_argument("--total-prompts", type=int, default=int(os.environ.get("BENCH_TOTAL_PROMPTS", 128)))
+    ap.add_argument("--rollout-tp", type=int, default=int(os.environ.get("BENCH_ROLLOUT_TP", 1)),
+                    help="tensor-parallel size of the colocated rollout engine (TP groups of consecutive ranks)")
+    ap.add_argument("--no-selfcheck", action="store_true")
     ap.add_argument("--model", default=os.environ.get("BENCH_MODEL", "llama3-8b"))
     ap.add_argument("--prompts-per-gpu", type=int, default=int(os.environ.get("BENCH_PROMPTS_PER_GPU", 16)))
     ap.add_argument("--n", type=int, default=int(os.environ.get("BENCH_N", 8)))
     ap.add_argument("--prompt-len-max", type=int, default=int(os.environ.get("BENCH_PROMPT_LEN", 256)))
     ap.add_argument("--response-length", type=int, default=int(os.environ.get("BENCH_RESPONSE_LEN", 512)))
     ap.add_argument("--max-token-len", type=int, default=int(os.environ.get("BENCH_MAX_TOKEN_LEN", 16384)))
+    ap.add_argument("--mode", default="colocated", choices=["colocated", "disagg"],
+                    help="colocated: every GPU rolls out and trains; disagg: N/2 rollout GPUs (TP engine servers behind the C++ "
+                         "manager) stream to N/2 ZeRO trainers with a weight push every step (BASELINE config 3)")
     ap.add_argument("--comm", default=os.environ.get("BENCH_COMM", "p2p"), choices=["p2p", "nccl"])
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--rollout-weight-dtype", default="bf16", choices=["bf16", "fp8"],
@@ -50,8 +63,9 @@ def reference_arm(args) -> int:
     """The reference (Terra-Flux/PolyRL) installs here only with --no-deps; its own entry point
     (python -m rlboost.verl_stream.trainer.main_stream) imports hydra / ray / omegaconf / tensordict / verl /
     sglang and spawns the Rust manager with `cargo run` — none of which exist on this image (no network)."""
-    why = ("reference needs ray, sglang==0.5.5, hydra-core, omegaconf, tensordict, rpyc, verl (empty submodule) and a Rust "
-           "toolchain (cargo); none are installed/installable offline — see baseline/install_attempt*.log, DESIGN.md")
+    why = ("reference installs with --no-deps (baseline/_ref) but cannot run: its entry point needs ray, sglang==0.5.5, hydra-core, "
+           "omegaconf, tensordict, rpyc and a Rust toolchain (cargo run for the manager); none are installed/installable offline — "
+           "see baseline/install_attempt*.log, DESIGN.md section 5")
     if int(os.environ.get("RANK", 0)) == 0:
         print(json.dumps({"impl": "reference", "unavailable": why}), flush=True)
     return 0
@@ -120,15 +134,162 @@ class ClockSampler:
                 "power_w_max": max(pw), "samples": len(sm)}
 
 
+LIB_ENV = {"POLYRL_GEMM_BACKEND": "cublas", "POLYRL_CE_BACKEND": "torch", "POLYRL_DECODE_GEMM": "cublas"}
+
+
+def build_job(args, world, device, library: bool):
+    """Construct the colocated job.  ``library`` flips ONLY the backend switches (cuBLAS GEMMs / materialised-logits CE / cuBLAS
+    decode GEMMs / NCCL collectives); shapes, memory policy and algorithm are the same as the product arm."""
+    from polyrl_b200.config.schema import load_config
+    from polyrl_b200.trainer.colocated import ColocatedPPO
+
+    for k, v in LIB_ENV.items():
+        if library:
+            os.environ[k] = v
+        else:
+            os.environ.pop(k, None)
+    P, n, R = args.P, args.n, args.response_length
+    cfg = load_config(overrides=[
+        f"actor_rollout_ref.model.path={args.model}", "algorithm.adv_estimator=grpo", f"actor_rollout_ref.rollout.n={n}",
+        f"data.max_prompt_length={args.prompt_len_max}", f"data.max_response_length={R}",
+        f"data.train_batch_size={P * world}", f"actor_rollout_ref.actor.ppo_mini_batch_size={P * world}",
+        "actor_rollout_ref.actor.use_dynamic_bsz=True", f"actor_rollout_ref.actor.ppo_max_token_len_per_gpu={args.max_token_len}",
+        "actor_rollout_ref.rollout.log_prob_use_dynamic_bsz=True",
+        f"actor_rollout_ref.rollout.log_prob_max_token_len_per_gpu={args.max_token_len}",
+        f"actor_rollout_ref.rollout.max_num_seqs={P * n}", f"actor_rollout_ref.rollout.cuda_graph={not args.no_graph}",
+        f"actor_rollout_ref.actor.fsdp_config.comm_backend={'nccl' if library else args.comm}",
+        "actor_rollout_ref.rollout.free_cache_engine=True",
+        f"actor_rollout_ref.rollout.tensor_model_parallel_size={args.rollout_tp}",
+        f"trainer.n_gpus_per_node={world}", "actor_rollout_ref.actor.optim.lr=1e-6",
+        f"actor_rollout_ref.rollout.weight_dtype={args.rollout_weight_dtype}",
+    ])
+    return ColocatedPPO(cfg, device=device, group=None)
+
+
+def selfcheck(ppo, world, device) -> dict:
+    """Cross-rank correctness evidence for the driver (the multi-GPU unit tests skip on its 1-GPU test box): peer-memory
+    reduce-scatter vs NCCL on a bucket of this engine's size class, bit-identical bf16 replicas on every rank after an optimizer
+    step, and TP lock-step of the rollout engine when --rollout-tp > 1."""
+    import torch
+    import torch.distributed as dist
+
+    out: dict = {"world": world}
+    eng = ppo.worker.actor_engine
+    if world > 1:
+        # (a) replica checksum: every rank must hold the same bf16 parameters after the step's all-gather
+        cs = torch.zeros(2, device=device, dtype=torch.float64)
+        for u in eng.units[:8]:
+            full = u._resident if getattr(u, "_resident", None) is not None else None
+            if full is None:
+                continue
+            f = full.float()
+            cs[0] += f.double().sum()
+            cs[1] += f.double().abs().sum()
+        lo, hi = cs.clone(), cs.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        out["replica_checksum_equal_across_ranks"] = bool(torch.equal(lo, hi))
+        out["replica_checksum"] = [float(lo[0]), float(lo[1])]
+        # (b) peer-memory reduce-scatter vs NCCL reduce-scatter on the same data
+        if eng.comm == "p2p" and eng.heap is not None and hasattr(eng, "selfcheck_reduce_scatter"):
+            out.update(eng.selfcheck_reduce_scatter())
+    tp = getattr(ppo.worker, "rollout_tp", 1)
+    if tp > 1 and hasattr(ppo.worker.rollout, "lockstep_digest"):
+        d = torch.tensor([ppo.worker.rollout.lockstep_digest()], device=device, dtype=torch.int64)
+        lo, hi = d.clone(), d.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN, group=ppo.worker.tp_group)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX, group=ppo.worker.tp_group)
+        out["tp_lockstep"] = bool(torch.equal(lo, hi))
+    return out
+
+
+def run_arm(args, ppo, world, rank, local_rank, device, steps, warmup, with_clocks: bool):
+    import torch
+    import torch.distributed as dist
+
+    from polyrl_b200 import ops
+    from polyrl_b200.data.synthetic import SyntheticPromptDataset
+    from polyrl_b200.protocol import DataProto, collate_fn
+
+    P = args.P
+    mcfg = ppo.worker.model_cfg
+    ds = SyntheticPromptDataset(mcfg.vocab_size, 1 << 20, (64, 192), args.prompt_len_max, mcfg.pad_token_id, seed=1)
+
+    def host_batch(step: int) -> DataProto:
+        base = (step * world + rank) * P
+        b = DataProto.from_single_dict(collate_fn([ds[base + i] for i in range(P)]))
+        b.batch = b.batch.pin_memory()           # inputs start in pinned host memory every step
+        b.meta_info["ignore_eos"] = False
+        return b
+
+    h2d_bytes = sum(v.numel() * v.element_size() for v in host_batch(0).batch.values())
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    check = {}
+    for w in range(warmup):
+        ppo.step(host_batch(w))
+        if w == 0 and with_clocks and not args.no_selfcheck:
+            check = selfcheck(ppo, world, device)
+    sync_all()
+    sampler = ClockSampler(local_rank)
+    if with_clocks:
+        sampler.start()
+    launches0 = ops.total_launches()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    d2h_bytes, samples, tokens = 0, 0, 0
+    t_wall0 = time.perf_counter()
+    gen_intervals, last_timing = [], {}
+    for k in range(steps):
+        hb = host_batch(warmup + k)              # host-side batch assembly is part of the e2e region
+        ev[k][0].record()
+        t_wall = time.time()
+        m = ppo.step(hb)                         # includes H2D of hb and D2H of losses/metrics (.item())
+        ev[k][1].record()
+        gen_intervals.append((t_wall, t_wall + m.get("timing_s/gen", 0.0)))
+        last_timing = {kk: round(v, 3) for kk, v in m.items() if kk.startswith("timing_s/")}
+        if rank == 0:
+            print("[bench] step", k, last_timing,
+                  "engine", {kk: round(float(v), 3) for kk, v in ppo.worker.rollout.stats.items()}, "cpus", len(os.sched_getaffinity(0)),
+                  "saved_act_layers", ppo.worker.actor_engine.saved_layers_last, "resident", ppo.worker.actor_engine.resident,
+                  "mem_GB", round(torch.cuda.max_memory_allocated() / 2**30, 1),
+                  "launches", dict(sorted(ops.LAUNCHES.items())), file=sys.stderr, flush=True)
+        d2h_bytes += 8 * sum(1 for v in m.values() if isinstance(v, float))
+        samples += int(m["num_samples"])
+        tokens += int(m.get("perf/total_num_tokens", 0))
+    sync_all()
+    t_wall = time.perf_counter() - t_wall0
+    clocks = sampler.stop() if with_clocks else {}
+    if with_clocks:
+        clocks.update(sampler.phase_medians(gen_intervals))
+    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+    t = torch.tensor([dev_ms, t_wall * 1e3, float(samples), float(ops.total_launches() - launches0), float(tokens)], device=device,
+                     dtype=torch.float64)
+    if world > 1:
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone()
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        dev_ms, wall_ms = tmax[0].item(), tmax[1].item()
+        total_samples, launches, total_tokens = tsum[2].item(), tsum[3].item(), tsum[4].item()
+    else:
+        dev_ms, wall_ms, total_samples, launches, total_tokens = (x.item() for x in t)
+    return {"dev_ms": dev_ms, "wall_ms": wall_ms, "samples": total_samples, "launches": launches, "tokens": total_tokens,
+            "clocks": clocks, "h2d": h2d_bytes, "d2h": int(d2h_bytes / max(1, steps)), "timing": last_timing, "selfcheck": check,
+            "saved_layers": ppo.worker.actor_engine.saved_layers_last, "resident": bool(ppo.worker.actor_engine.resident)}
+
+
 def main() -> int:
     args = parse()
     if args.impl == "reference":
         return reference_arm(args)
-    if args.impl == "baseline":
-        os.environ["POLYRL_GEMM_BACKEND"] = "cublas"
-        os.environ["POLYRL_CE_BACKEND"] = "torch"
-        os.environ["POLYRL_DECODE_GEMM"] = "cublas"
-        args.comm = "nccl"
+    if args.mode == "disagg":
+        from polyrl_b200.trainer.bench_disagg import main as disagg_main
+
+        return disagg_main(args)
 
     # stdout carries exactly ONE JSON line: keep NCCL's "NCCL version ..." banner (NCCL_DEBUG=VERSION) off it
     if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
@@ -152,109 +313,70 @@ def main() -> int:
         print(f"[bench] WORLD_SIZE={world} but --gpus={args.gpus}; using WORLD_SIZE", file=sys.stderr)
 
     from polyrl_b200 import ops
-    from polyrl_b200.config.schema import load_config
-    from polyrl_b200.data.synthetic import SyntheticPromptDataset
-    from polyrl_b200.protocol import DataProto, collate_fn
-    from polyrl_b200.trainer.colocated import ColocatedPPO
 
     ops.ext()   # fail loudly if the sm_100a extension is missing
-    P, n, R = args.prompts_per_gpu, args.n, args.response_length
-    per_gpu = P * n
-    cfg = load_config(overrides=[
-        f"actor_rollout_ref.model.path={args.model}", "algorithm.adv_estimator=grpo", f"actor_rollout_ref.rollout.n={n}",
-        f"data.max_prompt_length={args.prompt_len_max}", f"data.max_response_length={R}",
-        f"data.train_batch_size={P * world}", f"actor_rollout_ref.actor.ppo_mini_batch_size={P * world}",
-        "actor_rollout_ref.actor.use_dynamic_bsz=True", f"actor_rollout_ref.actor.ppo_max_token_len_per_gpu={args.max_token_len}",
-        "actor_rollout_ref.rollout.log_prob_use_dynamic_bsz=True",
-        f"actor_rollout_ref.rollout.log_prob_max_token_len_per_gpu={args.max_token_len}",
-        f"actor_rollout_ref.rollout.max_num_seqs={per_gpu}", f"actor_rollout_ref.rollout.cuda_graph={not args.no_graph}",
-        f"actor_rollout_ref.actor.fsdp_config.comm_backend={args.comm}", "actor_rollout_ref.rollout.free_cache_engine=True",
-        f"trainer.n_gpus_per_node={world}", "actor_rollout_ref.actor.optim.lr=1e-6",
-        f"actor_rollout_ref.rollout.weight_dtype={args.rollout_weight_dtype}",
-        *(["actor_rollout_ref.actor.fsdp_config.resident_params=false", "actor_rollout_ref.actor.fsdp_config.activation_checkpoint=full"]
-          if args.impl == "baseline" else []),
-    ])
-    ppo = ColocatedPPO(cfg, device=device, group=None)
-    mcfg = ppo.worker.model_cfg
-    ds = SyntheticPromptDataset(mcfg.vocab_size, 1 << 20, (64, 192), args.prompt_len_max, mcfg.pad_token_id, seed=1)
-
-    def host_batch(step: int) -> DataProto:
-        base = (step * world + rank) * P
-        b = DataProto.from_single_dict(collate_fn([ds[base + i] for i in range(P)]))
-        b.batch = b.batch.pin_memory()           # inputs start in pinned host memory every step
-        b.meta_info["ignore_eos"] = False
-        return b
-
-    h2d_bytes = sum(v.numel() * v.element_size() for v in host_batch(0).batch.values())
-
-    def sync_all():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for w in range(args.warmup):
-        ppo.step(host_batch(w))
-    sync_all()
-
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    launches0 = ops.total_launches()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    d2h_bytes = 0
-    samples = 0
-    t_wall0 = time.perf_counter()
-    gen_intervals = []
-    for k in range(args.steps):
-        hb = host_batch(args.warmup + k)         # host-side batch assembly is part of the e2e region
-        ev[k][0].record()
-        t_wall = time.time()
-        m = ppo.step(hb)                         # includes H2D of hb and D2H of losses/metrics (.item())
-        ev[k][1].record()
-        gen_intervals.append((t_wall, t_wall + m.get("timing_s/gen", 0.0)))
-        if rank == 0:
-            print("[bench] step", k, {kk: round(v, 3) for kk, v in m.items() if kk.startswith("timing_s/")},
-                  "engine", {kk: round(float(v), 3) for kk, v in ppo.worker.rollout.stats.items()}, "cpus", len(os.sched_getaffinity(0)),
-                  "saved_act_layers", ppo.worker.actor_engine.saved_layers_last, "resident", ppo.worker.actor_engine.resident,
-                  "mem_GB", round(torch.cuda.max_memory_allocated() / 2**30, 1),
-                  "launches", dict(sorted(ops.LAUNCHES.items())), file=sys.stderr, flush=True)
-        d2h_bytes += 8 * sum(1 for v in m.values() if isinstance(v, float))
-        samples += int(m["num_samples"])
-    sync_all()
-    t_wall = time.perf_counter() - t_wall0
-    clocks = sampler.stop()
-    clocks.update(sampler.phase_medians(gen_intervals))
-    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
-    t = torch.tensor([dev_ms, t_wall * 1e3, float(samples), float(ops.total_launches() - launches0)], device=device, dtype=torch.float64)
-    if world > 1:
-        tmax = t.clone()
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        tsum = t.clone()
-        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-        dev_ms, wall_ms, total_samples, launches = tmax[0].item(), tmax[1].item(), tsum[2].item(), tsum[3].item()
+    if args.scaling == "strong":
+        if args.total_prompts % world:
+            raise SystemExit(f"--total-prompts {args.total_prompts} not divisible by {world} GPUs")
+        args.P = args.total_prompts // world
     else:
-        dev_ms, wall_ms, total_samples, launches = t[0].item(), t[1].item(), t[2].item(), t[3].item()
-    value = total_samples / (dev_ms / 1e3)
-    e2e = total_samples / (wall_ms / 1e3)
+        args.P = args.prompts_per_gpu
+    n, R = args.n, args.response_length
+    per_gpu = args.P * n
+
+    own_only_library = args.impl == "baseline"
+    ppo = build_job(args, world, device, library=own_only_library)
+    res = run_arm(args, ppo, world, rank, local_rank, device, args.steps, args.warmup, with_clocks=True)
+    value = res["samples"] / (res["dev_ms"] / 1e3)
+    e2e = res["samples"] / (res["wall_ms"] / 1e3)
+    parallelism = (f"colocated dp{world} rollout replicas" if args.rollout_tp == 1 else
+                   f"colocated {world // args.rollout_tp} x TP{args.rollout_tp} rollout engines") + \
+                  (f" + zero x{world} ({'nccl' if own_only_library else args.comm}; fp32 master/moments/grads sharded, bf16 replica "
+                   f"{'resident' if res['resident'] or world == 1 else 'gathered per layer'})")
+    num_layers = ppo.worker.model_cfg.num_layers
+
+    base = None
+    if not own_only_library and args.baseline_steps > 0:
+        # ---- library baseline, same invocation, same memory policy: tear the product job down, rebuild with the switches
+        del ppo
+        import gc
+
+        gc.collect()
+        torch.cuda.empty_cache()
+        ppo_b = build_job(args, world, device, library=True)
+        rb = run_arm(args, ppo_b, world, rank, local_rank, device, args.baseline_steps, max(1, min(args.warmup, 2)), with_clocks=False)
+        bval = rb["samples"] / (rb["dev_ms"] / 1e3)
+        base = {"value": round(bval, 4), "unit": "samples/s", "steps": args.baseline_steps, "ms_per_step": round(rb["dev_ms"] / args.baseline_steps, 2),
+                "what": "same framework, same invocation, same memory policy; GEMMs -> cuBLAS (+ eager SwiGLU), linear-CE -> chunked "
+                        "materialised logits, decode GEMMs -> cuBLAS, collectives -> NCCL (BASELINE.md section 3)",
+                "timing_s": rb["timing"], "saved_act_layers": rb["saved_layers"]}
+        for k in LIB_ENV:
+            os.environ.pop(k, None)
+
     if rank == 0:
         out = {
             "metric": "PPO-step samples/sec (rollout+update, device-timed max over ranks)", "value": round(value, 4),
             "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": round(dev_ms / args.steps, 2), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": round(res["dev_ms"] / args.steps, 2), "higher_is_better": True, "scaling": args.scaling,
+            "vs_baseline": round(value / base["value"], 4) if base else None,
             "dtype": "bf16", "data": "synthetic GSM8K-shaped prompts (64-192 tok), random-init weights",
-            "config": {"model": args.model, "algorithm": "GRPO", "global_batch": P * world, "samples_per_step": per_gpu * world,
-                       "n": n, "seq_len": args.prompt_len_max + R, "response_length": R,
-                       "parallelism": f"colocated dp{world} rollout replicas + zero x{world} ({args.comm}; fp32 master/moments/grads "
-                                      f"sharded, bf16 replica {'resident' if ppo.worker.actor_engine.resident or world == 1 else 'gathered per layer'})",
-                       "activation_checkpoint": f"auto: {ppo.worker.actor_engine.saved_layers_last}/{ppo.worker.model_cfg.num_layers} blocks "
-                                                "saved, rest recomputed",
+            "config": {"model": args.model, "algorithm": "GRPO", "global_batch": args.P * world, "samples_per_step": per_gpu * world,
+                       "n": n, "seq_len": args.prompt_len_max + R, "response_length": R, "parallelism": parallelism,
+                       "activation_checkpoint": f"auto: {res['saved_layers']}/{num_layers} blocks saved, rest recomputed",
+                       "max_tokens_per_microbatch": args.max_token_len,
                        "l2": "working set >> L2: 16 GB bf16 weights + KV cache streamed every step; no cache reuse across iterations",
                        "optimizer": "AdamW fp32 master+moments, grad clip 1.0", "old_log_prob_recompute": True,
-                       "cuda_graph_decode": not args.no_graph, "rollout_weight_dtype": args.rollout_weight_dtype},
-            "clocks": clocks,
-            "e2e": {"value": round(e2e, 4), "unit": "samples/s", "h2d_bytes_per_step": h2d_bytes,
-                    "d2h_bytes_per_step": int(d2h_bytes / max(1, args.steps)) + per_gpu * R * 12},
-            "gpu_launches": int(launches), "impl": args.impl,
-            "tokens_per_s": round(value * (args.prompt_len_max / 2 + R), 1),
+                       "cuda_graph_decode": not args.no_graph, "rollout_weight_dtype": args.rollout_weight_dtype,
+                       "rollout_tp": args.rollout_tp},
+            "clocks": res["clocks"],
+            "e2e": {"value": round(e2e, 4), "unit": "samples/s", "h2d_bytes_per_step": res["h2d"],
+                    "d2h_bytes_per_step": res["d2h"] + per_gpu * R * 12},
+            "gpu_launches": int(res["launches"]), "impl": args.impl,
+            "tokens_per_s": round(res["tokens"] / (res["dev_ms"] / 1e3), 1),
+            "timing_s": res["timing"], "selfcheck": res["selfcheck"],
+            "baseline": base,
+            "vs_baseline_note": "BASELINE.md publishes no comparable number and the reference cannot run offline; vs_baseline = value / "
+                                "the library-baseline arm timed in this same invocation (see 'baseline')" if base else None,
         }
         print(json.dumps(out), flush=True)
     if world > 1:

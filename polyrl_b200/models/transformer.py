@@ -175,7 +175,8 @@ def moe_mlp_static(cfg: ModelConfig, w: dict, h: torch.Tensor) -> torch.Tensor:
     order = torch.argsort(flat_e, stable=True)
     sorted_e = flat_e[order]
     tok = torch.div(order, k, rounding_mode="floor")
-    counts = torch.bincount(flat_e, minlength=e)
+    # scatter_add instead of bincount: bincount reads its max back to the host, which a CUDA-graph capture cannot do
+    counts = torch.zeros(e, dtype=torch.long, device=flat_e.device).scatter_add_(0, flat_e, torch.ones_like(flat_e))
     start = counts.cumsum(0) - counts
     slot = torch.arange(t * k, device=h.device) - start[sorted_e]                 # position of the assignment inside its expert
     x = h.new_zeros(e, t, h.shape[1])

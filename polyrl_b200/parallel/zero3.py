@@ -575,6 +575,31 @@ class Zero3Engine:
     def mark_grad_slot_busy(self, slot, ev) -> None:
         self._grad_slot_events[id(slot)] = ev
 
+    @torch.no_grad()
+    def selfcheck_reduce_scatter(self, numel: int = 1 << 22) -> dict:
+        """Evidence for a multi-GPU run without a unit-test harness (bench.py ``selfcheck``): the peer-memory reduce-scatter +
+        fp32 accumulate kernel against NCCL ``reduce_scatter_tensor`` on the same rank-dependent bf16 data."""
+        if self.comm != "p2p" or self.world == 1:
+            return {}
+        w = self.world
+        chunk = min(numel // w, (self._grad_slots[0].local.numel() // w) // 8 * 8)
+        slot = self.next_grad_slot()
+        self.wait_grad_slot_free(slot)
+        g = torch.Generator(device=self.device).manual_seed(1234 + self.rank)
+        src = torch.randn(chunk * w, device=self.device, generator=g).to(self.param_dtype)
+        slot.local[: chunk * w].copy_(src)
+        acc = torch.zeros(chunk, device=self.device, dtype=torch.float32)
+        torch.cuda.synchronize(self.device)
+        self.heap.barrier(2)          # channel 2: this check runs on the current stream (channel 1 belongs to the comm stream)
+        self.C.p2p_reduce_scatter_accum(slot.peer_ptrs(), self.rank * chunk, acc, 1.0 / w, self.rank, None, self.comm_ctas)
+        self.heap.barrier(2)
+        want = torch.empty(chunk, device=self.device, dtype=torch.float32)
+        dist.reduce_scatter_tensor(want, src.float(), op=dist.ReduceOp.SUM, group=self.group)
+        want.mul_(1.0 / w)
+        err = (acc - want).abs().max()
+        dist.all_reduce(err, op=dist.ReduceOp.MAX, group=self.group)
+        return {"p2p_reduce_scatter_vs_nccl_max_abs_err": float(err), "p2p_reduce_scatter_elems_per_rank": int(chunk)}
+
     # ---- model functions ----------------------------------------------------------------------
     def _build_runners(self) -> None:
         cfg = self.cfg

@@ -654,7 +654,13 @@ class RolloutEngine:
         base = r.params.seed if r.params.seed is not None else self._base_seed
         return (zlib.crc32(f"{base}/{r.rid}".encode()) << 12) + step * 1000003
 
+    def lockstep_digest(self) -> int:
+        """Order-sensitive checksum of every token this engine has appended so far: the ranks of one TP group must agree on it
+        (bench.py selfcheck, tests/tp_worker.py)."""
+        return int(getattr(self, "_tok_digest", 0))
+
     def _append_token(self, r: Request, tok: int, lp: float) -> None:
+        self._tok_digest = (getattr(self, "_tok_digest", 0) * 1000003 + int(tok) + 1) & 0x7FFFFFFFFFFFFFFF
         r.output_ids.append(int(tok))
         r.logprobs.append(float(lp))
         p = r.params
