@@ -134,7 +134,8 @@ class ClockSampler:
                 "power_w_max": max(pw), "samples": len(sm)}
 
 
-LIB_ENV = {"POLYRL_GEMM_BACKEND": "cublas", "POLYRL_CE_BACKEND": "torch", "POLYRL_DECODE_GEMM": "cublas"}
+# library arm: backend switches + a larger transient reserve for the materialised [chunk, V] fp32 logits of the eager CE
+LIB_ENV = {"POLYRL_GEMM_BACKEND": "cublas", "POLYRL_CE_BACKEND": "torch", "POLYRL_DECODE_GEMM": "cublas", "POLYRL_ACT_RESERVE_GB": "30"}
 
 
 def build_job(args, world, device, library: bool):
@@ -295,12 +296,44 @@ def main() -> int:
     if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
         os.environ["NCCL_DEBUG"] = "WARN"
 
-    import torch
-    import torch.distributed as dist
-
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
+
+    # ---- library baseline FIRST, as a child process per rank (own rendezvous port): its memory, CUDA graphs and symmetric heaps are
+    # gone when it exits, so the product arm below runs on a clean device with the same shapes and the same memory policy
+    base, base_err = None, None
+    if args.impl == "own" and args.baseline_steps > 0:
+        env = dict(os.environ)
+        env["MASTER_PORT"] = str(int(os.environ.get("MASTER_PORT", "29500")) + 13)
+        env["BENCH_CHILD"] = "1"
+        env["TORCHELASTIC_USE_AGENT_STORE"] = "False"      # the children rendezvous on their own port: child rank 0 hosts the store
+        cmd = [sys.executable, os.path.abspath(__file__), "--impl", "baseline", "--gpus", str(args.gpus), "--steps", str(args.baseline_steps),
+               "--warmup", str(max(1, min(args.warmup, 2))), "--baseline-steps", "0", "--no-selfcheck", "--model", args.model,
+               "--prompts-per-gpu", str(args.prompts_per_gpu), "--n", str(args.n), "--prompt-len-max", str(args.prompt_len_max),
+               "--response-length", str(args.response_length), "--max-token-len", str(args.max_token_len), "--scaling", args.scaling,
+               "--total-prompts", str(args.total_prompts), "--rollout-tp", str(args.rollout_tp),
+               "--rollout-weight-dtype", args.rollout_weight_dtype] + (["--no-graph"] if args.no_graph else [])
+        try:
+            r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=float(os.environ.get("BENCH_BASELINE_TIMEOUT_S", 900)))
+            lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+            if rank == 0:
+                sys.stderr.write(r.stderr[-6000:])
+                if r.returncode == 0 and lines:
+                    b = json.loads(lines[-1])
+                    base = {"value": b["value"], "unit": b["unit"], "steps": b["steps"], "ms_per_step": b["ms_per_step"],
+                            "what": "same framework, child process of this invocation, same shapes and memory policy; GEMMs -> cuBLAS (+ eager "
+                                    "SwiGLU), linear-CE -> chunked materialised logits, decode GEMMs -> cuBLAS, collectives -> NCCL "
+                                    "(BASELINE.md section 3)",
+                            "timing_s": b.get("timing_s"), "activation_checkpoint": b["config"]["activation_checkpoint"]}
+                else:
+                    base_err = f"baseline child rc={r.returncode}: {r.stderr[-300:]}"
+        except Exception as e:      # never let the comparison arm take the product number down with it
+            base_err = f"{type(e).__name__}: {str(e)[:200]}"
+
+    import torch
+    import torch.distributed as dist
+
     if not torch.cuda.is_available():
         print(json.dumps({"error": "bench.py needs a CUDA device"}))
         return 1
@@ -335,24 +368,6 @@ def main() -> int:
                    f"{'resident' if res['resident'] or world == 1 else 'gathered per layer'})")
     num_layers = ppo.worker.model_cfg.num_layers
 
-    base = None
-    if not own_only_library and args.baseline_steps > 0:
-        # ---- library baseline, same invocation, same memory policy: tear the product job down, rebuild with the switches
-        del ppo
-        import gc
-
-        gc.collect()
-        torch.cuda.empty_cache()
-        ppo_b = build_job(args, world, device, library=True)
-        rb = run_arm(args, ppo_b, world, rank, local_rank, device, args.baseline_steps, max(1, min(args.warmup, 2)), with_clocks=False)
-        bval = rb["samples"] / (rb["dev_ms"] / 1e3)
-        base = {"value": round(bval, 4), "unit": "samples/s", "steps": args.baseline_steps, "ms_per_step": round(rb["dev_ms"] / args.baseline_steps, 2),
-                "what": "same framework, same invocation, same memory policy; GEMMs -> cuBLAS (+ eager SwiGLU), linear-CE -> chunked "
-                        "materialised logits, decode GEMMs -> cuBLAS, collectives -> NCCL (BASELINE.md section 3)",
-                "timing_s": rb["timing"], "saved_act_layers": rb["saved_layers"]}
-        for k in LIB_ENV:
-            os.environ.pop(k, None)
-
     if rank == 0:
         out = {
             "metric": "PPO-step samples/sec (rollout+update, device-timed max over ranks)", "value": round(value, 4),
@@ -374,9 +389,9 @@ def main() -> int:
             "gpu_launches": int(res["launches"]), "impl": args.impl,
             "tokens_per_s": round(res["tokens"] / (res["dev_ms"] / 1e3), 1),
             "timing_s": res["timing"], "selfcheck": res["selfcheck"],
-            "baseline": base,
+            "baseline": base if base else ({"unavailable": base_err} if base_err else None),
             "vs_baseline_note": "BASELINE.md publishes no comparable number and the reference cannot run offline; vs_baseline = value / "
-                                "the library-baseline arm timed in this same invocation (see 'baseline')" if base else None,
+                                "the library-baseline arm timed by this same invocation just before the product arm (see 'baseline')" if base else None,
         }
         print(json.dumps(out), flush=True)
     if world > 1:

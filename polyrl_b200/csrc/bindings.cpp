@@ -48,6 +48,22 @@ int prl_vmm_unmap(int64_t);
 int prl_vmm_free(int64_t);
 int prl_vmm_is_mapped(int64_t);
 int prl_p2p_reduce_scatter_accum(void* const*, int64_t, float*, int64_t, float, int, int, float*, int, cudaStream_t);
+int prl_nvls_supported(int);
+int64_t prl_nvls_round_size(int64_t, int, int);
+int64_t prl_nvls_create(int64_t, int);
+int64_t prl_nvls_mc_create(int64_t, int);
+int prl_nvls_export_fd(int64_t);
+int64_t prl_nvls_import_fd(int, int64_t, int);
+int prl_nvls_mc_add_device(int64_t, int);
+int prl_nvls_mc_bind(int64_t, int64_t);
+int64_t prl_nvls_map(int64_t, int);
+int prl_nvls_unmap(int64_t);
+int prl_nvls_release(int64_t);
+int prl_close_fd(int);
+int prl_nvls_allreduce(const void*, void*, const void*, int64_t, void* const*, int, int, uint32_t*, int, cudaStream_t);
+int prl_nvls_allreduce_oneshot(const void*, void*, const void*, int64_t, void* const*, int, int, uint32_t*, int, cudaStream_t);
+int prl_nvls_reduce_scatter_accum(const void*, int64_t, float*, int64_t, float, float*, int, cudaStream_t);
+int prl_nvls_bcast_store(const void*, void*, int64_t, int, cudaStream_t);
 int prl_skinny_workspace_floats(int, int, int);
 int prl_skinny_gemm(const void*, const void*, void*, const void*, const void*, const float*, const float*, float*, int*, int, int, int, int64_t, int64_t, int64_t, int, int, int, cudaStream_t);
 int prl_stream_gemm(const void*, const void*, void*, const void*, const void*, const float*, const float*, int, int, int, int64_t, int64_t, int64_t, int, int, int, cudaStream_t);
@@ -532,6 +548,53 @@ at::Tensor ag_gemm_bf16(const at::Tensor& a, const std::vector<int64_t>& shard_p
 
 }  // namespace
 
+// ---- NVLS: multicast-mapped symmetric heap + multimem collectives (csrc/nvls.cu)
+void nvls_allreduce(int64_t mc_in, int64_t mc_out, const c10::optional<at::Tensor>& residual, int64_t bytes,
+                    const std::vector<int64_t>& flag_ptrs, int64_t rank, at::Tensor state, int64_t ctas) {
+  TORCH_CHECK(state.is_cuda() && state.scalar_type() == at::kInt && state.numel() >= 3);
+  c10::cuda::CUDAGuard g(state.device());
+  std::vector<void*> fp = to_ptrs(flag_ptrs);
+  const void* r = nullptr;
+  if (residual.has_value()) { CHECK_BF16(*residual); TORCH_CHECK(residual->is_contiguous() && residual->numel() * 2 >= bytes); r = residual->data_ptr(); }
+  check(prl_nvls_allreduce(reinterpret_cast<const void*>(mc_in), reinterpret_cast<void*>(mc_out), r, bytes, fp.data(),
+                           static_cast<int>(rank), static_cast<int>(fp.size()), reinterpret_cast<uint32_t*>(state.data_ptr<int>()),
+                           static_cast<int>(ctas), cur_stream()), "nvls_allreduce");
+}
+
+// one barrier + in-switch reduction of the whole buffer into a LOCAL output tensor (+ residual)
+at::Tensor nvls_allreduce_oneshot(int64_t mc_in, at::Tensor out, const c10::optional<at::Tensor>& residual,
+                                  const std::vector<int64_t>& flag_ptrs, int64_t rank, at::Tensor state, int64_t ctas) {
+  CHECK_BF16(out);
+  TORCH_CHECK(out.is_contiguous() && state.is_cuda() && state.scalar_type() == at::kInt && state.numel() >= 3);
+  const int64_t bytes = out.numel() * 2;
+  TORCH_CHECK(bytes % 16 == 0, "all-reduce size must be a multiple of 16 bytes");
+  c10::cuda::CUDAGuard g(out.device());
+  std::vector<void*> fp = to_ptrs(flag_ptrs);
+  const void* r = nullptr;
+  if (residual.has_value()) { CHECK_BF16(*residual); TORCH_CHECK(residual->is_contiguous() && residual->numel() == out.numel()); r = residual->data_ptr(); }
+  check(prl_nvls_allreduce_oneshot(reinterpret_cast<const void*>(mc_in), out.data_ptr(), r, bytes, fp.data(), static_cast<int>(rank),
+                                   static_cast<int>(fp.size()), reinterpret_cast<uint32_t*>(state.data_ptr<int>()),
+                                   static_cast<int>(ctas), cur_stream()), "nvls_allreduce_oneshot");
+  return out;
+}
+
+void nvls_reduce_scatter_accum(int64_t mc_grads, int64_t shard_off_elems, at::Tensor acc, double scale,
+                               const c10::optional<at::Tensor>& sumsq, int64_t ctas) {
+  CHECK_F32(acc);
+  TORCH_CHECK(acc.is_contiguous());
+  c10::cuda::CUDAGuard g(acc.device());
+  float* ss = sumsq.has_value() ? sumsq->data_ptr<float>() : nullptr;
+  check(prl_nvls_reduce_scatter_accum(reinterpret_cast<const void*>(mc_grads), shard_off_elems, acc.data_ptr<float>(), acc.numel(),
+                                      static_cast<float>(scale), ss, static_cast<int>(ctas), cur_stream()), "nvls_reduce_scatter_accum");
+}
+
+void nvls_bcast_store(const at::Tensor& src, int64_t mc_dst, int64_t ctas) {
+  TORCH_CHECK(src.is_cuda() && src.is_contiguous());
+  c10::cuda::CUDAGuard g(src.device());
+  check(prl_nvls_bcast_store(src.data_ptr(), reinterpret_cast<void*>(mc_dst), src.numel() * src.element_size(), static_cast<int>(ctas),
+                             cur_stream()), "nvls_bcast_store");
+}
+
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("gemm_bf16", &gemm_bf16, py::arg("a"), py::arg("b"), py::arg("residual") = py::none(),
         py::arg("out") = py::none(), py::arg("force_bn") = 0);
@@ -574,6 +637,22 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("vmm_free", &vmm_free);
   m.def("vmm_is_mapped", &vmm_is_mapped);
   m.def("vmm_granularity", [](int64_t d) { return prl_vmm_granularity(static_cast<int>(d)); });
+  m.def("nvls_supported", [](int64_t d) { return prl_nvls_supported(static_cast<int>(d)); });
+  m.def("nvls_round_size", [](int64_t b, int64_t d, int64_t w) { return prl_nvls_round_size(b, static_cast<int>(d), static_cast<int>(w)); });
+  m.def("nvls_create", [](int64_t b, int64_t d) { return prl_nvls_create(b, static_cast<int>(d)); });
+  m.def("nvls_mc_create", [](int64_t b, int64_t w) { return prl_nvls_mc_create(b, static_cast<int>(w)); });
+  m.def("nvls_export_fd", [](int64_t id) { return prl_nvls_export_fd(id); });
+  m.def("nvls_import_fd", [](int64_t fd, int64_t b, int64_t d) { return prl_nvls_import_fd(static_cast<int>(fd), b, static_cast<int>(d)); });
+  m.def("nvls_mc_add_device", [](int64_t id, int64_t d) { return prl_nvls_mc_add_device(id, static_cast<int>(d)); });
+  m.def("nvls_mc_bind", [](int64_t mc, int64_t mem) { return prl_nvls_mc_bind(mc, mem); });
+  m.def("nvls_map", [](int64_t id, int64_t d) { return prl_nvls_map(id, static_cast<int>(d)); });
+  m.def("nvls_unmap", [](int64_t va) { return prl_nvls_unmap(va); });
+  m.def("nvls_release", [](int64_t id) { return prl_nvls_release(id); });
+  m.def("close_fd", [](int64_t fd) { return prl_close_fd(static_cast<int>(fd)); });
+  m.def("nvls_allreduce", &nvls_allreduce);
+  m.def("nvls_allreduce_oneshot", &nvls_allreduce_oneshot);
+  m.def("nvls_reduce_scatter_accum", &nvls_reduce_scatter_accum);
+  m.def("nvls_bcast_store", &nvls_bcast_store);
   m.def("p2p_barrier", &p2p_barrier);
   m.def("p2p_copy", &p2p_copy);
   m.def("p2p_push_fp8", &p2p_push_fp8);

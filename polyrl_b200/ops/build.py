@@ -34,6 +34,7 @@ CU_SOURCES = [
     "decode_attn.cu",
     "sampling.cu",
     "p2p.cu",
+    "nvls.cu",
 ]
 HEADERS = ["common.cuh", "gemm_sm100.cuh", "gemm2_sm100.cuh"]
 NVCC_FLAGS = [

@@ -241,6 +241,10 @@ def linear_swiglu(x: torch.Tensor, wgu: torch.Tensor) -> torch.Tensor:
     if _is_kernel_tensor(x) and wgu.dtype == torch.bfloat16 and not _cublas():
         return _LinearSwigluFn.apply(x, wgu)
     gu = torch.nn.functional.linear(x, wgu.to(x.dtype))
+    if x.is_cuda and x.dtype == torch.bfloat16:
+        # library arm on GPUs: what an HF decoder layer does — act_fn(gate) * up in bf16, three eager kernels
+        g, u = ref.split_gate_up(gu)
+        return torch.nn.functional.silu(g) * u
     return ref.swiglu(gu)
 
 

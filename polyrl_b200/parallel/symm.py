@@ -110,3 +110,23 @@ class SymmetricHeap:
             except Exception:
                 pass
         self._allocs.clear()
+
+
+def make_heap(group=None, device: torch.device | None = None):
+    """Symmetric heap factory: the VMM / multicast heap (``parallel/nvls.py``) where the driver supports it, the legacy CUDA-IPC
+    heap otherwise or when ``POLYRL_HEAP=ipc``.  Every rank of ``group`` takes the same branch (the support flag is all-reduced)."""
+    import os
+
+    if os.environ.get("POLYRL_HEAP", "nvls") != "ipc":
+        try:
+            from .nvls import NvlsHeap
+
+            ok = torch.tensor([1 if ext().nvls_supported((device or torch.device("cuda", torch.cuda.current_device())).index) else 0],
+                              device=device, dtype=torch.int32)
+            if dist.is_initialized() and (dist.get_world_size(group) > 1):
+                dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+            if int(ok.item()):
+                return NvlsHeap(group=group, device=device)
+        except Exception as e:      # noqa: BLE001
+            print(f"[symm] NVLS heap unavailable ({e}); using the CUDA-IPC heap", flush=True)
+    return SymmetricHeap(group=group, device=device)

@@ -27,6 +27,8 @@ import math
 import zlib
 from typing import Callable, Sequence
 
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -469,7 +471,7 @@ class Zero3Engine:
         self._offload_stream = None
         self._offload_force = False          # tests: run the hooks on CPU tensors too
         self._fold, self._folded = False, {}
-        self.act_reserve_bytes = 16 << 30
+        self.act_reserve_bytes = int(float(os.environ.get("POLYRL_ACT_RESERVE_GB", "16")) * (1 << 30))
         self.saved_layers_last = 0
         self.grad_scale = 1.0
         self.lr, self.betas, self.eps, self.weight_decay, self.max_grad_norm = lr, betas, eps, weight_decay, max_grad_norm
@@ -673,7 +675,14 @@ class Zero3Engine:
         if c.num_experts:                       # every token passes through k experts of width moe_intermediate_size (+ its copies)
             inter = c.num_experts_per_tok * (c.moe_intermediate_size + c.hidden_size)
         qkv = (c.num_heads + 2 * c.num_kv_heads) * c.head_dim
-        return 2 * (5 * c.hidden_size + qkv + 3 * inter) + 64
+        per = 2 * (5 * c.hidden_size + qkv + 3 * inter) + 64
+        import os
+
+        if os.environ.get("POLYRL_GEMM_BACKEND", "tcgen05") == "cublas":
+            # library arm: the eager SwiGLU keeps silu(gate) and the gate/up views alive for autograd on top of the fused path's
+            # saved tensors; the same "save what fits" policy therefore fits fewer blocks
+            per += 2 * 3 * inter
+        return per
 
     def _plan_activation_saving(self, tokens: int) -> None:
         n = len(self.layer_runners)

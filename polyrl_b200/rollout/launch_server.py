@@ -46,7 +46,7 @@ def main(argv=None) -> int:
         # one process per TP rank (torchrun); rank 0 owns the HTTP front-end, the others mirror its commands
         import torch.distributed as dist
 
-        from ..parallel.symm import SymmetricHeap
+        from ..parallel.symm import SymmetricHeap, make_heap
         from .tp import TPContext
 
         tp_rank = int(os.environ["RANK"])
@@ -55,7 +55,7 @@ def main(argv=None) -> int:
             a.device = f"cuda:{int(os.environ.get('LOCAL_RANK', 0))}"
             torch.cuda.set_device(a.device)
             dist.init_process_group("nccl", device_id=torch.device(a.device))
-            heap = SymmetricHeap(group=None, device=torch.device(a.device))
+            heap = make_heap(group=None, device=torch.device(a.device))
         else:                                  # CPU plumbing path (library all-reduce)
             os.environ.setdefault("GLOO_SOCKET_IFNAME", "lo")
             dist.init_process_group("gloo")

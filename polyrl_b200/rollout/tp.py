@@ -49,8 +49,23 @@ class TPContext:
         #   "nccl":   library GEMM + NCCL all-reduce (baseline)
         import os
 
-        self.ar_mode = os.environ.get("POLYRL_TP_ALLREDUCE", "oneshot")
+        #   "nvls":   library GEMM into a multicast-mapped buffer -> ONE kernel: rank barrier + `multimem.ld_reduce` of the whole
+        #             buffer inside the NVSwitch (+ fused residual); needs the VMM/multicast heap (parallel/nvls.py)
+        self.ar_mode = os.environ.get("POLYRL_TP_ALLREDUCE", "auto")
         rows = ((min(max_batch, 256) + 7) // 8) * 8
+        self.nvls_ar = None
+        if self.ar_mode == "auto" and tp_world <= 2:
+            self.ar_mode = "oneshot"            # measured at TP=2: peer-pointer one-shot 18.2 us vs multimem 21.8 us (profiles/)
+        if self.ar_mode in ("auto", "nvls"):
+            if getattr(heap, "multicast", False):
+                from ..parallel.nvls import NvlsOneShotAllReduce
+
+                self.nvls_ar = NvlsOneShotAllReduce(heap, rows * cfg.hidden_size)
+                self.ar_mode = "nvls"
+            elif self.ar_mode == "nvls":
+                raise RuntimeError("POLYRL_TP_ALLREDUCE=nvls needs a multicast-capable symmetric heap (parallel/nvls.py)")
+            else:
+                self.ar_mode = "oneshot"
         self.ar_bufs = [heap.alloc(rows * cfg.hidden_size, torch.bfloat16) for _ in range(2)]   # alternate: see row_parallel
         self.ar_turn = 0
         heap.barrier()
@@ -93,6 +108,12 @@ class TPContext:
                      decode: bool = True) -> torch.Tensor:
         b = x_local.shape[0]
         small = self.heap is not None and x_local.is_cuda and decode and b <= 256 and b <= self.max_batch
+        if small and self.ar_mode == "nvls":
+            h = w_local.shape[0]
+            part = self.nvls_ar.next_input(b * h).view(b, h)
+            torch.mm(x_local, w_local.t(), out=part)
+            out = torch.empty(b, h, device=x_local.device, dtype=torch.bfloat16)
+            return self.nvls_ar.reduce(out, residual.contiguous() if residual is not None else None)
         if small and self.ar_mode == "oneshot":
             # Two symmetric buffers alternate: a rank may overwrite buffer p for call c+2 only after passing the barrier of
             # call c+1, which every peer reaches after it finished READING buffer p in call c.  (Decode issues an even

@@ -95,9 +95,9 @@ def run_rollout_rank(cfg: PPOConfig, rank: int, trainer_ranks, rollout_ranks, de
         tp_rank, replica = rollout_ranks.index(rank) % tp, rollout_ranks.index(rank) // tp
         heap = None
         if torch.device(device).type == "cuda":
-            from ..parallel.symm import SymmetricHeap
+            from ..parallel.symm import SymmetricHeap, make_heap
 
-            heap = SymmetricHeap(group=nccl_group, device=torch.device(device))
+            heap = make_heap(group=nccl_group, device=torch.device(device))
         tp_ctx = TPContext(model_cfg, heap, tp_rank, tp, max_batch=r.max_num_seqs, group=nccl_group)
     eng = RolloutEngine(model_cfg, device, max_num_seqs=r.max_num_seqs, max_model_len=max_len,
                         gpu_memory_utilization=r.gpu_memory_utilization, use_cuda_graph=r.cuda_graph,

@@ -201,9 +201,9 @@ class ActorRolloutRefWorker:
                 self.tp_rank = self.rank % self.rollout_tp
                 heap = None
                 if self.device.type == "cuda":
-                    from ..parallel.symm import SymmetricHeap
+                    from ..parallel.symm import SymmetricHeap, make_heap
 
-                    heap = SymmetricHeap(group=self.tp_group, device=self.device)
+                    heap = make_heap(group=self.tp_group, device=self.device)
                 tp_ctx = TPContext(self.model_cfg, heap, self.tp_rank, self.rollout_tp,
                                    max_batch=r.max_num_seqs * self.rollout_tp, group=self.tp_group)
             # a TP replica serves the prompts of all its ranks: tp x the per-GPU sequence slots (each holds 1/tp of the KV heads)

@@ -59,7 +59,9 @@ def test_ulysses_sp_nccl_and_peer_memory():
     """SP=2 == no SP (bf16 tolerances), and the NVLink peer-memory all-to-all == the NCCL all-to-all."""
     v = _torchrun("ulysses_worker.py", 2, 29657, "ULYSSES_RESULTS")
     assert float(v["lp_err"]) < 5e-2 and float(v["w_err"]) < 0.15      # measured 0 / 1.9e-2 (bf16 + AdamW at lr 1e-2)
-    assert float(v["peer_lp_err"]) < 1e-6 and float(v["peer_w_err"]) < 1e-6
+    # forward log-probs are bit-identical; the updated weights go through the flash-attn backward, whose dq accumulation uses
+    # atomics (run-to-run 1.5e-5 on 2x B200), so the weight comparison is tight but not exact
+    assert float(v["peer_lp_err"]) < 1e-6 and float(v["peer_w_err"]) < 1e-4
 
 
 def test_vocab_parallel_linear_ce_kernels():

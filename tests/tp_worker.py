@@ -16,7 +16,7 @@ def main():
     dev = torch.device("cuda", int(os.environ["LOCAL_RANK"]))
     dist.init_process_group("nccl", device_id=dev)
     from polyrl_b200.models import TransformerWeights, get_model_config
-    from polyrl_b200.parallel.symm import SymmetricHeap
+    from polyrl_b200.parallel.symm import make_heap
     from polyrl_b200.rollout.engine import RolloutEngine, SamplingParams
     from polyrl_b200.rollout.tp import TPContext
 
@@ -28,8 +28,9 @@ def main():
     sp = SamplingParams(max_new_tokens=40, temperature=0.0, ignore_eos=True)
     res = {}
     for graph in (False, True):
-        heap = SymmetricHeap(device=dev)
+        heap = make_heap(device=dev)
         tp = TPContext(cfg, heap, rank, world, max_batch=16)
+        res[f"ar_mode_graph{int(graph)}"] = tp.ar_mode
         eng = RolloutEngine(cfg, dev, max_num_seqs=16, max_model_len=128, kv_cache_tokens=16 * 128, use_cuda_graph=graph, tp=tp)
         eng.set_weights(w.embed, w.layers, w.head)
         out = [g[0].output_ids for g in eng.generate(prompts, sp)]
@@ -50,8 +51,9 @@ def main():
         # fused row-parallel GEMM -> all-reduce (one kernel, NVLink peer stores) vs cuBLAS + NCCL all-reduce, at the
         # Llama-3-8B decode shapes (B=128; o-proj K=4096/W, down-proj K=14336/W), both replayed from CUDA graphs
         big = get_model_config("llama3-8b", num_layers=1)
-        heap = SymmetricHeap(device=dev)
+        heap = make_heap(device=dev)
         tp = TPContext(big, heap, rank, world, max_batch=128)
+        have_nvls = tp.nvls_ar is not None
         B, H = 128, big.hidden_size
         torch.manual_seed(11)
         timing = {}
@@ -70,6 +72,11 @@ def main():
                 for wt in wts:
                     tp.row_parallel(x, wt, resid)
 
+            def nvls():
+                tp.ar_mode = "nvls"
+                for wt in wts:
+                    tp.row_parallel(x, wt, resid)
+
             def lib():
                 for wt in wts:
                     y = torch.nn.functional.linear(x, wt)
@@ -79,14 +86,21 @@ def main():
             tp.ar_mode = "oneshot"
             got1 = tp.row_parallel(x, wts[0], resid).float()
             tp.row_parallel(x, wts[1], resid)                    # keep the buffer alternation even
+            if have_nvls:
+                tp.ar_mode = "nvls"
+                got2 = tp.row_parallel(x, wts[0], resid).float()
+                tp.row_parallel(x, wts[1], resid)
             tp.ar_mode = "fused"
             got = tp.row_parallel(x, wts[0], resid).float()
             y = torch.nn.functional.linear(x, wts[0]).float()
             dist.all_reduce(y)
             timing[f"{name}_err"] = round(((got - (y + resid.float())).norm() / (y + resid.float()).norm()).item(), 5)
             timing[f"{name}_oneshot_err"] = round(((got1 - (y + resid.float())).norm() / (y + resid.float()).norm()).item(), 5)
+            if have_nvls:
+                timing[f"{name}_nvls_err"] = round(((got2 - (y + resid.float())).norm() / (y + resid.float()).norm()).item(), 5)
             out = {}
             for label, fn in (("fused_gemm_allreduce", fused), ("cublas_plus_oneshot_p2p_allreduce", oneshot),
+                              *((("cublas_plus_nvls_multimem_allreduce", nvls),) if have_nvls else ()),
                               ("cublas_plus_nccl_allreduce", lib)):
                 s_ = torch.cuda.Stream()
                 s_.wait_stream(torch.cuda.current_stream())
