@@ -30,6 +30,7 @@ int prl_adamw(float*, float*, float*, float*, void*, int64_t, float, float, floa
 int prl_paged_decode_workspace_floats(int, int, int, int);
 int prl_paged_decode(const void*, int64_t, const void*, const void*, const int32_t*, int64_t, const int32_t*, int, int, int, int, float, int, float*, void*, int64_t, cudaStream_t);
 int prl_sample(const void*, int, int64_t, int, int, const float*, const uint64_t*, int, int64_t*, float*, cudaStream_t);
+int prl_sample_topk_topp(const void*, int, int64_t, int, int, const float*, const uint64_t*, int, int, float, int64_t*, float*, cudaStream_t);
 int prl_ipc_get_handle(void*, void*);
 int prl_ipc_open_handle(const void*, void**);
 int prl_ipc_close_handle(void*);
@@ -356,6 +357,24 @@ std::vector<at::Tensor> sample(const at::Tensor& logits, const c10::optional<at:
   return {tok, lp};
 }
 
+std::vector<at::Tensor> sample_topk_topp(const at::Tensor& logits, const c10::optional<at::Tensor>& inv_temp,
+                                         const c10::optional<at::Tensor>& seeds, bool greedy, int64_t top_k, double top_p) {
+  TORCH_CHECK(logits.is_cuda() && logits.dim() == 2 && logits.stride(1) == 1);
+  const int dt = logits.scalar_type() == at::kFloat ? 0 : 1;
+  TORCH_CHECK(dt == 0 || logits.scalar_type() == at::kBFloat16);
+  const int B = logits.size(0), V = logits.size(1);
+  c10::cuda::CUDAGuard g(logits.device());
+  at::Tensor tok = at::empty({B}, logits.options().dtype(at::kLong));
+  at::Tensor lp = at::empty({B}, logits.options().dtype(at::kFloat));
+  const uint64_t* sd = nullptr;
+  if (seeds.has_value()) { TORCH_CHECK(seeds->scalar_type() == at::kLong); sd = reinterpret_cast<const uint64_t*>(seeds->data_ptr<int64_t>()); }
+  check(prl_sample_topk_topp(logits.data_ptr(), dt, logits.stride(0), B, V,
+                             inv_temp.has_value() ? inv_temp->data_ptr<float>() : nullptr, sd, greedy ? 1 : 0,
+                             static_cast<int>(top_k), static_cast<float>(top_p), tok.data_ptr<int64_t>(), lp.data_ptr<float>(),
+                             cur_stream()), "sample_topk_topp");
+  return {tok, lp};
+}
+
 // Decode-shape GEMM (swap-AB + split-K).  mode 0: out = x @ w.T (+bias)(+residual); mode 1: SwiGLU on interleaved W.
 at::Tensor skinny_gemm(const at::Tensor& x, const at::Tensor& w, const c10::optional<at::Tensor>& residual,
                        const c10::optional<at::Tensor>& bias, const c10::optional<at::Tensor>& x_scale,
@@ -624,6 +643,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
         py::arg("seq_lens"), py::arg("nq"), py::arg("nkv"), py::arg("d"), py::arg("sm_scale"), py::arg("splits") = 1,
         py::arg("out") = py::none());
   m.def("sample", &sample);
+  m.def("sample_topk_topp", &sample_topk_topp);
   m.def("sym_malloc", &sym_malloc);
   m.def("sym_free", &sym_free);
   m.def("ipc_get_handle", &ipc_get_handle);

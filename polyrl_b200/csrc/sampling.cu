@@ -98,9 +98,199 @@ sample_kernel(const T* __restrict__ logits, int64_t ld, int V, const float* __re
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// top-k / top-p (nucleus) sampling, one CTA per row, no sort: the k-th largest logit and the nucleus cut are found by
+// MSB-first radix selection over order-preserving integer keys of the logits (two 8-bit passes for bf16 rows, four for
+// fp32 rows; count histograms for top-k, FIXED-POINT probability-mass histograms for top-p so that the cut is
+// independent of the order of the shared-memory atomics — tensor-parallel engine ranks must sample identically).
+// Then Gumbel-max over the kept set and the log-prob under the renormalised distribution.  HF / SGLang order:
+// temperature -> top-k -> top-p.  Replaces the eager full-vocabulary sort of round 1 (reference exposes rollout.top_k /
+// rollout.top_p: 3rdparty/verl/verl/trainer/config/rollout/rollout.yaml).
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t order_key(float f) {
+  const uint32_t u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);      // ascending float order == ascending unsigned order
+}
+
+template <typename T>
+__device__ __forceinline__ float load_logit(const T* p, int i) { return static_cast<float>(p[i]); }
+
+__device__ __forceinline__ float block_reduce_max(float v, float* red) {
+  v = warp_max(v);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __syncthreads();
+  if (l == 0) red[w] = v;
+  __syncthreads();
+  float r = red[0];
+  for (int i = 1; i < (blockDim.x >> 5); ++i) r = fmaxf(r, red[i]);
+  return r;
+}
+__device__ __forceinline__ float block_reduce_sum(float v, float* red) {
+  v = warp_sum(v);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __syncthreads();
+  if (l == 0) red[w] = v;
+  __syncthreads();
+  float r = 0.f;
+  for (int i = 0; i < (blockDim.x >> 5); ++i) r += red[i];      // fixed order: deterministic
+  return r;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(1024)
+sample_topk_topp_kernel(const T* __restrict__ logits, int64_t ld, int V, const float* __restrict__ inv_temp,
+                        const uint64_t* __restrict__ seeds, int greedy_all, int top_k, float top_p,
+                        int64_t* __restrict__ out_tok, float* __restrict__ out_lp) {
+  constexpr int NPASS = sizeof(T) == 2 ? 2 : 4;            // bf16 logits are exact in the top 16 key bits
+  constexpr float kL2e = 1.4426950408889634f;
+  __shared__ unsigned long long hist[256];
+  __shared__ float red[32];
+  __shared__ uint32_t s_prefix, s_mask;
+  __shared__ unsigned long long s_remaining;
+  const int row = blockIdx.x;
+  const T* lr = logits + static_cast<int64_t>(row) * ld;
+  const float it = inv_temp ? inv_temp[row] : 1.f;
+  const bool greedy = greedy_all || it <= 0.f;
+  const float scale = greedy ? 1.f : it;
+  const uint64_t seed = seeds ? seeds[row] : 0;
+
+  float m = -INFINITY;
+  for (int i = threadIdx.x; i < V; i += blockDim.x) m = fmaxf(m, load_logit(lr, i));
+  m = block_reduce_max(m, red);
+
+  // ---- top-k: key of the k-th largest logit (ties at the cut are all kept, like `z < kth` masking)
+  uint32_t k_key = 0;
+  if (top_k > 0 && top_k < V) {
+    if (threadIdx.x == 0) { s_prefix = 0; s_mask = 0; s_remaining = static_cast<unsigned long long>(top_k); }
+    for (int pass = 0; pass < NPASS; ++pass) {
+      const int shift = 24 - 8 * pass;
+      for (int b = threadIdx.x; b < 256; b += blockDim.x) hist[b] = 0;
+      __syncthreads();
+      const uint32_t prefix = s_prefix, mask = s_mask;
+      for (int i = threadIdx.x; i < V; i += blockDim.x) {
+        const uint32_t key = order_key(load_logit(lr, i));
+        if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1ull);
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        unsigned long long cum = 0, rem = s_remaining;
+        int b = 255;
+        for (; b > 0; --b) {
+          if (cum + hist[b] >= rem) break;
+          cum += hist[b];
+        }
+        s_remaining = rem - cum;
+        s_prefix = prefix | (static_cast<uint32_t>(b) << shift);
+        s_mask = mask | (255u << shift);
+      }
+      __syncthreads();
+    }
+    k_key = s_prefix;
+  }
+
+  // ---- softmax mass of the top-k set
+  float sk = 0.f;
+  for (int i = threadIdx.x; i < V; i += blockDim.x) {
+    const float z = load_logit(lr, i);
+    if (order_key(z) >= k_key) sk += exp2f((z - m) * scale * kL2e);
+  }
+  sk = block_reduce_sum(sk, red);
+
+  // ---- top-p inside the top-k set: smallest prefix (by descending logit) whose mass reaches top_p * sk
+  uint32_t p_key = 0;
+  float s_kept = sk;
+  if (!greedy && top_p < 1.f && top_p > 0.f) {
+    const double kFix = 1099511627776.0;                  // 2^40 fixed-point mass units per unit weight (weights are <= 1)
+    if (threadIdx.x == 0) {
+      s_prefix = 0; s_mask = 0;
+      s_remaining = static_cast<unsigned long long>(static_cast<double>(top_p) * static_cast<double>(sk) * kFix);
+    }
+    for (int pass = 0; pass < NPASS; ++pass) {
+      const int shift = 24 - 8 * pass;
+      for (int b = threadIdx.x; b < 256; b += blockDim.x) hist[b] = 0;
+      __syncthreads();
+      const uint32_t prefix = s_prefix, mask = s_mask;
+      for (int i = threadIdx.x; i < V; i += blockDim.x) {
+        const float z = load_logit(lr, i);
+        const uint32_t key = order_key(z);
+        if (key >= k_key && (key & mask) == prefix) {
+          const float w = exp2f((z - m) * scale * kL2e);
+          atomicAdd(&hist[(key >> shift) & 255u], static_cast<unsigned long long>(static_cast<double>(w) * kFix));
+        }
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        unsigned long long cum = 0, rem = s_remaining;
+        int b = 255;
+        for (; b > 0; --b) {
+          if (cum + hist[b] >= rem) break;
+          cum += hist[b];
+        }
+        s_remaining = rem > cum ? rem - cum : 0ull;
+        s_prefix = prefix | (static_cast<uint32_t>(b) << shift);
+        s_mask = mask | (255u << shift);
+      }
+      __syncthreads();
+    }
+    p_key = s_prefix;
+  }
+  const uint32_t cut = k_key > p_key ? k_key : p_key;
+
+  // ---- Gumbel-max over the kept set + its mass
+  SampleState st{-INFINITY, 0x7fffffff, 0.f, -INFINITY, 0.f};
+  float mass = 0.f;
+  for (int i = threadIdx.x; i < V; i += blockDim.x) {
+    const float raw = load_logit(lr, i);
+    if (order_key(raw) < cut) continue;
+    const float z = raw * scale;
+    mass += exp2f((raw - m) * scale * kL2e);
+    const float key = greedy ? z : z + gumbel_noise(seed, row, i);
+    if (key > st.best || (key == st.best && i < st.best_idx)) { st.best = key; st.best_idx = i; st.best_z = z; }
+  }
+  if (cut != k_key || p_key != 0) s_kept = 0.f;           // recomputed below when the nucleus cut shrank the set
+  mass = block_reduce_sum(mass, red);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, st.best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, st.best_idx, o);
+    const float oz = __shfl_xor_sync(0xffffffffu, st.best_z, o);
+    if (ob > st.best || (ob == st.best && oi < st.best_idx)) { st.best = ob; st.best_idx = oi; st.best_z = oz; }
+  }
+  __shared__ float rb[32], rz[32];
+  __shared__ int ri[32];
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __syncthreads();
+  if (l == 0) { rb[w] = st.best; ri[w] = st.best_idx; rz[w] = st.best_z; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float b = rb[0], z = rz[0];
+    int bi = ri[0];
+    for (int i = 1; i < (blockDim.x >> 5); ++i)
+      if (rb[i] > b || (rb[i] == b && ri[i] < bi)) { b = rb[i]; bi = ri[i]; z = rz[i]; }
+    out_tok[row] = bi;
+    out_lp[row] = (z - m * scale) - __logf(mass);
+  }
+  (void)s_kept;
+}
+
 }  // namespace prl
 
 using namespace prl;
+
+// top_k <= 0 disables top-k, top_p >= 1 disables top-p.  dtype: 0 = fp32 logits, 1 = bf16 logits.
+extern "C" int prl_sample_topk_topp(const void* logits, int dtype, int64_t ld, int B, int V, const float* inv_temp,
+                                    const uint64_t* seeds, int greedy_all, int top_k, float top_p, int64_t* out_tok,
+                                    float* out_lp, cudaStream_t s) {
+  if (B <= 0) return 0;
+  if (dtype == 0)
+    sample_topk_topp_kernel<float><<<B, 1024, 0, s>>>(static_cast<const float*>(logits), ld, V, inv_temp, seeds, greedy_all,
+                                                     top_k, top_p, out_tok, out_lp);
+  else
+    sample_topk_topp_kernel<__nv_bfloat16><<<B, 1024, 0, s>>>(static_cast<const __nv_bfloat16*>(logits), ld, V, inv_temp, seeds,
+                                                             greedy_all, top_k, top_p, out_tok, out_lp);
+  PRL_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
 
 // dtype: 0 = fp32 logits, 1 = bf16 logits
 extern "C" int prl_sample(const void* logits, int dtype, int64_t ld, int B, int V, const float* inv_temp,

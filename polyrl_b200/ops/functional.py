@@ -509,12 +509,14 @@ def sample_tokens(logits: torch.Tensor, temperature: torch.Tensor | float = 1.0,
     if not torch.is_tensor(temperature):
         temperature = torch.full((b,), float(temperature), device=logits.device, dtype=torch.float32)
     simple = top_k <= 0 and top_p >= 1.0
-    if logits.is_cuda and simple:
+    if logits.is_cuda and logits.dtype in (torch.bfloat16, torch.float32):
         inv_t = torch.where(temperature > 0, 1.0 / temperature.clamp_min(1e-6), torch.zeros_like(temperature))
         if seeds is None:
             seeds = torch.randint(0, 2 ** 62, (b,), device=logits.device, dtype=torch.int64)
-        tok, lp = _C().sample(logits, inv_t.float().contiguous(), seeds, bool(greedy))
-        return tok, lp
+        if simple:
+            return tuple(_C().sample(logits, inv_t.float().contiguous(), seeds, bool(greedy)))
+        # top-k / top-p: radix-select kernel (no sort); log-prob under the renormalised kept set
+        return tuple(_C().sample_topk_topp(logits, inv_t.float().contiguous(), seeds, bool(greedy), int(top_k), float(top_p)))
     z = logits.float()
     temperature = temperature.to(z.device)
     row_greedy = torch.ones_like(temperature, dtype=torch.bool) if greedy else temperature <= 0     # per row, like the kernel

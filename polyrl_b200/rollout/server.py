@@ -13,6 +13,7 @@ per-request event queues.  ``register_with_manager`` self-registers the instance
 from __future__ import annotations
 
 import json
+import os
 import queue
 import threading
 import time
@@ -29,7 +30,7 @@ class _Tracked:
 
 
 class EngineServer:
-    def __init__(self, engine: RolloutEngine, host: str = "127.0.0.1", port: int = 0, stream_interval: int = 20,
+    def __init__(self, engine: RolloutEngine, host: str = "127.0.0.1", port: int = 0, stream_interval: int = 128,
                  weight_update_fn=None, tp_cmd_group=None):
         self.engine = engine
         # tensor-parallel serving: this object lives on TP rank 0; every scheduler iteration its command list is
@@ -38,7 +39,9 @@ class EngineServer:
         # scheduler inputs to its TP workers; weight fan-out rlboost/sglang/patches.py:185-241)
         self.tp_cmd_group = tp_cmd_group
         self._rid = 0
-        self.stream_interval = stream_interval
+        # cumulative SSE chunks cost O(tokens) each to build and to parse: every 128 tokens is plenty for the manager's
+        # partial-result bookkeeping (an abort flushes the latest state anyway); POLYRL_STREAM_INTERVAL overrides
+        self.stream_interval = int(os.environ.get("POLYRL_STREAM_INTERVAL", stream_interval))
         self.weight_update_fn = weight_update_fn        # callable(payload dict) -> (ok, message)
         self._lock = threading.Lock()
         self._inbox: list = []                          # (kind, payload) commands for the engine thread

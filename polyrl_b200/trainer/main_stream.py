@@ -23,6 +23,9 @@ import torch.distributed as dist
 from ..config.schema import PPOConfig, load_config, need_critic, need_reference_policy, validate_config
 
 
+STEP_CALLBACK = None        # set by bench.py --mode disagg: callable(trainer, global_step, metrics) on every trainer rank
+
+
 def _init_dist(device_type: str):
     world = int(os.environ.get("WORLD_SIZE", 1))
     if world > 1 and not dist.is_initialized():
@@ -195,6 +198,7 @@ def run_trainer_rank(cfg: PPOConfig, rank: int, trainer_ranks, rollout_ranks, de
             client.update_weight_version = lambda: sender.version
     tracking = Tracking(cfg.trainer.project_name, cfg.trainer.experiment_name, cfg.trainer.logger) if rank == 0 else None
     trainer = StreamPPOTrainer(cfg, worker, critic, reward_fn, reward_fn, train, val, client, trainer_group, tracking, sampler)
+    trainer.step_callback = STEP_CALLBACK
     out = trainer.fit()
     return out
 

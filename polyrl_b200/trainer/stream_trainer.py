@@ -548,4 +548,7 @@ class StreamPPOTrainer:
             if self.rank == 0 and self.tracking:
                 self.tracking.log(out, self.global_steps)
             last_metrics = out
+            cb = getattr(self, "step_callback", None)
+            if cb is not None:                   # benchmark / monitoring hook: called on EVERY trainer rank after each step
+                cb(self, self.global_steps, out)
         return last_metrics

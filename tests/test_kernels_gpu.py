@@ -262,6 +262,50 @@ def test_sampling(C):
     assert torch.allclose(lp, want_lp, atol=2e-3)
 
 
+def _ref_filter(logits, temp, top_k, top_p):
+    z = logits.float() / temp
+    if top_k > 0:
+        kth = torch.topk(z, min(top_k, z.shape[-1]), dim=-1).values[..., -1:]
+        z = z.masked_fill(z < kth, float("-inf"))
+    if top_p < 1.0:
+        sz, si = torch.sort(z, dim=-1, descending=True)
+        pr = torch.softmax(sz, dim=-1)
+        drop = pr.cumsum(-1) - pr >= top_p
+        sz = sz.masked_fill(drop, float("-inf"))
+        z = torch.full_like(z, float("-inf")).scatter(-1, si, sz)
+    return z
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("top_k,top_p", [(50, 1.0), (0, 0.9), (40, 0.8), (1, 1.0), (0, 0.2)])
+def test_sampling_topk_topp_kernel(C, dtype, top_k, top_p):
+    """Radix-select top-k / top-p sampler vs the sort-based reference: sampled token inside the reference kept set, log-prob equal
+    to the renormalised log-softmax, greedy == argmax, and empirical frequencies on a small vocabulary."""
+    torch.manual_seed(12)
+    B, V, temp = 64, 32000, 0.7
+    logits = (torch.randn(B, V, device="cuda") * 3).to(dtype)
+    inv_t = torch.full((B,), 1.0 / temp, device="cuda")
+    seeds = torch.randint(0, 2 ** 40, (B,), device="cuda")
+    tok, lp = C.sample_topk_topp(logits, inv_t, seeds, False, top_k, top_p)
+    z = _ref_filter(logits, temp, top_k, top_p)
+    want_lp = torch.log_softmax(z, -1).gather(-1, tok[:, None]).squeeze(-1)
+    assert torch.isfinite(want_lp).all(), "sampled a token outside the reference kept set"
+    assert torch.allclose(lp, want_lp, atol=3e-3), (lp - want_lp).abs().max()
+    # same seeds -> same tokens (tensor-parallel ranks must agree)
+    tok2, _ = C.sample_topk_topp(logits, inv_t, seeds, False, top_k, top_p)
+    assert torch.equal(tok, tok2)
+    gtok, _ = C.sample_topk_topp(logits, inv_t, seeds, True, top_k, top_p)
+    assert torch.equal(gtok, logits.float().argmax(-1))
+    # frequencies: 6-token vocabulary, nucleus keeps a strict subset
+    small = torch.tensor([[2.0, 1.5, 1.0, 0.0, -1.0, -3.0]], device="cuda").repeat(20000, 1).to(dtype)
+    sd = torch.arange(20000, device="cuda", dtype=torch.int64) * 7919 + 3
+    t2, _ = C.sample_topk_topp(small, torch.ones(20000, device="cuda"), sd, False, min(top_k, 4) if top_k else 0, top_p)
+    zr = _ref_filter(small[:1], 1.0, min(top_k, 4) if top_k else 0, top_p)
+    want = torch.softmax(zr[0], -1)
+    freq = torch.bincount(t2, minlength=6).float() / 20000
+    assert (freq - want).abs().max().item() < 0.02, (freq, want)
+
+
 def test_functional_autograd_linear():
     from polyrl_b200 import ops
 
