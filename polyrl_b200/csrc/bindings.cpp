@@ -31,6 +31,7 @@ int prl_paged_decode_workspace_floats(int, int, int, int);
 int prl_paged_decode(const void*, int64_t, const void*, const void*, const int32_t*, int64_t, const int32_t*, int, int, int, int, float, int, float*, void*, int64_t, cudaStream_t);
 int prl_sample(const void*, int, int64_t, int, int, const float*, const uint64_t*, int, int64_t*, float*, cudaStream_t);
 int prl_sample_topk_topp(const void*, int, int64_t, int, int, const float*, const uint64_t*, int, int, float, int64_t*, float*, cudaStream_t);
+int prl_attn_fwd(const void*, const void*, const void*, void*, float*, const int32_t*, const int32_t*, int, int, int, int, int, int64_t, int64_t, int64_t, int64_t, float, int, int, long long*, cudaStream_t);
 int prl_ipc_get_handle(void*, void*);
 int prl_ipc_open_handle(const void*, void**);
 int prl_ipc_close_handle(void*);
@@ -375,6 +376,33 @@ std::vector<at::Tensor> sample_topk_topp(const at::Tensor& logits, const c10::op
   return {tok, lp};
 }
 
+// varlen causal flash-attention forward on tcgen05 (csrc/attn_fwd.cu).  q:[Tq,nq,128] k,v:[Tk,nkv,128] (row-strided views allowed)
+std::vector<at::Tensor> attn_fwd(const at::Tensor& q, const at::Tensor& k, const at::Tensor& v, const at::Tensor& cu_q,
+                                 const at::Tensor& cu_k, double sm_scale, bool causal, bool want_lse,
+                                 const c10::optional<at::Tensor>& dbg) {
+  CHECK_BF16(q); CHECK_BF16(k); CHECK_BF16(v);
+  TORCH_CHECK(q.dim() == 3 && k.dim() == 3 && v.dim() == 3 && q.size(2) == 128 && k.size(2) == 128 && v.size(2) == 128,
+              "attn_fwd: head_dim must be 128");
+  TORCH_CHECK(q.stride(2) == 1 && q.stride(1) == 128 && k.stride(2) == 1 && k.stride(1) == 128 && v.stride(2) == 1 && v.stride(1) == 128,
+              "attn_fwd: heads must be contiguous inside a token row");
+  TORCH_CHECK(q.stride(0) % 8 == 0 && k.stride(0) % 8 == 0 && v.stride(0) % 8 == 0);
+  TORCH_CHECK((reinterpret_cast<uintptr_t>(q.data_ptr()) & 15) == 0 && (reinterpret_cast<uintptr_t>(k.data_ptr()) & 15) == 0 &&
+              (reinterpret_cast<uintptr_t>(v.data_ptr()) & 15) == 0, "attn_fwd: 16-byte aligned operands");
+  TORCH_CHECK(cu_q.is_cuda() && cu_q.scalar_type() == at::kInt && cu_q.is_contiguous() && cu_k.is_cuda() &&
+              cu_k.scalar_type() == at::kInt && cu_k.is_contiguous() && cu_q.numel() == cu_k.numel());
+  const int Tq = q.size(0), Tk = k.size(0), nq = q.size(1), nkv = k.size(1), B = cu_q.numel() - 1;
+  c10::cuda::CUDAGuard g(q.device());
+  at::Tensor o = at::empty({Tq, nq, 128}, q.options());
+  at::Tensor lse = want_lse ? at::empty({nq, Tq}, q.options().dtype(at::kFloat)) : at::Tensor();
+  check(prl_attn_fwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), want_lse ? lse.data_ptr<float>() : nullptr,
+                     cu_q.data_ptr<int>(), cu_k.data_ptr<int>(), B, Tq, Tk, nq, nkv, q.stride(0), k.stride(0), v.stride(0),
+                     static_cast<int64_t>(nq) * 128, static_cast<float>(sm_scale), causal ? 1 : 0, Tq / 128 + B,
+                     dbg.has_value() ? reinterpret_cast<long long*>(dbg->data_ptr<int64_t>()) : nullptr, cur_stream()),
+        "attn_fwd");
+  if (want_lse) return {o, lse};
+  return {o};
+}
+
 // Decode-shape GEMM (swap-AB + split-K).  mode 0: out = x @ w.T (+bias)(+residual); mode 1: SwiGLU on interleaved W.
 at::Tensor skinny_gemm(const at::Tensor& x, const at::Tensor& w, const c10::optional<at::Tensor>& residual,
                        const c10::optional<at::Tensor>& bias, const c10::optional<at::Tensor>& x_scale,
@@ -642,6 +670,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("paged_decode", &paged_decode, py::arg("q"), py::arg("k_cache"), py::arg("v_cache"), py::arg("block_table"),
         py::arg("seq_lens"), py::arg("nq"), py::arg("nkv"), py::arg("d"), py::arg("sm_scale"), py::arg("splits") = 1,
         py::arg("out") = py::none());
+  m.def("attn_fwd", &attn_fwd, py::arg("q"), py::arg("k"), py::arg("v"), py::arg("cu_q"), py::arg("cu_k"), py::arg("sm_scale"),
+        py::arg("causal") = true, py::arg("want_lse") = true, py::arg("dbg") = py::none());
   m.def("sample", &sample);
   m.def("sample_topk_topp", &sample_topk_topp);
   m.def("sym_malloc", &sym_malloc);

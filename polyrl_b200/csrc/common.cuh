@@ -319,6 +319,13 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
+// single MUFU.EX2 (no range-reduction branches): 2^-inf = 0, fine for softmax weights
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);

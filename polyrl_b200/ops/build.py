@@ -32,6 +32,7 @@ CU_SOURCES = [
     "elementwise.cu",
     "optim.cu",
     "decode_attn.cu",
+    "attn_fwd.cu",
     "sampling.cu",
     "p2p.cu",
     "nvls.cu",

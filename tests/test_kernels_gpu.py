@@ -272,7 +272,11 @@ def _ref_filter(logits, temp, top_k, top_p):
         pr = torch.softmax(sz, dim=-1)
         drop = pr.cumsum(-1) - pr >= top_p
         sz = sz.masked_fill(drop, float("-inf"))
-        z = torch.full_like(z, float("-inf")).scatter(-1, si, sz)
+        kept = torch.full_like(z, float("-inf")).scatter(-1, si, sz)
+        # ties at the nucleus boundary: a sort cuts a group of equal logits at an arbitrary member, the kernel keeps the whole
+        # group (bf16 logits tie often) -> make the reference tie-inclusive
+        thr = torch.where(torch.isfinite(kept), kept, torch.full_like(kept, float("inf"))).amin(-1, keepdim=True)
+        z = z.masked_fill(z < thr, float("-inf"))
     return z
 
 
