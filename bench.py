@@ -330,6 +330,7 @@ def main() -> int:
                     base_err = f"baseline child rc={r.returncode}: {r.stderr[-300:]}"
         except Exception as e:      # never let the comparison arm take the product number down with it
             base_err = f"{type(e).__name__}: {str(e)[:200]}"
+        time.sleep(float(os.environ.get("BENCH_COOLDOWN_S", 10)))     # let the power/thermal state settle before the product arm
 
     import torch
     import torch.distributed as dist

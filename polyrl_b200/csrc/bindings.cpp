@@ -32,6 +32,7 @@ int prl_paged_decode(const void*, int64_t, const void*, const void*, const int32
 int prl_sample(const void*, int, int64_t, int, int, const float*, const uint64_t*, int, int64_t*, float*, cudaStream_t);
 int prl_sample_topk_topp(const void*, int, int64_t, int, int, const float*, const uint64_t*, int, int, float, int64_t*, float*, cudaStream_t);
 int prl_attn_fwd(const void*, const void*, const void*, void*, float*, const int32_t*, const int32_t*, int, int, int, int, int, int64_t, int64_t, int64_t, int64_t, float, int, int, long long*, cudaStream_t);
+int prl_attn_bwd(const void*, const void*, const void*, const void*, const void*, const float*, float*, float*, void*, void*, const int32_t*, const int32_t*, int, int, int, int, int, int64_t, int64_t, int64_t, int64_t, int64_t, float, int, int, cudaStream_t);
 int prl_ipc_get_handle(void*, void*);
 int prl_ipc_open_handle(const void*, void**);
 int prl_ipc_close_handle(void*);
@@ -403,6 +404,29 @@ std::vector<at::Tensor> attn_fwd(const at::Tensor& q, const at::Tensor& k, const
   return {o};
 }
 
+// flash-attention backward (csrc/attn_bwd.cu): returns (dq, dk, dv) in bf16, shapes of q / k / v (contiguous)
+std::vector<at::Tensor> attn_bwd(const at::Tensor& q, const at::Tensor& k, const at::Tensor& v, const at::Tensor& o,
+                                 const at::Tensor& d_o, const at::Tensor& lse, const at::Tensor& cu_q, const at::Tensor& cu_k,
+                                 double sm_scale, bool causal) {
+  CHECK_BF16(q); CHECK_BF16(k); CHECK_BF16(v); CHECK_BF16(o); CHECK_BF16(d_o); CHECK_F32(lse);
+  for (const at::Tensor* t : {&q, &k, &v, &o, &d_o}) {
+    TORCH_CHECK(t->dim() == 3 && t->size(2) == 128 && t->stride(2) == 1 && t->stride(1) == 128 && t->stride(0) % 8 == 0 &&
+                (reinterpret_cast<uintptr_t>(t->data_ptr()) & 15) == 0, "attn_bwd: [T, heads, 128] row-strided bf16 operands");
+  }
+  const int Tq = q.size(0), Tk = k.size(0), nq = q.size(1), nkv = k.size(1), B = cu_q.numel() - 1;
+  TORCH_CHECK(lse.is_contiguous() && lse.size(0) == nq && lse.size(1) == Tq);
+  c10::cuda::CUDAGuard g(q.device());
+  at::Tensor dq_acc = at::zeros({Tq, nq, 128}, q.options().dtype(at::kFloat));
+  at::Tensor dk = at::empty({Tk, nkv, 128}, q.options());
+  at::Tensor dv = at::empty({Tk, nkv, 128}, q.options());
+  at::Tensor dsum = at::empty({nq, Tq}, q.options().dtype(at::kFloat));
+  check(prl_attn_bwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), d_o.data_ptr(), lse.data_ptr<float>(),
+                     dsum.data_ptr<float>(), dq_acc.data_ptr<float>(), dk.data_ptr(), dv.data_ptr(), cu_q.data_ptr<int>(),
+                     cu_k.data_ptr<int>(), B, Tq, Tk, nq, nkv, q.stride(0), k.stride(0), v.stride(0), o.stride(0), d_o.stride(0),
+                     static_cast<float>(sm_scale), causal ? 1 : 0, Tk / 128 + B, cur_stream()), "attn_bwd");
+  return {dq_acc.to(at::kBFloat16), dk, dv};
+}
+
 // Decode-shape GEMM (swap-AB + split-K).  mode 0: out = x @ w.T (+bias)(+residual); mode 1: SwiGLU on interleaved W.
 at::Tensor skinny_gemm(const at::Tensor& x, const at::Tensor& w, const c10::optional<at::Tensor>& residual,
                        const c10::optional<at::Tensor>& bias, const c10::optional<at::Tensor>& x_scale,
@@ -672,6 +696,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
         py::arg("out") = py::none());
   m.def("attn_fwd", &attn_fwd, py::arg("q"), py::arg("k"), py::arg("v"), py::arg("cu_q"), py::arg("cu_k"), py::arg("sm_scale"),
         py::arg("causal") = true, py::arg("want_lse") = true, py::arg("dbg") = py::none());
+  m.def("attn_bwd", &attn_bwd);
   m.def("sample", &sample);
   m.def("sample_topk_topp", &sample_topk_topp);
   m.def("sym_malloc", &sym_malloc);

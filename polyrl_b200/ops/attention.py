@@ -1,16 +1,64 @@
 """Packed (varlen) causal self-attention for training / prefill.
 
-Backends, in order: flash-attn varlen (library call, the same provider the reference uses —
-3rdparty/verl/verl/models/transformers/monkey_patch.py:108) on CUDA; PyTorch SDPA over a padded
-[B, S] view otherwise (CPU tests, or CUDA when flash-attn cannot be imported).  Decode-time
-attention is NOT here: it is the hand-written paged kernel in csrc/decode_attn.cu.
+Backends, in order: the own tcgen05 / TMEM flash-attention kernels (csrc/attn_fwd.cu, csrc/attn_bwd.cu: head_dim 128, bf16,
+GQA, bottom-right aligned causal mask for prefill behind a cached prefix) on CUDA; the flash-attn varlen library (what the
+reference calls, 3rdparty/verl/verl/models/transformers/monkey_patch.py:108) for other head sizes / dtypes or when
+``POLYRL_ATTN_BACKEND=flash``; PyTorch SDPA over a padded [B, S] view otherwise (CPU tests).  Decode-time attention is NOT
+here: it is the hand-written paged kernel in csrc/decode_attn.cu.
 """
 from __future__ import annotations
 
 import torch
 import torch.nn.functional as F
 
+import os
+
 _FLASH = None
+
+
+def _own_ok(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor) -> bool:
+    return (q.is_cuda and q.dtype == torch.bfloat16 and k.dtype == torch.bfloat16 and v.dtype == torch.bfloat16
+            and q.shape[-1] == 128 and k.shape[-1] == 128 and q.shape[1] % k.shape[1] == 0
+            and os.environ.get("POLYRL_ATTN_BACKEND", "own") == "own" and os.environ.get("POLYRL_GEMM_BACKEND", "tcgen05") != "cublas")
+
+
+def _rows(t: torch.Tensor) -> torch.Tensor:
+    """[T, heads, 128] view whose heads are contiguous inside a token row (row pitch free): what the kernels' TMA maps need."""
+    if t.stride(2) != 1 or t.stride(1) != t.shape[2] or t.stride(0) % 8 != 0 or t.data_ptr() % 16 != 0:
+        t = t.contiguous()
+    return t
+
+
+class _OwnAttnFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, q, k, v, cu_q, cu_k, scale, causal):
+        from . import ext
+
+        q, k, v = _rows(q), _rows(k), _rows(v)
+        need = q.requires_grad or k.requires_grad or v.requires_grad
+        outs = ext().attn_fwd(q, k, v, cu_q, cu_k, float(scale), bool(causal), bool(need))
+        if need:
+            ctx.save_for_backward(q, k, v, outs[0], outs[1], cu_q, cu_k)
+            ctx.scale, ctx.causal = float(scale), bool(causal)
+        return outs[0]
+
+    @staticmethod
+    def backward(ctx, do):
+        from . import ext
+
+        q, k, v, o, lse, cu_q, cu_k = ctx.saved_tensors
+        dq, dk, dv = ext().attn_bwd(q, k, v, o, _rows(do), lse, cu_q, cu_k, ctx.scale, ctx.causal)
+        return dq, dk, dv, None, None, None, None
+
+
+def _own_attention(q, k, v, cu_q, cu_k, scale, causal=True):
+    cu_q = cu_q if cu_q.dtype == torch.int32 else cu_q.to(torch.int32)
+    cu_k = cu_k if cu_k.dtype == torch.int32 else cu_k.to(torch.int32)
+    if torch.is_grad_enabled() and (q.requires_grad or k.requires_grad or v.requires_grad):
+        return _OwnAttnFn.apply(q, k, v, cu_q.contiguous(), cu_k.contiguous(), scale, causal)
+    from . import ext
+
+    return ext().attn_fwd(_rows(q), _rows(k), _rows(v), cu_q.contiguous(), cu_k.contiguous(), float(scale), bool(causal), False)[0]
 
 
 def _flash():
@@ -58,6 +106,8 @@ def attention_varlen(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, cu_seqle
     """q:[T,nq,d], k/v:[T,nkv,d] packed over sequences delimited by ``cu_seqlens`` (int32 [B+1])."""
     if scale is None:
         scale = q.shape[-1] ** -0.5
+    if _own_ok(q, k, v):
+        return _own_attention(q, k, v, cu_seqlens, cu_seqlens, scale, causal)
     fa = _flash() if q.is_cuda and q.dtype in (torch.bfloat16, torch.float16) else False
     if fa:
         return fa(q, k, v, cu_seqlens, cu_seqlens, int(max_seqlen), int(max_seqlen), 0.0, softmax_scale=scale,
@@ -71,6 +121,8 @@ def attention_varlen_prefix(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, c
     then the new tokens); causal mask aligned bottom-right.  q:[Tq,nq,d], k/v:[Tk,nkv,d]."""
     if scale is None:
         scale = q.shape[-1] ** -0.5
+    if _own_ok(q, k, v):
+        return _own_attention(q, k, v, cu_q, cu_k, scale, True)
     fa = _flash() if q.is_cuda and q.dtype in (torch.bfloat16, torch.float16) else False
     if fa:
         return fa(q, k, v, cu_q, cu_k, int(max_q), int(max_k), 0.0, softmax_scale=scale, causal=True)

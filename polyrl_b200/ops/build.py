@@ -33,6 +33,7 @@ CU_SOURCES = [
     "optim.cu",
     "decode_attn.cu",
     "attn_fwd.cu",
+    "attn_bwd.cu",
     "sampling.cu",
     "p2p.cu",
     "nvls.cu",

@@ -262,6 +262,51 @@ def test_sampling(C):
     assert torch.allclose(lp, want_lp, atol=2e-3)
 
 
+def _ref_attn(q, k, v, cu_q, cu_k):
+    nq, nkv = q.shape[1], k.shape[1]
+    out = torch.empty_like(q, dtype=torch.float32)
+    cq, ck = cu_q.tolist(), cu_k.tolist()
+    for i in range(len(cq) - 1):
+        qs, ks, vs = q[cq[i]:cq[i + 1]].float(), k[ck[i]:ck[i + 1]].float(), v[ck[i]:ck[i + 1]].float()
+        lq, lk = qs.shape[0], ks.shape[0]
+        ks, vs = ks.repeat_interleave(nq // nkv, dim=1), vs.repeat_interleave(nq // nkv, dim=1)
+        s = torch.einsum("qhd,khd->hqk", qs, ks) * (q.shape[-1] ** -0.5)
+        mask = torch.arange(lk, device=q.device)[None, :] <= (torch.arange(lq, device=q.device)[:, None] + (lk - lq))
+        out[cq[i]:cq[i + 1]] = torch.einsum("hqk,khd->qhd", torch.softmax(s.masked_fill(~mask[None], float("-inf")), -1), vs)
+    return out
+
+
+@pytest.mark.parametrize("lq,lk,nq,nkv", [
+    ([640, 700, 33, 128, 1, 257, 129], None, 8, 2),           # packed self-attention, ragged tile edges, GQA 4:1
+    ([64, 1, 200, 128], [364, 18, 328, 1152], 4, 4),          # prefill behind a cached prefix (bottom-right aligned causal)
+    ([1500], None, 4, 1),
+])
+def test_tcgen05_flash_attention_fwd_bwd(lq, lk, nq, nkv):
+    """Own tcgen05 flash-attention forward + backward vs an fp32 PyTorch reference (through the public op, autograd)."""
+    from polyrl_b200.ops.attention import attention_varlen_prefix
+
+    torch.manual_seed(30)
+    lk = lk or lq
+    cu_q = torch.tensor([0] + list(torch.tensor(lq).cumsum(0)), device="cuda", dtype=torch.int32)
+    cu_k = torch.tensor([0] + list(torch.tensor(lk).cumsum(0)), device="cuda", dtype=torch.int32)
+    Tq, Tk, d = int(cu_q[-1]), int(cu_k[-1]), 128
+    q = (torch.randn(Tq, nq, d, device="cuda") * 0.5).to(torch.bfloat16).requires_grad_(True)
+    k = (torch.randn(Tk, nkv, d, device="cuda") * 0.5).to(torch.bfloat16).requires_grad_(True)
+    v = (torch.randn(Tk, nkv, d, device="cuda") * 0.5).to(torch.bfloat16).requires_grad_(True)
+    do = (torch.randn(Tq, nq, d, device="cuda") * 0.5).to(torch.bfloat16)
+    o = attention_varlen_prefix(q, k, v, cu_q, cu_k, max(lq), max(lk))
+    o.backward(do)
+    qf, kf, vf = (t.detach().float().requires_grad_(True) for t in (q, k, v))
+    want = _ref_attn(qf, kf, vf, cu_q, cu_k)
+    want.backward(do.float())
+    assert _rel_err(o, want) < 5e-3
+    assert _rel_err(q.grad, qf.grad) < 1e-2 and _rel_err(k.grad, kf.grad) < 1e-2 and _rel_err(v.grad, vf.grad) < 1e-2
+    with torch.no_grad():                      # inference path (no lse, strided views of a packed qkv row)
+        qkv = torch.cat([q.detach().reshape(Tq, -1), k.detach()[:Tq].reshape(Tq, -1) if Tk >= Tq else k.detach().reshape(Tk, -1)], dim=1)
+        o2 = attention_varlen_prefix(q.detach(), k.detach(), v.detach(), cu_q, cu_k, max(lq), max(lk))
+        assert torch.equal(o2, o.detach()) and qkv.is_cuda
+
+
 def _ref_filter(logits, temp, top_k, top_p):
     z = logits.float() / temp
     if top_k > 0:
