@@ -69,7 +69,7 @@ int prl_nvls_reduce_scatter_accum(const void*, int64_t, float*, int64_t, float, 
 int prl_nvls_bcast_store(const void*, void*, int64_t, int, cudaStream_t);
 int prl_skinny_workspace_floats(int, int, int);
 int prl_skinny_gemm(const void*, const void*, void*, const void*, const void*, const float*, const float*, float*, int*, int, int, int, int64_t, int64_t, int64_t, int, int, int, cudaStream_t);
-int prl_stream_gemm(const void*, const void*, void*, const void*, const void*, const float*, const float*, int, int, int, int64_t, int64_t, int64_t, int, int, int, cudaStream_t);
+int prl_stream_gemm(const void*, const void*, void*, const void*, const void*, const float*, const float*, int, int, int, int64_t, int64_t, int64_t, int, int, int, int, cudaStream_t);
 int prl_skinny_gemm_tp(const void*, const void*, void*, const void*, const void*, const float*, const float*, float*, int*, int, int, int, int64_t, int64_t, int64_t, int, int, int, int, int, uint32_t*, int*, int64_t, void* const*, void* const*, cudaStream_t);
 int prl_ag_gemm_bf16(const void*, void* const*, void*, void*, uint32_t*, uint32_t, int, int, int, int64_t, int64_t, int, int, int, cudaStream_t);
 }
@@ -463,7 +463,7 @@ at::Tensor skinny_gemm(const at::Tensor& x, const at::Tensor& w, const c10::opti
 at::Tensor stream_gemm(const at::Tensor& x, const at::Tensor& w, const c10::optional<at::Tensor>& residual,
                        const c10::optional<at::Tensor>& bias, const c10::optional<at::Tensor>& x_scale,
                        const c10::optional<at::Tensor>& w_scale, int64_t mode, int64_t splits,
-                       c10::optional<at::Tensor> out_opt) {
+                       c10::optional<at::Tensor> out_opt, int64_t pair) {
   TORCH_CHECK(x.is_cuda() && w.is_cuda() && x.dim() == 2 && w.dim() == 2 && x.stride(1) == 1 && w.stride(1) == 1);
   const bool fp8 = x.element_size() == 1;
   TORCH_CHECK(fp8 == (w.element_size() == 1), "x and w must both be bf16 or both fp8");
@@ -487,7 +487,7 @@ at::Tensor stream_gemm(const at::Tensor& x, const at::Tensor& w, const c10::opti
   const float* ws = w_scale.has_value() ? w_scale->data_ptr<float>() : nullptr;
   TORCH_CHECK(!fp8 || (xs && ws), "fp8 stream GEMM needs x_scale and w_scale");
   check(prl_stream_gemm(x.data_ptr(), w.data_ptr(), out.data_ptr(), r, bs, xs, ws, B, N, K, x.stride(0), w.stride(0), out.stride(0),
-                        static_cast<int>(mode), fp8 ? 1 : 0, static_cast<int>(splits), cur_stream()), "stream_gemm");
+                        static_cast<int>(mode), fp8 ? 1 : 0, static_cast<int>(splits), static_cast<int>(pair), cur_stream()), "stream_gemm");
   return out;
 }
 
@@ -679,7 +679,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("skinny_gemm_tp", &skinny_gemm_tp);
   m.def("stream_gemm", &stream_gemm, py::arg("x"), py::arg("w"), py::arg("residual") = py::none(), py::arg("bias") = py::none(),
         py::arg("x_scale") = py::none(), py::arg("w_scale") = py::none(), py::arg("mode") = 0, py::arg("splits") = 0,
-        py::arg("out") = py::none());
+        py::arg("out") = py::none(), py::arg("pair") = -1);
   m.def("linear_ce_fwd", &linear_ce_fwd);
   m.def("linear_ce_dz", &linear_ce_dz);
   m.def("rmsnorm_fwd", &rmsnorm_fwd);

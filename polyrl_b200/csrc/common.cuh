@@ -83,6 +83,13 @@ __device__ __forceinline__ void tma_load_2d_hint(const CUtensorMap* m, uint64_t*
       ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(hint)
       : "memory");
 }
+// Pull a tile into L2 only (no shared-memory destination, no barrier): lets a streaming kernel keep far more bytes in flight
+// than its shared-memory ring holds — the ring then only has to cover L2 latency, not HBM latency.
+__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* m, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(m)), "r"(c0),
+               "r"(c1)
+               : "memory");
+}
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* smem_src, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
                    reinterpret_cast<uint64_t>(m)),

@@ -39,7 +39,7 @@ struct StreamParams {
   const float* x_scale;        // optional fp8: per batch row
   const float* w_scale;        // optional fp8: per weight row
   int64_t ldo;
-  int B, N, K, BP, S, kb_per_split, swiglu, tiles, dbg, nacc;
+  int B, N, K, BP, S, kb_per_split, swiglu, tiles, dbg, nacc, pf;
 };
 
 __device__ __forceinline__ void st_shared_cluster_f32(uint32_t addr, float v) {
@@ -51,14 +51,20 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t cta) {
   return r;
 }
 
-template <bool FP8>
+// PAIR = true: the CTAs of a cluster are organised as S CTA PAIRS (cta_group::2).  A pair owns 256 weight rows (128 per CTA)
+// and one k-range; each CTA stages half of the activation k-block and the leader issues ONE tcgen05.mma (M = 256) per K=16
+// step for both — 256 weight rows per ~128-clk instruction instead of 128 rows per ~190 clk (profiles/r2_decode_gemm_
+// experiments.md), which is what lifts the per-SM weight rate above the HBM share.
+template <bool FP8, bool PAIR>
 __global__ void __launch_bounds__(kSgThreads, 1)
 stream_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmX, StreamParams p) {
   constexpr int BLOCK_K = FP8 ? 128 : 64;
   constexpr int A_BYTES = 128 * 128;
+  constexpr int NC = PAIR ? 2 : 1;                     // CTAs that share one accumulator tile / MMA
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int b_bytes = p.BP * 128;
+  const int b_rows = p.BP / NC;                        // activation rows staged by THIS CTA
+  const int b_bytes = b_rows * 128;
   const int stage_bytes = A_BYTES + b_bytes;
   int stages = kSgSmemBudget / stage_bytes;
   if (stages > 8) stages = 8;
@@ -72,21 +78,31 @@ stream_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int S = p.S;
-  const int split = static_cast<int>(blockIdx.x) % S;                 // == rank inside the cluster
-  const int tile = static_cast<int>(blockIdx.x) / S;
+  const int crank = static_cast<int>(blockIdx.x) % (S * NC);         // rank inside the cluster
+  const int split = crank / NC;                                       // k-range owned by this CTA (pair)
+  const int r2 = crank % NC;                                          // CTA inside the pair (0 = MMA leader)
+  const int tile = static_cast<int>(blockIdx.x) / (S * NC);           // 128 (single) or 256 (pair) weight rows
   const int num_kb_total = (p.K + BLOCK_K - 1) / BLOCK_K;
   const int kb0 = split * p.kb_per_split;
   const int kb1 = min(num_kb_total, kb0 + p.kb_per_split);
   const int nkb = max(0, kb1 - kb0);
-  // SwiGLU tile t: features [64t, 64t+64): gate rows 256*(t/2) + 64*(t%2) .., up rows 128 further
-  const int row_g = p.swiglu ? (tile >> 1) * 256 + (tile & 1) * 64 : tile * 128;
-  const int row_u = p.swiglu ? row_g + 128 : row_g + 64;
-  // NACC independent accumulators: back-to-back tcgen05.mma into ONE accumulator serialise on the TMEM read-modify-write
-  // (~140 clk per dependent 128x128x16 MMA, measured); the four K=16 steps of a k-block rotate over NACC accumulators
-  // that the epilogue sums.
-  const int NACC = p.nacc;
+  // weight rows of this CTA's 128 TMEM lanes: lanes [0,64) <- row_g.., lanes [64,128) <- row_u..
+  //   plain:  128 consecutive rows.   SwiGLU: 64 gate rows + the 64 matching up rows of the [128 gate | 128 up] block layout
+  int row_g, row_u, n_tile0;
+  if (p.swiglu) {
+    const int t64 = tile * NC + r2;                                   // 64-feature tile index
+    row_g = (t64 >> 1) * 256 + (t64 & 1) * 64;
+    row_u = row_g + 128;
+    n_tile0 = t64 * 64;
+  } else {
+    row_g = (tile * NC + r2) * 128;
+    row_u = row_g + 64;
+    n_tile0 = row_g;
+  }
+  const int NACC = PAIR ? 1 : p.nacc;
   uint32_t tmem_cols = 32;
   while (tmem_cols < static_cast<uint32_t>(p.BP * NACC)) tmem_cols <<= 1;
+  const uint16_t pair_mask = static_cast<uint16_t>(3u << (2 * split));
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmW);
@@ -95,34 +111,57 @@ stream_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
     mbar_init(acc_bar, 1);
     fence_barrier_init();
   }
-  if (warp == 1) { tmem_alloc(tmem_slot, tmem_cols); tmem_relinquish(); }
+  if (warp == 1) {
+    if constexpr (PAIR) { tmem_alloc_2sm(tmem_slot, tmem_cols); tmem_relinquish_2sm(); }
+    else { tmem_alloc(tmem_slot, tmem_cols); tmem_relinquish(); }
+  }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (PAIR) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
+      // L2 prefetch `pf` k-blocks ahead of the ring: HBM latency under load (~2-3 us) x 23 B/clk per SM is more than the
+      // ~128 KB of weights the ring can hold, so the ring alone cannot keep the HBM share of one SM in flight
+      const int pf = p.pf;
+      for (int kb = kb0; kb < min(kb1, kb0 + pf); ++kb) {
+        tma_prefetch_l2_2d(&tmW, kb * BLOCK_K, row_g);
+        tma_prefetch_l2_2d(&tmW, kb * BLOCK_K, row_u);
+      }
       for (int kb = kb0; kb < kb1; ++kb) {
         if ((p.dbg & 2) && kb - kb0 >= stages) break;              // experiment: MMA-only (ring loaded once)
+        if (kb + pf < kb1) {
+          tma_prefetch_l2_2d(&tmW, (kb + pf) * BLOCK_K, row_g);
+          tma_prefetch_l2_2d(&tmW, (kb + pf) * BLOCK_K, row_u);
+        }
         mbar_wait(&empty_bar[stage], phase ^ 1);
-        mbar_expect_tx(&full_bar[stage], stage_bytes);
-        // weights are read exactly once: do not let them displace the activations in L2
-        tma_load_2d_hint(&tmW, &full_bar[stage], smem_a + stage * A_BYTES, kb * BLOCK_K, row_g, kEvictFirst);
-        tma_load_2d_hint(&tmW, &full_bar[stage], smem_a + stage * A_BYTES + 64 * 128, kb * BLOCK_K, row_u, kEvictFirst);
-        tma_load_2d_hint(&tmX, &full_bar[stage], smem_b + stage * b_bytes, kb * BLOCK_K, 0, kEvictLast);
+        uint8_t* sa = smem_a + stage * A_BYTES;
+        uint8_t* sb = smem_b + stage * b_bytes;
+        if constexpr (PAIR) {
+          if (r2 == 0) mbar_expect_tx(&full_bar[stage], 2 * stage_bytes);      // both CTAs' bytes are counted on the leader
+          tma_load_2d_2sm(&tmW, &full_bar[stage], sa, kb * BLOCK_K, row_g, kEvictFirst);
+          tma_load_2d_2sm(&tmW, &full_bar[stage], sa + 64 * 128, kb * BLOCK_K, row_u, kEvictFirst);
+          tma_load_2d_2sm(&tmX, &full_bar[stage], sb, kb * BLOCK_K, r2 * b_rows, kEvictLast);
+        } else {
+          mbar_expect_tx(&full_bar[stage], stage_bytes);
+          // weights are read exactly once: do not let them displace the activations in L2
+          tma_load_2d_hint(&tmW, &full_bar[stage], sa, kb * BLOCK_K, row_g, kEvictFirst);
+          tma_load_2d_hint(&tmW, &full_bar[stage], sa + 64 * 128, kb * BLOCK_K, row_u, kEvictFirst);
+          tma_load_2d_hint(&tmX, &full_bar[stage], sb, kb * BLOCK_K, 0, kEvictLast);
+        }
         if (++stage == stages) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = FP8 ? umma_idesc(128, p.BP, 0, 0) : umma_idesc(128, p.BP, 1, 1);
+    if (lane == 0 && r2 == 0) {
+      const uint32_t idesc = FP8 ? umma_idesc(128 * NC, p.BP, 0, 0) : umma_idesc(128 * NC, p.BP, 1, 1);
       int stage = 0; uint32_t phase = 0;
       for (int kb = 0; kb < nkb; ++kb) {
         if (!((p.dbg & 2) && kb >= stages)) mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        if (p.dbg & 1) {                                           // experiment: stream-only (no MMA)
+        if (!PAIR && (p.dbg & 1)) {                                // experiment: stream-only (no MMA)
           mbar_arrive(&empty_bar[stage]);
           if (++stage == stages) { stage = 0; phase ^= 1; }
           continue;
@@ -133,13 +172,20 @@ stream_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
         for (int k = 0; k < 4; ++k) {
           const int a = k & (NACC - 1);
           const uint32_t acc = (kb != 0) || (k >= NACC);
-          if constexpr (FP8) umma_f8_ss(tmem_base + a * p.BP, da + 2 * k, db + 2 * k, idesc, acc);
-          else umma_bf16_ss(tmem_base + a * p.BP, da + 2 * k, db + 2 * k, idesc, acc);
+          if constexpr (PAIR) {
+            umma_bf16_ss_2sm(tmem_base, da + 2 * k, db + 2 * k, idesc, acc);
+          } else {
+            if constexpr (FP8) umma_f8_ss(tmem_base + a * p.BP, da + 2 * k, db + 2 * k, idesc, acc);
+            else umma_bf16_ss(tmem_base + a * p.BP, da + 2 * k, db + 2 * k, idesc, acc);
+          }
         }
-        if (!(p.dbg & 2)) umma_commit(&empty_bar[stage]);
+        if constexpr (PAIR) umma_commit_2sm(&empty_bar[stage], pair_mask);
+        else if (!(p.dbg & 2)) umma_commit(&empty_bar[stage]);
         if (++stage == stages) { stage = 0; phase ^= 1; }
       }
-      if (p.dbg & 1) mbar_arrive(acc_bar); else umma_commit(acc_bar);
+      if constexpr (PAIR) umma_commit_2sm(acc_bar, pair_mask);
+      else if (p.dbg & 1) mbar_arrive(acc_bar);
+      else umma_commit(acc_bar);
     }
   }
 
@@ -156,7 +202,7 @@ stream_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
   if (epi_warp) {
     if (nkb > 0) { mbar_wait(acc_bar, 0); tc_fence_after(); }
   }
-  if (S > 1) cluster_sync_all();                                 // every ring of the cluster is idle from here on
+  if (S * NC > 1) cluster_sync_all();                            // every ring of the cluster is idle from here on
   else __syncthreads();
   if (epi_warp) {
     const uint32_t lane_base = static_cast<uint32_t>(quad * 32) << 16;
@@ -185,7 +231,7 @@ stream_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
         if (q >= num_chunks) break;
         const int owner = q % S, slot = q / S;
         const uint32_t local = inbox_u32 + static_cast<uint32_t>((((split * LC + slot) * 8) * 128 + r) * 4);
-        const uint32_t dst = S > 1 ? mapa_u32(local, owner) : local;
+        const uint32_t dst = S > 1 ? mapa_u32(local, owner * NC + r2) : local;
 #pragma unroll
         for (int i = 0; i < 8; ++i)
           st_shared_cluster_f32(dst + i * 512, __uint_as_float(v[qq * 8 + i]) * ws_row);   // 32 lanes -> 128 contiguous bytes
@@ -193,12 +239,11 @@ stream_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
     }
   }
   tc_fence_before();
-  if (S > 1) cluster_sync_all();                                 // all partial chunks have landed in their owners
+  if (S * NC > 1) cluster_sync_all();                            // all partial chunks have landed in their owners
   else __syncthreads();
   if (epi_warp) {
     const int et = (warp - 2) * 32 + lane;                       // 0..127
-    const int feats = p.swiglu ? 64 : 128;                       // output features of this tile
-    const int n_tile0 = tile * feats;
+    const int feats = p.swiglu ? 64 : 128;                       // output features of this CTA
     const int n_out = p.swiglu ? p.N / 2 : p.N;
     const int segs = feats >> 3;
     const int seg = et % segs, bsub = et / segs;
@@ -250,8 +295,11 @@ stream_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
     }
   }
   tc_fence_before();
-  __syncthreads();
-  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, tmem_cols); }
+  if constexpr (PAIR) cluster_sync_all(); else __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    if constexpr (PAIR) tmem_dealloc_2sm(tmem_base, tmem_cols); else tmem_dealloc(tmem_base, tmem_cols);
+  }
 }
 
 using EncodeTiledFn3 = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -280,13 +328,14 @@ static int sg_tmap(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols
   return r == CUDA_SUCCESS ? 0 : -static_cast<int>(r);
 }
 
-template <bool FP8>
+template <bool FP8, bool PAIR>
 static int launch_stream(const void* X, const void* W, StreamParams p, int64_t ldx_bytes, int64_t ldw_bytes, cudaStream_t s) {
   constexpr int EB = FP8 ? 1 : 2;
+  constexpr int NC = PAIR ? 2 : 1;
   CUtensorMap tmW, tmX;
   if (sg_tmap(&tmW, W, p.N, p.K, ldw_bytes, 64, EB)) return -61;       // two 64-row boxes per stage (gate | up halves)
-  if (sg_tmap(&tmX, X, p.B, p.K, ldx_bytes, p.BP, EB)) return -62;
-  auto kern = stream_gemm_kernel<FP8>;
+  if (sg_tmap(&tmX, X, p.B, p.K, ldx_bytes, p.BP / NC, EB)) return -62;
+  auto kern = stream_gemm_kernel<FP8, PAIR>;
   static bool attr = false;
   const int smem = kSgSmemBudget + 1024 + 256;
   if (!attr) {
@@ -294,13 +343,13 @@ static int launch_stream(const void* X, const void* W, StreamParams p, int64_t l
     attr = true;
   }
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(p.tiles * p.S);
+  cfg.gridDim = dim3(p.tiles * p.S * NC);
   cfg.blockDim = dim3(kSgThreads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = s;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeClusterDimension;
-  at[0].val.clusterDim.x = p.S;
+  at[0].val.clusterDim.x = p.S * NC;
   at[0].val.clusterDim.y = 1;
   at[0].val.clusterDim.z = 1;
   cfg.attrs = at;
@@ -315,10 +364,11 @@ using namespace prl;
 
 // mode: 0 = store (+bias, +residual), 1 = SwiGLU (W block-interleaved [128 gate | 128 up] per 256 rows, out is [B, N/2]).
 // dtype: 0 = bf16, 1 = fp8 e4m3 (x_scale per batch row, w_scale per weight row required).
-// splits: cluster size S in 1..8 (0 = auto: the S that puts tiles x S CTAs closest to, but not above, one wave).
+// splits: k-splits S per cluster (0 = auto).  pair: 1 = CTA pairs (cta_group::2, 256 weight rows per MMA, bf16 only),
+// 0 = single CTAs, -1 = auto (pairs whenever the shape allows).
 extern "C" int prl_stream_gemm(const void* X, const void* W, void* out, const void* res, const void* bias, const float* x_scale,
                                const float* w_scale, int B, int N, int K, int64_t ldx, int64_t ldw, int64_t ldo, int mode,
-                               int dtype, int splits, cudaStream_t stream) {
+                               int dtype, int splits, int pair, cudaStream_t stream) {
   if (B <= 0 || B > 256) return -60;
   StreamParams p;
   {
@@ -337,27 +387,37 @@ extern "C" int prl_stream_gemm(const void* X, const void* W, void* out, const vo
   if (n_out % 8 != 0 || ldo % 8 != 0) return -65;
   const int block_k = dtype == 1 ? 128 : 64;
   const int num_kb = (K + block_k - 1) / block_k;
-  p.tiles = (N + 127) / 128;
+  const int tiles128 = (N + 127) / 128;
+  bool use_pair = pair == 1 || (pair < 0 && dtype == 0 && tiles128 % 2 == 0 && p.BP >= 32);
+  if (use_pair && (dtype != 0 || tiles128 % 2 != 0)) return -68;
+  const int NC = use_pair ? 2 : 1;
+  p.tiles = tiles128 / NC;
   int S = splits;
   if (S <= 0) {
-    // one wave of clusters: a cluster of S needs S SMs of one GPC, so count ~140 usable SMs for S >= 3
+    // one wave of clusters (a cluster needs all its SMs inside one GPC: count ~132 usable SMs beyond 2-CTA clusters), every
+    // split keeps >= 8 k-blocks
     S = 1;
-    for (int s = 2; s <= 8; ++s) {
-      const int usable = s <= 2 ? 148 : 140;
-      if (p.tiles * s <= usable && num_kb / s >= 8) S = s;
+    for (int s = 2; s * NC <= 8; ++s) {
+      const int usable = s * NC <= 2 ? 148 : 132;
+      if (p.tiles * s * NC <= usable && num_kb / s >= 8) S = s;
     }
   }
-  if (S > 8 || S > num_kb) return -66;
+  if (S * NC > 8 || S > num_kb) return -66;
   p.kb_per_split = (num_kb + S - 1) / S;
   if ((S - 1) * p.kb_per_split >= num_kb) return -67;              // every rank of the cluster must own >= 1 k-block
   p.S = S;
   {
     const char* e = getenv("PRL_STREAM_NACC");
-    int na = e ? atoi(e) : 4;
+    int na = e ? atoi(e) : 1;
     while (na > 1 && na * p.BP > 512) na >>= 1;
     p.nacc = (na == 1 || na == 2 || na == 4) ? na : 1;
   }
+  {
+    const char* e = getenv("PRL_STREAM_PF");                        // L2 prefetch distance in k-blocks (0 = off)
+    p.pf = e ? atoi(e) : 0;                        // measured: prefetching only adds traffic (profiles/r2_decode_gemm_experiments.md)
+  }
   const int eb = dtype == 1 ? 1 : 2;
-  return dtype == 1 ? launch_stream<true>(X, W, p, ldx * eb, ldw * eb, stream)
-                    : launch_stream<false>(X, W, p, ldx * eb, ldw * eb, stream);
+  if (use_pair) return launch_stream<false, true>(X, W, p, ldx * eb, ldw * eb, stream);
+  return dtype == 1 ? launch_stream<true, false>(X, W, p, ldx * eb, ldw * eb, stream)
+                    : launch_stream<false, false>(X, W, p, ldx * eb, ldw * eb, stream);
 }

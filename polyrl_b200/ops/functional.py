@@ -79,11 +79,16 @@ def _use_skinny(x2: torch.Tensor, w: torch.Tensor) -> bool:
 
 
 def skinny_linear(x2: torch.Tensor, w: torch.Tensor, bias=None, residual=None, mode: int = 0, splits: int = 0) -> torch.Tensor:
-    ws, ctr = _skinny_buffers(x2.device)
+    """Own decode-shape GEMM: the round-2 stream GEMM (cluster split-K + DSMEM reduce-scatter, csrc/decode_gemm.cu); the round-1
+    swap-AB kernel remains behind ``POLYRL_DECODE_GEMM_IMPL=skinny`` (it still backs the fused TP all-reduce epilogue)."""
     if x2.stride(-1) != 1 or x2.stride(0) % 8 != 0:
         x2 = x2.contiguous()
     if residual is not None and not residual.is_contiguous():
         residual = residual.contiguous()
+    n_out = w.shape[0] // 2 if mode == 1 else w.shape[0]
+    if os.environ.get("POLYRL_DECODE_GEMM_IMPL", "stream") == "stream" and n_out % 8 == 0:
+        return _C().stream_gemm(x2, w, residual, bias, None, None, mode, splits, None, -1)
+    ws, ctr = _skinny_buffers(x2.device)
     return _C().skinny_gemm(x2, w, residual, bias, None, None, ws, ctr, mode, splits)
 
 
@@ -128,8 +133,11 @@ def _linear_fp8(x: torch.Tensor, w: Fp8Weight, bias=None, residual=None, swiglu:
         xq, xs = quantize_fp8_rowwise(x)
         n = w.q.shape[0]
         if x.shape[0] <= _SKINNY_MAX_ROWS and n >= 128 and (not swiglu or n % 256 == 0):
-            wsb, ctr = _skinny_buffers(x.device)              # swap-AB split-K kernel: fp8 operands, fused scales/residual/SwiGLU
+            # stream GEMM: fp8 operands, fused scales / residual / SwiGLU, cluster split-K
             r = residual.contiguous() if residual is not None else None
+            if (n // 2 if swiglu else n) % 8 == 0 and os.environ.get("POLYRL_DECODE_GEMM_IMPL", "stream") == "stream":
+                return _C().stream_gemm(xq, w.q, r, bias, xs, w.scale, 1 if swiglu else 0, 0, None, 0)
+            wsb, ctr = _skinny_buffers(x.device)
             return _C().skinny_gemm(xq, w.q, r, bias, xs, w.scale, wsb, ctr, 1 if swiglu else 0, 0)
         y = _C().gemm_fp8(xq, w.q, xs, w.scale, 0)
     else:                                                       # CPU emulation: same quantisation, fp32 matmul

@@ -41,18 +41,23 @@ def main():
     ctr = torch.zeros(4096, device="cuda", dtype=torch.int32)
     ok = True
     # ---------------- correctness
-    for (B, N, K, mode, splits) in [(128, 4096, 4096, 0, 1), (128, 4096, 4096, 0, 4), (128, 6144, 4096, 0, 3),
-                                    (128, 4096, 14336, 0, 4), (64, 1024, 512, 0, 0), (7, 512, 256, 0, 2),
-                                    (200, 4096, 4096, 0, 2), (33, 1000, 4096, 0, 5), (128, 28672, 4096, 1, 1),
-                                    (96, 2048, 1024, 1, 3), (128, 128256, 1024, 0, 1), (256, 4096, 4096, 0, 8),
-                                    (128, 4096, 4096, 0, 0), (72, 2048, 2048, 1, 7)]:
+    for (B, N, K, mode, splits, pair) in [(128, 4096, 4096, 0, 1, 0), (128, 4096, 4096, 0, 4, 0), (128, 6144, 4096, 0, 3, 0),
+                                          (128, 4096, 14336, 0, 4, 0), (64, 1024, 512, 0, 0, 0), (7, 512, 256, 0, 2, 0),
+                                          (200, 4096, 4096, 0, 2, 0), (33, 1000, 4096, 0, 5, 0), (128, 28672, 4096, 1, 1, 0),
+                                          (96, 2048, 1024, 1, 3, 0), (128, 128256, 1024, 0, 1, 0), (256, 4096, 4096, 0, 8, 0),
+                                          (128, 4096, 4096, 0, 0, 0), (72, 2048, 2048, 1, 7, 0),
+                                          (128, 4096, 4096, 0, 1, 1), (128, 4096, 4096, 0, 4, 1), (128, 6144, 4096, 0, 2, 1),
+                                          (128, 4096, 14336, 0, 4, 1), (64, 1024, 512, 0, 1, 1), (40, 512, 256, 0, 2, 1),
+                                          (200, 4096, 4096, 0, 2, 1), (128, 28672, 4096, 1, 1, 1), (96, 2048, 1024, 1, 3, 1),
+                                          (128, 128256, 1024, 0, 1, 1), (256, 4096, 4096, 0, 4, 1), (128, 4096, 4096, 0, 0, -1),
+                                          (128, 28672, 4096, 1, 0, -1)]:
         torch.manual_seed(B + N)
         x = torch.randn(B, K, device="cuda", dtype=torch.bfloat16)
         w = (torch.randn(N, K, device="cuda") * 0.05).to(torch.bfloat16)
         n_out = N // 2 if mode else N
         r = torch.randn(B, n_out, device="cuda", dtype=torch.bfloat16) if not mode else None
         bias = torch.randn(N, device="cuda", dtype=torch.bfloat16) if not mode else None
-        got = C.stream_gemm(x, w, r, bias, None, None, mode, splits)
+        got = C.stream_gemm(x, w, r, bias, None, None, mode, splits, None, pair)
         torch.cuda.synchronize()
         z = x.float() @ w.float().t()
         if mode:
@@ -63,7 +68,7 @@ def main():
         e = rel_err(got, want)
         good = e < 6e-3
         ok &= good
-        print(json.dumps({"check": "stream_gemm", "B": B, "N": N, "K": K, "mode": mode, "splits": splits,
+        print(json.dumps({"check": "stream_gemm", "B": B, "N": N, "K": K, "mode": mode, "splits": splits, "pair": pair,
                           "rel_err": round(e, 5), "ok": bool(good)}), flush=True)
     print(json.dumps({"all_checks_ok": bool(ok)}), flush=True)
     if not ok or "--check" in sys.argv:
@@ -87,16 +92,17 @@ def main():
             rec["r1_kernel_ms"] = round(t_old, 4)
             best = None
             tiles = (N + 127) // 128
-            for splits in range(1, 9):
-                if tiles * splits > 296 and splits > 1:
-                    break
-                t = graph_time([(lambda w=w: C.stream_gemm(x, w, None, None, None, None, mode, splits)) for w in Ws])
-                rec[f"stream_s{splits}_ms"] = round(t, 4)
-                if best is None or t < best[0]:
-                    best = (t, splits)
-            t_auto = graph_time([(lambda w=w: C.stream_gemm(x, w, None, None, None, None, mode, 0)) for w in Ws])
+            for pair in (0, 1):
+                for splits in range(1, 9 if not pair else 5):
+                    if tiles * splits > 296 and splits > 1:
+                        break
+                    t = graph_time([(lambda w=w: C.stream_gemm(x, w, None, None, None, None, mode, splits, None, pair)) for w in Ws])
+                    rec[f"stream_{'pair' if pair else 'single'}_s{splits}_ms"] = round(t, 4)
+                    if best is None or t < best[0]:
+                        best = (t, splits, pair)
+            t_auto = graph_time([(lambda w=w: C.stream_gemm(x, w, None, None, None, None, mode, 0, None, -1)) for w in Ws])
             rec["stream_auto_ms"] = round(t_auto, 4)
-            rec["best"] = {"ms": round(best[0], 4), "splits": best[1]}
+            rec["best"] = {"ms": round(best[0], 4), "splits": best[1], "pair": best[2]}
             rec["best_GBps"] = round(N * K * 2 / best[0] / 1e6, 1)
             rec["best_hbm_frac_of_measured_6569.6"] = round(N * K * 2 / best[0] / 1e6 / 6569.6, 3)
             rec["cublas_hbm_frac_of_measured"] = round(N * K * 2 / t_l / 1e6 / 6569.6, 3)

@@ -387,6 +387,40 @@ def test_skinny_gemm(C, B, N, K, splits):
     assert int(ctr.abs().sum().item()) == 0
 
 
+@pytest.mark.parametrize("B,N,K,mode,splits,pair", [
+    (128, 4096, 4096, 0, 4, 0), (128, 6144, 4096, 0, 3, 0), (33, 1000, 4096, 0, 5, 0), (7, 512, 256, 0, 2, 0),
+    (96, 2048, 1024, 1, 3, 0), (128, 4096, 4096, 0, 4, 1), (40, 512, 256, 0, 2, 1), (96, 2048, 1024, 1, 3, 1),
+    (256, 4096, 4096, 0, 0, -1), (128, 28672, 1024, 1, 0, -1),
+])
+def test_stream_gemm_cluster_splitk(C, B, N, K, mode, splits, pair):
+    """Decode stream GEMM (cluster split-K, DSMEM reduce-scatter, single CTAs and CTA pairs) vs fp32 matmul."""
+    torch.manual_seed(22)
+    x = torch.randn(B, K, device="cuda", dtype=torch.bfloat16)
+    w = (torch.randn(N, K, device="cuda") * 0.05).to(torch.bfloat16)
+    z = x.float() @ w.float().t()
+    if mode:
+        got = C.stream_gemm(x, w, None, None, None, None, 1, splits, None, pair)
+        want = ref.swiglu(z.to(torch.bfloat16)).float() if False else (lambda g, u: torch.nn.functional.silu(g) * u)(*ref.split_gate_up(z))
+    else:
+        r = torch.randn(B, N, device="cuda", dtype=torch.bfloat16)
+        bias = torch.randn(N, device="cuda", dtype=torch.bfloat16)
+        got = C.stream_gemm(x, w, r, bias, None, None, 0, splits, None, pair)
+        want = z + bias.float() + r.float()
+    assert _rel_err(got, want) < 6e-3
+
+
+def test_stream_gemm_fp8(C):
+    torch.manual_seed(23)
+    B, N, K = 96, 2048, 1024
+    x = torch.randn(B, K, device="cuda", dtype=torch.bfloat16)
+    w = (torch.randn(N, K, device="cuda") * 0.05).to(torch.bfloat16)
+    xq, xs = C.quant_fp8_rowwise(x)
+    wq, wsc = C.quant_fp8_rowwise(w)
+    got = C.stream_gemm(xq, wq, None, None, xs, wsc, 0, 2, None, 0)
+    want = (xq.float() * xs[:, None]) @ (wq.float() * wsc[:, None]).t()
+    assert _rel_err(got, want) < 6e-3
+
+
 def test_skinny_gemm_swiglu_and_fp8(C):
     torch.manual_seed(21)
     B, F, K = 96, 2048, 1024
