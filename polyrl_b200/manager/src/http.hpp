@@ -1,19 +1,28 @@
-// Minimal HTTP/1.1 server (thread per connection, keep-alive, chunked streaming responses) and blocking
-// client (content-length / chunked bodies, incremental line callbacks for SSE / NDJSON).  POSIX sockets.
+// Minimal HTTP/1.1 server and blocking client (content-length / chunked bodies, incremental line callbacks for SSE / NDJSON).
+// Server: one epoll REACTOR thread owns the listening socket and every idle keep-alive connection (EPOLLONESHOT); a readable
+// connection is handed to a BOUNDED worker pool for exactly one request and re-armed afterwards, so idle connections cost no
+// thread and the thread count is bounded whatever the number of clients (reference: tokio/axum tasks,
+// rollout-manager/src/handlers.rs:442-564).  POSIX sockets + epoll.
 #pragma once
 #include <arpa/inet.h>
 #include <netdb.h>
 #include <netinet/in.h>
 #include <netinet/tcp.h>
 #include <poll.h>
+#include <pthread.h>
+#include <sys/epoll.h>
 #include <sys/socket.h>
 #include <unistd.h>
 
 #include <atomic>
 #include <cerrno>
+#include <condition_variable>
 #include <cstring>
+#include <deque>
 #include <functional>
 #include <map>
+#include <memory>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -36,6 +45,65 @@ inline bool send_all(int fd, const char* p, size_t n) {
   return true;
 }
 inline bool send_all(int fd, const std::string& s) { return send_all(fd, s.data(), s.size()); }
+
+// Bounded pool of worker threads with small stacks.  Threads are created lazily up to `max_threads` and never exceed it; work
+// beyond that queues.  Used for request handlers (bounded by --http-workers) and for the blocking per-request engine streams
+// (bounded by --max-inflight-requests) — the round-1 manager spawned one detached thread per request instead.
+class WorkerPool {
+ public:
+  explicit WorkerPool(size_t max_threads, size_t stack_bytes = 512 * 1024) : max_(max_threads ? max_threads : 1), stack_(stack_bytes) {}
+  ~WorkerPool() { shutdown(); }
+  void submit(std::function<void()> fn) {
+    std::unique_lock<std::mutex> lk(mu_);
+    q_.push_back(std::move(fn));
+    if (idle_ == 0 && threads_ < max_) {
+      ++threads_;
+      lk.unlock();
+      pthread_attr_t at;
+      pthread_attr_init(&at);
+      pthread_attr_setstacksize(&at, stack_);
+      pthread_attr_setdetachstate(&at, PTHREAD_CREATE_DETACHED);
+      pthread_t t;
+      if (pthread_create(&t, &at, &WorkerPool::entry, this) != 0) { std::lock_guard<std::mutex> g(mu_); --threads_; }
+      pthread_attr_destroy(&at);
+      lk.lock();
+    }
+    cv_.notify_one();
+  }
+  size_t threads() { std::lock_guard<std::mutex> g(mu_); return threads_; }
+  size_t peak_queue() { std::lock_guard<std::mutex> g(mu_); return peak_q_; }
+  void shutdown() {
+    std::unique_lock<std::mutex> lk(mu_);
+    stop_ = true;
+    cv_.notify_all();
+    done_.wait_for(lk, std::chrono::seconds(2), [&] { return threads_ == 0; });
+  }
+
+ private:
+  static void* entry(void* self) { static_cast<WorkerPool*>(self)->run(); return nullptr; }
+  void run() {
+    std::unique_lock<std::mutex> lk(mu_);
+    for (;;) {
+      ++idle_;
+      cv_.wait(lk, [&] { return stop_ || !q_.empty(); });
+      --idle_;
+      if (q_.empty()) break;                 // stop_ with nothing left to do
+      if (q_.size() > peak_q_) peak_q_ = q_.size();
+      auto fn = std::move(q_.front());
+      q_.pop_front();
+      lk.unlock();
+      try { fn(); } catch (...) {}
+      lk.lock();
+    }
+    --threads_;
+    done_.notify_all();
+  }
+  std::mutex mu_;
+  std::condition_variable cv_, done_;
+  std::deque<std::function<void()>> q_;
+  size_t max_, stack_, threads_ = 0, idle_ = 0, peak_q_ = 0;
+  bool stop_ = false;
+};
 
 // Buffered reader over a socket with an optional per-read timeout (ms; <0 = block forever).
 class SockReader {
@@ -82,6 +150,7 @@ class SockReader {
     compact();
     return 1;
   }
+  bool pending() const { return off_ < buf_.size(); }     // bytes of a pipelined request already buffered
   int read_some(std::string& out) {   // whatever is buffered, or one recv
     if (buf_.size() == off_) { int r = fill(); if (r != 1) return r; }
     out.assign(buf_, off_, std::string::npos);
@@ -138,9 +207,10 @@ using Handler = std::function<void(const HttpRequest&, HttpResponder&)>;
 
 class HttpServer {
  public:
+  explicit HttpServer(size_t workers = 64) : pool_(workers) {}
   void route(const std::string& method, const std::string& path, Handler h) { routes_[method + " " + path] = std::move(h); }
   bool listen(const std::string& host, int port) {
-    lfd_ = ::socket(AF_INET, SOCK_STREAM, 0);
+    lfd_ = ::socket(AF_INET, SOCK_STREAM | SOCK_NONBLOCK, 0);
     if (lfd_ < 0) return false;
     int one = 1;
     setsockopt(lfd_, SOL_SOCKET, SO_REUSEADDR, &one, sizeof one);
@@ -149,91 +219,137 @@ class HttpServer {
     a.sin_port = htons(static_cast<uint16_t>(port));
     a.sin_addr.s_addr = host.empty() || host == "0.0.0.0" ? INADDR_ANY : inet_addr(host.c_str());
     if (::bind(lfd_, reinterpret_cast<sockaddr*>(&a), sizeof a) < 0) return false;
-    if (::listen(lfd_, 1024) < 0) return false;
+    if (::listen(lfd_, 4096) < 0) return false;
     socklen_t len = sizeof a;
     getsockname(lfd_, reinterpret_cast<sockaddr*>(&a), &len);
     port_ = ntohs(a.sin_port);
-    return true;
+    ep_ = ::epoll_create1(0);
+    if (ep_ < 0) return false;
+    epoll_event ev{};
+    ev.events = EPOLLIN;
+    ev.data.ptr = nullptr;                      // nullptr = the listening socket
+    return ::epoll_ctl(ep_, EPOLL_CTL_ADD, lfd_, &ev) == 0;
   }
   int port() const { return port_; }
+  size_t worker_threads() { return pool_.threads(); }
+  size_t open_connections() { std::lock_guard<std::mutex> g(mu_); return conns_.size(); }
+  // Reactor: accepts, and dispatches every connection that becomes readable to the worker pool for ONE request.
   void serve_forever() {
+    std::vector<epoll_event> evs(256);
     while (!stop_.load()) {
-      pollfd p{lfd_, POLLIN, 0};
-      int r = ::poll(&p, 1, 200);
-      if (r <= 0) continue;
-      int fd = ::accept(lfd_, nullptr, nullptr);
-      if (fd < 0) continue;
-      int one = 1;
-      setsockopt(fd, IPPROTO_TCP, TCP_NODELAY, &one, sizeof one);
-      std::thread([this, fd] { this->handle_conn(fd); }).detach();
+      int n = ::epoll_wait(ep_, evs.data(), static_cast<int>(evs.size()), 200);
+      for (int i = 0; i < n; ++i) {
+        if (evs[i].data.ptr == nullptr) {
+          for (;;) {
+            int fd = ::accept4(lfd_, nullptr, nullptr, SOCK_CLOEXEC);
+            if (fd < 0) break;
+            int one = 1;
+            setsockopt(fd, IPPROTO_TCP, TCP_NODELAY, &one, sizeof one);
+            auto c = std::make_shared<Conn>(fd);
+            { std::lock_guard<std::mutex> g(mu_); conns_[fd] = c; }
+            arm(c.get(), EPOLL_CTL_ADD);
+          }
+        } else {
+          Conn* raw = static_cast<Conn*>(evs[i].data.ptr);
+          std::shared_ptr<Conn> c;
+          { std::lock_guard<std::mutex> g(mu_); auto it = conns_.find(raw->fd); if (it != conns_.end() && it->second.get() == raw) c = it->second; }
+          if (c) pool_.submit([this, c] { this->serve_ready(c); });
+        }
+      }
     }
-    ::close(lfd_);
+    // lfd_ / ep_ stay open: workers may still be finishing a request (epoll_ctl on ep_) while the process winds down —
+    // the ThreadSanitizer build flags closing them here as a race; main() leaves through _exit()
   }
   void stop() { stop_.store(true); }
 
  private:
-  void handle_conn(int fd) {
-    SockReader rd(fd, 300000);
+  struct Conn {
+    explicit Conn(int f) : fd(f), rd(f, 300000) {}
+    int fd;
+    SockReader rd;
+  };
+  void arm(Conn* c, int op) {
+    epoll_event ev{};
+    ev.events = EPOLLIN | EPOLLRDHUP | EPOLLONESHOT;        // one-shot: exactly one worker owns the connection at a time
+    ev.data.ptr = c;
+    ::epoll_ctl(ep_, op, c->fd, &ev);
+  }
+  void drop(const std::shared_ptr<Conn>& c) {
+    ::epoll_ctl(ep_, EPOLL_CTL_DEL, c->fd, nullptr);
+    { std::lock_guard<std::mutex> g(mu_); conns_.erase(c->fd); }
+    ::close(c->fd);
+  }
+  void serve_ready(const std::shared_ptr<Conn>& c) {
     for (;;) {
-      HttpRequest req;
-      std::string line;
-      if (rd.read_line(line) != 1) break;
-      if (line.empty()) continue;
-      size_t s1 = line.find(' '), s2 = line.rfind(' ');
-      if (s1 == std::string::npos || s2 == s1) break;
-      req.method = line.substr(0, s1);
-      std::string target = line.substr(s1 + 1, s2 - s1 - 1);
-      size_t q = target.find('?');
-      req.path = q == std::string::npos ? target : target.substr(0, q);
-      req.query = q == std::string::npos ? "" : target.substr(q + 1);
-      bool ok = true;
-      for (;;) {
-        if (rd.read_line(line) != 1) { ok = false; break; }
-        if (line.empty()) break;
-        size_t c = line.find(':');
-        if (c == std::string::npos) continue;
-        std::string k = lower(line.substr(0, c));
-        size_t v = c + 1;
-        while (v < line.size() && line[v] == ' ') ++v;
-        req.headers[k] = line.substr(v);
-      }
-      if (!ok) break;
-      auto te = req.headers.find("transfer-encoding");
-      if (te != req.headers.end() && lower(te->second).find("chunked") != std::string::npos) {
-        for (;;) {
-          if (rd.read_line(line) != 1) { ok = false; break; }
-          size_t n = strtoul(line.c_str(), nullptr, 16);
-          if (n == 0) { rd.read_line(line); break; }
-          std::string part;
-          if (rd.read_exact(n, part) != 1) { ok = false; break; }
-          req.body += part;
-          rd.read_line(line);
-        }
-      } else {
-        auto cl = req.headers.find("content-length");
-        size_t n = cl == req.headers.end() ? 0 : strtoul(cl->second.c_str(), nullptr, 10);
-        if (n > 0 && rd.read_exact(n, req.body) != 1) ok = false;
-      }
-      if (!ok) break;
-      HttpResponder resp(fd);
-      auto it = routes_.find(req.method + " " + req.path);
-      if (it == routes_.end()) {
-        resp.send(404, "{\"error\":\"not found\"}");
-      } else {
-        try {
-          it->second(req, resp);
-        } catch (const std::exception& e) {
-          if (!resp.sent()) resp.send(500, std::string("{\"error\":\"") + e.what() + "\"}");
-        }
-        if (!resp.sent()) resp.send(500, "{\"error\":\"handler produced no response\"}");
-      }
-      auto conn = req.headers.find("connection");
-      if (conn != req.headers.end() && lower(conn->second) == "close") break;
+      const int rc = handle_one(*c);
+      if (rc != 1) { drop(c); return; }
+      if (!c->rd.pending()) break;              // pipelined request already buffered: serve it now
     }
-    ::close(fd);
+    arm(c.get(), EPOLL_CTL_MOD);                // idle again: back to the reactor
+  }
+  // returns 1 = request served, keep the connection; 0 = close
+  int handle_one(Conn& c) {
+    SockReader& rd = c.rd;
+    const int fd = c.fd;
+    HttpRequest req;
+    std::string line;
+    do {
+      if (rd.read_line(line) != 1) return 0;
+    } while (line.empty());
+    size_t s1 = line.find(' '), s2 = line.rfind(' ');
+    if (s1 == std::string::npos || s2 == s1) return 0;
+    req.method = line.substr(0, s1);
+    std::string target = line.substr(s1 + 1, s2 - s1 - 1);
+    size_t q = target.find('?');
+    req.path = q == std::string::npos ? target : target.substr(0, q);
+    req.query = q == std::string::npos ? "" : target.substr(q + 1);
+    for (;;) {
+      if (rd.read_line(line) != 1) return 0;
+      if (line.empty()) break;
+      size_t cpos = line.find(':');
+      if (cpos == std::string::npos) continue;
+      std::string k = lower(line.substr(0, cpos));
+      size_t v = cpos + 1;
+      while (v < line.size() && line[v] == ' ') ++v;
+      req.headers[k] = line.substr(v);
+    }
+    auto te = req.headers.find("transfer-encoding");
+    if (te != req.headers.end() && lower(te->second).find("chunked") != std::string::npos) {
+      for (;;) {
+        if (rd.read_line(line) != 1) return 0;
+        size_t n = strtoul(line.c_str(), nullptr, 16);
+        if (n == 0) { rd.read_line(line); break; }
+        std::string part;
+        if (rd.read_exact(n, part) != 1) return 0;
+        req.body += part;
+        rd.read_line(line);
+      }
+    } else {
+      auto cl = req.headers.find("content-length");
+      size_t n = cl == req.headers.end() ? 0 : strtoul(cl->second.c_str(), nullptr, 10);
+      if (n > 0 && rd.read_exact(n, req.body) != 1) return 0;
+    }
+    HttpResponder resp(fd);
+    auto it = routes_.find(req.method + " " + req.path);
+    if (it == routes_.end()) {
+      resp.send(404, "{\"error\":\"not found\"}");
+    } else {
+      try {
+        it->second(req, resp);
+      } catch (const std::exception& e) {
+        if (!resp.sent()) resp.send(500, std::string("{\"error\":\"") + e.what() + "\"}");
+      }
+      if (!resp.sent()) resp.send(500, "{\"error\":\"handler produced no response\"}");
+    }
+    auto conn = req.headers.find("connection");
+    if (conn != req.headers.end() && lower(conn->second) == "close") return 0;
+    return 1;
   }
   std::map<std::string, Handler> routes_;
-  int lfd_ = -1, port_ = 0;
+  WorkerPool pool_;
+  std::mutex mu_;
+  std::map<int, std::shared_ptr<Conn>> conns_;
+  int lfd_ = -1, ep_ = -1, port_ = 0;
   std::atomic<bool> stop_{false};
 };
 

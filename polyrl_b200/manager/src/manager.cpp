@@ -69,6 +69,7 @@ class AppState {
   LoadBalanceState balance;
   std::atomic<uint64_t> latest_weight_version{0};
   std::atomic<bool> shutting_down{false};
+  WorkerPool* gen_pool = nullptr;          // bounded pool for the blocking per-request engine streams (set in main)
 
   explicit AppState(const ManagerConfig& c) : cfg(c), balance(c.initial_local_gen_s) {}
 
@@ -478,10 +479,15 @@ static void install_routes(HttpServer& srv, AppState& st) {
   srv.route("POST", "/batch_generate_requests", [&](const HttpRequest& req, HttpResponder& rsp) {
     Json b;
     if (!Json::try_parse(req.body, b) || !b.is_array() || b.size() == 0) { rsp.send(400, err_json("no requests provided").dump()); return; }
+    struct Line {
+      std::string text;
+      Clock::time_point when;
+      size_t tokens = 0, subs = 0;             // counted once, where the result object still exists (no re-parse of the line)
+    };
     struct Shared {
       std::mutex mu;
       std::condition_variable cv;
-      std::deque<std::pair<std::string, Clock::time_point>> results;
+      std::deque<Line> results;
       size_t finished = 0;
     };
     auto sh = std::make_shared<Shared>();
@@ -490,11 +496,14 @@ static void install_routes(HttpServer& srv, AppState& st) {
     for (auto& item : b.arr()) {
       int64_t id = item[static_cast<size_t>(0)].as_int();
       Json body = item[static_cast<size_t>(1)];
-      std::thread([&st, sh, id, body] {
+      st.gen_pool->submit([&st, sh, id, body] {
         Json out, line = Json::object();
         GenError e;
         line["id"] = id;
+        Line res;
         if (process_single_generate_request(st, body, out, e)) {
+          res.tokens = count_output_tokens(out, true);
+          res.subs = out.is_array() ? out.size() : 1;
           line["success"] = true;
           line["data"] = out;
         } else {
@@ -506,10 +515,11 @@ static void install_routes(HttpServer& srv, AppState& st) {
           if (!e.partial.is_null()) eo["partial_response"] = e.partial;
           line["error"] = eo;
         }
-        std::string s = line.dump() + "\n";
-        { std::lock_guard<std::mutex> g(sh->mu); sh->results.emplace_back(std::move(s), Clock::now()); ++sh->finished; }
+        res.text = line.dump() + "\n";
+        res.when = Clock::now();
+        { std::lock_guard<std::mutex> g(sh->mu); sh->results.push_back(std::move(res)); ++sh->finished; }
         sh->cv.notify_all();
-      }).detach();
+      });
     }
     // ---- time-boxed local generation window
     const uint64_t max_gen_s = st.balance.max_local_gen_s();
@@ -533,20 +543,17 @@ static void install_routes(HttpServer& srv, AppState& st) {
     size_t sent = 0, total_tokens = 0, total_sub = 0;
     Clock::time_point latest = t_start;
     while (sent < total) {
-      std::pair<std::string, Clock::time_point> item;
+      Line item;
       {
         std::unique_lock<std::mutex> lk(sh->mu);
         sh->cv.wait(lk, [&] { return !sh->results.empty(); });
         item = std::move(sh->results.front());
         sh->results.pop_front();
       }
-      latest = std::max(latest, item.second);
-      Json parsed;
-      if (Json::try_parse(item.first, parsed) && parsed["success"].as_bool()) {
-        total_tokens += count_output_tokens(parsed["data"], true);
-        total_sub += parsed["data"].is_array() ? parsed["data"].size() : 1;
-      }
-      if (!rsp.write_chunk(item.first)) break;    // client went away
+      latest = std::max(latest, item.when);
+      total_tokens += item.tokens;
+      total_sub += item.subs;
+      if (!rsp.write_chunk(item.text)) break;    // client went away
       ++sent;
     }
     rsp.end_stream();
@@ -726,6 +733,7 @@ int main(int argc, char** argv) {
   std::string config_file;
   std::vector<std::string> cli_endpoints;
   int cli_max_assigned = -1;
+  int http_workers = 64, max_inflight = 2048;
   std::string cli_device, cli_proto, cli_bind;
   for (int i = 1; i < argc; ++i) {
     std::string a = argv[i];
@@ -740,6 +748,8 @@ int main(int argc, char** argv) {
     else if (a == "--stats-interval-ms") { std::string v; val(v); cfg.stats_interval_ms = atoi(v.c_str()); }
     else if (a == "--health-interval-ms") { std::string v; val(v); cfg.health_interval_ms = atoi(v.c_str()); }
     else if (a == "--wait-full-local-window") cfg.wait_full_local_window = true;
+    else if (a == "--http-workers") { std::string v; val(v); http_workers = std::max(4, atoi(v.c_str())); }
+    else if (a == "--max-inflight-requests") { std::string v; val(v); max_inflight = std::max(8, atoi(v.c_str())); }
     else if (a == "--log-level") { std::string v; val(v); g_log_level = v == "debug" ? 2 : (v == "error" ? 0 : 1); }
     else if (a == "--help" || a == "-h") {
       printf("rollout-manager [--config-file F] [--bind-addr H:P] [--weight-sender-rpyc-endpoints E...] "
@@ -768,7 +778,9 @@ int main(int argc, char** argv) {
   int port = 5000;
   if (!split_host_port(cfg.bind_addr, host, port) && cfg.bind_addr.find(':') == std::string::npos) host = cfg.bind_addr;
   AppState state(cfg);
-  HttpServer srv;
+  WorkerPool gen_pool(static_cast<size_t>(max_inflight));      // blocking engine streams: bounded, queued beyond the bound
+  state.gen_pool = &gen_pool;
+  HttpServer srv(static_cast<size_t>(http_workers));
   install_routes(srv, state);
   if (!srv.listen(host, port)) { logf(0, "cannot bind %s", cfg.bind_addr.c_str()); return 1; }
   g_srv = &srv;

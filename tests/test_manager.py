@@ -233,3 +233,52 @@ def test_thread_sanitizer_build_is_race_free(tmp_path):
         m.close(); bad.stop(); good.stop(); log.close()
     report = (tmp_path / "tsan.log").read_text()
     assert "ThreadSanitizer" not in report, report[:4000]
+
+
+def _thread_count(pid: int) -> int:
+    with open(f"/proc/{pid}/status") as f:
+        for line in f:
+            if line.startswith("Threads:"):
+                return int(line.split()[1])
+    return -1
+
+
+def test_scale_1024_groups_8_engines_bounded_threads_and_kill_mid_stream(manager_bin):
+    """Reactor + bounded pools at the scale SURVEY 7.4(7) asks for: 1024 request groups over 8 engines, one engine crashing
+    mid-stream (its partials must continue elsewhere), while the manager's thread count stays under the configured bound
+    (round 1 spawned one detached thread per request: > 1024 threads here)."""
+    import threading
+
+    m = Manager(manager_bin, "--max-inflight-requests", "96", "--http-workers", "16", "--max-assigned-batches-per-stats-check", "4096")
+    engines = [FakeEngine(token_delay_s=0.0005, stream_interval=8) for _ in range(7)] + [FakeEngine(token_delay_s=0.0005, die_after_tokens=6)]
+    peak = [0]
+    stop = threading.Event()
+
+    def watch():
+        while not stop.is_set():
+            peak[0] = max(peak[0], _thread_count(m.p.pid))
+            time.sleep(0.02)
+
+    try:
+        assert _http("POST", m.url + "/register_local_rollout_instances", [["127.0.0.1", e.port] for e in engines])[0] == 200
+        threading.Thread(target=watch, daemon=True).start()
+        reqs = [[i + 1, {"input_ids": [[3, i % 97, i // 97]] * 2, "sampling_params": {"max_new_tokens": 10}}] for i in range(1024)]
+        res = _batch(m, reqs, timeout=300)
+        stop.set()
+        assert len(res) == 1024
+        ok = 0
+        for i in range(1024):
+            r = res[i + 1]
+            assert r["success"], r
+            for sub in r["data"]:
+                assert _tokens(sub) == reference_generation([3, i % 97, i // 97], 10)
+            ok += 1
+        assert ok == 1024
+        # reactor (1) + stats worker + main + <= 16 handler workers + <= 96 stream workers + health checks
+        assert 0 < peak[0] <= 16 + 96 + 24, peak[0]
+        assert engines[-1].generate_calls > 0                           # the dying engine did take work before it was evicted
+    finally:
+        stop.set()
+        m.close()
+        for e in engines:
+            e.stop()
