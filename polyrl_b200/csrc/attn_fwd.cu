@@ -303,6 +303,7 @@ static EncodeTiledFn4 af_encode_fn() {
 }
 // rows x cols bf16 matrix with row pitch ld_bytes; box = 64 columns (128 B) x box_rows rows, 128B swizzle
 int af_tmap(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld_bytes, uint32_t box_rows) {
+  ensure_thread_ctx();
   auto fn = af_encode_fn();
   if (!fn) return -1;
   cuuint64_t gdim[2] = {cols, rows};

@@ -133,8 +133,12 @@ at::Tensor gemm2_bf16(const at::Tensor& a, const at::Tensor& b, bool a_mn, bool 
     TORCH_CHECK(residual->sizes() == d.sizes() && residual->stride(0) == d.stride(0) && residual->stride(1) == 1);
     r = residual->data_ptr();
   }
-  check(prl_gemm2_bf16(a.data_ptr(), b.data_ptr(), d.data_ptr(), r, M, N, K, a.stride(0), b.stride(0), d.stride(0),
-                       a_mn ? 1 : 0, b_mn ? 1 : 0, static_cast<int>(force_bn), cur_stream()), "gemm2_bf16");
+  TORCH_CHECK(a.stride(0) >= a.size(1) && b.stride(0) >= b.size(1), "gemm2_bf16: row pitch shorter than the row");
+  const int rc = prl_gemm2_bf16(a.data_ptr(), b.data_ptr(), d.data_ptr(), r, M, N, K, a.stride(0), b.stride(0), d.stride(0),
+                                a_mn ? 1 : 0, b_mn ? 1 : 0, static_cast<int>(force_bn), cur_stream());
+  TORCH_CHECK(rc == 0, "polyrl_b200 kernel 'gemm2_bf16' failed with code ", rc, " (M=", M, " N=", N, " K=", K, " a_mn=", a_mn,
+              " b_mn=", b_mn, " lda=", a.stride(0), " ldb=", b.stride(0), " ldd=", d.stride(0), " a=", a.data_ptr(), " b=",
+              b.data_ptr(), " dev=", a.get_device(), ")");
   return d;
 }
 

@@ -344,6 +344,16 @@ __device__ __forceinline__ float2 unpack_bf16(uint32_t u) {
 
 }  // namespace prl
 
+// cuTensorMapEncodeTiled is a driver call and needs a context bound to the calling thread.  A fresh thread (an autograd worker
+// whose first op is one of our GEMMs on a cached buffer) has made no runtime call yet, so bind the primary context once.
+inline void ensure_thread_ctx() {
+  static thread_local bool bound = false;
+  if (!bound) {
+    cudaFree(nullptr);
+    bound = true;
+  }
+}
+
 #define PRL_CUDA_CHECK(x)                                                                          \
   do {                                                                                             \
     cudaError_t e__ = (x);                                                                         \

@@ -261,8 +261,12 @@ inline EncodeTiledFn get_encode_fn() {
 // 2-D K-major operand: `rows` x `cols` elements, row pitch `ld_bytes`; box = 128 bytes x box_rows.
 inline int make_tmap_kmajor(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld_bytes,
                             uint32_t box_rows, int elem_bytes) {
+  ensure_thread_ctx();
   EncodeTiledFn fn = get_encode_fn();
-  if (!fn) return -1;
+  if (!fn) {
+    fprintf(stderr, "[prl] cuTensorMapEncodeTiled entry point not found\n");
+    return -1;
+  }
   cuuint64_t gdim[2] = {cols, rows};
   cuuint64_t gstride[1] = {ld_bytes};
   cuuint32_t box[2] = {static_cast<cuuint32_t>(128 / elem_bytes), box_rows};
@@ -270,6 +274,10 @@ inline int make_tmap_kmajor(CUtensorMap* m, const void* ptr, uint64_t rows, uint
   CUtensorMapDataType dt = elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_UINT8;
   CUresult r = fn(m, dt, 2, const_cast<void*>(ptr), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    fprintf(stderr, "[prl] cuTensorMapEncodeTiled -> %d (ptr=%p rows=%llu cols=%llu ld_bytes=%llu box_rows=%u elem=%d)\n",
+            static_cast<int>(r), ptr, static_cast<unsigned long long>(rows), static_cast<unsigned long long>(cols),
+            static_cast<unsigned long long>(ld_bytes), box_rows, elem_bytes);
   return r == CUDA_SUCCESS ? 0 : -static_cast<int>(r);
 }
 

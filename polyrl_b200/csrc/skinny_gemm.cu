@@ -268,6 +268,7 @@ static EncodeTiledFn2 sk_encode_fn() {
   return fn;
 }
 static int sk_tmap(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld_bytes, uint32_t box_rows, int eb) {
+  ensure_thread_ctx();
   auto fn = sk_encode_fn();
   if (!fn) return -1;
   cuuint64_t gdim[2] = {cols, rows};

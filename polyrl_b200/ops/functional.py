@@ -24,7 +24,7 @@ def _is_kernel_tensor(x: torch.Tensor) -> bool:
 
 def _g2_operand(t: torch.Tensor) -> torch.Tensor:
     """Operand of the CTA-pair GEMM family: unit inner stride, row pitch a multiple of 8 elements, 16-byte aligned base."""
-    if t.stride(-1) != 1 or t.stride(0) % 8 != 0 or t.data_ptr() % 16 != 0:
+    if t.stride(-1) != 1 or t.stride(0) % 8 != 0 or t.stride(0) < t.shape[-1] or t.data_ptr() % 16 != 0:
         t = t.contiguous()
     return t
 

@@ -39,7 +39,8 @@ def main():
     assert torch.equal(y, want)
 
     assert local_expert_range(cfg, world, rank) == (2 * rank, 2 * rank + 2)
-    eng = EPTrainEngine(cfg, dev, dist.group.WORLD, lr=1e-2, weight_decay=0.0, seed=11)
+    lr = 1e-3 if cuda else 1e-2
+    eng = EPTrainEngine(cfg, dev, dist.group.WORLD, lr=lr, weight_decay=0.0, seed=11)
     assert eng.master["layers.0.ewgu"].shape[0] == 2 and eng.master["layers.0.router"].shape[0] == 8
 
     def batch(r: int, step: int):
@@ -53,6 +54,12 @@ def main():
     w = TransformerWeights(cfg, device=dev, dtype=torch.float32, init=False)
     w.load_state_dict({n: t.to(dev) for n, t in w_cpu.state_dict().items()})
     params = {n: t.requires_grad_(True) for n, t in w.named_tensors()}
+    # On the GPU the oracle runs the same bf16 kernels from a bf16 copy of its fp32 master weights (what the engine does), without
+    # expert parallelism: the comparison then isolates dispatch / combine / gradient reduction from bf16-vs-fp32 rounding.
+    cw = w
+    if cuda:
+        cw = TransformerWeights(cfg, device=dev, dtype=torch.bfloat16, init=False)
+    cparams = {n: t.requires_grad_(True) for n, t in cw.named_tensors()} if cuda else params
     m = {n: torch.zeros_like(t) for n, t in params.items()}
     v = {n: torch.zeros_like(t) for n, t in params.items()}
     lp_err = gn_err = 0.0
@@ -61,30 +68,44 @@ def main():
         lp, ent = eng.forward_logprob_entropy(inp, labels, 1.0)
         (-(lp.mean()) + 0.01 * ent.mean()).backward()
         st = eng.step()
-        for p in params.values():
+        for p in cparams.values():
             p.grad = None
+        if cuda:
+            with torch.no_grad():
+                for n, p in cparams.items():
+                    p.copy_(params[n])
         mine = None
         for r in range(world):
             ri, rl = batch(r, step)
-            h = tf.forward_hidden(cfg, w, ri)
-            rlp, rent = ref.linear_cross_entropy(h, tf.lm_head_weight(cfg, w.head, w.embed), rl, 1.0)
+            h = tf.forward_hidden(cfg, cw, ri)
+            if cuda:
+                from polyrl_b200 import ops
+                rlp, rent = ops.linear_cross_entropy(h, tf.lm_head_weight(cfg, cw.head, cw.embed), rl, 1.0)
+            else:
+                rlp, rent = ref.linear_cross_entropy(h, tf.lm_head_weight(cfg, cw.head, cw.embed), rl, 1.0)
             ((-(rlp.mean()) + 0.01 * rent.mean()) / world).backward()
             if r == rank:
-                mine = rlp.detach()
-        gn = torch.sqrt(sum(p.grad.pow(2).sum() for p in params.values())).item()
+                mine = rlp.detach().float()
+        grads = {n: cparams[n].grad.float() for n in params}
+        gn = torch.sqrt(sum(g.pow(2).sum() for g in grads.values())).item()
         coef = min(1.0, 1.0 / (gn + 1e-6))
         with torch.no_grad():
             for n, p in params.items():
-                ref.adamw_step(p, m[n], v[n], p.grad, 1e-2, 0.9, 0.999, 1e-8, 0.0, step + 1, coef)
+                ref.adamw_step(p, m[n], v[n], grads[n], lr, 0.9, 0.999, 1e-8, 0.0, step + 1, coef)
         lp_err = max(lp_err, (lp.detach().float() - mine).abs().max().item())
         gn_err = max(gn_err, abs(st["grad_norm"] - gn))
     got = eng.gather_full_state()
     want = {n: t.detach() for n, t in w.named_tensors()}
     assert set(got) == set(want)
-    w_err = max(((got[n] - want[n]).norm() / (want[n].norm() + 1e-9)).item() for n in want)
+    errs = {n: ((got[n].float() - want[n]).norm() / (want[n].norm() + 1e-9)).item() for n in want}
+    worst = max(errs, key=errs.get)
+    w_err = errs[worst]
     t = torch.tensor([lp_err, gn_err, w_err], device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    tol = (0.2, 5e-2, 0.1) if cuda else (1e-4, 1e-4, 2e-3)            # bf16 kernels vs the fp32 oracle (routing may flip near ties)
+    # GPU: same-precision oracle; what is left is summation order (atomics, all-reduce) and Adam amplifying it where |g| ~ noise
+    tol = (0.2, 2e-2, 0.05) if cuda else (1e-4, 1e-4, 2e-3)
+    if rank == 0:
+        print(f"EP_TRAIN lp_err={t[0]:.3e} gn_err={t[1]:.3e} w_err={t[2]:.3e} worst={worst}", flush=True)
     assert t[0] < tol[0] and t[1] < tol[1] and t[2] < tol[2], t
     if rank == 0:
         print(f"EP_TRAIN_OK lp_err={t[0]:.2e} gn_err={t[1]:.2e} w_err={t[2]:.2e}", flush=True)

@@ -70,6 +70,31 @@ def test_gemm2_cta_pair_layouts(C, a_mn, b_mn, M, N, K, bn, res):
     assert _rel_err(d, want) < 5e-3
 
 
+def test_gemm2_from_fresh_thread(C):
+    """Tensor-map encode is a driver call: a thread that has made no CUDA runtime call yet (an autograd worker whose first op is
+    one of our GEMMs writing into a cached buffer) must still be able to launch."""
+    import threading
+
+    a = torch.randn(160, 512, device="cuda", dtype=torch.bfloat16)
+    b = torch.randn(512, 1024, device="cuda", dtype=torch.bfloat16)
+    out = torch.empty(160, 1024, device="cuda", dtype=torch.bfloat16)
+    torch.cuda.synchronize()
+    err: list = []
+
+    def run():
+        try:
+            C.gemm2_bf16(a, b, False, True, None, out, 0)
+        except Exception as e:            # noqa: BLE001
+            err.append(e)
+
+    t = threading.Thread(target=run)
+    t.start()
+    t.join()
+    torch.cuda.synchronize()
+    assert not err, err
+    assert _rel_err(out, a.float() @ b.float()) < 5e-3
+
+
 def test_gemm2_accum_f32(C):
     torch.manual_seed(5)
     M, N, K = 520, 392, 1032
