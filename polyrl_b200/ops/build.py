@@ -48,6 +48,9 @@ NVCC_FLAGS = [
 ]
 
 
+LAST_BUILD: dict = {}          # what the last build() call did (clean / incremental / up-to-date), printed by __graft_entry__.build()
+
+
 def _nvcc() -> str:
     cuda_home = os.environ.get("CUDA_HOME", "/usr/local/cuda")
     return str(Path(cuda_home) / "bin" / "nvcc")
@@ -97,9 +100,16 @@ def build(force: bool = False, verbose: bool = False) -> Path:
             "g++", "-O2", "-std=c++17", "-fPIC", "-DTORCH_EXTENSION_NAME=_C", "-DTORCH_API_INCLUDE_EXTENSION_H",
             f"-D_GLIBCXX_USE_CXX11_ABI={int(torch._C._GLIBCXX_USE_CXX11_ABI)}", *inc, "-c", str(bsrc), "-o", str(bobj),
         ])
+    import time
+
+    t0 = time.time()
     if jobs:
         with cf.ThreadPoolExecutor(max_workers=min(8, len(jobs))) as ex:
             list(ex.map(lambda c: _run(c, verbose), jobs))
+    global LAST_BUILD
+    LAST_BUILD = {"build_mode": "clean" if len(jobs) == len(objs) else ("incremental" if jobs else "up-to-date"),
+                  "objects_compiled": len(jobs), "objects_total": len(objs), "compile_s": round(time.time() - t0, 1),
+                  "arch": "compute_100a/sm_100a", "nvcc_flags": NVCC_FLAGS}
     if jobs or force or not OUT.exists():
         lib_dirs = ce.library_paths("cuda") if "device_type" in ce.library_paths.__code__.co_varnames else ce.library_paths(True)
         tmp_out = OUT.with_suffix(".so.tmp")           # link next to the target, then rename: readers never see a half-written .so
@@ -118,6 +128,9 @@ def main() -> None:
     ap.add_argument("--verbose", action="store_true")
     a = ap.parse_args()
     print(build(a.force, a.verbose))
+    import json
+
+    print(json.dumps(LAST_BUILD))
 
 
 if __name__ == "__main__":
