@@ -33,6 +33,34 @@ def _g2_ok(*dims: int) -> bool:
     return all(d % 8 == 0 for d in dims)
 
 
+# ---- gradient sink: weight gradients written by the wgrad GEMM straight into caller-provided storage ----
+# The ZeRO engine registers, per weight of the unit whose backward is about to run, a view of the symmetric reduce-scatter slot
+# (parallel/zero3.py::_UnitFn.backward).  The wgrad GEMM's TMA store then lands in the buffer the peers will read: no staging
+# copy of the unit's gradients (2 x 16 GB of HBM traffic per micro-batch for an 8B model).
+_GRAD_SINK: dict[int, torch.Tensor] = {}
+
+
+class grad_sink:
+    def __init__(self, mapping: dict[int, torch.Tensor]):
+        self.mapping = mapping
+
+    def __enter__(self):
+        _GRAD_SINK.update(self.mapping)
+        return self
+
+    def __exit__(self, *exc):
+        for k in self.mapping:
+            _GRAD_SINK.pop(k, None)
+        return False
+
+
+def _sink_for(w: torch.Tensor) -> torch.Tensor | None:
+    if not _GRAD_SINK:
+        return None
+    t = _GRAD_SINK.get(w.data_ptr())
+    return t if t is not None and t.shape == w.shape and t.dtype == w.dtype else None
+
+
 def mm_nn(dy: torch.Tensor, w: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
     """dgrad: ``dy[M, N] @ w[N, K]`` -> [M, K].  ``w`` is consumed as an MN-major tcgen05 operand (no transpose copy)."""
     if _cublas() or not (_is_kernel_tensor(dy) and w.dtype == torch.bfloat16 and _g2_ok(dy.shape[1], w.shape[1])):
@@ -181,7 +209,7 @@ class _LinearFn(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             dx = mm_nn(dy2, w).reshape(ctx.x_shape)
         if ctx.needs_input_grad[1]:
-            dw = mm_tn(dy2, x2)
+            dw = mm_tn(dy2, x2, out=_sink_for(w))
         if ctx.has_res and ctx.needs_input_grad[2]:
             dres = dy
         return dx, dw, dres
@@ -236,7 +264,7 @@ class _LinearSwigluFn(torch.autograd.Function):
         dh2 = dh.reshape(-1, dh.shape[-1]).contiguous()
         dgu = _C().swiglu_bwd(gu, dh2)
         dx = mm_nn(dgu, wgu).reshape(ctx.x_shape) if ctx.needs_input_grad[0] else None
-        dw = mm_tn(dgu, x2) if ctx.needs_input_grad[1] else None
+        dw = mm_tn(dgu, x2, out=_sink_for(wgu)) if ctx.needs_input_grad[1] else None
         return dx, dw
 
 

@@ -35,6 +35,7 @@ import torch.distributed as dist
 from ..models.config import ModelConfig
 from ..models import transformer as tf
 from ..ops import reference as ref
+from .. import ops
 
 
 def _ceil_to(x: int, m: int) -> int:
@@ -74,6 +75,7 @@ class ShardedUnit:
         self._full_event = None
         self._resident: torch.Tensor | None = None      # persistent full bf16 replica (engine.resident mode)
         self._pending_rs = None       # event of the last async reduce-scatter into grad_acc
+        self._sink_slot = None        # reduce-scatter slot the running backward writes its wgrads into (engine._make_grad_sink)
 
     # ---- initialisation ---------------------------------------------------------------------
     def init_random(self, cfg: ModelConfig, seed: int) -> None:
@@ -200,9 +202,11 @@ class ShardedUnit:
         # stage into a param-major padded flat buffer
         gdtype = eng.param_dtype
         if eng.comm == "p2p":
-            slot = eng.next_grad_slot()
+            slot, self._sink_slot = self._sink_slot, None       # backward already wrote the big wgrads into this slot
+            if slot is None:
+                slot = eng.next_grad_slot()
+                eng.wait_grad_slot_free(slot)
             flat = slot.local[: self.full_numel]
-            eng.wait_grad_slot_free(slot)
         else:
             flat = eng.pool_acquire(self.full_numel, tag="grad_flat", dtype=gdtype)
         for g, numel, chunk, fo in zip(grads, self.numels, self.chunks, self.full_offsets):
@@ -210,7 +214,11 @@ class ShardedUnit:
             if g is None:
                 seg.zero_()
             else:
-                seg[:numel].copy_(g.reshape(-1))
+                if g.data_ptr() != seg.data_ptr():             # not produced in place by the gradient sink
+                    seg[:numel].copy_(g.reshape(-1))
+                    eng.grad_stage_stats["copied"] += numel
+                else:
+                    eng.grad_stage_stats["in_place"] += numel
                 if chunk * w > numel:
                     seg[numel:].zero_()
         scale_eff = scale / w            # data-parallel mean over ranks
@@ -384,8 +392,10 @@ class _UnitFn(torch.autograd.Function):
         pairs = [(o, g) for o, g in zip(outs, grad_out) if g is not None and o.requires_grad]
         diff_ins = [t for t in ins if t.requires_grad]
         flat_leaves = [p for l in leaves for p in l]
-        grads = torch.autograd.grad([o for o, _ in pairs], diff_ins + flat_leaves, [g for _, g in pairs],
-                                    allow_unused=True)
+        sink = runner.engine._make_grad_sink(runner.units, leaves)
+        with ops.functional.grad_sink(sink):
+            grads = torch.autograd.grad([o for o, _ in pairs], diff_ins + flat_leaves, [g for _, g in pairs],
+                                        allow_unused=True)
         gin = list(grads[: len(diff_ins)])
         gpar = grads[len(diff_ins):]
         k = 0
@@ -491,6 +501,8 @@ class Zero3Engine:
         self._grad_slots: list = []
         self._grad_slot_events: dict = {}
         self._grad_slot_idx = 0
+        self.grad_sink_enabled = os.environ.get("POLYRL_GRAD_SINK", "0") == "1"
+        self.grad_stage_stats = {"copied": 0, "in_place": 0}          # elements staged by copy vs written in place by wgrad
 
         # LoRA (models/lora.py): the base units are frozen (bf16 shard only), one small trainable adapter unit per block
         self.lora = lora if trainable else None
@@ -563,6 +575,24 @@ class Zero3Engine:
 
     def pool_release(self, t: torch.Tensor, tag: str = "full") -> None:
         self._pool.setdefault((tag, t.numel(), t.dtype), []).append(t)
+
+    def _make_grad_sink(self, units, leaves) -> dict:
+        """{weight data_ptr: view of the reduce-scatter slot} for the 2-D weights of the (single) trainable unit whose backward is
+        about to run: the wgrad GEMMs store there directly (ops/functional.py::grad_sink), accumulate_grads skips the copy."""
+        if not (self.comm == "p2p" and self.world > 1 and self.use_kernels and self.grad_sink_enabled):
+            return {}
+        trainable = [(u, l) for u, l in zip(units, leaves) if l]
+        if len(trainable) != 1:
+            return {}
+        u, l = trainable[0]
+        slot = self.next_grad_slot()
+        self.wait_grad_slot_free(slot)
+        u._sink_slot = slot
+        sink = {}
+        for p, numel, fo in zip(l, u.numels, u.full_offsets):
+            if p.dim() == 2 and fo % 8 == 0 and p.shape[1] % 8 == 0 and p.shape[0] % 8 == 0 and p.is_contiguous():
+                sink[p.data_ptr()] = slot.local[fo:fo + numel].view(p.shape)
+        return sink
 
     def next_grad_slot(self):
         s = self._grad_slots[self._grad_slot_idx % len(self._grad_slots)]

@@ -165,10 +165,13 @@ def main():
     st_ref, w_ref = run(ref_eng)
     for comm in ("p2p", "nccl"):
         eng = Zero3Engine(cfg, dev, comm=comm, lr=1e-2, weight_decay=0.0, seed=5)
+        eng.grad_sink_enabled = True      # opt-in (POLYRL_GRAD_SINK=1): wgrads written straight into the reduce-scatter slot
         st, w = run(eng)
         err = max(rel(w[k], w_ref[k]) for k in w_ref)
         results[f"zero3_{comm}_weight_err"] = err
         results[f"zero3_{comm}_gradnorm"] = (round(st["grad_norm"], 4), round(st_ref["grad_norm"], 4))
+        if comm == "p2p":                 # wgrad GEMMs store straight into the reduce-scatter slot (gradient sink)
+            results["zero3_p2p_grad_staging"] = dict(eng.grad_stage_stats)
         dist.barrier()
 
     # ---- 5. trainer->rollout weight push over peer memory (all ranks train, all ranks host a replica buffer)

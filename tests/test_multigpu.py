@@ -29,6 +29,8 @@ def test_peer_memory_paths_match_nccl():
     assert res["reduce_scatter_accum_err"] < 1e-5 and res["reduce_scatter_sumsq_err"] < 1e-3
     assert res["ag_gemm_err"] < 5e-3
     assert res["zero3_p2p_weight_err"] < 2e-2 and res["zero3_nccl_weight_err"] < 2e-2
+    st = res["zero3_p2p_grad_staging"]                       # the big 2-D weights' gradients are produced in the slot, not copied
+    assert st["in_place"] > 3 * st["copied"], st
 
 
 def test_tensor_parallel_rollout_engine():
