@@ -169,10 +169,13 @@ class WorkerGroup:
         return True
 
     def start_worker_aliveness_check(self, every_n_seconds: float = 1.0) -> None:
+        self._alive_stop = threading.Event()
+
         def loop():
-            while True:
-                time.sleep(every_n_seconds)
+            while not self._alive_stop.wait(every_n_seconds):
                 for i in range(self.world_size):
+                    if self._alive_stop.is_set():         # an orderly shutdown is in progress: exiting workers are expected
+                        return
                     if not self._is_worker_alive(i):
                         print(f"[controller] worker {i} died; aborting the driver", flush=True)
                         signal.raise_signal(signal.SIGABRT)
@@ -181,11 +184,16 @@ class WorkerGroup:
         self._alive_thread = threading.Thread(target=loop, daemon=True)
         self._alive_thread.start()
 
+    def stop_worker_aliveness_check(self) -> None:
+        ev = getattr(self, "_alive_stop", None)
+        if ev is not None:
+            ev.set()
+
     def _execute(self, idx: int, method: str, args: list, kwargs: dict) -> Future:
         raise NotImplementedError
 
     def shutdown(self) -> None:
-        return None
+        self.stop_worker_aliveness_check()
 
 
 class _View(WorkerGroup):
@@ -229,6 +237,7 @@ class LocalWorkerGroup(WorkerGroup):
         return self._pools[idx].submit(getattr(self.workers[idx], method), *args, **kwargs)
 
     def shutdown(self) -> None:
+        self.stop_worker_aliveness_check()
         for p in self._pools:
             p.shutdown(wait=False)
 
@@ -325,6 +334,7 @@ class MPWorkerGroup(WorkerGroup):
         return self.procs[idx].is_alive()
 
     def shutdown(self) -> None:
+        self.stop_worker_aliveness_check()
         for c in self.conns:
             try:
                 c.send(None)
@@ -380,5 +390,31 @@ class RayWorkerGroup(WorkerGroup):
 
         ref = self.actors[idx].call.remote(method, args, kwargs)
         f: Future = Future()
-        threading.Thread(target=lambda: f.set_result(ray.get(ref)), daemon=True).start()
+
+        def wait():
+            try:
+                f.set_result(ray.get(ref))
+            except Exception as e:           # noqa: BLE001  (actor died / method raised: surface it on the future)
+                f.set_exception(e)
+
+        threading.Thread(target=wait, daemon=True).start()
         return f
+
+    def _is_worker_alive(self, idx: int) -> bool:
+        import ray
+
+        try:
+            ray.get(self.actors[idx].call.remote("_ping", [], {}), timeout=60)
+            return True
+        except Exception:                    # noqa: BLE001
+            return False
+
+    def shutdown(self) -> None:
+        import ray
+
+        self.stop_worker_aliveness_check()
+        for a in self.actors:
+            try:
+                ray.kill(a)
+            except Exception:                # noqa: BLE001
+                pass

@@ -1,0 +1,330 @@
+"""Single-controller PPO / GRPO: ONE driver process owns the data loader, rewards, advantages and the control flow; the model
+work runs in a ``WorkerGroup`` (one OS process per GPU, or Ray actors, or in-process workers) whose methods are called through
+the ``@register`` dispatch protocol.
+
+This is the reference's execution model — ``RayPPOTrainer.fit`` driving ``RayWorkerGroup``s of fused
+actor / rollout / ref (+ critic) workers (3rdparty/verl/verl/trainer/ppo/ray_trainer.py:968-1214,
+verl/single_controller/ray/base.py:262-444, verl/workers/fsdp_workers.py:134-1100) — on this framework's own controller
+(``polyrl_b200/controller``).  The SPMD trainers (``trainer/stream_trainer.py``, ``trainer/colocated.py``) stay the fast path:
+there a batch never leaves the device between phases; here every phase costs one host round trip per worker, which is what
+the reference pays through the Ray object store.  Both drive the same ``ActorRolloutRefWorker`` / ``CriticWorker``.
+
+    python -m polyrl_b200.trainer.controller_ppo controller.backend=mp trainer.n_gpus_per_node=2 ...   # one process per GPU
+    python -m polyrl_b200.trainer.controller_ppo controller.backend=ray ...                            # Ray actors (if installed)
+"""
+from __future__ import annotations
+
+import os
+import sys
+import time
+import uuid
+from typing import Callable
+
+import numpy as np
+import torch
+
+from ..algos import core_algos
+from ..config.schema import PPOConfig, load_config, need_critic, need_reference_policy
+from ..controller import ClassWithInitArgs, Dispatch, Execute, LocalWorkerGroup, MPWorkerGroup, Worker, register
+from ..protocol import DataProto, collate_fn
+from ..utils import metrics as M
+from ..utils.profiler import marked_timer
+from . import core
+
+
+class PPOWorker(Worker):
+    """Fused actor + rollout (+ ref) (+ critic) worker of one GPU, exposed to the driver through ``@register`` methods.
+    DataProto arguments arrive on the host (they crossed a pipe / the Ray object store), are moved to the device for the call
+    and results go back to the host."""
+
+    def __init__(self, config: PPOConfig, init_dist: bool = True):
+        super().__init__()
+        self.config = config
+        self.inner = None
+        self.critic = None
+        want_cuda = torch.cuda.is_available() and config.trainer.device != "cpu"
+        self.device = torch.device(f"cuda:{int(os.environ.get('LOCAL_RANK', 0))}" if want_cuda else "cpu")
+        if init_dist and self.world_size > 1:
+            import torch.distributed as dist
+
+            if not dist.is_initialized():
+                if want_cuda:
+                    torch.cuda.set_device(self.device)
+                    dist.init_process_group("nccl", rank=self.rank, world_size=self.world_size, device_id=self.device)
+                else:
+                    dist.init_process_group("gloo", rank=self.rank, world_size=self.world_size)
+
+    # ---- helpers
+    def _in(self, data: DataProto) -> DataProto:
+        return data.to(self.device)
+
+    @staticmethod
+    def _out(data: DataProto) -> DataProto:
+        return data.to("cpu")
+
+    # ---- lifecycle
+    @register(dispatch_mode=Dispatch.ONE_TO_ALL)
+    def init_model(self) -> dict:
+        from ..workers.hybrid_worker import ActorRolloutRefWorker, CriticWorker
+
+        cfg = self.config
+        role = "actor_rollout_ref" if need_reference_policy(cfg) else "actor_rollout"
+        self.inner = ActorRolloutRefWorker(cfg, role=role, device=self.device, group=None)
+        self.inner.init_model()
+        if need_critic(cfg):
+            self.critic = CriticWorker(cfg, device=self.device, group=None)
+            self.critic.init_model(heap=self.inner.actor_engine.heap)
+        mc = self.inner.model_cfg
+        return {"rank": self.rank, "vocab_size": mc.vocab_size, "eos_token_id": mc.eos_token_id, "pad_token_id": mc.pad_token_id,
+                "num_params": self.inner.actor_engine.num_params()}
+
+    # ---- rollout / inference
+    @register(dispatch_mode=Dispatch.DP_COMPUTE_PROTO)
+    def generate_sequences(self, prompts: DataProto) -> DataProto:
+        return self._out(self.inner.generate_sequences(self._in(prompts)))
+
+    @register(dispatch_mode=Dispatch.DP_COMPUTE_PROTO)
+    def compute_log_prob(self, data: DataProto) -> DataProto:
+        return self._out(self.inner.compute_log_prob(self._in(data)))
+
+    @register(dispatch_mode=Dispatch.DP_COMPUTE_PROTO)
+    def compute_ref_log_prob(self, data: DataProto) -> DataProto:
+        return self._out(self.inner.compute_ref_log_prob(self._in(data)))
+
+    @register(dispatch_mode=Dispatch.DP_COMPUTE_PROTO)
+    def compute_values(self, data: DataProto) -> DataProto:
+        return self._out(self.critic.compute_values(self._in(data)))
+
+    # ---- updates: the driver sends one mini-batch per call; every worker trains on its chunk, gradients are averaged by ZeRO
+    @register(dispatch_mode=Dispatch.DP_COMPUTE_PROTO)
+    def update_actor(self, data: DataProto) -> DataProto:
+        return self.inner.update_actor_stream(self._in(data))
+
+    @register(dispatch_mode=Dispatch.DP_COMPUTE_PROTO)
+    def update_critic(self, data: DataProto) -> DataProto:
+        return self.critic.update_critic_stream(self._in(data))
+
+    @register(dispatch_mode=Dispatch.ONE_TO_ALL)
+    def update_weight(self) -> bool:
+        return bool(self.inner.update_weight_remote())
+
+    # ---- checkpoints
+    @register(dispatch_mode=Dispatch.ONE_TO_ALL)
+    def save_checkpoint(self, path: str, global_step: int = 0, max_ckpt_to_keep: int | None = None) -> None:
+        self.inner.save_checkpoint(os.path.join(path, "actor"), None, global_step, max_ckpt_to_keep)
+        if self.critic is not None:
+            self.critic.save_checkpoint(os.path.join(path, "critic"), None, global_step, max_ckpt_to_keep)
+
+    @register(dispatch_mode=Dispatch.ONE_TO_ALL)
+    def load_checkpoint(self, path: str) -> None:
+        self.inner.load_checkpoint(os.path.join(path, "actor"))
+        if self.critic is not None:
+            self.critic.load_checkpoint(os.path.join(path, "critic"))
+
+    @register(dispatch_mode=Dispatch.RANK_ZERO, execute_mode=Execute.RANK_ZERO)
+    def weights_checksum(self) -> float:
+        s = 0.0
+        for _, t in self.inner.actor_engine.named_full_tensors():
+            s += float(t.double().abs().sum())
+        return s
+
+    @register(dispatch_mode=Dispatch.ONE_TO_ALL)
+    def teardown(self) -> None:
+        import torch.distributed as dist
+
+        if dist.is_initialized():
+            dist.barrier()
+            dist.destroy_process_group()
+
+
+def make_worker_group(config: PPOConfig, backend: str, world_size: int, env: dict | None = None):
+    cia = ClassWithInitArgs(PPOWorker, config)
+    if backend == "local":
+        if world_size != 1:
+            raise ValueError("the in-process backend runs one worker (collectives need one process per rank)")
+        return LocalWorkerGroup(1, ClassWithInitArgs(PPOWorker, config, init_dist=False))
+    if backend == "mp":
+        return MPWorkerGroup(world_size, cia, env=env)
+    if backend == "ray":
+        from ..controller.worker_group import RayWorkerGroup
+
+        return RayWorkerGroup(world_size, cia, env=env)
+    raise ValueError(f"unknown controller backend {backend!r} (local | mp | ray)")
+
+
+class ControllerPPOTrainer:
+    """Driver-side loop.  ``reward_fn(batch) -> [B] scores or [B, R] token scores``; defaults to the synthetic token reward."""
+
+    def __init__(self, config: PPOConfig, worker_group, train_dataset, val_dataset=None, reward_fn: Callable | None = None,
+                 tracking=None, sampler=None):
+        self.config, self.wg = config, worker_group
+        self.train_dataset, self.val_dataset, self.reward_fn, self.tracking = train_dataset, val_dataset, reward_fn, tracking
+        self.sampler = sampler
+        self.kl_ctrl = (core_algos.get_kl_controller(config.algorithm.kl_ctrl) if config.algorithm.use_kl_in_reward else None)
+        self.global_step = 0
+        self.model_info = self.wg.init_model()[0]
+        self.wg.start_worker_aliveness_check(1.0)
+
+    # ---- data
+    def _batches(self):
+        bs = self.config.data.train_batch_size
+        order = list(self.sampler) if self.sampler is not None else list(range(len(self.train_dataset)))
+        for i in range(0, len(order) - bs + 1, bs):
+            yield DataProto.from_single_dict(collate_fn([self.train_dataset[j] for j in order[i:i + bs]]))
+
+    def _reward(self, batch: DataProto) -> torch.Tensor:
+        mask = batch.batch["response_mask"]
+        if self.reward_fn is not None:
+            scores = self.reward_fn(batch)
+            if torch.is_tensor(scores) and scores.dim() == 2:
+                return scores
+        else:
+            from ..data.synthetic import synthetic_token_reward
+
+            resp, lens = batch.batch["responses"].numpy(), mask.sum(-1).numpy()
+            rm = batch.non_tensor_batch["reward_model"]
+            v = self.model_info["vocab_size"]
+            scores = [synthetic_token_reward(resp[i, : lens[i]], rm[i]["ground_truth"], v) for i in range(len(batch))]
+        return core.place_outcome_rewards(scores, mask)
+
+    # ---- one PPO step
+    def step(self, prompts: DataProto) -> dict:
+        cfg, algo, wg = self.config, self.config.algorithm, self.wg
+        n = cfg.actor_rollout_ref.rollout.n
+        timing: dict[str, float] = {}
+        t_step = time.time()
+        if "uid" not in prompts.non_tensor_batch:
+            prompts.non_tensor_batch["uid"] = np.array([str(uuid.uuid4()) for _ in range(len(prompts))], dtype=object)
+        with marked_timer("gen", timing):
+            batch = wg.generate_sequences(prompts)
+        with marked_timer("reward", timing):
+            batch.batch["token_level_scores"] = self._reward(batch)
+        with marked_timer("old_log_prob", timing):
+            batch.meta_info["temperature"] = cfg.actor_rollout_ref.rollout.temperature
+            old = wg.compute_log_prob(batch)
+            batch.batch["old_log_probs"] = old.batch["old_log_probs"]
+            entropy = core_algos.masked_mean(old.batch["entropys"], batch.batch["response_mask"].float()).item()
+        if need_reference_policy(cfg):
+            with marked_timer("ref", timing):
+                batch.batch["ref_log_prob"] = wg.compute_ref_log_prob(batch).batch["ref_log_prob"]
+        if need_critic(cfg):
+            with marked_timer("values", timing):
+                batch.batch["values"] = wg.compute_values(batch).batch["values"]
+        metrics: dict = {}
+        with marked_timer("adv", timing):
+            if algo.use_kl_in_reward:
+                batch, klm = core.apply_kl_penalty(batch, self.kl_ctrl, algo.kl_penalty)
+                metrics.update(klm)
+            else:
+                batch.batch["token_level_rewards"] = batch.batch["token_level_scores"]
+            batch = core.compute_advantage(batch, algo.adv_estimator, algo.gamma, algo.lam, n, algo.norm_adv_by_std_in_grpo, algo)
+        # the driver balances nothing here: whole GRPO groups stay adjacent, chunks are contiguous slices (DP_COMPUTE_PROTO)
+        upd: dict[str, list] = {}
+        with marked_timer("update_actor", timing):
+            mini = cfg.actor_rollout_ref.actor.ppo_mini_batch_size * n
+            bounds = list(range(mini, len(batch) + 1, mini)) or [len(batch)]
+            if bounds[-1] != len(batch):
+                bounds.append(len(batch))
+            start = 0
+            for bi, end in enumerate(bounds):
+                part = batch.slice(start, end)
+                if len(part) % wg.world_size != 0:
+                    raise ValueError(f"mini-batch of {len(part)} samples does not split over {wg.world_size} workers")
+                part.meta_info = {**batch.meta_info, "is_opt_step": True, "is_lr_step": bi == len(bounds) - 1}
+                if need_critic(cfg):
+                    M.append_to_dict(upd, wg.update_critic(part).meta_info["metrics"])
+                if not need_critic(cfg) or self.global_step >= cfg.trainer.critic_warmup:
+                    M.append_to_dict(upd, wg.update_actor(part).meta_info["metrics"])
+                start = end
+        with marked_timer("update_weight", timing):
+            wg.update_weight()
+        self.global_step += 1
+        mask = batch.batch["response_mask"].float()
+        metrics.update({k: float(np.mean(v)) for k, v in upd.items()})
+        metrics.update({
+            "critic/score/mean": batch.batch["token_level_scores"].sum(-1).mean().item(),
+            "critic/advantages/mean": core_algos.masked_mean(batch.batch["advantages"], mask).item(),
+            "response_length/mean": mask.sum(-1).mean().item(), "actor/entropy_old": entropy,
+            "perf/total_num_tokens": int(batch.batch["attention_mask"].sum().item()), "num_samples": len(batch),
+        })
+        timing["step"] = time.time() - t_step
+        metrics.update({f"timing_s/{k}": v for k, v in timing.items()})
+        return metrics
+
+    def validate(self) -> dict:
+        if self.val_dataset is None or len(self.val_dataset) == 0:
+            return {}
+        w = self.wg.world_size
+        rows = [self.val_dataset[i] for i in range(len(self.val_dataset) - len(self.val_dataset) % w or len(self.val_dataset))]
+        prompts = DataProto.from_single_dict(collate_fn(rows))
+        prompts.meta_info.update({"validate": True, "do_sample": self.config.actor_rollout_ref.rollout.val_kwargs.get("do_sample", False), "n": 1})
+        out = self.wg.generate_sequences(prompts)
+        scores = self._reward(out).sum(-1)
+        return {"val-core/score/mean@1": scores.mean().item(), "val-aux/response_length/mean": out.batch["response_mask"].sum(-1).float().mean().item()}
+
+    def fit(self, max_steps: int | None = None) -> list[dict]:
+        cfg = self.config
+        total = max_steps or cfg.trainer.total_training_steps or 10 ** 9
+        history: list[dict] = []
+        if cfg.trainer.val_before_train and self.val_dataset is not None:
+            v = self.validate()
+            if self.tracking is not None:
+                self.tracking.log(v, step=0)
+        for epoch in range(max(1, cfg.trainer.total_epochs)):
+            for prompts in self._batches():
+                m = self.step(prompts)
+                if cfg.trainer.test_freq > 0 and self.global_step % cfg.trainer.test_freq == 0:
+                    m.update(self.validate())
+                if cfg.trainer.save_freq > 0 and self.global_step % cfg.trainer.save_freq == 0:
+                    path = os.path.join(cfg.trainer.default_local_dir, f"global_step_{self.global_step}")
+                    self.wg.save_checkpoint(path, self.global_step, cfg.trainer.max_actor_ckpt_to_keep)
+                if self.tracking is not None:
+                    self.tracking.log(m, step=self.global_step)
+                history.append(m)
+                if self.global_step >= total:
+                    return history
+        return history
+
+    def shutdown(self) -> None:
+        try:
+            self.wg.teardown()
+        except Exception:
+            pass
+        self.wg.shutdown()
+
+
+def main(argv: list[str] | None = None) -> int:
+    argv = list(sys.argv[1:] if argv is None else argv)
+    backend = "mp"
+    rest = []
+    for a in argv:
+        if a.startswith("controller.backend="):
+            backend = a.split("=", 1)[1]
+        else:
+            rest.append(a)
+    cfg = load_config(overrides=rest)
+    world = max(1, cfg.trainer.n_gpus_per_node * cfg.trainer.nnodes)
+    from ..models import get_model_config
+    from .main_stream import build_datasets
+
+    mc = get_model_config(cfg.actor_rollout_ref.model.path, **cfg.actor_rollout_ref.model.override_config)
+    train, val, sampler, tok = build_datasets(cfg, mc)
+    reward_fn = None
+    if tok is not None:
+        from ..data.reward_manager import load_reward_manager
+
+        reward_fn = load_reward_manager(cfg, tok)
+    from ..utils.tracking import Tracking
+
+    tracking = Tracking(cfg.trainer.project_name, cfg.trainer.experiment_name, cfg.trainer.logger)
+    wg = make_worker_group(cfg, backend, world)
+    trainer = ControllerPPOTrainer(cfg, wg, train, val, reward_fn, tracking, sampler)
+    try:
+        trainer.fit()
+    finally:
+        trainer.shutdown()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
