@@ -296,7 +296,8 @@ class FilterGroupsConfig(BaseConfig):
     samples all got the same ``metric`` carry no learning signal under group-normalised advantages and are taken out of the loss."""
     enable: bool = False
     metric: str = "seq_reward"            # seq_reward | seq_final_reward | acc | score (per-sample scalar looked up in the batch)
-    max_num_gen_batches: int = 0          # accepted for config compatibility; the streaming trainer never re-generates
+    max_num_gen_batches: int = 0          # recipes.dapo: give up after this many generation batches per step (0 = keep trying);
+                                          # the streaming trainer masks groups instead and never re-generates
 
 
 @dataclass
@@ -321,6 +322,7 @@ class DataConfig(BaseConfig):
     max_prompt_length: int = 512
     max_response_length: int = 512
     train_batch_size: int = 1024
+    gen_batch_size: int | None = None      # recipes.dapo: prompts per generation batch (default: train_batch_size)
     val_batch_size: int | None = None
     shuffle: bool = True
     seed: int = 1

@@ -280,7 +280,7 @@ class DataProto:
 
     def select_idxs(self, idxs) -> "DataProto":
         if isinstance(idxs, list):
-            idxs = torch.tensor(idxs)
+            idxs = torch.tensor(idxs, dtype=torch.bool if idxs and isinstance(idxs[0], bool) else torch.long)   # [] stays an index
         if isinstance(idxs, np.ndarray):
             idxs_np, idxs_t = idxs, torch.from_numpy(idxs)
         else:

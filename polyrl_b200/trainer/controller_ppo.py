@@ -187,18 +187,31 @@ class ControllerPPOTrainer:
             scores = [synthetic_token_reward(resp[i, : lens[i]], rm[i]["ground_truth"], v) for i in range(len(batch))]
         return core.place_outcome_rewards(scores, mask)
 
-    # ---- one PPO step
-    def step(self, prompts: DataProto) -> dict:
-        cfg, algo, wg = self.config, self.config.algorithm, self.wg
-        n = cfg.actor_rollout_ref.rollout.n
-        timing: dict[str, float] = {}
-        t_step = time.time()
+    # ---- one PPO step = rollout_and_score -> compute_advantages -> train_on (recipes override the pieces)
+    def rollout_and_score(self, prompts: DataProto, timing: dict) -> DataProto:
+        """Generation + rewards for one batch of prompts (n samples each, whole groups adjacent)."""
         if "uid" not in prompts.non_tensor_batch:
             prompts.non_tensor_batch["uid"] = np.array([str(uuid.uuid4()) for _ in range(len(prompts))], dtype=object)
         with marked_timer("gen", timing):
-            batch = wg.generate_sequences(prompts)
+            batch = self.wg.generate_sequences(prompts)
         with marked_timer("reward", timing):
             batch.batch["token_level_scores"] = self._reward(batch)
+        return batch
+
+    def compute_advantages(self, batch: DataProto, metrics: dict) -> DataProto:
+        cfg, algo = self.config, self.config.algorithm
+        if algo.use_kl_in_reward:
+            batch, klm = core.apply_kl_penalty(batch, self.kl_ctrl, algo.kl_penalty)
+            metrics.update(klm)
+        else:
+            batch.batch["token_level_rewards"] = batch.batch["token_level_scores"]
+        return core.compute_advantage(batch, algo.adv_estimator, algo.gamma, algo.lam, cfg.actor_rollout_ref.rollout.n,
+                                      algo.norm_adv_by_std_in_grpo, algo)
+
+    def train_on(self, batch: DataProto, timing: dict) -> dict:
+        """old log-probs (+ ref, values), advantages, mini-batch updates, weight hand-off.  Returns the step metrics."""
+        cfg, wg = self.config, self.wg
+        n = cfg.actor_rollout_ref.rollout.n
         with marked_timer("old_log_prob", timing):
             batch.meta_info["temperature"] = cfg.actor_rollout_ref.rollout.temperature
             old = wg.compute_log_prob(batch)
@@ -212,12 +225,7 @@ class ControllerPPOTrainer:
                 batch.batch["values"] = wg.compute_values(batch).batch["values"]
         metrics: dict = {}
         with marked_timer("adv", timing):
-            if algo.use_kl_in_reward:
-                batch, klm = core.apply_kl_penalty(batch, self.kl_ctrl, algo.kl_penalty)
-                metrics.update(klm)
-            else:
-                batch.batch["token_level_rewards"] = batch.batch["token_level_scores"]
-            batch = core.compute_advantage(batch, algo.adv_estimator, algo.gamma, algo.lam, n, algo.norm_adv_by_std_in_grpo, algo)
+            batch = self.compute_advantages(batch, metrics)
         # the driver balances nothing here: whole GRPO groups stay adjacent, chunks are contiguous slices (DP_COMPUTE_PROTO)
         upd: dict[str, list] = {}
         with marked_timer("update_actor", timing):
@@ -247,6 +255,13 @@ class ControllerPPOTrainer:
             "response_length/mean": mask.sum(-1).mean().item(), "actor/entropy_old": entropy,
             "perf/total_num_tokens": int(batch.batch["attention_mask"].sum().item()), "num_samples": len(batch),
         })
+        return metrics
+
+    def step(self, prompts: DataProto) -> dict:
+        timing: dict[str, float] = {}
+        t_step = time.time()
+        batch = self.rollout_and_score(prompts, timing)
+        metrics = self.train_on(batch, timing)
         timing["step"] = time.time() - t_step
         metrics.update({f"timing_s/{k}": v for k, v in timing.items()})
         return metrics
