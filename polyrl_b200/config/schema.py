@@ -253,9 +253,20 @@ class CriticConfig(BaseConfig):
 
 
 @dataclass
+class OverlongBufferConfig(BaseConfig):
+    """DAPO soft over-long punishment (reference: verl/workers/reward_manager/dapo.py, reward_model.overlong_buffer.*): responses
+    longer than ``max_response_length - len`` lose up to ``penalty_factor`` linearly over the last ``len`` tokens."""
+    enable: bool = False
+    len: int = 0
+    penalty_factor: float = 1.0
+    log: bool = False
+
+
+@dataclass
 class RewardModelConfig(BaseConfig):
     enable: bool = False
     reward_manager: str = "naive"       # naive | batch | dapo | prime
+    overlong_buffer: OverlongBufferConfig = field(default_factory=OverlongBufferConfig)
     use_reward_loop: bool = False       # async per-sample reward loop (data/reward_loop.py; managers naive | dapo)
     reward_loop_concurrency: int = 64
     genrm_endpoints: list = field(default_factory=list)   # "host:port" engine servers judging responses (generative reward model)

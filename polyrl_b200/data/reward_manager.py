@@ -167,6 +167,11 @@ def load_reward_manager(config, tokenizer=None, num_examine: int = 0, **kwargs):
             fn = GenerativeRewardModel(list(rm.genrm_endpoints), tokenizer, max_new_tokens=rm.genrm_max_new_tokens).compute_score
         return RewardLoopManager(name if name in ("naive", "dapo") else "naive", tokenizer, max_concurrency=rm.reward_loop_concurrency,
                                  compute_score=fn, reward_fn_key=config.data.reward_fn_key, **kwargs)
+    ob = getattr(rm, "overlong_buffer", None)
+    if name == "dapo" and ob is not None and ob.enable:
+        kwargs.setdefault("max_resp_len", config.data.max_response_length)
+        kwargs.setdefault("overlong_buffer_len", ob.len)
+        kwargs.setdefault("penalty_factor", ob.penalty_factor)
     return get_reward_manager_cls(name)(tokenizer=tokenizer, num_examine=num_examine, compute_score=fn,
                                         reward_fn_key=config.data.reward_fn_key, **kwargs)
 
