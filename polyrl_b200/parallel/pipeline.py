@@ -9,8 +9,8 @@ the schedule (send activation + receive gradient, send gradient + receive next a
 
 Capability parity: the reference's Megatron back-end pipeline parallelism (``pipeline_model_parallel_size``,
 3rdparty/verl/verl/utils/megatron/pipeline_parallel.py:22-49, workers/megatron_workers.py forward_backward_func / 1F1B schedule of
-megatron.core.pipeline_parallel.schedules).  Not interleaved (no virtual stages); tensor parallelism inside a stage is the separate
-``TPTrainEngine``.  On one NVSwitch box ZeRO / TP are the faster layouts — this engine is for models whose optimizer state has to
+megatron.core.pipeline_parallel.schedules).  ``InterleavedPipelineEngine`` (below) adds virtual stages; tensor parallelism inside a stage is the
+separate ``TPTrainEngine``.  On one NVSwitch box ZeRO / TP are the faster layouts — this engine is for models whose optimizer state has to
 be split by depth, and for multi-node layouts where only neighbour traffic should cross the slow links.
 """
 from __future__ import annotations
@@ -262,3 +262,217 @@ class PipelineEngine:
             for k, v in p.items():
                 out.setdefault(k, v)
         return out
+
+
+# =====================================================================================================================
+# Interleaved (virtual-stage) 1F1B
+# =====================================================================================================================
+def build_interleaved_schedule(pp: int, v: int, m: int, forward_only: bool = False) -> list[list[tuple | None]]:
+    """Tick table of the interleaved schedule: ``table[t][rank]`` is ``('F' | 'B', vstage, micro_batch)`` or None.
+
+    The model is cut into ``S = pp * v`` virtual stages, vstage ``s`` lives on rank ``s % pp`` (chunk ``s // pp`` of that rank), so a
+    micro-batch visits every rank ``v`` times and the pipeline bubble shrinks by ``v`` (Megatron-LM interleaved 1F1B).  The table is
+    produced by a deterministic list-scheduling simulation that every rank runs identically: one action per rank per tick; a forward
+    needs the previous vstage's forward of that micro-batch from an EARLIER tick, a backward needs the next vstage's backward and
+    its own forward; a ready backward wins except right after a backward, when a ready forward goes first (1F1B alternation; this reaches
+    Megatron's tick count 2 v m + 2 (pp - 1)), and a rank stops issuing forwards while it already holds the Megatron
+    warm-up depth ``2 (pp - rank - 1) + (v - 1) pp + 1`` of live activations.  Because the table is global knowledge, every
+    neighbour exchange of a tick is known to both ends and is issued as one grouped send/recv — no dead-lock on stream-ordered
+    transports."""
+    S = pp * v
+    INF = 1 << 60
+    done_f = [[INF] * m for _ in range(S)]
+    done_b = [[INF] * m for _ in range(S)]
+    next_f = [0] * S                      # micro-batches run in order on every vstage
+    next_b = [0] * S
+    live = [0] * pp
+    cap = [INF if forward_only else 2 * (pp - r - 1) + (v - 1) * pp + 1 for r in range(pp)]
+    total = S * m * (1 if forward_only else 2)
+    table: list[list[tuple | None]] = []
+    last: list[str | None] = [None] * pp
+    n_done, t, relaxed = 0, 0, False
+    while n_done < total:
+        row: list[tuple | None] = [None] * pp
+        for r in range(pp):
+            mine = range(r, S, pp)
+            pick = None
+            f_ready = any(next_f[s] < m and (s == 0 or done_f[s - 1][next_f[s]] < t) for s in mine)
+            # steady state alternates: right after a backward the rank takes a forward if one is ready (one-forward-one-backward)
+            if not forward_only and not (last[r] == "B" and f_ready and live[r] < cap[r]):
+                cand = []
+                for s in mine:
+                    k = next_b[s]
+                    if k < m and done_f[s][k] < t and (s == S - 1 or done_b[s + 1][k] < t):
+                        cand.append((k // pp, -(s // pp), k % pp, s, k))
+                if cand:
+                    _, _, _, s, k = min(cand)
+                    pick = ("B", s, k)
+            if pick is None and (live[r] < cap[r] or relaxed):
+                cand = []
+                for s in mine:
+                    k = next_f[s]
+                    if k < m and (s == 0 or done_f[s - 1][k] < t):
+                        cand.append((k // pp, s // pp, k % pp, s, k))
+                if cand:
+                    _, _, _, s, k = min(cand)
+                    pick = ("F", s, k)
+            row[r] = pick
+            if pick is not None:
+                last[r] = pick[0]
+        progressed = False
+        for r, a in enumerate(row):
+            if a is None:
+                continue
+            progressed = True
+            kind, s, k = a
+            if kind == "F":
+                done_f[s][k] = t
+                next_f[s] += 1
+                live[r] += 0 if forward_only else 1
+            else:
+                done_b[s][k] = t
+                next_b[s] += 1
+                live[r] -= 1
+            n_done += 1
+        if progressed:
+            table.append(row)
+            relaxed = False
+            t += 1
+        else:
+            if relaxed:
+                raise RuntimeError("interleaved pipeline schedule cannot make progress")
+            relaxed = True                # the activation cap can only stall when m is not a multiple of pp: lift it for one tick
+    return table
+
+
+class InterleavedPipelineEngine(PipelineEngine):
+    """``PipelineEngine`` with ``virtual_stages`` model chunks per rank (Megatron's virtual pipeline parallelism,
+    ``virtual_pipeline_model_parallel_size``; reference: 3rdparty/verl/verl/workers/megatron_workers.py:204-211 passes it through to
+    mcore).  Same parameters, optimizer step, tied-embedding handling and export as the base engine; only the layer placement and
+    the schedule differ."""
+
+    def __init__(self, cfg: ModelConfig, device, pp_group, dp_group=None, virtual_stages: int = 2, **kw):
+        self.v = int(virtual_stages)
+        pp = dist.get_world_size(pp_group)
+        if self.v < 1 or cfg.num_layers < pp * self.v:
+            raise ValueError(f"{cfg.num_layers} layers cannot fill {pp} x {self.v} virtual pipeline stages")
+        self._ranges = stage_layers(cfg.num_layers, pp * self.v)
+        super().__init__(cfg, device, pp_group, dp_group, **kw)
+
+    def load_full(self, embed: dict, layers: list[dict], head: dict) -> None:
+        self.chunks = [self._ranges[c * self.pp + self.stage] for c in range(self.v)]
+        owned = [i for lo, hi in self.chunks for i in range(lo, hi)]
+        self.lo, self.hi = owned[0], owned[0]                        # the base loader takes no layers; they are added below
+        super().load_full(embed, layers, head)
+        extra = {f"layers.{i}.{k}": t.clone() for i in owned for k, t in layers[i].items()}
+        for k, t in extra.items():
+            self.master[k] = t.to(self.device, torch.float32)
+            self.params[k] = self.master[k].to(self.dtype).clone().requires_grad_(True)
+            self.exp_avg[k] = torch.zeros_like(self.master[k])
+            self.exp_avg_sq[k] = torch.zeros_like(self.master[k])
+
+    # ---- one virtual stage
+    def _chunk_forward(self, s: int, inp: tf.PackedInput, x_in: torch.Tensor | None) -> torch.Tensor:
+        lo, hi = self._ranges[s]
+        x = torch.nn.functional.embedding(inp.input_ids, self.params["embed"]) if s == 0 else x_in
+        for i in range(lo, hi):
+            x = tf.layer_forward(self.cfg, self.layer(i), x, inp)
+        return x
+
+    def _run_table(self, table, micro_batches, on_forward, on_backward) -> None:
+        """Execute this rank's column of the tick table; after every tick exchange what the table says crosses a rank boundary."""
+        pp, S = self.pp, self.pp * self.v
+        ranks = dist.get_process_group_ranks(self.pp_group)
+        inbox_act: dict = {}
+        inbox_grad: dict = {}
+        for row in table:
+            mine = row[self.stage]
+            out_act = out_grad = None
+            if mine is not None:
+                kind, s, k = mine
+                if kind == "F":
+                    out_act = on_forward(s, k, inbox_act.pop((s, k), None))
+                else:
+                    out_grad = on_backward(s, k, inbox_grad.pop((s, k), None))
+            # messages of this tick, in one global order both ends agree on
+            msgs = []
+            for r, a in enumerate(row):
+                if a is None:
+                    continue
+                kind, s, k = a
+                if kind == "F" and s < S - 1:
+                    msgs.append((r, (s + 1) % pp, 0, s + 1, k))
+                elif kind == "B" and s > 0:
+                    msgs.append((r, (s - 1) % pp, 1, s - 1, k))
+            ops_ = []
+            for src, dst, kind, s, k in sorted(msgs):
+                if src == self.stage:
+                    t = (out_act if kind == 0 else out_grad).contiguous()
+                    ops_.append(dist.P2POp(dist.isend, t, ranks[dst]))
+                if dst == self.stage:
+                    buf = torch.empty(self._shape(micro_batches[k][0]), device=self.device, dtype=self.dtype)
+                    (inbox_act if kind == 0 else inbox_grad)[(s, k)] = buf
+                    ops_.append(dist.P2POp(dist.irecv, buf, ranks[src]))
+            if ops_:
+                for w in dist.batch_isend_irecv(ops_):
+                    w.wait()
+
+    # ---- training step
+    def train_batch(self, micro_batches, loss_fn, temperature: float = 1.0) -> list[float]:
+        S, m = self.pp * self.v, len(micro_batches)
+        table = build_interleaved_schedule(self.pp, self.v, m)
+        held: dict = {}
+        losses: dict[int, float] = {}
+        self.peak_in_flight = 0
+
+        def fwd(s, k, x_in):
+            inp, labels = micro_batches[k]
+            if x_in is not None:
+                x_in.requires_grad_(True)
+            out = self._chunk_forward(s, inp, x_in)
+            if s == S - 1:
+                lp, ent = self._head(out, labels, temperature)
+                out = loss_fn(lp, ent, k)
+                losses[k] = float(out.detach())
+            held[(s, k)] = (x_in, out)
+            self.peak_in_flight = max(self.peak_in_flight, len(held))
+            return None if s == S - 1 else out.detach()
+
+        def bwd(s, k, grad_out):
+            x_in, out = held.pop((s, k))
+            if s == S - 1:
+                out.backward()
+            else:
+                torch.autograd.backward(out, grad_out)
+            return None if x_in is None else x_in.grad
+
+        self._run_table(table, micro_batches, fwd, bwd)
+        self.last_schedule_ticks = len(table)
+        return [losses[k] for k in sorted(losses)]
+
+    @torch.no_grad()
+    def forward_only(self, micro_batches, temperature: float = 1.0, broadcast: bool = True):
+        S = self.pp * self.v
+        table = build_interleaved_schedule(self.pp, self.v, len(micro_batches), forward_only=True)
+        out: dict[int, tuple] = {}
+
+        def fwd(s, k, x_in):
+            inp, labels = micro_batches[k]
+            x = self._chunk_forward(s, inp, x_in)
+            if s == S - 1:
+                out[k] = self._head(x, labels, temperature)
+                return None
+            return x
+
+        self._run_table(table, micro_batches, fwd, None)
+        res_local = [out[k] for k in sorted(out)]
+        if not broadcast:
+            return res_local
+        src = dist.get_process_group_ranks(self.pp_group)[-1]
+        res = []
+        for k, (inp, _) in enumerate(micro_batches):
+            t = int(inp.input_ids.shape[0])
+            buf = torch.stack([o.float() for o in out[k]]) if self.last else torch.empty(2, t, device=self.device, dtype=torch.float32)
+            dist.broadcast(buf, src=src, group=self.pp_group)
+            res.append((buf[0], buf[1]))
+        return res

@@ -185,14 +185,19 @@ class PipelineLMEngine(ZeroEngine):
     engine with ``pipeline_model_parallel_size > 1`` (verl/workers/engine/megatron/transformer_impl.py).  Every stage of a pipeline
     receives the same batch; losses and metrics exist on the last stage and are broadcast to the others."""
 
-    def __init__(self, model, device, pp_group, dp_group=None, lr: float = 1e-6, lr_schedule=None, micro_batch_size: int = 8, **engine_kw):
+    def __init__(self, model, device, pp_group, dp_group=None, lr: float = 1e-6, lr_schedule=None, micro_batch_size: int = 8,
+                 virtual_stages: int = 1, **engine_kw):
         super().__init__(model, device, group=None, lr=lr, lr_schedule=lr_schedule, micro_batch_size=micro_batch_size, **engine_kw)
-        self.pp_group, self.dp_group = pp_group, dp_group
+        self.pp_group, self.dp_group, self.virtual_stages = pp_group, dp_group, int(virtual_stages)
 
     def initialize(self) -> None:
-        from ..parallel.pipeline import PipelineEngine
+        from ..parallel.pipeline import InterleavedPipelineEngine, PipelineEngine
 
-        self.engine = PipelineEngine(self.model_cfg, self.device, self.pp_group, self.dp_group, lr=self.base_lr, **self.engine_kw)
+        if self.virtual_stages > 1:       # Megatron's virtual_pipeline_model_parallel_size: interleaved 1F1B over model chunks
+            self.engine = InterleavedPipelineEngine(self.model_cfg, self.device, self.pp_group, self.dp_group,
+                                                    virtual_stages=self.virtual_stages, lr=self.base_lr, **self.engine_kw)
+        else:
+            self.engine = PipelineEngine(self.model_cfg, self.device, self.pp_group, self.dp_group, lr=self.base_lr, **self.engine_kw)
         self.ckpt = None
 
     def _packed(self, mb: dict):

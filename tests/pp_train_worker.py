@@ -21,7 +21,15 @@ def main():
 
     assert stage_layers(7, 3) == [(0, 3), (3, 5), (5, 7)]
     worst = {}
-    for name, pp, tied, n_layers, n_micro in (("pp2xdp2", 2, False, 4, 4), ("pp4_tied", 4, True, 5, 6), ("pp4_few_micro", 4, False, 4, 2)):
+    from polyrl_b200.parallel.pipeline import InterleavedPipelineEngine, build_interleaved_schedule
+
+    # interleaved schedule: Megatron's tick count when the micro-batch count is a multiple of pp, and the warm-up activation cap
+    for pp_, v_, m_ in ((2, 2, 4), (4, 2, 8), (4, 4, 16)):
+        tab = build_interleaved_schedule(pp_, v_, m_)
+        assert len(tab) == 2 * v_ * m_ + 2 * (pp_ - 1), (pp_, v_, m_, len(tab))
+    for name, pp, tied, n_layers, n_micro, virt in (("pp2xdp2", 2, False, 4, 4, 1), ("pp4_tied", 4, True, 5, 6, 1),
+                                                    ("pp4_few_micro", 4, False, 4, 2, 1), ("pp2v2xdp2", 2, False, 5, 4, 2),
+                                                    ("pp4v2_tied", 4, True, 8, 6, 2)):
         dp = world // pp
         pp_group = dp_group = None
         for d in range(dp):
@@ -33,8 +41,14 @@ def main():
             if s == rank % pp:
                 dp_group = g
         cfg = get_model_config("tiny-llama", num_layers=n_layers, tie_word_embeddings=tied)
-        eng = PipelineEngine(cfg, dev, pp_group, dp_group if dp > 1 else None, lr=1e-2, weight_decay=0.0, seed=11)
-        assert eng.hi - eng.lo >= 1 and (("embed" in eng.master) == (eng.first or (eng.last and tied)))
+        if virt > 1:
+            eng = InterleavedPipelineEngine(cfg, dev, pp_group, dp_group if dp > 1 else None, virtual_stages=virt, lr=1e-2,
+                                            weight_decay=0.0, seed=11)
+            assert len(eng.chunks) == virt and all(hi > lo for lo, hi in eng.chunks)
+        else:
+            eng = PipelineEngine(cfg, dev, pp_group, dp_group if dp > 1 else None, lr=1e-2, weight_decay=0.0, seed=11)
+            assert eng.hi - eng.lo >= 1
+        assert ("embed" in eng.master) == (eng.first or (eng.last and tied))
 
         def micro(dp_rank: int, k: int, step: int):
             gen = torch.Generator().manual_seed(1000 * step + 50 * dp_rank + k)
@@ -51,7 +65,8 @@ def main():
         for step in range(2):
             mbs = [micro(rank // pp, k, step) for k in range(n_micro)]
             losses = eng.train_batch(mbs, lambda lp, ent, k: (-(lp.mean()) + 0.01 * ent.mean()) / n_micro)
-            assert eng.peak_in_flight <= min(pp - eng.stage, n_micro), (eng.peak_in_flight, eng.stage)
+            cap = min(pp - eng.stage, n_micro) if virt == 1 else min(2 * (pp - eng.stage - 1) + (virt - 1) * pp + 1, virt * n_micro)
+            assert eng.peak_in_flight <= cap, (eng.peak_in_flight, eng.stage, cap)
             st = eng.step()
             for p in params.values():
                 p.grad = None
