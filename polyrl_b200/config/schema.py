@@ -97,6 +97,9 @@ class CheckpointConfig(BaseConfig):
 
 @dataclass
 class ProfilerConfig(BaseConfig):
+    """Per-role profiler switch (reference: verl/utils/profiler/config.py ProfilerConfig): which ranks of this role record, and
+    tool options merged over ``global_profiler.global_tool_config`` — ``{"nsys": {"discrete": bool}, "torch": {"step_start": int,
+    "step_end": int}, "torch_memory": {"trace_alloc_max_entries": int, "stack_depth": int}}``."""
     enable: bool = False
     all_ranks: bool = False
     ranks: list = field(default_factory=list)
@@ -250,6 +253,7 @@ class CriticConfig(BaseConfig):
     ppo_epochs: int = 1
     fsdp_config: FSDPConfig = field(default_factory=FSDPConfig)
     checkpoint: CheckpointConfig = field(default_factory=CheckpointConfig)
+    profiler: ProfilerConfig = field(default_factory=ProfilerConfig)
 
 
 @dataclass

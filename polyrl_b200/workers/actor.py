@@ -192,6 +192,9 @@ class DataParallelPPOActor:
             if is_opt_step and mi == len(mbs) - 1:
                 self.engine.arm_norm_fold()         # the last reduce-scatter of the mini-batch also produces the grad norm
             (loss * scale).backward()
+            prof = getattr(self, "profiler", None)
+            if prof is not None:
+                prof.step()                         # torch-profiler step window counts micro-batches (tool_config.torch.step_*)
             for k, v in m.items():
                 metrics.setdefault(k, []).append(v)
         if is_opt_step:

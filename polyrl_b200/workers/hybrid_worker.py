@@ -65,6 +65,8 @@ def maybe_load_pretrained(engine, path: str, rank: int = 0) -> int:
         print(f"[worker] loaded {n} tensors from {p}", flush=True)
     return n
 
+from ..utils.profiler import DistProfiler  # noqa: E402
+
 
 class ActorRolloutRefWorker:
     """role in {"actor_rollout", "actor_rollout_ref", "actor", "rollout", "ref"}."""
@@ -221,6 +223,7 @@ class ActorRolloutRefWorker:
         maybe_load_pretrained(engine, path, self.rank)
 
     # ------------------------------------------------------------------ weight sync (colocated)
+    @DistProfiler.annotate("update_weight_remote")
     def update_weight_remote(self) -> bool:
         """Publish the current actor weights to the rollout engine.  world==1: the engine *aliases* the
         trainer's bf16 shard (zero copies).  world>1: every rank gathers a full bf16 replica into
@@ -334,6 +337,7 @@ class ActorRolloutRefWorker:
             self._in_rollout_mode = False
 
     # ------------------------------------------------------------------ rollout
+    @DistProfiler.annotate("generate_sequences")
     @torch.no_grad()
     def generate_sequences(self, prompts: DataProto) -> DataProto:
         """Generate ``n`` responses per prompt with the colocated engine (sync path / validation)."""
@@ -493,6 +497,7 @@ class ActorRolloutRefWorker:
             return None
 
     # ------------------------------------------------------------------ log-probs
+    @DistProfiler.annotate("compute_log_prob")
     @torch.no_grad()
     def compute_log_prob(self, data: DataProto) -> DataProto:
         r = self.config.actor_rollout_ref.rollout
@@ -503,6 +508,7 @@ class ActorRolloutRefWorker:
         lp, ent = self.actor.compute_log_prob(data)
         return DataProto.from_dict({"old_log_probs": lp, "entropys": ent}, meta_info={"temperature": r.temperature})
 
+    @DistProfiler.annotate("compute_ref_log_prob")
     @torch.no_grad()
     def compute_ref_log_prob(self, data: DataProto) -> DataProto:
         ref = self.config.actor_rollout_ref.ref
@@ -514,6 +520,7 @@ class ActorRolloutRefWorker:
         return DataProto.from_dict({"ref_log_prob": lp})
 
     # ------------------------------------------------------------------ update
+    @DistProfiler.annotate("update_actor_stream")
     def update_actor_stream(self, data: DataProto) -> DataProto:
         meta = data.meta_info
         is_opt = meta.get("is_opt_step", True)
@@ -584,10 +591,19 @@ class ActorRolloutRefWorker:
         if self.rollout is not None:
             self.update_weight_remote()
 
-    def start_profile(self, **kw) -> None:
+    def _ensure_profiler(self):
         from ..utils.profiler import DistProfiler
 
-        self.profiler = self.profiler or DistProfiler(self.rank, self.config.global_profiler)
+        if self.profiler is None:
+            role_cfg = self.config.actor_rollout_ref.actor.profiler
+            # a role config that was never enabled means "no per-role filter": the trainer's global_profiler.steps decide
+            self.profiler = DistProfiler(self.rank, self.config.global_profiler, role_cfg if role_cfg.enable else None, role=self.role)
+            if self.actor is not None:
+                self.actor.profiler = self.profiler
+        return self.profiler
+
+    def start_profile(self, **kw) -> None:
+        self._ensure_profiler()
         self.profiler.start(**kw)
 
     def stop_profile(self) -> None:
@@ -640,6 +656,18 @@ class CriticWorker:
             device = f"cuda:{int(os.environ.get('LOCAL_RANK', 0))}" if torch.cuda.is_available() else "cpu"
         self.device = torch.device(device)
         self.lr_step = 0
+        self.profiler = None
+
+    def start_profile(self, **kw) -> None:
+        if self.profiler is None:
+            role_cfg = getattr(self.config.critic, "profiler", None)
+            self.profiler = DistProfiler(self.rank, self.config.global_profiler, role_cfg if (role_cfg is not None and role_cfg.enable) else None,
+                                         role="critic")
+        self.profiler.start(**kw)
+
+    def stop_profile(self) -> None:
+        if self.profiler is not None:
+            self.profiler.stop()
 
     def init_model(self, heap=None) -> None:
         cfg = self.config
@@ -658,6 +686,7 @@ class CriticWorker:
                                 loss_agg_mode=c.loss_agg_mode, grad_clip=c.grad_clip, cliprange_value=c.cliprange_value)
         self.critic = DataParallelPPOCritic(self.engine, rt, dp_group=self.group)
 
+    @DistProfiler.annotate("compute_values")
     @torch.no_grad()
     def compute_values(self, data: DataProto) -> DataProto:
         c = self.config.critic
@@ -666,6 +695,7 @@ class CriticWorker:
         data.meta_info.setdefault("use_dynamic_bsz", c.use_dynamic_bsz)
         return DataProto.from_dict({"values": self.critic.compute_values(data)})
 
+    @DistProfiler.annotate("update_critic_stream")
     def update_critic_stream(self, data: DataProto) -> DataProto:
         meta = data.meta_info
         is_opt = meta.get("is_opt_step", True)

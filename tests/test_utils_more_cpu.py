@@ -354,3 +354,46 @@ def test_tcp_receiver_recovers_from_an_incomplete_transfer():
         st.close()
     finally:
         rx.close()
+
+
+def test_dist_profiler_rank_filter_discrete_ranges_and_torch_window(tmp_path, monkeypatch):
+    """Per-role rank filter, discrete nsys capture ranges per annotated phase, torch traces limited to a micro-step window."""
+    from types import SimpleNamespace as NS
+
+    from polyrl_b200.utils.profiler import DistProfiler
+
+    g = NS(tool="nsys", save_path=str(tmp_path), global_tool_config={"nsys": {"discrete": True}})
+    role = NS(enable=True, all_ranks=False, ranks=[1], tool_config={})
+    assert not DistProfiler(0, g, role).this_rank and DistProfiler(1, g, role).this_rank
+    assert DistProfiler(3, g, NS(enable=True, all_ranks=True, ranks=[], tool_config={})).this_rank
+
+    class W:
+        def __init__(self, prof):
+            self.profiler = prof
+
+        @DistProfiler.annotate("gen")
+        def gen(self, x):
+            return x + 1
+
+    p = DistProfiler(1, g, role, role="actor")
+    w = W(p)
+    assert w.gen(1) == 2 and p.ranges_opened == 0          # outside a profiled step nothing is captured
+    p.start()
+    w.gen(1), w.gen(2)
+    p.stop()
+    assert p.ranges_opened == 2                              # one capture range per annotated call
+    muted = W(DistProfiler(0, g, role))
+    muted.profiler.start()
+    muted.gen(1)
+    assert muted.profiler.ranges_opened == 0                 # filtered rank
+    # torch tool with a step window: only micro-steps [1, 3) are recorded -> exactly one trace file
+    g2 = NS(tool="torch", save_path=str(tmp_path / "tr"), global_tool_config={})
+    r2 = NS(enable=True, all_ranks=True, ranks=[], tool_config={"torch": {"step_start": 1, "step_end": 3}})
+    t = DistProfiler(0, g2, r2, role="actor")
+    t.start()
+    for _ in range(5):
+        torch.ones(4).sum()
+        t.step()
+    t.stop()
+    files = list((tmp_path / "tr").glob("trace_actor_rank0_*.json"))
+    assert len(files) == 1 and t.ranges_opened == 1
