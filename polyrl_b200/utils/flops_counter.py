@@ -43,12 +43,46 @@ class FlopsCounter:
         per_layer = h * (c.q_size + 2 * c.kv_size) + c.q_size * h + mlp
         return per_layer * c.num_layers + v * h           # lm_head included, input embedding lookup excluded
 
-    def estimate_flops(self, batch_seqlens: list[int], delta_time: float, forward_only: bool = False) -> tuple[float, float]:
+    def _attn_flops(self, batch_seqlens: list[int]) -> float:
+        """QK^T + PV, fwd+bwd, counted without the causal discount (the reference's convention).  Sliding-window layers
+        (``sliding_window`` + ``layer_types`` / ``max_window_layers``) attend to at most ``window`` keys per query."""
         c = self.cfg
+        full = sum(s * s for s in batch_seqlens)
+        win = getattr(c, "sliding_window", None)
+        if not win:
+            return 12.0 * c.num_layers * c.q_size * full
+        windowed = sum(s * min(s, int(win)) for s in batch_seqlens)
+        types = getattr(c, "layer_types", None)
+        if types:
+            n_win = sum(1 for t in types if "sliding" in str(t))
+        else:
+            mwl = getattr(c, "max_window_layers", None)          # HF Qwen2: layers with index >= max_window_layers slide
+            n_win = c.num_layers if mwl is None else max(0, c.num_layers - int(mwl))
+        return 12.0 * c.q_size * ((c.num_layers - n_win) * full + n_win * windowed)
+
+    def _vision_flops(self, images_seqlens: list[int]) -> float:
+        """ViT tower (Qwen2-VL / 2.5-VL layout, models/vision.py), fwd+bwd: ``images_seqlens`` = patches per image (before the
+        spatial merge).  Dense 6·N_vit·patches + 12·depth·dim·Σ p² attention (full attention inside an image) + the merger MLP."""
+        v = self.cfg.vision
+        if not v or not images_seqlens:
+            return 0.0
+        dim, depth = int(v["embed_dim"]), int(v["depth"])
+        inter = int(v.get("intermediate_size") or dim * float(v.get("mlp_ratio", 4)))
+        mlp = (3 if v.get("arch") == "qwen2_5" else 2) * dim * inter
+        per_block = 4 * dim * dim + mlp
+        patches = sum(images_seqlens)
+        in_ch = int(v.get("in_channels", 3)) * int(v.get("temporal_patch_size", 2)) * int(v["patch_size"]) ** 2
+        merge = int(v.get("spatial_merge_size", 2)) ** 2
+        merger = (dim * merge) * (dim * merge) + (dim * merge) * self.cfg.hidden_size          # per merged token
+        dense = 6.0 * (per_block * depth + in_ch * dim) * patches + 6.0 * merger * (patches / merge)
+        return dense + 12.0 * depth * dim * sum(p * p for p in images_seqlens)
+
+    def estimate_flops(self, batch_seqlens: list[int], delta_time: float, forward_only: bool = False,
+                       images_seqlens: list[int] | None = None) -> tuple[float, float]:
+        """(achieved TFLOP/s, device peak TFLOP/s).  Families: llama / qwen2 / qwen3 dense (gated MLP), gpt2 (plain MLP), MoE
+        (routed experts only), sliding-window variants, vision-language models (pass ``images_seqlens``)."""
         tokens = sum(batch_seqlens)
-        dense = 6 * self._dense_params() * tokens
-        attn = 12 * c.num_layers * c.q_size * sum(s * s for s in batch_seqlens)
-        total = dense + attn
+        total = 6.0 * self._dense_params() * tokens + self._attn_flops(batch_seqlens) + self._vision_flops(images_seqlens or [])
         if forward_only:
             total /= 3
         return total / max(delta_time, 1e-9) / 1e12, get_device_flops("T")

@@ -27,6 +27,22 @@ def test_flops_counter_matches_6nd_rule():
     fwd, _ = fc.estimate_flops([512] * 32, 1.0, forward_only=True)
     assert abs(fwd * 3 - tf_s) / tf_s < 1e-9
     assert DEVICE_PEAK_BF16["B200"] == 2.25e15
+    # vision-language: the tower's FLOPs are added per image (patch count before the merge); the text part is unchanged
+    vl = get_model_config("qwen2-vl-7b") if "qwen2-vl-7b" in __import__("polyrl_b200.models.config", fromlist=["PRESETS"]).PRESETS else None
+    if vl is not None:
+        fv = FlopsCounter(vl)
+        base, _ = fv.estimate_flops([1024], 1.0)
+        with_img, _ = fv.estimate_flops([1024], 1.0, images_seqlens=[1024])
+        vit = (with_img - base) * 1e12
+        assert 6 * 0.6e9 * 1024 < vit < 6 * 0.75e9 * 1024 * 1.3          # ~0.67 B-parameter tower + its attention
+    # sliding-window layers attend to at most `window` keys
+    import dataclasses
+
+    sw = dataclasses.replace(cfg) if dataclasses.is_dataclass(cfg) else cfg
+    object.__setattr__(sw, "sliding_window", 128)
+    object.__setattr__(sw, "max_window_layers", 0)
+    short, _ = FlopsCounter(sw).estimate_flops([512] * 32, 1.0)
+    assert short < tf_s and abs((tf_s - short) * 1e12 - 12 * cfg.num_layers * cfg.q_size * 32 * (512 * 512 - 512 * 128)) / (tf_s * 1e12) < 1e-9
 
 
 def test_model_merger_roundtrip_and_hf_names(tmp_path):
