@@ -2,6 +2,7 @@
 // Kernel translation units are torch-free (raw pointers + cudaStream_t) so they compile in seconds;
 // this file is the only one that sees torch headers.
 #include <ATen/cuda/CUDAContext.h>
+#include "kv_manager.hpp"
 #include <c10/cuda/CUDAGuard.h>
 #include <torch/extension.h>
 
@@ -671,6 +672,22 @@ void nvls_bcast_store(const at::Tensor& src, int64_t mc_dst, int64_t ctas) {
 }
 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
+  py::class_<prl::KvPageManager>(m, "KvPageManager")
+      .def(py::init<int64_t, int64_t>(), py::arg("num_blocks"), py::arg("page_size"))
+      .def_property_readonly("num_blocks", &prl::KvPageManager::num_blocks)
+      .def("available", &prl::KvPageManager::available)
+      .def("ref", &prl::KvPageManager::ref)
+      .def("alloc", &prl::KvPageManager::alloc)
+      .def("share", &prl::KvPageManager::share)
+      .def("release", &prl::KvPageManager::release)
+      .def("page_keys", &prl::KvPageManager::page_keys)
+      .def("match", &prl::KvPageManager::match)
+      .def("insert", &prl::KvPageManager::insert)
+      .def("evict", &prl::KvPageManager::evict)
+      .def("flush", &prl::KvPageManager::flush)
+      .def("cached_pages", &prl::KvPageManager::cached_pages)
+      .def_property_readonly("hits", &prl::KvPageManager::hits)
+      .def_property_readonly("misses", &prl::KvPageManager::misses);
   m.def("gemm_bf16", &gemm_bf16, py::arg("a"), py::arg("b"), py::arg("residual") = py::none(),
         py::arg("out") = py::none(), py::arg("force_bn") = 0);
   m.def("gemm2_bf16", &gemm2_bf16, py::arg("a"), py::arg("b"), py::arg("a_mn") = false, py::arg("b_mn") = false,

@@ -25,7 +25,7 @@ class _CountingExt:
         fn = self._cache.get(name)
         if fn is None:
             raw = getattr(self._mod, name)
-            if not callable(raw):
+            if not callable(raw) or isinstance(raw, type):       # attributes and host-side classes (KvPageManager) are not launches
                 return raw
 
             def fn(*a, _raw=raw, _n=name, **kw):

@@ -39,6 +39,7 @@ CU_SOURCES = [
     "nvls.cu",
 ]
 HEADERS = ["common.cuh", "gemm_sm100.cuh", "gemm2_sm100.cuh"]
+HOST_HEADERS = ["kv_manager.hpp"]          # included by bindings.cpp only
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",
@@ -91,7 +92,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     bsrc = CSRC / "bindings.cpp"
     bobj = BUILD / "bindings.o"
     objs.append(bobj)
-    if force or _newer(bsrc, bobj, []):
+    if force or _newer(bsrc, bobj, [CSRC / h for h in HOST_HEADERS]):
         inc = []
         for p in ce.include_paths("cuda") if "device_type" in ce.include_paths.__code__.co_varnames else ce.include_paths(True):
             inc += ["-isystem", p]

@@ -16,6 +16,7 @@ CUDA graph and replayed; the host only feeds page-table deltas and reads back to
 from __future__ import annotations
 
 import itertools
+import os
 import time
 import zlib
 from collections import deque
@@ -180,6 +181,78 @@ class PrefixCache:
             self._drop(b)
 
 
+class NativeBlockAllocator:
+    """``BlockAllocator`` API over the C++ ``KvPageManager`` (csrc/kv_manager.hpp)."""
+
+    def __init__(self, num_blocks: int, mgr=None):
+        from ..ops import ext
+
+        self.num_blocks = num_blocks
+        self.mgr = mgr or ext().KvPageManager(num_blocks, PAGE)
+
+    def available(self) -> int:
+        return self.mgr.available()
+
+    def alloc(self, n: int) -> list[int]:
+        try:
+            return self.mgr.alloc(n)
+        except RuntimeError as e:
+            raise MemoryError(str(e)) from None
+
+    def share(self, blocks: list[int]) -> None:
+        self.mgr.share(blocks)
+
+    def release(self, blocks: list[int]) -> None:
+        self.mgr.release(blocks)
+
+
+class NativePrefixCache:
+    """``PrefixCache`` API over the same C++ object as the allocator (page keys are hashed natively, one call per request)."""
+
+    def __init__(self, alloc: NativeBlockAllocator):
+        self.alloc, self.mgr = alloc, alloc.mgr
+
+    def page_keys(self, tokens: list[int], max_pages: int) -> list[int]:
+        return self.mgr.page_keys(tokens, max_pages)
+
+    def match(self, keys: list[int]) -> list[int]:
+        return self.mgr.match(keys)
+
+    def insert(self, keys: list[int], blocks: list[int]) -> None:
+        self.mgr.insert(keys, blocks)
+
+    def evict(self, want: int) -> int:
+        return self.mgr.evict(want)
+
+    def flush(self) -> None:
+        self.mgr.flush()
+
+    @property
+    def by_key(self):
+        return range(self.mgr.cached_pages())
+
+    @property
+    def hits(self) -> int:
+        return self.mgr.hits
+
+    @property
+    def misses(self) -> int:
+        return self.mgr.misses
+
+
+def make_kv_manager(num_blocks: int, prefix_cache: bool):
+    """(allocator, prefix cache or None): the native page manager unless ``POLYRL_NATIVE_KV=0`` or the extension is not built."""
+    if os.environ.get("POLYRL_NATIVE_KV", "1") == "1":
+        try:
+            alloc = NativeBlockAllocator(num_blocks)
+            return alloc, (NativePrefixCache(alloc) if prefix_cache else None)
+        except Exception:            # noqa: BLE001  (no extension in this environment: pure-Python bookkeeping)
+            if torch.cuda.is_available():
+                raise
+    alloc = BlockAllocator(num_blocks)
+    return alloc, (PrefixCache(alloc) if prefix_cache else None)
+
+
 class RolloutEngine:
     def __init__(self, cfg: ModelConfig, device, max_num_seqs: int = 256, max_model_len: int = 2048,
                  kv_cache_tokens: int | None = None, gpu_memory_utilization: float = 0.5, dtype=None,
@@ -330,13 +403,11 @@ class RolloutEngine:
             self.k_cache, self.v_cache = self._kv_views
             for t in (*self.k_cache, *self.v_cache):
                 t.zero_()                              # fresh physical pages: masked tail slots must hold finite values
-            self.alloc = BlockAllocator(self._kv_blocks)
-            self.prefix_cache = PrefixCache(self.alloc) if self.enable_prefix_cache else None
+            self.alloc, self.prefix_cache = make_kv_manager(self._kv_blocks, self.enable_prefix_cache)
             return
         self.k_cache = [torch.zeros(shape, device=self.device, dtype=self.dtype) for _ in range(c.num_layers)]
         self.v_cache = [torch.zeros(shape, device=self.device, dtype=self.dtype) for _ in range(c.num_layers)]
-        self.alloc = BlockAllocator(num_blocks)
-        self.prefix_cache = PrefixCache(self.alloc) if self.enable_prefix_cache else None
+        self.alloc, self.prefix_cache = make_kv_manager(num_blocks, self.enable_prefix_cache)
         self._graphs.clear()
 
     def release_memory(self, tags=("kv_cache",)) -> None:
@@ -455,7 +526,7 @@ class RolloutEngine:
             keys: list[int] = []
             if donor is None and self.prefix_cache is not None and r.mm is None:     # placeholder ids do not identify an image
                 # at least the last prompt token must be recomputed (its logits seed the first sampled token)
-                keys = PrefixCache.page_keys(r.prompt_ids, (len(r.prompt_ids) - 1) // PAGE)
+                keys = self.prefix_cache.page_keys(r.prompt_ids, (len(r.prompt_ids) - 1) // PAGE)
                 cached = self.prefix_cache.match(keys)
                 self.alloc.share(cached)            # pin before any eviction below can touch them
             fresh = need - (full_prompt_pages if donor is not None else len(cached))
@@ -501,7 +572,7 @@ class RolloutEngine:
                 # every FULL page whose KV is final: prompt + generated tokens except the last one (never fed back)
                 toks = r.prompt_ids + r.output_ids
                 n_full = max(0, (len(toks) - 1)) // PAGE
-                self.prefix_cache.insert(PrefixCache.page_keys(toks, n_full), r.blocks[:n_full])
+                self.prefix_cache.insert(self.prefix_cache.page_keys(toks, n_full), r.blocks[:n_full])
             self.alloc.release(r.blocks)
         r.blocks = []
 

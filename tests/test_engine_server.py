@@ -512,3 +512,61 @@ def test_tcp_push_survives_a_vanished_instance():
     s = TrainerWeightSender("127.0.0.1:1", sync=None)
     s._tcp_push(eng, 0, ["127.0.0.1:9"])                # nobody listens there
     assert s.failed_targets == ["127.0.0.1:9"]
+
+
+def test_native_kv_manager_matches_python_reference():
+    """C++ KvPageManager (csrc/kv_manager.hpp) vs the Python BlockAllocator + PrefixCache under a random op sequence: same free
+    counts, same hit lengths, same eviction results, ref counts consistent."""
+    import random
+
+    from polyrl_b200.ops import have_ext
+    from polyrl_b200.rollout.engine import PAGE, BlockAllocator, NativeBlockAllocator, NativePrefixCache, PrefixCache
+
+    if not have_ext():
+        pytest.skip("extension not built")
+    rng = random.Random(5)
+    nb = 40
+    pa, na = BlockAllocator(nb), NativeBlockAllocator(nb)
+    pc, nc = PrefixCache(pa), NativePrefixCache(na)
+    live: list[tuple[list[int], list[int], list[int]]] = []       # (tokens, python blocks, native blocks)
+    vocab = 7
+    prefixes = [[rng.randrange(vocab) for _ in range(3 * PAGE)] for _ in range(3)]      # shared "system prompts"
+    for step in range(600):
+        op = rng.random()
+        if op < 0.5:                                              # admit a request: match prefix, allocate the rest
+            base = prefixes[rng.randrange(len(prefixes))]
+            toks = base[: rng.randrange(0, 4) * PAGE] + [rng.randrange(vocab) for _ in range(rng.randrange(1, 3) * PAGE + rng.randrange(PAGE))]
+            n_pages = (len(toks) - 1) // PAGE
+            pk, nk = PrefixCache.page_keys(toks, n_pages), nc.page_keys(toks, n_pages)
+            assert len(pk) == len(nk) == n_pages
+            ph, nh = pc.match(pk), nc.match(nk)
+            assert len(ph) == len(nh), (step, len(ph), len(nh))
+            pa.share(ph), na.share(nh)
+            need = (len(toks) + PAGE - 1) // PAGE - len(ph)
+            if need > pa.available():
+                assert pc.evict(need - pa.available()) == nc.evict(need - na.available())
+            if need > pa.available():
+                pa.release(ph), na.release(nh)
+                with pytest.raises(MemoryError):
+                    na.alloc(need)
+                continue
+            live.append((toks, ph + pa.alloc(need), nh + na.alloc(need)))
+        elif live:                                                # finish a request: publish its full pages, release
+            toks, pb, nbk = live.pop(rng.randrange(len(live)))
+            n_full = (len(toks) - 1) // PAGE
+            if op < 0.9:
+                pc.insert(PrefixCache.page_keys(toks, n_full), pb[:n_full])
+                nc.insert(nc.page_keys(toks, n_full), nbk[:n_full])
+            pa.release(pb), na.release(nbk)
+        assert pa.available() == na.available(), step
+        assert len(pc.by_key) == len(nc.by_key), step
+    assert pc.hits == nc.hits and pc.misses == nc.misses and pc.hits > 0
+    for _, pb, nbk in live:
+        pa.release(pb), na.release(nbk)
+    pc.flush(), nc.flush()
+    assert pa.available() == na.available() == nb - 1 and not nc.by_key
+    # chained keys: changing an early token changes every later key; equal prefixes share keys
+    a = nc.page_keys(list(range(3 * PAGE)), 3)
+    b = nc.page_keys([99] + list(range(1, 3 * PAGE)), 3)
+    c = nc.page_keys(list(range(2 * PAGE)) + [0] * PAGE, 3)
+    assert len(set(a)) == 3 and all(x != y for x, y in zip(a, b)) and a[:2] == c[:2] and a[2] != c[2]
