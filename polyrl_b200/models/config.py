@@ -34,6 +34,11 @@ class ModelConfig:
     bos_token_id: int = 1
     name: str = "custom"
     value_head: bool = False         # critic: scalar head instead of lm_head
+    # Mistral-style local attention: every query sees at most ``sliding_window`` keys.  The kernels implement full causal
+    # attention, which is the same thing while sequences are no longer than the window (RL rollouts of a few K tokens against
+    # Mistral's 4096 / 32768) — longer sequences are rejected instead of silently attending too far (models/transformer.py).
+    sliding_window: int | None = None
+    hf_model_type: str = ""          # the HF model_type this config was read from (export writes it back)
     # mixture-of-experts MLPs (Qwen3-MoE layout): every block routes each token to ``num_experts_per_tok`` of ``num_experts`` SwiGLU
     # experts of width ``moe_intermediate_size``; 0 experts = dense MLP
     num_experts: int = 0
@@ -117,7 +122,7 @@ class ModelConfig:
 
     @classmethod
     def from_hf_config(cls, hf: dict) -> "ModelConfig":
-        """Translate a HuggingFace ``config.json`` dict (Llama / Qwen2 / Qwen3 / GPT-2)."""
+        """Translate a HuggingFace ``config.json`` dict (Llama / Mistral / Qwen2 / Qwen3 / Qwen3-MoE / Qwen2-VL / GPT-2)."""
         mt = hf.get("model_type", "llama")
         if mt == "gpt2":
             return cls(family="gpt2", vocab_size=hf["vocab_size"], hidden_size=hf["n_embd"],
@@ -165,6 +170,8 @@ class ModelConfig:
                    qkv_bias=(mt == "qwen2") or hf.get("attention_bias", False), qk_norm=(mt == "qwen3"),
                    tie_word_embeddings=hf.get("tie_word_embeddings", False), eos_token_id=eos, extra_eos_token_ids=extra_eos,
                    bos_token_id=hf.get("bos_token_id") or eos, pad_token_id=hf.get("pad_token_id") or eos,
+                   sliding_window=(hf.get("sliding_window") if (mt == "mistral" or hf.get("use_sliding_window")) else None),
+                   hf_model_type=mt if mt in ("mistral",) else "",
                    name=hf.get("_name_or_path", mt), **vis_kw, **moe_kw)
 
 
@@ -175,6 +182,9 @@ PRESETS: dict[str, dict] = {
     "llama3-70b": dict(family="llama", vocab_size=128256, hidden_size=8192, intermediate_size=28672, num_layers=80,
                        num_heads=64, num_kv_heads=8, max_position_embeddings=8192, rope_theta=500000.0,
                        rms_norm_eps=1e-5, eos_token_id=128001, bos_token_id=128000, pad_token_id=128001),
+    "mistral-7b": dict(family="llama", vocab_size=32768, hidden_size=4096, intermediate_size=14336, num_layers=32, num_heads=32,
+                       num_kv_heads=8, max_position_embeddings=32768, rope_theta=1000000.0, rms_norm_eps=1e-5, eos_token_id=2,
+                       bos_token_id=1, pad_token_id=2, hf_model_type="mistral"),
     "qwen2-7b": dict(family="llama", vocab_size=152064, hidden_size=3584, intermediate_size=18944, num_layers=28,
                      num_heads=28, num_kv_heads=4, max_position_embeddings=32768, rope_theta=1000000.0,
                      rms_norm_eps=1e-6, qkv_bias=True, eos_token_id=151643, bos_token_id=151643, pad_token_id=151643),

@@ -210,10 +210,14 @@ def hf_config_dict(cfg: ModelConfig) -> dict:
                 "rope_scaling": {"type": "mrope", "mrope_section": list(cfg.mrope_section)}, "rope_theta": cfg.rope_theta}
     mt = "qwen3" if cfg.qk_norm else ("qwen2" if cfg.qkv_bias else "llama")
     arch = {"qwen3": "Qwen3ForCausalLM", "qwen2": "Qwen2ForCausalLM", "llama": "LlamaForCausalLM"}[mt]
+    if getattr(cfg, "hf_model_type", "") == "mistral" and mt == "llama":
+        mt, arch = "mistral", "MistralForCausalLM"
     moe = {}
+    if cfg.sliding_window:
+        moe["sliding_window"] = int(cfg.sliding_window)
     if cfg.num_experts:
         mt, arch = "qwen3_moe", "Qwen3MoeForCausalLM"
-        moe = {"num_experts": cfg.num_experts, "num_experts_per_tok": cfg.num_experts_per_tok, "moe_intermediate_size": cfg.moe_intermediate_size,
+        moe = {**moe, "num_experts": cfg.num_experts, "num_experts_per_tok": cfg.num_experts_per_tok, "moe_intermediate_size": cfg.moe_intermediate_size,
                "norm_topk_prob": cfg.norm_topk_prob, "decoder_sparse_step": 1, "mlp_only_layers": []}
     return {**moe, "model_type": mt, "architectures": [arch], "vocab_size": cfg.vocab_size, "hidden_size": cfg.hidden_size,
             "intermediate_size": cfg.intermediate_size, "num_hidden_layers": cfg.num_layers, "num_attention_heads": cfg.num_heads,

@@ -242,6 +242,9 @@ def layer_forward(cfg: ModelConfig, w: dict, x: torch.Tensor, inp: PackedInput, 
     makes this a prefill step that also fills the paged KV cache (rollout engine)."""
     nq, nkv, d = cfg.num_heads, cfg.num_kv_heads, cfg.head_dim
     t = x.shape[0]
+    if cfg.sliding_window and inp.max_seqlen > cfg.sliding_window:
+        raise NotImplementedError(f"sequence of {inp.max_seqlen} tokens exceeds the model's attention window "
+                                  f"({cfg.sliding_window}); windowed attention is not implemented, only the full-causal case")
     if cfg.family == "llama":
         lora = "_lora_scale" in w
         if lora:

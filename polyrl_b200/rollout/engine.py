@@ -259,6 +259,9 @@ class RolloutEngine:
                  use_cuda_graph: bool = True, max_prefill_tokens: int = 16384, seed: int = 0, tp=None,
                  weight_dtype: str = "bf16", steps_per_sync: int | None = None, enable_prefix_cache: bool = False,
                  kv_vmm: bool | None = None):
+        if cfg.sliding_window and max_model_len > cfg.sliding_window:
+            raise NotImplementedError(f"max_model_len {max_model_len} exceeds the model's attention window {cfg.sliding_window}: "
+                                      "windowed decode attention is not implemented (full-causal only)")
         # decode steps launched back to back per host round trip (tokens are read back once per window; a sequence that
         # ends mid-window rides along for a few ignored tokens).  1 = one-step lag only.
         import os as _os

@@ -18,12 +18,15 @@ def _hf(name):
                   max_position_embeddings=256, rope_theta=10000.0)
     if name == "llama":
         return transformers.LlamaForCausalLM(transformers.LlamaConfig(rms_norm_eps=1e-5, tie_word_embeddings=False, attention_bias=False, **common))
+    if name == "mistral":
+        return transformers.MistralForCausalLM(transformers.MistralConfig(rms_norm_eps=1e-5, tie_word_embeddings=False, sliding_window=64,
+                                                                          **common))
     if name == "qwen2":
         return transformers.Qwen2ForCausalLM(transformers.Qwen2Config(rms_norm_eps=1e-6, tie_word_embeddings=False, **common))
     return transformers.Qwen3ForCausalLM(transformers.Qwen3Config(rms_norm_eps=1e-6, head_dim=32, tie_word_embeddings=True, attention_bias=False, **common))
 
 
-@pytest.mark.parametrize("name", ["llama", "qwen2", "qwen3"])
+@pytest.mark.parametrize("name", ["llama", "mistral", "qwen2", "qwen3"])
 def test_logits_match_hf(name):
     torch.manual_seed(0)
     m = _hf(name).eval().float()
@@ -45,6 +48,14 @@ def test_logits_match_hf(name):
         got = forward_hidden(cfg, w, inp) @ lm_head_weight(cfg, w.head, w.embed).t()
     keep = mask.bool()
     assert (got - want[keep]).abs().max().item() < 2e-4
+    if name == "mistral":                                           # the window is recorded, exported, and enforced
+        from polyrl_b200.models.hf_io import hf_config_dict
+
+        out = hf_config_dict(cfg)
+        assert cfg.sliding_window == 64 and out["model_type"] == "mistral" and out["sliding_window"] == 64
+        long_ids = torch.randint(0, 320, (1, 80))
+        with pytest.raises(NotImplementedError, match="attention window"):
+            forward_hidden(cfg, w, pack_padded(long_ids, torch.ones_like(long_ids))[0])
     back = tf.export_hf_state_dict(cfg, sd)                         # export restores every HF tensor bit for bit
     hf_sd = m.state_dict()
     assert all(torch.equal(back[k], hf_sd[k]) for k in back if k in hf_sd) and len([k for k in back if k in hf_sd]) >= len(hf_sd) - 1
