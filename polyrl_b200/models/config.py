@@ -49,6 +49,7 @@ class ModelConfig:
     # stack rotates with 3-axis (t, h, w) M-RoPE.  ``vision`` holds the tower shape (see models/vision.py), None = text only.
     vision: dict | None = None
     mrope_section: tuple = ()        # rotary frequency split between the (t, h, w) position streams, sums to head_dim / 2
+    mrope_interleaved: bool = False  # Qwen3-VL: the three streams alternate frequency by frequency instead of owning contiguous chunks
     image_token_id: int = -1
     video_token_id: int = -1
     vision_start_token_id: int = -1
@@ -132,6 +133,24 @@ class ModelConfig:
                        eos_token_id=hf.get("eos_token_id", 50256), bos_token_id=hf.get("bos_token_id", 50256),
                        pad_token_id=hf.get("pad_token_id") or hf.get("eos_token_id", 50256), name=hf.get("_name_or_path", "gpt2"))
         vis_kw: dict = {}
+        if mt == "qwen3_vl":
+            vc = dict(hf.get("vision_config") or {})
+            top = hf
+            hf = {**{k: v for k, v in hf.items() if k not in ("text_config", "vision_config")}, **(hf.get("text_config") or {})}
+            rope = hf.get("rope_parameters") or hf.get("rope_scaling") or {}
+            hf.setdefault("rope_theta", rope.get("rope_theta", 5000000.0))
+            vision = dict(arch="qwen3", depth=vc["depth"], embed_dim=vc["hidden_size"], num_heads=vc["num_heads"],
+                          patch_size=vc["patch_size"], spatial_merge_size=vc.get("spatial_merge_size", 2),
+                          temporal_patch_size=vc.get("temporal_patch_size", 2), in_channels=vc.get("in_channels", 3),
+                          intermediate_size=vc["intermediate_size"], hidden_act=vc.get("hidden_act", "gelu_pytorch_tanh"),
+                          num_position_embeddings=vc.get("num_position_embeddings", 2304),
+                          deepstack_visual_indexes=list(vc.get("deepstack_visual_indexes", ())))
+            vis_kw = dict(vision=vision, mrope_section=tuple(rope.get("mrope_section", ())),
+                          mrope_interleaved=bool(rope.get("mrope_interleaved", True)), image_token_id=top.get("image_token_id", -1),
+                          video_token_id=top.get("video_token_id", -1), vision_start_token_id=top.get("vision_start_token_id", -1),
+                          vision_end_token_id=top.get("vision_end_token_id", -1))
+            hf["tie_word_embeddings"] = top.get("tie_word_embeddings", hf.get("tie_word_embeddings", False))
+            mt = "qwen3"
         if mt in ("qwen2_vl", "qwen2_5_vl"):
             # transformers >= 4.5x nests the text stack under text_config; older checkpoints keep it flat
             vc = dict(hf.get("vision_config") or {})
@@ -228,6 +247,22 @@ PRESETS: dict[str, dict] = {
                           vision=dict(depth=2, embed_dim=64, num_heads=4, patch_size=4, spatial_merge_size=2,
                                       temporal_patch_size=2, in_channels=3, mlp_ratio=2),
                           mrope_section=(4, 6, 6), image_token_id=500, video_token_id=501, vision_start_token_id=499, vision_end_token_id=498),
+    "tiny-qwen3-vl": dict(family="llama", vocab_size=512, hidden_size=128, intermediate_size=256, num_layers=4, num_heads=4,
+                          num_kv_heads=2, head_dim=32, max_position_embeddings=512, rope_theta=10000.0, rms_norm_eps=1e-6,
+                          qk_norm=True, eos_token_id=1, bos_token_id=2, pad_token_id=0,
+                          vision=dict(arch="qwen3", depth=3, embed_dim=64, intermediate_size=96, num_heads=4, patch_size=4,
+                                      spatial_merge_size=2, temporal_patch_size=2, in_channels=3, hidden_act="gelu_pytorch_tanh",
+                                      num_position_embeddings=36, deepstack_visual_indexes=[0, 2]),
+                          mrope_section=(6, 5, 5), mrope_interleaved=True, image_token_id=500, video_token_id=501,
+                          vision_start_token_id=499, vision_end_token_id=498),
+    "qwen3-vl-8b": dict(family="llama", vocab_size=151936, hidden_size=4096, intermediate_size=12288, num_layers=36, num_heads=32,
+                        num_kv_heads=8, head_dim=128, max_position_embeddings=262144, rope_theta=5000000.0, rms_norm_eps=1e-6,
+                        qk_norm=True, eos_token_id=151645, bos_token_id=151643, pad_token_id=151643,
+                        vision=dict(arch="qwen3", depth=27, embed_dim=1152, intermediate_size=4304, num_heads=16, patch_size=16,
+                                    spatial_merge_size=2, temporal_patch_size=2, in_channels=3, hidden_act="gelu_pytorch_tanh",
+                                    num_position_embeddings=2304, deepstack_visual_indexes=[8, 16, 24]),
+                        mrope_section=(24, 20, 20), mrope_interleaved=True, image_token_id=151655, video_token_id=151656,
+                        vision_start_token_id=151652, vision_end_token_id=151653),
     # kernel-friendly VLM test config (head_dim 128 for the CUDA decode / rope kernels)
     "tiny-qwen2-vl-128": dict(family="llama", vocab_size=1024, hidden_size=512, intermediate_size=1024, num_layers=2, num_heads=4,
                               num_kv_heads=2, head_dim=128, max_position_embeddings=1024, rope_theta=10000.0, rms_norm_eps=1e-6,

@@ -194,6 +194,21 @@ def hf_config_dict(cfg: ModelConfig) -> dict:
                 "tie_word_embeddings": cfg.tie_word_embeddings, "eos_token_id": cfg.eos_token_id, "bos_token_id": cfg.bos_token_id,
                 "pad_token_id": cfg.pad_token_id,
                 "rope_parameters": {"rope_type": "default", "rope_theta": cfg.rope_theta, "mrope_section": list(cfg.mrope_section)}}
+        if cfg.vision.get("arch") == "qwen3":
+            v = cfg.vision
+            text.update(model_type="qwen3_vl_text", head_dim=cfg.head_dim, attention_bias=False,
+                        rope_parameters={"rope_type": "default", "rope_theta": cfg.rope_theta, "mrope_section": list(cfg.mrope_section),
+                                         "mrope_interleaved": bool(cfg.mrope_interleaved)})
+            vis = {"depth": v["depth"], "hidden_size": v["embed_dim"], "hidden_act": v.get("hidden_act", "gelu_pytorch_tanh"),
+                   "intermediate_size": v["intermediate_size"], "num_heads": v["num_heads"], "in_channels": v.get("in_channels", 3),
+                   "patch_size": v["patch_size"], "spatial_merge_size": v.get("spatial_merge_size", 2),
+                   "temporal_patch_size": v.get("temporal_patch_size", 2), "out_hidden_size": cfg.hidden_size,
+                   "num_position_embeddings": v["num_position_embeddings"],
+                   "deepstack_visual_indexes": list(v.get("deepstack_visual_indexes") or ())}
+            return {"model_type": "qwen3_vl", "architectures": ["Qwen3VLForConditionalGeneration"], "text_config": text,
+                    "vision_config": vis, "image_token_id": cfg.image_token_id, "video_token_id": cfg.video_token_id,
+                    "vision_start_token_id": cfg.vision_start_token_id, "vision_end_token_id": cfg.vision_end_token_id,
+                    "tie_word_embeddings": cfg.tie_word_embeddings, "torch_dtype": "bfloat16"}
         v25 = cfg.vision.get("arch") == "qwen2_5"
         vis = {k: v for k, v in cfg.vision.items() if k != "arch"}
         if v25:

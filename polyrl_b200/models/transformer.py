@@ -439,8 +439,12 @@ class TransformerWeights:
 
 def forward_hidden(cfg: ModelConfig, weights: TransformerWeights, inp: PackedInput) -> torch.Tensor:
     x = embed_forward(cfg, weights.embed, inp)
-    for w in weights.layers:
+    for i, w in enumerate(weights.layers):
         x = layer_forward(cfg, w, x, inp)
+        if inp.image_embeds is not None and cfg.vision is not None:
+            from .vision import deepstack_add
+
+            x = deepstack_add(cfg, x, inp.input_ids, inp.image_embeds, i)          # Qwen3-VL DeepStack (no-op otherwise)
     return final_norm(cfg, weights.head, x)
 
 

@@ -1,4 +1,5 @@
-"""Vision-language support (Qwen2-VL family): ViT tower, patch merger, M-RoPE positions, image preprocessing.
+"""Vision-language support (Qwen2-VL, Qwen2.5-VL and Qwen3-VL families): ViT tower, patch merger, DeepStack, M-RoPE positions,
+image preprocessing.
 
 The reference trains VLMs by monkey-patching the HF Qwen2-VL classes (3rdparty/verl/verl/models/transformers/qwen2_vl.py:
 ``get_rope_index`` :36-150, flash-attention forward with 3-axis rotary :153-318, ``process_position_ids``) and feeds images through
@@ -52,9 +53,32 @@ def is_v25(cfg: ModelConfig) -> bool:
     return _v(cfg).get("arch", "qwen2") == "qwen2_5"
 
 
+def is_v3(cfg: ModelConfig) -> bool:
+    """Qwen3-VL tower: LayerNorm blocks with a plain GELU-tanh MLP, biased patch embedding, learned position embeddings that are
+    bilinearly interpolated to the image grid, full attention inside a frame, and DeepStack — the outputs of the
+    ``deepstack_visual_indexes`` blocks go through their own mergers and are added to the hidden states of the first decoder
+    layers at the image-token positions (reference: 3rdparty/verl/verl/models/transformers/qwen3_vl.py)."""
+    return _v(cfg).get("arch", "qwen2") == "qwen3"
+
+
+def deepstack_levels(cfg: ModelConfig) -> int:
+    if cfg.vision is None or cfg.vision.get("arch") != "qwen3":
+        return 0
+    return len(cfg.vision.get("deepstack_visual_indexes") or ())
+
+
+def embed_width(cfg: ModelConfig) -> int:
+    """Columns of the tower output: the merged embedding followed by one block of ``hidden_size`` columns per DeepStack level."""
+    return cfg.hidden_size * (1 + deepstack_levels(cfg))
+
+
 def vision_block_specs(cfg: ModelConfig) -> ParamSpec:
     v = _v(cfg)
     e = v["embed_dim"]
+    if is_v3(cfg):
+        f = int(v["intermediate_size"])
+        return [("ln1_w", (e,)), ("ln1_b", (e,)), ("wqkv", (3 * e, e)), ("bqkv", (3 * e,)), ("wo", (e, e)), ("bo", (e,)),
+                ("ln2_w", (e,)), ("ln2_b", (e,)), ("wfc", (f, e)), ("bfc", (f,)), ("wproj", (e, f)), ("bproj", (e,))]
     if is_v25(cfg):
         f = int(v["intermediate_size"])
         return [("ln1_w", (e,)), ("wqkv", (3 * e, e)), ("bqkv", (3 * e,)), ("wo", (e, e)), ("bo", (e,)), ("ln2_w", (e,)),
@@ -69,8 +93,15 @@ def vision_stem_specs(cfg: ModelConfig) -> ParamSpec:
     v = _v(cfg)
     e, m = v["embed_dim"], v["embed_dim"] * v["spatial_merge_size"] ** 2
     ln = [("merger_ln_w", (e,))] if is_v25(cfg) else [("merger_ln_w", (e,)), ("merger_ln_b", (e,))]
-    return [("patch_embed", (e, patch_dim(cfg))), *ln, ("merger_w1", (m, m)),
+    base = [("patch_embed", (e, patch_dim(cfg))), *ln, ("merger_w1", (m, m)),
             ("merger_b1", (m,)), ("merger_w2", (cfg.hidden_size, m)), ("merger_b2", (cfg.hidden_size,))]
+    if not is_v3(cfg):
+        return base
+    extra = [("patch_embed_b", (e,)), ("pos_embed", (int(v["num_position_embeddings"]), e))]
+    for k in range(deepstack_levels(cfg)):           # DeepStack mergers normalise AFTER the merge-block shuffle (width m)
+        extra += [(f"ds{k}_ln_w", (m,)), (f"ds{k}_ln_b", (m,)), (f"ds{k}_w1", (m, m)), (f"ds{k}_b1", (m,)),
+                  (f"ds{k}_w2", (cfg.hidden_size, m)), (f"ds{k}_b2", (cfg.hidden_size,))]
+    return base + extra
 
 
 def vision_unit_specs(cfg: ModelConfig) -> ParamSpec:
@@ -101,7 +132,7 @@ def vision_num_params(cfg: ModelConfig) -> int:
 def _init(name: str, t: torch.Tensor, g) -> None:
     if name.endswith("_w") and "ln" in name:
         t.fill_(1.0)
-    elif name.startswith("b") or name.endswith("_b") or name.startswith("merger_b"):
+    elif name.startswith("b") or name.endswith("_b") or name.startswith("merger_b") or (name.startswith("ds") and "_b" in name):
         t.zero_()
     else:
         t.normal_(0.0, 0.02, generator=g)
@@ -205,11 +236,51 @@ def vision_block(cfg: ModelConfig, w: dict, x: torch.Tensor, cos, sin, cu: torch
         return x + F.linear(F.silu(F.linear(h, w["wg"], w["bg"])) * F.linear(h, w["wu"], w["bu"]), w["wproj"], w["bproj"])
     h = F.layer_norm(x, (e,), w["ln2_w"], w["ln2_b"], 1e-6)
     h = F.linear(h, w["wfc"], w["bfc"])
+    if v.get("arch") == "qwen3":
+        act = v.get("hidden_act", "gelu_pytorch_tanh")
+        h = F.gelu(h, approximate="tanh") if act == "gelu_pytorch_tanh" else (F.gelu(h) if act == "gelu" else F.silu(h))
+        return x + F.linear(h, w["wproj"], w["bproj"])
     return x + F.linear(h * torch.sigmoid(1.702 * h), w["wproj"], w["bproj"])          # quick-GELU
 
 
-def vision_stem_in(cfg: ModelConfig, stem: dict, pixel_values: torch.Tensor) -> torch.Tensor:
-    return F.linear(pixel_values.to(stem["patch_embed"].dtype), stem["patch_embed"])
+def interpolated_pos_embed(cfg: ModelConfig, table: torch.Tensor, grid_thw) -> torch.Tensor:
+    """Qwen3-VL: the learned [side x side] position table bilinearly resampled to every image's (h, w) patch grid, repeated over
+    its frames and emitted in the merge-block patch order of the preprocessor -> [N, E]."""
+    v = _v(cfg)
+    m = v["spatial_merge_size"]
+    side = int(round(table.shape[0] ** 0.5))
+    out = []
+    for t, h, w in _grid_list(grid_thw):
+        ys = torch.linspace(0, side - 1, h, device=table.device)
+        xs = torch.linspace(0, side - 1, w, device=table.device)
+        y0, x0 = ys.long(), xs.long()
+        y1, x1 = (y0 + 1).clamp(max=side - 1), (x0 + 1).clamp(max=side - 1)
+        dy, dx = (ys - y0).to(table.dtype), (xs - x0).to(table.dtype)
+        tab = table.view(side, side, -1)
+        pe = (tab[y0][:, x0] * ((1 - dy)[:, None] * (1 - dx)[None, :]).unsqueeze(-1)
+              + tab[y0][:, x1] * ((1 - dy)[:, None] * dx[None, :]).unsqueeze(-1)
+              + tab[y1][:, x0] * (dy[:, None] * (1 - dx)[None, :]).unsqueeze(-1)
+              + tab[y1][:, x1] * (dy[:, None] * dx[None, :]).unsqueeze(-1))                      # [h, w, E]
+        pe = pe.view(h // m, m, w // m, m, -1).permute(0, 2, 1, 3, 4).reshape(h * w, -1)
+        out.append(pe.repeat(t, 1))
+    return torch.cat(out, dim=0)
+
+
+def vision_stem_in(cfg: ModelConfig, stem: dict, pixel_values: torch.Tensor, grid_thw=None) -> torch.Tensor:
+    x = F.linear(pixel_values.to(stem["patch_embed"].dtype), stem["patch_embed"], stem.get("patch_embed_b"))
+    if "pos_embed" in stem:
+        if grid_thw is None:
+            raise ValueError("the Qwen3-VL tower needs the image grids for its position embeddings")
+        x = x + interpolated_pos_embed(cfg, stem["pos_embed"], grid_thw).to(x.dtype)
+    return x
+
+
+def deepstack_merge(cfg: ModelConfig, stem: dict, k: int, x: torch.Tensor) -> torch.Tensor:
+    """DeepStack merger k on an intermediate block output: merge-block rows concatenated, LayerNorm over the merged width, MLP."""
+    v = _v(cfg)
+    mdim = v["embed_dim"] * v["spatial_merge_size"] ** 2
+    h = F.layer_norm(x.view(-1, mdim), (mdim,), stem[f"ds{k}_ln_w"], stem[f"ds{k}_ln_b"], 1e-6)
+    return F.linear(F.gelu(F.linear(h, stem[f"ds{k}_w1"], stem[f"ds{k}_b1"])), stem[f"ds{k}_w2"], stem[f"ds{k}_b2"])
 
 
 def vision_stem_out(cfg: ModelConfig, stem: dict, x: torch.Tensor) -> torch.Tensor:
@@ -251,9 +322,19 @@ def frame_cu_seqlens(grid_thw, device) -> tuple[torch.Tensor, int]:
 
 def vision_forward(cfg: ModelConfig, vw: "VisionWeights", pixel_values: torch.Tensor, grid_thw) -> torch.Tensor:
     """pixel_values [N, C*Tp*P*P] (N = sum t*h*w) -> merged image embeddings [N / merge^2, hidden_size]."""
-    x = vision_stem_in(cfg, vw.stem, pixel_values)
+    x = vision_stem_in(cfg, vw.stem, pixel_values, grid_thw)
     cos, sin = vision_rotary(cfg, grid_thw, x.device)
     cu, mx = frame_cu_seqlens(grid_thw, x.device)
+    if is_v3(cfg):
+        # the merged embedding and the DeepStack levels travel as ONE [n, hidden * (1 + levels)] tensor (embed_width): every
+        # consumer that slices rows (chunked prefill, SP slicing, ZeRO unit outputs) keeps working unchanged
+        taps = list(_v(cfg).get("deepstack_visual_indexes") or ())
+        feats: list = [None] * len(taps)
+        for i, b in enumerate(vw.blocks):
+            x = vision_block(cfg, b, x, cos, sin, cu, mx)
+            if i in taps:
+                feats[taps.index(i)] = deepstack_merge(cfg, vw.stem, taps.index(i), x)
+        return torch.cat([vision_stem_out(cfg, vw.stem, x), *feats], dim=-1)
     if not is_v25(cfg):
         for b in vw.blocks:
             x = vision_block(cfg, b, x, cos, sin, cu, mx)
@@ -285,7 +366,18 @@ def merge_image_embeds(cfg: ModelConfig, x: torch.Tensor, input_ids: torch.Tenso
     idx = mask.nonzero(as_tuple=True)[0]
     if idx.numel() != image_embeds.shape[0]:
         raise ValueError(f"{idx.numel()} image placeholder tokens but {image_embeds.shape[0]} image embedding rows")
-    return x.index_copy(0, idx, image_embeds.to(x.dtype))
+    return x.index_copy(0, idx, image_embeds[:, : x.shape[-1]].to(x.dtype))
+
+
+def deepstack_add(cfg: ModelConfig, x: torch.Tensor, input_ids: torch.Tensor, image_embeds: torch.Tensor | None, layer_idx: int) -> torch.Tensor:
+    """Qwen3-VL DeepStack: after decoder layer ``layer_idx`` (< number of levels) add that level's visual features to the hidden
+    states at the image / video placeholder positions.  No-op for other towers, text-only batches and deeper layers."""
+    if image_embeds is None or layer_idx >= deepstack_levels(cfg) or image_embeds.shape[0] == 0:
+        return x
+    hsz = x.shape[-1]
+    mask = (input_ids == cfg.image_token_id) | (input_ids == cfg.video_token_id)
+    idx = mask.nonzero(as_tuple=True)[0]
+    return x.index_add(0, idx, image_embeds[:, hsz * (layer_idx + 1): hsz * (layer_idx + 2)].to(x.dtype))
 
 
 # --------------------------------------------------------------------------------------------
@@ -301,7 +393,10 @@ def mrope_positions(cfg: ModelConfig, input_ids, grid_thw, second_per_grid_ts=No
     ids = input_ids.tolist() if isinstance(input_ids, torch.Tensor) else list(input_ids)
     v = _v(cfg)
     m = v["spatial_merge_size"]
-    grids = iter(_grid_list(grid_thw) if grid_thw is not None else [])
+    glist = _grid_list(grid_thw) if grid_thw is not None else []
+    if is_v3(cfg):        # Qwen3-VL prompts separate the frames of a video by timestamp text: one placeholder run per frame
+        glist = [(1, h, w) for t, h, w in glist for _ in range(t)]
+    grids = iter(glist)
     secs = iter(second_per_grid_ts if second_per_grid_ts is not None else [])
     pos = torch.empty(3, len(ids), dtype=torch.long)
     i, p = 0, 0
@@ -338,7 +433,14 @@ def mrope_tables(cfg: ModelConfig, pos3: torch.Tensor, cos: torch.Tensor, sin: t
     """Per-token rotary tables [T, head_dim / 2]: frequency i reads position stream s(i) given by ``mrope_section``.  Feeding them to
     the rope op with positions arange(T) reuses the 1-D kernel unchanged."""
     sec = torch.tensor(cfg.mrope_section, device=pos3.device)
-    stream = torch.repeat_interleave(torch.arange(3, device=pos3.device), sec)            # [d/2] -> 0/1/2
+    if getattr(cfg, "mrope_interleaved", False):
+        # Qwen3-VL: frequencies cycle t, h, w, t, h, w, ... (h / w only inside their first 3 * section entries), the rest reads t
+        i = torch.arange(int(sec.sum()), device=pos3.device)
+        stream = torch.zeros_like(i)
+        stream[(i % 3 == 1) & (i < 3 * sec[1])] = 1
+        stream[(i % 3 == 2) & (i < 3 * sec[2])] = 2
+    else:
+        stream = torch.repeat_interleave(torch.arange(3, device=pos3.device), sec)        # [d/2] -> 0/1/2
     p = pos3.to(cos.device)[stream.to(cos.device)]                                         # [d/2, T]
     f = torch.arange(cos.shape[1], device=cos.device).unsqueeze(1)                        # [d/2, 1]
     return cos[p, f].t().contiguous(), sin[p, f].t().contiguous()
@@ -451,7 +553,24 @@ _BLOCK_MAP_25 = {"ln1_w": "norm1.weight", "wqkv": "attn.qkv.weight", "bqkv": "at
                  "wu": "mlp.up_proj.weight", "bu": "mlp.up_proj.bias", "wproj": "mlp.down_proj.weight", "bproj": "mlp.down_proj.bias"}
 
 
+_BLOCK_MAP_3 = {**{k: v for k, v in _BLOCK_MAP.items() if not k.startswith(("wfc", "bfc", "wproj", "bproj"))},
+                "wfc": "mlp.linear_fc1.weight", "bfc": "mlp.linear_fc1.bias", "wproj": "mlp.linear_fc2.weight", "bproj": "mlp.linear_fc2.bias"}
+
+
+def _stem_map_3(cfg: ModelConfig) -> dict:
+    out = {"patch_embed_b": "patch_embed.proj.bias", "pos_embed": "pos_embed.weight", "merger_ln_w": "merger.norm.weight",
+           "merger_ln_b": "merger.norm.bias", "merger_w1": "merger.linear_fc1.weight", "merger_b1": "merger.linear_fc1.bias",
+           "merger_w2": "merger.linear_fc2.weight", "merger_b2": "merger.linear_fc2.bias"}
+    for k in range(deepstack_levels(cfg)):
+        pre = f"deepstack_merger_list.{k}."
+        out.update({f"ds{k}_ln_w": pre + "norm.weight", f"ds{k}_ln_b": pre + "norm.bias", f"ds{k}_w1": pre + "linear_fc1.weight",
+                    f"ds{k}_b1": pre + "linear_fc1.bias", f"ds{k}_w2": pre + "linear_fc2.weight", f"ds{k}_b2": pre + "linear_fc2.bias"})
+    return out
+
+
 def _maps(cfg: ModelConfig) -> tuple[dict, dict]:
+    if is_v3(cfg):
+        return _stem_map_3(cfg), _BLOCK_MAP_3
     if is_v25(cfg):
         return {k: v for k, v in _STEM_MAP.items() if k != "merger_ln_b"}, _BLOCK_MAP_25
     return _STEM_MAP, _BLOCK_MAP

@@ -767,10 +767,12 @@ class Zero3Engine:
                 ph = (inp.input_ids == self.cfg.image_token_id) | (inp.input_ids == self.cfg.video_token_id)
                 before = int(ph[:lo].sum())
                 here = int(ph[lo:lo + n_loc].sum())
-                x = self.embed_runner(local, ids, pos, img[before:before + here])
+                img_loc = img[before:before + here]
+                x = self.embed_runner(local, ids, pos, img_loc)
             else:
+                img_loc = None
                 x = self.embed_runner(local, ids, pos)
-            x = self._run_layers(local, x)
+            x = self._run_layers(local, x, img_loc)
             return GatherSeq.apply(x, sp, True)[:total]      # full hidden on every SP rank; grads scaled by sp on the way back
         if inp.pixel_values is not None:
             if self.vision_runner is None:
@@ -779,10 +781,24 @@ class Zero3Engine:
             img = self.vision_runner(grid, inp.pixel_values.to(self.device, self.param_dtype))
             x = self.embed_runner(inp, inp.input_ids, inp.position_ids, img)
         else:
+            img = None
             x = self.embed_runner(inp, inp.input_ids, inp.position_ids)
-        return self._run_layers(inp, x)
+        return self._run_layers(inp, x, img)
 
-    def _run_layers(self, inp: tf.PackedInput, x: torch.Tensor) -> torch.Tensor:
+    def _run_layers(self, inp: tf.PackedInput, x: torch.Tensor, img: torch.Tensor | None = None) -> torch.Tensor:
+        levels = 0
+        if img is not None and self.cfg.vision is not None:
+            from ..models.vision import deepstack_add, deepstack_levels
+
+            levels = deepstack_levels(self.cfg)
+        if levels:
+            # Qwen3-VL DeepStack: level i of the tower output is added after decoder layer i, outside the layer units so that
+            # plain autograd carries the gradient back into the ``vision`` unit's output
+            for i, r in enumerate(self.layer_runners):
+                x = r(inp, x)
+                if i < levels:
+                    x = deepstack_add(self.cfg, x, inp.input_ids, img, i)
+            return x
         if self.moe_aux:
             auxs = []
             for r in self.layer_runners:

@@ -644,6 +644,10 @@ class RolloutEngine:
                 x = layer_prefill_tp(self.tp, cfg, w, x, inp, (self.k_cache[i], self.v_cache[i], slot_t))
             else:
                 x = tf.layer_forward(cfg, w, x, inp, kv_sink=(self.k_cache[i], self.v_cache[i], slot_t))
+            if inp.image_embeds is not None:
+                from ..models.vision import deepstack_add
+
+                x = deepstack_add(self.full_cfg, x, inp.input_ids, inp.image_embeds, i)      # Qwen3-VL DeepStack (no-op otherwise)
         self.stats["prefill_tokens"] += len(ids)
         done_ids = {id(r) for r in donors if r.prefilled >= len(r.prompt_ids)}
         reqs = [r for r in reqs if not r.finished and (id(r) in done_ids or (r.donor is not None and id(r.donor) in done_ids))]
@@ -721,7 +725,7 @@ class RolloutEngine:
             if e >= len(r.prompt_ids):
                 r.image_embeds = None
         pos_t = torch.cat(pos, dim=1).contiguous().to(dev)
-        emb_t = torch.cat(emb, dim=0) if emb else torch.zeros(0, cfg.hidden_size, device=dev, dtype=self.dtype)
+        emb_t = torch.cat(emb, dim=0) if emb else torch.zeros(0, V.embed_width(cfg), device=dev, dtype=self.dtype)
         return pos_t, emb_t
 
     def _seed_for(self, r: Request, step: int) -> int:

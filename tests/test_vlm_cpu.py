@@ -131,12 +131,14 @@ def test_vision_state_dict_round_trip_and_param_count():
     assert cfg.num_params() == V.vision_num_params(cfg) + get_model_config("tiny-qwen2-vl", vision=None, mrope_section=()).num_params()
 
 
-def test_engine_generates_like_hf_with_images():
+@pytest.mark.parametrize("family", ["qwen2_vl", "qwen3_vl"])
+def test_engine_generates_like_hf_with_images(family):
     """Rollout engine on image prompts: greedy continuation equals HF generate (prefill with tower embeddings + M-RoPE, decode
-    with the per-request rotary offset), also when the prompt is prefilled in chunks and when n samples share the prompt."""
+    with the per-request rotary offset), also when the prompt is prefilled in chunks and when n samples share the prompt.
+    Qwen3-VL adds DeepStack: the per-level features are added after the first decoder layers of every prefill chunk."""
     from polyrl_b200.rollout.engine import RolloutEngine, SamplingParams
 
-    hc, model = _hf_tiny()
+    hc, model = _hf_tiny() if family == "qwen2_vl" else _hf_tiny_q3()
     cfg, w, vw = _ours(hc, model)
     g = torch.Generator().manual_seed(3)
     grids_a, grids_b = [(1, 4, 6)], [(1, 4, 4), (1, 8, 4)]
@@ -195,13 +197,15 @@ def _vlm_batch(cfg, seed=5):
     return inp, labels
 
 
-def test_zero_engine_trains_the_tower_like_plain_autograd():
+@pytest.mark.parametrize("preset", ["tiny-qwen2-vl", "tiny-qwen3-vl"])
+def test_zero_engine_trains_the_tower_like_plain_autograd(preset):
     """ZeRO engine with a ``vision`` unit: log-probs and the gradients of tower + text parameters equal plain autograd over the
-    functional model, in recompute and saved-activation modes; a frozen tower keeps its weights; HF export reloads in HF."""
+    functional model, in recompute and saved-activation modes; a frozen tower keeps its weights; HF export reloads in HF.
+    (Qwen3-VL: the DeepStack levels reach the decoder outside the layer units and still carry gradients into the tower.)"""
     from polyrl_b200.ops import reference as ref
     from polyrl_b200.parallel.zero3 import Zero3Engine
 
-    cfg = get_model_config("tiny-qwen2-vl")
+    cfg = get_model_config(preset)
     inp, labels = _vlm_batch(cfg)
     eng = Zero3Engine(cfg, "cpu", lr=1e-2, weight_decay=0.0, seed=3, max_grad_norm=1e9)
     full = {n: t.clone() for n, t in eng.named_full_tensors()}
@@ -626,3 +630,75 @@ def test_launch_server_serves_a_vlm_checkpoint_directory(tmp_path):
     finally:
         if p.poll() is None:
             p.terminate()
+
+
+# --------------------------------------------------------------------------------------------- Qwen3-VL
+def _hf_tiny_q3():
+    from transformers import Qwen3VLConfig, Qwen3VLForConditionalGeneration
+
+    torch.manual_seed(0)
+    hc = Qwen3VLConfig(
+        text_config=dict(vocab_size=512, hidden_size=128, intermediate_size=256, num_hidden_layers=4, num_attention_heads=4,
+                         num_key_value_heads=2, head_dim=32, max_position_embeddings=512, rms_norm_eps=1e-6,
+                         rope_parameters=dict(rope_type="default", rope_theta=10000.0, mrope_section=[6, 5, 5], mrope_interleaved=True)),
+        vision_config=dict(depth=3, hidden_size=64, intermediate_size=96, num_heads=4, patch_size=4, spatial_merge_size=2,
+                           temporal_patch_size=2, in_channels=3, out_hidden_size=128, num_position_embeddings=36,
+                           deepstack_visual_indexes=[0, 2], hidden_act="gelu_pytorch_tanh"),
+        image_token_id=500, video_token_id=501, vision_start_token_id=499, vision_end_token_id=498, tie_word_embeddings=False)
+    hc._attn_implementation = "eager"
+    model = Qwen3VLForConditionalGeneration(hc).eval().float()
+    with torch.no_grad():
+        for n, p in model.named_parameters():
+            if p.dim() == 1:
+                p.add_(0.1 * torch.randn_like(p))
+    return hc, model
+
+
+def test_qwen3_vl_tower_deepstack_and_logits_match_hf():
+    """Qwen3-VL: learned + interpolated position embeddings, GELU-tanh LayerNorm blocks, DeepStack features added after the first
+    decoder layers, interleaved M-RoPE (reference: 3rdparty/verl/verl/models/transformers/qwen3_vl.py)."""
+    hc, model = _hf_tiny_q3()
+    cfg, w, vw = _ours(hc, model)
+    assert V.is_v3(cfg) and V.deepstack_levels(cfg) == 2 and cfg.mrope_interleaved and cfg.qk_norm and not cfg.qkv_bias
+    g = torch.Generator().manual_seed(1)
+    grids = [(1, 4, 6), (1, 8, 4)]
+    pix = torch.randn(sum(t * h * w_ for t, h, w_ in grids), V.patch_dim(cfg), generator=g)
+    grid_t = torch.tensor(grids)
+    with torch.no_grad():
+        out = model.model.visual(pix, grid_thw=grid_t)
+        mine = V.vision_forward(cfg, vw, pix, grids)
+    n_tok = sum(V.num_image_tokens(cfg, grids))
+    assert mine.shape == (n_tok, V.embed_width(cfg)) == (n_tok, 3 * cfg.hidden_size)
+    assert (mine[:, : cfg.hidden_size] - out.pooler_output).abs().max() < 2e-4
+    for k, f in enumerate(out.deepstack_features):
+        assert (mine[:, cfg.hidden_size * (k + 1): cfg.hidden_size * (k + 2)] - f).abs().max() < 2e-4
+
+    n0, n1 = V.num_image_tokens(cfg, grids)
+    ids = [2, 11, 12, 499] + [500] * n0 + [498, 13, 14, 15, 499] + [500] * n1 + [498, 16, 17]
+    ids_t = torch.tensor([ids])
+    mm_type = (ids_t == 500).int()
+    with torch.no_grad():
+        ref_logits = model(input_ids=ids_t, pixel_values=pix, image_grid_thw=grid_t, mm_token_type_ids=mm_type).logits[0]
+    pos3, delta = V.mrope_positions(cfg, ids, grids)
+    hf_pos, hf_delta = model.model.get_rope_index(ids_t, mm_type, image_grid_thw=grid_t)
+    assert torch.equal(pos3, hf_pos[:, 0]) and delta == int(hf_delta[0, 0])
+    t = len(ids)
+    inp = tf.PackedInput(torch.tensor(ids), pos3[0].clone(), torch.tensor([0, t], dtype=torch.int32), t, mrope_pos=pos3,
+                         image_embeds=mine)
+    with torch.no_grad():
+        logits = tf.logits_forward(cfg, w.head, w.embed, tf.forward_hidden(cfg, w, inp))
+    assert (logits - ref_logits).abs().max() < 5e-4
+    # without the DeepStack columns the logits must differ (the levels are really consumed)
+    inp2 = tf.PackedInput(torch.tensor(ids), pos3[0].clone(), torch.tensor([0, t], dtype=torch.int32), t, mrope_pos=pos3,
+                          image_embeds=torch.cat([mine[:, : cfg.hidden_size], torch.zeros_like(mine[:, cfg.hidden_size:])], dim=-1))
+    with torch.no_grad():
+        assert (tf.logits_forward(cfg, w.head, w.embed, tf.forward_hidden(cfg, w, inp2)) - ref_logits).abs().max() > 1e-3
+    # checkpoint names round-trip and the exported config parses back to the same model
+    sd = model.state_dict()
+    back = V.export_hf_vision_state_dict(cfg, V.convert_hf_vision_state_dict(cfg, sd))
+    vis_keys = [k for k in sd if k.startswith("model.visual.")]
+    assert set(back) == set(vis_keys) and all(torch.equal(back[k].reshape(sd[k].shape), sd[k]) for k in vis_keys)
+    from polyrl_b200.models.hf_io import hf_config_dict
+
+    cfg2 = ModelConfig.from_hf_config(hf_config_dict(cfg))
+    assert cfg2.vision == cfg.vision and cfg2.mrope_section == cfg.mrope_section and cfg2.mrope_interleaved
