@@ -449,6 +449,15 @@ def mrope_tables(cfg: ModelConfig, pos3: torch.Tensor, cos: torch.Tensor, sin: t
 # --------------------------------------------------------------------------------------------
 # image preprocessing (PIL / tensor -> patches)
 # --------------------------------------------------------------------------------------------
+def norm_stats(cfg: ModelConfig) -> tuple[torch.Tensor, torch.Tensor]:
+    """Per-channel (mean, std) of the family's image processor: CLIP statistics for Qwen2-VL / 2.5-VL, 0.5 / 0.5 for Qwen3-VL;
+    ``vision.image_mean`` / ``vision.image_std`` override."""
+    v = _v(cfg)
+    default_mean, default_std = ((0.5, 0.5, 0.5), (0.5, 0.5, 0.5)) if v.get("arch") == "qwen3" else (CLIP_MEAN, CLIP_STD)
+    mean, std = v.get("image_mean") or default_mean, v.get("image_std") or default_std
+    return torch.tensor(mean, dtype=torch.float32).view(3, 1, 1), torch.tensor(std, dtype=torch.float32).view(3, 1, 1)
+
+
 def smart_resize(height: int, width: int, factor: int, min_pixels: int, max_pixels: int) -> tuple[int, int]:
     """Closest (h, w) that are multiples of ``factor``, keep the aspect ratio and fit the pixel budget."""
     if max(height, width) / max(1, min(height, width)) > 200:
@@ -498,7 +507,8 @@ def preprocess_image(cfg: ModelConfig, image, min_pixels: int | None = None, max
     import numpy as np
 
     x = torch.from_numpy(np.asarray(image).copy()).permute(2, 0, 1).float() / 255.0
-    x = (x - torch.tensor(CLIP_MEAN).view(3, 1, 1)) / torch.tensor(CLIP_STD).view(3, 1, 1)
+    mean, std = norm_stats(cfg)
+    x = (x - mean) / std
     return patchify(cfg, x.unsqueeze(0))
 
 
@@ -516,7 +526,7 @@ def preprocess_video(cfg: ModelConfig, frames, min_pixels: int | None = None, ma
     if not imgs:
         raise ValueError("empty video")
     h, w = smart_resize(imgs[0].height, imgs[0].width, factor, min_pixels, max_pixels)
-    mean, std = torch.tensor(CLIP_MEAN).view(3, 1, 1), torch.tensor(CLIP_STD).view(3, 1, 1)
+    mean, std = norm_stats(cfg)
     xs = [(torch.from_numpy(np.asarray(im.convert("RGB").resize((w, h), resample=Image.BICUBIC)).copy()).permute(2, 0, 1).float() / 255.0 - mean) / std
           for im in imgs]
     return patchify(cfg, torch.stack(xs))

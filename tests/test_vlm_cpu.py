@@ -702,3 +702,18 @@ def test_qwen3_vl_tower_deepstack_and_logits_match_hf():
 
     cfg2 = ModelConfig.from_hf_config(hf_config_dict(cfg))
     assert cfg2.vision == cfg.vision and cfg2.mrope_section == cfg.mrope_section and cfg2.mrope_interleaved
+
+
+def test_qwen3_vl_preprocess_matches_hf_processor():
+    from PIL import Image
+    from transformers.models.qwen2_vl.image_processing_qwen2_vl import Qwen2VLImageProcessor
+
+    cfg = get_model_config("qwen3-vl-8b")
+    rng = np.random.default_rng(1)
+    img = Image.fromarray(rng.integers(0, 255, size=(90, 150, 3), dtype=np.uint8))
+    mine, grid = V.preprocess_image(cfg, img, min_pixels=64 * 64, max_pixels=32 * 32 * 64)
+    proc = Qwen2VLImageProcessor(min_pixels=64 * 64, max_pixels=32 * 32 * 64, patch_size=16, merge_size=2, temporal_patch_size=2,
+                                 image_mean=[0.5, 0.5, 0.5], image_std=[0.5, 0.5, 0.5])          # the Qwen3-VL processor settings
+    out = proc(images=[img], return_tensors="pt")
+    assert tuple(out["image_grid_thw"][0].tolist()) == grid and mine.shape == out["pixel_values"].shape
+    assert (mine - out["pixel_values"]).abs().max() < 0.05 and (mine - out["pixel_values"]).abs().mean() < 5e-3
