@@ -75,7 +75,8 @@ def test_ulysses_sp_equivalence_gloo():
     assert r.returncode == 0 and line, r.stdout[-2000:] + r.stderr[-2000:]
     vals = dict(kv.split("=") for kv in line[0].split()[1:])
     assert float(vals["lp_err"]) < 1e-4 and float(vals["w_err"]) < 1e-3
-    assert float(vals["vlm_lp_err"]) < 1e-4 and float(vals["vlm_w_err"]) < 1e-3      # image rows / 3-axis positions sliced with the tokens
+    for fam in ("tiny-qwen2-vl", "tiny-qwen3-vl"):          # image rows (+ DeepStack rows) / 3-axis positions sliced with the tokens
+        assert float(vals[f"vlm_lp_err[{fam}]"]) < 1e-4 and float(vals[f"vlm_w_err[{fam}]"]) < 1e-3
 
 
 def test_hsdp_equivalence_gloo():

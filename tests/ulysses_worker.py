@@ -55,29 +55,31 @@ def main():
         from polyrl_b200.models import transformer as tf
         from polyrl_b200.models import vision as V
 
-        vcfg = get_model_config("tiny-qwen2-vl")
-        g = torch.Generator().manual_seed(9)
-        grids = [(1, 4, 4), (1, 4, 8)]
-        pix = torch.randn(16 + 32, V.patch_dim(vcfg), generator=g)
-        a = V.expand_image_placeholders(vcfg, [2, 11, 499, 500, 498, 12, 13, 499, 500, 498, 14, 15, 16], grids)
-        b = [2, 31, 32, 33, 34, 35, 36, 37]
-        pa, _ = V.mrope_positions(vcfg, a, grids)
-        pos3 = torch.cat([pa, torch.arange(len(b)).expand(3, -1)], dim=1).contiguous()
-        vin = tf.PackedInput(torch.tensor(a + b), pos3[0].clone(), torch.tensor([0, len(a), len(a) + len(b)], dtype=torch.int32),
-                             max(len(a), len(b)), mrope_pos=pos3, pixel_values=pix, grid_thw=grids)
-        assert vin.input_ids.numel() % world != 0                      # exercises the tail padding of the slices
-        vlabels = torch.randint(0, 400, (vin.input_ids.numel(),), generator=g)
-        vouts = {}
-        for name, sp_group in (("nosp", None), ("sp", dist.group.WORLD)):
-            eng = Zero3Engine(vcfg, dev, comm="nccl", lr=1e-2, weight_decay=0.0, seed=7, sp_group=sp_group)
-            lp, ent = eng.forward_logprob_entropy(vin, vlabels, 1.0)
-            (-(lp.mean()) + 0.01 * ent.mean()).backward()
-            eng.step()
-            vouts[name] = (lp.detach().float(), {n: t.float().clone() for n, t in eng.named_full_tensors()})
-        v_lp = (vouts["sp"][0] - vouts["nosp"][0]).abs().max().item()
-        v_w = max(((vouts["sp"][1][k] - vouts["nosp"][1][k]).norm() / (vouts["nosp"][1][k].norm() + 1e-9)).item() for k in vouts["sp"][1])
-        assert any(k.startswith("vision.") for k in vouts["sp"][1])
-        extra += f" vlm_lp_err={v_lp:.3e} vlm_w_err={v_w:.3e}"
+        for preset in ("tiny-qwen2-vl", "tiny-qwen3-vl"):      # Qwen3-VL: the DeepStack rows are sliced with the image rows
+            vcfg = get_model_config(preset)
+            g = torch.Generator().manual_seed(9)
+            grids = [(1, 4, 4), (1, 4, 8)]
+            pix = torch.randn(16 + 32, V.patch_dim(vcfg), generator=g)
+            a = V.expand_image_placeholders(vcfg, [2, 11, 499, 500, 498, 12, 13, 499, 500, 498, 14, 15, 16], grids)
+            b = [2, 31, 32, 33, 34, 35, 36, 37]
+            pa, _ = V.mrope_positions(vcfg, a, grids)
+            pos3 = torch.cat([pa, torch.arange(len(b)).expand(3, -1)], dim=1).contiguous()
+            vin = tf.PackedInput(torch.tensor(a + b), pos3[0].clone(), torch.tensor([0, len(a), len(a) + len(b)], dtype=torch.int32),
+                                 max(len(a), len(b)), mrope_pos=pos3, pixel_values=pix, grid_thw=grids)
+            assert vin.input_ids.numel() % world != 0                      # exercises the tail padding of the slices
+            vlabels = torch.randint(0, 400, (vin.input_ids.numel(),), generator=g)
+            vouts = {}
+            for name, sp_group in (("nosp", None), ("sp", dist.group.WORLD)):
+                eng = Zero3Engine(vcfg, dev, comm="nccl", lr=1e-2, weight_decay=0.0, seed=7, sp_group=sp_group)
+                lp, ent = eng.forward_logprob_entropy(vin, vlabels, 1.0)
+                (-(lp.mean()) + 0.01 * ent.mean()).backward()
+                eng.step()
+                vouts[name] = (lp.detach().float(), {n: t.float().clone() for n, t in eng.named_full_tensors()})
+            v_lp = (vouts["sp"][0] - vouts["nosp"][0]).abs().max().item()
+            v_w = max(((vouts["sp"][1][k] - vouts["nosp"][1][k]).norm() / (vouts["nosp"][1][k].norm() + 1e-9)).item() for k in vouts["sp"][1])
+            assert any(k.startswith("vision.") for k in vouts["sp"][1])
+            assert v_lp < 1e-4 and v_w < 1e-3, (preset, v_lp, v_w)
+            extra += f" vlm_lp_err[{preset}]={v_lp:.3e} vlm_w_err[{preset}]={v_w:.3e}"
     if rank == 0:
         print(f"ULYSSES_RESULTS lp_err={lp_err:.3e} w_err={w_err:.3e}{extra}", flush=True)
     dist.barrier()
