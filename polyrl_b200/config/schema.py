@@ -86,6 +86,10 @@ class PolicyLossConfig(BaseConfig):
     dpo_beta: float = 0.1                # loss_mode=online_dpo (SPIN-style pairs, rollout.n = 2)
     dpo_label_smoothing: float = 0.0
     dpo_loss_type: str = "sigmoid"       # sigmoid | ipo
+    flowrl_beta: float = 15.0            # loss_mode=flowrl: reward scale of the trajectory-balance target
+    flowrl_logz_layers: int = 3          # depth of the log-partition head on the mean prompt hidden state
+    flowrl_logz_dropout: float = 0.1
+    flowrl_logz_lr: float = 1e-4
 
 
 @dataclass
@@ -520,7 +524,8 @@ def need_critic(cfg: PPOConfig) -> bool:
 
 
 def need_reference_policy(cfg: PPOConfig) -> bool:
-    return cfg.algorithm.use_kl_in_reward or cfg.actor_rollout_ref.actor.use_kl_loss
+    a = cfg.actor_rollout_ref.actor
+    return cfg.algorithm.use_kl_in_reward or a.use_kl_loss or a.policy_loss.loss_mode == "flowrl"      # FlowRL's target uses pi_ref
 
 
 def validate_config(cfg: PPOConfig, n_gpus: int | None = None) -> None:

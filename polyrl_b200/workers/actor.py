@@ -78,6 +78,18 @@ class PackedBatch:
         self.sel = src[tgt_valid]                        # packed rows to project through the LM head
         self.labels = input_ids[:, s - r:][tgt_valid]
         self.valid = tgt_valid                           # [b, R]
+        self._grid, self._mask = grid, mask
+
+    def prompt_mean(self, hidden: torch.Tensor) -> torch.Tensor:
+        """Mean hidden state over every sample's prompt tokens (columns before the response, the last prompt token excluded —
+        its hidden state already predicts the first response token) -> [b, H] fp32.  FlowRL's log-Z head reads this."""
+        cols = self.s - self.r - 1
+        pm = self._mask[:, :cols]
+        rows = self._grid[:, :cols][pm]
+        owner = torch.arange(self.b, device=hidden.device).unsqueeze(1).expand(self.b, cols)[pm]
+        sums = torch.zeros(self.b, hidden.shape[-1], device=hidden.device, dtype=torch.float32)
+        sums = sums.index_add(0, owner, hidden.index_select(0, rows).float())
+        return sums / pm.sum(-1, keepdim=True).clamp(min=1).float()
 
     def scatter(self, values: torch.Tensor, fill: float = 0.0) -> torch.Tensor:
         out = values.new_full((self.b, self.r), fill)
@@ -123,8 +135,8 @@ class DataParallelPPOActor:
             out.append((data.slice(i, min(i + micro_bsz, n)), idx))
         return out
 
-    def _forward_micro_batch(self, mb: DataProto, temperature: float, calculate_entropy: bool = True):
-        """-> (entropy [b,R], log_probs [b,R]) for the response tokens."""
+    def _forward_micro_batch(self, mb: DataProto, temperature: float, calculate_entropy: bool = True, return_prompt_hidden: bool = False):
+        """-> (entropy [b,R], log_probs [b,R]) for the response tokens (+ the mean prompt hidden state [b,H] on request)."""
         ids = mb.batch["input_ids"]
         r = mb.batch["responses"].shape[-1]
         pb = PackedBatch(ids, mb.batch["attention_mask"], mb.batch.get("position_ids"), r)
@@ -132,6 +144,8 @@ class DataParallelPPOActor:
         hidden = self.engine.forward_hidden(pb.inp)
         h_sel = hidden.index_select(0, pb.sel)
         lp, ent = self.engine.head_lp_runner(float(temperature), h_sel, pb.labels)
+        if return_prompt_hidden:
+            return pb.scatter(ent), pb.scatter(lp), pb.prompt_mean(hidden)
         return pb.scatter(ent), pb.scatter(lp)
 
     # ------------------------------------------------------------------ inference
@@ -261,3 +275,78 @@ class DataParallelPPOCritic:
             st = self.engine.step(lr)
             metrics.setdefault("critic/grad_norm", []).append(st["grad_norm"])
         return metrics
+
+
+class FlowRLActor(DataParallelPPOActor):
+    """Actor of the FlowRL recipe (``policy_loss.loss_mode = flowrl``; reference: recipe/flowrl/flowrl_actor.py): the update
+    minimises the trajectory-balance residual with a learned log-partition head on the mean prompt hidden state.  The head is a
+    small replicated fp32 module with its own AdamW; its gradients are averaged over the data-parallel group at the optimizer
+    step, the policy's gradients flow through the ZeRO engine as usual."""
+
+    def __init__(self, engine: Zero3Engine, config: ActorConfig, dp_group=None, seed: int = 0):
+        super().__init__(engine, config, dp_group)
+        from ..algos.flowrl import LogZHead
+
+        pl = config.policy_loss or {}
+        gen = torch.Generator().manual_seed(seed + 4242)
+        cpu_state = torch.random.get_rng_state()
+        torch.manual_seed(int(torch.randint(0, 2 ** 31 - 1, (1,), generator=gen)))          # identical init on every rank
+        self.log_z = LogZHead(engine.cfg.hidden_size, int(pl.get("flowrl_logz_layers", 3)), float(pl.get("flowrl_logz_dropout", 0.1)))
+        torch.random.set_rng_state(cpu_state)
+        self.log_z.to(engine.device)
+        self.beta = float(pl.get("flowrl_beta", 15.0))
+        self.log_z_opt = torch.optim.AdamW(self.log_z.parameters(), lr=float(pl.get("flowrl_logz_lr", 1e-4)), weight_decay=0.0)
+
+    def update_policy_stream(self, data: DataProto, is_opt_step: bool = True, lr: float | None = None) -> dict:
+        from ..algos.flowrl import flowrl_objective
+
+        cfg = self.config
+        if "ref_log_prob" not in data.batch:
+            raise ValueError("FlowRL needs the reference log-probs (the recipe enables the reference policy)")
+        temperature = data.meta_info.get("temperature", 1.0)
+        metrics: dict[str, list] = {}
+        n = len(data)
+        mbs = list(self._micro_batches(data, cfg.ppo_micro_batch_size_per_gpu, cfg.ppo_max_token_len_per_gpu, cfg.use_dynamic_bsz))
+        grad_accum = max(1, cfg.ppo_mini_batch_size // max(1, (cfg.ppo_micro_batch_size_per_gpu or n)))
+        self.log_z.train()
+        for mi, (mb, idx) in enumerate(mbs):
+            b = mb.batch
+            scale = (len(mb) / cfg.ppo_mini_batch_size) if cfg.use_dynamic_bsz else 1.0 / grad_accum
+            _, lp, pm = self._forward_micro_batch(mb, temperature, calculate_entropy=False, return_prompt_hidden=True)
+            loss, m = flowrl_objective(lp, b["ref_log_prob"], b["old_log_probs"], self.log_z(pm), b["advantages"], b["response_mask"],
+                                       cfg.clip_ratio_low, cfg.clip_ratio_high, self.beta)
+            if is_opt_step and mi == len(mbs) - 1:
+                self.engine.arm_norm_fold()
+            (loss * scale).backward()
+            prof = getattr(self, "profiler", None)
+            if prof is not None:
+                prof.step()
+            for k, v in m.items():
+                metrics.setdefault(k, []).append(v)
+        if is_opt_step:
+            st = self.engine.step(lr)
+            metrics.setdefault("actor/grad_norm", []).append(st["grad_norm"])
+            if st["skipped"]:
+                metrics.setdefault("actor/skipped_steps", []).append(1.0)
+            import torch.distributed as dist
+
+            params = [p for p in self.log_z.parameters() if p.grad is not None]
+            if dist.is_initialized() and dist.get_world_size(self.dp_group) > 1:
+                for p in params:
+                    dist.all_reduce(p.grad, group=self.dp_group)
+                    p.grad /= dist.get_world_size(self.dp_group)
+            if not st["skipped"]:
+                torch.nn.utils.clip_grad_norm_(params, cfg.grad_clip if cfg.grad_clip > 0 else 1e9)
+                self.log_z_opt.step()
+            self.log_z_opt.zero_grad(set_to_none=True)
+        return metrics
+
+    # the head travels in the worker's checkpoint "extra" dict
+    def extra_state(self) -> dict:
+        return {"log_z": {k: v.detach().cpu() for k, v in self.log_z.state_dict().items()}, "log_z_opt": self.log_z_opt.state_dict()}
+
+    def load_extra_state(self, st: dict | None) -> None:
+        if st and "log_z" in st:
+            self.log_z.load_state_dict(st["log_z"])
+            if st.get("log_z_opt"):
+                self.log_z_opt.load_state_dict(st["log_z_opt"])

@@ -174,7 +174,12 @@ class ActorRolloutRefWorker:
                                     use_kl_loss=a.use_kl_loss, kl_loss_coef=a.kl_loss_coef, kl_loss_type=a.kl_loss_type,
                                     ppo_epochs=a.ppo_epochs, policy_loss_mode=a.policy_loss.loss_mode,
                                     policy_loss=a.policy_loss.to_dict(), grad_clip=a.grad_clip)
-            self.actor = DataParallelPPOActor(self.actor_engine, rt, dp_group=self.group)
+            if a.policy_loss.loss_mode == "flowrl":
+                from .actor import FlowRLActor
+
+                self.actor = FlowRLActor(self.actor_engine, rt, dp_group=self.group, seed=seed)
+            else:
+                self.actor = DataParallelPPOActor(self.actor_engine, rt, dp_group=self.group)
         if self.has_ref:
             # reference policy = frozen copy of the initial actor weights (same seed => identical init)
             self.ref_engine = Zero3Engine(self.model_cfg, self.device, group=self.shard_group, comm=comm, trainable=False,
@@ -571,7 +576,10 @@ class ActorRolloutRefWorker:
     # ------------------------------------------------------------------ checkpoint / profile
     def save_checkpoint(self, local_path: str, hdfs_path: str | None = None, global_step: int = 0,
                         max_ckpt_to_keep: int | None = None) -> None:
-        self._ckpt_manager().save(local_path, global_step, max_ckpt_to_keep, extra={"lr_step": self.lr_step})
+        extra = {"lr_step": self.lr_step}
+        if hasattr(self.actor, "extra_state"):
+            extra["actor_extra"] = self.actor.extra_state()          # e.g. FlowRL's log-Z head
+        self._ckpt_manager().save(local_path, global_step, max_ckpt_to_keep, extra=extra)
 
     def _ckpt_manager(self):
         """ONE manager per worker, configured from ``actor.checkpoint.{save,load}_contents`` (e.g. ``hf_model``)."""
@@ -588,6 +596,8 @@ class ActorRolloutRefWorker:
             return
         extra = self._ckpt_manager().load(local_path)
         self.lr_step = (extra or {}).get("lr_step", 0)
+        if hasattr(self.actor, "load_extra_state"):
+            self.actor.load_extra_state((extra or {}).get("actor_extra"))
         if self.rollout is not None:
             self.update_weight_remote()
 

@@ -8,7 +8,7 @@ from polyrl_b200.config.schema import load_config
 from polyrl_b200.data.synthetic import SyntheticPromptDataset
 from polyrl_b200.models import get_model_config
 from polyrl_b200.protocol import DataProto
-from polyrl_b200.recipes import RECIPES, dapo, entropy, gspo, spin, sppo
+from polyrl_b200.recipes import RECIPES, dapo, entropy, flowrl, gspo, spin, sppo
 from polyrl_b200.trainer.controller_ppo import make_worker_group
 
 BASE = ["trainer.device=cpu", "actor_rollout_ref.model.path=tiny-llama", "data.max_prompt_length=32", "data.max_response_length=10",
@@ -74,6 +74,7 @@ def test_dapo_gives_up_after_max_gen_batches():
     ("sppo", sppo, ["actor_rollout_ref.rollout.n=4"]),
     ("spin", spin, []),
     ("gspo", gspo, ["actor_rollout_ref.rollout.n=4"]),
+    ("flowrl", flowrl, ["actor_rollout_ref.rollout.n=4"]),
     ("entropy", entropy, ["actor_rollout_ref.rollout.n=4", "actor_rollout_ref.actor.policy_loss.loss_mode=kl_cov", "data.gen_batch_size=4"]),
 ])
 def test_recipe_runs_one_step(name, mod, extra):
@@ -88,3 +89,64 @@ def test_recipe_runs_one_step(name, mod, extra):
         assert 0.0 <= m["sppo/win_prob_mean"] <= 1.0 and "actor/sppo_log_ratio" in m
     if name == "spin":
         assert "spin/pair_margin" in m
+    if name == "flowrl":
+        assert {"actor/log_z", "actor/flowrl_residual", "actor/importance_weight", "actor/ref_kl"} <= set(m) and "timing_s/ref" in m
+
+
+def test_flowrl_objective_and_head_learning(tmp_path):
+    """Trajectory balance: zero loss exactly when log Z + mean log pi = beta r + mean log pi_ref; the head's gradient moves log Z
+    towards the target; tokens outside the trust region leave the averages; the head survives a worker checkpoint."""
+    from polyrl_b200.algos.flowrl import LogZHead, flowrl_objective
+
+    torch.manual_seed(0)
+    b, r = 4, 6
+    lp = -torch.rand(b, r)
+    ref = -torch.rand(b, r)
+    adv = torch.randn(b, 1).expand(b, r).contiguous()
+    mask = torch.ones(b, r)
+    mask[0, 4:] = 0
+    m = mask
+    target = 2.0 * ((adv * m).sum(-1) / m.sum(-1)) + (ref * m).sum(-1) / m.sum(-1) - (lp * m).sum(-1) / m.sum(-1)
+    loss, met = flowrl_objective(lp, ref, lp.clone(), target, adv, mask, 0.2, 0.2, beta=2.0)
+    assert loss.item() < 1e-10 and abs(met["actor/importance_weight"] - 1.0) < 1e-6 and met["actor/cispo_mask_ratio"] == 0.0
+    z = torch.zeros(b, requires_grad=True)
+    loss, _ = flowrl_objective(lp, ref, lp.clone(), z, adv, mask, 0.2, 0.2, beta=2.0)
+    loss.backward()
+    assert torch.allclose(z.grad, -2 * target / b, atol=1e-6)          # d/dz mean((z - target)^2)
+    old = lp.clone()
+    old[1, 0] = lp[1, 0] - 1.0                                        # ratio e^1 > 1 + clip with a positive advantage -> dropped
+    adv2 = adv.abs()
+    _, met = flowrl_objective(lp, ref, old, target, adv2, mask, 0.2, 0.2, beta=2.0)
+    assert met["actor/cispo_mask_ratio"] > 0
+    head = LogZHead(16, num_layers=3, dropout=0.0)
+    assert head(torch.randn(5, 16)).shape == (5,)
+    # end to end through a worker: one update changes the head, a checkpoint restores it
+    from polyrl_b200.config.schema import load_config, need_reference_policy
+    from polyrl_b200.workers.actor import FlowRLActor
+    from polyrl_b200.workers.hybrid_worker import ActorRolloutRefWorker
+
+    cfg = load_config(overrides=flowrl.DEFAULTS + BASE + ["actor_rollout_ref.rollout.n=2", "data.train_batch_size=2",
+                                                          "actor_rollout_ref.actor.ppo_mini_batch_size=2"])
+    assert need_reference_policy(cfg)
+    w = ActorRolloutRefWorker(cfg, role="actor_rollout_ref", device="cpu")
+    w.init_model()
+    assert isinstance(w.actor, FlowRLActor)
+    before = {k: v.clone() for k, v in w.actor.log_z.state_dict().items()}
+    from polyrl_b200.data.synthetic import SyntheticPromptDataset
+    from polyrl_b200.protocol import DataProto, collate_fn
+
+    ds = SyntheticPromptDataset(w.model_cfg.vocab_size, 8, (8, 16), 32)
+    batch = w.generate_sequences(DataProto.from_single_dict(collate_fn([ds[0], ds[1]])))
+    batch.meta_info["temperature"] = 1.0
+    batch.batch["old_log_probs"] = w.compute_log_prob(batch).batch["old_log_probs"]
+    batch.batch["ref_log_prob"] = w.compute_ref_log_prob(batch).batch["ref_log_prob"]
+    batch.batch["advantages"] = torch.randn(len(batch), 1).expand(-1, batch.batch["responses"].shape[1]) * batch.batch["response_mask"]
+    batch.meta_info.update(is_opt_step=True, is_lr_step=True)
+    w.update_actor_stream(batch)
+    after = w.actor.log_z.state_dict()
+    assert any(not torch.equal(after[k], before[k]) for k in before)
+    w.save_checkpoint(str(tmp_path / "ck"), None, 1, None)
+    w2 = ActorRolloutRefWorker(cfg, role="actor_rollout_ref", device="cpu")
+    w2.init_model()
+    w2.load_checkpoint(str(tmp_path / "ck"))
+    assert all(torch.equal(w2.actor.log_z.state_dict()[k], after[k]) for k in after)
