@@ -28,8 +28,13 @@ from ..ops.functional import rope_and_cache_, _skinny_buffers
 
 class TPContext:
     def __init__(self, cfg: ModelConfig, heap, tp_rank: int, tp_world: int, max_batch: int, group=None):
-        if cfg.num_heads % tp_world or cfg.num_kv_heads % tp_world or (cfg.intermediate_size // 128) % tp_world:
-            raise ValueError("heads, kv heads and intermediate_size/128 must be divisible by the TP size")
+        if cfg.num_heads % tp_world or cfg.num_kv_heads % tp_world:
+            raise ValueError("heads and kv heads must be divisible by the TP size")
+        if cfg.num_experts:
+            if cfg.num_experts % tp_world:
+                raise ValueError(f"{cfg.num_experts} experts cannot be split over {tp_world} TP ranks")
+        elif (cfg.intermediate_size // 128) % tp_world:
+            raise ValueError("intermediate_size/128 must be divisible by the TP size")
         self.cfg, self.heap, self.rank, self.world, self.group = cfg, heap, tp_rank, tp_world, group
         self.max_batch = max_batch
         if heap is None:            # CPU / gloo (plumbing tests) or explicit library mode: all-reduce through torch.distributed
@@ -73,11 +78,13 @@ class TPContext:
     def local_cfg(self) -> ModelConfig:
         """Model config as seen by one TP rank (for KV-cache sizing and the attention kernels)."""
         c = self.cfg
-        if c.num_experts:
-            raise NotImplementedError("tensor-parallel rollout of mixture-of-experts models")
         d = c.to_dict()
+        # mixture of experts: attention is head-sharded as usual, the experts are SHARDED WHOLE over the TP ranks (rank r owns
+        # experts [r E/W, (r+1) E/W)); activations are replicated inside a TP group, so no dispatch all-to-all is needed — every
+        # rank runs the tokens routed to its experts and the partial outputs meet in the same all-reduce a dense row-parallel
+        # down-projection uses
         d.update(num_heads=c.num_heads // self.world, num_kv_heads=c.num_kv_heads // self.world,
-                 intermediate_size=c.intermediate_size // self.world, head_dim=c.head_dim)
+                 intermediate_size=c.intermediate_size if c.num_experts else c.intermediate_size // self.world, head_dim=c.head_dim)
         out = ModelConfig(**d)
         out.hidden_size = c.hidden_size
         return out
@@ -97,6 +104,11 @@ class TPContext:
         if "bqkv" in w:
             out["bqkv"] = torch.cat([w["bqkv"][q0:q0 + nq * d], w["bqkv"][k0:k0 + nkv * d], w["bqkv"][v0:v0 + nkv * d]]).contiguous()
         out["wo"] = w["wo"][:, q0:q0 + nq * d]                      # [H, nq_local*d] view, row pitch = full
+        if c.num_experts:
+            el = c.num_experts // W
+            out["router"] = w["router"]                               # replicated: every rank routes every token identically
+            out["ewgu"], out["ewd"] = w["ewgu"][r * el:(r + 1) * el], w["ewd"][r * el:(r + 1) * el]
+            return out
         f2 = 2 * c.intermediate_size // W
         out["wgu"] = w["wgu"][r * f2:(r + 1) * f2]                  # contiguous rows (block-interleaved layout)
         fl = c.intermediate_size // W
@@ -137,6 +149,82 @@ class TPContext:
         return y + residual if residual is not None else y
 
 
+def allreduce_partial(tp: TPContext, part: torch.Tensor, residual: torch.Tensor | None, decode: bool) -> torch.Tensor:
+    """Sum a [b, H] partial result over the TP ranks (+ residual) through the same transports as ``row_parallel``."""
+    b, h = part.shape
+    small = tp.heap is not None and part.is_cuda and decode and b <= 256 and b <= tp.max_batch
+    if small and tp.ar_mode == "nvls":
+        tp.nvls_ar.next_input(b * h).view(b, h).copy_(part)
+        out = torch.empty(b, h, device=part.device, dtype=torch.bfloat16)
+        return tp.nvls_ar.reduce(out, residual.contiguous() if residual is not None else None)
+    if small and tp.ar_mode in ("oneshot", "fused"):
+        buf = tp.ar_bufs[tp.ar_turn]
+        tp.ar_turn ^= 1
+        buf.local[: b * h].view(b, h).copy_(part)
+        tp.heap.barrier()
+        out = torch.empty(b, h, device=part.device, dtype=torch.bfloat16)
+        tp.C.p2p_allreduce(buf.ptrs, 0, out, residual.contiguous() if residual is not None else None, 0)
+        return out
+    y = part.contiguous()
+    dist.all_reduce(y, group=tp.group)
+    return y + residual if residual is not None else y
+
+
+def moe_partial(tp: TPContext, cfg: ModelConfig, w: dict, h: torch.Tensor, static: bool) -> torch.Tensor:
+    """This rank's share of a mixture-of-experts MLP: the (replicated) router picks top-k experts per token, the rank computes
+    the assignments that fall on ITS experts and returns the weighted partial sum [T, H] (zero rows for tokens routed elsewhere).
+    ``static`` keeps every shape fixed and avoids host reads (CUDA-graph decode): assignments are scattered into an
+    [E_local + 1, T, H] buffer whose last row collects the other ranks' assignments and is never multiplied."""
+    import torch.nn.functional as F
+
+    from ..ops import reference as ref
+
+    t, k, e = h.shape[0], cfg.num_experts_per_tok, cfg.num_experts
+    el = e // tp.world
+    e0 = tp.rank * el
+    probs = torch.softmax(F.linear(h, w["router"].to(h.dtype)).float(), dim=-1)
+    top_w, top_e = torch.topk(probs, k, dim=-1)
+    if cfg.norm_topk_prob:
+        top_w = top_w / top_w.sum(-1, keepdim=True)
+    flat_e = top_e.reshape(-1)
+    order = torch.argsort(flat_e, stable=True)
+    sorted_e = flat_e[order]
+    tok = torch.div(order, k, rounding_mode="floor")
+    gate = top_w.reshape(-1)[order].to(h.dtype)
+    mine = (sorted_e >= e0) & (sorted_e < e0 + el)
+    if static:
+        counts = torch.zeros(e, dtype=torch.long, device=h.device).scatter_add_(0, flat_e, torch.ones_like(flat_e))
+        start = counts.cumsum(0) - counts
+        slot = torch.arange(t * k, device=h.device) - start[sorted_e]
+        row = torch.where(mine, sorted_e - e0, torch.full_like(sorted_e, el))
+        x = h.new_zeros(el + 1, t, h.shape[1])
+        x[row, slot] = h.index_select(0, tok)
+        gu = torch.bmm(x[:el], w["ewgu"].to(h.dtype).transpose(1, 2))
+        a = ref.swiglu(gu.reshape(el * t, -1)).reshape(el, t, -1)
+        y = torch.bmm(a, w["ewd"].to(h.dtype).transpose(1, 2))
+        y = torch.cat([y, y.new_zeros(1, t, h.shape[1])], dim=0)[row, slot] * gate.unsqueeze(-1)
+        return torch.zeros(t, h.shape[1], dtype=y.dtype, device=h.device).index_add(0, tok, y)
+    counts = torch.bincount(flat_e, minlength=e).tolist()
+    xs = h.index_select(0, tok)
+    out = torch.zeros(t, h.shape[1], dtype=h.dtype, device=h.device)
+    lo = 0
+    for ei, n in enumerate(counts):
+        if n and e0 <= ei < e0 + el:
+            a = ops.linear_swiglu(xs[lo:lo + n], w["ewgu"][ei - e0])
+            y = ops.linear(a, w["ewd"][ei - e0]) * gate[lo:lo + n].unsqueeze(-1)
+            out = out.index_add(0, tok[lo:lo + n], y.to(out.dtype))
+        lo += n
+    return out
+
+
+def _mlp_tp(tp: TPContext, lcfg: ModelConfig, w: dict, x: torch.Tensor, decode: bool) -> torch.Tensor:
+    h = ops.rmsnorm(x, w["ln2"], lcfg.rms_norm_eps)
+    if "router" in w:
+        part = moe_partial(tp, tp.cfg, w, h, static=decode and x.is_cuda and tf._MOE_STATIC_DECODE())
+        return allreduce_partial(tp, part.to(x.dtype), x, decode)
+    return tp.row_parallel(ops.linear_swiglu(h, w["wgu"]), w["wd"], x, decode=decode)
+
+
 def layer_decode_tp(tp: TPContext, lcfg: ModelConfig, w: dict, x: torch.Tensor, inp: tf.DecodeInput, k_cache, v_cache) -> torch.Tensor:
     nq, nkv, d = lcfg.num_heads, lcfg.num_kv_heads, lcfg.head_dim
     h = ops.rmsnorm(x, w["ln1"], lcfg.rms_norm_eps)
@@ -146,9 +234,7 @@ def layer_decode_tp(tp: TPContext, lcfg: ModelConfig, w: dict, x: torch.Tensor, 
     a = ops.paged_decode_attention(qkv[:, : nq * d], k_cache, v_cache, inp.block_table, inp.seq_lens, nq, nkv, d, d ** -0.5,
                                    max_len=inp.max_len)
     x = tp.row_parallel(a, w["wo"], x)
-    h = ops.rmsnorm(x, w["ln2"], lcfg.rms_norm_eps)
-    a = ops.linear_swiglu(h, w["wgu"])
-    return tp.row_parallel(a, w["wd"], x)
+    return _mlp_tp(tp, lcfg, w, x, decode=True)
 
 
 def layer_prefill_tp(tp: TPContext, lcfg: ModelConfig, w: dict, x: torch.Tensor, inp: tf.PackedInput, kv_sink) -> torch.Tensor:
@@ -163,6 +249,4 @@ def layer_prefill_tp(tp: TPContext, lcfg: ModelConfig, w: dict, x: torch.Tensor,
     v = qkv[:, (nq + nkv) * d:].view(t, nkv, d)
     a = attention_varlen(q, k, v, inp.cu_seqlens, inp.max_seqlen, causal=True).reshape(t, nq * d)
     x = tp.row_parallel(a, w["wo"], x, decode=False)
-    h = ops.rmsnorm(x, w["ln2"], lcfg.rms_norm_eps)
-    a = ops.linear_swiglu(h, w["wgu"])
-    return tp.row_parallel(a, w["wd"], x, decode=False)
+    return _mlp_tp(tp, lcfg, w, x, decode=False)

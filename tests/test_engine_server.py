@@ -309,6 +309,8 @@ def test_tp_rollout_cpu_gloo_engine_and_colocated_worker():
     assert "tok_ok=1" in line[0] and "lock=1" in line[0] and "slice_ok=1" in line[0] and "differ=1" in line[0] and "zero3_tp_slices_ok=1" in line[0]
     vlm = [l for l in r.stdout.splitlines() if l.startswith("TP_CPU_VLM")]          # image prompts through the TP engine / worker
     assert vlm and "tok_ok=1" in vlm[0] and float(vlm[0].split("worker_err=")[1]) < 1e-4
+    moe = [l for l in r.stdout.splitlines() if l.startswith("TP_CPU_MOE")]          # experts sharded whole over the TP ranks
+    assert moe and "tok_ok=1" in moe[0] and float(moe[0].split("lp_err=")[1]) < 1e-4
 
 
 def test_prefix_cache_unit_semantics():

@@ -203,3 +203,27 @@ def test_static_shape_expert_path_matches_the_grouped_loop(monkeypatch):
         eng.set_weights(w.embed, w.layers, w.head)
         outs[flag] = [q[0].output_ids for q in eng.generate([[5, 6, 7, 8], [20, 21, 22]], SamplingParams(max_new_tokens=8, temperature=0.0, ignore_eos=True))]
     assert outs["0"] == outs["1"]
+
+
+def test_tp_expert_sharding_partials_sum_to_the_full_moe():
+    """rollout/tp.py::moe_partial: every TP rank computes the assignments routed to ITS experts; the partial sums (dynamic grouping
+    and the static-shape graph-capturable variant with its spill row) add up to the single-device mixture."""
+    from types import SimpleNamespace
+
+    from polyrl_b200.models import TransformerWeights, get_model_config
+    from polyrl_b200.models import transformer as tf
+    from polyrl_b200.rollout.tp import moe_partial
+
+    cfg = get_model_config("tiny-qwen3-moe")
+    w = TransformerWeights(cfg, "cpu", torch.float32, seed=2).layers[0]
+    h = torch.randn(13, cfg.hidden_size)
+    want = tf.moe_mlp(cfg, w, h)
+    for world in (2, 4):
+        el = cfg.num_experts // world
+        for static in (False, True):
+            total = torch.zeros_like(want)
+            for r in range(world):
+                tp = SimpleNamespace(rank=r, world=world)
+                wl = {"router": w["router"], "ewgu": w["ewgu"][r * el:(r + 1) * el], "ewd": w["ewd"][r * el:(r + 1) * el]}
+                total += moe_partial(tp, cfg, wl, h, static)
+            assert (total - want).abs().max() < 1e-5, (world, static)

@@ -102,6 +102,20 @@ def main():
     lp_tr = wv.compute_log_prob(vo).batch["old_log_probs"]
     assert vo.batch["rollout_log_probs"].abs().min() > 1e-3 and vo.batch["response_mask"].sum() == 12
     vlm_worker_err = (lp_tr - vo.batch["rollout_log_probs"]).abs().max().item()            # TP engine == trainer forward
+    # ---- mixture of experts through the TP engine: experts sharded whole over the ranks, partial outputs all-reduced
+    mcfg = get_model_config("tiny-qwen3-moe")
+    mw = TransformerWeights(mcfg, "cpu", torch.float32, seed=13)
+    outs_m = []
+    for ctx in (TPContext(mcfg, None, rank, world, max_batch=8, group=dist.group.WORLD), None):
+        e = RolloutEngine(mcfg, "cpu", max_num_seqs=8, max_model_len=64, use_cuda_graph=False, seed=3, tp=ctx)
+        e.set_weights(mw.embed, mw.layers, mw.head)
+        if ctx is not None:
+            assert e.layer_w[0]["ewgu"].shape[0] == mcfg.num_experts // world and "wgu" not in e.layer_w[0]
+        outs_m.append([(q[0].output_ids, q[0].logprobs) for q in e.generate(prompts, sp)])
+    moe_tok_ok = all(a[0] == b[0] for a, b in zip(*outs_m))
+    moe_lp_err = max(abs(x - y) for a, b in zip(*outs_m) for x, y in zip(a[1], b[1]))
+    if rank == 0:
+        print(f"TP_CPU_MOE tok_ok={int(moe_tok_ok)} lp_err={moe_lp_err:.2e}", flush=True)
     if rank == 0:
         print(f"TP_CPU_VLM tok_ok={int(vlm_tok_ok)} lp_err={vlm_lp_err:.2e} worker_err={vlm_worker_err:.2e}", flush=True)
     if rank == 0:
