@@ -572,3 +572,21 @@ def test_native_kv_manager_matches_python_reference():
     b = nc.page_keys([99] + list(range(1, 3 * PAGE)), 3)
     c = nc.page_keys(list(range(2 * PAGE)) + [0] * PAGE, 3)
     assert len(set(a)) == 3 and all(x != y for x, y in zip(a, b)) and a[:2] == c[:2] and a[2] != c[2]
+
+
+def test_kv_manager_cpp_under_sanitizers(tmp_path):
+    """The C++ KV page manager's own stress test (csrc/tests_cpp/test_kv_manager.cpp) built with ASAN + UBSAN: 20 000 random
+    admit / finish / evict / flush operations with reference-count invariants checked after each."""
+    import shutil
+    import subprocess
+    from pathlib import Path
+
+    if shutil.which("g++") is None:
+        pytest.skip("no g++")
+    src = Path(__file__).resolve().parent.parent / "polyrl_b200" / "csrc" / "tests_cpp" / "test_kv_manager.cpp"
+    exe = tmp_path / "test_kv_manager"
+    b = subprocess.run(["g++", "-std=c++17", "-O1", "-g", "-fsanitize=address,undefined", "-fno-omit-frame-pointer", str(src), "-o", str(exe)],
+                       capture_output=True, text=True, timeout=300)
+    assert b.returncode == 0, b.stderr[-2000:]
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "KV_MANAGER_OK" in r.stdout and "runtime error" not in r.stderr, r.stdout[-500:] + r.stderr[-2000:]
