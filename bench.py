@@ -34,7 +34,7 @@ def parse():
                          "reference (unavailable offline); baseline = ONLY this framework with the named ops routed through stock "
                          "libraries (BASELINE.md section 3): cuBLAS GEMMs + unfused SwiGLU, materialised-logits chunked CE, cuBLAS "
                          "decode GEMMs, NCCL collectives.  Memory policy (resident replica, saved activations) is IDENTICAL to own")
-    ap.add_argument("--baseline-steps", type=int, default=int(os.environ.get("BENCH_BASELINE_STEPS", 2)),
+    ap.add_argument("--baseline-steps", type=int, default=int(os.environ.get("BENCH_BASELINE_STEPS", 3)),
                     help="after the own arm, rebuild the job with the library switches and time this many steps in the same "
                          "invocation -> vs_baseline (0 = skip)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
@@ -309,7 +309,7 @@ def main() -> int:
         env["BENCH_CHILD"] = "1"
         env["TORCHELASTIC_USE_AGENT_STORE"] = "False"      # the children rendezvous on their own port: child rank 0 hosts the store
         cmd = [sys.executable, os.path.abspath(__file__), "--impl", "baseline", "--gpus", str(args.gpus), "--steps", str(args.baseline_steps),
-               "--warmup", str(max(1, min(args.warmup, 2))), "--baseline-steps", "0", "--no-selfcheck", "--model", args.model,
+               "--warmup", str(3 if args.warmup >= 3 else max(1, args.warmup)), "--baseline-steps", "0", "--no-selfcheck", "--model", args.model,
                "--prompts-per-gpu", str(args.prompts_per_gpu), "--n", str(args.n), "--prompt-len-max", str(args.prompt_len_max),
                "--response-length", str(args.response_length), "--max-token-len", str(args.max_token_len), "--scaling", args.scaling,
                "--total-prompts", str(args.total_prompts), "--rollout-tp", str(args.rollout_tp),
