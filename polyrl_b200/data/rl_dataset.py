@@ -106,6 +106,61 @@ def load_image(obj):
     return Image.fromarray(np.asarray(obj, dtype=np.uint8))
 
 
+def load_video(obj, fps: float = 2.0, nframes: int | None = None, min_frames: int = 4, max_frames: int = 768,
+               frame_factor: int = 2) -> tuple[list, float]:
+    """Dataset video cell -> (frames as PIL images, sampling rate in frames / second).
+
+    Accepts a frame list (passed through), ``{"frames": [...], "fps": f}``, or a video FILE — a path, ``{"path" | "video": path,
+    "fps": f, "nframes": n, "video_start": s, "video_end": s}`` — decoded with OpenCV.  Frames are sampled uniformly: ``nframes``
+    if given, else ``fps`` frames per second of footage clamped to [min_frames, max_frames], and the count is rounded to a multiple
+    of ``frame_factor`` (the tower's temporal patch) like the reference's ``fetch_video`` (verl/utils/dataset/vision_utils.py:
+    63-125 -> qwen_vl_utils)."""
+    if isinstance(obj, (list, tuple, np.ndarray)) and not isinstance(obj, (str, bytes)):
+        return [load_image(f) for f in obj], float(fps)
+    spec = dict(obj) if isinstance(obj, dict) else {"path": obj}
+    if spec.get("frames") is not None:
+        return [load_image(f) for f in spec["frames"]], float(spec.get("fps", fps))
+    path = spec.get("path") or spec.get("video")
+    if not path:
+        raise ValueError(f"video cell without frames / path: {list(spec)}")
+    try:
+        import cv2
+    except ImportError as e:                                   # pragma: no cover
+        raise RuntimeError("decoding video files needs OpenCV (cv2); pass the video as a list of frames instead") from e
+    from PIL import Image
+
+    cap = cv2.VideoCapture(str(path))
+    if not cap.isOpened():
+        raise FileNotFoundError(f"cannot open video {path!r}")
+    total = int(cap.get(cv2.CAP_PROP_FRAME_COUNT))
+    src_fps = float(cap.get(cv2.CAP_PROP_FPS)) or 30.0
+    first = max(0, int(round(float(spec.get("video_start", 0.0)) * src_fps)))
+    last = min(total - 1, int(round(float(spec["video_end"]) * src_fps))) if spec.get("video_end") is not None else total - 1
+    span = max(1, last - first + 1)
+    want_fps = float(spec.get("fps", fps))
+    n = spec.get("nframes", nframes)
+    if n is None:
+        n = span / src_fps * want_fps
+        n = min(max(n, min_frames), max_frames, span)
+    n = max(frame_factor, int(round(float(n) / frame_factor)) * frame_factor)
+    n = min(n, max(frame_factor, span // frame_factor * frame_factor))
+    idx = np.linspace(first, last, n).round().astype(int).tolist()
+    frames, pos = [], -1
+    for i in idx:
+        if i != pos + 1:
+            cap.set(cv2.CAP_PROP_POS_FRAMES, i)
+        ok, bgr = cap.read()
+        pos = i
+        if not ok:                                             # container reported more frames than it holds: repeat the last one
+            if not frames:
+                raise ValueError(f"no decodable frame in {path!r}")
+            frames.append(frames[-1])
+            continue
+        frames.append(Image.fromarray(cv2.cvtColor(bgr, cv2.COLOR_BGR2RGB)))
+    cap.release()
+    return frames, n / (span / src_fps)
+
+
 class RLHFDataset(Dataset):
     """``model_cfg`` with a vision tower turns on the multi-modal path: rows may carry ``image_key`` (list of images) and mark their
     place in the prompt with ``<image>``; items then hold ``multi_modal_inputs`` (patches + grids), prompt ids with one placeholder
@@ -143,8 +198,8 @@ class RLHFDataset(Dataset):
 
     def _tokenize_mm(self, row: dict):
         """-> (prompt ids with expanded placeholders, pixel_values [N, patch_dim], grids, seconds per temporal patch of the videos).
-        ``<image>`` / ``<video>`` marks in the prompt consume the row's images / videos in order; a video is a list of frames (or
-        ``{"frames": [...], "fps": f}``)."""
+        ``<image>`` / ``<video>`` marks in the prompt consume the row's images / videos in order; a video is a list of frames,
+        ``{"frames": [...], "fps": f}``, or a video file (path / ``{"path": ..., "fps": ..., "nframes": ...}``, see ``load_video``)."""
         import re
 
         from ..models import vision as V
@@ -166,8 +221,8 @@ class RLHFDataset(Dataset):
                 tok = cfg.image_token_id
             elif seg == self.VIDEO_MARK:
                 vid = next(it_vid)
-                frames, fps = (vid["frames"], float(vid.get("fps", 2.0))) if isinstance(vid, dict) else (vid, 2.0)
-                pv, g = V.preprocess_video(cfg, [load_image(f) for f in frames], self.min_pixels, self.max_pixels)
+                frames, fps = load_video(vid, frame_factor=tp)         # frame lists pass through, files are decoded (OpenCV)
+                pv, g = V.preprocess_video(cfg, frames, self.min_pixels, self.max_pixels)
                 secs.append(tp / fps)
                 tok = cfg.video_token_id
             else:

@@ -717,3 +717,31 @@ def test_qwen3_vl_preprocess_matches_hf_processor():
     out = proc(images=[img], return_tensors="pt")
     assert tuple(out["image_grid_thw"][0].tolist()) == grid and mine.shape == out["pixel_values"].shape
     assert (mine - out["pixel_values"]).abs().max() < 0.05 and (mine - out["pixel_values"]).abs().mean() < 5e-3
+
+
+def test_video_files_are_decoded_and_sampled(tmp_path):
+    """Video FILES in dataset rows (reference: vision_utils.process_video / qwen_vl_utils fetch_video): uniform sampling at the
+    requested rate, frame count a multiple of the temporal patch, start / end windows, frame lists untouched."""
+    cv2 = pytest.importorskip("cv2")
+    from polyrl_b200.data.rl_dataset import load_video
+
+    path = str(tmp_path / "clip.avi")
+    wr = cv2.VideoWriter(path, cv2.VideoWriter_fourcc(*"MJPG"), 10.0, (32, 24))
+    assert wr.isOpened()
+    for i in range(40):                                              # 4 seconds at 10 fps, brightness encodes the frame index
+        wr.write(np.full((24, 32, 3), 5 * i + 20, dtype=np.uint8))
+    wr.release()
+    frames, rate = load_video(path, fps=2.0, min_frames=4)
+    assert len(frames) == 8 and abs(rate - 2.0) < 1e-6 and frames[0].size == (32, 24)
+    lum = [np.asarray(f).mean() for f in frames]
+    assert all(b > a for a, b in zip(lum, lum[1:])) and abs(lum[0] - 20) < 6 and abs(lum[-1] - (5 * 39 + 20)) < 6
+    assert len(load_video({"path": path, "nframes": 5})[0]) == 4            # rounded to the temporal patch
+    f2, r2 = load_video({"video": path, "video_start": 1.0, "video_end": 2.0, "fps": 4.0})
+    assert len(f2) == 4 and 60 < np.asarray(f2[0]).mean() < 85             # starts at frame 10
+    assert len(load_video([np.zeros((8, 8, 3), dtype=np.uint8)] * 3)[0]) == 3
+    with pytest.raises(FileNotFoundError):
+        load_video(str(tmp_path / "missing.mp4"))
+    # through the tower preprocessing: the decoded clip becomes (t, gh, gw) patches
+    cfg = get_model_config("tiny-qwen2-vl")
+    pv, grid = V.preprocess_video(cfg, frames, min_pixels=16 * 16, max_pixels=32 * 32)
+    assert grid[0] == 4 and pv.shape[0] == grid[0] * grid[1] * grid[2]
