@@ -111,8 +111,19 @@ class ProfilerConfig(BaseConfig):
 
 
 @dataclass
+class MegatronConfig(BaseConfig):
+    """Model-parallel layout of a ``strategy=megatron`` role (reference keys: actor.megatron.{tensor,pipeline,virtual_pipeline}_model_
+    parallel_size, verl/trainer/config/actor/megatron_actor.yaml).  Served by the stand-alone engines ``parallel/pipeline.py`` and
+    ``parallel/tp_train.py`` through the single-controller trainer (``trainer/controller_ppo.py::PipelinePPOWorker``)."""
+    tensor_model_parallel_size: int = 1
+    pipeline_model_parallel_size: int = 1
+    virtual_pipeline_model_parallel_size: int | None = None
+
+
+@dataclass
 class ActorConfig(BaseConfig):
     strategy: str = "fsdp"
+    megatron: MegatronConfig = field(default_factory=MegatronConfig)
     ppo_mini_batch_size: int = 256
     ppo_micro_batch_size: int | None = None
     ppo_micro_batch_size_per_gpu: int | None = None
@@ -541,8 +552,9 @@ def validate_config(cfg: PPOConfig, n_gpus: int | None = None) -> None:
         raise ValueError(f"train_batch_size*n ({real_bsz}) must be divisible by the number of trainer GPUs ({n_train})")
     if a.ppo_epochs != 1:
         raise ValueError("the streaming trainer requires actor.ppo_epochs == 1")
-    if a.strategy not in ("fsdp", "fsdp2", "zero3"):
-        raise NotImplementedError(f"actor strategy {a.strategy!r}: only ZeRO-3/FSDP is supported by the streaming path")
+    if a.strategy not in ("fsdp", "fsdp2", "zero3", "megatron"):
+        raise NotImplementedError(f"actor strategy {a.strategy!r}: fsdp | fsdp2 | zero3 (streaming + controller trainers) or megatron "
+                                  "(pipeline-parallel actor through trainer/controller_ppo.py)")
     if not a.use_dynamic_bsz:
         if a.ppo_micro_batch_size_per_gpu is None and a.ppo_micro_batch_size is None:
             raise ValueError("set actor.ppo_micro_batch_size_per_gpu (or enable use_dynamic_bsz)")

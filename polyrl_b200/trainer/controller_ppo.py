@@ -25,7 +25,8 @@ import torch
 
 from ..algos import core_algos
 from ..config.schema import PPOConfig, load_config, need_critic, need_reference_policy
-from ..controller import ClassWithInitArgs, Dispatch, Execute, LocalWorkerGroup, MPWorkerGroup, Worker, register
+from ..controller import (ClassWithInitArgs, Dispatch, Execute, LocalWorkerGroup, MPWorkerGroup, Worker,
+                          make_nd_compute_dataproto_dispatch_fn, register)
 from ..protocol import DataProto, collate_fn
 from ..utils import metrics as M
 from ..utils.profiler import marked_timer
@@ -137,7 +138,149 @@ class PPOWorker(Worker):
             dist.destroy_process_group()
 
 
+class PipelinePPOWorker(Worker):
+    """``actor.strategy = megatron``: the actor is PIPELINE-parallel (``actor.megatron.pipeline_model_parallel_size`` stages x data
+    parallel replicas, optional virtual stages) on ``parallel/pipeline.py`` through the ``BaseEngine`` role worker
+    (``workers/roles.py::ActorWorker``), the way the reference's Megatron workers sit behind the same trainer
+    (3rdparty/verl/verl/workers/megatron_workers.py:204-600).  Dispatch uses the nd-mesh protocol: every stage of a pipeline
+    receives its replica's chunk, results are collected from the last stage.  Rollout stays data-parallel over ALL workers: each
+    one holds a full-model engine that is refreshed from the gathered pipeline state after every update (the role of the
+    reference's Megatron -> inference-engine resharding).  GRPO-style algorithms only (no critic / reference policy here)."""
+
+    def __init__(self, config: PPOConfig):
+        super().__init__()
+        import torch.distributed as dist
+
+        self.config = config
+        if need_critic(config) or need_reference_policy(config):
+            raise NotImplementedError("the pipeline-parallel actor worker supports critic-free algorithms without a reference policy")
+        want_cuda = torch.cuda.is_available() and config.trainer.device != "cpu"
+        self.device = torch.device(f"cuda:{int(os.environ.get('LOCAL_RANK', 0))}" if want_cuda else "cpu")
+        if not dist.is_initialized():
+            if want_cuda:
+                torch.cuda.set_device(self.device)
+                dist.init_process_group("nccl", rank=self.rank, world_size=self.world_size, device_id=self.device)
+            else:
+                dist.init_process_group("gloo", rank=self.rank, world_size=self.world_size)
+        mg = config.actor_rollout_ref.actor.megatron
+        self.pp = int(mg.pipeline_model_parallel_size)
+        if self.pp < 2 or self.world_size % self.pp:
+            raise ValueError(f"pipeline_model_parallel_size={self.pp} must be >= 2 and divide the {self.world_size} workers")
+        if mg.tensor_model_parallel_size != 1:
+            raise NotImplementedError("tensor parallelism inside pipeline stages (use parallel/tp_train.py on its own)")
+        self.dp = self.world_size // self.pp
+        self.pp_group = self.dp_group = None
+        for d in range(self.dp):                        # every process creates every group, in the same order
+            g = dist.new_group(list(range(d * self.pp, (d + 1) * self.pp)))
+            if d == self.rank // self.pp:
+                self.pp_group = g
+        for st in range(self.pp):
+            g = dist.new_group(list(range(st, self.world_size, self.pp)))
+            if st == self.rank % self.pp:
+                self.dp_group = g
+        self._register_dispatch_collect_info("actor", dp_rank=self.rank // self.pp, is_collect=self.rank % self.pp == self.pp - 1,
+                                             dp_size=self.dp)
+        self.actor = self.rollout = self.roll_w = None
+
+    @register(dispatch_mode=Dispatch.ONE_TO_ALL)
+    def init_model(self) -> dict:
+        from ..models import TransformerWeights, get_model_config
+        from ..rollout.engine import RolloutEngine
+        from ..workers.engine_api import get_engine_cls
+        from ..workers.hybrid_worker import lr_at_step
+        from ..workers.roles import ActorWorker
+
+        cfg = self.config
+        arr, a = cfg.actor_rollout_ref, cfg.actor_rollout_ref.actor
+        self.model_cfg = get_model_config(arr.model.path, **arr.model.override_config)
+        total = a.optim.total_training_steps if a.optim.total_training_steps > 0 else (cfg.trainer.total_training_steps or 0)
+        eng = get_engine_cls("language_model", "pp")(
+            self.model_cfg, self.device, self.pp_group, self.dp_group if self.dp > 1 else None, lr=a.optim.lr,
+            lr_schedule=lambda step: lr_at_step(a.optim, step, total), micro_batch_size=a.ppo_micro_batch_size_per_gpu or 8,
+            virtual_stages=int(a.megatron.virtual_pipeline_model_parallel_size or 1), weight_decay=a.optim.weight_decay,
+            max_grad_norm=a.grad_clip, seed=cfg.data.seed)
+        self.actor = ActorWorker(eng, ppo_mini_batch_size=1 << 30, ppo_epochs=1, clip_ratio=a.clip_ratio, loss_agg_mode=a.loss_agg_mode,
+                                 loss_config=a)
+        self.actor.init_model()
+        r = arr.rollout
+        self.roll_w = TransformerWeights(self.model_cfg, device=self.device, dtype=eng.engine.dtype, init=False)
+        self.rollout = RolloutEngine(self.model_cfg, self.device, max_num_seqs=r.max_num_seqs,
+                                     max_model_len=r.max_model_len or (cfg.data.max_prompt_length + cfg.data.max_response_length),
+                                     gpu_memory_utilization=r.gpu_memory_utilization, use_cuda_graph=r.cuda_graph,
+                                     max_prefill_tokens=r.max_num_batched_tokens, seed=cfg.data.seed + 17 * self.rank)
+        self._refresh_rollout_weights()
+        mc = self.model_cfg
+        return {"rank": self.rank, "vocab_size": mc.vocab_size, "eos_token_id": mc.eos_token_id, "pad_token_id": mc.pad_token_id,
+                "num_params": mc.num_params(), "pp": self.pp, "dp": self.dp, "stage_params": eng.engine.num_local_params()}
+
+    def _refresh_rollout_weights(self) -> None:
+        full = self.actor.engine.engine.gather_full_state()              # every stage's fp32 masters, on every rank
+        with torch.no_grad():
+            self.roll_w.load_state_dict({k: v.to(self.device) for k, v in full.items()})
+        self.rollout.set_weights(self.roll_w.embed, self.roll_w.layers, self.roll_w.head)
+
+    @register(dispatch_mode=Dispatch.DP_COMPUTE_PROTO)
+    def generate_sequences(self, prompts: DataProto) -> DataProto:
+        from ..workers.hybrid_worker import ActorRolloutRefWorker
+
+        # reuse the hybrid worker's request building / post-processing on this worker's engine
+        shim = getattr(self, "_gen_shim", None)
+        if shim is None:
+            shim = self._gen_shim = object.__new__(ActorRolloutRefWorker)
+            shim.config, shim.device, shim.rollout, shim.model_cfg = self.config, self.device, self.rollout, self.model_cfg
+            shim.rank, shim.world, shim.rollout_tp, shim.tp_group, shim.tp_rank = self.rank, self.world_size, 1, None, 0
+            shim.profiler = None
+            shim._remote_client = None
+        return shim.generate_sequences(prompts.to(self.device)).to("cpu")
+
+    @register(dispatch_mode=make_nd_compute_dataproto_dispatch_fn("actor"))
+    def compute_log_prob(self, data: DataProto) -> DataProto:
+        data.meta_info.setdefault("temperature", self.config.actor_rollout_ref.rollout.temperature)
+        return self.actor.compute_log_prob(data.to(self.device)).to("cpu")
+
+    @register(dispatch_mode=make_nd_compute_dataproto_dispatch_fn("actor"))
+    def update_actor(self, data: DataProto) -> DataProto:
+        data.meta_info.setdefault("temperature", self.config.actor_rollout_ref.rollout.temperature)
+        m = self.actor.update_actor(data.to(self.device))
+        return DataProto(meta_info={"metrics": {k: [v] for k, v in m.items()}})
+
+    @register(dispatch_mode=Dispatch.ONE_TO_ALL)
+    def update_weight(self) -> bool:
+        self._refresh_rollout_weights()
+        return True
+
+    @register(dispatch_mode=Dispatch.ONE_TO_ALL)
+    def save_checkpoint(self, path: str, global_step: int = 0, max_ckpt_to_keep: int | None = None) -> None:
+        self.actor.save_checkpoint(os.path.join(path, "actor"), global_step, max_ckpt_to_keep)
+
+    @register(dispatch_mode=Dispatch.ONE_TO_ALL)
+    def load_checkpoint(self, path: str) -> None:
+        self.actor.load_checkpoint(os.path.join(path, "actor"))
+        self._refresh_rollout_weights()
+
+    @register(dispatch_mode=Dispatch.RANK_ZERO, execute_mode=Execute.RANK_ZERO)
+    def weights_checksum(self) -> float:
+        return float(sum(t.double().abs().sum() for _, t in self.roll_w.named_tensors()))
+
+    @register(dispatch_mode=Dispatch.ONE_TO_ALL)
+    def teardown(self) -> None:
+        import torch.distributed as dist
+
+        if dist.is_initialized():
+            dist.barrier()
+            dist.destroy_process_group()
+
+
 def make_worker_group(config: PPOConfig, backend: str, world_size: int, env: dict | None = None):
+    if config.actor_rollout_ref.actor.strategy == "megatron":
+        if backend == "local":
+            raise ValueError("the pipeline-parallel actor needs one process per stage (controller.backend=mp | ray)")
+        cia = ClassWithInitArgs(PipelinePPOWorker, config)
+        if backend == "ray":
+            from ..controller.worker_group import RayWorkerGroup
+
+            return RayWorkerGroup(world_size, cia, env=env)
+        return MPWorkerGroup(world_size, cia, env=env)
     cia = ClassWithInitArgs(PPOWorker, config)
     if backend == "local":
         if world_size != 1:
