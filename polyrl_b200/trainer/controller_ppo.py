@@ -139,8 +139,9 @@ class PPOWorker(Worker):
 
 
 class PipelinePPOWorker(Worker):
-    """``actor.strategy = megatron``: the actor is PIPELINE-parallel (``actor.megatron.pipeline_model_parallel_size`` stages x data
-    parallel replicas, optional virtual stages) on ``parallel/pipeline.py`` through the ``BaseEngine`` role worker
+    """``actor.strategy = megatron``: the actor is MODEL-parallel — pipeline (``actor.megatron.pipeline_model_parallel_size`` stages,
+    optional virtual stages, ``parallel/pipeline.py``) or tensor parallel (``tensor_model_parallel_size``, ``parallel/tp_train.py``)
+    x data-parallel replicas — through the ``BaseEngine`` role worker
     (``workers/roles.py::ActorWorker``), the way the reference's Megatron workers sit behind the same trainer
     (3rdparty/verl/verl/workers/megatron_workers.py:204-600).  Dispatch uses the nd-mesh protocol: every stage of a pipeline
     receives its replica's chunk, results are collected from the last stage.  Rollout stays data-parallel over ALL workers: each
@@ -164,10 +165,14 @@ class PipelinePPOWorker(Worker):
                 dist.init_process_group("gloo", rank=self.rank, world_size=self.world_size)
         mg = config.actor_rollout_ref.actor.megatron
         self.pp = int(mg.pipeline_model_parallel_size)
+        self.tp = int(mg.tensor_model_parallel_size)
+        if self.tp > 1 and self.pp > 1:
+            raise NotImplementedError("tensor parallelism inside pipeline stages: choose tensor_ OR pipeline_model_parallel_size > 1")
+        self.use_tp = self.tp > 1
+        if self.use_tp:
+            self.pp = self.tp            # one model-parallel group per replica; below "pp" is the size of that group
         if self.pp < 2 or self.world_size % self.pp:
-            raise ValueError(f"pipeline_model_parallel_size={self.pp} must be >= 2 and divide the {self.world_size} workers")
-        if mg.tensor_model_parallel_size != 1:
-            raise NotImplementedError("tensor parallelism inside pipeline stages (use parallel/tp_train.py on its own)")
+            raise ValueError(f"model-parallel size {self.pp} must be >= 2 and divide the {self.world_size} workers")
         self.dp = self.world_size // self.pp
         self.pp_group = self.dp_group = None
         for d in range(self.dp):                        # every process creates every group, in the same order
@@ -178,8 +183,9 @@ class PipelinePPOWorker(Worker):
             g = dist.new_group(list(range(st, self.world_size, self.pp)))
             if st == self.rank % self.pp:
                 self.dp_group = g
-        self._register_dispatch_collect_info("actor", dp_rank=self.rank // self.pp, is_collect=self.rank % self.pp == self.pp - 1,
-                                             dp_size=self.dp)
+        # collect from the last pipeline stage (the head lives there) or from TP rank 0 (every TP rank holds the same result)
+        collect = (self.rank % self.pp == 0) if self.use_tp else (self.rank % self.pp == self.pp - 1)
+        self._register_dispatch_collect_info("actor", dp_rank=self.rank // self.pp, is_collect=collect, dp_size=self.dp)
         self.actor = self.rollout = self.roll_w = None
 
     @register(dispatch_mode=Dispatch.ONE_TO_ALL)
@@ -194,11 +200,17 @@ class PipelinePPOWorker(Worker):
         arr, a = cfg.actor_rollout_ref, cfg.actor_rollout_ref.actor
         self.model_cfg = get_model_config(arr.model.path, **arr.model.override_config)
         total = a.optim.total_training_steps if a.optim.total_training_steps > 0 else (cfg.trainer.total_training_steps or 0)
-        eng = get_engine_cls("language_model", "pp")(
-            self.model_cfg, self.device, self.pp_group, self.dp_group if self.dp > 1 else None, lr=a.optim.lr,
-            lr_schedule=lambda step: lr_at_step(a.optim, step, total), micro_batch_size=a.ppo_micro_batch_size_per_gpu or 8,
-            virtual_stages=int(a.megatron.virtual_pipeline_model_parallel_size or 1), weight_decay=a.optim.weight_decay,
-            max_grad_norm=a.grad_clip, seed=cfg.data.seed)
+        common = dict(lr=a.optim.lr, lr_schedule=lambda step: lr_at_step(a.optim, step, total),
+                      micro_batch_size=a.ppo_micro_batch_size_per_gpu or 8, weight_decay=a.optim.weight_decay,
+                      max_grad_norm=a.grad_clip, seed=cfg.data.seed)
+        if self.use_tp:
+            from ..workers.engine_api import TensorParallelLMEngine
+
+            eng = TensorParallelLMEngine(self.model_cfg, self.device, self.pp_group, self.dp_group if self.dp > 1 else None, **common)
+        else:
+            eng = get_engine_cls("language_model", "pp")(
+                self.model_cfg, self.device, self.pp_group, self.dp_group if self.dp > 1 else None,
+                virtual_stages=int(a.megatron.virtual_pipeline_model_parallel_size or 1), **common)
         self.actor = ActorWorker(eng, ppo_mini_batch_size=1 << 30, ppo_epochs=1, clip_ratio=a.clip_ratio, loss_agg_mode=a.loss_agg_mode,
                                  loss_config=a)
         self.actor.init_model()
@@ -211,7 +223,9 @@ class PipelinePPOWorker(Worker):
         self._refresh_rollout_weights()
         mc = self.model_cfg
         return {"rank": self.rank, "vocab_size": mc.vocab_size, "eos_token_id": mc.eos_token_id, "pad_token_id": mc.pad_token_id,
-                "num_params": mc.num_params(), "pp": self.pp, "dp": self.dp, "stage_params": eng.engine.num_local_params()}
+                "num_params": mc.num_params(), "pp": 1 if self.use_tp else self.pp, "tp": self.tp, "dp": self.dp,
+                "stage_params": (eng.engine.num_local_params() if hasattr(eng.engine, "num_local_params")
+                                 else sum(v.numel() for v in eng.engine.master.values()))}
 
     def _refresh_rollout_weights(self) -> None:
         full = self.actor.engine.engine.gather_full_state()              # every stage's fp32 masters, on every rank

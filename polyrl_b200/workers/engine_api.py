@@ -180,6 +180,24 @@ class ZeroEngineWithValueHead(ZeroEngine):
     value_head = True
 
 
+class TensorParallelLMEngine(ZeroEngine):
+    """``BaseEngine`` surface over ``parallel.tp_train.TPTrainEngine`` (dp x tp, optional Megatron sequence parallelism) — the
+    reference's Megatron engine with ``tensor_model_parallel_size > 1``.  Every rank of a TP group receives the same batch and
+    produces the same log-probs / metrics."""
+
+    def __init__(self, model, device, tp_group, dp_group=None, lr: float = 1e-6, lr_schedule=None, micro_batch_size: int = 8,
+                 sequence_parallel: bool = False, **engine_kw):
+        super().__init__(model, device, group=None, lr=lr, lr_schedule=lr_schedule, micro_batch_size=micro_batch_size, **engine_kw)
+        self.tp_group, self.dp_group, self.sequence_parallel = tp_group, dp_group, sequence_parallel
+
+    def initialize(self) -> None:
+        from ..parallel.tp_train import TPTrainEngine
+
+        self.engine = TPTrainEngine(self.model_cfg, self.device, self.tp_group, self.dp_group, lr=self.base_lr,
+                                    sequence_parallel=self.sequence_parallel, **self.engine_kw)
+        self.ckpt = None
+
+
 class PipelineLMEngine(ZeroEngine):
     """``BaseEngine`` surface over ``parallel.pipeline.PipelineEngine`` (dp x pp, 1F1B) — the role of the reference's Megatron
     engine with ``pipeline_model_parallel_size > 1`` (verl/workers/engine/megatron/transformer_impl.py).  Every stage of a pipeline
