@@ -118,6 +118,7 @@ class MegatronConfig(BaseConfig):
     tensor_model_parallel_size: int = 1
     pipeline_model_parallel_size: int = 1
     virtual_pipeline_model_parallel_size: int | None = None
+    expert_model_parallel_size: int = 1            # MoE: experts split over this many workers (= all workers), dense part data-parallel
 
 
 @dataclass

@@ -169,9 +169,14 @@ class PipelinePPOWorker(Worker):
         if self.tp > 1 and self.pp > 1:
             raise NotImplementedError("tensor parallelism inside pipeline stages: choose tensor_ OR pipeline_model_parallel_size > 1")
         self.use_tp = self.tp > 1
+        self.use_ep = int(mg.expert_model_parallel_size) > 1
+        if self.use_ep:
+            if self.tp > 1 or self.pp > 1 or int(mg.expert_model_parallel_size) != self.world_size:
+                raise NotImplementedError("expert parallelism spans all workers and does not combine with tensor / pipeline parallelism here")
+            self.pp = 1                  # no replication of data inside a model-parallel group: every worker has its own chunk
         if self.use_tp:
             self.pp = self.tp            # one model-parallel group per replica; below "pp" is the size of that group
-        if self.pp < 2 or self.world_size % self.pp:
+        if (self.pp < 2 and not self.use_ep) or self.world_size % self.pp:
             raise ValueError(f"model-parallel size {self.pp} must be >= 2 and divide the {self.world_size} workers")
         self.dp = self.world_size // self.pp
         self.pp_group = self.dp_group = None
@@ -203,7 +208,13 @@ class PipelinePPOWorker(Worker):
         common = dict(lr=a.optim.lr, lr_schedule=lambda step: lr_at_step(a.optim, step, total),
                       micro_batch_size=a.ppo_micro_batch_size_per_gpu or 8, weight_decay=a.optim.weight_decay,
                       max_grad_norm=a.grad_clip, seed=cfg.data.seed)
-        if self.use_tp:
+        if self.use_ep:
+            import torch.distributed as dist
+
+            from ..workers.engine_api import ExpertParallelLMEngine
+
+            eng = ExpertParallelLMEngine(self.model_cfg, self.device, dist.group.WORLD, **common)
+        elif self.use_tp:
             from ..workers.engine_api import TensorParallelLMEngine
 
             eng = TensorParallelLMEngine(self.model_cfg, self.device, self.pp_group, self.dp_group if self.dp > 1 else None, **common)
@@ -223,7 +234,8 @@ class PipelinePPOWorker(Worker):
         self._refresh_rollout_weights()
         mc = self.model_cfg
         return {"rank": self.rank, "vocab_size": mc.vocab_size, "eos_token_id": mc.eos_token_id, "pad_token_id": mc.pad_token_id,
-                "num_params": mc.num_params(), "pp": 1 if self.use_tp else self.pp, "tp": self.tp, "dp": self.dp,
+                "num_params": mc.num_params(), "pp": 1 if (self.use_tp or self.use_ep) else self.pp, "tp": self.tp, "ep": self.world_size if self.use_ep else 1,
+                "dp": self.dp,
                 "stage_params": (eng.engine.num_local_params() if hasattr(eng.engine, "num_local_params")
                                  else sum(v.numel() for v in eng.engine.master.values()))}
 

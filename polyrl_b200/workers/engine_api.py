@@ -198,6 +198,22 @@ class TensorParallelLMEngine(ZeroEngine):
         self.ckpt = None
 
 
+class ExpertParallelLMEngine(ZeroEngine):
+    """``BaseEngine`` surface over ``parallel.expert.EPTrainEngine``: the experts of a mixture-of-experts model are split over the
+    group, the dense part is data-parallel — every rank trains on its OWN batch chunk and the dispatch / combine all-to-alls
+    require all ranks to run the same number of micro-batches."""
+
+    def __init__(self, model, device, ep_group, lr: float = 1e-6, lr_schedule=None, micro_batch_size: int = 8, **engine_kw):
+        super().__init__(model, device, group=None, lr=lr, lr_schedule=lr_schedule, micro_batch_size=micro_batch_size, **engine_kw)
+        self.ep_group = ep_group
+
+    def initialize(self) -> None:
+        from ..parallel.expert import EPTrainEngine
+
+        self.engine = EPTrainEngine(self.model_cfg, self.device, self.ep_group, lr=self.base_lr, **self.engine_kw)
+        self.ckpt = None
+
+
 class PipelineLMEngine(ZeroEngine):
     """``BaseEngine`` surface over ``parallel.pipeline.PipelineEngine`` (dp x pp, 1F1B) — the role of the reference's Megatron
     engine with ``pipeline_model_parallel_size > 1`` (verl/workers/engine/megatron/transformer_impl.py).  Every stage of a pipeline

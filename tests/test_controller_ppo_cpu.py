@@ -68,20 +68,23 @@ PP2 = ["actor_rollout_ref.actor.megatron.pipeline_model_parallel_size=2"]
 
 @pytest.mark.parametrize("world,extra", [(2, PP2), (4, PP2 + ["actor_rollout_ref.actor.megatron.virtual_pipeline_model_parallel_size=2",
                                                              "actor_rollout_ref.model.override_config={num_layers: 4}"]),
-                                         (2, ["actor_rollout_ref.actor.megatron.tensor_model_parallel_size=2"])])
+                                         (2, ["actor_rollout_ref.actor.megatron.tensor_model_parallel_size=2"]),
+                                         (2, ["actor_rollout_ref.actor.megatron.expert_model_parallel_size=2",
+                                              "actor_rollout_ref.model.path=tiny-qwen3-moe"])])
 def test_controller_drives_a_pipeline_parallel_actor(world, extra):
     """actor.strategy=megatron: GRPO through the single controller with a pipeline-parallel actor (pp=2; 4 workers = 2 pipelines
     with interleaved virtual stages), data-parallel rollout engines refreshed from the gathered pipeline state.  The log-probs the
     pipeline computes for the sampled responses must equal the rollout engines' own (same weights on both sides)."""
     cfg = load_config(overrides=OV + [f"trainer.n_gpus_per_node={world}", "actor_rollout_ref.actor.strategy=megatron",
                                       "actor_rollout_ref.actor.ppo_micro_batch_size_per_gpu=4", *extra])
-    tp = "tensor_model_parallel_size=2" in extra[0]
-    mc = get_model_config("tiny-llama", **cfg.actor_rollout_ref.model.override_config)
+    tp, ep = "tensor_model_parallel_size=2" in extra[0], "expert_model_parallel_size=2" in extra[0]
+    mc = get_model_config(cfg.actor_rollout_ref.model.path, **cfg.actor_rollout_ref.model.override_config)
     ds = SyntheticPromptDataset(mc.vocab_size, 32, (8, 24), 32)
     wg = make_worker_group(cfg, "mp", world)
     tr = ControllerPPOTrainer(cfg, wg, ds)
     try:
-        assert (tr.model_info["tp"] if tp else tr.model_info["pp"]) == 2 and tr.model_info["dp"] == world // 2
+        assert (tr.model_info["ep"] if ep else tr.model_info["tp"] if tp else tr.model_info["pp"]) == 2
+        assert tr.model_info["dp"] == (world if ep else world // 2)
         assert tr.model_info["stage_params"] < mc.num_params()
         from polyrl_b200.protocol import DataProto, collate_fn
 
