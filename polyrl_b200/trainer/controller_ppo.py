@@ -153,8 +153,8 @@ class PipelinePPOWorker(Worker):
         import torch.distributed as dist
 
         self.config = config
-        if need_critic(config) or need_reference_policy(config):
-            raise NotImplementedError("the pipeline-parallel actor worker supports critic-free algorithms without a reference policy")
+        if need_critic(config):
+            raise NotImplementedError("the model-parallel actor worker supports critic-free algorithms (GRPO / RLOO / ...)")
         want_cuda = torch.cuda.is_available() and config.trainer.device != "cpu"
         self.device = torch.device(f"cuda:{int(os.environ.get('LOCAL_RANK', 0))}" if want_cuda else "cpu")
         if not dist.is_initialized():
@@ -197,7 +197,9 @@ class PipelinePPOWorker(Worker):
     def init_model(self) -> dict:
         from ..models import TransformerWeights, get_model_config
         from ..rollout.engine import RolloutEngine
-        from ..workers.engine_api import get_engine_cls
+        import torch.distributed as dist
+
+        from ..workers.engine_api import ExpertParallelLMEngine, TensorParallelLMEngine, get_engine_cls
         from ..workers.hybrid_worker import lr_at_step
         from ..workers.roles import ActorWorker
 
@@ -209,14 +211,8 @@ class PipelinePPOWorker(Worker):
                       micro_batch_size=a.ppo_micro_batch_size_per_gpu or 8, weight_decay=a.optim.weight_decay,
                       max_grad_norm=a.grad_clip, seed=cfg.data.seed)
         if self.use_ep:
-            import torch.distributed as dist
-
-            from ..workers.engine_api import ExpertParallelLMEngine
-
             eng = ExpertParallelLMEngine(self.model_cfg, self.device, dist.group.WORLD, **common)
         elif self.use_tp:
-            from ..workers.engine_api import TensorParallelLMEngine
-
             eng = TensorParallelLMEngine(self.model_cfg, self.device, self.pp_group, self.dp_group if self.dp > 1 else None, **common)
         else:
             eng = get_engine_cls("language_model", "pp")(
@@ -225,6 +221,20 @@ class PipelinePPOWorker(Worker):
         self.actor = ActorWorker(eng, ppo_mini_batch_size=1 << 30, ppo_epochs=1, clip_ratio=a.clip_ratio, loss_agg_mode=a.loss_agg_mode,
                                  loss_config=a)
         self.actor.init_model()
+        self.ref = None
+        if need_reference_policy(cfg):
+            # frozen copy of the initial policy with the same model-parallel layout (same seed => identical initial weights)
+            ref_kw = {**common, "lr": 0.0, "lr_schedule": None}
+            if self.use_ep:
+                ref_eng = ExpertParallelLMEngine(self.model_cfg, self.device, dist.group.WORLD, **ref_kw)
+            elif self.use_tp:
+                ref_eng = TensorParallelLMEngine(self.model_cfg, self.device, self.pp_group, self.dp_group if self.dp > 1 else None, **ref_kw)
+            else:
+                ref_eng = get_engine_cls("language_model", "pp")(
+                    self.model_cfg, self.device, self.pp_group, self.dp_group if self.dp > 1 else None,
+                    virtual_stages=int(a.megatron.virtual_pipeline_model_parallel_size or 1), **ref_kw)
+            self.ref = ActorWorker(ref_eng)
+            self.ref.init_model()
         r = arr.rollout
         self.roll_w = TransformerWeights(self.model_cfg, device=self.device, dtype=eng.engine.dtype, init=False)
         self.rollout = RolloutEngine(self.model_cfg, self.device, max_num_seqs=r.max_num_seqs,
@@ -263,6 +273,12 @@ class PipelinePPOWorker(Worker):
     def compute_log_prob(self, data: DataProto) -> DataProto:
         data.meta_info.setdefault("temperature", self.config.actor_rollout_ref.rollout.temperature)
         return self.actor.compute_log_prob(data.to(self.device)).to("cpu")
+
+    @register(dispatch_mode=make_nd_compute_dataproto_dispatch_fn("actor"))
+    def compute_ref_log_prob(self, data: DataProto) -> DataProto:
+        data.meta_info.setdefault("temperature", self.config.actor_rollout_ref.rollout.temperature)
+        out = self.ref.compute_log_prob(data.to(self.device))
+        return DataProto.from_dict({"ref_log_prob": out.batch["old_log_probs"]}).to("cpu")
 
     @register(dispatch_mode=make_nd_compute_dataproto_dispatch_fn("actor"))
     def update_actor(self, data: DataProto) -> DataProto:

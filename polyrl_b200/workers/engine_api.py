@@ -305,12 +305,35 @@ def sft_loss(out: dict, mb: dict):
 def ppo_loss(config=None, clip_ratio: float = 0.2, loss_agg_mode: str = "token-mean"):
     from ..algos import core_algos
 
+    # ``config`` may be the actor config tree (policy_loss.loss_mode, entropy_coeff, use_kl_loss, ...) or None (plain dual-clip PPO)
+    def get(name, default):
+        return getattr(config, name, default) if config is not None else default
+
+    pl = get("policy_loss", None)
+    mode = (pl.get("loss_mode") if isinstance(pl, dict) else getattr(pl, "loss_mode", None)) or "vanilla"
+    loss_impl = core_algos.get_policy_loss_fn(mode)
+    ent_coeff = float(get("entropy_coeff", 0.0) or 0.0)
+    use_kl, kl_coef, kl_type = bool(get("use_kl_loss", False)), float(get("kl_loss_coef", 0.001)), get("kl_loss_type", "low_var_kl")
+
     def fn(out: dict, mb: dict):
         dev = out["log_probs"].device
         mask = mb["response_mask"].to(dev).float()
-        pg, m = core_algos.compute_policy_loss_vanilla(mb["old_log_probs"].to(dev), out["log_probs"], mb["advantages"].to(dev), mask,
-                                                       loss_agg_mode=loss_agg_mode, config=config, cliprange=clip_ratio)
-        return pg, {"actor/pg_loss": pg.item(), **m}
+        kw = dict(cliprange=clip_ratio) if mode == "vanilla" else {}
+        riw = mb.get("rollout_is_weights")
+        pg, m = loss_impl(mb["old_log_probs"].to(dev), out["log_probs"], mb["advantages"].to(dev), mask, loss_agg_mode=loss_agg_mode,
+                          config=config, rollout_is_weights=riw.to(dev) if riw is not None else None, **kw)
+        loss, metrics = pg, {"actor/pg_loss": pg.item(), **m}
+        if ent_coeff != 0.0:
+            ent = core_algos.agg_loss(out["entropy"], mask, loss_agg_mode)
+            loss = loss - ent_coeff * ent
+            metrics["actor/entropy"] = ent.item()
+        if use_kl:
+            if "ref_log_prob" not in mb:
+                raise ValueError("use_kl_loss needs ref_log_prob in the batch")
+            kl = core_algos.agg_loss(core_algos.kl_penalty(out["log_probs"], mb["ref_log_prob"].to(dev), kl_type), mask, loss_agg_mode)
+            loss = loss + kl_coef * kl
+            metrics.update({"actor/kl_loss": kl.item(), "actor/kl_coef": kl_coef})
+        return loss, metrics
     return fn
 
 

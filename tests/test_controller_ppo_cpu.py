@@ -69,6 +69,8 @@ PP2 = ["actor_rollout_ref.actor.megatron.pipeline_model_parallel_size=2"]
 @pytest.mark.parametrize("world,extra", [(2, PP2), (4, PP2 + ["actor_rollout_ref.actor.megatron.virtual_pipeline_model_parallel_size=2",
                                                              "actor_rollout_ref.model.override_config={num_layers: 4}"]),
                                          (2, ["actor_rollout_ref.actor.megatron.tensor_model_parallel_size=2"]),
+                                         (2, PP2 + ["actor_rollout_ref.actor.use_kl_loss=True", "actor_rollout_ref.actor.kl_loss_coef=0.01",
+                                                    "actor_rollout_ref.actor.entropy_coeff=0.001", "actor_rollout_ref.actor.optim.lr=1e-3"]),
                                          (2, ["actor_rollout_ref.actor.megatron.expert_model_parallel_size=2",
                                               "actor_rollout_ref.model.path=tiny-qwen3-moe"])])
 def test_controller_drives_a_pipeline_parallel_actor(world, extra):
@@ -96,5 +98,8 @@ def test_controller_drives_a_pipeline_parallel_actor(world, extra):
         hist = tr.fit(max_steps=2)
         assert len(hist) == 2 and all(m["num_samples"] == 16 and m["actor/grad_norm"] > 0 for m in hist)
         assert wg.weights_checksum() != before                                            # the update reached the rollout engines
+        if any("use_kl_loss=True" in e for e in extra):                                   # reference policy + KL / entropy terms
+            assert all("actor/kl_loss" in m and "actor/entropy" in m and "timing_s/ref" in m for m in hist)
+            assert hist[0]["actor/kl_loss"] < 1e-7 < hist[1]["actor/kl_loss"]             # identical at step 1, drifting after the update
     finally:
         tr.shutdown()
