@@ -68,6 +68,22 @@ def maybe_load_pretrained(engine, path: str, rank: int = 0) -> int:
 from ..utils.profiler import DistProfiler  # noqa: E402
 
 
+def auto_fsdp_size(configured: int, world: int, comm: str, rank: int = 0, local_world: int | None = None) -> int:
+    """Shard-group size of the ZeRO engine.  An explicit ``fsdp_config.fsdp_size`` wins.  Otherwise a job that spans several nodes
+    (torchrun exports LOCAL_WORLD_SIZE < WORLD_SIZE) with the peer-memory backend shards INSIDE each node — the symmetric heap and
+    its NVLink kernels only exist within one NVSwitch domain — and replicates across nodes, where the gradient all-reduce of the
+    HSDP replica group runs over NCCL / the network (reference: fsdp_size / device-mesh (ddp, fsdp), fsdp_workers.py:99-118)."""
+    if configured and configured > 0:
+        return configured
+    lw = local_world if local_world is not None else int(os.environ.get("LOCAL_WORLD_SIZE", world) or world)
+    if comm == "p2p" and 0 < lw < world and world % lw == 0:
+        if rank == 0:
+            print(f"[worker] {world} ranks over {world // lw} nodes: ZeRO shards inside each node ({lw} GPUs, peer memory), "
+                  f"replicas across nodes (NCCL)", flush=True)
+        return lw
+    return configured
+
+
 class ActorRolloutRefWorker:
     """role in {"actor_rollout", "actor_rollout_ref", "actor", "rollout", "ref"}."""
 
@@ -116,7 +132,7 @@ class ActorRolloutRefWorker:
                 if g == self.dp_rank:
                     self.sp_group = grp
         # HSDP: fsdp_size < world => shard inside consecutive blocks of fsdp_size ranks, replicate across blocks
-        fs = arr.actor.fsdp_config.fsdp_size
+        fs = auto_fsdp_size(arr.actor.fsdp_config.fsdp_size, self.world, comm, self.rank)
         self.shard_group, self.replica_group = self.group, None
         if dist.is_initialized() and 0 < fs < self.world:
             if self.world % fs != 0:

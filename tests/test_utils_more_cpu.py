@@ -413,3 +413,12 @@ def test_dist_profiler_rank_filter_discrete_ranges_and_torch_window(tmp_path, mo
     t.stop()
     files = list((tmp_path / "tr").glob("trace_actor_rank0_*.json"))
     assert len(files) == 1 and t.ranges_opened == 1
+
+
+def test_multi_node_jobs_shard_inside_the_node():
+    from polyrl_b200.workers.hybrid_worker import auto_fsdp_size
+
+    assert auto_fsdp_size(-1, 16, "p2p", rank=1, local_world=8) == 8          # 2 nodes x 8 GPUs: HSDP 8 x 2
+    assert auto_fsdp_size(-1, 8, "p2p", rank=1, local_world=8) == -1          # one node: plain ZeRO over all ranks
+    assert auto_fsdp_size(-1, 16, "nccl", rank=1, local_world=8) == -1        # library collectives span nodes themselves
+    assert auto_fsdp_size(4, 16, "p2p", rank=1, local_world=8) == 4           # explicit setting wins
