@@ -422,3 +422,64 @@ def test_multi_node_jobs_shard_inside_the_node():
     assert auto_fsdp_size(-1, 8, "p2p", rank=1, local_world=8) == -1          # one node: plain ZeRO over all ranks
     assert auto_fsdp_size(-1, 16, "nccl", rank=1, local_world=8) == -1        # library collectives span nodes themselves
     assert auto_fsdp_size(4, 16, "p2p", rank=1, local_world=8) == 4           # explicit setting wins
+
+
+def test_offline_generation_and_evaluation_entry_points(tmp_path):
+    """main_generation (engine-backed batch sampling to parquet / jsonl) + main_eval (per-data-source scores of a generations file);
+    reference: verl/trainer/main_generation.py, main_eval.py."""
+    import json
+
+    from polyrl_b200.trainer import main_eval, main_generation
+
+    rows = [{"prompt": [5, 6, 7, 8 + i], "data_source": "openai/gsm8k", "reward_model": {"ground_truth": str(i)}} for i in range(5)]
+    src = tmp_path / "prompts.jsonl"
+    src.write_text("\n".join(json.dumps(r) for r in rows))
+    out = tmp_path / "gen" / "out.parquet"
+    assert main_generation.main(["--model", "tiny-llama", "--data", str(src), "--output", str(out), "--n-samples", "3",
+                                 "--response-length", "6", "--batch-size", "2"]) == 0
+    import pyarrow.parquet as pq
+
+    got = pq.read_table(str(out)).to_pylist()
+    assert len(got) == 5 and all(len(g["response_ids"]) == 3 and all(len(x) <= 6 for x in g["response_ids"]) for g in got)
+    assert got[2]["prompt"] == rows[2]["prompt"]
+    with pytest.raises(ValueError):
+        main_generation.generate("tiny-llama", rows, n_samples=2, temperature=0.0)
+    # evaluation on text responses: gsm8k scorer looks for "#### <answer>"
+    ev = [{"data_source": "openai/gsm8k", "reward_model": {"ground_truth": "7"}, "responses": ["so #### 7", "maybe #### 8"]},
+          {"data_source": "openai/gsm8k", "reward_model": {"ground_truth": "3"}, "responses": ["#### 4", "#### 5"]},
+          {"data_source": "other", "reward_model": {"ground_truth": "x"}, "responses": ["x"]}]
+    custom = tmp_path / "rw.py"
+    custom.write_text("def compute_score(data_source, solution_str, ground_truth, extra_info=None):\n    return float(solution_str.strip() == ground_truth)\n")
+    m = main_eval.evaluate(ev[:2], workers=1)
+    assert m["test_score/openai/gsm8k"] == 0.25 and m["test_score/openai/gsm8k/best@2"] == 0.5 and m["num_prompts/openai/gsm8k"] == 2.0
+    m2 = main_eval.evaluate(ev[2:], custom_reward=f"{custom}:compute_score", workers=1)
+    assert m2["test_score/other"] == 1.0
+
+
+def test_command_line_tools(tmp_path, capsys):
+    """init_random_model (HF checkpoint that HF itself loads), print_cfg, diagnose, rollout_viewer."""
+    import json
+
+    from polyrl_b200.tools import diagnose, init_random_model, print_cfg, rollout_viewer
+
+    out = tmp_path / "rand"
+    assert init_random_model.main(["--model", "tiny-llama", "--out", str(out), "--override", "num_layers=1", "--dtype", "float32"]) == 0
+    import transformers
+
+    m = transformers.AutoModelForCausalLM.from_pretrained(str(out))
+    assert m.config.num_hidden_layers == 1 and sum(p.numel() for p in m.parameters()) > 0
+    capsys.readouterr()
+    assert print_cfg.main(["--json", "actor_rollout_ref.rollout.n=4", "actor_rollout_ref.actor.use_dynamic_bsz=True"]) == 0
+    cfg = json.loads(capsys.readouterr().out)
+    assert cfg["actor_rollout_ref"]["rollout"]["n"] == 4
+    info = diagnose.collect()
+    assert info["python"] and "extension" in info and "optional_modules" in info and info["optional_modules"]["transformers"]
+    d = tmp_path / "dump"
+    d.mkdir()
+    (d / "train_1.jsonl").write_text("\n".join(json.dumps({"step": 1, "score": s, "input": f"q{s}", "output": f"a #### {s}"}) for s in (0.0, 1.0, 0.5)))
+    (d / "train_2.jsonl").write_text(json.dumps({"step": 2, "score": 0.25, "input": "q", "output": "zzz"}))
+    rows = rollout_viewer.load(str(d))
+    assert len(rows) == 4 and rollout_viewer.stats(rows)[1]["mean"] == 0.5
+    assert [r["score"] for r in rollout_viewer.select(rows, step=1, min_score=0.4)] == [1.0, 0.5]
+    assert len(rollout_viewer.select(rows, grep="zzz")) == 1
+    assert rollout_viewer.main([str(d), "--stats"]) == 0 and rollout_viewer.main([str(d), "--top", "2"]) == 0
