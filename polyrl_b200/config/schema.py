@@ -240,6 +240,7 @@ class ModelCfg(BaseConfig):
     freeze_vision_tower: bool = False     # vision-language models: train the text stack only (verl model.freeze_vision_tower)
     override_config: dict = field(default_factory=dict)
     tokenizer_path: str | None = None
+    use_shm: bool = False                 # copy the checkpoint directory to /dev/shm once per node before loading (verl model.use_shm)
 
 
 @dataclass

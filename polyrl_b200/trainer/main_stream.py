@@ -46,6 +46,9 @@ def build_datasets(cfg: PPOConfig, model_cfg, tokenizer=None):
     from ..data.synthetic import SyntheticPromptDataset
 
     d = cfg.data
+    from ..utils.fs import stage_path
+
+    d.train_files, d.val_files = stage_path(d.train_files), stage_path(d.val_files)        # remote (hdfs://) datasets: once per node
     if d.synthetic or not d.train_files:
         train = SyntheticPromptDataset(model_cfg.vocab_size, d.synthetic_num_samples, tuple(d.synthetic_prompt_len_range),
                                        d.max_prompt_length, model_cfg.pad_token_id, seed=d.seed)

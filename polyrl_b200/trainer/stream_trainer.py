@@ -410,6 +410,14 @@ class StreamPPOTrainer:
             write_latest(self._ckpt_root(), self.global_steps)
         if dist.is_initialized() and self.world > 1:
             dist.barrier(group=self.group)
+        if t.default_hdfs_dir and self.rank == 0:
+            # second copy of the step (HDFS through the `hdfs` CLI, or any mounted directory): reference trainer.default_hdfs_dir
+            from ..utils.fs import mirror_checkpoint
+
+            try:
+                mirror_checkpoint(root, t.default_hdfs_dir)
+            except Exception as e:                  # noqa: BLE001  (a failed mirror must not stop training)
+                print(f"[trainer] checkpoint mirror to {t.default_hdfs_dir!r} failed: {e}", flush=True)
         keeps = [k for k in (t.max_actor_ckpt_to_keep, t.max_critic_ckpt_to_keep if self.use_critic else None) if k]
         if keeps and self.rank == 0:
             from ..utils.checkpoint import rotate_checkpoints

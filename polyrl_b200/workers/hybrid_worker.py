@@ -115,6 +115,10 @@ class ActorRolloutRefWorker:
     def init_model(self) -> None:
         cfg = self.config
         arr = cfg.actor_rollout_ref
+        from ..utils.fs import is_non_local, stage_path
+
+        if is_non_local(arr.model.path) or getattr(arr.model, "use_shm", False):      # hdfs:// checkpoints are fetched once per node
+            arr.model.path = stage_path(arr.model.path, use_shm=bool(getattr(arr.model, "use_shm", False)))
         self.model_cfg = get_model_config(arr.model.path, **arr.model.override_config)
         comm = arr.actor.fsdp_config.comm_backend
         opt = arr.actor.optim

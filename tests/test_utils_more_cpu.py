@@ -483,3 +483,58 @@ def test_command_line_tools(tmp_path, capsys):
     assert [r["score"] for r in rollout_viewer.select(rows, step=1, min_score=0.4)] == [1.0, 0.5]
     assert len(rollout_viewer.select(rows, grep="zzz")) == 1
     assert rollout_viewer.main([str(d), "--stats"]) == 0 and rollout_viewer.main([str(d), "--top", "2"]) == 0
+
+
+def test_fs_staging_and_checkpoint_mirror(tmp_path, monkeypatch):
+    """utils/fs.py: local paths pass through, hdfs:// paths go through the `hdfs dfs` CLI into an md5-named cache (fetched once),
+    checkpoints are mirrored to trainer.default_hdfs_dir (plain directory or hdfs://)."""
+    import stat
+
+    from polyrl_b200.utils import fs
+
+    # a fake `hdfs` executable that maps hdfs://ns/<p> onto <tmp>/remote/<p>
+    remote = tmp_path / "remote"
+    remote.mkdir()
+    bindir = tmp_path / "bin"
+    bindir.mkdir()
+    script = bindir / "hdfs"
+    script.write_text(f"""#!/bin/bash
+# usage: hdfs dfs -get|-put|-cp|-test|-mkdir ...
+shift
+map() {{ echo "$1" | sed "s#^hdfs://ns#{remote}#"; }}
+case "$1" in
+  -get) cp -r "$(map "$3")" "$4" ;;
+  -put) mkdir -p "$(dirname "$(map "$4")")"; cp -r "$3" "$(map "$4")" ;;
+  -cp) cp -r "$(map "$3")" "$(map "$4")" ;;
+  -test) test -e "$(map "$3")" ;;
+  -mkdir) mkdir -p "$(map "$3")" ;;
+  *) exit 2 ;;
+esac
+""")
+    script.chmod(script.stat().st_mode | stat.S_IEXEC)
+    monkeypatch.setenv("PATH", f"{bindir}:{__import__('os').environ['PATH']}")
+    monkeypatch.setenv("POLYRL_CACHE_DIR", str(tmp_path / "cache"))
+    (remote / "models" / "m1").mkdir(parents=True)
+    (remote / "models" / "m1" / "config.json").write_text("{}")
+    assert fs.is_non_local("hdfs://ns/models/m1") and not fs.is_non_local("/data/x") and not fs.is_non_local("file:///data/x")
+    assert fs.exists("hdfs://ns/models/m1") and not fs.exists("hdfs://ns/models/none")
+    loc = fs.copy_to_local("hdfs://ns/models/m1")
+    assert (tmp_path / "cache") in __import__("pathlib").Path(loc).parents and (__import__("pathlib").Path(loc) / "config.json").exists()
+    (remote / "models" / "m1" / "config.json").write_text('{"changed": 1}')
+    assert fs.copy_to_local("hdfs://ns/models/m1") == loc and (__import__("pathlib").Path(loc) / "config.json").read_text() == "{}"   # cached
+    assert fs.stage_path(["hdfs://ns/models/m1", "/plain/path"]) == [loc, "/plain/path"]
+    assert fs.copy_to_local("file:///plain/path") == "/plain/path" and fs.copy_to_local(None) is None
+    # checkpoint mirror: to a directory and to hdfs://
+    ck = tmp_path / "ckpt" / "global_step_3"
+    (ck / "actor").mkdir(parents=True)
+    (ck / "actor" / "w.pt").write_text("x")
+    (ck.parent / "latest_checkpointed_iteration.txt").write_text("3")
+    dst = fs.mirror_checkpoint(ck, tmp_path / "mirror")
+    assert (tmp_path / "mirror" / "global_step_3" / "actor" / "w.pt").exists() and (tmp_path / "mirror" / "latest_checkpointed_iteration.txt").read_text() == "3"
+    assert dst.endswith("global_step_3")
+    fs.mirror_checkpoint(ck, "hdfs://ns/ckpts")
+    assert (remote / "ckpts" / "global_step_3" / "actor" / "w.pt").exists()
+    assert fs.mirror_checkpoint(ck, None) is None
+    monkeypatch.setenv("PATH", "/nonexistent")
+    with pytest.raises(RuntimeError, match="hdfs"):
+        fs.exists("hdfs://ns/x")
