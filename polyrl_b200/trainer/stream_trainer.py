@@ -263,6 +263,14 @@ class StreamPPOTrainer:
                 if diff.numel():
                     metrics.setdefault("training/rollout_probs_diff_mean", []).append(diff.mean().item())
                     metrics.setdefault("training/rollout_probs_diff_max", []).append(diff.max().item())
+                    metrics.setdefault("training/rollout_probs_diff_std", []).append(diff.std().item() if diff.numel() > 1 else 0.0)
+                    # Pearson correlation of the engine's and the trainer's token probabilities (reference:
+                    # verl/utils/debug/metrics.py calculate_debug_metrics): drops when the two forward passes disagree systematically
+                    a = local.batch["rollout_log_probs"][m].float().exp()
+                    b = local.batch["old_log_probs"][m].float().exp()
+                    if a.numel() > 1 and float(a.std()) > 0 and float(b.std()) > 0:
+                        metrics.setdefault("training/rollout_actor_probs_pearson_corr", []).append(
+                            float(torch.corrcoef(torch.stack([a, b]))[0, 1]))
         rc = cfg.algorithm.rollout_correction
         if (rc.rollout_is or rc.rollout_rs) and "rollout_log_probs" in local.batch:
             from ..algos.rollout_corr import compute_rollout_correction
