@@ -52,7 +52,34 @@ class Gsm8kInteraction(BaseInteraction):
         return float(gsm8k.compute_score(st["response"], st["ground_truth"], method="strict", format_score=0.0, score=1.0))
 
 
-_INTERACTIONS = {"gsm8k": Gsm8kInteraction, "base": BaseInteraction}
+class WeatherInteraction(BaseInteraction):
+    """Demo environment for tool-use trajectories (reference: verl/interactions/weather_interaction.py): the simulated user is
+    satisfied — and the turn scores 1 — once the assistant's reply contains a weather report (a temperature reading), otherwise
+    it asks again, up to ``max_turns`` (config)."""
+
+    def start_interaction(self, instance_id=None, **kwargs):
+        iid = super().start_interaction(instance_id, **kwargs)
+        self._instances[iid] = {"turns": 0, "reward": 0.0, **kwargs}
+        return iid
+
+    def generate_response(self, instance_id, messages, **kwargs):
+        import re
+
+        st = self._instances[instance_id]
+        st["turns"] += 1
+        last = next((str(m["content"]) for m in reversed(messages) if m.get("role") == "assistant"), "")
+        if re.search(r"-?\d+(\.\d+)?\s*(°|degrees|deg)\s*[CF]?", last, flags=re.I):
+            st["reward"] = 1.0
+            return True, "Thanks, that is the weather report I was looking for.", 1.0, {}
+        if st["turns"] >= int(self.config.get("max_turns", 3)):
+            return True, "Never mind.", 0.0, {}
+        return False, "I still need the current temperature. Please call the weather tool and report it.", 0.0, {}
+
+    def calculate_score(self, instance_id, **kwargs) -> float:
+        return float(self._instances[instance_id]["reward"])
+
+
+_INTERACTIONS = {"gsm8k": Gsm8kInteraction, "weather": WeatherInteraction, "base": BaseInteraction}
 
 
 def get_interaction_cls(name: str):
