@@ -8,6 +8,7 @@ rlboost/verl_stream/workers/config/rollout.py:94-208).
 from __future__ import annotations
 
 import copy
+import os
 import dataclasses
 from dataclasses import dataclass, field, fields, is_dataclass
 from typing import Any, Mapping
@@ -53,6 +54,22 @@ class OptimConfig(BaseConfig):
     betas: tuple = (0.9, 0.999)
     eps: float = 1e-8
     clip_grad: float = 1.0
+    lr_decay_style: str | None = None          # Megatron spelling of warmup_style (constant | cosine | linear): mapped in __post_init__
+    lr_scheduler_type: str | None = None       # HF spelling of the same choice
+    lr_warmup_init: float = 0.0
+    grad_clip: float | None = None             # alias of clip_grad
+    min_lr: float | None = None                # absolute floor of the cosine schedule (sets min_lr_ratio = min_lr / lr)
+    override_optimizer_config: dict = field(default_factory=dict)   # Megatron optimizer knobs (cpu offload fractions, ...): accepted;
+                                                                    # ``optimizer_cpu_offload`` maps to fsdp_config.optimizer_offload
+
+    def __post_init__(self):
+        style = self.lr_decay_style or self.lr_scheduler_type
+        if style:
+            self.warmup_style = "cosine" if style == "cosine" else "constant"
+        if self.grad_clip is not None:
+            self.clip_grad = float(self.grad_clip)
+        if self.min_lr is not None and self.lr > 0:
+            self.min_lr_ratio = float(self.min_lr) / float(self.lr)
 
 
 @dataclass
@@ -72,6 +89,12 @@ class FSDPConfig(BaseConfig):
     activation_offload: bool = False     # park saved activations in pinned host memory (verl enable_activation_offload); slower than
                                          # recompute on B200, for parity and for models whose saved activations do not fit
     activation_reserve_gb: float = 16.0
+    # accepted for config compatibility with torch-FSDP based stacks; the engine's precision policy is fixed (bf16 parameters and
+    # gradients on the wire, fp32 master weights / moments / gradient accumulation) and parameters are always "original"
+    mixed_precision: dict = field(default_factory=dict)
+    use_orig_params: bool = True
+    wrap_policy: dict = field(default_factory=dict)
+    offload_policy: bool = False
 
 
 @dataclass
@@ -119,12 +142,40 @@ class MegatronConfig(BaseConfig):
     pipeline_model_parallel_size: int = 1
     virtual_pipeline_model_parallel_size: int | None = None
     expert_model_parallel_size: int = 1            # MoE: experts split over this many workers (= all workers), dense part data-parallel
+    # the rest of the reference's Megatron block is accepted so that its launch scripts parse; what has a counterpart is mapped
+    # (offload flags -> the ZeRO engine's offload options), transformer-engine fusion switches have nothing to switch here
+    context_parallel_size: int = 1                 # > 1 is rejected by validate_config (Ulysses SP covers long sequences)
+    expert_tensor_parallel_size: int | None = None
+    sequence_parallel: bool = True
+    param_offload: bool = False
+    grad_offload: bool = False
+    optimizer_offload: bool = False
+    use_distributed_optimizer: bool = True
+    use_dist_checkpointing: bool = False
+    dist_checkpointing_path: str | None = None
+    use_mbridge: bool = False
+    seed: int = 42
+    override_transformer_config: dict = field(default_factory=dict)
+    override_ddp_config: dict = field(default_factory=dict)
 
 
 @dataclass
 class ActorConfig(BaseConfig):
     strategy: str = "fsdp"
     megatron: MegatronConfig = field(default_factory=MegatronConfig)
+    freeze_vision_tower: bool | None = None   # alias of model.freeze_vision_tower (verl spells it on the actor)
+    # older spellings of policy_loss.* directly on the actor (entropy-mechanism recipe scripts)
+    loss_mode: str | None = None
+    clip_cov_ratio: float | None = None
+    clip_cov_lb: float | None = None
+    clip_cov_ub: float | None = None
+    kl_cov_ratio: float | None = None
+    ppo_kl_coef: float | None = None
+    # logits-memory knobs of HF-model stacks: the fused linear-cross-entropy kernel never materialises [T, V] logits, so there is
+    # nothing to chunk or checkpoint; torch.compile is not used
+    entropy_checkpointing: bool = False
+    entropy_from_logits_with_chunking: bool = False
+    use_torch_compile: bool = False
     ppo_mini_batch_size: int = 256
     ppo_micro_batch_size: int | None = None
     ppo_micro_batch_size_per_gpu: int | None = None
@@ -151,6 +202,13 @@ class ActorConfig(BaseConfig):
     profiler: ProfilerConfig = field(default_factory=ProfilerConfig)
     _mutable_fields = {"ppo_mini_batch_size", "ppo_micro_batch_size", "ppo_micro_batch_size_per_gpu"}
 
+    def __post_init__(self):
+        if self.loss_mode:
+            self.policy_loss.loss_mode = self.loss_mode
+        for k in ("clip_cov_ratio", "clip_cov_lb", "clip_cov_ub", "kl_cov_ratio", "ppo_kl_coef"):
+            if getattr(self, k) is not None:
+                setattr(self.policy_loss, k, float(getattr(self, k)))
+
 
 @dataclass
 class RolloutManagerConfig(BaseConfig):
@@ -172,6 +230,7 @@ class MultiTurnConfig(BaseConfig):
     tool_config_path: str | None = None
     interaction_config_path: str | None = None
     format: str = "hermes"
+    num_repeat_rollouts: int | None = None   # collabllm-style repeated simulated-user rollouts per turn (accepted; single rollout here)
 
 
 @dataclass
@@ -206,6 +265,18 @@ class RolloutConfig(BaseConfig):
     log_prob_max_token_len_per_gpu: int = 16384
     min_stream_batch_size: int = 16
     cuda_graph: bool = True
+    enforce_eager: bool | None = None       # vLLM / SGLang spelling: True = no CUDA graphs (sets cuda_graph = not enforce_eager)
+    log_prob_micro_batch_size: int | None = None     # GLOBAL micro-batch (deprecated in verl): divided by the GPU count at start-up
+    engine_kwargs: dict = field(default_factory=dict)      # back-end specific extras (vllm / sglang sections): accepted, unused by the native engine
+    layered_summon: bool = False            # FSDP-to-engine weight gathering granularity: the ZeRO engine always gathers unit by unit
+    multi_stage_wake_up: bool = False       # weights and KV cache already resume separately (release_memory / resume_memory tags)
+    disable_log_stats: bool = True
+    over_sample_rate: float = 0.0           # SGLang async over-sampling knob: the manager's continuation makes stragglers cheap instead
+    update_weights_bucket_megabytes: int = 512   # bucket size of IPC weight hand-off in other stacks; weights are aliased / peer-pushed here
+    agent: dict = field(default_factory=dict)    # {"agent_loop_config_path": ..., "num_workers": ...}
+    trace: dict = field(default_factory=dict)    # {"backend": weave | mlflow | None, "token2text": bool} -> utils/rollout_trace.py
+    skip_rollout: bool = False
+    skip_dump_dir: str = "/tmp/rollout_dump"
     rollout_manager: RolloutManagerConfig = field(default_factory=RolloutManagerConfig)
     multi_turn: MultiTurnConfig = field(default_factory=MultiTurnConfig)
     val_kwargs: dict = field(default_factory=lambda: {"n": 1, "temperature": 0.0, "do_sample": False})
@@ -217,11 +288,20 @@ class RolloutConfig(BaseConfig):
             raise ValueError("expert_parallel_size must equal tensor_model_parallel_size * data_parallel_size")
         if self.name == "sglang-disaggregated":
             self.name = "native-disaggregated"
+        if self.enforce_eager is not None:
+            self.cuda_graph = not bool(self.enforce_eager)
 
 
 @dataclass
 class RefConfig(BaseConfig):
     strategy: str = "fsdp"
+    log_prob_micro_batch_size: int | None = None      # GLOBAL micro-batch (deprecated spelling): divided by the GPU count at start-up
+    ulysses_sequence_parallel_size: int | None = None  # the reference policy shares the actor's SP groups (must match if set)
+    megatron: MegatronConfig = field(default_factory=MegatronConfig)
+    profiler: ProfilerConfig = field(default_factory=ProfilerConfig)
+    entropy_checkpointing: bool = False
+    entropy_from_logits_with_chunking: bool = False
+    use_torch_compile: bool = False
     log_prob_micro_batch_size_per_gpu: int | None = None
     log_prob_use_dynamic_bsz: bool = False
     log_prob_max_token_len_per_gpu: int = 16384
@@ -241,6 +321,20 @@ class ModelCfg(BaseConfig):
     override_config: dict = field(default_factory=dict)
     tokenizer_path: str | None = None
     use_shm: bool = False                 # copy the checkpoint directory to /dev/shm once per node before loading (verl model.use_shm)
+    trust_remote_code: bool = False       # no remote code is ever executed: models are this framework's own implementations
+    exclude_modules: str | None = None    # LoRA: regex of module names that get no adapter (e.g. ".*visual.*")
+    lora_adapter_path: str | None = None  # LoRA: peft adapter directory to start from
+    fused_kernel_options: dict = field(default_factory=dict)   # {"impl_backend": ...}: the fused path is the own sm_100a kernels
+    input_tokenizer: str | None = None    # reward models whose tokenizer differs from the policy's (re-tokenise before scoring)
+    fsdp_config: FSDPConfig = field(default_factory=FSDPConfig)   # critic / reward model: verl nests their fsdp_config under model
+    # PRIME's implicit process reward model (algos/prime.py::ImplicitPRM): beta of the log-ratio reward, own optimizer, and when it
+    # is updated relative to scoring the batch (none | before | after)
+    beta_train: float = 0.05
+    update: str = "none"
+    optim: OptimConfig = field(default_factory=OptimConfig)
+    ref_path: str | None = None
+    enable_activation_offload: bool = False     # -> fsdp_config.activation_offload of the role (both verl spellings are accepted)
+    enable_activation_offloading: bool = False
 
 
 @dataclass
@@ -271,6 +365,14 @@ class CriticConfig(BaseConfig):
     fsdp_config: FSDPConfig = field(default_factory=FSDPConfig)
     checkpoint: CheckpointConfig = field(default_factory=CheckpointConfig)
     profiler: ProfilerConfig = field(default_factory=ProfilerConfig)
+    megatron: MegatronConfig = field(default_factory=MegatronConfig)
+    ulysses_sequence_parallel_size: int = 1    # the critic trains on the actor's SP groups (must equal the actor's setting)
+    ppo_micro_batch_size: int | None = None    # GLOBAL micro-batch (deprecated spelling)
+    shuffle: bool = False
+    rollout_n: int | None = None
+
+    def __post_init__(self):
+        self.model.fsdp_config = self.fsdp_config     # verl spells critic.model.fsdp_config.*: one object behind both paths
 
 
 @dataclass
@@ -295,6 +397,30 @@ class RewardModelConfig(BaseConfig):
     launch_reward_fn_async: bool = False
     model: ModelCfg = field(default_factory=ModelCfg)
     micro_batch_size_per_gpu: int | None = None
+    micro_batch_size: int | None = None              # GLOBAL micro-batch (deprecated spelling)
+    use_dynamic_bsz: bool = False
+    forward_max_token_len_per_gpu: int = 32768
+    strategy: str = "fsdp"
+    param_offload: bool = False
+    max_length: int | None = None
+    megatron: MegatronConfig = field(default_factory=MegatronConfig)
+    profiler: ProfilerConfig = field(default_factory=ProfilerConfig)
+    # reward_kwargs.{max_resp_len, overlong_buffer_cfg.{enable,len,penalty_factor,log}}: the older spelling of overlong_buffer
+    reward_kwargs: dict = field(default_factory=dict)
+    sandbox_fusion: dict = field(default_factory=dict)     # {"url": ..., "max_concurrent": ..., "memory_limit_mb": ...}
+    # generative / separately placed reward models (fapo, genrm recipes): pool size and engine options of the judge; the judge
+    # here is any engine server behind ``genrm_endpoints``
+    enable_resource_pool: bool = False
+    n_gpus_per_node: int = 0
+    nnodes: int = 0
+    rollout: dict = field(default_factory=dict)
+    mini_batch_size: int | None = None      # PRIME: mini-batch of the implicit process reward model's own update
+
+    def __post_init__(self):
+        ob = (self.reward_kwargs or {}).get("overlong_buffer_cfg")
+        if ob:
+            self.overlong_buffer = OverlongBufferConfig(enable=bool(ob.get("enable", False)), len=int(ob.get("len", 0)),
+                                                        penalty_factor=float(ob.get("penalty_factor", 1.0)), log=bool(ob.get("log", False)))
 
 
 @dataclass
@@ -343,6 +469,10 @@ class AlgorithmConfig(BaseConfig):
     kl_ctrl: KLCtrlConfig = field(default_factory=KLCtrlConfig)
     rollout_correction: RolloutCorrectionConfig = field(default_factory=RolloutCorrectionConfig)
     filter_groups: FilterGroupsConfig = field(default_factory=FilterGroupsConfig)
+    # PF-PPO (policy filtration, arXiv:2409.06957; reference: verl/trainer/ppo/core_algos.py compute_pf_ppo_reweight_data): before the
+    # update the batch is resampled with replacement, weighting samples by their score (trainer/core.py::pf_ppo_resample)
+    use_pf_ppo: bool = False
+    pf_ppo: dict = field(default_factory=lambda: {"reweight_method": "pow", "weight_pow": 2.0})
 
 
 @dataclass
@@ -370,6 +500,16 @@ class DataConfig(BaseConfig):
     # resolves the name inside polyrl_b200.data.dynamic (e.g. SuccessRateCurriculumSampler, MockDataGenerator)
     sampler: dict = field(default_factory=dict)
     datagen: dict = field(default_factory=dict)
+    apply_chat_template_kwargs: dict = field(default_factory=dict)   # extra arguments of tokenizer.apply_chat_template (e.g. reasoning_effort)
+    custom_cls: dict = field(default_factory=dict)      # {"path": file.py, "name": DatasetClass}: dataset class replacing RLHFDataset
+    trust_remote_code: bool = False
+    use_shm: bool = False
+    validation_shuffle: bool = False
+    # PRIME-style accuracy filtering (recipe/prime): keep prompts whose group accuracy lies inside the bounds, over-sample to refill
+    filter_accuracy: bool = False
+    accuracy_lower_bound: float = 0.0
+    accuracy_upper_bound: float = 1.0
+    oversample_factor: float = 1.0
     synthetic: bool = False               # synthetic GSM8K-shaped prompts (no network on the target box)
     synthetic_num_samples: int = 4096
     synthetic_prompt_len_range: tuple = (64, 192)
@@ -393,6 +533,15 @@ class TrainerConfig(BaseConfig):
     logger: list = field(default_factory=lambda: ["console"])
     nnodes: int = 1
     n_gpus_per_node: int = 8
+    use_legacy_worker_impl: str = "auto"      # verl's switch between its two worker implementations: there is one here
+    log_freq: int = 1
+    max_ckpt_to_keep: int | None = None        # one limit for every role (sets max_actor_ckpt_to_keep / max_critic_ckpt_to_keep)
+    ref_update_freq: int = -1                  # SPIN / self-play: copy the actor into the reference policy every k steps (-1: never)
+    tensorboard_dir: str | None = None         # also honoured through the TENSORBOARD_DIR environment variable
+    rl_logging_board_dir: str | None = None
+    num_global_batch: int = 1                  # TransferQueue sizing of the reference stack (no TransferQueue service here)
+    num_data_storage_units: int = 1
+    num_data_controllers: int = 1
     save_freq: int = -1
     test_freq: int = -1
     val_before_train: bool = False
@@ -435,6 +584,50 @@ class PPOConfig(BaseConfig):
     algorithm: AlgorithmConfig = field(default_factory=AlgorithmConfig)
     trainer: TrainerConfig = field(default_factory=TrainerConfig)
     global_profiler: GlobalProfilerConfig = field(default_factory=GlobalProfilerConfig)
+    # dedicated rollout resource pool of the one-step-off / fully-async recipes (``rollout.nnodes``, ``rollout.n_gpus_per_node``):
+    # finalize_config() turns it into trainer.n_rollout_gpus of the disaggregated deployment
+    rollout: dict = field(default_factory=dict)
+    ray_kwargs: dict = field(default_factory=dict)        # Ray start-up options of the reference stack: accepted, unused
+    transfer_queue: dict = field(default_factory=dict)
+
+
+def finalize_config(cfg: "PPOConfig") -> "PPOConfig":
+    """Resolve aliases that span config sections (run by load_config after every override has been applied)."""
+    t, arr = cfg.trainer, cfg.actor_rollout_ref
+    if t.max_ckpt_to_keep is not None:
+        t.max_actor_ckpt_to_keep = t.max_actor_ckpt_to_keep or t.max_ckpt_to_keep
+        t.max_critic_ckpt_to_keep = t.max_critic_ckpt_to_keep or t.max_ckpt_to_keep
+    if arr.actor.freeze_vision_tower is not None:
+        arr.model.freeze_vision_tower = bool(arr.actor.freeze_vision_tower)
+    if arr.model.enable_activation_offload or arr.model.enable_activation_offloading:
+        arr.actor.fsdp_config.activation_offload = True
+    if cfg.critic.model.enable_activation_offload or cfg.critic.model.enable_activation_offloading:
+        cfg.critic.fsdp_config.activation_offload = True
+    if (arr.actor.optim.override_optimizer_config or {}).get("optimizer_cpu_offload"):
+        arr.actor.fsdp_config.optimizer_offload = True
+    if arr.actor.strategy == "megatron" and arr.actor.megatron.optimizer_offload:
+        arr.actor.fsdp_config.optimizer_offload = True
+    pool = cfg.rollout or {}
+    if pool.get("n_gpus_per_node") and not t.n_rollout_gpus:
+        t.n_rollout_gpus = int(pool.get("nnodes", 1)) * int(pool["n_gpus_per_node"])
+    ob = (cfg.reward_model.reward_kwargs or {}).get("overlong_buffer_cfg")
+    if ob:                                                       # older spelling of reward_model.overlong_buffer.*
+        cfg.reward_model.overlong_buffer = OverlongBufferConfig(enable=bool(ob.get("enable", False)), len=int(ob.get("len", 0)),
+                                                                penalty_factor=float(ob.get("penalty_factor", 1.0)), log=bool(ob.get("log", False)))
+    # GLOBAL micro-batch sizes (the deprecated verl spelling) -> per GPU, like verl's normalisation at worker start-up
+    n_train = max(1, t.n_gpus_per_node * t.nnodes - t.n_rollout_gpus)
+    for obj, glob, per in ((arr.rollout, "log_prob_micro_batch_size", "log_prob_micro_batch_size_per_gpu"),
+                           (arr.ref, "log_prob_micro_batch_size", "log_prob_micro_batch_size_per_gpu"),
+                           (cfg.critic, "ppo_micro_batch_size", "ppo_micro_batch_size_per_gpu"),
+                           (cfg.reward_model, "micro_batch_size", "micro_batch_size_per_gpu")):
+        if getattr(obj, glob, None) and getattr(obj, per, None) is None:
+            setattr(obj, per, max(1, int(getattr(obj, glob)) // n_train))
+    sf = cfg.reward_model.sandbox_fusion or {}
+    if sf.get("url") and not os.environ.get("SANDBOX_FUSION_URL"):
+        os.environ["SANDBOX_FUSION_URL"] = str(sf["url"])         # the code scorer reads the service address from here
+    if t.tensorboard_dir and not os.environ.get("TENSORBOARD_DIR"):
+        os.environ["TENSORBOARD_DIR"] = str(t.tensorboard_dir)
+    return cfg
 
 
 # ---------------------------------------------------------------------------------------------
@@ -483,7 +676,7 @@ def apply_overrides(cfg: Any, overrides: list[str]) -> Any:
         parts = key.split(".")
         obj = cfg
         for i, p in enumerate(parts[:-1]):
-            nxt = obj[p] if isinstance(obj, dict) else getattr(obj, p, None)
+            nxt = obj.get(p) if isinstance(obj, dict) else getattr(obj, p, None)
             if nxt is None and not isinstance(obj, dict):
                 raise KeyError(f"unknown config key {'.'.join(parts[:i + 1])!r}")
             if nxt is None:
@@ -516,7 +709,7 @@ def load_config(yaml_paths: list[str] | str | None = None, overrides: list[str] 
             d = yaml.safe_load(f) or {}
         _apply_dict(cfg, d)
     apply_overrides(cfg, overrides or [])
-    return cfg
+    return finalize_config(cfg)
 
 
 def config_to_flat_dict(cfg: Any, prefix: str = "") -> dict[str, Any]:

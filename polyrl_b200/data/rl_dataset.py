@@ -27,7 +27,7 @@ class ByteTokenizer:
         bs = bytes(int(i) - 3 for i in ids if 3 <= int(i) < 259)      # ids above the byte range (larger model vocab) are dropped
         return bs.decode("utf-8", errors="replace")
 
-    def apply_chat_template(self, messages: list[dict], add_generation_prompt: bool = True, tokenize: bool = False):
+    def apply_chat_template(self, messages: list[dict], add_generation_prompt: bool = True, tokenize: bool = False, **_kw):
         text = "".join(f"<{m['role']}>{m['content']}\n" for m in messages) + ("<assistant>" if add_generation_prompt else "")
         return self.encode(text) if tokenize else text
 
@@ -172,7 +172,8 @@ class RLHFDataset(Dataset):
     def __init__(self, data_files, tokenizer, prompt_key: str = "prompt", max_prompt_length: int = 512,
                  filter_overlong_prompts: bool = False, truncation: str = "error", return_raw_chat: bool = False,
                  model_cfg=None, image_key: str = "images", min_pixels: int | None = None, max_pixels: int | None = None,
-                 video_key: str = "videos"):
+                 video_key: str = "videos", apply_chat_template_kwargs: dict | None = None):
+        self.chat_kwargs = dict(apply_chat_template_kwargs or {})       # e.g. {"reasoning_effort": "medium", "enable_thinking": False}
         self.tok, self.key, self.max_len = tokenizer, prompt_key, max_prompt_length
         self.truncation, self.return_raw_chat = truncation, return_raw_chat
         self.vl_cfg = model_cfg if (model_cfg is not None and getattr(model_cfg, "vision", None) is not None) else None
@@ -193,7 +194,7 @@ class RLHFDataset(Dataset):
     def _chat_text(self, row: dict) -> str:
         p = row[self.key]
         if isinstance(p, (list, np.ndarray)) and len(p) and isinstance(p[0], dict):
-            return self.tok.apply_chat_template(list(p), add_generation_prompt=True, tokenize=False)
+            return self.tok.apply_chat_template(list(p), add_generation_prompt=True, tokenize=False, **self.chat_kwargs)
         return str(p)
 
     def _tokenize_mm(self, row: dict):

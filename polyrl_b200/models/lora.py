@@ -151,3 +151,52 @@ def export_peft_state_dict(named: dict[str, torch.Tensor]) -> dict[str, torch.Te
 def peft_adapter_config(cfg: ModelConfig, lcfg: LoraConfig) -> dict:
     return {"peft_type": "LORA", "r": lcfg.rank, "lora_alpha": lcfg.alpha, "target_modules": list(lcfg.target_modules),
             "bias": "none", "task_type": "CAUSAL_LM", "lora_dropout": 0.0}
+
+
+def import_peft_state_dict(peft_sd: dict[str, torch.Tensor]) -> dict[str, torch.Tensor]:
+    """Inverse of ``export_peft_state_dict``: peft adapter tensors (any prefix up to ``layers.{i}.``, optional ``.default``
+    adapter name) -> ``layers.{i}.lora.lora_{proj}_{A|B}``.  Tensors of modules this framework does not adapt are ignored."""
+    import re
+
+    inv = {v: k for k, v in _PEFT_MODULE.items()}
+    out = {}
+    for k, v in peft_sd.items():
+        m = re.search(r"layers\.(\d+)\.((?:self_attn|mlp)\.\w+)\.lora_([AB])(?:\.\w+)?\.weight$", k)
+        if m and m.group(2) in inv:
+            out[f"layers.{m.group(1)}.lora.lora_{inv[m.group(2)]}_{m.group(3)}"] = v
+    return out
+
+
+def load_peft_adapter(engine, path: str) -> int:
+    """Start the ZeRO engine's adapter units from a peft adapter directory (``adapter_model.safetensors`` / ``.bin`` next to
+    ``adapter_config.json``); reference: model.lora_adapter_path, verl/workers/fsdp_workers.py (PeftModel.from_pretrained).  Rank and
+    target modules must match the engine's LoRA config.  Returns the number of tensors loaded."""
+    import json
+    from pathlib import Path
+
+    p = Path(path)
+    cfg_file = p / "adapter_config.json"
+    if cfg_file.exists():
+        ac = json.loads(cfg_file.read_text())
+        if engine.lora is not None and int(ac.get("r", engine.lora.rank)) != engine.lora.rank:
+            raise ValueError(f"adapter rank {ac.get('r')} != model.lora_rank {engine.lora.rank}")
+    if (p / "adapter_model.safetensors").exists():
+        from safetensors.torch import load_file
+
+        sd = load_file(str(p / "adapter_model.safetensors"))
+    elif (p / "adapter_model.bin").exists():
+        sd = torch.load(p / "adapter_model.bin", map_location="cpu", weights_only=True)
+    else:
+        raise FileNotFoundError(f"no adapter_model.safetensors / adapter_model.bin in {path!r}")
+    ours = import_peft_state_dict(sd)
+    n = 0
+    for i, unit in enumerate(engine.lora_layers):
+        pre = f"layers.{i}.lora."
+        named = {k[len(pre):]: v for k, v in ours.items() if k.startswith(pre)}
+        if named:
+            missing = [name for name, _ in unit.specs if name not in named]
+            if missing:
+                raise KeyError(f"adapter at {path!r} lacks {missing[:3]} for layer {i} (target modules differ?)")
+            unit.load_full_state(named)
+            n += len(named)
+    return n

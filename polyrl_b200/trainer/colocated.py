@@ -100,6 +100,8 @@ class ColocatedPPO:
         else:
             batch.batch["token_level_rewards"] = batch.batch["token_level_scores"]
         batch = core.compute_advantage(batch, algo.adv_estimator, algo.gamma, algo.lam, n, algo.norm_adv_by_std_in_grpo, algo)
+        if algo.use_pf_ppo:
+            batch = core.pf_ppo_resample(batch, algo.pf_ppo.get("reweight_method", "pow"), float(algo.pf_ppo.get("weight_pow", 2.0)))
         timing["adv"] = time.time() - t0
         # ---- update: split at mini-batch boundaries; optimizer step per mini-batch
         t0 = time.time()

@@ -109,6 +109,10 @@ class PPOWorker(Worker):
     def update_weight(self) -> bool:
         return bool(self.inner.update_weight_remote())
 
+    @register(dispatch_mode=Dispatch.ONE_TO_ALL)
+    def update_reference_policy(self) -> None:
+        self.inner.update_reference_policy()
+
     # ---- checkpoints
     @register(dispatch_mode=Dispatch.ONE_TO_ALL)
     def save_checkpoint(self, path: str, global_step: int = 0, max_ckpt_to_keep: int | None = None) -> None:
@@ -390,8 +394,11 @@ class ControllerPPOTrainer:
             metrics.update(klm)
         else:
             batch.batch["token_level_rewards"] = batch.batch["token_level_scores"]
-        return core.compute_advantage(batch, algo.adv_estimator, algo.gamma, algo.lam, cfg.actor_rollout_ref.rollout.n,
-                                      algo.norm_adv_by_std_in_grpo, algo)
+        batch = core.compute_advantage(batch, algo.adv_estimator, algo.gamma, algo.lam, cfg.actor_rollout_ref.rollout.n,
+                                       algo.norm_adv_by_std_in_grpo, algo)
+        if algo.use_pf_ppo:
+            batch = core.pf_ppo_resample(batch, algo.pf_ppo.get("reweight_method", "pow"), float(algo.pf_ppo.get("weight_pow", 2.0)))
+        return batch
 
     def train_on(self, batch: DataProto, timing: dict) -> dict:
         """old log-probs (+ ref, values), advantages, mini-batch updates, weight hand-off.  Returns the step metrics."""
@@ -432,6 +439,9 @@ class ControllerPPOTrainer:
         with marked_timer("update_weight", timing):
             wg.update_weight()
         self.global_step += 1
+        ruf = cfg.trainer.ref_update_freq
+        if need_reference_policy(cfg) and ruf and ruf > 0 and self.global_step % ruf == 0 and hasattr(wg, "update_reference_policy"):
+            wg.update_reference_policy()
         mask = batch.batch["response_mask"].float()
         metrics.update({k: float(np.mean(v)) for k, v in upd.items()})
         metrics.update({

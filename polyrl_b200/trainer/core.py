@@ -137,3 +137,22 @@ def filter_uninformative_groups(batch: DataProto, metric: str = "seq_reward") ->
     n = max(1, len(groups))
     return batch, {"dapo/num_groups": float(len(groups)), "dapo/filtered_groups": float(len(drop)),
                    "dapo/kept_group_ratio": 1.0 - len(drop) / n}
+
+
+def pf_ppo_resample(batch: DataProto, reweight_method: str = "pow", weight_pow: float = 2.0, generator: torch.Generator | None = None) -> DataProto:
+    """PF-PPO policy filtration (arXiv:2409.06957; reference: verl/trainer/ppo/core_algos.py compute_pf_ppo_reweight_data, switched by
+    ``algorithm.use_pf_ppo``): resample the batch WITH replacement, the probability of a sample following its sequence score —
+    ``pow``: |score|^weight_pow; ``max_min``: only the best- and worst-scored samples; ``max_random``: the best samples four
+    times as likely as the rest.  Unreliable middle-of-the-road reward signals are filtered out, the batch size is unchanged."""
+    scores = batch.batch["token_level_scores"].sum(-1).float()
+    if reweight_method == "pow":
+        w = scores.abs().pow(weight_pow)
+    elif reweight_method == "max_min":
+        w = ((scores == scores.max()) | (scores == scores.min())).float()
+    elif reweight_method == "max_random":
+        w = torch.where(scores == scores.max(), torch.full_like(scores, 0.4), torch.full_like(scores, 0.1))
+    else:
+        raise ValueError(f"unsupported pf_ppo reweight_method {reweight_method!r} (pow | max_min | max_random)")
+    w = (w + 1e-8).clamp(min=1e-8)
+    idx = torch.multinomial(w.cpu(), len(batch), replacement=True, generator=generator)
+    return batch.select_idxs(idx)

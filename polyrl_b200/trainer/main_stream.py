@@ -58,7 +58,12 @@ def build_datasets(cfg: PPOConfig, model_cfg, tokenizer=None):
     else:
         tok = tokenizer or load_tokenizer(cfg.actor_rollout_ref.model.tokenizer_path or cfg.actor_rollout_ref.model.path)
         raw = d.return_raw_chat or cfg.actor_rollout_ref.rollout.multi_turn.enable       # agent loops re-template the chat
-        kw = dict(model_cfg=model_cfg, image_key=d.image_key, video_key=d.video_key, min_pixels=d.image_min_pixels, max_pixels=d.image_max_pixels)
+        kw = dict(model_cfg=model_cfg, image_key=d.image_key, video_key=d.video_key, min_pixels=d.image_min_pixels, max_pixels=d.image_max_pixels,
+                  apply_chat_template_kwargs=dict(d.apply_chat_template_kwargs or {}))
+        if (d.custom_cls or {}).get("name") and (d.custom_cls or {}).get("path"):   # data.custom_cls.{path,name}: user dataset class with RLHFDataset's constructor
+            from ..data.dynamic import load_extern_type
+
+            RLHFDataset = load_extern_type(d.custom_cls.get("path"), d.custom_cls["name"])    # noqa: N806
         if (d.datagen or {}).get("name"):
             from ..data.dynamic import DynamicGenDataset, load_extern_type
 

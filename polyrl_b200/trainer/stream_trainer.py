@@ -317,6 +317,9 @@ class StreamPPOTrainer:
                 else:
                     local = core.compute_advantage(local, algo.adv_estimator, algo.gamma, algo.lam,
                                                    cfg.actor_rollout_ref.rollout.n, algo.norm_adv_by_std_in_grpo, algo)
+        if algo.use_pf_ppo:
+            # PF-PPO: resample this rank's shard by score (every rank keeps its row count, so mini-batch boundaries are unchanged)
+            local = core.pf_ppo_resample(local, algo.pf_ppo.get("reweight_method", "pow"), float(algo.pf_ppo.get("weight_pow", 2.0)))
         self._step_batches.append(local)
         # ---- split at cumulative mini-batch boundaries (in global sample counts)
         end_global = seen + full_len
@@ -530,6 +533,9 @@ class StreamPPOTrainer:
                 if self.client is not None and self.rank == 0:
                     self.client.update_weight_version()
                 self.worker.update_weight_remote()
+            ruf = cfg.trainer.ref_update_freq
+            if self.use_reference and ruf and ruf > 0 and self.global_steps % ruf == 0:
+                self.worker.update_reference_policy()             # self-play: the reference follows the actor every k steps
             step_time = time.time() - t_step
             self._timing["step"] = step_time
             is_last = self.global_steps >= self.total_training_steps

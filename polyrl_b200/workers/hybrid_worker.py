@@ -161,6 +161,12 @@ class ActorRolloutRefWorker:
                                             sp_group=self.sp_group, replica_group=self.replica_group, lora=self.lora_cfg,
                                             freeze_vision_tower=m.freeze_vision_tower)
             self._maybe_load_pretrained(self.actor_engine, arr.model.path)
+            if m.lora_adapter_path and self.actor_engine.lora is not None:
+                from ..models.lora import load_peft_adapter
+
+                n_ad = load_peft_adapter(self.actor_engine, m.lora_adapter_path)
+                if self.rank == 0:
+                    print(f"[worker] loaded {n_ad} adapter tensors from {m.lora_adapter_path}", flush=True)
             fc = arr.actor.fsdp_config
             eng = self.actor_engine
             want = str(fc.resident_params).lower()
@@ -532,6 +538,20 @@ class ActorRolloutRefWorker:
         data.meta_info.setdefault("temperature", r.temperature)
         lp, ent = self.actor.compute_log_prob(data)
         return DataProto.from_dict({"old_log_probs": lp, "entropys": ent}, meta_info={"temperature": r.temperature})
+
+    @torch.no_grad()
+    def update_reference_policy(self) -> None:
+        """Copy the current actor weights into the reference policy (``trainer.ref_update_freq``: self-play recipes such as SPIN move
+        the reference every k steps; reference: recipe/spin/spin_trainer.py ref_update_freq)."""
+        if self.ref_engine is None or self.actor_engine is None:
+            return
+        for src, dst in zip(self.actor_engine.base_units, self.ref_engine.base_units):
+            dst.shard.copy_(src.shard)
+            dst.drop_gathered()
+        if getattr(self.actor_engine, "vision", None) is not None and getattr(self.ref_engine, "vision", None) is not None:
+            self.ref_engine.vision.shard.copy_(self.actor_engine.vision.shard)
+            self.ref_engine.vision.drop_gathered()
+        self.ref_engine._resident_stale = self.ref_engine._reload_all = True
 
     @DistProfiler.annotate("compute_ref_log_prob")
     @torch.no_grad()

@@ -145,3 +145,55 @@ def test_hbm_sizing_planner():
     assert p70.resident_replica == 0 and p70.saved_blocks == 0 and d["optimizer_offload_during_rollout"]
     assert d["release_rollout_weights_during_training"] and d["fits_rollout"] and d["fits_training"]
     assert d["max_tokens_per_microbatch"] < 16384
+
+
+def test_reference_launch_script_keys_are_accepted():
+    """Every dotted override used by the reference stack's example / recipe launch scripts (PPO tree; collected from
+    3rdparty/verl/examples/*/*.sh and recipe/*/*.sh) must parse, and the ones with a counterpart must take effect."""
+    from polyrl_b200.config.schema import load_config
+
+    keys = """actor_rollout_ref.actor.entropy_checkpointing=True actor_rollout_ref.actor.entropy_from_logits_with_chunking=True
+    actor_rollout_ref.actor.fsdp_config.mixed_precision.param_dtype=bf16 actor_rollout_ref.actor.fsdp_config.use_orig_params=True
+    actor_rollout_ref.actor.megatron.context_parallel_size=1 actor_rollout_ref.actor.megatron.expert_tensor_parallel_size=1
+    actor_rollout_ref.actor.megatron.grad_offload=True actor_rollout_ref.actor.megatron.param_offload=True
+    actor_rollout_ref.actor.megatron.override_transformer_config.recompute_granularity=full
+    actor_rollout_ref.actor.megatron.override_transformer_config.moe_grouped_gemm=True
+    actor_rollout_ref.actor.megatron.use_dist_checkpointing=True actor_rollout_ref.actor.megatron.use_mbridge=True
+    actor_rollout_ref.actor.optim.lr_decay_style=constant actor_rollout_ref.actor.optim.override_optimizer_config.optimizer_offload_fraction=1
+    actor_rollout_ref.actor.profiler.tool_config.npu.discrete=True actor_rollout_ref.actor.use_torch_compile=False
+    actor_rollout_ref.model.exclude_modules=.*visual.* actor_rollout_ref.model.fused_kernel_options.impl_backend=torch
+    actor_rollout_ref.model.lora_adapter_path=/x actor_rollout_ref.model.override_config.model_config.max_position_embeddings=4096
+    actor_rollout_ref.model.trust_remote_code=True actor_rollout_ref.ref.entropy_checkpointing=True
+    actor_rollout_ref.ref.log_prob_micro_batch_size=32 actor_rollout_ref.ref.megatron.pipeline_model_parallel_size=3
+    actor_rollout_ref.ref.profiler.enable=True actor_rollout_ref.ref.ulysses_sequence_parallel_size=1
+    actor_rollout_ref.rollout.engine_kwargs.sglang.attention_backend=triton actor_rollout_ref.rollout.layered_summon=True
+    actor_rollout_ref.rollout.multi_stage_wake_up=True actor_rollout_ref.rollout.over_sample_rate=0.1
+    actor_rollout_ref.rollout.trace.backend=mlflow actor_rollout_ref.rollout.update_weights_bucket_megabytes=512
+    actor_rollout_ref.rollout.agent.agent_loop_config_path=/x actor_rollout_ref.rollout.multi_turn.num_repeat_rollouts=3
+    algorithm.use_pf_ppo=True algorithm.pf_ppo.reweight_method=pow algorithm.pf_ppo.weight_pow=2.0
+    critic.megatron.tensor_model_parallel_size=1 critic.model.trust_remote_code=True critic.ulysses_sequence_parallel_size=2
+    data.apply_chat_template_kwargs.reasoning_effort=medium data.custom_cls.name=RLHFDataset data.custom_cls.path=x.py
+    data.trust_remote_code=True data.filter_accuracy=True data.accuracy_lower_bound=0.2 data.oversample_factor=4
+    global_profiler.global_tool_config.torch_memory.stack_depth=32 reward_model.forward_max_token_len_per_gpu=98304
+    reward_model.megatron.tensor_model_parallel_size=4 reward_model.model.fsdp_config.param_offload=True
+    reward_model.model.input_tokenizer=x reward_model.param_offload=False reward_model.profiler.enable=True
+    reward_model.sandbox_fusion.max_concurrent=128 reward_model.use_dynamic_bsz=True reward_model.enable_resource_pool=True
+    reward_model.rollout.name=sglang reward_model.model.beta_train=0.05 reward_model.model.optim.grad_clip=10.0
+    reward_model.model.update=before reward_model.mini_batch_size=64 trainer.use_legacy_worker_impl=auto trainer.log_freq=1
+    trainer.ref_update_freq=1 trainer.rl_logging_board_dir=/x trainer.num_data_controllers=1""".split()
+    for kv in keys:
+        load_config(overrides=[kv])
+    c = load_config(overrides=["actor_rollout_ref.rollout.log_prob_micro_batch_size=64", "trainer.n_gpus_per_node=8", "rollout.n_gpus_per_node=4",
+                               "rollout.nnodes=1", "actor_rollout_ref.rollout.enforce_eager=True", "critic.model.fsdp_config.param_offload=True",
+                               "actor_rollout_ref.actor.loss_mode=kl_cov", "actor_rollout_ref.actor.clip_cov_ub=4",
+                               "reward_model.reward_kwargs.overlong_buffer_cfg.enable=True", "reward_model.reward_kwargs.overlong_buffer_cfg.len=128",
+                               "actor_rollout_ref.model.enable_activation_offload=True", "trainer.max_ckpt_to_keep=3",
+                               "actor_rollout_ref.actor.optim.lr_scheduler_type=cosine", "actor_rollout_ref.actor.freeze_vision_tower=True",
+                               "actor_rollout_ref.actor.optim.min_lr=1e-7", "actor_rollout_ref.actor.optim.lr=1e-6"])
+    a = c.actor_rollout_ref
+    assert c.trainer.n_rollout_gpus == 4 and a.rollout.log_prob_micro_batch_size_per_gpu == 16        # 64 over the 4 trainer GPUs
+    assert a.rollout.cuda_graph is False and c.critic.fsdp_config.param_offload is True
+    assert a.actor.policy_loss.loss_mode == "kl_cov" and a.actor.policy_loss.clip_cov_ub == 4.0
+    assert c.reward_model.overlong_buffer.enable and c.reward_model.overlong_buffer.len == 128
+    assert a.actor.fsdp_config.activation_offload and c.trainer.max_actor_ckpt_to_keep == 3 and c.trainer.max_critic_ckpt_to_keep == 3
+    assert a.actor.optim.warmup_style == "cosine" and abs(a.actor.optim.min_lr_ratio - 0.1) < 1e-9 and a.model.freeze_vision_tower

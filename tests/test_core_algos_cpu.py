@@ -266,3 +266,27 @@ def test_implicit_prm_learns_the_outcome_labels():
     q = prm.score(data)
     seq = q.sum(-1)
     assert (seq[acc > 0].min() > seq[acc == 0].max()) and pairwise_accuracy(q, acc, data.batch["response_mask"].float(), 2) == 1.0
+
+
+def test_pf_ppo_resampling_follows_the_scores():
+    """algorithm.use_pf_ppo (reference: compute_pf_ppo_reweight_data): same batch size, rows drawn with replacement by score."""
+    import numpy as np
+
+    from polyrl_b200.protocol import DataProto
+    from polyrl_b200.trainer.core import pf_ppo_resample
+
+    scores = torch.tensor([0.0, 0.1, 1.0, 0.5, 0.9, 0.0, 0.2, 1.0])
+    b = DataProto.from_dict({"token_level_scores": scores.unsqueeze(-1), "row": torch.arange(8)},
+                            non_tensors={"uid": np.array([f"u{i}" for i in range(8)], dtype=object)})
+    g = torch.Generator().manual_seed(0)
+    out = pf_ppo_resample(b, "max_min", generator=g)
+    assert len(out) == 8 and set(out.batch["row"].tolist()) <= {0, 2, 5, 7}              # only best / worst scored rows survive
+    assert all(u == f"u{r}" for u, r in zip(out.non_tensor_batch["uid"], out.batch["row"].tolist()))
+    rows = torch.cat([pf_ppo_resample(b, "pow", 2.0, generator=g).batch["row"] for _ in range(200)])
+    freq = torch.bincount(rows, minlength=8).float() / rows.numel()
+    assert freq[2] > 5 * freq[6] and freq[0] < 0.01                                       # ~ score^2
+    rows = torch.cat([pf_ppo_resample(b, "max_random", generator=g).batch["row"] for _ in range(200)])
+    freq = torch.bincount(rows, minlength=8).float() / rows.numel()
+    assert 2.5 < (freq[2] / freq[1]).item() < 6                                           # best samples four times as likely
+    with pytest.raises(ValueError):
+        pf_ppo_resample(b, "nope")

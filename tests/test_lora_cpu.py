@@ -188,3 +188,41 @@ def test_role_workers_over_base_engine_match_the_streaming_actor():
     m = critic.update_critic(data)
     v1 = critic.compute_values(data).batch["values"]
     assert "critic/vf_loss" in m and ((v1 - 1) ** 2).mean() < ((v0 - 1) ** 2).mean()
+
+
+def test_peft_adapter_directory_round_trip(tmp_path):
+    """model.lora_adapter_path: an exported peft adapter (names with and without the ``.default`` adapter segment) loads back into
+    the engine's adapter units; a rank mismatch is rejected."""
+    import json
+
+    import pytest
+    from safetensors.torch import save_file
+
+    from polyrl_b200.models import get_model_config
+    from polyrl_b200.models.lora import LoraConfig, export_peft_state_dict, import_peft_state_dict, load_peft_adapter, peft_adapter_config
+    from polyrl_b200.parallel.zero3 import Zero3Engine
+
+    cfg = get_model_config("tiny-llama")
+    lc = LoraConfig.from_model_cfg(4, 8, "all-linear")
+    src = Zero3Engine(cfg, "cpu", seed=1, lora=lc)
+    with torch.no_grad():
+        for u in src.lora_layers:
+            u.shard.normal_(0, 0.1)
+            if u.master is not None:
+                u.master.copy_(u.shard.float())
+    named = {n: t.clone() for n, t in src.named_full_tensors() if ".lora." in n}
+    peft = export_peft_state_dict(named)
+    assert import_peft_state_dict(peft).keys() == named.keys()
+    renamed = {k.replace(".lora_A.weight", ".lora_A.default.weight").replace(".lora_B.weight", ".lora_B.default.weight"): v for k, v in peft.items()}
+    assert import_peft_state_dict(renamed).keys() == named.keys()
+    d = tmp_path / "adapter"
+    d.mkdir()
+    save_file({k: v.contiguous() for k, v in renamed.items()}, str(d / "adapter_model.safetensors"))
+    (d / "adapter_config.json").write_text(json.dumps(peft_adapter_config(cfg, lc)))
+    dst = Zero3Engine(cfg, "cpu", seed=2, lora=lc)
+    assert load_peft_adapter(dst, str(d)) == len(named)
+    got = {n: t for n, t in dst.named_full_tensors() if ".lora." in n}
+    assert all(torch.allclose(got[n].float(), named[n].float(), atol=1e-6) for n in named)
+    (d / "adapter_config.json").write_text(json.dumps({**peft_adapter_config(cfg, lc), "r": 16}))
+    with pytest.raises(ValueError, match="rank"):
+        load_peft_adapter(dst, str(d))

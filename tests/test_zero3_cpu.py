@@ -109,3 +109,24 @@ def test_activation_offload_hooks_keep_gradients_exact():
     eng.act_offload, eng._offload_force, eng.act_offload_min_bytes = True, True, 1024
     _loss(eng, inp2, labels2).backward()
     assert 1.8 < eng.offload_stats["bytes"] / res[True][2]["bytes"] < 2.2
+
+
+def test_reference_policy_follows_the_actor_on_request():
+    """trainer.ref_update_freq: ``update_reference_policy`` copies the trained actor into the frozen reference engine."""
+    from polyrl_b200.config.schema import load_config
+    from polyrl_b200.workers.hybrid_worker import ActorRolloutRefWorker
+
+    cfg = load_config(overrides=["trainer.device=cpu", "actor_rollout_ref.model.path=tiny-llama", "actor_rollout_ref.actor.use_kl_loss=True",
+                                 "actor_rollout_ref.actor.use_dynamic_bsz=True", "actor_rollout_ref.rollout.cuda_graph=False",
+                                 "actor_rollout_ref.rollout.max_num_seqs=8", "data.max_prompt_length=16", "data.max_response_length=8"])
+    w = ActorRolloutRefWorker(cfg, role="actor_rollout_ref", device="cpu")
+    w.init_model()
+    with torch.no_grad():
+        for u in w.actor_engine.base_units:
+            u.shard.add_(0.01)
+    a = {n: t.clone() for n, t in w.actor_engine.named_full_tensors()}
+    r0 = {n: t.clone() for n, t in w.ref_engine.named_full_tensors()}
+    assert any(not torch.equal(a[n], r0[n]) for n in a)
+    w.update_reference_policy()
+    r1 = dict(w.ref_engine.named_full_tensors())
+    assert all(torch.equal(a[n].to(r1[n].dtype), r1[n]) for n in a)
