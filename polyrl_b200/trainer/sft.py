@@ -41,6 +41,17 @@ class SFTDataConfig(BaseConfig):
     synthetic: bool = False
     synthetic_num_samples: int = 64
     seed: int = 1
+    # spellings of the reference's SFT configs (verl/trainer/config/sft_trainer*.yaml): resolved by finalize_sft_config
+    messages_key: str | None = None                 # = multiturn_messages_key
+    multiturn: dict = field(default_factory=dict)   # {"enable": bool, "messages_key": ..., "tools_key": ...}
+    micro_batch_size: int | None = None             # GLOBAL micro-batch: divided by the world size
+    max_token_len_per_gpu: int | None = None        # token budget of a micro-batch when use_dynamic_bsz (sequences are packed)
+    use_dynamic_bsz: bool = False
+    pad_mode: str = "right"                         # right | no_padding (packed; what the engine does internally either way)
+    prompt_dict_keys: list | None = None
+    response_dict_keys: list | None = None
+    use_shm: bool = False
+    apply_chat_template_kwargs: dict = field(default_factory=dict)
 
 
 @dataclass
@@ -51,6 +62,28 @@ class SFTModelConfig(BaseConfig):
     lora_rank: int = 0
     lora_alpha: int = 16
     target_modules: str = "all-linear"
+    partial_pretrain: str | None = None             # older spelling of path
+    strategy: str = "fsdp"
+    use_remove_padding: bool = True                 # always: sequences are packed
+    use_liger: bool = False                         # third-party fused kernels of other stacks: the own fused kernels are always on
+    trust_remote_code: bool = False
+    enable_gradient_checkpointing: bool = True
+    fsdp_config: dict = field(default_factory=dict)
+
+
+@dataclass
+class SFTEngineConfig(BaseConfig):
+    """Parallel layout block of the reference's newer SFT trainer (``engine.*``)."""
+    strategy: str = "fsdp"
+    fsdp_size: int = -1
+    ulysses_sequence_parallel_size: int = 1
+    tensor_model_parallel_size: int = 1
+    pipeline_model_parallel_size: int = 1
+    virtual_pipeline_model_parallel_size: int | None = None
+    context_parallel_size: int = 1
+    use_mbridge: bool = False
+    param_offload: bool = False
+    optimizer_offload: bool = False
 
 
 @dataclass
@@ -64,6 +97,16 @@ class SFTTrainerConfig(BaseConfig):
     ulysses_sequence_parallel_size: int = 1
     comm_backend: str = "p2p"
     logger: list = field(default_factory=lambda: ["console"])
+    total_training_steps: int | None = None         # = total_steps
+    test_freq: int | None = None                    # = eval_freq
+    project_name: str = "polyrl_b200_sft"
+    experiment_name: str = "sft"
+    resume_mode: str = "auto"
+    resume_from_path: str | None = None
+    max_ckpt_to_keep: int | None = None
+    nnodes: int = 1
+    n_gpus_per_node: int = 8
+    seed: int = 1
 
 
 @dataclass
@@ -72,6 +115,35 @@ class SFTConfig(BaseConfig):
     model: SFTModelConfig = field(default_factory=SFTModelConfig)
     optim: OptimConfig = field(default_factory=lambda: OptimConfig(lr=1e-5))
     trainer: SFTTrainerConfig = field(default_factory=SFTTrainerConfig)
+    engine: SFTEngineConfig = field(default_factory=SFTEngineConfig)
+    checkpoint: dict = field(default_factory=dict)          # {"save_contents": [...], "load_contents": [...]}
+    ulysses_sequence_parallel_size: int | None = None       # top-level spelling of the older fsdp_sft_trainer config
+    use_remove_padding: bool = True
+
+
+def finalize_sft_config(cfg: SFTConfig, world: int = 1) -> SFTConfig:
+    """Map the reference's spellings onto the fields the trainer reads."""
+    d, m, t, e = cfg.data, cfg.model, cfg.trainer, cfg.engine
+    if m.partial_pretrain:
+        m.path = m.partial_pretrain
+    mt = d.multiturn or {}
+    if mt.get("enable") or d.messages_key:
+        d.multiturn_messages_key = d.multiturn_messages_key or mt.get("messages_key") or d.messages_key or "messages"
+    if d.micro_batch_size and d.micro_batch_size_per_gpu == SFTDataConfig.micro_batch_size_per_gpu:
+        d.micro_batch_size_per_gpu = max(1, int(d.micro_batch_size) // max(1, world))
+    if d.use_dynamic_bsz and d.max_token_len_per_gpu:
+        d.micro_batch_size_per_gpu = max(1, int(d.max_token_len_per_gpu) // max(1, int(d.max_length)))
+    if t.total_training_steps:
+        t.total_steps = int(t.total_training_steps)
+    if t.test_freq is not None:
+        t.eval_freq = int(t.test_freq)
+    sp = cfg.ulysses_sequence_parallel_size or e.ulysses_sequence_parallel_size
+    if sp and sp > 1:
+        t.ulysses_sequence_parallel_size = int(sp)
+    if e.tensor_model_parallel_size > 1 or e.pipeline_model_parallel_size > 1 or e.context_parallel_size > 1:
+        raise NotImplementedError("the SFT trainer runs on the ZeRO engine (+ Ulysses SP): tensor / pipeline / context parallel "
+                                  "layouts are not available here")
+    return cfg
 
 
 class SFTDataset(Dataset):
@@ -303,6 +375,7 @@ def main(argv=None) -> int:
     cfg = SFTConfig()
     apply_overrides(cfg, a.overrides)
     world = int(os.environ.get("WORLD_SIZE", 1))
+    finalize_sft_config(cfg, world)
     cuda = cfg.trainer.device == "cuda" and torch.cuda.is_available()
     if world > 1 and not dist.is_initialized():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")

@@ -197,3 +197,30 @@ def test_reference_launch_script_keys_are_accepted():
     assert c.reward_model.overlong_buffer.enable and c.reward_model.overlong_buffer.len == 128
     assert a.actor.fsdp_config.activation_offload and c.trainer.max_actor_ckpt_to_keep == 3 and c.trainer.max_critic_ckpt_to_keep == 3
     assert a.actor.optim.warmup_style == "cosine" and abs(a.actor.optim.min_lr_ratio - 0.1) < 1e-9 and a.model.freeze_vision_tower
+
+
+def test_reference_sft_script_keys_are_accepted():
+    """The SFT trainer takes the reference's sft_trainer / fsdp_sft_trainer override names."""
+    from polyrl_b200.config.schema import apply_overrides
+    from polyrl_b200.trainer.sft import SFTConfig, finalize_sft_config
+
+    keys = """checkpoint.save_contents=[model,optimizer,extra] data.max_length=16384 data.max_token_len_per_gpu=65536 data.messages_key=messages
+    data.micro_batch_size=64 data.multiturn.enable=true data.multiturn.tools_key=tools data.pad_mode=no_padding data.use_dynamic_bsz=True
+    engine.fsdp_size=8 engine.strategy=fsdp engine.ulysses_sequence_parallel_size=2 engine.use_mbridge=False model.partial_pretrain=tiny-llama
+    model.strategy=fsdp model.use_liger=False model.use_remove_padding=True optim.betas=[0.9,0.95] optim.clip_grad=1.0 optim.lr_decay_style=cosine
+    optim.lr_warmup_init=0 optim.min_lr=2e-6 optim.weight_decay=0.1 trainer.experiment_name=x trainer.max_ckpt_to_keep=5 trainer.project_name=p
+    trainer.resume_mode=auto trainer.test_freq=10 trainer.total_training_steps=50 ulysses_sequence_parallel_size=2 use_remove_padding=true""".split()
+    for kv in keys:
+        apply_overrides(SFTConfig(), [kv])
+    c = SFTConfig()
+    apply_overrides(c, ["model.partial_pretrain=tiny-llama", "data.multiturn.enable=true", "data.multiturn.messages_key=msgs", "data.micro_batch_size=16",
+                        "trainer.total_training_steps=7", "trainer.test_freq=2", "engine.ulysses_sequence_parallel_size=2"])
+    finalize_sft_config(c, world=4)
+    assert (c.model.path, c.data.multiturn_messages_key, c.data.micro_batch_size_per_gpu) == ("tiny-llama", "msgs", 4)
+    assert (c.trainer.total_steps, c.trainer.eval_freq, c.trainer.ulysses_sequence_parallel_size) == (7, 2, 2)
+    import pytest
+
+    bad = SFTConfig()
+    apply_overrides(bad, ["engine.tensor_model_parallel_size=2"])
+    with pytest.raises(NotImplementedError):
+        finalize_sft_config(bad)
