@@ -66,6 +66,15 @@ def evaluate(rows: list[dict], response_key: str = "responses", data_source_key:
 
 
 def main(argv: list[str] | None = None) -> int:
+    from .main_generation import _translate_dotted
+
+    argv = list(sys.argv[1:] if argv is None else argv)
+    fn_name = next((a.split("=", 1)[1] for a in argv if a.startswith("custom_reward_function.name=")), None)
+    argv = _translate_dotted(argv, {"data.path": "--data", "data.response_key": "--response-key", "data.data_source_key": "--data-source-key",
+                                    "data.reward_model_key": "--reward-model-key", "custom_reward_function.path": "--custom-reward"})
+    if fn_name and "--custom-reward" in argv:
+        i = argv.index("--custom-reward") + 1
+        argv[i] = f"{argv[i]}:{fn_name}"
     ap = argparse.ArgumentParser(description=__doc__, formatter_class=argparse.RawDescriptionHelpFormatter)
     ap.add_argument("--data", required=True)
     ap.add_argument("--response-key", default="responses")

@@ -90,7 +90,28 @@ def generate(model: str, rows: list[dict], n_samples: int = 1, temperature: floa
     return [{**rows[i], **out[i]} for i in range(len(rows))] if rank == 0 else []
 
 
+_DOTTED = {"model.path": "--model", "data.path": "--data", "data.output_path": "--output", "data.prompt_key": "--prompt-key",
+           "data.n_samples": "--n-samples", "data.batch_size": "--batch-size", "rollout.temperature": "--temperature",
+           "rollout.top_p": "--top-p", "rollout.top_k": "--top-k", "rollout.prompt_length": "--prompt-length",
+           "rollout.response_length": "--response-length", "model.tokenizer_path": "--tokenizer"}
+
+
+def _translate_dotted(argv: list[str], table: dict[str, str]) -> list[str]:
+    """``key=value`` overrides in the reference's generation.yaml / evaluation.yaml naming -> this CLI's flags; other dotted keys
+    (trainer.nnodes, rollout.tensor_model_parallel_size, ray settings ...) are accepted and ignored."""
+    out: list[str] = []
+    for a in argv:
+        if not a.startswith("-") and "=" in a and "." in a.split("=", 1)[0]:
+            k, v = a.split("=", 1)
+            if k.lstrip("+") in table:
+                out += [table[k.lstrip("+")], v]
+            continue
+        out.append(a)
+    return out
+
+
 def main(argv: list[str] | None = None) -> int:
+    argv = _translate_dotted(list(sys.argv[1:] if argv is None else argv), _DOTTED)
     ap = argparse.ArgumentParser(description=__doc__, formatter_class=argparse.RawDescriptionHelpFormatter)
     ap.add_argument("--model", required=True, help="HF checkpoint directory or a preset name (random init)")
     ap.add_argument("--data", required=True, help="parquet / jsonl / json with the prompts")
