@@ -471,6 +471,9 @@ class AlgorithmConfig(BaseConfig):
     filter_groups: FilterGroupsConfig = field(default_factory=FilterGroupsConfig)
     # PF-PPO (policy filtration, arXiv:2409.06957; reference: verl/trainer/ppo/core_algos.py compute_pf_ppo_reweight_data): before the
     # update the batch is resampled with replacement, weighting samples by their score (trainer/core.py::pf_ppo_resample)
+    # PRIME (recipes/prime.py): weights of the outcome reward and of the implicit process reward in the advantage
+    reward_gt_coef: float = 5.0
+    reward_dpo_coef: float = 5.0
     use_pf_ppo: bool = False
     pf_ppo: dict = field(default_factory=lambda: {"reweight_method": "pow", "weight_pow": 2.0})
 

@@ -113,6 +113,38 @@ class PPOWorker(Worker):
     def update_reference_policy(self) -> None:
         self.inner.update_reference_policy()
 
+    # ---- implicit process reward model (PRIME recipe): a policy-shaped trainable LM scored against a frozen copy of itself
+    @register(dispatch_mode=Dispatch.ONE_TO_ALL)
+    def init_prm(self) -> int:
+        from ..algos.prime import ImplicitPRM
+        from ..models import get_model_config
+        from ..parallel.zero3 import Zero3Engine
+        from ..workers.hybrid_worker import maybe_load_pretrained
+
+        rm = self.config.reward_model
+        path = rm.model.path if rm.model.path != "tiny-llama" or self.config.actor_rollout_ref.model.path == "tiny-llama" else self.config.actor_rollout_ref.model.path
+        mcfg = get_model_config(path, **(rm.model.override_config or {}))
+        comm = rm.model.fsdp_config.comm_backend if self.device.type == "cuda" else "nccl"
+        heap = self.inner.actor_engine.heap if self.inner is not None and self.inner.actor_engine is not None else None
+        o = rm.model.optim
+        prm = Zero3Engine(mcfg, self.device, comm=comm, trainable=True, seed=self.config.data.seed, lr=o.lr, betas=tuple(o.betas), eps=o.eps,
+                          weight_decay=o.weight_decay, max_grad_norm=o.clip_grad, heap=heap)
+        ref = Zero3Engine(mcfg, self.device, comm=comm, trainable=False, seed=self.config.data.seed, heap=heap)
+        for e in (prm, ref):
+            maybe_load_pretrained(e, rm.model.ref_path if (e is ref and rm.model.ref_path) else path, self.rank)
+        self.prm = ImplicitPRM(prm, ref, beta=rm.model.beta_train, micro_batch_size=rm.micro_batch_size_per_gpu or 8)
+        return prm.num_params()
+
+    @register(dispatch_mode=Dispatch.DP_COMPUTE_PROTO)
+    def compute_prm_score(self, data: DataProto) -> DataProto:
+        return DataProto.from_dict({"prm_scores": self.prm.score(self._in(data)).float()}).to("cpu")
+
+    @register(dispatch_mode=Dispatch.DP_COMPUTE_PROTO)
+    def update_prm(self, data: DataProto) -> DataProto:
+        data = self._in(data)
+        m = self.prm.update(data, data.batch["acc"])
+        return DataProto(meta_info={"metrics": {k: [v] for k, v in m.items()}})
+
     # ---- checkpoints
     @register(dispatch_mode=Dispatch.ONE_TO_ALL)
     def save_checkpoint(self, path: str, global_step: int = 0, max_ckpt_to_keep: int | None = None) -> None:

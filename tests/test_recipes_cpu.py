@@ -8,7 +8,7 @@ from polyrl_b200.config.schema import load_config
 from polyrl_b200.data.synthetic import SyntheticPromptDataset
 from polyrl_b200.models import get_model_config
 from polyrl_b200.protocol import DataProto
-from polyrl_b200.recipes import RECIPES, dapo, entropy, flowrl, gspo, spin, sppo
+from polyrl_b200.recipes import RECIPES, dapo, entropy, flowrl, gspo, prime, spin, sppo
 from polyrl_b200.trainer.controller_ppo import make_worker_group
 
 BASE = ["trainer.device=cpu", "actor_rollout_ref.model.path=tiny-llama", "data.max_prompt_length=32", "data.max_response_length=10",
@@ -150,3 +150,30 @@ def test_flowrl_objective_and_head_learning(tmp_path):
     w2.init_model()
     w2.load_checkpoint(str(tmp_path / "ck"))
     assert all(torch.equal(w2.actor.log_z.state_dict()[k], after[k]) for k in after)
+
+
+def test_prime_recipe_filters_by_accuracy_and_trains_the_prm():
+    """PRIME: over-sampled generation, accuracy-band group filter, online PRM update before scoring, combined advantages."""
+    b = DataProto.from_dict({"acc": torch.tensor([1.0, 1.0, 0.0, 1.0, 0.0, 0.0])}, non_tensors={"uid": np.array(list("aabbcc"), dtype=object)})
+    kept, k, g = prime.filter_by_accuracy(b, 0.2, 0.8)
+    assert (k, g) == (1, 3) and list(kept.non_tensor_batch["uid"]) == ["b", "b"]
+
+    def reward_fn(batch):                       # a learnable-looking signal: 1 when the first response token is even
+        return (batch.batch["responses"][:, 0] % 2 == 0).float()
+
+    tr = _trainer(prime.PRIMETrainer, prime.DEFAULTS, ["actor_rollout_ref.rollout.n=4", "data.train_batch_size=2", "data.oversample_factor=2",
+                                                       "actor_rollout_ref.actor.ppo_mini_batch_size=2", "reward_model.model.optim.lr=1e-3"],
+                  reward_fn)
+    try:
+        assert tr.prm_params > 0
+        before = tr.wg.workers[0].prm.engine.named_full_tensors()
+        before = {n: t.clone() for n, t in before}
+        hist = tr.fit(max_steps=1)
+        after = dict(tr.wg.workers[0].prm.engine.named_full_tensors())
+    finally:
+        tr.shutdown()
+    m = hist[0]
+    assert m["num_samples"] in (4, 8) and m["actor/grad_norm"] > 0 and 0.0 < m["prime/kept_group_ratio"] <= 1.0
+    assert {"reward_model/prm_ce_loss", "reward_model/pairwise_acc", "reward_model/process_reward_mean", "prime/acc_mean"} <= set(m)
+    assert 0.2 <= m["prime/acc_mean"] <= 0.8                                            # only mixed groups were trained on
+    assert any(not torch.equal(after[n], before[n]) for n in before)                    # the PRM itself was updated
