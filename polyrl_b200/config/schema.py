@@ -58,6 +58,7 @@ class OptimConfig(BaseConfig):
     lr_scheduler_type: str | None = None       # HF spelling of the same choice
     lr_warmup_init: float = 0.0
     grad_clip: float | None = None             # alias of clip_grad
+    lr_decay_steps: int | None = None          # Megatron: length of the decay phase (sets total_training_steps when that is unset)
     min_lr: float | None = None                # absolute floor of the cosine schedule (sets min_lr_ratio = min_lr / lr)
     override_optimizer_config: dict = field(default_factory=dict)   # Megatron optimizer knobs (cpu offload fractions, ...): accepted;
                                                                     # ``optimizer_cpu_offload`` maps to fsdp_config.optimizer_offload
@@ -68,6 +69,8 @@ class OptimConfig(BaseConfig):
             self.warmup_style = "cosine" if style == "cosine" else "constant"
         if self.grad_clip is not None:
             self.clip_grad = float(self.grad_clip)
+        if self.lr_decay_steps and self.total_training_steps <= 0:
+            self.total_training_steps = int(self.lr_decay_steps)
         if self.min_lr is not None and self.lr > 0:
             self.min_lr_ratio = float(self.min_lr) / float(self.lr)
 
@@ -271,6 +274,7 @@ class RolloutConfig(BaseConfig):
     layered_summon: bool = False            # FSDP-to-engine weight gathering granularity: the ZeRO engine always gathers unit by unit
     multi_stage_wake_up: bool = False       # weights and KV cache already resume separately (release_memory / resume_memory tags)
     disable_log_stats: bool = True
+    skip_tokenizer_init: bool = True        # the engine works on token ids; text never enters it
     over_sample_rate: float = 0.0           # SGLang async over-sampling knob: the manager's continuation makes stragglers cheap instead
     update_weights_bucket_megabytes: int = 512   # bucket size of IPC weight hand-off in other stacks; weights are aliased / peer-pushed here
     agent: dict = field(default_factory=dict)    # {"agent_loop_config_path": ..., "num_workers": ...}
@@ -322,6 +326,7 @@ class ModelCfg(BaseConfig):
     tokenizer_path: str | None = None
     use_shm: bool = False                 # copy the checkpoint directory to /dev/shm once per node before loading (verl model.use_shm)
     trust_remote_code: bool = False       # no remote code is ever executed: models are this framework's own implementations
+    use_liger: bool = False               # third-party fused kernels of other stacks: the own fused kernels are always on
     exclude_modules: str | None = None    # LoRA: regex of module names that get no adapter (e.g. ".*visual.*")
     lora_adapter_path: str | None = None  # LoRA: peft adapter directory to start from
     fused_kernel_options: dict = field(default_factory=dict)   # {"impl_backend": ...}: the fused path is the own sm_100a kernels
@@ -403,6 +408,7 @@ class RewardModelConfig(BaseConfig):
     strategy: str = "fsdp"
     param_offload: bool = False
     max_length: int | None = None
+    ulysses_sequence_parallel_size: int = 1
     megatron: MegatronConfig = field(default_factory=MegatronConfig)
     profiler: ProfilerConfig = field(default_factory=ProfilerConfig)
     # reward_kwargs.{max_resp_len, overlong_buffer_cfg.{enable,len,penalty_factor,log}}: the older spelling of overlong_buffer
@@ -590,6 +596,11 @@ class PPOConfig(BaseConfig):
     # dedicated rollout resource pool of the one-step-off / fully-async recipes (``rollout.nnodes``, ``rollout.n_gpus_per_node``):
     # finalize_config() turns it into trainer.n_rollout_gpus of the disaggregated deployment
     rollout: dict = field(default_factory=dict)
+    # fully-async recipe block (recipe/fully_async_policy): what maps onto this framework's streaming trainer is applied by
+    # finalize_config — staleness_threshold >= 1 -> trainer.one_step_off (generation runs one policy version ahead),
+    # use_rollout_log_probs -> rollout_correction.bypass_mode (engine log-probs serve as old log-probs); partial rollouts are the
+    # manager's token-level continuation and always on; parameter sync happens every optimizer step
+    async_training: dict = field(default_factory=dict)
     ray_kwargs: dict = field(default_factory=dict)        # Ray start-up options of the reference stack: accepted, unused
     transfer_queue: dict = field(default_factory=dict)
 
@@ -610,6 +621,11 @@ def finalize_config(cfg: "PPOConfig") -> "PPOConfig":
         arr.actor.fsdp_config.optimizer_offload = True
     if arr.actor.strategy == "megatron" and arr.actor.megatron.optimizer_offload:
         arr.actor.fsdp_config.optimizer_offload = True
+    at = cfg.async_training or {}
+    if float(at.get("staleness_threshold", 0) or 0) >= 1:
+        t.one_step_off = True
+    if at.get("use_rollout_log_probs"):
+        cfg.algorithm.rollout_correction.bypass_mode = True
     pool = cfg.rollout or {}
     if pool.get("n_gpus_per_node") and not t.n_rollout_gpus:
         t.n_rollout_gpus = int(pool.get("nnodes", 1)) * int(pool["n_gpus_per_node"])
