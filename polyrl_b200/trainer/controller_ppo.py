@@ -438,9 +438,13 @@ class ControllerPPOTrainer:
         n = cfg.actor_rollout_ref.rollout.n
         with marked_timer("old_log_prob", timing):
             batch.meta_info["temperature"] = cfg.actor_rollout_ref.rollout.temperature
-            old = wg.compute_log_prob(batch)
-            batch.batch["old_log_probs"] = old.batch["old_log_probs"]
-            entropy = core_algos.masked_mean(old.batch["entropys"], batch.batch["response_mask"].float()).item()
+            if cfg.algorithm.rollout_correction.bypass_mode and "rollout_log_probs" in batch.batch:
+                batch.batch["old_log_probs"] = batch.batch["rollout_log_probs"].float()      # engine log-probs serve as pi_old
+                entropy = float("nan")
+            else:
+                old = wg.compute_log_prob(batch)
+                batch.batch["old_log_probs"] = old.batch["old_log_probs"]
+                entropy = core_algos.masked_mean(old.batch["entropys"], batch.batch["response_mask"].float()).item()
         if need_reference_policy(cfg):
             with marked_timer("ref", timing):
                 batch.batch["ref_log_prob"] = wg.compute_ref_log_prob(batch).batch["ref_log_prob"]

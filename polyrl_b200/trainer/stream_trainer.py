@@ -253,11 +253,17 @@ class StreamPPOTrainer:
         local = self._balance_and_shard(ibatch, metrics)
         local.meta_info["temperature"] = cfg.actor_rollout_ref.rollout.temperature
         with marked_timer("old_log_prob", t):
-            old = self.worker.compute_log_prob(local)
-            local.batch["old_log_probs"] = old.batch["old_log_probs"]
-            metrics.setdefault("actor/entropy_rollout", []).append(
-                core_algos.masked_mean(old.batch["entropys"], local.batch["response_mask"].float()).item())
-            if "rollout_log_probs" in local.batch:
+            bypass = cfg.algorithm.rollout_correction.bypass_mode and "rollout_log_probs" in local.batch
+            if bypass:
+                # rollout_correction.bypass_mode (reference: rollout_corr_helper / fully-async use_rollout_log_probs): the engine's
+                # own log-probs serve as pi_old — no recompute pass; the ratio then also absorbs the engine / trainer mismatch
+                local.batch["old_log_probs"] = local.batch["rollout_log_probs"].to(torch.float32)
+            else:
+                old = self.worker.compute_log_prob(local)
+                local.batch["old_log_probs"] = old.batch["old_log_probs"]
+                metrics.setdefault("actor/entropy_rollout", []).append(
+                    core_algos.masked_mean(old.batch["entropys"], local.batch["response_mask"].float()).item())
+            if "rollout_log_probs" in local.batch and not bypass:
                 m = local.batch["response_mask"].bool()
                 diff = (local.batch["rollout_log_probs"] - local.batch["old_log_probs"]).abs()[m]
                 if diff.numel():

@@ -103,3 +103,12 @@ def test_controller_drives_a_pipeline_parallel_actor(world, extra):
             assert hist[0]["actor/kl_loss"] < 1e-7 < hist[1]["actor/kl_loss"]             # identical at step 1, drifting after the update
     finally:
         tr.shutdown()
+
+
+def test_bypass_mode_uses_engine_log_probs_as_old_policy():
+    """algorithm.rollout_correction.bypass_mode (= async_training.use_rollout_log_probs): no recompute pass; at step 1 the ratio is
+    the engine / trainer mismatch only, so the clip fraction is zero and ppo_kl tiny."""
+    hist, _, _ = _run("local", 1, 1, extra=["async_training.use_rollout_log_probs=True"])
+    m = hist[0]
+    assert m["actor/grad_norm"] > 0 and m["actor/entropy_old"] != m["actor/entropy_old"]          # NaN: no entropy pass was run
+    assert m["actor/pg_clipfrac"] == 0.0 and abs(m["actor/ppo_kl"]) < 1e-3
