@@ -26,7 +26,11 @@ from ..config.schema import PPOConfig, load_config, need_critic, need_reference_
 STEP_CALLBACK = None        # set by bench.py --mode disagg: callable(trainer, global_step, metrics) on every trainer rank
 
 
-def _init_dist(device_type: str):
+def _init_dist(device_type: str, timeout_s: int | None = None):
+    """``timeout_s`` = actor_rollout_ref.nccl_timeout: how long a collective may wait for a straggling rank before the job aborts."""
+    import datetime
+
+    kw = {"timeout": datetime.timedelta(seconds=int(timeout_s))} if timeout_s else {}
     world = int(os.environ.get("WORLD_SIZE", 1))
     if world > 1 and not dist.is_initialized():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
@@ -35,9 +39,9 @@ def _init_dist(device_type: str):
             os.environ.setdefault("GLOO_SOCKET_IFNAME", "lo")       # single node: never resolve the (possibly unresolvable) hostname
         if device_type == "cuda":
             torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", 0)))
-            dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ.get("LOCAL_RANK", 0))))
+            dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ.get("LOCAL_RANK", 0))), **kw)
         else:
-            dist.init_process_group("gloo")
+            dist.init_process_group("gloo", **kw)
     return int(os.environ.get("RANK", 0)), world
 
 
@@ -219,7 +223,7 @@ def main(argv: list[str] | None = None) -> int:
     a = ap.parse_args(argv)
     cfg = load_config(a.config_file, a.overrides)
     device_type = cfg.trainer.device if (cfg.trainer.device != "cuda" or torch.cuda.is_available()) else "cpu"
-    rank, world = _init_dist(device_type)
+    rank, world = _init_dist(device_type, cfg.actor_rollout_ref.nccl_timeout)
     if os.environ.get("POLYRL_DUMP_STACKS_AFTER_S"):
         # hang diagnosis: every rank writes the Python stacks of all its threads to a file after N seconds (and every N after that)
         import faulthandler

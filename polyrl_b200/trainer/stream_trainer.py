@@ -364,6 +364,7 @@ class StreamPPOTrainer:
         cfg = self.config
         bs = cfg.data.val_batch_size or len(self.val_dataset)
         scores, sources, uids = [], [], []
+        val_samples: list[tuple] = []        # trainer.log_val_generations: a few (input, output, score) triples per validation
         # trainers without a colocated engine (disaggregated deployments) validate through the rollout manager like training
         # does (reference: stream_ray_trainer.py _validate -> generate_sequences on the remote rollout); rank 0 owns the client
         remote = getattr(self.worker, "rollout", None) is None
@@ -392,6 +393,15 @@ class StreamPPOTrainer:
                 r = fn(out)
                 r = r if torch.is_tensor(r) else r["reward_tensor"]
             self._dump_generations(out, r.sum(-1).tolist(), cfg.trainer.validation_data_dir, "val")
+            if cfg.trainer.log_val_generations > 0 and self.rank == 0 and len(val_samples) < cfg.trainer.log_val_generations:
+                tok = getattr(self, "tokenizer", None)
+                pr, rs = out.batch["prompts"].cpu(), out.batch["responses"].cpu()
+                pm = out.batch["attention_mask"][:, : pr.shape[1]].bool().cpu()
+                rmk = out.batch["attention_mask"][:, pr.shape[1]:].bool().cpu()
+                for j in range(min(len(out), cfg.trainer.log_val_generations - len(val_samples))):
+                    p_ids, r_ids = pr[j][pm[j]].tolist(), rs[j][rmk[j]].tolist()
+                    val_samples.append((tok.decode(p_ids) if tok is not None else p_ids, tok.decode(r_ids) if tok is not None else r_ids,
+                                        float(r[j].sum())))
             scores += r.sum(-1).tolist()
             sources += list(out.non_tensor_batch.get("data_source", ["unknown"] * len(out)))
             uids += [str(uuid.uuid4()) for _ in range(len(out))]
@@ -401,6 +411,11 @@ class StreamPPOTrainer:
             scores = [s for g in gathered for s in g[0]]
             sources = [s for g in gathered for s in g[1]]
             uids = [s for g in gathered for s in g[2]]
+        if val_samples:
+            from ..utils.tracking import ValidationGenerationsLogger
+
+            ValidationGenerationsLogger(cfg.trainer.project_name, cfg.trainer.experiment_name).log(
+                cfg.trainer.logger, val_samples, self.global_steps)
         res = M.process_validation_metrics(sources, uids, {"reward": scores})
         out = {}
         for ds, vars_ in res.items():
@@ -512,8 +527,12 @@ class StreamPPOTrainer:
                     r_ = cfg.actor_rollout_ref.rollout
                     handle_next = self.client.submit(lookahead, {"temperature": r_.temperature, "top_p": r_.top_p, "top_k": r_.top_k})
             do_profile = bool(prof.tool and prof.steps and self.global_steps in prof.steps)
-            if do_profile:
+            # global_profiler.profile_continuous_steps: consecutive profiled steps share ONE capture (start at the first, stop
+            # after the last) instead of one capture per step
+            cont = bool(prof.profile_continuous_steps)
+            if do_profile and not (cont and getattr(self, "_profiling", False)):
                 self.worker.start_profile()
+                self._profiling = True
             self._timing = {}
             self._step_batches = []
             metrics: dict = {}
@@ -551,8 +570,9 @@ class StreamPPOTrainer:
             if self._should_save(is_last, step_time):
                 with marked_timer("save_checkpoint", self._timing):
                     self._save_checkpoint()
-            if do_profile:
+            if do_profile and not (cont and prof.steps and (self.global_steps + 1) in prof.steps and not is_last):
                 self.worker.stop_profile()
+                self._profiling = False
             # ---- metrics
             full = DataProto.concat(self._step_batches)
             self._data_feedback(full)
