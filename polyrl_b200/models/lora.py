@@ -19,6 +19,8 @@ from ..ops import reference as ref
 from .config import ModelConfig
 
 ALL_LINEAR = ("q_proj", "k_proj", "v_proj", "o_proj", "gate_proj", "up_proj", "down_proj")
+_PEFT_MODULE_NAMES = {"q_proj": "self_attn.q_proj", "k_proj": "self_attn.k_proj", "v_proj": "self_attn.v_proj", "o_proj": "self_attn.o_proj",
+                      "gate_proj": "mlp.gate_proj", "up_proj": "mlp.up_proj", "down_proj": "mlp.down_proj"}
 
 
 @dataclass
@@ -32,7 +34,9 @@ class LoraConfig:
         return self.alpha / self.rank
 
     @classmethod
-    def from_model_cfg(cls, rank: int, alpha: float, target_modules) -> "LoraConfig | None":
+    def from_model_cfg(cls, rank: int, alpha: float, target_modules, exclude_modules: str | None = None) -> "LoraConfig | None":
+        """``exclude_modules``: regex over HF-style module names (``model.layers.0.self_attn.q_proj``, ``visual...``); a target whose
+        name matches gets no adapter (verl model.exclude_modules, e.g. ".*visual.*" — the vision tower never carries adapters here)."""
         if not rank or rank <= 0:
             return None
         if target_modules in (None, "all-linear", "all_linear"):
@@ -44,6 +48,13 @@ class LoraConfig:
         bad = [t for t in tm if t not in ALL_LINEAR]
         if bad:
             raise ValueError(f"unsupported LoRA target module(s) {bad}; supported: {ALL_LINEAR}")
+        if exclude_modules:
+            import re
+
+            pat = re.compile(exclude_modules)
+            tm = tuple(t for t in tm if not pat.fullmatch(f"model.layers.0.{_PEFT_MODULE_NAMES[t]}") and not pat.fullmatch(t))
+            if not tm:
+                raise ValueError(f"exclude_modules={exclude_modules!r} removes every LoRA target")
         return cls(rank=int(rank), alpha=float(alpha), target_modules=tm)
 
 

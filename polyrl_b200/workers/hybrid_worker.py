@@ -153,7 +153,7 @@ class ActorRolloutRefWorker:
         from ..models.lora import LoraConfig
 
         m = arr.model
-        self.lora_cfg = LoraConfig.from_model_cfg(m.lora_rank, m.lora_alpha, m.target_modules)
+        self.lora_cfg = LoraConfig.from_model_cfg(m.lora_rank, m.lora_alpha, m.target_modules, m.exclude_modules)
         if self.has_actor:
             self.actor_engine = Zero3Engine(self.model_cfg, self.device, group=self.shard_group, comm=comm, trainable=True,
                                             seed=seed, lr=opt.lr, betas=tuple(opt.betas), eps=opt.eps,
