@@ -682,11 +682,58 @@ class RewardModelWorker:
         self.engine = Zero3Engine(self.model_cfg, self.device, group=self.group, comm="nccl", trainable=False,
                                   seed=self.config.data.seed + 2, heap=heap)
         maybe_load_pretrained(self.engine, rm.model.path, dist.get_rank(self.group) if dist.is_initialized() else 0)
-        rt = ActorRuntimeConfig(ppo_micro_batch_size_per_gpu=rm.micro_batch_size_per_gpu)
+        rt = ActorRuntimeConfig(ppo_micro_batch_size_per_gpu=rm.micro_batch_size_per_gpu, use_dynamic_bsz=rm.use_dynamic_bsz,
+                                ppo_max_token_len_per_gpu=rm.forward_max_token_len_per_gpu)
         self.scorer = DataParallelPPOCritic(self.engine, rt, dp_group=self.group)
+        # reward models with their own vocabulary / chat template (verl reward_model.model.input_tokenizer): the policy's tokens are
+        # decoded and re-encoded with the reward model's tokenizer before scoring
+        self.src_tok = self.rm_tok = None
+        if rm.model.input_tokenizer:
+            from ..data.rl_dataset import load_tokenizer
+
+            self.src_tok = load_tokenizer(rm.model.input_tokenizer)
+            self.rm_tok = load_tokenizer(rm.model.tokenizer_path or rm.model.path)
+
+    def _switch_tokenizer(self, data: DataProto) -> DataProto:
+        """(prompt, response) pairs re-tokenised for the reward model: left-padded prompt + right-padded response of the SAME
+        widths as the input batch (longer re-encodings are truncated from the prompt's left / the response's right)."""
+        ids, mask = data.batch["input_ids"], data.batch["attention_mask"].bool()
+        r = data.batch["responses"].shape[1]
+        p = ids.shape[1] - r
+        pad = self.rm_tok.pad_token_id or 0
+        out_ids = torch.full_like(ids, pad)
+        out_mask = torch.zeros_like(data.batch["attention_mask"])
+        for i in range(ids.shape[0]):
+            prompt = self.src_tok.decode(ids[i, :p][mask[i, :p]].tolist())
+            resp = self.src_tok.decode(ids[i, p:][mask[i, p:]].tolist())
+            pi = list(self.rm_tok.encode(prompt, add_special_tokens=False))[-p:]
+            ri = list(self.rm_tok.encode(resp, add_special_tokens=False))[:r]
+            if pi:
+                out_ids[i, p - len(pi):p] = torch.tensor(pi, dtype=ids.dtype, device=ids.device)
+                out_mask[i, p - len(pi):p] = 1
+            if ri:
+                out_ids[i, p:p + len(ri)] = torch.tensor(ri, dtype=ids.dtype, device=ids.device)
+                out_mask[i, p:p + len(ri)] = 1
+        pos = (out_mask.cumsum(-1) - 1).clamp_min(0)
+        new = DataProto.from_dict({"input_ids": out_ids, "attention_mask": out_mask, "position_ids": pos, "responses": out_ids[:, p:],
+                                   "response_mask": out_mask[:, p:]})
+        new.meta_info = dict(data.meta_info)
+        return new
 
     @torch.no_grad()
     def compute_rm_score(self, data: DataProto) -> DataProto:
+        if self.rm_tok is not None:
+            scored = self.compute_rm_score_tokens(self._switch_tokenizer(data))
+            # the scalar goes back onto the last valid token of the ORIGINAL response
+            mask = data.batch["response_mask"] if "response_mask" in data.batch else data.batch["attention_mask"][:, -data.batch["responses"].shape[1]:]
+            last = (mask.sum(-1).long() - 1).clamp_min(0)
+            out = torch.zeros(mask.shape, dtype=torch.float32, device=mask.device)
+            out[torch.arange(out.shape[0], device=out.device), last] = scored.batch["rm_scores"].sum(-1).to(out.device)
+            return DataProto.from_dict({"rm_scores": out * (mask.sum(-1, keepdim=True) > 0)})
+        return self.compute_rm_score_tokens(data)
+
+    @torch.no_grad()
+    def compute_rm_score_tokens(self, data: DataProto) -> DataProto:
         data.meta_info.setdefault("micro_batch_size", self.config.reward_model.micro_batch_size_per_gpu)
         values = self.scorer.compute_values(data)                     # value BEFORE each response token
         mask = data.batch["response_mask"] if "response_mask" in data.batch else data.batch["attention_mask"][:, -values.shape[1]:]

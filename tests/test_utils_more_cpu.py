@@ -538,3 +538,39 @@ esac
     monkeypatch.setenv("PATH", "/nonexistent")
     with pytest.raises(RuntimeError, match="hdfs"):
         fs.exists("hdfs://ns/x")
+
+
+def test_reward_model_worker_scores_and_switches_tokenizers():
+    """RewardModelWorker: a value-head model scores (prompt, response) on the last response token; with
+    reward_model.model.input_tokenizer the pair is decoded and re-encoded for the reward model first (same score position in the
+    original response)."""
+    from polyrl_b200.config.schema import load_config
+    from polyrl_b200.protocol import DataProto
+    from polyrl_b200.workers.hybrid_worker import RewardModelWorker
+
+    def batch():
+        ids = torch.randint(40, 120, (3, 20))
+        mask = torch.ones(3, 20, dtype=torch.long)
+        mask[0, :3] = 0                     # left-padded prompt
+        mask[1, 17:] = 0                    # short response
+        return DataProto.from_dict({"input_ids": ids, "attention_mask": mask, "position_ids": (mask.cumsum(-1) - 1).clamp_min(0),
+                                    "responses": ids[:, -8:], "response_mask": mask[:, -8:]})
+
+    torch.manual_seed(0)
+    cfg = load_config(overrides=["trainer.device=cpu", "reward_model.enable=True", "reward_model.model.path=tiny-llama",
+                                 "reward_model.micro_batch_size_per_gpu=2"])
+    w = RewardModelWorker(cfg, device="cpu")
+    w.init_model()
+    b = batch()
+    s = w.compute_rm_score(b).batch["rm_scores"]
+    last = b.batch["response_mask"].sum(-1) - 1
+    assert s.shape == (3, 8) and all(float(s[i].abs().sum()) == float(s[i, last[i]].abs()) for i in range(3)) and s.abs().sum() > 0
+    cfg2 = load_config(overrides=["trainer.device=cpu", "reward_model.enable=True", "reward_model.model.path=tiny-llama",
+                                  "reward_model.micro_batch_size_per_gpu=2", "reward_model.model.input_tokenizer=byte",
+                                  "reward_model.model.tokenizer_path=byte"])
+    w2 = RewardModelWorker(cfg2, device="cpu")
+    w2.init_model()
+    s2 = w2.compute_rm_score(b).batch["rm_scores"]
+    assert s2.shape == (3, 8) and all(float(s2[i].abs().sum()) == float(s2[i, last[i]].abs()) for i in range(3))
+    sw = w2._switch_tokenizer(b)
+    assert sw.batch["input_ids"].shape == b.batch["input_ids"].shape and sw.batch["attention_mask"][:, 12:].sum() > 0
