@@ -75,6 +75,12 @@ class PPOWorker(Worker):
         if need_critic(cfg):
             self.critic = CriticWorker(cfg, device=self.device, group=None)
             self.critic.init_model(heap=self.inner.actor_engine.heap)
+        self.rm = None
+        if cfg.reward_model.enable:
+            from ..workers.hybrid_worker import RewardModelWorker
+
+            self.rm = RewardModelWorker(cfg, device=self.device, group=None)
+            self.rm.init_model(heap=self.inner.actor_engine.heap)
         mc = self.inner.model_cfg
         return {"rank": self.rank, "vocab_size": mc.vocab_size, "eos_token_id": mc.eos_token_id, "pad_token_id": mc.pad_token_id,
                 "num_params": self.inner.actor_engine.num_params()}
@@ -91,6 +97,10 @@ class PPOWorker(Worker):
     @register(dispatch_mode=Dispatch.DP_COMPUTE_PROTO)
     def compute_ref_log_prob(self, data: DataProto) -> DataProto:
         return self._out(self.inner.compute_ref_log_prob(self._in(data)))
+
+    @register(dispatch_mode=Dispatch.DP_COMPUTE_PROTO)
+    def compute_rm_score(self, data: DataProto) -> DataProto:
+        return self._out(self.rm.compute_rm_score(self._in(data)))
 
     @register(dispatch_mode=Dispatch.DP_COMPUTE_PROTO)
     def compute_values(self, data: DataProto) -> DataProto:
@@ -399,6 +409,8 @@ class ControllerPPOTrainer:
             scores = self.reward_fn(batch)
             if torch.is_tensor(scores) and scores.dim() == 2:
                 return scores
+        elif "rm_scores" in batch.batch:
+            return batch.batch["rm_scores"]                  # reward model only (no rule-based scorer configured)
         else:
             from ..data.synthetic import synthetic_token_reward
 
@@ -416,6 +428,8 @@ class ControllerPPOTrainer:
         with marked_timer("gen", timing):
             batch = self.wg.generate_sequences(prompts)
         with marked_timer("reward", timing):
+            if self.config.reward_model.enable and hasattr(self.wg, "compute_rm_score"):
+                batch.batch["rm_scores"] = self.wg.compute_rm_score(batch).batch["rm_scores"]      # model-based reward
             batch.batch["token_level_scores"] = self._reward(batch)
         return batch
 

@@ -210,6 +210,11 @@ def run_trainer_rank(cfg: PPOConfig, rank: int, trainer_ranks, rollout_ranks, de
             client.update_weight_version = lambda: sender.version
     tracking = Tracking(cfg.trainer.project_name, cfg.trainer.experiment_name, cfg.trainer.logger) if rank == 0 else None
     trainer = StreamPPOTrainer(cfg, worker, critic, reward_fn, reward_fn, train, val, client, trainer_group, tracking, sampler)
+    if cfg.reward_model.enable:
+        from ..workers.hybrid_worker import RewardModelWorker
+
+        trainer.rm = RewardModelWorker(cfg, device=device, group=trainer_group)
+        trainer.rm.init_model(heap=worker.actor_engine.heap)
     trainer.step_callback = STEP_CALLBACK
     out = trainer.fit()
     return out

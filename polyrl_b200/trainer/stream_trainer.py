@@ -68,6 +68,26 @@ class StreamPPOTrainer:
         self.total_training_steps = config.trainer.total_training_steps or n_batches * config.trainer.total_epochs
         config.actor_rollout_ref.actor.optim.total_training_steps = self.total_training_steps
         self._esi_deadline = float(os.environ.get("POLYRL_ESI_EXPIRATION_TS", "0") or 0)
+        self.rm = None              # model-based reward (reward_model.enable): RewardModelWorker set by the entry point
+
+    def _model_reward(self, batch: DataProto) -> None:
+        """reward_model.enable: the value-head reward model scores the batch — every rank takes a contiguous slice, the slices are
+        all-gathered — and the result rides along as ``rm_scores``, which the reward managers use instead of (or combine with) the
+        rule-based scorers (reference: ray_trainer.py compute_rm_score before compute_reward)."""
+        if self.rm is None or "rm_scores" in batch.batch:
+            return
+        n = len(batch)
+        per = (n + self.world - 1) // self.world
+        lo, hi = min(n, self.rank * per), min(n, (self.rank + 1) * per)
+        r = batch.batch["responses"].shape[1]
+        mine = torch.zeros(per, r, device=self.device)
+        if hi > lo:
+            mine[: hi - lo] = self.rm.compute_rm_score(batch.slice(lo, hi)).batch["rm_scores"].to(self.device)
+        if self.world > 1:
+            parts = [torch.zeros_like(mine) for _ in range(self.world)]
+            dist.all_gather(parts, mine, group=self.group)
+            mine = torch.cat(parts)
+        batch.batch["rm_scores"] = mine[:n]
 
     # ------------------------------------------------------------------ data
     def _iter_batches(self):
@@ -195,6 +215,8 @@ class StreamPPOTrainer:
         return batch.chunk(dp)[dp_rank]       # ranks of one Ulysses SP group share the same shard
 
     def _reward(self, batch: DataProto) -> torch.Tensor:
+        if self.reward_fn is None and "rm_scores" in batch.batch:
+            return batch.batch["rm_scores"].to(self.device)            # reward model only (no rule-based scorer configured)
         if self.reward_fn is None:
             from ..data.synthetic import synthetic_token_reward
 
@@ -235,6 +257,7 @@ class StreamPPOTrainer:
         cfg, algo = self.config, self.config.algorithm
         t = self._timing
         with marked_timer("reward", t):
+            self._model_reward(ibatch)
             ibatch.batch["token_level_scores"] = self._reward(ibatch)
             self._dump_generations(ibatch, ibatch.batch["token_level_scores"].sum(-1).tolist(), self.config.trainer.rollout_data_dir, "train")
         full_len = len(ibatch)

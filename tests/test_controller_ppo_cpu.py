@@ -112,3 +112,10 @@ def test_bypass_mode_uses_engine_log_probs_as_old_policy():
     m = hist[0]
     assert m["actor/grad_norm"] > 0 and m["actor/entropy_old"] != m["actor/entropy_old"]          # NaN: no entropy pass was run
     assert m["actor/pg_clipfrac"] == 0.0 and abs(m["actor/ppo_kl"]) < 1e-3
+
+
+def test_model_based_reward_through_the_controller():
+    """reward_model.enable: the workers' value-head reward model scores the rollouts (no rule-based scorer), GRPO trains on it."""
+    hist, _, _ = _run("mp", 2, 1, extra=["reward_model.enable=True", "reward_model.model.path=tiny-llama", "reward_model.micro_batch_size_per_gpu=4"])
+    m = hist[0]
+    assert m["num_samples"] == 16 and m["actor/grad_norm"] > 0 and m["critic/score/mean"] != 0.0

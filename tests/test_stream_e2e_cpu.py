@@ -273,3 +273,21 @@ def test_disaggregated_two_trainers_one_rollout_gloo_ws3():
     r = _run(3, ov + ["trainer.one_step_off=True", "trainer.total_training_steps=3"])      # the prefetched batch reaches both trainers
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "step:3" in r.stdout
+
+
+def test_model_based_reward_and_val_generation_log_gloo_ws2(tmp_path):
+    """reward_model.enable in the streaming trainer: every trainer rank scores its slice with the value-head reward model, the slices
+    are all-gathered and drive GRPO; trainer.log_val_generations writes a few validation samples per validation pass."""
+    ov = COMMON + ["actor_rollout_ref.model.path=tiny-llama", "algorithm.adv_estimator=grpo", "trainer.n_gpus_per_node=2",
+                   "trainer.total_training_steps=1", "reward_model.enable=True", "reward_model.model.path=tiny-llama",
+                   "reward_model.micro_batch_size_per_gpu=4", "trainer.test_freq=1", "data.val_batch_size=8", "trainer.log_val_generations=3",
+                   "trainer.project_name=t", f"trainer.experiment_name=rm{os.getpid()}"]
+    r = _run(2, ov)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "step:1" in r.stdout and "critic/score/mean" in r.stdout and "val-core/" in r.stdout
+    logs = list((ROOT / "outputs" / "val_generations" / "t" / f"rm{os.getpid()}").glob("*.jsonl")) if (ROOT / "outputs").exists() else []
+    logs += list(__import__("pathlib").Path("outputs/val_generations/t").glob(f"rm{os.getpid()}/*.jsonl"))
+    assert logs and len(logs[0].read_text().splitlines()) == 3
+    import shutil
+
+    shutil.rmtree(logs[0].parent, ignore_errors=True)
