@@ -249,6 +249,14 @@ class ActorRolloutRefWorker:
                                          kv_vmm=True if r.kv_vmm else None)
             if self.has_actor:
                 self.update_weight_remote()
+            if r.skip_rollout:
+                # debugging aid (verl rollout.skip_rollout / skip_dump_dir): generations are dumped once and replayed afterwards,
+                # so the training half of a step can be iterated on a fixed batch without running the engine
+                from ..utils.rollout_skip import RolloutSkip
+
+                self._rollout_skip = RolloutSkip(os.path.join(r.skip_dump_dir, f"rank{self.rank}"), cfg.trainer.experiment_name, r.n,
+                                                 cfg.data.train_batch_size)
+                self._rollout_skip.wrap_generate_sequences(self)
 
     def _maybe_load_pretrained(self, engine, path: str) -> None:
         maybe_load_pretrained(engine, path, self.rank)

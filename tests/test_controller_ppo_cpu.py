@@ -119,3 +119,13 @@ def test_model_based_reward_through_the_controller():
     hist, _, _ = _run("mp", 2, 1, extra=["reward_model.enable=True", "reward_model.model.path=tiny-llama", "reward_model.micro_batch_size_per_gpu=4"])
     m = hist[0]
     assert m["num_samples"] == 16 and m["actor/grad_norm"] > 0 and m["critic/score/mean"] != 0.0
+
+
+def test_skip_rollout_replays_dumped_generations(tmp_path):
+    """rollout.skip_rollout: the first run dumps its generations, a second run with the same dump dir replays them (identical
+    responses, the engine is not asked to generate)."""
+    extra = ["actor_rollout_ref.rollout.skip_rollout=True", f"actor_rollout_ref.rollout.skip_dump_dir={tmp_path}/dump"]
+    h1, _, ck1 = _run("local", 1, 1, extra=extra)
+    assert list((tmp_path / "dump" / "rank0").glob("*_step0.pt"))
+    h2, _, ck2 = _run("local", 1, 1, extra=extra + ["data.seed=1"])
+    assert h1[0]["response_length/mean"] == h2[0]["response_length/mean"] and abs(ck1 - ck2) <= 1e-9 * ck1
