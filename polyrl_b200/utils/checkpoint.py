@@ -82,11 +82,24 @@ def rotate_checkpoints(latest_path: str | Path, keep: int) -> list[str]:
 
 
 class ShardedCheckpointManager:
-    def __init__(self, engine, model_cfg, save_contents=("model", "optimizer", "extra"), load_contents=None):
+    def __init__(self, engine, model_cfg, save_contents=("model", "optimizer", "extra"), load_contents=None, async_save: bool = False):
         self.engine, self.model_cfg = engine, model_cfg
         self.save_contents = set(save_contents)
         self.load_contents = set(load_contents or save_contents)
         self.saved: list[str] = []
+        # checkpoint.async_save: the state is snapshotted to host memory synchronously (training may mutate the device tensors right
+        # after), the files are written by a background thread; the next save / load / wait() joins it first
+        self.async_save = bool(async_save)
+        self._writer = None
+        self._writer_error: BaseException | None = None
+
+    def wait(self) -> None:
+        w, self._writer = self._writer, None
+        if w is not None:
+            w.join()
+        if self._writer_error is not None:
+            e, self._writer_error = self._writer_error, None
+            raise RuntimeError(f"asynchronous checkpoint write failed: {e!r}") from e
 
     def _names(self, path: str):
         w, r = self.engine.world, self.engine.rank
@@ -96,31 +109,58 @@ class ShardedCheckpointManager:
 
     def save(self, path: str, global_step: int = 0, max_ckpt_to_keep: int | None = None, extra: dict | None = None) -> None:
         eng = self.engine
+        self.wait()
         Path(path).mkdir(parents=True, exist_ok=True)
         mp, op, ep = self._names(path)
+        files: list[tuple] = []                # (host-memory object, file): written inline or by the background thread
+
+        def host(t):                           # async: a private host copy (``.cpu()`` of a CPU tensor would alias live memory)
+            c = t.detach().cpu()
+            return c.clone() if (self.async_save and c.data_ptr() == t.data_ptr()) else c
+
         if "model" in self.save_contents:
-            torch.save({u.name: {"shard": u.shard.cpu(), "master": None if u.master is None else u.master.cpu()}
-                        for u in eng.units}, mp)
+            files.append(({u.name: {"shard": host(u.shard), "master": None if u.master is None else host(u.master)} for u in eng.units}, mp))
         if "optimizer" in self.save_contents and eng.trainable:
-            torch.save({"opt_step": eng.opt_step,
-                        "units": {u.name: {"exp_avg": u.exp_avg.cpu(), "exp_avg_sq": u.exp_avg_sq.cpu()} for u in eng.units
-                                  if u.exp_avg is not None}}, op)
+            files.append(({"opt_step": eng.opt_step,
+                           "units": {u.name: {"exp_avg": host(u.exp_avg), "exp_avg_sq": host(u.exp_avg_sq)} for u in eng.units
+                                     if u.exp_avg is not None}}, op))
         if "hf_model" in self.save_contents:
             from ..models.hf_io import save_hf
 
             save_hf(eng, self.model_cfg, Path(path) / "huggingface")      # consolidated HF directory (every rank gathers, rank 0 writes)
         if "extra" in self.save_contents:
-            torch.save({"extra": extra or {}, "rng": _rng_state(eng.device), "global_step": global_step}, ep)
-        if eng.rank == 0:
-            self.model_cfg.save(Path(path) / "config.json")
-        if dist.is_initialized() and eng.world > 1:
-            dist.barrier(group=eng.group)
+            files.append(({"extra": extra or {}, "rng": _rng_state(eng.device), "global_step": global_step}, ep))
+
+        def write():
+            for obj, f in files:
+                tmp = Path(str(f) + ".tmp")
+                torch.save(obj, tmp)
+                os.replace(tmp, f)
+            if eng.rank == 0:
+                self.model_cfg.save(Path(path) / "config.json")
+
+        if self.async_save:
+            import threading
+
+            def run():
+                try:
+                    write()
+                except BaseException as e:          # noqa: BLE001  (surfaced by the next wait())
+                    self._writer_error = e
+
+            self._writer = threading.Thread(target=run, name="ckpt-writer", daemon=False)
+            self._writer.start()
+        else:
+            write()
+            if dist.is_initialized() and eng.world > 1:
+                dist.barrier(group=eng.group)
         self.saved.append(path)
         if max_ckpt_to_keep and max_ckpt_to_keep > 0 and eng.rank == 0:
             rotate_checkpoints(path, max_ckpt_to_keep)
 
     def load(self, path: str) -> dict | None:
         eng = self.engine
+        self.wait()
         mp, op, ep = self._names(path)
         if not mp.exists():
             raise FileNotFoundError(f"{mp} not found (checkpoints are per-rank; world size must match)")

@@ -636,7 +636,7 @@ class ActorRolloutRefWorker:
 
             ck = self.config.actor_rollout_ref.actor.checkpoint
             self._ckpt_mgr = ShardedCheckpointManager(self.actor_engine, self.model_cfg, tuple(ck.save_contents),
-                                                      tuple(ck.load_contents))
+                                                      tuple(ck.load_contents), async_save=ck.async_save)
         return self._ckpt_mgr
 
     def load_checkpoint(self, local_path: str | None, hdfs_path: str | None = None, del_local_after_load: bool = False) -> None:

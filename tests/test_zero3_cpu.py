@@ -130,3 +130,26 @@ def test_reference_policy_follows_the_actor_on_request():
     w.update_reference_policy()
     r1 = dict(w.ref_engine.named_full_tensors())
     assert all(torch.equal(a[n].to(r1[n].dtype), r1[n]) for n in a)
+
+
+def test_async_checkpoint_snapshot_is_isolated_from_later_updates(tmp_path):
+    """checkpoint.async_save: the state is copied to host memory at save() time and written in the background — weights changed
+    right after save() do not leak into the file; load() joins the writer first."""
+    from polyrl_b200.models import get_model_config
+    from polyrl_b200.parallel.zero3 import Zero3Engine
+    from polyrl_b200.utils.checkpoint import ShardedCheckpointManager
+
+    cfg = get_model_config("tiny-llama")
+    eng = Zero3Engine(cfg, "cpu", seed=4)
+    mgr = ShardedCheckpointManager(eng, cfg, async_save=True)
+    want = {n: t.clone() for n, t in eng.named_full_tensors()}
+    mgr.save(str(tmp_path / "global_step_1" / "actor"), 1, None, extra={"lr_step": 7})
+    with torch.no_grad():
+        for u in eng.units:
+            u.shard.add_(1.0)
+            if u.master is not None:
+                u.master.add_(1.0)
+    extra = mgr.load(str(tmp_path / "global_step_1" / "actor"))
+    got = dict(eng.named_full_tensors())
+    assert extra["lr_step"] == 7 and all(torch.equal(got[n], want[n]) for n in want)
+    mgr.wait()
