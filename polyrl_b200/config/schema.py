@@ -14,6 +14,7 @@ from dataclasses import dataclass, field, fields, is_dataclass
 from typing import Any, Mapping
 
 import yaml
+from pathlib import Path
 
 
 class BaseConfig(Mapping):
@@ -58,6 +59,12 @@ class OptimConfig(BaseConfig):
     lr_scheduler_type: str | None = None       # HF spelling of the same choice
     lr_warmup_init: float = 0.0
     grad_clip: float | None = None             # alias of clip_grad
+    optimizer: str = "AdamW"                   # the fused AdamW kernel is the only optimizer
+    optimizer_impl: str = "polyrl_b200"
+    weight_decay_incr_style: str = "constant"
+    lr_wsd_decay_style: str = "exponential"
+    lr_wsd_decay_steps: int | None = None
+    use_checkpoint_opt_param_scheduler: bool = False
     lr_decay_steps: int | None = None          # Megatron: length of the decay phase (sets total_training_steps when that is unset)
     min_lr: float | None = None                # absolute floor of the cosine schedule (sets min_lr_ratio = min_lr / lr)
     override_optimizer_config: dict = field(default_factory=dict)   # Megatron optimizer knobs (cpu offload fractions, ...): accepted;
@@ -98,6 +105,12 @@ class FSDPConfig(BaseConfig):
     use_orig_params: bool = True
     wrap_policy: dict = field(default_factory=dict)
     offload_policy: bool = False
+    strategy: str = "fsdp"
+    forward_only: bool = False
+    ulysses_sequence_parallel_size: int | None = None
+    entropy_from_logits_with_chunking: bool = False
+    entropy_checkpointing: bool = False
+    use_torch_compile: bool = False
 
 
 @dataclass
@@ -134,6 +147,8 @@ class ProfilerConfig(BaseConfig):
     all_ranks: bool = False
     ranks: list = field(default_factory=list)
     tool_config: dict = field(default_factory=dict)
+    tool: str | None = None              # per-role tool (defaults to global_profiler.tool)
+    save_path: str | None = None
 
 
 @dataclass
@@ -160,6 +175,8 @@ class MegatronConfig(BaseConfig):
     seed: int = 42
     override_transformer_config: dict = field(default_factory=dict)
     override_ddp_config: dict = field(default_factory=dict)
+    override_mcore_model_config: dict = field(default_factory=dict)
+    forward_only: bool = False
 
 
 @dataclass
@@ -179,6 +196,10 @@ class ActorConfig(BaseConfig):
     entropy_checkpointing: bool = False
     entropy_from_logits_with_chunking: bool = False
     use_torch_compile: bool = False
+    use_fused_kernels: bool = True            # always: the fused sm_100a kernels are the implementation
+    use_remove_padding: bool = True           # always: batches are packed
+    data_loader_seed: int | None = None
+    load_weight: bool = True
     ppo_mini_batch_size: int = 256
     ppo_micro_batch_size: int | None = None
     ppo_micro_batch_size_per_gpu: int | None = None
@@ -233,6 +254,8 @@ class MultiTurnConfig(BaseConfig):
     tool_config_path: str | None = None
     interaction_config_path: str | None = None
     format: str = "hermes"
+    use_inference_chat_template: bool = False
+    tokenization_sanity_check_mode: str = "strict"   # strict | ignore_strippable | disable
     num_repeat_rollouts: int | None = None   # collabllm-style repeated simulated-user rollouts per turn (accepted; single rollout here)
 
 
@@ -274,6 +297,10 @@ class RolloutConfig(BaseConfig):
     layered_summon: bool = False            # FSDP-to-engine weight gathering granularity: the ZeRO engine always gathers unit by unit
     multi_stage_wake_up: bool = False       # weights and KV cache already resume separately (release_memory / resume_memory tags)
     disable_log_stats: bool = True
+    layer_name_map: dict = field(default_factory=dict)
+    ignore_eos: bool = False                 # generate up to the response length regardless of EOS (benchmarking)
+    cudagraph_capture_sizes: list | None = None   # batch sizes to capture decode graphs for (default: the engine's buckets)
+    profiler: ProfilerConfig = field(default_factory=ProfilerConfig)
     skip_tokenizer_init: bool = True        # the engine works on token ids; text never enters it
     over_sample_rate: float = 0.0           # SGLang async over-sampling knob: the manager's continuation makes stragglers cheap instead
     update_weights_bucket_megabytes: int = 512   # bucket size of IPC weight hand-off in other stacks; weights are aliased / peer-pushed here
@@ -306,6 +333,8 @@ class RefConfig(BaseConfig):
     entropy_checkpointing: bool = False
     entropy_from_logits_with_chunking: bool = False
     use_torch_compile: bool = False
+    load_weight: bool = True
+    model: dict = field(default_factory=dict)   # reference policy from a different checkpoint: {"path": ...}
     log_prob_micro_batch_size_per_gpu: int | None = None
     log_prob_use_dynamic_bsz: bool = False
     log_prob_max_token_len_per_gpu: int = 16384
@@ -326,6 +355,9 @@ class ModelCfg(BaseConfig):
     tokenizer_path: str | None = None
     use_shm: bool = False                 # copy the checkpoint directory to /dev/shm once per node before loading (verl model.use_shm)
     trust_remote_code: bool = False       # no remote code is ever executed: models are this framework's own implementations
+    external_lib: str | None = None       # python module imported before model construction (custom architectures in HF stacks)
+    hf_config_path: str | None = None     # config directory when it differs from the weights directory
+    custom_chat_template: str | None = None   # Jinja chat template that replaces the tokenizer's own
     use_liger: bool = False               # third-party fused kernels of other stacks: the own fused kernels are always on
     exclude_modules: str | None = None    # LoRA: regex of module names that get no adapter (e.g. ".*visual.*")
     lora_adapter_path: str | None = None  # LoRA: peft adapter directory to start from
@@ -371,6 +403,11 @@ class CriticConfig(BaseConfig):
     checkpoint: CheckpointConfig = field(default_factory=CheckpointConfig)
     profiler: ProfilerConfig = field(default_factory=ProfilerConfig)
     megatron: MegatronConfig = field(default_factory=MegatronConfig)
+    forward_micro_batch_size: int | None = None
+    forward_micro_batch_size_per_gpu: int | None = None
+    nccl_timeout: int = 600
+    load_weight: bool = True
+    data_loader_seed: int | None = None
     ulysses_sequence_parallel_size: int = 1    # the critic trains on the actor's SP groups (must equal the actor's setting)
     ppo_micro_batch_size: int | None = None    # GLOBAL micro-batch (deprecated spelling)
     shuffle: bool = False
@@ -409,6 +446,8 @@ class RewardModelConfig(BaseConfig):
     param_offload: bool = False
     max_length: int | None = None
     ulysses_sequence_parallel_size: int = 1
+    nccl_timeout: int = 600
+    load_weight: bool = True
     megatron: MegatronConfig = field(default_factory=MegatronConfig)
     profiler: ProfilerConfig = field(default_factory=ProfilerConfig)
     # reward_kwargs.{max_resp_len, overlong_buffer_cfg.{enable,len,penalty_factor,log}}: the older spelling of overlong_buffer
@@ -452,6 +491,12 @@ class RolloutCorrectionConfig(BaseConfig):
     rollout_rs_threshold_lower: float | None = None
     rollout_token_veto_threshold: float | None = None
     bypass_mode: bool = False
+    bypass_old_logprob_for_rollout: bool = False     # older spelling of bypass_mode
+    use_pure_rollout_correction: bool = False
+
+    def __post_init__(self):
+        if self.bypass_old_logprob_for_rollout:
+            self.bypass_mode = True
 
 
 @dataclass
@@ -480,6 +525,15 @@ class AlgorithmConfig(BaseConfig):
     # PRIME (recipes/prime.py): weights of the outcome reward and of the implicit process reward in the advantage
     reward_gt_coef: float = 5.0
     reward_dpo_coef: float = 5.0
+    # flat spellings of rollout_correction.* used by older configs (mapped by finalize_config)
+    rollout_is: bool | str | None = None
+    rollout_is_threshold: float | None = None
+    rollout_rs: bool | str | None = None
+    rollout_rs_threshold: float | None = None
+    rollout_rs_threshold_lower: float | None = None
+    rollout_token_veto_threshold: float | None = None
+    bypass_old_logprob_for_rollout: bool | None = None
+    use_pure_rollout_correction: bool | None = None
     use_pf_ppo: bool = False
     pf_ppo: dict = field(default_factory=lambda: {"reweight_method": "pow", "weight_pow": 2.0})
 
@@ -514,6 +568,15 @@ class DataConfig(BaseConfig):
     trust_remote_code: bool = False
     use_shm: bool = False
     validation_shuffle: bool = False
+    tokenizer: str | None = None            # tokenizer path when it differs from the model's
+    train_max_samples: int = -1             # use only the first N rows of the training / validation files (-1: all)
+    val_max_samples: int = -1
+    tool_config_path: str | None = None
+    return_raw_input_ids: bool = False
+    return_full_prompt: bool = False
+    return_multi_modal_inputs: bool = True
+    image_patch_size: int = 14
+    filter_overlong_prompts_workers: int = 1
     # PRIME-style accuracy filtering (recipe/prime): keep prompts whose group accuracy lies inside the bounds, over-sample to refill
     filter_accuracy: bool = False
     accuracy_lower_bound: float = 0.0
@@ -544,6 +607,8 @@ class TrainerConfig(BaseConfig):
     n_gpus_per_node: int = 8
     use_legacy_worker_impl: str = "auto"      # verl's switch between its two worker implementations: there is one here
     log_freq: int = 1
+    del_local_ckpt_after_load: bool = False
+    ray_wait_register_center_timeout: int = 300
     max_ckpt_to_keep: int | None = None        # one limit for every role (sets max_actor_ckpt_to_keep / max_critic_ckpt_to_keep)
     ref_update_freq: int = -1                  # SPIN / self-play: copy the actor into the reference policy every k steps (-1: never)
     tensorboard_dir: str | None = None         # also honoured through the TENSORBOARD_DIR environment variable
@@ -621,6 +686,14 @@ def finalize_config(cfg: "PPOConfig") -> "PPOConfig":
         arr.actor.fsdp_config.optimizer_offload = True
     if arr.actor.strategy == "megatron" and arr.actor.megatron.optimizer_offload:
         arr.actor.fsdp_config.optimizer_offload = True
+    rc = cfg.algorithm.rollout_correction
+    for k in ("rollout_is", "rollout_is_threshold", "rollout_rs", "rollout_rs_threshold", "rollout_rs_threshold_lower",
+              "rollout_token_veto_threshold"):
+        v = getattr(cfg.algorithm, k)
+        if v is not None:
+            setattr(rc, k, v)
+    if cfg.algorithm.bypass_old_logprob_for_rollout:
+        rc.bypass_mode = True
     at = cfg.async_training or {}
     if float(at.get("staleness_threshold", 0) or 0) >= 1:
         t.one_step_off = True
@@ -667,15 +740,80 @@ def _coerce(value: Any, target: Any) -> Any:
     return parsed
 
 
-def _apply_dict(obj: Any, d: Mapping, path: str = "") -> None:
+_HYDRA_KEYS = ("hydra", "defaults", "_target_", "_recursive_", "_convert_", "_partial_")
+
+
+def _resolve_interpolations(node: Any, root: Mapping, depth: int = 0) -> Any:
+    """``${a.b.c}`` / ``${oc.select:a.b.c,default}`` / ``${oc.env:VAR,default}`` of Hydra / OmegaConf YAML files, resolved against the
+    file's own tree (``root``).  References that the file does not define (they point into Hydra's composed defaults) resolve to
+    None, i.e. the value keeps this framework's default."""
+    import re
+
+    if isinstance(node, Mapping):
+        return {k: _resolve_interpolations(v, root, depth) for k, v in node.items()}
+    if isinstance(node, list):
+        return [_resolve_interpolations(v, root, depth) for v in node]
+    if not isinstance(node, str) or "${" not in node or depth > 8:
+        return node
+
+    def lookup(path: str):
+        cur: Any = root
+        for part in path.strip().split("."):
+            if not isinstance(cur, Mapping) or part not in cur:
+                return None
+            cur = cur[part]
+        return cur
+
+    def one(expr: str):
+        expr = expr.strip()
+        if expr.startswith("oc.select:"):
+            key, _, default = expr[len("oc.select:"):].partition(",")
+            v = lookup(key)
+            return yaml.safe_load(default) if v is None and default.strip() else v
+        if expr.startswith("oc.env:"):
+            key, _, default = expr[len("oc.env:"):].partition(",")
+            return os.environ.get(key.strip(), yaml.safe_load(default) if default.strip() else None)
+        return lookup(expr)
+
+    m = re.fullmatch(r"\$\{([^{}]+)\}", node.strip())
+    if m:
+        return _resolve_interpolations(one(m.group(1)), root, depth + 1)
+    out = re.sub(r"\$\{([^{}]+)\}", lambda mm: str(one(mm.group(1))), node)
+    return _resolve_interpolations(out, root, depth + 1)
+
+
+def _apply_dict(obj: Any, d: Mapping, path: str = "", lenient: bool = False) -> None:
+    """``lenient`` (YAML files written for the reference stack): Hydra bookkeeping keys are skipped, unresolved interpolations keep
+    the default, and keys this framework does not have are reported once instead of aborting the load."""
     for k, v in d.items():
+        if k in _HYDRA_KEYS:
+            continue
+        if isinstance(obj, dict):
+            obj[k] = dict(v) if isinstance(v, Mapping) else v
+            continue
         if not hasattr(obj, k):
+            if lenient:
+                _UNKNOWN_YAML_KEYS.append(path + k)
+                continue
             raise KeyError(f"unknown config key {path + k!r}")
         cur = getattr(obj, k)
+        if lenient and isinstance(v, str) and v.strip() == "???":
+            continue                                    # OmegaConf's mandatory-value marker: keep the default
+        if v is None and lenient and cur is not None and not isinstance(cur, (str, int, float, bool)):
+            continue                                    # "null" for a structured field: keep the default tree
         if is_dataclass(cur) and isinstance(v, Mapping):
-            _apply_dict(cur, v, path + k + ".")
+            _apply_dict(cur, v, path + k + ".", lenient)
+            if hasattr(cur, "__post_init__"):
+                cur.__post_init__()
+        elif isinstance(cur, dict) and isinstance(v, Mapping):
+            cur.update({kk: vv for kk, vv in v.items() if kk not in _HYDRA_KEYS})
         else:
+            if v is None and lenient and isinstance(cur, (int, float, bool)) and not isinstance(cur, str):
+                continue                                # unresolved ${...}: keep the default
             setattr(obj, k, _coerce(v, cur) if not isinstance(v, Mapping) else dict(v))
+
+
+_UNKNOWN_YAML_KEYS: list[str] = []
 
 
 def apply_overrides(cfg: Any, overrides: list[str]) -> Any:
@@ -726,7 +864,14 @@ def load_config(yaml_paths: list[str] | str | None = None, overrides: list[str] 
     for p in yaml_paths or []:
         with open(p) as f:
             d = yaml.safe_load(f) or {}
-        _apply_dict(cfg, d)
+        hydra_style = any(k in d for k in ("hydra", "defaults")) or "${" in Path(p).read_text()
+        if hydra_style:
+            d = _resolve_interpolations(d, d)
+        del _UNKNOWN_YAML_KEYS[:]
+        _apply_dict(cfg, d, lenient=hydra_style)
+        if _UNKNOWN_YAML_KEYS and int(os.environ.get("RANK", 0)) == 0:
+            print(f"[config] {p}: ignored {len(_UNKNOWN_YAML_KEYS)} key(s) without a counterpart here: "
+                  f"{', '.join(_UNKNOWN_YAML_KEYS[:12])}{' ...' if len(_UNKNOWN_YAML_KEYS) > 12 else ''}", flush=True)
     apply_overrides(cfg, overrides or [])
     return finalize_config(cfg)
 

@@ -60,7 +60,9 @@ def build_datasets(cfg: PPOConfig, model_cfg, tokenizer=None):
                                      d.max_prompt_length, model_cfg.pad_token_id, seed=d.seed + 7)
         tok = None
     else:
-        tok = tokenizer or load_tokenizer(cfg.actor_rollout_ref.model.tokenizer_path or cfg.actor_rollout_ref.model.path)
+        tok = tokenizer or load_tokenizer(d.tokenizer or cfg.actor_rollout_ref.model.tokenizer_path or cfg.actor_rollout_ref.model.path)
+        if cfg.actor_rollout_ref.model.custom_chat_template and hasattr(tok, "chat_template"):
+            tok.chat_template = cfg.actor_rollout_ref.model.custom_chat_template          # verl model.custom_chat_template
         raw = d.return_raw_chat or cfg.actor_rollout_ref.rollout.multi_turn.enable       # agent loops re-template the chat
         kw = dict(model_cfg=model_cfg, image_key=d.image_key, video_key=d.video_key, min_pixels=d.image_min_pixels, max_pixels=d.image_max_pixels,
                   apply_chat_template_kwargs=dict(d.apply_chat_template_kwargs or {}))
@@ -78,6 +80,10 @@ def build_datasets(cfg: PPOConfig, model_cfg, tokenizer=None):
             train = RLHFDataset(d.train_files, tok, d.prompt_key, d.max_prompt_length, d.filter_overlong_prompts, d.truncation, raw, **kw)
         val = (RLHFDataset(d.val_files, tok, d.prompt_key, d.max_prompt_length, d.filter_overlong_prompts, d.truncation, raw, **kw)
                if d.val_files else None)
+    # data.train_max_samples / val_max_samples: only the first N rows (quick experiments on a slice of a big file)
+    for ds, cap in ((train, d.train_max_samples), (val, d.val_max_samples)):
+        if ds is not None and cap and cap > 0 and hasattr(ds, "rows") and len(ds.rows) > cap:
+            ds.rows = ds.rows[:cap]
     if (d.sampler or {}).get("class_name"):
         from ..data.dynamic import load_extern_type
 

@@ -391,7 +391,7 @@ class ActorRolloutRefWorker:
             temperature = 0.0
         resp_len = meta.get("response_length", cfg.data.max_response_length)
         sp = SamplingParams(max_new_tokens=resp_len, temperature=temperature, top_p=meta.get("top_p", r.top_p),
-                            top_k=meta.get("top_k", r.top_k), n=n, ignore_eos=meta.get("ignore_eos", False))
+                            top_k=meta.get("top_k", r.top_k), n=n, ignore_eos=meta.get("ignore_eos", r.ignore_eos))
         raw = prompts.non_tensor_batch.get("raw_prompt_ids")
         if raw is None:
             ids, mask = prompts.batch["input_ids"], prompts.batch["attention_mask"].bool()

@@ -224,3 +224,53 @@ def test_reference_sft_script_keys_are_accepted():
     apply_overrides(bad, ["engine.tensor_model_parallel_size=2"])
     with pytest.raises(NotImplementedError):
         finalize_sft_config(bad)
+
+
+def test_hydra_style_yaml_files_load(tmp_path):
+    """YAML files written for the reference stack (Hydra ``defaults`` / ``hydra`` blocks, ``_target_`` markers, ``${...}`` and
+    ``oc.select`` interpolation, ``???`` mandatory markers, a few keys without counterpart) load with their values applied."""
+    from polyrl_b200.config import schema as S
+
+    y = tmp_path / "ppo_stream_trainer.yaml"
+    y.write_text("""
+hydra:
+  searchpath: [file://somewhere]
+defaults:
+  - ppo_trainer
+  - _self_
+data:
+  train_batch_size: 64
+  max_prompt_length: 256
+  tokenizer: null
+actor_rollout_ref:
+  model:
+    path: ???
+  actor:
+    _target_: some.module.ActorConfig
+    ppo_mini_batch_size: ${data.train_batch_size}
+    optim: {lr: 2e-6, total_training_steps: "${oc.select:trainer.total_training_steps,-1}"}
+    unknown_knob: 3
+  rollout:
+    _target_: x.RolloutConfig
+    name: sglang-disaggregated
+    n: 4
+    prompt_length: ${data.max_prompt_length}
+    rollout_manager: {port: 5001, endpoint: null}
+    min_stream_batch_size: 8
+trainer:
+  total_training_steps: 12
+  logger: ["console"]
+""")
+    c = S.load_config(str(y), overrides=["actor_rollout_ref.rollout.n=8"])
+    a = c.actor_rollout_ref
+    assert c.data.train_batch_size == 64 and a.actor.ppo_mini_batch_size == 64 and a.rollout.prompt_length == 256
+    assert a.actor.optim.lr == 2e-6 and a.actor.optim.total_training_steps == 12 and c.trainer.total_training_steps == 12
+    assert a.rollout.name == "native-disaggregated" and a.rollout.rollout_manager.port == 5001 and a.rollout.n == 8
+    assert a.model.path == "tiny-llama"                                  # "???" keeps the default
+    assert S._UNKNOWN_YAML_KEYS == ["actor_rollout_ref.actor.unknown_knob"]
+    strict = tmp_path / "own.yaml"
+    strict.write_text("data: {train_batch_size: 8, nonsense: 1}\n")
+    import pytest
+
+    with pytest.raises(KeyError):
+        S.load_config(str(strict))                                       # the framework's own files stay strict
