@@ -133,6 +133,14 @@ class ModelConfig:
                        eos_token_id=hf.get("eos_token_id", 50256), bos_token_id=hf.get("bos_token_id", 50256),
                        pad_token_id=hf.get("pad_token_id") or hf.get("eos_token_id", 50256), name=hf.get("_name_or_path", "gpt2"))
         vis_kw: dict = {}
+        vl_moe_kw: dict = {}
+        if mt == "qwen3_vl_moe":             # Qwen3-VL tower + DeepStack on a Qwen3-MoE text stack (always-normalised top-k routing)
+            tc = dict(hf.get("text_config") or {})
+            if tc.get("mlp_only_layers") or tc.get("decoder_sparse_step", 1) != 1:
+                raise NotImplementedError("mixed dense / sparse layer stacks (mlp_only_layers, decoder_sparse_step != 1)")
+            vl_moe_kw = dict(num_experts=tc.get("num_experts") or tc["num_local_experts"], num_experts_per_tok=tc["num_experts_per_tok"],
+                             moe_intermediate_size=tc["moe_intermediate_size"], norm_topk_prob=True)
+            mt = "qwen3_vl"
         if mt == "qwen3_vl":
             vc = dict(hf.get("vision_config") or {})
             top = hf
@@ -191,7 +199,7 @@ class ModelConfig:
                    bos_token_id=hf.get("bos_token_id") or eos, pad_token_id=hf.get("pad_token_id") or eos,
                    sliding_window=(hf.get("sliding_window") if (mt == "mistral" or hf.get("use_sliding_window")) else None),
                    hf_model_type=mt if mt in ("mistral",) else "",
-                   name=hf.get("_name_or_path", mt), **vis_kw, **moe_kw)
+                   name=hf.get("_name_or_path", mt), **vis_kw, **{**moe_kw, **vl_moe_kw})
 
 
 PRESETS: dict[str, dict] = {

@@ -205,6 +205,13 @@ def hf_config_dict(cfg: ModelConfig) -> dict:
                    "temporal_patch_size": v.get("temporal_patch_size", 2), "out_hidden_size": cfg.hidden_size,
                    "num_position_embeddings": v["num_position_embeddings"],
                    "deepstack_visual_indexes": list(v.get("deepstack_visual_indexes") or ())}
+            if cfg.num_experts:
+                text.update(model_type="qwen3_vl_moe_text", num_experts=cfg.num_experts, num_experts_per_tok=cfg.num_experts_per_tok,
+                            moe_intermediate_size=cfg.moe_intermediate_size, decoder_sparse_step=1, mlp_only_layers=[])
+                return {"model_type": "qwen3_vl_moe", "architectures": ["Qwen3VLMoeForConditionalGeneration"], "text_config": text,
+                        "vision_config": vis, "image_token_id": cfg.image_token_id, "video_token_id": cfg.video_token_id,
+                        "vision_start_token_id": cfg.vision_start_token_id, "vision_end_token_id": cfg.vision_end_token_id,
+                        "tie_word_embeddings": cfg.tie_word_embeddings, "torch_dtype": "bfloat16"}
             return {"model_type": "qwen3_vl", "architectures": ["Qwen3VLForConditionalGeneration"], "text_config": text,
                     "vision_config": vis, "image_token_id": cfg.image_token_id, "video_token_id": cfg.video_token_id,
                     "vision_start_token_id": cfg.vision_start_token_id, "vision_end_token_id": cfg.vision_end_token_id,

@@ -745,3 +745,46 @@ def test_video_files_are_decoded_and_sampled(tmp_path):
     cfg = get_model_config("tiny-qwen2-vl")
     pv, grid = V.preprocess_video(cfg, frames, min_pixels=16 * 16, max_pixels=32 * 32)
     assert grid[0] == 4 and pv.shape[0] == grid[0] * grid[1] * grid[2]
+
+
+def test_qwen3_vl_moe_logits_match_hf():
+    """Qwen3-VL-MoE = the Qwen3-VL tower / DeepStack / interleaved M-RoPE on a mixture-of-experts text stack (stacked expert tensors)."""
+    from transformers import Qwen3VLMoeConfig, Qwen3VLMoeForConditionalGeneration
+
+    torch.manual_seed(0)
+    hc = Qwen3VLMoeConfig(
+        text_config=dict(vocab_size=512, hidden_size=128, intermediate_size=256, num_hidden_layers=2, num_attention_heads=4,
+                         num_key_value_heads=2, head_dim=32, max_position_embeddings=512, num_experts=4, num_experts_per_tok=2,
+                         moe_intermediate_size=128, decoder_sparse_step=1, mlp_only_layers=[],
+                         rope_parameters=dict(rope_type="default", rope_theta=10000.0, mrope_section=[6, 5, 5], mrope_interleaved=True)),
+        vision_config=dict(depth=2, hidden_size=64, intermediate_size=96, num_heads=4, patch_size=4, spatial_merge_size=2,
+                           temporal_patch_size=2, in_channels=3, out_hidden_size=128, num_position_embeddings=36, deepstack_visual_indexes=[0]),
+        image_token_id=500, video_token_id=501, vision_start_token_id=499, vision_end_token_id=498, tie_word_embeddings=False)
+    hc._attn_implementation = "eager"
+    model = Qwen3VLMoeForConditionalGeneration(hc).eval().float()
+    with torch.no_grad():
+        for n, p in model.named_parameters():
+            if p.dim() == 1:
+                p.add_(0.1 * torch.randn_like(p))
+            elif "experts" in n:
+                p.normal_(0, 0.05)                       # HF leaves the stacked expert tensors uninitialised (torch.empty)
+    cfg, w, vw = _ours(hc, model)
+    assert cfg.num_experts == 4 and cfg.norm_topk_prob and V.is_v3(cfg) and V.deepstack_levels(cfg) == 1
+    g = torch.Generator().manual_seed(1)
+    grids = [(1, 4, 4)]
+    pix = torch.randn(16, V.patch_dim(cfg), generator=g)
+    n0 = V.num_image_tokens(cfg, grids)[0]
+    ids = [2, 11, 499] + [500] * n0 + [498, 13, 14, 15]
+    ids_t = torch.tensor([ids])
+    with torch.no_grad():
+        ref_logits = model(input_ids=ids_t, pixel_values=pix, image_grid_thw=torch.tensor(grids), mm_token_type_ids=(ids_t == 500).int()).logits[0]
+        img = V.vision_forward(cfg, vw, pix, grids)
+        pos3, _ = V.mrope_positions(cfg, ids, grids)
+        t = len(ids)
+        inp = tf.PackedInput(torch.tensor(ids), pos3[0].clone(), torch.tensor([0, t], dtype=torch.int32), t, mrope_pos=pos3, image_embeds=img)
+        logits = tf.logits_forward(cfg, w.head, w.embed, tf.forward_hidden(cfg, w, inp))
+    assert (logits - ref_logits).abs().max() < 5e-4
+    from polyrl_b200.models.hf_io import hf_config_dict
+
+    cfg2 = ModelConfig.from_hf_config(hf_config_dict(cfg))
+    assert cfg2.num_experts == 4 and cfg2.vision == cfg.vision
