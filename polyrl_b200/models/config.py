@@ -179,6 +179,9 @@ class ModelConfig:
             hf["tie_word_embeddings"] = top.get("tie_word_embeddings", hf.get("tie_word_embeddings", False))
             mt = "qwen2"
         moe_kw: dict = {}
+        if mt == "mixtral":                  # llama attention + top-k of num_local_experts SwiGLU experts of width intermediate_size
+            moe_kw = dict(num_experts=hf["num_local_experts"], num_experts_per_tok=hf["num_experts_per_tok"],
+                          moe_intermediate_size=hf["intermediate_size"], norm_topk_prob=True)
         if mt == "qwen3_moe":
             if hf.get("mlp_only_layers") or hf.get("decoder_sparse_step", 1) != 1:
                 raise NotImplementedError("mixed dense / sparse layer stacks (mlp_only_layers, decoder_sparse_step != 1)")
@@ -193,12 +196,13 @@ class ModelConfig:
                    intermediate_size=hf["intermediate_size"], num_layers=hf["num_hidden_layers"],
                    num_heads=hf["num_attention_heads"], num_kv_heads=hf.get("num_key_value_heads", hf["num_attention_heads"]),
                    head_dim=hf.get("head_dim") or 0, max_position_embeddings=hf.get("max_position_embeddings", 8192),
-                   rope_theta=hf.get("rope_theta", 10000.0), rms_norm_eps=hf.get("rms_norm_eps", 1e-6),
+                   rope_theta=(hf.get("rope_theta") or (hf.get("rope_parameters") or hf.get("rope_scaling") or {}).get("rope_theta") or 10000.0),
+                   rms_norm_eps=hf.get("rms_norm_eps", 1e-6),
                    qkv_bias=(mt == "qwen2") or hf.get("attention_bias", False), qk_norm=(mt == "qwen3"),
                    tie_word_embeddings=hf.get("tie_word_embeddings", False), eos_token_id=eos, extra_eos_token_ids=extra_eos,
                    bos_token_id=hf.get("bos_token_id") or eos, pad_token_id=hf.get("pad_token_id") or eos,
-                   sliding_window=(hf.get("sliding_window") if (mt == "mistral" or hf.get("use_sliding_window")) else None),
-                   hf_model_type=mt if mt in ("mistral",) else "",
+                   sliding_window=(hf.get("sliding_window") if (mt in ("mistral", "mixtral") or hf.get("use_sliding_window")) else None),
+                   hf_model_type=mt if mt in ("mistral", "mixtral") else "",
                    name=hf.get("_name_or_path", mt), **vis_kw, **{**moe_kw, **vl_moe_kw})
 
 

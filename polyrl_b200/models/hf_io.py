@@ -108,10 +108,21 @@ def _convert_layer(cfg: ModelConfig, ck: HFCheckpoint, i: int) -> dict[str, torc
                     "transformer.ln_f.weight": torch.empty(0), "transformer.ln_f.bias": torch.empty(0)})
     else:
         keys = _layer_keys(cfg, i)
-        if cfg.num_experts and keys[-1] not in ck.weight_map and f"model.language_model.{keys[-1][6:]}" not in ck.weight_map:
-            # older checkpoints store one module per expert
-            p = f"model.layers.{i}."
-            keys = keys[:-2] + [f"{p}mlp.experts.{e}.{n}_proj.weight" for e in range(cfg.num_experts) for n in ("gate", "up", "down")]
+        p = f"model.layers.{i}."
+
+        def has(k: str) -> bool:
+            return k in ck.weight_map or f"model.language_model.{k[6:]}" in ck.weight_map
+
+        if cfg.num_experts and not has(p + "mlp.experts.gate_up_proj"):
+            # checkpoints written before the stacked expert layout: one module per expert
+            stacked = {p + "mlp.gate.weight", p + "mlp.experts.gate_up_proj", p + "mlp.experts.down_proj"}
+            keys = [k for k in keys if k not in stacked]
+            if has(p + "block_sparse_moe.gate.weight"):             # Mixtral: block_sparse_moe.experts.{e}.w1 (gate) / w3 (up) / w2 (down)
+                keys += [p + "block_sparse_moe.gate.weight"] + [f"{p}block_sparse_moe.experts.{e}.{n}.weight"
+                                                                for e in range(cfg.num_experts) for n in ("w1", "w2", "w3")]
+            else:
+                keys += [p + "mlp.gate.weight"] + [f"{p}mlp.experts.{e}.{n}_proj.weight" for e in range(cfg.num_experts)
+                                                   for n in ("gate", "up", "down")]
         sub = {k.replace(f"model.layers.{i}.", "model.layers.0."): ck.get(k) for k in keys}
         sub.update({"model.embed_tokens.weight": torch.empty(0), "model.norm.weight": torch.empty(0), "lm_head.weight": torch.empty(0)})
     conv = tf.convert_hf_state_dict(_one_layer_cfg(cfg), sub)
@@ -237,6 +248,14 @@ def hf_config_dict(cfg: ModelConfig) -> dict:
     moe = {}
     if cfg.sliding_window:
         moe["sliding_window"] = int(cfg.sliding_window)
+    if cfg.num_experts and getattr(cfg, "hf_model_type", "") == "mixtral":
+        return {"model_type": "mixtral", "architectures": ["MixtralForCausalLM"], "vocab_size": cfg.vocab_size, "hidden_size": cfg.hidden_size,
+                "intermediate_size": cfg.moe_intermediate_size, "num_hidden_layers": cfg.num_layers, "num_attention_heads": cfg.num_heads,
+                "num_key_value_heads": cfg.num_kv_heads, "head_dim": cfg.head_dim, "max_position_embeddings": cfg.max_position_embeddings,
+                "rope_theta": cfg.rope_theta, "rms_norm_eps": cfg.rms_norm_eps, "tie_word_embeddings": cfg.tie_word_embeddings,
+                "num_local_experts": cfg.num_experts, "num_experts_per_tok": cfg.num_experts_per_tok, "sliding_window": cfg.sliding_window,
+                "hidden_act": "silu", "torch_dtype": "bfloat16", "eos_token_id": cfg.eos_token_id, "bos_token_id": cfg.bos_token_id,
+                "pad_token_id": cfg.pad_token_id}
     if cfg.num_experts:
         mt, arch = "qwen3_moe", "Qwen3MoeForCausalLM"
         moe = {**moe, "num_experts": cfg.num_experts, "num_experts_per_tok": cfg.num_experts_per_tok, "moe_intermediate_size": cfg.moe_intermediate_size,

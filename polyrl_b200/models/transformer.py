@@ -507,6 +507,13 @@ def convert_hf_state_dict(cfg: ModelConfig, hf_sd: dict[str, torch.Tensor]) -> d
         out[f"layers.{i}.wo"] = hf_sd[p + "self_attn.o_proj.weight"]
         if cfg.num_experts:
             fm = cfg.moe_intermediate_size
+            if p + "block_sparse_moe.gate.weight" in hf_sd:      # Mixtral checkpoints on disk: block_sparse_moe.experts.{e}.w1 / w3 / w2
+                q = p + "block_sparse_moe."
+                out[f"layers.{i}.router"] = hf_sd[q + "gate.weight"]
+                pairs = [(hf_sd[f"{q}experts.{e}.w1.weight"], hf_sd[f"{q}experts.{e}.w3.weight"]) for e in range(cfg.num_experts)]
+                out[f"layers.{i}.ewd"] = torch.stack([hf_sd[f"{q}experts.{e}.w2.weight"] for e in range(cfg.num_experts)])
+                out[f"layers.{i}.ewgu"] = torch.stack([ref.interleave_gate_up(g, u) for g, u in pairs])
+                continue
             out[f"layers.{i}.router"] = hf_sd[p + "mlp.gate.weight"]
             if p + "mlp.experts.gate_up_proj" in hf_sd:          # stacked layout [E, 2f, h] (gate rows then up rows)
                 gu, dn = hf_sd[p + "mlp.experts.gate_up_proj"], hf_sd[p + "mlp.experts.down_proj"]

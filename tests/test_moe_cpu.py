@@ -227,3 +227,60 @@ def test_tp_expert_sharding_partials_sum_to_the_full_moe():
                 wl = {"router": w["router"], "ewgu": w["ewgu"][r * el:(r + 1) * el], "ewd": w["ewd"][r * el:(r + 1) * el]}
                 total += moe_partial(tp, cfg, wl, h, static)
             assert (total - want).abs().max() < 1e-5, (world, static)
+
+
+def test_mixtral_logits_match_hf_and_legacy_checkpoint_names_load(tmp_path):
+    """Mixtral family: llama attention + top-2 of N SwiGLU experts.  Logits equal HF MixtralForCausalLM; a checkpoint directory in
+    the on-disk naming of the released weights (block_sparse_moe.experts.{e}.w1/w2/w3) loads through the lazy reader."""
+    import transformers
+    from safetensors.torch import save_file
+
+    from polyrl_b200.models import TransformerWeights, forward_hidden, lm_head_weight, pack_padded
+    from polyrl_b200.models import transformer as tf
+    from polyrl_b200.models.config import ModelConfig
+    from polyrl_b200.models.hf_io import hf_config_dict, load_state_dict
+
+    torch.manual_seed(0)
+    hc = transformers.MixtralConfig(vocab_size=320, hidden_size=128, intermediate_size=128, num_hidden_layers=2, num_attention_heads=4,
+                                    num_key_value_heads=2, max_position_embeddings=256, num_local_experts=4, num_experts_per_tok=2,
+                                    sliding_window=None, rms_norm_eps=1e-5, tie_word_embeddings=False)
+    m = transformers.MixtralForCausalLM(hc).eval().float()
+    with torch.no_grad():
+        for n, p in m.named_parameters():
+            if "experts" in n:
+                p.normal_(0, 0.05)
+            elif p.dim() == 1:
+                p.add_(0.1 * torch.randn_like(p))
+    cfg = ModelConfig.from_hf_config(hc.to_dict())
+    assert cfg.num_experts == 4 and cfg.moe_intermediate_size == 128 and cfg.norm_topk_prob and not cfg.qk_norm
+    sd = tf.convert_hf_state_dict(cfg, m.state_dict())
+    w = TransformerWeights(cfg, "cpu", torch.float32, init=False)
+    w.load_state_dict(sd)
+    ids = torch.randint(0, 320, (2, 19))
+    with torch.no_grad():
+        want = m(ids).logits
+        inp, _ = pack_padded(ids, torch.ones_like(ids))
+        got = forward_hidden(cfg, w, inp) @ lm_head_weight(cfg, w.head, w.embed).t()
+    assert (got - want.reshape(-1, 320)).abs().max() < 3e-4
+    assert hf_config_dict(cfg)["model_type"] == "mixtral" and hf_config_dict(cfg)["num_local_experts"] == 4
+    # released-checkpoint naming on disk
+    legacy = {}
+    for k, v in m.state_dict().items():
+        if ".mlp.experts.gate_up_proj" in k:
+            pre = k.replace("mlp.experts.gate_up_proj", "block_sparse_moe.experts.")
+            for e in range(4):
+                legacy[f"{pre}{e}.w1.weight"], legacy[f"{pre}{e}.w3.weight"] = v[e, :128].clone(), v[e, 128:].clone()
+        elif ".mlp.experts.down_proj" in k:
+            pre = k.replace("mlp.experts.down_proj", "block_sparse_moe.experts.")
+            for e in range(4):
+                legacy[f"{pre}{e}.w2.weight"] = v[e].clone()
+        elif ".mlp.gate.weight" in k:
+            legacy[k.replace("mlp.gate.weight", "block_sparse_moe.gate.weight")] = v.clone()
+        else:
+            legacy[k] = v.clone()
+    d = tmp_path / "mixtral"
+    d.mkdir()
+    save_file(legacy, str(d / "model.safetensors"))
+    (d / "config.json").write_text(__import__("json").dumps(hc.to_dict()))
+    back = load_state_dict(cfg, d)
+    assert all(torch.equal(back[k], sd[k]) for k in sd)
