@@ -25,6 +25,10 @@ class ModelConfig:
     max_position_embeddings: int = 8192
     rope_theta: float = 10000.0
     rms_norm_eps: float = 1e-6
+    # long-context rotary scaling (HF rope_scaling / rope_parameters): {"rope_type": "llama3" | "linear" | "yarn", "factor": f,
+    # "original_max_position_embeddings": n, "low_freq_factor", "high_freq_factor" (llama3), "beta_fast", "beta_slow", "mscale",
+    # "attention_factor" (yarn)}; None / "default" = plain RoPE.  Applied once when the cos / sin tables are built.
+    rope_scaling: dict | None = None
     qkv_bias: bool = False           # Qwen2
     qk_norm: bool = False            # Qwen3: per-head RMSNorm on q and k (weights [head_dim]) before RoPE
     tie_word_embeddings: bool = False
@@ -197,13 +201,26 @@ class ModelConfig:
                    num_heads=hf["num_attention_heads"], num_kv_heads=hf.get("num_key_value_heads", hf["num_attention_heads"]),
                    head_dim=hf.get("head_dim") or 0, max_position_embeddings=hf.get("max_position_embeddings", 8192),
                    rope_theta=(hf.get("rope_theta") or (hf.get("rope_parameters") or hf.get("rope_scaling") or {}).get("rope_theta") or 10000.0),
-                   rms_norm_eps=hf.get("rms_norm_eps", 1e-6),
+                   rope_scaling=_rope_scaling_of(hf), rms_norm_eps=hf.get("rms_norm_eps", 1e-6),
                    qkv_bias=(mt == "qwen2") or hf.get("attention_bias", False), qk_norm=(mt == "qwen3"),
                    tie_word_embeddings=hf.get("tie_word_embeddings", False), eos_token_id=eos, extra_eos_token_ids=extra_eos,
                    bos_token_id=hf.get("bos_token_id") or eos, pad_token_id=hf.get("pad_token_id") or eos,
                    sliding_window=(hf.get("sliding_window") if (mt in ("mistral", "mixtral") or hf.get("use_sliding_window")) else None),
                    hf_model_type=mt if mt in ("mistral", "mixtral") else "",
                    name=hf.get("_name_or_path", mt), **vis_kw, **{**moe_kw, **vl_moe_kw})
+
+
+def _rope_scaling_of(hf: dict) -> dict | None:
+    rp = dict(hf.get("rope_scaling") or hf.get("rope_parameters") or {})
+    kind = rp.get("rope_type") or rp.get("type") or "default"
+    if kind in ("default", "mrope") or not rp:
+        return None
+    keep = ("factor", "original_max_position_embeddings", "low_freq_factor", "high_freq_factor", "beta_fast", "beta_slow", "mscale",
+            "mscale_all_dim", "attention_factor", "truncate")
+    out = {"rope_type": kind, **{k: rp[k] for k in keep if rp.get(k) is not None}}
+    if "original_max_position_embeddings" not in out and hf.get("original_max_position_embeddings"):
+        out["original_max_position_embeddings"] = hf["original_max_position_embeddings"]
+    return out
 
 
 PRESETS: dict[str, dict] = {

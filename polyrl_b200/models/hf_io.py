@@ -264,6 +264,7 @@ def hf_config_dict(cfg: ModelConfig) -> dict:
             "intermediate_size": cfg.intermediate_size, "num_hidden_layers": cfg.num_layers, "num_attention_heads": cfg.num_heads,
             "num_key_value_heads": cfg.num_kv_heads, "head_dim": cfg.head_dim, "max_position_embeddings": cfg.max_position_embeddings,
             "rope_theta": cfg.rope_theta, "rms_norm_eps": cfg.rms_norm_eps, "tie_word_embeddings": cfg.tie_word_embeddings,
+            **({"rope_scaling": dict(cfg.rope_scaling)} if cfg.rope_scaling else {}),
             "attention_bias": bool(cfg.qkv_bias and mt == "llama"), "hidden_act": "silu", "torch_dtype": "bfloat16",
             "eos_token_id": cfg.eos_token_id, "bos_token_id": cfg.bos_token_id, "pad_token_id": cfg.pad_token_id}
 

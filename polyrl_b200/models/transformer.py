@@ -97,10 +97,64 @@ def init_param_(name: str, t: torch.Tensor, cfg: ModelConfig, generator: torch.G
 _ROPE_CACHE: dict = {}
 
 
+def scaled_inv_freq(cfg: ModelConfig) -> tuple[torch.Tensor, float]:
+    """(inverse frequencies [head_dim / 2], attention factor) under ``cfg.rope_scaling`` — the long-context schemes HF checkpoints
+    declare (transformers ``modeling_rope_utils``: linear, llama3, yarn).  The factor multiplies cos and sin (YaRN's temperature)."""
+    import math
+
+    d, base = cfg.head_dim, float(cfg.rope_theta)
+    inv = 1.0 / (base ** (torch.arange(0, d, 2, dtype=torch.float32) / d))
+    rs = cfg.rope_scaling
+    if not rs or rs.get("rope_type", "default") == "default":
+        return inv, 1.0
+    kind, factor = rs["rope_type"], float(rs.get("factor", 1.0))
+    if kind == "linear":
+        return inv / factor, 1.0
+    orig = float(rs.get("original_max_position_embeddings") or cfg.max_position_embeddings)
+    if kind == "llama3":
+        lo_f, hi_f = float(rs.get("low_freq_factor", 1.0)), float(rs.get("high_freq_factor", 4.0))
+        wavelen = 2 * math.pi / inv
+        smooth = ((orig / wavelen - lo_f) / (hi_f - lo_f)).clamp(0.0, 1.0)
+        scaled = torch.where(wavelen > orig / lo_f, inv / factor, inv)                       # long wavelengths: fully interpolated
+        mid = (wavelen <= orig / lo_f) & (wavelen >= orig / hi_f)
+        return torch.where(mid, (1 - smooth) * inv / factor + smooth * inv, scaled), 1.0
+    if kind == "yarn":
+        beta_fast, beta_slow = float(rs.get("beta_fast", 32.0)), float(rs.get("beta_slow", 1.0))
+
+        def corr_dim(rot: float) -> float:
+            return d * math.log(orig / (rot * 2 * math.pi)) / (2 * math.log(base))
+
+        low, high = corr_dim(beta_fast), corr_dim(beta_slow)
+        if rs.get("truncate", True):
+            low, high = math.floor(low), math.ceil(high)
+        low, high = max(low, 0), min(high, d - 1)
+        if low == high:
+            high += 0.001
+        ramp = ((torch.arange(d // 2, dtype=torch.float32) - low) / (high - low)).clamp(0.0, 1.0)
+        extrap_w = 1.0 - ramp
+        inv_s = (inv / factor) * (1 - extrap_w) + inv * extrap_w
+
+        def mscale(scale: float, m: float = 1.0) -> float:
+            return 1.0 if scale <= 1 else 0.1 * m * math.log(scale) + 1.0
+
+        af = rs.get("attention_factor")
+        if af is None:
+            ms, msa = rs.get("mscale"), rs.get("mscale_all_dim")
+            af = mscale(factor, ms) / mscale(factor, msa) if (ms and msa) else mscale(factor)
+        return inv_s, float(af)
+    raise NotImplementedError(f"rope scaling type {kind!r} (supported: linear, llama3, yarn)")
+
+
 def rope_tables(cfg: ModelConfig, device) -> tuple[torch.Tensor, torch.Tensor]:
-    key = (cfg.head_dim, cfg.rope_theta, cfg.max_position_embeddings, str(device))
+    rs_key = tuple(sorted((k, str(v)) for k, v in (cfg.rope_scaling or {}).items()))
+    key = (cfg.head_dim, cfg.rope_theta, cfg.max_position_embeddings, str(device), rs_key)
     if key not in _ROPE_CACHE:
-        _ROPE_CACHE[key] = ref.rope_tables(cfg.max_position_embeddings, cfg.head_dim, cfg.rope_theta, device=device)
+        if not cfg.rope_scaling:
+            _ROPE_CACHE[key] = ref.rope_tables(cfg.max_position_embeddings, cfg.head_dim, cfg.rope_theta, device=device)
+        else:
+            inv, af = scaled_inv_freq(cfg)
+            fr = torch.outer(torch.arange(cfg.max_position_embeddings, dtype=torch.float32), inv).to(device)
+            _ROPE_CACHE[key] = ((fr.cos() * af).contiguous(), (fr.sin() * af).contiguous())
     return _ROPE_CACHE[key]
 
 

@@ -186,3 +186,35 @@ def test_critic_loads_backbone_from_hf_dir_and_keeps_value_head(tmp_path):
     want = tf.convert_hf_state_dict(cw.model_cfg, m.state_dict())
     assert torch.allclose(got["layers.1.wd"].float(), want["layers.1.wd"].float(), atol=1e-6) and "v_head" in got and "lm_head" not in got
     assert got["v_head"][0].abs().sum() > 0
+
+
+@pytest.mark.parametrize("scaling", [
+    dict(rope_type="llama3", factor=8.0, low_freq_factor=1.0, high_freq_factor=4.0, original_max_position_embeddings=64),
+    dict(rope_type="linear", factor=4.0),
+    dict(rope_type="yarn", factor=4.0, original_max_position_embeddings=64),
+])
+def test_long_context_rope_scaling_matches_hf(scaling):
+    """Llama-3.1-style / linear / YaRN rotary scaling declared in the HF config: logits equal HF on sequences longer than the
+    original context, and the exported config carries the scaling back."""
+    torch.manual_seed(0)
+    hc = transformers.LlamaConfig(vocab_size=320, hidden_size=128, intermediate_size=256, num_hidden_layers=2, num_attention_heads=4,
+                                  num_key_value_heads=2, max_position_embeddings=256, rms_norm_eps=1e-5, tie_word_embeddings=False,
+                                  rope_parameters={**scaling, "rope_theta": 10000.0})
+    m = transformers.LlamaForCausalLM(hc).eval().float()
+    cfg = ModelConfig.from_hf_config(m.config.to_dict())
+    assert cfg.rope_scaling["rope_type"] == scaling["rope_type"]
+    w = TransformerWeights(cfg, "cpu", torch.float32, init=False)
+    w.load_state_dict(tf.convert_hf_state_dict(cfg, m.state_dict()))
+    ids = torch.randint(0, 320, (2, 150))
+    with torch.no_grad():
+        want = m(ids).logits
+        inp, _ = pack_padded(ids, torch.ones_like(ids))
+        got = forward_hidden(cfg, w, inp) @ lm_head_weight(cfg, w.head, w.embed).t()
+    assert (got - want.reshape(-1, 320)).abs().max().item() < 3e-4
+    plain = ModelConfig.from_hf_config({**m.config.to_dict(), "rope_parameters": {"rope_type": "default", "rope_theta": 10000.0}})
+    with torch.no_grad():
+        off = forward_hidden(plain, w, inp) @ lm_head_weight(cfg, w.head, w.embed).t()
+    assert (off - want.reshape(-1, 320)).abs().max().item() > 1e-3            # the scaling really matters at these lengths
+    from polyrl_b200.models.hf_io import hf_config_dict
+
+    assert ModelConfig.from_hf_config(hf_config_dict(cfg)).rope_scaling == cfg.rope_scaling
