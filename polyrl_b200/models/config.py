@@ -29,6 +29,12 @@ class ModelConfig:
     # "original_max_position_embeddings": n, "low_freq_factor", "high_freq_factor" (llama3), "beta_fast", "beta_slow", "mscale",
     # "attention_factor" (yarn)}; None / "default" = plain RoPE.  Applied once when the cos / sin tables are built.
     rope_scaling: dict | None = None
+    # GLM family: only the first ``partial_rotary_factor * head_dim`` features of a head rotate; ``rope_interleaved`` says the HF
+    # checkpoint pairs features (2j, 2j+1) — the converters permute the q / k rows so that OUR weights always pair (j, j + d/2) and
+    # non-rotating features sit on table entries with cos = 1, sin = 0: the rope / attention kernels stay untouched.
+    partial_rotary_factor: float = 1.0
+    rope_interleaved: bool = False
+    sandwich_norm: bool = False      # GLM-4: extra RMSNorm on the attention output and on the MLP output, before the residual adds
     qkv_bias: bool = False           # Qwen2
     qk_norm: bool = False            # Qwen3: per-head RMSNorm on q and k (weights [head_dim]) before RoPE
     tie_word_embeddings: bool = False
@@ -96,6 +102,8 @@ class ModelConfig:
                 per += 2 * self.head_dim
             if self.qkv_bias:
                 per += self.q_size + 2 * self.kv_size
+            if self.sandwich_norm:
+                per += 2 * h
         else:
             per = 4 * h * h + 2 * h * f + 9 * h + f + 4 * h
         emb = v * h * (1 if self.tie_word_embeddings else 2)
@@ -182,6 +190,11 @@ class ModelConfig:
                 vision_end_token_id=top.get("vision_end_token_id", -1))
             hf["tie_word_embeddings"] = top.get("tie_word_embeddings", hf.get("tie_word_embeddings", False))
             mt = "qwen2"
+        glm_kw: dict = {}
+        if mt in ("glm", "glm4"):            # partial interleaved rotary, fused gate_up projection; GLM-4 adds the sandwich norms
+            rp = hf.get("rope_parameters") or hf.get("rope_scaling") or {}
+            glm_kw = dict(partial_rotary_factor=float(rp.get("partial_rotary_factor") or hf.get("partial_rotary_factor") or 0.5),
+                          rope_interleaved=True, sandwich_norm=(mt == "glm4"))
         moe_kw: dict = {}
         if mt == "mixtral":                  # llama attention + top-k of num_local_experts SwiGLU experts of width intermediate_size
             moe_kw = dict(num_experts=hf["num_local_experts"], num_experts_per_tok=hf["num_experts_per_tok"],
@@ -206,8 +219,8 @@ class ModelConfig:
                    tie_word_embeddings=hf.get("tie_word_embeddings", False), eos_token_id=eos, extra_eos_token_ids=extra_eos,
                    bos_token_id=hf.get("bos_token_id") or eos, pad_token_id=hf.get("pad_token_id") or eos,
                    sliding_window=(hf.get("sliding_window") if (mt in ("mistral", "mixtral") or hf.get("use_sliding_window")) else None),
-                   hf_model_type=mt if mt in ("mistral", "mixtral") else "",
-                   name=hf.get("_name_or_path", mt), **vis_kw, **{**moe_kw, **vl_moe_kw})
+                   hf_model_type=mt if mt in ("mistral", "mixtral", "glm", "glm4") else "",
+                   name=hf.get("_name_or_path", mt), **vis_kw, **{**moe_kw, **vl_moe_kw}, **glm_kw)
 
 
 def _rope_scaling_of(hf: dict) -> dict | None:
@@ -255,6 +268,18 @@ PRESETS: dict[str, dict] = {
     "tiny-qwen3": dict(family="llama", vocab_size=512, hidden_size=256, intermediate_size=512, num_layers=2, num_heads=4,
                        num_kv_heads=2, head_dim=64, max_position_embeddings=512, rope_theta=1000000.0, rms_norm_eps=1e-6,
                        qk_norm=True, tie_word_embeddings=True, eos_token_id=1, bos_token_id=2, pad_token_id=0),
+    "tiny-glm4": dict(family="llama", vocab_size=512, hidden_size=256, intermediate_size=512, num_layers=2, num_heads=4, num_kv_heads=2,
+                      head_dim=64, max_position_embeddings=512, rope_theta=10000.0, rms_norm_eps=1e-5, qkv_bias=True,
+                      partial_rotary_factor=0.5, rope_interleaved=True, sandwich_norm=True, hf_model_type="glm4",
+                      eos_token_id=1, bos_token_id=2, pad_token_id=0),
+    "glm-4-9b": dict(family="llama", vocab_size=151552, hidden_size=4096, intermediate_size=13696, num_layers=40, num_heads=32,
+                     num_kv_heads=2, head_dim=128, max_position_embeddings=131072, rope_theta=10000.0, rms_norm_eps=1.5625e-07,
+                     qkv_bias=True, partial_rotary_factor=0.5, rope_interleaved=True, hf_model_type="glm",
+                     eos_token_id=151329, extra_eos_token_ids=(151336, 151338), bos_token_id=151329, pad_token_id=151329),
+    "glm-4-9b-0414": dict(family="llama", vocab_size=151552, hidden_size=4096, intermediate_size=13696, num_layers=40, num_heads=32,
+                          num_kv_heads=2, head_dim=128, max_position_embeddings=32768, rope_theta=10000.0, rms_norm_eps=1e-5,
+                          qkv_bias=True, partial_rotary_factor=0.5, rope_interleaved=True, sandwich_norm=True, hf_model_type="glm4",
+                          eos_token_id=151329, extra_eos_token_ids=(151336, 151338), bos_token_id=151329, pad_token_id=151329),
     "qwen2-vl-7b": dict(family="llama", vocab_size=152064, hidden_size=3584, intermediate_size=18944, num_layers=28,
                         num_heads=28, num_kv_heads=4, max_position_embeddings=32768, rope_theta=1000000.0,
                         rms_norm_eps=1e-6, qkv_bias=True, eos_token_id=151645, bos_token_id=151643, pad_token_id=151643,

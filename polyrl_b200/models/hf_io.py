@@ -84,8 +84,12 @@ def _layer_keys(cfg: ModelConfig, i: int) -> list[str]:
     keys = [p + "input_layernorm.weight", p + "post_attention_layernorm.weight", p + "self_attn.o_proj.weight"]
     if cfg.num_experts:
         keys += [p + "mlp.gate.weight", p + "mlp.experts.gate_up_proj", p + "mlp.experts.down_proj"]
+    elif getattr(cfg, "hf_model_type", "") in ("glm", "glm4", "glm4v"):
+        keys += [p + "mlp.gate_up_proj.weight", p + "mlp.down_proj.weight"]
     else:
         keys += [p + "mlp.gate_proj.weight", p + "mlp.up_proj.weight", p + "mlp.down_proj.weight"]
+    if cfg.sandwich_norm:
+        keys += [p + "post_self_attn_layernorm.weight", p + "post_mlp_layernorm.weight"]
     keys += [p + f"self_attn.{n}_proj.weight" for n in "qkv"]
     if cfg.qkv_bias:
         keys += [p + f"self_attn.{n}_proj.bias" for n in "qkv"]
@@ -256,6 +260,17 @@ def hf_config_dict(cfg: ModelConfig) -> dict:
                 "num_local_experts": cfg.num_experts, "num_experts_per_tok": cfg.num_experts_per_tok, "sliding_window": cfg.sliding_window,
                 "hidden_act": "silu", "torch_dtype": "bfloat16", "eos_token_id": cfg.eos_token_id, "bos_token_id": cfg.bos_token_id,
                 "pad_token_id": cfg.pad_token_id}
+    if getattr(cfg, "hf_model_type", "") in ("glm", "glm4"):
+        gmt = cfg.hf_model_type
+        return {"model_type": gmt, "architectures": ["GlmForCausalLM" if gmt == "glm" else "Glm4ForCausalLM"], "vocab_size": cfg.vocab_size,
+                "hidden_size": cfg.hidden_size, "intermediate_size": cfg.intermediate_size, "num_hidden_layers": cfg.num_layers,
+                "num_attention_heads": cfg.num_heads, "num_key_value_heads": cfg.num_kv_heads, "head_dim": cfg.head_dim,
+                "max_position_embeddings": cfg.max_position_embeddings, "rms_norm_eps": cfg.rms_norm_eps, "attention_bias": bool(cfg.qkv_bias),
+                "partial_rotary_factor": cfg.partial_rotary_factor, "rope_theta": cfg.rope_theta,
+                "rope_parameters": {"rope_type": "default", "rope_theta": cfg.rope_theta, "partial_rotary_factor": cfg.partial_rotary_factor},
+                "tie_word_embeddings": cfg.tie_word_embeddings, "hidden_act": "silu", "torch_dtype": "bfloat16",
+                "eos_token_id": [cfg.eos_token_id, *cfg.extra_eos_token_ids] if cfg.extra_eos_token_ids else cfg.eos_token_id,
+                "bos_token_id": cfg.bos_token_id, "pad_token_id": cfg.pad_token_id}
     if cfg.num_experts:
         mt, arch = "qwen3_moe", "Qwen3MoeForCausalLM"
         moe = {**moe, "num_experts": cfg.num_experts, "num_experts_per_tok": cfg.num_experts_per_tok, "moe_intermediate_size": cfg.moe_intermediate_size,

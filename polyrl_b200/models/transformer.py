@@ -39,6 +39,8 @@ def layer_param_specs(cfg: ModelConfig) -> ParamSpec:
         if cfg.qk_norm:
             specs += [("q_norm", (cfg.head_dim,)), ("k_norm", (cfg.head_dim,))]
         specs += [("wo", (h, cfg.q_size)), ("ln2", (h,))]
+        if cfg.sandwich_norm:
+            specs += [("ln_attn", (h,)), ("ln_mlp", (h,))]
         if cfg.num_experts:            # router + stacked experts (gate/up rows interleaved per expert like the dense ``wgu``)
             fm = cfg.moe_intermediate_size
             specs += [("router", (cfg.num_experts, h)), ("ewgu", (cfg.num_experts, 2 * fm, h)), ("ewd", (cfg.num_experts, h, fm))]
@@ -78,7 +80,7 @@ def init_param_(name: str, t: torch.Tensor, cfg: ModelConfig, generator: torch.G
             bound = 1.0 / math.sqrt(t.shape[-1])
             t.uniform_(-bound, bound, generator=generator)
         return
-    if base in ("ln1", "ln2", "norm_w", "ln1_w", "ln2_w", "q_norm", "k_norm", "merger_ln_w"):
+    if base in ("ln1", "ln2", "ln_attn", "ln_mlp", "norm_w", "ln1_w", "ln2_w", "q_norm", "k_norm", "merger_ln_w"):
         t.fill_(1.0)
     elif base.startswith("b") or base.endswith("_b") or base.startswith("merger_b"):
         t.zero_()
@@ -97,12 +99,40 @@ def init_param_(name: str, t: torch.Tensor, cfg: ModelConfig, generator: torch.G
 _ROPE_CACHE: dict = {}
 
 
+def rotary_dim(cfg: ModelConfig) -> int:
+    """Features of a head that rotate (``partial_rotary_factor``; the rest passes through unchanged)."""
+    return int(cfg.head_dim * cfg.partial_rotary_factor) if cfg.partial_rotary_factor < 1.0 else cfg.head_dim
+
+
+def rope_feature_perm(cfg: ModelConfig) -> torch.Tensor | None:
+    """perm [head_dim] with ours[j] = checkpoint[perm[j]] inside every q / k head, or None when the layouts agree.  Our kernels
+    rotate the pair (j, j + d/2) with table column j.  A checkpoint that pairs (2j, 2j+1) (``rope_interleaved``) or rotates only its
+    first r features gets its rotating pairs moved to columns j < r/2 and the pass-through features to the columns whose table
+    entries are cos = 1, sin = 0.  q . k is invariant under a common permutation of the head features, so attention is unchanged."""
+    d, r = cfg.head_dim, rotary_dim(cfg)
+    if not cfg.rope_interleaved and r == d:
+        return None
+    perm = torch.empty(d, dtype=torch.long)
+    j = torch.arange(r // 2)
+    first, second = (2 * j, 2 * j + 1) if cfg.rope_interleaved else (j, j + r // 2)
+    perm[: r // 2], perm[d // 2: d // 2 + r // 2] = first, second
+    rest = torch.arange(r, d)
+    perm[r // 2: d // 2], perm[d // 2 + r // 2:] = rest[: (d - r) // 2], rest[(d - r) // 2:]
+    return perm
+
+
+def _permute_heads(t: torch.Tensor, perm: torch.Tensor, d: int, inverse: bool = False) -> torch.Tensor:
+    """Apply ``perm`` to the feature index inside every head of a [n_heads * d, ...] projection weight or bias."""
+    idx = torch.argsort(perm) if inverse else perm
+    return t.reshape(-1, d, *t.shape[1:])[:, idx.to(t.device)].reshape(t.shape)
+
+
 def scaled_inv_freq(cfg: ModelConfig) -> tuple[torch.Tensor, float]:
     """(inverse frequencies [head_dim / 2], attention factor) under ``cfg.rope_scaling`` — the long-context schemes HF checkpoints
     declare (transformers ``modeling_rope_utils``: linear, llama3, yarn).  The factor multiplies cos and sin (YaRN's temperature)."""
     import math
 
-    d, base = cfg.head_dim, float(cfg.rope_theta)
+    d, base = rotary_dim(cfg), float(cfg.rope_theta)
     inv = 1.0 / (base ** (torch.arange(0, d, 2, dtype=torch.float32) / d))
     rs = cfg.rope_scaling
     if not rs or rs.get("rope_type", "default") == "default":
@@ -147,14 +177,18 @@ def scaled_inv_freq(cfg: ModelConfig) -> tuple[torch.Tensor, float]:
 
 def rope_tables(cfg: ModelConfig, device) -> tuple[torch.Tensor, torch.Tensor]:
     rs_key = tuple(sorted((k, str(v)) for k, v in (cfg.rope_scaling or {}).items()))
-    key = (cfg.head_dim, cfg.rope_theta, cfg.max_position_embeddings, str(device), rs_key)
+    key = (cfg.head_dim, cfg.rope_theta, cfg.max_position_embeddings, str(device), rs_key, rotary_dim(cfg))
     if key not in _ROPE_CACHE:
-        if not cfg.rope_scaling:
+        if not cfg.rope_scaling and rotary_dim(cfg) == cfg.head_dim:
             _ROPE_CACHE[key] = ref.rope_tables(cfg.max_position_embeddings, cfg.head_dim, cfg.rope_theta, device=device)
         else:
             inv, af = scaled_inv_freq(cfg)
-            fr = torch.outer(torch.arange(cfg.max_position_embeddings, dtype=torch.float32), inv).to(device)
-            _ROPE_CACHE[key] = ((fr.cos() * af).contiguous(), (fr.sin() * af).contiguous())
+            fr = torch.outer(torch.arange(cfg.max_position_embeddings, dtype=torch.float32), inv)
+            cos, sin = fr.cos() * af, fr.sin() * af
+            pad = cfg.head_dim // 2 - cos.shape[1]           # pass-through features: identity rotation
+            if pad:
+                cos, sin = F.pad(cos, (0, pad), value=1.0), F.pad(sin, (0, pad), value=0.0)
+            _ROPE_CACHE[key] = (cos.to(device).contiguous(), sin.to(device).contiguous())
     return _ROPE_CACHE[key]
 
 
@@ -329,18 +363,30 @@ def layer_forward(cfg: ModelConfig, w: dict, x: torch.Tensor, inp: PackedInput, 
         else:
             a = attention_varlen(q, k, v, inp.cu_seqlens, inp.max_seqlen, causal=True)
         a = a.reshape(t, nq * d)
-        x = ops.linear(a, w["wo"], residual=x)
-        if lora and L.has_lora(w, "o_proj"):
-            x = x + L.single_delta(w, a, "o_proj")
+        if cfg.sandwich_norm:
+            o = ops.linear(a, w["wo"])
+            if lora and L.has_lora(w, "o_proj"):
+                o = o + L.single_delta(w, a, "o_proj")
+            x = x + ops.rmsnorm(o, w["ln_attn"], cfg.rms_norm_eps)
+        else:
+            x = ops.linear(a, w["wo"], residual=x)
+            if lora and L.has_lora(w, "o_proj"):
+                x = x + L.single_delta(w, a, "o_proj")
         if w.get("_skip_mlp"):              # callers that supply their own MLP (expert parallelism, parallel/expert.py)
             return x
         h = ops.rmsnorm(x, w["ln2"], cfg.rms_norm_eps)
         if "router" in w:
-            return x + moe_mlp(cfg, w, h, aux_out)
+            y = moe_mlp(cfg, w, h, aux_out)
+            return x + (ops.rmsnorm(y, w["ln_mlp"], cfg.rms_norm_eps) if cfg.sandwich_norm else y)
         if lora and L.has_lora(w, "gate_proj", "up_proj"):
             a = ref.swiglu(ops.linear(h, w["wgu"]) + L.gate_up_delta(cfg, w, h))    # adapters act before the activation
         else:
             a = ops.linear_swiglu(h, w["wgu"])
+        if cfg.sandwich_norm:
+            y = ops.linear(a, w["wd"])
+            if lora and L.has_lora(w, "down_proj"):
+                y = y + L.single_delta(w, a, "down_proj")
+            return x + ops.rmsnorm(y, w["ln_mlp"], cfg.rms_norm_eps)
         y = ops.linear(a, w["wd"], residual=x)
         if lora and L.has_lora(w, "down_proj"):
             y = y + L.single_delta(w, a, "down_proj")
@@ -407,11 +453,17 @@ def layer_decode(cfg: ModelConfig, w: dict, x: torch.Tensor, inp: DecodeInput, k
                         k_cache.shape[2])
         a = ops.paged_decode_attention(qkv[:, : nq * d], k_cache, v_cache, inp.block_table, inp.seq_lens, nq, nkv, d,
                                        scale, max_len=inp.max_len)
-        x = ops.linear(a, w["wo"], residual=x)
+        if cfg.sandwich_norm:
+            x = x + ops.rmsnorm(ops.linear(a, w["wo"]), w["ln_attn"], cfg.rms_norm_eps)
+        else:
+            x = ops.linear(a, w["wo"], residual=x)
         h = ops.rmsnorm(x, w["ln2"], cfg.rms_norm_eps)
         if "router" in w:
-            return x + (moe_mlp_static(cfg, w, h) if _MOE_STATIC_DECODE() else moe_mlp(cfg, w, h))
+            y = moe_mlp_static(cfg, w, h) if _MOE_STATIC_DECODE() else moe_mlp(cfg, w, h)
+            return x + (ops.rmsnorm(y, w["ln_mlp"], cfg.rms_norm_eps) if cfg.sandwich_norm else y)
         a = ops.linear_swiglu(h, w["wgu"])
+        if cfg.sandwich_norm:
+            return x + ops.rmsnorm(ops.linear(a, w["wd"]), w["ln_mlp"], cfg.rms_norm_eps)
         return ops.linear(a, w["wd"], residual=x)
     h = F.layer_norm(x, (cfg.hidden_size,), w["ln1_w"], w["ln1_b"], cfg.rms_norm_eps)
     qkv = F.linear(h, w["wqkv"], w["bqkv"])
@@ -553,11 +605,16 @@ def convert_hf_state_dict(cfg: ModelConfig, hf_sd: dict[str, torch.Tensor]) -> d
         p = f"model.layers.{i}."
         out[f"layers.{i}.ln1"] = hf_sd[p + "input_layernorm.weight"]
         out[f"layers.{i}.ln2"] = hf_sd[p + "post_attention_layernorm.weight"]
-        out[f"layers.{i}.wqkv"] = torch.cat([hf_sd[p + f"self_attn.{n}_proj.weight"] for n in "qkv"], dim=0)
+        perm = rope_feature_perm(cfg)
+        fix = (lambda t, n: _permute_heads(t, perm, cfg.head_dim) if (perm is not None and n in "qk") else t)
+        out[f"layers.{i}.wqkv"] = torch.cat([fix(hf_sd[p + f"self_attn.{n}_proj.weight"], n) for n in "qkv"], dim=0)
         if cfg.qkv_bias:
-            out[f"layers.{i}.bqkv"] = torch.cat([hf_sd[p + f"self_attn.{n}_proj.bias"] for n in "qkv"], dim=0)
+            out[f"layers.{i}.bqkv"] = torch.cat([fix(hf_sd[p + f"self_attn.{n}_proj.bias"], n) for n in "qkv"], dim=0)
         if cfg.qk_norm:
-            out[f"layers.{i}.q_norm"], out[f"layers.{i}.k_norm"] = hf_sd[p + "self_attn.q_norm.weight"], hf_sd[p + "self_attn.k_norm.weight"]
+            qn, kn = hf_sd[p + "self_attn.q_norm.weight"], hf_sd[p + "self_attn.k_norm.weight"]
+            out[f"layers.{i}.q_norm"], out[f"layers.{i}.k_norm"] = (qn, kn) if perm is None else (qn[perm], kn[perm])
+        if cfg.sandwich_norm:
+            out[f"layers.{i}.ln_attn"], out[f"layers.{i}.ln_mlp"] = hf_sd[p + "post_self_attn_layernorm.weight"], hf_sd[p + "post_mlp_layernorm.weight"]
         out[f"layers.{i}.wo"] = hf_sd[p + "self_attn.o_proj.weight"]
         if cfg.num_experts:
             fm = cfg.moe_intermediate_size
@@ -578,7 +635,11 @@ def convert_hf_state_dict(cfg: ModelConfig, hf_sd: dict[str, torch.Tensor]) -> d
                 out[f"layers.{i}.ewd"] = torch.stack([hf_sd[f"{p}mlp.experts.{e}.down_proj.weight"] for e in range(cfg.num_experts)])
             out[f"layers.{i}.ewgu"] = torch.stack([ref.interleave_gate_up(g, u) for g, u in pairs])
             continue
-        out[f"layers.{i}.wgu"] = ref.interleave_gate_up(hf_sd[p + "mlp.gate_proj.weight"], hf_sd[p + "mlp.up_proj.weight"])
+        if p + "mlp.gate_up_proj.weight" in hf_sd:               # GLM: one fused projection, gate rows then up rows
+            gu = hf_sd[p + "mlp.gate_up_proj.weight"]
+            out[f"layers.{i}.wgu"] = ref.interleave_gate_up(gu[: gu.shape[0] // 2], gu[gu.shape[0] // 2:])
+        else:
+            out[f"layers.{i}.wgu"] = ref.interleave_gate_up(hf_sd[p + "mlp.gate_proj.weight"], hf_sd[p + "mlp.up_proj.weight"])
         out[f"layers.{i}.wd"] = hf_sd[p + "mlp.down_proj.weight"]
     return out
 
@@ -599,17 +660,22 @@ def export_hf_state_dict(cfg: ModelConfig, sd: dict[str, torch.Tensor]) -> dict[
     out = {"model.embed_tokens.weight": sd["embed"], "model.norm.weight": sd["norm_w"]}
     out["lm_head.weight"] = sd["embed"] if cfg.tie_word_embeddings else sd["lm_head"]
     q, kv = cfg.q_size, cfg.kv_size
+    perm = rope_feature_perm(cfg)
+    back = (lambda t: t) if perm is None else (lambda t: _permute_heads(t, perm, cfg.head_dim, inverse=True))
+    fused_gu = getattr(cfg, "hf_model_type", "") in ("glm", "glm4", "glm4v")
     for i in range(cfg.num_layers):
         p = f"model.layers.{i}."
         w = sd[f"layers.{i}.wqkv"]
         out[p + "self_attn.q_proj.weight"], out[p + "self_attn.k_proj.weight"], out[p + "self_attn.v_proj.weight"] = (
-            w[:q], w[q:q + kv], w[q + kv:])
+            back(w[:q]), back(w[q:q + kv]), w[q + kv:])
         if cfg.qkv_bias:
             b = sd[f"layers.{i}.bqkv"]
             out[p + "self_attn.q_proj.bias"], out[p + "self_attn.k_proj.bias"], out[p + "self_attn.v_proj.bias"] = (
-                b[:q], b[q:q + kv], b[q + kv:])
+                back(b[:q]), back(b[q:q + kv]), b[q + kv:])
         if cfg.qk_norm:
-            out[p + "self_attn.q_norm.weight"], out[p + "self_attn.k_norm.weight"] = sd[f"layers.{i}.q_norm"], sd[f"layers.{i}.k_norm"]
+            out[p + "self_attn.q_norm.weight"], out[p + "self_attn.k_norm.weight"] = back(sd[f"layers.{i}.q_norm"]), back(sd[f"layers.{i}.k_norm"])
+        if cfg.sandwich_norm:
+            out[p + "post_self_attn_layernorm.weight"], out[p + "post_mlp_layernorm.weight"] = sd[f"layers.{i}.ln_attn"], sd[f"layers.{i}.ln_mlp"]
         out[p + "self_attn.o_proj.weight"] = sd[f"layers.{i}.wo"]
         if cfg.num_experts:                                      # stacked HF layout
             gus = [ref.deinterleave_gate_up(sd[f"layers.{i}.ewgu"][e]) for e in range(cfg.num_experts)]
@@ -618,7 +684,10 @@ def export_hf_state_dict(cfg: ModelConfig, sd: dict[str, torch.Tensor]) -> dict[
             out[p + "mlp.experts.down_proj"] = sd[f"layers.{i}.ewd"]
         else:
             g, u = ref.deinterleave_gate_up(sd[f"layers.{i}.wgu"])
-            out[p + "mlp.gate_proj.weight"], out[p + "mlp.up_proj.weight"] = g, u
+            if fused_gu:
+                out[p + "mlp.gate_up_proj.weight"] = torch.cat([g, u], dim=0)
+            else:
+                out[p + "mlp.gate_proj.weight"], out[p + "mlp.up_proj.weight"] = g, u
             out[p + "mlp.down_proj.weight"] = sd[f"layers.{i}.wd"]
         out[p + "input_layernorm.weight"] = sd[f"layers.{i}.ln1"]
         out[p + "post_attention_layernorm.weight"] = sd[f"layers.{i}.ln2"]

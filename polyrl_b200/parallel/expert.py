@@ -172,6 +172,8 @@ class EPTrainEngine:
                  weight_decay: float = 0.01, max_grad_norm: float = 1.0, seed: int = 0, dtype=None):
         if not cfg.num_experts:
             raise ValueError("expert parallelism needs a mixture-of-experts model")
+        if cfg.sandwich_norm:
+            raise NotImplementedError("expert parallelism for blocks with output norms (sandwich_norm)")
         self.cfg, self.device, self.group = cfg, torch.device(device), ep_group
         self.ep, self.rank = dist.get_world_size(ep_group), dist.get_rank(ep_group)
         self.e_lo, self.e_hi = local_expert_range(cfg, self.ep, self.rank)

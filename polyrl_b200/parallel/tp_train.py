@@ -130,7 +130,7 @@ def shard_layer(cfg: ModelConfig, w: dict, rank: int, tp: int) -> dict:
     d, nq, nkv = cfg.head_dim, cfg.num_heads // tp, cfg.num_kv_heads // tp
     q0, k0, v0 = rank * nq * d, cfg.q_size + rank * nkv * d, cfg.q_size + cfg.kv_size + rank * nkv * d
     out = {"ln1": w["ln1"].clone(), "ln2": w["ln2"].clone()}
-    for k in ("q_norm", "k_norm"):
+    for k in ("q_norm", "k_norm", "ln_attn", "ln_mlp"):
         if k in w:
             out[k] = w[k].clone()
     out["wqkv"] = torch.cat([w["wqkv"][q0:q0 + nq * d], w["wqkv"][k0:k0 + nkv * d], w["wqkv"][v0:v0 + nkv * d]]).contiguous()
@@ -149,6 +149,8 @@ def tp_layer_forward(lcfg: ModelConfig, w: dict, x: torch.Tensor, inp: tf.Packed
     holds this rank's T/tp token rows: norms and residual adds then run on 1/tp of the tokens, the all-reduces become an
     all-gather into / a reduce-scatter out of each GEMM region (same bytes on the wire, 1/tp of the norm/residual activations)."""
     nq, nkv, d = lcfg.num_heads, lcfg.num_kv_heads, lcfg.head_dim
+    # GLM-4: the summed projection outputs are normalised before the residual add
+    post = (lambda y, k: ops.rmsnorm(y, w[k], lcfg.rms_norm_eps)) if lcfg.sandwich_norm else (lambda y, k: y)
     if sequence_parallel:
         h = _GatherFromSP.apply(ops.rmsnorm(x, w["ln1"], lcfg.rms_norm_eps), group)
         t = h.shape[0]
@@ -157,9 +159,9 @@ def tp_layer_forward(lcfg: ModelConfig, w: dict, x: torch.Tensor, inp: tf.Packed
         qkv = ops.apply_rope(qkv, pos, cos, sin, nq, nkv, d)
         a = attention_varlen(qkv[:, : nq * d].view(t, nq, d), qkv[:, nq * d:(nq + nkv) * d].view(t, nkv, d),
                              qkv[:, (nq + nkv) * d:].view(t, nkv, d), inp.cu_seqlens, inp.max_seqlen, causal=True).reshape(t, nq * d)
-        x = x + _ScatterToSP.apply(ops.linear(a, w["wo"]), group)
+        x = x + post(_ScatterToSP.apply(ops.linear(a, w["wo"]), group), "ln_attn")
         h = _GatherFromSP.apply(ops.rmsnorm(x, w["ln2"], lcfg.rms_norm_eps), group)
-        return x + _ScatterToSP.apply(ops.linear(ops.linear_swiglu(h, w["wgu"]), w["wd"]), group)
+        return x + post(_ScatterToSP.apply(ops.linear(ops.linear_swiglu(h, w["wgu"]), w["wd"]), group), "ln_mlp")
     t = x.shape[0]
     h = _CopyToTP.apply(ops.rmsnorm(x, w["ln1"], lcfg.rms_norm_eps), group)
     qkv = tf.qk_norm_(lcfg, w, ops.linear(h, w["wqkv"], bias=w.get("bqkv")))
@@ -169,10 +171,10 @@ def tp_layer_forward(lcfg: ModelConfig, w: dict, x: torch.Tensor, inp: tf.Packed
     k = qkv[:, nq * d:(nq + nkv) * d].view(t, nkv, d)
     v = qkv[:, (nq + nkv) * d:].view(t, nkv, d)
     a = attention_varlen(q, k, v, inp.cu_seqlens, inp.max_seqlen, causal=True).reshape(t, nq * d)
-    x = x + _ReduceFromTP.apply(ops.linear(a, w["wo"]), group)
+    x = x + post(_ReduceFromTP.apply(ops.linear(a, w["wo"]), group), "ln_attn")
     h = _CopyToTP.apply(ops.rmsnorm(x, w["ln2"], lcfg.rms_norm_eps), group)
     a = ops.linear_swiglu(h, w["wgu"])
-    return x + _ReduceFromTP.apply(ops.linear(a, w["wd"]), group)
+    return x + post(_ReduceFromTP.apply(ops.linear(a, w["wd"]), group), "ln_mlp")
 
 
 class TPTrainEngine:
@@ -180,7 +182,7 @@ class TPTrainEngine:
     slices; ``step()`` averages gradients over ``dp_group``, clips by the global norm (sharded params counted once per TP
     rank, replicated params once) and applies AdamW."""
 
-    REPLICATED = ("ln1", "ln2", "embed", "norm_w", "q_norm", "k_norm")
+    REPLICATED = ("ln1", "ln2", "ln_attn", "ln_mlp", "embed", "norm_w", "q_norm", "k_norm")
 
     def __init__(self, cfg: ModelConfig, device, tp_group, dp_group=None, lr: float = 1e-6, betas=(0.9, 0.999), eps: float = 1e-8,
                  weight_decay: float = 0.01, max_grad_norm: float = 1.0, seed: int = 0, dtype=None, sequence_parallel: bool = False):
@@ -318,7 +320,7 @@ class TPTrainEngine:
         for i in range(cfg.num_layers):
             pre = f"layers.{i}."
             out[pre + "ln1"], out[pre + "ln2"] = self.master[pre + "ln1"].clone(), self.master[pre + "ln2"].clone()
-            for k in ("q_norm", "k_norm"):
+            for k in ("q_norm", "k_norm", "ln_attn", "ln_mlp"):
                 if pre + k in self.master:
                     out[pre + k] = self.master[pre + k].clone()
             qkv = gather(self.master[pre + "wqkv"])

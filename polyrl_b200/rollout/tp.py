@@ -97,7 +97,7 @@ class TPContext:
         d, nq, nkv = c.head_dim, c.num_heads // W, c.num_kv_heads // W
         q0, k0, v0 = r * nq * d, c.q_size + r * nkv * d, c.q_size + c.kv_size + r * nkv * d
         out = {"ln1": w["ln1"], "ln2": w["ln2"]}
-        for k in ("q_norm", "k_norm"):              # Qwen3 per-head gains are shared by every head: replicated
+        for k in ("q_norm", "k_norm", "ln_attn", "ln_mlp"):   # per-head gains (Qwen3) and output norms (GLM-4): replicated
             if k in w:
                 out[k] = w[k]
         out["wqkv"] = torch.cat([w["wqkv"][q0:q0 + nq * d], w["wqkv"][k0:k0 + nkv * d], w["wqkv"][v0:v0 + nkv * d]], dim=0).contiguous()
@@ -217,12 +217,21 @@ def moe_partial(tp: TPContext, cfg: ModelConfig, w: dict, h: torch.Tensor, stati
     return out
 
 
+def _row_out(tp: TPContext, lcfg: ModelConfig, w: dict, a: torch.Tensor, wname: str, norm: str, x: torch.Tensor, decode: bool) -> torch.Tensor:
+    """Row-parallel projection + residual; GLM-4 normalises the (all-reduced) projection output before the residual add."""
+    if lcfg.sandwich_norm:
+        return x + ops.rmsnorm(tp.row_parallel(a, w[wname], None, decode=decode), w[norm], lcfg.rms_norm_eps)
+    return tp.row_parallel(a, w[wname], x, decode=decode)
+
+
 def _mlp_tp(tp: TPContext, lcfg: ModelConfig, w: dict, x: torch.Tensor, decode: bool) -> torch.Tensor:
     h = ops.rmsnorm(x, w["ln2"], lcfg.rms_norm_eps)
     if "router" in w:
+        if lcfg.sandwich_norm:
+            raise NotImplementedError("mixture-of-experts blocks with output norms under tensor-parallel rollout")
         part = moe_partial(tp, tp.cfg, w, h, static=decode and x.is_cuda and tf._MOE_STATIC_DECODE())
         return allreduce_partial(tp, part.to(x.dtype), x, decode)
-    return tp.row_parallel(ops.linear_swiglu(h, w["wgu"]), w["wd"], x, decode=decode)
+    return _row_out(tp, lcfg, w, ops.linear_swiglu(h, w["wgu"]), "wd", "ln_mlp", x, decode)
 
 
 def layer_decode_tp(tp: TPContext, lcfg: ModelConfig, w: dict, x: torch.Tensor, inp: tf.DecodeInput, k_cache, v_cache) -> torch.Tensor:
@@ -233,7 +242,7 @@ def layer_decode_tp(tp: TPContext, lcfg: ModelConfig, w: dict, x: torch.Tensor, 
     rope_and_cache_(qkv, inp.position_ids, cos, sin, nq, nkv, d, k_cache, v_cache, inp.slot_mapping, k_cache.shape[2])
     a = ops.paged_decode_attention(qkv[:, : nq * d], k_cache, v_cache, inp.block_table, inp.seq_lens, nq, nkv, d, d ** -0.5,
                                    max_len=inp.max_len)
-    x = tp.row_parallel(a, w["wo"], x)
+    x = _row_out(tp, lcfg, w, a, "wo", "ln_attn", x, True)
     return _mlp_tp(tp, lcfg, w, x, decode=True)
 
 
@@ -248,5 +257,5 @@ def layer_prefill_tp(tp: TPContext, lcfg: ModelConfig, w: dict, x: torch.Tensor,
     k = qkv[:, nq * d:(nq + nkv) * d].view(t, nkv, d)
     v = qkv[:, (nq + nkv) * d:].view(t, nkv, d)
     a = attention_varlen(q, k, v, inp.cu_seqlens, inp.max_seqlen, causal=True).reshape(t, nq * d)
-    x = tp.row_parallel(a, w["wo"], x, decode=False)
+    x = _row_out(tp, lcfg, w, a, "wo", "ln_attn", x, False)
     return _mlp_tp(tp, lcfg, w, x, decode=False)

@@ -218,3 +218,49 @@ def test_long_context_rope_scaling_matches_hf(scaling):
     from polyrl_b200.models.hf_io import hf_config_dict
 
     assert ModelConfig.from_hf_config(hf_config_dict(cfg)).rope_scaling == cfg.rope_scaling
+
+
+@pytest.mark.parametrize("family", ["glm", "glm4"])
+def test_glm_families_match_hf(family, tmp_path):
+    """GLM-4-9B-style (``glm``: partial interleaved rotary, fused gate_up projection, qkv bias) and GLM-4-0414-style (``glm4``: the
+    same plus RMSNorms on the attention and MLP outputs): logits equal HF, greedy generation through the paged engine equals HF
+    generate, and an exported checkpoint loads back into HF with identical logits."""
+    from polyrl_b200.models import hf_io
+    from polyrl_b200.rollout.engine import RolloutEngine, SamplingParams
+
+    torch.manual_seed(0)
+    cls, ccls = ((transformers.GlmForCausalLM, transformers.GlmConfig) if family == "glm"
+                 else (transformers.Glm4ForCausalLM, transformers.Glm4Config))
+    hc = ccls(vocab_size=320, hidden_size=128, intermediate_size=256, num_hidden_layers=2, num_attention_heads=4, num_key_value_heads=2,
+              head_dim=32, max_position_embeddings=128, rms_norm_eps=1e-5, attention_bias=True, pad_token_id=0, eos_token_id=[1, 2],
+              tie_word_embeddings=False)
+    m = cls(hc).eval().float()
+    with torch.no_grad():                                   # norms away from their all-ones init so a missing one shows
+        for n, p_ in m.named_parameters():
+            if "layernorm" in n or n.endswith("norm.weight"):
+                p_.add_(0.1 * torch.randn_like(p_))
+    cfg = ModelConfig.from_hf_config(m.config.to_dict())
+    assert cfg.partial_rotary_factor == 0.5 and cfg.rope_interleaved and cfg.sandwich_norm == (family == "glm4")
+    w = TransformerWeights(cfg, "cpu", torch.float32, init=False)
+    w.load_state_dict(tf.convert_hf_state_dict(cfg, m.state_dict()))
+    ids = torch.randint(3, 320, (2, 40))
+    with torch.no_grad():
+        want = m(ids).logits
+        inp, _ = pack_padded(ids, torch.ones_like(ids))
+        got = forward_hidden(cfg, w, inp) @ lm_head_weight(cfg, w.head, w.embed).t()
+    assert (got - want.reshape(-1, 320)).abs().max().item() < 3e-4
+    # decode path (paged KV, per-token rope) against HF greedy generation
+    eng = RolloutEngine(cfg, "cpu", max_num_seqs=2, max_model_len=96, kv_cache_tokens=2 * 96)
+    eng.set_weights(w.embed, w.layers, w.head)
+    prompt = ids[0, :17].tolist()
+    out = eng.generate([prompt], SamplingParams(max_new_tokens=8, temperature=0.0, ignore_eos=True))[0][0]
+    with torch.no_grad():
+        hf_out = m.generate(torch.tensor([prompt]), max_new_tokens=8, do_sample=False, eos_token_id=None, pad_token_id=0)[0, 17:].tolist()
+    assert out.output_ids == hf_out
+    # export -> HF
+    sd = tf.export_hf_state_dict(cfg, w.state_dict())
+    m2 = cls(ccls(**{k: v for k, v in hf_io.hf_config_dict(cfg).items() if k not in ("architectures", "torch_dtype", "model_type")})).eval().float()
+    missing, unexpected = m2.load_state_dict(sd, strict=False)
+    assert not unexpected and all("rotary" in k for k in missing), (missing, unexpected)
+    with torch.no_grad():
+        assert (m2(ids).logits - want).abs().max().item() < 1e-5

@@ -147,6 +147,14 @@ def test_tensor_parallel_training_dp2_tp2_gloo():
     assert r.returncode == 0 and line, r.stdout[-2000:] + r.stderr[-2000:]
     vals = dict(kv.split("=") for kv in line[0].split()[1:])
     assert float(vals["lp_err"]) < 1e-3 and float(vals["gn_err"]) < 1e-4 and float(vals["w_err"]) < 2e-3
+    # GLM-4 blocks (RMSNorm on the summed projection outputs, partial rotary, qkv bias) under sequence parallelism
+    r = run_torchrun([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=4", "--master-addr", "127.0.0.1",
+                        "--master-port", "29754", str(ROOT / "tests" / "tp_train_worker.py")], capture_output=True, text=True, timeout=600,
+                       env={**env, "TP_TRAIN_SP": "1", "TP_TRAIN_MODEL": "tiny-glm4"})
+    line = [l for l in r.stdout.splitlines() if l.startswith("TP_TRAIN_RESULTS")]
+    assert r.returncode == 0 and line, r.stdout[-2000:] + r.stderr[-2000:]
+    vals = dict(kv.split("=") for kv in line[0].split()[1:])
+    assert float(vals["lp_err"]) < 1e-3 and float(vals["gn_err"]) < 1e-4 and float(vals["w_err"]) < 2e-3
 
 
 def test_one_step_off_policy_gloo_ws2(tmp_path):

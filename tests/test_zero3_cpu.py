@@ -153,3 +153,34 @@ def test_async_checkpoint_snapshot_is_isolated_from_later_updates(tmp_path):
     got = dict(eng.named_full_tensors())
     assert extra["lr_step"] == 7 and all(torch.equal(got[n], want[n]) for n in want)
     mgr.wait()
+
+
+def test_sandwich_norm_family_trains_through_the_sharded_engine():
+    """GLM-4 blocks (RMSNorm on the attention and MLP outputs, partial rotary): the engine's loss and every gradient-driven update
+    equal plain autograd over the functional model with the same weights, in every activation-checkpoint mode."""
+    from polyrl_b200.models import transformer as tf
+    from polyrl_b200.ops import reference as ref
+
+    cfg = get_model_config("tiny-glm4")
+    _, inp, labels = _data(cfg, 3)
+    eng = Zero3Engine(cfg, "cpu", lr=1e-2, weight_decay=0.0, seed=6)
+    names = [n for n, _ in eng.named_full_tensors()]
+    assert any(n.endswith("ln_attn") for n in names) and any(n.endswith("ln_mlp") for n in names)
+    w = tf.TransformerWeights(cfg, "cpu", torch.float32, init=False)
+    w.load_state_dict({n: t.clone() for n, t in eng.named_full_tensors()})
+    w.requires_grad_(True)
+    h = tf.forward_hidden(cfg, w, inp)
+    logits = h @ tf.lm_head_weight(cfg, w.head, w.embed).t()
+    lp_ref = torch.log_softmax(logits.float(), -1).gather(1, labels[:, None]).squeeze(1)
+    lp, _ = eng.forward_logprob_entropy(inp, labels, 1.0)
+    assert torch.allclose(lp, lp_ref, atol=1e-5)
+    (-lp_ref.mean()).backward()
+    (-lp.mean()).backward()
+    gn = math.sqrt(sum(float(t.grad.pow(2).sum()) for _, t in w.named_tensors() if t.grad is not None))
+    st = eng.step()
+    assert abs(st["grad_norm"] - gn) < 1e-4 * max(1.0, gn)
+    for mode in ("none", "1"):
+        e2 = Zero3Engine(cfg, "cpu", lr=1e-2, weight_decay=0.0, seed=6)
+        e2.act_ckpt = mode
+        (-e2.forward_logprob_entropy(inp, labels, 1.0)[0].mean()).backward()
+        assert abs(e2.step()["grad_norm"] - gn) < 1e-4 * max(1.0, gn)

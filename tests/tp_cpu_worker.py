@@ -114,6 +114,21 @@ def main():
         outs_m.append([(q[0].output_ids, q[0].logprobs) for q in e.generate(prompts, sp)])
     moe_tok_ok = all(a[0] == b[0] for a, b in zip(*outs_m))
     moe_lp_err = max(abs(x - y) for a, b in zip(*outs_m) for x, y in zip(a[1], b[1]))
+    # ---- GLM-4 blocks (output norms after the row-parallel all-reduces, partial rotary, qkv bias) through the TP engine
+    gcfg = get_model_config("tiny-glm4")
+    gw = TransformerWeights(gcfg, "cpu", torch.float32, seed=17)
+    for lw in gw.layers:
+        for k in ("ln_attn", "ln_mlp"):
+            lw[k].add_(0.2 * torch.randn(lw[k].shape, generator=torch.Generator().manual_seed(3)))
+    outs_g = []
+    for ctx in (TPContext(gcfg, None, rank, world, max_batch=8, group=dist.group.WORLD), None):
+        e = RolloutEngine(gcfg, "cpu", max_num_seqs=8, max_model_len=64, use_cuda_graph=False, seed=3, tp=ctx)
+        e.set_weights(gw.embed, gw.layers, gw.head)
+        outs_g.append([(q[0].output_ids, q[0].logprobs) for q in e.generate(prompts, sp)])
+    glm_tok_ok = all(a[0] == b[0] for a, b in zip(*outs_g))
+    glm_lp_err = max(abs(x - y) for a, b in zip(*outs_g) for x, y in zip(a[1], b[1]))
+    if rank == 0:
+        print(f"TP_CPU_GLM tok_ok={int(glm_tok_ok)} lp_err={glm_lp_err:.2e}", flush=True)
     if rank == 0:
         print(f"TP_CPU_MOE tok_ok={int(moe_tok_ok)} lp_err={moe_lp_err:.2e}", flush=True)
     if rank == 0:

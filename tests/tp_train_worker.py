@@ -36,7 +36,7 @@ def main():
         g = dist.new_group(list(range(t, world, tp)))
         if t == rank % tp:
             dp_group = g
-    cfg = get_model_config("tiny-llama-128" if cuda else "tiny-llama")
+    cfg = get_model_config(os.environ.get("TP_TRAIN_MODEL") or ("tiny-llama-128" if cuda else "tiny-llama"))
     dtype = torch.bfloat16 if cuda else torch.float32
     sp_mode = os.environ.get("TP_TRAIN_SP", "0") == "1"                 # Megatron sequence parallelism inside the TP group
     eng = TPTrainEngine(cfg, dev, tp_group, dp_group if dp > 1 else None, lr=1e-2, weight_decay=0.0, seed=11, dtype=dtype,
