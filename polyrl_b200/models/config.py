@@ -82,8 +82,9 @@ class ModelConfig:
         if self.vision is not None:
             if self.family != "llama":
                 raise ValueError("vision towers attach to the llama family only")
-            if not self.mrope_section or sum(self.mrope_section) != self.head_dim // 2:
-                raise ValueError("mrope_section must split head_dim / 2 rotary frequencies")
+            rot = int(self.head_dim * self.partial_rotary_factor) if self.partial_rotary_factor < 1.0 else self.head_dim
+            if not self.mrope_section or sum(self.mrope_section) != rot // 2:
+                raise ValueError("mrope_section must split the rotary_dim / 2 rotary frequencies")
 
     @property
     def q_size(self) -> int:
@@ -171,6 +172,26 @@ class ModelConfig:
                           vision_end_token_id=top.get("vision_end_token_id", -1))
             hf["tie_word_embeddings"] = top.get("tie_word_embeddings", hf.get("tie_word_embeddings", False))
             mt = "qwen3"
+        if mt == "glm4v":                    # GLM-4V tower on a GLM-4 text stack (output norms, partial interleaved rotary) with M-RoPE
+            vc = dict(hf.get("vision_config") or {})
+            top = hf
+            hf = {**{k: v for k, v in hf.items() if k not in ("text_config", "vision_config")}, **(hf.get("text_config") or {})}
+            rope = hf.get("rope_parameters") or hf.get("rope_scaling") or {}
+            hf.setdefault("rope_theta", rope.get("rope_theta", 10000.0))
+            side = int(vc.get("image_size", 336)) // int(vc["patch_size"])
+            vision = dict(arch="glm4v", depth=vc["depth"], embed_dim=vc["hidden_size"], num_heads=vc["num_heads"], patch_size=vc["patch_size"],
+                          spatial_merge_size=vc.get("spatial_merge_size", 2), temporal_patch_size=vc.get("temporal_patch_size", 2),
+                          in_channels=vc.get("in_channels", 3), intermediate_size=vc["intermediate_size"],
+                          attention_bias=bool(vc.get("attention_bias", False)), rms_norm_eps=vc.get("rms_norm_eps", 1e-5),
+                          num_position_embeddings=side * side, image_size=int(vc.get("image_size", 336)))
+            # GLM-4V wraps images in <|begin_of_image|> ... <|end_of_image|>; video frames reuse the image placeholder
+            vis_kw = dict(vision=vision, mrope_section=tuple(rope.get("mrope_section", (8, 12, 12))),
+                          image_token_id=top.get("image_token_id", -1), video_token_id=top.get("video_token_id", -1),
+                          vision_start_token_id=top.get("image_start_token_id", -1), vision_end_token_id=top.get("image_end_token_id", -1))
+            hf["tie_word_embeddings"] = top.get("tie_word_embeddings", hf.get("tie_word_embeddings", False))
+            hf.setdefault("attention_bias", True)
+            hf["_glm4v"] = True
+            mt = "glm4"
         if mt in ("qwen2_vl", "qwen2_5_vl"):
             # transformers >= 4.5x nests the text stack under text_config; older checkpoints keep it flat
             vc = dict(hf.get("vision_config") or {})
@@ -193,7 +214,8 @@ class ModelConfig:
         glm_kw: dict = {}
         if mt in ("glm", "glm4"):            # partial interleaved rotary, fused gate_up projection; GLM-4 adds the sandwich norms
             rp = hf.get("rope_parameters") or hf.get("rope_scaling") or {}
-            glm_kw = dict(partial_rotary_factor=float(rp.get("partial_rotary_factor") or hf.get("partial_rotary_factor") or 0.5),
+            default_prf = 1.0 if hf.get("_glm4v") else 0.5            # HF: Glm4vTextConfig rotates the whole head unless told otherwise
+            glm_kw = dict(partial_rotary_factor=float(rp.get("partial_rotary_factor") or hf.get("partial_rotary_factor") or default_prf),
                           rope_interleaved=True, sandwich_norm=(mt == "glm4"))
         moe_kw: dict = {}
         if mt == "mixtral":                  # llama attention + top-k of num_local_experts SwiGLU experts of width intermediate_size
@@ -219,7 +241,7 @@ class ModelConfig:
                    tie_word_embeddings=hf.get("tie_word_embeddings", False), eos_token_id=eos, extra_eos_token_ids=extra_eos,
                    bos_token_id=hf.get("bos_token_id") or eos, pad_token_id=hf.get("pad_token_id") or eos,
                    sliding_window=(hf.get("sliding_window") if (mt in ("mistral", "mixtral") or hf.get("use_sliding_window")) else None),
-                   hf_model_type=mt if mt in ("mistral", "mixtral", "glm", "glm4") else "",
+                   hf_model_type=("glm4v" if hf.get("_glm4v") else mt) if mt in ("mistral", "mixtral", "glm", "glm4") else "",
                    name=hf.get("_name_or_path", mt), **vis_kw, **{**moe_kw, **vl_moe_kw}, **glm_kw)
 
 
@@ -295,6 +317,23 @@ PRESETS: dict[str, dict] = {
                                       fullatt_block_indexes=[7, 15, 23, 31]),
                           mrope_section=(16, 24, 24), image_token_id=151655, video_token_id=151656, vision_start_token_id=151652,
                           vision_end_token_id=151653),
+    "tiny-glm4v": dict(family="llama", vocab_size=512, hidden_size=128, intermediate_size=256, num_layers=2, num_heads=4, num_kv_heads=2,
+                       head_dim=32, max_position_embeddings=512, rope_theta=10000.0, rms_norm_eps=1e-5, qkv_bias=True,
+                       partial_rotary_factor=0.5, rope_interleaved=True, sandwich_norm=True, hf_model_type="glm4v",
+                       eos_token_id=1, bos_token_id=2, pad_token_id=0,
+                       vision=dict(arch="glm4v", depth=2, embed_dim=64, num_heads=4, patch_size=4, spatial_merge_size=2, temporal_patch_size=2,
+                                   in_channels=3, intermediate_size=96, attention_bias=False, rms_norm_eps=1e-5, num_position_embeddings=36,
+                                   image_size=24),
+                       mrope_section=(2, 3, 3), image_token_id=500, video_token_id=501, vision_start_token_id=499, vision_end_token_id=498),
+    "glm-4.1v-9b": dict(family="llama", vocab_size=151552, hidden_size=4096, intermediate_size=13696, num_layers=40, num_heads=32,
+                        num_kv_heads=2, head_dim=128, max_position_embeddings=65536, rope_theta=10000.0, rms_norm_eps=1e-5, qkv_bias=True,
+                        partial_rotary_factor=0.5, rope_interleaved=True, sandwich_norm=True, hf_model_type="glm4v",
+                        eos_token_id=151329, extra_eos_token_ids=(151336, 151338, 151348), bos_token_id=151329, pad_token_id=151329,
+                        vision=dict(arch="glm4v", depth=24, embed_dim=1536, num_heads=12, patch_size=14, spatial_merge_size=2,
+                                    temporal_patch_size=2, in_channels=3, intermediate_size=13696, attention_bias=False, rms_norm_eps=1e-5,
+                                    num_position_embeddings=576, image_size=336),
+                        mrope_section=(8, 12, 12), image_token_id=151343, video_token_id=151344, vision_start_token_id=151339,
+                        vision_end_token_id=151340),
     "tiny-qwen2-vl": dict(family="llama", vocab_size=512, hidden_size=128, intermediate_size=256, num_layers=2, num_heads=4,
                           num_kv_heads=2, head_dim=32, max_position_embeddings=512, rope_theta=10000.0, rms_norm_eps=1e-6,
                           qkv_bias=True, eos_token_id=1, bos_token_id=2, pad_token_id=0,

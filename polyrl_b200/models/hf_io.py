@@ -209,6 +209,21 @@ def hf_config_dict(cfg: ModelConfig) -> dict:
                 "tie_word_embeddings": cfg.tie_word_embeddings, "eos_token_id": cfg.eos_token_id, "bos_token_id": cfg.bos_token_id,
                 "pad_token_id": cfg.pad_token_id,
                 "rope_parameters": {"rope_type": "default", "rope_theta": cfg.rope_theta, "mrope_section": list(cfg.mrope_section)}}
+        if cfg.vision.get("arch") == "glm4v":
+            v = cfg.vision
+            text.update(model_type="glm4v_text", attention_bias=bool(cfg.qkv_bias),
+                        rope_parameters={"rope_type": "default", "rope_theta": cfg.rope_theta, "mrope_section": list(cfg.mrope_section),
+                                         "partial_rotary_factor": cfg.partial_rotary_factor})
+            vis = {"depth": v["depth"], "hidden_size": v["embed_dim"], "hidden_act": "silu", "intermediate_size": v["intermediate_size"],
+                   "num_heads": v["num_heads"], "in_channels": v.get("in_channels", 3), "patch_size": v["patch_size"],
+                   "image_size": v.get("image_size", int(round(v["num_position_embeddings"] ** 0.5)) * v["patch_size"]),
+                   "spatial_merge_size": v.get("spatial_merge_size", 2), "temporal_patch_size": v.get("temporal_patch_size", 2),
+                   "out_hidden_size": cfg.hidden_size, "attention_bias": bool(v.get("attention_bias", False)),
+                   "rms_norm_eps": v.get("rms_norm_eps", 1e-5)}
+            return {"model_type": "glm4v", "architectures": ["Glm4vForConditionalGeneration"], "text_config": text, "vision_config": vis,
+                    "image_token_id": cfg.image_token_id, "video_token_id": cfg.video_token_id,
+                    "image_start_token_id": cfg.vision_start_token_id, "image_end_token_id": cfg.vision_end_token_id,
+                    "tie_word_embeddings": cfg.tie_word_embeddings, "torch_dtype": "bfloat16"}
         if cfg.vision.get("arch") == "qwen3":
             v = cfg.vision
             text.update(model_type="qwen3_vl_text", head_dim=cfg.head_dim, attention_bias=False,

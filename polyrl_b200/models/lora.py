@@ -185,6 +185,11 @@ def load_peft_adapter(engine, path: str) -> int:
     import json
     from pathlib import Path
 
+    from .transformer import rope_feature_perm
+
+    if rope_feature_perm(engine.cfg) is not None:
+        raise NotImplementedError("peft adapters for checkpoints whose rotary layout is permuted at load time (GLM family): "
+                                  "the q / k adapter rows would need the same permutation")
     p = Path(path)
     cfg_file = p / "adapter_config.json"
     if cfg_file.exists():

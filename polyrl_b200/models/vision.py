@@ -61,6 +61,13 @@ def is_v3(cfg: ModelConfig) -> bool:
     return _v(cfg).get("arch", "qwen2") == "qwen3"
 
 
+def is_glm4v(cfg: ModelConfig) -> bool:
+    """GLM-4V tower: bias-free RMSNorm / SwiGLU blocks with full attention inside a frame, RMSNorm after the patch embedding, a
+    learned position table resampled BICUBICALLY at every patch centre, a strided-convolution merge of each merge^2 cell and a
+    gated MLP merger (reference: 3rdparty/verl/verl/models/transformers/glm4v.py)."""
+    return _v(cfg).get("arch", "qwen2") == "glm4v"
+
+
 def deepstack_levels(cfg: ModelConfig) -> int:
     if cfg.vision is None or cfg.vision.get("arch") != "qwen3":
         return 0
@@ -79,6 +86,11 @@ def vision_block_specs(cfg: ModelConfig) -> ParamSpec:
         f = int(v["intermediate_size"])
         return [("ln1_w", (e,)), ("ln1_b", (e,)), ("wqkv", (3 * e, e)), ("bqkv", (3 * e,)), ("wo", (e, e)), ("bo", (e,)),
                 ("ln2_w", (e,)), ("ln2_b", (e,)), ("wfc", (f, e)), ("bfc", (f,)), ("wproj", (e, f)), ("bproj", (e,))]
+    if is_glm4v(cfg):
+        f = int(cfg.hidden_size)                       # the block MLP is as wide as the tower OUTPUT (HF: out_hidden_size)
+        bias = [("bqkv", (3 * e,))] if v.get("attention_bias") else []
+        return [("ln1_w", (e,)), ("wqkv", (3 * e, e)), *bias, ("wo", (e, e)), ("ln2_w", (e,)), ("wg", (f, e)), ("wu", (f, e)),
+                ("wproj", (e, f))]
     if is_v25(cfg):
         f = int(v["intermediate_size"])
         return [("ln1_w", (e,)), ("wqkv", (3 * e, e)), ("bqkv", (3 * e,)), ("wo", (e, e)), ("bo", (e,)), ("ln2_w", (e,)),
@@ -92,6 +104,12 @@ def vision_stem_specs(cfg: ModelConfig) -> ParamSpec:
     """Patch embedding + merger (everything outside the blocks)."""
     v = _v(cfg)
     e, m = v["embed_dim"], v["embed_dim"] * v["spatial_merge_size"] ** 2
+    if is_glm4v(cfg):
+        o, c = cfg.hidden_size, int(v["intermediate_size"])
+        return [("patch_embed", (e, patch_dim(cfg))), ("patch_embed_b", (e,)), ("post_conv_ln_w", (e,)),
+                ("pos_embed", (int(v["num_position_embeddings"]), e)), ("post_ln_w", (e,)), ("downsample_w", (o, m)), ("downsample_b", (o,)),
+                ("merger_proj", (o, o)), ("merger_ln_w", (o,)), ("merger_ln_b", (o,)), ("merger_wg", (c, o)), ("merger_wu", (c, o)),
+                ("merger_wd", (o, c))]
     ln = [("merger_ln_w", (e,))] if is_v25(cfg) else [("merger_ln_w", (e,)), ("merger_ln_b", (e,))]
     base = [("patch_embed", (e, patch_dim(cfg))), *ln, ("merger_w1", (m, m)),
             ("merger_b1", (m,)), ("merger_w2", (cfg.hidden_size, m)), ("merger_b2", (cfg.hidden_size,))]
@@ -225,15 +243,16 @@ def vision_block(cfg: ModelConfig, w: dict, x: torch.Tensor, cos, sin, cu: torch
     v = _v(cfg)
     e, nh = v["embed_dim"], v["num_heads"]
     n = x.shape[0]
-    v25 = "ln1_b" not in w
-    h = _rms(x, w["ln1_w"]) if v25 else F.layer_norm(x, (e,), w["ln1_w"], w["ln1_b"], 1e-6)
-    qkv = F.linear(h, w["wqkv"], w["bqkv"]).view(n, 3, nh, e // nh)
+    v25 = "ln1_b" not in w                          # RMSNorm + SwiGLU blocks: Qwen2.5-VL (biased) and GLM-4V (bias-free)
+    eps = float(v.get("rms_norm_eps", 1e-6))
+    h = _rms(x, w["ln1_w"], eps) if v25 else F.layer_norm(x, (e,), w["ln1_w"], w["ln1_b"], 1e-6)
+    qkv = F.linear(h, w["wqkv"], w.get("bqkv")).view(n, 3, nh, e // nh)
     q, k = _rot_half(qkv[:, 0], cos, sin), _rot_half(qkv[:, 1], cos, sin)
     a = attention_varlen(q.contiguous(), k.contiguous(), qkv[:, 2].contiguous(), cu, max_len, causal=False)
-    x = x + F.linear(a.reshape(n, e), w["wo"], w["bo"])
+    x = x + F.linear(a.reshape(n, e), w["wo"], w.get("bo"))
     if v25:
-        h = _rms(x, w["ln2_w"])
-        return x + F.linear(F.silu(F.linear(h, w["wg"], w["bg"])) * F.linear(h, w["wu"], w["bu"]), w["wproj"], w["bproj"])
+        h = _rms(x, w["ln2_w"], eps)
+        return x + F.linear(F.silu(F.linear(h, w["wg"], w.get("bg"))) * F.linear(h, w["wu"], w.get("bu")), w["wproj"], w.get("bproj"))
     h = F.layer_norm(x, (e,), w["ln2_w"], w["ln2_b"], 1e-6)
     h = F.linear(h, w["wfc"], w["bfc"])
     if v.get("arch") == "qwen3":
@@ -266,8 +285,30 @@ def interpolated_pos_embed(cfg: ModelConfig, table: torch.Tensor, grid_thw) -> t
     return torch.cat(out, dim=0)
 
 
+def bicubic_pos_embed(cfg: ModelConfig, table: torch.Tensor, grid_thw) -> torch.Tensor:
+    """GLM-4V: the learned [side x side] position table sampled bicubically at the centre of every patch of every image (patch
+    (r, c) of an h x w grid reads the table at ((c + .5) / w, (r + .5) / h), border-clamped), in the preprocessor's patch order."""
+    m = _v(cfg)["spatial_merge_size"]
+    side = int(round(table.shape[0] ** 0.5))
+    rows, cols, hs, ws = [], [], [], []
+    for t, h, w in _grid_list(grid_thw):
+        r = torch.arange(h).view(h // m, m, 1, 1).expand(h // m, m, w // m, m).permute(0, 2, 1, 3).reshape(-1).repeat(t)
+        c = torch.arange(w).view(1, 1, w // m, m).expand(h // m, m, w // m, m).permute(0, 2, 1, 3).reshape(-1).repeat(t)
+        rows.append(r), cols.append(c), hs.append(torch.full_like(r, h)), ws.append(torch.full_like(c, w))
+    r, c, hh, ww = (torch.cat(z).to(device=table.device, dtype=torch.float32) for z in (rows, cols, hs, ws))
+    grid = torch.stack(((c + 0.5) / ww * 2 - 1, (r + 0.5) / hh * 2 - 1), dim=-1).view(1, -1, 1, 2)
+    tab = table.float().view(side, side, -1).permute(2, 0, 1).unsqueeze(0)
+    out = F.grid_sample(tab, grid, mode="bicubic", align_corners=False, padding_mode="border")
+    return out[0, :, :, 0].t().to(table.dtype)
+
+
 def vision_stem_in(cfg: ModelConfig, stem: dict, pixel_values: torch.Tensor, grid_thw=None) -> torch.Tensor:
     x = F.linear(pixel_values.to(stem["patch_embed"].dtype), stem["patch_embed"], stem.get("patch_embed_b"))
+    if "post_conv_ln_w" in stem:                     # GLM-4V
+        if grid_thw is None:
+            raise ValueError("the GLM-4V tower needs the image grids for its position embeddings")
+        x = _rms(x, stem["post_conv_ln_w"], float(_v(cfg).get("rms_norm_eps", 1e-5)))
+        return x + bicubic_pos_embed(cfg, stem["pos_embed"], grid_thw).to(x.dtype)
     if "pos_embed" in stem:
         if grid_thw is None:
             raise ValueError("the Qwen3-VL tower needs the image grids for its position embeddings")
@@ -286,6 +327,13 @@ def deepstack_merge(cfg: ModelConfig, stem: dict, k: int, x: torch.Tensor) -> to
 def vision_stem_out(cfg: ModelConfig, stem: dict, x: torch.Tensor) -> torch.Tensor:
     v = _v(cfg)
     e, m2 = v["embed_dim"], v["spatial_merge_size"] ** 2
+    if "downsample_w" in stem:                       # GLM-4V: norm, merge^2 cell -> one row by a strided convolution, gated merger
+        x = _rms(x, stem["post_ln_w"], float(v.get("rms_norm_eps", 1e-5)))
+        cells = x.view(-1, m2, e).transpose(1, 2).reshape(-1, e * m2)            # conv weight order: (channel, row, col)
+        y = F.linear(cells, stem["downsample_w"], stem["downsample_b"])
+        y = F.linear(y, stem["merger_proj"])
+        y = F.gelu(F.layer_norm(y, (y.shape[-1],), stem["merger_ln_w"], stem["merger_ln_b"], 1e-5))
+        return F.linear(F.silu(F.linear(y, stem["merger_wg"])) * F.linear(y, stem["merger_wu"]), stem["merger_wd"])
     h = _rms(x, stem["merger_ln_w"]) if "merger_ln_b" not in stem else F.layer_norm(x, (e,), stem["merger_ln_w"], stem["merger_ln_b"], 1e-6)
     h = h.view(-1, e * m2)
     return F.linear(F.gelu(F.linear(h, stem["merger_w1"], stem["merger_b1"])), stem["merger_w2"], stem["merger_b2"])
@@ -394,7 +442,7 @@ def mrope_positions(cfg: ModelConfig, input_ids, grid_thw, second_per_grid_ts=No
     v = _v(cfg)
     m = v["spatial_merge_size"]
     glist = _grid_list(grid_thw) if grid_thw is not None else []
-    if is_v3(cfg):        # Qwen3-VL prompts separate the frames of a video by timestamp text: one placeholder run per frame
+    if is_v3(cfg) or is_glm4v(cfg):   # prompts separate the frames of a video by timestamp text: one placeholder run per frame
         glist = [(1, h, w) for t, h, w in glist for _ in range(t)]
     grids = iter(glist)
     secs = iter(second_per_grid_ts if second_per_grid_ts is not None else [])
@@ -441,6 +489,8 @@ def mrope_tables(cfg: ModelConfig, pos3: torch.Tensor, cos: torch.Tensor, sin: t
         stream[(i % 3 == 2) & (i < 3 * sec[2])] = 2
     else:
         stream = torch.repeat_interleave(torch.arange(3, device=pos3.device), sec)        # [d/2] -> 0/1/2
+    if stream.numel() < cos.shape[1]:               # partial rotary (GLM): the pass-through columns hold cos = 1 / sin = 0 anyway
+        stream = F.pad(stream, (0, cos.shape[1] - stream.numel()))
     p = pos3.to(cos.device)[stream.to(cos.device)]                                         # [d/2, T]
     f = torch.arange(cos.shape[1], device=cos.device).unsqueeze(1)                        # [d/2, 1]
     return cos[p, f].t().contiguous(), sin[p, f].t().contiguous()
@@ -453,23 +503,28 @@ def norm_stats(cfg: ModelConfig) -> tuple[torch.Tensor, torch.Tensor]:
     """Per-channel (mean, std) of the family's image processor: CLIP statistics for Qwen2-VL / 2.5-VL, 0.5 / 0.5 for Qwen3-VL;
     ``vision.image_mean`` / ``vision.image_std`` override."""
     v = _v(cfg)
-    default_mean, default_std = ((0.5, 0.5, 0.5), (0.5, 0.5, 0.5)) if v.get("arch") == "qwen3" else (CLIP_MEAN, CLIP_STD)
+    default_mean, default_std = ((0.5, 0.5, 0.5), (0.5, 0.5, 0.5)) if v.get("arch") == "qwen3" else (CLIP_MEAN, CLIP_STD)   # GLM-4V: CLIP
     mean, std = v.get("image_mean") or default_mean, v.get("image_std") or default_std
     return torch.tensor(mean, dtype=torch.float32).view(3, 1, 1), torch.tensor(std, dtype=torch.float32).view(3, 1, 1)
 
 
-def smart_resize(height: int, width: int, factor: int, min_pixels: int, max_pixels: int) -> tuple[int, int]:
-    """Closest (h, w) that are multiples of ``factor``, keep the aspect ratio and fit the pixel budget."""
+def smart_resize(height: int, width: int, factor: int, min_pixels: int, max_pixels: int, frames: int = 1) -> tuple[int, int]:
+    """Closest (h, w) that are multiples of ``factor``, keep the aspect ratio and fit the pixel budget.  ``frames`` > 1 is the
+    GLM-4V rule: the budget counts frames x height x width voxels (a still image counts as one temporal patch of frames), and an
+    image smaller than one merge cell is first scaled up to it."""
+    if frames > 1 and (height < factor or width < factor):
+        scale = max(factor / height, factor / width)
+        height, width = int(height * scale), int(width * scale)
     if max(height, width) / max(1, min(height, width)) > 200:
         raise ValueError("aspect ratio above 200")
     h = max(factor, round(height / factor) * factor)
     w = max(factor, round(width / factor) * factor)
-    if h * w > max_pixels:
-        beta = math.sqrt(height * width / max_pixels)
+    if frames * h * w > max_pixels:
+        beta = math.sqrt(frames * height * width / max_pixels)
         h = max(factor, math.floor(height / beta / factor) * factor)
         w = max(factor, math.floor(width / beta / factor) * factor)
-    elif h * w < min_pixels:
-        beta = math.sqrt(min_pixels / (height * width))
+    elif frames * h * w < min_pixels:
+        beta = math.sqrt(min_pixels / (frames * height * width))
         h = math.ceil(height * beta / factor) * factor
         w = math.ceil(width * beta / factor) * factor
     return h, w
@@ -495,6 +550,9 @@ def preprocess_image(cfg: ModelConfig, image, min_pixels: int | None = None, max
 
     v = _v(cfg)
     factor = v["patch_size"] * v["spatial_merge_size"]
+    if is_glm4v(cfg):                                  # GLM-4V processor defaults (budget in frames x pixels, see smart_resize)
+        min_pixels = min_pixels or 112 * 112
+        max_pixels = max_pixels or factor * factor * v["temporal_patch_size"] * 6144
     min_pixels = min_pixels or 4 * factor * factor
     max_pixels = max_pixels or 1280 * factor * factor
     if not isinstance(image, Image.Image):
@@ -502,7 +560,8 @@ def preprocess_image(cfg: ModelConfig, image, min_pixels: int | None = None, max
 
         image = Image.fromarray(np.asarray(image, dtype="uint8"))
     image = image.convert("RGB")
-    h, w = smart_resize(image.height, image.width, factor, min_pixels, max_pixels)
+    h, w = smart_resize(image.height, image.width, factor, min_pixels, max_pixels,
+                        frames=v["temporal_patch_size"] if is_glm4v(cfg) else 1)
     image = image.resize((w, h), resample=Image.BICUBIC)
     import numpy as np
 
@@ -578,7 +637,18 @@ def _stem_map_3(cfg: ModelConfig) -> dict:
     return out
 
 
+_STEM_MAP_GLM = {"patch_embed_b": "patch_embed.proj.bias", "post_conv_ln_w": "post_conv_layernorm.weight",
+                 "pos_embed": "embeddings.position_embedding.weight", "post_ln_w": "post_layernorm.weight",
+                 "downsample_w": "downsample.weight", "downsample_b": "downsample.bias", "merger_proj": "merger.proj.weight",
+                 "merger_ln_w": "merger.post_projection_norm.weight", "merger_ln_b": "merger.post_projection_norm.bias",
+                 "merger_wg": "merger.gate_proj.weight", "merger_wu": "merger.up_proj.weight", "merger_wd": "merger.down_proj.weight"}
+
+
 def _maps(cfg: ModelConfig) -> tuple[dict, dict]:
+    if is_glm4v(cfg):
+        drop = () if _v(cfg).get("attention_bias") else ("bqkv",)
+        return _STEM_MAP_GLM, {k: v for k, v in _BLOCK_MAP_25.items() if k in ("ln1_w", "wqkv", "bqkv", "wo", "ln2_w", "wg", "wu", "wproj")
+                               and k not in drop}
     if is_v3(cfg):
         return _stem_map_3(cfg), _BLOCK_MAP_3
     if is_v25(cfg):
@@ -592,7 +662,8 @@ def convert_hf_vision_state_dict(cfg: ModelConfig, hf_sd: dict[str, torch.Tensor
     stem_map, block_map = _maps(cfg)
     out = {"vision.patch_embed": hf_sd[p + "patch_embed.proj.weight"].reshape(_v(cfg)["embed_dim"], -1)}
     for ours, theirs in stem_map.items():
-        out[f"vision.{ours}"] = hf_sd[p + theirs]
+        t = hf_sd[p + theirs]
+        out[f"vision.{ours}"] = t.reshape(t.shape[0], -1) if ours == "downsample_w" else t       # Conv2d [O, E, m, m] -> linear
     for i in range(_v(cfg)["depth"]):
         for ours, theirs in block_map.items():
             out[f"vision.blocks.{i}.{ours}"] = hf_sd[f"{p}blocks.{i}.{theirs}"]
@@ -605,7 +676,9 @@ def export_hf_vision_state_dict(cfg: ModelConfig, sd: dict[str, torch.Tensor], p
         v["embed_dim"], v["in_channels"], v["temporal_patch_size"], v["patch_size"], v["patch_size"])}
     stem_map, block_map = _maps(cfg)
     for ours, theirs in stem_map.items():
-        out[prefix + theirs] = sd[f"vision.{ours}"]
+        t = sd[f"vision.{ours}"]
+        m = v["spatial_merge_size"]
+        out[prefix + theirs] = t.reshape(t.shape[0], v["embed_dim"], m, m) if ours == "downsample_w" else t
     for i in range(v["depth"]):
         for ours, theirs in block_map.items():
             out[f"{prefix}blocks.{i}.{theirs}"] = sd[f"vision.blocks.{i}.{ours}"]

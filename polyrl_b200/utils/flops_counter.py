@@ -68,12 +68,18 @@ class FlopsCounter:
             return 0.0
         dim, depth = int(v["embed_dim"]), int(v["depth"])
         inter = int(v.get("intermediate_size") or dim * float(v.get("mlp_ratio", 4)))
-        mlp = (3 if v.get("arch") == "qwen2_5" else 2) * dim * inter
+        glm = v.get("arch") == "glm4v"
+        if glm:                                   # block MLPs are as wide as the tower output; gated
+            inter = self.cfg.hidden_size
+        mlp = (3 if v.get("arch") in ("qwen2_5", "glm4v") else 2) * dim * inter
         per_block = 4 * dim * dim + mlp
         patches = sum(images_seqlens)
         in_ch = int(v.get("in_channels", 3)) * int(v.get("temporal_patch_size", 2)) * int(v["patch_size"]) ** 2
         merge = int(v.get("spatial_merge_size", 2)) ** 2
         merger = (dim * merge) * (dim * merge) + (dim * merge) * self.cfg.hidden_size          # per merged token
+        if glm:                                   # strided-conv cell merge + projection + gated MLP of width vision.intermediate_size
+            o = self.cfg.hidden_size
+            merger = (dim * merge) * o + o * o + 3 * o * int(v["intermediate_size"])
         dense = 6.0 * (per_block * depth + in_ch * dim) * patches + 6.0 * merger * (patches / merge)
         return dense + 12.0 * depth * dim * sum(p * p for p in images_seqlens)
 

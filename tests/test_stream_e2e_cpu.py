@@ -7,6 +7,8 @@ import sys as _sys
 _sys.path.insert(0, _os.path.dirname(_os.path.abspath(__file__)))
 from _spawn import run_torchrun  # noqa: E402
 import os
+
+import pytest
 import sys
 
 from pathlib import Path
@@ -75,7 +77,7 @@ def test_ulysses_sp_equivalence_gloo():
     assert r.returncode == 0 and line, r.stdout[-2000:] + r.stderr[-2000:]
     vals = dict(kv.split("=") for kv in line[0].split()[1:])
     assert float(vals["lp_err"]) < 1e-4 and float(vals["w_err"]) < 1e-3
-    for fam in ("tiny-qwen2-vl", "tiny-qwen3-vl"):          # image rows (+ DeepStack rows) / 3-axis positions sliced with the tokens
+    for fam in ("tiny-qwen2-vl", "tiny-qwen3-vl", "tiny-glm4v"):          # image rows (+ DeepStack rows) / 3-axis positions sliced with the tokens
         assert float(vals[f"vlm_lp_err[{fam}]"]) < 1e-4 and float(vals[f"vlm_w_err[{fam}]"]) < 1e-3
 
 
@@ -178,7 +180,8 @@ def test_colocated_ws2_bench_topology_gloo():
     assert "resident True" in lines[1] and "saved 2" in lines[1] and "n 16" in lines[1]
 
 
-def test_vlm_grpo_disaggregated_gloo_ws2(tmp_path):
+@pytest.mark.parametrize("model", ["tiny-qwen2-vl", "tiny-glm4v"])
+def test_vlm_grpo_disaggregated_gloo_ws2(tmp_path, model):
     """Vision-language GRPO through the whole streaming stack on CPU: image dataset (jsonl + PNG files, byte tokenizer) ->
     manager -> remote engine that runs the ViT tower at prefill -> actor update (tower + text) with KL to the reference ->
     broadcast weight sync including the tower -> validation."""
@@ -202,7 +205,7 @@ def test_vlm_grpo_disaggregated_gloo_ws2(tmp_path):
     f = tmp_path / "geo.jsonl"
     f.write_text("\n".join(json.dumps(r) for r in rows))
     ov = [o for o in COMMON if not o.startswith(("data.synthetic", "data.max_prompt_length"))] + [
-        "actor_rollout_ref.model.path=tiny-qwen2-vl", "actor_rollout_ref.model.tokenizer_path=byte", f"data.train_files={f}",
+        f"actor_rollout_ref.model.path={model}", "actor_rollout_ref.model.tokenizer_path=byte", f"data.train_files={f}",
         f"data.val_files={f}", "data.max_prompt_length=48", "data.image_min_pixels=64", "data.image_max_pixels=1024",
         "data.val_batch_size=8", "trainer.test_freq=2", "algorithm.adv_estimator=grpo", "actor_rollout_ref.actor.use_kl_loss=True",
         "trainer.n_rollout_gpus=1", "trainer.n_gpus_per_node=2", "trainer.total_training_steps=2",

@@ -131,14 +131,14 @@ def test_vision_state_dict_round_trip_and_param_count():
     assert cfg.num_params() == V.vision_num_params(cfg) + get_model_config("tiny-qwen2-vl", vision=None, mrope_section=()).num_params()
 
 
-@pytest.mark.parametrize("family", ["qwen2_vl", "qwen3_vl"])
+@pytest.mark.parametrize("family", ["qwen2_vl", "qwen3_vl", "glm4v"])
 def test_engine_generates_like_hf_with_images(family):
     """Rollout engine on image prompts: greedy continuation equals HF generate (prefill with tower embeddings + M-RoPE, decode
     with the per-request rotary offset), also when the prompt is prefilled in chunks and when n samples share the prompt.
     Qwen3-VL adds DeepStack: the per-level features are added after the first decoder layers of every prefill chunk."""
     from polyrl_b200.rollout.engine import RolloutEngine, SamplingParams
 
-    hc, model = _hf_tiny() if family == "qwen2_vl" else _hf_tiny_q3()
+    hc, model = {"qwen2_vl": _hf_tiny, "qwen3_vl": _hf_tiny_q3, "glm4v": _hf_tiny_glm4v}[family]()
     cfg, w, vw = _ours(hc, model)
     g = torch.Generator().manual_seed(3)
     grids_a, grids_b = [(1, 4, 6)], [(1, 4, 4), (1, 8, 4)]
@@ -197,7 +197,7 @@ def _vlm_batch(cfg, seed=5):
     return inp, labels
 
 
-@pytest.mark.parametrize("preset", ["tiny-qwen2-vl", "tiny-qwen3-vl"])
+@pytest.mark.parametrize("preset", ["tiny-qwen2-vl", "tiny-qwen3-vl", "tiny-glm4v"])
 def test_zero_engine_trains_the_tower_like_plain_autograd(preset):
     """ZeRO engine with a ``vision`` unit: log-probs and the gradients of tower + text parameters equal plain autograd over the
     functional model, in recompute and saved-activation modes; a frozen tower keeps its weights; HF export reloads in HF.
@@ -253,18 +253,20 @@ def test_zero_engine_trains_the_tower_like_plain_autograd(preset):
     assert not torch.equal(after["layers.0.wqkv"], full["layers.0.wqkv"])
 
 
-def test_vlm_hf_checkpoint_round_trip(tmp_path):
-    """save_hf of a VLM engine -> a directory HF's Qwen2VLForConditionalGeneration loads, with identical logits; and back into a
-    fresh engine / state dict through load_into_engine / load_state_dict."""
-    from transformers import Qwen2VLForConditionalGeneration
+@pytest.mark.parametrize("preset", ["tiny-qwen2-vl", "tiny-glm4v"])
+def test_vlm_hf_checkpoint_round_trip(tmp_path, preset):
+    """save_hf of a VLM engine -> a directory HF's Qwen2VLForConditionalGeneration / Glm4vForConditionalGeneration loads, with
+    identical logits; and back into a fresh engine / state dict through load_into_engine / load_state_dict."""
+    from transformers import Glm4vForConditionalGeneration, Qwen2VLForConditionalGeneration
 
     from polyrl_b200.models import hf_io
     from polyrl_b200.parallel.zero3 import Zero3Engine
 
-    cfg = get_model_config("tiny-qwen2-vl")
+    cfg = get_model_config(preset)
     eng = Zero3Engine(cfg, "cpu", seed=11)
     hf_io.save_hf(eng, cfg, tmp_path / "ck", dtype=torch.float32)
-    model = Qwen2VLForConditionalGeneration.from_pretrained(tmp_path / "ck", dtype=torch.float32).eval()
+    hf_cls = Glm4vForConditionalGeneration if preset == "tiny-glm4v" else Qwen2VLForConditionalGeneration
+    model = hf_cls.from_pretrained(tmp_path / "ck", dtype=torch.float32).eval()
     inp, _ = _vlm_batch(cfg)
     n0 = int(inp.cu_seqlens[1])
     ids_t = inp.input_ids[:n0].unsqueeze(0)
@@ -788,3 +790,89 @@ def test_qwen3_vl_moe_logits_match_hf():
 
     cfg2 = ModelConfig.from_hf_config(hf_config_dict(cfg))
     assert cfg2.num_experts == 4 and cfg2.vision == cfg.vision
+
+
+def _hf_tiny_glm4v():
+    from transformers import Glm4vConfig, Glm4vForConditionalGeneration
+
+    torch.manual_seed(0)
+    hc = Glm4vConfig(
+        text_config=dict(vocab_size=512, hidden_size=128, intermediate_size=256, num_hidden_layers=2, num_attention_heads=4,
+                         num_key_value_heads=2, max_position_embeddings=512, rms_norm_eps=1e-5, pad_token_id=0,
+                         rope_parameters=dict(rope_type="default", rope_theta=10000.0, mrope_section=[2, 3, 3], partial_rotary_factor=0.5)),
+        vision_config=dict(depth=2, hidden_size=64, intermediate_size=96, num_heads=4, patch_size=4, image_size=24, spatial_merge_size=2,
+                           temporal_patch_size=2, in_channels=3, out_hidden_size=128, attention_bias=True, rms_norm_eps=1e-5),
+        image_token_id=500, video_token_id=501, image_start_token_id=499, image_end_token_id=498, tie_word_embeddings=False)
+    hc._attn_implementation = "eager"
+    model = Glm4vForConditionalGeneration(hc).eval().float()
+    with torch.no_grad():
+        for n, p in model.named_parameters():
+            if p.dim() == 1:
+                p.add_(0.1 * torch.randn_like(p))
+    return hc, model
+
+
+def test_glm4v_tower_positions_and_logits_match_hf():
+    """GLM-4V: RMSNorm after the patch embedding, bicubically resampled position table, bias-free SwiGLU blocks, convolutional cell
+    merge + gated merger; GLM-4 text blocks (output norms, partial interleaved rotary) under M-RoPE
+    (reference: 3rdparty/verl/verl/models/transformers/glm4v.py)."""
+    hc, model = _hf_tiny_glm4v()
+    cfg, w, vw = _ours(hc, model)
+    assert V.is_glm4v(cfg) and cfg.sandwich_norm and cfg.partial_rotary_factor == 0.5 and cfg.rope_interleaved and cfg.qkv_bias
+    g = torch.Generator().manual_seed(1)
+    grids = [(1, 4, 6), (1, 8, 4)]
+    pix = torch.randn(sum(t * h * w_ for t, h, w_ in grids), V.patch_dim(cfg), generator=g)
+    grid_t = torch.tensor(grids)
+    with torch.no_grad():
+        out = model.model.visual(pix, grid_thw=grid_t).pooler_output
+        mine = V.vision_forward(cfg, vw, pix, grids)
+    assert mine.shape == out.shape == (sum(V.num_image_tokens(cfg, grids)), cfg.hidden_size)
+    assert (mine - out).abs().max() < 2e-4
+    n0, n1 = V.num_image_tokens(cfg, grids)
+    ids = [2, 11, 12, 499] + [500] * n0 + [498, 13, 14, 15, 499] + [500] * n1 + [498, 16, 17]
+    ids_t = torch.tensor([ids])
+    mm_type = (ids_t == 500).int()
+    with torch.no_grad():
+        ref_logits = model(input_ids=ids_t, pixel_values=pix, image_grid_thw=grid_t, mm_token_type_ids=mm_type).logits[0]
+    pos3, delta = V.mrope_positions(cfg, ids, grids)
+    hf_pos, hf_delta = model.model.get_rope_index(ids_t, mm_type, image_grid_thw=grid_t)
+    assert torch.equal(pos3, hf_pos[:, 0]) and delta == int(hf_delta[0, 0])
+    t = len(ids)
+    inp = tf.PackedInput(torch.tensor(ids), pos3[0].clone(), torch.tensor([0, t], dtype=torch.int32), t, mrope_pos=pos3, image_embeds=mine)
+    with torch.no_grad():
+        logits = tf.logits_forward(cfg, w.head, w.embed, tf.forward_hidden(cfg, w, inp))
+    assert (logits - ref_logits).abs().max() < 5e-4
+    # text-only positions (all three streams equal) are NOT what the model sees on image tokens
+    flat = tf.PackedInput(torch.tensor(ids), torch.arange(t), torch.tensor([0, t], dtype=torch.int32), t, image_embeds=mine)
+    with torch.no_grad():
+        assert (tf.logits_forward(cfg, w.head, w.embed, tf.forward_hidden(cfg, w, flat)) - ref_logits).abs().max() > 1e-3
+    # checkpoint names round-trip (tower and text stack) and the exported config parses back to the same model
+    sd = model.state_dict()
+    back = V.export_hf_vision_state_dict(cfg, V.convert_hf_vision_state_dict(cfg, sd))
+    vis_keys = [k for k in sd if k.startswith("model.visual.")]
+    assert set(back) == set(vis_keys) and all(torch.equal(back[k].reshape(sd[k].shape), sd[k]) for k in vis_keys)
+    txt = tf.export_hf_state_dict(cfg, w.state_dict())
+    for k, v in txt.items():
+        hk = k.replace("model.", "model.language_model.", 1) if k.startswith("model.") else k
+        assert torch.equal(v, sd[hk]), k
+    from polyrl_b200.models.hf_io import hf_config_dict
+
+    cfg2 = ModelConfig.from_hf_config(hf_config_dict(cfg))
+    assert cfg2.vision == cfg.vision and cfg2.mrope_section == cfg.mrope_section and cfg2.sandwich_norm and cfg2.partial_rotary_factor == 0.5
+
+
+def test_glm4v_preprocess_matches_hf_processor():
+    """GLM-4V image processor: CLIP statistics, the resize budget counts temporal-patch x height x width voxels."""
+    from PIL import Image
+    from transformers.models.glm4v.image_processing_glm4v import Glm4vImageProcessor
+
+    cfg = get_model_config("glm-4.1v-9b")
+    rng = np.random.default_rng(0)
+    proc = Glm4vImageProcessor()
+    for size in ((75, 131), (900, 40), (1900, 2400)):
+        img = Image.fromarray(rng.integers(0, 255, size=(*size, 3), dtype=np.uint8))
+        mine, grid = V.preprocess_image(cfg, img)
+        out = proc(images=[img], return_tensors="pt")
+        assert tuple(out["image_grid_thw"][0].tolist()) == grid, (size, grid, out["image_grid_thw"])
+        assert mine.shape == out["pixel_values"].shape
+        assert (mine - out["pixel_values"]).abs().mean() < 5e-3

@@ -55,7 +55,7 @@ def main():
         from polyrl_b200.models import transformer as tf
         from polyrl_b200.models import vision as V
 
-        for preset in ("tiny-qwen2-vl", "tiny-qwen3-vl"):      # Qwen3-VL: the DeepStack rows are sliced with the image rows
+        for preset in ("tiny-qwen2-vl", "tiny-qwen3-vl", "tiny-glm4v"):      # Qwen3-VL: the DeepStack rows are sliced with the image rows
             vcfg = get_model_config(preset)
             g = torch.Generator().manual_seed(9)
             grids = [(1, 4, 4), (1, 4, 8)]
