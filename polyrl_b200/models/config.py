@@ -55,6 +55,19 @@ class ModelConfig:
     num_experts_per_tok: int = 0
     moe_intermediate_size: int = 0
     norm_topk_prob: bool = True
+    # MoE variants.  ``dense_layers``: blocks that keep a dense SwiGLU MLP of width intermediate_size (Qwen mlp_only_layers /
+    # decoder_sparse_step, DeepSeek / GLM-4.5 first_k_dense_replace).  Shared expert: a dense SwiGLU MLP of width
+    # ``shared_expert_intermediate_size`` added to the routed output of every sparse block, optionally scaled by a learned sigmoid
+    # gate per token (Qwen2-MoE).  ``moe_router``: "softmax" (Mixtral / Qwen) or "sigmoid_group" (DeepSeek-V3 / GLM-4.5: sigmoid
+    # scores, selection on scores + a per-expert bias, experts restricted to the best ``topk_group`` of ``n_group`` groups,
+    # weights scaled by ``routed_scaling_factor``).
+    dense_layers: tuple = ()
+    shared_expert_intermediate_size: int = 0
+    shared_expert_gate: bool = False
+    moe_router: str = "softmax"
+    n_group: int = 1
+    topk_group: int = 1
+    routed_scaling_factor: float = 1.0
     # vision-language models (Qwen2-VL): a ViT tower feeds merged patch embeddings into the image-token positions and the text
     # stack rotates with 3-axis (t, h, w) M-RoPE.  ``vision`` holds the tower shape (see models/vision.py), None = text only.
     vision: dict | None = None
@@ -68,6 +81,7 @@ class ModelConfig:
     def __post_init__(self):
         self.extra_eos_token_ids = tuple(self.extra_eos_token_ids or ())        # json round trip gives a list
         self.mrope_section = tuple(self.mrope_section or ())
+        self.dense_layers = tuple(int(i) for i in (self.dense_layers or ()))
         if self.head_dim == 0:
             self.head_dim = self.hidden_size // self.num_heads
         if self.num_heads % self.num_kv_heads != 0:
@@ -77,8 +91,12 @@ class ModelConfig:
         if self.num_experts:
             if self.family != "llama" or not (0 < self.num_experts_per_tok <= self.num_experts) or self.moe_intermediate_size <= 0:
                 raise ValueError("MoE needs the llama family, 0 < num_experts_per_tok <= num_experts and moe_intermediate_size > 0")
-            if self.moe_intermediate_size % 128:
-                raise ValueError("moe_intermediate_size must be a multiple of 128 (gate / up rows are interleaved in 128-row blocks)")
+            if self.moe_intermediate_size % 128 or self.shared_expert_intermediate_size % 128:
+                raise ValueError("moe / shared-expert intermediate sizes must be multiples of 128 (gate / up rows are interleaved in 128-row blocks)")
+            if self.moe_router not in ("softmax", "sigmoid_group"):
+                raise ValueError(f"unknown moe_router {self.moe_router!r}")
+            if self.moe_router == "sigmoid_group" and (self.num_experts % self.n_group or self.topk_group > self.n_group):
+                raise ValueError("n_group must divide num_experts and topk_group <= n_group")
         if self.vision is not None:
             if self.family != "llama":
                 raise ValueError("vision towers attach to the llama family only")
@@ -97,7 +115,10 @@ class ModelConfig:
     def num_params(self) -> int:
         h, f, v = self.hidden_size, self.intermediate_size, self.vocab_size
         if self.family == "llama":
-            mlp = self.num_experts * (3 * h * self.moe_intermediate_size + h) if self.num_experts else 3 * h * f
+            mlp = 3 * h * f
+            if self.num_experts:
+                mlp = self.num_experts * (3 * h * self.moe_intermediate_size + h) + 3 * h * self.shared_expert_intermediate_size
+                mlp += (h if self.shared_expert_gate else 0) + (self.num_experts if self.moe_router == "sigmoid_group" else 0)
             per = h * (self.q_size + 2 * self.kv_size) + self.q_size * h + mlp + 2 * h
             if self.qk_norm:
                 per += 2 * self.head_dim
@@ -115,14 +136,18 @@ class ModelConfig:
             from .vision import vision_num_params
 
             vis = vision_num_params(self)
-        return per * self.num_layers + emb + h + vis
+        n_dense = len([i for i in self.dense_layers if i < self.num_layers]) if self.num_experts else 0
+        return per * self.num_layers - n_dense * (mlp - 3 * h * f) + emb + h + vis
+
+    def num_sparse_layers(self) -> int:
+        return (self.num_layers - len([i for i in self.dense_layers if i < self.num_layers])) if self.num_experts else 0
 
     def num_active_params(self) -> int:
         """Parameters touched per token (MoE: only the routed experts) — the FLOPs-relevant count."""
         if not self.num_experts:
             return self.num_params()
         idle = (self.num_experts - self.num_experts_per_tok) * 3 * self.hidden_size * self.moe_intermediate_size
-        return self.num_params() - idle * self.num_layers
+        return self.num_params() - idle * self.num_sparse_layers()
 
     def to_dict(self) -> dict:
         return asdict(self)
@@ -149,10 +174,8 @@ class ModelConfig:
         vl_moe_kw: dict = {}
         if mt == "qwen3_vl_moe":             # Qwen3-VL tower + DeepStack on a Qwen3-MoE text stack (always-normalised top-k routing)
             tc = dict(hf.get("text_config") or {})
-            if tc.get("mlp_only_layers") or tc.get("decoder_sparse_step", 1) != 1:
-                raise NotImplementedError("mixed dense / sparse layer stacks (mlp_only_layers, decoder_sparse_step != 1)")
             vl_moe_kw = dict(num_experts=tc.get("num_experts") or tc["num_local_experts"], num_experts_per_tok=tc["num_experts_per_tok"],
-                             moe_intermediate_size=tc["moe_intermediate_size"], norm_topk_prob=True)
+                             moe_intermediate_size=tc["moe_intermediate_size"], norm_topk_prob=True, dense_layers=_qwen_dense_layers(tc))
             mt = "qwen3_vl"
         if mt == "qwen3_vl":
             vc = dict(hf.get("vision_config") or {})
@@ -221,12 +244,24 @@ class ModelConfig:
         if mt == "mixtral":                  # llama attention + top-k of num_local_experts SwiGLU experts of width intermediate_size
             moe_kw = dict(num_experts=hf["num_local_experts"], num_experts_per_tok=hf["num_experts_per_tok"],
                           moe_intermediate_size=hf["intermediate_size"], norm_topk_prob=True)
-        if mt == "qwen3_moe":
-            if hf.get("mlp_only_layers") or hf.get("decoder_sparse_step", 1) != 1:
-                raise NotImplementedError("mixed dense / sparse layer stacks (mlp_only_layers, decoder_sparse_step != 1)")
+        if mt in ("qwen3_moe", "qwen2_moe"):
             moe_kw = dict(num_experts=hf.get("num_experts") or hf["num_local_experts"], num_experts_per_tok=hf["num_experts_per_tok"],
-                          moe_intermediate_size=hf["moe_intermediate_size"], norm_topk_prob=hf.get("norm_topk_prob", False))
-            mt = "qwen3"
+                          moe_intermediate_size=hf["moe_intermediate_size"], norm_topk_prob=hf.get("norm_topk_prob", False),
+                          dense_layers=_qwen_dense_layers(hf))
+            if mt == "qwen2_moe":            # + an always-on shared expert behind a per-token sigmoid gate; qkv bias like Qwen2
+                moe_kw.update(shared_expert_intermediate_size=hf.get("shared_expert_intermediate_size", 0),
+                              shared_expert_gate=bool(hf.get("shared_expert_intermediate_size", 0)))
+                hf = {**hf, "attention_bias": hf.get("qkv_bias", True)}
+            mt = "qwen3" if mt == "qwen3_moe" else "qwen2_moe"
+        if mt == "glm4_moe":                 # GLM-4.5: DeepSeek-style routing + shared experts, first layers dense, partial (non-interleaved) rotary
+            rp = hf.get("rope_parameters") or hf.get("rope_scaling") or {}
+            moe_kw = dict(num_experts=hf["n_routed_experts"], num_experts_per_tok=hf["num_experts_per_tok"],
+                          moe_intermediate_size=hf["moe_intermediate_size"], norm_topk_prob=hf.get("norm_topk_prob", True),
+                          dense_layers=tuple(range(min(int(hf.get("first_k_dense_replace", 0)), hf["num_hidden_layers"]))),
+                          shared_expert_intermediate_size=hf["moe_intermediate_size"] * int(hf.get("n_shared_experts") or 0),
+                          moe_router="sigmoid_group", n_group=int(hf.get("n_group") or 1), topk_group=int(hf.get("topk_group") or 1),
+                          routed_scaling_factor=float(hf.get("routed_scaling_factor", 1.0)))
+            glm_kw = dict(partial_rotary_factor=float(rp.get("partial_rotary_factor") or hf.get("partial_rotary_factor") or 0.5))
         eos = hf.get("eos_token_id", 2)
         extra_eos: tuple = ()
         if isinstance(eos, list):
@@ -237,12 +272,19 @@ class ModelConfig:
                    head_dim=hf.get("head_dim") or 0, max_position_embeddings=hf.get("max_position_embeddings", 8192),
                    rope_theta=(hf.get("rope_theta") or (hf.get("rope_parameters") or hf.get("rope_scaling") or {}).get("rope_theta") or 10000.0),
                    rope_scaling=_rope_scaling_of(hf), rms_norm_eps=hf.get("rms_norm_eps", 1e-6),
-                   qkv_bias=(mt == "qwen2") or hf.get("attention_bias", False), qk_norm=(mt == "qwen3"),
+                   qkv_bias=(mt == "qwen2") or bool(hf.get("attention_bias", False)),
+                   qk_norm=(mt == "qwen3") or (mt == "glm4_moe" and bool(hf.get("use_qk_norm", False))),
                    tie_word_embeddings=hf.get("tie_word_embeddings", False), eos_token_id=eos, extra_eos_token_ids=extra_eos,
                    bos_token_id=hf.get("bos_token_id") or eos, pad_token_id=hf.get("pad_token_id") or eos,
                    sliding_window=(hf.get("sliding_window") if (mt in ("mistral", "mixtral") or hf.get("use_sliding_window")) else None),
-                   hf_model_type=("glm4v" if hf.get("_glm4v") else mt) if mt in ("mistral", "mixtral", "glm", "glm4") else "",
+                   hf_model_type=("glm4v" if hf.get("_glm4v") else mt) if mt in ("mistral", "mixtral", "glm", "glm4", "qwen2_moe", "glm4_moe") else "",
                    name=hf.get("_name_or_path", mt), **vis_kw, **{**moe_kw, **vl_moe_kw}, **glm_kw)
+
+
+def _qwen_dense_layers(hf: dict) -> tuple:
+    """Qwen MoE stacks: block i is sparse unless listed in mlp_only_layers or (i + 1) is not a multiple of decoder_sparse_step."""
+    step, only = int(hf.get("decoder_sparse_step", 1) or 1), set(hf.get("mlp_only_layers") or ())
+    return tuple(i for i in range(hf["num_hidden_layers"]) if i in only or (i + 1) % step != 0)
 
 
 def _rope_scaling_of(hf: dict) -> dict | None:
@@ -372,6 +414,27 @@ PRESETS: dict[str, dict] = {
                            num_kv_heads=2, head_dim=32, max_position_embeddings=512, rope_theta=1000000.0, rms_norm_eps=1e-6,
                            qk_norm=True, num_experts=8, num_experts_per_tok=2, moe_intermediate_size=128, norm_topk_prob=True,
                            eos_token_id=1, bos_token_id=2, pad_token_id=0),
+    "tiny-glm4-moe": dict(family="llama", vocab_size=512, hidden_size=128, intermediate_size=256, num_layers=3, num_heads=4, num_kv_heads=2,
+                          head_dim=32, max_position_embeddings=512, rope_theta=10000.0, rms_norm_eps=1e-5, qkv_bias=True, qk_norm=True,
+                          partial_rotary_factor=0.5, num_experts=8, num_experts_per_tok=2, moe_intermediate_size=128, norm_topk_prob=True,
+                          dense_layers=(0,), shared_expert_intermediate_size=256, moe_router="sigmoid_group", n_group=4, topk_group=2,
+                          routed_scaling_factor=1.5, hf_model_type="glm4_moe", eos_token_id=1, bos_token_id=2, pad_token_id=0),
+    "tiny-qwen2-moe": dict(family="llama", vocab_size=512, hidden_size=128, intermediate_size=256, num_layers=2, num_heads=4, num_kv_heads=2,
+                           head_dim=32, max_position_embeddings=512, rope_theta=1000000.0, rms_norm_eps=1e-6, qkv_bias=True,
+                           num_experts=8, num_experts_per_tok=2, moe_intermediate_size=128, norm_topk_prob=False,
+                           shared_expert_intermediate_size=256, shared_expert_gate=True, hf_model_type="qwen2_moe",
+                           eos_token_id=1, bos_token_id=2, pad_token_id=0),
+    "qwen1.5-moe-a2.7b": dict(family="llama", vocab_size=151936, hidden_size=2048, intermediate_size=5632, num_layers=24, num_heads=16,
+                              num_kv_heads=16, max_position_embeddings=8192, rope_theta=1000000.0, rms_norm_eps=1e-6, qkv_bias=True,
+                              num_experts=60, num_experts_per_tok=4, moe_intermediate_size=1408, norm_topk_prob=False,
+                              shared_expert_intermediate_size=5632, shared_expert_gate=True, hf_model_type="qwen2_moe",
+                              eos_token_id=151643, bos_token_id=151643, pad_token_id=151643),
+    "glm-4.5-air": dict(family="llama", vocab_size=151552, hidden_size=4096, intermediate_size=10944, num_layers=46, num_heads=96,
+                        num_kv_heads=8, head_dim=128, max_position_embeddings=131072, rope_theta=1000000.0, rms_norm_eps=1e-5,
+                        qkv_bias=True, partial_rotary_factor=0.5, num_experts=128, num_experts_per_tok=8, moe_intermediate_size=1408,
+                        norm_topk_prob=True, dense_layers=(0,), shared_expert_intermediate_size=1408, moe_router="sigmoid_group",
+                        n_group=1, topk_group=1, routed_scaling_factor=1.0, hf_model_type="glm4_moe",
+                        eos_token_id=151329, extra_eos_token_ids=(151336, 151338), bos_token_id=151329, pad_token_id=151329),
     "tiny-qwen3-moe-128": dict(family="llama", vocab_size=1024, hidden_size=512, intermediate_size=1024, num_layers=2, num_heads=4,
                                num_kv_heads=2, head_dim=128, max_position_embeddings=1024, rope_theta=1000000.0, rms_norm_eps=1e-6,
                                qk_norm=True, num_experts=8, num_experts_per_tok=2, moe_intermediate_size=256, norm_topk_prob=True,

@@ -82,8 +82,15 @@ def _layer_keys(cfg: ModelConfig, i: int) -> list[str]:
                                 "mlp.c_proj.bias")]
     p = f"model.layers.{i}."
     keys = [p + "input_layernorm.weight", p + "post_attention_layernorm.weight", p + "self_attn.o_proj.weight"]
-    if cfg.num_experts:
+    if tf.is_sparse_layer(cfg, i):
         keys += [p + "mlp.gate.weight", p + "mlp.experts.gate_up_proj", p + "mlp.experts.down_proj"]
+        if cfg.moe_router == "sigmoid_group":
+            keys.append(p + "mlp.gate.e_score_correction_bias")
+        if cfg.shared_expert_intermediate_size:
+            sh = "mlp.shared_expert." if cfg.shared_expert_gate else "mlp.shared_experts."
+            keys += [p + sh + f"{n}_proj.weight" for n in ("gate", "up", "down")]
+            if cfg.shared_expert_gate:
+                keys.append(p + "mlp.shared_expert_gate.weight")
     elif getattr(cfg, "hf_model_type", "") in ("glm", "glm4", "glm4v"):
         keys += [p + "mlp.gate_up_proj.weight", p + "mlp.down_proj.weight"]
     else:
@@ -98,9 +105,11 @@ def _layer_keys(cfg: ModelConfig, i: int) -> list[str]:
     return keys
 
 
-def _one_layer_cfg(cfg: ModelConfig) -> ModelConfig:
+def _one_layer_cfg(cfg: ModelConfig, i: int = 0) -> ModelConfig:
+    """A one-block copy of the config whose block 0 has the MLP kind (sparse / dense) of block ``i``."""
     c = ModelConfig(**cfg.to_dict())
     c.num_layers = 1
+    c.dense_layers = (0,) if (cfg.num_experts and i in cfg.dense_layers) else ()
     return c
 
 
@@ -117,7 +126,7 @@ def _convert_layer(cfg: ModelConfig, ck: HFCheckpoint, i: int) -> dict[str, torc
         def has(k: str) -> bool:
             return k in ck.weight_map or f"model.language_model.{k[6:]}" in ck.weight_map
 
-        if cfg.num_experts and not has(p + "mlp.experts.gate_up_proj"):
+        if tf.is_sparse_layer(cfg, i) and not has(p + "mlp.experts.gate_up_proj"):
             # checkpoints written before the stacked expert layout: one module per expert
             stacked = {p + "mlp.gate.weight", p + "mlp.experts.gate_up_proj", p + "mlp.experts.down_proj"}
             keys = [k for k in keys if k not in stacked]
@@ -129,7 +138,7 @@ def _convert_layer(cfg: ModelConfig, ck: HFCheckpoint, i: int) -> dict[str, torc
                                                    for n in ("gate", "up", "down")]
         sub = {k.replace(f"model.layers.{i}.", "model.layers.0."): ck.get(k) for k in keys}
         sub.update({"model.embed_tokens.weight": torch.empty(0), "model.norm.weight": torch.empty(0), "lm_head.weight": torch.empty(0)})
-    conv = tf.convert_hf_state_dict(_one_layer_cfg(cfg), sub)
+    conv = tf.convert_hf_state_dict(_one_layer_cfg(cfg, i), sub)
     return {k[len("layers.0."):]: v for k, v in conv.items() if k.startswith("layers.0.")}
 
 
@@ -286,10 +295,29 @@ def hf_config_dict(cfg: ModelConfig) -> dict:
                 "tie_word_embeddings": cfg.tie_word_embeddings, "hidden_act": "silu", "torch_dtype": "bfloat16",
                 "eos_token_id": [cfg.eos_token_id, *cfg.extra_eos_token_ids] if cfg.extra_eos_token_ids else cfg.eos_token_id,
                 "bos_token_id": cfg.bos_token_id, "pad_token_id": cfg.pad_token_id}
+    if cfg.num_experts and getattr(cfg, "hf_model_type", "") == "glm4_moe":
+        first_dense = 0
+        while first_dense in cfg.dense_layers:
+            first_dense += 1
+        return {"model_type": "glm4_moe", "architectures": ["Glm4MoeForCausalLM"], "vocab_size": cfg.vocab_size, "hidden_size": cfg.hidden_size,
+                "intermediate_size": cfg.intermediate_size, "num_hidden_layers": cfg.num_layers, "num_attention_heads": cfg.num_heads,
+                "num_key_value_heads": cfg.num_kv_heads, "head_dim": cfg.head_dim, "max_position_embeddings": cfg.max_position_embeddings,
+                "rms_norm_eps": cfg.rms_norm_eps, "attention_bias": bool(cfg.qkv_bias), "use_qk_norm": bool(cfg.qk_norm),
+                "partial_rotary_factor": cfg.partial_rotary_factor, "rope_theta": cfg.rope_theta,
+                "rope_parameters": {"rope_type": "default", "rope_theta": cfg.rope_theta, "partial_rotary_factor": cfg.partial_rotary_factor},
+                "n_routed_experts": cfg.num_experts, "num_experts_per_tok": cfg.num_experts_per_tok,
+                "moe_intermediate_size": cfg.moe_intermediate_size, "norm_topk_prob": cfg.norm_topk_prob,
+                "n_shared_experts": cfg.shared_expert_intermediate_size // cfg.moe_intermediate_size, "n_group": cfg.n_group,
+                "topk_group": cfg.topk_group, "routed_scaling_factor": cfg.routed_scaling_factor, "first_k_dense_replace": first_dense,
+                "tie_word_embeddings": cfg.tie_word_embeddings, "hidden_act": "silu", "torch_dtype": "bfloat16",
+                "eos_token_id": cfg.eos_token_id, "bos_token_id": cfg.bos_token_id, "pad_token_id": cfg.pad_token_id}
     if cfg.num_experts:
         mt, arch = "qwen3_moe", "Qwen3MoeForCausalLM"
         moe = {**moe, "num_experts": cfg.num_experts, "num_experts_per_tok": cfg.num_experts_per_tok, "moe_intermediate_size": cfg.moe_intermediate_size,
-               "norm_topk_prob": cfg.norm_topk_prob, "decoder_sparse_step": 1, "mlp_only_layers": []}
+               "norm_topk_prob": cfg.norm_topk_prob, "decoder_sparse_step": 1, "mlp_only_layers": [int(i) for i in cfg.dense_layers]}
+        if getattr(cfg, "hf_model_type", "") == "qwen2_moe":
+            mt, arch = "qwen2_moe", "Qwen2MoeForCausalLM"
+            moe.update(shared_expert_intermediate_size=cfg.shared_expert_intermediate_size, qkv_bias=bool(cfg.qkv_bias))
     return {**moe, "model_type": mt, "architectures": [arch], "vocab_size": cfg.vocab_size, "hidden_size": cfg.hidden_size,
             "intermediate_size": cfg.intermediate_size, "num_hidden_layers": cfg.num_layers, "num_attention_heads": cfg.num_heads,
             "num_key_value_heads": cfg.num_kv_heads, "head_dim": cfg.head_dim, "max_position_embeddings": cfg.max_position_embeddings,

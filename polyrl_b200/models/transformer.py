@@ -29,7 +29,13 @@ ParamSpec = list[tuple[str, tuple[int, ...]]]
 # --------------------------------------------------------------------------------------------
 # parameter specs
 # --------------------------------------------------------------------------------------------
-def layer_param_specs(cfg: ModelConfig) -> ParamSpec:
+def is_sparse_layer(cfg: ModelConfig, i: int | None) -> bool:
+    """Block i carries a mixture-of-experts MLP (``i=None``: a generic block of the model — sparse for every MoE config)."""
+    return bool(cfg.num_experts) and (i is None or i not in cfg.dense_layers)
+
+
+def layer_param_specs(cfg: ModelConfig, i: int | None = None) -> ParamSpec:
+    """Parameters of decoder block ``i`` (MoE stacks may mix sparse and dense blocks: ``cfg.dense_layers``)."""
     h, f = cfg.hidden_size, cfg.intermediate_size
     qkv = cfg.q_size + 2 * cfg.kv_size
     if cfg.family == "llama":
@@ -41,9 +47,15 @@ def layer_param_specs(cfg: ModelConfig) -> ParamSpec:
         specs += [("wo", (h, cfg.q_size)), ("ln2", (h,))]
         if cfg.sandwich_norm:
             specs += [("ln_attn", (h,)), ("ln_mlp", (h,))]
-        if cfg.num_experts:            # router + stacked experts (gate/up rows interleaved per expert like the dense ``wgu``)
-            fm = cfg.moe_intermediate_size
+        if is_sparse_layer(cfg, i):    # router + stacked experts (gate/up rows interleaved per expert like the dense ``wgu``)
+            fm, fs = cfg.moe_intermediate_size, cfg.shared_expert_intermediate_size
             specs += [("router", (cfg.num_experts, h)), ("ewgu", (cfg.num_experts, 2 * fm, h)), ("ewd", (cfg.num_experts, h, fm))]
+            if cfg.moe_router == "sigmoid_group":
+                specs.append(("router_bias", (cfg.num_experts,)))        # selection-only score correction (no gradient reaches it)
+            if fs:
+                specs += [("swgu", (2 * fs, h)), ("swd", (h, fs))]
+                if cfg.shared_expert_gate:
+                    specs.append(("sgate", (1, h)))
         else:
             specs += [("wgu", (2 * f, h)), ("wd", (h, f))]
         return specs
@@ -82,11 +94,11 @@ def init_param_(name: str, t: torch.Tensor, cfg: ModelConfig, generator: torch.G
         return
     if base in ("ln1", "ln2", "ln_attn", "ln_mlp", "norm_w", "ln1_w", "ln2_w", "q_norm", "k_norm", "merger_ln_w"):
         t.fill_(1.0)
-    elif base.startswith("b") or base.endswith("_b") or base.startswith("merger_b"):
+    elif base.startswith("b") or base.endswith("_b") or base.startswith("merger_b") or base == "router_bias":
         t.zero_()
     else:
         std = 0.02
-        if base in ("wo", "wd", "wproj", "ewd"):
+        if base in ("wo", "wd", "wproj", "ewd", "swd"):
             std = 0.02 / math.sqrt(2 * cfg.num_layers)
         t.normal_(0.0, std, generator=generator)
         if base == "v_head":
@@ -219,6 +231,42 @@ def moe_load_balance_loss(cfg: ModelConfig, probs: torch.Tensor, top_e: torch.Te
     return e * (f * probs.mean(0)).sum()
 
 
+def moe_route(cfg: ModelConfig, w: dict, h: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """Router of a sparse block on rows h:[T,H] -> (weights [T,k] fp32, expert ids [T,k], scores [T,E] fp32 for the balance loss).
+    ``softmax``: fp32 softmax over all experts, top-k, optional renormalisation (Mixtral / Qwen MoE).  ``sigmoid_group``: sigmoid
+    scores; experts are CHOSEN on scores + ``router_bias`` inside the ``topk_group`` best of ``n_group`` expert groups (a group's
+    rank = sum of its two best biased scores) but WEIGHTED by the unbiased scores, renormalised and scaled by
+    ``routed_scaling_factor`` (DeepSeek-V3 / GLM-4.5; HF Glm4MoeMoE.route_tokens_to_experts)."""
+    k, e = cfg.num_experts_per_tok, cfg.num_experts
+    if cfg.moe_router == "sigmoid_group":
+        scores = torch.sigmoid(F.linear(h.float(), w["router"].float()))
+        choice = scores + w["router_bias"].float()
+        if cfg.n_group > 1:
+            grp = choice.view(-1, cfg.n_group, e // cfg.n_group).topk(2, dim=-1)[0].sum(-1)
+            keep = torch.zeros_like(grp).scatter_(1, grp.topk(cfg.topk_group, dim=-1)[1], 1.0).bool()
+            choice = choice.masked_fill(~keep.unsqueeze(-1).expand(-1, cfg.n_group, e // cfg.n_group).reshape(-1, e), 0.0)
+        top_e = choice.topk(k, dim=-1)[1]
+        top_w = scores.gather(1, top_e)
+        if cfg.norm_topk_prob:
+            top_w = top_w / (top_w.sum(-1, keepdim=True) + 1e-20)
+        return top_w * cfg.routed_scaling_factor, top_e, scores / scores.sum(-1, keepdim=True)   # balance term on normalised scores
+    probs = torch.softmax(F.linear(h, w["router"].to(h.dtype)).float(), dim=-1)
+    top_w, top_e = torch.topk(probs, k, dim=-1)
+    if cfg.norm_topk_prob:
+        top_w = top_w / top_w.sum(-1, keepdim=True)
+    return top_w, top_e, probs
+
+
+def shared_expert(w: dict, h: torch.Tensor) -> torch.Tensor | None:
+    """The always-on expert of a sparse block (None when the block has none); Qwen2-MoE scales it by a per-token sigmoid gate."""
+    if "swgu" not in w:
+        return None
+    y = ops.linear(ops.linear_swiglu(h, w["swgu"]), w["swd"])
+    if "sgate" in w:
+        y = y * torch.sigmoid(F.linear(h, w["sgate"].to(h.dtype)))
+    return y
+
+
 def moe_mlp(cfg: ModelConfig, w: dict, h: torch.Tensor, aux_out: list | None = None) -> torch.Tensor:
     """Token-choice top-k mixture of SwiGLU experts on rows h:[T,H] -> [T,H] (Qwen3-MoE semantics: fp32 softmax over all experts,
     top-k, optional renormalisation of the k weights).  Tokens are grouped by expert and every expert with work runs the same
@@ -226,12 +274,9 @@ def moe_mlp(cfg: ModelConfig, w: dict, h: torch.Tensor, aux_out: list | None = N
     Reference capability: HF Qwen3MoeSparseMoeBlock through verl's FSDP path (verl/models/transformers/ + fsdp_workers.py)."""
     t = h.shape[0]
     k = cfg.num_experts_per_tok
-    probs = torch.softmax(F.linear(h, w["router"].to(h.dtype)).float(), dim=-1)
-    top_w, top_e = torch.topk(probs, k, dim=-1)                                   # [T, k]
+    top_w, top_e, probs = moe_route(cfg, w, h)                                    # [T, k]
     if aux_out is not None:
         aux_out.append(moe_load_balance_loss(cfg, probs, top_e))
-    if cfg.norm_topk_prob:
-        top_w = top_w / top_w.sum(-1, keepdim=True)
     flat_e = top_e.reshape(-1)
     order = torch.argsort(flat_e, stable=True)                                     # assignments grouped by expert
     tok = torch.div(order, k, rounding_mode="floor")
@@ -246,7 +291,9 @@ def moe_mlp(cfg: ModelConfig, w: dict, h: torch.Tensor, aux_out: list | None = N
         outs.append(ops.linear(a, w["ewd"][e]))
         lo += n
     y = torch.cat(outs, dim=0) * gate_w.unsqueeze(-1)
-    return torch.zeros(t, h.shape[1], dtype=y.dtype, device=h.device).index_add(0, tok, y)
+    y = torch.zeros(t, h.shape[1], dtype=y.dtype, device=h.device).index_add(0, tok, y)
+    s = shared_expert(w, h)
+    return y if s is None else y + s
 
 
 def moe_mlp_static(cfg: ModelConfig, w: dict, h: torch.Tensor) -> torch.Tensor:
@@ -255,10 +302,7 @@ def moe_mlp_static(cfg: ModelConfig, w: dict, h: torch.Tensor) -> torch.Tensor:
     every token once, nothing is ever dropped) and all experts run as two batched GEMMs.  Padded rows cost FLOPs but no weight
     traffic beyond reading each expert once, which a decode step pays anyway — meant for T <= a few hundred rows."""
     t, k, e = h.shape[0], cfg.num_experts_per_tok, cfg.num_experts
-    probs = torch.softmax(F.linear(h, w["router"].to(h.dtype)).float(), dim=-1)
-    top_w, top_e = torch.topk(probs, k, dim=-1)
-    if cfg.norm_topk_prob:
-        top_w = top_w / top_w.sum(-1, keepdim=True)
+    top_w, top_e, _ = moe_route(cfg, w, h)
     flat_e = top_e.reshape(-1)
     order = torch.argsort(flat_e, stable=True)
     sorted_e = flat_e[order]
@@ -273,7 +317,9 @@ def moe_mlp_static(cfg: ModelConfig, w: dict, h: torch.Tensor) -> torch.Tensor:
     a = ref.swiglu(gu.reshape(e * t, -1)).reshape(e, t, -1)
     y = torch.bmm(a, w["ewd"].to(h.dtype).transpose(1, 2))[sorted_e, slot]          # [T*k, H] in assignment order
     y = y * top_w.reshape(-1)[order].to(h.dtype).unsqueeze(-1)
-    return torch.zeros(t, h.shape[1], dtype=y.dtype, device=h.device).index_add(0, tok, y)
+    y = torch.zeros(t, h.shape[1], dtype=y.dtype, device=h.device).index_add(0, tok, y)
+    s = shared_expert(w, h)
+    return y if s is None else y + s
 
 
 @dataclass
@@ -518,7 +564,7 @@ class TransformerWeights:
             return out
 
         self.embed = make(embed_param_specs(cfg))
-        self.layers = [make(layer_param_specs(cfg)) for _ in range(cfg.num_layers)]
+        self.layers = [make(layer_param_specs(cfg, i)) for i in range(cfg.num_layers)]
         self.head = make(head_param_specs(cfg))
 
     def named_tensors(self):
@@ -616,8 +662,16 @@ def convert_hf_state_dict(cfg: ModelConfig, hf_sd: dict[str, torch.Tensor]) -> d
         if cfg.sandwich_norm:
             out[f"layers.{i}.ln_attn"], out[f"layers.{i}.ln_mlp"] = hf_sd[p + "post_self_attn_layernorm.weight"], hf_sd[p + "post_mlp_layernorm.weight"]
         out[f"layers.{i}.wo"] = hf_sd[p + "self_attn.o_proj.weight"]
-        if cfg.num_experts:
+        if is_sparse_layer(cfg, i):
             fm = cfg.moe_intermediate_size
+            if p + "mlp.gate.e_score_correction_bias" in hf_sd:
+                out[f"layers.{i}.router_bias"] = hf_sd[p + "mlp.gate.e_score_correction_bias"]
+            for sh in ("mlp.shared_expert.", "mlp.shared_experts."):          # Qwen2-MoE / DeepSeek-style naming
+                if p + sh + "gate_proj.weight" in hf_sd:
+                    out[f"layers.{i}.swgu"] = ref.interleave_gate_up(hf_sd[p + sh + "gate_proj.weight"], hf_sd[p + sh + "up_proj.weight"])
+                    out[f"layers.{i}.swd"] = hf_sd[p + sh + "down_proj.weight"]
+            if p + "mlp.shared_expert_gate.weight" in hf_sd:
+                out[f"layers.{i}.sgate"] = hf_sd[p + "mlp.shared_expert_gate.weight"]
             if p + "block_sparse_moe.gate.weight" in hf_sd:      # Mixtral checkpoints on disk: block_sparse_moe.experts.{e}.w1 / w3 / w2
                 q = p + "block_sparse_moe."
                 out[f"layers.{i}.router"] = hf_sd[q + "gate.weight"]
@@ -677,11 +731,19 @@ def export_hf_state_dict(cfg: ModelConfig, sd: dict[str, torch.Tensor]) -> dict[
         if cfg.sandwich_norm:
             out[p + "post_self_attn_layernorm.weight"], out[p + "post_mlp_layernorm.weight"] = sd[f"layers.{i}.ln_attn"], sd[f"layers.{i}.ln_mlp"]
         out[p + "self_attn.o_proj.weight"] = sd[f"layers.{i}.wo"]
-        if cfg.num_experts:                                      # stacked HF layout
+        if is_sparse_layer(cfg, i):                              # stacked HF layout
             gus = [ref.deinterleave_gate_up(sd[f"layers.{i}.ewgu"][e]) for e in range(cfg.num_experts)]
             out[p + "mlp.gate.weight"] = sd[f"layers.{i}.router"]
             out[p + "mlp.experts.gate_up_proj"] = torch.stack([torch.cat([g, u], dim=0) for g, u in gus])
             out[p + "mlp.experts.down_proj"] = sd[f"layers.{i}.ewd"]
+            if f"layers.{i}.router_bias" in sd:
+                out[p + "mlp.gate.e_score_correction_bias"] = sd[f"layers.{i}.router_bias"]
+            if f"layers.{i}.swgu" in sd:
+                sh = "mlp.shared_expert." if cfg.shared_expert_gate else "mlp.shared_experts."
+                g, u = ref.deinterleave_gate_up(sd[f"layers.{i}.swgu"])
+                out[p + sh + "gate_proj.weight"], out[p + sh + "up_proj.weight"], out[p + sh + "down_proj.weight"] = g, u, sd[f"layers.{i}.swd"]
+            if f"layers.{i}.sgate" in sd:
+                out[p + "mlp.shared_expert_gate.weight"] = sd[f"layers.{i}.sgate"]
         else:
             g, u = ref.deinterleave_gate_up(sd[f"layers.{i}.wgu"])
             if fused_gu:

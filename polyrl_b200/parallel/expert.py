@@ -115,10 +115,7 @@ def ep_moe_mlp(cfg: ModelConfig, w: dict, h: torch.Tensor, group) -> torch.Tenso
     ep, rank = dist.get_world_size(group), dist.get_rank(group)
     per = cfg.num_experts // ep
     t, k = h.shape[0], cfg.num_experts_per_tok
-    probs = torch.softmax(F.linear(h, w["router"].to(h.dtype)).float(), dim=-1)
-    top_w, top_e = torch.topk(probs, k, dim=-1)
-    if cfg.norm_topk_prob:
-        top_w = top_w / top_w.sum(-1, keepdim=True)
+    top_w, top_e, _ = tf.moe_route(cfg, w, h)
     flat_e = top_e.reshape(-1)
     order = torch.argsort(flat_e, stable=True)                    # grouped by expert == grouped by destination rank
     tok = torch.div(order, k, rounding_mode="floor")
@@ -151,11 +148,16 @@ def ep_moe_mlp(cfg: ModelConfig, w: dict, h: torch.Tensor, group) -> torch.Tenso
     inv[perm] = torch.arange(perm.numel(), device=h.device)
     ys = _VarAllToAll.apply(ye.index_select(0, inv), recv_counts, send_counts, group)   # back to the token owners, assignment order
     y = ys * top_w.reshape(-1)[order].to(h.dtype).unsqueeze(-1)
-    return torch.zeros(t, h.shape[1], dtype=y.dtype, device=h.device).index_add(0, tok, y)
+    y = torch.zeros(t, h.shape[1], dtype=y.dtype, device=h.device).index_add(0, tok, y)
+    s = tf.shared_expert(w, h)                                    # replicated (data-parallel) like the rest of the dense part
+    return y if s is None else y + s
 
 
 def ep_layer_forward(cfg: ModelConfig, w: dict, x: torch.Tensor, inp: tf.PackedInput, group) -> torch.Tensor:
-    """A decoder block whose MoE MLP is expert-parallel: attention through the ordinary block code with the MLP swapped."""
+    """A decoder block whose MoE MLP is expert-parallel: attention through the ordinary block code with the MLP swapped.  Dense
+    blocks of a mixed stack run the ordinary block."""
+    if "router" not in w:
+        return tf.layer_forward(cfg, w, x, inp)
     dense = {k: v for k, v in w.items() if k not in ("router", "ewgu", "ewd")}
     dense["_skip_mlp"] = True
     xa = tf.layer_forward(cfg, dense, x, inp)                     # attention half (+ residual); see layer_forward
@@ -229,6 +231,7 @@ class EPTrainEngine:
         sq_d = sum((g.pow(2).sum() for k, g in grads.items() if not self.is_expert(k)), torch.zeros((), device=self.device))
         dist.all_reduce(sq_e, group=self.group)
         norm = float((sq_e + sq_d).sqrt().item())
+        self.last_grads = grads                    # mean gradients of the step just taken (tests / diagnostics)
         skipped = not math.isfinite(norm)
         if not skipped:
             self.opt_step += 1

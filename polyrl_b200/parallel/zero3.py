@@ -508,7 +508,7 @@ class Zero3Engine:
         self.lora = lora if trainable else None
         base_tr = None if self.lora is None else False
         self.embed = ShardedUnit("embed", tf.embed_param_specs(cfg), self, trainable=base_tr)
-        self.layers = [ShardedUnit(f"layers.{i}", tf.layer_param_specs(cfg), self, trainable=base_tr)
+        self.layers = [ShardedUnit(f"layers.{i}", tf.layer_param_specs(cfg, i), self, trainable=base_tr)
                        for i in range(cfg.num_layers)]
         self.head = ShardedUnit("head", tf.head_param_specs(cfg), self, trainable=base_tr)
         self.base_units = [self.embed, *self.layers, self.head]
@@ -657,7 +657,7 @@ class Zero3Engine:
             if self.moe_aux:        # MoE blocks also return their load-balancing term (a second, differentiable output)
                 aux: list = []
                 y = tf.layer_forward(cfg, w, x, inp, aux_out=aux)
-                return y, aux[0]
+                return y, (aux[0] if aux else y.new_zeros((), dtype=torch.float32))      # dense blocks of a mixed stack: no term
             return tf.layer_forward(cfg, w, x, inp)
 
         tied = cfg.tie_word_embeddings and not cfg.value_head
@@ -703,7 +703,7 @@ class Zero3Engine:
         c = self.cfg
         inter = getattr(c, "intermediate_size", 4 * c.hidden_size)
         if c.num_experts:                       # every token passes through k experts of width moe_intermediate_size (+ its copies)
-            inter = c.num_experts_per_tok * (c.moe_intermediate_size + c.hidden_size)
+            inter = c.num_experts_per_tok * (c.moe_intermediate_size + c.hidden_size) + c.shared_expert_intermediate_size
         qkv = (c.num_heads + 2 * c.num_kv_heads) * c.head_dim
         per = 2 * (5 * c.hidden_size + qkv + 3 * inter) + 64
         import os
@@ -804,7 +804,8 @@ class Zero3Engine:
             for r in self.layer_runners:
                 x, a = r(inp, x)
                 auxs.append(a)
-            self.last_aux_loss = torch.stack(auxs).mean()          # mean over blocks; add ``coef * last_aux_loss`` to the loss
+            # mean over the sparse blocks; add ``coef * last_aux_loss`` to the loss
+            self.last_aux_loss = torch.stack(auxs).sum() / max(1, self.cfg.num_sparse_layers())
             return x
         for r in self.layer_runners:
             x = r(inp, x)

@@ -104,10 +104,20 @@ class TPContext:
         if "bqkv" in w:
             out["bqkv"] = torch.cat([w["bqkv"][q0:q0 + nq * d], w["bqkv"][k0:k0 + nkv * d], w["bqkv"][v0:v0 + nkv * d]]).contiguous()
         out["wo"] = w["wo"][:, q0:q0 + nq * d]                      # [H, nq_local*d] view, row pitch = full
-        if c.num_experts:
+        if "router" in w:                                            # a sparse block (MoE stacks may also hold dense blocks)
             el = c.num_experts // W
             out["router"] = w["router"]                               # replicated: every rank routes every token identically
+            if "router_bias" in w:
+                out["router_bias"] = w["router_bias"]
             out["ewgu"], out["ewd"] = w["ewgu"][r * el:(r + 1) * el], w["ewd"][r * el:(r + 1) * el]
+            if "swgu" in w:                                           # shared expert: column / row parallel like a dense MLP
+                fs = c.shared_expert_intermediate_size // W
+                if c.shared_expert_intermediate_size % (128 * W) == 0:
+                    out["swgu"], out["swd"] = w["swgu"][r * 2 * fs:(r + 1) * 2 * fs], w["swd"][:, r * fs:(r + 1) * fs]
+                elif r == 0:                                          # too narrow to split into whole 128-row blocks: rank 0 runs it
+                    out["swgu"], out["swd"] = w["swgu"], w["swd"]
+                if "sgate" in w and "swgu" in out:
+                    out["sgate"] = w["sgate"]
             return out
         f2 = 2 * c.intermediate_size // W
         out["wgu"] = w["wgu"][r * f2:(r + 1) * f2]                  # contiguous rows (block-interleaved layout)
@@ -182,10 +192,7 @@ def moe_partial(tp: TPContext, cfg: ModelConfig, w: dict, h: torch.Tensor, stati
     t, k, e = h.shape[0], cfg.num_experts_per_tok, cfg.num_experts
     el = e // tp.world
     e0 = tp.rank * el
-    probs = torch.softmax(F.linear(h, w["router"].to(h.dtype)).float(), dim=-1)
-    top_w, top_e = torch.topk(probs, k, dim=-1)
-    if cfg.norm_topk_prob:
-        top_w = top_w / top_w.sum(-1, keepdim=True)
+    top_w, top_e, _ = tf.moe_route(cfg, w, h)
     flat_e = top_e.reshape(-1)
     order = torch.argsort(flat_e, stable=True)
     sorted_e = flat_e[order]
@@ -203,7 +210,7 @@ def moe_partial(tp: TPContext, cfg: ModelConfig, w: dict, h: torch.Tensor, stati
         a = ref.swiglu(gu.reshape(el * t, -1)).reshape(el, t, -1)
         y = torch.bmm(a, w["ewd"].to(h.dtype).transpose(1, 2))
         y = torch.cat([y, y.new_zeros(1, t, h.shape[1])], dim=0)[row, slot] * gate.unsqueeze(-1)
-        return torch.zeros(t, h.shape[1], dtype=y.dtype, device=h.device).index_add(0, tok, y)
+        return _add_shared(w, h, torch.zeros(t, h.shape[1], dtype=y.dtype, device=h.device).index_add(0, tok, y))
     counts = torch.bincount(flat_e, minlength=e).tolist()
     xs = h.index_select(0, tok)
     out = torch.zeros(t, h.shape[1], dtype=h.dtype, device=h.device)
@@ -214,7 +221,13 @@ def moe_partial(tp: TPContext, cfg: ModelConfig, w: dict, h: torch.Tensor, stati
             y = ops.linear(a, w["ewd"][ei - e0]) * gate[lo:lo + n].unsqueeze(-1)
             out = out.index_add(0, tok[lo:lo + n], y.to(out.dtype))
         lo += n
-    return out
+    return _add_shared(w, h, out)
+
+
+def _add_shared(w: dict, h: torch.Tensor, part: torch.Tensor) -> torch.Tensor:
+    """+ this rank's column slice of the shared expert (its sigmoid gate distributes over the partial sums)."""
+    s = tf.shared_expert(w, h)
+    return part if s is None else part + s.to(part.dtype)
 
 
 def _row_out(tp: TPContext, lcfg: ModelConfig, w: dict, a: torch.Tensor, wname: str, norm: str, x: torch.Tensor, decode: bool) -> torch.Tensor:

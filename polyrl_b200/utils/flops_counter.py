@@ -36,12 +36,14 @@ class FlopsCounter:
     def _dense_params(self) -> int:
         c = self.cfg
         h, f, v = c.hidden_size, c.intermediate_size, c.vocab_size
-        if c.num_experts:                                 # MoE: only the routed experts (+ the router) do work per token
-            mlp = c.num_experts_per_tok * 3 * h * c.moe_intermediate_size + c.num_experts * h
-        else:
-            mlp = 3 * h * f if c.family == "llama" else 2 * h * f
-        per_layer = h * (c.q_size + 2 * c.kv_size) + c.q_size * h + mlp
-        return per_layer * c.num_layers + v * h           # lm_head included, input embedding lookup excluded
+        dense_mlp = 3 * h * f if c.family == "llama" else 2 * h * f
+        attn = h * (c.q_size + 2 * c.kv_size) + c.q_size * h
+        if c.num_experts:                                 # MoE: only the routed (+ shared) experts and the router do work per token
+            sparse_mlp = (c.num_experts_per_tok * 3 * h * c.moe_intermediate_size + c.num_experts * h
+                          + 3 * h * c.shared_expert_intermediate_size + (h if c.shared_expert_gate else 0))
+            n_sparse = c.num_sparse_layers()
+            return attn * c.num_layers + sparse_mlp * n_sparse + dense_mlp * (c.num_layers - n_sparse) + v * h
+        return (attn + dense_mlp) * c.num_layers + v * h   # lm_head included, input embedding lookup excluded
 
     def _attn_flops(self, batch_seqlens: list[int]) -> float:
         """QK^T + PV, fwd+bwd, counted without the causal discount (the reference's convention).  Sliding-window layers

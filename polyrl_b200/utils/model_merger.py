@@ -24,7 +24,7 @@ def merge(ckpt_dir: str) -> tuple[ModelConfig, dict[str, torch.Tensor]]:
     if len(files) != world:
         raise ValueError(f"expected {world} shards, found {len(files)}")
     shards = [torch.load(f, map_location="cpu", weights_only=False) for f in files]
-    units = [("embed", tf.embed_param_specs(cfg))] + [(f"layers.{i}", tf.layer_param_specs(cfg)) for i in range(cfg.num_layers)] + \
+    units = [("embed", tf.embed_param_specs(cfg))] + [(f"layers.{i}", tf.layer_param_specs(cfg, i)) for i in range(cfg.num_layers)] + \
             [("head", tf.head_param_specs(cfg))]
     if cfg.vision is not None and "vision" in shards[0]:          # vision-language checkpoints carry the tower as one more unit
         from ..models.vision import vision_unit_specs

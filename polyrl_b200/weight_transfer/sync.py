@@ -33,7 +33,7 @@ class WeightLayout:
 
     def __init__(self, cfg: ModelConfig, n_trainers: int):
         self.units: list[tuple[str, tf.ParamSpec]] = [("embed", tf.embed_param_specs(cfg))]
-        self.units += [(f"layers.{i}", tf.layer_param_specs(cfg)) for i in range(cfg.num_layers)]
+        self.units += [(f"layers.{i}", tf.layer_param_specs(cfg, i)) for i in range(cfg.num_layers)]
         self.units.append(("head", tf.head_param_specs(cfg)))
         self.n_text = len(self.units)                 # vision-language models: the tower follows the text stack
         if cfg.vision is not None:

@@ -27,7 +27,7 @@ def main():
     # variable all-to-all: rank r sends (r + j + 1) rows to rank j
     send = [rank + j + 1 for j in range(world)]
     recv = [j + rank + 1 for j in range(world)]
-    cfg = get_model_config("tiny-qwen3-moe-128" if cuda else "tiny-qwen3-moe")
+    cfg = get_model_config(os.environ.get("EP_TRAIN_MODEL") or ("tiny-qwen3-moe-128" if cuda else "tiny-qwen3-moe"))
     if cuda and os.environ.get("EP_PEER") == "1":
         from polyrl_b200.parallel.expert import enable_peer_dispatch
         from polyrl_b200.parallel.symm import SymmetricHeap
@@ -41,7 +41,8 @@ def main():
     assert local_expert_range(cfg, world, rank) == (2 * rank, 2 * rank + 2)
     lr = 1e-3 if cuda else 1e-2
     eng = EPTrainEngine(cfg, dev, dist.group.WORLD, lr=lr, weight_decay=0.0, seed=11)
-    assert eng.master["layers.0.ewgu"].shape[0] == 2 and eng.master["layers.0.router"].shape[0] == 8
+    sl = next(i for i in range(cfg.num_layers) if i not in cfg.dense_layers)            # first sparse block
+    assert eng.master[f"layers.{sl}.ewgu"].shape[0] == 2 and eng.master[f"layers.{sl}.router"].shape[0] == 8
 
     def batch(r: int, step: int):
         gen = torch.Generator().manual_seed(900 + 10 * step + r)
@@ -86,13 +87,21 @@ def main():
             ((-(rlp.mean()) + 0.01 * rent.mean()) / world).backward()
             if r == rank:
                 mine = rlp.detach().float()
-        grads = {n: cparams[n].grad.float() for n in params}
+        # parameters that only steer discrete choices (the router's selection bias) receive no gradient
+        grads = {n: (cparams[n].grad.float() if cparams[n].grad is not None else torch.zeros_like(params[n])) for n in params}
         gn = torch.sqrt(sum(g.pow(2).sum() for g in grads.values())).item()
         coef = min(1.0, 1.0 / (gn + 1e-6))
         with torch.no_grad():
             for n, p in params.items():
                 ref.adamw_step(p, m[n], v[n], grads[n], lr, 0.9, 0.999, 1e-8, 0.0, step + 1, coef)
         lp_err = max(lp_err, (lp.detach().float() - mine).abs().max().item())
+        if os.environ.get("EP_TRAIN_DEBUG") and rank == 0:
+            for n in ("embed", "layers.0.wqkv", "layers.1.swgu", "layers.1.router"):
+                if n in grads and n in eng.last_grads:
+                    d = (eng.last_grads[n] - grads[n]).abs()
+                    small = (grads[n].abs() < 1e-7).float().mean().item()
+                    print(f"EP_TRAIN_DEBUG   {n}: max|dg|={d.max().item():.2e} max|g|={grads[n].abs().max().item():.2e} frac|g|<1e-7={small:.4f} nonzero={(grads[n] != 0).float().mean().item():.4f}", flush=True)
+            print(f"EP_TRAIN_DEBUG step={step} lp_err={(lp.detach().float() - mine).abs().max().item():.3e} gn={gn:.5f} eng_gn={st['grad_norm']:.5f}", flush=True)
         gn_err = max(gn_err, abs(st["grad_norm"] - gn))
     got = eng.gather_full_state()
     want = {n: t.detach() for n, t in w.named_tensors()}
@@ -104,6 +113,8 @@ def main():
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     # GPU: same-precision oracle; what is left is summation order (atomics, all-reduce) and Adam amplifying it where |g| ~ noise
     tol = (0.2, 2e-2, 0.05) if cuda else (1e-4, 1e-4, 2e-3)
+    if os.environ.get("EP_TRAIN_TOL"):
+        tol = tuple(float(x) for x in os.environ["EP_TRAIN_TOL"].split(","))
     if rank == 0:
         print(f"EP_TRAIN lp_err={t[0]:.3e} gn_err={t[1]:.3e} w_err={t[2]:.3e} worst={worst}", flush=True)
     assert t[0] < tol[0] and t[1] < tol[1] and t[2] < tol[2], t

@@ -1,10 +1,14 @@
 """Mixture-of-experts family (Qwen3-MoE layout) on CPU: logits equal HF, HF checkpoint round trip, the ZeRO engine trains router
 and experts like plain autograd, the rollout engine decodes it, the pipeline engine's stage function runs it."""
+import math
+
+import pytest
 import torch
 
 from polyrl_b200.models import hf_io
 from polyrl_b200.models import transformer as tf
 from polyrl_b200.models.config import ModelConfig, get_model_config
+from polyrl_b200.models.transformer import TransformerWeights, pack_padded
 
 
 def _hf_tiny():
@@ -214,19 +218,24 @@ def test_tp_expert_sharding_partials_sum_to_the_full_moe():
     from polyrl_b200.models import transformer as tf
     from polyrl_b200.rollout.tp import moe_partial
 
-    cfg = get_model_config("tiny-qwen3-moe")
-    w = TransformerWeights(cfg, "cpu", torch.float32, seed=2).layers[0]
-    h = torch.randn(13, cfg.hidden_size)
-    want = tf.moe_mlp(cfg, w, h)
-    for world in (2, 4):
-        el = cfg.num_experts // world
-        for static in (False, True):
-            total = torch.zeros_like(want)
-            for r in range(world):
-                tp = SimpleNamespace(rank=r, world=world)
-                wl = {"router": w["router"], "ewgu": w["ewgu"][r * el:(r + 1) * el], "ewd": w["ewd"][r * el:(r + 1) * el]}
-                total += moe_partial(tp, cfg, wl, h, static)
-            assert (total - want).abs().max() < 1e-5, (world, static)
+    from polyrl_b200.rollout.tp import TPContext
+
+    for preset, li in (("tiny-qwen3-moe", 0), ("tiny-glm4-moe", 1), ("tiny-qwen2-moe", 0)):
+        cfg = get_model_config(preset)
+        w = TransformerWeights(cfg, "cpu", torch.float32, seed=2).layers[li]
+        if "router_bias" in w:
+            w["router_bias"].normal_(0.0, 0.2, generator=torch.Generator().manual_seed(4))
+        h = torch.randn(13, cfg.hidden_size)
+        want = tf.moe_mlp(cfg, w, h)
+        for world in (2, 4):              # 4 ranks: the 256-wide shared experts no longer split into whole 128-row blocks -> rank 0 runs them
+            for static in (False, True):
+                total = torch.zeros_like(want)
+                for r in range(world):
+                    tp = SimpleNamespace(rank=r, world=world, cfg=cfg)
+                    wl = TPContext.shard_layer(tp, w)                 # the engine's own slicing (experts whole, shared expert column / row)
+                    wl = {k: v for k, v in wl.items() if k in ("router", "router_bias", "ewgu", "ewd", "swgu", "swd", "sgate")}
+                    total += moe_partial(tp, cfg, wl, h, static)
+                assert (total - want).abs().max() < 1e-5, (preset, world, static)
 
 
 def test_mixtral_logits_match_hf_and_legacy_checkpoint_names_load(tmp_path):
@@ -284,3 +293,100 @@ def test_mixtral_logits_match_hf_and_legacy_checkpoint_names_load(tmp_path):
     (d / "config.json").write_text(__import__("json").dumps(hc.to_dict()))
     back = load_state_dict(cfg, d)
     assert all(torch.equal(back[k], sd[k]) for k in sd)
+
+
+def _randomise_(model, skip=()):
+    """Move HF's all-ones / zero / uninitialised tensors to informative values (stacked experts come back uninitialised)."""
+    g = torch.Generator().manual_seed(7)
+    with torch.no_grad():
+        for n, p_ in model.named_parameters():
+            if "experts.gate_up_proj" in n or "experts.down_proj" in n:
+                p_.copy_(0.05 * torch.randn(p_.shape, generator=g))
+            elif p_.dim() == 1:
+                p_.add_(0.1 * torch.randn(p_.shape, generator=g))
+        for n, b in model.named_buffers():
+            if "e_score_correction_bias" in n:
+                b.copy_(0.2 * torch.randn(b.shape, generator=g))
+
+
+@pytest.mark.parametrize("family", ["qwen2_moe", "glm4_moe", "qwen3_moe_mixed"])
+def test_moe_variants_match_hf(family, tmp_path):
+    """Qwen2-MoE (shared expert behind a per-token sigmoid gate, qkv bias, a dense block via mlp_only_layers), GLM-4.5-style MoE
+    (sigmoid scores, bias-corrected group-limited selection, scaled weights, always-on shared experts, first block dense, partial
+    rotary, per-head QK norm) and a Qwen3-MoE stack with decoder_sparse_step = 2: logits equal HF, greedy decoding through the paged
+    engine equals the full forward, ZeRO gradients equal plain autograd, and the HF checkpoint directory round-trips."""
+    import transformers
+
+    from polyrl_b200.models import hf_io
+    from polyrl_b200.parallel.zero3 import Zero3Engine
+    from polyrl_b200.rollout.engine import RolloutEngine, SamplingParams
+
+    torch.manual_seed(0)
+    common = dict(vocab_size=320, hidden_size=128, intermediate_size=256, num_hidden_layers=3, num_attention_heads=4, num_key_value_heads=2,
+                  max_position_embeddings=128, rms_norm_eps=1e-5, tie_word_embeddings=False, pad_token_id=0)
+    if family == "qwen2_moe":
+        hc = transformers.Qwen2MoeConfig(**common, num_experts=8, num_experts_per_tok=2, moe_intermediate_size=128,
+                                         shared_expert_intermediate_size=256, norm_topk_prob=False, mlp_only_layers=[1], decoder_sparse_step=1)
+        m = transformers.Qwen2MoeForCausalLM(hc)
+    elif family == "glm4_moe":
+        hc = transformers.Glm4MoeConfig(**common, head_dim=32, n_routed_experts=8, num_experts_per_tok=2, moe_intermediate_size=128,
+                                        n_shared_experts=1, n_group=4, topk_group=2, routed_scaling_factor=1.5, norm_topk_prob=True,
+                                        first_k_dense_replace=1, use_qk_norm=True, attention_bias=True)
+        m = transformers.Glm4MoeForCausalLM(hc)
+    else:
+        hc = transformers.Qwen3MoeConfig(**common, head_dim=32, num_experts=8, num_experts_per_tok=2, moe_intermediate_size=128,
+                                         norm_topk_prob=True, mlp_only_layers=[], decoder_sparse_step=2)
+        m = transformers.Qwen3MoeForCausalLM(hc)
+    m = m.eval().float()
+    _randomise_(m)
+    cfg = ModelConfig.from_hf_config(m.config.to_dict())
+    sparse = [tf.is_sparse_layer(cfg, i) for i in range(3)]
+    assert sparse == {"qwen2_moe": [True, False, True], "glm4_moe": [False, True, True], "qwen3_moe_mixed": [False, True, False]}[family]
+    w = TransformerWeights(cfg, "cpu", torch.float32, init=False)
+    sd = m.state_dict()
+    w.load_state_dict(tf.convert_hf_state_dict(cfg, sd))
+    assert sum(t.numel() for _, t in w.named_tensors()) == cfg.num_params()
+    ids = torch.randint(3, 320, (2, 33))
+    with torch.no_grad():
+        want = m(ids).logits
+        inp, _ = pack_padded(ids, torch.ones_like(ids))
+        got = tf.forward_hidden(cfg, w, inp) @ tf.lm_head_weight(cfg, w.head, w.embed).t()
+    assert (got - want.reshape(-1, 320)).abs().max().item() < 3e-4
+    # paged engine (dynamic and static expert paths) vs the full forward
+    eng = RolloutEngine(cfg, "cpu", max_num_seqs=4, max_model_len=64, kv_cache_tokens=4 * 64)
+    eng.set_weights(w.embed, w.layers, w.head)
+    prompt = ids[0, :9].tolist()
+    out = eng.generate([prompt], SamplingParams(max_new_tokens=6, temperature=0.0, ignore_eos=True))[0][0].output_ids
+    with torch.no_grad():
+        hf_out = m.generate(torch.tensor([prompt]), max_new_tokens=6, do_sample=False, eos_token_id=None, pad_token_id=0)[0, 9:].tolist()
+    assert out == hf_out
+    h = torch.randn(5, cfg.hidden_size)
+    lw = w.layers[sparse.index(True)]
+    assert (tf.moe_mlp_static(cfg, lw, h) - tf.moe_mlp(cfg, lw, h)).abs().max() < 1e-5
+    # ZeRO engine: same log-probs and gradient norm as plain autograd
+    labels = torch.randint(0, 320, (inp.input_ids.numel(),))
+    e = Zero3Engine(cfg, "cpu", lr=1e-3, weight_decay=0.0, seed=2, max_grad_norm=1e9)
+    for u, src in [(e.embed, w.embed), (e.head, w.head)] + list(zip(e.layers, w.layers)):
+        u.load_full_state(src)
+    w.requires_grad_(True)
+    lp_o = torch.log_softmax((tf.forward_hidden(cfg, w, inp) @ tf.lm_head_weight(cfg, w.head, w.embed).t()).float(), -1).gather(1, labels[:, None]).squeeze(1)
+    (-lp_o.mean()).backward()
+    gn = math.sqrt(sum(float(t.grad.pow(2).sum()) for _, t in w.named_tensors() if t.grad is not None))
+    lp, _ = e.forward_logprob_entropy(inp, labels, 1.0)
+    assert (lp - lp_o.detach()).abs().max() < 1e-5
+    (-lp.mean()).backward()
+    assert abs(e.step()["grad_norm"] - gn) < 1e-4 * max(1.0, gn)
+    # checkpoint directory out and back, and HF reloads it with the same logits
+    w.requires_grad_(False)
+    e2 = Zero3Engine(cfg, "cpu", seed=5)
+    for u, src in [(e2.embed, w.embed), (e2.head, w.head)] + list(zip(e2.layers, w.layers)):
+        u.load_full_state(src)
+    hf_io.save_hf(e2, cfg, tmp_path / "ck", dtype=torch.float32)
+    m2 = type(m).from_pretrained(tmp_path / "ck", dtype=torch.float32).eval()
+    with torch.no_grad():
+        assert (m2(ids).logits - want).abs().max() < 1e-4
+    cfg2 = get_model_config(str(tmp_path / "ck"))
+    assert cfg2.dense_layers == cfg.dense_layers and cfg2.moe_router == cfg.moe_router and cfg2.shared_expert_intermediate_size == cfg.shared_expert_intermediate_size
+    back = hf_io.load_state_dict(cfg2, tmp_path / "ck")
+    mine = w.state_dict()
+    assert set(back) == set(mine) and all(torch.allclose(back[k], mine[k]) for k in mine)
