@@ -150,7 +150,10 @@ def _embed_head(cfg: ModelConfig, ck: HFCheckpoint) -> tuple[dict, dict]:
         return embed, head
     embed = {"embed": ck.get("model.embed_tokens.weight")}
     head = {"norm_w": ck.get("model.norm.weight")}
-    if not cfg.tie_word_embeddings:
+    if cfg.value_head:                       # reward-model / critic checkpoints carry ``score``; language-model checkpoints do not
+        if "score.weight" in ck.weight_map:
+            head.update(tf.value_head_from_hf(cfg, ck.get("score.weight"), ck.get("score.bias") if "score.bias" in ck.weight_map else None))
+    elif not cfg.tie_word_embeddings:
         head["lm_head"] = ck.get("lm_head.weight")
     return embed, head
 
@@ -207,6 +210,17 @@ def load_into_engine(engine, path: str | Path) -> int:
 
 
 def hf_config_dict(cfg: ModelConfig) -> dict:
+    """HF ``config.json`` of the model.  Value-head models (critics, reward models) are written as the family's
+    ``...ForTokenClassification`` with one label, the class the reference loads them with (verl/workers/fsdp_workers.py critic:
+    AutoModelForTokenClassification, num_labels = 1)."""
+    d = _lm_config_dict(cfg)
+    if cfg.value_head and cfg.vision is None and d.get("architectures"):
+        d["architectures"] = [d["architectures"][0].replace("ForCausalLM", "ForTokenClassification").replace("LMHeadModel", "ForTokenClassification")]
+        d.update(num_labels=1, id2label={"0": "LABEL_0"}, label2id={"LABEL_0": 0}, classifier_dropout=0.0)
+    return d
+
+
+def _lm_config_dict(cfg: ModelConfig) -> dict:
     if cfg.family == "gpt2":
         return {"model_type": "gpt2", "architectures": ["GPT2LMHeadModel"], "vocab_size": cfg.vocab_size, "n_embd": cfg.hidden_size,
                 "n_inner": cfg.intermediate_size, "n_layer": cfg.num_layers, "n_head": cfg.num_heads, "n_positions": cfg.max_position_embeddings,

@@ -76,7 +76,9 @@ def head_param_specs(cfg: ModelConfig) -> ParamSpec:
     if cfg.family == "gpt2":
         specs.append(("norm_b", (h,)))
     if cfg.value_head:
-        specs.append(("v_head", (8, h)))          # row 0 is the value projection; padded to 8 rows for alignment
+        # row 0 / element 0 are the value projection and its bias (HF ``score`` of a ...ForTokenClassification checkpoint with
+        # num_labels = 1); padded to 8 rows for alignment
+        specs += [("v_head", (8, h)), ("v_head_b", (8,))]
     elif not cfg.tie_word_embeddings:
         specs.append(("lm_head", (cfg.vocab_size, h)))
     return specs
@@ -470,7 +472,8 @@ def logits_forward(cfg: ModelConfig, head_w: dict, embed_w: dict, hidden: torch.
 
 
 def value_forward(cfg: ModelConfig, head_w: dict, hidden: torch.Tensor) -> torch.Tensor:
-    return F.linear(hidden, head_w["v_head"][:1].to(hidden.dtype)).squeeze(-1).float()
+    v = F.linear(hidden, head_w["v_head"][:1].to(hidden.dtype)).squeeze(-1).float()
+    return v + head_w["v_head_b"][0].float() if "v_head_b" in head_w else v
 
 
 # --------------------------------------------------------------------------------------------
@@ -627,6 +630,21 @@ def unpack_to_padded(values: torch.Tensor, idx: torch.Tensor, batch: int, seqlen
 # --------------------------------------------------------------------------------------------
 # HF checkpoint name mapping (import / export)
 # --------------------------------------------------------------------------------------------
+def value_head_from_hf(cfg: ModelConfig, score_w: torch.Tensor | None, score_b: torch.Tensor | None) -> dict[str, torch.Tensor]:
+    """``score.weight`` [1, H] (+ ``score.bias`` [1]) of a token-classification / reward-model checkpoint -> our padded value head.
+    Empty when the checkpoint has no scoring head (a critic started from a language model keeps its fresh head)."""
+    if score_w is None:
+        return {}
+    if score_w.shape[0] != 1:
+        raise ValueError(f"value / reward heads are scalar: score.weight has {score_w.shape[0]} labels")
+    w = score_w.new_zeros(8, cfg.hidden_size)
+    w[0] = score_w[0]
+    b = score_w.new_zeros(8)
+    if score_b is not None:
+        b[0] = score_b[0]
+    return {"v_head": w, "v_head_b": b}
+
+
 def convert_hf_state_dict(cfg: ModelConfig, hf_sd: dict[str, torch.Tensor]) -> dict[str, torch.Tensor]:
     """Map HF Llama / Qwen2 / Qwen3 / GPT-2 parameter names to ours (fusing q/k/v and interleaving gate/up; GPT-2's Conv1D
     weights are stored [in, out] and get transposed)."""
@@ -645,7 +663,9 @@ def convert_hf_state_dict(cfg: ModelConfig, hf_sd: dict[str, torch.Tensor]) -> d
     if any(k.startswith("model.language_model.") for k in hf_sd):        # VL checkpoints nest the text stack
         hf_sd = {k.replace("model.language_model.", "model.", 1): v for k, v in hf_sd.items()}
     out = {"embed": hf_sd["model.embed_tokens.weight"], "norm_w": hf_sd["model.norm.weight"]}
-    if not cfg.tie_word_embeddings:
+    if cfg.value_head:
+        out.update(value_head_from_hf(cfg, hf_sd.get("score.weight"), hf_sd.get("score.bias")))
+    elif not cfg.tie_word_embeddings:
         out["lm_head"] = hf_sd["lm_head.weight"]
     for i in range(cfg.num_layers):
         p = f"model.layers.{i}."
@@ -712,7 +732,11 @@ def export_hf_state_dict(cfg: ModelConfig, sd: dict[str, torch.Tensor]) -> dict[
             out[p + "mlp.c_proj.weight"], out[p + "mlp.c_proj.bias"] = sd[q + "wproj"].t().contiguous(), sd[q + "bproj"]
         return out
     out = {"model.embed_tokens.weight": sd["embed"], "model.norm.weight": sd["norm_w"]}
-    out["lm_head.weight"] = sd["embed"] if cfg.tie_word_embeddings else sd["lm_head"]
+    if cfg.value_head:                                           # critics / reward models: HF ...ForTokenClassification, num_labels = 1
+        out["score.weight"] = sd["v_head"][:1]
+        out["score.bias"] = sd["v_head_b"][:1] if "v_head_b" in sd else sd["v_head"].new_zeros(1)
+    else:
+        out["lm_head.weight"] = sd["embed"] if cfg.tie_word_embeddings else sd["lm_head"]
     q, kv = cfg.q_size, cfg.kv_size
     perm = rope_feature_perm(cfg)
     back = (lambda t: t) if perm is None else (lambda t: _permute_heads(t, perm, cfg.head_dim, inverse=True))

@@ -8,7 +8,7 @@ import torch
 
 from polyrl_b200.models import TransformerWeights, forward_hidden, lm_head_weight, pack_padded
 from polyrl_b200.models import transformer as tf
-from polyrl_b200.models.config import ModelConfig
+from polyrl_b200.models.config import ModelConfig, get_model_config
 
 transformers = pytest.importorskip("transformers")
 
@@ -264,3 +264,44 @@ def test_glm_families_match_hf(family, tmp_path):
     assert not unexpected and all("rotary" in k for k in missing), (missing, unexpected)
     with torch.no_grad():
         assert (m2(ids).logits - want).abs().max().item() < 1e-5
+
+
+def test_value_head_round_trips_through_hf_token_classification(tmp_path):
+    """Critics / reward models: an HF ``...ForTokenClassification`` checkpoint with one label (``score`` weight + bias) loads into the
+    value-head engine and gives the same per-token values; a value-head engine saved in HF format loads back into HF with equal
+    outputs; a plain LM checkpoint still initialises a critic (fresh head, loaded trunk)."""
+    from polyrl_b200.models import hf_io
+    from polyrl_b200.parallel.zero3 import Zero3Engine
+
+    torch.manual_seed(0)
+    hc = transformers.Qwen2Config(vocab_size=320, hidden_size=128, intermediate_size=256, num_hidden_layers=2, num_attention_heads=4,
+                                  num_key_value_heads=2, max_position_embeddings=128, rms_norm_eps=1e-6, tie_word_embeddings=False,
+                                  num_labels=1, classifier_dropout=0.0)
+    m = transformers.Qwen2ForTokenClassification(hc).eval().float()
+    with torch.no_grad():
+        m.score.bias.fill_(0.37)
+    m.save_pretrained(tmp_path / "rm", safe_serialization=True)
+    cfg = get_model_config(str(tmp_path / "rm"), value_head=True)
+    eng = Zero3Engine(cfg, "cpu", seed=3)
+    assert hf_io.load_into_engine(eng, tmp_path / "rm") > 0
+    ids = torch.randint(3, 320, (2, 19))
+    inp, _ = pack_padded(ids, torch.ones_like(ids))
+    with torch.no_grad():
+        want = m(ids).logits[..., 0].reshape(-1)
+        got = eng.forward_values(inp)
+    assert (got - want).abs().max() < 2e-4 and want.abs().max() > 0.1
+    # engine -> HF directory -> HF model
+    hf_io.save_hf(eng, cfg, tmp_path / "out", dtype=torch.float32)
+    m2 = transformers.AutoModelForTokenClassification.from_pretrained(tmp_path / "out", dtype=torch.float32).eval()
+    assert type(m2).__name__ == "Qwen2ForTokenClassification"
+    with torch.no_grad():
+        assert (m2(ids).logits[..., 0].reshape(-1) - want).abs().max() < 2e-4
+    # a language-model checkpoint: trunk loaded, head left as initialised
+    lm = transformers.Qwen2ForCausalLM(hc).eval().float()
+    lm.save_pretrained(tmp_path / "lm", safe_serialization=True)
+    crit = Zero3Engine(get_model_config(str(tmp_path / "lm"), value_head=True), "cpu", seed=4)
+    head0 = {n: t.clone() for n, t in crit.named_full_tensors() if n in ("v_head", "v_head_b")}
+    hf_io.load_into_engine(crit, tmp_path / "lm")
+    after = dict(crit.named_full_tensors())
+    assert all(torch.equal(after[n], head0[n]) for n in head0)
+    assert torch.equal(after["layers.0.wo"], lm.state_dict()["model.layers.0.self_attn.o_proj.weight"])
