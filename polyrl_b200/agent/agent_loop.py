@@ -258,10 +258,10 @@ class MultiTurnRollout:
         tr.response_mask += [1] * len(out)
         tr.logprobs += lps
         tr.assistant_turns += 1
+        text, calls = self.parser.extract_tool_calls(out)
+        tr.messages.append({"role": "assistant", "content": text})          # also when cut short: recipes read the conversation
         if req.finish_reason in ("length", "abort") or len(tr.response_ids) >= self.response_length:
             return self._terminate(tr, req.finish_reason if req.finish_reason != "stop" else "length")
-        text, calls = self.parser.extract_tool_calls(out)
-        tr.messages.append({"role": "assistant", "content": text})
         if calls and self.tools and tr.assistant_turns < self.max_assistant_turns:
             tr.state = AgentState.PROCESSING_TOOLS
             futures[self.pool.submit(self._run_tools, tr, calls)] = tr
@@ -289,7 +289,7 @@ class MultiTurnRollout:
             msgs = list(s.get("messages") or [])
             pids = list(map(int, s["prompt_ids"])) if s.get("prompt_ids") is not None else self.encode_prompt(msgs)
             mm0 = _engine_mm(s.get("multi_modal_inputs"))
-            trajs.append(_Traj(index=i, prompt_ids=pids, messages=msgs, extra=s, mm=mm0))
+            trajs.append(_Traj(index=i, prompt_ids=pids, messages=msgs, extra=s, mm=mm0, interaction_id=s.get("_interaction_id")))
         for tr in trajs:
             self._submit(tr, sampling)
         futures: dict[Future, _Traj] = {}
@@ -312,6 +312,7 @@ class MultiTurnRollout:
                 else:
                     self._terminate(tr, "length")
         outs = []
+        self.last_messages = [tr.messages for tr in trajs]           # final conversation of every trajectory (recipes score them)
         for tr in trajs:
             if tr.state != AgentState.TERMINATED:
                 self._terminate(tr)
@@ -394,6 +395,46 @@ def outputs_to_dataproto(outs: list[AgentLoopOutput], prompt_length: int, respon
             mm_arr[i] = o.multi_modal_inputs
         nt["multi_modal_inputs"] = mm_arr
     nt.update(non_tensors or {})
-    return DataProto.from_dict({"prompts": prompts, "responses": resp, "input_ids": torch.cat([prompts, resp], dim=1),
-                                "attention_mask": attention_mask, "position_ids": position_ids, "response_mask": r_loss,
-                                "rollout_log_probs": lps}, non_tensors=nt)
+    tensors = {"prompts": prompts, "responses": resp, "input_ids": torch.cat([prompts, resp], dim=1), "attention_mask": attention_mask,
+               "position_ids": position_ids, "response_mask": r_loss, "rollout_log_probs": lps}
+    if any(o.reward_score is not None for o in outs):
+        # an agent loop that scores its own trajectories (e.g. recipes/collabllm.py): the scalar sits on the last response token,
+        # the layout reward models use (``rm_scores``), so the reward managers / trainers pick it up unchanged
+        rm = torch.zeros(b, response_length, dtype=torch.float32)
+        for i, o in enumerate(outs):
+            n = min(len(o.response_ids), response_length)
+            if o.reward_score is not None and n:
+                rm[i, n - 1] = float(o.reward_score)
+        tensors["rm_scores"] = rm
+        keys = sorted({k for o in outs for k, v in o.metrics.items() if "/" in k and isinstance(v, (int, float))})
+        for k in keys:                                            # recipe metrics ride along per sample ("collabllm/accuracy", ...)
+            nt[k] = np.array([float(o.metrics.get(k, 0.0)) for o in outs], dtype=np.float64)
+    return DataProto.from_dict(tensors, non_tensors=nt)
+
+
+_AGENT_LOOPS: dict[str, Any] = {}
+
+
+def register_agent_loop(name: str, target) -> None:
+    """``target``: a MultiTurnRollout subclass or a dotted path to one (imported on first use)."""
+    _AGENT_LOOPS[name] = target
+
+
+def get_agent_loop_cls(name: str | None):
+    """Agent-loop class by registry name (``tool_agent``, ``single_turn_agent``, ``collabllm_agent``, ``react_agent``) or dotted path
+    (reference: ``rollout.agent.default_agent_loop`` + the ``_target_`` entries of agent_loop_config_path files)."""
+    import importlib
+
+    target = _AGENT_LOOPS.get(name or "tool_agent", name)
+    if isinstance(target, str):
+        mod, _, attr = target.rpartition(".")
+        if not mod:
+            raise KeyError(f"unknown agent loop {name!r} (registered: {sorted(_AGENT_LOOPS)})")
+        target = getattr(importlib.import_module(mod), attr)
+    return target
+
+
+register_agent_loop("tool_agent", ToolAgentLoop)
+register_agent_loop("single_turn_agent", SingleTurnAgentLoop)
+register_agent_loop("collabllm_agent", "polyrl_b200.recipes.collabllm.CollabLLMAgentLoop")
+register_agent_loop("react_agent", "polyrl_b200.agent.graph.ReactAgentLoop")

@@ -82,9 +82,18 @@ class WeatherInteraction(BaseInteraction):
 _INTERACTIONS = {"gsm8k": Gsm8kInteraction, "weather": WeatherInteraction, "base": BaseInteraction}
 
 
+def register_interaction(name: str, cls) -> None:
+    """Make an interaction class loadable by a short name in ``interaction_config_path`` files."""
+    _INTERACTIONS[name] = cls
+
+
+_LAZY_INTERACTIONS = {"collabllm": "polyrl_b200.recipes.collabllm.CollabLLMInteraction"}      # registered by their recipe modules
+
+
 def get_interaction_cls(name: str):
     if name in _INTERACTIONS:
         return _INTERACTIONS[name]
+    name = _LAZY_INTERACTIONS.get(name, name)
     mod, _, attr = name.rpartition(".")
     return getattr(importlib.import_module(mod), attr)
 

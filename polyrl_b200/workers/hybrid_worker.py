@@ -437,8 +437,16 @@ class ActorRolloutRefWorker:
         mt = self.config.actor_rollout_ref.rollout.multi_turn
         if getattr(self, "_multi_turn", None) is None:
             tok = load_tokenizer(self.config.actor_rollout_ref.model.tokenizer_path)
-            self._multi_turn = MultiTurnRollout(
-                self.rollout, tok, tools=load_tools(mt.tool_config_path), interactions=load_interactions(mt.interaction_config_path),
+            from ..agent import get_agent_loop_cls
+
+            agent_cfg = dict(self.config.actor_rollout_ref.rollout.agent or {})
+            name = agent_cfg.get("default_agent_loop")
+            if name in ("collabllm_agent",):
+                from ..recipes import collabllm  # noqa: F401 — registers the simulated-user interaction
+            loop_cls = get_agent_loop_cls(name) if name else MultiTurnRollout
+            self._multi_turn = loop_cls(
+                self.rollout, tok, **dict(agent_cfg.get("agent_loop_kwargs") or {}),
+                tools=load_tools(mt.tool_config_path), interactions=load_interactions(mt.interaction_config_path),
                 parser=mt.format, response_length=resp_len, max_assistant_turns=mt.max_assistant_turns,
                 max_user_turns=mt.max_user_turns, max_parallel_calls=mt.max_parallel_calls,
                 max_tool_response_length=mt.max_tool_response_length, tool_response_truncate_side=mt.tool_response_truncate_side,

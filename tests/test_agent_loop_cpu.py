@@ -125,6 +125,12 @@ def test_interaction_loop():
     assert o.turn_scores == [0.0, 1.0]
 
 
+def _scripted_user(messages, **kw):
+    """Simulated user for the worker-level CollabLLM test: one follow-up question, then done."""
+    mine = sum(m["role"] == "assistant" for m in messages)
+    return "and then?" if mine < 2 else "ok [[TERMINATE CHAT]]"
+
+
 def test_real_engine_smoke():
     """Random tiny model: whatever it emits, the loop must terminate with consistent bookkeeping."""
     from polyrl_b200.models import TransformerWeights, get_model_config
@@ -141,8 +147,13 @@ def test_real_engine_smoke():
         assert 0 < len(o.response_ids) <= 48 and len(o.response_ids) == len(o.response_mask)
 
 
-def test_worker_multi_turn_generate_and_update(tmp_path):
-    """Colocated worker with multi_turn.enable: trajectories with tool config flow through generate -> log-prob -> update."""
+import pytest
+
+
+@pytest.mark.parametrize("agent", [None, "react_agent", "collabllm_agent"])
+def test_worker_multi_turn_generate_and_update(tmp_path, agent):
+    """Colocated worker with multi_turn.enable: trajectories with tool config flow through generate -> log-prob -> update; the agent
+    loop class is selected by ``rollout.agent.default_agent_loop`` (graph-structured ReAct agent, CollabLLM forward sampling)."""
     import numpy as np
     import yaml
 
@@ -157,16 +168,31 @@ def test_worker_multi_turn_generate_and_update(tmp_path):
                              "actor_rollout_ref.rollout.cuda_graph=False", "actor_rollout_ref.rollout.multi_turn.enable=True",
                              f"actor_rollout_ref.rollout.multi_turn.tool_config_path={tools_yaml}",
                              "actor_rollout_ref.actor.ppo_mini_batch_size=2", "actor_rollout_ref.actor.ppo_micro_batch_size_per_gpu=2",
-                             "actor_rollout_ref.rollout.log_prob_micro_batch_size_per_gpu=4"])
+                             "actor_rollout_ref.rollout.log_prob_micro_batch_size_per_gpu=4"]
+                      + ([f"actor_rollout_ref.rollout.agent.default_agent_loop={agent}"] if agent else []))
+    nt = {"uid": np.array(["a", "b"], dtype=object)}
+    if agent == "collabllm_agent":
+        inter_yaml = tmp_path / "inter.yaml"
+        inter_yaml.write_text(yaml.safe_dump({"interaction": [{"name": "collabllm", "class_name": "collabllm",
+                                                               "config": {"user_model": "tests.test_agent_loop_cpu._scripted_user"}}]}))
+        cfg.actor_rollout_ref.rollout.multi_turn.interaction_config_path = str(inter_yaml)
+        cfg.actor_rollout_ref.rollout.agent["agent_loop_kwargs"] = {"num_repeat_rollouts": 2, "metric_weights": {"token_amount": -0.001, "interactivity": 1.0}}
+        ik = {"name": "collabllm", "single_turn_prompt": "find x", "ground_truth": "4"}
+        nt["interaction_kwargs"] = np.array([ik, ik], dtype=object)
+        nt["raw_prompt"] = np.array([[{"role": "user", "content": "hi"}], [{"role": "user", "content": "yo"}]], dtype=object)
     w = ActorRolloutRefWorker(cfg, role="actor_rollout", device="cpu")
     w.init_model()
     ids = torch.randint(3, 200, (2, 16))
     mask = torch.ones_like(ids)
     mask[0, :5] = 0
     prompts = DataProto.from_dict({"input_ids": ids, "attention_mask": mask, "position_ids": (mask.cumsum(-1) - 1).clamp_min(0)},
-                                  non_tensors={"uid": np.array(["a", "b"], dtype=object)})
+                                  non_tensors=nt)
     out = w.generate_sequences(prompts)
     assert out.batch["responses"].shape == (4, 24) and "__num_turns__" in out.non_tensor_batch
+    if agent:
+        assert type(w._multi_turn).__name__ == {"react_agent": "ReactAgentLoop", "collabllm_agent": "CollabLLMAgentLoop"}[agent]
+    if agent == "collabllm_agent":
+        assert "rm_scores" in out.batch and (out.non_tensor_batch["collabllm/num_futures"] == 2).all()
     assert (out.batch["response_mask"] <= out.batch["attention_mask"][:, -24:]).all()
     old = w.compute_log_prob(out)
     out = out.union(old)
@@ -401,3 +427,97 @@ def test_image_tool_responses_extend_the_vision_context(tmp_path):
     dp.meta_info.update(temperature=1.0, micro_batch_size=1)
     lp = wk.compute_log_prob(dp).batch["old_log_probs"]
     assert lp.shape == (1, 200) and torch.isfinite(lp).all() and (lp[0, :n][torch.tensor(o.response_mask, dtype=torch.bool)] < 0).all()
+
+
+def test_react_graph_agent_equals_the_tool_loop_and_custom_graphs_run_batched():
+    """agent/graph.py: the ReAct graph (model node <-> tools node, one thread per trajectory, every ``ctx.chat`` a request into the
+    shared engine) yields token for token the trajectory of the built-in tool loop; a custom graph adds a node that injects a user
+    message and scores the conversation; graph construction errors are reported at compile time; a crashing node ends only its
+    own trajectory."""
+    import pytest
+
+    from polyrl_b200.agent import get_agent_loop_cls
+    from polyrl_b200.agent.graph import END, GraphAgentLoop, StateGraph
+
+    tok = ByteTokenizer()
+
+    def policy(ctx: str) -> str:
+        if "<tool>" not in ctx:
+            return 'I will use a tool. <tool_call>{"name": "calculator", "arguments": {"expression": "6*7"}}</tool_call>'
+        if "are you sure" in ctx and "yes, 42" not in ctx:
+            return "yes, 42"
+        if "reward=" not in ctx:
+            ans = ctx.split("<tool>")[1].split("\n")[0]
+            return f'<tool_call>{{"name": "calc_gsm8k_reward", "arguments": {{"answer": "{ans}"}}}}</tool_call>'
+        return "The answer is 42. #### 42"
+
+    spec = {"tools": [{"class_name": "calculator"}, {"class_name": "calc_gsm8k_reward"}]}
+    sample = {"messages": [{"role": "user", "content": "what is 6*7?"}],
+              "tools_kwargs": {"calc_gsm8k_reward": {"create_kwargs": {"ground_truth": "42"}}}}
+    base = MultiTurnRollout(ScriptedEngine(tok, policy), tok, tools=load_tools(spec), response_length=600, max_assistant_turns=5)
+    want = base.generate([dict(sample) for _ in range(3)], {"temperature": 1.0})
+    react = get_agent_loop_cls("react_agent")(ScriptedEngine(tok, policy), tok, tools=load_tools(spec), response_length=600, max_assistant_turns=5)
+    got = react.generate([dict(sample) for _ in range(3)], {"temperature": 1.0})
+    for a, b in zip(got, want):
+        assert a.response_ids == b.response_ids and a.response_mask == b.response_mask and a.response_logprobs == b.response_logprobs
+        assert a.metrics["tool_calls"] == 2 and a.num_turns == b.num_turns and a.finish_reason == "stop"
+    assert [m["role"] for m in react.last_messages[0]] == ["user", "assistant", "tool", "assistant", "tool", "assistant"]
+
+    # a custom graph: model -> (tool calls -> tools -> model) | challenge once -> model | grade -> END
+    def model(state, ctx):
+        msg = ctx.chat(state["messages"])
+        return {"messages": [msg]} if msg is not None else {"exhausted": True}
+
+    def tools(state, ctx):
+        return {"messages": ctx.run_tools(state["messages"][-1]["tool_calls"])}
+
+    def challenge(state, ctx):
+        return {"messages": [{"role": "user", "content": "are you sure?"}], "challenged": True}
+
+    def grade(state, ctx):
+        if ctx.sample.get("boom"):
+            raise RuntimeError("grader crashed")
+        return {"reward_score": 1.0 if "42" in (state["messages"][-1].get("content") or "") else 0.0}
+
+    def route(state):
+        last = state["messages"][-1]
+        if state.get("exhausted"):
+            return "grade"
+        if last.get("tool_calls"):
+            return "tools"
+        return "challenge" if not state.get("challenged") else "grade"
+
+    g = (StateGraph().add_node("model", model).add_node("tools", tools).add_node("challenge", challenge).add_node("grade", grade)
+         .set_entry_point("model").add_conditional_edges("model", route).add_edge("tools", "model").add_edge("challenge", "model")
+         .add_edge("grade", END))
+    loop = GraphAgentLoop(ScriptedEngine(tok, policy), tok, graph_factory=g.compile, tools=load_tools(spec), response_length=900,
+                          max_assistant_turns=8)
+    outs = loop.generate([dict(sample), {**sample, "boom": True}], {"temperature": 1.0})
+    o = outs[0]
+    text = tok.decode(o.response_ids)
+    assert o.reward_score == 1.0 and "are you sure?" in text and "yes, 42" in text
+    ctx_text = tok.decode([t for t, m in zip(o.response_ids, o.response_mask) if not m])
+    assert "are you sure?" in ctx_text and "yes, 42" not in ctx_text          # injected turn: context; model turns: trained
+    assert outs[1].finish_reason.startswith("error: RuntimeError") and outs[1].reward_score is None and outs[1].response_ids
+    dp = outputs_to_dataproto(outs, prompt_length=64, response_length=900, pad_id=tok.pad_token_id)
+    assert float(dp.batch["rm_scores"][0].sum()) == 1.0 and float(dp.batch["rm_scores"][1].sum()) == 0.0
+    # budget: one assistant turn only -> chat returns None on the second call and the graph still terminates
+    tight = GraphAgentLoop(ScriptedEngine(tok, policy), tok, graph_factory=g.compile, tools=load_tools(spec), response_length=900,
+                           max_assistant_turns=1)
+    t = tight.generate([dict(sample)], {"temperature": 1.0})[0]
+    assert t.finish_reason == "length" and t.metrics["tool_calls"] == 1
+    # construction errors
+    with pytest.raises(ValueError):
+        StateGraph().add_node("a", model).compile()                           # no entry point
+    with pytest.raises(ValueError):
+        StateGraph().add_node("a", model).set_entry_point("a").compile()       # no way out of "a"
+    with pytest.raises(ValueError):
+        StateGraph().add_node("a", model).set_entry_point("a").add_edge("a", "nowhere").compile()
+    # chat() must extend the conversation the engine has seen
+    def bad(state, ctx):
+        ctx.chat(state["messages"])
+        return {"messages": [ctx.chat([{"role": "user", "content": "something else"}])]}
+
+    bg = StateGraph().add_node("bad", bad).set_entry_point("bad").add_edge("bad", END)
+    r = GraphAgentLoop(ScriptedEngine(tok, policy), tok, graph_factory=bg.compile, response_length=300).generate([dict(sample)])[0]
+    assert r.finish_reason.startswith("error: ValueError")

@@ -177,3 +177,61 @@ def test_prime_recipe_filters_by_accuracy_and_trains_the_prm():
     assert {"reward_model/prm_ce_loss", "reward_model/pairwise_acc", "reward_model/process_reward_mean", "prime/acc_mean"} <= set(m)
     assert 0.2 <= m["prime/acc_mean"] <= 0.8                                            # only mixed groups were trained on
     assert any(not torch.equal(after[n], before[n]) for n in before)                    # the PRM itself was updated
+
+
+def test_collabllm_multiturn_aware_reward_from_simulated_futures():
+    """CollabLLM agent loop: the trained response is ONE assistant turn; ``num_repeat_rollouts`` futures are sampled with a simulated
+    user (one more user turn each here, then the termination signal) inside the same engine; the reward of the trained turn is the
+    weighted mean of the conversation-level metrics of its futures and lands on the last response token as ``rm_scores``."""
+    from polyrl_b200.agent.agent_loop import get_agent_loop_cls, outputs_to_dataproto
+    from polyrl_b200.agent.interactions import load_interactions
+    from polyrl_b200.data.rl_dataset import load_tokenizer
+    from polyrl_b200.models import TransformerWeights
+    from polyrl_b200.recipes import collabllm as C
+    from polyrl_b200.rollout.engine import RolloutEngine
+
+    cfg = get_model_config("tiny-llama")
+    w = TransformerWeights(cfg, "cpu", torch.float32, seed=3)
+    eng = RolloutEngine(cfg, "cpu", max_num_seqs=16, max_model_len=512, kv_cache_tokens=16 * 512, enable_prefix_cache=True)
+    eng.set_weights(w.embed, w.layers, w.head)
+    tok = load_tokenizer("byte")
+    calls = []
+
+    def user(messages, **kw):                       # the simulator sees the dialogue from the user's side + its hidden goal
+        assert messages[0]["role"] == "system" and "find x" in messages[0]["content"] and messages[-1]["role"] == "user"
+        calls.append(len(messages))
+        mine = sum(m["role"] == "assistant" for m in messages)             # its own earlier lines
+        return "can you explain?" if mine < 2 else f"thanks {C.TERMINATION_SIGNAL}"
+
+    its = load_interactions({"interaction": [{"name": "collabllm", "class_name": "collabllm", "config": {"user_model": user}}]})
+    loop = get_agent_loop_cls("collabllm_agent")(eng, tok, interactions=its, num_repeat_rollouts=2, response_length=16,
+                                                 metric_weights={"token_amount": -0.01, "interactivity": 1.0, "bleu_score": 0.5},
+                                                 max_assistant_turns=4, max_user_turns=3)
+    ik = {"name": "collabllm", "single_turn_prompt": "find x", "ground_truth": "x = 4"}
+    samples = [{"messages": [{"role": "user", "content": f"help {i}"}], "interaction_kwargs": ik} for i in range(3)]
+    outs = loop.generate(samples, {"temperature": 1.0})
+    assert len(outs) == 3 and all(o.response_mask == [1] * len(o.response_ids) and 0 < len(o.response_ids) <= 16 for o in outs)
+    m = C.ConversationMetrics(tok)
+    for o in outs:
+        assert o.metrics["collabllm/num_futures"] == 2 and o.reward_score is not None
+        want = -0.01 * o.metrics["collabllm/token_amount"] + o.metrics["collabllm/interactivity"] + 0.5 * o.metrics["collabllm/bleu_score"]
+        assert abs(o.reward_score - want) < 1e-9
+        assert o.metrics["collabllm/token_amount"] > 0                       # futures hold at least the trained turn + one more
+    assert len(calls) >= 6                                                   # >= one simulated reply per future
+    dp = outputs_to_dataproto(outs, 64, 16, cfg.pad_token_id)
+    rm, mask = dp.batch["rm_scores"], dp.batch["attention_mask"][:, 64:]
+    last = mask.sum(-1) - 1
+    assert torch.allclose(rm[torch.arange(3), last], torch.tensor([o.reward_score for o in outs], dtype=torch.float32))
+    assert (rm != 0).sum() <= 3 and "collabllm/interactivity" in dp.non_tensor_batch
+    # metrics
+    assert C.bleu_score("the answer is x = 4", "the answer is x = 4") == pytest.approx(1.0)
+    assert 0 < C.bleu_score("the answer is x = 5 maybe", "the answer is x = 4") < 1 and C.bleu_score("", "a") == 0
+    conv = [{"role": "user", "content": "q"}, {"role": "assistant", "content": "which one?"}, {"role": "user", "content": "a"},
+            {"role": "assistant", "content": "x = 4"}]
+    assert m.interactivity(conv, {}) == 1.0 and m.bleu_score(conv, {"ground_truth": "x = 4"}) == pytest.approx(1.0)
+    judged = C.ConversationMetrics(tok, judge=lambda msgs, **kw: '{"accuracy": 1}' if "x = 4" in msgs[0]["content"] else '{"accuracy": 0}')
+    assert judged.accuracy(conv, {"ground_truth": "x = 4", "single_turn_prompt": "find x"}) == 1.0
+    r, per = C.multiturn_aware_reward([conv, conv[:2]], {"ground_truth": "x = 4"}, {"interactivity": 2.0}, m)
+    assert per["interactivity"] == 0.5 and r == 1.0                           # second future: only one assistant turn -> 0
+    rows = C.build_rl_rows([{"single_turn_prompt": "find x", "single_turn_completion": "x = 4", "chat": conv}])
+    assert len(rows) == 2 and rows[1]["prompt"] == conv[:3] and rows[0]["extra_info"]["interaction_kwargs"]["name"] == "collabllm"
