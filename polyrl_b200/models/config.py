@@ -68,6 +68,17 @@ class ModelConfig:
     n_group: int = 1
     topk_group: int = 1
     routed_scaling_factor: float = 1.0
+    # Multi-head latent attention (DeepSeek-V2/V3, Moonlight, Kimi text stacks; models/mla.py).  ``attn_type="mla"``: queries come
+    # from a low-rank bottleneck (``q_lora_rank``, 0 = a plain projection), keys / values from ONE shared latent of width
+    # ``kv_lora_rank`` per token plus ``qk_rope_head_dim`` rotary features shared by all heads; a head has ``qk_nope_head_dim``
+    # position-free + ``qk_rope_head_dim`` rotary query / key features (``head_dim`` = their sum) and ``v_head_dim`` value features.
+    # The rollout engine caches only the latent (kv_lora_rank + qk_rope_head_dim numbers per token and layer).
+    attn_type: str = "mha"
+    q_lora_rank: int = 0
+    kv_lora_rank: int = 0
+    qk_nope_head_dim: int = 0
+    qk_rope_head_dim: int = 0
+    v_head_dim: int = 0
     # vision-language models (Qwen2-VL): a ViT tower feeds merged patch embeddings into the image-token positions and the text
     # stack rotates with 3-axis (t, h, w) M-RoPE.  ``vision`` holds the tower shape (see models/vision.py), None = text only.
     vision: dict | None = None
@@ -82,6 +93,15 @@ class ModelConfig:
         self.extra_eos_token_ids = tuple(self.extra_eos_token_ids or ())        # json round trip gives a list
         self.mrope_section = tuple(self.mrope_section or ())
         self.dense_layers = tuple(int(i) for i in (self.dense_layers or ()))
+        if self.attn_type not in ("mha", "mla"):
+            raise ValueError(f"unknown attn_type {self.attn_type!r}")
+        if self.attn_type == "mla":
+            if self.family != "llama" or min(self.kv_lora_rank, self.qk_nope_head_dim, self.qk_rope_head_dim, self.v_head_dim) <= 0:
+                raise ValueError("MLA needs the llama family and kv_lora_rank / qk_nope_head_dim / qk_rope_head_dim / v_head_dim > 0")
+            if self.qk_rope_head_dim % 2 or self.qkv_bias or self.qk_norm or self.vision is not None:
+                raise ValueError("MLA: qk_rope_head_dim must be even; projection biases, per-head QK norm and vision towers are not supported")
+            self.head_dim = self.qk_nope_head_dim + self.qk_rope_head_dim
+            self.num_kv_heads = self.num_heads
         if self.head_dim == 0:
             self.head_dim = self.hidden_size // self.num_heads
         if self.num_heads % self.num_kv_heads != 0:
@@ -112,6 +132,27 @@ class ModelConfig:
     def kv_size(self) -> int:
         return self.num_kv_heads * self.head_dim
 
+    @property
+    def o_in_size(self) -> int:
+        """Input width of the attention output projection (heads x value features)."""
+        return self.num_heads * (self.v_head_dim if self.attn_type == "mla" else self.head_dim)
+
+    def kv_cache_layout(self) -> tuple[int, int, bool]:
+        """(heads, features per head, separate value pool) of one paged KV-cache entry.  MLA caches the shared latent + rotary key
+        features once per token; values are a prefix of the same entry, so no second pool exists."""
+        if self.attn_type == "mla":
+            return 1, self.kv_lora_rank + self.qk_rope_head_dim, False
+        return self.num_kv_heads, self.head_dim, True
+
+    def attn_num_params(self) -> int:
+        """Attention projection parameters of one block (norm gains of the MLA bottlenecks included)."""
+        h = self.hidden_size
+        if self.attn_type == "mla":
+            qk, r = self.num_heads * self.head_dim, self.kv_lora_rank
+            q = (h * self.q_lora_rank + self.q_lora_rank + self.q_lora_rank * qk) if self.q_lora_rank else h * qk
+            return q + h * (r + self.qk_rope_head_dim) + r + r * self.num_heads * (self.qk_nope_head_dim + self.v_head_dim) + self.o_in_size * h
+        return h * (self.q_size + 2 * self.kv_size) + self.q_size * h
+
     def num_params(self) -> int:
         h, f, v = self.hidden_size, self.intermediate_size, self.vocab_size
         if self.family == "llama":
@@ -119,7 +160,7 @@ class ModelConfig:
             if self.num_experts:
                 mlp = self.num_experts * (3 * h * self.moe_intermediate_size + h) + 3 * h * self.shared_expert_intermediate_size
                 mlp += (h if self.shared_expert_gate else 0) + (self.num_experts if self.moe_router == "sigmoid_group" else 0)
-            per = h * (self.q_size + 2 * self.kv_size) + self.q_size * h + mlp + 2 * h
+            per = self.attn_num_params() + mlp + 2 * h
             if self.qk_norm:
                 per += 2 * self.head_dim
             if self.qkv_bias:
@@ -262,6 +303,21 @@ class ModelConfig:
                           moe_router="sigmoid_group", n_group=int(hf.get("n_group") or 1), topk_group=int(hf.get("topk_group") or 1),
                           routed_scaling_factor=float(hf.get("routed_scaling_factor", 1.0)))
             glm_kw = dict(partial_rotary_factor=float(rp.get("partial_rotary_factor") or hf.get("partial_rotary_factor") or 0.5))
+        mla_kw: dict = {}
+        if mt == "deepseek_v3":              # MLA attention + DeepSeek-V3 routing (sigmoid, bias-corrected, group-limited), shared experts
+            if hf.get("attention_bias"):
+                raise NotImplementedError("deepseek_v3 checkpoints with attention_bias are not supported")
+            mla_kw = dict(attn_type="mla", q_lora_rank=int(hf.get("q_lora_rank") or 0), kv_lora_rank=int(hf["kv_lora_rank"]),
+                          qk_nope_head_dim=int(hf["qk_nope_head_dim"]), qk_rope_head_dim=int(hf["qk_rope_head_dim"]),
+                          v_head_dim=int(hf["v_head_dim"]), rope_interleaved=bool(hf.get("rope_interleave", True)))
+            if hf.get("n_routed_experts") and int(hf.get("first_k_dense_replace", 0)) < hf["num_hidden_layers"]:
+                moe_kw = dict(num_experts=hf["n_routed_experts"], num_experts_per_tok=hf["num_experts_per_tok"],
+                              moe_intermediate_size=hf["moe_intermediate_size"], norm_topk_prob=hf.get("norm_topk_prob", True),
+                              dense_layers=tuple(range(min(int(hf.get("first_k_dense_replace", 0)), hf["num_hidden_layers"]))),
+                              shared_expert_intermediate_size=hf["moe_intermediate_size"] * int(hf.get("n_shared_experts") or 0),
+                              moe_router="sigmoid_group", n_group=int(hf.get("n_group") or 1), topk_group=int(hf.get("topk_group") or 1),
+                              routed_scaling_factor=float(hf.get("routed_scaling_factor", 1.0)))
+            hf = {**hf, "head_dim": 0, "num_key_value_heads": hf["num_attention_heads"]}     # HF stores the rotary width as head_dim
         eos = hf.get("eos_token_id", 2)
         extra_eos: tuple = ()
         if isinstance(eos, list):
@@ -277,8 +333,8 @@ class ModelConfig:
                    tie_word_embeddings=hf.get("tie_word_embeddings", False), eos_token_id=eos, extra_eos_token_ids=extra_eos,
                    bos_token_id=hf.get("bos_token_id") or eos, pad_token_id=hf.get("pad_token_id") or eos,
                    sliding_window=(hf.get("sliding_window") if (mt in ("mistral", "mixtral") or hf.get("use_sliding_window")) else None),
-                   hf_model_type=("glm4v" if hf.get("_glm4v") else mt) if mt in ("mistral", "mixtral", "glm", "glm4", "qwen2_moe", "glm4_moe") else "",
-                   name=hf.get("_name_or_path", mt), **vis_kw, **{**moe_kw, **vl_moe_kw}, **glm_kw)
+                   hf_model_type=("glm4v" if hf.get("_glm4v") else mt) if mt in ("mistral", "mixtral", "glm", "glm4", "qwen2_moe", "glm4_moe", "deepseek_v3") else "",
+                   name=hf.get("_name_or_path", mt), **vis_kw, **{**moe_kw, **vl_moe_kw}, **{**glm_kw, **mla_kw})
 
 
 def _qwen_dense_layers(hf: dict) -> tuple:
@@ -435,6 +491,28 @@ PRESETS: dict[str, dict] = {
                         norm_topk_prob=True, dense_layers=(0,), shared_expert_intermediate_size=1408, moe_router="sigmoid_group",
                         n_group=1, topk_group=1, routed_scaling_factor=1.0, hf_model_type="glm4_moe",
                         eos_token_id=151329, extra_eos_token_ids=(151336, 151338), bos_token_id=151329, pad_token_id=151329),
+    # DeepSeek-V3 architecture (MLA + sigmoid group-limited routing); Moonlight-16B-A3B ships under the same model_type
+    "deepseek-v3": dict(family="llama", vocab_size=129280, hidden_size=7168, intermediate_size=18432, num_layers=61, num_heads=128,
+                        num_kv_heads=128, max_position_embeddings=163840, rope_theta=10000.0, rms_norm_eps=1e-6, attn_type="mla",
+                        q_lora_rank=1536, kv_lora_rank=512, qk_nope_head_dim=128, qk_rope_head_dim=64, v_head_dim=128, rope_interleaved=True,
+                        rope_scaling=dict(rope_type="yarn", factor=40.0, original_max_position_embeddings=4096, beta_fast=32.0, beta_slow=1.0,
+                                          mscale=1.0, mscale_all_dim=1.0),
+                        num_experts=256, num_experts_per_tok=8, moe_intermediate_size=2048, norm_topk_prob=True, dense_layers=(0, 1, 2),
+                        shared_expert_intermediate_size=2048, moe_router="sigmoid_group", n_group=8, topk_group=4, routed_scaling_factor=2.5,
+                        hf_model_type="deepseek_v3", eos_token_id=1, bos_token_id=0, pad_token_id=1),
+    "moonlight-16b-a3b": dict(family="llama", vocab_size=163840, hidden_size=2048, intermediate_size=11264, num_layers=27, num_heads=16,
+                              num_kv_heads=16, max_position_embeddings=8192, rope_theta=50000.0, rms_norm_eps=1e-5, attn_type="mla",
+                              q_lora_rank=0, kv_lora_rank=512, qk_nope_head_dim=128, qk_rope_head_dim=64, v_head_dim=128, rope_interleaved=True,
+                              num_experts=64, num_experts_per_tok=6, moe_intermediate_size=1408, norm_topk_prob=True, dense_layers=(0,),
+                              shared_expert_intermediate_size=2816, moe_router="sigmoid_group", n_group=1, topk_group=1,
+                              routed_scaling_factor=2.446, hf_model_type="deepseek_v3", eos_token_id=163585, bos_token_id=163584,
+                              pad_token_id=163839),
+    "tiny-deepseek-v3": dict(family="llama", vocab_size=512, hidden_size=128, intermediate_size=256, num_layers=3, num_heads=4, num_kv_heads=4,
+                             max_position_embeddings=512, rope_theta=10000.0, rms_norm_eps=1e-6, attn_type="mla", q_lora_rank=48,
+                             kv_lora_rank=32, qk_nope_head_dim=32, qk_rope_head_dim=16, v_head_dim=32, rope_interleaved=True,
+                             num_experts=8, num_experts_per_tok=2, moe_intermediate_size=128, norm_topk_prob=True, dense_layers=(0,),
+                             shared_expert_intermediate_size=128, moe_router="sigmoid_group", n_group=4, topk_group=2,
+                             routed_scaling_factor=2.5, hf_model_type="deepseek_v3", eos_token_id=1, bos_token_id=2, pad_token_id=0),
     "tiny-qwen3-moe-128": dict(family="llama", vocab_size=1024, hidden_size=512, intermediate_size=1024, num_layers=2, num_heads=4,
                                num_kv_heads=2, head_dim=128, max_position_embeddings=1024, rope_theta=1000000.0, rms_norm_eps=1e-6,
                                qk_norm=True, num_experts=8, num_experts_per_tok=2, moe_intermediate_size=256, norm_topk_prob=True,

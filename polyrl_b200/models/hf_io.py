@@ -97,6 +97,10 @@ def _layer_keys(cfg: ModelConfig, i: int) -> list[str]:
         keys += [p + "mlp.gate_proj.weight", p + "mlp.up_proj.weight", p + "mlp.down_proj.weight"]
     if cfg.sandwich_norm:
         keys += [p + "post_self_attn_layernorm.weight", p + "post_mlp_layernorm.weight"]
+    if cfg.attn_type == "mla":
+        a = p + "self_attn."
+        q = [a + "q_a_proj.weight", a + "q_a_layernorm.weight", a + "q_b_proj.weight"] if cfg.q_lora_rank else [a + "q_proj.weight"]
+        return keys + q + [a + "kv_a_proj_with_mqa.weight", a + "kv_a_layernorm.weight", a + "kv_b_proj.weight"]
     keys += [p + f"self_attn.{n}_proj.weight" for n in "qkv"]
     if cfg.qkv_bias:
         keys += [p + f"self_attn.{n}_proj.bias" for n in "qkv"]
@@ -306,6 +310,26 @@ def _lm_config_dict(cfg: ModelConfig) -> dict:
                 "max_position_embeddings": cfg.max_position_embeddings, "rms_norm_eps": cfg.rms_norm_eps, "attention_bias": bool(cfg.qkv_bias),
                 "partial_rotary_factor": cfg.partial_rotary_factor, "rope_theta": cfg.rope_theta,
                 "rope_parameters": {"rope_type": "default", "rope_theta": cfg.rope_theta, "partial_rotary_factor": cfg.partial_rotary_factor},
+                "tie_word_embeddings": cfg.tie_word_embeddings, "hidden_act": "silu", "torch_dtype": "bfloat16",
+                "eos_token_id": [cfg.eos_token_id, *cfg.extra_eos_token_ids] if cfg.extra_eos_token_ids else cfg.eos_token_id,
+                "bos_token_id": cfg.bos_token_id, "pad_token_id": cfg.pad_token_id}
+    if cfg.attn_type == "mla":           # DeepSeek-V3 architecture (a dense MLA stack is written as first_k_dense_replace = all layers)
+        first_dense = 0
+        while first_dense in cfg.dense_layers:
+            first_dense += 1
+        fm = cfg.moe_intermediate_size or cfg.intermediate_size
+        rp = {"rope_type": "default", "rope_theta": cfg.rope_theta, **(dict(cfg.rope_scaling) if cfg.rope_scaling else {})}
+        return {"model_type": "deepseek_v3", "architectures": ["DeepseekV3ForCausalLM"], "vocab_size": cfg.vocab_size, "hidden_size": cfg.hidden_size,
+                "intermediate_size": cfg.intermediate_size, "num_hidden_layers": cfg.num_layers, "num_attention_heads": cfg.num_heads,
+                "num_key_value_heads": cfg.num_heads, "max_position_embeddings": cfg.max_position_embeddings, "rms_norm_eps": cfg.rms_norm_eps,
+                "attention_bias": False, "q_lora_rank": cfg.q_lora_rank or None, "kv_lora_rank": cfg.kv_lora_rank,
+                "qk_nope_head_dim": cfg.qk_nope_head_dim, "qk_rope_head_dim": cfg.qk_rope_head_dim, "v_head_dim": cfg.v_head_dim,
+                "rope_interleave": bool(cfg.rope_interleaved), "rope_theta": cfg.rope_theta, "rope_parameters": rp,
+                **({"rope_scaling": dict(cfg.rope_scaling)} if cfg.rope_scaling else {}),
+                "n_routed_experts": cfg.num_experts or 1, "num_experts_per_tok": cfg.num_experts_per_tok or 1, "moe_intermediate_size": fm,
+                "norm_topk_prob": cfg.norm_topk_prob, "n_shared_experts": (cfg.shared_expert_intermediate_size // fm) if cfg.num_experts else 0,
+                "n_group": cfg.n_group, "topk_group": cfg.topk_group, "routed_scaling_factor": cfg.routed_scaling_factor,
+                "first_k_dense_replace": first_dense if cfg.num_experts else cfg.num_layers,
                 "tie_word_embeddings": cfg.tie_word_embeddings, "hidden_act": "silu", "torch_dtype": "bfloat16",
                 "eos_token_id": [cfg.eos_token_id, *cfg.extra_eos_token_ids] if cfg.extra_eos_token_ids else cfg.eos_token_id,
                 "bos_token_id": cfg.bos_token_id, "pad_token_id": cfg.pad_token_id}

@@ -39,12 +39,17 @@ def layer_param_specs(cfg: ModelConfig, i: int | None = None) -> ParamSpec:
     h, f = cfg.hidden_size, cfg.intermediate_size
     qkv = cfg.q_size + 2 * cfg.kv_size
     if cfg.family == "llama":
-        specs: ParamSpec = [("ln1", (h,)), ("wqkv", (qkv, h))]
-        if cfg.qkv_bias:
-            specs.append(("bqkv", (qkv,)))
-        if cfg.qk_norm:
-            specs += [("q_norm", (cfg.head_dim,)), ("k_norm", (cfg.head_dim,))]
-        specs += [("wo", (h, cfg.q_size)), ("ln2", (h,))]
+        if cfg.attn_type == "mla":          # latent attention: fused first-stage projection + up-projections (models/mla.py)
+            from . import mla
+
+            specs: ParamSpec = [("ln1", (h,)), *mla.param_specs(cfg), ("ln2", (h,))]
+        else:
+            specs = [("ln1", (h,)), ("wqkv", (qkv, h))]
+            if cfg.qkv_bias:
+                specs.append(("bqkv", (qkv,)))
+            if cfg.qk_norm:
+                specs += [("q_norm", (cfg.head_dim,)), ("k_norm", (cfg.head_dim,))]
+            specs += [("wo", (h, cfg.q_size)), ("ln2", (h,))]
         if cfg.sandwich_norm:
             specs += [("ln_attn", (h,)), ("ln_mlp", (h,))]
         if is_sparse_layer(cfg, i):    # router + stacked experts (gate/up rows interleaved per expert like the dense ``wgu``)
@@ -94,7 +99,7 @@ def init_param_(name: str, t: torch.Tensor, cfg: ModelConfig, generator: torch.G
             bound = 1.0 / math.sqrt(t.shape[-1])
             t.uniform_(-bound, bound, generator=generator)
         return
-    if base in ("ln1", "ln2", "ln_attn", "ln_mlp", "norm_w", "ln1_w", "ln2_w", "q_norm", "k_norm", "merger_ln_w"):
+    if base in ("ln1", "ln2", "ln_attn", "ln_mlp", "norm_w", "ln1_w", "ln2_w", "q_norm", "k_norm", "merger_ln_w", "q_a_ln", "kv_a_ln"):
         t.fill_(1.0)
     elif base.startswith("b") or base.endswith("_b") or base.startswith("merger_b") or base == "router_bias":
         t.zero_()
@@ -115,6 +120,8 @@ _ROPE_CACHE: dict = {}
 
 def rotary_dim(cfg: ModelConfig) -> int:
     """Features of a head that rotate (``partial_rotary_factor``; the rest passes through unchanged)."""
+    if cfg.attn_type == "mla":
+        return cfg.qk_rope_head_dim
     return int(cfg.head_dim * cfg.partial_rotary_factor) if cfg.partial_rotary_factor < 1.0 else cfg.head_dim
 
 
@@ -373,6 +380,14 @@ def embed_forward(cfg: ModelConfig, w: dict, inp: PackedInput) -> torch.Tensor:
     return x
 
 
+def _mlp_forward(cfg: ModelConfig, w: dict, x: torch.Tensor, aux_out: list | None = None) -> torch.Tensor:
+    """Second half of a llama-family block without adapters: x + MLP(norm(x)), dense SwiGLU or mixture of experts."""
+    h = ops.rmsnorm(x, w["ln2"], cfg.rms_norm_eps)
+    if "router" in w:
+        return x + moe_mlp(cfg, w, h, aux_out)
+    return ops.linear(ops.linear_swiglu(h, w["wgu"]), w["wd"], residual=x)
+
+
 def layer_forward(cfg: ModelConfig, w: dict, x: torch.Tensor, inp: PackedInput, kv_sink=None, aux_out: list | None = None) -> torch.Tensor:
     """One decoder block on packed activations x:[T,H].  ``kv_sink`` = (k_cache, v_cache, slot_mapping)
     makes this a prefill step that also fills the paged KV cache (rollout engine)."""
@@ -386,6 +401,13 @@ def layer_forward(cfg: ModelConfig, w: dict, x: torch.Tensor, inp: PackedInput, 
         if lora:
             from . import lora as L
         h = ops.rmsnorm(x, w["ln1"], cfg.rms_norm_eps)
+        if cfg.attn_type == "mla":
+            from . import mla
+
+            if lora:
+                raise NotImplementedError("LoRA adapters are not implemented for MLA attention")
+            x = ops.linear(mla.attention_forward(cfg, w, h, inp, kv_sink), w["wo"], residual=x)
+            return x if w.get("_skip_mlp") else _mlp_forward(cfg, w, x, aux_out)
         qkv = ops.linear(h, w["wqkv"], bias=w.get("bqkv"))
         if lora and L.has_lora(w, "q_proj", "k_proj", "v_proj"):
             qkv = qkv + L.qkv_delta(cfg, w, h)
@@ -494,6 +516,15 @@ def layer_decode(cfg: ModelConfig, w: dict, x: torch.Tensor, inp: DecodeInput, k
     nq, nkv, d = cfg.num_heads, cfg.num_kv_heads, cfg.head_dim
     b = x.shape[0]
     scale = d ** -0.5
+    if cfg.family == "llama" and cfg.attn_type == "mla":
+        from . import mla
+
+        h = ops.rmsnorm(x, w["ln1"], cfg.rms_norm_eps)
+        x = ops.linear(mla.attention_decode(cfg, w, h, inp, k_cache), w["wo"], residual=x)
+        h = ops.rmsnorm(x, w["ln2"], cfg.rms_norm_eps)
+        if "router" in w:
+            return x + (moe_mlp_static(cfg, w, h) if _MOE_STATIC_DECODE() else moe_mlp(cfg, w, h))
+        return ops.linear(ops.linear_swiglu(h, w["wgu"]), w["wd"], residual=x)
     if cfg.family == "llama":
         h = ops.rmsnorm(x, w["ln1"], cfg.rms_norm_eps)
         qkv = qk_norm_(cfg, w, ops.linear(h, w["wqkv"], bias=w.get("bqkv")))
@@ -645,6 +676,44 @@ def value_head_from_hf(cfg: ModelConfig, score_w: torch.Tensor | None, score_b: 
     return {"v_head": w, "v_head_b": b}
 
 
+def _convert_mlp(cfg: ModelConfig, hf_sd: dict, out: dict, i: int, p: str) -> None:
+    """MLP tensors of block ``i`` (HF prefix ``p``) into ``out``: dense SwiGLU (separate or fused gate_up) or router + experts
+    (stacked, one module per expert, or Mixtral's block_sparse_moe naming) + shared experts."""
+    if is_sparse_layer(cfg, i):
+        fm = cfg.moe_intermediate_size
+        if p + "mlp.gate.e_score_correction_bias" in hf_sd:
+            out[f"layers.{i}.router_bias"] = hf_sd[p + "mlp.gate.e_score_correction_bias"]
+        for sh in ("mlp.shared_expert.", "mlp.shared_experts."):          # Qwen2-MoE / DeepSeek-style naming
+            if p + sh + "gate_proj.weight" in hf_sd:
+                out[f"layers.{i}.swgu"] = ref.interleave_gate_up(hf_sd[p + sh + "gate_proj.weight"], hf_sd[p + sh + "up_proj.weight"])
+                out[f"layers.{i}.swd"] = hf_sd[p + sh + "down_proj.weight"]
+        if p + "mlp.shared_expert_gate.weight" in hf_sd:
+            out[f"layers.{i}.sgate"] = hf_sd[p + "mlp.shared_expert_gate.weight"]
+        if p + "block_sparse_moe.gate.weight" in hf_sd:      # Mixtral checkpoints on disk: block_sparse_moe.experts.{e}.w1 / w3 / w2
+            q = p + "block_sparse_moe."
+            out[f"layers.{i}.router"] = hf_sd[q + "gate.weight"]
+            pairs = [(hf_sd[f"{q}experts.{e}.w1.weight"], hf_sd[f"{q}experts.{e}.w3.weight"]) for e in range(cfg.num_experts)]
+            out[f"layers.{i}.ewd"] = torch.stack([hf_sd[f"{q}experts.{e}.w2.weight"] for e in range(cfg.num_experts)])
+            out[f"layers.{i}.ewgu"] = torch.stack([ref.interleave_gate_up(g, u) for g, u in pairs])
+            return
+        out[f"layers.{i}.router"] = hf_sd[p + "mlp.gate.weight"]
+        if p + "mlp.experts.gate_up_proj" in hf_sd:          # stacked layout [E, 2f, h] (gate rows then up rows)
+            gu, dn = hf_sd[p + "mlp.experts.gate_up_proj"], hf_sd[p + "mlp.experts.down_proj"]
+            pairs = [(gu[e, :fm], gu[e, fm:]) for e in range(cfg.num_experts)]
+            out[f"layers.{i}.ewd"] = dn.clone()
+        else:                                                # one module per expert
+            pairs = [(hf_sd[f"{p}mlp.experts.{e}.gate_proj.weight"], hf_sd[f"{p}mlp.experts.{e}.up_proj.weight"]) for e in range(cfg.num_experts)]
+            out[f"layers.{i}.ewd"] = torch.stack([hf_sd[f"{p}mlp.experts.{e}.down_proj.weight"] for e in range(cfg.num_experts)])
+        out[f"layers.{i}.ewgu"] = torch.stack([ref.interleave_gate_up(g, u) for g, u in pairs])
+        return
+    if p + "mlp.gate_up_proj.weight" in hf_sd:               # GLM: one fused projection, gate rows then up rows
+        gu = hf_sd[p + "mlp.gate_up_proj.weight"]
+        out[f"layers.{i}.wgu"] = ref.interleave_gate_up(gu[: gu.shape[0] // 2], gu[gu.shape[0] // 2:])
+    else:
+        out[f"layers.{i}.wgu"] = ref.interleave_gate_up(hf_sd[p + "mlp.gate_proj.weight"], hf_sd[p + "mlp.up_proj.weight"])
+    out[f"layers.{i}.wd"] = hf_sd[p + "mlp.down_proj.weight"]
+
+
 def convert_hf_state_dict(cfg: ModelConfig, hf_sd: dict[str, torch.Tensor]) -> dict[str, torch.Tensor]:
     """Map HF Llama / Qwen2 / Qwen3 / GPT-2 parameter names to ours (fusing q/k/v and interleaving gate/up; GPT-2's Conv1D
     weights are stored [in, out] and get transposed)."""
@@ -671,6 +740,12 @@ def convert_hf_state_dict(cfg: ModelConfig, hf_sd: dict[str, torch.Tensor]) -> d
         p = f"model.layers.{i}."
         out[f"layers.{i}.ln1"] = hf_sd[p + "input_layernorm.weight"]
         out[f"layers.{i}.ln2"] = hf_sd[p + "post_attention_layernorm.weight"]
+        if cfg.attn_type == "mla":
+            from . import mla
+
+            out.update({f"layers.{i}.{k}": v for k, v in mla.from_hf(cfg, hf_sd, p).items()})
+            _convert_mlp(cfg, hf_sd, out, i, p)
+            continue
         perm = rope_feature_perm(cfg)
         fix = (lambda t, n: _permute_heads(t, perm, cfg.head_dim) if (perm is not None and n in "qk") else t)
         out[f"layers.{i}.wqkv"] = torch.cat([fix(hf_sd[p + f"self_attn.{n}_proj.weight"], n) for n in "qkv"], dim=0)
@@ -682,40 +757,34 @@ def convert_hf_state_dict(cfg: ModelConfig, hf_sd: dict[str, torch.Tensor]) -> d
         if cfg.sandwich_norm:
             out[f"layers.{i}.ln_attn"], out[f"layers.{i}.ln_mlp"] = hf_sd[p + "post_self_attn_layernorm.weight"], hf_sd[p + "post_mlp_layernorm.weight"]
         out[f"layers.{i}.wo"] = hf_sd[p + "self_attn.o_proj.weight"]
-        if is_sparse_layer(cfg, i):
-            fm = cfg.moe_intermediate_size
-            if p + "mlp.gate.e_score_correction_bias" in hf_sd:
-                out[f"layers.{i}.router_bias"] = hf_sd[p + "mlp.gate.e_score_correction_bias"]
-            for sh in ("mlp.shared_expert.", "mlp.shared_experts."):          # Qwen2-MoE / DeepSeek-style naming
-                if p + sh + "gate_proj.weight" in hf_sd:
-                    out[f"layers.{i}.swgu"] = ref.interleave_gate_up(hf_sd[p + sh + "gate_proj.weight"], hf_sd[p + sh + "up_proj.weight"])
-                    out[f"layers.{i}.swd"] = hf_sd[p + sh + "down_proj.weight"]
-            if p + "mlp.shared_expert_gate.weight" in hf_sd:
-                out[f"layers.{i}.sgate"] = hf_sd[p + "mlp.shared_expert_gate.weight"]
-            if p + "block_sparse_moe.gate.weight" in hf_sd:      # Mixtral checkpoints on disk: block_sparse_moe.experts.{e}.w1 / w3 / w2
-                q = p + "block_sparse_moe."
-                out[f"layers.{i}.router"] = hf_sd[q + "gate.weight"]
-                pairs = [(hf_sd[f"{q}experts.{e}.w1.weight"], hf_sd[f"{q}experts.{e}.w3.weight"]) for e in range(cfg.num_experts)]
-                out[f"layers.{i}.ewd"] = torch.stack([hf_sd[f"{q}experts.{e}.w2.weight"] for e in range(cfg.num_experts)])
-                out[f"layers.{i}.ewgu"] = torch.stack([ref.interleave_gate_up(g, u) for g, u in pairs])
-                continue
-            out[f"layers.{i}.router"] = hf_sd[p + "mlp.gate.weight"]
-            if p + "mlp.experts.gate_up_proj" in hf_sd:          # stacked layout [E, 2f, h] (gate rows then up rows)
-                gu, dn = hf_sd[p + "mlp.experts.gate_up_proj"], hf_sd[p + "mlp.experts.down_proj"]
-                pairs = [(gu[e, :fm], gu[e, fm:]) for e in range(cfg.num_experts)]
-                out[f"layers.{i}.ewd"] = dn.clone()
-            else:                                                # one module per expert
-                pairs = [(hf_sd[f"{p}mlp.experts.{e}.gate_proj.weight"], hf_sd[f"{p}mlp.experts.{e}.up_proj.weight"]) for e in range(cfg.num_experts)]
-                out[f"layers.{i}.ewd"] = torch.stack([hf_sd[f"{p}mlp.experts.{e}.down_proj.weight"] for e in range(cfg.num_experts)])
-            out[f"layers.{i}.ewgu"] = torch.stack([ref.interleave_gate_up(g, u) for g, u in pairs])
-            continue
-        if p + "mlp.gate_up_proj.weight" in hf_sd:               # GLM: one fused projection, gate rows then up rows
-            gu = hf_sd[p + "mlp.gate_up_proj.weight"]
-            out[f"layers.{i}.wgu"] = ref.interleave_gate_up(gu[: gu.shape[0] // 2], gu[gu.shape[0] // 2:])
-        else:
-            out[f"layers.{i}.wgu"] = ref.interleave_gate_up(hf_sd[p + "mlp.gate_proj.weight"], hf_sd[p + "mlp.up_proj.weight"])
-        out[f"layers.{i}.wd"] = hf_sd[p + "mlp.down_proj.weight"]
+        _convert_mlp(cfg, hf_sd, out, i, p)
     return out
+
+
+def _export_mlp(cfg: ModelConfig, sd: dict, out: dict, i: int, p: str, fused_gu: bool) -> None:
+    """MLP tensors and the two block norms of block ``i`` in HF names (inverse of ``_convert_mlp``)."""
+    if is_sparse_layer(cfg, i):                              # stacked HF layout
+        gus = [ref.deinterleave_gate_up(sd[f"layers.{i}.ewgu"][e]) for e in range(cfg.num_experts)]
+        out[p + "mlp.gate.weight"] = sd[f"layers.{i}.router"]
+        out[p + "mlp.experts.gate_up_proj"] = torch.stack([torch.cat([g, u], dim=0) for g, u in gus])
+        out[p + "mlp.experts.down_proj"] = sd[f"layers.{i}.ewd"]
+        if f"layers.{i}.router_bias" in sd:
+            out[p + "mlp.gate.e_score_correction_bias"] = sd[f"layers.{i}.router_bias"]
+        if f"layers.{i}.swgu" in sd:
+            sh = "mlp.shared_expert." if cfg.shared_expert_gate else "mlp.shared_experts."
+            g, u = ref.deinterleave_gate_up(sd[f"layers.{i}.swgu"])
+            out[p + sh + "gate_proj.weight"], out[p + sh + "up_proj.weight"], out[p + sh + "down_proj.weight"] = g, u, sd[f"layers.{i}.swd"]
+        if f"layers.{i}.sgate" in sd:
+            out[p + "mlp.shared_expert_gate.weight"] = sd[f"layers.{i}.sgate"]
+    else:
+        g, u = ref.deinterleave_gate_up(sd[f"layers.{i}.wgu"])
+        if fused_gu:
+            out[p + "mlp.gate_up_proj.weight"] = torch.cat([g, u], dim=0)
+        else:
+            out[p + "mlp.gate_proj.weight"], out[p + "mlp.up_proj.weight"] = g, u
+        out[p + "mlp.down_proj.weight"] = sd[f"layers.{i}.wd"]
+    out[p + "input_layernorm.weight"] = sd[f"layers.{i}.ln1"]
+    out[p + "post_attention_layernorm.weight"] = sd[f"layers.{i}.ln2"]
 
 
 def export_hf_state_dict(cfg: ModelConfig, sd: dict[str, torch.Tensor]) -> dict[str, torch.Tensor]:
@@ -743,6 +812,12 @@ def export_hf_state_dict(cfg: ModelConfig, sd: dict[str, torch.Tensor]) -> dict[
     fused_gu = getattr(cfg, "hf_model_type", "") in ("glm", "glm4", "glm4v")
     for i in range(cfg.num_layers):
         p = f"model.layers.{i}."
+        if cfg.attn_type == "mla":
+            from . import mla
+
+            out.update(mla.to_hf(cfg, sd, f"layers.{i}.", p))
+            _export_mlp(cfg, sd, out, i, p, fused_gu)
+            continue
         w = sd[f"layers.{i}.wqkv"]
         out[p + "self_attn.q_proj.weight"], out[p + "self_attn.k_proj.weight"], out[p + "self_attn.v_proj.weight"] = (
             back(w[:q]), back(w[q:q + kv]), w[q + kv:])
@@ -755,26 +830,5 @@ def export_hf_state_dict(cfg: ModelConfig, sd: dict[str, torch.Tensor]) -> dict[
         if cfg.sandwich_norm:
             out[p + "post_self_attn_layernorm.weight"], out[p + "post_mlp_layernorm.weight"] = sd[f"layers.{i}.ln_attn"], sd[f"layers.{i}.ln_mlp"]
         out[p + "self_attn.o_proj.weight"] = sd[f"layers.{i}.wo"]
-        if is_sparse_layer(cfg, i):                              # stacked HF layout
-            gus = [ref.deinterleave_gate_up(sd[f"layers.{i}.ewgu"][e]) for e in range(cfg.num_experts)]
-            out[p + "mlp.gate.weight"] = sd[f"layers.{i}.router"]
-            out[p + "mlp.experts.gate_up_proj"] = torch.stack([torch.cat([g, u], dim=0) for g, u in gus])
-            out[p + "mlp.experts.down_proj"] = sd[f"layers.{i}.ewd"]
-            if f"layers.{i}.router_bias" in sd:
-                out[p + "mlp.gate.e_score_correction_bias"] = sd[f"layers.{i}.router_bias"]
-            if f"layers.{i}.swgu" in sd:
-                sh = "mlp.shared_expert." if cfg.shared_expert_gate else "mlp.shared_experts."
-                g, u = ref.deinterleave_gate_up(sd[f"layers.{i}.swgu"])
-                out[p + sh + "gate_proj.weight"], out[p + sh + "up_proj.weight"], out[p + sh + "down_proj.weight"] = g, u, sd[f"layers.{i}.swd"]
-            if f"layers.{i}.sgate" in sd:
-                out[p + "mlp.shared_expert_gate.weight"] = sd[f"layers.{i}.sgate"]
-        else:
-            g, u = ref.deinterleave_gate_up(sd[f"layers.{i}.wgu"])
-            if fused_gu:
-                out[p + "mlp.gate_up_proj.weight"] = torch.cat([g, u], dim=0)
-            else:
-                out[p + "mlp.gate_proj.weight"], out[p + "mlp.up_proj.weight"] = g, u
-            out[p + "mlp.down_proj.weight"] = sd[f"layers.{i}.wd"]
-        out[p + "input_layernorm.weight"] = sd[f"layers.{i}.ln1"]
-        out[p + "post_attention_layernorm.weight"] = sd[f"layers.{i}.ln2"]
+        _export_mlp(cfg, sd, out, i, p, fused_gu)
     return out

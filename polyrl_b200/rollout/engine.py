@@ -370,7 +370,8 @@ class RolloutEngine:
 
     def kv_bytes_per_token(self) -> int:
         c = self.cfg
-        return 2 * c.num_layers * c.num_kv_heads * c.head_dim * torch.empty(0, dtype=self.dtype).element_size()
+        heads, width, two = c.kv_cache_layout()          # MLA: one shared latent entry per token, no separate value pool
+        return (2 if two else 1) * c.num_layers * heads * width * torch.empty(0, dtype=self.dtype).element_size()
 
     def init_kv_cache(self) -> None:
         """(Re)create the paged KV pool (``resume_memory_occupation(['kv_cache'])``)."""
@@ -388,7 +389,15 @@ class RolloutEngine:
         tokens = min(tokens, self.max_num_seqs * self.max_blocks_per_seq * PAGE + PAGE)
         num_blocks = max(2, tokens // PAGE)
         c = self.cfg
-        shape = (num_blocks, c.num_kv_heads, PAGE, c.head_dim)
+        kv_heads, kv_width, two_pools = c.kv_cache_layout()
+        shape = (num_blocks, kv_heads, PAGE, kv_width)
+        if not two_pools:
+            # latent attention: the value pool is a prefix view of the key pool (models/mla.py), nothing extra is allocated
+            self.k_cache = [torch.zeros(shape, device=self.device, dtype=self.dtype) for _ in range(c.num_layers)]
+            self.v_cache = [k[..., : c.kv_lora_rank] for k in self.k_cache]
+            self.alloc, self.prefix_cache = make_kv_manager(num_blocks, self.enable_prefix_cache)
+            self._graphs.clear()
+            return
         if self.kv_vmm:
             if self._vmm is None:                      # sized once; later resumes re-back the same virtual range
                 from ..utils.vmm import VmmBuffer
@@ -762,7 +771,8 @@ class RolloutEngine:
         x = torch.nn.functional.embedding(ids, self.embed_w["embed"]).to(self.dtype)
         if cfg.family == "gpt2":
             x = x + torch.nn.functional.embedding(pos, self.embed_w["pos_embed"]).to(self.dtype)
-        fused = self.tp is None and cfg.family == "llama" and self.is_cuda and self.dtype == torch.bfloat16 and not cfg.num_experts
+        fused = (self.tp is None and cfg.family == "llama" and self.is_cuda and self.dtype == torch.bfloat16 and not cfg.num_experts
+                 and cfg.attn_type == "mha")
         delta = None
         for i, w in enumerate(self.layer_w):
             if self.tp is not None:

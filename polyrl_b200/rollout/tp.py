@@ -28,6 +28,8 @@ from ..ops.functional import rope_and_cache_, _skinny_buffers
 
 class TPContext:
     def __init__(self, cfg: ModelConfig, heap, tp_rank: int, tp_world: int, max_batch: int, group=None):
+        if cfg.attn_type != "mha":
+            raise NotImplementedError("tensor-parallel rollout is not implemented for MLA attention (run data-parallel engines)")
         if cfg.num_heads % tp_world or cfg.num_kv_heads % tp_world:
             raise ValueError("heads and kv heads must be divisible by the TP size")
         if cfg.num_experts:

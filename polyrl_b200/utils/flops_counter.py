@@ -37,7 +37,7 @@ class FlopsCounter:
         c = self.cfg
         h, f, v = c.hidden_size, c.intermediate_size, c.vocab_size
         dense_mlp = 3 * h * f if c.family == "llama" else 2 * h * f
-        attn = h * (c.q_size + 2 * c.kv_size) + c.q_size * h
+        attn = c.attn_num_params()
         if c.num_experts:                                 # MoE: only the routed (+ shared) experts and the router do work per token
             sparse_mlp = (c.num_experts_per_tok * 3 * h * c.moe_intermediate_size + c.num_experts * h
                           + 3 * h * c.shared_expert_intermediate_size + (h if c.shared_expert_gate else 0))
@@ -51,6 +51,8 @@ class FlopsCounter:
         c = self.cfg
         full = sum(s * s for s in batch_seqlens)
         win = getattr(c, "sliding_window", None)
+        if c.attn_type == "mla":                # QK^T over nope + rope features, PV over v_head_dim features
+            return 12.0 * c.num_layers * c.num_heads * 0.5 * (c.head_dim + c.v_head_dim) * full
         if not win:
             return 12.0 * c.num_layers * c.q_size * full
         windowed = sum(s * min(s, int(win)) for s in batch_seqlens)

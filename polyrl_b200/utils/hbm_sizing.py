@@ -17,6 +17,8 @@ GB = float(1 << 30)
 
 
 def count_params(c: ModelConfig) -> int:
+    if c.num_experts or c.attn_type != "mha" or c.vision is not None:
+        return c.num_params()
     h, f, v, L = c.hidden_size, c.intermediate_size, c.vocab_size, c.num_layers
     qkv = (c.num_heads + 2 * c.num_kv_heads) * c.head_dim
     per_layer = h * qkv + c.num_heads * c.head_dim * h + 3 * h * f + 2 * h
@@ -72,6 +74,8 @@ def plan(model: str | ModelConfig, n_gpus: int = 8, rollout_tp: int = 1, tokens_
     elif not resident and n_gpus > 1:
         p.rollout_weights = replica
     kv_tok = 2 * c.num_layers * (c.num_kv_heads // max(1, rollout_tp) or 1) * c.head_dim * 2
+    if c.attn_type == "mla":                    # one shared latent entry per token and layer (models/mla.py)
+        kv_tok = c.num_layers * c.kv_cache_layout()[1] * 2
     p.kv_cache = max_num_seqs * max_model_len * kv_tok / GB
     Pc = 0 if not critic else (P if critic is True else count_params(get_model_config(critic)))
     critic_opt = 16 * Pc / n_gpus / GB

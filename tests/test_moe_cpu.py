@@ -390,3 +390,119 @@ def test_moe_variants_match_hf(family, tmp_path):
     back = hf_io.load_state_dict(cfg2, tmp_path / "ck")
     mine = w.state_dict()
     assert set(back) == set(mine) and all(torch.allclose(back[k], mine[k]) for k in mine)
+
+
+@pytest.mark.parametrize("variant", ["q_lora_interleaved", "plain_q_yarn", "dense"])
+def test_deepseek_v3_mla_matches_hf(variant, tmp_path):
+    """DeepSeek-V3 architecture (multi-head latent attention + sigmoid group-limited routing + shared experts; Moonlight ships under
+    the same model_type): logits equal HF ``DeepseekV3ForCausalLM`` with the query bottleneck and interleaved rotary weights, with a
+    plain query projection under YaRN (mscale folded into the softmax scale), and as a dense MLA stack; greedy decoding through the
+    paged engine — which caches only the latent and decodes in the absorbed form — equals HF ``generate``, also with chunked prefill
+    behind a cached prefix; ZeRO gradients equal plain autograd; the HF checkpoint directory round-trips."""
+    import transformers
+
+    from polyrl_b200.models import hf_io
+    from polyrl_b200.parallel.zero3 import Zero3Engine
+    from polyrl_b200.rollout.engine import RolloutEngine, SamplingParams
+
+    torch.manual_seed(0)
+    kw = dict(q_lora_rank=48, rope_interleave=True)
+    if variant == "plain_q_yarn":
+        kw = dict(q_lora_rank=None, rope_interleave=False,
+                  rope_parameters=dict(rope_type="yarn", factor=4.0, original_max_position_embeddings=32, beta_fast=32.0, beta_slow=1.0,
+                                       mscale=1.0, mscale_all_dim=0.8, rope_theta=10000.0))
+    n_layers = 3
+    hc = transformers.DeepseekV3Config(
+        vocab_size=320, hidden_size=128, intermediate_size=256, moe_intermediate_size=128, num_hidden_layers=n_layers, num_attention_heads=4,
+        num_key_value_heads=4, n_shared_experts=1, n_routed_experts=8, routed_scaling_factor=2.5, kv_lora_rank=32, qk_rope_head_dim=16,
+        v_head_dim=32, qk_nope_head_dim=32, n_group=4, topk_group=2, num_experts_per_tok=2,
+        first_k_dense_replace=n_layers if variant == "dense" else 1, norm_topk_prob=True, max_position_embeddings=128, rms_norm_eps=1e-6,
+        pad_token_id=0, tie_word_embeddings=False, **kw)
+    m = transformers.DeepseekV3ForCausalLM(hc).eval().float()
+    _randomise_(m)
+    cfg = ModelConfig.from_hf_config(m.config.to_dict())
+    assert cfg.attn_type == "mla" and cfg.head_dim == 48 and cfg.kv_cache_layout() == (1, 48, False)
+    assert bool(cfg.num_experts) == (variant != "dense") and cfg.dense_layers == (() if variant == "dense" else (0,))
+    w = TransformerWeights(cfg, "cpu", torch.float32, init=False)
+    w.load_state_dict(tf.convert_hf_state_dict(cfg, m.state_dict()))
+    assert sum(t.numel() for _, t in w.named_tensors()) == cfg.num_params()
+    ids = torch.randint(3, 320, (2, 33))
+    with torch.no_grad():
+        want = m(ids).logits
+        inp, _ = pack_padded(ids, torch.ones_like(ids))
+        got = tf.forward_hidden(cfg, w, inp) @ tf.lm_head_weight(cfg, w.head, w.embed).t()
+    assert (got - want.reshape(-1, 320)).abs().max().item() < 3e-4
+    # paged engine over the latent pool: one entry of kv_lora_rank + rope numbers per token and layer, no value pool
+    eng = RolloutEngine(cfg, "cpu", max_num_seqs=4, max_model_len=64, kv_cache_tokens=4 * 64)
+    eng.set_weights(w.embed, w.layers, w.head)
+    eng.init_kv_cache()
+    assert eng.k_cache[0].shape[1:] == (1, eng.k_cache[0].shape[2], 48) and eng.v_cache[0].data_ptr() == eng.k_cache[0].data_ptr()
+    assert eng.kv_bytes_per_token() == n_layers * 48 * 4
+    prompt = ids[0, :21].tolist()
+    with torch.no_grad():
+        hf_out = m.generate(torch.tensor([prompt]), max_new_tokens=6, do_sample=False, eos_token_id=None, pad_token_id=0)[0, 21:].tolist()
+    sp = SamplingParams(max_new_tokens=6, temperature=0.0, ignore_eos=True)
+    assert eng.generate([prompt], sp)[0][0].output_ids == hf_out
+    # chunked prefill (later chunks attend over the cached latent prefix) and the n-samples-share-a-prefill path
+    eng2 = RolloutEngine(cfg, "cpu", max_num_seqs=4, max_model_len=64, kv_cache_tokens=4 * 64, max_prefill_tokens=8)
+    eng2.set_weights(w.embed, w.layers, w.head)
+    outs = eng2.generate([prompt], SamplingParams(max_new_tokens=6, temperature=0.0, ignore_eos=True, n=2))[0]
+    assert [o.output_ids for o in outs] == [hf_out, hf_out]
+    # ZeRO engine: same log-probs and gradient norm as plain autograd
+    labels = torch.randint(0, 320, (inp.input_ids.numel(),))
+    e = Zero3Engine(cfg, "cpu", lr=1e-3, weight_decay=0.0, seed=2, max_grad_norm=1e9)
+    for u, src in [(e.embed, w.embed), (e.head, w.head)] + list(zip(e.layers, w.layers)):
+        u.load_full_state(src)
+    w.requires_grad_(True)
+    lp_o = torch.log_softmax((tf.forward_hidden(cfg, w, inp) @ tf.lm_head_weight(cfg, w.head, w.embed).t()).float(), -1).gather(1, labels[:, None]).squeeze(1)
+    (-lp_o.mean()).backward()
+    gn = math.sqrt(sum(float(t.grad.pow(2).sum()) for _, t in w.named_tensors() if t.grad is not None))
+    lp, _ = e.forward_logprob_entropy(inp, labels, 1.0)
+    assert (lp - lp_o.detach()).abs().max() < 1e-5
+    (-lp.mean()).backward()
+    assert abs(e.step()["grad_norm"] - gn) < 1e-4 * max(1.0, gn)
+    # checkpoint directory out and back, and HF reloads it with the same logits
+    w.requires_grad_(False)
+    e2 = Zero3Engine(cfg, "cpu", seed=5)
+    for u, src in [(e2.embed, w.embed), (e2.head, w.head)] + list(zip(e2.layers, w.layers)):
+        u.load_full_state(src)
+    hf_io.save_hf(e2, cfg, tmp_path / "ck", dtype=torch.float32)
+    m2 = transformers.DeepseekV3ForCausalLM.from_pretrained(tmp_path / "ck", dtype=torch.float32).eval()
+    with torch.no_grad():
+        assert (m2(ids).logits - want).abs().max() < 1e-4
+    cfg2 = get_model_config(str(tmp_path / "ck"))
+    assert (cfg2.attn_type, cfg2.q_lora_rank, cfg2.kv_lora_rank, cfg2.rope_interleaved, cfg2.rope_scaling, cfg2.dense_layers, cfg2.num_experts) == \
+        (cfg.attn_type, cfg.q_lora_rank, cfg.kv_lora_rank, cfg.rope_interleaved, cfg.rope_scaling, cfg.dense_layers, cfg.num_experts)
+    back = hf_io.load_state_dict(cfg2, tmp_path / "ck")
+    mine = w.state_dict()
+    assert set(back) == set(mine) and all(torch.allclose(back[k], mine[k]) for k in mine)
+
+
+def test_deepseek_v3_worker_rollout_logprob_update():
+    """The MLA + MoE preset through the hybrid worker: rollout over the latent cache, old log-probs, one streamed PPO update;
+    engine log-probs agree with the trainer's recomputation (same weights, fp32)."""
+    import numpy as np
+
+    from polyrl_b200.config.schema import load_config
+    from polyrl_b200.protocol import DataProto
+    from polyrl_b200.workers.hybrid_worker import ActorRolloutRefWorker
+
+    g = torch.Generator().manual_seed(3)
+    c = load_config(None, ["trainer.device=cpu", "actor_rollout_ref.model.path=tiny-deepseek-v3", "data.max_prompt_length=12",
+                           "data.max_response_length=6", "actor_rollout_ref.rollout.max_num_seqs=8", "actor_rollout_ref.rollout.n=2",
+                           "actor_rollout_ref.rollout.cuda_graph=False", "actor_rollout_ref.actor.ppo_mini_batch_size=4",
+                           "actor_rollout_ref.actor.ppo_micro_batch_size_per_gpu=2", "actor_rollout_ref.actor.router_aux_loss_coef=0.01"])
+    wk = ActorRolloutRefWorker(c, role="actor_rollout", device="cpu")
+    wk.init_model()
+    pids = torch.randint(3, 200, (2, 12), generator=g)
+    dp = DataProto.from_dict({"input_ids": pids, "attention_mask": torch.ones_like(pids), "position_ids": torch.arange(12).expand(2, -1).contiguous()},
+                             non_tensors={"uid": np.array(["a", "b"], dtype=object)})
+    dp.meta_info.update(temperature=1.0, ignore_eos=True)
+    out = wk.generate_sequences(dp)
+    out = out.union(wk.compute_log_prob(out))
+    mask = out.batch["response_mask"].bool()
+    assert (out.batch["rollout_log_probs"] - out.batch["old_log_probs"])[mask].abs().max() < 1e-4
+    out.batch["advantages"] = torch.randn(4, 6, generator=g) * out.batch["response_mask"]
+    out.meta_info.update({"is_opt_step": True})
+    m = wk.update_actor_stream(out).meta_info["metrics"]
+    assert np.isfinite(m["actor/grad_norm"]).all() and "actor/router_aux_loss" in m

@@ -238,6 +238,11 @@ def test_expert_parallel_training_gloo_ws4():
                         "--master-port", "29762", str(ROOT / "tests" / "ep_train_worker.py")], capture_output=True, text=True, timeout=600,
                        env={**env, "EP_TRAIN_MODEL": "tiny-glm4-moe", "EP_TRAIN_TOL": "2e-3,1e-4,2e-2"})
     assert r.returncode == 0 and "EP_TRAIN_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+    # DeepSeek-V3 architecture: the same routing on top of multi-head latent attention (models/mla.py)
+    r = run_torchrun([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=4", "--master-addr", "127.0.0.1",
+                        "--master-port", "29763", str(ROOT / "tests" / "ep_train_worker.py")], capture_output=True, text=True, timeout=600,
+                       env={**env, "EP_TRAIN_MODEL": "tiny-deepseek-v3", "EP_TRAIN_TOL": "2e-3,1e-4,2e-2"})
+    assert r.returncode == 0 and "EP_TRAIN_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
 
 
 def test_elastic_external_instance_joins_a_running_job(tmp_path):
