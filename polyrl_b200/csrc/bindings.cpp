@@ -3,6 +3,7 @@
 // this file is the only one that sees torch headers.
 #include <ATen/cuda/CUDAContext.h>
 #include "kv_manager.hpp"
+#include "scheduler.hpp"
 #include <c10/cuda/CUDAGuard.h>
 #include <torch/extension.h>
 
@@ -671,7 +672,36 @@ void nvls_bcast_store(const at::Tensor& src, int64_t mc_dst, int64_t ctas) {
                              cur_stream()), "nvls_bcast_store");
 }
 
+static at::Tensor vec_i64(const std::vector<int64_t>& v) {
+  return at::tensor(c10::ArrayRef<int64_t>(v.data(), v.size()), at::TensorOptions().dtype(at::kLong));
+}
+
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
+  py::class_<prl::EngineScheduler>(m, "EngineScheduler")
+      .def(py::init<prl::KvPageManager*, int64_t, int64_t, bool>(), py::arg("kv"), py::arg("max_num_seqs"), py::arg("page_size"),
+           py::arg("prefix_cache"), py::keep_alive<1, 2>())
+      .def("add", &prl::EngineScheduler::add, py::arg("prompt"), py::arg("max_new"), py::arg("group"), py::arg("cacheable"))
+      .def("remove_waiting", &prl::EngineScheduler::remove_waiting)
+      .def("num_waiting", &prl::EngineScheduler::num_waiting)
+      .def("num_free_slots", &prl::EngineScheduler::num_free_slots)
+      .def("num_live", &prl::EngineScheduler::num_live)
+      .def("admit", &prl::EngineScheduler::admit)
+      .def("info", [](const prl::EngineScheduler& s, int64_t h) {        // (slot, blocks, shared_prefix_blocks, cached_tokens, donor)
+        const prl::SchedRequest& r = s.get(h);
+        return py::make_tuple(r.slot, r.blocks, r.shared_prefix_blocks, r.cached_tokens, r.donor);
+      })
+      .def("prefill_arrays", [](const prl::EngineScheduler& s, const std::vector<std::tuple<int64_t, int64_t, int64_t>>& spans, bool gather) {
+        const prl::PrefillArrays a = s.prefill_arrays(spans, gather);
+        return py::make_tuple(vec_i64(a.ids), vec_i64(a.pos), vec_i64(a.slots), vec_i64(a.lens), vec_i64(a.g_blk), vec_i64(a.g_off), vec_i64(a.klens));
+      })
+      .def("block_rows", [](const prl::EngineScheduler& s, const std::vector<int64_t>& handles, int64_t width) {
+        const std::vector<int32_t> rows = s.block_rows(handles, width);
+        return at::tensor(c10::ArrayRef<int32_t>(rows.data(), rows.size()), at::TensorOptions().dtype(at::kInt))
+            .reshape({static_cast<int64_t>(handles.size()), width});
+      })
+      .def("move_slots", &prl::EngineScheduler::move_slots)
+      .def("free_slots", &prl::EngineScheduler::free_slots)
+      .def("finish", &prl::EngineScheduler::finish, py::arg("handle"), py::arg("tokens"), py::arg("to_cache"));
   py::class_<prl::KvPageManager>(m, "KvPageManager")
       .def(py::init<int64_t, int64_t>(), py::arg("num_blocks"), py::arg("page_size"))
       .def_property_readonly("num_blocks", &prl::KvPageManager::num_blocks)

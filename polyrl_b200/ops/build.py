@@ -39,7 +39,7 @@ CU_SOURCES = [
     "nvls.cu",
 ]
 HEADERS = ["common.cuh", "gemm_sm100.cuh", "gemm2_sm100.cuh"]
-HOST_HEADERS = ["kv_manager.hpp"]          # included by bindings.cpp only
+HOST_HEADERS = ["kv_manager.hpp", "scheduler.hpp"]          # included by bindings.cpp only
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",

@@ -74,6 +74,7 @@ class Request:
     mrope_pos: object = None
     mrope_delta: int = 0
     image_embeds: object = None            # tower output, computed at the first prefill chunk and dropped after the last
+    h: int = -1                            # handle inside the native scheduler (csrc/scheduler.hpp), -1 = not registered
 
     @property
     def decoding(self) -> bool:
@@ -304,6 +305,7 @@ class RolloutEngine:
         self.k_cache: list[torch.Tensor] = []
         self.v_cache: list[torch.Tensor] = []
         self.alloc: BlockAllocator | None = None
+        self.sched = None                              # native scheduler (csrc/scheduler.hpp), created with the KV pool
         self.waiting: deque[Request] = deque()
         self.running: dict[int, Request] = {}          # slot -> request
         self.free_slots = list(range(max_num_seqs - 1, -1, -1))
@@ -396,6 +398,7 @@ class RolloutEngine:
             self.k_cache = [torch.zeros(shape, device=self.device, dtype=self.dtype) for _ in range(c.num_layers)]
             self.v_cache = [k[..., : c.kv_lora_rank] for k in self.k_cache]
             self.alloc, self.prefix_cache = make_kv_manager(num_blocks, self.enable_prefix_cache)
+            self._make_scheduler()
             self._graphs.clear()
             return
         if self.kv_vmm:
@@ -416,18 +419,32 @@ class RolloutEngine:
             for t in (*self.k_cache, *self.v_cache):
                 t.zero_()                              # fresh physical pages: masked tail slots must hold finite values
             self.alloc, self.prefix_cache = make_kv_manager(self._kv_blocks, self.enable_prefix_cache)
+            self._make_scheduler()
             return
         self.k_cache = [torch.zeros(shape, device=self.device, dtype=self.dtype) for _ in range(c.num_layers)]
         self.v_cache = [torch.zeros(shape, device=self.device, dtype=self.dtype) for _ in range(c.num_layers)]
         self.alloc, self.prefix_cache = make_kv_manager(num_blocks, self.enable_prefix_cache)
+        self._make_scheduler()
         self._graphs.clear()
+
+    def _make_scheduler(self) -> None:
+        """Native admission scheduler over the native page manager (csrc/scheduler.hpp); ``POLYRL_NATIVE_SCHED=0`` keeps the Python
+        reference implementation below (`_admit`, the planning half of `_prefill`, `_finish`), which the tests compare it against."""
+        self.sched = None
+        if os.environ.get("POLYRL_NATIVE_SCHED", "1") == "1" and isinstance(self.alloc, NativeBlockAllocator):
+            if self.running:
+                raise RuntimeError("KV pool re-created with sequences running")
+            self.sched = ops.ext().EngineScheduler(self.alloc.mgr, self.max_num_seqs, PAGE, self.prefix_cache is not None)
+            self.free_slots = list(range(self.max_num_seqs - 1, -1, -1))
+            for r in self.waiting:
+                r.h = -1
 
     def release_memory(self, tags=("kv_cache",)) -> None:
         """Free engine memory so the trainer can use it (colocated mode).  Requires no running requests."""
         if "kv_cache" in tags:
             if self.running or self.waiting:
                 raise RuntimeError("cannot release the KV cache with requests in flight")
-            self.k_cache, self.v_cache, self.alloc, self.prefix_cache = [], [], None, None
+            self.k_cache, self.v_cache, self.alloc, self.prefix_cache, self.sched = [], [], None, None, None
             if self.kv_vmm and self._vmm is not None:
                 torch.cuda.synchronize(self.device)        # nothing may still read the pool
                 self._vmm.unmap()                          # graphs stay valid: same addresses after the next resume
@@ -502,6 +519,9 @@ class RolloutEngine:
         for r in list(self.waiting):
             if abort_all or r.rid == rid:
                 self.waiting.remove(r)
+                if r.h >= 0 and self.sched is not None:
+                    self.sched.remove_waiting(r.h)
+                r.h = -1
                 r.finish_reason = "abort"
                 out.append(r)
         self._drain_pending()
@@ -527,6 +547,8 @@ class RolloutEngine:
 
     def _admit(self) -> list[Request]:
         """Pop waiting requests that fit (slots, KV pages reserved up front, prefill token budget)."""
+        if self.sched is not None:
+            return self._admit_native()
         admitted, tokens = [], 0
         shared: dict = {}
         while self.waiting and self.free_slots:
@@ -571,6 +593,27 @@ class RolloutEngine:
             tokens += 0 if donor is not None else len(r.prompt_ids) - r.prefilled
         return admitted
 
+    def _admit_native(self) -> list[Request]:
+        """``_admit`` through the C++ scheduler: same decisions, the per-request results are mirrored onto the Request objects."""
+        for r in self.waiting:                     # registration is lazy so the native queue always has the order of self.waiting
+            if r.h < 0:
+                r.h = self.sched.add(r.prompt_ids, r.params.max_new_tokens, id(r.group) if r.group is not None else -1, r.mm is None)
+        admitted, by_h = [], {}
+        for h in self.sched.admit(self.max_prefill_tokens):
+            r = self.waiting.popleft()
+            slot, blocks, shared, cached, donor = self.sched.info(h)
+            if r.h != h or self.free_slots.pop() != slot:
+                raise RuntimeError("native scheduler out of step with the engine's request queue")
+            r.slot, r.blocks, r.shared_prefix_blocks = slot, blocks, shared
+            if donor >= 0:
+                r.donor, r.prefilled = by_h[donor], 0
+            else:
+                r.cached_tokens = r.prefilled = cached
+            by_h[h] = r
+            self.running[slot] = r
+            admitted.append(r)
+        return admitted
+
     def _finish(self, r: Request, reason: str) -> None:
         r.finish_reason = reason
         if r.slot >= 0:
@@ -579,6 +622,11 @@ class RolloutEngine:
             self.st_seq_lens[r.slot] = 0
             self.free_slots.append(r.slot)
             r.slot = -1
+        if r.h >= 0 and self.sched is not None:
+            to_cache = self.prefix_cache is not None and reason != "abort" and r.mm is None
+            self.sched.finish(r.h, (r.prompt_ids + r.output_ids) if to_cache else [], to_cache)
+            r.h, r.blocks = -1, []
+            return
         if r.blocks and self.alloc is not None:
             if self.prefix_cache is not None and reason != "abort" and r.mm is None:
                 # every FULL page whose KV is final: prompt + generated tokens except the last one (never fed back)
@@ -623,28 +671,37 @@ class RolloutEngine:
         ids, pos, slots, lens = [], [], [], []
         any_cached = any(c > 0 for c, _ in spans)
         g_blk, g_off, klens = [], [], []
-        for r, (c, e) in zip(donors, spans):
-            ids += r.prompt_ids[c:e]
-            pos += list(range(c, e))
-            slots += [r.blocks[t // PAGE] * PAGE + t % PAGE for t in range(c, e)]
-            lens.append(e - c)
+        native = self.sched is not None and all(r.h >= 0 for r in donors)
+        if native:       # one pass in C++ over every token of the chunk (csrc/scheduler.hpp::prefill_arrays)
+            ids_t, pos_t, slots_t, lens_t, g_blk, g_off, klens_t = self.sched.prefill_arrays(
+                [(r.h, c, e) for r, (c, e) in zip(donors, spans)], any_cached)
+            lens, klens = lens_t.tolist(), klens_t.tolist()
+            for r, (c, e) in zip(donors, spans):
+                r.prefilled = e
+        else:
+            for r, (c, e) in zip(donors, spans):
+                ids += r.prompt_ids[c:e]
+                pos += list(range(c, e))
+                slots += [r.blocks[t // PAGE] * PAGE + t % PAGE for t in range(c, e)]
+                lens.append(e - c)
+                if any_cached:
+                    g_blk += [r.blocks[t // PAGE] for t in range(e)]
+                    g_off += [t % PAGE for t in range(e)]
+                    klens.append(e)
+                r.prefilled = e
+            ids_t, pos_t, slots_t = (torch.tensor(v, dtype=torch.long) for v in (ids, pos, slots))
             if any_cached:
-                g_blk += [r.blocks[t // PAGE] for t in range(e)]
-                g_off += [t % PAGE for t in range(e)]
-                klens.append(e)
-            r.prefilled = e
+                g_blk, g_off = torch.tensor(g_blk, dtype=torch.long), torch.tensor(g_off, dtype=torch.long)
         cu = torch.zeros(len(donors) + 1, dtype=torch.int32)
         cu[1:] = torch.tensor(lens, dtype=torch.int32).cumsum(0)
-        inp = tf.PackedInput(torch.tensor(ids, dtype=torch.long, device=dev), torch.tensor(pos, dtype=torch.long, device=dev),
-                             cu.to(dev), max(lens))
+        inp = tf.PackedInput(ids_t.to(dev), pos_t.to(dev), cu.to(dev), max(lens))
         if any(r.mm is not None for r in donors):
             inp.mrope_pos, inp.image_embeds = self._mm_prefill_inputs(donors, spans)
         if any_cached:
             cu_k = torch.zeros(len(donors) + 1, dtype=torch.int32)
             cu_k[1:] = torch.tensor(klens, dtype=torch.int32).cumsum(0)
-            inp.kv_gather = (torch.tensor(g_blk, dtype=torch.long, device=dev), torch.tensor(g_off, dtype=torch.long, device=dev),
-                             cu_k.to(dev), max(klens))
-        slot_t = torch.tensor(slots, dtype=torch.long, device=dev)
+            inp.kv_gather = (g_blk.to(dev), g_off.to(dev), cu_k.to(dev), max(klens))
+        slot_t = slots_t.to(dev)
         x = tf.embed_forward(cfg, self.embed_w, inp).to(self.dtype)
         for i, w in enumerate(self.layer_w):
             if self.tp is not None:
@@ -657,7 +714,7 @@ class RolloutEngine:
                 from ..models.vision import deepstack_add
 
                 x = deepstack_add(self.full_cfg, x, inp.input_ids, inp.image_embeds, i)      # Qwen3-VL DeepStack (no-op otherwise)
-        self.stats["prefill_tokens"] += len(ids)
+        self.stats["prefill_tokens"] += int(ids_t.numel())
         done_ids = {id(r) for r in donors if r.prefilled >= len(r.prompt_ids)}
         reqs = [r for r in reqs if not r.finished and (id(r) in done_ids or (r.donor is not None and id(r.donor) in done_ids))]
         self._prefill_queue = [r for r in self._prefill_queue if not r.finished and not any(r is q for q in reqs)]
@@ -696,8 +753,7 @@ class RolloutEngine:
                 continue
             n = r.num_tokens            # tokens so far; the new token sits at position n-1 (+ the M-RoPE offset of image prompts)
             live.append((r.slot, t, n - 1 + r.mrope_delta, n, 1, r.params.temperature, self._seed_for(r, 1)))
-            row = r.blocks + [0] * (self.st_block_table.shape[1] - len(r.blocks))
-            rows.append(row)
+            rows.append(r)
         if live:
             cols = list(zip(*live))
             sl = torch.tensor(cols[0], dtype=torch.long, device=dev)
@@ -707,7 +763,12 @@ class RolloutEngine:
             self.st_active[sl] = torch.tensor(cols[4], dtype=torch.long, device=dev)
             self.st_temp[sl] = torch.tensor(cols[5], dtype=torch.float32, device=dev)
             self.st_seeds[sl] = torch.tensor(cols[6], dtype=torch.long, device=dev)
-            self.st_block_table[sl] = torch.tensor(rows, dtype=torch.int32, device=dev)
+            width = self.st_block_table.shape[1]
+            if self.sched is not None and all(r.h >= 0 for r in rows):
+                table = self.sched.block_rows([r.h for r in rows], width)
+            else:
+                table = torch.tensor([r.blocks + [0] * (width - len(r.blocks)) for r in rows], dtype=torch.int32)
+            self.st_block_table[sl] = table.to(dev)
 
     def _mm_prefill_inputs(self, donors: list[Request], spans: list[tuple[int, int]]):
         """M-RoPE positions [3, T] and tower embeddings for the image-token rows of this prefill chunk.  The tower runs once per
@@ -842,6 +903,8 @@ class RolloutEngine:
         if not high:
             return
         low_free = sorted(s for s in range(bucket) if s not in self.running)
+        if self.sched is not None:
+            self.sched.move_slots([(self.running[src].h, dst) for src, dst in zip(high, low_free)])
         for src, dst in zip(high, low_free):
             r = self.running.pop(src)
             for t in (self.st_input_ids, self.st_positions, self.st_seq_lens, self.st_active, self.st_temp,
