@@ -105,9 +105,8 @@ def expand_kv(cfg: ModelConfig, w: dict, entry: torch.Tensor) -> tuple[torch.Ten
 def attention_forward(cfg: ModelConfig, w: dict, h: torch.Tensor, inp, kv_sink=None) -> torch.Tensor:
     """Attention of one block on packed rows (training, old-log-prob, engine prefill): h:[T,H] normed input -> [T, nh * v] (the
     input of ``wo``).  ``kv_sink`` = (latent pool [blocks, 1, page, r + rope], _, slot mapping): also appends this chunk's cache
-    entries, and with ``inp.kv_gather`` attends over the cached prefix as well (chunked prefill / prefix cache)."""
-    if inp.sp_group is not None:
-        raise NotImplementedError("Ulysses sequence parallelism is not implemented for MLA attention")
+    entries, and with ``inp.kv_gather`` attends over the cached prefix as well (chunked prefill / prefix cache).  Under Ulysses
+    sequence parallelism (``inp.sp_group``) h holds this rank's token slice."""
     t = h.shape[0]
     dv = cfg.v_head_dim
     q, entry = project(cfg, w, h, inp.position_ids)
@@ -123,6 +122,13 @@ def attention_forward(cfg: ModelConfig, w: dict, h: torch.Tensor, inp, kv_sink=N
             return attention_varlen_prefix(q, k, v, inp.cu_seqlens, cu_k, inp.max_seqlen, max_k, scale=scale)[..., :dv].reshape(t, -1)
     k, v = expand_kv(cfg, w, entry)
     v = F.pad(v, (0, cfg.head_dim - dv))
+    if inp.sp_group is not None:
+        # Ulysses SP: the projections ran on this rank's token slice; the expanded per-head q / k / v swap tokens for heads around
+        # the attention (reference capability: 3rdparty/verl/verl/models/transformers/kimi_vl.py, Ulysses over the DeepSeek-V3 MLA)
+        from ..parallel.ulysses import ulysses_attention
+
+        a = ulysses_attention(q, k, v, inp.cu_seqlens, inp.max_seqlen, inp.sp_group, inp.total_tokens, causal=True, scale=scale)
+        return a[..., :dv].reshape(t, -1)
     return attention_varlen(q, k, v, inp.cu_seqlens, inp.max_seqlen, causal=True, scale=scale)[..., :dv].reshape(t, -1)
 
 

@@ -139,7 +139,7 @@ def validate_sp(num_heads: int, num_kv_heads: int, sp: int) -> None:
 
 
 def ulysses_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, cu_seqlens: torch.Tensor, max_seqlen: int, group,
-                      total_tokens: int, causal: bool = True) -> torch.Tensor:
+                      total_tokens: int, causal: bool = True, scale: float | None = None) -> torch.Tensor:
     """q:[T/sp, nq, d], k/v:[T/sp, nkv, d] (local token slice, all heads) -> [T/sp, nq, d].
 
     ``cu_seqlens`` describe the FULL packed stream (identical on every SP rank); the tail padding tokens (beyond
@@ -159,5 +159,5 @@ def ulysses_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, cu_seql
     if t_full > total_tokens:        # padding tail = one extra sequence
         cu = torch.cat([cu_seqlens, cu_seqlens.new_tensor([t_full])])
         max_seqlen = max(max_seqlen, t_full - total_tokens)
-    o = attention_varlen(qf, kf, vf, cu, max_seqlen, causal=causal)
+    o = attention_varlen(qf, kf, vf, cu, max_seqlen, causal=causal, scale=scale)
     return gather_heads_scatter_seq(o, group)

@@ -28,8 +28,6 @@ from ..ops.functional import rope_and_cache_, _skinny_buffers
 
 class TPContext:
     def __init__(self, cfg: ModelConfig, heap, tp_rank: int, tp_world: int, max_batch: int, group=None):
-        if cfg.attn_type != "mha":
-            raise NotImplementedError("tensor-parallel rollout is not implemented for MLA attention (run data-parallel engines)")
         if cfg.num_heads % tp_world or cfg.num_kv_heads % tp_world:
             raise ValueError("heads and kv heads must be divisible by the TP size")
         if cfg.num_experts:
@@ -102,10 +100,23 @@ class TPContext:
         for k in ("q_norm", "k_norm", "ln_attn", "ln_mlp"):   # per-head gains (Qwen3) and output norms (GLM-4): replicated
             if k in w:
                 out[k] = w[k]
-        out["wqkv"] = torch.cat([w["wqkv"][q0:q0 + nq * d], w["wqkv"][k0:k0 + nkv * d], w["wqkv"][v0:v0 + nkv * d]], dim=0).contiguous()
-        if "bqkv" in w:
-            out["bqkv"] = torch.cat([w["bqkv"][q0:q0 + nq * d], w["bqkv"][k0:k0 + nkv * d], w["bqkv"][v0:v0 + nkv * d]]).contiguous()
-        out["wo"] = w["wo"][:, q0:q0 + nq * d]                      # [H, nq_local*d] view, row pitch = full
+        if c.attn_type == "mla":
+            # latent attention: the heads are split (query / key-value up-projections by head rows, output projection by head
+            # columns); the latent bottlenecks — and therefore the paged latent cache — are replicated on every TP rank
+            up, dv = c.qk_nope_head_dim + c.v_head_dim, c.v_head_dim
+            out["kv_a_ln"] = w["kv_a_ln"]
+            out["wkv_up"] = w["wkv_up"][r * nq * up:(r + 1) * nq * up]
+            out["wo"] = w["wo"][:, r * nq * dv:(r + 1) * nq * dv]
+            if c.q_lora_rank:
+                out["wa"], out["q_a_ln"] = w["wa"], w["q_a_ln"]
+                out["wq_up"] = w["wq_up"][q0:q0 + nq * d]
+            else:                                                     # plain query projection fused into ``wa``: local head rows + the latent rows
+                out["wa"] = torch.cat([w["wa"][q0:q0 + nq * d], w["wa"][c.q_size:]], dim=0).contiguous()
+        else:
+            out["wqkv"] = torch.cat([w["wqkv"][q0:q0 + nq * d], w["wqkv"][k0:k0 + nkv * d], w["wqkv"][v0:v0 + nkv * d]], dim=0).contiguous()
+            if "bqkv" in w:
+                out["bqkv"] = torch.cat([w["bqkv"][q0:q0 + nq * d], w["bqkv"][k0:k0 + nkv * d], w["bqkv"][v0:v0 + nkv * d]]).contiguous()
+            out["wo"] = w["wo"][:, q0:q0 + nq * d]                      # [H, nq_local*d] view, row pitch = full
         if "router" in w:                                            # a sparse block (MoE stacks may also hold dense blocks)
             el = c.num_experts // W
             out["router"] = w["router"]                               # replicated: every rank routes every token identically
@@ -252,6 +263,11 @@ def _mlp_tp(tp: TPContext, lcfg: ModelConfig, w: dict, x: torch.Tensor, decode: 
 def layer_decode_tp(tp: TPContext, lcfg: ModelConfig, w: dict, x: torch.Tensor, inp: tf.DecodeInput, k_cache, v_cache) -> torch.Tensor:
     nq, nkv, d = lcfg.num_heads, lcfg.num_kv_heads, lcfg.head_dim
     h = ops.rmsnorm(x, w["ln1"], lcfg.rms_norm_eps)
+    if lcfg.attn_type == "mla":         # local heads over the replicated latent cache, then the usual row-parallel output projection
+        from ..models import mla
+
+        x = _row_out(tp, lcfg, w, mla.attention_decode(lcfg, w, h, inp, k_cache), "wo", "ln_attn", x, True)
+        return _mlp_tp(tp, lcfg, w, x, decode=True)
     qkv = tf.qk_norm_(lcfg, w, ops.linear(h, w["wqkv"], bias=w.get("bqkv")))
     cos, sin = tf.rope_tables(lcfg, x.device)
     rope_and_cache_(qkv, inp.position_ids, cos, sin, nq, nkv, d, k_cache, v_cache, inp.slot_mapping, k_cache.shape[2])
@@ -265,6 +281,11 @@ def layer_prefill_tp(tp: TPContext, lcfg: ModelConfig, w: dict, x: torch.Tensor,
     nq, nkv, d = lcfg.num_heads, lcfg.num_kv_heads, lcfg.head_dim
     t = x.shape[0]
     h = ops.rmsnorm(x, w["ln1"], lcfg.rms_norm_eps)
+    if lcfg.attn_type == "mla":
+        from ..models import mla
+
+        x = _row_out(tp, lcfg, w, mla.attention_forward(lcfg, w, h, inp, kv_sink), "wo", "ln_attn", x, False)
+        return _mlp_tp(tp, lcfg, w, x, decode=False)
     qkv = tf.qk_norm_(lcfg, w, ops.linear(h, w["wqkv"], bias=w.get("bqkv")))
     pos, cos, sin = inp.rope_inputs(lcfg, x.device)              # 1-D positions, or per-token M-RoPE tables (VLM prompts)
     qkv = rope_and_cache_(qkv, pos, cos, sin, nq, nkv, d, *kv_sink)

@@ -313,6 +313,8 @@ def test_tp_rollout_cpu_gloo_engine_and_colocated_worker():
     assert moe and "tok_ok=1" in moe[0] and float(moe[0].split("lp_err=")[1]) < 1e-4
     glm = [l for l in r.stdout.splitlines() if l.startswith("TP_CPU_GLM")]          # GLM-4 output norms after the row-parallel sums
     assert glm and "tok_ok=1" in glm[0] and float(glm[0].split("lp_err=")[1]) < 1e-4
+    mla = [l for l in r.stdout.splitlines() if l.startswith("TP_CPU_MLA")]          # DeepSeek-V3 latent attention: heads split, latent cache replicated
+    assert mla and "tok_ok=1" in mla[0] and float(mla[0].split("lp_err=")[1]) < 1e-4
 
 
 def test_prefix_cache_unit_semantics():

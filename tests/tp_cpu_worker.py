@@ -114,6 +114,23 @@ def main():
         outs_m.append([(q[0].output_ids, q[0].logprobs) for q in e.generate(prompts, sp)])
     moe_tok_ok = all(a[0] == b[0] for a, b in zip(*outs_m))
     moe_lp_err = max(abs(x - y) for a, b in zip(*outs_m) for x, y in zip(a[1], b[1]))
+    # ---- DeepSeek-V3 blocks: latent attention with the heads split over the ranks and the latent cache replicated, on top of the
+    # expert-sharded MoE; with the query bottleneck and with the plain query projection fused into the first-stage GEMM
+    mla_ok, mla_err = True, 0.0
+    for qlr in (48, 0):
+        dcfg = get_model_config("tiny-deepseek-v3", q_lora_rank=qlr)
+        dw = TransformerWeights(dcfg, "cpu", torch.float32, seed=19)
+        outs_d = []
+        for ctx in (TPContext(dcfg, None, rank, world, max_batch=8, group=dist.group.WORLD), None):
+            e = RolloutEngine(dcfg, "cpu", max_num_seqs=8, max_model_len=64, use_cuda_graph=False, seed=3, tp=ctx)
+            e.set_weights(dw.embed, dw.layers, dw.head)
+            if ctx is not None:
+                assert e.layer_w[1]["wkv_up"].shape[0] == dw.layers[1]["wkv_up"].shape[0] // world and e.cfg.num_heads == dcfg.num_heads // world
+            outs_d.append([(q[0].output_ids, q[0].logprobs) for q in e.generate(prompts, sp)])
+        mla_ok = mla_ok and all(a[0] == b[0] for a, b in zip(*outs_d))
+        mla_err = max(mla_err, max(abs(x - y) for a, b in zip(*outs_d) for x, y in zip(a[1], b[1])))
+    if rank == 0:
+        print(f"TP_CPU_MLA tok_ok={int(mla_ok)} lp_err={mla_err:.2e}", flush=True)
     # ---- GLM-4 blocks (output norms after the row-parallel all-reduces, partial rotary, qkv bias) through the TP engine
     gcfg = get_model_config("tiny-glm4")
     gw = TransformerWeights(gcfg, "cpu", torch.float32, seed=17)

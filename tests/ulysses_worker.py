@@ -80,6 +80,27 @@ def main():
             assert any(k.startswith("vision.") for k in vouts["sp"][1])
             assert v_lp < 1e-4 and v_w < 1e-3, (preset, v_lp, v_w)
             extra += f" vlm_lp_err[{preset}]={v_lp:.3e} vlm_w_err[{preset}]={v_w:.3e}"
+    # ---- multi-head latent attention under SP (the reference's kimi_vl.py capability: Ulysses over the DeepSeek-V3 attention)
+    if not cuda:
+        mcfg = get_model_config("tiny-deepseek-v3")
+        torch.manual_seed(6)
+        mids = torch.randint(3, mcfg.vocab_size, (3, 19))
+        mmask = torch.ones_like(mids)
+        mmask[2, 11:] = 0
+        minp, _ = pack_padded(mids, mmask)
+        assert minp.input_ids.numel() % world != 0
+        mlabels = torch.randint(0, mcfg.vocab_size, (minp.input_ids.numel(),))
+        mouts = {}
+        for name, sp_group in (("nosp", None), ("sp", dist.group.WORLD)):
+            eng = Zero3Engine(mcfg, dev, comm="nccl", lr=1e-2, weight_decay=0.0, seed=7, sp_group=sp_group)
+            lp, ent = eng.forward_logprob_entropy(minp, mlabels, 1.0)
+            (-(lp.mean()) + 0.01 * ent.mean()).backward()
+            eng.step()
+            mouts[name] = (lp.detach().float(), {n: t.float().clone() for n, t in eng.named_full_tensors()})
+        m_lp = (mouts["sp"][0] - mouts["nosp"][0]).abs().max().item()
+        m_w = max(((mouts["sp"][1][k] - mouts["nosp"][1][k]).norm() / (mouts["nosp"][1][k].norm() + 1e-9)).item() for k in mouts["sp"][1])
+        assert m_lp < 1e-4 and m_w < 1e-3, (m_lp, m_w)
+        extra += f" mla_lp_err={m_lp:.3e} mla_w_err={m_w:.3e}"
     if rank == 0:
         print(f"ULYSSES_RESULTS lp_err={lp_err:.3e} w_err={w_err:.3e}{extra}", flush=True)
     dist.barrier()
