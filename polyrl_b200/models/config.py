@@ -74,6 +74,9 @@ class ModelConfig:
     # position-free + ``qk_rope_head_dim`` rotary query / key features (``head_dim`` = their sum) and ``v_head_dim`` value features.
     # The rollout engine caches only the latent (kv_lora_rank + qk_rope_head_dim numbers per token and layer).
     attn_type: str = "mha"
+    # dense MLP kind: "swiglu" (gate / up / down, every other family) or "xielu" (Apertus: up -> xIELU -> down with two learned
+    # scalars per block; xIELU(x) = a_p x^2 + b x for x > 0, a_n (expm1(min(x, eps)) - x) + b x otherwise)
+    mlp_act: str = "swiglu"
     q_lora_rank: int = 0
     kv_lora_rank: int = 0
     qk_nope_head_dim: int = 0
@@ -93,6 +96,8 @@ class ModelConfig:
         self.extra_eos_token_ids = tuple(self.extra_eos_token_ids or ())        # json round trip gives a list
         self.mrope_section = tuple(self.mrope_section or ())
         self.dense_layers = tuple(int(i) for i in (self.dense_layers or ()))
+        if self.mlp_act not in ("swiglu", "xielu") or (self.mlp_act == "xielu" and (self.family != "llama" or self.num_experts)):
+            raise ValueError("mlp_act is 'swiglu' or 'xielu' (dense llama-family stacks only)")
         if self.attn_type not in ("mha", "mla"):
             raise ValueError(f"unknown attn_type {self.attn_type!r}")
         if self.attn_type == "mla":
@@ -156,7 +161,7 @@ class ModelConfig:
     def num_params(self) -> int:
         h, f, v = self.hidden_size, self.intermediate_size, self.vocab_size
         if self.family == "llama":
-            mlp = 3 * h * f
+            mlp = 3 * h * f if self.mlp_act == "swiglu" else 2 * h * f + 2
             if self.num_experts:
                 mlp = self.num_experts * (3 * h * self.moe_intermediate_size + h) + 3 * h * self.shared_expert_intermediate_size
                 mlp += (h if self.shared_expert_gate else 0) + (self.num_experts if self.moe_router == "sigmoid_group" else 0)
@@ -178,7 +183,7 @@ class ModelConfig:
 
             vis = vision_num_params(self)
         n_dense = len([i for i in self.dense_layers if i < self.num_layers]) if self.num_experts else 0
-        return per * self.num_layers - n_dense * (mlp - 3 * h * f) + emb + h + vis
+        return per * self.num_layers - n_dense * (mlp - 3 * h * f) + emb + h + vis      # (dense blocks of MoE stacks are SwiGLU)
 
     def num_sparse_layers(self) -> int:
         return (self.num_layers - len([i for i in self.dense_layers if i < self.num_layers])) if self.num_experts else 0
@@ -303,6 +308,11 @@ class ModelConfig:
                           moe_router="sigmoid_group", n_group=int(hf.get("n_group") or 1), topk_group=int(hf.get("topk_group") or 1),
                           routed_scaling_factor=float(hf.get("routed_scaling_factor", 1.0)))
             glm_kw = dict(partial_rotary_factor=float(rp.get("partial_rotary_factor") or hf.get("partial_rotary_factor") or 0.5))
+        act_kw: dict = {}
+        if mt == "apertus":                  # Qwen3-style attention (per-head QK norm) + a non-gated xIELU MLP
+            if hf.get("hidden_act", "xielu") != "xielu":
+                raise NotImplementedError(f"apertus with hidden_act={hf.get('hidden_act')!r}")
+            act_kw = dict(mlp_act="xielu")
         mla_kw: dict = {}
         if mt == "deepseek_v3":              # MLA attention + DeepSeek-V3 routing (sigmoid, bias-corrected, group-limited), shared experts
             if hf.get("attention_bias"):
@@ -329,12 +339,12 @@ class ModelConfig:
                    rope_theta=(hf.get("rope_theta") or (hf.get("rope_parameters") or hf.get("rope_scaling") or {}).get("rope_theta") or 10000.0),
                    rope_scaling=_rope_scaling_of(hf), rms_norm_eps=hf.get("rms_norm_eps", 1e-6),
                    qkv_bias=(mt == "qwen2") or bool(hf.get("attention_bias", False)),
-                   qk_norm=(mt == "qwen3") or (mt == "glm4_moe" and bool(hf.get("use_qk_norm", False))),
+                   qk_norm=(mt in ("qwen3", "apertus")) or (mt == "glm4_moe" and bool(hf.get("use_qk_norm", False))),
                    tie_word_embeddings=hf.get("tie_word_embeddings", False), eos_token_id=eos, extra_eos_token_ids=extra_eos,
                    bos_token_id=hf.get("bos_token_id") or eos, pad_token_id=hf.get("pad_token_id") or eos,
                    sliding_window=(hf.get("sliding_window") if (mt in ("mistral", "mixtral") or hf.get("use_sliding_window")) else None),
-                   hf_model_type=("glm4v" if hf.get("_glm4v") else mt) if mt in ("mistral", "mixtral", "glm", "glm4", "qwen2_moe", "glm4_moe", "deepseek_v3") else "",
-                   name=hf.get("_name_or_path", mt), **vis_kw, **{**moe_kw, **vl_moe_kw}, **{**glm_kw, **mla_kw})
+                   hf_model_type=("glm4v" if hf.get("_glm4v") else mt) if mt in ("mistral", "mixtral", "glm", "glm4", "qwen2_moe", "glm4_moe", "deepseek_v3", "apertus") else "",
+                   name=hf.get("_name_or_path", mt), **vis_kw, **{**moe_kw, **vl_moe_kw}, **{**glm_kw, **mla_kw, **act_kw})
 
 
 def _qwen_dense_layers(hf: dict) -> tuple:
@@ -513,6 +523,15 @@ PRESETS: dict[str, dict] = {
                              num_experts=8, num_experts_per_tok=2, moe_intermediate_size=128, norm_topk_prob=True, dense_layers=(0,),
                              shared_expert_intermediate_size=128, moe_router="sigmoid_group", n_group=4, topk_group=2,
                              routed_scaling_factor=2.5, hf_model_type="deepseek_v3", eos_token_id=1, bos_token_id=2, pad_token_id=0),
+    "apertus-8b": dict(family="llama", vocab_size=131072, hidden_size=4096, intermediate_size=21504, num_layers=32, num_heads=32,
+                       num_kv_heads=8, head_dim=128, max_position_embeddings=65536, rope_theta=12000000.0, rms_norm_eps=1e-5, qk_norm=True,
+                       mlp_act="xielu", hf_model_type="apertus",
+                       rope_scaling=dict(rope_type="llama3", factor=8.0, original_max_position_embeddings=8192, low_freq_factor=1.0,
+                                         high_freq_factor=4.0),
+                       eos_token_id=68, bos_token_id=1, pad_token_id=3),
+    "tiny-apertus": dict(family="llama", vocab_size=512, hidden_size=256, intermediate_size=512, num_layers=2, num_heads=4, num_kv_heads=2,
+                         head_dim=64, max_position_embeddings=512, rope_theta=10000.0, rms_norm_eps=1e-5, qk_norm=True, mlp_act="xielu",
+                         hf_model_type="apertus", eos_token_id=1, bos_token_id=2, pad_token_id=0),
     "tiny-qwen3-moe-128": dict(family="llama", vocab_size=1024, hidden_size=512, intermediate_size=1024, num_layers=2, num_heads=4,
                                num_kv_heads=2, head_dim=128, max_position_embeddings=1024, rope_theta=1000000.0, rms_norm_eps=1e-6,
                                qk_norm=True, num_experts=8, num_experts_per_tok=2, moe_intermediate_size=256, norm_topk_prob=True,

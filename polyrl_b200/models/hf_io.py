@@ -82,6 +82,11 @@ def _layer_keys(cfg: ModelConfig, i: int) -> list[str]:
                                 "mlp.c_proj.bias")]
     p = f"model.layers.{i}."
     keys = [p + "input_layernorm.weight", p + "post_attention_layernorm.weight", p + "self_attn.o_proj.weight"]
+    if cfg.mlp_act == "xielu":               # Apertus naming: its own norm names, no gate projection, activation scalars
+        keys = [p + "attention_layernorm.weight", p + "feedforward_layernorm.weight", p + "self_attn.o_proj.weight", p + "mlp.up_proj.weight",
+                p + "mlp.down_proj.weight", p + "mlp.act_fn.alpha_p", p + "mlp.act_fn.alpha_n"]
+        keys += [p + f"self_attn.{n}_proj.weight" for n in "qkv"] + [p + "self_attn.q_norm.weight", p + "self_attn.k_norm.weight"]
+        return keys + ([p + f"self_attn.{n}_proj.bias" for n in "qkv"] if cfg.qkv_bias else [])
     if tf.is_sparse_layer(cfg, i):
         keys += [p + "mlp.gate.weight", p + "mlp.experts.gate_up_proj", p + "mlp.experts.down_proj"]
         if cfg.moe_router == "sigmoid_group":
@@ -289,6 +294,15 @@ def _lm_config_dict(cfg: ModelConfig) -> dict:
                 "rope_scaling": {"type": "mrope", "mrope_section": list(cfg.mrope_section)}, "rope_theta": cfg.rope_theta}
     mt = "qwen3" if cfg.qk_norm else ("qwen2" if cfg.qkv_bias else "llama")
     arch = {"qwen3": "Qwen3ForCausalLM", "qwen2": "Qwen2ForCausalLM", "llama": "LlamaForCausalLM"}[mt]
+    if cfg.mlp_act == "xielu":
+        rp = {"rope_type": "default", "rope_theta": cfg.rope_theta, **(dict(cfg.rope_scaling) if cfg.rope_scaling else {})}
+        return {"model_type": "apertus", "architectures": ["ApertusForCausalLM"], "vocab_size": cfg.vocab_size, "hidden_size": cfg.hidden_size,
+                "intermediate_size": cfg.intermediate_size, "num_hidden_layers": cfg.num_layers, "num_attention_heads": cfg.num_heads,
+                "num_key_value_heads": cfg.num_kv_heads, "head_dim": cfg.head_dim, "max_position_embeddings": cfg.max_position_embeddings,
+                "rope_theta": cfg.rope_theta, "rope_parameters": rp, **({"rope_scaling": dict(cfg.rope_scaling)} if cfg.rope_scaling else {}),
+                "rms_norm_eps": cfg.rms_norm_eps, "tie_word_embeddings": cfg.tie_word_embeddings, "attention_bias": bool(cfg.qkv_bias),
+                "hidden_act": "xielu", "qk_norm": True, "torch_dtype": "bfloat16", "eos_token_id": cfg.eos_token_id,
+                "bos_token_id": cfg.bos_token_id, "pad_token_id": cfg.pad_token_id}
     if getattr(cfg, "hf_model_type", "") == "mistral" and mt == "llama":
         mt, arch = "mistral", "MistralForCausalLM"
     moe = {}

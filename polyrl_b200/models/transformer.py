@@ -61,6 +61,8 @@ def layer_param_specs(cfg: ModelConfig, i: int | None = None) -> ParamSpec:
                 specs += [("swgu", (2 * fs, h)), ("swd", (h, fs))]
                 if cfg.shared_expert_gate:
                     specs.append(("sgate", (1, h)))
+        elif cfg.mlp_act == "xielu":   # Apertus: up -> xIELU (two learned scalars) -> down
+            specs += [("wup", (f, h)), ("wd", (h, f)), ("act_ap", (1,)), ("act_an", (1,))]
         else:
             specs += [("wgu", (2 * f, h)), ("wd", (h, f))]
         return specs
@@ -98,6 +100,9 @@ def init_param_(name: str, t: torch.Tensor, cfg: ModelConfig, generator: torch.G
         else:
             bound = 1.0 / math.sqrt(t.shape[-1])
             t.uniform_(-bound, bound, generator=generator)
+        return
+    if base in ("act_ap", "act_an"):                # HF XIELUActivation: softplus^-1 of 0.8 and of 0.8 - beta
+        t.fill_(math.log(math.expm1(0.8 if base == "act_ap" else 0.8 - XIELU_BETA)))
         return
     if base in ("ln1", "ln2", "ln_attn", "ln_mlp", "norm_w", "ln1_w", "ln2_w", "q_norm", "k_norm", "merger_ln_w", "q_a_ln", "kv_a_ln"):
         t.fill_(1.0)
@@ -380,11 +385,30 @@ def embed_forward(cfg: ModelConfig, w: dict, inp: PackedInput) -> torch.Tensor:
     return x
 
 
+XIELU_BETA, XIELU_EPS = 0.5, -1e-6
+
+
+def xielu(x: torch.Tensor, ap: torch.Tensor, an: torch.Tensor) -> torch.Tensor:
+    """xIELU with learned scalars (pre-softplus ``ap`` / ``an``), fp32 math: a_p x^2 + b x above zero, a_n (expm1(min(x, eps)) - x) + b x
+    below (HF ``XIELUActivation._xielu_python``)."""
+    xf = x.float()
+    a_p, a_n = F.softplus(ap.float()), XIELU_BETA + F.softplus(an.float())
+    y = torch.where(xf > 0, a_p * xf * xf + XIELU_BETA * xf, (torch.expm1(xf.clamp(max=XIELU_EPS)) - xf) * a_n + XIELU_BETA * xf)
+    return y.to(x.dtype)
+
+
+def xielu_mlp(w: dict, h: torch.Tensor, residual: torch.Tensor | None = None) -> torch.Tensor:
+    """Apertus MLP: down(xIELU(up(h))) (+ residual)."""
+    return ops.linear(xielu(ops.linear(h, w["wup"]), w["act_ap"], w["act_an"]), w["wd"], residual=residual)
+
+
 def _mlp_forward(cfg: ModelConfig, w: dict, x: torch.Tensor, aux_out: list | None = None) -> torch.Tensor:
     """Second half of a llama-family block without adapters: x + MLP(norm(x)), dense SwiGLU or mixture of experts."""
     h = ops.rmsnorm(x, w["ln2"], cfg.rms_norm_eps)
     if "router" in w:
         return x + moe_mlp(cfg, w, h, aux_out)
+    if "wup" in w:
+        return xielu_mlp(w, h, x)
     return ops.linear(ops.linear_swiglu(h, w["wgu"]), w["wd"], residual=x)
 
 
@@ -448,6 +472,10 @@ def layer_forward(cfg: ModelConfig, w: dict, x: torch.Tensor, inp: PackedInput, 
         if "router" in w:
             y = moe_mlp(cfg, w, h, aux_out)
             return x + (ops.rmsnorm(y, w["ln_mlp"], cfg.rms_norm_eps) if cfg.sandwich_norm else y)
+        if "wup" in w:
+            if lora:
+                raise NotImplementedError("LoRA adapters are not implemented for the xIELU MLP")
+            return xielu_mlp(w, h, x)
         if lora and L.has_lora(w, "gate_proj", "up_proj"):
             a = ref.swiglu(ops.linear(h, w["wgu"]) + L.gate_up_delta(cfg, w, h))    # adapters act before the activation
         else:
@@ -524,6 +552,8 @@ def layer_decode(cfg: ModelConfig, w: dict, x: torch.Tensor, inp: DecodeInput, k
         h = ops.rmsnorm(x, w["ln2"], cfg.rms_norm_eps)
         if "router" in w:
             return x + (moe_mlp_static(cfg, w, h) if _MOE_STATIC_DECODE() else moe_mlp(cfg, w, h))
+        if "wup" in w:
+            return xielu_mlp(w, h, x)
         return ops.linear(ops.linear_swiglu(h, w["wgu"]), w["wd"], residual=x)
     if cfg.family == "llama":
         h = ops.rmsnorm(x, w["ln1"], cfg.rms_norm_eps)
@@ -541,6 +571,8 @@ def layer_decode(cfg: ModelConfig, w: dict, x: torch.Tensor, inp: DecodeInput, k
         if "router" in w:
             y = moe_mlp_static(cfg, w, h) if _MOE_STATIC_DECODE() else moe_mlp(cfg, w, h)
             return x + (ops.rmsnorm(y, w["ln_mlp"], cfg.rms_norm_eps) if cfg.sandwich_norm else y)
+        if "wup" in w:
+            return xielu_mlp(w, h, x)
         a = ops.linear_swiglu(h, w["wgu"])
         if cfg.sandwich_norm:
             return x + ops.rmsnorm(ops.linear(a, w["wd"]), w["ln_mlp"], cfg.rms_norm_eps)
@@ -706,6 +738,11 @@ def _convert_mlp(cfg: ModelConfig, hf_sd: dict, out: dict, i: int, p: str) -> No
             out[f"layers.{i}.ewd"] = torch.stack([hf_sd[f"{p}mlp.experts.{e}.down_proj.weight"] for e in range(cfg.num_experts)])
         out[f"layers.{i}.ewgu"] = torch.stack([ref.interleave_gate_up(g, u) for g, u in pairs])
         return
+    if cfg.mlp_act == "xielu":                               # Apertus: no gate; the activation's two learned scalars live under act_fn
+        out[f"layers.{i}.wup"], out[f"layers.{i}.wd"] = hf_sd[p + "mlp.up_proj.weight"], hf_sd[p + "mlp.down_proj.weight"]
+        out[f"layers.{i}.act_ap"] = hf_sd[p + "mlp.act_fn.alpha_p"].reshape(1)
+        out[f"layers.{i}.act_an"] = hf_sd[p + "mlp.act_fn.alpha_n"].reshape(1)
+        return
     if p + "mlp.gate_up_proj.weight" in hf_sd:               # GLM: one fused projection, gate rows then up rows
         gu = hf_sd[p + "mlp.gate_up_proj.weight"]
         out[f"layers.{i}.wgu"] = ref.interleave_gate_up(gu[: gu.shape[0] // 2], gu[gu.shape[0] // 2:])
@@ -738,8 +775,9 @@ def convert_hf_state_dict(cfg: ModelConfig, hf_sd: dict[str, torch.Tensor]) -> d
         out["lm_head"] = hf_sd["lm_head.weight"]
     for i in range(cfg.num_layers):
         p = f"model.layers.{i}."
-        out[f"layers.{i}.ln1"] = hf_sd[p + "input_layernorm.weight"]
-        out[f"layers.{i}.ln2"] = hf_sd[p + "post_attention_layernorm.weight"]
+        apertus = p + "attention_layernorm.weight" in hf_sd
+        out[f"layers.{i}.ln1"] = hf_sd[p + ("attention_layernorm.weight" if apertus else "input_layernorm.weight")]
+        out[f"layers.{i}.ln2"] = hf_sd[p + ("feedforward_layernorm.weight" if apertus else "post_attention_layernorm.weight")]
         if cfg.attn_type == "mla":
             from . import mla
 
@@ -776,6 +814,13 @@ def _export_mlp(cfg: ModelConfig, sd: dict, out: dict, i: int, p: str, fused_gu:
             out[p + sh + "gate_proj.weight"], out[p + sh + "up_proj.weight"], out[p + sh + "down_proj.weight"] = g, u, sd[f"layers.{i}.swd"]
         if f"layers.{i}.sgate" in sd:
             out[p + "mlp.shared_expert_gate.weight"] = sd[f"layers.{i}.sgate"]
+    elif cfg.mlp_act == "xielu":
+        out[p + "mlp.up_proj.weight"], out[p + "mlp.down_proj.weight"] = sd[f"layers.{i}.wup"], sd[f"layers.{i}.wd"]
+        out[p + "mlp.act_fn.alpha_p"], out[p + "mlp.act_fn.alpha_n"] = sd[f"layers.{i}.act_ap"].reshape(1), sd[f"layers.{i}.act_an"].reshape(1)
+        out[p + "mlp.act_fn.beta"] = sd[f"layers.{i}.act_ap"].new_tensor(XIELU_BETA)
+        out[p + "mlp.act_fn.eps"] = sd[f"layers.{i}.act_ap"].new_tensor(XIELU_EPS)
+        out[p + "attention_layernorm.weight"], out[p + "feedforward_layernorm.weight"] = sd[f"layers.{i}.ln1"], sd[f"layers.{i}.ln2"]
+        return
     else:
         g, u = ref.deinterleave_gate_up(sd[f"layers.{i}.wgu"])
         if fused_gu:

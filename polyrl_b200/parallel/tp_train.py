@@ -188,6 +188,8 @@ class TPTrainEngine:
                  weight_decay: float = 0.01, max_grad_norm: float = 1.0, seed: int = 0, dtype=None, sequence_parallel: bool = False):
         if cfg.family != "llama":
             raise NotImplementedError("TP training is implemented for the llama / qwen block family")
+        if cfg.mlp_act != "swiglu":
+            raise NotImplementedError("TP training is implemented for SwiGLU MLPs (the xIELU family trains on the ZeRO / pipeline engines)")
         if cfg.attn_type != "mha":
             raise NotImplementedError("TP training is not implemented for MLA attention (use the ZeRO, pipeline or expert-parallel engine)")
         self.sequence_parallel = sequence_parallel      # Megatron SP (reference: megatron.yaml sequence_parallel, utils/megatron/sequence_parallel.py)

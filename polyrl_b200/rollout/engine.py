@@ -833,7 +833,7 @@ class RolloutEngine:
         if cfg.family == "gpt2":
             x = x + torch.nn.functional.embedding(pos, self.embed_w["pos_embed"]).to(self.dtype)
         fused = (self.tp is None and cfg.family == "llama" and self.is_cuda and self.dtype == torch.bfloat16 and not cfg.num_experts
-                 and cfg.attn_type == "mha")
+                 and cfg.attn_type == "mha" and cfg.mlp_act == "swiglu")
         delta = None
         for i, w in enumerate(self.layer_w):
             if self.tp is not None:

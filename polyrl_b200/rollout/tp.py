@@ -132,6 +132,11 @@ class TPContext:
                 if "sgate" in w and "swgu" in out:
                     out["sgate"] = w["sgate"]
             return out
+        if "wup" in w:                                               # xIELU MLP: element-wise activation, plain column / row split
+            fl = c.intermediate_size // W
+            out["wup"], out["wd"] = w["wup"][r * fl:(r + 1) * fl], w["wd"][:, r * fl:(r + 1) * fl]
+            out["act_ap"], out["act_an"] = w["act_ap"], w["act_an"]
+            return out
         f2 = 2 * c.intermediate_size // W
         out["wgu"] = w["wgu"][r * f2:(r + 1) * f2]                  # contiguous rows (block-interleaved layout)
         fl = c.intermediate_size // W
@@ -257,6 +262,8 @@ def _mlp_tp(tp: TPContext, lcfg: ModelConfig, w: dict, x: torch.Tensor, decode: 
             raise NotImplementedError("mixture-of-experts blocks with output norms under tensor-parallel rollout")
         part = moe_partial(tp, tp.cfg, w, h, static=decode and x.is_cuda and tf._MOE_STATIC_DECODE())
         return allreduce_partial(tp, part.to(x.dtype), x, decode)
+    if "wup" in w:
+        return _row_out(tp, lcfg, w, tf.xielu(ops.linear(h, w["wup"]), w["act_ap"], w["act_an"]), "wd", "ln_mlp", x, decode)
     return _row_out(tp, lcfg, w, ops.linear_swiglu(h, w["wgu"]), "wd", "ln_mlp", x, decode)
 
 

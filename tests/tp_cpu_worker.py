@@ -129,6 +129,16 @@ def main():
             outs_d.append([(q[0].output_ids, q[0].logprobs) for q in e.generate(prompts, sp)])
         mla_ok = mla_ok and all(a[0] == b[0] for a, b in zip(*outs_d))
         mla_err = max(mla_err, max(abs(x - y) for a, b in zip(*outs_d) for x, y in zip(a[1], b[1])))
+    # ---- Apertus blocks: non-gated xIELU MLP split column / row wise
+    acfg = get_model_config("tiny-apertus")
+    aw = TransformerWeights(acfg, "cpu", torch.float32, seed=23)
+    outs_a = []
+    for ctx in (TPContext(acfg, None, rank, world, max_batch=8, group=dist.group.WORLD), None):
+        e = RolloutEngine(acfg, "cpu", max_num_seqs=8, max_model_len=64, use_cuda_graph=False, seed=3, tp=ctx)
+        e.set_weights(aw.embed, aw.layers, aw.head)
+        outs_a.append([(q[0].output_ids, q[0].logprobs) for q in e.generate(prompts, sp)])
+    mla_ok = mla_ok and all(a[0] == b[0] for a, b in zip(*outs_a))
+    mla_err = max(mla_err, max(abs(x - y) for a, b in zip(*outs_a) for x, y in zip(a[1], b[1])))
     if rank == 0:
         print(f"TP_CPU_MLA tok_ok={int(mla_ok)} lp_err={mla_err:.2e}", flush=True)
     # ---- GLM-4 blocks (output norms after the row-parallel all-reduces, partial rotary, qkv bias) through the TP engine
