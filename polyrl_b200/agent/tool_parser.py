@@ -70,6 +70,32 @@ class JsonBlockToolParser(ToolParser):
         return self._rx.sub("", text), calls
 
 
+@ToolParser.register("gpt-oss")
+class GptOssToolParser(ToolParser):
+    """OpenAI harmony format (gpt-oss models): an assistant turn is a run of ``<|start|>assistant<|channel|>CH ...<|message|>BODY``
+    segments closed by ``<|end|>`` / ``<|call|>`` / ``<|return|>``.  A tool call is a segment addressed ``to=functions.NAME`` whose
+    body is the JSON arguments and which ends with ``<|call|>``.  Reasoning in the ``analysis`` channel may itself mention tool-call
+    markup, so it is removed before calls are searched (also when the leading ``<|start|>assistant`` belongs to the prompt).
+    Capability parity: 3rdparty/verl/verl/experimental/agent_loop/tool_parser.py:110-160 (GptOssToolParser); arguments are passed on
+    unvalidated, the tool schema check happens at execution."""
+    _cot = re.compile(r"(?:<\|start\|>assistant)?<\|channel\|>analysis<\|message\|>.*?<\|end\|>", re.DOTALL)
+    # header = everything between the role and <|message|>: channel name, recipient (before or after the channel) and content type
+    _call = re.compile(r"(?:<\|start\|>assistant)?(?P<head>(?:(?!<\|message\|>|<\|start\|>).)*?to=functions\.(?P<name>[^\s<]+)(?:(?!<\|message\|>|<\|start\|>).)*?)"
+                       r"<\|message\|>(?P<args>.*?)<\|call\|>", re.DOTALL)
+
+    def extract_tool_calls(self, response_ids):
+        text = self.tokenizer.decode(response_ids, skip_special_tokens=False)
+        pad = getattr(self.tokenizer, "pad_token", None)
+        if pad:
+            text = text.replace(pad, "")
+        text = self._cot.sub("", text)
+        calls = [FunctionCall(name=m.group("name"), arguments=m.group("args").strip()) for m in self._call.finditer(text)
+                 if "<|channel|>" in m.group("head")]
+        if not calls:
+            return text, []
+        return self._call.sub(lambda m: "" if "<|channel|>" in m.group("head") else m.group(0), text), calls
+
+
 def get_tool_parser(name: str, tokenizer) -> ToolParser:
     if name not in ToolParser._registry:
         raise ValueError(f"unknown tool parser {name!r} (have {sorted(ToolParser._registry)})")

@@ -60,6 +60,29 @@ def test_hermes_parser():
     assert "<tool_call>" not in content
 
 
+def test_gpt_oss_harmony_parser():
+    """gpt-oss (harmony) tool calls: calls are the segments addressed to=functions.NAME and closed by <|call|>; tool-call markup inside
+    the analysis channel (chain of thought) is not a call, also when the prompt already holds the leading <|start|>assistant;
+    padding is dropped; a plain final answer has no calls (reference: tests/experimental/agent_loop/test_gpt_oss_tool_parser.py)."""
+    from polyrl_b200.agent import get_tool_parser
+
+    class Tok(ByteTokenizer):
+        pad_token = "<|pad|>"
+
+    tok = Tok()
+    p = get_tool_parser("gpt-oss", tok)
+    txt = ('<|channel|>analysis<|message|>maybe to=functions.fake <|constrain|>json<|message|>{"x":1}<|call|> no<|end|>'
+           '<|start|>assistant<|channel|>commentary to=functions.get_weather <|constrain|>json<|message|>{"city": "Paris"}<|call|><|pad|><|pad|>')
+    content, calls = p.extract_tool_calls(tok.encode(txt))
+    assert [(c.name, json.loads(c.arguments)) for c in calls] == [("get_weather", {"city": "Paris"})] and content == ""
+    two = ('<|start|>assistant<|channel|>analysis<|message|>think<|end|><|start|>assistant to=functions.calc<|channel|>commentary json'
+           '<|message|>{"a": 2}<|call|><|start|>assistant<|channel|>commentary to=functions.b <|constrain|>json<|message|>{}<|call|>')
+    _, calls = p.extract_tool_calls(tok.encode(two))
+    assert [c.name for c in calls] == ["calc", "b"] and calls[0].arguments == '{"a": 2}'
+    final = "<|start|>assistant<|channel|>final<|message|>The answer is 4<|return|>"
+    assert p.extract_tool_calls(tok.encode(final)) == (final, [])
+
+
 def test_tool_loop_masks_and_rewards():
     tok = ByteTokenizer()
 
