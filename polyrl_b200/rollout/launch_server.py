@@ -11,6 +11,7 @@ import argparse
 import os
 
 import torch
+from pathlib import Path
 
 from ..models import TransformerWeights, get_model_config
 from .engine import RolloutEngine
@@ -36,6 +37,10 @@ def main(argv=None) -> int:
     ap.add_argument("--transfer-agent-sender-group-idx", type=int, default=0)
     ap.add_argument("--num-transfer-engines-per-group", type=int, default=1)
     ap.add_argument("--enable-prefix-cache", action="store_true", help="cross-request KV page reuse (radix-cache equivalent)")
+    ap.add_argument("--tokenizer-path", default=None, help="HF tokenizer directory (or 'byte'): enables the OpenAI-compatible /v1/completions "
+                                                           "and /v1/chat/completions routes; default: --model-path when it holds a tokenizer")
+    ap.add_argument("--served-model-name", default=None)
+    ap.add_argument("--tool-call-parser", default=None, help="hermes | gpt-oss | json_block: parse tool calls of chat completions into tool_calls")
     ap.add_argument("--tp-size", type=int, default=1, help="tensor-parallel degree; launch with torchrun --nproc-per-node TP")
     a = ap.parse_args(argv)
     cfg = get_model_config(a.model_path)
@@ -104,8 +109,15 @@ def main(argv=None) -> int:
                 return False, str(e)
         return True, "ok"
 
+    tokenizer = None
+    tok_path = a.tokenizer_path or (a.model_path if any((Path(a.model_path) / f).exists() for f in ("tokenizer.json", "tokenizer_config.json")) else None)
+    if tok_path:
+        from ..data.rl_dataset import load_tokenizer
+
+        tokenizer = load_tokenizer(tok_path)
     srv = EngineServer(eng, host=a.host, port=a.port, stream_interval=a.stream_interval, weight_update_fn=on_update,
-                       tp_cmd_group=cmd_group).start()
+                       tp_cmd_group=cmd_group, tokenizer=tokenizer, model_name=a.served_model_name or a.model_path,
+                       tool_parser=a.tool_call_parser).start()
     if a.rollout_manager_address:
         import time as _t
 

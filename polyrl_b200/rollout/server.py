@@ -31,8 +31,11 @@ class _Tracked:
 
 class EngineServer:
     def __init__(self, engine: RolloutEngine, host: str = "127.0.0.1", port: int = 0, stream_interval: int = 128,
-                 weight_update_fn=None, tp_cmd_group=None):
+                 weight_update_fn=None, tp_cmd_group=None, tokenizer=None, model_name: str | None = None, tool_parser: str | None = None):
         self.engine = engine
+        # OpenAI-compatible text front-end (/v1/completions, /v1/chat/completions, /v1/models): needs a tokenizer; the token-id
+        # /generate route the manager and the trainers use does not
+        self.tokenizer, self.model_name, self.tool_parser = tokenizer, model_name or engine.full_cfg.name, tool_parser
         # tensor-parallel serving: this object lives on TP rank 0; every scheduler iteration its command list is
         # broadcast over ``tp_cmd_group`` (a gloo group of the TP ranks) so that followers (``run_tp_follower``) apply the
         # same requests / aborts / weight updates and then take the same engine step (reference: SGLang broadcasts
@@ -72,6 +75,9 @@ class EngineServer:
                 elif path == "/get_server_info":
                     info = srv.engine.server_info()
                     self._json(200, {"internal_states": [info], "weight_version": srv.weight_version})
+                elif path == "/v1/models":
+                    self._json(200, {"object": "list", "data": [{"id": srv.model_name, "object": "model", "owned_by": "polyrl_b200",
+                                                                  "max_model_len": srv.engine.max_model_len}]})
                 else:
                     self._json(404, {"error": "not found"})
 
@@ -86,6 +92,10 @@ class EngineServer:
                 path = self.path.split("?")[0]
                 if path == "/generate":
                     srv._handle_generate(self, body)
+                elif path in ("/v1/chat/completions", "/v1/completions"):
+                    from .openai_api import handle_openai
+
+                    handle_openai(srv, self, body, chat=path.endswith("chat/completions"))
                 elif path == "/abort_request":
                     srv._command("abort", body)
                     self._json(200, {"success": True})
@@ -163,6 +173,14 @@ class EngineServer:
         done.wait(timeout=600)
         return result.get("ok", False), result.get("msg", "timeout")
 
+    def submit(self, prompts: list[list[int]], sp: SamplingParams, mm=None) -> tuple[str, "queue.Queue"]:
+        """Queue token-id prompts for the engine thread; events (index, payload, finished) arrive on the returned queue."""
+        q: queue.Queue = queue.Queue()
+        key = f"g{id(q)}"
+        with self._lock:
+            self._inbox.append(("generate", (key, prompts, sp, q, mm), None))
+        return key, q
+
     def _handle_generate(self, h, body: dict):
         ids = body.get("input_ids")
         if ids is None:
@@ -178,10 +196,7 @@ class EngineServer:
 
             img = body["image_data"]
             mm = [decode_mm_wire(d) if d is not None else None for d in img] if isinstance(img, list) else [decode_mm_wire(img)] * len(prompts)
-        q: queue.Queue = queue.Queue()
-        key = f"g{id(q)}"
-        with self._lock:
-            self._inbox.append(("generate", (key, prompts, sp, q, mm), None))
+        key, q = self.submit(prompts, sp, mm)
         n = len(prompts)
         latest = [None] * n
         if stream:

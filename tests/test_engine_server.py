@@ -671,3 +671,104 @@ def test_native_scheduler_matches_python_scheduler(monkeypatch):
     assert a.prefix_cache.hits == b.prefix_cache.hits > 0 and a.sched.num_live() == 0
     moved = sum(1 for t0, t1 in zip(trace_a, trace_a[1:]) for r0, r1 in zip(t0, t1) if r0[1] >= 0 and r1[1] >= 0 and r0[1] != r1[1])
     assert moved > 0                 # slot compaction happened (and stayed mirrored in the native free list)
+
+
+def test_openai_compatible_routes(tmp_path):
+    """/v1/models, /v1/completions and /v1/chat/completions on the engine server: n choices per prompt, token-id and text prompts,
+    log-probs that are the engine's own, string stops, usage accounting, SSE streaming whose deltas concatenate to the blocking
+    answer, tool calls parsed into ``tool_calls``; and the offline ``main_generation_server`` entry point against the same server."""
+    from polyrl_b200.data.rl_dataset import ByteTokenizer
+    from polyrl_b200.trainer import main_generation_server as mgs
+
+    cfg = get_model_config("tiny-llama")
+    w = TransformerWeights(cfg, "cpu", torch.float32, seed=4)
+    eng = RolloutEngine(cfg, "cpu", max_num_seqs=8, max_model_len=128, use_cuda_graph=False, seed=2)
+    eng.set_weights(w.embed, w.layers, w.head)
+    tok = ByteTokenizer()
+    srv = EngineServer(eng, stream_interval=3, tokenizer=tok, model_name="tiny", tool_parser="hermes").start()
+    try:
+        ep = srv.endpoint
+        with urllib.request.urlopen(f"http://{ep}/v1/models", timeout=10) as r:
+            assert json.loads(r.read())["data"][0]["id"] == "tiny"
+        msgs = [{"role": "user", "content": "hi there"}]
+        out = mgs._post(ep, "/v1/chat/completions", {"messages": msgs, "n": 3, "max_tokens": 9, "temperature": 1.0, "seed": 5,
+                                                      "logprobs": True, "ignore_eos": True})
+        assert out["object"] == "chat.completion" and [c["index"] for c in out["choices"]] == [0, 1, 2]
+        p_len = len(tok.apply_chat_template(msgs, tokenize=True))
+        assert out["usage"] == {"prompt_tokens": p_len, "completion_tokens": 27, "total_tokens": p_len + 27}
+        c0 = out["choices"][0]
+        assert c0["finish_reason"] == "length" and len(c0["logprobs"]["content"]) == 9 and all(i["logprob"] <= 0 for i in c0["logprobs"]["content"])
+        assert len({json.dumps(c["logprobs"]["content"]) for c in out["choices"]}) > 1            # samples differ
+        # the same request through the token-id route gives the same tokens (same seed, same request ids are not needed at T=0)
+        ids = tok.apply_chat_template(msgs, tokenize=True)
+        g = mgs._post(ep, "/generate", {"input_ids": ids, "sampling_params": {"max_new_tokens": 9, "temperature": 0.0, "ignore_eos": True}})
+        o0 = mgs._post(ep, "/v1/completions", {"prompt": ids, "max_tokens": 9, "temperature": 0.0, "logprobs": True, "ignore_eos": True})
+        assert o0["object"] == "text_completion" and o0["choices"][0]["text"] == tok.decode(g["output_ids"])
+        assert [round(x, 5) for x in o0["choices"][0]["logprobs"]["token_logprobs"]] == [round(l, 5) for l, _, _ in g["meta_info"]["output_token_logprobs"]]
+        # text prompts (a batch of two), string stop applied to the decoded text
+        full = mgs._post(ep, "/v1/completions", {"prompt": ["abc", "xyz"], "max_tokens": 12, "temperature": 0.0, "ignore_eos": True})
+        assert len(full["choices"]) == 2
+        t0 = full["choices"][0]["text"]
+        if len(t0) > 2:
+            cut = mgs._post(ep, "/v1/completions", {"prompt": "abc", "max_tokens": 12, "temperature": 0.0, "ignore_eos": True, "stop": [t0[2]]})
+            assert cut["choices"][0]["text"] == t0[: t0.find(t0[2])] and cut["choices"][0]["finish_reason"] == "stop"
+        # streaming: deltas concatenate to the blocking answer
+        req = urllib.request.Request(f"http://{ep}/v1/chat/completions", data=json.dumps(
+            {"messages": msgs, "max_tokens": 10, "temperature": 0.0, "stream": True, "ignore_eos": True}).encode(), headers={"Content-Type": "application/json"})
+        chunks = []
+        with urllib.request.urlopen(req, timeout=60) as r:
+            for line in r.read().decode().splitlines():
+                if line.startswith("data: ") and line != "data: [DONE]":
+                    chunks.append(json.loads(line[6:]))
+        assert all(c["object"] == "chat.completion.chunk" for c in chunks) and chunks[-1]["choices"][0]["finish_reason"] == "length"
+        block = mgs._post(ep, "/v1/chat/completions", {"messages": msgs, "max_tokens": 10, "temperature": 0.0, "ignore_eos": True})
+        assert "".join(c["choices"][0]["delta"].get("content", "") for c in chunks) == block["choices"][0]["message"]["content"]
+        # bad requests are 400s, not hangs
+        for bad in ({"messages": []}, {"prompt": 7}):
+            try:
+                mgs._post(ep, "/v1/chat/completions" if "messages" in bad else "/v1/completions", bad)
+                assert False
+            except urllib.error.HTTPError as e:
+                assert e.code == 400
+        # tool calls: what the parser finds in the generated ids becomes tool_calls (exercised on the choice builder directly —
+        # a random-init model does not emit the markup)
+        from polyrl_b200.rollout.openai_api import _choice
+
+        txt = 'ok <tool_call>{"name": "calculator", "arguments": {"expression": "6*7"}}</tool_call>'
+        pl = {"output_ids": tok.encode(txt), "meta_info": {"finish_reason": {"type": "stop"}, "output_token_logprobs": []}}
+        ch = _choice(srv, pl, 0, True, [], False, True)
+        assert ch["finish_reason"] == "tool_calls" and ch["message"]["tool_calls"][0]["function"]["name"] == "calculator"
+        assert json.loads(ch["message"]["tool_calls"][0]["function"]["arguments"]) == {"expression": "6*7"}
+        # offline generation through the running server
+        data = tmp_path / "p.jsonl"
+        data.write_text("\n".join(json.dumps({"prompt": [{"role": "user", "content": f"q{i}"}], "k": i}) for i in range(5)))
+        assert mgs.main(["--model", "tiny", "--data", str(data), "--output", str(tmp_path / "o.jsonl"), "--n-samples", "2",
+                         "--response-length", "6", "--server", ep]) == 0
+        rows = [json.loads(l) for l in (tmp_path / "o.jsonl").read_text().splitlines()]
+        assert [r["k"] for r in rows] == list(range(5)) and all(len(r["responses"]) == 2 for r in rows)
+    finally:
+        srv.stop()
+
+
+def test_generation_server_entry_starts_its_own_replicas(tmp_path):
+    """``main_generation_server`` end to end on CPU: it starts two ``launch_server`` replicas (dummy weights, byte tokenizer), splits
+    the prompts over them, collects n samples per prompt through /v1/chat/completions and shuts the replicas down."""
+    import os
+
+    from polyrl_b200.trainer import main_generation_server as mgs
+
+    data = tmp_path / "p.jsonl"
+    data.write_text("\n".join(json.dumps({"prompt": f"question {i}"}) for i in range(6)))
+    env_before = dict(os.environ)
+    os.environ["PYTHONPATH"] = str(_os.path.dirname(_os.path.dirname(_os.path.abspath(__file__)))) + os.pathsep + os.environ.get("PYTHONPATH", "")
+    try:
+        rc = mgs.main(["--model", "tiny-llama", "--data", str(data), "--output", str(tmp_path / "o.jsonl"), "--n-samples", "2",
+                       "--response-length", "5", "--prompt-length", "64", "--num-replicas", "2", "--base-port", "31840", "--tokenizer", "byte",
+                       "--load-format", "dummy", "--device", "cpu", "--max-num-seqs", "8"])
+    finally:
+        os.environ.clear()
+        os.environ.update(env_before)
+    assert rc == 0
+    rows = [json.loads(l) for l in (tmp_path / "o.jsonl").read_text().splitlines()]
+    assert len(rows) == 6 and all(len(r["responses"]) == 2 and all(isinstance(t, str) for t in r["responses"]) for r in rows)
+    assert not mgs._healthy("127.0.0.1:31840") and not mgs._healthy("127.0.0.1:31841")          # replicas are gone
