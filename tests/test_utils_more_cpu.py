@@ -89,6 +89,104 @@ def test_tracking_backends_and_validation_logger(tmp_path, monkeypatch):
         pass
 
 
+def test_tracking_external_backends_through_fake_clients(tmp_path, monkeypatch):
+    """The wandb / trackio / mlflow / swanlab / clearml adapters and the per-backend validation-generation tables, driven against
+    recording stand-ins for the client libraries (none is installed here): init arguments, metric routing, mlflow key sanitisation
+    and flattened params, clearml title / series split, the wandb table that grows by one row per step; a backend whose library is
+    missing is skipped without stopping the run."""
+    import sys
+    import types
+
+    from polyrl_b200.utils import tracking as T
+
+    calls: list = []
+
+    def rec(name):
+        return lambda *a, **k: calls.append((name, a, k))
+
+    wandb = types.ModuleType("wandb")
+    wandb.init, wandb.log, wandb.finish = rec("wandb.init"), rec("wandb.log"), rec("wandb.finish")
+    wandb.Settings = lambda **k: ("settings", k)
+    wandb.Table = lambda columns, data: {"columns": columns, "data": data}
+    trackio = types.ModuleType("trackio")
+    trackio.init, trackio.log, trackio.finish = rec("trackio.init"), rec("trackio.log"), rec("trackio.finish")
+    mlflow = types.ModuleType("mlflow")
+    for f in ("set_tracking_uri", "start_run", "log_params", "log_metrics", "end_run", "log_text"):
+        setattr(mlflow, f, rec("mlflow." + f))
+    mlflow.set_experiment = lambda name: types.SimpleNamespace(experiment_id="17")
+    swanlab = types.ModuleType("swanlab")
+    for f in ("login", "init", "log", "finish"):
+        setattr(swanlab, f, rec("swanlab." + f))
+    swanlab.Text = lambda text, caption=None: ("text", caption, text)
+
+    class FakeLogger:
+        report_scalar, report_text, report_table = (staticmethod(rec("clearml.scalar")), staticmethod(rec("clearml.text")),
+                                                    staticmethod(rec("clearml.table")))
+
+    class FakeTask:
+        _cur = None
+
+        @classmethod
+        def init(cls, **k):
+            calls.append(("clearml.init", (), k))
+            cls._cur = cls()
+            return cls._cur
+
+        @classmethod
+        def current_task(cls):
+            return cls._cur
+
+        def connect_configuration(self, cfg, name=None):
+            calls.append(("clearml.connect", (cfg,), {"name": name}))
+
+        def get_logger(self):
+            return FakeLogger()
+
+        def close(self):
+            calls.append(("clearml.close", (), {}))
+
+    clearml = types.ModuleType("clearml")
+    clearml.Task = FakeTask
+    for name, mod in (("wandb", wandb), ("trackio", trackio), ("mlflow", mlflow), ("swanlab", swanlab), ("clearml", clearml)):
+        monkeypatch.setitem(sys.modules, name, mod)
+    monkeypatch.setenv("WANDB_ENTITY", "team")
+    monkeypatch.setenv("SWANLAB_API_KEY", "k")
+    monkeypatch.setenv("SWANLAB_MODE", "local")
+    monkeypatch.delenv("MLFLOW_TRACKING_URI", raising=False)
+    monkeypatch.chdir(tmp_path)
+    cfg = {"trainer": {"wandb_proxy": "http://p:1", "n_gpus": 8}, "data": {"files": ["a", "b"]}}
+    t = T.Tracking("proj", "exp", ["tracking", "trackio", "mlflow", "swanlab", "clearml", "vemlp_wandb"], config=cfg)
+    assert set(t.loggers) == {"wandb", "trackio", "mlflow", "swanlab", "clearml"}          # volcengine client missing: skipped
+    by = lambda n: [c for c in calls if c[0] == n]                                            # noqa: E731
+    assert by("wandb.init")[0][2] == {"project": "proj", "name": "exp", "config": cfg, "entity": "team", "settings": ("settings", {"https_proxy": "http://p:1"})}
+    assert by("mlflow.set_tracking_uri")[0][1] == ("sqlite:////tmp/mlruns.db",) and by("mlflow.start_run")[0][2] == {"experiment_id": "17", "run_name": "exp"}
+    assert by("mlflow.log_params")[0][1][0] == {"trainer/wandb_proxy": "http://p:1", "trainer/n_gpus": 8, "data/files/list_len": 2, "data/files/0": "a", "data/files/1": "b"}
+    assert by("swanlab.login")[0][1] == ("k",) and by("swanlab.init")[0][2]["mode"] == "local" and by("swanlab.init")[0][2]["config"]["FRAMEWORK"] == "polyrl_b200"
+    assert by("clearml.init")[0][2]["task_name"] == "exp" and by("clearml.connect")[0][1][0] == cfg
+    t.log({"val-core/gsm8k/acc/mean@4": 0.5, "actor/pg_loss": torch.tensor(0.25), "note": "hi"}, step=3)
+    assert by("wandb.log")[0][2] == {"step": 3} and by("trackio.log")[0][1][0]["note"] == "hi"
+    assert by("mlflow.log_metrics")[0][2] == {"metrics": {"val-core/gsm8k/acc/mean_at_4": 0.5, "actor/pg_loss": 0.25}, "step": 3}
+    sc = {(c[2]["title"], c[2]["series"]): c[2]["value"] for c in by("clearml.scalar")}
+    assert sc == {("val-core", "gsm8k/acc/mean@4"): 0.5, ("actor", "pg_loss"): 0.25} and "note = hi" in by("clearml.text")[0][1][0]
+    t.log({"x": 1.0}, step=4, backend=["mlflow"])
+    assert len(by("mlflow.log_metrics")) == 2 and len(by("wandb.log")) == 1
+    # validation generations in every backend's own form
+    vg = T.ValidationGenerationsLogger("proj", "exp", root=str(tmp_path / "val"))
+    T.ValidationGenerationsLogger._wandb_rows.clear()
+    vg.log(["wandb", "swanlab", "mlflow", "clearml", "tensorboard", "vemlp_wandb"], [("q1", "a1", 1.0), ("q2", "a2", 0.0)], step=5)
+    vg.log(["wandb"], [("q3", "a3", 0.5)], step=6)
+    tables = [c[1][0]["val/generations"] for c in by("wandb.log")[1:]]
+    assert tables[0]["columns"] == ["step", "input_1", "output_1", "score_1", "input_2", "output_2", "score_2"] and tables[0]["data"] == [[5, "q1", "a1", 1.0, "q2", "a2", 0.0]]
+    assert tables[1]["data"] == [[5, "q1", "a1", 1.0, "q2", "a2", 0.0], [6, "q3", "a3", 0.5, None, None, None]]       # one row per step
+    assert [c[1] for c in by("swanlab.log")[-1][1][0]["val/generations"]] == ["sample 1", "sample 2"]
+    assert json.loads(by("mlflow.log_text")[0][1][0])[1] == {"input": "q2", "output": "a2", "score": 0.0} and by("mlflow.log_text")[0][1][1] == "val_step5.json"
+    assert list(by("clearml.table")[0][2]["table_plot"]["output"]) == ["a1", "a2"]
+    assert (tmp_path / "val" / "proj" / "exp" / "5.jsonl").exists() and list(tmp_path.rglob("events.out.tfevents*"))
+    t.finish()
+    assert by("wandb.finish") and by("mlflow.end_run") and by("swanlab.finish") and by("clearml.close") and not t.loggers
+    assert T.sanitize_mlflow_key("a b:c/d-e.f(g)@2") == "a b:c/d-e.f_g__at_2"
+
+
 def test_profiler_timers_and_annotate():
     from polyrl_b200.utils import profiler as P
 
