@@ -3,6 +3,8 @@ model server that scripts tool calls)."""
 import itertools
 import json
 
+import pytest
+
 import torch
 
 from polyrl_b200.agent import (CalculatorTool, Gsm8kInteraction, Gsm8kTool, HermesToolParser, MultiTurnRollout, ToolSchema,
@@ -243,7 +245,121 @@ def test_rollout_trace_file_backend(tmp_path):
     with rollout_trace_attr(step=5, sample_index=2, rollout_n=1):
         assert t.work(4, k=3) == 12
     rows = [_json.loads(l) for l in cfg.path.read_text().splitlines()]
-    assert len(rows) == 1 and rows[0]["step"] == 5 and rows[0]["output"] == 12 and rows[0]["inputs"]["kwargs"] == {"k": 3}
+    assert len(rows) == 1 and rows[0]["step"] == 5 and rows[0]["output"] == 12 and rows[0]["inputs"] == {"x": 4, "k": 3}
+    RolloutTraceConfig.reset()
+
+
+def test_rollout_trace_weave_mlflow_async_and_token2text(tmp_path, monkeypatch):
+    """The weave and mlflow trace back-ends against recording stand-ins for the client libraries (neither is installed): one call /
+    span per traced op with named inputs inside the per-sample attribute scope, exceptions reported, async methods traced, and
+    ``token2text`` adding the decoded prompt / response next to the ids."""
+    import asyncio
+    import contextlib
+    import sys
+    import types
+
+    from polyrl_b200.utils.rollout_trace import RolloutTraceConfig, rollout_trace_attr, rollout_trace_op
+
+    log: list = []
+
+    class Out:
+        def __init__(self):
+            self.prompt_ids, self.response_ids, self.reward = [3 + ord("h"), 3 + ord("i")], [3 + ord("o"), 3 + ord("k")], 1.0
+
+    class Agent:
+        tokenizer = ByteTokenizer()
+
+        @rollout_trace_op
+        async def run(self, prompt, n=1):
+            await asyncio.sleep(0)
+            return Out()
+
+        @rollout_trace_op
+        def boom(self, x):
+            raise ValueError("bad " + str(x))
+
+    # ---- weave
+    class Client:
+        def create_call(self, op, inputs, attributes):
+            log.append(("create", op, inputs, attributes))
+            return len(log)
+
+        def finish_call(self, call, output=None, exception=None):
+            log.append(("finish", call, output, repr(exception) if exception else None))
+
+    scope: list = [{}]
+    weave = types.ModuleType("weave")
+    weave.init = lambda project: Client()
+
+    @contextlib.contextmanager
+    def attributes(d):
+        scope.append(d)
+        try:
+            yield
+        finally:
+            scope.pop()
+
+    weave.attributes = attributes
+    ctx_mod = types.ModuleType("weave.trace.context")
+    ctx_mod.call_context = types.SimpleNamespace(call_attributes=types.SimpleNamespace(get=lambda: scope[-1]))
+    for name, mod in (("weave", weave), ("weave.trace", types.ModuleType("weave.trace")), ("weave.trace.context", ctx_mod)):
+        monkeypatch.setitem(sys.modules, name, mod)
+    RolloutTraceConfig.reset()
+    RolloutTraceConfig.init("proj", "exp", "weave", token2text=True)
+    a = Agent()
+    with rollout_trace_attr(step=2, sample_index=7, rollout_n=1, validate=True):
+        out = asyncio.run(a.run("hello", n=4))
+        with pytest.raises(ValueError):
+            a.boom(5)
+    assert isinstance(out, Out)
+    assert log[0][:3] == ("create", "test_rollout_trace_weave_mlflow_async_and_token2text.<locals>.Agent.run", {"prompt": "hello", "n": 4})
+    assert log[0][3] == {"step": 2, "sample_index": 7, "rollout_n": 1, "validate": True, "experiment_name": "exp"}
+    assert log[1][2]["prompt_text"] == "hi" and log[1][2]["response_text"] == "ok" and log[1][2]["reward"] == 1.0 and log[1][3] is None
+    assert log[2][2] == {"x": 5} and "bad 5" in log[3][3]
+    # ---- mlflow
+    log.clear()
+
+    class Span:
+        trace_id = "t1"
+
+        def __init__(self, name):
+            self.name = name
+
+        def set_inputs(self, i):
+            log.append(("inputs", self.name, i))
+
+        def set_outputs(self, o):
+            log.append(("outputs", self.name, o))
+
+    @contextlib.contextmanager
+    def start_span(name):
+        log.append(("open", name))
+        try:
+            yield Span(name)
+        finally:
+            log.append(("close", name))
+
+    mlflow = types.ModuleType("mlflow")
+    mlflow.start_span = start_span
+    mlflow.set_trace_tag = lambda tid, k, v: log.append(("tag", tid, k, v))
+    mlflow.set_tracking_uri = lambda uri: log.append(("uri", uri))
+    mlflow.set_experiment = lambda name: log.append(("experiment", name))
+    mlflow.config = types.SimpleNamespace(enable_async_logging=lambda: log.append(("async",)))
+    monkeypatch.setitem(sys.modules, "mlflow", mlflow)
+    monkeypatch.delenv("MLFLOW_TRACKING_URI", raising=False)
+    RolloutTraceConfig.reset()
+    RolloutTraceConfig.init("proj", "exp", "mlflow")
+    assert log[:3] == [("async",), ("uri", "sqlite:////tmp/mlruns.db"), ("experiment", "proj")]
+    with rollout_trace_attr(step=3, sample_index=0, name="agent_loop"):
+        asyncio.run(a.run("q"))
+        with pytest.raises(ValueError):
+            a.boom(1)
+    names = [e[:2] for e in log[3:] if e[0] in ("open", "close")]
+    run, boom = "Agent.run", "Agent.boom"
+    assert [n[0] for n in names] == ["open", "open", "close", "open", "close", "close"] and names[0][1] == "agent_loop" and names[1][1].endswith(run) and names[3][1].endswith(boom)
+    assert ("tag", "t1", "step", "3") in log and ("tag", "t1", "experiment_name", "exp") in log
+    outs = [e for e in log if e[0] == "outputs"]
+    assert len(outs) == 1 and isinstance(outs[0][2], Out)              # token2text off: the object itself; the failed call has no output
     RolloutTraceConfig.reset()
 
 
