@@ -120,7 +120,7 @@ class ModelConfig:
                 raise ValueError("moe / shared-expert intermediate sizes must be multiples of 128 (gate / up rows are interleaved in 128-row blocks)")
             if self.moe_router not in ("softmax", "sigmoid_group"):
                 raise ValueError(f"unknown moe_router {self.moe_router!r}")
-            if self.moe_router == "sigmoid_group" and (self.num_experts % self.n_group or self.topk_group > self.n_group):
+            if self.n_group > 1 and (self.num_experts % self.n_group or self.topk_group > self.n_group):
                 raise ValueError("n_group must divide num_experts and topk_group <= n_group")
         if self.vision is not None:
             if self.family != "llama":
@@ -314,6 +314,22 @@ class ModelConfig:
                 raise NotImplementedError(f"apertus with hidden_act={hf.get('hidden_act')!r}")
             act_kw = dict(mlp_act="xielu")
         mla_kw: dict = {}
+        if mt == "deepseek_v2":              # MLA attention (complex-pair rotary = interleaved weights) + softmax routing, optionally group-limited
+            if hf.get("attention_bias"):
+                raise NotImplementedError("deepseek_v2 checkpoints with attention_bias are not supported")
+            mla_kw = dict(attn_type="mla", q_lora_rank=int(hf.get("q_lora_rank") or 0), kv_lora_rank=int(hf["kv_lora_rank"]),
+                          qk_nope_head_dim=int(hf["qk_nope_head_dim"]), qk_rope_head_dim=int(hf["qk_rope_head_dim"]),
+                          v_head_dim=int(hf["v_head_dim"]), rope_interleaved=True)
+            if hf.get("n_routed_experts") and int(hf.get("first_k_dense_replace", 0)) < hf["num_hidden_layers"]:
+                grouped = hf.get("topk_method", "greedy") == "group_limited_greedy"
+                moe_kw = dict(num_experts=hf["n_routed_experts"], num_experts_per_tok=hf["num_experts_per_tok"],
+                              moe_intermediate_size=hf["moe_intermediate_size"], norm_topk_prob=False,
+                              dense_layers=tuple(range(min(int(hf.get("first_k_dense_replace", 0)), hf["num_hidden_layers"]))),
+                              shared_expert_intermediate_size=hf["moe_intermediate_size"] * int(hf.get("n_shared_experts") or 0),
+                              moe_router="softmax", n_group=int(hf.get("n_group") or 1) if grouped else 1,
+                              topk_group=int(hf.get("topk_group") or 1) if grouped else 1,
+                              routed_scaling_factor=float(hf.get("routed_scaling_factor", 1.0)))
+            hf = {**hf, "head_dim": 0, "num_key_value_heads": hf["num_attention_heads"]}
         if mt == "deepseek_v3":              # MLA attention + DeepSeek-V3 routing (sigmoid, bias-corrected, group-limited), shared experts
             if hf.get("attention_bias"):
                 raise NotImplementedError("deepseek_v3 checkpoints with attention_bias are not supported")
@@ -343,7 +359,7 @@ class ModelConfig:
                    tie_word_embeddings=hf.get("tie_word_embeddings", False), eos_token_id=eos, extra_eos_token_ids=extra_eos,
                    bos_token_id=hf.get("bos_token_id") or eos, pad_token_id=hf.get("pad_token_id") or eos,
                    sliding_window=(hf.get("sliding_window") if (mt in ("mistral", "mixtral") or hf.get("use_sliding_window")) else None),
-                   hf_model_type=("glm4v" if hf.get("_glm4v") else mt) if mt in ("mistral", "mixtral", "glm", "glm4", "qwen2_moe", "glm4_moe", "deepseek_v3", "apertus") else "",
+                   hf_model_type=("glm4v" if hf.get("_glm4v") else mt) if mt in ("mistral", "mixtral", "glm", "glm4", "qwen2_moe", "glm4_moe", "deepseek_v2", "deepseek_v3", "apertus") else "",
                    name=hf.get("_name_or_path", mt), **vis_kw, **{**moe_kw, **vl_moe_kw}, **{**glm_kw, **mla_kw, **act_kw})
 
 
@@ -517,6 +533,14 @@ PRESETS: dict[str, dict] = {
                               shared_expert_intermediate_size=2816, moe_router="sigmoid_group", n_group=1, topk_group=1,
                               routed_scaling_factor=2.446, hf_model_type="deepseek_v3", eos_token_id=163585, bos_token_id=163584,
                               pad_token_id=163839),
+    "deepseek-v2-lite": dict(family="llama", vocab_size=102400, hidden_size=2048, intermediate_size=10944, num_layers=27, num_heads=16,
+                             num_kv_heads=16, max_position_embeddings=163840, rope_theta=10000.0, rms_norm_eps=1e-6, attn_type="mla",
+                             q_lora_rank=0, kv_lora_rank=512, qk_nope_head_dim=128, qk_rope_head_dim=64, v_head_dim=128, rope_interleaved=True,
+                             rope_scaling=dict(rope_type="yarn", factor=40.0, original_max_position_embeddings=4096, beta_fast=32.0, beta_slow=1.0,
+                                               mscale=0.707, mscale_all_dim=0.707),
+                             num_experts=64, num_experts_per_tok=6, moe_intermediate_size=1408, norm_topk_prob=False, dense_layers=(0,),
+                             shared_expert_intermediate_size=2816, moe_router="softmax", routed_scaling_factor=1.0,
+                             hf_model_type="deepseek_v2", eos_token_id=100001, bos_token_id=100000, pad_token_id=100001),
     "tiny-deepseek-v3": dict(family="llama", vocab_size=512, hidden_size=128, intermediate_size=256, num_layers=3, num_heads=4, num_kv_heads=4,
                              max_position_embeddings=512, rope_theta=10000.0, rms_norm_eps=1e-6, attn_type="mla", q_lora_rank=48,
                              kv_lora_rank=32, qk_nope_head_dim=32, qk_rope_head_dim=16, v_head_dim=32, rope_interleaved=True,

@@ -333,6 +333,20 @@ def _lm_config_dict(cfg: ModelConfig) -> dict:
             first_dense += 1
         fm = cfg.moe_intermediate_size or cfg.intermediate_size
         rp = {"rope_type": "default", "rope_theta": cfg.rope_theta, **(dict(cfg.rope_scaling) if cfg.rope_scaling else {})}
+        if cfg.moe_router == "softmax" and (cfg.num_experts or getattr(cfg, "hf_model_type", "") == "deepseek_v2"):      # DeepSeek-V2 / V2-Lite
+            return {"model_type": "deepseek_v2", "architectures": ["DeepseekV2ForCausalLM"], "vocab_size": cfg.vocab_size, "hidden_size": cfg.hidden_size,
+                    "intermediate_size": cfg.intermediate_size, "num_hidden_layers": cfg.num_layers, "num_attention_heads": cfg.num_heads,
+                    "num_key_value_heads": cfg.num_heads, "max_position_embeddings": cfg.max_position_embeddings, "rms_norm_eps": cfg.rms_norm_eps,
+                    "attention_bias": False, "q_lora_rank": cfg.q_lora_rank or None, "kv_lora_rank": cfg.kv_lora_rank,
+                    "qk_nope_head_dim": cfg.qk_nope_head_dim, "qk_rope_head_dim": cfg.qk_rope_head_dim, "v_head_dim": cfg.v_head_dim,
+                    "rope_theta": cfg.rope_theta, "rope_parameters": rp, **({"rope_scaling": dict(cfg.rope_scaling)} if cfg.rope_scaling else {}),
+                    "n_routed_experts": cfg.num_experts or None, "num_experts_per_tok": cfg.num_experts_per_tok or None, "moe_intermediate_size": fm,
+                    "n_shared_experts": (cfg.shared_expert_intermediate_size // fm) if cfg.num_experts else None,
+                    "topk_method": "group_limited_greedy" if cfg.n_group > 1 else "greedy", "n_group": cfg.n_group, "topk_group": cfg.topk_group,
+                    "routed_scaling_factor": cfg.routed_scaling_factor, "norm_topk_prob": False,
+                    "first_k_dense_replace": first_dense if cfg.num_experts else cfg.num_layers,
+                    "tie_word_embeddings": cfg.tie_word_embeddings, "hidden_act": "silu", "torch_dtype": "bfloat16",
+                    "eos_token_id": cfg.eos_token_id, "bos_token_id": cfg.bos_token_id, "pad_token_id": cfg.pad_token_id}
         return {"model_type": "deepseek_v3", "architectures": ["DeepseekV3ForCausalLM"], "vocab_size": cfg.vocab_size, "hidden_size": cfg.hidden_size,
                 "intermediate_size": cfg.intermediate_size, "num_hidden_layers": cfg.num_layers, "num_attention_heads": cfg.num_heads,
                 "num_key_value_heads": cfg.num_heads, "max_position_embeddings": cfg.max_position_embeddings, "rms_norm_eps": cfg.rms_norm_eps,

@@ -265,9 +265,16 @@ def moe_route(cfg: ModelConfig, w: dict, h: torch.Tensor) -> tuple[torch.Tensor,
             top_w = top_w / (top_w.sum(-1, keepdim=True) + 1e-20)
         return top_w * cfg.routed_scaling_factor, top_e, scores / scores.sum(-1, keepdim=True)   # balance term on normalised scores
     probs = torch.softmax(F.linear(h, w["router"].to(h.dtype)).float(), dim=-1)
-    top_w, top_e = torch.topk(probs, k, dim=-1)
+    choice = probs
+    if cfg.n_group > 1:        # DeepSeek-V2 group_limited_greedy: experts of the topk_group groups with the best single expert
+        grp = probs.view(-1, cfg.n_group, e // cfg.n_group).max(-1).values
+        keep = torch.zeros_like(grp).scatter_(1, grp.topk(cfg.topk_group, dim=-1)[1], 1.0).bool()
+        choice = probs.masked_fill(~keep.unsqueeze(-1).expand(-1, cfg.n_group, e // cfg.n_group).reshape(-1, e), 0.0)
+    top_w, top_e = torch.topk(choice, k, dim=-1)
     if cfg.norm_topk_prob:
         top_w = top_w / top_w.sum(-1, keepdim=True)
+    if cfg.routed_scaling_factor != 1.0:
+        top_w = top_w * cfg.routed_scaling_factor
     return top_w, top_e, probs
 
 

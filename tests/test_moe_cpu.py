@@ -392,7 +392,7 @@ def test_moe_variants_match_hf(family, tmp_path):
     assert set(back) == set(mine) and all(torch.allclose(back[k], mine[k]) for k in mine)
 
 
-@pytest.mark.parametrize("variant", ["q_lora_interleaved", "plain_q_yarn", "dense"])
+@pytest.mark.parametrize("variant", ["q_lora_interleaved", "plain_q_yarn", "dense", "v2_group_limited", "v2_lite_greedy"])
 def test_deepseek_v3_mla_matches_hf(variant, tmp_path):
     """DeepSeek-V3 architecture (multi-head latent attention + sigmoid group-limited routing + shared experts; Moonlight ships under
     the same model_type): logits equal HF ``DeepseekV3ForCausalLM`` with the query bottleneck and interleaved rotary weights, with a
@@ -412,15 +412,28 @@ def test_deepseek_v3_mla_matches_hf(variant, tmp_path):
                   rope_parameters=dict(rope_type="yarn", factor=4.0, original_max_position_embeddings=32, beta_fast=32.0, beta_slow=1.0,
                                        mscale=1.0, mscale_all_dim=0.8, rope_theta=10000.0))
     n_layers = 3
-    hc = transformers.DeepseekV3Config(
+    v2 = variant.startswith("v2")
+    if v2:        # DeepSeek-V2 / V2-Lite: the same attention with complex-pair rotary, softmax routing (optionally group-limited), scaled weights
+        hc = transformers.DeepseekV2Config(
+            vocab_size=320, hidden_size=128, intermediate_size=256, moe_intermediate_size=128, num_hidden_layers=n_layers, num_attention_heads=4,
+            num_key_value_heads=4, n_shared_experts=2, n_routed_experts=8, routed_scaling_factor=16.0 if variant == "v2_group_limited" else 1.0,
+            kv_lora_rank=32, q_lora_rank=48 if variant == "v2_group_limited" else None, qk_rope_head_dim=16, v_head_dim=32, qk_nope_head_dim=32,
+            topk_method="group_limited_greedy" if variant == "v2_group_limited" else "greedy", n_group=4, topk_group=2, num_experts_per_tok=2,
+            first_k_dense_replace=1, max_position_embeddings=128, rms_norm_eps=1e-6, pad_token_id=0, tie_word_embeddings=False)
+    hc = hc if v2 else transformers.DeepseekV3Config(
         vocab_size=320, hidden_size=128, intermediate_size=256, moe_intermediate_size=128, num_hidden_layers=n_layers, num_attention_heads=4,
         num_key_value_heads=4, n_shared_experts=1, n_routed_experts=8, routed_scaling_factor=2.5, kv_lora_rank=32, qk_rope_head_dim=16,
         v_head_dim=32, qk_nope_head_dim=32, n_group=4, topk_group=2, num_experts_per_tok=2,
         first_k_dense_replace=n_layers if variant == "dense" else 1, norm_topk_prob=True, max_position_embeddings=128, rms_norm_eps=1e-6,
         pad_token_id=0, tie_word_embeddings=False, **kw)
-    m = transformers.DeepseekV3ForCausalLM(hc).eval().float()
+    m = (transformers.DeepseekV2ForCausalLM if v2 else transformers.DeepseekV3ForCausalLM)(hc).eval().float()
+    for mod in m.modules():          # transformers 5.5: DeepseekV2Moe's group-limited branch reads an attribute its __init__ never sets
+        if "topk_method" in vars(mod):
+            mod.num_experts = hc.n_routed_experts
     _randomise_(m)
     cfg = ModelConfig.from_hf_config(m.config.to_dict())
+    if v2:
+        assert cfg.moe_router == "softmax" and cfg.shared_expert_intermediate_size == 256 and cfg.n_group == (4 if variant == "v2_group_limited" else 1)
     assert cfg.attn_type == "mla" and cfg.head_dim == 48 and cfg.kv_cache_layout() == (1, 48, False)
     assert bool(cfg.num_experts) == (variant != "dense") and cfg.dense_layers == (() if variant == "dense" else (0,))
     w = TransformerWeights(cfg, "cpu", torch.float32, init=False)
@@ -467,10 +480,14 @@ def test_deepseek_v3_mla_matches_hf(variant, tmp_path):
     for u, src in [(e2.embed, w.embed), (e2.head, w.head)] + list(zip(e2.layers, w.layers)):
         u.load_full_state(src)
     hf_io.save_hf(e2, cfg, tmp_path / "ck", dtype=torch.float32)
-    m2 = transformers.DeepseekV3ForCausalLM.from_pretrained(tmp_path / "ck", dtype=torch.float32).eval()
+    m2 = type(m).from_pretrained(tmp_path / "ck", dtype=torch.float32).eval()
+    for mod in m2.modules():
+        if "topk_method" in vars(mod):
+            mod.num_experts = cfg.num_experts
     with torch.no_grad():
         assert (m2(ids).logits - want).abs().max() < 1e-4
     cfg2 = get_model_config(str(tmp_path / "ck"))
+    assert (cfg2.moe_router, cfg2.n_group, cfg2.routed_scaling_factor) == (cfg.moe_router, cfg.n_group, cfg.routed_scaling_factor)
     assert (cfg2.attn_type, cfg2.q_lora_rank, cfg2.kv_lora_rank, cfg2.rope_interleaved, cfg2.rope_scaling, cfg2.dense_layers, cfg2.num_experts) == \
         (cfg.attn_type, cfg.q_lora_rank, cfg.kv_lora_rank, cfg.rope_interleaved, cfg.rope_scaling, cfg.dense_layers, cfg.num_experts)
     back = hf_io.load_state_dict(cfg2, tmp_path / "ck")
