@@ -139,10 +139,10 @@ def paged_latent_attention(q: torch.Tensor, pool: torch.Tensor, block_table: tor
     b = q.shape[0]
     page = pool.shape[2]
     ent = pool[block_table.long(), 0].reshape(b, block_table.shape[1] * page, pool.shape[-1])          # [B, L, r + rope]
-    s = torch.einsum("bhc,blc->bhl", q.float(), ent.float()) * scale
+    s = torch.bmm(q, ent.transpose(1, 2)).float() * scale                                              # tensor-core GEMM in the cache dtype, fp32 softmax
     dead = torch.arange(ent.shape[1], device=q.device)[None, :] >= seq_lens.long().clamp(min=1)[:, None]      # idle slots: finite rows
     p = torch.softmax(s.masked_fill(dead[:, None, :], float("-inf")), dim=-1)
-    return torch.einsum("bhl,blc->bhc", p, ent[..., :r].float()).to(q.dtype)
+    return torch.bmm(p.to(ent.dtype), ent[..., :r])
 
 
 def attention_decode(cfg: ModelConfig, w: dict, h: torch.Tensor, inp, pool: torch.Tensor) -> torch.Tensor:
