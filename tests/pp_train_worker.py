@@ -40,7 +40,7 @@ def main():
             g = dist.new_group(list(range(s, world, pp)))
             if s == rank % pp:
                 dp_group = g
-        cfg = get_model_config("tiny-llama", num_layers=n_layers, tie_word_embeddings=tied)
+        cfg = get_model_config(os.environ.get("PP_TRAIN_MODEL", "tiny-llama"), num_layers=n_layers, tie_word_embeddings=tied)
         if virt > 1:
             eng = InterleavedPipelineEngine(cfg, dev, pp_group, dp_group if dp > 1 else None, virtual_stages=virt, lr=1e-2,
                                             weight_decay=0.0, seed=11)
