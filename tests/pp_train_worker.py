@@ -79,6 +79,9 @@ def main():
                     loss = (-(rlp.mean()) + 0.01 * rent.mean()) / n_micro
                     (loss / dp).backward()
                     ref_losses[(d, k)] = loss.item()
+            for p in params.values():                 # selection-only parameters (router score bias) get no gradient
+                if p.grad is None:
+                    p.grad = torch.zeros_like(p)
             gn = torch.sqrt(sum(p.grad.pow(2).sum() for p in params.values())).item()
             coef = min(1.0, 1.0 / (gn + 1e-6))
             with torch.no_grad():

@@ -222,6 +222,11 @@ def test_pipeline_parallel_training_1f1b_gloo_ws4():
     r = run_torchrun([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=4", "--master-addr", "127.0.0.1",
                         "--master-port", "29758", str(ROOT / "tests" / "pp_train_worker.py")], capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0 and "PP_TRAIN_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+    # the same schedules over DeepSeek-V3 blocks (latent attention, dense first block, sigmoid group-limited experts + shared expert)
+    r = run_torchrun([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=4", "--master-addr", "127.0.0.1",
+                        "--master-port", "29759", str(ROOT / "tests" / "pp_train_worker.py")], capture_output=True, text=True, timeout=600,
+                       env={**env, "PP_TRAIN_MODEL": "tiny-deepseek-v3"})
+    assert r.returncode == 0 and "PP_TRAIN_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
 
 
 def test_expert_parallel_training_gloo_ws4():
