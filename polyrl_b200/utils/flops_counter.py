@@ -36,8 +36,8 @@ class FlopsCounter:
     def _dense_params(self) -> int:
         c = self.cfg
         h, f, v = c.hidden_size, c.intermediate_size, c.vocab_size
-        dense_mlp = 3 * h * f if c.family == "llama" else 2 * h * f
-        attn = c.attn_num_params()
+        dense_mlp = 3 * h * f if (c.family == "llama" and c.mlp_act == "swiglu") else 2 * h * f      # gated vs plain / xIELU MLP
+        attn = c.attn_num_params() - ((c.kv_lora_rank + c.q_lora_rank) if c.attn_type == "mla" else 0)      # projections only, not the latent norm gains
         if c.num_experts:                                 # MoE: only the routed (+ shared) experts and the router do work per token
             sparse_mlp = (c.num_experts_per_tok * 3 * h * c.moe_intermediate_size + c.num_experts * h
                           + 3 * h * c.shared_expert_intermediate_size + (h if c.shared_expert_gate else 0))

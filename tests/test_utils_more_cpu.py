@@ -45,6 +45,37 @@ def test_flops_counter_matches_6nd_rule():
     assert short < tf_s and abs((tf_s - short) * 1e12 - 12 * cfg.num_layers * cfg.q_size * 32 * (512 * 512 - 512 * 128)) / (tf_s * 1e12) < 1e-9
 
 
+def test_flops_counter_latent_attention_and_plain_mlp_families():
+    """FLOPs-relevant parameters = all parameters minus the input embedding, the norm gains / activation scalars and the idle experts:
+    holds for the multi-head-latent-attention MoE stacks (DeepSeek-V3, V2-Lite, Moonlight) and the non-gated xIELU MLP (Apertus);
+    MLA attention FLOPs count nope + rope query / key features and v_head_dim value features."""
+    from polyrl_b200.models import get_model_config
+    from polyrl_b200.utils.flops_counter import FlopsCounter
+
+    for name in ("deepseek-v3", "deepseek-v2-lite", "moonlight-16b-a3b", "apertus-8b"):
+        c = get_model_config(name)
+        fc = FlopsCounter(c)
+        small = c.num_layers * 2 * c.hidden_size + c.hidden_size                     # block norms + final norm
+        if c.attn_type == "mla":
+            small += c.num_layers * (c.kv_lora_rank + c.q_lora_rank)                    # latent norm gains
+        if c.mlp_act == "xielu":
+            small += 2 * c.num_layers
+        if c.qk_norm:
+            small += 2 * c.head_dim * c.num_layers                                      # per-head q / k norm gains
+        if c.moe_router == "sigmoid_group":
+            small += c.num_sparse_layers() * c.num_experts                              # selection-only score bias
+        want = c.num_active_params() - c.vocab_size * c.hidden_size - small
+        assert abs(fc._dense_params() - want) / want < 1e-9, name
+        if c.attn_type == "mla":
+            a, _ = fc.estimate_flops([1024], 1.0)
+            b, _ = fc.estimate_flops([2048], 1.0)
+            quad = ((b - 2 * a) * 1e12) / (12.0 * c.num_layers * (2048 ** 2 - 2 * 1024 ** 2))
+            assert abs(quad - c.num_heads * 0.5 * (c.head_dim + c.v_head_dim)) / quad < 1e-6
+    v3 = get_model_config("deepseek-v3")
+    assert 6.6e11 < v3.num_params() < 6.9e11 and 3.6e10 < v3.num_active_params() < 3.9e10          # 671 B total / 37 B active
+    assert get_model_config("deepseek-v2-lite").kv_cache_layout() == (1, 576, False)
+
+
 def test_model_merger_roundtrip_and_hf_names(tmp_path):
     from polyrl_b200.models import get_model_config
     from polyrl_b200.models import transformer as tf
