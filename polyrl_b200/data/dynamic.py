@@ -16,12 +16,11 @@ from .rl_dataset import RLHFDataset
 
 def load_extern_type(path: str | None, name: str):
     """Class ``name`` from a python file (or from this module when ``path`` is empty)."""
+    from ..utils.import_utils import load_extern_type as _load
+
     if not path:
         return globals()[name]
-    spec = importlib.util.spec_from_file_location("polyrl_extern", path)
-    mod = importlib.util.module_from_spec(spec)
-    spec.loader.exec_module(mod)
-    return getattr(mod, name)
+    return _load(path, name)
 
 
 class AbstractDataGenerator(ABC):

@@ -116,6 +116,9 @@ class ActorRolloutRefWorker:
         cfg = self.config
         arr = cfg.actor_rollout_ref
         from ..utils.fs import is_non_local, stage_path
+        from ..utils.import_utils import import_external_libs
+
+        import_external_libs(getattr(arr.model, "external_lib", None))     # user registrations (presets, reward functions, tools) as an import side effect
 
         if is_non_local(arr.model.path) or getattr(arr.model, "use_shm", False):      # hdfs:// checkpoints are fetched once per node
             arr.model.path = stage_path(arr.model.path, use_shm=bool(getattr(arr.model, "use_shm", False)))

@@ -703,3 +703,111 @@ def test_reward_model_worker_scores_and_switches_tokenizers():
     assert s2.shape == (3, 8) and all(float(s2[i].abs().sum()) == float(s2[i, last[i]].abs()) for i in range(3))
     sw = w2._switch_tokenizer(b)
     assert sw.batch["input_ids"].shape == b.batch["input_ids"].shape and sw.batch["attention_mask"][:, 12:].sum() > 0
+
+
+def _slow_square(x, delay=0.0):
+    import time as _t
+
+    _t.sleep(delay)
+    return x * x
+
+
+def _raises(x):
+    raise KeyError(x)
+
+
+def test_py_functional_groupwise_import_utils_and_dtypes(tmp_path, monkeypatch):
+    """The small utility surface users of the reference stack rely on (its tests: test_timeout_decorator_cpu, test_temp_env_on_cpu,
+    test_groupwise, test_import_utils_on_cpu): wall-clock limits in a child process and through SIGALRM, scoped environment
+    overrides, conflict-checked dict union, nested namespaces, run-time extensible enums, group statistics equal to a per-group
+    loop, external-library / extern-type loading, precision names."""
+    import os
+    import warnings
+
+    from polyrl_b200.utils import groupwise, import_utils, py_functional as P
+    from polyrl_b200.utils.torch_dtypes import PrecisionType
+
+    # ---- timeout_limit: child-process mode (kills a call that never returns), exceptions travel back, signal mode
+    assert P.timeout_limit(5.0)(_slow_square)(7) == 49
+    with pytest.raises(TimeoutError):
+        P.timeout_limit(0.3)(_slow_square)(3, delay=5.0)
+    with pytest.raises(KeyError):
+        P.timeout_limit(5.0)(_raises)("k")
+    with pytest.raises(TimeoutError):
+        P.timeout_limit(0.2, use_signals=True)(_slow_square)(3, delay=5.0)
+    assert P.timeout_limit(2.0, use_signals=True)(_slow_square)(4) == 16
+    # ---- temp_env_var restores (also on error, also for previously unset keys)
+    monkeypatch.setenv("PRL_T", "old")
+    monkeypatch.delenv("PRL_U", raising=False)
+    with P.temp_env_var("PRL_T", "new"), P.temp_env_var("PRL_U", "1"):
+        assert os.environ["PRL_T"] == "new" and os.environ["PRL_U"] == "1"
+        with P.temp_env_var("PRL_T", None):
+            assert "PRL_T" not in os.environ
+        assert os.environ["PRL_T"] == "new"
+    assert os.environ["PRL_T"] == "old" and "PRL_U" not in os.environ
+    with pytest.raises(RuntimeError):
+        with P.temp_env_var("PRL_U", "x"):
+            raise RuntimeError
+    assert "PRL_U" not in os.environ
+    # ---- dict helpers, namespaces, dynamic enums
+    assert P.union_two_dict({"a": 1, "t": torch.ones(2)}, {"b": 2, "a": 1, "t": torch.ones(2)})["b"] == 2
+    with pytest.raises(ValueError):
+        P.union_two_dict({"a": 1}, {"a": 2})
+    acc = P.append_to_dict(P.append_to_dict({}, {"loss": 1.0}, "actor/"), {"loss": 2.0}, "actor/")
+    assert acc == {"actor/loss": [1.0, 2.0]}
+    ns = P.NestedNamespace({"actor": {"optim": {"lr": 1e-6}, "stages": [{"n": 1}, {"n": 2}]}})
+    assert ns.actor.optim.lr == 1e-6 and ns.actor.stages[1].n == 2 and ns.to_dict() == {"actor": {"optim": {"lr": 1e-6}, "stages": [{"n": 1}, {"n": 2}]}}
+
+    class Estimator(P.DynamicEnum):
+        pass
+
+    class Other(P.DynamicEnum):
+        pass
+
+    g, r = Estimator.register("grpo"), Estimator.register("rloo")
+    assert Estimator.GRPO is g and r.value == 1 and Estimator["RLOO"] is r and "GRPO" in Estimator and len(Estimator) == 2 and list(Estimator) == [g, r]
+    assert len(Other) == 0 and Estimator.from_name("nope") is None
+    with pytest.raises(ValueError):
+        Estimator.register("GRPO")
+    Estimator.remove("grpo")
+    assert not hasattr(Estimator, "GRPO") and len(Estimator) == 1
+    # ---- group statistics
+    gen = torch.Generator().manual_seed(0)
+    scores = torch.randn(23, generator=gen)
+    uids = [f"u{int(i)}" for i in torch.randint(0, 6, (22,), generator=gen)] + ["lonely"]
+    gi = groupwise.as_torch_index(uids)
+    assert gi[-1].item() == gi.max().item() and gi[0].item() == 0
+    mean, std, cnt = groupwise.group_mean_std(scores, gi)
+    for k in range(int(gi.max()) + 1):
+        sel = scores[gi == k]
+        if sel.numel() == 1:
+            assert mean[k] == 0 and std[k] == 1 and cnt[k] == 1
+        else:
+            assert abs(mean[k] - sel.mean()) < 1e-5 and abs(std[k] - sel.std(unbiased=True).clamp_min(1e-3)) < 1e-4 and cnt[k] == sel.numel()
+    assert torch.equal(groupwise.as_torch_index(torch.tensor([5, 5, 9, 5, 2])), torch.tensor([0, 0, 1, 0, 2]))
+    assert all(t.numel() == 0 for t in groupwise.group_mean_std(torch.empty(0), torch.empty(0, dtype=torch.long)))
+    # ---- import utils
+    assert import_utils.is_available("torch") and not import_utils.is_available("definitely_not_installed_xyz") and not import_utils.is_sglang_available()
+    (tmp_path / "prl_ext_lib.py").write_text("REGISTERED = []\nREGISTERED.append('hello')\n\nclass MyReward:\n    tag = 'mine'\n")
+    monkeypatch.syspath_prepend(str(tmp_path))
+    mods = import_utils.import_external_libs("prl_ext_lib, json")
+    assert mods[0].REGISTERED == ["hello"] and import_utils.import_external_libs(None) == []
+    cls = import_utils.load_extern_type(str(tmp_path / "prl_ext_lib.py"), "MyReward")
+    assert cls.tag == "mine" and import_utils.load_extern_type(str(tmp_path / "prl_ext_lib.py"), "MyReward") is cls          # cached module
+    assert import_utils.load_extern_type("pkg://json", "dumps") is json.dumps
+    with pytest.raises(AttributeError):
+        import_utils.load_extern_type(str(tmp_path / "prl_ext_lib.py"), "Missing")
+    with pytest.raises(FileNotFoundError):
+        import_utils.load_extern_type(str(tmp_path / "nope.py"), "X")
+
+    @import_utils.deprecated("new_fn")
+    def old_fn(x):
+        return x + 1
+
+    with warnings.catch_warnings(record=True) as rec:
+        warnings.simplefilter("always")
+        assert old_fn(1) == 2
+    assert rec and "new_fn" in str(rec[0].message) and issubclass(rec[0].category, FutureWarning)
+    # ---- precision names
+    assert PrecisionType.to_dtype("bf16") is torch.bfloat16 and PrecisionType.to_dtype("16-mixed") is torch.float16 and PrecisionType.to_dtype(torch.float32) is torch.float32
+    assert PrecisionType.is_bf16("torch.bfloat16") and PrecisionType.is_fp32("float") and PrecisionType.to_str("half") == "fp16" and not PrecisionType.supported("int8")
