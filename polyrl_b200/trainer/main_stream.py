@@ -39,6 +39,9 @@ def _init_dist(device_type: str, timeout_s: int | None = None):
             os.environ.setdefault("GLOO_SOCKET_IFNAME", "lo")       # single node: never resolve the (possibly unresolvable) hostname
         if device_type == "cuda":
             torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", 0)))
+            from ..utils.affinity import set_numa_affinity
+
+            set_numa_affinity(int(os.environ.get("LOCAL_RANK", 0)))          # opt-in: POLYRL_NUMA_AFFINITY=1
             dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ.get("LOCAL_RANK", 0))), **kw)
         else:
             dist.init_process_group("gloo", **kw)

@@ -811,3 +811,36 @@ def test_py_functional_groupwise_import_utils_and_dtypes(tmp_path, monkeypatch):
     # ---- precision names
     assert PrecisionType.to_dtype("bf16") is torch.bfloat16 and PrecisionType.to_dtype("16-mixed") is torch.float16 and PrecisionType.to_dtype(torch.float32) is torch.float32
     assert PrecisionType.is_bf16("torch.bfloat16") and PrecisionType.is_fp32("float") and PrecisionType.to_str("half") == "fp16" and not PrecisionType.supported("int8")
+
+
+def test_numa_affinity_uses_the_gpus_cpu_mask(monkeypatch):
+    """``set_numa_affinity``: opt-in, maps the local rank through CUDA_VISIBLE_DEVICES to the NVML index, applies the intersection of
+    the GPU's CPU mask with the CPUs this process may use, and survives NVML errors (driven against a stand-in pynvml)."""
+    import os
+    import sys
+    import types
+
+    from polyrl_b200.utils import affinity
+
+    if not hasattr(os, "sched_setaffinity"):
+        pytest.skip("no sched_setaffinity")
+    allowed = sorted(os.sched_getaffinity(0))
+    asked: list = []
+    nv = types.ModuleType("pynvml")
+    nv.nvmlInit = lambda: None
+    nv.nvmlShutdown = lambda: None
+    nv.nvmlDeviceGetHandleByIndex = lambda i: asked.append(i) or i
+    keep = allowed[: max(1, len(allowed) // 2)]
+    mask_bits = sum(1 << c for c in keep) | (1 << 1000)                        # plus a CPU this container does not have
+    nv.nvmlDeviceGetCpuAffinity = lambda h, words: [(mask_bits >> (64 * w)) & ((1 << 64) - 1) for w in range(max(words, 16))]
+    monkeypatch.setitem(sys.modules, "pynvml", nv)
+    monkeypatch.delenv("POLYRL_NUMA_AFFINITY", raising=False)
+    try:
+        assert affinity.set_numa_affinity(0) is None and not asked                # off by default
+        monkeypatch.setenv("POLYRL_NUMA_AFFINITY", "1")
+        monkeypatch.setenv("CUDA_VISIBLE_DEVICES", "4,6")
+        assert affinity.set_numa_affinity(1) == keep and asked == [6] and sorted(os.sched_getaffinity(0)) == keep
+        nv.nvmlDeviceGetHandleByIndex = lambda i: (_ for _ in ()).throw(RuntimeError("nvml down"))
+        assert affinity.set_numa_affinity(0) is None                               # reported, not raised
+    finally:
+        os.sched_setaffinity(0, allowed)
